@@ -1,0 +1,224 @@
+/*
+ * orc_tail.c -- restatement of internal/mct/mct.go (RCT, ICT, DC shift) and of
+ * the tail of the reference decoder: decoder.go:321-348 (inverse MCT + DC
+ * shift) and decoder.createImage decoder.go:417-599 (clamp, precision scaling,
+ * packing into the Go image Pix layouts).  Also the threaded whole-path driver
+ * used as the CPU baseline.  Oracle / test infrastructure only.
+ */
+#include "oracle.h"
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define WADD(a, b) ((int32_t)((uint32_t)(a) + (uint32_t)(b)))
+#define WSUB(a, b) ((int32_t)((uint32_t)(a) - (uint32_t)(b)))
+#define WMUL(a, b) ((int32_t)((uint32_t)(a) * (uint32_t)(b)))
+
+void orc_fwd_rct(int32_t *r, int32_t *g, int32_t *b, size_t n)      /* mct.go:28-38 */
+{
+    for (size_t i = 0; i < n; i++) {
+        int32_t y = WADD(WADD(r[i], WMUL(2, g[i])), b[i]) >> 2;
+        int32_t u = WSUB(b[i], g[i]), v = WSUB(r[i], g[i]);
+        r[i] = y; g[i] = u; b[i] = v;
+    }
+}
+
+void orc_inv_rct(int32_t *y, int32_t *u, int32_t *v, size_t n)      /* mct.go:56-66 */
+{
+    for (size_t i = 0; i < n; i++) {
+        int32_t g = WSUB(y[i], WADD(u[i], v[i]) >> 2);
+        int32_t r = WADD(v[i], g), b = WADD(u[i], g);
+        y[i] = r; u[i] = g; v[i] = b;
+    }
+}
+
+void orc_fwd_ict(double *r, double *g, double *b, size_t n)         /* mct.go:14-24 */
+{
+    for (size_t i = 0; i < n; i++) {
+        double y  = 0.299 * r[i] + 0.587 * g[i] + 0.114 * b[i];
+        double cb = -0.16875 * r[i] - 0.33126 * g[i] + 0.5 * b[i];
+        double cr = 0.5 * r[i] - 0.41869 * g[i] - 0.08131 * b[i];
+        r[i] = y; g[i] = cb; b[i] = cr;
+    }
+}
+
+void orc_inv_ict(double *y, double *cb, double *cr, size_t n)       /* mct.go:43-53 */
+{
+    for (size_t i = 0; i < n; i++) {
+        double r = y[i] + 1.402 * cr[i];
+        double g = y[i] - 0.34413 * cb[i] - 0.71414 * cr[i];
+        double b = y[i] + 1.772 * cb[i];
+        y[i] = r; cb[i] = g; cr[i] = b;
+    }
+}
+
+void orc_dc_shift_forward(int32_t *d, size_t n, int prec)           /* mct.go:96-101 */
+{
+    int32_t s = (int32_t)((uint32_t)1 << (prec - 1));
+    for (size_t i = 0; i < n; i++) d[i] = WSUB(d[i], s);
+}
+
+void orc_dc_shift_inverse(int32_t *d, size_t n, int prec)           /* mct.go:113-118 */
+{
+    int32_t s = (int32_t)((uint32_t)1 << (prec - 1));
+    for (size_t i = 0; i < n; i++) d[i] = WADD(d[i], s);
+}
+
+/* decoder.go:321-348 */
+void orc_decoder_tail(int32_t *const *comps, int ncomp, size_t n, int mct, int reversible,
+                      const uint8_t *prec, const uint8_t *sgnd)
+{
+    if (mct != 0 && ncomp >= 3) {
+        if (reversible) {
+            orc_inv_rct(comps[0], comps[1], comps[2], n);
+        } else {
+            double *f[3];
+            for (int c = 0; c < 3; c++) {
+                f[c] = malloc(sizeof(double) * (n ? n : 1));
+                for (size_t i = 0; i < n; i++) f[c][i] = (double)comps[c][i];
+            }
+            orc_inv_ict(f[0], f[1], f[2], n);
+            for (int c = 0; c < 3; c++) {
+                for (size_t i = 0; i < n; i++) comps[c][i] = (int32_t)(f[c][i] + 0.5);  /* truncating */
+                free(f[c]);
+            }
+        }
+    }
+    for (int c = 0; c < ncomp; c++)
+        if (!sgnd[c]) orc_dc_shift_inverse(comps[c], n, prec[c]);
+}
+
+static inline int32_t clamp_i32(int32_t v, int32_t lo, int32_t hi)   /* decoder.go:591-599 */
+{
+    return v < lo ? lo : (v > hi ? hi : v);
+}
+
+/* decoder.createImage decoder.go:417-588.  `v*65535/maxVal` is evaluated in
+ * int32 like the reference (the product wraps for 16-bit samples). */
+int orc_create_image(const int32_t *const *comps, int w, int h, int ncomp, int prec, uint8_t *pix)
+{
+    int32_t maxv = (int32_t)(((uint64_t)1 << prec) - 1);
+    size_t n = (size_t)w * h;
+    if (ncomp != 1 && ncomp != 3 && ncomp != 4) return -1;         /* decoder.go:585-586 */
+    int nch = ncomp == 1 ? 1 : 4;
+    if (prec <= 8) {
+        for (size_t i = 0; i < n; i++) {
+            for (int c = 0; c < nch; c++) {
+                int32_t v;
+                if (c < ncomp) {
+                    v = clamp_i32(comps[c][i], 0, maxv);
+                    if (prec != 8) v = WMUL(v, 255) / maxv;
+                } else v = 255;                                      /* opaque alpha for 3 components */
+                pix[i * nch + c] = (uint8_t)v;
+            }
+        }
+        return nch;
+    }
+    for (size_t i = 0; i < n; i++) {
+        for (int c = 0; c < nch; c++) {
+            int32_t v;
+            if (c < ncomp) {
+                v = clamp_i32(comps[c][i], 0, maxv);
+                v = WMUL(v, 65535) / maxv;
+            } else v = 65535;
+            uint16_t u = (uint16_t)v;
+            pix[(i * nch + c) * 2] = (uint8_t)(u >> 8);              /* Go image.Gray16/RGBA64: big-endian */
+            pix[(i * nch + c) * 2 + 1] = (uint8_t)u;
+        }
+    }
+    return nch * 2;
+}
+
+/* ---------------- whole-path driver (CPU baseline) ---------------------------- */
+typedef struct {
+    const orc_image_t *img; const orc_tilecomp_t *tcs; uint32_t n_tc;
+    const orc_cblk_t *cbs; uint32_t n_cb; const uint8_t *blob;
+    int32_t **planes;            /* per tile-component coefficient planes */
+    volatile uint32_t next;      /* work counter */
+    int stage;
+} job_t;
+
+static void *worker(void *arg)
+{
+    job_t *j = (job_t *)arg;
+    for (;;) {
+        uint32_t i = __atomic_fetch_add(&j->next, 1, __ATOMIC_RELAXED);
+        if (j->stage == 0) {                       /* block entropy decode */
+            if (i >= j->n_cb) break;
+            const orc_cblk_t *cb = &j->cbs[i];
+            const orc_tilecomp_t *tc = &j->tcs[cb->tilecomp];
+            int tw = (int)(tc->x1 - tc->x0);
+            int32_t *tmp = malloc(sizeof(int32_t) * (size_t)cb->w * cb->h + 4);
+            if (cb->data_len == 0) memset(tmp, 0, sizeof(int32_t) * (size_t)cb->w * cb->h);  /* tcd.go:394-396 */
+            else if (j->img->ht) orc_ht_decode(j->blob + cb->data_off, (int)cb->data_len, cb->w, cb->h, tmp);
+            else orc_t1_decode(j->blob + cb->data_off, (int)cb->data_len, cb->w, cb->h, cb->num_bps, cb->band, tmp);
+            int32_t *plane = j->planes[cb->tilecomp];
+            for (int y = 0; y < cb->h; y++)
+                memcpy(plane + (size_t)(cb->y0 + y) * tw + cb->x0, tmp + (size_t)y * cb->w, sizeof(int32_t) * cb->w);
+            free(tmp);
+        } else {                                   /* inverse DWT per tile-component */
+            if (i >= j->n_tc) break;
+            const orc_tilecomp_t *tc = &j->tcs[i];
+            orc_apply_inverse_dwt(j->planes[i], (int)(tc->x1 - tc->x0), (int)(tc->y1 - tc->y0),
+                                  j->img->nlevels, j->img->reversible);
+        }
+    }
+    return NULL;
+}
+
+static void run_stage(job_t *j, int stage, int threads)
+{
+    j->stage = stage; j->next = 0;
+    if (threads <= 1) { worker(j); return; }
+    pthread_t *th = malloc(sizeof(pthread_t) * (size_t)threads);
+    for (int t = 0; t < threads; t++) pthread_create(&th[t], NULL, worker, j);
+    for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+    free(th);
+}
+
+int orc_decode_image(const orc_image_t *img, const orc_tilecomp_t *tcs, uint32_t n_tc,
+                     const orc_cblk_t *cbs, uint32_t n_cb, const uint8_t *blob, uint64_t blob_len,
+                     uint8_t *out_pix, uint64_t out_stride, int threads)
+{
+    if (!img || !tcs || !out_pix || img->ncomp == 0 || img->ncomp > 4) return -1;
+    for (uint32_t i = 0; i < n_cb; i++) {
+        if (cbs[i].tilecomp >= n_tc) return -1;
+        if (cbs[i].data_off + cbs[i].data_len > blob_len) return -2;
+    }
+    job_t j; memset(&j, 0, sizeof j);
+    j.img = img; j.tcs = tcs; j.n_tc = n_tc; j.cbs = cbs; j.n_cb = n_cb; j.blob = blob;
+    j.planes = calloc(n_tc ? n_tc : 1, sizeof(int32_t *));
+    for (uint32_t i = 0; i < n_tc; i++) {
+        size_t n = (size_t)(tcs[i].x1 - tcs[i].x0) * (tcs[i].y1 - tcs[i].y0);
+        j.planes[i] = calloc(n ? n : 1, sizeof(int32_t));           /* tcd.go:283 zero Data */
+    }
+    run_stage(&j, 0, threads);
+    run_stage(&j, 1, threads);
+
+    size_t W = img->width, H = img->height, n = W * H;
+    int32_t *comps[4] = {0, 0, 0, 0};
+    for (int c = 0; c < img->ncomp; c++) comps[c] = calloc(n ? n : 1, sizeof(int32_t));
+    for (uint32_t i = 0; i < n_tc; i++) {                           /* decoder.go:398-410 */
+        const orc_tilecomp_t *tc = &tcs[i];
+        if (tc->comp >= img->ncomp) continue;
+        size_t tw = tc->x1 - tc->x0;
+        for (uint32_t y = tc->y0; y < tc->y1 && y < H; y++)
+            for (uint32_t x = tc->x0; x < tc->x1 && x < W; x++)
+                comps[tc->comp][(size_t)y * W + x] = j.planes[i][(size_t)(y - tc->y0) * tw + (x - tc->x0)];
+    }
+    orc_decoder_tail(comps, img->ncomp, n, img->mct, img->reversible, img->prec, img->sgnd);
+    int bpp = img->ncomp == 1 ? (img->prec[0] <= 8 ? 1 : 2) : (img->prec[0] <= 8 ? 4 : 8);
+    int rc = 0;
+    if (out_stride == W * (size_t)bpp) {
+        if (orc_create_image((const int32_t *const *)comps, (int)W, (int)H, img->ncomp, img->prec[0], out_pix) < 0) rc = -3;
+    } else {
+        uint8_t *tmp = malloc(n * (size_t)bpp + 1);
+        if (orc_create_image((const int32_t *const *)comps, (int)W, (int)H, img->ncomp, img->prec[0], tmp) < 0) rc = -3;
+        else for (size_t y = 0; y < H; y++) memcpy(out_pix + y * out_stride, tmp + y * W * bpp, W * (size_t)bpp);
+        free(tmp);
+    }
+    for (int c = 0; c < img->ncomp; c++) free(comps[c]);
+    for (uint32_t i = 0; i < n_tc; i++) free(j.planes[i]);
+    free(j.planes);
+    return rc;
+}

@@ -1,0 +1,200 @@
+"""ctypes binding of oracle/liboracle.so (the CPU restatement of the reference path).
+
+Test infrastructure only -- imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  Builds the library with oracle/Makefile on first use.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+_lib = None
+
+u8p = C.POINTER(C.c_uint8)
+i32p = C.POINTER(C.c_int32)
+f64p = C.POINTER(C.c_double)
+
+
+class CBlk(C.Structure):  # == j2k_cblk_t
+    _fields_ = [("data_off", C.c_uint64), ("data_len", C.c_uint32), ("tilecomp", C.c_uint32),
+                ("x0", C.c_uint16), ("y0", C.c_uint16), ("w", C.c_uint16), ("h", C.c_uint16),
+                ("band", C.c_uint8), ("level", C.c_uint8), ("num_bps", C.c_uint8), ("num_passes", C.c_uint8),
+                ("step", C.c_float)]
+
+
+class TileComp(C.Structure):  # == j2k_tilecomp_t
+    _fields_ = [("comp", C.c_uint32), ("x0", C.c_uint32), ("y0", C.c_uint32), ("x1", C.c_uint32),
+                ("y1", C.c_uint32), ("coeff_off", C.c_uint64)]
+
+
+class Image(C.Structure):  # == j2k_image_t
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("ncomp", C.c_uint16),
+                ("prec", C.c_uint8 * 4), ("sgnd", C.c_uint8 * 4), ("mct", C.c_uint8),
+                ("reversible", C.c_uint8), ("nlevels", C.c_uint8), ("ht", C.c_uint8),
+                ("mode", C.c_uint8), ("out_fmt", C.c_uint8)]
+
+
+def build(force=False):
+    so = os.path.join(ORACLE_DIR, "liboracle.so")
+    srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".c", ".h", ".inc"))]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "liboracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        L = _lib
+        L.orc_mq_encode.restype = C.c_int
+        L.orc_t1_encode.restype = C.c_int
+        L.orc_ht_encode.restype = C.c_int
+        L.orc_create_image.restype = C.c_int
+        L.orc_decode_image.restype = C.c_int
+        L.orc_t1_zc_lut.restype = u8p
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+def mq_encode(ctxs, bits):
+    ctxs = np.ascontiguousarray(ctxs, np.uint8)
+    bits = np.ascontiguousarray(bits, np.uint8)
+    out = np.zeros(2 * len(bits) + 64, np.uint8)
+    n = lib().orc_mq_encode(_p(ctxs, u8p), _p(bits, u8p), len(bits), _p(out, u8p), len(out))
+    assert n >= 0
+    return out[:n].tobytes()
+
+
+def mq_decode(data, ctxs):
+    ctxs = np.ascontiguousarray(ctxs, np.uint8)
+    buf = np.frombuffer(bytes(data), np.uint8) if len(data) else np.zeros(1, np.uint8)
+    out = np.zeros(len(ctxs), np.uint8)
+    lib().orc_mq_decode(_p(buf, u8p), len(data), _p(ctxs, u8p), len(ctxs), _p(out, u8p))
+    return out
+
+
+def t1_encode(coeffs, w, h, band):
+    """-> (bytes, num_bps); bytes == b'' for an all-zero block (Go nil)."""
+    c = np.ascontiguousarray(coeffs, np.int32).reshape(-1)
+    assert c.size == w * h
+    out = np.zeros(w * h * 4 + 16384, np.uint8)
+    nb = C.c_int(0)
+    n = lib().orc_t1_encode(_p(c, i32p), w, h, band, _p(out, u8p), len(out), C.byref(nb))
+    assert n >= 0
+    return out[:n].tobytes(), nb.value
+
+
+def t1_decode(data, w, h, num_bps, band):
+    buf = np.frombuffer(bytes(data), np.uint8) if len(data) else np.zeros(1, np.uint8)
+    out = np.zeros(w * h, np.int32)
+    lib().orc_t1_decode(_p(buf, u8p), len(data), w, h, num_bps, band, _p(out, i32p))
+    return out
+
+
+def ht_encode(coeffs, w, h, band=0):
+    c = np.ascontiguousarray(coeffs, np.int32).reshape(-1)
+    assert c.size == w * h
+    out = np.zeros(max(w * h * 2, 64) * 2 + 64, np.uint8)
+    n = lib().orc_ht_encode(_p(c, i32p), w, h, band, _p(out, u8p), len(out))
+    if n < 0:
+        raise OverflowError("reference HT encoder would index out of range")
+    return out[:n].tobytes()
+
+
+def ht_decode(data, w, h):
+    buf = np.frombuffer(bytes(data), np.uint8) if len(data) else np.zeros(1, np.uint8)
+    out = np.zeros(w * h, np.int32)
+    lib().orc_ht_decode(_p(buf, u8p), len(data), w, h, _p(out, i32p))
+    return out
+
+
+def _inplace(fn, arr, *args):
+    fn(arr.ctypes.data_as(C.c_void_p), *args)
+    return arr
+
+
+def fwd53(d): d = np.array(d, np.int32); return _inplace(lib().orc_fwd53, d, len(d))
+def inv53(d): d = np.array(d, np.int32); return _inplace(lib().orc_inv53, d, len(d))
+def fwd97(d): d = np.array(d, np.float64); return _inplace(lib().orc_fwd97, d, len(d))
+def inv97(d): d = np.array(d, np.float64); return _inplace(lib().orc_inv97, d, len(d))
+def fwd2d53(d, w, h): d = np.array(d, np.int32).reshape(-1); return _inplace(lib().orc_fwd2d53, d, w, h)
+def inv2d53(d, w, h): d = np.array(d, np.int32).reshape(-1); return _inplace(lib().orc_inv2d53, d, w, h)
+def fwd2d97(d, w, h): d = np.array(d, np.float64).reshape(-1); return _inplace(lib().orc_fwd2d97, d, w, h)
+def inv2d97(d, w, h): d = np.array(d, np.float64).reshape(-1); return _inplace(lib().orc_inv2d97, d, w, h)
+def decompose53(d, w, h, L): d = np.array(d, np.int32).reshape(-1); return _inplace(lib().orc_decompose53, d, w, h, L)
+def reconstruct53(d, w, h, L): d = np.array(d, np.int32).reshape(-1); return _inplace(lib().orc_reconstruct53, d, w, h, L)
+def decompose97(d, w, h, L): d = np.array(d, np.float64).reshape(-1); return _inplace(lib().orc_decompose97, d, w, h, L)
+def reconstruct97(d, w, h, L): d = np.array(d, np.float64).reshape(-1); return _inplace(lib().orc_reconstruct97, d, w, h, L)
+
+
+def apply_inverse_dwt(d, w, h, levels, reversible):
+    d = np.array(d, np.int32).reshape(-1)
+    return _inplace(lib().orc_apply_inverse_dwt, d, w, h, levels, int(reversible))
+
+
+def quantize(d, step):
+    d = np.ascontiguousarray(d, np.float64)
+    out = np.zeros(d.size, np.int32)
+    lib().orc_quantize(_p(d, f64p), C.c_double(step), _p(out, i32p), C.c_size_t(d.size))
+    return out
+
+
+def _three(fn, a, b, c, dt):
+    a, b, c = (np.array(x, dt).reshape(-1) for x in (a, b, c))
+    fn(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), c.ctypes.data_as(C.c_void_p), C.c_size_t(a.size))
+    return a, b, c
+
+
+def fwd_rct(r, g, b): return _three(lib().orc_fwd_rct, r, g, b, np.int32)
+def inv_rct(y, u, v): return _three(lib().orc_inv_rct, y, u, v, np.int32)
+def fwd_ict(r, g, b): return _three(lib().orc_fwd_ict, r, g, b, np.float64)
+def inv_ict(y, cb, cr): return _three(lib().orc_inv_ict, y, cb, cr, np.float64)
+
+
+def dc_shift_inverse(d, prec):
+    d = np.array(d, np.int32).reshape(-1)
+    lib().orc_dc_shift_inverse(_p(d, i32p), C.c_size_t(d.size), prec)
+    return d
+
+
+def dc_shift_forward(d, prec):
+    d = np.array(d, np.int32).reshape(-1)
+    lib().orc_dc_shift_forward(_p(d, i32p), C.c_size_t(d.size), prec)
+    return d
+
+
+def decoder_tail(comps, mct, reversible, prec, sgnd):
+    comps = [np.array(c, np.int32).reshape(-1) for c in comps]
+    arr = (i32p * len(comps))(*[_p(c, i32p) for c in comps])
+    pr = (C.c_uint8 * 4)(*(list(prec) + [0] * (4 - len(prec))))
+    sg = (C.c_uint8 * 4)(*(list(sgnd) + [0] * (4 - len(sgnd))))
+    lib().orc_decoder_tail(arr, len(comps), C.c_size_t(comps[0].size), int(mct), int(reversible), pr, sg)
+    return comps
+
+
+def create_image(comps, w, h, prec):
+    comps = [np.ascontiguousarray(c, np.int32).reshape(-1) for c in comps]
+    arr = (i32p * max(len(comps), 1))(*[_p(c, i32p) for c in comps])
+    pix = np.zeros(w * h * 8, np.uint8)
+    bpp = lib().orc_create_image(arr, w, h, len(comps), prec, _p(pix, u8p))
+    if bpp < 0:
+        raise ValueError("unsupported number of components: %d" % len(comps))
+    return pix[: w * h * bpp].copy(), bpp
+
+
+def decode_image(img, tcs, cbs, blob, out_stride, out_size, threads=1):
+    """img: Image; tcs: ctypes array of TileComp; cbs: ctypes array of CBlk; blob: np.uint8."""
+    out = np.zeros(out_size, np.uint8)
+    blob = np.ascontiguousarray(blob, np.uint8)
+    rc = lib().orc_decode_image(C.byref(img), tcs, len(tcs), cbs, len(cbs), _p(blob, u8p),
+                                C.c_uint64(blob.size), _p(out, u8p), C.c_uint64(out_stride), threads)
+    if rc != 0:
+        raise RuntimeError("orc_decode_image rc=%d" % rc)
+    return out
