@@ -1,20 +1,10 @@
 /*
- * orc_t1.c -- restatement of the reference EBCOT tier-1 block coder
- * (internal/entropy/t1.go, t1_luts.go, t1_fast5.go).  Oracle / test
- * infrastructure only.
- *
- * Reference behaviour kept on purpose:
- *  - significance-propagation and magnitude-refinement passes scan in RASTER
- *    order (t1.go:1298-1299, 1334-1335); only the cleanup pass scans 4-row
- *    stripes column by column (t1.go:1353-1354);
- *  - every bit-plane runs all three passes, including the first;
- *  - run-length mode only when the full 4-row column exists (t1.go:1196);
- *  - the ZC table of t1_luts.go:35-110 and the sign rule of t1.go:387-460
- *    (vc is not negated when hc != 0);
- *  - all MQ contexts start in state 0 (UNI in 92).
+ * gen_t1.c -- restatement of the reference EBCOT tier-1 ENCODER: T1.SetData (t1.go:292-304) and
+ * T1.Encode = EncodeFast5 (t1_fast5.go:10-899; same decisions as EncodeSafe t1.go:923-947), with the
+ * context rules of t1.go:349-479 / t1_luts.go:35-110.  Part of datagen/ (synthetic-input generator).
  */
-#include "oracle.h"
-#include "orc_mq.h"
+#include "datagen.h"
+#include "gen_mq.h"
 #include <stdlib.h>
 #include <string.h>
 
@@ -35,14 +25,14 @@ static void zc_lut_init(void)
             int vcount = ((p >> 2) & 1) + ((p >> 3) & 1);
             int dcount = ((p >> 4) & 1) + ((p >> 5) & 1) + ((p >> 6) & 1) + ((p >> 7) & 1);
             int ctx;
-            if (band == ORC_BAND_HH) {
+            if (band == GEN_BAND_HH) {
                 int hv = hcount + vcount;
                 if (hv >= 3) ctx = 8;
                 else if (hv == 2) ctx = dcount >= 2 ? 7 : (dcount >= 1 ? 6 : 5);
                 else if (hv == 1) ctx = dcount >= 2 ? 4 : 3;
                 else ctx = dcount >= 2 ? 2 : (dcount >= 1 ? 1 : 0);
             } else {
-                if (band == ORC_BAND_HL) { int t = hcount; hcount = vcount; vcount = t; }
+                if (band == GEN_BAND_HL) { int t = hcount; hcount = vcount; vcount = t; }
                 if (hcount == 2) ctx = 8;
                 else if (hcount == 1) ctx = vcount >= 1 ? 7 : (dcount >= 1 ? 6 : 5);
                 else if (vcount == 2) ctx = 4;
@@ -55,7 +45,6 @@ static void zc_lut_init(void)
     g_zc_ready = 1;
 }
 
-const uint8_t *orc_t1_zc_lut(void) { zc_lut_init(); return g_zc_lut; }
 
 typedef struct {
     int w, h, stride, band;
@@ -102,18 +91,18 @@ static int sc_context(const t1_state *t, int i, int *pred)
     *pred = 0;
     if (hc < 0) { *pred = 1; hc = -hc; }
     if (hc == 0 && vc < 0) { *pred = 1; vc = -vc; }
-    int ctx = ORC_CTX_SC0;
-    if (hc == 1) ctx = ORC_CTX_SC0 + (vc == 1 ? 4 : (vc == 0 ? 2 : 1));
-    else if (hc == 0) ctx = ORC_CTX_SC0 + (vc == 1 ? 1 : 0);
-    else if (hc == 2) ctx = ORC_CTX_SC0 + 3;
+    int ctx = GEN_CTX_SC0;
+    if (hc == 1) ctx = GEN_CTX_SC0 + (vc == 1 ? 4 : (vc == 0 ? 2 : 1));
+    else if (hc == 0) ctx = GEN_CTX_SC0 + (vc == 1 ? 1 : 0);
+    else if (hc == 2) ctx = GEN_CTX_SC0 + 3;
     return ctx;
 }
 
 /* getMRContext t1.go:463-479 */
 static int mr_context(const t1_state *t, int i)
 {
-    if (t->flags[i] & F_REFINE) return ORC_CTX_MAG0 + 2;
-    return has_sig_neighbor(t, i) ? ORC_CTX_MAG0 + 1 : ORC_CTX_MAG0;
+    if (t->flags[i] & F_REFINE) return GEN_CTX_MAG0 + 2;
+    return has_sig_neighbor(t, i) ? GEN_CTX_MAG0 + 1 : GEN_CTX_MAG0;
 }
 
 /* canUseRunLength t1.go:1195-1208 */
@@ -128,65 +117,86 @@ static int can_run_length(const t1_state *t, int x, int y)
     return 1;
 }
 
-/* ============================ decoder ======================================== */
+/* ============================ encoder ======================================== */
+/* SetData t1.go:292-304 + EncodeFast5 t1_fast5.go:10-899 (same decisions as
+ * EncodeSafe t1.go:923-947; the directional-flag shortcut only skips samples
+ * that have no significant neighbour). */
 
-static void dec_sign(t1_state *t, orc_mqdec *mq, int i)            /* t1.go:1322-1328 */
+static void enc_sign(t1_state *t, gen_mqenc *mq, int i)            /* t1.go:482-555 */
 {
     int pred, ctx = sc_context(t, i, &pred);
-    if (orc_mqdec_decode(mq, ctx) ^ pred) t->flags[i] |= F_NEG;
+    int sign = (t->flags[i] & F_NEG) ? 1 : 0;
+    gen_mqenc_encode(mq, ctx, sign ^ pred);
 }
 
-static void dec_new_sig(t1_state *t, orc_mqdec *mq, int x, int y, int32_t bit)
-{
-    int i = FIDX(t, x, y);
-    t->mag[y * t->w + x] = bit;
-    dec_sign(t, mq, i);
-    t->flags[i] |= F_SIG;
-}
-
-void orc_t1_decode(const uint8_t *data, int len, int w, int h, int num_bps, int band, int32_t *out)
+int gen_t1_encode(const int32_t *coeffs, int w, int h, int band, uint8_t *out, int cap, int *num_bps)
 {
     zc_lut_init();
     t1_state t;
     t.w = w; t.h = h; t.stride = w + 2; t.band = band;
     t.flags = (uint8_t *)calloc((size_t)(w + 2) * (h + 2), 1);
-    t.mag = out;                                  /* decode magnitudes in place, sign applied last */
-    memset(out, 0, sizeof(int32_t) * (size_t)w * h);
-    orc_mqdec mq;
-    orc_mqdec_init(&mq, data, len);               /* t1.go:1264 */
+    t.mag = (int32_t *)malloc(sizeof(int32_t) * (size_t)w * h);
+    int32_t maxv = 0;
+    for (int y = 0; y < h; y++) {
+        for (int x = 0; x < w; x++) {
+            int32_t v = coeffs[y * w + x];
+            if (v < 0) { v = (int32_t)(0u - (uint32_t)v); t.flags[FIDX(&t, x, y)] |= F_NEG; }
+            t.mag[y * w + x] = v;
+            if (v > maxv) maxv = v;
+        }
+    }
+    int nbps = 0;
+    for (int32_t m = maxv; m > 0; m >>= 1) nbps++;                  /* t1_fast5.go:23-27 */
+    if (num_bps) *num_bps = nbps;
+    if (maxv == 0) { free(t.flags); free(t.mag); return 0; }        /* t1_fast5.go:20-22 -> nil */
 
-    for (int bp = num_bps - 1; bp >= 0; bp--) {   /* t1.go:1275-1279 */
+    int tmpcap = w * h * 4 + 16384;
+    uint8_t *buf = (uint8_t *)malloc((size_t)tmpcap);
+    gen_mqenc mq;
+    gen_mqenc_init(&mq, buf, tmpcap);
+
+    for (int bp = nbps - 1; bp >= 0; bp--) {
         int32_t bit = (int32_t)((uint32_t)1 << bp);
-        /* significance propagation, raster order t1.go:1295-1319 */
+        /* SPP t1.go:558-639 */
         for (int y = 0; y < h; y++) {
             for (int x = 0; x < w; x++) {
                 int i = FIDX(&t, x, y);
                 if (t.flags[i] & F_SIG) continue;
                 if (!has_sig_neighbor(&t, i)) continue;
-                if (orc_mqdec_decode(&mq, zc_context(&t, i))) dec_new_sig(&t, &mq, x, y, bit);
+                int sig = (t.mag[y * w + x] & bit) != 0;
+                gen_mqenc_encode(&mq, zc_context(&t, i), sig);
+                if (sig) { enc_sign(&t, &mq, i); t.flags[i] |= F_SIG; }
                 t.flags[i] |= F_VISIT;
             }
         }
-        /* magnitude refinement, raster order t1.go:1331-1347 */
+        /* MRP t1.go:642-683 */
         for (int y = 0; y < h; y++) {
             for (int x = 0; x < w; x++) {
                 int i = FIDX(&t, x, y);
                 if (!(t.flags[i] & F_SIG) || (t.flags[i] & F_VISIT)) continue;
-                if (orc_mqdec_decode(&mq, mr_context(&t, i))) t.mag[y * w + x] |= bit;
+                gen_mqenc_encode(&mq, mr_context(&t, i), (t.mag[y * w + x] & bit) != 0);
                 t.flags[i] |= F_REFINE;
             }
         }
-        /* cleanup, 4-row stripes column by column t1.go:1350-1381 */
+        /* cleanup t1.go:686-770, run length t1.go:816-914 */
         for (int y = 0; y < h; y += 4) {
             for (int x = 0; x < w; x++) {
-                if (can_run_length(&t, x, y)) {   /* decodeRunLength t1.go:1384-1410 */
-                    if (!orc_mqdec_decode(&mq, ORC_CTX_RL)) continue;
-                    int pos = orc_mqdec_decode(&mq, ORC_CTX_UNI) << 1;
-                    pos |= orc_mqdec_decode(&mq, ORC_CTX_UNI);
-                    dec_new_sig(&t, &mq, x, y + pos, bit);
-                    for (int k = pos + 1; k < 4 && y + k < h; k++) {
-                        int i = FIDX(&t, x, y + k);
-                        if (orc_mqdec_decode(&mq, zc_context(&t, i))) dec_new_sig(&t, &mq, x, y + k, bit);
+                if (can_run_length(&t, x, y)) {
+                    int first = -1;
+                    for (int k = 0; k < 4; k++)
+                        if (t.mag[(y + k) * w + x] & bit) { first = k; break; }
+                    if (first < 0) { gen_mqenc_encode(&mq, GEN_CTX_RL, 0); continue; }
+                    gen_mqenc_encode(&mq, GEN_CTX_RL, 1);
+                    gen_mqenc_encode(&mq, GEN_CTX_UNI, (first >> 1) & 1);
+                    gen_mqenc_encode(&mq, GEN_CTX_UNI, first & 1);
+                    int i = FIDX(&t, x, y + first);
+                    enc_sign(&t, &mq, i);
+                    t.flags[i] |= F_SIG;
+                    for (int k = first + 1; k < 4 && y + k < h; k++) {
+                        i = FIDX(&t, x, y + k);
+                        int sig = (t.mag[(y + k) * w + x] & bit) != 0;
+                        gen_mqenc_encode(&mq, zc_context(&t, i), sig);
+                        if (sig) { enc_sign(&t, &mq, i); t.flags[i] |= F_SIG; }
                     }
                     continue;
                 }
@@ -194,16 +204,17 @@ void orc_t1_decode(const uint8_t *data, int len, int w, int h, int num_bps, int 
                     int i = FIDX(&t, x, yy);
                     if (t.flags[i] & F_VISIT) { t.flags[i] &= (uint8_t)~F_VISIT; continue; }
                     if (t.flags[i] & F_SIG) continue;
-                    if (orc_mqdec_decode(&mq, zc_context(&t, i))) dec_new_sig(&t, &mq, x, yy, bit);
+                    int sig = (t.mag[yy * w + x] & bit) != 0;
+                    gen_mqenc_encode(&mq, zc_context(&t, i), sig);
+                    if (sig) { enc_sign(&t, &mq, i); t.flags[i] |= F_SIG; }
                 }
             }
         }
     }
-    /* apply signs t1.go:1282-1289 (Go int32 negation wraps) */
-    for (int y = 0; y < h; y++)
-        for (int x = 0; x < w; x++)
-            if (t.flags[FIDX(&t, x, y)] & F_NEG)
-                out[y * w + x] = (int32_t)(0u - (uint32_t)out[y * w + x]);
-    free(t.flags);
+    const uint8_t *start;
+    int n = gen_mqenc_flush(&mq, &start);                            /* t1_fast5.go:878-898 */
+    if (n > cap) n = -1;
+    if (n > 0) memcpy(out, start, (size_t)n);
+    free(buf); free(t.flags); free(t.mag);
+    return n;
 }
-

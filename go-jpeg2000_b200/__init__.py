@@ -1,0 +1,324 @@
+"""go-jpeg2000_b200 -- B200 (sm_100a) JPEG 2000 tile-component decode path behind a C ABI.
+
+The product is csrc/ -> libj2kgpu.so (include/j2kgpu.h).  This Python package is the thin host
+mirror used by tests and bench.py: ctypes structs identical to the C ones, and functions named after
+the reference functions they stand in for (reference = mrjoshuak/go-jpeg2000):
+
+    t1_decode / ht_decode          entropy.T1.Decode (t1.go:1261) / entropy.HTDecoder.Decode (ht.go:93)
+    reconstruct_multilevel53/97    dwt.ReconstructMultiLevel53/97 (dwt.go:534, 561)
+    apply_inverse_dwt              tcd.TileDecoder.ApplyInverseDWT (tcd.go:416)
+    inverse_rct / inverse_ict      mct.InverseRCT / InverseICT (mct.go:56, 43)
+    dc_level_shift_inverse         mct.DCLevelShiftInverse (mct.go:113)
+    create_image                   decoder.createImage (decoder.go:417)
+    decode_tiles                   decoder.decodeTiles (decoder.go:282) -- the whole path
+
+There is no CPU fallback: if libj2kgpu.so is missing or no CUDA device is present, import / Context()
+raise.  (The directory name carries a hyphen, so load it with importlib -- see load_package() in
+__graft_entry__.py -- under the module name go_jpeg2000_b200.)
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libj2kgpu.so")
+
+MODE_REF, MODE_ISO = 0, 1
+BAND_LL, BAND_HL, BAND_LH, BAND_HH = 0, 1, 2, 3
+FMT_AUTO, FMT_GRAY8, FMT_GRAY16, FMT_RGBA8, FMT_RGBA64 = 0, 1, 2, 3, 4
+E_ARG, E_RANGE, E_UNSUPPORTED, E_CUDA, E_NOMEM, E_NODEVICE = -1, -2, -3, -4, -5, -6
+
+u8p = C.POINTER(C.c_uint8)
+i32p = C.POINTER(C.c_int32)
+f64p = C.POINTER(C.c_double)
+
+
+class Image(C.Structure):          # j2k_image_t
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("ncomp", C.c_uint16),
+                ("prec", C.c_uint8 * 4), ("sgnd", C.c_uint8 * 4), ("mct", C.c_uint8),
+                ("reversible", C.c_uint8), ("nlevels", C.c_uint8), ("ht", C.c_uint8),
+                ("mode", C.c_uint8), ("out_fmt", C.c_uint8)]
+
+
+class TileComp(C.Structure):       # j2k_tilecomp_t
+    _fields_ = [("comp", C.c_uint32), ("x0", C.c_uint32), ("y0", C.c_uint32), ("x1", C.c_uint32),
+                ("y1", C.c_uint32), ("coeff_off", C.c_uint64)]
+
+
+class CBlk(C.Structure):           # j2k_cblk_t
+    _fields_ = [("data_off", C.c_uint64), ("data_len", C.c_uint32), ("tilecomp", C.c_uint32),
+                ("x0", C.c_uint16), ("y0", C.c_uint16), ("w", C.c_uint16), ("h", C.c_uint16),
+                ("band", C.c_uint8), ("level", C.c_uint8), ("num_bps", C.c_uint8), ("num_passes", C.c_uint8),
+                ("step", C.c_float)]
+
+
+class BatchItem(C.Structure):      # j2k_batch_item_t
+    _fields_ = [("image", Image),
+                ("tilecomps", C.POINTER(TileComp)), ("n_tilecomps", C.c_uint32),
+                ("cblks", C.POINTER(CBlk)), ("n_cblks", C.c_uint32),
+                ("blob", u8p), ("blob_len", C.c_uint64),
+                ("out_pix", u8p), ("out_stride", C.c_uint64)]
+
+
+class BlkJob(C.Structure):         # j2k_blkjob_t
+    _fields_ = [("data_off", C.c_uint64), ("data_len", C.c_uint32), ("out_off", C.c_uint32),
+                ("w", C.c_uint16), ("h", C.c_uint16), ("band", C.c_uint8), ("num_bps", C.c_uint8),
+                ("rsv0", C.c_uint8), ("rsv1", C.c_uint8)]
+
+
+EXPORTS = [
+    "j2kgpu_abi_version", "j2kgpu_create", "j2kgpu_destroy", "j2kgpu_strerror", "j2kgpu_last_error",
+    "j2kgpu_set_stream", "j2kgpu_launch_count", "j2kgpu_decode", "j2kgpu_decode_batch",
+    "j2kgpu_job_create", "j2kgpu_job_destroy", "j2kgpu_job_blob_bytes", "j2kgpu_job_out_bytes",
+    "j2kgpu_job_out_offset", "j2kgpu_job_run", "j2kgpu_job_run_entropy", "j2kgpu_job_run_dwt_mct",
+    "j2kgpu_job_run_host", "j2kgpu_sync", "j2kgpu_t1_decode_blocks", "j2kgpu_ht_decode_blocks",
+    "j2kgpu_idwt53", "j2kgpu_idwt97", "j2kgpu_apply_inverse_dwt", "j2kgpu_inverse_rct",
+    "j2kgpu_inverse_ict", "j2kgpu_dc_level_shift_inverse", "j2kgpu_mct_dc_pack",
+]
+
+_lib = None
+
+
+class J2KError(RuntimeError):
+    def __init__(self, code, detail=""):
+        self.code = code
+        super().__init__("j2kgpu error %d: %s" % (code, detail))
+
+
+def lib():
+    """Load libj2kgpu.so.  Fails loudly when it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("libj2kgpu.so not built: run __graft_entry__.build() "
+                              "(make -C go-jpeg2000_b200/csrc); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.j2kgpu_strerror.restype = C.c_char_p
+        L.j2kgpu_last_error.restype = C.c_char_p
+        L.j2kgpu_last_error.argtypes = [C.c_void_p]
+        L.j2kgpu_launch_count.restype = C.c_uint64
+        L.j2kgpu_launch_count.argtypes = [C.c_void_p]
+        for name in ("j2kgpu_job_blob_bytes", "j2kgpu_job_out_bytes"):
+            getattr(L, name).restype = C.c_uint64
+            getattr(L, name).argtypes = [C.c_void_p]
+        L.j2kgpu_job_out_offset.restype = C.c_uint64
+        L.j2kgpu_job_out_offset.argtypes = [C.c_void_p, C.c_uint32]
+        L.j2kgpu_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.j2kgpu_destroy.argtypes = [C.c_void_p]
+        L.j2kgpu_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        L.j2kgpu_sync.argtypes = [C.c_void_p]
+        L.j2kgpu_decode.argtypes = [C.c_void_p, C.POINTER(Image), C.POINTER(TileComp), C.c_uint32,
+                                    C.POINTER(CBlk), C.c_uint32, u8p, C.c_uint64, u8p, C.c_uint64]
+        L.j2kgpu_decode_batch.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(BatchItem)]
+        L.j2kgpu_job_create.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(BatchItem), C.POINTER(C.c_void_p)]
+        L.j2kgpu_job_destroy.argtypes = [C.c_void_p]
+        L.j2kgpu_job_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.j2kgpu_job_run_entropy.argtypes = [C.c_void_p, C.c_void_p]
+        L.j2kgpu_job_run_dwt_mct.argtypes = [C.c_void_p, C.c_void_p]
+        L.j2kgpu_job_run_host.argtypes = [C.c_void_p, C.POINTER(BatchItem)]
+        for name in ("j2kgpu_t1_decode_blocks", "j2kgpu_ht_decode_blocks"):
+            getattr(L, name).argtypes = [C.c_void_p, C.c_int, C.POINTER(BlkJob), C.c_uint32, u8p, C.c_uint64,
+                                         i32p, C.c_uint64]
+        L.j2kgpu_idwt53.argtypes = [C.c_void_p, C.c_int, i32p, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.j2kgpu_idwt97.argtypes = [C.c_void_p, C.c_int, f64p, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.j2kgpu_apply_inverse_dwt.argtypes = [C.c_void_p, C.c_int, i32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
+        L.j2kgpu_inverse_rct.argtypes = [C.c_void_p, i32p, i32p, i32p, C.c_uint64]
+        L.j2kgpu_inverse_ict.argtypes = [C.c_void_p, f64p, f64p, f64p, C.c_uint64]
+        L.j2kgpu_dc_level_shift_inverse.argtypes = [C.c_void_p, i32p, C.c_uint64, C.c_int]
+        L.j2kgpu_mct_dc_pack.argtypes = [C.c_void_p, C.POINTER(Image), C.POINTER(i32p), C.c_int, u8p, C.c_uint64]
+        _lib = L
+    return _lib
+
+
+def fmt_bpp(ncomp, prec):
+    """bytes per output pixel, as decoder.createImage picks the Go image type (decoder.go:427-523)"""
+    return (1 if prec <= 8 else 2) if ncomp == 1 else (4 if prec <= 8 else 8)
+
+
+def make_image(width, height, ncomp, prec, sgnd=0, mct=1, reversible=1, nlevels=5, ht=0, mode=MODE_REF):
+    im = Image()
+    im.width, im.height, im.ncomp = width, height, ncomp
+    precs = list(prec) if isinstance(prec, (list, tuple)) else [prec] * ncomp
+    sg = list(sgnd) if isinstance(sgnd, (list, tuple)) else [sgnd] * ncomp
+    for c in range(min(ncomp, 4)):
+        im.prec[c] = precs[c]
+        im.sgnd[c] = sg[c]
+    im.mct, im.reversible, im.nlevels, im.ht, im.mode, im.out_fmt = mct, reversible, nlevels, ht, mode, FMT_AUTO
+    return im
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+class Context:
+    """One j2kgpu_ctx (one GPU, one stream, calls serialised) -- the object a Go decoder would hold."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        rc = lib().j2kgpu_create(device, C.byref(self._h))
+        if rc != 0:
+            raise J2KError(rc, lib().j2kgpu_strerror(rc).decode())
+
+    def close(self):
+        if self._h:
+            lib().j2kgpu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise J2KError(rc, lib().j2kgpu_last_error(self._h).decode() or lib().j2kgpu_strerror(rc).decode())
+
+    @property
+    def launches(self):
+        return int(lib().j2kgpu_launch_count(self._h))
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(lib().j2kgpu_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def sync(self):
+        self._check(lib().j2kgpu_sync(self._h))
+
+    # ---- entropy stage ------------------------------------------------------------------------
+    def _decode_blocks(self, fn, blocks, mode):
+        """blocks: list of (bytes, w, h, num_bps, band) -> list of int32 arrays (w*h each)"""
+        n = len(blocks)
+        jobs = (BlkJob * max(n, 1))()
+        blob = bytearray()
+        off = 0
+        for i, (data, w, h, nbps, band) in enumerate(blocks):
+            jobs[i] = BlkJob(len(blob), len(data), off, w, h, band, nbps, 0, 0)
+            blob += bytes(data)
+            off += w * h
+        blob_np = np.frombuffer(bytes(blob), np.uint8) if blob else np.zeros(1, np.uint8)
+        out = np.zeros(max(off, 1), np.int32)
+        self._check(fn(self._h, mode, jobs, n, _p(blob_np, u8p), len(blob), _p(out, i32p), off))
+        res, o = [], 0
+        for (_, w, h, _, _) in blocks:
+            res.append(out[o:o + w * h].copy())
+            o += w * h
+        return res
+
+    def t1_decode_blocks(self, blocks, mode=MODE_REF):
+        return self._decode_blocks(lib().j2kgpu_t1_decode_blocks, blocks, mode)
+
+    def ht_decode_blocks(self, blocks, mode=MODE_REF):
+        return self._decode_blocks(lib().j2kgpu_ht_decode_blocks, blocks, mode)
+
+    def t1_decode(self, data, w, h, num_bps, band, mode=MODE_REF):
+        """entropy.T1.Decode(data, numBPS, bandType) on a fresh NewT1(w, h)  (t1.go:1261)"""
+        return self.t1_decode_blocks([(data, w, h, num_bps, band)], mode)[0]
+
+    def ht_decode(self, data, w, h, num_bitplanes=0, band=0, mode=MODE_REF):
+        """entropy.HTDecoder.Decode(data, numBitplanes, bandType) on a fresh NewHTDecoder(w, h)  (ht.go:93)"""
+        return self.ht_decode_blocks([(data, w, h, num_bitplanes, band)], mode)[0]
+
+    # ---- DWT stage ----------------------------------------------------------------------------
+    def reconstruct_multilevel53(self, data, width, height, levels, mode=MODE_REF):
+        d = np.array(data, np.int32).reshape(-1)
+        assert d.size == width * height
+        self._check(lib().j2kgpu_idwt53(self._h, mode, _p(d, i32p), width, height, levels))
+        return d
+
+    def reconstruct_multilevel97(self, data, width, height, levels, mode=MODE_REF):
+        d = np.array(data, np.float64).reshape(-1)
+        assert d.size == width * height
+        self._check(lib().j2kgpu_idwt97(self._h, mode, _p(d, f64p), width, height, levels))
+        return d
+
+    def apply_inverse_dwt(self, data, width, height, levels, reversible, mode=MODE_REF):
+        d = np.array(data, np.int32).reshape(-1)
+        assert d.size == width * height
+        self._check(lib().j2kgpu_apply_inverse_dwt(self._h, mode, _p(d, i32p), width, height, levels, int(reversible)))
+        return d
+
+    # ---- MCT / DC / pack ------------------------------------------------------------------------
+    def inverse_rct(self, y, u, v):
+        y, u, v = (np.array(a, np.int32).reshape(-1) for a in (y, u, v))
+        self._check(lib().j2kgpu_inverse_rct(self._h, _p(y, i32p), _p(u, i32p), _p(v, i32p), y.size))
+        return y, u, v
+
+    def inverse_ict(self, y, cb, cr):
+        y, cb, cr = (np.array(a, np.float64).reshape(-1) for a in (y, cb, cr))
+        self._check(lib().j2kgpu_inverse_ict(self._h, _p(y, f64p), _p(cb, f64p), _p(cr, f64p), y.size))
+        return y, cb, cr
+
+    def dc_level_shift_inverse(self, data, precision):
+        d = np.array(data, np.int32).reshape(-1)
+        self._check(lib().j2kgpu_dc_level_shift_inverse(self._h, _p(d, i32p), d.size, precision))
+        return d
+
+    def mct_dc_pack(self, img, comps, apply_tail=True):
+        comps = [np.ascontiguousarray(c, np.int32).reshape(-1) for c in comps]
+        bpp = fmt_bpp(img.ncomp, img.prec[0])
+        stride = img.width * bpp
+        pix = np.zeros(max(stride * img.height, 1), np.uint8)
+        arr = (i32p * max(len(comps), 1))(*[_p(c, i32p) for c in comps])
+        self._check(lib().j2kgpu_mct_dc_pack(self._h, C.byref(img), arr, int(apply_tail), _p(pix, u8p), stride))
+        return pix[: stride * img.height]
+
+    def create_image(self, comps, width, height, prec):
+        """decoder.createImage (decoder.go:417): planar components -> Pix; raises for a bad component count"""
+        img = make_image(width, height, len(comps), prec, sgnd=1, mct=0)
+        return self.mct_dc_pack(img, comps, apply_tail=False)
+
+    # ---- whole path -------------------------------------------------------------------------------
+    def decode_tiles(self, img, tilecomps, cblks, blob, out_stride=None):
+        """decoder.decodeTiles (decoder.go:282): job tables + compressed blob -> packed pixels (host buffers)"""
+        bpp = fmt_bpp(img.ncomp, img.prec[0])
+        stride = out_stride or img.width * bpp
+        blob = np.ascontiguousarray(blob, np.uint8)
+        out = np.zeros(max(stride * img.height, 1), np.uint8)
+        self._check(lib().j2kgpu_decode(self._h, C.byref(img), tilecomps, len(tilecomps), cblks, len(cblks),
+                                        _p(blob, u8p), blob.size, _p(out, u8p), stride))
+        return out[: stride * img.height]
+
+    def decode_batch(self, items):
+        arr = (BatchItem * len(items))(*items)
+        self._check(lib().j2kgpu_decode_batch(self._h, len(items), arr))
+
+
+class Job:
+    """A validated, uploaded batch (j2kgpu_job): run it with device pointers, repeatedly."""
+
+    def __init__(self, ctx, items):
+        self.ctx = ctx
+        self._items = (BatchItem * len(items))(*items)
+        self._h = C.c_void_p()
+        ctx._check(lib().j2kgpu_job_create(ctx._h, len(items), self._items, C.byref(self._h)))
+        self.blob_bytes = int(lib().j2kgpu_job_blob_bytes(self._h))
+        self.out_bytes = int(lib().j2kgpu_job_out_bytes(self._h))
+        self.n = len(items)
+
+    def out_offset(self, i):
+        return int(lib().j2kgpu_job_out_offset(self._h, i))
+
+    def run(self, d_blob_ptr, d_out_ptr):
+        self.ctx._check(lib().j2kgpu_job_run(self._h, C.c_void_p(d_blob_ptr), C.c_void_p(d_out_ptr)))
+
+    def run_entropy(self, d_blob_ptr):
+        self.ctx._check(lib().j2kgpu_job_run_entropy(self._h, C.c_void_p(d_blob_ptr)))
+
+    def run_dwt_mct(self, d_out_ptr):
+        self.ctx._check(lib().j2kgpu_job_run_dwt_mct(self._h, C.c_void_p(d_out_ptr)))
+
+    def run_host(self):
+        self.ctx._check(lib().j2kgpu_job_run_host(self._h, self._items))
+
+    def close(self):
+        if self._h:
+            lib().j2kgpu_job_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,654 @@
+// api.cu -- the C ABI of libj2kgpu.so (include/j2kgpu.h): context, job flattening / validation,
+// whole-path launch sequence, host-buffer staging and the per-stage entry points.
+// There is no CPU fallback anywhere in this file: every entry point either runs CUDA kernels or
+// returns an error.
+#include "common.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <tuple>
+
+cudaError_t launch_t1_ref_stage(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, int32_t *d_coef,
+                                int max_bps, cudaStream_t s);
+
+// ---- errors ------------------------------------------------------------------------------------------
+int j2k_set_err(j2kgpu_ctx *ctx, int code, const char *fmt, ...)
+{
+    if (ctx) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        ctx->err = buf;
+    }
+    return code;
+}
+
+int j2k_cuda_err(j2kgpu_ctx *ctx, cudaError_t e, const char *what)
+{
+    return j2k_set_err(ctx, J2KGPU_E_CUDA, "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+}
+
+int j2k_reserve(j2kgpu_ctx *ctx, DevBuf &b, size_t bytes, bool pinned_host)
+{
+    if (bytes <= b.cap) return J2KGPU_OK;
+    size_t cap = bytes + bytes / 4 + 4096;
+    if (b.p) {
+        if (pinned_host) cudaFreeHost(b.p); else cudaFree(b.p);
+        b.p = nullptr; b.cap = 0;
+    }
+    cudaError_t e = pinned_host ? cudaMallocHost(&b.p, cap) : cudaMalloc(&b.p, cap);
+    if (e != cudaSuccess) { b.p = nullptr; return j2k_set_err(ctx, J2KGPU_E_NOMEM, "allocating %zu bytes: %s", cap, cudaGetErrorString(e)); }
+    b.cap = cap;
+    return J2KGPU_OK;
+}
+
+int j2k_resolve_fmt(int ncomp, int prec, int fmt)
+{
+    int want = ncomp == 1 ? (prec <= 8 ? J2KGPU_FMT_GRAY8 : J2KGPU_FMT_GRAY16)
+                          : (prec <= 8 ? J2KGPU_FMT_RGBA8 : J2KGPU_FMT_RGBA64);      // decoder.go:427-523
+    if (fmt == J2KGPU_FMT_AUTO || fmt == want) return want;
+    return -1;
+}
+
+int j2k_fmt_bpp(int fmt)
+{
+    switch (fmt) {
+    case J2KGPU_FMT_GRAY8: return 1;
+    case J2KGPU_FMT_GRAY16: return 2;
+    case J2KGPU_FMT_RGBA8: return 4;
+    case J2KGPU_FMT_RGBA64: return 8;
+    }
+    return 0;
+}
+
+static int make_tail(j2kgpu_ctx *ctx, const j2k_image_t &im, TailParams &tp)
+{
+    if (im.ncomp != 1 && im.ncomp != 3 && im.ncomp != 4)
+        return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "unsupported number of components: %d", (int)im.ncomp);   // decoder.go:585-586
+    for (int c = 0; c < im.ncomp; c++)
+        if (im.prec[c] < 1 || im.prec[c] > 16)
+            return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "component %d precision %d outside 1..16", c, (int)im.prec[c]);
+    memset(&tp, 0, sizeof tp);
+    tp.ncomp = im.ncomp;
+    for (int c = 0; c < 4; c++) { tp.prec[c] = c < im.ncomp ? im.prec[c] : 8; tp.sgnd[c] = c < im.ncomp ? (im.sgnd[c] != 0) : 1; }
+    tp.mct = (im.mct != 0 && im.ncomp >= 3);                                            // decoder.go:322
+    tp.reversible = im.reversible != 0;
+    tp.iso = im.mode == J2KGPU_MODE_ISO;
+    tp.fmt = j2k_resolve_fmt(im.ncomp, im.prec[0], im.out_fmt);
+    if (tp.fmt < 0) return j2k_set_err(ctx, J2KGPU_E_ARG, "out_fmt %d does not match ncomp/precision", (int)im.out_fmt);
+    return J2KGPU_OK;
+}
+
+// ---- context -------------------------------------------------------------------------------------------
+extern "C" int j2kgpu_abi_version(void) { return J2KGPU_ABI_VERSION; }
+
+extern "C" const char *j2kgpu_strerror(int code)
+{
+    switch (code) {
+    case J2KGPU_OK: return "ok";
+    case J2KGPU_E_ARG: return "invalid argument";
+    case J2KGPU_E_RANGE: return "offset or block out of range";
+    case J2KGPU_E_UNSUPPORTED: return "unsupported configuration";
+    case J2KGPU_E_CUDA: return "CUDA error";
+    case J2KGPU_E_NOMEM: return "out of memory";
+    case J2KGPU_E_NODEVICE: return "no CUDA device";
+    }
+    return "unknown error";
+}
+
+extern "C" int j2kgpu_create(int device, j2kgpu_ctx **out)
+{
+    if (!out) return J2KGPU_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return J2KGPU_E_NODEVICE;
+    if (device < 0 || device >= ndev) return J2KGPU_E_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return J2KGPU_E_CUDA;
+    j2kgpu_ctx *ctx = new (std::nothrow) j2kgpu_ctx();
+    if (!ctx) return J2KGPU_E_NOMEM;
+    ctx->device = device;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return J2KGPU_E_CUDA; }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return J2KGPU_OK;
+}
+
+static void free_buf(DevBuf &b, bool pinned) { if (b.p) { if (pinned) cudaFreeHost(b.p); else cudaFree(b.p); } b.p = nullptr; b.cap = 0; }
+
+extern "C" void j2kgpu_destroy(j2kgpu_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_buf(ctx->d_in, false); free_buf(ctx->d_out, false); free_buf(ctx->d_aux, false); free_buf(ctx->d_tab, false);
+    free_buf(ctx->h_in, true); free_buf(ctx->h_out, true);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+extern "C" const char *j2kgpu_last_error(const j2kgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int j2kgpu_set_stream(j2kgpu_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return J2KGPU_E_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return J2KGPU_OK;
+}
+
+extern "C" uint64_t j2kgpu_launch_count(const j2kgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int j2kgpu_sync(j2kgpu_ctx *ctx)
+{
+    if (!ctx) return J2KGPU_E_ARG;
+    J2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return J2KGPU_OK;
+}
+
+// ---- job ---------------------------------------------------------------------------------------------
+static uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+static void job_free(j2kgpu_job *job)
+{
+    if (!job) return;
+    if (job->ctx) cudaSetDevice(job->ctx->device);
+    cudaFree(job->d_cblks); cudaFree(job->d_tcs); cudaFree(job->d_tiles); cudaFree(job->d_coef); cudaFree(job->d_tmp);
+    cudaFree(job->d_blob); cudaFree(job->d_pix);
+    if (job->h_blob) cudaFreeHost(job->h_blob);
+    if (job->h_pix) cudaFreeHost(job->h_pix);
+    delete job;
+}
+
+extern "C" void j2kgpu_job_destroy(j2kgpu_job *job)
+{
+    if (!job) return;
+    if (job->ctx) { std::lock_guard<std::mutex> g(job->ctx->mu); cudaStreamSynchronize(job->ctx->stream); }
+    job_free(job);
+}
+
+static bool same_header(const j2k_image_t &a, const j2k_image_t &b)
+{
+    return a.ncomp == b.ncomp && !memcmp(a.prec, b.prec, 4) && !memcmp(a.sgnd, b.sgnd, 4) && a.mct == b.mct &&
+           a.reversible == b.reversible && a.nlevels == b.nlevels && a.ht == b.ht && a.mode == b.mode &&
+           a.out_fmt == b.out_fmt;
+}
+
+static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *items, j2kgpu_job **out)
+{
+    if (!ctx || !out || !items || n_img == 0) return j2k_set_err(ctx, J2KGPU_E_ARG, "null or empty batch");
+    *out = nullptr;
+    const j2k_image_t &hdr = items[0].image;
+    TailParams tp;
+    int rc = make_tail(ctx, hdr, tp);
+    if (rc) return rc;
+    if (hdr.mode != J2KGPU_MODE_REF)
+        return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "mode %d: only J2KGPU_MODE_REF is built in this revision", (int)hdr.mode);
+    if (hdr.nlevels > J2K_MAX_LEVELS) return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "nlevels %d > %d", (int)hdr.nlevels, J2K_MAX_LEVELS);
+    const int bpp = j2k_fmt_bpp(tp.fmt);
+
+    j2kgpu_job *job = new (std::nothrow) j2kgpu_job();
+    if (!job) return j2k_set_err(ctx, J2KGPU_E_NOMEM, "job");
+    job->ctx = ctx; job->n_img = n_img; job->hdr = hdr; job->tail = tp; job->nlevels = hdr.nlevels;
+
+    std::vector<DevTileComp> tcs;
+    std::vector<DevTile> tiles;
+    std::vector<DevCblk> cbs;
+    uint64_t coef_elems = 0, tmp_elems = 0, blob_bytes = 0, out_bytes = 0;
+    int max_bps = 0;
+    bool need_clear = false;
+
+    for (uint32_t ii = 0; ii < n_img; ii++) {
+        const j2k_batch_item_t &it = items[ii];
+        const j2k_image_t &im = it.image;
+        if (!same_header(im, hdr)) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_ARG, "item %u: header differs from item 0", ii); }
+        if (im.width == 0 || im.height == 0) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_ARG, "item %u: empty image", ii); }
+        if ((!it.tilecomps && it.n_tilecomps) || (!it.cblks && it.n_cblks) || (!it.blob && it.blob_len)) {
+            job_free(job); return j2k_set_err(ctx, J2KGPU_E_ARG, "item %u: null table", ii);
+        }
+        if (it.out_stride < (uint64_t)im.width * bpp || it.out_stride % bpp) {
+            job_free(job); return j2k_set_err(ctx, J2KGPU_E_ARG, "item %u: out_stride %llu too small or not a multiple of %d", ii, (unsigned long long)it.out_stride, bpp);
+        }
+        const uint32_t tc_base = (uint32_t)tcs.size();
+        job->blob_off.push_back(blob_bytes);
+        job->out_off.push_back(out_bytes);
+        job->out_size.push_back(it.out_stride * im.height);
+
+        std::map<std::tuple<uint32_t, uint32_t, uint32_t, uint32_t>, uint32_t> tile_of;
+        std::vector<uint64_t> covered(it.n_tilecomps, 0);
+        for (uint32_t t = 0; t < it.n_tilecomps; t++) {
+            const j2k_tilecomp_t &tc = it.tilecomps[t];
+            if (tc.comp >= im.ncomp || tc.x1 <= tc.x0 || tc.y1 <= tc.y0) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_ARG, "item %u tile-component %u: bad bounds/component", ii, t); }
+            DevTileComp d{};
+            d.w = tc.x1 - tc.x0; d.h = tc.y1 - tc.y0;
+            if ((uint64_t)d.w * d.h > (1ull << 31)) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "tile-component too large"); }
+            d.coef_off = coef_elems;
+            coef_elems = align_up(coef_elems + (uint64_t)d.w * d.h, 32);
+            d.tmp_elems = (uint32_t)align_up((uint64_t)((d.w + 1) / 2) * ((d.h + 1) / 2), 32);
+            d.tmp_off = tmp_elems;
+            tmp_elems += 2ull * d.tmp_elems;
+            tcs.push_back(d);
+            if (d.w > job->max_w) job->max_w = d.w;
+            if (d.h > job->max_h) job->max_h = d.h;
+            auto key = std::make_tuple(tc.x0, tc.y0, tc.x1, tc.y1);
+            auto f = tile_of.find(key);
+            uint32_t ti;
+            if (f == tile_of.end()) {
+                DevTile tl{};
+                for (int c = 0; c < 4; c++) tl.tc[c] = 0xFFFFFFFFu;
+                tl.img_x0 = tc.x0; tl.img_y0 = tc.y0; tl.w = d.w; tl.h = d.h;
+                tl.out_off = out_bytes; tl.out_stride = it.out_stride; tl.img_w = im.width; tl.img_h = im.height;
+                ti = (uint32_t)tiles.size();
+                tiles.push_back(tl);
+                tile_of[key] = ti;
+            } else ti = f->second;
+            if (tiles[ti].tc[tc.comp] != 0xFFFFFFFFu) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_ARG, "item %u: duplicate tile-component", ii); }
+            tiles[ti].tc[tc.comp] = tc_base + t;
+        }
+        for (auto &kv : tile_of)
+            for (int c = 0; c < im.ncomp; c++)
+                if (tiles[kv.second].tc[c] == 0xFFFFFFFFu) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_ARG, "item %u: a tile lacks component %d (subsampled components are not supported)", ii, c); }
+
+        for (uint32_t b = 0; b < it.n_cblks; b++) {
+            const j2k_cblk_t &cb = it.cblks[b];
+            if (cb.tilecomp >= it.n_tilecomps) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_RANGE, "item %u block %u: tile-component %u out of range", ii, b, cb.tilecomp); }
+            const DevTileComp &d = tcs[tc_base + cb.tilecomp];
+            if (cb.w == 0 || cb.h == 0) continue;
+            if (cb.w > 64 || cb.h > 64) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "item %u block %u: %ux%u exceeds 64x64", ii, b, cb.w, cb.h); }
+            if ((uint32_t)cb.x0 + cb.w > d.w || (uint32_t)cb.y0 + cb.h > d.h) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_RANGE, "item %u block %u: outside its tile-component", ii, b); }
+            if (cb.data_off > it.blob_len || cb.data_len > it.blob_len - cb.data_off) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_RANGE, "item %u block %u: data outside blob", ii, b); }
+            if (cb.num_bps > 31 || cb.band > 3) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "item %u block %u: num_bps %d / band %d", ii, b, (int)cb.num_bps, (int)cb.band); }
+            DevCblk o{};
+            o.data_off = blob_bytes + cb.data_off; o.data_len = cb.data_len;
+            o.out_off = d.coef_off + (uint64_t)cb.y0 * d.w + cb.x0; o.out_stride = d.w;
+            o.w = cb.w; o.h = cb.h; o.band = cb.band; o.num_bps = cb.num_bps; o.level = cb.level; o.num_passes = cb.num_passes;
+            cbs.push_back(o);
+            covered[cb.tilecomp] += (uint64_t)cb.w * cb.h;
+            if (cb.data_len && cb.num_bps > max_bps) max_bps = cb.num_bps;
+        }
+        for (uint32_t t = 0; t < it.n_tilecomps; t++)
+            if (covered[t] != (uint64_t)tcs[tc_base + t].w * tcs[tc_base + t].h) need_clear = true;
+        blob_bytes += it.blob_len;
+        out_bytes = align_up(out_bytes + it.out_stride * im.height, 256);
+    }
+    job->n_tc = (uint32_t)tcs.size(); job->n_tiles = (uint32_t)tiles.size(); job->n_cb = (uint32_t)cbs.size();
+    job->coef_elems = coef_elems; job->blob_bytes = blob_bytes; job->out_bytes = out_bytes; job->max_bps = max_bps;
+    job->tmp_bytes = tmp_elems * (hdr.reversible ? 4 : 8);
+    job->need_clear = need_clear;                  // some plane is not fully covered by its blocks
+
+    cudaSetDevice(ctx->device);
+    cudaError_t e = cudaSuccess;
+    auto up = [&](void **dst, const void *src, size_t bytes) {
+        if (e != cudaSuccess) return;
+        e = cudaMalloc(dst, bytes ? bytes : 16);
+        if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    };
+    up((void **)&job->d_cblks, cbs.data(), cbs.size() * sizeof(DevCblk));
+    up((void **)&job->d_tcs, tcs.data(), tcs.size() * sizeof(DevTileComp));
+    up((void **)&job->d_tiles, tiles.data(), tiles.size() * sizeof(DevTile));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&job->d_coef, (coef_elems ? coef_elems : 4) * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&job->d_tmp, job->tmp_bytes ? job->tmp_bytes : 16);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);          // tables are read from host vectors
+    if (e != cudaSuccess) { job_free(job); return j2k_cuda_err(ctx, e, "job upload"); }
+    *out = job;
+    return J2KGPU_OK;
+}
+
+extern "C" int j2kgpu_job_create(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *items, j2kgpu_job **out)
+{
+    if (!ctx) return J2KGPU_E_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    return job_build(ctx, n_img, items, out);
+}
+
+extern "C" uint64_t j2kgpu_job_blob_bytes(const j2kgpu_job *job) { return job ? job->blob_bytes : 0; }
+extern "C" uint64_t j2kgpu_job_out_bytes(const j2kgpu_job *job) { return job ? job->out_bytes : 0; }
+extern "C" uint64_t j2kgpu_job_out_offset(const j2kgpu_job *job, uint32_t item)
+{
+    return (job && item < job->n_img) ? job->out_off[item] : 0;
+}
+
+static int run_entropy(j2kgpu_job *job, const void *d_blob)
+{
+    j2kgpu_ctx *ctx = job->ctx;
+    if (job->need_clear)
+        J2K_CUDA(ctx, cudaMemsetAsync(job->d_coef, 0, job->coef_elems * sizeof(int32_t), ctx->stream));
+    if (job->n_cb == 0) return J2KGPU_OK;
+    cudaError_t e = job->hdr.ht ? launch_ht_ref(job->d_cblks, job->n_cb, (const uint8_t *)d_blob, job->d_coef, ctx->stream)
+                                : launch_t1_ref(job->d_cblks, job->n_cb, (const uint8_t *)d_blob, job->d_coef, job->max_bps, ctx->stream);
+    if (e != cudaSuccess) return j2k_cuda_err(ctx, e, "entropy kernel launch");
+    ctx->launches++;
+    return J2KGPU_OK;
+}
+
+static int run_dwt_mct(j2kgpu_job *job, void *d_out)
+{
+    j2kgpu_ctx *ctx = job->ctx;
+    IdwtLaunch p{};
+    p.d_tcs = job->d_tcs; p.n_tc = job->n_tc; p.d_tiles = job->d_tiles; p.n_tiles = job->n_tiles;
+    p.d_coef = job->d_coef; p.d_tmp = job->d_tmp; p.nlevels = job->nlevels;
+    p.max_w = job->max_w; p.max_h = job->max_h; p.reversible = job->hdr.reversible != 0; p.f64_io = 0;
+    p.d_plane_out = nullptr; p.d_pix = (uint8_t *)d_out; p.tail = job->tail;
+    for (int lvl = job->nlevels - 1; lvl >= 0; lvl--) {
+        p.lvl = lvl;
+        IdwtLaunch q = p;
+        if (lvl > 0) q.d_tiles = nullptr;
+        int nl = 0;
+        cudaError_t e = launch_idwt_level(q, ctx->stream, &nl);
+        if (e != cudaSuccess) return j2k_cuda_err(ctx, e, "idwt level launch");
+        ctx->launches += nl;
+    }
+    if (job->nlevels == 0) {
+        p.lvl = 0;
+        int nl = 0;
+        cudaError_t e = launch_idwt_level(p, ctx->stream, &nl);
+        if (e != cudaSuccess) return j2k_cuda_err(ctx, e, "idwt level launch");
+        ctx->launches += nl;
+    }
+    return J2KGPU_OK;
+}
+
+extern "C" int j2kgpu_job_run_entropy(j2kgpu_job *job, const void *d_blob)
+{
+    if (!job || (!d_blob && job->blob_bytes)) return J2KGPU_E_ARG;
+    std::lock_guard<std::mutex> g(job->ctx->mu);
+    cudaSetDevice(job->ctx->device);
+    return run_entropy(job, d_blob);
+}
+
+extern "C" int j2kgpu_job_run_dwt_mct(j2kgpu_job *job, void *d_out)
+{
+    if (!job || !d_out) return J2KGPU_E_ARG;
+    std::lock_guard<std::mutex> g(job->ctx->mu);
+    cudaSetDevice(job->ctx->device);
+    return run_dwt_mct(job, d_out);
+}
+
+extern "C" int j2kgpu_job_run(j2kgpu_job *job, const void *d_blob, void *d_out)
+{
+    if (!job || !d_out || (!d_blob && job->blob_bytes)) return J2KGPU_E_ARG;
+    std::lock_guard<std::mutex> g(job->ctx->mu);
+    cudaSetDevice(job->ctx->device);
+    int rc = run_entropy(job, d_blob);
+    if (rc) return rc;
+    return run_dwt_mct(job, d_out);
+}
+
+static int run_host_locked(j2kgpu_job *job, const j2k_batch_item_t *items)
+{
+    j2kgpu_ctx *ctx = job->ctx;
+    cudaSetDevice(ctx->device);
+    if (!job->d_blob) J2K_CUDA(ctx, cudaMalloc(&job->d_blob, job->blob_bytes ? job->blob_bytes : 16));
+    if (!job->d_pix) J2K_CUDA(ctx, cudaMalloc(&job->d_pix, job->out_bytes ? job->out_bytes : 16));
+    for (uint32_t i = 0; i < job->n_img; i++) {
+        if (!items[i].out_pix) return j2k_set_err(ctx, J2KGPU_E_ARG, "item %u: null out_pix", i);
+        if (items[i].blob_len)
+            J2K_CUDA(ctx, cudaMemcpyAsync((uint8_t *)job->d_blob + job->blob_off[i], items[i].blob, items[i].blob_len,
+                                          cudaMemcpyHostToDevice, ctx->stream));
+    }
+    int rc = run_entropy(job, job->d_blob);
+    if (rc) return rc;
+    rc = run_dwt_mct(job, job->d_pix);
+    if (rc) return rc;
+    for (uint32_t i = 0; i < job->n_img; i++)
+        J2K_CUDA(ctx, cudaMemcpyAsync(items[i].out_pix, (uint8_t *)job->d_pix + job->out_off[i], job->out_size[i],
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+    J2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return J2KGPU_OK;
+}
+
+extern "C" int j2kgpu_job_run_host(j2kgpu_job *job, const j2k_batch_item_t *items)
+{
+    if (!job || !items) return J2KGPU_E_ARG;
+    std::lock_guard<std::mutex> g(job->ctx->mu);
+    return run_host_locked(job, items);
+}
+
+extern "C" int j2kgpu_decode_batch(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *items)
+{
+    if (!ctx) return J2KGPU_E_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    j2kgpu_job *job = nullptr;
+    int rc = job_build(ctx, n_img, items, &job);
+    if (rc) return rc;
+    rc = run_host_locked(job, items);
+    cudaStreamSynchronize(ctx->stream);
+    job_free(job);
+    return rc;
+}
+
+extern "C" int j2kgpu_decode(j2kgpu_ctx *ctx, const j2k_image_t *img,
+                             const j2k_tilecomp_t *tilecomps, uint32_t n_tilecomps,
+                             const j2k_cblk_t *cblks, uint32_t n_cblks,
+                             const uint8_t *blob, uint64_t blob_len,
+                             uint8_t *out_pix, uint64_t out_stride)
+{
+    if (!ctx) return J2KGPU_E_ARG;
+    if (!img || !out_pix) return j2k_set_err(ctx, J2KGPU_E_ARG, "null image or output");
+    j2k_batch_item_t it;
+    memset(&it, 0, sizeof it);
+    it.image = *img; it.tilecomps = tilecomps; it.n_tilecomps = n_tilecomps; it.cblks = cblks; it.n_cblks = n_cblks;
+    it.blob = blob; it.blob_len = blob_len; it.out_pix = out_pix; it.out_stride = out_stride;
+    return j2kgpu_decode_batch(ctx, 1, &it);
+}
+
+// ---- per-stage entry points -------------------------------------------------------------------------------
+static int stage_blocks(j2kgpu_ctx *ctx, int mode, int ht, const j2k_blkjob_t *jobs, uint32_t n,
+                        const uint8_t *blob, uint64_t blob_len, int32_t *out, uint64_t out_len)
+{
+    if (!ctx) return J2KGPU_E_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (mode != J2KGPU_MODE_REF) return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "mode %d not built", mode);
+    if ((!jobs && n) || (!blob && blob_len) || (!out && out_len)) return j2k_set_err(ctx, J2KGPU_E_ARG, "null argument");
+    if (n == 0) return J2KGPU_OK;
+    cudaSetDevice(ctx->device);
+    std::vector<DevCblk> cbs(n);
+    int max_bps = 1;
+    for (uint32_t i = 0; i < n; i++) {
+        const j2k_blkjob_t &j = jobs[i];
+        if (j.w == 0 || j.h == 0 || j.w > 64 || j.h > 64) return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "block %u: size %ux%u", i, j.w, j.h);
+        if (j.data_off > blob_len || j.data_len > blob_len - j.data_off) return j2k_set_err(ctx, J2KGPU_E_RANGE, "block %u: data outside blob", i);
+        if ((uint64_t)j.out_off + (uint64_t)j.w * j.h > out_len) return j2k_set_err(ctx, J2KGPU_E_RANGE, "block %u: output outside buffer", i);
+        if (j.num_bps > 31 || j.band > 3) return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "block %u: num_bps %d / band %d", i, (int)j.num_bps, (int)j.band);
+        DevCblk &o = cbs[i];
+        memset(&o, 0, sizeof o);
+        o.data_off = j.data_off; o.data_len = j.data_len; o.out_off = j.out_off; o.out_stride = j.w;
+        o.w = j.w; o.h = j.h; o.band = j.band; o.num_bps = j.num_bps;
+        if (j.num_bps > max_bps) max_bps = j.num_bps;
+    }
+    int rc;
+    if ((rc = j2k_reserve(ctx, ctx->d_tab, n * sizeof(DevCblk), false))) return rc;
+    if ((rc = j2k_reserve(ctx, ctx->d_in, blob_len + 16, false))) return rc;
+    if ((rc = j2k_reserve(ctx, ctx->d_out, out_len * sizeof(int32_t) + 16, false))) return rc;
+    J2K_CUDA(ctx, cudaMemcpyAsync(ctx->d_tab.p, cbs.data(), n * sizeof(DevCblk), cudaMemcpyHostToDevice, ctx->stream));
+    if (blob_len) J2K_CUDA(ctx, cudaMemcpyAsync(ctx->d_in.p, blob, blob_len, cudaMemcpyHostToDevice, ctx->stream));
+    J2K_CUDA(ctx, cudaMemsetAsync(ctx->d_out.p, 0, out_len * sizeof(int32_t), ctx->stream));
+    cudaError_t e = ht ? launch_ht_ref((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, (int32_t *)ctx->d_out.p, ctx->stream)
+                       : launch_t1_ref_stage((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, (int32_t *)ctx->d_out.p, max_bps, ctx->stream);
+    if (e != cudaSuccess) return j2k_cuda_err(ctx, e, "entropy kernel launch");
+    ctx->launches++;
+    J2K_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_out.p, out_len * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    J2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return J2KGPU_OK;
+}
+
+extern "C" int j2kgpu_t1_decode_blocks(j2kgpu_ctx *ctx, int mode, const j2k_blkjob_t *jobs, uint32_t n,
+                                       const uint8_t *blob, uint64_t blob_len, int32_t *out, uint64_t out_len)
+{
+    return stage_blocks(ctx, mode, 0, jobs, n, blob, blob_len, out, out_len);
+}
+
+extern "C" int j2kgpu_ht_decode_blocks(j2kgpu_ctx *ctx, int mode, const j2k_blkjob_t *jobs, uint32_t n,
+                                       const uint8_t *blob, uint64_t blob_len, int32_t *out, uint64_t out_len)
+{
+    return stage_blocks(ctx, mode, 1, jobs, n, blob, blob_len, out, out_len);
+}
+
+// one plane through every level; kind 0: int32 5-3, 1: float64 9-7, 2: int32 -> 9-7 -> int32(v+0.5)
+static int stage_idwt(j2kgpu_ctx *ctx, int mode, void *data, uint32_t w, uint32_t h, uint32_t levels, int kind)
+{
+    if (!ctx) return J2KGPU_E_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (mode != J2KGPU_MODE_REF) return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "mode %d not built", mode);
+    if (!data && w && h) return j2k_set_err(ctx, J2KGPU_E_ARG, "null data");
+    if (w == 0 || h == 0) return J2KGPU_OK;
+    if (levels == 0 && kind != 2) return J2KGPU_OK;                           // dwt.go:545: no levels, nothing to do
+    if (levels > J2K_MAX_LEVELS) return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "levels %u > %d", levels, J2K_MAX_LEVELS);
+    if ((uint64_t)w * h > (1ull << 31)) return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "plane too large");
+    cudaSetDevice(ctx->device);
+    const size_t n = (size_t)w * h;
+    const size_t in_el = kind == 1 ? 8 : 4, out_el = kind == 1 ? 8 : 4, tmp_el = kind == 0 ? 4 : 8;
+    DevTileComp tc{};
+    tc.w = w; tc.h = h; tc.coef_off = 0; tc.tmp_off = 0;
+    tc.tmp_elems = (uint32_t)align_up((uint64_t)((w + 1) / 2) * ((h + 1) / 2), 32);
+    int rc;
+    if ((rc = j2k_reserve(ctx, ctx->d_tab, sizeof tc, false))) return rc;
+    if ((rc = j2k_reserve(ctx, ctx->d_in, n * in_el, false))) return rc;
+    if ((rc = j2k_reserve(ctx, ctx->d_out, n * out_el, false))) return rc;
+    if ((rc = j2k_reserve(ctx, ctx->d_aux, 2ull * tc.tmp_elems * tmp_el, false))) return rc;
+    J2K_CUDA(ctx, cudaMemcpyAsync(ctx->d_tab.p, &tc, sizeof tc, cudaMemcpyHostToDevice, ctx->stream));
+    J2K_CUDA(ctx, cudaMemcpyAsync(ctx->d_in.p, data, n * in_el, cudaMemcpyHostToDevice, ctx->stream));
+    IdwtLaunch p{};
+    p.d_tcs = (const DevTileComp *)ctx->d_tab.p; p.n_tc = 1; p.d_tiles = nullptr; p.n_tiles = 0;
+    p.d_coef = (const int32_t *)ctx->d_in.p; p.d_tmp = ctx->d_aux.p; p.nlevels = (int)levels;
+    p.max_w = w; p.max_h = h; p.reversible = kind == 0; p.f64_io = kind == 1;
+    p.d_plane_out = (int32_t *)ctx->d_out.p; p.d_pix = nullptr;
+    // levels == 0 (kind 2 only): tcd.go:428-435 still runs int32 -> float64 -> int32(v + 0.5), which maps a
+    // negative integer n to n + 1 (truncation); one pass-through launch reproduces it
+    for (int lvl = levels ? (int)levels - 1 : 0; lvl >= 0; lvl--) {
+        p.lvl = lvl;
+        int nl = 0;
+        cudaError_t e = launch_idwt_level(p, ctx->stream, &nl);
+        if (e != cudaSuccess) return j2k_cuda_err(ctx, e, "idwt level launch");
+        ctx->launches += nl;
+    }
+    J2K_CUDA(ctx, cudaMemcpyAsync(data, ctx->d_out.p, n * out_el, cudaMemcpyDeviceToHost, ctx->stream));
+    J2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return J2KGPU_OK;
+}
+
+extern "C" int j2kgpu_idwt53(j2kgpu_ctx *ctx, int mode, int32_t *data, uint32_t width, uint32_t height, uint32_t levels)
+{
+    return stage_idwt(ctx, mode, data, width, height, levels, 0);
+}
+
+extern "C" int j2kgpu_idwt97(j2kgpu_ctx *ctx, int mode, double *data, uint32_t width, uint32_t height, uint32_t levels)
+{
+    return stage_idwt(ctx, mode, data, width, height, levels, 1);
+}
+
+extern "C" int j2kgpu_apply_inverse_dwt(j2kgpu_ctx *ctx, int mode, int32_t *data, uint32_t width, uint32_t height,
+                                        uint32_t levels, int reversible)
+{
+    return stage_idwt(ctx, mode, data, width, height, levels, reversible ? 0 : 2);
+}
+
+static int stage_tail(j2kgpu_ctx *ctx, const TailParams &tp, const int32_t *const *comps, int32_t *const *planes_out,
+                      uint32_t width, uint32_t height, int apply_tail, uint8_t *out_pix, uint64_t out_stride)
+{
+    const uint64_t n = (uint64_t)width * height;
+    if (n == 0) return J2KGPU_OK;
+    cudaSetDevice(ctx->device);
+    const int nc = tp.ncomp;
+    int rc;
+    if ((rc = j2k_reserve(ctx, ctx->d_in, n * 4 * nc, false))) return rc;
+    const int32_t *d_c[4] = {nullptr, nullptr, nullptr, nullptr};
+    int32_t *d_o[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int c = 0; c < nc; c++) {
+        if (!comps[c]) return j2k_set_err(ctx, J2KGPU_E_ARG, "null component %d", c);
+        int32_t *p = (int32_t *)ctx->d_in.p + (size_t)c * n;
+        J2K_CUDA(ctx, cudaMemcpyAsync(p, comps[c], n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        d_c[c] = p;
+    }
+    for (int c = nc; c < 4; c++) d_c[c] = d_c[0];
+    if (planes_out) {
+        if ((rc = j2k_reserve(ctx, ctx->d_aux, n * 4 * nc, false))) return rc;
+        for (int c = 0; c < 4; c++) d_o[c] = (int32_t *)ctx->d_aux.p + (size_t)(c < nc ? c : 0) * n;
+    }
+    uint8_t *d_pix = nullptr;
+    if (out_pix) {
+        if ((rc = j2k_reserve(ctx, ctx->d_out, out_stride * height, false))) return rc;
+        d_pix = (uint8_t *)ctx->d_out.p;
+    }
+    cudaError_t e = launch_tail(d_c, planes_out ? d_o : nullptr, d_pix, out_stride, width, height, tp, apply_tail, ctx->stream);
+    if (e != cudaSuccess) return j2k_cuda_err(ctx, e, "tail kernel launch");
+    ctx->launches++;
+    if (planes_out)
+        for (int c = 0; c < nc; c++)
+            J2K_CUDA(ctx, cudaMemcpyAsync(planes_out[c], d_o[c], n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_pix) J2K_CUDA(ctx, cudaMemcpyAsync(out_pix, d_pix, out_stride * height, cudaMemcpyDeviceToHost, ctx->stream));
+    J2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return J2KGPU_OK;
+}
+
+extern "C" int j2kgpu_inverse_rct(j2kgpu_ctx *ctx, int32_t *y, int32_t *u, int32_t *v, uint64_t n)
+{
+    if (!ctx) return J2KGPU_E_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (n == 0) return J2KGPU_OK;
+    if (!y || !u || !v) return j2k_set_err(ctx, J2KGPU_E_ARG, "null plane");
+    if (n > 0xFFFFFFFFull) return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "plane too large");
+    TailParams tp{};
+    tp.ncomp = 3; tp.mct = 1; tp.reversible = 1; tp.fmt = J2KGPU_FMT_RGBA8;
+    for (int c = 0; c < 4; c++) { tp.prec[c] = 8; tp.sgnd[c] = 1; }            // signed: no DC shift
+    const int32_t *in[4] = {y, u, v, nullptr};
+    int32_t *out[4] = {y, u, v, nullptr};
+    return stage_tail(ctx, tp, in, out, (uint32_t)n, 1, 1, nullptr, 0);
+}
+
+extern "C" int j2kgpu_inverse_ict(j2kgpu_ctx *ctx, double *y, double *cb, double *cr, uint64_t n)
+{
+    if (!ctx) return J2KGPU_E_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (n == 0) return J2KGPU_OK;
+    if (!y || !cb || !cr) return j2k_set_err(ctx, J2KGPU_E_ARG, "null plane");
+    cudaSetDevice(ctx->device);
+    int rc;
+    if ((rc = j2k_reserve(ctx, ctx->d_in, n * 8 * 3, false))) return rc;
+    double *d = (double *)ctx->d_in.p;
+    J2K_CUDA(ctx, cudaMemcpyAsync(d, y, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    J2K_CUDA(ctx, cudaMemcpyAsync(d + n, cb, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    J2K_CUDA(ctx, cudaMemcpyAsync(d + 2 * n, cr, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    cudaError_t e = launch_inverse_ict_f64(d, d + n, d + 2 * n, n, ctx->stream);
+    if (e != cudaSuccess) return j2k_cuda_err(ctx, e, "ict kernel launch");
+    ctx->launches++;
+    J2K_CUDA(ctx, cudaMemcpyAsync(y, d, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    J2K_CUDA(ctx, cudaMemcpyAsync(cb, d + n, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    J2K_CUDA(ctx, cudaMemcpyAsync(cr, d + 2 * n, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    J2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return J2KGPU_OK;
+}
+
+extern "C" int j2kgpu_dc_level_shift_inverse(j2kgpu_ctx *ctx, int32_t *data, uint64_t n, int precision)
+{
+    if (!ctx) return J2KGPU_E_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (n == 0) return J2KGPU_OK;
+    if (!data) return j2k_set_err(ctx, J2KGPU_E_ARG, "null data");
+    if (precision < 1 || precision > 31) return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "precision %d", precision);
+    if (n > 0xFFFFFFFFull) return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "plane too large");
+    TailParams tp{};
+    tp.ncomp = 1; tp.mct = 0; tp.reversible = 1; tp.fmt = J2KGPU_FMT_GRAY8;
+    for (int c = 0; c < 4; c++) { tp.prec[c] = precision; tp.sgnd[c] = c != 0; }
+    const int32_t *in[4] = {data, nullptr, nullptr, nullptr};
+    int32_t *out[4] = {data, nullptr, nullptr, nullptr};
+    return stage_tail(ctx, tp, in, out, (uint32_t)n, 1, 1, nullptr, 0);
+}
+
+extern "C" int j2kgpu_mct_dc_pack(j2kgpu_ctx *ctx, const j2k_image_t *img, const int32_t *const *comps,
+                                  int apply_tail, uint8_t *out_pix, uint64_t out_stride)
+{
+    if (!ctx) return J2KGPU_E_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!img || !comps || !out_pix) return j2k_set_err(ctx, J2KGPU_E_ARG, "null argument");
+    TailParams tp;
+    int rc = make_tail(ctx, *img, tp);
+    if (rc) return rc;
+    const int bpp = j2k_fmt_bpp(tp.fmt);
+    if (out_stride < (uint64_t)img->width * bpp || out_stride % bpp) return j2k_set_err(ctx, J2KGPU_E_ARG, "bad out_stride");
+    return stage_tail(ctx, tp, comps, nullptr, img->width, img->height, apply_tail, out_pix, out_stride);
+}

@@ -1,0 +1,130 @@
+// common.h -- internal declarations shared by the CUDA translation units of libj2kgpu.so.
+// Public boundary: include/j2kgpu.h.  Nothing here is exported.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+#include <vector>
+#include <mutex>
+
+#include "../../include/j2kgpu.h"
+
+#define J2K_MAX_LEVELS 10
+
+// ---- device-side tables (uploaded once per job) ---------------------------------------------
+struct DevCblk {                 // one code block, 32 bytes
+    uint64_t data_off;           // into the job blob
+    uint64_t out_off;            // int32 element offset of sample (0,0) in the coefficient arena
+    uint32_t data_len;
+    uint32_t out_stride;         // row stride of the destination plane, in elements
+    uint16_t w, h;
+    uint8_t  band, num_bps, level, num_passes;
+};
+
+struct DevTileComp {             // one tile-component plane
+    uint64_t coef_off;           // int32 element offset of the plane in the coefficient arena
+    uint64_t tmp_off;            // element offset of this plane's two ping-pong level buffers in the scratch arena
+    uint32_t w, h;               // plane size
+    uint32_t tmp_elems;          // elements in ONE ping-pong buffer (= w_1 * h_1)
+    uint32_t pad;
+};
+
+struct DevTile {                 // ncomp tile-components that share a footprint: unit of the fused last level
+    uint32_t tc[4];              // tile-component indices per component
+    uint32_t img_x0, img_y0;     // position of the tile inside the image
+    uint32_t w, h;               // tile-component size (equal for all components)
+    uint64_t out_off;            // byte offset of the owning image's pixel buffer in d_out
+    uint64_t out_stride;         // bytes per output row of the owning image
+    uint32_t img_w, img_h;       // clipping bounds (decoder.go:398-410)
+};
+
+struct TailParams {              // image-wide constants of the MCT / DC / pack epilogue
+    int ncomp;
+    int prec[4];
+    int sgnd[4];
+    int mct;                     // inverse MCT requested and ncomp >= 3
+    int reversible;
+    int fmt;                     // J2KGPU_FMT_* (resolved, never AUTO)
+    int iso;                     // 1: ISO packing (no int32-overflow quirk)
+};
+
+// ---- context -----------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0;
+};
+
+struct j2kgpu_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;       // stream in use (own or external)
+    std::mutex mu;
+    std::string err;
+    uint64_t launches = 0;
+    // grow-only scratch used by the host-buffer entry points
+    DevBuf d_in, d_out, d_aux, d_tab;
+    DevBuf h_in, h_out;                  // pinned staging
+};
+
+struct j2kgpu_job {
+    j2kgpu_ctx *ctx = nullptr;
+    uint32_t n_img = 0, n_tc = 0, n_tiles = 0, n_cb = 0;
+    j2k_image_t hdr{};                   // shared header fields
+    TailParams tail{};
+    int nlevels = 0;
+    uint32_t max_w = 0, max_h = 0;       // largest tile-component
+    int max_bps = 0;
+    bool need_clear = false;
+    DevCblk *d_cblks = nullptr;
+    DevTileComp *d_tcs = nullptr;
+    DevTile *d_tiles = nullptr;
+    int32_t *d_coef = nullptr;  uint64_t coef_elems = 0;
+    void *d_tmp = nullptr;      uint64_t tmp_bytes = 0;
+    uint64_t blob_bytes = 0, out_bytes = 0;
+    std::vector<uint64_t> blob_off, out_off, out_size;
+    // staging for run_host
+    void *d_blob = nullptr; void *d_pix = nullptr;
+    void *h_blob = nullptr; void *h_pix = nullptr;
+};
+
+// ---- error helpers -----------------------------------------------------------------------------
+int j2k_set_err(j2kgpu_ctx *ctx, int code, const char *fmt, ...);
+int j2k_cuda_err(j2kgpu_ctx *ctx, cudaError_t e, const char *what);
+#define J2K_CUDA(ctx, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return j2k_cuda_err((ctx), e__, #call); } while (0)
+int j2k_reserve(j2kgpu_ctx *ctx, DevBuf &b, size_t bytes, bool pinned_host);
+
+// ---- kernel launchers (each returns a cudaError_t; all asynchronous on `s`) ---------------------
+// entropy stage: one warp per code block
+cudaError_t launch_t1_ref(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, int32_t *d_coef,
+                          int max_bps, cudaStream_t s);
+cudaError_t launch_ht_ref(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, int32_t *d_coef,
+                          cudaStream_t s);
+
+// inverse DWT, REF (dense-prefix) addressing.  One call = one decomposition level of every
+// tile-component in the table.  `lvl` counts from 0 (full resolution).  For lvl > 0 the output goes to the
+// tile-component's ping-pong buffer; for lvl == 0 it goes to `d_plane_out` (int32 planes at coef_off, in place
+// is NOT allowed) or, when tiles != nullptr, through the fused MCT + DC + pack epilogue into d_pix.
+struct IdwtLaunch {
+    const DevTileComp *d_tcs; uint32_t n_tc;
+    const DevTile *d_tiles; uint32_t n_tiles;      // only for the fused last level
+    const int32_t *d_coef;                          // coefficient arena
+    void *d_tmp;                                    // ping-pong arena (int32 for 5-3, double for 9-7)
+    int nlevels, lvl;
+    uint32_t max_w, max_h;                          // largest tile-component (grid sizing)
+    int reversible;
+    int f64_io;                                     // 9-7 stage API: coefficient arena and output planes are double
+    int32_t *d_plane_out;                           // lvl == 0 without tiles: output planes (same offsets as coef)
+    uint8_t *d_pix;                                 // lvl == 0 with tiles: packed pixels
+    TailParams tail;
+};
+cudaError_t launch_idwt_level(const IdwtLaunch &p, cudaStream_t s, int *n_launches);
+
+// unfused tail: planar int32 components -> (inverse MCT, DC shift) -> planes and/or packed pixels
+cudaError_t launch_tail(const int32_t *const d_comps[4], int32_t *const d_planes_out[4], uint8_t *d_pix,
+                        uint64_t out_stride, uint32_t width, uint32_t height, const TailParams &tp,
+                        int apply_tail, cudaStream_t s);
+cudaError_t launch_inverse_ict_f64(double *y, double *cb, double *cr, uint64_t n, cudaStream_t s);
+
+int j2k_resolve_fmt(int ncomp, int prec, int fmt);
+int j2k_fmt_bpp(int fmt);

@@ -1,0 +1,428 @@
+// idwt.cu -- inverse 5-3 (int32) / 9-7 (float64) lifting DWT, one decomposition level per launch,
+// shared-memory tiled with halo, with the fused "last level + inverse MCT + DC shift + clamp + pack"
+// epilogue (sm_100a).
+//
+// Replaces dwt.Inverse53/Inverse97 (reference internal/dwt/dwt.go:122-147, 213-262), Inverse2D53/97
+// (dwt.go:410-429, 454-473), ReconstructMultiLevel53/97 (dwt.go:534-573), tcd.ApplyInverseDWT
+// (internal/tcd/tcd.go:416-437) and, in the fused epilogue, mct.InverseRCT/InverseICT (mct.go:43-66),
+// mct.DCLevelShiftInverse (mct.go:113-118), decoder.go:321-348 and createImage (decoder.go:417-588).
+//
+// REF addressing: level l of the reference works IN PLACE on the dense prefix
+// data[0 : w_l*h_l] of the plane (stride w_l).  Here a level is out of place: element i of the level's
+// input comes from the previous (coarser) level's dense output when i < w_{l+1}*h_{l+1} and from the
+// coefficient plane otherwise, and the output goes to a ping-pong buffer -- every coefficient is read
+// from HBM exactly once over the whole reconstruction, and the last level never writes the plane at
+// all: it feeds the pixel epilogue from shared memory / registers.
+//
+// Per CTA: an output tile TH x TW of the level image.  The tile plus HALO interleaved samples on each
+// side is gathered into a shared-memory patch in INTERLEAVED order (the reference's interleave() is
+// folded into the gather; the gather walks each band row contiguously so global loads coalesce),
+// then columns are lifted, then rows ("columns first, then rows", dwt.go:411-428), with the reference's
+// exact edge expressions.  9-7 uses __dmul_rn/__dadd_rn so that no FMA is contracted (Go/amd64 never
+// fuses) -- REF parity for float64 is bit-exact.
+#include "common.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int TW = 64;          // output tile width  (even)
+constexpr int TH = 32;          // output tile height (even)
+
+enum { EPI_STORE = 0, EPI_ROUND_I32 = 1, EPI_PIXELS = 2 };
+
+__device__ __forceinline__ int lvl_dim(int full, int lvl) { return (full + (1 << lvl) - 1) >> lvl; }
+
+// ---- lifting policies -------------------------------------------------------------------------------
+struct Lift53 {
+    typedef int32_t T;
+    static constexpr int HALO = 2;
+    static constexpr int STEPS = 2;
+    static __device__ __forceinline__ T from_i32(int32_t v) { return v; }
+    static __device__ __forceinline__ T scale(T v, int) { return v; }
+    static constexpr bool kScale = false;
+    // step 0: even samples  x -= (l + r + 2) >> 2        (dwt.go:132-138)
+    // step 1: odd samples   x += (l + r) >> 1, last odd of an even-length line: x += l   (dwt.go:141-146)
+    static __device__ __forceinline__ T apply(int step, T x, T l, T r, bool has_l, bool has_r)
+    {
+        uint32_t ux = (uint32_t)x, ul = (uint32_t)l, ur = (uint32_t)r;
+        if (step == 0) {
+            if (!has_l) ul = ur;
+            if (!has_r) ur = ul;
+            return (T)(ux - (uint32_t)((int32_t)(ul + ur + 2u) >> 2));
+        }
+        if (!has_r) return (T)(ux + ul);
+        return (T)(ux + (uint32_t)((int32_t)(ul + ur) >> 1));
+    }
+};
+
+struct Lift97 {
+    typedef double T;
+    static constexpr int HALO = 4;
+    static constexpr int STEPS = 4;
+    static constexpr bool kScale = true;
+    static __device__ __forceinline__ T from_i32(int32_t v) { return (double)v; }        // tcd.go:429-431
+    static __device__ __forceinline__ T scale(T v, int odd)                               // dwt.go:222-227
+    {
+        return __dmul_rn(v, odd ? 0.812893066115961 : 1.230174104914001);
+    }
+    // steps: delta (even), gamma (odd), beta (even), alpha (odd): x -= c * (l + r); at a line end the
+    // reference uses (2c) * neighbour, which is bit-identical to c * (n + n).   (dwt.go:229-261)
+    static __device__ __forceinline__ T apply(int step, T x, T l, T r, bool has_l, bool has_r)
+    {
+        const double c = step == 0 ? 0.443506852043971 : step == 1 ? 0.882911075530934
+                       : step == 2 ? -0.052980118572961 : -1.586134342059924;
+        if (!has_l) l = r;
+        if (!has_r) r = l;
+        return __dsub_rn(x, __dmul_rn(c, __dadd_rn(l, r)));
+    }
+};
+
+// ---- pixel epilogue: decoder.go:321-348 + createImage decoder.go:417-588 ----------------------------
+__device__ __forceinline__ int32_t clampi(int32_t v, int32_t lo, int32_t hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+__device__ __forceinline__ void tail_mct_dc(int32_t v[4], const TailParams &tp)
+{
+    if (tp.mct) {
+        if (tp.reversible) {                                   // mct.go:56-66
+            uint32_t y = (uint32_t)v[0], u = (uint32_t)v[1], w = (uint32_t)v[2];
+            uint32_t g = y - (uint32_t)((int32_t)(u + w) >> 2);
+            v[0] = (int32_t)(w + g); v[1] = (int32_t)g; v[2] = (int32_t)(u + g);
+        } else {                                               // mct.go:43-53 via decoder.go:326-340
+            double y = (double)v[0], cb = (double)v[1], cr = (double)v[2];
+            double r = __dadd_rn(y, __dmul_rn(1.402, cr));
+            double g = __dsub_rn(__dsub_rn(y, __dmul_rn(0.34413, cb)), __dmul_rn(0.71414, cr));
+            double b = __dadd_rn(y, __dmul_rn(1.772, cb));
+            v[0] = __double2int_rz(__dadd_rn(r, 0.5));          // int32(v + 0.5) truncates toward zero
+            v[1] = __double2int_rz(__dadd_rn(g, 0.5));
+            v[2] = __double2int_rz(__dadd_rn(b, 0.5));
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+        if (c < tp.ncomp && !tp.sgnd[c]) v[c] = (int32_t)((uint32_t)v[c] + (1u << (tp.prec[c] - 1)));   // mct.go:113-118
+}
+
+// scaled sample value exactly as createImage computes it (int32 product wraps in REF mode)
+__device__ __forceinline__ uint32_t pack_value(int32_t v, int prec, int32_t maxv, bool iso)
+{
+    v = clampi(v, 0, maxv);
+    if (prec <= 8) {
+        if (prec != 8) v = (int32_t)((uint32_t)v * 255u) / maxv;
+        return (uint32_t)v & 0xFF;
+    }
+    if (iso) return (uint32_t)(((uint64_t)(uint32_t)v * 65535u) / (uint32_t)maxv) & 0xFFFF;
+    v = (int32_t)((uint32_t)v * 65535u) / maxv;
+    return (uint32_t)v & 0xFFFF;
+}
+
+__device__ __forceinline__ void store_pixel(uint8_t *row, uint32_t x, const int32_t v[4], const TailParams &tp)
+{
+    const int prec = tp.prec[0];
+    const int32_t maxv = (int32_t)((1u << prec) - 1u);
+    switch (tp.fmt) {
+    case J2KGPU_FMT_GRAY8:
+        row[x] = (uint8_t)pack_value(v[0], prec, maxv, tp.iso);
+        break;
+    case J2KGPU_FMT_GRAY16: {
+        uint32_t p = pack_value(v[0], prec, maxv, tp.iso);
+        *(uint16_t *)(row + 2 * (size_t)x) = (uint16_t)((p >> 8) | ((p & 0xFF) << 8));      // big-endian
+        break;
+    }
+    case J2KGPU_FMT_RGBA8: {
+        uint32_t r = pack_value(v[0], prec, maxv, tp.iso), g = pack_value(v[1], prec, maxv, tp.iso),
+                 b = pack_value(v[2], prec, maxv, tp.iso);
+        uint32_t a = tp.ncomp == 4 ? pack_value(v[3], prec, maxv, tp.iso) : 255u;
+        *(uint32_t *)(row + 4 * (size_t)x) = r | (g << 8) | (b << 16) | (a << 24);
+        break;
+    }
+    default: {   // RGBA64, big-endian 16-bit channels
+        uint32_t r = pack_value(v[0], prec, maxv, tp.iso), g = pack_value(v[1], prec, maxv, tp.iso),
+                 b = pack_value(v[2], prec, maxv, tp.iso);
+        uint32_t a = tp.ncomp == 4 ? pack_value(v[3], prec, maxv, tp.iso) : 65535u;
+        uint32_t lo = ((r >> 8) | ((r & 0xFF) << 8)) | (((g >> 8) | ((g & 0xFF) << 8)) << 16);
+        uint32_t hi = ((b >> 8) | ((b & 0xFF) << 8)) | (((a >> 8) | ((a & 0xFF) << 8)) << 16);
+        *(uint2 *)(row + 8 * (size_t)x) = make_uint2(lo, hi);
+        break;
+    }
+    }
+}
+
+// ---- one level of one tile-component into the shared patch -------------------------------------------
+struct LevelGeom {
+    int w, h;          // level image size
+    int nlx, nly;      // number of low-pass columns / rows
+    uint32_t nprev;    // elements taken from the previous level's output
+};
+
+template <class L, bool IN_F64>
+__device__ __forceinline__ typename L::T load_src(uint32_t lin, uint32_t nprev, const typename L::T *prev,
+                                                  const void *coef)
+{
+    if (lin < nprev) return prev[lin];
+    if (IN_F64) return (typename L::T)((const double *)coef)[lin];
+    return L::from_i32(((const int32_t *)coef)[lin]);
+}
+
+template <class L, bool IN_F64>
+__device__ void transform_tile(typename L::T *P, const LevelGeom &g, int x0, int y0,
+                               const typename L::T *prev, const void *coef, bool no_xform)
+{
+    typedef typename L::T T;
+    constexpr int HALO = L::HALO, PW = TW + 2 * HALO, PH = TH + 2 * HALO, PP = PW + 1;
+    const int tid = threadIdx.x;
+    const bool do_v = g.h >= 2 && !no_xform, do_h = g.w >= 2 && !no_xform;
+
+    // gather: patch row j <-> interleaved row y0-HALO+j; walk de-interleaved column order so that
+    // consecutive threads read consecutive addresses of the band row
+    for (int e = tid; e < PH * PW; e += kThreads) {
+        int j = e / PW, k = e - j * PW;
+        int i = (k < PW / 2) ? 2 * k : 2 * (k - PW / 2) + 1;
+        int yy = y0 - HALO + j, xx = x0 - HALO + i;
+        if (yy < 0 || yy >= g.h || xx < 0 || xx >= g.w) continue;
+        int ry = do_v ? ((yy & 1) ? g.nly + (yy >> 1) : (yy >> 1)) : yy;
+        int cx = do_h ? ((xx & 1) ? g.nlx + (xx >> 1) : (xx >> 1)) : xx;
+        T v = load_src<L, IN_F64>((uint32_t)ry * (uint32_t)g.w + (uint32_t)cx, g.nprev, prev, coef);
+        if (L::kScale) {                                   // 9-7: K on even / 1/K on odd, per direction
+            if (do_v) v = L::scale(v, yy & 1);
+        }
+        P[j * PP + i] = v;
+    }
+    __syncthreads();
+
+    // ---- columns (vertical) ----
+    if (do_v) {
+#pragma unroll
+        for (int s = 0; s < L::STEPS; s++) {
+            const int margin = L::STEPS - 2 - s;
+            int ya = y0 - (margin > 0 ? margin : 0), yb = y0 + TH + margin;       // inclusive range
+            if (ya < 0) ya = 0;
+            if (yb > g.h - 1) yb = g.h - 1;
+            if ((ya & 1) != (s & 1)) ya++;
+            const int nrows = yb >= ya ? ((yb - ya) >> 1) + 1 : 0;
+            for (int e = tid; e < nrows * PW; e += kThreads) {
+                int r = e / PW, i = e - r * PW;
+                int yy = ya + 2 * r, j = yy - (y0 - HALO);
+                int xx = x0 - HALO + i;
+                if (xx < 0 || xx >= g.w) continue;
+                bool hl = yy - 1 >= 0, hr = yy + 1 < g.h;
+                T l = hl ? P[(j - 1) * PP + i] : T(0), rr = hr ? P[(j + 1) * PP + i] : T(0);
+                P[j * PP + i] = L::apply(s, P[j * PP + i], l, rr, hl, hr);
+            }
+            __syncthreads();
+        }
+    }
+    // ---- rows (horizontal), only the TH output rows ----
+    if (do_h) {
+        if (L::kScale) {
+            for (int e = tid; e < TH * PW; e += kThreads) {
+                int r = e / PW, i = e - r * PW;
+                int yy = y0 + r, xx = x0 - HALO + i;
+                if (yy >= g.h || xx < 0 || xx >= g.w) continue;
+                int j = r + HALO;
+                P[j * PP + i] = L::scale(P[j * PP + i], xx & 1);
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int s = 0; s < L::STEPS; s++) {
+            const int margin = L::STEPS - 2 - s;
+            int xa = x0 - (margin > 0 ? margin : 0), xb = x0 + TW + margin;
+            if (xa < 0) xa = 0;
+            if (xb > g.w - 1) xb = g.w - 1;
+            if ((xa & 1) != (s & 1)) xa++;
+            const int ncols = xb >= xa ? ((xb - xa) >> 1) + 1 : 0;
+            for (int e = tid; e < TH * ncols; e += kThreads) {
+                int r = e / ncols, c = e - r * ncols;
+                int yy = y0 + r;
+                if (yy >= g.h) continue;
+                int xx = xa + 2 * c, i = xx - (x0 - HALO), j = r + HALO;
+                bool hl = xx - 1 >= 0, hr = xx + 1 < g.w;
+                T l = hl ? P[j * PP + i - 1] : T(0), rr = hr ? P[j * PP + i + 1] : T(0);
+                P[j * PP + i] = L::apply(s, P[j * PP + i], l, rr, hl, hr);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---- kernel: one level, every tile-component (EPI_STORE / EPI_ROUND_I32) ------------------------------
+template <class L, bool IN_F64, int EPI>
+__global__ void __launch_bounds__(kThreads)
+k_idwt_level(const DevTileComp *__restrict__ tcs, const void *__restrict__ coef, typename L::T *tmp,
+             void *out_planes, int nlevels, int lvl)
+{
+    typedef typename L::T T;
+    constexpr int HALO = L::HALO, PW = TW + 2 * HALO, PH = TH + 2 * HALO, PP = PW + 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *P = (T *)smem_raw;
+
+    const DevTileComp tc = tcs[blockIdx.z];
+    LevelGeom g;
+    g.w = lvl_dim((int)tc.w, lvl); g.h = lvl_dim((int)tc.h, lvl);
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    if (x0 >= g.w || y0 >= g.h) return;
+    g.nlx = (g.w + 1) >> 1; g.nly = (g.h + 1) >> 1;
+    const bool no_xform = nlevels == 0;
+    g.nprev = (lvl + 1 < nlevels) ? (uint32_t)g.nlx * (uint32_t)g.nly : 0u;
+    T *pp0 = tmp + tc.tmp_off, *pp1 = pp0 + tc.tmp_elems;
+    const T *prev = ((lvl + 1) & 1) ? pp1 : pp0;
+    const void *cbase = IN_F64 ? (const void *)((const double *)coef + tc.coef_off)
+                               : (const void *)((const int32_t *)coef + tc.coef_off);
+    transform_tile<L, IN_F64>(P, g, x0, y0, prev, cbase, no_xform);
+
+    for (int e = threadIdx.x; e < TH * TW; e += kThreads) {
+        int r = e / TW, c = e - r * TW;
+        int yy = y0 + r, xx = x0 + c;
+        if (yy >= g.h || xx >= g.w) continue;
+        T v = P[(r + HALO) * PP + c + HALO];
+        size_t o = (size_t)yy * g.w + xx;
+        if (lvl > 0) {
+            ((lvl & 1) ? pp1 : pp0)[o] = v;
+        } else if (EPI == EPI_ROUND_I32) {
+            ((int32_t *)out_planes)[tc.coef_off + o] = __double2int_rz(__dadd_rn((double)v, 0.5));   // tcd.go:433-435
+        } else {
+            ((T *)out_planes)[tc.coef_off + o] = v;
+        }
+    }
+}
+
+// ---- kernel: last level of every tile, fused with inverse MCT + DC shift + clamp + pack ---------------
+template <class L>
+__global__ void __launch_bounds__(kThreads)
+k_idwt_last_pixels(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__ tiles,
+                   const int32_t *__restrict__ coef, typename L::T *tmp, uint8_t *pix, int nlevels,
+                   TailParams tp)
+{
+    typedef typename L::T T;
+    constexpr int HALO = L::HALO, PW = TW + 2 * HALO, PP = PW + 1;
+    constexpr int PER = TH * TW / kThreads;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *P = (T *)smem_raw;
+
+    const DevTile tile = tiles[blockIdx.z];
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    if (x0 >= (int)tile.w || y0 >= (int)tile.h) return;
+    LevelGeom g;
+    g.w = (int)tile.w; g.h = (int)tile.h;
+    g.nlx = (g.w + 1) >> 1; g.nly = (g.h + 1) >> 1;
+    g.nprev = nlevels > 1 ? (uint32_t)g.nlx * (uint32_t)g.nly : 0u;
+
+    int32_t acc[4][PER];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        if (c >= tp.ncomp) break;
+        const DevTileComp tc = tcs[tile.tc[c]];
+        const T *prev = tmp + tc.tmp_off + tc.tmp_elems;          // level 1 wrote ping-pong buffer 1
+        transform_tile<L, false>(P, g, x0, y0, prev, coef + tc.coef_off, nlevels == 0);
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            int e = threadIdx.x + k * kThreads;
+            int r = e / TW, cc = e - r * TW;
+            T v = P[(r + HALO) * PP + cc + HALO];
+            if (sizeof(T) == 8) acc[c][k] = __double2int_rz(__dadd_rn((double)v, 0.5));   // tcd.go:433-435
+            else acc[c][k] = (int32_t)v;
+        }
+        __syncthreads();
+    }
+    uint8_t *img = pix + tile.out_off;
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        int e = threadIdx.x + k * kThreads;
+        int r = e / TW, cc = e - r * TW;
+        int yy = y0 + r, xx = x0 + cc;
+        if (yy >= g.h || xx >= g.w) continue;
+        uint32_t gx = tile.img_x0 + xx, gy = tile.img_y0 + yy;
+        if (gx >= tile.img_w || gy >= tile.img_h) continue;      // decoder.go:398-410 clipping
+        int32_t v[4] = {acc[0][k], tp.ncomp > 1 ? acc[1][k] : 0, tp.ncomp > 2 ? acc[2][k] : 0,
+                        tp.ncomp > 3 ? acc[3][k] : 0};
+        tail_mct_dc(v, tp);
+        store_pixel(img + (size_t)gy * tile.out_stride, gx, v, tp);
+    }
+}
+
+// ---- unfused tail over whole planes (stage entry points) ------------------------------------------------
+__global__ void k_tail(const int32_t *c0, const int32_t *c1, const int32_t *c2, const int32_t *c3,
+                       int32_t *o0, int32_t *o1, int32_t *o2, int32_t *o3, uint8_t *pix, uint64_t out_stride,
+                       uint32_t width, uint32_t height, TailParams tp, int apply_tail)
+{
+    uint64_t n = (uint64_t)width * height;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        int32_t v[4] = {c0[i], tp.ncomp > 1 ? c1[i] : 0, tp.ncomp > 2 ? c2[i] : 0, tp.ncomp > 3 ? c3[i] : 0};
+        if (apply_tail) tail_mct_dc(v, tp);
+        if (o0) { o0[i] = v[0]; if (tp.ncomp > 1) o1[i] = v[1]; if (tp.ncomp > 2) o2[i] = v[2]; if (tp.ncomp > 3) o3[i] = v[3]; }
+        if (pix) {
+            uint32_t y = (uint32_t)(i / width), x = (uint32_t)(i - (uint64_t)y * width);
+            store_pixel(pix + (size_t)y * out_stride, x, v, tp);
+        }
+    }
+}
+
+__global__ void k_inverse_ict_f64(double *y, double *cb, double *cr, uint64_t n)       // mct.go:43-53
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        double a = y[i], b = cb[i], c = cr[i];
+        y[i]  = __dadd_rn(a, __dmul_rn(1.402, c));
+        cb[i] = __dsub_rn(__dsub_rn(a, __dmul_rn(0.34413, b)), __dmul_rn(0.71414, c));
+        cr[i] = __dadd_rn(a, __dmul_rn(1.772, b));
+    }
+}
+
+template <class L>
+constexpr size_t patch_bytes() { return sizeof(typename L::T) * (size_t)(TH + 2 * L::HALO) * (TW + 2 * L::HALO + 1); }
+
+template <class L, bool IN_F64, int EPI>
+cudaError_t run_level(const IdwtLaunch &p, dim3 grid, cudaStream_t s)
+{
+    k_idwt_level<L, IN_F64, EPI><<<grid, kThreads, patch_bytes<L>(), s>>>(
+        p.d_tcs, (const void *)p.d_coef, (typename L::T *)p.d_tmp, (void *)p.d_plane_out, p.nlevels, p.lvl);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_idwt_level(const IdwtLaunch &p, cudaStream_t s, int *n_launches)
+{
+    const int lvl = p.lvl;
+    uint32_t lw = (p.max_w + (1u << lvl) - 1) >> lvl, lh = (p.max_h + (1u << lvl) - 1) >> lvl;
+    if (lw == 0 || lh == 0) return cudaSuccess;
+    if (n_launches) (*n_launches)++;
+    const bool pixels = (lvl == 0 && p.d_tiles != nullptr);
+    dim3 grid((lw + TW - 1) / TW, (lh + TH - 1) / TH, pixels ? p.n_tiles : p.n_tc);
+    if (grid.z == 0) return cudaSuccess;
+    if (pixels) {
+        if (p.reversible)
+            k_idwt_last_pixels<Lift53><<<grid, kThreads, patch_bytes<Lift53>(), s>>>(
+                p.d_tcs, p.d_tiles, p.d_coef, (int32_t *)p.d_tmp, p.d_pix, p.nlevels, p.tail);
+        else
+            k_idwt_last_pixels<Lift97><<<grid, kThreads, patch_bytes<Lift97>(), s>>>(
+                p.d_tcs, p.d_tiles, p.d_coef, (double *)p.d_tmp, p.d_pix, p.nlevels, p.tail);
+        return cudaGetLastError();
+    }
+    if (p.reversible) return run_level<Lift53, false, EPI_STORE>(p, grid, s);
+    if (p.f64_io)     return run_level<Lift97, true, EPI_STORE>(p, grid, s);
+    return run_level<Lift97, false, EPI_ROUND_I32>(p, grid, s);
+}
+
+cudaError_t launch_tail(const int32_t *const d_comps[4], int32_t *const d_planes_out[4], uint8_t *d_pix,
+                        uint64_t out_stride, uint32_t width, uint32_t height, const TailParams &tp,
+                        int apply_tail, cudaStream_t s)
+{
+    uint64_t n = (uint64_t)width * height;
+    if (n == 0) return cudaSuccess;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_tail<<<blocks, 256, 0, s>>>(d_comps[0], d_comps[1], d_comps[2], d_comps[3],
+                                  d_planes_out ? d_planes_out[0] : nullptr, d_planes_out ? d_planes_out[1] : nullptr,
+                                  d_planes_out ? d_planes_out[2] : nullptr, d_planes_out ? d_planes_out[3] : nullptr,
+                                  d_pix, out_stride, width, height, tp, apply_tail);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_inverse_ict_f64(double *y, double *cb, double *cr, uint64_t n, cudaStream_t s)
+{
+    if (n == 0) return cudaSuccess;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_inverse_ict_f64<<<blocks, 256, 0, s>>>(y, cb, cr, n);
+    return cudaGetLastError();
+}

@@ -1,0 +1,372 @@
+// t1_ref.cu -- EBCOT tier-1 block decoder, REF semantics, one warp per code block (sm_100a).
+//
+// Replaces entropy.T1.Decode (reference internal/entropy/t1.go:1261-1410) together with
+// MQDecoder (internal/entropy/mqc.go:370-497) and the context rules of t1.go:349-479 /
+// t1_luts.go:35-110.  REF quirks kept: raster-order SPP/MRP, stripe-order cleanup, run-length
+// only on full 4-row columns, all MQ contexts start in state 0 (UNI 92), no pass truncation.
+//
+// Design (not a port of the Go loops): the (w+2)(h+2) byte flag array and the int32 magnitude
+// array of the reference become ROW BITMAPS -- one 64-bit word per code-block row for each of
+// significance / sign / visited / refined, plus one bitmap per magnitude bit-plane -- held in
+// shared memory (about 2 KB + 512 B per bit-plane per block instead of 21 KB).  Neighbourhood
+// tests are 64-bit shifts of three row words; the candidate set of a whole row is one boolean
+// expression; the zero-coding context is a 9-bit window (3 rows x 3 columns) indexing a 512-entry
+// table in constant memory.  The MQ decision chain is inherently serial, so the 32 lanes execute
+// it in lock-step on warp-uniform registers (no divergence, shared-memory loads are broadcasts);
+// the lanes split the work that IS parallel: clearing state, assembling magnitudes from the
+// bit-plane bitmaps, applying signs and the coalesced store into the tile-component plane.
+#include "common.h"
+
+namespace {
+
+constexpr int kWarpsPerCta = 4;
+constexpr int kCtxZC = 0, kCtxSC = 9, kCtxMag = 14, kCtxRL = 17, kCtxUni = 18, kNumCtx = 19;
+
+__constant__ uint32_t c_mq[94];          // qe | nmps << 16 | nlps << 24      (mqc.go:21-116)
+__constant__ uint8_t  c_zc9[4 * 512];    // band, 3x3 significance window -> ZC context (t1_luts.go:35-110)
+__constant__ uint8_t  c_sc[256];         // W,E,N,S (sig,neg) pairs -> (SC context - 9) << 1 | prediction (t1.go:387-460)
+
+struct MQ {
+    uint32_t A, C, CT;
+    int bp, len;
+    uint32_t cur;                        // data[bp] when bp < len
+    const uint8_t *d;
+};
+
+// byteIn, mqc.go:402-439
+__device__ __forceinline__ void mq_bytein(MQ &m)
+{
+    if (m.bp >= m.len) { m.C += 0xFF00; m.CT = 8; return; }
+    uint32_t nxt = (m.bp + 1 < m.len) ? (uint32_t)__ldg(m.d + m.bp + 1) : 0xFFu;
+    if (m.cur == 0xFF) {
+        if (nxt > 0x8F) { m.C += 0xFF00; m.CT = 8; }
+        else { m.bp++; m.cur = nxt; m.C += nxt << 9; m.CT = 7; }
+    } else {
+        m.bp++; m.cur = nxt; m.C += nxt << 8; m.CT = 8;
+    }
+}
+
+// NewMQDecoder, mqc.go:370-399
+__device__ __forceinline__ void mq_init(MQ &m, const uint8_t *d, int len)
+{
+    m.d = d; m.len = len; m.A = 0x8000; m.CT = 0; m.bp = 0;
+    if (len == 0) { m.C = 0xFFu << 16; m.cur = 0; }
+    else { m.cur = __ldg(d); m.C = m.cur << 16; }
+    mq_bytein(m);
+    m.C <<= 7;
+    m.CT -= 7;
+    m.A = 0x8000;
+}
+
+// Decode + renormDec, mqc.go:443-497.  ctxs = 19 state indices in shared memory (warp-uniform).
+__device__ __forceinline__ uint32_t mq_decode(MQ &m, uint8_t *ctxs, int ctx)
+{
+    uint32_t st = ctxs[ctx];
+    uint32_t row = c_mq[st];
+    uint32_t qe = row & 0xFFFF;
+    uint32_t mps = st & 1, d;
+    m.A -= qe;
+    if ((m.C >> 16) < qe) {
+        if (m.A < qe) { d = mps;     st = (row >> 16) & 0xFF; }
+        else          { d = mps ^ 1; st = row >> 24; }
+        m.A = qe;
+    } else {
+        m.C -= qe << 16;
+        if (m.A & 0x8000) return mps;
+        if (m.A < qe) { d = mps ^ 1; st = row >> 24; }
+        else          { d = mps;     st = (row >> 16) & 0xFF; }
+    }
+    ctxs[ctx] = (uint8_t)st;
+    do {
+        if (m.CT == 0) mq_bytein(m);
+        m.A <<= 1; m.C <<= 1; m.CT--;
+    } while ((m.A & 0x8000) == 0);
+    return d;
+}
+
+// bits (x-1, x, x+1) of a row word as a 3-bit value; columns outside 0..63 read as 0
+__device__ __forceinline__ uint32_t win3(uint64_t row, int x)
+{
+    return (uint32_t)(x ? (row >> (x - 1)) : (row << 1)) & 7u;
+}
+
+// decodeSign t1.go:1322-1328 with getSCContext t1.go:387-460; returns 1 for negative
+__device__ __forceinline__ uint32_t decode_sign(MQ &m, uint8_t *ctxs, int x,
+                                                uint64_t sup, uint64_t smid, uint64_t sdn,
+                                                uint64_t nup, uint64_t nmid, uint64_t ndn)
+{
+    uint32_t ms = win3(smid, x), mn = win3(nmid, x);
+    uint32_t idx = (ms & 1) | ((mn & 1) << 1) | ((ms >> 2) << 2) | ((mn >> 2) << 3) |
+                   ((uint32_t)((sup >> x) & 1) << 4) | ((uint32_t)((nup >> x) & 1) << 5) |
+                   ((uint32_t)((sdn >> x) & 1) << 6) | ((uint32_t)((ndn >> x) & 1) << 7);
+    uint32_t e = c_sc[idx];
+    return mq_decode(m, ctxs, kCtxSC + (e >> 1)) ^ (e & 1);
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_t1_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob,
+         int32_t *__restrict__ coef, int plane_words /* 64 * max_bps */, int skip_empty)
+{
+    extern __shared__ uint64_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t blk = blockIdx.x * kWarpsPerCta + warp;
+    if (blk >= n) return;
+    const DevCblk cb = cblks[blk];
+    const int w = cb.w, h = cb.h, nbps = cb.num_bps, band = cb.band & 3;
+
+    const int words = 66 + 64 * 3 + plane_words + 4;
+    uint64_t *base = smem + (size_t)warp * words;
+    uint64_t *sig = base + 1;            // rows -1 .. 64
+    uint64_t *neg = base + 66;
+    uint64_t *visit = base + 130;
+    uint64_t *refine = base + 194;
+    uint64_t *planes = base + 258;       // [bp][row]
+    uint8_t *ctxs = (uint8_t *)(base + 258 + plane_words);
+
+    int32_t *out = coef + cb.out_off;
+    const uint32_t ostride = cb.out_stride;
+
+    if ((cb.data_len == 0 && skip_empty) || nbps == 0) {          // tcd.go:394-396: not coded -> zeros
+        for (int y = 0; y < h; y++)
+            for (int x = lane; x < w; x += 32) out[(size_t)y * ostride + x] = 0;
+        return;
+    }
+
+    for (int i = lane; i < 258 + 64 * nbps; i += 32) base[i] = 0;
+    if (lane < kNumCtx) ctxs[lane] = (lane == kCtxUni) ? 92 : 0;   // mqc.go:378-383
+    __syncwarp();
+
+    MQ mq;
+    mq_init(mq, blob + cb.data_off, (int)cb.data_len);
+    const uint64_t wmask = (w >= 64) ? ~0ull : ((1ull << w) - 1);
+    const uint8_t *zc = c_zc9 + band * 512;
+
+    for (int bp = nbps - 1; bp >= 0; bp--) {
+        uint64_t *plane = planes + bp * 64;
+
+        // ---- significance propagation, raster order (t1.go:1295-1319) ----
+        for (int y = 0; y < h; y++) {
+            const uint64_t up = sig[y - 1], dn = sig[y + 1];
+            uint64_t mid = sig[y];
+            const uint64_t nbs = up | (up << 1) | (up >> 1) | dn | (dn << 1) | (dn >> 1);
+            if (((nbs | mid) & wmask) == 0) continue;               // nothing can be a candidate
+            const uint64_t nup = y > 0 ? neg[y - 1] : 0, ndn = y < 63 ? neg[y + 1] : 0;
+            uint64_t nmid = neg[y], todo = wmask, vis = 0, bits = 0;
+            for (;;) {
+                uint64_t cand = ~mid & (nbs | (mid << 1) | (mid >> 1)) & todo;
+                if (!cand) break;
+                int x = __ffsll((long long)cand) - 1;
+                todo = (x >= 63) ? 0 : (todo & (~0ull << (x + 1)));
+                uint32_t idx9 = win3(up, x) | (win3(mid, x) << 3) | (win3(dn, x) << 6);
+                if (mq_decode(mq, ctxs, kCtxZC + zc[idx9])) {
+                    bits |= 1ull << x;
+                    if (decode_sign(mq, ctxs, x, up, mid, dn, nup, nmid, ndn)) nmid |= 1ull << x;
+                    mid |= 1ull << x;
+                }
+                vis |= 1ull << x;
+            }
+            sig[y] = mid; neg[y] = nmid; visit[y] = vis;
+            if (bits) plane[y] |= bits;
+        }
+
+        // ---- magnitude refinement, raster order (t1.go:1331-1347) ----
+        for (int y = 0; y < h; y++) {
+            const uint64_t mid = sig[y];
+            uint64_t cand = mid & ~visit[y];
+            if (!cand) continue;
+            const uint64_t up = sig[y - 1], dn = sig[y + 1], ref = refine[y];
+            uint64_t bits = 0;
+            refine[y] = ref | cand;
+            while (cand) {
+                int x = __ffsll((long long)cand) - 1;
+                cand &= cand - 1;
+                int ctx;
+                if ((ref >> x) & 1) ctx = kCtxMag + 2;
+                else ctx = kCtxMag + ((win3(up, x) | win3(dn, x) | (win3(mid, x) & 5)) ? 1 : 0);
+                if (mq_decode(mq, ctxs, ctx)) bits |= 1ull << x;
+            }
+            if (bits) plane[y] |= bits;
+        }
+
+        // ---- cleanup, 4-row stripes, column by column (t1.go:1350-1410) ----
+        for (int y0 = 0; y0 < h; y0 += 4) {
+            uint64_t s[6], ng[6], v[4], pb[4];
+#pragma unroll
+            for (int k = 0; k < 6; k++) { s[k] = sig[y0 - 1 + k]; ng[k] = neg[(y0 - 1 + k) & 63]; }
+            // neg[] has rows 0..63 only: rows -1 and 64 are never negative, mask them out
+            if (y0 == 0) ng[0] = 0;
+            if (y0 + 4 >= 64) ng[5] = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) { v[k] = visit[(y0 + k) & 63]; pb[k] = 0; }
+            const bool full = (y0 + 4 <= h);
+            const int rows = full ? 4 : (h - y0);
+            for (int x = 0; x < w; x++) {
+                bool rl = false;
+                int pos = 0;
+                if (full) {
+                    uint32_t any = win3(s[0], x) | win3(s[1], x) | win3(s[2], x) | win3(s[3], x) |
+                                   win3(s[4], x) | win3(s[5], x) |
+                                   (uint32_t)(((v[0] | v[1] | v[2] | v[3]) >> x) & 1);
+                    if (any == 0) {                               // canUseRunLength t1.go:1195-1208
+                        if (!mq_decode(mq, ctxs, kCtxRL)) continue;
+                        pos = (int)(mq_decode(mq, ctxs, kCtxUni) << 1);
+                        pos |= (int)mq_decode(mq, ctxs, kCtxUni);
+                        rl = true;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (k >= rows) break;
+                    bool newsig;
+                    if (rl) {
+                        if (k < pos) continue;
+                        if (k == pos) newsig = true;
+                        else {
+                            uint32_t idx9 = win3(s[k], x) | (win3(s[k + 1], x) << 3) | (win3(s[k + 2], x) << 6);
+                            newsig = mq_decode(mq, ctxs, kCtxZC + zc[idx9]) != 0;
+                        }
+                    } else {
+                        if ((v[k] >> x) & 1) continue;            // visited in SPP: flag cleared below
+                        if ((s[k + 1] >> x) & 1) continue;
+                        uint32_t idx9 = win3(s[k], x) | (win3(s[k + 1], x) << 3) | (win3(s[k + 2], x) << 6);
+                        newsig = mq_decode(mq, ctxs, kCtxZC + zc[idx9]) != 0;
+                    }
+                    if (newsig) {
+                        pb[k] |= 1ull << x;
+                        if (decode_sign(mq, ctxs, x, s[k], s[k + 1], s[k + 2], ng[k], ng[k + 1], ng[k + 2]))
+                            ng[k + 1] |= 1ull << x;
+                        s[k + 1] |= 1ull << x;
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (k < rows) {
+                    sig[y0 + k] = s[k + 1]; neg[y0 + k] = ng[k + 1]; visit[y0 + k] = 0;
+                    if (pb[k]) plane[y0 + k] |= pb[k];
+                }
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- assemble magnitudes, apply signs (t1.go:1282-1289), coalesced store ----
+    for (int y = 0; y < h; y++) {
+        uint32_t m0 = 0, m1 = 0;
+        for (int bp = 0; bp < nbps; bp++) {
+            uint64_t pr = planes[bp * 64 + y];
+            m0 |= (uint32_t)((pr >> lane) & 1) << bp;
+            m1 |= (uint32_t)((pr >> (lane + 32)) & 1) << bp;
+        }
+        uint64_t nr = neg[y];
+        if (lane < w)      out[(size_t)y * ostride + lane]      = (int32_t)(((nr >> lane) & 1) ? 0u - m0 : m0);
+        if (lane + 32 < w) out[(size_t)y * ostride + lane + 32] = (int32_t)(((nr >> (lane + 32)) & 1) ? 0u - m1 : m1);
+    }
+}
+
+// ---- host-side table construction -------------------------------------------------------------------
+// ISO/IEC 15444-1 Table C.2 rows (Qe, NMPS, NLPS, SWITCH); the reference's 94-entry table
+// (mqc.go:21-116) is this machine expanded to index 2*state + mps, entry 46 being UNI.
+const uint16_t kQe[47] = {
+    0x5601, 0x3401, 0x1801, 0x0AC1, 0x0521, 0x0221, 0x5601, 0x5401, 0x4801, 0x3801, 0x3001, 0x2401,
+    0x1C01, 0x1601, 0x5601, 0x5401, 0x5101, 0x4801, 0x3801, 0x3401, 0x3001, 0x2801, 0x2401, 0x2201,
+    0x1C01, 0x1801, 0x1601, 0x1401, 0x1201, 0x1101, 0x0AC1, 0x09C1, 0x08A1, 0x0521, 0x0441, 0x02A1,
+    0x0221, 0x0141, 0x0111, 0x0085, 0x0049, 0x0025, 0x0015, 0x0009, 0x0005, 0x0001, 0x5601};
+const uint8_t kNmps[47] = {1, 2, 3, 4, 5, 38, 7, 8, 9, 10, 11, 12, 13, 29, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24,
+                           25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 40, 41, 42, 43, 44, 45, 45, 46};
+const uint8_t kNlps[47] = {1, 6, 9, 12, 29, 33, 6, 14, 14, 14, 17, 18, 20, 21, 14, 14, 15, 16, 17, 18, 19, 19, 20, 21,
+                           22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 40, 41, 42, 43, 46};
+const uint8_t kSwitch[47] = {1, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 1};
+
+int zc_context(int band, int hc, int vc, int dc)                 // t1_luts.go:52-107
+{
+    if (band == J2KGPU_BAND_HH) {
+        int hv = hc + vc;
+        if (hv >= 3) return 8;
+        if (hv == 2) return dc >= 2 ? 7 : (dc >= 1 ? 6 : 5);
+        if (hv == 1) return dc >= 2 ? 4 : 3;
+        return dc >= 2 ? 2 : (dc >= 1 ? 1 : 0);
+    }
+    if (band == J2KGPU_BAND_HL) { int t = hc; hc = vc; vc = t; }
+    if (hc == 2) return 8;
+    if (hc == 1) return vc >= 1 ? 7 : (dc >= 1 ? 6 : 5);
+    if (vc == 2) return 4;
+    if (vc == 1) return dc >= 1 ? 3 : 2;
+    return dc >= 2 ? 1 : 0;
+}
+
+cudaError_t upload_tables()
+{
+    static bool done = false;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> g(mu);
+    if (done) return cudaSuccess;
+    uint32_t mq[94];
+    for (int i = 0; i < 47; i++)
+        for (int m = 0; m < 2; m++) {
+            uint32_t nm = 2u * kNmps[i] + m, nl = 2u * kNlps[i] + (m ^ kSwitch[i]);
+            mq[2 * i + m] = kQe[i] | (nm << 16) | (nl << 24);
+        }
+    uint8_t zc[4 * 512];
+    for (int band = 0; band < 4; band++)
+        for (int i = 0; i < 512; i++) {
+            // window bit layout: row (up, mid, down) * 3 + column (x-1, x, x+1)
+            int nw = i & 1, n = (i >> 1) & 1, ne = (i >> 2) & 1, w = (i >> 3) & 1, e = (i >> 5) & 1,
+                sw = (i >> 6) & 1, s = (i >> 7) & 1, se = (i >> 8) & 1;
+            zc[band * 512 + i] = (uint8_t)zc_context(band, w + e, n + s, nw + ne + sw + se);
+        }
+    uint8_t sc[256];
+    for (int i = 0; i < 256; i++) {                                // t1.go:392-457
+        int hc = 0, vc = 0;
+        if (i & 1)  hc += (i & 2) ? -1 : 1;
+        if (i & 4)  hc += (i & 8) ? -1 : 1;
+        if (i & 16) vc += (i & 32) ? -1 : 1;
+        if (i & 64) vc += (i & 128) ? -1 : 1;
+        int pred = 0, ctx = 0;
+        if (hc < 0) { pred = 1; hc = -hc; }
+        if (hc == 0 && vc < 0) { pred = 1; vc = -vc; }
+        if (hc == 1) ctx = vc == 1 ? 4 : (vc == 0 ? 2 : 1);
+        else if (hc == 0) ctx = vc == 1 ? 1 : 0;
+        else if (hc == 2) ctx = 3;
+        sc[i] = (uint8_t)((ctx << 1) | pred);
+    }
+    cudaError_t e;
+    if ((e = cudaMemcpyToSymbol(c_mq, mq, sizeof mq)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_zc9, zc, sizeof zc)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_sc, sc, sizeof sc)) != cudaSuccess) return e;
+    done = true;
+    return cudaSuccess;
+}
+
+}  // namespace
+
+static cudaError_t launch_t1_ref_impl(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, int32_t *d_coef,
+                                      int max_bps, int skip_empty, cudaStream_t s)
+{
+    if (n == 0) return cudaSuccess;
+    cudaError_t e = upload_tables();
+    if (e != cudaSuccess) return e;
+    if (max_bps < 1) max_bps = 1;
+    int plane_words = 64 * max_bps;
+    size_t smem = (size_t)kWarpsPerCta * (66 + 64 * 3 + plane_words + 4) * sizeof(uint64_t);
+    if (smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(k_t1_ref, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    uint32_t grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
+    k_t1_ref<<<grid, kWarpsPerCta * 32, smem, s>>>(d_cblks, n, d_blob, d_coef, plane_words, skip_empty);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_t1_ref(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, int32_t *d_coef,
+                          int max_bps, cudaStream_t s)
+{
+    return launch_t1_ref_impl(d_cblks, n, d_blob, d_coef, max_bps, 1, s);
+}
+
+// stage API form: T1.Decode is also defined for empty data (decodes the 0xFF fill, mqc.go:387-388)
+cudaError_t launch_t1_ref_stage(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, int32_t *d_coef,
+                                int max_bps, cudaStream_t s)
+{
+    return launch_t1_ref_impl(d_cblks, n, d_blob, d_coef, max_bps, 0, s);
+}

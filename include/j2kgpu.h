@@ -1,0 +1,190 @@
+/*
+ * j2kgpu.h -- C ABI of the B200 (sm_100a) JPEG 2000 tile-component decode path.
+ *
+ * This is the drop-in boundary for mrjoshuak/go-jpeg2000 (reference, pure Go):
+ * the reference has NO FFI of its own, so each entry point below
+ * replaces one Go-internal function and cites it.  A cgo binding
+ * (go/j2kgpu_cgo.go, shown in INTEGRATION.md) swaps the body of
+ * decoder.decodeTiles (decoder.go:311-359) for one call to j2kgpu_decode().
+ *
+ * Rules of the boundary (cgo-safe):
+ *  - POD only; tables hold offsets, never pointers; host byte order.
+ *  - The caller owns every host buffer.  The library copies what it needs before
+ *    returning and keeps no host pointer after the call.
+ *  - Calls are blocking unless the name ends in _async.  A ctx serialises its
+ *    calls (one decode at a time); use one ctx per goroutine / GPU.
+ *  - Errors: 0 = OK, negative = J2KGPU_E_*; j2kgpu_last_error(ctx) holds the
+ *    sticky detail (CUDA error string, offending index).  Nothing aborts or
+ *    panics on malformed input (reference fuzz contract, fuzz_test.go:10-63).
+ *  - There is no CPU fallback: without a CUDA device j2kgpu_create() fails.
+ */
+#ifndef J2KGPU_H
+#define J2KGPU_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define J2KGPU_ABI_VERSION 1
+
+/* ---- status codes ---------------------------------------------------------- */
+enum {
+    J2KGPU_OK            = 0,
+    J2KGPU_E_ARG         = -1,   /* null pointer, zero size, inconsistent table        */
+    J2KGPU_E_RANGE       = -2,   /* block outside its tile-component / blob, bad offset  */
+    J2KGPU_E_UNSUPPORTED = -3,   /* component count (decoder.go:585), block > 64x64, ... */
+    J2KGPU_E_CUDA        = -4,   /* CUDA runtime error, see j2kgpu_last_error()          */
+    J2KGPU_E_NOMEM       = -5,
+    J2KGPU_E_NODEVICE    = -6
+};
+
+/* conformance mode */
+enum {
+    J2KGPU_MODE_REF = 0,   /* bit-exact to the reference's stage functions (parity contract) */
+    J2KGPU_MODE_ISO = 1    /* ISO/IEC 15444-1/-15 semantics (what real codestreams need)     */
+};
+
+/* band type, internal/entropy/t1.go:125-130 */
+enum { J2KGPU_BAND_LL = 0, J2KGPU_BAND_HL = 1, J2KGPU_BAND_LH = 2, J2KGPU_BAND_HH = 3 };
+
+/* output pixel layout == the Go image types chosen by createImage (decoder.go:417-588) */
+enum {
+    J2KGPU_FMT_AUTO    = 0,   /* pick from ncomp/prec exactly like createImage          */
+    J2KGPU_FMT_GRAY8   = 1,   /* image.Gray    1 B/px                                   */
+    J2KGPU_FMT_GRAY16  = 2,   /* image.Gray16  2 B/px big-endian                        */
+    J2KGPU_FMT_RGBA8   = 3,   /* image.RGBA    4 B/px, A = 255 for 3 components         */
+    J2KGPU_FMT_RGBA64  = 4    /* image.RGBA64  8 B/px big-endian, A = 65535             */
+};
+
+/* ---- job description (flattened codestream.Header + tcd model) ------------ */
+
+/* one image: codestream.Header fields the path reads (header.go:8-48) */
+typedef struct {
+    uint32_t width, height;     /* image area: Xsiz-XOsiz, Ysiz-YOsiz (decoder.go:286-287)   */
+    uint16_t ncomp;             /* 1, 3 or 4 (decoder.go:427,585)                           */
+    uint8_t  prec[4];           /* ComponentInfo[c].Precision()                              */
+    uint8_t  sgnd[4];           /* ComponentInfo[c].IsSigned()                               */
+    uint8_t  mct;               /* COD MultipleComponentXf (decoder.go:322)                  */
+    uint8_t  reversible;        /* CodingStyle.IsReversible(): 1 = 5-3/RCT, 0 = 9-7/ICT      */
+    uint8_t  nlevels;           /* NumDecompositions                                         */
+    uint8_t  ht;                /* Header.IsHTJ2K() (header.go:241-257)                      */
+    uint8_t  mode;              /* J2KGPU_MODE_*                                             */
+    uint8_t  out_fmt;           /* J2KGPU_FMT_*                                              */
+} j2k_image_t;
+
+/* one tile-component (tcd.TileComponent, tcd.go:272-283): bounds in image
+ * coordinates relative to the image origin; the coefficient plane is
+ * (x1-x0) x (y1-y0) int32, row-major. */
+typedef struct {
+    uint32_t comp;
+    uint32_t x0, y0, x1, y1;
+    uint64_t coeff_off;         /* reserved (device arena offset); set 0                    */
+} j2k_tilecomp_t;
+
+/* one code block (tcd.CodeBlock, tcd.go:18-41) */
+typedef struct {
+    uint64_t data_off;          /* into blob                                                 */
+    uint32_t data_len;          /* 0 => block not coded => all-zero (tcd.go:394-396)         */
+    uint32_t tilecomp;          /* index into the tile-component table                       */
+    uint16_t x0, y0, w, h;      /* placement inside the tile-component plane; w,h <= 64      */
+    uint8_t  band;              /* J2KGPU_BAND_*                                             */
+    uint8_t  level;             /* decomposition level of the band (ISO mode)                */
+    uint8_t  num_bps;           /* CodeBlock.TotalBitPlanes: bit length of max|x|            */
+    uint8_t  num_passes;        /* ISO mode: coding passes present (0 = all); REF: ignored   */
+    float    step;              /* ISO mode dequantisation step; REF: ignored                */
+} j2k_cblk_t;
+
+/* one image of a batch (cfg5: many frames, one call) */
+typedef struct {
+    j2k_image_t           image;
+    const j2k_tilecomp_t *tilecomps;  uint32_t n_tilecomps;
+    const j2k_cblk_t     *cblks;      uint32_t n_cblks;
+    const uint8_t        *blob;       uint64_t blob_len;
+    uint8_t              *out_pix;    uint64_t out_stride;   /* bytes per output row          */
+} j2k_batch_item_t;
+
+/* stage-level block job (entropy stage in isolation) */
+typedef struct {
+    uint64_t data_off;  uint32_t data_len;
+    uint32_t out_off;           /* element offset into the int32 output array               */
+    uint16_t w, h;
+    uint8_t  band, num_bps, rsv0, rsv1;
+} j2k_blkjob_t;
+
+typedef struct j2kgpu_ctx j2kgpu_ctx;
+typedef struct j2kgpu_job j2kgpu_job;
+
+/* ---- context ---------------------------------------------------------------- */
+int         j2kgpu_abi_version(void);
+int         j2kgpu_create(int device, j2kgpu_ctx **out);
+void        j2kgpu_destroy(j2kgpu_ctx *ctx);
+const char *j2kgpu_strerror(int code);
+const char *j2kgpu_last_error(const j2kgpu_ctx *ctx);
+/* Use an externally owned CUDA stream (cudaStream_t, e.g. torch's current stream)
+ * for all work of this ctx; NULL restores the ctx's own stream. */
+int         j2kgpu_set_stream(j2kgpu_ctx *ctx, void *cuda_stream);
+/* kernels launched by this ctx since creation (bench.py's gpu_launches) */
+uint64_t    j2kgpu_launch_count(const j2kgpu_ctx *ctx);
+
+/* ---- whole path: replaces decoder.decodeTiles (decoder.go:282-360) ---------- *
+ * blocks -> coefficient planes (DecodeCodeBlock tcd.go:393) -> ApplyInverseDWT
+ * (tcd.go:416) -> inverse MCT + DC shift (decoder.go:321-348) -> createImage
+ * (decoder.go:417).  Host buffers in, host pixels out (H2D/D2H inside).       */
+int j2kgpu_decode(j2kgpu_ctx *ctx, const j2k_image_t *img,
+                  const j2k_tilecomp_t *tilecomps, uint32_t n_tilecomps,
+                  const j2k_cblk_t *cblks, uint32_t n_cblks,
+                  const uint8_t *blob, uint64_t blob_len,
+                  uint8_t *out_pix, uint64_t out_stride);
+/* many images in one call; all items must share ncomp/prec/sgnd/mct/reversible/
+ * nlevels/ht/mode (geometry may differ). */
+int j2kgpu_decode_batch(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *items);
+
+/* ---- device-resident form (inputs and outputs stay in HBM) ------------------ *
+ * A job is a batch whose tables have been validated, flattened and uploaded.
+ * j2kgpu_job_run launches the whole path on the ctx stream with DEVICE pointers
+ * and returns without synchronising (CUDA-graph friendly).  d_blob holds the
+ * items' blobs back to back in item order; d_out holds the items' pixel buffers
+ * back to back (item i at byte offset j2kgpu_job_out_offset(job, i)).          */
+int      j2kgpu_job_create(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *items, j2kgpu_job **out);
+void     j2kgpu_job_destroy(j2kgpu_job *job);
+uint64_t j2kgpu_job_blob_bytes(const j2kgpu_job *job);
+uint64_t j2kgpu_job_out_bytes(const j2kgpu_job *job);
+uint64_t j2kgpu_job_out_offset(const j2kgpu_job *job, uint32_t item);
+int      j2kgpu_job_run(j2kgpu_job *job, const void *d_blob, void *d_out);
+/* stage subsets of the same job, for per-stage timing: entropy only / DWT+MCT+pack only */
+int      j2kgpu_job_run_entropy(j2kgpu_job *job, const void *d_blob);
+int      j2kgpu_job_run_dwt_mct(j2kgpu_job *job, void *d_out);
+/* host-buffer run of a prepared job (pinned staging + H2D + kernels + D2H, blocking) */
+int      j2kgpu_job_run_host(j2kgpu_job *job, const j2k_batch_item_t *items);
+int      j2kgpu_sync(j2kgpu_ctx *ctx);
+
+/* ---- per-stage entry points (differential tests against the oracle) --------- */
+/* entropy.T1.Decode (t1.go:1261) over n blocks; out = concatenated w*h int32 */
+int j2kgpu_t1_decode_blocks(j2kgpu_ctx *ctx, int mode, const j2k_blkjob_t *jobs, uint32_t n,
+                            const uint8_t *blob, uint64_t blob_len, int32_t *out, uint64_t out_len);
+/* entropy.HTDecoder.Decode (ht.go:93) over n blocks */
+int j2kgpu_ht_decode_blocks(j2kgpu_ctx *ctx, int mode, const j2k_blkjob_t *jobs, uint32_t n,
+                            const uint8_t *blob, uint64_t blob_len, int32_t *out, uint64_t out_len);
+/* dwt.ReconstructMultiLevel53 (dwt.go:534): in place on a host buffer */
+int j2kgpu_idwt53(j2kgpu_ctx *ctx, int mode, int32_t *data, uint32_t width, uint32_t height, uint32_t levels);
+/* dwt.ReconstructMultiLevel97 (dwt.go:561): float64, in place */
+int j2kgpu_idwt97(j2kgpu_ctx *ctx, int mode, double *data, uint32_t width, uint32_t height, uint32_t levels);
+/* tcd.TileDecoder.ApplyInverseDWT (tcd.go:416): int32 plane in place, 9-7 through float64 */
+int j2kgpu_apply_inverse_dwt(j2kgpu_ctx *ctx, int mode, int32_t *data, uint32_t width, uint32_t height,
+                             uint32_t levels, int reversible);
+/* mct.InverseRCT (mct.go:56) / mct.InverseICT (mct.go:43) / mct.DCLevelShiftInverse (mct.go:113) */
+int j2kgpu_inverse_rct(j2kgpu_ctx *ctx, int32_t *y, int32_t *u, int32_t *v, uint64_t n);
+int j2kgpu_inverse_ict(j2kgpu_ctx *ctx, double *y, double *cb, double *cr, uint64_t n);
+int j2kgpu_dc_level_shift_inverse(j2kgpu_ctx *ctx, int32_t *data, uint64_t n, int precision);
+/* decoder.go:321-348 + createImage (decoder.go:417): planar int32 components -> Pix.
+ * apply_tail != 0 runs inverse MCT + DC shift first; 0 packs the planes as they are. */
+int j2kgpu_mct_dc_pack(j2kgpu_ctx *ctx, const j2k_image_t *img, const int32_t *const *comps,
+                       int apply_tail, uint8_t *out_pix, uint64_t out_stride);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* J2KGPU_H */

@@ -35,50 +35,33 @@ extern "C" {
 enum { ORC_BAND_LL = 0, ORC_BAND_HL = 1, ORC_BAND_LH = 2, ORC_BAND_HH = 3 };
 
 /* ---- MQ coder (internal/entropy/mqc.go) -------------------------------- */
-/* Encode n (ctx,bit) decisions; returns number of bytes written to out (<= cap),
- * or -1 if cap is too small.  mqc.go:185-349 */
-int  orc_mq_encode(const uint8_t *ctxs, const uint8_t *bits, int n, uint8_t *out, int cap);
 /* Decode n decisions with the given context sequence.  mqc.go:370-497 */
 void orc_mq_decode(const uint8_t *data, int len, const uint8_t *ctxs, int n, uint8_t *bits_out);
 
 /* ---- EBCOT tier-1 (internal/entropy/t1.go, t1_luts.go, t1_fast5.go) ---- */
-/* T1.SetData + T1.Encode: returns byte count (0 == nil, all-zero block), -1 if
- * cap too small; *num_bps receives the bit length of max|x| (t1_fast5.go:13-28). */
-int  orc_t1_encode(const int32_t *coeffs, int w, int h, int band, uint8_t *out, int cap, int *num_bps);
 /* T1.Decode on a fresh T1 (t1.go:1261-1292).  out has w*h entries. */
 void orc_t1_decode(const uint8_t *data, int len, int w, int h, int num_bps, int band, int32_t *out);
 /* the ZC context table (t1_luts.go:35-110), 4*256 entries, for table tests */
 const uint8_t *orc_t1_zc_lut(void);
 
 /* ---- HT block coder (internal/entropy/ht.go, ht_luts.go) --------------- */
-int  orc_ht_encode(const int32_t *coeffs, int w, int h, int band, uint8_t *out, int cap);
 /* HTDecoder.Decode on a fresh (zeroed) decoder, ht.go:93-150. */
 void orc_ht_decode(const uint8_t *data, int len, int w, int h, int32_t *out);
 
 /* ---- DWT (internal/dwt/dwt.go) ------------------------------------------ */
-void orc_fwd53(int32_t *d, int n);                      /* dwt.go:73-118  */
 void orc_inv53(int32_t *d, int n);                      /* dwt.go:122-147 */
-void orc_fwd97(double *d, int n);                       /* dwt.go:161-210 */
 void orc_inv97(double *d, int n);                       /* dwt.go:213-262 */
-void orc_fwd2d53(int32_t *d, int w, int h);             /* dwt.go:356-407 */
 void orc_inv2d53(int32_t *d, int w, int h);             /* dwt.go:410-429 */
-void orc_fwd2d97(double *d, int w, int h);              /* dwt.go:432-451 */
 void orc_inv2d97(double *d, int w, int h);              /* dwt.go:454-473 */
-void orc_decompose53(int32_t *d, int w, int h, int levels);   /* dwt.go:524-531 */
 void orc_reconstruct53(int32_t *d, int w, int h, int levels); /* dwt.go:534-548 */
-void orc_decompose97(double *d, int w, int h, int levels);    /* dwt.go:551-558 */
 void orc_reconstruct97(double *d, int w, int h, int levels);  /* dwt.go:561-573 */
-void orc_quantize(const double *in, double step, int32_t *out, size_t n);   /* dwt.go:500-511 */
 void orc_dequantize(const int32_t *in, double step, double *out, size_t n); /* dwt.go:514-520 */
 /* TileDecoder.ApplyInverseDWT, internal/tcd/tcd.go:416-437 */
 void orc_apply_inverse_dwt(int32_t *d, int w, int h, int levels, int reversible);
 
 /* ---- MCT / DC shift (internal/mct/mct.go) ------------------------------- */
-void orc_fwd_rct(int32_t *r, int32_t *g, int32_t *b, size_t n);   /* mct.go:28-38  */
 void orc_inv_rct(int32_t *y, int32_t *u, int32_t *v, size_t n);   /* mct.go:56-66  */
-void orc_fwd_ict(double *r, double *g, double *b, size_t n);      /* mct.go:14-24  */
 void orc_inv_ict(double *y, double *cb, double *cr, size_t n);    /* mct.go:43-53  */
-void orc_dc_shift_forward(int32_t *d, size_t n, int prec);        /* mct.go:96-101 */
 void orc_dc_shift_inverse(int32_t *d, size_t n, int prec);        /* mct.go:113-118 */
 
 /* ---- decoder tail (decoder.go) ------------------------------------------- */

@@ -25,14 +25,7 @@ static const double kDelta = 0.443506852043971;
 static const double kK     = 1.230174104914001;
 static const double kKInv  = 0.812893066115961;
 
-/* deinterleave / interleave dwt.go:265-306 */
-static void deinterleave_i(int32_t *d, int n, int32_t *tmp)
-{
-    int half = (n + 1) / 2;
-    for (int i = 0, j = 0; i < n; i += 2, j++) tmp[j] = d[i];
-    for (int i = 1, j = half; i < n; i += 2, j++) tmp[j] = d[i];
-    memcpy(d, tmp, sizeof(int32_t) * (size_t)n);
-}
+/* interleave dwt.go:287-306, 329-346 */
 static void interleave_i(int32_t *d, int n, int32_t *tmp)
 {
     int half = (n + 1) / 2;
@@ -40,30 +33,12 @@ static void interleave_i(int32_t *d, int n, int32_t *tmp)
     for (int i = 0, j = 0; j < half; i += 2, j++) d[i] = tmp[j];
     for (int i = 1, j = half; j < n; i += 2, j++) d[i] = tmp[j];
 }
-static void deinterleave_f(double *d, int n, double *tmp)
-{
-    int half = (n + 1) / 2;
-    for (int i = 0, j = 0; i < n; i += 2, j++) tmp[j] = d[i];
-    for (int i = 1, j = half; i < n; i += 2, j++) tmp[j] = d[i];
-    memcpy(d, tmp, sizeof(double) * (size_t)n);
-}
 static void interleave_f(double *d, int n, double *tmp)
 {
     int half = (n + 1) / 2;
     memcpy(tmp, d, sizeof(double) * (size_t)n);
     for (int i = 0, j = 0; j < half; i += 2, j++) d[i] = tmp[j];
     for (int i = 1, j = half; j < n; i += 2, j++) d[i] = tmp[j];
-}
-
-static void fwd53_t(int32_t *d, int n, int32_t *tmp)     /* dwt.go:73-118 */
-{
-    if (n < 2) return;
-    for (int i = 1; i < n - 1; i += 2) d[i] = WSUB(d[i], WADD(d[i - 1], d[i + 1]) >> 1);
-    if ((n & 1) == 0) d[n - 1] = WSUB(d[n - 1], d[n - 2]);
-    d[0] = WADD(d[0], WADD(WADD(d[1], d[1]), 2) >> 2);
-    for (int i = 2; i < n - 1; i += 2) d[i] = WADD(d[i], WADD(WADD(d[i - 1], d[i + 1]), 2) >> 2);
-    if (n & 1) d[n - 1] = WADD(d[n - 1], WADD(WADD(d[n - 2], d[n - 2]), 2) >> 2);
-    deinterleave_i(d, n, tmp);
 }
 
 static void inv53_t(int32_t *d, int n, int32_t *tmp)     /* dwt.go:122-147 */
@@ -75,24 +50,6 @@ static void inv53_t(int32_t *d, int n, int32_t *tmp)     /* dwt.go:122-147 */
     if (n & 1) d[n - 1] = WSUB(d[n - 1], WADD(WADD(d[n - 2], d[n - 2]), 2) >> 2);
     for (int i = 1; i < n - 1; i += 2) d[i] = WADD(d[i], WADD(d[i - 1], d[i + 1]) >> 1);
     if ((n & 1) == 0) d[n - 1] = WADD(d[n - 1], d[n - 2]);
-}
-
-static void fwd97_t(double *d, int n, double *tmp)       /* dwt.go:161-210 */
-{
-    if (n < 2) return;
-    for (int i = 1; i < n - 1; i += 2) d[i] += kAlpha * (d[i - 1] + d[i + 1]);
-    if ((n & 1) == 0) d[n - 1] += (2 * kAlpha) * d[n - 2];
-    d[0] += (2 * kBeta) * d[1];
-    for (int i = 2; i < n - 1; i += 2) d[i] += kBeta * (d[i - 1] + d[i + 1]);
-    if (n & 1) d[n - 1] += (2 * kBeta) * d[n - 2];
-    for (int i = 1; i < n - 1; i += 2) d[i] += kGamma * (d[i - 1] + d[i + 1]);
-    if ((n & 1) == 0) d[n - 1] += (2 * kGamma) * d[n - 2];
-    d[0] += (2 * kDelta) * d[1];
-    for (int i = 2; i < n - 1; i += 2) d[i] += kDelta * (d[i - 1] + d[i + 1]);
-    if (n & 1) d[n - 1] += (2 * kDelta) * d[n - 2];
-    for (int i = 0; i < n; i += 2) d[i] *= kKInv;
-    for (int i = 1; i < n; i += 2) d[i] *= kK;
-    deinterleave_f(d, n, tmp);
 }
 
 static void inv97_t(double *d, int n, double *tmp)       /* dwt.go:213-262 */
@@ -113,23 +70,8 @@ static void inv97_t(double *d, int n, double *tmp)       /* dwt.go:213-262 */
     if ((n & 1) == 0) d[n - 1] -= (2 * kAlpha) * d[n - 2];
 }
 
-void orc_fwd53(int32_t *d, int n) { if (n < 2) return; int32_t *t = malloc(sizeof(int32_t) * (size_t)n); fwd53_t(d, n, t); free(t); }
 void orc_inv53(int32_t *d, int n) { if (n < 2) return; int32_t *t = malloc(sizeof(int32_t) * (size_t)n); inv53_t(d, n, t); free(t); }
-void orc_fwd97(double *d, int n) { if (n < 2) return; double *t = malloc(sizeof(double) * (size_t)n); fwd97_t(d, n, t); free(t); }
 void orc_inv97(double *d, int n) { if (n < 2) return; double *t = malloc(sizeof(double) * (size_t)n); inv97_t(d, n, t); free(t); }
-
-void orc_fwd2d53(int32_t *d, int w, int h)               /* rows then columns, dwt.go:356-407 */
-{
-    int m = w > h ? w : h;
-    int32_t *tmp = malloc(sizeof(int32_t) * (size_t)m), *col = malloc(sizeof(int32_t) * (size_t)h);
-    for (int y = 0; y < h; y++) fwd53_t(d + (size_t)y * w, w, tmp);
-    for (int x = 0; x < w; x++) {
-        for (int y = 0; y < h; y++) col[y] = d[(size_t)y * w + x];
-        fwd53_t(col, h, tmp);
-        for (int y = 0; y < h; y++) d[(size_t)y * w + x] = col[y];
-    }
-    free(tmp); free(col);
-}
 
 void orc_inv2d53(int32_t *d, int w, int h)               /* columns then rows, dwt.go:410-429 */
 {
@@ -141,19 +83,6 @@ void orc_inv2d53(int32_t *d, int w, int h)               /* columns then rows, d
         for (int y = 0; y < h; y++) d[(size_t)y * w + x] = col[y];
     }
     for (int y = 0; y < h; y++) inv53_t(d + (size_t)y * w, w, tmp);
-    free(tmp); free(col);
-}
-
-void orc_fwd2d97(double *d, int w, int h)                /* dwt.go:432-451 */
-{
-    int m = w > h ? w : h;
-    double *tmp = malloc(sizeof(double) * (size_t)m), *col = malloc(sizeof(double) * (size_t)h);
-    for (int y = 0; y < h; y++) fwd97_t(d + (size_t)y * w, w, tmp);
-    for (int x = 0; x < w; x++) {
-        for (int y = 0; y < h; y++) col[y] = d[(size_t)y * w + x];
-        fwd97_t(col, h, tmp);
-        for (int y = 0; y < h; y++) d[(size_t)y * w + x] = col[y];
-    }
     free(tmp); free(col);
 }
 
@@ -170,11 +99,6 @@ void orc_inv2d97(double *d, int w, int h)                /* dwt.go:454-473 */
     free(tmp); free(col);
 }
 
-void orc_decompose53(int32_t *d, int w, int h, int levels)     /* dwt.go:524-531 */
-{
-    for (int l = 0; l < levels; l++) { orc_fwd2d53(d, w, h); w = (w + 1) / 2; h = (h + 1) / 2; }
-}
-
 void orc_reconstruct53(int32_t *d, int w, int h, int levels)   /* dwt.go:534-548 */
 {
     if (levels <= 0) return;
@@ -184,11 +108,6 @@ void orc_reconstruct53(int32_t *d, int w, int h, int levels)   /* dwt.go:534-548
     free(ws); free(hs);
 }
 
-void orc_decompose97(double *d, int w, int h, int levels)      /* dwt.go:551-558 */
-{
-    for (int l = 0; l < levels; l++) { orc_fwd2d97(d, w, h); w = (w + 1) / 2; h = (h + 1) / 2; }
-}
-
 void orc_reconstruct97(double *d, int w, int h, int levels)    /* dwt.go:561-573 */
 {
     if (levels <= 0) return;
@@ -196,13 +115,6 @@ void orc_reconstruct97(double *d, int w, int h, int levels)    /* dwt.go:561-573
     for (int l = 0; l < levels; l++) { ws[l] = w; hs[l] = h; w = (w + 1) / 2; h = (h + 1) / 2; }
     for (int l = levels - 1; l >= 0; l--) orc_inv2d97(d, ws[l], hs[l]);
     free(ws); free(hs);
-}
-
-void orc_quantize(const double *in, double step, int32_t *out, size_t n)   /* dwt.go:500-511 */
-{
-    double inv = 1.0 / step;
-    for (size_t i = 0; i < n; i++)
-        out[i] = in[i] >= 0 ? (int32_t)floor(in[i] * inv + 0.5) : (int32_t)ceil(in[i] * inv - 0.5);
 }
 
 void orc_dequantize(const int32_t *in, double step, double *out, size_t n) /* dwt.go:514-520 */

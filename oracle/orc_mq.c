@@ -46,95 +46,6 @@ void orc_mq_tables_init(void)
     g_tables_ready = 1;
 }
 
-/* ---- encoder: NewMQEncoder mqc.go:185-201 ---------------------------------- */
-void orc_mqenc_init(orc_mqenc *e, uint8_t *buf, int cap)
-{
-    orc_mq_tables_init();
-    e->A = 0x8000; e->C = 0; e->CT = 12;
-    e->buf = buf; e->cap = cap; e->bp = 0; e->overflow = 0;
-    if (cap > 0) buf[0] = 0;                 /* the dummy byte "bp[-1]" */
-    else e->overflow = 1;
-    memset(e->ctx, 0, sizeof e->ctx);        /* every context starts in state 0 ... */
-    e->ctx[ORC_CTX_UNI] = 92;                /* ... except UNI (mqc.go:194-199)      */
-}
-
-static void enc_put(orc_mqenc *e, uint8_t b)
-{
-    e->bp++;
-    if (e->bp >= e->cap) { e->overflow = 1; e->bp = e->cap - 1; return; }
-    e->buf[e->bp] = b;
-}
-
-/* byteOut mqc.go:270-310 */
-static void enc_byte_out(orc_mqenc *e)
-{
-    if (e->overflow) return;
-    if (e->buf[e->bp] == 0xFF) {
-        enc_put(e, (uint8_t)(e->C >> 20));
-        e->C &= 0xFFFFF; e->CT = 7;
-    } else if ((e->C & 0x8000000u) == 0) {
-        enc_put(e, (uint8_t)(e->C >> 19));
-        e->C &= 0x7FFFF; e->CT = 8;
-    } else {
-        e->buf[e->bp]++;
-        if (e->buf[e->bp] == 0xFF) {
-            e->C &= 0x7FFFFFFu;
-            enc_put(e, (uint8_t)(e->C >> 20));
-            e->C &= 0xFFFFF; e->CT = 7;
-        } else {
-            enc_put(e, (uint8_t)(e->C >> 19));
-            e->C &= 0x7FFFF; e->CT = 8;
-        }
-    }
-}
-
-/* renormEnc mqc.go:258-267 */
-static void enc_renorm(orc_mqenc *e)
-{
-    while ((e->A & 0x8000) == 0) {
-        e->A <<= 1; e->C <<= 1; e->CT--;
-        if (e->CT == 0) enc_byte_out(e);
-    }
-}
-
-/* Encode mqc.go:224-255 */
-void orc_mqenc_encode(orc_mqenc *e, int ctx, int d)
-{
-    uint8_t s = e->ctx[ctx];
-    uint32_t qe = orc_mq_qe[s];
-    int mps = s & 1;
-    e->A -= qe;
-    if ((d & 1) == mps) {
-        if ((e->A & 0x8000) == 0) {
-            if (e->A < qe) e->A = qe; else e->C += qe;
-            e->ctx[ctx] = orc_mq_nmps[s];
-            enc_renorm(e);
-        } else {
-            e->C += qe;
-        }
-    } else {
-        if (e->A < qe) e->C += qe; else e->A = qe;
-        e->ctx[ctx] = orc_mq_nlps[s];
-        enc_renorm(e);
-    }
-}
-
-/* Flush mqc.go:313-341 (setbits, two byteOuts, drop trailing 0xFF and the dummy byte) */
-int orc_mqenc_flush(orc_mqenc *e, const uint8_t **start)
-{
-    uint32_t tempC = e->C + e->A;
-    e->C |= 0xFFFF;
-    if (e->C >= tempC) e->C -= 0x8000;
-    e->C <<= e->CT; enc_byte_out(e);
-    e->C <<= e->CT; enc_byte_out(e);
-    if (e->overflow) { *start = NULL; return -1; }
-    int end = e->bp + 1;
-    if (end > 0 && e->buf[end - 1] == 0xFF) end--;
-    if (end > 1) { *start = e->buf + 1; return end - 1; }
-    *start = NULL;
-    return 0;
-}
-
 /* ---- decoder: NewMQDecoder mqc.go:370-399 ---------------------------------- */
 static void dec_byte_in(orc_mqdec *d);
 
@@ -199,25 +110,7 @@ int orc_mqdec_decode(orc_mqdec *d, int ctx)
     return mps;
 }
 
-/* ---- flat test entry points -------------------------------------------------- */
-int orc_mq_encode(const uint8_t *ctxs, const uint8_t *bits, int n, uint8_t *out, int cap)
-{
-    int tmpcap = 2 * n + 64;
-    uint8_t stackbuf[4096];
-    uint8_t *buf = stackbuf;
-    uint8_t *heap = NULL;
-    if (tmpcap > (int)sizeof stackbuf) { heap = (uint8_t *)__builtin_malloc((size_t)tmpcap); buf = heap; }
-    orc_mqenc e;
-    orc_mqenc_init(&e, buf, tmpcap);
-    for (int i = 0; i < n; i++) orc_mqenc_encode(&e, ctxs[i], bits[i]);
-    const uint8_t *start;
-    int len = orc_mqenc_flush(&e, &start);
-    if (len > cap) len = -1;
-    if (len > 0) memcpy(out, start, (size_t)len);
-    if (heap) __builtin_free(heap);
-    return len;
-}
-
+/* ---- flat test entry point ---------------------------------------------------- */
 void orc_mq_decode(const uint8_t *data, int len, const uint8_t *ctxs, int n, uint8_t *bits_out)
 {
     orc_mqdec d;

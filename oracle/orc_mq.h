@@ -17,19 +17,10 @@ void orc_mq_tables_init(void);
 
 typedef struct {
     uint32_t A, C, CT;
-    uint8_t *buf; int cap; int bp; int overflow;
-    uint8_t ctx[ORC_NUM_CTX];
-} orc_mqenc;
-
-typedef struct {
-    uint32_t A, C, CT;
     const uint8_t *data; int len; int bp;
     uint8_t ctx[ORC_NUM_CTX];
 } orc_mqdec;
 
-void orc_mqenc_init(orc_mqenc *e, uint8_t *buf, int cap);
-void orc_mqenc_encode(orc_mqenc *e, int ctx, int d);
-int  orc_mqenc_flush(orc_mqenc *e, const uint8_t **start);   /* returns length, *start = first payload byte */
 void orc_mqdec_init(orc_mqdec *d, const uint8_t *data, int len);
 int  orc_mqdec_decode(orc_mqdec *d, int ctx);
 #endif

@@ -14,31 +14,12 @@
 #define WSUB(a, b) ((int32_t)((uint32_t)(a) - (uint32_t)(b)))
 #define WMUL(a, b) ((int32_t)((uint32_t)(a) * (uint32_t)(b)))
 
-void orc_fwd_rct(int32_t *r, int32_t *g, int32_t *b, size_t n)      /* mct.go:28-38 */
-{
-    for (size_t i = 0; i < n; i++) {
-        int32_t y = WADD(WADD(r[i], WMUL(2, g[i])), b[i]) >> 2;
-        int32_t u = WSUB(b[i], g[i]), v = WSUB(r[i], g[i]);
-        r[i] = y; g[i] = u; b[i] = v;
-    }
-}
-
 void orc_inv_rct(int32_t *y, int32_t *u, int32_t *v, size_t n)      /* mct.go:56-66 */
 {
     for (size_t i = 0; i < n; i++) {
         int32_t g = WSUB(y[i], WADD(u[i], v[i]) >> 2);
         int32_t r = WADD(v[i], g), b = WADD(u[i], g);
         y[i] = r; u[i] = g; v[i] = b;
-    }
-}
-
-void orc_fwd_ict(double *r, double *g, double *b, size_t n)         /* mct.go:14-24 */
-{
-    for (size_t i = 0; i < n; i++) {
-        double y  = 0.299 * r[i] + 0.587 * g[i] + 0.114 * b[i];
-        double cb = -0.16875 * r[i] - 0.33126 * g[i] + 0.5 * b[i];
-        double cr = 0.5 * r[i] - 0.41869 * g[i] - 0.08131 * b[i];
-        r[i] = y; g[i] = cb; b[i] = cr;
     }
 }
 
@@ -50,12 +31,6 @@ void orc_inv_ict(double *y, double *cb, double *cr, size_t n)       /* mct.go:43
         double b = y[i] + 1.772 * cb[i];
         y[i] = r; cb[i] = g; cr[i] = b;
     }
-}
-
-void orc_dc_shift_forward(int32_t *d, size_t n, int prec)           /* mct.go:96-101 */
-{
-    int32_t s = (int32_t)((uint32_t)1 << (prec - 1));
-    for (size_t i = 0; i < n; i++) d[i] = WSUB(d[i], s);
 }
 
 void orc_dc_shift_inverse(int32_t *d, size_t n, int prec)           /* mct.go:113-118 */

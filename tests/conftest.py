@@ -29,3 +29,30 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+def load_package():
+    """import go-jpeg2000_b200/ (hyphenated directory) under the module name go_jpeg2000_b200"""
+    import importlib.util
+    name = "go_jpeg2000_b200"
+    if name in sys.modules:
+        return sys.modules[name]
+    pkg_dir = os.path.join(ROOT, "go-jpeg2000_b200")
+    spec = importlib.util.spec_from_file_location(name, os.path.join(pkg_dir, "__init__.py"),
+                                                  submodule_search_locations=[pkg_dir])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.fixture(scope="session")
+def j2k():
+    return load_package()
+
+
+@pytest.fixture(scope="session")
+def gpu_ctx(j2k):
+    ctx = j2k.Context(0)
+    yield ctx
+    ctx.close()

@@ -6,11 +6,17 @@ cpu_baseline / --impl reference legs.  Builds the library with oracle/Makefile o
 import ctypes as C
 import os
 import subprocess
+import sys
 
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+# encoder-side helpers come from the input generator (datagen/), re-exported for the tests' convenience
+from datagen import (mq_encode, t1_encode, ht_encode, fwd53, fwd97, fwd2d53, fwd2d97, decompose53, decompose97,  # noqa: E402,F401
+                     quantize, fwd_rct, fwd_ict, dc_shift_forward, encode_blocks)
 _lib = None
 
 u8p = C.POINTER(C.c_uint8)
@@ -50,9 +56,6 @@ def lib():
     if _lib is None:
         _lib = C.CDLL(build())
         L = _lib
-        L.orc_mq_encode.restype = C.c_int
-        L.orc_t1_encode.restype = C.c_int
-        L.orc_ht_encode.restype = C.c_int
         L.orc_create_image.restype = C.c_int
         L.orc_decode_image.restype = C.c_int
         L.orc_t1_zc_lut.restype = u8p
@@ -63,13 +66,6 @@ def _p(a, t):
     return a.ctypes.data_as(t)
 
 
-def mq_encode(ctxs, bits):
-    ctxs = np.ascontiguousarray(ctxs, np.uint8)
-    bits = np.ascontiguousarray(bits, np.uint8)
-    out = np.zeros(2 * len(bits) + 64, np.uint8)
-    n = lib().orc_mq_encode(_p(ctxs, u8p), _p(bits, u8p), len(bits), _p(out, u8p), len(out))
-    assert n >= 0
-    return out[:n].tobytes()
 
 
 def mq_decode(data, ctxs):
@@ -80,15 +76,6 @@ def mq_decode(data, ctxs):
     return out
 
 
-def t1_encode(coeffs, w, h, band):
-    """-> (bytes, num_bps); bytes == b'' for an all-zero block (Go nil)."""
-    c = np.ascontiguousarray(coeffs, np.int32).reshape(-1)
-    assert c.size == w * h
-    out = np.zeros(w * h * 4 + 16384, np.uint8)
-    nb = C.c_int(0)
-    n = lib().orc_t1_encode(_p(c, i32p), w, h, band, _p(out, u8p), len(out), C.byref(nb))
-    assert n >= 0
-    return out[:n].tobytes(), nb.value
 
 
 def t1_decode(data, w, h, num_bps, band):
@@ -98,14 +85,6 @@ def t1_decode(data, w, h, num_bps, band):
     return out
 
 
-def ht_encode(coeffs, w, h, band=0):
-    c = np.ascontiguousarray(coeffs, np.int32).reshape(-1)
-    assert c.size == w * h
-    out = np.zeros(max(w * h * 2, 64) * 2 + 64, np.uint8)
-    n = lib().orc_ht_encode(_p(c, i32p), w, h, band, _p(out, u8p), len(out))
-    if n < 0:
-        raise OverflowError("reference HT encoder would index out of range")
-    return out[:n].tobytes()
 
 
 def ht_decode(data, w, h):
@@ -120,17 +99,11 @@ def _inplace(fn, arr, *args):
     return arr
 
 
-def fwd53(d): d = np.array(d, np.int32); return _inplace(lib().orc_fwd53, d, len(d))
 def inv53(d): d = np.array(d, np.int32); return _inplace(lib().orc_inv53, d, len(d))
-def fwd97(d): d = np.array(d, np.float64); return _inplace(lib().orc_fwd97, d, len(d))
 def inv97(d): d = np.array(d, np.float64); return _inplace(lib().orc_inv97, d, len(d))
-def fwd2d53(d, w, h): d = np.array(d, np.int32).reshape(-1); return _inplace(lib().orc_fwd2d53, d, w, h)
 def inv2d53(d, w, h): d = np.array(d, np.int32).reshape(-1); return _inplace(lib().orc_inv2d53, d, w, h)
-def fwd2d97(d, w, h): d = np.array(d, np.float64).reshape(-1); return _inplace(lib().orc_fwd2d97, d, w, h)
 def inv2d97(d, w, h): d = np.array(d, np.float64).reshape(-1); return _inplace(lib().orc_inv2d97, d, w, h)
-def decompose53(d, w, h, L): d = np.array(d, np.int32).reshape(-1); return _inplace(lib().orc_decompose53, d, w, h, L)
 def reconstruct53(d, w, h, L): d = np.array(d, np.int32).reshape(-1); return _inplace(lib().orc_reconstruct53, d, w, h, L)
-def decompose97(d, w, h, L): d = np.array(d, np.float64).reshape(-1); return _inplace(lib().orc_decompose97, d, w, h, L)
 def reconstruct97(d, w, h, L): d = np.array(d, np.float64).reshape(-1); return _inplace(lib().orc_reconstruct97, d, w, h, L)
 
 
@@ -139,11 +112,6 @@ def apply_inverse_dwt(d, w, h, levels, reversible):
     return _inplace(lib().orc_apply_inverse_dwt, d, w, h, levels, int(reversible))
 
 
-def quantize(d, step):
-    d = np.ascontiguousarray(d, np.float64)
-    out = np.zeros(d.size, np.int32)
-    lib().orc_quantize(_p(d, f64p), C.c_double(step), _p(out, i32p), C.c_size_t(d.size))
-    return out
 
 
 def _three(fn, a, b, c, dt):
@@ -152,9 +120,7 @@ def _three(fn, a, b, c, dt):
     return a, b, c
 
 
-def fwd_rct(r, g, b): return _three(lib().orc_fwd_rct, r, g, b, np.int32)
 def inv_rct(y, u, v): return _three(lib().orc_inv_rct, y, u, v, np.int32)
-def fwd_ict(r, g, b): return _three(lib().orc_fwd_ict, r, g, b, np.float64)
 def inv_ict(y, cb, cr): return _three(lib().orc_inv_ict, y, cb, cr, np.float64)
 
 
@@ -164,10 +130,6 @@ def dc_shift_inverse(d, prec):
     return d
 
 
-def dc_shift_forward(d, prec):
-    d = np.array(d, np.int32).reshape(-1)
-    lib().orc_dc_shift_forward(_p(d, i32p), C.c_size_t(d.size), prec)
-    return d
 
 
 def decoder_tail(comps, mct, reversible, prec, sgnd):

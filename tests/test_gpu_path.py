@@ -1,0 +1,135 @@
+"""GPU parity, whole path through j2kgpu_decode / j2kgpu_decode_batch / j2kgpu_job_* (C ABI): pixels identical
+to the oracle's whole REF path (orc_decode_image) on the same job, and -- lossless -- identical to the source
+image (encode -> decode round trip, the size-independent property used at full BASELINE sizes)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from datagen import jobs
+
+pytestmark = pytest.mark.gpu
+
+
+def hdr(j2k, job):
+    return j2k.make_image(job["width"], job["height"], job["ncomp"], job["prec"], sgnd=job["sgnd"], mct=job["mct"],
+                          reversible=job["reversible"], nlevels=job["nlevels"], ht=job["ht"])
+
+
+def oracle_pixels(job):
+    img = O.Image()
+    img.width, img.height, img.ncomp = job["width"], job["height"], job["ncomp"]
+    for c in range(job["ncomp"]):
+        img.prec[c], img.sgnd[c] = job["prec"], job["sgnd"]
+    img.mct, img.reversible, img.nlevels, img.ht = job["mct"], job["reversible"], job["nlevels"], job["ht"]
+    bpp = (1 if job["prec"] <= 8 else 2) if job["ncomp"] == 1 else (4 if job["prec"] <= 8 else 8)
+    stride = job["width"] * bpp
+    return O.decode_image(img, jobs.as_ctypes(job["tilecomps"], O.TileComp), jobs.as_ctypes(job["cblks"], O.CBlk),
+                          job["blob"], stride, stride * job["height"], threads=4)
+
+
+def gpu_pixels(j2k, ctx, job):
+    return ctx.decode_tiles(hdr(j2k, job), jobs.as_ctypes(job["tilecomps"], j2k.TileComp),
+                            jobs.as_ctypes(job["cblks"], j2k.CBlk), job["blob"])
+
+
+CASES = [  # w, h, ncomp, prec, tile_w, tile_h, levels, reversible, ht
+    (96, 80, 3, 8, None, None, 3, 1, 0),
+    (130, 70, 3, 8, 64, 64, 2, 1, 0),          # ragged last tile column / row
+    (64, 64, 1, 8, None, None, 5, 1, 0),
+    (100, 60, 1, 12, 48, 32, 2, 1, 0),         # Gray16
+    (70, 50, 3, 16, None, None, 3, 1, 0),      # RGBA64 + overflow quirk
+    (96, 64, 3, 8, None, None, 3, 0, 0),       # 9-7 + ICT
+    (200, 120, 3, 12, 128, 128, 4, 0, 0),      # 12-bit lossy, tiles
+    (128, 128, 3, 8, 64, 64, 3, 1, 1),         # reference "HT" coder
+    (96, 96, 1, 8, None, None, 0, 1, 0),       # zero decomposition levels
+    (512, 512, 3, 8, None, None, 5, 1, 0),     # BASELINE cfg1: 512x512 RGB 8-bit lossless 5-3, 1 tile, 64x64 blocks
+]
+
+
+@pytest.mark.parametrize("w,h,ncomp,prec,tw,th,levels,rev,ht", CASES)
+def test_whole_path_matches_oracle(j2k, gpu_ctx, w, h, ncomp, prec, tw, th, levels, rev, ht):
+    s = jobs.synth_image(w, h, ncomp, prec, seed=1000 + w + h)
+    job = jobs.build_ref_job(s, prec, tw, th, nlevels=levels, reversible=bool(rev), ht=bool(ht), threads=4)
+    got = gpu_pixels(j2k, gpu_ctx, job)
+    assert np.array_equal(got, oracle_pixels(job))
+    if rev and not ht and prec == 8:                     # lossless round trip: decode(encode(x)) == x
+        pix = got.reshape(h, w, -1)
+        for c in range(ncomp):
+            assert np.array_equal(pix[:, :, c], s[c].astype(np.uint8))
+
+
+def test_uncoded_blocks_and_partial_coverage(j2k, gpu_ctx):
+    """tcd.go:394-396: len(Data)==0 -> block stays zero; planes not covered by any block stay zero"""
+    s = jobs.synth_image(128, 64, 3, 8, seed=5)
+    job = jobs.build_ref_job(s, 8, nlevels=2, reversible=True, threads=2)
+    cb = job["cblks"].copy()
+    cb["data_len"][::3] = 0
+    job["cblks"] = cb[np.arange(len(cb)) % 5 != 4]        # drop every fifth block entirely
+    assert np.array_equal(gpu_pixels(j2k, gpu_ctx, job), oracle_pixels(job))
+
+
+def test_batch_and_job_api(j2k, gpu_ctx):
+    """j2kgpu_decode_batch and the device-resident j2kgpu_job_run agree with per-image decode"""
+    import torch
+    jl = [jobs.build_ref_job(jobs.synth_image(96, 64, 3, 8, seed=40 + i), 8, 64, 64, nlevels=3, reversible=True, threads=2)
+          for i in range(3)]
+    want = [oracle_pixels(j) for j in jl]
+    keep, items, outs = [], [], []
+    for j in jl:
+        tcs, cbs = jobs.as_ctypes(j["tilecomps"], j2k.TileComp), jobs.as_ctypes(j["cblks"], j2k.CBlk)
+        blob = np.ascontiguousarray(j["blob"])
+        out = np.zeros(96 * 64 * 4, np.uint8)
+        keep += [tcs, cbs, blob]
+        outs.append(out)
+        items.append(j2k.BatchItem(hdr(j2k, j), tcs, len(tcs), cbs, len(cbs), blob.ctypes.data_as(j2k.u8p), blob.size,
+                                   out.ctypes.data_as(j2k.u8p), 96 * 4))
+    gpu_ctx.decode_batch(items)
+    for o, w_ in zip(outs, want):
+        assert np.array_equal(o, w_)
+    # device-resident: blobs back to back in HBM, pixels stay in HBM, torch owns memory and stream
+    job = j2k.Job(gpu_ctx, items)
+    d_blob = torch.from_numpy(np.concatenate([j["blob"] for j in jl])).cuda()
+    d_out = torch.zeros(job.out_bytes, dtype=torch.uint8, device="cuda")
+    gpu_ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    n0 = gpu_ctx.launches
+    job.run(d_blob.data_ptr(), d_out.data_ptr())
+    torch.cuda.synchronize()
+    assert gpu_ctx.launches - n0 == 4                     # 1 entropy + 3 DWT levels (last fused with MCT/pack)
+    host = d_out.cpu().numpy()
+    for i, w_ in enumerate(want):
+        assert np.array_equal(host[job.out_offset(i): job.out_offset(i) + w_.size], w_)
+    for o in outs:
+        o[:] = 0
+    job.run_host()
+    for o, w_ in zip(outs, want):
+        assert np.array_equal(o, w_)
+    gpu_ctx.set_stream(0)
+    job.close()
+
+
+def test_path_argument_errors(j2k, gpu_ctx):
+    s = jobs.synth_image(64, 64, 3, 8, seed=9)
+    job = jobs.build_ref_job(s, 8, nlevels=2, reversible=True, threads=2)
+    tcs, cbs = jobs.as_ctypes(job["tilecomps"], j2k.TileComp), jobs.as_ctypes(job["cblks"], j2k.CBlk)
+    bad = hdr(j2k, job)
+    bad.ncomp = 2
+    with pytest.raises(j2k.J2KError) as e:
+        gpu_ctx.decode_tiles(bad, tcs, cbs, job["blob"])
+    assert e.value.code == j2k.E_UNSUPPORTED              # decoder.go:585-586
+    cb2 = job["cblks"].copy()
+    cb2["data_off"][3] = len(job["blob"]) + 10
+    with pytest.raises(j2k.J2KError) as e:
+        gpu_ctx.decode_tiles(hdr(j2k, job), tcs, jobs.as_ctypes(cb2, j2k.CBlk), job["blob"])
+    assert e.value.code == j2k.E_RANGE
+    cb3 = job["cblks"].copy()
+    cb3["x0"][0] = 60
+    with pytest.raises(j2k.J2KError) as e:
+        gpu_ctx.decode_tiles(hdr(j2k, job), tcs, jobs.as_ctypes(cb3, j2k.CBlk), job["blob"])
+    assert e.value.code == j2k.E_RANGE
+    # garbage bytes never fault (fuzz contract): corrupt the blob and compare with the oracle
+    blob = job["blob"].copy()
+    blob[::7] ^= 0xA5
+    job["blob"] = blob
+    assert np.array_equal(gpu_pixels(j2k, gpu_ctx, job), oracle_pixels(job))
