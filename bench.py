@@ -1,0 +1,343 @@
+#!/usr/bin/env python3
+"""bench.py -- decoded Mpixels/s of the B200 JPEG 2000 tile-component decode path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--coder ht|ebcot] [--frames F]
+
+One "step" = one pass of the whole hot path (block entropy decode -> inverse DWT -> inverse RCT -> DC shift ->
+clamp -> RGBA pack) over one batch of F frames of BASELINE configs[1]: 3840x2160 RGB 8-bit lossless,
+5 decomposition levels (6 resolutions), 512x512 tiles, RCT, 64x64 code blocks, block bitstreams produced by the
+reference encoder restated in datagen/ (REF semantics).  Inputs are resident in HBM when the
+timed region starts (`value`); `e2e` times the same batch through the host-buffer C-ABI call with pinned host
+buffers, H2D and D2H inside the timed region.  Timing: CUDA events on the launching stream, barrier +
+synchronize on both sides, max over ranks.  The batch working set (F x (99.5 MB coefficients + 33 MB pixels))
+is larger than the 126 MB L2, so no explicit L2 flush is needed between steps.
+
+Extra objects on the JSON line: roofline (fused last-level IDWT+RCT+DC+pack kernel, algorithmic bytes
+4*W*H*C + W*H*bpp per frame over its CUDA-event time, against MEASURED_PEAKS.json), cpu_baseline (the C oracle,
+a restatement of the reference's Go stage functions, all host threads, bounded sample), clocks.
+
+--impl reference times the CPU implementation alone (oracle port; the Go reference cannot run: no Go toolchain).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+W, H, NCOMP, PREC, TILE, LEVELS = 3840, 2160, 3, 8, 512, 5
+METRIC = "decoded_mpixels_per_s"
+UNIT = "Mpixel/s"
+
+
+def workload_name(coder, frames):
+    return ("cfg2: %dx%d RGB 8-bit lossless 5-3, %d levels, %dx%d tiles, RCT, 64x64 blocks, %s block coder "
+            "(REF semantics), batch of %d frames" % (W, H, LEVELS, TILE, TILE,
+                                                    "reference HT" if coder == "ht" else "EBCOT/MQ", frames))
+
+
+def build_frame(coder, seed, threads):
+    from datagen import jobs
+    s = jobs.synth_image(W, H, NCOMP, PREC, seed=seed)
+    return jobs.build_ref_job(s, PREC, TILE, TILE, nlevels=LEVELS, reversible=True, ht=(coder == "ht"), threads=threads)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_image(O, job):
+    img = O.Image()
+    img.width, img.height, img.ncomp = job["width"], job["height"], job["ncomp"]
+    for c in range(job["ncomp"]):
+        img.prec[c], img.sgnd[c] = job["prec"], job["sgnd"]
+    img.mct, img.reversible, img.nlevels, img.ht = job["mct"], job["reversible"], job["nlevels"], job["ht"]
+    return img
+
+
+def cpu_decode_time(job, threads, reps):
+    """seconds per frame of the oracle's whole path (orc_decode_image) with `threads` host threads"""
+    import oracle_lib as O
+    from datagen import jobs
+    img = oracle_image(O, job)
+    tcs, cbs = jobs.as_ctypes(job["tilecomps"], O.TileComp), jobs.as_ctypes(job["cblks"], O.CBlk)
+    blob = np.ascontiguousarray(job["blob"])
+    out = np.zeros(W * H * 4, np.uint8)
+    fn = O.lib().orc_decode_image
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        rc = fn(C.byref(img), tcs, len(tcs), cbs, len(cbs), blob.ctypes.data_as(O.u8p), C.c_uint64(blob.size),
+                out.ctypes.data_as(O.u8p), C.c_uint64(W * 4), threads)
+        dt = time.perf_counter() - t0
+        assert rc == 0
+        best = dt if best is None else min(best, dt)
+    return best, out
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path on the host cores (oracle port, all threads)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    job = build_frame(args.coder, 1002, threads)
+    for _ in range(min(args.warmup, 1)):
+        cpu_decode_time(job, threads, 1)
+    times = []
+    for _ in range(max(1, args.steps)):
+        t, _ = cpu_decode_time(job, threads, 1)
+        times.append(t)
+    tot = sum(times)
+    val = (W * H / 1e6) * len(times) / tot
+    sample = "1 frame of the workload per step (of %d in the GPU arm's batch)" % args.frames
+    line = {"impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": round(1e3 * tot / len(times), 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": workload_name(args.coder, args.frames), "mode": "REF", "sample": sample},
+            "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                             "note": "C restatement of the reference's Go stage functions (oracle/), not Go: no Go toolchain on the box"},
+            "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from datagen import jobs
+    from __graft_entry__ import load_package
+    j2k = load_package()
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = j2k.Context(local)
+    # an explicit torch stream: the library launches on it and the CUDA events below are recorded on it
+    # (torch's legacy default stream has handle 0, which j2kgpu_set_stream reads as "use the ctx's own stream")
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    ctx.set_stream(stream.cuda_stream)
+
+    threads = max(1, (os.cpu_count() or 1) // max(1, world))
+    F = args.frames
+    # two distinct synthetic frames per rank, alternated through the batch (each item owns its bytes in HBM)
+    base = [build_frame(args.coder, 1002 + 17 * rank + i, threads) for i in range(min(2, F))]
+    frames = [base[i % len(base)] for i in range(F)]
+    bpp, stride = 4, W * 4
+    keep, items, host_out = [], [], []
+    for j in frames:
+        tcs, cbs = jobs.as_ctypes(j["tilecomps"], j2k.TileComp), jobs.as_ctypes(j["cblks"], j2k.CBlk)
+        hb = torch.from_numpy(np.ascontiguousarray(j["blob"])).pin_memory()
+        ho = torch.empty(stride * H, dtype=torch.uint8).pin_memory()
+        keep += [tcs, cbs, hb]
+        host_out.append(ho)
+        img = j2k.make_image(W, H, NCOMP, PREC, nlevels=LEVELS, ht=j["ht"])
+        items.append(j2k.BatchItem(img, tcs, len(tcs), cbs, len(cbs), C.cast(hb.data_ptr(), j2k.u8p), hb.numel(),
+                                   C.cast(ho.data_ptr(), j2k.u8p), stride))
+    job = j2k.Job(ctx, items)
+    d_blob = torch.cat([torch.from_numpy(np.ascontiguousarray(j["blob"])) for j in frames]).cuda()
+    d_out = torch.empty(job.out_bytes, dtype=torch.uint8, device="cuda")
+    n_blocks = sum(len(j["cblks"]) for j in frames)
+    blob_bytes = int(d_blob.numel())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- correctness guard on the exact bench inputs: frame 0 must match the source image (lossless EBCOT) ----
+    job.run(d_blob.data_ptr(), d_out.data_ptr())
+    torch.cuda.synchronize()
+    first = d_out[: stride * H].cpu().numpy().reshape(H, W, 4)
+    if args.coder == "ebcot":
+        src = frames[0]["samples"]
+        for c in range(3):
+            assert np.array_equal(first[:, :, c], src[c].astype(np.uint8)), "bench inputs decode incorrectly"
+
+    # ---- device-resident timing ------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        job.run(d_blob.data_ptr(), d_out.data_ptr())
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    l0 = ctx.launches
+    ev[0].record(stream)
+    for _ in range(args.steps):
+        job.run(d_blob.data_ptr(), d_out.data_ptr())
+    ev[1].record(stream)
+    barrier()
+    ms_total = ev[0].elapsed_time(ev[1])
+    launches = ctx.launches - l0
+
+    # ---- per-stage / per-kernel timing (same inputs, same stream) -----------------------------------------
+    def time_fn(fn, reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ts = []
+        for _ in range(reps):
+            a.record(stream)
+            fn()
+            b.record(stream)
+            b.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.mean(ts)), float(np.min(ts))
+
+    reps = max(3, min(args.steps, 10))
+    job.run_entropy(d_blob.data_ptr())
+    ent_ms, _ = time_fn(lambda: job.run_entropy(d_blob.data_ptr()), reps)
+    dwt_ms, _ = time_fn(lambda: job.run_dwt_mct(d_out.data_ptr()), reps)
+    # the dominant kernel alone: levels 4..1 refill the ping-pong buffers outside the timed pair of events
+    last_ts = []
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(reps):
+        for lvl in range(LEVELS - 1, 0, -1):
+            job.run_level(lvl)
+        a.record(stream)
+        job.run_level(0, d_out.data_ptr())
+        b.record(stream)
+        b.synchronize()
+        last_ts.append(a.elapsed_time(b))
+    last_ms = float(np.mean(last_ts))
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside) -------------
+    for _ in range(max(1, min(args.warmup, 2))):
+        job.run_host()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        job.run_host()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d = blob_bytes
+    d2h = stride * H * F
+    assert np.array_equal(host_out[0].numpy().reshape(H, W, 4), first), "host path differs from device path"
+
+    # ---- reduce over ranks (max time) -----------------------------------------------------------------------
+    if world > 1:
+        t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, e2e_s = float(t[0]), float(t[1])
+    mpix_step = W * H * F * world / 1e6
+    value = mpix_step * args.steps / (ms_total / 1e3)
+    e2e_val = mpix_step * e2e_steps / e2e_s
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        alg_bytes = (4 * W * H * NCOMP + W * H * bpp) * F          # SURVEY.md 8(d), per launch of the fused kernel
+        achieved = alg_bytes / (last_ms / 1e3) / 1e9
+        stage_gbs = alg_bytes / (dwt_ms / 1e3) / 1e9
+        cpu_threads = os.cpu_count() or 1
+        cpu_t, _ = cpu_decode_time(frames[0], cpu_threads, 1 if args.coder == "ebcot" else 2)
+        cpu_val = (W * H / 1e6) / cpu_t
+        line = {
+            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": workload_name(args.coder, F), "mode": "REF", "frames_per_gpu_per_step": F,
+                       "code_blocks_per_step": n_blocks * world, "l2": "working set > L2 (no flush needed)",
+                       "parallelism": "frames sharded across GPUs, no collective"},
+            "e2e": {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": round(1e3 * e2e_s / e2e_steps, 3), "api": "j2kgpu_job_run_host (pinned host buffers)"},
+            "gpu_launches": int(launches),
+            "stages_ms": {"entropy": round(ent_ms, 4), "dwt_mct_pack": round(dwt_ms, 4), "last_level_fused": round(last_ms, 4)},
+            "roofline": {"bound": "hbm", "kernel": "k_idwt_last_pixels<Lift53> (last IDWT level + RCT + DC + clamp + RGBA pack)",
+                         "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "traffic": None,
+                         "dwt_mct_stage_gbs": round(stage_gbs, 1), "dwt_mct_stage_frac": round(stage_gbs / peak, 4)},
+            "cpu_baseline": {"value": round(cpu_val, 2), "unit": UNIT, "cores": cpu_threads, "kind": "port",
+                             "sample": "1 frame of the batch, whole path, all host threads",
+                             "note": "C restatement of the reference's Go stage functions (oracle/); Go itself is absent"},
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    job.close()
+    ctx.set_stream(0)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--coder", default="ht", choices=["ht", "ebcot"])
+    ap.add_argument("--frames", type=int, default=8, help="frames per GPU per step")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

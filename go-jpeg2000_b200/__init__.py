@@ -72,6 +72,7 @@ EXPORTS = [
     "j2kgpu_set_stream", "j2kgpu_launch_count", "j2kgpu_decode", "j2kgpu_decode_batch",
     "j2kgpu_job_create", "j2kgpu_job_destroy", "j2kgpu_job_blob_bytes", "j2kgpu_job_out_bytes",
     "j2kgpu_job_out_offset", "j2kgpu_job_run", "j2kgpu_job_run_entropy", "j2kgpu_job_run_dwt_mct",
+    "j2kgpu_job_run_level",
     "j2kgpu_job_run_host", "j2kgpu_sync", "j2kgpu_t1_decode_blocks", "j2kgpu_ht_decode_blocks",
     "j2kgpu_idwt53", "j2kgpu_idwt97", "j2kgpu_apply_inverse_dwt", "j2kgpu_inverse_rct",
     "j2kgpu_inverse_ict", "j2kgpu_dc_level_shift_inverse", "j2kgpu_mct_dc_pack",
@@ -116,6 +117,7 @@ def lib():
         L.j2kgpu_job_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.j2kgpu_job_run_entropy.argtypes = [C.c_void_p, C.c_void_p]
         L.j2kgpu_job_run_dwt_mct.argtypes = [C.c_void_p, C.c_void_p]
+        L.j2kgpu_job_run_level.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.j2kgpu_job_run_host.argtypes = [C.c_void_p, C.POINTER(BatchItem)]
         for name in ("j2kgpu_t1_decode_blocks", "j2kgpu_ht_decode_blocks"):
             getattr(L, name).argtypes = [C.c_void_p, C.c_int, C.POINTER(BlkJob), C.c_uint32, u8p, C.c_uint64,
@@ -308,6 +310,9 @@ class Job:
 
     def run_dwt_mct(self, d_out_ptr):
         self.ctx._check(lib().j2kgpu_job_run_dwt_mct(self._h, C.c_void_p(d_out_ptr)))
+
+    def run_level(self, lvl, d_out_ptr=0):
+        self.ctx._check(lib().j2kgpu_job_run_level(self._h, lvl, C.c_void_p(d_out_ptr)))
 
     def run_host(self):
         self.ctx._check(lib().j2kgpu_job_run_host(self._h, self._items))

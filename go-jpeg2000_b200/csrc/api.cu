@@ -47,6 +47,57 @@ int j2k_reserve(j2kgpu_ctx *ctx, DevBuf &b, size_t bytes, bool pinned_host)
     return J2KGPU_OK;
 }
 
+// ---- ctx-level device buffer pool (grow-only cache) ------------------------------------------------------
+struct PoolTag { size_t cap; };
+static std::map<void *, size_t> &pool_sizes()
+{
+    static std::map<void *, size_t> m;
+    return m;
+}
+static std::mutex g_pool_mu;
+
+void *j2k_pool_alloc(j2kgpu_ctx *ctx, size_t bytes, cudaError_t *err)
+{
+    *err = cudaSuccess;
+    if (bytes == 0) bytes = 16;
+    int best = -1;
+    for (size_t i = 0; i < ctx->pool.size(); i++)
+        if (ctx->pool[i].cap >= bytes && ctx->pool[i].cap <= 2 * bytes + (1u << 20) &&
+            (best < 0 || ctx->pool[i].cap < ctx->pool[best].cap)) best = (int)i;
+    if (best >= 0) {
+        void *p = ctx->pool[best].p;
+        ctx->pool.erase(ctx->pool.begin() + best);
+        return p;
+    }
+    void *p = nullptr;
+    size_t cap = (bytes + 255) / 256 * 256;
+    *err = cudaMalloc(&p, cap);
+    if (*err != cudaSuccess) {                      // drop the cache and retry once
+        for (auto &b : ctx->pool) { std::lock_guard<std::mutex> g(g_pool_mu); pool_sizes().erase(b.p); cudaFree(b.p); }
+        ctx->pool.clear();
+        *err = cudaMalloc(&p, cap);
+        if (*err != cudaSuccess) return nullptr;
+    }
+    std::lock_guard<std::mutex> g(g_pool_mu);
+    pool_sizes()[p] = cap;
+    return p;
+}
+
+void j2k_pool_free(j2kgpu_ctx *ctx, void *p)
+{
+    if (!p) return;
+    size_t cap = 0;
+    { std::lock_guard<std::mutex> g(g_pool_mu); auto it = pool_sizes().find(p); if (it != pool_sizes().end()) cap = it->second; }
+    if (cap == 0 || ctx->pool.size() >= 64) {
+        std::lock_guard<std::mutex> g(g_pool_mu);
+        pool_sizes().erase(p);
+        cudaFree(p);
+        return;
+    }
+    DevBuf b; b.p = p; b.cap = cap;
+    ctx->pool.push_back(b);
+}
+
 int j2k_resolve_fmt(int ncomp, int prec, int fmt)
 {
     int want = ncomp == 1 ? (prec <= 8 ? J2KGPU_FMT_GRAY8 : J2KGPU_FMT_GRAY16)
@@ -127,6 +178,8 @@ extern "C" void j2kgpu_destroy(j2kgpu_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     free_buf(ctx->d_in, false); free_buf(ctx->d_out, false); free_buf(ctx->d_aux, false); free_buf(ctx->d_tab, false);
     free_buf(ctx->h_in, true); free_buf(ctx->h_out, true);
+    for (auto &b : ctx->pool) { { std::lock_guard<std::mutex> g(g_pool_mu); pool_sizes().erase(b.p); } cudaFree(b.p); }
+    ctx->pool.clear();
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -156,9 +209,11 @@ static uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 static void job_free(j2kgpu_job *job)
 {
     if (!job) return;
-    if (job->ctx) cudaSetDevice(job->ctx->device);
-    cudaFree(job->d_cblks); cudaFree(job->d_tcs); cudaFree(job->d_tiles); cudaFree(job->d_coef); cudaFree(job->d_tmp);
-    cudaFree(job->d_blob); cudaFree(job->d_pix);
+    if (job->ctx) {
+        cudaSetDevice(job->ctx->device);
+        void *ps[] = {job->d_cblks, job->d_tcs, job->d_tiles, job->d_coef, job->d_tmp, job->d_blob, job->d_pix};
+        for (void *p : ps) j2k_pool_free(job->ctx, p);
+    }
     if (job->h_blob) cudaFreeHost(job->h_blob);
     if (job->h_pix) cudaFreeHost(job->h_pix);
     delete job;
@@ -167,7 +222,7 @@ static void job_free(j2kgpu_job *job)
 extern "C" void j2kgpu_job_destroy(j2kgpu_job *job)
 {
     if (!job) return;
-    if (job->ctx) { std::lock_guard<std::mutex> g(job->ctx->mu); cudaStreamSynchronize(job->ctx->stream); }
+    if (job->ctx) { std::lock_guard<std::mutex> g(job->ctx->mu); cudaStreamSynchronize(job->ctx->stream); job_free(job); return; }
     job_free(job);
 }
 
@@ -201,6 +256,7 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
     uint64_t coef_elems = 0, tmp_elems = 0, blob_bytes = 0, out_bytes = 0;
     int max_bps = 0;
     bool need_clear = false;
+    uint32_t stream_levels = hdr.nlevels ? ((1u << hdr.nlevels) - 1) : 0;
 
     for (uint32_t ii = 0; ii < n_img; ii++) {
         const j2k_batch_item_t &it = items[ii];
@@ -232,6 +288,8 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
             d.tmp_off = tmp_elems;
             tmp_elems += 2ull * d.tmp_elems;
             tcs.push_back(d);
+            for (int l = 0; l < hdr.nlevels; l++)
+                if (!j2k_stream_ok(d.w, d.h, l)) stream_levels &= ~(1u << l);
             if (d.w > job->max_w) job->max_w = d.w;
             if (d.h > job->max_h) job->max_h = d.h;
             auto key = std::make_tuple(tc.x0, tc.y0, tc.x1, tc.y1);
@@ -278,20 +336,21 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
     job->n_tc = (uint32_t)tcs.size(); job->n_tiles = (uint32_t)tiles.size(); job->n_cb = (uint32_t)cbs.size();
     job->coef_elems = coef_elems; job->blob_bytes = blob_bytes; job->out_bytes = out_bytes; job->max_bps = max_bps;
     job->tmp_bytes = tmp_elems * (hdr.reversible ? 4 : 8);
-    job->need_clear = need_clear;                  // some plane is not fully covered by its blocks
+    job->need_clear = need_clear;
+    job->stream_levels = stream_levels;                  // some plane is not fully covered by its blocks
 
     cudaSetDevice(ctx->device);
     cudaError_t e = cudaSuccess;
     auto up = [&](void **dst, const void *src, size_t bytes) {
         if (e != cudaSuccess) return;
-        e = cudaMalloc(dst, bytes ? bytes : 16);
+        *dst = j2k_pool_alloc(ctx, bytes, &e);
         if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
     };
     up((void **)&job->d_cblks, cbs.data(), cbs.size() * sizeof(DevCblk));
     up((void **)&job->d_tcs, tcs.data(), tcs.size() * sizeof(DevTileComp));
     up((void **)&job->d_tiles, tiles.data(), tiles.size() * sizeof(DevTile));
-    if (e == cudaSuccess) e = cudaMalloc((void **)&job->d_coef, (coef_elems ? coef_elems : 4) * sizeof(int32_t));
-    if (e == cudaSuccess) e = cudaMalloc(&job->d_tmp, job->tmp_bytes ? job->tmp_bytes : 16);
+    if (e == cudaSuccess) job->d_coef = (int32_t *)j2k_pool_alloc(ctx, coef_elems * sizeof(int32_t), &e);
+    if (e == cudaSuccess) job->d_tmp = j2k_pool_alloc(ctx, job->tmp_bytes, &e);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);          // tables are read from host vectors
     if (e != cudaSuccess) { job_free(job); return j2k_cuda_err(ctx, e, "job upload"); }
     *out = job;
@@ -332,7 +391,7 @@ static int run_dwt_mct(j2kgpu_job *job, void *d_out)
     p.d_tcs = job->d_tcs; p.n_tc = job->n_tc; p.d_tiles = job->d_tiles; p.n_tiles = job->n_tiles;
     p.d_coef = job->d_coef; p.d_tmp = job->d_tmp; p.nlevels = job->nlevels;
     p.max_w = job->max_w; p.max_h = job->max_h; p.reversible = job->hdr.reversible != 0; p.f64_io = 0;
-    p.d_plane_out = nullptr; p.d_pix = (uint8_t *)d_out; p.tail = job->tail;
+    p.d_plane_out = nullptr; p.d_pix = (uint8_t *)d_out; p.tail = job->tail; p.stream_levels = job->stream_levels;
     for (int lvl = job->nlevels - 1; lvl >= 0; lvl--) {
         p.lvl = lvl;
         IdwtLaunch q = p;
@@ -368,6 +427,24 @@ extern "C" int j2kgpu_job_run_dwt_mct(j2kgpu_job *job, void *d_out)
     return run_dwt_mct(job, d_out);
 }
 
+extern "C" int j2kgpu_job_run_level(j2kgpu_job *job, int lvl, void *d_out)
+{
+    if (!job || lvl < 0 || lvl >= (job->nlevels ? job->nlevels : 1) || (lvl == 0 && !d_out)) return J2KGPU_E_ARG;
+    j2kgpu_ctx *ctx = job->ctx;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    cudaSetDevice(ctx->device);
+    IdwtLaunch p{};
+    p.d_tcs = job->d_tcs; p.n_tc = job->n_tc; p.d_tiles = lvl == 0 ? job->d_tiles : nullptr; p.n_tiles = job->n_tiles;
+    p.d_coef = job->d_coef; p.d_tmp = job->d_tmp; p.nlevels = job->nlevels; p.lvl = lvl;
+    p.max_w = job->max_w; p.max_h = job->max_h; p.reversible = job->hdr.reversible != 0; p.f64_io = 0;
+    p.d_plane_out = nullptr; p.d_pix = (uint8_t *)d_out; p.tail = job->tail; p.stream_levels = job->stream_levels;
+    int nl = 0;
+    cudaError_t e = launch_idwt_level(p, ctx->stream, &nl);
+    if (e != cudaSuccess) return j2k_cuda_err(ctx, e, "idwt level launch");
+    ctx->launches += nl;
+    return J2KGPU_OK;
+}
+
 extern "C" int j2kgpu_job_run(j2kgpu_job *job, const void *d_blob, void *d_out)
 {
     if (!job || !d_out || (!d_blob && job->blob_bytes)) return J2KGPU_E_ARG;
@@ -382,8 +459,9 @@ static int run_host_locked(j2kgpu_job *job, const j2k_batch_item_t *items)
 {
     j2kgpu_ctx *ctx = job->ctx;
     cudaSetDevice(ctx->device);
-    if (!job->d_blob) J2K_CUDA(ctx, cudaMalloc(&job->d_blob, job->blob_bytes ? job->blob_bytes : 16));
-    if (!job->d_pix) J2K_CUDA(ctx, cudaMalloc(&job->d_pix, job->out_bytes ? job->out_bytes : 16));
+    cudaError_t pe = cudaSuccess;
+    if (!job->d_blob) { job->d_blob = j2k_pool_alloc(ctx, job->blob_bytes, &pe); if (pe != cudaSuccess) return j2k_cuda_err(ctx, pe, "blob staging"); }
+    if (!job->d_pix) { job->d_pix = j2k_pool_alloc(ctx, job->out_bytes, &pe); if (pe != cudaSuccess) return j2k_cuda_err(ctx, pe, "pixel staging"); }
     for (uint32_t i = 0; i < job->n_img; i++) {
         if (!items[i].out_pix) return j2k_set_err(ctx, J2KGPU_E_ARG, "item %u: null out_pix", i);
         if (items[i].blob_len)
@@ -517,6 +595,10 @@ static int stage_idwt(j2kgpu_ctx *ctx, int mode, void *data, uint32_t w, uint32_
     p.d_coef = (const int32_t *)ctx->d_in.p; p.d_tmp = ctx->d_aux.p; p.nlevels = (int)levels;
     p.max_w = w; p.max_h = h; p.reversible = kind == 0; p.f64_io = kind == 1;
     p.d_plane_out = (int32_t *)ctx->d_out.p; p.d_pix = nullptr;
+    p.stream_levels = 0;
+    if (kind == 0)
+        for (int l = 1; l < (int)levels; l++)                 // level 0 of the stage API stores planes: tiled kernel
+            if (j2k_stream_ok(w, h, l)) p.stream_levels |= 1u << l;
     // levels == 0 (kind 2 only): tcd.go:428-435 still runs int32 -> float64 -> int32(v + 0.5), which maps a
     // negative integer n to n + 1 (truncation); one pass-through launch reproduces it
     for (int lvl = levels ? (int)levels - 1 : 0; lvl >= 0; lvl--) {

@@ -65,7 +65,11 @@ struct j2kgpu_ctx {
     // grow-only scratch used by the host-buffer entry points
     DevBuf d_in, d_out, d_aux, d_tab;
     DevBuf h_in, h_out;                  // pinned staging
+    // device buffers released by finished jobs, reused by the next job (repeated decode calls do not cudaMalloc)
+    std::vector<DevBuf> pool;
 };
+void *j2k_pool_alloc(j2kgpu_ctx *ctx, size_t bytes, cudaError_t *err);
+void j2k_pool_free(j2kgpu_ctx *ctx, void *p);
 
 struct j2kgpu_job {
     j2kgpu_ctx *ctx = nullptr;
@@ -76,6 +80,7 @@ struct j2kgpu_job {
     uint32_t max_w = 0, max_h = 0;       // largest tile-component
     int max_bps = 0;
     bool need_clear = false;
+    uint32_t stream_levels = 0;
     DevCblk *d_cblks = nullptr;
     DevTileComp *d_tcs = nullptr;
     DevTile *d_tiles = nullptr;
@@ -83,6 +88,7 @@ struct j2kgpu_job {
     void *d_tmp = nullptr;      uint64_t tmp_bytes = 0;
     uint64_t blob_bytes = 0, out_bytes = 0;
     std::vector<uint64_t> blob_off, out_off, out_size;
+    std::vector<std::pair<void *, size_t>> owned;   // device allocations taken from the ctx pool
     // staging for run_host
     void *d_blob = nullptr; void *d_pix = nullptr;
     void *h_blob = nullptr; void *h_pix = nullptr;
@@ -114,11 +120,19 @@ struct IdwtLaunch {
     uint32_t max_w, max_h;                          // largest tile-component (grid sizing)
     int reversible;
     int f64_io;                                     // 9-7 stage API: coefficient arena and output planes are double
+    uint32_t stream_levels;                         // bit l set: level l of every tile-component fits the streaming kernel
     int32_t *d_plane_out;                           // lvl == 0 without tiles: output planes (same offsets as coef)
     uint8_t *d_pix;                                 // lvl == 0 with tiles: packed pixels
     TailParams tail;
 };
 cudaError_t launch_idwt_level(const IdwtLaunch &p, cudaStream_t s, int *n_launches);
+cudaError_t launch_idwt53_stream(const IdwtLaunch &p, cudaStream_t s);
+// level l fits the streaming kernel when its width is a multiple of 4 and its height is even (>= 2)
+static inline bool j2k_stream_ok(uint32_t w, uint32_t h, int lvl)
+{
+    uint32_t wl = (w + (1u << lvl) - 1) >> lvl, hl = (h + (1u << lvl) - 1) >> lvl;
+    return wl >= 4 && (wl & 3) == 0 && hl >= 2 && (hl & 1) == 0;
+}
 
 // unfused tail: planar int32 components -> (inverse MCT, DC shift) -> planes and/or packed pixels
 cudaError_t launch_tail(const int32_t *const d_comps[4], int32_t *const d_planes_out[4], uint8_t *d_pix,

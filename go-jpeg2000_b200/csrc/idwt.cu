@@ -21,6 +21,7 @@
 // exact edge expressions.  9-7 uses __dmul_rn/__dadd_rn so that no FMA is contracted (Go/amd64 never
 // fuses) -- REF parity for float64 is bit-exact.
 #include "common.h"
+#include "tail.cuh"
 
 namespace {
 
@@ -76,76 +77,6 @@ struct Lift97 {
         return __dsub_rn(x, __dmul_rn(c, __dadd_rn(l, r)));
     }
 };
-
-// ---- pixel epilogue: decoder.go:321-348 + createImage decoder.go:417-588 ----------------------------
-__device__ __forceinline__ int32_t clampi(int32_t v, int32_t lo, int32_t hi) { return v < lo ? lo : (v > hi ? hi : v); }
-
-__device__ __forceinline__ void tail_mct_dc(int32_t v[4], const TailParams &tp)
-{
-    if (tp.mct) {
-        if (tp.reversible) {                                   // mct.go:56-66
-            uint32_t y = (uint32_t)v[0], u = (uint32_t)v[1], w = (uint32_t)v[2];
-            uint32_t g = y - (uint32_t)((int32_t)(u + w) >> 2);
-            v[0] = (int32_t)(w + g); v[1] = (int32_t)g; v[2] = (int32_t)(u + g);
-        } else {                                               // mct.go:43-53 via decoder.go:326-340
-            double y = (double)v[0], cb = (double)v[1], cr = (double)v[2];
-            double r = __dadd_rn(y, __dmul_rn(1.402, cr));
-            double g = __dsub_rn(__dsub_rn(y, __dmul_rn(0.34413, cb)), __dmul_rn(0.71414, cr));
-            double b = __dadd_rn(y, __dmul_rn(1.772, cb));
-            v[0] = __double2int_rz(__dadd_rn(r, 0.5));          // int32(v + 0.5) truncates toward zero
-            v[1] = __double2int_rz(__dadd_rn(g, 0.5));
-            v[2] = __double2int_rz(__dadd_rn(b, 0.5));
-        }
-    }
-#pragma unroll
-    for (int c = 0; c < 4; c++)
-        if (c < tp.ncomp && !tp.sgnd[c]) v[c] = (int32_t)((uint32_t)v[c] + (1u << (tp.prec[c] - 1)));   // mct.go:113-118
-}
-
-// scaled sample value exactly as createImage computes it (int32 product wraps in REF mode)
-__device__ __forceinline__ uint32_t pack_value(int32_t v, int prec, int32_t maxv, bool iso)
-{
-    v = clampi(v, 0, maxv);
-    if (prec <= 8) {
-        if (prec != 8) v = (int32_t)((uint32_t)v * 255u) / maxv;
-        return (uint32_t)v & 0xFF;
-    }
-    if (iso) return (uint32_t)(((uint64_t)(uint32_t)v * 65535u) / (uint32_t)maxv) & 0xFFFF;
-    v = (int32_t)((uint32_t)v * 65535u) / maxv;
-    return (uint32_t)v & 0xFFFF;
-}
-
-__device__ __forceinline__ void store_pixel(uint8_t *row, uint32_t x, const int32_t v[4], const TailParams &tp)
-{
-    const int prec = tp.prec[0];
-    const int32_t maxv = (int32_t)((1u << prec) - 1u);
-    switch (tp.fmt) {
-    case J2KGPU_FMT_GRAY8:
-        row[x] = (uint8_t)pack_value(v[0], prec, maxv, tp.iso);
-        break;
-    case J2KGPU_FMT_GRAY16: {
-        uint32_t p = pack_value(v[0], prec, maxv, tp.iso);
-        *(uint16_t *)(row + 2 * (size_t)x) = (uint16_t)((p >> 8) | ((p & 0xFF) << 8));      // big-endian
-        break;
-    }
-    case J2KGPU_FMT_RGBA8: {
-        uint32_t r = pack_value(v[0], prec, maxv, tp.iso), g = pack_value(v[1], prec, maxv, tp.iso),
-                 b = pack_value(v[2], prec, maxv, tp.iso);
-        uint32_t a = tp.ncomp == 4 ? pack_value(v[3], prec, maxv, tp.iso) : 255u;
-        *(uint32_t *)(row + 4 * (size_t)x) = r | (g << 8) | (b << 16) | (a << 24);
-        break;
-    }
-    default: {   // RGBA64, big-endian 16-bit channels
-        uint32_t r = pack_value(v[0], prec, maxv, tp.iso), g = pack_value(v[1], prec, maxv, tp.iso),
-                 b = pack_value(v[2], prec, maxv, tp.iso);
-        uint32_t a = tp.ncomp == 4 ? pack_value(v[3], prec, maxv, tp.iso) : 65535u;
-        uint32_t lo = ((r >> 8) | ((r & 0xFF) << 8)) | (((g >> 8) | ((g & 0xFF) << 8)) << 16);
-        uint32_t hi = ((b >> 8) | ((b & 0xFF) << 8)) | (((a >> 8) | ((a & 0xFF) << 8)) << 16);
-        *(uint2 *)(row + 8 * (size_t)x) = make_uint2(lo, hi);
-        break;
-    }
-    }
-}
 
 // ---- one level of one tile-component into the shared patch -------------------------------------------
 struct LevelGeom {
@@ -389,6 +320,8 @@ cudaError_t launch_idwt_level(const IdwtLaunch &p, cudaStream_t s, int *n_launch
     const bool pixels = (lvl == 0 && p.d_tiles != nullptr);
     dim3 grid((lw + TW - 1) / TW, (lh + TH - 1) / TH, pixels ? p.n_tiles : p.n_tc);
     if (grid.z == 0) return cudaSuccess;
+    if (p.reversible && p.nlevels > 0 && ((p.stream_levels >> lvl) & 1) && (lvl > 0 || pixels))
+        return launch_idwt53_stream(p, s);
     if (pixels) {
         if (p.reversible)
             k_idwt_last_pixels<Lift53><<<grid, kThreads, patch_bytes<Lift53>(), s>>>(

@@ -157,6 +157,9 @@ int      j2kgpu_job_run(j2kgpu_job *job, const void *d_blob, void *d_out);
 /* stage subsets of the same job, for per-stage timing: entropy only / DWT+MCT+pack only */
 int      j2kgpu_job_run_entropy(j2kgpu_job *job, const void *d_blob);
 int      j2kgpu_job_run_dwt_mct(j2kgpu_job *job, void *d_out);
+/* one inverse-DWT level of the job (lvl = nlevels-1 .. 0; level 0 is the fused IDWT+MCT+DC+pack kernel and
+ * needs d_out); levels must be run coarse to fine after the entropy stage -- used to time a single kernel */
+int      j2kgpu_job_run_level(j2kgpu_job *job, int lvl, void *d_out);
 /* host-buffer run of a prepared job (pinned staging + H2D + kernels + D2H, blocking) */
 int      j2kgpu_job_run_host(j2kgpu_job *job, const j2k_batch_item_t *items);
 int      j2kgpu_sync(j2kgpu_ctx *ctx);

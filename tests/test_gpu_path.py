@@ -45,6 +45,11 @@ CASES = [  # w, h, ncomp, prec, tile_w, tile_h, levels, reversible, ht
     (128, 128, 3, 8, 64, 64, 3, 1, 1),         # reference "HT" coder
     (96, 96, 1, 8, None, None, 0, 1, 0),       # zero decomposition levels
     (512, 512, 3, 8, None, None, 5, 1, 0),     # BASELINE cfg1: 512x512 RGB 8-bit lossless 5-3, 1 tile, 64x64 blocks
+    (256, 128, 1, 8, 128, 128, 3, 1, 0),       # streaming kernel, 1 component (Gray8)
+    (256, 192, 4, 8, None, None, 4, 1, 0),     # streaming kernel, 4 components (RGBA with coded alpha)
+    (384, 256, 3, 12, 128, 128, 3, 1, 0),      # streaming kernel, RGBA64 epilogue
+    (264, 136, 3, 8, 128, 128, 2, 1, 0),       # 8-wide / 8-high edge tiles (one active quad pair per warp)
+    (1024, 192, 3, 8, None, None, 2, 1, 0),    # several warps across one tile row (30-quad ranges + halo lanes)
 ]
 
 
@@ -92,10 +97,17 @@ def test_batch_and_job_api(j2k, gpu_ctx):
     job = j2k.Job(gpu_ctx, items)
     d_blob = torch.from_numpy(np.concatenate([j["blob"] for j in jl])).cuda()
     d_out = torch.zeros(job.out_bytes, dtype=torch.uint8, device="cuda")
-    gpu_ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.Stream()
+    assert stream.cuda_stream != 0
+    gpu_ctx.set_stream(stream.cuda_stream)
+    torch.cuda.synchronize()                              # uploads above ran on torch's default stream
     n0 = gpu_ctx.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
     job.run(d_blob.data_ptr(), d_out.data_ptr())
-    torch.cuda.synchronize()
+    ev1.record(stream)
+    stream.synchronize()
+    assert ev0.elapsed_time(ev1) > 0.02                   # the kernels really ran on the caller's stream
     assert gpu_ctx.launches - n0 == 4                     # 1 entropy + 3 DWT levels (last fused with MCT/pack)
     host = d_out.cpu().numpy()
     for i, w_ in enumerate(want):
@@ -119,7 +131,7 @@ def test_path_argument_errors(j2k, gpu_ctx):
         gpu_ctx.decode_tiles(bad, tcs, cbs, job["blob"])
     assert e.value.code == j2k.E_UNSUPPORTED              # decoder.go:585-586
     cb2 = job["cblks"].copy()
-    cb2["data_off"][3] = len(job["blob"]) + 10
+    cb2["data_off"][1] = len(job["blob"]) + 10
     with pytest.raises(j2k.J2KError) as e:
         gpu_ctx.decode_tiles(hdr(j2k, job), tcs, jobs.as_ctypes(cb2, j2k.CBlk), job["blob"])
     assert e.value.code == j2k.E_RANGE
