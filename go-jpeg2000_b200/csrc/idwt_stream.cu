@@ -53,7 +53,7 @@ __device__ __forceinline__ int2 ld2(const Src &s, uint32_t lin)
 }
 
 template <int NC, bool PIXELS>
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(kWarps * 32, 3)
 k_idwt53_stream(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__ tiles,
                 const int32_t *__restrict__ coef, int32_t *__restrict__ tmp, uint8_t *__restrict__ pix,
                 int nlevels, int lvl, int strip_pairs, TailParams tp)
@@ -180,28 +180,40 @@ k_idwt53_stream(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__
     }
 
     // ---- stream the strip: step k finishes rows 2k-2 (even) and 2k-1 (odd) ----
+    // The band rows of step k+1 are requested before step k is computed (register double buffer), so a warp
+    // always has one full step of loads (NC x 4 x 256 B) in flight behind its arithmetic.
+    int lo[NC][4], hi[NC][4];
+    if (ka + 1 < nly) {
+#pragma unroll
+        for (int c = 0; c < NC; c++) { load_row(c, ka + 1, lo[c]); load_row(c, nly + ka + 1, hi[c]); }
+    }
     for (int k = ka + 1; k <= kb; k++) {
         int o[NC][4];
         if (k < nly) {
+            int nlo[NC][4], nhi[NC][4];
+            const bool more = (k + 1 <= kb) && (k + 1 < nly);
+            if (more) {
+#pragma unroll
+                for (int c = 0; c < NC; c++) { load_row(c, k + 1, nlo[c]); load_row(c, nly + k + 1, nhi[c]); }
+            }
             int e[NC][4];
 #pragma unroll
-            for (int c = 0; c < NC; c++) {
-                int lo[4], hi[4];
-                load_row(c, k, lo);
-                load_row(c, nly + k, hi);
+            for (int c = 0; c < NC; c++)
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    e[c][j] = even_upd(lo[j], hp[c][j], hi[j]);
+                    e[c][j] = even_upd(lo[c][j], hp[c][j], hi[c][j]);
                     o[c][j] = odd_upd(hp[c][j], ep[c][j], e[c][j]);
-                    hp[c][j] = hi[j];
+                    hp[c][j] = hi[c][j];
                 }
-            }
             emit_row(2 * k - 2, ep);
             emit_row(2 * k - 1, o);
 #pragma unroll
             for (int c = 0; c < NC; c++)
 #pragma unroll
-                for (int j = 0; j < 4; j++) ep[c][j] = e[c][j];
+                for (int j = 0; j < 4; j++) {
+                    ep[c][j] = e[c][j];
+                    if (more) { lo[c][j] = nlo[c][j]; hi[c][j] = nhi[c][j]; }
+                }
         } else {                                                       // bottom edge (h even): last odd row += x[n-2]
 #pragma unroll
             for (int c = 0; c < NC; c++)
