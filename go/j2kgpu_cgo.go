@@ -1,0 +1,97 @@
+//go:build cuda
+
+// Package jpeg2000: cgo binding of libj2kgpu.so (include/j2kgpu.h).
+//
+// Drop this file next to decoder.go in mrjoshuak/go-jpeg2000 and build with `-tags cuda`; it replaces the
+// body of decoder.decodeTiles from tcd.NewTileDecoder onward (decoder.go:311-359) with ONE blocking C call.
+// Everything above it (readFormat, parseCodestream, the tier-2 walk that fills the job tables) stays in Go.
+// UNCOMPILED in this repository: there is no Go toolchain in the build image (see INTEGRATION.md).
+package jpeg2000
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/include
+#cgo LDFLAGS: -L${SRCDIR}/lib -lj2kgpu
+#include <stdlib.h>
+#include "j2kgpu.h"
+*/
+import "C"
+
+import (
+	"fmt"
+	"image"
+	"os"
+	"strconv"
+	"sync"
+	"unsafe"
+)
+
+// gpuCtx is one j2kgpu_ctx (one GPU, one stream).  A ctx serialises its calls, so a pool keeps one per
+// concurrently decoding goroutine; J2KGPU_DEVICE selects the device.
+type gpuCtx struct{ h *C.j2kgpu_ctx }
+
+var gpuPool = sync.Pool{New: func() interface{} {
+	dev, _ := strconv.Atoi(os.Getenv("J2KGPU_DEVICE"))
+	var h *C.j2kgpu_ctx
+	if rc := C.j2kgpu_create(C.int(dev), &h); rc != 0 {
+		return fmt.Errorf("j2kgpu_create: %s", C.GoString(C.j2kgpu_strerror(rc)))
+	}
+	return &gpuCtx{h}
+}}
+
+// gpuJob is what the Go tier-2 walk produces: flat tables (no Go pointers inside) plus one blob.
+type gpuJob struct {
+	img       C.j2k_image_t
+	tilecomps []C.j2k_tilecomp_t
+	cblks     []C.j2k_cblk_t
+	blob      []byte
+}
+
+// decodeTilesGPU is decoder.decodeTiles on the GPU: it returns the same image types createImage would
+// (decoder.go:417-588) with Pix filled by the library; errors are wrapped like decoder.go:47.
+func (d *decoder) decodeTilesGPU(job *gpuJob) (image.Image, error) {
+	v := gpuPool.Get()
+	ctx, ok := v.(*gpuCtx)
+	if !ok {
+		return nil, fmt.Errorf("decoding tiles: %w", v.(error))
+	}
+	defer gpuPool.Put(ctx)
+
+	w, h := int(job.img.width), int(job.img.height)
+	var out image.Image
+	var pix []uint8
+	var stride int
+	prec8 := job.img.prec[0] <= 8
+	switch {
+	case job.img.ncomp == 1 && prec8:
+		im := image.NewGray(image.Rect(0, 0, w, h))
+		out, pix, stride = im, im.Pix, im.Stride
+	case job.img.ncomp == 1:
+		im := image.NewGray16(image.Rect(0, 0, w, h))
+		out, pix, stride = im, im.Pix, im.Stride
+	case prec8:
+		im := image.NewRGBA(image.Rect(0, 0, w, h))
+		out, pix, stride = im, im.Pix, im.Stride
+	default:
+		im := image.NewRGBA64(image.Rect(0, 0, w, h))
+		out, pix, stride = im, im.Pix, im.Stride
+	}
+	var tc *C.j2k_tilecomp_t
+	var cb *C.j2k_cblk_t
+	var blob *C.uint8_t
+	if len(job.tilecomps) > 0 {
+		tc = &job.tilecomps[0]
+	}
+	if len(job.cblks) > 0 {
+		cb = &job.cblks[0]
+	}
+	if len(job.blob) > 0 {
+		blob = (*C.uint8_t)(unsafe.Pointer(&job.blob[0]))
+	}
+	rc := C.j2kgpu_decode(ctx.h, &job.img, tc, C.uint32_t(len(job.tilecomps)), cb, C.uint32_t(len(job.cblks)),
+		blob, C.uint64_t(len(job.blob)), (*C.uint8_t)(unsafe.Pointer(&pix[0])), C.uint64_t(stride))
+	if rc != 0 {
+		return nil, fmt.Errorf("decoding tiles: %s: %s", C.GoString(C.j2kgpu_strerror(rc)),
+			C.GoString(C.j2kgpu_last_error(ctx.h)))
+	}
+	return out, nil
+}
