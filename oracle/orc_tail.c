@@ -111,7 +111,11 @@ typedef struct {
     int32_t **planes;            /* per tile-component coefficient planes */
     volatile uint32_t next;      /* work counter */
     int stage;
+    /* stage 2: image tail over row chunks */
+    int32_t *comps[4]; uint8_t *out_pix; uint64_t out_stride; int bpp; int rc;
 } job_t;
+
+#define TAIL_ROWS 16
 
 static void *worker(void *arg)
 {
@@ -131,6 +135,23 @@ static void *worker(void *arg)
             for (int y = 0; y < cb->h; y++)
                 memcpy(plane + (size_t)(cb->y0 + y) * tw + cb->x0, tmp + (size_t)y * cb->w, sizeof(int32_t) * cb->w);
             free(tmp);
+        } else if (j->stage == 2) {                /* decoder tail + createImage on a chunk of rows (elementwise) */
+            size_t W = j->img->width, H = j->img->height;
+            size_t y0 = (size_t)i * TAIL_ROWS;
+            if (y0 >= H) break;
+            size_t rows = H - y0 < TAIL_ROWS ? H - y0 : TAIL_ROWS;
+            int32_t *c[4] = {0, 0, 0, 0};
+            for (int k = 0; k < j->img->ncomp; k++) c[k] = j->comps[k] + y0 * W;
+            orc_decoder_tail(c, j->img->ncomp, rows * W, j->img->mct, j->img->reversible, j->img->prec, j->img->sgnd);
+            if (j->out_stride == W * (size_t)j->bpp) {
+                if (orc_create_image((const int32_t *const *)c, (int)W, (int)rows, j->img->ncomp, j->img->prec[0],
+                                     j->out_pix + y0 * j->out_stride) < 0) j->rc = -3;
+            } else {
+                uint8_t *tmp = malloc(rows * W * (size_t)j->bpp + 1);
+                if (orc_create_image((const int32_t *const *)c, (int)W, (int)rows, j->img->ncomp, j->img->prec[0], tmp) < 0) j->rc = -3;
+                else for (size_t y = 0; y < rows; y++) memcpy(j->out_pix + (y0 + y) * j->out_stride, tmp + y * W * j->bpp, W * (size_t)j->bpp);
+                free(tmp);
+            }
         } else {                                   /* inverse DWT per tile-component */
             if (i >= j->n_tc) break;
             const orc_tilecomp_t *tc = &j->tcs[i];
@@ -181,17 +202,15 @@ int orc_decode_image(const orc_image_t *img, const orc_tilecomp_t *tcs, uint32_t
             for (uint32_t x = tc->x0; x < tc->x1 && x < W; x++)
                 comps[tc->comp][(size_t)y * W + x] = j.planes[i][(size_t)(y - tc->y0) * tw + (x - tc->x0)];
     }
-    orc_decoder_tail(comps, img->ncomp, n, img->mct, img->reversible, img->prec, img->sgnd);
     int bpp = img->ncomp == 1 ? (img->prec[0] <= 8 ? 1 : 2) : (img->prec[0] <= 8 ? 4 : 8);
-    int rc = 0;
-    if (out_stride == W * (size_t)bpp) {
-        if (orc_create_image((const int32_t *const *)comps, (int)W, (int)H, img->ncomp, img->prec[0], out_pix) < 0) rc = -3;
-    } else {
-        uint8_t *tmp = malloc(n * (size_t)bpp + 1);
-        if (orc_create_image((const int32_t *const *)comps, (int)W, (int)H, img->ncomp, img->prec[0], tmp) < 0) rc = -3;
-        else for (size_t y = 0; y < H; y++) memcpy(out_pix + y * out_stride, tmp + y * W * bpp, W * (size_t)bpp);
-        free(tmp);
+    if (img->ncomp != 1 && img->ncomp != 3 && img->ncomp != 4) j.rc = -3;          /* decoder.go:585-586 */
+    else {
+        for (int c = 0; c < img->ncomp; c++) j.comps[c] = comps[c];
+        j.out_pix = out_pix; j.out_stride = out_stride; j.bpp = bpp;
+        run_stage(&j, 2, threads);
     }
+    int rc = j.rc;
+    (void)n;
     for (int c = 0; c < img->ncomp; c++) free(comps[c]);
     for (uint32_t i = 0; i < n_tc; i++) free(j.planes[i]);
     free(j.planes);
