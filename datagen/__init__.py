@@ -40,6 +40,7 @@ def lib():
         _lib.gen_t1_encode.restype = C.c_int
         _lib.gen_ht_encode.restype = C.c_int
         _lib.gen_encode_blocks.restype = C.c_int64
+        _lib.gen_iso_ht_encode.restype = C.c_int
     return _lib
 
 
@@ -74,6 +75,17 @@ def ht_encode(coeffs, w, h, band=0):
     n = lib().gen_ht_encode(_p(c, i32p), w, h, band, _p(out, u8p), len(out))
     if n < 0:
         raise OverflowError("reference HT encoder would index out of range")
+    return out[:n].tobytes()
+
+
+def iso_ht_encode(coeffs, w, h):
+    """conformant HT cleanup-pass encoder (T.814); b'' for an all-zero block"""
+    c = np.ascontiguousarray(coeffs, np.int32).reshape(-1)
+    assert c.size == w * h
+    out = np.zeros(w * h * 5 + 8192, np.uint8)
+    n = lib().gen_iso_ht_encode(_p(c, i32p), w, h, _p(out, u8p), len(out))
+    if n < 0:
+        raise ValueError("HT encode failed (magnitude too large?)")
     return out[:n].tobytes()
 
 

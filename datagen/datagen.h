@@ -20,6 +20,8 @@ int  gen_mq_encode(const uint8_t *ctxs, const uint8_t *bits, int n, uint8_t *out
 int  gen_t1_encode(const int32_t *coeffs, int w, int h, int band, uint8_t *out, int cap, int *num_bps);
 /* HTEncoder.Encode ht.go:942-1045; -1 where the reference would index out of range */
 int  gen_ht_encode(const int32_t *coeffs, int w, int h, int band, uint8_t *out, int cap);
+/* ISO/IEC 15444-15 HT cleanup-pass encoder (conformant; see gen_iso_ht.c) */
+int  gen_iso_ht_encode(const int32_t *coeffs, int w, int h, uint8_t *out, int cap);
 void gen_fwd53(int32_t *d, int n);                              /* dwt.go:73-118  */
 void gen_fwd97(double *d, int n);                               /* dwt.go:161-210 */
 void gen_fwd2d53(int32_t *d, int w, int h);                     /* dwt.go:356-407 */

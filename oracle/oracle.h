@@ -48,6 +48,10 @@ const uint8_t *orc_t1_zc_lut(void);
 /* HTDecoder.Decode on a fresh (zeroed) decoder, ht.go:93-150. */
 void orc_ht_decode(const uint8_t *data, int len, int w, int h, int32_t *out);
 
+/* ---- ISO-mode checkers (not restatements of the reference; see the file headers) ------ */
+/* ISO/IEC 15444-15 HT cleanup decoder: out = sign * (mu << (num_bps-1)); returns 0 or <0 if malformed */
+int  iso_ht_decode(const uint8_t *data, int len, int w, int h, int num_bps, int32_t *out);
+
 /* ---- DWT (internal/dwt/dwt.go) ------------------------------------------ */
 void orc_inv53(int32_t *d, int n);                      /* dwt.go:122-147 */
 void orc_inv97(double *d, int n);                       /* dwt.go:213-262 */

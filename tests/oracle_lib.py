@@ -59,6 +59,7 @@ def lib():
         L.orc_create_image.restype = C.c_int
         L.orc_decode_image.restype = C.c_int
         L.orc_t1_zc_lut.restype = u8p
+        L.iso_ht_decode.restype = C.c_int
     return _lib
 
 
@@ -92,6 +93,13 @@ def ht_decode(data, w, h):
     out = np.zeros(w * h, np.int32)
     lib().orc_ht_decode(_p(buf, u8p), len(data), w, h, _p(out, i32p))
     return out
+
+
+def iso_ht_decode(data, w, h, num_bps=1):
+    buf = np.frombuffer(bytes(data), np.uint8) if len(data) else np.zeros(1, np.uint8)
+    out = np.zeros(w * h, np.int32)
+    rc = lib().iso_ht_decode(_p(buf, u8p), len(data), w, h, num_bps, _p(out, i32p))
+    return out, rc
 
 
 def _inplace(fn, arr, *args):
