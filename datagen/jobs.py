@@ -116,3 +116,31 @@ def as_ctypes(arr, ctype):
     n = len(arr)
     buf = (ctype * max(n, 1)).from_buffer_copy(arr.tobytes() if n else bytes(C.sizeof(ctype)))
     return buf
+
+
+def build_iso_job(samples, prec, tile_w=None, tile_h=None, nlevels=5, mct=1, cb=64):
+    """ISO-mode (J2KGPU_MODE_ISO) job: the same source image as a conformant HTJ2K codestream (lossless 5-3, RCT,
+    HT cleanup-only blocks) plus the flat tables a tier-2 parser would hand to j2kgpu_decode.  Block placement
+    (x0, y0) is in the tile-component's Mallat plane; num_bps = Mb - missing_msbs = 1 (HT cleanup carries every
+    magnitude bit), num_passes = 1."""
+    from . import codestream as cs
+    ncomp, H, W = samples.shape
+    tile_w, tile_h = tile_w or W, tile_h or H
+    data, info = cs.write_htj2k(samples, prec, tile_w, tile_h, nlevels, mct=mct, cb=cb)
+    ntx = cs.cdiv(W, tile_w)
+    tcs, tc_index = [], {}
+    for ty in range(cs.cdiv(H, tile_h)):
+        for tx in range(ntx):
+            for c in range(ncomp):
+                tc_index[(ty * ntx + tx, c)] = len(tcs)
+                tcs.append((c, tx * tile_w, ty * tile_h, min((tx + 1) * tile_w, W), min((ty + 1) * tile_h, H), 0))
+    blks = info["blocks"]
+    cblks = np.zeros(len(blks), CBLK_DT)
+    blob = bytearray()
+    for i, b in enumerate(blks):
+        cblks[i] = (len(blob), len(b["data"]), tc_index[(b["tile"], b["comp"])], b["px"], b["py"], b["w"], b["h"],
+                    b["band"], b["level"], 1, 1, 1.0)
+        blob += b["data"]
+    return dict(width=W, height=H, ncomp=ncomp, prec=prec, sgnd=0, mct=1 if (mct and ncomp >= 3) else 0, reversible=1,
+                nlevels=nlevels, ht=1, mode=1, tilecomps=np.array(tcs, TILECOMP_DT), cblks=cblks,
+                blob=np.frombuffer(bytes(blob), np.uint8).copy(), samples=samples, codestream=data)

@@ -5,6 +5,7 @@
 #include "common.h"
 
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -241,14 +242,20 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
     TailParams tp;
     int rc = make_tail(ctx, hdr, tp);
     if (rc) return rc;
-    if (hdr.mode != J2KGPU_MODE_REF)
-        return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "mode %d: only J2KGPU_MODE_REF is built in this revision", (int)hdr.mode);
+    if (hdr.mode != J2KGPU_MODE_REF && hdr.mode != J2KGPU_MODE_ISO)
+        return j2k_set_err(ctx, J2KGPU_E_ARG, "unknown mode %d", (int)hdr.mode);
+    const bool iso = hdr.mode == J2KGPU_MODE_ISO;
+    if (iso && !hdr.ht)
+        return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "ISO mode: only HT code blocks (ISO/IEC 15444-15) are built in this revision");
+    if (iso && !hdr.reversible)
+        return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "ISO mode: only the reversible 5-3 path is built in this revision");
     if (hdr.nlevels > J2K_MAX_LEVELS) return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "nlevels %d > %d", (int)hdr.nlevels, J2K_MAX_LEVELS);
     const int bpp = j2k_fmt_bpp(tp.fmt);
 
     j2kgpu_job *job = new (std::nothrow) j2kgpu_job();
     if (!job) return j2k_set_err(ctx, J2KGPU_E_NOMEM, "job");
-    job->ctx = ctx; job->n_img = n_img; job->hdr = hdr; job->tail = tp; job->nlevels = hdr.nlevels;
+    job->ctx = ctx; job->n_img = n_img; job->hdr = hdr; job->tail = tp; job->nlevels = hdr.nlevels; job->iso = iso;
+    if (const char *e = getenv("J2KGPU_HT_MAP")) job->ht_map = (atoi(e) == 1) ? 1 : 32;
 
     std::vector<DevTileComp> tcs;
     std::vector<DevTile> tiles;
@@ -290,6 +297,11 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
             tcs.push_back(d);
             for (int l = 0; l < hdr.nlevels; l++)
                 if (!j2k_stream_ok(d.w, d.h, l)) stream_levels &= ~(1u << l);
+            if (iso && ((tc.x0 | tc.y0) & ((1u << hdr.nlevels) - 1))) {
+                job_free(job);
+                return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "ISO mode: tile origin (%u,%u) is not a multiple of 2^nlevels", tc.x0, tc.y0);
+            }
+            if (iso && (d.w & 3)) stream_levels = 0;          // Mallat rows must stay 8-byte aligned for the streaming kernel
             if (d.w > job->max_w) job->max_w = d.w;
             if (d.h > job->max_h) job->max_h = d.h;
             auto key = std::make_tuple(tc.x0, tc.y0, tc.x1, tc.y1);
@@ -319,6 +331,8 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
             if (cb.w > 64 || cb.h > 64) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "item %u block %u: %ux%u exceeds 64x64", ii, b, cb.w, cb.h); }
             if ((uint32_t)cb.x0 + cb.w > d.w || (uint32_t)cb.y0 + cb.h > d.h) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_RANGE, "item %u block %u: outside its tile-component", ii, b); }
             if (cb.data_off > it.blob_len || cb.data_len > it.blob_len - cb.data_off) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_RANGE, "item %u block %u: data outside blob", ii, b); }
+            if (iso && (cb.num_bps < 1 || cb.num_bps > 30) && cb.data_len) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "item %u block %u: num_bps %d outside 1..30", ii, b, (int)cb.num_bps); }
+            if (iso && cb.num_passes > 1) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "item %u block %u: HT SigProp/MagRef passes are not built in this revision", ii, b); }
             if (cb.num_bps > 31 || cb.band > 3) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "item %u block %u: num_bps %d / band %d", ii, b, (int)cb.num_bps, (int)cb.band); }
             DevCblk o{};
             o.data_off = blob_bytes + cb.data_off; o.data_len = cb.data_len;
@@ -377,8 +391,10 @@ static int run_entropy(j2kgpu_job *job, const void *d_blob)
     if (job->need_clear)
         J2K_CUDA(ctx, cudaMemsetAsync(job->d_coef, 0, job->coef_elems * sizeof(int32_t), ctx->stream));
     if (job->n_cb == 0) return J2KGPU_OK;
-    cudaError_t e = job->hdr.ht ? launch_ht_ref(job->d_cblks, job->n_cb, (const uint8_t *)d_blob, job->d_coef, ctx->stream)
-                                : launch_t1_ref(job->d_cblks, job->n_cb, (const uint8_t *)d_blob, job->d_coef, job->max_bps, ctx->stream);
+    cudaError_t e;
+    if (job->iso) e = launch_ht_iso(job->d_cblks, job->n_cb, (const uint8_t *)d_blob, job->d_coef, job->d_steps, 0, job->ht_map, ctx->stream);
+    else if (job->hdr.ht) e = launch_ht_ref(job->d_cblks, job->n_cb, (const uint8_t *)d_blob, job->d_coef, ctx->stream);
+    else e = launch_t1_ref(job->d_cblks, job->n_cb, (const uint8_t *)d_blob, job->d_coef, job->max_bps, ctx->stream);
     if (e != cudaSuccess) return j2k_cuda_err(ctx, e, "entropy kernel launch");
     ctx->launches++;
     return J2KGPU_OK;
@@ -391,7 +407,7 @@ static int run_dwt_mct(j2kgpu_job *job, void *d_out)
     p.d_tcs = job->d_tcs; p.n_tc = job->n_tc; p.d_tiles = job->d_tiles; p.n_tiles = job->n_tiles;
     p.d_coef = job->d_coef; p.d_tmp = job->d_tmp; p.nlevels = job->nlevels;
     p.max_w = job->max_w; p.max_h = job->max_h; p.reversible = job->hdr.reversible != 0; p.f64_io = 0;
-    p.d_plane_out = nullptr; p.d_pix = (uint8_t *)d_out; p.tail = job->tail; p.stream_levels = job->stream_levels;
+    p.d_plane_out = nullptr; p.d_pix = (uint8_t *)d_out; p.tail = job->tail; p.stream_levels = job->stream_levels; p.iso = job->iso;
     for (int lvl = job->nlevels - 1; lvl >= 0; lvl--) {
         p.lvl = lvl;
         IdwtLaunch q = p;
@@ -437,7 +453,7 @@ extern "C" int j2kgpu_job_run_level(j2kgpu_job *job, int lvl, void *d_out)
     p.d_tcs = job->d_tcs; p.n_tc = job->n_tc; p.d_tiles = lvl == 0 ? job->d_tiles : nullptr; p.n_tiles = job->n_tiles;
     p.d_coef = job->d_coef; p.d_tmp = job->d_tmp; p.nlevels = job->nlevels; p.lvl = lvl;
     p.max_w = job->max_w; p.max_h = job->max_h; p.reversible = job->hdr.reversible != 0; p.f64_io = 0;
-    p.d_plane_out = nullptr; p.d_pix = (uint8_t *)d_out; p.tail = job->tail; p.stream_levels = job->stream_levels;
+    p.d_plane_out = nullptr; p.d_pix = (uint8_t *)d_out; p.tail = job->tail; p.stream_levels = job->stream_levels; p.iso = job->iso;
     int nl = 0;
     cudaError_t e = launch_idwt_level(p, ctx->stream, &nl);
     if (e != cudaSuccess) return j2k_cuda_err(ctx, e, "idwt level launch");
@@ -520,7 +536,7 @@ static int stage_blocks(j2kgpu_ctx *ctx, int mode, int ht, const j2k_blkjob_t *j
 {
     if (!ctx) return J2KGPU_E_ARG;
     std::lock_guard<std::mutex> g(ctx->mu);
-    if (mode != J2KGPU_MODE_REF) return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "mode %d not built", mode);
+    if (mode != J2KGPU_MODE_REF && !(mode == J2KGPU_MODE_ISO && ht)) return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "mode %d not built for this coder", mode);
     if ((!jobs && n) || (!blob && blob_len) || (!out && out_len)) return j2k_set_err(ctx, J2KGPU_E_ARG, "null argument");
     if (n == 0) return J2KGPU_OK;
     cudaSetDevice(ctx->device);
@@ -545,7 +561,11 @@ static int stage_blocks(j2kgpu_ctx *ctx, int mode, int ht, const j2k_blkjob_t *j
     J2K_CUDA(ctx, cudaMemcpyAsync(ctx->d_tab.p, cbs.data(), n * sizeof(DevCblk), cudaMemcpyHostToDevice, ctx->stream));
     if (blob_len) J2K_CUDA(ctx, cudaMemcpyAsync(ctx->d_in.p, blob, blob_len, cudaMemcpyHostToDevice, ctx->stream));
     J2K_CUDA(ctx, cudaMemsetAsync(ctx->d_out.p, 0, out_len * sizeof(int32_t), ctx->stream));
-    cudaError_t e = ht ? launch_ht_ref((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, (int32_t *)ctx->d_out.p, ctx->stream)
+    int ht_map = 32;
+    if (const char *ev = getenv("J2KGPU_HT_MAP")) ht_map = (atoi(ev) == 1) ? 1 : 32;
+    cudaError_t e = (ht && mode == J2KGPU_MODE_ISO)
+                        ? launch_ht_iso((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, (int32_t *)ctx->d_out.p, nullptr, 0, ht_map, ctx->stream)
+                    : ht ? launch_ht_ref((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, (int32_t *)ctx->d_out.p, ctx->stream)
                        : launch_t1_ref_stage((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, (int32_t *)ctx->d_out.p, max_bps, ctx->stream);
     if (e != cudaSuccess) return j2k_cuda_err(ctx, e, "entropy kernel launch");
     ctx->launches++;
@@ -571,7 +591,8 @@ static int stage_idwt(j2kgpu_ctx *ctx, int mode, void *data, uint32_t w, uint32_
 {
     if (!ctx) return J2KGPU_E_ARG;
     std::lock_guard<std::mutex> g(ctx->mu);
-    if (mode != J2KGPU_MODE_REF) return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "mode %d not built", mode);
+    if (mode != J2KGPU_MODE_REF && !(mode == J2KGPU_MODE_ISO && kind == 0))
+        return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "mode %d not built for this transform", mode);
     if (!data && w && h) return j2k_set_err(ctx, J2KGPU_E_ARG, "null data");
     if (w == 0 || h == 0) return J2KGPU_OK;
     if (levels == 0 && kind != 2) return J2KGPU_OK;                           // dwt.go:545: no levels, nothing to do
@@ -596,7 +617,8 @@ static int stage_idwt(j2kgpu_ctx *ctx, int mode, void *data, uint32_t w, uint32_
     p.max_w = w; p.max_h = h; p.reversible = kind == 0; p.f64_io = kind == 1;
     p.d_plane_out = (int32_t *)ctx->d_out.p; p.d_pix = nullptr;
     p.stream_levels = 0;
-    if (kind == 0)
+    p.iso = mode == J2KGPU_MODE_ISO;
+    if (kind == 0 && !(p.iso && (w & 3)))
         for (int l = 1; l < (int)levels; l++)                 // level 0 of the stage API stores planes: tiled kernel
             if (j2k_stream_ok(w, h, l)) p.stream_levels |= 1u << l;
     // levels == 0 (kind 2 only): tcd.go:428-435 still runs int32 -> float64 -> int32(v + 0.5), which maps a

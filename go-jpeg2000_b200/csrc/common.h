@@ -81,6 +81,9 @@ struct j2kgpu_job {
     int max_bps = 0;
     bool need_clear = false;
     uint32_t stream_levels = 0;
+    int iso = 0;                         // J2KGPU_MODE_ISO
+    int ht_map = 32;                     // ISO HT: code blocks per warp (32 = thread per block, 1 = warp per block)
+    float *d_steps = nullptr;            // ISO irreversible: dequantisation step per block
     DevCblk *d_cblks = nullptr;
     DevTileComp *d_tcs = nullptr;
     DevTile *d_tiles = nullptr;
@@ -106,6 +109,9 @@ cudaError_t launch_t1_ref(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_b
                           int max_bps, cudaStream_t s);
 cudaError_t launch_ht_ref(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, int32_t *d_coef,
                           cudaStream_t s);
+// ISO/IEC 15444-15 cleanup decoder; blocks_per_warp = 1 (warp per block) or 32 (thread per block)
+cudaError_t launch_ht_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, int32_t *d_coef,
+                          const float *d_steps, int irrev, int blocks_per_warp, cudaStream_t s);
 
 // inverse DWT, REF (dense-prefix) addressing.  One call = one decomposition level of every
 // tile-component in the table.  `lvl` counts from 0 (full resolution).  For lvl > 0 the output goes to the
@@ -120,6 +126,7 @@ struct IdwtLaunch {
     uint32_t max_w, max_h;                          // largest tile-component (grid sizing)
     int reversible;
     int f64_io;                                     // 9-7 stage API: coefficient arena and output planes are double
+    int iso;                                        // 1: Mallat addressing + ISO order (rows, then columns)
     uint32_t stream_levels;                         // bit l set: level l of every tile-component fits the streaming kernel
     int32_t *d_plane_out;                           // lvl == 0 without tiles: output planes (same offsets as coef)
     uint8_t *d_pix;                                 // lvl == 0 with tiles: packed pixels

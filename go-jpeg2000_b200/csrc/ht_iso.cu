@@ -1,0 +1,343 @@
+// ht_iso.cu -- ISO/IEC 15444-15 (ITU-T T.814) HT cleanup-pass block decoder for J2KGPU_MODE_ISO (sm_100a).
+//
+// What north_star calls "HTJ2K cleanup decoding (MEL, VLC and MagSgn bitstreams)".  The reference's ht.go is
+// not conformant and is covered by ht_ref.cu; this kernel follows the published algorithm
+// (T.814 clause 7): MagSgn forward from byte 0, MEL forward from Lcup-Scup, VLC backward from Lcup-2, 2x2 quads
+// in pairs, CxtVLC tables, U-VLC, exponent predictor from the previous quad row.  Checked in the test suite against
+// a CPU statement of the same algorithm that is itself pinned by OpenJPEG decoding the same streams.
+//
+// Mapping.  The three bit streams of a block are strictly sequential, so a block is one serial chain of about
+// 50 instructions per quad whatever the mapping.  Two mappings of the same device function are built:
+//   BLOCKS_PER_WARP = 1   one warp per code block: all lanes run the chain on uniform registers, lane 0 stores;
+//   BLOCKS_PER_WARP = 32  one thread per code block: 32 independent chains per warp (divergent but short
+//                         branches), 32x fewer warp-instructions for the same work.
+// The launcher picks by J2KGPU_HT_MAP (default: thread-per-block; see DESIGN.md for the ncu comparison).
+// Per-block state: stream cursors and 64-bit bit buffers in registers; previous-row significance as a 64-bit
+// column mask; previous-row exponents as 64 bytes of shared memory, updated in place with a one-column carry.
+// Every sample of the block is written exactly once (zeros included), two rows x two columns per quad.
+#include "common.h"
+
+namespace {
+
+#include "ht_vlc_tables.inc"
+__device__ const uint16_t d_tbl0[1024] = HT_VLC_TBL0_INIT;
+__device__ const uint16_t d_tbl1[1024] = HT_VLC_TBL1_INIT;
+
+constexpr int kThreads = 128;
+
+struct Mel {
+    int pos, left; uint32_t tmp; int bits; bool unstuff;
+    int k, zeros; bool one_after;
+};
+struct Vlc { int pos, left; uint64_t tmp; int bits; bool unstuff; };
+struct Ms  { int pos, left; uint64_t tmp; int bits; bool unstuff; };
+
+__device__ __forceinline__ int mel_exp(int k)
+{
+    // {0,0,0,1,1,1,2,2,2,3,3,4,5} packed 4 bits each
+    return (int)((0x5433222111000ull >> (4 * k)) & 0xF);
+}
+
+__device__ __forceinline__ int mel_bit(Mel &m, const uint8_t *d)
+{
+    if (m.bits == 0) {
+        uint32_t b = 0xFF;
+        if (m.left > 0) {
+            b = __ldg(d + m.pos); m.pos++; m.left--;
+            if (m.left == 0) b |= 0x0F;                 // last byte is shared with the VLC stream
+        }
+        m.bits = m.unstuff ? 7 : 8;
+        m.tmp = m.unstuff ? (b & 0x7F) : b;
+        m.unstuff = (b == 0xFF);
+    }
+    m.bits--;
+    return (int)((m.tmp >> m.bits) & 1);
+}
+
+__device__ __forceinline__ int mel_event(Mel &m, const uint8_t *d)
+{
+    if (m.zeros == 0 && !m.one_after) {
+        const int e = mel_exp(m.k);
+        if (mel_bit(m, d)) {
+            m.zeros = 1 << e;
+            if (m.k < 12) m.k++;
+        } else {
+            int r = 0;
+            for (int i = 0; i < e; i++) r = (r << 1) | mel_bit(m, d);
+            m.zeros = r; m.one_after = true;
+            if (m.k > 0) m.k--;
+        }
+    }
+    if (m.zeros > 0) { m.zeros--; return 0; }
+    m.one_after = false;
+    return 1;
+}
+
+__device__ __forceinline__ uint32_t vlc_peek(Vlc &v, const uint8_t *d)
+{
+    while (v.bits <= 32) {
+        uint32_t b = 0;
+        if (v.left > 0) { b = __ldg(d + v.pos); v.pos--; v.left--; }
+        const int nb = (v.unstuff && (b & 0x7F) == 0x7F) ? 7 : 8;
+        v.tmp |= (uint64_t)b << v.bits;
+        v.bits += nb;
+        v.unstuff = b > 0x8F;
+    }
+    return (uint32_t)v.tmp;
+}
+__device__ __forceinline__ void vlc_skip(Vlc &v, int n) { v.tmp >>= n; v.bits -= n; }
+
+__device__ __forceinline__ uint32_t ms_get(Ms &s, const uint8_t *d, int n)
+{
+    while (s.bits <= 32) {
+        uint32_t b = 0xFF;
+        if (s.left > 0) { b = __ldg(d + s.pos); s.pos++; s.left--; }
+        const int nb = s.unstuff ? 7 : 8;
+        s.tmp |= (uint64_t)b << s.bits;
+        s.bits += nb;
+        s.unstuff = (b == 0xFF);
+    }
+    const uint32_t v = (uint32_t)s.tmp & ((n >= 32) ? 0xFFFFFFFFu : ((1u << n) - 1u));
+    s.tmp >>= n; s.bits -= n;
+    return v;
+}
+
+// U-VLC prefix rows (T.814 Table 3): prefix_len | suffix_len << 2 | base << 5, indexed by the 3 LSBs
+__device__ __forceinline__ uint32_t uvlc_row(uint32_t b3)
+{
+    // {183, 33, 66, 33, 103, 33, 66, 33}
+    return (uint32_t)((0x2142216721422100ull | 0xB7ull) >> (8 * b3)) & 0xFF;
+}
+
+__device__ int uvlc_decode(uint32_t vlc, int mode, bool initial, int &u0, int &u1)
+{
+    u0 = 0; u1 = 0;
+    if (mode == 0) return 0;
+    if (mode == 1 || mode == 2) {
+        const uint32_t t = uvlc_row(vlc & 7);
+        const int pl = t & 3, sl = (t >> 2) & 7;
+        vlc >>= pl;
+        const int u = (int)((t >> 5) + (vlc & ((1u << sl) - 1)));
+        if (mode == 1) u0 = u; else u1 = u;
+        return pl + sl;
+    }
+    const uint32_t t1 = uvlc_row(vlc & 7);
+    const int p1 = t1 & 3;
+    vlc >>= p1;
+    if (mode == 3 && initial && p1 > 2) {                 // u0 > 2, so u1 is 1 or 2: a single bit
+        u1 = (int)(vlc & 1) + 1;
+        vlc >>= 1;
+        const int sl = (t1 >> 2) & 7;
+        u0 = (int)((t1 >> 5) + (vlc & ((1u << sl) - 1)));
+        return p1 + 1 + sl;
+    }
+    const uint32_t t2 = uvlc_row(vlc & 7);
+    const int p2 = t2 & 3;
+    vlc >>= p2;
+    const int s1 = (t1 >> 2) & 7, s2 = (t2 >> 2) & 7;
+    u0 = (int)((t1 >> 5) + (vlc & ((1u << s1) - 1)));
+    vlc >>= s1;
+    u1 = (int)((t2 >> 5) + (vlc & ((1u << s2) - 1)));
+    if (mode == 4) { u0 += 2; u1 += 2; }
+    return p1 + p2 + s1 + s2;
+}
+
+// columns (c-1, c, c+1, c+2) of a 64-bit column mask as 4 bits; columns outside 0..63 read 0
+__device__ __forceinline__ uint32_t win4(uint64_t m, int c)
+{
+    return (uint32_t)(c ? (m >> (c - 1)) : (m << 1)) & 0xF;
+}
+
+// value written for one decoded sample: reversible -> integer; irreversible -> dequantised float bits
+__device__ __forceinline__ int32_t sample_value(uint32_t mu, uint32_t sign, int shift, float step, bool irrev)
+{
+    if (!irrev) {
+        const uint32_t mag = mu << shift;
+        return (int32_t)(sign ? 0u - mag : mag);
+    }
+    // mid-point reconstruction: (mu + 1/2) * 2^shift * step
+    const float f = ((float)mu + 0.5f) * (float)(1u << shift) * step;
+    return __float_as_int(sign ? -f : f);
+}
+
+// One block, one thread's worth of control flow.  `ex` = 64 exponent bytes of the previous quad row's bottom
+// samples (element c at ex[c * ex_stride]).  `do_store`: this thread performs the global stores.
+__device__ void ht_decode_block(const DevCblk &cb, const uint8_t *__restrict__ blob, int32_t *__restrict__ coef,
+                                const uint16_t *s_tbl, uint8_t *ex, int ex_stride, bool do_store, float step, bool irrev)
+{
+    const int w = cb.w, h = cb.h;
+    int32_t *out = coef + cb.out_off;
+    const size_t ostride = cb.out_stride;
+    const uint8_t *d = blob + cb.data_off;
+    const int lcup = (int)cb.data_len;
+    bool ok = lcup >= 2 && cb.num_bps >= 1 && cb.num_bps <= 30;
+    int scup = 0;
+    if (ok) {
+        scup = ((int)__ldg(d + lcup - 1) << 4) + (int)(__ldg(d + lcup - 2) & 0x0F);
+        ok = scup >= 2 && scup <= lcup && scup <= 4079;
+    }
+    if (!ok) {                                               // not coded or malformed: the block is zero
+        if (do_store)
+            for (int y = 0; y < h; y++)
+                for (int x = 0; x < w; x++) out[(size_t)y * ostride + x] = 0;
+        return;
+    }
+    const int shift = cb.num_bps - 1;
+    Mel mel; mel.pos = lcup - scup; mel.left = scup - 1; mel.tmp = 0; mel.bits = 0; mel.unstuff = false;
+    mel.k = 0; mel.zeros = 0; mel.one_after = false;
+    Vlc vlc;
+    {
+        const uint32_t b = __ldg(d + lcup - 2);
+        vlc.pos = lcup - 3; vlc.left = scup - 2;
+        vlc.tmp = b >> 4;
+        vlc.bits = 4 - (((vlc.tmp & 7) == 7) ? 1 : 0);
+        vlc.unstuff = (b | 0x0F) > 0x8F;
+    }
+    Ms ms; ms.pos = 0; ms.left = lcup - scup; ms.tmp = 0; ms.bits = 0; ms.unstuff = false;
+
+    const int nq = (w + 1) >> 1;
+    for (int c = 0; c < 64; c++) ex[c * ex_stride] = 0;
+    uint64_t sigprev = 0;
+    bool bad = false;
+    const bool vec_ok = ((cb.out_off | ostride) & 1) == 0;
+
+    for (int y = 0; y < h; y += 2) {
+        const bool initial = (y == 0);
+        const uint16_t *tbl = s_tbl + (initial ? 0 : 1024);
+        const bool row2 = (y + 1 < h);
+        uint64_t signew = 0;
+        int cw = 0;
+        int e_carry = 0;                                     // previous-row exponent of column 2q-1
+        for (int q = 0; q < nq; q += 2) {
+            const bool pair = (q + 1 < nq);
+            uint32_t qinf0 = 0, qinf1 = 0;
+            // ---- CxtVLC of the two quads ----
+            {
+                int c_q = cw;
+                if (!initial) { const uint32_t s4 = win4(sigprev, 2 * q); c_q |= ((s4 | (s4 >> 1)) & 1) | ((((s4 >> 2) | (s4 >> 3)) & 1) << 2); }
+                uint32_t e = tbl[(c_q << 7) | (vlc_peek(vlc, d) & 0x7F)];
+                if (c_q == 0 && !mel_event(mel, d)) e = 0;
+                vlc_skip(vlc, e & 7);
+                qinf0 = e;
+                const uint32_t rho = (e >> 4) & 0xF;
+                cw = initial ? (int)(((rho | (rho >> 1)) & 1) | (((rho >> 2) & 1) << 1) | (((rho >> 3) & 1) << 2))
+                             : (int)((((rho >> 2) | (rho >> 3)) & 1) << 1);
+            }
+            if (pair) {
+                int c_q = cw;
+                if (!initial) { const uint32_t s4 = win4(sigprev, 2 * q + 2); c_q |= ((s4 | (s4 >> 1)) & 1) | ((((s4 >> 2) | (s4 >> 3)) & 1) << 2); }
+                uint32_t e = tbl[(c_q << 7) | (vlc_peek(vlc, d) & 0x7F)];
+                if (c_q == 0 && !mel_event(mel, d)) e = 0;
+                vlc_skip(vlc, e & 7);
+                qinf1 = e;
+                const uint32_t rho = (e >> 4) & 0xF;
+                cw = initial ? (int)(((rho | (rho >> 1)) & 1) | (((rho >> 2) & 1) << 1) | (((rho >> 3) & 1) << 2))
+                             : (int)((((rho >> 2) | (rho >> 3)) & 1) << 1);
+            }
+            // ---- U-VLC ----
+            int mode = (int)(((qinf0 >> 3) & 1) | (((qinf1 >> 3) & 1) << 1));
+            if (initial && mode == 3 && mel_event(mel, d)) mode = 4;
+            int u0 = 0, u1 = 0;
+            if (mode) vlc_skip(vlc, uvlc_decode(vlc_peek(vlc, d), mode, initial, u0, u1));
+            // ---- exponent predictor kappa from the previous quad row (columns 2q-1 .. 2q+4) ----
+            const int c0 = 2 * q;
+            const int eA = e_carry, eB = ex[c0 * ex_stride], eC = (c0 + 1 < 64) ? ex[(c0 + 1) * ex_stride] : 0,
+                      eD = (c0 + 2 < 64) ? ex[(c0 + 2) * ex_stride] : 0, eE = (c0 + 3 < 64) ? ex[(c0 + 3) * ex_stride] : 0,
+                      eF = (c0 + 4 < 64) ? ex[(c0 + 4) * ex_stride] : 0;
+            int U0 = u0 + 1, U1 = u1 + 1;
+            if (!initial) {
+                const uint32_t r0 = (qinf0 >> 4) & 0xF, r1 = (qinf1 >> 4) & 0xF;
+                if (r0 & (r0 - 1)) { const int E = max(max(eA, eB), max(eC, eD)); U0 = u0 + max(1, E - 1); }
+                if (r1 & (r1 - 1)) { const int E = max(max(eC, eD), max(eE, eF)); U1 = u1 + max(1, E - 1); }
+            }
+            e_carry = eE;                                    // column 2(q+2)-1 before this pair overwrites it
+            if (U0 > 31 || U1 > 31) bad = true;
+            U0 = min(U0, 31); U1 = min(U1, 31);
+            // ---- MagSgn + store, quad by quad ----
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                if (i == 1 && !pair) break;
+                const uint32_t e = i ? qinf1 : qinf0;
+                const int U = i ? U1 : U0;
+                const int xq = c0 + 2 * i;
+                int32_t v[4];
+                int enew[2] = {0, 0};
+#pragma unroll
+                for (int n = 0; n < 4; n++) {
+                    v[n] = 0;
+                    if ((e >> (4 + n)) & 1) {
+                        const int m = U - (int)((e >> (12 + n)) & 1);
+                        uint32_t val = ms_get(ms, d, m);
+                        const uint32_t sign = val & 1;
+                        val |= ((e >> (8 + n)) & 1) << m;
+                        val |= 1;
+                        v[n] = sample_value((val >> 1) + 1, sign, shift, step, irrev);
+                        if (n & 1) enew[n >> 1] = 32 - __clz((int)val);
+                    }
+                }
+                const bool colB = (xq + 1 < w);
+                ex[xq * ex_stride] = (uint8_t)enew[0];
+                if (xq + 1 < 64) ex[(xq + 1) * ex_stride] = (uint8_t)enew[1];
+                signew |= ((uint64_t)((e >> 5) & 1) << xq) | ((uint64_t)((e >> 7) & 1) << (xq + 1));
+                // significance outside the block is a malformed stream: the whole block decodes to zero
+                if ((!colB && (e & 0xC0)) || (!row2 && (e & 0xA0))) bad = true;
+                if (do_store) {
+                    int32_t *p0 = out + (size_t)y * ostride + xq;
+                    if (colB && vec_ok) {
+                        *reinterpret_cast<int2 *>(p0) = make_int2(v[0], v[2]);
+                        if (row2) *reinterpret_cast<int2 *>(p0 + ostride) = make_int2(v[1], v[3]);
+                    } else {
+                        p0[0] = v[0];
+                        if (colB) p0[1] = v[2];
+                        if (row2) { p0[ostride] = v[1]; if (colB) p0[ostride + 1] = v[3]; }
+                    }
+                }
+            }
+        }
+        sigprev = signew;
+    }
+    if (bad && do_store)
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++) out[(size_t)y * ostride + x] = 0;
+}
+
+template <int BLOCKS_PER_WARP>
+__global__ void __launch_bounds__(kThreads)
+k_ht_iso(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob,
+         int32_t *__restrict__ coef, const float *__restrict__ steps, int irrev)
+{
+    __shared__ uint16_t s_tbl[2048];
+    __shared__ uint8_t s_ex[64 * kThreads];
+    for (int i = threadIdx.x; i < 1024; i += kThreads) { s_tbl[i] = d_tbl0[i]; s_tbl[1024 + i] = d_tbl1[i]; }
+    __syncthreads();
+    uint32_t blk;
+    bool do_store;
+    uint8_t *ex;
+    if (BLOCKS_PER_WARP == 32) {
+        blk = blockIdx.x * kThreads + threadIdx.x;
+        do_store = true;
+        ex = s_ex + threadIdx.x;                              // column-major: element c at ex[c * kThreads]
+    } else {
+        blk = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+        do_store = (threadIdx.x & 31) == 0;
+        ex = s_ex + (threadIdx.x >> 5);                       // lanes of a warp share one column (same values)
+    }
+    if (blk >= n) return;
+    const DevCblk cb = cblks[blk];
+    ht_decode_block(cb, blob, coef, s_tbl, ex, kThreads, do_store, steps ? steps[blk] : 1.0f, irrev != 0);
+}
+
+}  // namespace
+
+cudaError_t launch_ht_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, int32_t *d_coef,
+                          const float *d_steps, int irrev, int blocks_per_warp, cudaStream_t s)
+{
+    if (n == 0) return cudaSuccess;
+    if (blocks_per_warp == 32) {
+        k_ht_iso<32><<<(n + kThreads - 1) / kThreads, kThreads, 0, s>>>(d_cblks, n, d_blob, d_coef, d_steps, irrev);
+    } else {
+        const uint32_t per = kThreads / 32;
+        k_ht_iso<1><<<(n + per - 1) / per, kThreads, 0, s>>>(d_cblks, n, d_blob, d_coef, d_steps, irrev);
+    }
+    return cudaGetLastError();
+}

@@ -82,19 +82,33 @@ struct Lift97 {
 struct LevelGeom {
     int w, h;          // level image size
     int nlx, nly;      // number of low-pass columns / rows
-    uint32_t nprev;    // elements taken from the previous level's output
+    uint32_t nprev;    // REF: elements taken from the previous level's output; ISO: non-zero if LL comes from it
+    uint32_t W;        // ISO: row stride of the Mallat coefficient plane (full tile-component width)
 };
 
-template <class L, bool IN_F64>
-__device__ __forceinline__ typename L::T load_src(uint32_t lin, uint32_t nprev, const typename L::T *prev,
-                                                  const void *coef)
+// REF (dense prefix): interleaved (yy, xx) -> linear index in the level image, prev below nprev.
+// ISO (Mallat): LL from the previous level's dense output (or the plane when coarsest), HL/LH/HH from the plane.
+template <class L, bool IN_F64, bool ISO>
+__device__ __forceinline__ typename L::T load_src(const LevelGeom &g, int yy, int xx, bool do_v, bool do_h,
+                                                  const typename L::T *prev, const void *coef)
 {
-    if (lin < nprev) return prev[lin];
+    const int by = do_v ? (yy >> 1) : yy, bx = do_h ? (xx >> 1) : xx;
+    const bool hy = do_v && (yy & 1), hx = do_h && (xx & 1);
+    if (ISO) {
+        if (!hy && !hx && g.nprev) return prev[(uint32_t)by * (uint32_t)g.nlx + (uint32_t)bx];
+        const uint32_t lin = (uint32_t)(hy ? g.nly + by : by) * g.W + (uint32_t)(hx ? g.nlx + bx : bx);
+        if (IN_F64) return (typename L::T)((const double *)coef)[lin];
+        return L::from_i32(((const int32_t *)coef)[lin]);
+    }
+    const uint32_t lin = (uint32_t)(hy ? g.nly + by : by) * (uint32_t)g.w + (uint32_t)(hx ? g.nlx + bx : bx);
+    if (lin < g.nprev) return prev[lin];
     if (IN_F64) return (typename L::T)((const double *)coef)[lin];
     return L::from_i32(((const int32_t *)coef)[lin]);
 }
 
-template <class L, bool IN_F64>
+// REF: columns first, then rows (reference dwt.go:411-428).  ISO: rows first, then columns (15444-1 F.3.2:
+// HOR_SR before VER_SR) -- with integer lifting the order is observable.
+template <class L, bool IN_F64, bool ISO>
 __device__ void transform_tile(typename L::T *P, const LevelGeom &g, int x0, int y0,
                                const typename L::T *prev, const void *coef, bool no_xform)
 {
@@ -110,18 +124,28 @@ __device__ void transform_tile(typename L::T *P, const LevelGeom &g, int x0, int
         int i = (k < PW / 2) ? 2 * k : 2 * (k - PW / 2) + 1;
         int yy = y0 - HALO + j, xx = x0 - HALO + i;
         if (yy < 0 || yy >= g.h || xx < 0 || xx >= g.w) continue;
-        int ry = do_v ? ((yy & 1) ? g.nly + (yy >> 1) : (yy >> 1)) : yy;
-        int cx = do_h ? ((xx & 1) ? g.nlx + (xx >> 1) : (xx >> 1)) : xx;
-        T v = load_src<L, IN_F64>((uint32_t)ry * (uint32_t)g.w + (uint32_t)cx, g.nprev, prev, coef);
-        if (L::kScale) {                                   // 9-7: K on even / 1/K on odd, per direction
-            if (do_v) v = L::scale(v, yy & 1);
+        T v = load_src<L, IN_F64, ISO>(g, yy, xx, do_v, do_h, prev, coef);
+        if (L::kScale) {                                   // 9-7: K on even / 1/K on odd, first direction here
+            if (ISO) { if (do_h) v = L::scale(v, xx & 1); }
+            else if (do_v) v = L::scale(v, yy & 1);
         }
         P[j * PP + i] = v;
     }
     __syncthreads();
 
-    // ---- columns (vertical) ----
-    if (do_v) {
+    // vertical lifting over patch columns [ca, cb); horizontal lifting over patch rows [ra, rb)
+    auto vpass = [&](int ca, int cb, bool prescale) {
+        if (!do_v) return;
+        const int nc = cb - ca;
+        if (prescale && L::kScale) {
+            for (int e = tid; e < PH * nc; e += kThreads) {
+                int j = e / nc, i = ca + (e - j * nc);
+                int yy = y0 - HALO + j, xx = x0 - HALO + i;
+                if (yy < 0 || yy >= g.h || xx < 0 || xx >= g.w) continue;
+                P[j * PP + i] = L::scale(P[j * PP + i], yy & 1);
+            }
+            __syncthreads();
+        }
 #pragma unroll
         for (int s = 0; s < L::STEPS; s++) {
             const int margin = L::STEPS - 2 - s;
@@ -130,8 +154,8 @@ __device__ void transform_tile(typename L::T *P, const LevelGeom &g, int x0, int
             if (yb > g.h - 1) yb = g.h - 1;
             if ((ya & 1) != (s & 1)) ya++;
             const int nrows = yb >= ya ? ((yb - ya) >> 1) + 1 : 0;
-            for (int e = tid; e < nrows * PW; e += kThreads) {
-                int r = e / PW, i = e - r * PW;
+            for (int e = tid; e < nrows * nc; e += kThreads) {
+                int r = e / nc, i = ca + (e - r * nc);
                 int yy = ya + 2 * r, j = yy - (y0 - HALO);
                 int xx = x0 - HALO + i;
                 if (xx < 0 || xx >= g.w) continue;
@@ -141,15 +165,15 @@ __device__ void transform_tile(typename L::T *P, const LevelGeom &g, int x0, int
             }
             __syncthreads();
         }
-    }
-    // ---- rows (horizontal), only the TH output rows ----
-    if (do_h) {
-        if (L::kScale) {
-            for (int e = tid; e < TH * PW; e += kThreads) {
+    };
+    auto hpass = [&](int ra, int rb, bool prescale) {
+        if (!do_h) return;
+        const int nr = rb - ra;
+        if (prescale && L::kScale) {
+            for (int e = tid; e < nr * PW; e += kThreads) {
                 int r = e / PW, i = e - r * PW;
-                int yy = y0 + r, xx = x0 - HALO + i;
-                if (yy >= g.h || xx < 0 || xx >= g.w) continue;
-                int j = r + HALO;
+                int j = ra + r, yy = y0 - HALO + j, xx = x0 - HALO + i;
+                if (yy < 0 || yy >= g.h || xx < 0 || xx >= g.w) continue;
                 P[j * PP + i] = L::scale(P[j * PP + i], xx & 1);
             }
             __syncthreads();
@@ -162,22 +186,29 @@ __device__ void transform_tile(typename L::T *P, const LevelGeom &g, int x0, int
             if (xb > g.w - 1) xb = g.w - 1;
             if ((xa & 1) != (s & 1)) xa++;
             const int ncols = xb >= xa ? ((xb - xa) >> 1) + 1 : 0;
-            for (int e = tid; e < TH * ncols; e += kThreads) {
+            for (int e = tid; e < nr * ncols; e += kThreads) {
                 int r = e / ncols, c = e - r * ncols;
-                int yy = y0 + r;
-                if (yy >= g.h) continue;
-                int xx = xa + 2 * c, i = xx - (x0 - HALO), j = r + HALO;
+                int j = ra + r, yy = y0 - HALO + j;
+                if (yy < 0 || yy >= g.h) continue;
+                int xx = xa + 2 * c, i = xx - (x0 - HALO);
                 bool hl = xx - 1 >= 0, hr = xx + 1 < g.w;
                 T l = hl ? P[j * PP + i - 1] : T(0), rr = hr ? P[j * PP + i + 1] : T(0);
                 P[j * PP + i] = L::apply(s, P[j * PP + i], l, rr, hl, hr);
             }
             __syncthreads();
         }
+    };
+    if (ISO) {
+        hpass(0, PH, false);                  // every patch row, horizontally scaled in the gather
+        vpass(HALO, HALO + TW, true);         // then the TW output columns
+    } else {
+        vpass(0, PW, false);                  // every patch column, vertically scaled in the gather
+        hpass(HALO, HALO + TH, true);         // then the TH output rows
     }
 }
 
 // ---- kernel: one level, every tile-component (EPI_STORE / EPI_ROUND_I32) ------------------------------
-template <class L, bool IN_F64, int EPI>
+template <class L, bool IN_F64, int EPI, bool ISO>
 __global__ void __launch_bounds__(kThreads)
 k_idwt_level(const DevTileComp *__restrict__ tcs, const void *__restrict__ coef, typename L::T *tmp,
              void *out_planes, int nlevels, int lvl)
@@ -195,11 +226,12 @@ k_idwt_level(const DevTileComp *__restrict__ tcs, const void *__restrict__ coef,
     g.nlx = (g.w + 1) >> 1; g.nly = (g.h + 1) >> 1;
     const bool no_xform = nlevels == 0;
     g.nprev = (lvl + 1 < nlevels) ? (uint32_t)g.nlx * (uint32_t)g.nly : 0u;
+    g.W = tc.w;
     T *pp0 = tmp + tc.tmp_off, *pp1 = pp0 + tc.tmp_elems;
     const T *prev = ((lvl + 1) & 1) ? pp1 : pp0;
     const void *cbase = IN_F64 ? (const void *)((const double *)coef + tc.coef_off)
                                : (const void *)((const int32_t *)coef + tc.coef_off);
-    transform_tile<L, IN_F64>(P, g, x0, y0, prev, cbase, no_xform);
+    transform_tile<L, IN_F64, ISO>(P, g, x0, y0, prev, cbase, no_xform);
 
     for (int e = threadIdx.x; e < TH * TW; e += kThreads) {
         int r = e / TW, c = e - r * TW;
@@ -218,7 +250,7 @@ k_idwt_level(const DevTileComp *__restrict__ tcs, const void *__restrict__ coef,
 }
 
 // ---- kernel: last level of every tile, fused with inverse MCT + DC shift + clamp + pack ---------------
-template <class L>
+template <class L, bool ISO>
 __global__ void __launch_bounds__(kThreads)
 k_idwt_last_pixels(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__ tiles,
                    const int32_t *__restrict__ coef, typename L::T *tmp, uint8_t *pix, int nlevels,
@@ -237,6 +269,7 @@ k_idwt_last_pixels(const DevTileComp *__restrict__ tcs, const DevTile *__restric
     g.w = (int)tile.w; g.h = (int)tile.h;
     g.nlx = (g.w + 1) >> 1; g.nly = (g.h + 1) >> 1;
     g.nprev = nlevels > 1 ? (uint32_t)g.nlx * (uint32_t)g.nly : 0u;
+    g.W = tile.w;
 
     int32_t acc[4][PER];
 #pragma unroll
@@ -244,7 +277,7 @@ k_idwt_last_pixels(const DevTileComp *__restrict__ tcs, const DevTile *__restric
         if (c >= tp.ncomp) break;
         const DevTileComp tc = tcs[tile.tc[c]];
         const T *prev = tmp + tc.tmp_off + tc.tmp_elems;          // level 1 wrote ping-pong buffer 1
-        transform_tile<L, false>(P, g, x0, y0, prev, coef + tc.coef_off, nlevels == 0);
+        transform_tile<L, false, ISO>(P, g, x0, y0, prev, coef + tc.coef_off, nlevels == 0);
 #pragma unroll
         for (int k = 0; k < PER; k++) {
             int e = threadIdx.x + k * kThreads;
@@ -304,8 +337,12 @@ constexpr size_t patch_bytes() { return sizeof(typename L::T) * (size_t)(TH + 2 
 template <class L, bool IN_F64, int EPI>
 cudaError_t run_level(const IdwtLaunch &p, dim3 grid, cudaStream_t s)
 {
-    k_idwt_level<L, IN_F64, EPI><<<grid, kThreads, patch_bytes<L>(), s>>>(
-        p.d_tcs, (const void *)p.d_coef, (typename L::T *)p.d_tmp, (void *)p.d_plane_out, p.nlevels, p.lvl);
+    if (p.iso)
+        k_idwt_level<L, IN_F64, EPI, true><<<grid, kThreads, patch_bytes<L>(), s>>>(
+            p.d_tcs, (const void *)p.d_coef, (typename L::T *)p.d_tmp, (void *)p.d_plane_out, p.nlevels, p.lvl);
+    else
+        k_idwt_level<L, IN_F64, EPI, false><<<grid, kThreads, patch_bytes<L>(), s>>>(
+            p.d_tcs, (const void *)p.d_coef, (typename L::T *)p.d_tmp, (void *)p.d_plane_out, p.nlevels, p.lvl);
     return cudaGetLastError();
 }
 
@@ -323,11 +360,14 @@ cudaError_t launch_idwt_level(const IdwtLaunch &p, cudaStream_t s, int *n_launch
     if (p.reversible && p.nlevels > 0 && ((p.stream_levels >> lvl) & 1) && (lvl > 0 || pixels))
         return launch_idwt53_stream(p, s);
     if (pixels) {
-        if (p.reversible)
-            k_idwt_last_pixels<Lift53><<<grid, kThreads, patch_bytes<Lift53>(), s>>>(
+        if (p.reversible && p.iso)
+            k_idwt_last_pixels<Lift53, true><<<grid, kThreads, patch_bytes<Lift53>(), s>>>(
+                p.d_tcs, p.d_tiles, p.d_coef, (int32_t *)p.d_tmp, p.d_pix, p.nlevels, p.tail);
+        else if (p.reversible)
+            k_idwt_last_pixels<Lift53, false><<<grid, kThreads, patch_bytes<Lift53>(), s>>>(
                 p.d_tcs, p.d_tiles, p.d_coef, (int32_t *)p.d_tmp, p.d_pix, p.nlevels, p.tail);
         else
-            k_idwt_last_pixels<Lift97><<<grid, kThreads, patch_bytes<Lift97>(), s>>>(
+            k_idwt_last_pixels<Lift97, false><<<grid, kThreads, patch_bytes<Lift97>(), s>>>(
                 p.d_tcs, p.d_tiles, p.d_coef, (double *)p.d_tmp, p.d_pix, p.nlevels, p.tail);
         return cudaGetLastError();
     }

@@ -41,18 +41,19 @@ __device__ __forceinline__ int odd_last(int x, int l)             // x += l     
 }
 
 struct Src {
-    const int32_t *prev;     // dense output of the coarser level (elements [0, nprev))
-    const int32_t *coef;     // coefficient plane (elements [nprev, w*h))
-    uint32_t nprev;
+    const int32_t *prev;     // dense output of the coarser level
+    const int32_t *coef;     // coefficient plane
+    uint32_t nprev;          // REF: elements [0, nprev) of the level image come from prev; ISO: non-zero if LL does
 };
 
+// REF (dense prefix): one linear index space, prev below nprev
 __device__ __forceinline__ int2 ld2(const Src &s, uint32_t lin)
 {
     const int32_t *p = lin < s.nprev ? s.prev : s.coef;
     return __ldg(reinterpret_cast<const int2 *>(p + lin));
 }
 
-template <int NC, bool PIXELS>
+template <int NC, bool PIXELS, bool ISO>
 __global__ void __launch_bounds__(kWarps * 32, 3)
 k_idwt53_stream(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__ tiles,
                 const int32_t *__restrict__ coef, int32_t *__restrict__ tmp, uint8_t *__restrict__ pix,
@@ -100,14 +101,47 @@ k_idwt53_stream(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__
 
     int hp[NC][4], ep[NC][4];      // Hi[k-1] and E[k-1] of the lane's 4 columns, order L0, L1, H0, H1
 
+    // r = row of the level image in band order (rows [0, nly) low-pass, [nly, h) high-pass); v = L0, L1, H0, H1
+    const uint32_t planeW = (uint32_t)W0;            // ISO: stride of the Mallat plane
     auto load_row = [&](int c, int r, int v[4]) {
         if (qvalid) {
-            const uint32_t lin = (uint32_t)r * uw;
-            const int2 a = ld2(src[c], lin + colL), b = ld2(src[c], lin + colH);
+            int2 a, b;
+            if (ISO) {
+                const int32_t *rowp = src[c].coef + (size_t)r * planeW;
+                b = __ldg(reinterpret_cast<const int2 *>(rowp + colH));
+                if (r < nly && src[c].nprev) a = __ldg(reinterpret_cast<const int2 *>(src[c].prev + (size_t)r * (uint32_t)nlx + colL));
+                else a = __ldg(reinterpret_cast<const int2 *>(rowp + colL));
+            } else {
+                const uint32_t lin = (uint32_t)r * uw;
+                a = ld2(src[c], lin + colL); b = ld2(src[c], lin + colH);
+            }
             v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
         } else {
             v[0] = v[1] = v[2] = v[3] = 0;
         }
+    };
+    // horizontal synthesis of one row held as (L0, L1, H0, H1) per lane -> 4 interleaved samples; every lane
+    // takes part in the two shuffles (lane 0 / 31 are halo lanes)
+    auto hsynth = [&](const int V[4], int X[4]) {
+        const int VL0 = V[0], VL1 = V[1], VH0 = V[2], VH1 = V[3];
+        int left = __shfl_up_sync(0xffffffffu, VH1, 1);
+        if (q == 0) left = VH0;                                       // x[0] -= (x[1] + x[1] + 2) >> 2
+        const int X0 = even_upd(VL0, left, VH0);
+        const int X2 = even_upd(VL1, VH0, VH1);
+        const int right = __shfl_down_sync(0xffffffffu, X0, 1);
+        X[0] = X0;
+        X[1] = odd_upd(VH0, X0, X2);
+        X[2] = X2;
+        X[3] = (q == nq - 1) ? odd_last(VH1, X2) : odd_upd(VH1, X2, right);
+    };
+    // raw band-row pair k of component c (loads only, so that they can be issued one step ahead)
+    auto load_pair = [&](int c, int k, int lo[4], int hi[4]) {
+        load_row(c, k, lo); load_row(c, nly + k, hi);
+    };
+    // bring a raw row into the domain the vertical lifting works in: REF = band columns (the horizontal
+    // synthesis happens on finished rows), ISO = interleaved columns (horizontal synthesis first)
+    auto to_domain = [&](int v[4]) {
+        if (ISO) { int x[4]; hsynth(v, x); v[0] = x[0]; v[1] = x[1]; v[2] = x[2]; v[3] = x[3]; }
     };
 
     // pixel addressing of this lane's 4 output columns
@@ -120,16 +154,12 @@ k_idwt53_stream(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__
         int X[NC][4];
 #pragma unroll
         for (int c = 0; c < NC; c++) {
-            const int VL0 = V[c][0], VL1 = V[c][1], VH0 = V[c][2], VH1 = V[c][3];
-            int left = __shfl_up_sync(0xffffffffu, VH1, 1);
-            if (q == 0) left = VH0;                                   // x[0] -= (x[1] + x[1] + 2) >> 2
-            const int X0 = even_upd(VL0, left, VH0);
-            const int X2 = even_upd(VL1, VH0, VH1);
-            const int right = __shfl_down_sync(0xffffffffu, X0, 1);
-            X[c][0] = X0;
-            X[c][1] = odd_upd(VH0, X0, X2);
-            X[c][2] = X2;
-            X[c][3] = (q == nq - 1) ? odd_last(VH1, X2) : odd_upd(VH1, X2, right);
+            if (ISO) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) X[c][j] = V[c][j];
+            } else {
+                hsynth(V[c], X[c]);
+            }
         }
         if (!store_lane) return;
         if (!PIXELS) {
@@ -168,9 +198,10 @@ k_idwt53_stream(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__
 #pragma unroll
     for (int c = 0; c < NC; c++) {
         int lo[4], hi[4];
-        load_row(c, ka, lo);
-        load_row(c, nly + ka, hi);
+        load_pair(c, ka, lo, hi);
         if (ka > 0) load_row(c, nly + ka - 1, hp[c]);
+        to_domain(lo); to_domain(hi);
+        if (ka > 0) to_domain(hp[c]);
         else {
 #pragma unroll
             for (int j = 0; j < 4; j++) hp[c][j] = hi[j];              // top edge: Hi[-1] := Hi[0]
@@ -185,7 +216,7 @@ k_idwt53_stream(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__
     int lo[NC][4], hi[NC][4];
     if (ka + 1 < nly) {
 #pragma unroll
-        for (int c = 0; c < NC; c++) { load_row(c, ka + 1, lo[c]); load_row(c, nly + ka + 1, hi[c]); }
+        for (int c = 0; c < NC; c++) load_pair(c, ka + 1, lo[c], hi[c]);
     }
     for (int k = ka + 1; k <= kb; k++) {
         int o[NC][4];
@@ -194,9 +225,11 @@ k_idwt53_stream(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__
             const bool more = (k + 1 <= kb) && (k + 1 < nly);
             if (more) {
 #pragma unroll
-                for (int c = 0; c < NC; c++) { load_row(c, k + 1, nlo[c]); load_row(c, nly + k + 1, nhi[c]); }
+                for (int c = 0; c < NC; c++) load_pair(c, k + 1, nlo[c], nhi[c]);
             }
             int e[NC][4];
+#pragma unroll
+            for (int c = 0; c < NC; c++) { to_domain(lo[c]); to_domain(hi[c]); }
 #pragma unroll
             for (int c = 0; c < NC; c++)
 #pragma unroll
@@ -228,8 +261,12 @@ k_idwt53_stream(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__
 template <int NC, bool PIXELS>
 cudaError_t run(const IdwtLaunch &p, dim3 grid, int strip_pairs, cudaStream_t s)
 {
-    k_idwt53_stream<NC, PIXELS><<<grid, kWarps * 32, 0, s>>>(p.d_tcs, p.d_tiles, p.d_coef, (int32_t *)p.d_tmp,
-                                                              p.d_pix, p.nlevels, p.lvl, strip_pairs, p.tail);
+    if (p.iso)
+        k_idwt53_stream<NC, PIXELS, true><<<grid, kWarps * 32, 0, s>>>(p.d_tcs, p.d_tiles, p.d_coef, (int32_t *)p.d_tmp,
+                                                                        p.d_pix, p.nlevels, p.lvl, strip_pairs, p.tail);
+    else
+        k_idwt53_stream<NC, PIXELS, false><<<grid, kWarps * 32, 0, s>>>(p.d_tcs, p.d_tiles, p.d_coef, (int32_t *)p.d_tmp,
+                                                                         p.d_pix, p.nlevels, p.lvl, strip_pairs, p.tail);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,108 @@
+"""GPU parity, ISO mode (J2KGPU_MODE_ISO): conformant HTJ2K decode through the C ABI.
+
+Checkers: oracle/iso_ht.c (pinned by OpenJPEG, tests/test_iso_codestream.py) for the block decoder; the ISO
+inverse 5-3 = reference Inverse2D53 applied to the transpose (ISO does rows first, the reference columns first);
+and, end to end, the source image of a lossless codestream AND OpenJPEG's own decode of the same bytes."""
+import io
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from datagen import iso_ht_encode, jobs
+
+pytestmark = pytest.mark.gpu
+ISO = 1
+
+
+def test_iso_ht_blocks_vs_oracle(gpu_ctx):
+    rng = np.random.default_rng(31)
+    blocks, want = [], []
+    for t in range(400):
+        w, h = int(rng.integers(1, 65)), int(rng.integers(1, 65))
+        nb = int(rng.integers(1, 16))
+        d = rng.integers(-(1 << nb) + 1, 1 << nb, w * h).astype(np.int32)
+        d[rng.random(w * h) < rng.uniform(0, 0.97)] = 0
+        enc = iso_ht_encode(d, w, h)
+        nbps = int(rng.integers(1, 4))
+        blocks.append((enc, w, h, nbps, 0))
+        want.append(d << (nbps - 1))
+    for mp in ("32", "1"):
+        import os
+        os.environ["J2KGPU_HT_MAP"] = mp                       # thread-per-block and warp-per-block mappings
+        for i, (got, w_) in enumerate(zip(gpu_ctx.ht_decode_blocks(blocks, mode=ISO), want)):
+            assert np.array_equal(got, w_), (mp, i)
+    os.environ.pop("J2KGPU_HT_MAP", None)
+
+
+def test_iso_ht_garbage_vs_oracle(gpu_ctx):
+    """malformed segments decode to zero exactly as the checker does; nothing faults"""
+    rng = np.random.default_rng(32)
+    blocks = [(b"", 8, 8, 1, 0), (b"\x00\x00", 8, 8, 1, 0), (b"\xff\xff\xff", 8, 8, 1, 0)]
+    for _ in range(300):
+        n = int(rng.integers(2, 600))
+        s = rng.integers(0, 256, n).astype(np.uint8)
+        if rng.random() < 0.4:
+            s[rng.random(n) < 0.3] = 0xFF
+        scup = int(rng.integers(2, min(n, 4079) + 1))
+        s[-1], s[-2] = scup >> 4, (s[-2] & 0xF0) | (scup & 0xF)
+        blocks.append((s.tobytes(), int(rng.integers(1, 65)), int(rng.integers(1, 65)), 1, 0))
+    for i, ((s, w, h, nb, _), got) in enumerate(zip(blocks, gpu_ctx.ht_decode_blocks(blocks, mode=ISO))):
+        assert np.array_equal(got, O.iso_ht_decode(s, w, h, nb)[0]), i
+
+
+def iso_inverse53(plane, w, h, levels):
+    """ISO 15444-1 inverse 5-3 on a Mallat plane: per level, rows first then columns = Inverse2D53 of the transpose"""
+    a = np.array(plane, np.int32).reshape(h, w).copy()
+    dims = [(w, h)]
+    for _ in range(levels - 1):
+        dims.append(((dims[-1][0] + 1) // 2, (dims[-1][1] + 1) // 2))
+    for (lw, lh) in reversed(dims):
+        sub = np.ascontiguousarray(a[:lh, :lw].T)
+        a[:lh, :lw] = O.inv2d53(sub, lh, lw).reshape(lw, lh).T
+    return a.reshape(-1)
+
+
+@pytest.mark.parametrize("w,h,levels", [(8, 8, 1), (64, 64, 5), (16, 12, 2), (37, 23, 3), (1, 9, 2), (130, 70, 3),
+                                         (256, 256, 5), (512, 512, 5), (640, 360, 5), (264, 136, 2)])
+def test_iso_idwt53_vs_transposed_reference(gpu_ctx, w, h, levels):
+    rng = np.random.default_rng(w * 7 + h)
+    c = rng.integers(-3000, 3000, w * h).astype(np.int32)
+    assert np.array_equal(gpu_ctx.reconstruct_multilevel53(c, w, h, levels, mode=ISO), iso_inverse53(c, w, h, levels))
+
+
+def iso_pixels(j2k, ctx, job):
+    img = j2k.make_image(job["width"], job["height"], job["ncomp"], job["prec"], mct=job["mct"], reversible=1,
+                         nlevels=job["nlevels"], ht=1, mode=ISO)
+    return ctx.decode_tiles(img, jobs.as_ctypes(job["tilecomps"], j2k.TileComp), jobs.as_ctypes(job["cblks"], j2k.CBlk),
+                            job["blob"])
+
+
+@pytest.mark.parametrize("w,h,ncomp,prec,tw,th,nl", [
+    (64, 64, 1, 8, None, None, 0), (128, 128, 1, 8, None, None, 2), (256, 256, 3, 8, None, None, 5),
+    (200, 150, 3, 8, None, None, 3), (512, 512, 3, 8, 256, 256, 5), (333, 211, 3, 8, 128, 128, 4),
+    (640, 360, 1, 12, None, None, 5), (300, 200, 3, 16, None, None, 4), (1024, 512, 3, 8, 512, 512, 5),
+])
+def test_iso_whole_path_lossless_htj2k(j2k, gpu_ctx, w, h, ncomp, prec, tw, th, nl):
+    s = jobs.synth_image(w, h, ncomp, prec, seed=w + 3 * h)
+    job = jobs.build_iso_job(s, prec, tw, th, nl)
+    got = iso_pixels(j2k, gpu_ctx, job)
+    if prec <= 8:
+        pix = got.reshape(h, w, -1)
+        for c in range(ncomp):
+            assert np.array_equal(pix[:, :, c], s[c].astype(np.uint8)), c     # decode(encode(x)) == x
+        if ncomp == 3:
+            assert (pix[:, :, 3] == 255).all()
+        # and the same codestream decoded by OpenJPEG (independent ISO decoder) gives the same pixels
+        Image = pytest.importorskip("PIL.Image")
+        im = Image.open(io.BytesIO(job["codestream"]))
+        im.load()
+        a = np.array(im)
+        a = a[:, :, None] if a.ndim == 2 else a
+        assert np.array_equal(pix[:, :, :ncomp], a)
+    else:
+        val = got.reshape(h, w, -1, 2).astype(np.int64)
+        val = (val[..., 0] << 8) | val[..., 1]
+        maxv = (1 << prec) - 1
+        for c in range(ncomp):
+            assert np.array_equal(val[:, :, c], s[c].astype(np.int64) * 65535 // maxv)   # ISO packing: no int32 wrap
