@@ -156,6 +156,97 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def build_items(j2k, jobs, frames, mode):
+    """pinned host buffers + batch items for a list of frame jobs"""
+    import torch
+    stride = W * 4
+    keep, items, host_out = [], [], []
+    for j in frames:
+        tcs, cbs = jobs.as_ctypes(j["tilecomps"], j2k.TileComp), jobs.as_ctypes(j["cblks"], j2k.CBlk)
+        hb = torch.from_numpy(np.ascontiguousarray(j["blob"])).pin_memory()
+        ho = torch.empty(stride * H, dtype=torch.uint8).pin_memory()
+        keep += [tcs, cbs, hb]
+        host_out.append(ho)
+        img = j2k.make_image(W, H, NCOMP, PREC, nlevels=LEVELS, ht=j["ht"], mode=mode)
+        items.append(j2k.BatchItem(img, tcs, len(tcs), cbs, len(cbs), C.cast(hb.data_ptr(), j2k.u8p), hb.numel(),
+                                   C.cast(ho.data_ptr(), j2k.u8p), stride))
+    return items, host_out, keep
+
+
+def measure(args, ctx, j2k, jobs, frames, mode, stream, world, barrier, steps, check_lossless):
+    """device-resident and end-to-end timing of one workload; returns a dict of raw measurements"""
+    import torch
+    stride = W * 4
+    F = len(frames)
+    items, host_out, keep = build_items(j2k, jobs, frames, mode)
+    job = j2k.Job(ctx, items)
+    d_blob = torch.cat([torch.from_numpy(np.ascontiguousarray(j["blob"])) for j in frames] + [torch.zeros(64, dtype=torch.uint8)]).cuda()
+    d_out = torch.empty(job.out_bytes, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    # correctness guard on the exact bench inputs
+    job.run(d_blob.data_ptr(), d_out.data_ptr())
+    stream.synchronize()
+    first = d_out[: stride * H].cpu().numpy().reshape(H, W, 4)
+    if check_lossless:
+        src = frames[0]["samples"]
+        for c in range(3):
+            assert np.array_equal(first[:, :, c], src[c].astype(np.uint8)), "bench inputs decode incorrectly"
+    for _ in range(args.warmup):
+        job.run(d_blob.data_ptr(), d_out.data_ptr())
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    l0 = ctx.launches
+    ev[0].record(stream)
+    for _ in range(steps):
+        job.run(d_blob.data_ptr(), d_out.data_ptr())
+    ev[1].record(stream)
+    barrier()
+    ms_total = ev[0].elapsed_time(ev[1])
+    launches = ctx.launches - l0
+
+    def time_fn(fn, reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ts = []
+        for _ in range(reps):
+            a.record(stream)
+            fn()
+            b.record(stream)
+            b.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.mean(ts))
+
+    reps = max(3, min(steps, 10))
+    ent_ms = time_fn(lambda: job.run_entropy(d_blob.data_ptr()), reps)
+    dwt_ms = time_fn(lambda: job.run_dwt_mct(d_out.data_ptr()), reps)
+    last_ts = []
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(reps):                      # the dominant kernel alone: coarser levels refill the ping-pong buffers first
+        for lvl in range(LEVELS - 1, 0, -1):
+            job.run_level(lvl)
+        a.record(stream)
+        job.run_level(0, d_out.data_ptr())
+        b.record(stream)
+        b.synchronize()
+        last_ts.append(a.elapsed_time(b))
+    last_ms = float(np.mean(last_ts))
+    # end to end through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timed region)
+    for _ in range(2):
+        job.run_host()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(steps, 5))
+    for _ in range(e2e_steps):
+        job.run_host()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    assert np.array_equal(host_out[0].numpy().reshape(H, W, 4), first), "host path differs from device path"
+    res = dict(ms_total=ms_total, steps=steps, launches=int(launches), ent_ms=ent_ms, dwt_ms=dwt_ms, last_ms=last_ms,
+               e2e_s=e2e_s, e2e_steps=e2e_steps, h2d=int(d_blob.numel()) - 64, d2h=stride * H * F,
+               n_blocks=sum(len(j["cblks"]) for j in frames), F=F)
+    job.close()
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -172,34 +263,12 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = j2k.Context(local)
-    # an explicit torch stream: the library launches on it and the CUDA events below are recorded on it
+    # an explicit torch stream: the library launches on it and the CUDA events are recorded on it
     # (torch's legacy default stream has handle 0, which j2kgpu_set_stream reads as "use the ctx's own stream")
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
-
-    threads = max(1, (os.cpu_count() or 1) // max(1, world))
-    F = args.frames
-    # two distinct synthetic frames per rank, alternated through the batch (each item owns its bytes in HBM)
-    base = [build_frame(args.coder, 1002 + 17 * rank + i, threads) for i in range(min(2, F))]
-    frames = [base[i % len(base)] for i in range(F)]
-    bpp, stride = 4, W * 4
-    keep, items, host_out = [], [], []
-    for j in frames:
-        tcs, cbs = jobs.as_ctypes(j["tilecomps"], j2k.TileComp), jobs.as_ctypes(j["cblks"], j2k.CBlk)
-        hb = torch.from_numpy(np.ascontiguousarray(j["blob"])).pin_memory()
-        ho = torch.empty(stride * H, dtype=torch.uint8).pin_memory()
-        keep += [tcs, cbs, hb]
-        host_out.append(ho)
-        img = j2k.make_image(W, H, NCOMP, PREC, nlevels=LEVELS, ht=j["ht"])
-        items.append(j2k.BatchItem(img, tcs, len(tcs), cbs, len(cbs), C.cast(hb.data_ptr(), j2k.u8p), hb.numel(),
-                                   C.cast(ho.data_ptr(), j2k.u8p), stride))
-    job = j2k.Job(ctx, items)
-    d_blob = torch.cat([torch.from_numpy(np.ascontiguousarray(j["blob"])) for j in frames]).cuda()
-    d_out = torch.empty(job.out_bytes, dtype=torch.uint8, device="cuda")
-    n_blocks = sum(len(j["cblks"]) for j in frames)
-    blob_bytes = int(d_blob.numel())
 
     def barrier():
         torch.cuda.synchronize()
@@ -207,115 +276,94 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- correctness guard on the exact bench inputs: frame 0 must match the source image (lossless EBCOT) ----
-    job.run(d_blob.data_ptr(), d_out.data_ptr())
-    torch.cuda.synchronize()
-    first = d_out[: stride * H].cpu().numpy().reshape(H, W, 4)
-    if args.coder == "ebcot":
-        src = frames[0]["samples"]
-        for c in range(3):
-            assert np.array_equal(first[:, :, c], src[c].astype(np.uint8)), "bench inputs decode incorrectly"
+    def reduce_max(*vals):
+        if world == 1:
+            return vals
+        t = torch.tensor(list(vals), dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return tuple(float(x) for x in t)
 
-    # ---- device-resident timing ------------------------------------------------------------------------
-    for _ in range(args.warmup):
-        job.run(d_blob.data_ptr(), d_out.data_ptr())
-    barrier()
+    threads = max(1, (os.cpu_count() or 1) // max(1, world))
+    F = args.frames
+    mpix_step = W * H * F * world / 1e6
+    alg_bytes = (4 * W * H * NCOMP + W * H * 4) * F               # SURVEY.md 8(d), per launch of the fused kernel
+    peak, peak_src = peaks()
+
+    def summarize(m):
+        ms_total, e2e_s = reduce_max(m["ms_total"], m["e2e_s"])
+        ach = alg_bytes / (m["last_ms"] / 1e3) / 1e9
+        stg = alg_bytes / (m["dwt_ms"] / 1e3) / 1e9
+        return dict(value=round(mpix_step * m["steps"] / (ms_total / 1e3), 1), ms_per_step=round(ms_total / m["steps"], 4),
+                    e2e=dict(value=round(mpix_step * m["e2e_steps"] / e2e_s, 1), unit=UNIT, h2d_bytes_per_step=m["h2d"],
+                             d2h_bytes_per_step=m["d2h"], ms_per_step=round(1e3 * e2e_s / m["e2e_steps"], 3),
+                             api="j2kgpu_job_run_host (pinned host buffers)"),
+                    gpu_launches=m["launches"], code_blocks_per_step=m["n_blocks"] * world,
+                    stages_ms=dict(entropy=round(m["ent_ms"], 4), dwt_mct_pack=round(m["dwt_ms"], 4),
+                                   last_level_fused=round(m["last_ms"], 4)),
+                    roofline=dict(bound="hbm", achieved=round(ach, 1), peak=peak, unit="GB/s", frac=round(ach / peak, 4),
+                                  dwt_mct_stage_gbs=round(stg, 1), dwt_mct_stage_frac=round(stg / peak, 4)))
+
     sampler = ClockSampler(local)
+    # ---- headline: REF semantics (bit-identical to the reference's stage functions) -----------------------------------
+    base = [build_frame(args.coder, 1002 + 17 * rank + i, threads) for i in range(min(2, F))]
+    frames = [base[i % len(base)] for i in range(F)]
     if rank == 0:
         sampler.start()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    l0 = ctx.launches
-    ev[0].record(stream)
-    for _ in range(args.steps):
-        job.run(d_blob.data_ptr(), d_out.data_ptr())
-    ev[1].record(stream)
-    barrier()
-    ms_total = ev[0].elapsed_time(ev[1])
-    launches = ctx.launches - l0
-
-    # ---- per-stage / per-kernel timing (same inputs, same stream) -----------------------------------------
-    def time_fn(fn, reps):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ts = []
-        for _ in range(reps):
-            a.record(stream)
-            fn()
-            b.record(stream)
-            b.synchronize()
-            ts.append(a.elapsed_time(b))
-        return float(np.mean(ts)), float(np.min(ts))
-
-    reps = max(3, min(args.steps, 10))
-    job.run_entropy(d_blob.data_ptr())
-    ent_ms, _ = time_fn(lambda: job.run_entropy(d_blob.data_ptr()), reps)
-    dwt_ms, _ = time_fn(lambda: job.run_dwt_mct(d_out.data_ptr()), reps)
-    # the dominant kernel alone: levels 4..1 refill the ping-pong buffers outside the timed pair of events
-    last_ts = []
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for _ in range(reps):
-        for lvl in range(LEVELS - 1, 0, -1):
-            job.run_level(lvl)
-        a.record(stream)
-        job.run_level(0, d_out.data_ptr())
-        b.record(stream)
-        b.synchronize()
-        last_ts.append(a.elapsed_time(b))
-    last_ms = float(np.mean(last_ts))
+    m_ref = measure(args, ctx, j2k, jobs, frames, 0, stream, world, barrier, args.steps, args.coder == "ebcot")
     clocks = sampler.stop() if rank == 0 else None
+    main = summarize(m_ref)
 
-    # ---- end to end through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside) -------------
-    for _ in range(max(1, min(args.warmup, 2))):
-        job.run_host()
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 5))
-    for _ in range(e2e_steps):
-        job.run_host()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    h2d = blob_bytes
-    d2h = stride * H * F
-    assert np.array_equal(host_out[0].numpy().reshape(H, W, 4), first), "host path differs from device path"
-
-    # ---- reduce over ranks (max time) -----------------------------------------------------------------------
-    if world > 1:
-        t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e_s = float(t[0]), float(t[1])
-    mpix_step = W * H * F * world / 1e6
-    value = mpix_step * args.steps / (ms_total / 1e3)
-    e2e_val = mpix_step * e2e_steps / e2e_s
+    extra = {}
+    if not args.no_extra:
+        # ---- real HTJ2K (ISO/IEC 15444-15), same geometry: conformant codestream, cross-checked with OpenJPEG ----
+        iso_base = [jobs.build_iso_job(jobs.synth_image(W, H, NCOMP, PREC, seed=2002 + 17 * rank + i), PREC, TILE, TILE, LEVELS)
+                    for i in range(min(2, F))]
+        iso_frames = [iso_base[i % len(iso_base)] for i in range(F)]
+        m_iso = measure(args, ctx, j2k, jobs, iso_frames, 1, stream, world, barrier, args.steps, True)
+        extra["iso_htj2k"] = summarize(m_iso)
+        extra["iso_htj2k"]["workload"] = ("configs[1] as a conformant HTJ2K codestream (lossless 5-3, RCT, HT cleanup-only blocks), "
+                                          "J2KGPU_MODE_ISO, %d frames; pixels == source image == OpenJPEG decode" % F)
+        if rank == 0:
+            try:
+                import io
+                from PIL import Image
+                t0 = time.perf_counter()
+                im = Image.open(io.BytesIO(iso_base[0]["codestream"]))
+                im.load()
+                dt = time.perf_counter() - t0
+                extra["iso_htj2k"]["openjpeg_cpu"] = dict(value=round(W * H / 1e6 / dt, 2), unit=UNIT,
+                                                          note="OpenJPEG 2.5.4 via Pillow, same codestream, 1 frame, context only")
+            except Exception as e:  # pragma: no cover
+                extra["iso_htj2k"]["openjpeg_cpu"] = dict(error=str(e)[:100])
+        # ---- classic EBCOT/MQ, REF semantics ----------------------------------------------------------------
+        if args.coder != "ebcot":
+            eb = [build_frame("ebcot", 3002 + 17 * rank, threads)]
+            eb_frames = [eb[0]] * F
+            m_eb = measure(args, ctx, j2k, jobs, eb_frames, 0, stream, world, barrier, max(2, min(args.steps, 3)), True)
+            extra["ebcot_ref"] = summarize(m_eb)
+            extra["ebcot_ref"]["workload"] = workload_name("ebcot", F)
 
     if rank == 0:
-        peak, peak_src = peaks()
-        alg_bytes = (4 * W * H * NCOMP + W * H * bpp) * F          # SURVEY.md 8(d), per launch of the fused kernel
-        achieved = alg_bytes / (last_ms / 1e3) / 1e9
-        stage_gbs = alg_bytes / (dwt_ms / 1e3) / 1e9
         cpu_threads = os.cpu_count() or 1
         cpu_t, _ = cpu_decode_time(frames[0], cpu_threads, 1 if args.coder == "ebcot" else 2)
         cpu_val = (W * H / 1e6) / cpu_t
         line = {
-            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True,
+            "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": workload_name(args.coder, F), "mode": "REF", "frames_per_gpu_per_step": F,
-                       "code_blocks_per_step": n_blocks * world, "l2": "working set > L2 (no flush needed)",
+                       "code_blocks_per_step": main["code_blocks_per_step"], "l2": "working set > L2 (no flush needed)",
                        "parallelism": "frames sharded across GPUs, no collective"},
-            "e2e": {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": round(1e3 * e2e_s / e2e_steps, 3), "api": "j2kgpu_job_run_host (pinned host buffers)"},
-            "gpu_launches": int(launches),
-            "stages_ms": {"entropy": round(ent_ms, 4), "dwt_mct_pack": round(dwt_ms, 4), "last_level_fused": round(last_ms, 4)},
-            "roofline": {"bound": "hbm", "kernel": "k_idwt_last_pixels<Lift53> (last IDWT level + RCT + DC + clamp + RGBA pack)",
-                         "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "traffic": None,
-                         "dwt_mct_stage_gbs": round(stage_gbs, 1), "dwt_mct_stage_frac": round(stage_gbs / peak, 4)},
+            "e2e": main["e2e"], "gpu_launches": main["gpu_launches"], "stages_ms": main["stages_ms"],
+            "roofline": dict(main["roofline"], kernel="k_idwt53_stream<3,1> (last IDWT level + RCT + DC + clamp + RGBA pack)",
+                             peak_source=peak_src, algorithmic_bytes_per_launch=alg_bytes, traffic=None),
             "cpu_baseline": {"value": round(cpu_val, 2), "unit": UNIT, "cores": cpu_threads, "kind": "port",
                              "sample": "1 frame of the batch, whole path, all host threads",
                              "note": "C restatement of the reference's Go stage functions (oracle/); Go itself is absent"},
             "clocks": clocks,
         }
+        line.update(extra)
         print(json.dumps(line))
-    job.close()
     ctx.set_stream(0)
     ctx.close()
     if world > 1:
@@ -330,6 +378,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--coder", default="ht", choices=["ht", "ebcot"])
     ap.add_argument("--frames", type=int, default=8, help="frames per GPU per step")
+    ap.add_argument("--no-extra", action="store_true", help="skip the ISO HTJ2K and EBCOT side measurements")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
