@@ -13,6 +13,19 @@
 
 #define J2K_MAX_LEVELS 10
 
+// Kernel launch / dynamic shared memory spelled as macros so that tools/emu can build these same sources for the
+// CPU fiber emulator (a debugging aid; the product is the nvcc build below).
+#define J2K_UNPAREN(...) __VA_ARGS__
+#ifdef J2K_EMU
+#define J2K_LAUNCH(K, G, B, SM, ST, ...) emu::launch(dim3(G), dim3(B), (SM), [&]() { J2K_UNPAREN K(__VA_ARGS__); })
+#define J2K_DYN_SMEM(T, name) T *name = reinterpret_cast<T *>(emu::dyn_smem)
+#define J2K_LOCKSTEP_LANE(lane) ((lane) == 0)
+#else
+#define J2K_LOCKSTEP_LANE(lane) true
+#define J2K_LAUNCH(K, G, B, SM, ST, ...) J2K_UNPAREN K<<<(G), (B), (SM), (ST)>>>(__VA_ARGS__)
+#define J2K_DYN_SMEM(T, name) extern __shared__ __align__(16) unsigned char j2k_dyn_smem_[]; T *name = reinterpret_cast<T *>(j2k_dyn_smem_)
+#endif
+
 // ---- device-side tables (uploaded once per job) ---------------------------------------------
 struct DevCblk {                 // one code block, 32 bytes
     uint64_t data_off;           // into the job blob

@@ -334,10 +334,10 @@ cudaError_t launch_ht_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_b
 {
     if (n == 0) return cudaSuccess;
     if (blocks_per_warp == 32) {
-        k_ht_iso<32><<<(n + kThreads - 1) / kThreads, kThreads, 0, s>>>(d_cblks, n, d_blob, d_coef, d_steps, irrev);
+        J2K_LAUNCH((k_ht_iso<32>), (n + kThreads - 1) / kThreads, kThreads, 0, s, d_cblks, n, d_blob, d_coef, d_steps, irrev);
     } else {
         const uint32_t per = kThreads / 32;
-        k_ht_iso<1><<<(n + per - 1) / per, kThreads, 0, s>>>(d_cblks, n, d_blob, d_coef, d_steps, irrev);
+        J2K_LAUNCH((k_ht_iso<1>), (n + per - 1) / per, kThreads, 0, s, d_cblks, n, d_blob, d_coef, d_steps, irrev);
     }
     return cudaGetLastError();
 }

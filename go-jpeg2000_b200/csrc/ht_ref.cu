@@ -308,6 +308,6 @@ cudaError_t launch_ht_ref(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_b
 {
     if (n == 0) return cudaSuccess;
     uint32_t grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
-    k_ht_ref<<<grid, kWarpsPerCta * 32, 0, s>>>(d_cblks, n, d_blob, d_coef);
+    J2K_LAUNCH((k_ht_ref), grid, kWarpsPerCta * 32, 0, s, d_cblks, n, d_blob, d_coef);
     return cudaGetLastError();
 }

@@ -215,8 +215,7 @@ k_idwt_level(const DevTileComp *__restrict__ tcs, const void *__restrict__ coef,
 {
     typedef typename L::T T;
     constexpr int HALO = L::HALO, PW = TW + 2 * HALO, PH = TH + 2 * HALO, PP = PW + 1;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *P = (T *)smem_raw;
+    J2K_DYN_SMEM(T, P);
 
     const DevTileComp tc = tcs[blockIdx.z];
     LevelGeom g;
@@ -259,8 +258,7 @@ k_idwt_last_pixels(const DevTileComp *__restrict__ tcs, const DevTile *__restric
     typedef typename L::T T;
     constexpr int HALO = L::HALO, PW = TW + 2 * HALO, PP = PW + 1;
     constexpr int PER = TH * TW / kThreads;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *P = (T *)smem_raw;
+    J2K_DYN_SMEM(T, P);
 
     const DevTile tile = tiles[blockIdx.z];
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
@@ -338,11 +336,11 @@ template <class L, bool IN_F64, int EPI>
 cudaError_t run_level(const IdwtLaunch &p, dim3 grid, cudaStream_t s)
 {
     if (p.iso)
-        k_idwt_level<L, IN_F64, EPI, true><<<grid, kThreads, patch_bytes<L>(), s>>>(
-            p.d_tcs, (const void *)p.d_coef, (typename L::T *)p.d_tmp, (void *)p.d_plane_out, p.nlevels, p.lvl);
+        J2K_LAUNCH((k_idwt_level<L, IN_F64, EPI, true>), grid, kThreads, patch_bytes<L>(), s,
+                   p.d_tcs, (const void *)p.d_coef, (typename L::T *)p.d_tmp, (void *)p.d_plane_out, p.nlevels, p.lvl);
     else
-        k_idwt_level<L, IN_F64, EPI, false><<<grid, kThreads, patch_bytes<L>(), s>>>(
-            p.d_tcs, (const void *)p.d_coef, (typename L::T *)p.d_tmp, (void *)p.d_plane_out, p.nlevels, p.lvl);
+        J2K_LAUNCH((k_idwt_level<L, IN_F64, EPI, false>), grid, kThreads, patch_bytes<L>(), s,
+                   p.d_tcs, (const void *)p.d_coef, (typename L::T *)p.d_tmp, (void *)p.d_plane_out, p.nlevels, p.lvl);
     return cudaGetLastError();
 }
 
@@ -361,14 +359,14 @@ cudaError_t launch_idwt_level(const IdwtLaunch &p, cudaStream_t s, int *n_launch
         return launch_idwt53_stream(p, s);
     if (pixels) {
         if (p.reversible && p.iso)
-            k_idwt_last_pixels<Lift53, true><<<grid, kThreads, patch_bytes<Lift53>(), s>>>(
-                p.d_tcs, p.d_tiles, p.d_coef, (int32_t *)p.d_tmp, p.d_pix, p.nlevels, p.tail);
+            J2K_LAUNCH((k_idwt_last_pixels<Lift53, true>), grid, kThreads, patch_bytes<Lift53>(), s,
+                       p.d_tcs, p.d_tiles, p.d_coef, (int32_t *)p.d_tmp, p.d_pix, p.nlevels, p.tail);
         else if (p.reversible)
-            k_idwt_last_pixels<Lift53, false><<<grid, kThreads, patch_bytes<Lift53>(), s>>>(
-                p.d_tcs, p.d_tiles, p.d_coef, (int32_t *)p.d_tmp, p.d_pix, p.nlevels, p.tail);
+            J2K_LAUNCH((k_idwt_last_pixels<Lift53, false>), grid, kThreads, patch_bytes<Lift53>(), s,
+                       p.d_tcs, p.d_tiles, p.d_coef, (int32_t *)p.d_tmp, p.d_pix, p.nlevels, p.tail);
         else
-            k_idwt_last_pixels<Lift97, false><<<grid, kThreads, patch_bytes<Lift97>(), s>>>(
-                p.d_tcs, p.d_tiles, p.d_coef, (double *)p.d_tmp, p.d_pix, p.nlevels, p.tail);
+            J2K_LAUNCH((k_idwt_last_pixels<Lift97, false>), grid, kThreads, patch_bytes<Lift97>(), s,
+                       p.d_tcs, p.d_tiles, p.d_coef, (double *)p.d_tmp, p.d_pix, p.nlevels, p.tail);
         return cudaGetLastError();
     }
     if (p.reversible) return run_level<Lift53, false, EPI_STORE>(p, grid, s);
@@ -384,7 +382,7 @@ cudaError_t launch_tail(const int32_t *const d_comps[4], int32_t *const d_planes
     if (n == 0) return cudaSuccess;
     int blocks = (int)((n + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    k_tail<<<blocks, 256, 0, s>>>(d_comps[0], d_comps[1], d_comps[2], d_comps[3],
+    J2K_LAUNCH((k_tail), blocks, 256, 0, s, d_comps[0], d_comps[1], d_comps[2], d_comps[3],
                                   d_planes_out ? d_planes_out[0] : nullptr, d_planes_out ? d_planes_out[1] : nullptr,
                                   d_planes_out ? d_planes_out[2] : nullptr, d_planes_out ? d_planes_out[3] : nullptr,
                                   d_pix, out_stride, width, height, tp, apply_tail);
@@ -396,6 +394,6 @@ cudaError_t launch_inverse_ict_f64(double *y, double *cb, double *cr, uint64_t n
     if (n == 0) return cudaSuccess;
     int blocks = (int)((n + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    k_inverse_ict_f64<<<blocks, 256, 0, s>>>(y, cb, cr, n);
+    J2K_LAUNCH((k_inverse_ict_f64), blocks, 256, 0, s, y, cb, cr, n);
     return cudaGetLastError();
 }

@@ -262,11 +262,11 @@ template <int NC, bool PIXELS>
 cudaError_t run(const IdwtLaunch &p, dim3 grid, int strip_pairs, cudaStream_t s)
 {
     if (p.iso)
-        k_idwt53_stream<NC, PIXELS, true><<<grid, kWarps * 32, 0, s>>>(p.d_tcs, p.d_tiles, p.d_coef, (int32_t *)p.d_tmp,
-                                                                        p.d_pix, p.nlevels, p.lvl, strip_pairs, p.tail);
+        J2K_LAUNCH((k_idwt53_stream<NC, PIXELS, true>), grid, kWarps * 32, 0, s, p.d_tcs, p.d_tiles, p.d_coef,
+                   (int32_t *)p.d_tmp, p.d_pix, p.nlevels, p.lvl, strip_pairs, p.tail);
     else
-        k_idwt53_stream<NC, PIXELS, false><<<grid, kWarps * 32, 0, s>>>(p.d_tcs, p.d_tiles, p.d_coef, (int32_t *)p.d_tmp,
-                                                                         p.d_pix, p.nlevels, p.lvl, strip_pairs, p.tail);
+        J2K_LAUNCH((k_idwt53_stream<NC, PIXELS, false>), grid, kWarps * 32, 0, s, p.d_tcs, p.d_tiles, p.d_coef,
+                   (int32_t *)p.d_tmp, p.d_pix, p.nlevels, p.lvl, strip_pairs, p.tail);
     return cudaGetLastError();
 }
 

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
 k_t1_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob,
          int32_t *__restrict__ coef, int plane_words /* 64 * max_bps */, int skip_empty)
 {
-    extern __shared__ uint64_t smem[];
+    J2K_DYN_SMEM(uint64_t, smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t blk = blockIdx.x * kWarpsPerCta + warp;
     if (blk >= n) return;
@@ -141,7 +141,9 @@ k_t1_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
     const uint64_t wmask = (w >= 64) ? ~0ull : ((1ull << w) - 1);
     const uint8_t *zc = c_zc9 + band * 512;
 
-    for (int bp = nbps - 1; bp >= 0; bp--) {
+    // the serial MQ chain is executed redundantly by all 32 lanes in lock-step (idempotent shared-memory updates);
+    // the CPU fiber emulator (tools/emu) has no lock-step, so there lane 0 alone runs it
+    for (int bp = nbps - 1; bp >= 0 && J2K_LOCKSTEP_LANE(lane); bp--) {
         uint64_t *plane = planes + bp * 64;
 
         // ---- significance propagation, raster order (t1.go:1295-1319) ----
@@ -354,7 +356,7 @@ static cudaError_t launch_t1_ref_impl(const DevCblk *d_cblks, uint32_t n, const 
         if (e != cudaSuccess) return e;
     }
     uint32_t grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
-    k_t1_ref<<<grid, kWarpsPerCta * 32, smem, s>>>(d_cblks, n, d_blob, d_coef, plane_words, skip_empty);
+    J2K_LAUNCH((k_t1_ref), grid, kWarpsPerCta * 32, smem, s, d_cblks, n, d_blob, d_coef, plane_words, skip_empty);
     return cudaGetLastError();
 }
 
