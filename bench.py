@@ -167,7 +167,7 @@ def build_items(j2k, jobs, frames, mode):
         ho = torch.empty(stride * H, dtype=torch.uint8).pin_memory()
         keep += [tcs, cbs, hb]
         host_out.append(ho)
-        img = j2k.make_image(W, H, NCOMP, PREC, nlevels=LEVELS, ht=j["ht"], mode=mode)
+        img = j2k.make_image(W, H, NCOMP, PREC, nlevels=LEVELS, ht=j["ht"], mode=mode, coef_bits=j.get("coef_bits", 0))
         items.append(j2k.BatchItem(img, tcs, len(tcs), cbs, len(cbs), C.cast(hb.data_ptr(), j2k.u8p), hb.numel(),
                                    C.cast(ho.data_ptr(), j2k.u8p), stride))
     return items, host_out, keep
@@ -242,7 +242,7 @@ def measure(args, ctx, j2k, jobs, frames, mode, stream, world, barrier, steps, c
     assert np.array_equal(host_out[0].numpy().reshape(H, W, 4), first), "host path differs from device path"
     res = dict(ms_total=ms_total, steps=steps, launches=int(launches), ent_ms=ent_ms, dwt_ms=dwt_ms, last_ms=last_ms,
                e2e_s=e2e_s, e2e_steps=e2e_steps, h2d=int(d_blob.numel()) - 64, d2h=stride * H * F,
-               n_blocks=sum(len(j["cblks"]) for j in frames), F=F)
+               n_blocks=sum(len(j["cblks"]) for j in frames), F=F, fused_levels=job.fused_levels, coef_bytes=job.coef_bytes)
     job.close()
     return res
 
@@ -298,6 +298,7 @@ def run_ours(args):
                              d2h_bytes_per_step=m["d2h"], ms_per_step=round(1e3 * e2e_s / m["e2e_steps"], 3),
                              api="j2kgpu_job_run_host (pinned host buffers)"),
                     gpu_launches=m["launches"], code_blocks_per_step=m["n_blocks"] * world,
+                    plan=dict(idwt_levels_in_last_kernel=m["fused_levels"], coef_plane_bytes_per_sample=m["coef_bytes"]),
                     stages_ms=dict(entropy=round(m["ent_ms"], 4), dwt_mct_pack=round(m["dwt_ms"], 4),
                                    last_level_fused=round(m["last_ms"], 4)),
                     roofline=dict(bound="hbm", achieved=round(ach, 1), peak=peak, unit="GB/s", frac=round(ach / peak, 4),
@@ -354,8 +355,10 @@ def run_ours(args):
             "config": {"workload": workload_name(args.coder, F), "mode": "REF", "frames_per_gpu_per_step": F,
                        "code_blocks_per_step": main["code_blocks_per_step"], "l2": "working set > L2 (no flush needed)",
                        "parallelism": "frames sharded across GPUs, no collective"},
-            "e2e": main["e2e"], "gpu_launches": main["gpu_launches"], "stages_ms": main["stages_ms"],
-            "roofline": dict(main["roofline"], kernel="k_idwt53_stream<3,1> (last IDWT level + RCT + DC + clamp + RGBA pack)",
+            "e2e": main["e2e"], "gpu_launches": main["gpu_launches"], "stages_ms": main["stages_ms"], "plan": main["plan"],
+            "roofline": dict(main["roofline"], kernel="k_idwt53_fused<3> (IDWT levels 1+0 + RCT + DC + clamp + RGBA pack)"
+                             if main["plan"]["idwt_levels_in_last_kernel"] == 2 else
+                             "k_idwt53_stream<3,1> (last IDWT level + RCT + DC + clamp + RGBA pack)",
                              peak_source=peak_src, algorithmic_bytes_per_launch=alg_bytes, traffic=None),
             "cpu_baseline": {"value": round(cpu_val, 2), "unit": UNIT, "cores": cpu_threads, "kind": "port",
                              "sample": "1 frame of the batch, whole path, all host threads",

@@ -143,4 +143,5 @@ def build_iso_job(samples, prec, tile_w=None, tile_h=None, nlevels=5, mct=1, cb=
         blob += b["data"]
     return dict(width=W, height=H, ncomp=ncomp, prec=prec, sgnd=0, mct=1 if (mct and ncomp >= 3) else 0, reversible=1,
                 nlevels=nlevels, ht=1, mode=1, tilecomps=np.array(tcs, TILECOMP_DT), cblks=cblks,
-                blob=np.frombuffer(bytes(blob), np.uint8).copy(), samples=samples, codestream=data)
+                blob=np.frombuffer(bytes(blob), np.uint8).copy(), samples=samples, codestream=data,
+                coef_bits=max(info["eps"]) + info["guard"] - 1)      # max Mb over bands (QCD exponent + guard bits - 1)

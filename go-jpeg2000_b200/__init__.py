@@ -38,7 +38,7 @@ class Image(C.Structure):          # j2k_image_t
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("ncomp", C.c_uint16),
                 ("prec", C.c_uint8 * 4), ("sgnd", C.c_uint8 * 4), ("mct", C.c_uint8),
                 ("reversible", C.c_uint8), ("nlevels", C.c_uint8), ("ht", C.c_uint8),
-                ("mode", C.c_uint8), ("out_fmt", C.c_uint8)]
+                ("mode", C.c_uint8), ("out_fmt", C.c_uint8), ("coef_bits", C.c_uint8), ("rsv", C.c_uint8 * 3)]
 
 
 class TileComp(C.Structure):       # j2k_tilecomp_t
@@ -72,7 +72,7 @@ EXPORTS = [
     "j2kgpu_set_stream", "j2kgpu_launch_count", "j2kgpu_decode", "j2kgpu_decode_batch",
     "j2kgpu_job_create", "j2kgpu_job_destroy", "j2kgpu_job_blob_bytes", "j2kgpu_job_out_bytes",
     "j2kgpu_job_out_offset", "j2kgpu_job_run", "j2kgpu_job_run_entropy", "j2kgpu_job_run_dwt_mct",
-    "j2kgpu_job_run_level",
+    "j2kgpu_job_run_level", "j2kgpu_job_fused_levels", "j2kgpu_job_coef_bytes",
     "j2kgpu_job_run_host", "j2kgpu_sync", "j2kgpu_t1_decode_blocks", "j2kgpu_ht_decode_blocks",
     "j2kgpu_idwt53", "j2kgpu_idwt97", "j2kgpu_apply_inverse_dwt", "j2kgpu_inverse_rct",
     "j2kgpu_inverse_ict", "j2kgpu_dc_level_shift_inverse", "j2kgpu_mct_dc_pack",
@@ -119,6 +119,8 @@ def lib():
         L.j2kgpu_job_run_dwt_mct.argtypes = [C.c_void_p, C.c_void_p]
         L.j2kgpu_job_run_level.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.j2kgpu_job_run_host.argtypes = [C.c_void_p, C.POINTER(BatchItem)]
+        L.j2kgpu_job_fused_levels.argtypes = [C.c_void_p]
+        L.j2kgpu_job_coef_bytes.argtypes = [C.c_void_p]
         for name in ("j2kgpu_t1_decode_blocks", "j2kgpu_ht_decode_blocks"):
             getattr(L, name).argtypes = [C.c_void_p, C.c_int, C.POINTER(BlkJob), C.c_uint32, u8p, C.c_uint64,
                                          i32p, C.c_uint64]
@@ -138,7 +140,7 @@ def fmt_bpp(ncomp, prec):
     return (1 if prec <= 8 else 2) if ncomp == 1 else (4 if prec <= 8 else 8)
 
 
-def make_image(width, height, ncomp, prec, sgnd=0, mct=1, reversible=1, nlevels=5, ht=0, mode=MODE_REF):
+def make_image(width, height, ncomp, prec, sgnd=0, mct=1, reversible=1, nlevels=5, ht=0, mode=MODE_REF, coef_bits=0):
     im = Image()
     im.width, im.height, im.ncomp = width, height, ncomp
     precs = list(prec) if isinstance(prec, (list, tuple)) else [prec] * ncomp
@@ -147,6 +149,7 @@ def make_image(width, height, ncomp, prec, sgnd=0, mct=1, reversible=1, nlevels=
         im.prec[c] = precs[c]
         im.sgnd[c] = sg[c]
     im.mct, im.reversible, im.nlevels, im.ht, im.mode, im.out_fmt = mct, reversible, nlevels, ht, mode, FMT_AUTO
+    im.coef_bits = coef_bits
     return im
 
 
@@ -298,6 +301,8 @@ class Job:
         self.blob_bytes = int(lib().j2kgpu_job_blob_bytes(self._h))
         self.out_bytes = int(lib().j2kgpu_job_out_bytes(self._h))
         self.n = len(items)
+        self.fused_levels = int(lib().j2kgpu_job_fused_levels(self._h))
+        self.coef_bytes = int(lib().j2kgpu_job_coef_bytes(self._h))
 
     def out_offset(self, i):
         return int(lib().j2kgpu_job_out_offset(self._h, i))

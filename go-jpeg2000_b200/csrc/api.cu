@@ -15,6 +15,8 @@
 cudaError_t launch_t1_ref_stage(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, int32_t *d_coef,
                                 int max_bps, cudaStream_t s);
 
+static bool env_flag(const char *name) { const char *e = getenv(name); return e && *e && *e != '0'; }
+
 // ---- errors ------------------------------------------------------------------------------------------
 int j2k_set_err(j2kgpu_ctx *ctx, int code, const char *fmt, ...)
 {
@@ -45,6 +47,15 @@ int j2k_reserve(j2kgpu_ctx *ctx, DevBuf &b, size_t bytes, bool pinned_host)
     cudaError_t e = pinned_host ? cudaMallocHost(&b.p, cap) : cudaMalloc(&b.p, cap);
     if (e != cudaSuccess) { b.p = nullptr; return j2k_set_err(ctx, J2KGPU_E_NOMEM, "allocating %zu bytes: %s", cap, cudaGetErrorString(e)); }
     b.cap = cap;
+    return J2KGPU_OK;
+}
+
+int j2k_ctx_copy_streams(j2kgpu_ctx *ctx)
+{
+    if (ctx->s_in) return J2KGPU_OK;
+    J2K_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    J2K_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    J2K_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
     return J2KGPU_OK;
 }
 
@@ -181,6 +192,9 @@ extern "C" void j2kgpu_destroy(j2kgpu_ctx *ctx)
     free_buf(ctx->h_in, true); free_buf(ctx->h_out, true);
     for (auto &b : ctx->pool) { { std::lock_guard<std::mutex> g(g_pool_mu); pool_sizes().erase(b.p); } cudaFree(b.p); }
     ctx->pool.clear();
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+    if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -215,6 +229,8 @@ static void job_free(j2kgpu_job *job)
         void *ps[] = {job->d_cblks, job->d_tcs, job->d_tiles, job->d_coef, job->d_tmp, job->d_blob, job->d_pix};
         for (void *p : ps) j2k_pool_free(job->ctx, p);
     }
+    for (cudaEvent_t e : job->ev_in) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : job->ev_done) if (e) cudaEventDestroy(e);
     if (job->h_blob) cudaFreeHost(job->h_blob);
     if (job->h_pix) cudaFreeHost(job->h_pix);
     delete job;
@@ -264,6 +280,7 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
     int max_bps = 0;
     bool need_clear = false;
     uint32_t stream_levels = hdr.nlevels ? ((1u << hdr.nlevels) - 1) : 0;
+    bool fused_ok = hdr.reversible && hdr.nlevels >= 1 && !env_flag("J2KGPU_NO_FUSE");
 
     for (uint32_t ii = 0; ii < n_img; ii++) {
         const j2k_batch_item_t &it = items[ii];
@@ -277,6 +294,9 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
             job_free(job); return j2k_set_err(ctx, J2KGPU_E_ARG, "item %u: out_stride %llu too small or not a multiple of %d", ii, (unsigned long long)it.out_stride, bpp);
         }
         const uint32_t tc_base = (uint32_t)tcs.size();
+        job->item_cb.push_back((uint32_t)cbs.size());
+        job->item_tc.push_back(tc_base);
+        job->item_tile.push_back((uint32_t)tiles.size());
         job->blob_off.push_back(blob_bytes);
         job->out_off.push_back(out_bytes);
         job->out_size.push_back(it.out_stride * im.height);
@@ -290,6 +310,7 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
             d.w = tc.x1 - tc.x0; d.h = tc.y1 - tc.y0;
             if ((uint64_t)d.w * d.h > (1ull << 31)) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "tile-component too large"); }
             d.coef_off = coef_elems;
+            job->tc_coef_off.push_back(coef_elems);
             coef_elems = align_up(coef_elems + (uint64_t)d.w * d.h, 32);
             d.tmp_elems = (uint32_t)align_up((uint64_t)((d.w + 1) / 2) * ((d.h + 1) / 2), 32);
             d.tmp_off = tmp_elems;
@@ -297,6 +318,7 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
             tcs.push_back(d);
             for (int l = 0; l < hdr.nlevels; l++)
                 if (!j2k_stream_ok(d.w, d.h, l)) stream_levels &= ~(1u << l);
+            if (!j2k_fused_ok(d.w, d.h)) fused_ok = false;
             if (iso && ((tc.x0 | tc.y0) & ((1u << hdr.nlevels) - 1))) {
                 job_free(job);
                 return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "ISO mode: tile origin (%u,%u) is not a multiple of 2^nlevels", tc.x0, tc.y0);
@@ -347,7 +369,17 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
         blob_bytes += it.blob_len;
         out_bytes = align_up(out_bytes + it.out_stride * im.height, 256);
     }
+    job->item_cb.push_back((uint32_t)cbs.size());
+    job->item_tc.push_back((uint32_t)tcs.size());
+    job->item_tile.push_back((uint32_t)tiles.size());
     job->n_tc = (uint32_t)tcs.size(); job->n_tiles = (uint32_t)tiles.size(); job->n_cb = (uint32_t)cbs.size();
+    // int16 coefficient planes when every magnitude provably fits: EBCOT magnitudes are < 2^num_bps; a conformant
+    // codestream bounds them by coef_bits (Mb); the reference's HT coder has no bound (ht.go:664-684) and stays int32
+    if (!env_flag("J2KGPU_COEF32")) {
+        if (!iso && !hdr.ht) job->coef16 = max_bps <= 15;
+        if (iso && hdr.reversible) job->coef16 = hdr.coef_bits >= 1 && hdr.coef_bits <= 14;
+    }
+    job->fused_ok = fused_ok;
     job->coef_elems = coef_elems; job->blob_bytes = blob_bytes; job->out_bytes = out_bytes; job->max_bps = max_bps;
     job->tmp_bytes = tmp_elems * (hdr.reversible ? 4 : 8);
     job->need_clear = need_clear;
@@ -363,7 +395,7 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
     up((void **)&job->d_cblks, cbs.data(), cbs.size() * sizeof(DevCblk));
     up((void **)&job->d_tcs, tcs.data(), tcs.size() * sizeof(DevTileComp));
     up((void **)&job->d_tiles, tiles.data(), tiles.size() * sizeof(DevTile));
-    if (e == cudaSuccess) job->d_coef = (int32_t *)j2k_pool_alloc(ctx, coef_elems * sizeof(int32_t), &e);
+    if (e == cudaSuccess) job->d_coef = j2k_pool_alloc(ctx, coef_elems * (job->coef16 ? 2 : 4) + 64, &e);
     if (e == cudaSuccess) job->d_tmp = j2k_pool_alloc(ctx, job->tmp_bytes, &e);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);          // tables are read from host vectors
     if (e != cudaSuccess) { job_free(job); return j2k_cuda_err(ctx, e, "job upload"); }
@@ -385,44 +417,70 @@ extern "C" uint64_t j2kgpu_job_out_offset(const j2kgpu_job *job, uint32_t item)
     return (job && item < job->n_img) ? job->out_off[item] : 0;
 }
 
-static int run_entropy(j2kgpu_job *job, const void *d_blob)
+// ---- launch sequences over the items [ia, ib) of a job, on stream `st` ------------------------------------------------
+static int run_entropy(j2kgpu_job *job, const void *d_blob, uint32_t ia, uint32_t ib, cudaStream_t st)
 {
     j2kgpu_ctx *ctx = job->ctx;
-    if (job->need_clear)
-        J2K_CUDA(ctx, cudaMemsetAsync(job->d_coef, 0, job->coef_elems * sizeof(int32_t), ctx->stream));
-    if (job->n_cb == 0) return J2KGPU_OK;
+    const size_t esz = job->coef16 ? 2 : 4;
+    if (job->need_clear) {
+        const uint32_t ta = job->item_tc[ia], tb = job->item_tc[ib];
+        if (tb > ta) {
+            const uint64_t ea = job->tc_coef_off[ta], eb = tb < job->n_tc ? job->tc_coef_off[tb] : job->coef_elems;
+            J2K_CUDA(ctx, cudaMemsetAsync((uint8_t *)job->d_coef + ea * esz, 0, (eb - ea) * esz, st));
+        }
+    }
+    const uint32_t ca = job->item_cb[ia], n = job->item_cb[ib] - ca;
+    if (n == 0) return J2KGPU_OK;
+    const DevCblk *cbs = job->d_cblks + ca;
     cudaError_t e;
-    if (job->iso) e = launch_ht_iso(job->d_cblks, job->n_cb, (const uint8_t *)d_blob, job->d_coef, job->d_steps, 0, job->ht_map, ctx->stream);
-    else if (job->hdr.ht) e = launch_ht_ref(job->d_cblks, job->n_cb, (const uint8_t *)d_blob, job->d_coef, ctx->stream);
-    else e = launch_t1_ref(job->d_cblks, job->n_cb, (const uint8_t *)d_blob, job->d_coef, job->max_bps, ctx->stream);
+    if (job->iso) e = launch_ht_iso(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, job->d_steps, 0, job->hdr.coef_bits, job->ht_map, st);
+    else if (job->hdr.ht) e = launch_ht_ref(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, st);
+    else e = launch_t1_ref(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, job->max_bps, st);
     if (e != cudaSuccess) return j2k_cuda_err(ctx, e, "entropy kernel launch");
     ctx->launches++;
     return J2KGPU_OK;
 }
 
-static int run_dwt_mct(j2kgpu_job *job, void *d_out)
+static void fill_launch(const j2kgpu_job *job, IdwtLaunch &p, void *d_out, uint32_t ia, uint32_t ib)
 {
-    j2kgpu_ctx *ctx = job->ctx;
-    IdwtLaunch p{};
-    p.d_tcs = job->d_tcs; p.n_tc = job->n_tc; p.d_tiles = job->d_tiles; p.n_tiles = job->n_tiles;
-    p.d_coef = job->d_coef; p.d_tmp = job->d_tmp; p.nlevels = job->nlevels;
+    p = IdwtLaunch{};
+    p.d_tcs = job->d_tcs; p.d_tiles = job->d_tiles;
+    p.tc_first = job->item_tc[ia]; p.n_tc = job->item_tc[ib] - p.tc_first;
+    p.tile_first = job->item_tile[ia]; p.n_tiles = job->item_tile[ib] - p.tile_first;
+    p.d_coef = job->d_coef; p.coef16 = job->coef16; p.d_tmp = job->d_tmp; p.nlevels = job->nlevels;
     p.max_w = job->max_w; p.max_h = job->max_h; p.reversible = job->hdr.reversible != 0; p.f64_io = 0;
     p.d_plane_out = nullptr; p.d_pix = (uint8_t *)d_out; p.tail = job->tail; p.stream_levels = job->stream_levels; p.iso = job->iso;
-    for (int lvl = job->nlevels - 1; lvl >= 0; lvl--) {
-        p.lvl = lvl;
-        IdwtLaunch q = p;
-        if (lvl > 0) q.d_tiles = nullptr;
-        int nl = 0;
-        cudaError_t e = launch_idwt_level(q, ctx->stream, &nl);
-        if (e != cudaSuccess) return j2k_cuda_err(ctx, e, "idwt level launch");
-        ctx->launches += nl;
+}
+
+// one level of the reconstruction; with the fused kernel, level 1 is part of the level-0 launch
+static int run_level(j2kgpu_job *job, const IdwtLaunch &base, int lvl, cudaStream_t st)
+{
+    j2kgpu_ctx *ctx = job->ctx;
+    IdwtLaunch q = base;
+    q.lvl = lvl;
+    if (job->fused_ok && lvl <= 1) {
+        if (lvl == 1) return J2KGPU_OK;
+        cudaError_t e = launch_idwt53_fused(q, st);
+        if (e != cudaSuccess) return j2k_cuda_err(ctx, e, "fused idwt launch");
+        ctx->launches++;
+        return J2KGPU_OK;
     }
-    if (job->nlevels == 0) {
-        p.lvl = 0;
-        int nl = 0;
-        cudaError_t e = launch_idwt_level(p, ctx->stream, &nl);
-        if (e != cudaSuccess) return j2k_cuda_err(ctx, e, "idwt level launch");
-        ctx->launches += nl;
+    if (lvl > 0) q.d_tiles = nullptr;
+    int nl = 0;
+    cudaError_t e = launch_idwt_level(q, st, &nl);
+    if (e != cudaSuccess) return j2k_cuda_err(ctx, e, "idwt level launch");
+    ctx->launches += nl;
+    return J2KGPU_OK;
+}
+
+static int run_dwt_mct(j2kgpu_job *job, void *d_out, uint32_t ia, uint32_t ib, cudaStream_t st)
+{
+    IdwtLaunch p;
+    fill_launch(job, p, d_out, ia, ib);
+    if (p.n_tiles == 0) return J2KGPU_OK;
+    for (int lvl = job->nlevels ? job->nlevels - 1 : 0; lvl >= 0; lvl--) {
+        int rc = run_level(job, p, lvl, st);
+        if (rc) return rc;
     }
     return J2KGPU_OK;
 }
@@ -432,7 +490,7 @@ extern "C" int j2kgpu_job_run_entropy(j2kgpu_job *job, const void *d_blob)
     if (!job || (!d_blob && job->blob_bytes)) return J2KGPU_E_ARG;
     std::lock_guard<std::mutex> g(job->ctx->mu);
     cudaSetDevice(job->ctx->device);
-    return run_entropy(job, d_blob);
+    return run_entropy(job, d_blob, 0, job->n_img, job->ctx->stream);
 }
 
 extern "C" int j2kgpu_job_run_dwt_mct(j2kgpu_job *job, void *d_out)
@@ -440,7 +498,7 @@ extern "C" int j2kgpu_job_run_dwt_mct(j2kgpu_job *job, void *d_out)
     if (!job || !d_out) return J2KGPU_E_ARG;
     std::lock_guard<std::mutex> g(job->ctx->mu);
     cudaSetDevice(job->ctx->device);
-    return run_dwt_mct(job, d_out);
+    return run_dwt_mct(job, d_out, 0, job->n_img, job->ctx->stream);
 }
 
 extern "C" int j2kgpu_job_run_level(j2kgpu_job *job, int lvl, void *d_out)
@@ -449,48 +507,74 @@ extern "C" int j2kgpu_job_run_level(j2kgpu_job *job, int lvl, void *d_out)
     j2kgpu_ctx *ctx = job->ctx;
     std::lock_guard<std::mutex> g(ctx->mu);
     cudaSetDevice(ctx->device);
-    IdwtLaunch p{};
-    p.d_tcs = job->d_tcs; p.n_tc = job->n_tc; p.d_tiles = lvl == 0 ? job->d_tiles : nullptr; p.n_tiles = job->n_tiles;
-    p.d_coef = job->d_coef; p.d_tmp = job->d_tmp; p.nlevels = job->nlevels; p.lvl = lvl;
-    p.max_w = job->max_w; p.max_h = job->max_h; p.reversible = job->hdr.reversible != 0; p.f64_io = 0;
-    p.d_plane_out = nullptr; p.d_pix = (uint8_t *)d_out; p.tail = job->tail; p.stream_levels = job->stream_levels; p.iso = job->iso;
-    int nl = 0;
-    cudaError_t e = launch_idwt_level(p, ctx->stream, &nl);
-    if (e != cudaSuccess) return j2k_cuda_err(ctx, e, "idwt level launch");
-    ctx->launches += nl;
-    return J2KGPU_OK;
+    IdwtLaunch p;
+    fill_launch(job, p, d_out, 0, job->n_img);
+    return run_level(job, p, lvl, ctx->stream);
 }
+
+extern "C" int j2kgpu_job_fused_levels(const j2kgpu_job *job) { return job ? (job->fused_ok ? 2 : 1) : 0; }
+extern "C" int j2kgpu_job_coef_bytes(const j2kgpu_job *job) { return job ? (job->coef16 ? 2 : 4) : 0; }
 
 extern "C" int j2kgpu_job_run(j2kgpu_job *job, const void *d_blob, void *d_out)
 {
     if (!job || !d_out || (!d_blob && job->blob_bytes)) return J2KGPU_E_ARG;
     std::lock_guard<std::mutex> g(job->ctx->mu);
     cudaSetDevice(job->ctx->device);
-    int rc = run_entropy(job, d_blob);
+    int rc = run_entropy(job, d_blob, 0, job->n_img, job->ctx->stream);
     if (rc) return rc;
-    return run_dwt_mct(job, d_out);
+    return run_dwt_mct(job, d_out, 0, job->n_img, job->ctx->stream);
 }
 
+// Host-buffer run.  The batch is cut into chunks of whole items; chunk c's host->device copy runs on the copy-in
+// stream, its kernels on the ctx stream and its device->host copy on the copy-out stream, chained by events, so
+// that the PCIe transfers of neighbouring chunks overlap the kernels (the two copy engines work in both directions
+// at once).  A single-item batch degenerates to copy, compute, copy.
 static int run_host_locked(j2kgpu_job *job, const j2k_batch_item_t *items)
 {
     j2kgpu_ctx *ctx = job->ctx;
     cudaSetDevice(ctx->device);
     cudaError_t pe = cudaSuccess;
-    if (!job->d_blob) { job->d_blob = j2k_pool_alloc(ctx, job->blob_bytes, &pe); if (pe != cudaSuccess) return j2k_cuda_err(ctx, pe, "blob staging"); }
+    if (!job->d_blob) { job->d_blob = j2k_pool_alloc(ctx, job->blob_bytes + 64, &pe); if (pe != cudaSuccess) return j2k_cuda_err(ctx, pe, "blob staging"); }
     if (!job->d_pix) { job->d_pix = j2k_pool_alloc(ctx, job->out_bytes, &pe); if (pe != cudaSuccess) return j2k_cuda_err(ctx, pe, "pixel staging"); }
-    for (uint32_t i = 0; i < job->n_img; i++) {
-        if (!items[i].out_pix) return j2k_set_err(ctx, J2KGPU_E_ARG, "item %u: null out_pix", i);
-        if (items[i].blob_len)
-            J2K_CUDA(ctx, cudaMemcpyAsync((uint8_t *)job->d_blob + job->blob_off[i], items[i].blob, items[i].blob_len,
-                                          cudaMemcpyHostToDevice, ctx->stream));
-    }
-    int rc = run_entropy(job, job->d_blob);
-    if (rc) return rc;
-    rc = run_dwt_mct(job, job->d_pix);
-    if (rc) return rc;
     for (uint32_t i = 0; i < job->n_img; i++)
-        J2K_CUDA(ctx, cudaMemcpyAsync(items[i].out_pix, (uint8_t *)job->d_pix + job->out_off[i], job->out_size[i],
-                                      cudaMemcpyDeviceToHost, ctx->stream));
+        if (!items[i].out_pix) return j2k_set_err(ctx, J2KGPU_E_ARG, "item %u: null out_pix", i);
+    int rc = j2k_ctx_copy_streams(ctx);
+    if (rc) return rc;
+    // chunks of about 1/8 of the batch, at least one item each
+    const uint32_t n = job->n_img;
+    const uint32_t per = n >= 16 ? (n + 7) / 8 : 1;
+    const uint32_t nchunk = (n + per - 1) / per;
+    if (job->ev_in.size() < nchunk) {
+        const size_t old = job->ev_in.size();
+        job->ev_in.resize(nchunk, nullptr); job->ev_done.resize(nchunk, nullptr);
+        for (size_t c = old; c < nchunk; c++) {
+            J2K_CUDA(ctx, cudaEventCreateWithFlags(&job->ev_in[c], cudaEventDisableTiming));
+            J2K_CUDA(ctx, cudaEventCreateWithFlags(&job->ev_done[c], cudaEventDisableTiming));
+        }
+    }
+    // the copy streams start after whatever the caller queued on the ctx stream
+    J2K_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
+    J2K_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_start, 0));
+    J2K_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_start, 0));
+    for (uint32_t c = 0; c < nchunk; c++) {
+        const uint32_t ia = c * per, ib = ia + per < n ? ia + per : n;
+        for (uint32_t i = ia; i < ib; i++)
+            if (items[i].blob_len)
+                J2K_CUDA(ctx, cudaMemcpyAsync((uint8_t *)job->d_blob + job->blob_off[i], items[i].blob, items[i].blob_len,
+                                              cudaMemcpyHostToDevice, ctx->s_in));
+        J2K_CUDA(ctx, cudaEventRecord(job->ev_in[c], ctx->s_in));
+        J2K_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, job->ev_in[c], 0));
+        rc = run_entropy(job, job->d_blob, ia, ib, ctx->stream);
+        if (rc) return rc;
+        rc = run_dwt_mct(job, job->d_pix, ia, ib, ctx->stream);
+        if (rc) return rc;
+        J2K_CUDA(ctx, cudaEventRecord(job->ev_done[c], ctx->stream));
+        J2K_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, job->ev_done[c], 0));
+        for (uint32_t i = ia; i < ib; i++)
+            J2K_CUDA(ctx, cudaMemcpyAsync(items[i].out_pix, (uint8_t *)job->d_pix + job->out_off[i], job->out_size[i],
+                                          cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+    J2K_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
     J2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return J2KGPU_OK;
 }
@@ -564,8 +648,8 @@ static int stage_blocks(j2kgpu_ctx *ctx, int mode, int ht, const j2k_blkjob_t *j
     int ht_map = 32;
     if (const char *ev = getenv("J2KGPU_HT_MAP")) ht_map = (atoi(ev) == 1) ? 1 : 32;
     cudaError_t e = (ht && mode == J2KGPU_MODE_ISO)
-                        ? launch_ht_iso((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, (int32_t *)ctx->d_out.p, nullptr, 0, ht_map, ctx->stream)
-                    : ht ? launch_ht_ref((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, (int32_t *)ctx->d_out.p, ctx->stream)
+                        ? launch_ht_iso((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, nullptr, 0, 0, ht_map, ctx->stream)
+                    : ht ? launch_ht_ref((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, ctx->stream)
                        : launch_t1_ref_stage((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, (int32_t *)ctx->d_out.p, max_bps, ctx->stream);
     if (e != cudaSuccess) return j2k_cuda_err(ctx, e, "entropy kernel launch");
     ctx->launches++;

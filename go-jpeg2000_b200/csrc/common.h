@@ -72,6 +72,8 @@ struct j2kgpu_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;       // stream in use (own or external)
+    cudaStream_t s_in = nullptr, s_out = nullptr;   // copy-in / copy-out streams of the pipelined host-buffer run
+    cudaEvent_t ev_start = nullptr;
     std::mutex mu;
     std::string err;
     uint64_t launches = 0;
@@ -96,11 +98,16 @@ struct j2kgpu_job {
     uint32_t stream_levels = 0;
     int iso = 0;                         // J2KGPU_MODE_ISO
     int ht_map = 32;                     // ISO HT: code blocks per warp (32 = thread per block, 1 = warp per block)
+    int coef16 = 0;                      // coefficient arena holds int16 (every magnitude provably < 2^15) instead of int32
+    int fused_ok = 0;                    // levels 1 + 0 + pixel epilogue run as one kernel (idwt_fused.cu)
+    std::vector<uint32_t> item_cb, item_tc, item_tile;   // first block / tile-component / tile of each item (+ end)
+    std::vector<uint64_t> tc_coef_off;                   // coefficient-arena offset of each tile-component (host copy)
+    std::vector<cudaEvent_t> ev_in, ev_done;             // per chunk of the pipelined host-buffer run
     float *d_steps = nullptr;            // ISO irreversible: dequantisation step per block
     DevCblk *d_cblks = nullptr;
     DevTileComp *d_tcs = nullptr;
     DevTile *d_tiles = nullptr;
-    int32_t *d_coef = nullptr;  uint64_t coef_elems = 0;
+    void *d_coef = nullptr;     uint64_t coef_elems = 0;   // int32 or int16 elements (coef16)
     void *d_tmp = nullptr;      uint64_t tmp_bytes = 0;
     uint64_t blob_bytes = 0, out_bytes = 0;
     std::vector<uint64_t> blob_off, out_off, out_size;
@@ -115,16 +122,18 @@ int j2k_set_err(j2kgpu_ctx *ctx, int code, const char *fmt, ...);
 int j2k_cuda_err(j2kgpu_ctx *ctx, cudaError_t e, const char *what);
 #define J2K_CUDA(ctx, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return j2k_cuda_err((ctx), e__, #call); } while (0)
 int j2k_reserve(j2kgpu_ctx *ctx, DevBuf &b, size_t bytes, bool pinned_host);
+int j2k_ctx_copy_streams(j2kgpu_ctx *ctx);
 
 // ---- kernel launchers (each returns a cudaError_t; all asynchronous on `s`) ---------------------
 // entropy stage: one warp per code block
-cudaError_t launch_t1_ref(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, int32_t *d_coef,
+// d_coef: coefficient arena, int16 elements when coef16 else int32
+cudaError_t launch_t1_ref(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
                           int max_bps, cudaStream_t s);
-cudaError_t launch_ht_ref(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, int32_t *d_coef,
+cudaError_t launch_ht_ref(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
                           cudaStream_t s);
 // ISO/IEC 15444-15 cleanup decoder; blocks_per_warp = 1 (warp per block) or 32 (thread per block)
-cudaError_t launch_ht_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, int32_t *d_coef,
-                          const float *d_steps, int irrev, int blocks_per_warp, cudaStream_t s);
+cudaError_t launch_ht_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
+                          const float *d_steps, int irrev, int coef_bits, int blocks_per_warp, cudaStream_t s);
 
 // inverse DWT, REF (dense-prefix) addressing.  One call = one decomposition level of every
 // tile-component in the table.  `lvl` counts from 0 (full resolution).  For lvl > 0 the output goes to the
@@ -133,7 +142,9 @@ cudaError_t launch_ht_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_b
 struct IdwtLaunch {
     const DevTileComp *d_tcs; uint32_t n_tc;
     const DevTile *d_tiles; uint32_t n_tiles;      // only for the fused last level
-    const int32_t *d_coef;                          // coefficient arena
+    const void *d_coef;                             // coefficient arena (int32, or int16 when coef16; double when f64_io)
+    int coef16;
+    uint32_t tc_first, tile_first;                  // sub-range of the tables this launch covers (batch pipelining)
     void *d_tmp;                                    // ping-pong arena (int32 for 5-3, double for 9-7)
     int nlevels, lvl;
     uint32_t max_w, max_h;                          // largest tile-component (grid sizing)
@@ -147,6 +158,10 @@ struct IdwtLaunch {
 };
 cudaError_t launch_idwt_level(const IdwtLaunch &p, cudaStream_t s, int *n_launches);
 cudaError_t launch_idwt53_stream(const IdwtLaunch &p, cudaStream_t s);
+// levels 1 and 0 of every tile + inverse MCT + DC shift + clamp + pack in one kernel (5-3; see idwt_fused.cu)
+cudaError_t launch_idwt53_fused(const IdwtLaunch &p, cudaStream_t s);
+// a tile-component fits the fused kernel when its width is a multiple of 8 and its height a multiple of 4
+static inline bool j2k_fused_ok(uint32_t w, uint32_t h) { return w >= 8 && (w & 7) == 0 && h >= 4 && (h & 3) == 0; }
 // level l fits the streaming kernel when its width is a multiple of 4 and its height is even (>= 2)
 static inline bool j2k_stream_ok(uint32_t w, uint32_t h, int lvl)
 {

@@ -162,11 +162,12 @@ __device__ __forceinline__ int32_t sample_value(uint32_t mu, uint32_t sign, int 
 
 // One block, one thread's worth of control flow.  `ex` = 64 exponent bytes of the previous quad row's bottom
 // samples (element c at ex[c * ex_stride]).  `do_store`: this thread performs the global stores.
-__device__ void ht_decode_block(const DevCblk &cb, const uint8_t *__restrict__ blob, int32_t *__restrict__ coef,
-                                const uint16_t *s_tbl, uint8_t *ex, int ex_stride, bool do_store, float step, bool irrev)
+template <typename OT>
+__device__ void ht_decode_block(const DevCblk &cb, const uint8_t *__restrict__ blob, OT *__restrict__ coef,
+                                const uint16_t *s_tbl, uint8_t *ex, int ex_stride, bool do_store, float step, bool irrev, int coef_bits)
 {
     const int w = cb.w, h = cb.h;
-    int32_t *out = coef + cb.out_off;
+    OT *out = coef + cb.out_off;
     const size_t ostride = cb.out_stride;
     const uint8_t *d = blob + cb.data_off;
     const int lcup = (int)cb.data_len;
@@ -252,6 +253,9 @@ __device__ void ht_decode_block(const DevCblk &cb, const uint8_t *__restrict__ b
             }
             e_carry = eE;                                    // column 2(q+2)-1 before this pair overwrites it
             if (U0 > 31 || U1 > 31) bad = true;
+            // magnitude bound of the codestream (Mb = coef_bits): every decoded mu is <= 2^(U-1), and a conformant
+            // encoder never needs U > Mb - p + 1; beyond that the block is malformed (and would not fit the int16 arena)
+            if (coef_bits && (U0 + shift > coef_bits + 1 || U1 + shift > coef_bits + 1)) bad = true;
             U0 = min(U0, 31); U1 = min(U1, 31);
             // ---- MagSgn + store, quad by quad ----
 #pragma unroll
@@ -282,14 +286,19 @@ __device__ void ht_decode_block(const DevCblk &cb, const uint8_t *__restrict__ b
                 // significance outside the block is a malformed stream: the whole block decodes to zero
                 if ((!colB && (e & 0xC0)) || (!row2 && (e & 0xA0))) bad = true;
                 if (do_store) {
-                    int32_t *p0 = out + (size_t)y * ostride + xq;
+                    OT *p0 = out + (size_t)y * ostride + xq;
                     if (colB && vec_ok) {
-                        *reinterpret_cast<int2 *>(p0) = make_int2(v[0], v[2]);
-                        if (row2) *reinterpret_cast<int2 *>(p0 + ostride) = make_int2(v[1], v[3]);
+                        if (sizeof(OT) == 4) {
+                            *reinterpret_cast<int2 *>(p0) = make_int2(v[0], v[2]);
+                            if (row2) *reinterpret_cast<int2 *>(p0 + ostride) = make_int2(v[1], v[3]);
+                        } else {
+                            *reinterpret_cast<uint32_t *>(p0) = ((uint32_t)v[0] & 0xFFFFu) | ((uint32_t)v[2] << 16);
+                            if (row2) *reinterpret_cast<uint32_t *>(p0 + ostride) = ((uint32_t)v[1] & 0xFFFFu) | ((uint32_t)v[3] << 16);
+                        }
                     } else {
-                        p0[0] = v[0];
-                        if (colB) p0[1] = v[2];
-                        if (row2) { p0[ostride] = v[1]; if (colB) p0[ostride + 1] = v[3]; }
+                        p0[0] = (OT)v[0];
+                        if (colB) p0[1] = (OT)v[2];
+                        if (row2) { p0[ostride] = (OT)v[1]; if (colB) p0[ostride + 1] = (OT)v[3]; }
                     }
                 }
             }
@@ -301,10 +310,10 @@ __device__ void ht_decode_block(const DevCblk &cb, const uint8_t *__restrict__ b
             for (int x = 0; x < w; x++) out[(size_t)y * ostride + x] = 0;
 }
 
-template <int BLOCKS_PER_WARP>
+template <int BLOCKS_PER_WARP, typename OT>
 __global__ void __launch_bounds__(kThreads)
 k_ht_iso(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob,
-         int32_t *__restrict__ coef, const float *__restrict__ steps, int irrev)
+         OT *__restrict__ coef, const float *__restrict__ steps, int irrev, int coef_bits)
 {
     __shared__ uint16_t s_tbl[2048];
     __shared__ uint8_t s_ex[64 * kThreads];
@@ -324,20 +333,28 @@ k_ht_iso(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
     }
     if (blk >= n) return;
     const DevCblk cb = cblks[blk];
-    ht_decode_block(cb, blob, coef, s_tbl, ex, kThreads, do_store, steps ? steps[blk] : 1.0f, irrev != 0);
+    ht_decode_block(cb, blob, coef, s_tbl, ex, kThreads, do_store, steps ? steps[blk] : 1.0f, irrev != 0, coef_bits);
 }
 
 }  // namespace
 
-cudaError_t launch_ht_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, int32_t *d_coef,
-                          const float *d_steps, int irrev, int blocks_per_warp, cudaStream_t s)
+template <typename OT>
+static void launch_ht_iso_t(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, OT *d_coef,
+                            const float *d_steps, int irrev, int coef_bits, int blocks_per_warp, cudaStream_t s)
 {
-    if (n == 0) return cudaSuccess;
     if (blocks_per_warp == 32) {
-        J2K_LAUNCH((k_ht_iso<32>), (n + kThreads - 1) / kThreads, kThreads, 0, s, d_cblks, n, d_blob, d_coef, d_steps, irrev);
+        J2K_LAUNCH((k_ht_iso<32, OT>), (n + kThreads - 1) / kThreads, kThreads, 0, s, d_cblks, n, d_blob, d_coef, d_steps, irrev, coef_bits);
     } else {
         const uint32_t per = kThreads / 32;
-        J2K_LAUNCH((k_ht_iso<1>), (n + per - 1) / per, kThreads, 0, s, d_cblks, n, d_blob, d_coef, d_steps, irrev);
+        J2K_LAUNCH((k_ht_iso<1, OT>), (n + per - 1) / per, kThreads, 0, s, d_cblks, n, d_blob, d_coef, d_steps, irrev, coef_bits);
     }
+}
+
+cudaError_t launch_ht_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
+                          const float *d_steps, int irrev, int coef_bits, int blocks_per_warp, cudaStream_t s)
+{
+    if (n == 0) return cudaSuccess;
+    if (coef16 && !irrev) launch_ht_iso_t<int16_t>(d_cblks, n, d_blob, (int16_t *)d_coef, d_steps, irrev, coef_bits, blocks_per_warp, s);
+    else launch_ht_iso_t<int32_t>(d_cblks, n, d_blob, (int32_t *)d_coef, d_steps, irrev, coef_bits, blocks_per_warp, s);
     return cudaGetLastError();
 }

@@ -230,9 +230,10 @@ __device__ __forceinline__ int32_t magsgn_sample(Fwd &ms, uint32_t emb)
     return (int32_t)(sign ? 0u - m : m);
 }
 
+template <typename OT>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 k_ht_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob,
-         int32_t *__restrict__ coef)
+         OT *__restrict__ coef)
 {
     __shared__ uint8_t s_sigma[kWarpsPerCta][20];       // quadCols + 1 <= 17 for w <= 64
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -240,7 +241,7 @@ k_ht_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
     if (blk >= n) return;
     const DevCblk cb = cblks[blk];
     const int w = cb.w, h = cb.h, len = (int)cb.data_len;
-    int32_t *out = coef + cb.out_off;
+    OT *out = coef + cb.out_off;
     const uint32_t ostride = cb.out_stride;
     const uint8_t *d = blob + cb.data_off;
 
@@ -290,12 +291,12 @@ k_ht_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
             for (int i = 0; i < 4 && qx * 4 + i < w; i++)
                 if (rho1 & (1u << i)) {
                     int32_t v = magsgn_sample(ms, u0);
-                    if (lane == 0) out[(size_t)y * ostride + qx * 4 + i] = v;
+                    if (lane == 0) out[(size_t)y * ostride + qx * 4 + i] = (OT)v;
                 }
             for (int i = 0; i < 4 && (qx + 1) * 4 + i < w; i++)
                 if (rho2 & (1u << i)) {
                     int32_t v = magsgn_sample(ms, u1);
-                    if (lane == 0) out[(size_t)y * ostride + (qx + 1) * 4 + i] = v;
+                    if (lane == 0) out[(size_t)y * ostride + (qx + 1) * 4 + i] = (OT)v;
                 }
         }
     }
@@ -303,11 +304,12 @@ k_ht_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
 
 }  // namespace
 
-cudaError_t launch_ht_ref(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, int32_t *d_coef,
+cudaError_t launch_ht_ref(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
                           cudaStream_t s)
 {
     if (n == 0) return cudaSuccess;
     uint32_t grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
-    J2K_LAUNCH((k_ht_ref), grid, kWarpsPerCta * 32, 0, s, d_cblks, n, d_blob, d_coef);
+    if (coef16) J2K_LAUNCH((k_ht_ref<int16_t>), grid, kWarpsPerCta * 32, 0, s, d_cblks, n, d_blob, (int16_t *)d_coef);
+    else J2K_LAUNCH((k_ht_ref<int32_t>), grid, kWarpsPerCta * 32, 0, s, d_cblks, n, d_blob, (int32_t *)d_coef);
     return cudaGetLastError();
 }

@@ -84,7 +84,13 @@ struct LevelGeom {
     int nlx, nly;      // number of low-pass columns / rows
     uint32_t nprev;    // REF: elements taken from the previous level's output; ISO: non-zero if LL comes from it
     uint32_t W;        // ISO: row stride of the Mallat coefficient plane (full tile-component width)
+    int coef16;        // coefficient plane holds int16 instead of int32
 };
+
+__device__ __forceinline__ int32_t ld_coef_i32(const void *coef, uint32_t lin, int coef16)
+{
+    return coef16 ? (int32_t)((const int16_t *)coef)[lin] : ((const int32_t *)coef)[lin];
+}
 
 // REF (dense prefix): interleaved (yy, xx) -> linear index in the level image, prev below nprev.
 // ISO (Mallat): LL from the previous level's dense output (or the plane when coarsest), HL/LH/HH from the plane.
@@ -98,12 +104,12 @@ __device__ __forceinline__ typename L::T load_src(const LevelGeom &g, int yy, in
         if (!hy && !hx && g.nprev) return prev[(uint32_t)by * (uint32_t)g.nlx + (uint32_t)bx];
         const uint32_t lin = (uint32_t)(hy ? g.nly + by : by) * g.W + (uint32_t)(hx ? g.nlx + bx : bx);
         if (IN_F64) return (typename L::T)((const double *)coef)[lin];
-        return L::from_i32(((const int32_t *)coef)[lin]);
+        return L::from_i32(ld_coef_i32(coef, lin, g.coef16));
     }
     const uint32_t lin = (uint32_t)(hy ? g.nly + by : by) * (uint32_t)g.w + (uint32_t)(hx ? g.nlx + bx : bx);
     if (lin < g.nprev) return prev[lin];
     if (IN_F64) return (typename L::T)((const double *)coef)[lin];
-    return L::from_i32(((const int32_t *)coef)[lin]);
+    return L::from_i32(ld_coef_i32(coef, lin, g.coef16));
 }
 
 // REF: columns first, then rows (reference dwt.go:411-428).  ISO: rows first, then columns (15444-1 F.3.2:
@@ -211,7 +217,7 @@ __device__ void transform_tile(typename L::T *P, const LevelGeom &g, int x0, int
 template <class L, bool IN_F64, int EPI, bool ISO>
 __global__ void __launch_bounds__(kThreads)
 k_idwt_level(const DevTileComp *__restrict__ tcs, const void *__restrict__ coef, typename L::T *tmp,
-             void *out_planes, int nlevels, int lvl)
+             void *out_planes, int nlevels, int lvl, int coef16)
 {
     typedef typename L::T T;
     constexpr int HALO = L::HALO, PW = TW + 2 * HALO, PH = TH + 2 * HALO, PP = PW + 1;
@@ -226,9 +232,11 @@ k_idwt_level(const DevTileComp *__restrict__ tcs, const void *__restrict__ coef,
     const bool no_xform = nlevels == 0;
     g.nprev = (lvl + 1 < nlevels) ? (uint32_t)g.nlx * (uint32_t)g.nly : 0u;
     g.W = tc.w;
+    g.coef16 = coef16;
     T *pp0 = tmp + tc.tmp_off, *pp1 = pp0 + tc.tmp_elems;
     const T *prev = ((lvl + 1) & 1) ? pp1 : pp0;
     const void *cbase = IN_F64 ? (const void *)((const double *)coef + tc.coef_off)
+                      : coef16 ? (const void *)((const int16_t *)coef + tc.coef_off)
                                : (const void *)((const int32_t *)coef + tc.coef_off);
     transform_tile<L, IN_F64, ISO>(P, g, x0, y0, prev, cbase, no_xform);
 
@@ -252,8 +260,8 @@ k_idwt_level(const DevTileComp *__restrict__ tcs, const void *__restrict__ coef,
 template <class L, bool ISO>
 __global__ void __launch_bounds__(kThreads)
 k_idwt_last_pixels(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__ tiles,
-                   const int32_t *__restrict__ coef, typename L::T *tmp, uint8_t *pix, int nlevels,
-                   TailParams tp)
+                   const void *__restrict__ coef, typename L::T *tmp, uint8_t *pix, int nlevels,
+                   TailParams tp, int coef16)
 {
     typedef typename L::T T;
     constexpr int HALO = L::HALO, PW = TW + 2 * HALO, PP = PW + 1;
@@ -268,6 +276,7 @@ k_idwt_last_pixels(const DevTileComp *__restrict__ tcs, const DevTile *__restric
     g.nlx = (g.w + 1) >> 1; g.nly = (g.h + 1) >> 1;
     g.nprev = nlevels > 1 ? (uint32_t)g.nlx * (uint32_t)g.nly : 0u;
     g.W = tile.w;
+    g.coef16 = coef16;
 
     int32_t acc[4][PER];
 #pragma unroll
@@ -275,7 +284,9 @@ k_idwt_last_pixels(const DevTileComp *__restrict__ tcs, const DevTile *__restric
         if (c >= tp.ncomp) break;
         const DevTileComp tc = tcs[tile.tc[c]];
         const T *prev = tmp + tc.tmp_off + tc.tmp_elems;          // level 1 wrote ping-pong buffer 1
-        transform_tile<L, false, ISO>(P, g, x0, y0, prev, coef + tc.coef_off, nlevels == 0);
+        const void *cbase = coef16 ? (const void *)((const int16_t *)coef + tc.coef_off)
+                                   : (const void *)((const int32_t *)coef + tc.coef_off);
+        transform_tile<L, false, ISO>(P, g, x0, y0, prev, cbase, nlevels == 0);
 #pragma unroll
         for (int k = 0; k < PER; k++) {
             int e = threadIdx.x + k * kThreads;
@@ -336,11 +347,11 @@ template <class L, bool IN_F64, int EPI>
 cudaError_t run_level(const IdwtLaunch &p, dim3 grid, cudaStream_t s)
 {
     if (p.iso)
-        J2K_LAUNCH((k_idwt_level<L, IN_F64, EPI, true>), grid, kThreads, patch_bytes<L>(), s,
-                   p.d_tcs, (const void *)p.d_coef, (typename L::T *)p.d_tmp, (void *)p.d_plane_out, p.nlevels, p.lvl);
+        J2K_LAUNCH((k_idwt_level<L, IN_F64, EPI, true>), grid, kThreads, patch_bytes<L>(), s, p.d_tcs + p.tc_first,
+                   p.d_coef, (typename L::T *)p.d_tmp, (void *)p.d_plane_out, p.nlevels, p.lvl, p.coef16);
     else
-        J2K_LAUNCH((k_idwt_level<L, IN_F64, EPI, false>), grid, kThreads, patch_bytes<L>(), s,
-                   p.d_tcs, (const void *)p.d_coef, (typename L::T *)p.d_tmp, (void *)p.d_plane_out, p.nlevels, p.lvl);
+        J2K_LAUNCH((k_idwt_level<L, IN_F64, EPI, false>), grid, kThreads, patch_bytes<L>(), s, p.d_tcs + p.tc_first,
+                   p.d_coef, (typename L::T *)p.d_tmp, (void *)p.d_plane_out, p.nlevels, p.lvl, p.coef16);
     return cudaGetLastError();
 }
 
@@ -360,13 +371,13 @@ cudaError_t launch_idwt_level(const IdwtLaunch &p, cudaStream_t s, int *n_launch
     if (pixels) {
         if (p.reversible && p.iso)
             J2K_LAUNCH((k_idwt_last_pixels<Lift53, true>), grid, kThreads, patch_bytes<Lift53>(), s,
-                       p.d_tcs, p.d_tiles, p.d_coef, (int32_t *)p.d_tmp, p.d_pix, p.nlevels, p.tail);
+                       p.d_tcs, p.d_tiles + p.tile_first, p.d_coef, (int32_t *)p.d_tmp, p.d_pix, p.nlevels, p.tail, p.coef16);
         else if (p.reversible)
             J2K_LAUNCH((k_idwt_last_pixels<Lift53, false>), grid, kThreads, patch_bytes<Lift53>(), s,
-                       p.d_tcs, p.d_tiles, p.d_coef, (int32_t *)p.d_tmp, p.d_pix, p.nlevels, p.tail);
+                       p.d_tcs, p.d_tiles + p.tile_first, p.d_coef, (int32_t *)p.d_tmp, p.d_pix, p.nlevels, p.tail, p.coef16);
         else
             J2K_LAUNCH((k_idwt_last_pixels<Lift97, false>), grid, kThreads, patch_bytes<Lift97>(), s,
-                       p.d_tcs, p.d_tiles, p.d_coef, (double *)p.d_tmp, p.d_pix, p.nlevels, p.tail);
+                       p.d_tcs, p.d_tiles + p.tile_first, p.d_coef, (double *)p.d_tmp, p.d_pix, p.nlevels, p.tail, p.coef16);
         return cudaGetLastError();
     }
     if (p.reversible) return run_level<Lift53, false, EPI_STORE>(p, grid, s);

@@ -40,23 +40,32 @@ __device__ __forceinline__ int odd_last(int x, int l)             // x += l     
     return (int)((uint32_t)x + (uint32_t)l);
 }
 
+// two adjacent elements of a coefficient plane (CT = int32_t, or int16_t when the job's magnitudes fit 15 bits)
+__device__ __forceinline__ int2 ldpair(const int32_t *p) { return __ldg(reinterpret_cast<const int2 *>(p)); }
+__device__ __forceinline__ int2 ldpair(const int16_t *p)
+{
+    const uint32_t r = __ldg(reinterpret_cast<const uint32_t *>(p));
+    return make_int2((int)(int16_t)(r & 0xFFFFu), (int)r >> 16);
+}
+
+template <typename CT>
 struct Src {
     const int32_t *prev;     // dense output of the coarser level
-    const int32_t *coef;     // coefficient plane
+    const CT *coef;          // coefficient plane
     uint32_t nprev;          // REF: elements [0, nprev) of the level image come from prev; ISO: non-zero if LL does
 };
 
 // REF (dense prefix): one linear index space, prev below nprev
-__device__ __forceinline__ int2 ld2(const Src &s, uint32_t lin)
+template <typename CT>
+__device__ __forceinline__ int2 ld2(const Src<CT> &s, uint32_t lin)
 {
-    const int32_t *p = lin < s.nprev ? s.prev : s.coef;
-    return __ldg(reinterpret_cast<const int2 *>(p + lin));
+    return lin < s.nprev ? ldpair(s.prev + lin) : ldpair(s.coef + lin);
 }
 
-template <int NC, bool PIXELS, bool ISO>
+template <int NC, bool PIXELS, bool ISO, typename CT>
 __global__ void __launch_bounds__(kWarps * 32, 3)
 k_idwt53_stream(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__ tiles,
-                const int32_t *__restrict__ coef, int32_t *__restrict__ tmp, uint8_t *__restrict__ pix,
+                const CT *__restrict__ coef, int32_t *__restrict__ tmp, uint8_t *__restrict__ pix,
                 int nlevels, int lvl, int strip_pairs, TailParams tp)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -85,7 +94,7 @@ k_idwt53_stream(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__
     const int ka = strip * strip_pairs;
     const int kb = min(ka + strip_pairs, nly);
 
-    Src src[NC];
+    Src<CT> src[NC];
     int32_t *dst = nullptr;
 #pragma unroll
     for (int c = 0; c < NC; c++) {
@@ -107,10 +116,10 @@ k_idwt53_stream(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__
         if (qvalid) {
             int2 a, b;
             if (ISO) {
-                const int32_t *rowp = src[c].coef + (size_t)r * planeW;
-                b = __ldg(reinterpret_cast<const int2 *>(rowp + colH));
-                if (r < nly && src[c].nprev) a = __ldg(reinterpret_cast<const int2 *>(src[c].prev + (size_t)r * (uint32_t)nlx + colL));
-                else a = __ldg(reinterpret_cast<const int2 *>(rowp + colL));
+                const CT *rowp = src[c].coef + (size_t)r * planeW;
+                b = ldpair(rowp + colH);
+                if (r < nly && src[c].nprev) a = ldpair(src[c].prev + (size_t)r * (uint32_t)nlx + colL);
+                else a = ldpair(rowp + colL);
             } else {
                 const uint32_t lin = (uint32_t)r * uw;
                 a = ld2(src[c], lin + colL); b = ld2(src[c], lin + colH);
@@ -258,16 +267,25 @@ k_idwt53_stream(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__
     }
 }
 
+template <int NC, bool PIXELS, typename CT>
+cudaError_t run_ct(const IdwtLaunch &p, dim3 grid, int strip_pairs, cudaStream_t s)
+{
+    // pixel launches index tile-components through the tile table (absolute), plain levels through blockIdx.y
+    const DevTileComp *tcs = PIXELS ? p.d_tcs : p.d_tcs + p.tc_first;
+    const DevTile *tiles = p.d_tiles ? p.d_tiles + p.tile_first : nullptr;
+    if (p.iso)
+        J2K_LAUNCH((k_idwt53_stream<NC, PIXELS, true, CT>), grid, kWarps * 32, 0, s, tcs, tiles, (const CT *)p.d_coef,
+                   (int32_t *)p.d_tmp, p.d_pix, p.nlevels, p.lvl, strip_pairs, p.tail);
+    else
+        J2K_LAUNCH((k_idwt53_stream<NC, PIXELS, false, CT>), grid, kWarps * 32, 0, s, tcs, tiles, (const CT *)p.d_coef,
+                   (int32_t *)p.d_tmp, p.d_pix, p.nlevels, p.lvl, strip_pairs, p.tail);
+    return cudaGetLastError();
+}
+
 template <int NC, bool PIXELS>
 cudaError_t run(const IdwtLaunch &p, dim3 grid, int strip_pairs, cudaStream_t s)
 {
-    if (p.iso)
-        J2K_LAUNCH((k_idwt53_stream<NC, PIXELS, true>), grid, kWarps * 32, 0, s, p.d_tcs, p.d_tiles, p.d_coef,
-                   (int32_t *)p.d_tmp, p.d_pix, p.nlevels, p.lvl, strip_pairs, p.tail);
-    else
-        J2K_LAUNCH((k_idwt53_stream<NC, PIXELS, false>), grid, kWarps * 32, 0, s, p.d_tcs, p.d_tiles, p.d_coef,
-                   (int32_t *)p.d_tmp, p.d_pix, p.nlevels, p.lvl, strip_pairs, p.tail);
-    return cudaGetLastError();
+    return p.coef16 ? run_ct<NC, PIXELS, int16_t>(p, grid, strip_pairs, s) : run_ct<NC, PIXELS, int32_t>(p, grid, strip_pairs, s);
 }
 
 }  // namespace

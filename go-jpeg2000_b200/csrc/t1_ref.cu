@@ -103,9 +103,11 @@ __device__ __forceinline__ uint32_t decode_sign(MQ &m, uint8_t *ctxs, int x,
     return mq_decode(m, ctxs, kCtxSC + (e >> 1)) ^ (e & 1);
 }
 
+// OT = element type of the coefficient arena: int32_t, or int16_t when every block of the job has num_bps <= 15
+template <typename OT>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 k_t1_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob,
-         int32_t *__restrict__ coef, int plane_words /* 64 * max_bps */, int skip_empty)
+         OT *__restrict__ coef, int plane_words /* 64 * max_bps */, int skip_empty)
 {
     J2K_DYN_SMEM(uint64_t, smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -123,7 +125,7 @@ k_t1_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
     uint64_t *planes = base + 258;       // [bp][row]
     uint8_t *ctxs = (uint8_t *)(base + 258 + plane_words);
 
-    int32_t *out = coef + cb.out_off;
+    OT *out = coef + cb.out_off;
     const uint32_t ostride = cb.out_stride;
 
     if ((cb.data_len == 0 && skip_empty) || nbps == 0) {          // tcd.go:394-396: not coded -> zeros
@@ -261,8 +263,8 @@ k_t1_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
             m1 |= (uint32_t)((pr >> (lane + 32)) & 1) << bp;
         }
         uint64_t nr = neg[y];
-        if (lane < w)      out[(size_t)y * ostride + lane]      = (int32_t)(((nr >> lane) & 1) ? 0u - m0 : m0);
-        if (lane + 32 < w) out[(size_t)y * ostride + lane + 32] = (int32_t)(((nr >> (lane + 32)) & 1) ? 0u - m1 : m1);
+        if (lane < w)      out[(size_t)y * ostride + lane]      = (OT)(int32_t)(((nr >> lane) & 1) ? 0u - m0 : m0);
+        if (lane + 32 < w) out[(size_t)y * ostride + lane + 32] = (OT)(int32_t)(((nr >> (lane + 32)) & 1) ? 0u - m1 : m1);
     }
 }
 
@@ -342,7 +344,7 @@ cudaError_t upload_tables()
 
 }  // namespace
 
-static cudaError_t launch_t1_ref_impl(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, int32_t *d_coef,
+static cudaError_t launch_t1_ref_impl(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
                                       int max_bps, int skip_empty, cudaStream_t s)
 {
     if (n == 0) return cudaSuccess;
@@ -352,23 +354,27 @@ static cudaError_t launch_t1_ref_impl(const DevCblk *d_cblks, uint32_t n, const 
     int plane_words = 64 * max_bps;
     size_t smem = (size_t)kWarpsPerCta * (66 + 64 * 3 + plane_words + 4) * sizeof(uint64_t);
     if (smem > 48 * 1024) {
-        e = cudaFuncSetAttribute(k_t1_ref, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = coef16 ? cudaFuncSetAttribute(k_t1_ref<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                   : cudaFuncSetAttribute(k_t1_ref<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     uint32_t grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
-    J2K_LAUNCH((k_t1_ref), grid, kWarpsPerCta * 32, smem, s, d_cblks, n, d_blob, d_coef, plane_words, skip_empty);
+    if (coef16)
+        J2K_LAUNCH((k_t1_ref<int16_t>), grid, kWarpsPerCta * 32, smem, s, d_cblks, n, d_blob, (int16_t *)d_coef, plane_words, skip_empty);
+    else
+        J2K_LAUNCH((k_t1_ref<int32_t>), grid, kWarpsPerCta * 32, smem, s, d_cblks, n, d_blob, (int32_t *)d_coef, plane_words, skip_empty);
     return cudaGetLastError();
 }
 
-cudaError_t launch_t1_ref(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, int32_t *d_coef,
+cudaError_t launch_t1_ref(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
                           int max_bps, cudaStream_t s)
 {
-    return launch_t1_ref_impl(d_cblks, n, d_blob, d_coef, max_bps, 1, s);
+    return launch_t1_ref_impl(d_cblks, n, d_blob, d_coef, coef16, max_bps, 1, s);
 }
 
 // stage API form: T1.Decode is also defined for empty data (decodes the 0xFF fill, mqc.go:387-388)
 cudaError_t launch_t1_ref_stage(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, int32_t *d_coef,
                                 int max_bps, cudaStream_t s)
 {
-    return launch_t1_ref_impl(d_cblks, n, d_blob, d_coef, max_bps, 0, s);
+    return launch_t1_ref_impl(d_cblks, n, d_blob, d_coef, 0, max_bps, 0, s);
 }

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define J2KGPU_ABI_VERSION 1
+#define J2KGPU_ABI_VERSION 2
 
 /* ---- status codes ---------------------------------------------------------- */
 enum {
@@ -73,6 +73,13 @@ typedef struct {
     uint8_t  ht;                /* Header.IsHTJ2K() (header.go:241-257)                      */
     uint8_t  mode;              /* J2KGPU_MODE_*                                             */
     uint8_t  out_fmt;           /* J2KGPU_FMT_*                                              */
+    uint8_t  coef_bits;         /* ISO mode: upper bound on the magnitude bits of any coefficient, i.e. max over
+                                 * bands of Mb = guard bits + exponent - 1 (QCD/QCC); 0 = unknown.  When <= 14 the
+                                 * library keeps the coefficient planes as int16 in HBM (half the DWT read traffic);
+                                 * a block whose decoded magnitudes exceed the bound is malformed and decodes to
+                                 * zero.  REF mode ignores it (EBCOT bounds come from num_bps, the reference HT
+                                 * coder has no bound).                                                       */
+    uint8_t  rsv[3];            /* set 0                                                      */
 } j2k_image_t;
 
 /* one tile-component (tcd.TileComponent, tcd.go:272-283): bounds in image
@@ -160,7 +167,12 @@ int      j2kgpu_job_run_dwt_mct(j2kgpu_job *job, void *d_out);
 /* one inverse-DWT level of the job (lvl = nlevels-1 .. 0; level 0 is the fused IDWT+MCT+DC+pack kernel and
  * needs d_out); levels must be run coarse to fine after the entropy stage -- used to time a single kernel */
 int      j2kgpu_job_run_level(j2kgpu_job *job, int lvl, void *d_out);
-/* host-buffer run of a prepared job (pinned staging + H2D + kernels + D2H, blocking) */
+/* how the job was planned: 2 when inverse-DWT levels 1 and 0 run as one fused kernel (then run_level(1) is a
+ * no-op and run_level(0) runs both), else 1; bytes per element of the coefficient planes in HBM (2 or 4) */
+int      j2kgpu_job_fused_levels(const j2kgpu_job *job);
+int      j2kgpu_job_coef_bytes(const j2kgpu_job *job);
+/* host-buffer run of a prepared job: H2D, kernels and D2H pipelined over chunks of the batch on three streams;
+ * blocking.  Give pinned host buffers for the copies to overlap the kernels. */
 int      j2kgpu_job_run_host(j2kgpu_job *job, const j2k_batch_item_t *items);
 int      j2kgpu_sync(j2kgpu_ctx *ctx);
 

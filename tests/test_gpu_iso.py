@@ -71,9 +71,9 @@ def test_iso_idwt53_vs_transposed_reference(gpu_ctx, w, h, levels):
     assert np.array_equal(gpu_ctx.reconstruct_multilevel53(c, w, h, levels, mode=ISO), iso_inverse53(c, w, h, levels))
 
 
-def iso_pixels(j2k, ctx, job):
+def iso_pixels(j2k, ctx, job, coef_bits=0):
     img = j2k.make_image(job["width"], job["height"], job["ncomp"], job["prec"], mct=job["mct"], reversible=1,
-                         nlevels=job["nlevels"], ht=1, mode=ISO)
+                         nlevels=job["nlevels"], ht=1, mode=ISO, coef_bits=coef_bits)
     return ctx.decode_tiles(img, jobs.as_ctypes(job["tilecomps"], j2k.TileComp), jobs.as_ctypes(job["cblks"], j2k.CBlk),
                             job["blob"])
 
@@ -106,3 +106,26 @@ def test_iso_whole_path_lossless_htj2k(j2k, gpu_ctx, w, h, ncomp, prec, tw, th, 
         maxv = (1 << prec) - 1
         for c in range(ncomp):
             assert np.array_equal(val[:, :, c], s[c].astype(np.int64) * 65535 // maxv)   # ISO packing: no int32 wrap
+
+
+@pytest.mark.parametrize("w,h,ncomp,tw,th,nl", [(256, 256, 3, None, None, 5), (1024, 512, 3, 512, 512, 5),
+                                                 (640, 360, 1, None, None, 5), (333, 211, 3, 128, 128, 4)])
+def test_iso_int16_planes_with_coef_bits(j2k, gpu_ctx, w, h, ncomp, tw, th, nl):
+    """j2k_image_t.coef_bits (max Mb of the codestream) <= 14 switches the coefficient planes to int16: same pixels"""
+    s = jobs.synth_image(w, h, ncomp, 8, seed=5 * w + h)
+    job = jobs.build_iso_job(s, 8, tw, th, nl)
+    assert job["coef_bits"] <= 14
+    a = iso_pixels(j2k, gpu_ctx, job)
+    b = iso_pixels(j2k, gpu_ctx, job, coef_bits=job["coef_bits"])
+    assert np.array_equal(a, b)
+    pix = b.reshape(h, w, -1)
+    for c in range(ncomp):
+        assert np.array_equal(pix[:, :, c], s[c].astype(np.uint8))
+
+
+def test_iso_coef_bits_violation_zeroes_blocks(j2k, gpu_ctx):
+    """a declared magnitude bound that the stream exceeds marks the block malformed (zero), it never overflows int16"""
+    s = jobs.synth_image(128, 128, 1, 8, seed=3)
+    job = jobs.build_iso_job(s, 8, None, None, 2)
+    got = iso_pixels(j2k, gpu_ctx, job, coef_bits=2).reshape(128, 128)
+    assert got.shape == (128, 128) and not np.array_equal(got, s[0].astype(np.uint8))

@@ -108,7 +108,8 @@ def test_batch_and_job_api(j2k, gpu_ctx):
     ev1.record(stream)
     stream.synchronize()
     assert ev0.elapsed_time(ev1) > 0.02                   # the kernels really ran on the caller's stream
-    assert gpu_ctx.launches - n0 == 4                     # 1 entropy + 3 DWT levels (last fused with MCT/pack)
+    assert job.fused_levels == 2 and job.coef_bytes == 2  # 64- and 32-wide tiles fit the fused kernel; 8-bit EBCOT fits int16
+    assert gpu_ctx.launches - n0 == 3                     # 1 entropy + level 2 + fused (levels 1, 0, MCT, DC, pack)
     host = d_out.cpu().numpy()
     for i, w_ in enumerate(want):
         assert np.array_equal(host[job.out_offset(i): job.out_offset(i) + w_.size], w_)
@@ -119,6 +120,76 @@ def test_batch_and_job_api(j2k, gpu_ctx):
         assert np.array_equal(o, w_)
     gpu_ctx.set_stream(0)
     job.close()
+
+
+def _run_items(j2k, ctx, jl, env=None, mode=0, coef_bits=0):
+    """decode a list of jobs as ONE batch through j2kgpu_job_create + j2kgpu_job_run_host (the pipelined host path)"""
+    import os
+    keep, items, outs = [], [], []
+    for j in jl:
+        tcs, cbs = jobs.as_ctypes(j["tilecomps"], j2k.TileComp), jobs.as_ctypes(j["cblks"], j2k.CBlk)
+        blob = np.ascontiguousarray(j["blob"])
+        bpp = j2k.fmt_bpp(j["ncomp"], j["prec"])
+        out = np.zeros(j["width"] * j["height"] * bpp, np.uint8)
+        keep += [tcs, cbs, blob]
+        outs.append(out)
+        img = j2k.make_image(j["width"], j["height"], j["ncomp"], j["prec"], sgnd=j["sgnd"], mct=j["mct"],
+                             reversible=j["reversible"], nlevels=j["nlevels"], ht=j["ht"], mode=mode, coef_bits=coef_bits)
+        items.append(j2k.BatchItem(img, tcs, len(tcs), cbs, len(cbs), blob.ctypes.data_as(j2k.u8p), blob.size,
+                                   out.ctypes.data_as(j2k.u8p), j["width"] * bpp))
+    old = {k: os.environ.get(k) for k in (env or {})}
+    os.environ.update(env or {})
+    try:
+        job = j2k.Job(ctx, items)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    flags = (job.fused_levels, job.coef_bytes)
+    job.run_host()
+    job.close()
+    return outs, flags
+
+
+@pytest.mark.parametrize("w,h,ncomp,prec,tw,th,levels,ht", [
+    (512, 256, 3, 8, 256, 256, 5, 0),      # EBCOT: int16 planes + fused kernel
+    (512, 256, 3, 8, 256, 256, 5, 1),      # reference HT coder: no magnitude bound -> int32 planes + fused kernel
+    (1024, 128, 3, 8, None, None, 2, 1),   # several warps per row (28-quad ranges + 2 halo lanes each side), coarsest = level 1
+    (256, 64, 3, 8, None, None, 1, 0),     # a single decomposition level (no level 1 inside the fused kernel)
+    (192, 96, 1, 8, 96, 96, 3, 0),         # 1 component, Gray8
+    (160, 72, 4, 8, None, None, 3, 0),     # 4 components; 72 rows: strips shorter than the ring depth at the bottom
+    (384, 256, 3, 12, 128, 128, 4, 0),     # RGBA64 epilogue
+])
+def test_fused_and_int16_variants_agree(j2k, gpu_ctx, w, h, ncomp, prec, tw, th, levels, ht):
+    """the fused levels-1+0 kernel and the int16 coefficient planes are optimisations: every combination of
+    {fused, per-level} x {int16, int32} gives the oracle's pixels"""
+    s = jobs.synth_image(w, h, ncomp, prec, seed=77 + w)
+    job = jobs.build_ref_job(s, prec, tw, th, nlevels=levels, reversible=True, ht=bool(ht), threads=4)
+    want = oracle_pixels(job)
+    seen = set()
+    for env in ({}, {"J2KGPU_NO_FUSE": "1"}, {"J2KGPU_COEF32": "1"}, {"J2KGPU_NO_FUSE": "1", "J2KGPU_COEF32": "1"}):
+        outs, flags = _run_items(j2k, gpu_ctx, [job], env)
+        assert np.array_equal(outs[0], want), env
+        seen.add(flags)
+    assert (2, 4) in seen and (1, 4) in seen
+    if not ht:
+        assert (2, 2) in seen and (1, 2) in seen      # EBCOT magnitudes are bounded by num_bps <= 15
+    else:
+        assert (2, 2) not in seen                     # ht.go:664-684 has no magnitude bound: never int16
+
+
+def test_pipelined_host_run_many_items(j2k, gpu_ctx):
+    """j2kgpu_job_run_host cuts a batch of >= 16 items into chunks (copy-in / kernels / copy-out on three streams)"""
+    jl = []
+    for i in range(19):
+        w, h = (64, 32) if i % 3 else (96, 64)
+        jl.append(jobs.build_ref_job(jobs.synth_image(w, h, 3, 8, seed=300 + i), 8, 32, 32, nlevels=2, reversible=True,
+                                     ht=bool(i % 2 == 0) and False, threads=2))
+    outs, _ = _run_items(j2k, gpu_ctx, jl)
+    for o, j in zip(outs, jl):
+        assert np.array_equal(o, oracle_pixels(j))
 
 
 def test_path_argument_errors(j2k, gpu_ctx):
