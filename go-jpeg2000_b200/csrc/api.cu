@@ -380,6 +380,10 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
         if (iso && hdr.reversible) job->coef16 = hdr.coef_bits >= 1 && hdr.coef_bits <= 14;
     }
     job->fused_ok = fused_ok;
+    job->fast_epi = tp.fmt == J2KGPU_FMT_RGBA8 && tp.ncomp == 3 && tp.mct && tp.reversible && !env_flag("J2KGPU_NO_FAST_EPI");
+    for (int c = 0; c < 3; c++) if (tp.prec[c] != 8 || tp.sgnd[c]) job->fast_epi = 0;
+    for (const DevTile &t : tiles)
+        if ((t.out_stride & 15) || (t.out_off & 15) || (t.img_x0 & 3) || t.img_x0 + t.w > t.img_w || t.img_y0 + t.h > t.img_h) job->fast_epi = 0;
     job->coef_elems = coef_elems; job->blob_bytes = blob_bytes; job->out_bytes = out_bytes; job->max_bps = max_bps;
     job->tmp_bytes = tmp_elems * (hdr.reversible ? 4 : 8);
     job->need_clear = need_clear;
@@ -447,7 +451,7 @@ static void fill_launch(const j2kgpu_job *job, IdwtLaunch &p, void *d_out, uint3
     p.d_tcs = job->d_tcs; p.d_tiles = job->d_tiles;
     p.tc_first = job->item_tc[ia]; p.n_tc = job->item_tc[ib] - p.tc_first;
     p.tile_first = job->item_tile[ia]; p.n_tiles = job->item_tile[ib] - p.tile_first;
-    p.d_coef = job->d_coef; p.coef16 = job->coef16; p.d_tmp = job->d_tmp; p.nlevels = job->nlevels;
+    p.d_coef = job->d_coef; p.coef16 = job->coef16; p.d_tmp = job->d_tmp; p.nlevels = job->nlevels; p.fast_epi = job->fast_epi;
     p.max_w = job->max_w; p.max_h = job->max_h; p.reversible = job->hdr.reversible != 0; p.f64_io = 0;
     p.d_plane_out = nullptr; p.d_pix = (uint8_t *)d_out; p.tail = job->tail; p.stream_levels = job->stream_levels; p.iso = job->iso;
 }

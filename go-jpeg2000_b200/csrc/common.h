@@ -20,7 +20,11 @@
 #define J2K_LAUNCH(K, G, B, SM, ST, ...) emu::launch(dim3(G), dim3(B), (SM), [&]() { J2K_UNPAREN K(__VA_ARGS__); })
 #define J2K_DYN_SMEM(T, name) T *name = reinterpret_cast<T *>(emu::dyn_smem)
 #define J2K_LOCKSTEP_LANE(lane) ((lane) == 0)
+#define J2K_NOINLINE __attribute__((noinline))
+#define J2K_OPAQUE_PTR(p) ((void)0)
 #else
+#define J2K_OPAQUE_PTR(p) asm volatile("" : "+l"(p))
+#define J2K_NOINLINE __noinline__
 #define J2K_LOCKSTEP_LANE(lane) true
 #define J2K_LAUNCH(K, G, B, SM, ST, ...) J2K_UNPAREN K<<<(G), (B), (SM), (ST)>>>(__VA_ARGS__)
 #define J2K_DYN_SMEM(T, name) extern __shared__ __align__(16) unsigned char j2k_dyn_smem_[]; T *name = reinterpret_cast<T *>(j2k_dyn_smem_)
@@ -100,6 +104,7 @@ struct j2kgpu_job {
     int ht_map = 32;                     // ISO HT: code blocks per warp (32 = thread per block, 1 = warp per block)
     int coef16 = 0;                      // coefficient arena holds int16 (every magnitude provably < 2^15) instead of int32
     int fused_ok = 0;                    // levels 1 + 0 + pixel epilogue run as one kernel (idwt_fused.cu)
+    int fast_epi = 0;                    // every tile qualifies for the fused kernel's fixed RGBA8 epilogue
     std::vector<uint32_t> item_cb, item_tc, item_tile;   // first block / tile-component / tile of each item (+ end)
     std::vector<uint64_t> tc_coef_off;                   // coefficient-arena offset of each tile-component (host copy)
     std::vector<cudaEvent_t> ev_in, ev_done;             // per chunk of the pipelined host-buffer run
@@ -145,6 +150,7 @@ struct IdwtLaunch {
     const void *d_coef;                             // coefficient arena (int32, or int16 when coef16; double when f64_io)
     int coef16;
     uint32_t tc_first, tile_first;                  // sub-range of the tables this launch covers (batch pipelining)
+    int fast_epi;                                   // fused kernel: 3 x 8-bit unsigned, RCT, RGBA8, tiles inside the image, aligned rows
     void *d_tmp;                                    // ping-pong arena (int32 for 5-3, double for 9-7)
     int nlevels, lvl;
     uint32_t max_w, max_h;                          // largest tile-component (grid sizing)

@@ -97,7 +97,23 @@ __device__ __forceinline__ int2 slot_pair(const uint2 *s, int16_t)
     return make_int2((int)(int16_t)(r & 0xFFFFu), (int)r >> 16);
 }
 
-template <int NC, typename CT, bool ISO>
+// generic pixel store of one lane's 4 columns of one row (any format / precision / MCT): kept out of line
+template <int NC>
+__device__ J2K_NOINLINE void put_quad_generic(uint8_t *orow, uint32_t gx0, uint32_t img_w, const int *X, TailParams tp)
+{
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+        if (gx0 + p >= img_w) continue;
+        int32_t v[4] = {X[p], NC > 1 ? X[(NC > 1 ? 4 : 0) + p] : 0, NC > 2 ? X[(NC > 2 ? 8 : 0) + p] : 0,
+                        NC > 3 ? X[(NC > 3 ? 12 : 0) + p] : 0};
+        tail_mct_dc(v, tp);
+        store_pixel(orow, gx0 + p, v, tp);
+    }
+}
+
+// FAST: 3 unsigned 8-bit components, RCT, RGBA8 output, every tile inside the image and 16-byte aligned rows
+// (checked on the host): the epilogue is 8 instructions per pixel and one 16-byte streaming store per lane and row.
+template <int NC, typename CT, bool ISO, bool FAST>
 __global__ void __launch_bounds__(kWarps * 32, (NC <= 3 ? 4 : 3))
 k_idwt53_fused(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__ tiles, const CT *__restrict__ coef,
                const int32_t *__restrict__ tmp, uint8_t *__restrict__ pix, int nlevels, int strip_pairs, TailParams tp)
@@ -115,12 +131,13 @@ k_idwt53_fused(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__ 
     const int q = wi * kOwn - 2 + lane;
     const bool qvalid = q >= 0 && q < nq;
     const bool store_lane = qvalid && lane >= 2 && lane <= 29;
+    const bool q_first = q == 0, q_last = q == nq - 1;
     const int qc = qvalid ? q : 0;
     const int ka = strip * strip_pairs, kb = min(ka + strip_pairs, nly);
     const int rlast = min(kb, nly - 1);               // last level-0 band row pair this strip reads
     const bool l1on = nlevels >= 2, l2on = nlevels >= 3;
-    const int nlx1 = nq, nly1 = nly >> 1, w1 = nlx;   // level-1 image: w1 x nly, low-pass part nlx1 x nly1
-    const int half0 = nly >> 1;                       // REF: level-0 band rows below this come from the level-1 output
+    const int nlx1 = nq, nly1 = nly >> 1;             // level-1 image: nlx x nly, low-pass part nlx1 x nly1
+    const int half0 = nly >> 1;                       // REF: level-0 band rows below this ARE the level-1 output
 
     const CT *plane[NC];
     const int32_t *prev2[NC];
@@ -129,211 +146,156 @@ k_idwt53_fused(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__ 
         const DevTileComp tc = tcs[tile.tc[c]];
         plane[c] = coef + tc.coef_off;
         prev2[c] = tmp + tc.tmp_off;                  // level 2 wrote ping-pong buffer 0
+        J2K_OPAQUE_PTR(plane[c]);                     // keep the base pointers in registers: every address below is
+        J2K_OPAQUE_PTR(prev2[c]);                     // base + 32-bit offset (one IMAD.WIDE), not a 64-bit carry chain
     }
     uint2 *ring = ring_all + (size_t)warp * (kDepth * NC * 4 * 32) + lane;
     const uint32_t uw = (uint32_t)w;
     const uint32_t col0 = 2u * (uint32_t)qc;          // level-0 L column pair; H pair at nlx + col0
 
-    // which parts of level-0 band row r (r < nly) are the level-1 output
-    auto l0_L_from_l1 = [&](int r) { return l1on && (ISO || r < half0); };
-    auto l0_H_from_l1 = [&](int r) { return l1on && !ISO && r < half0; };
-
     // ---- level-0 band row pair r -> ring slot r % kDepth (the parts that come from the coefficient planes) ----
+    // rows are issued in increasing order: o_iss is the element offset of (row r, column col0), advanced per call
+    const uint32_t d_hi = (uint32_t)nly * uw;
+    uint32_t o_iss = 0;
     auto issue_l0 = [&](int r) {
-        if (!qvalid) return;
         const int s = r & (kDepth - 1);
-        const bool fl = l0_L_from_l1(r), fh = l0_H_from_l1(r);
+        const bool fl = l1on && (ISO || r < half0), fh = l1on && !ISO && r < half0;   // those parts are level-1 output
+        const uint32_t o0 = o_iss, o1 = o_iss + (uint32_t)nlx, o2 = o_iss + d_hi, o3 = o2 + (uint32_t)nlx;
+        uint2 *sl = ring + (size_t)(s * NC * 4) * 32;
 #pragma unroll
         for (int c = 0; c < NC; c++) {
-            uint2 *sl = ring + (size_t)((s * NC + c) * 4) * 32;
-            const CT *lo = plane[c] + (size_t)((uint32_t)r * uw + col0);
-            const CT *hi = plane[c] + (size_t)((uint32_t)(nly + r) * uw + col0);
-            if (!fl) cp_async<2 * sizeof(CT)>(sl, lo);
-            if (!fh) cp_async<2 * sizeof(CT)>(sl + 32, lo + nlx);
-            cp_async<2 * sizeof(CT)>(sl + 64, hi);
-            cp_async<2 * sizeof(CT)>(sl + 96, hi + nlx);
+            if (!fl) cp_async<2 * sizeof(CT)>(sl + c * 128, plane[c] + o0);
+            if (!fh) cp_async<2 * sizeof(CT)>(sl + c * 128 + 32, plane[c] + o1);
+            cp_async<2 * sizeof(CT)>(sl + c * 128 + 64, plane[c] + o2);
+            cp_async<2 * sizeof(CT)>(sl + c * 128 + 96, plane[c] + o3);
         }
     };
 
     // ---- horizontal synthesis; every lane takes part in the two shuffles ----
-    // level 0: a row held as (L0, L1, H0, H1) per lane -> 4 interleaved samples
-    auto hsynth0 = [&](const int V[4], int X[4]) {
+    // level 0: a row held as (L0, L1, H0, H1) per lane -> 4 interleaved samples, in place
+    auto hsynth0 = [&](int V[4]) {
         const int VL0 = V[0], VL1 = V[1], VH0 = V[2], VH1 = V[3];
         int left = __shfl_up_sync(0xffffffffu, VH1, 1);
-        if (q == 0) left = VH0;                                       // x[0] -= (x[1] + x[1] + 2) >> 2
+        left = q_first ? VH0 : left;                                  // x[0] -= (x[1] + x[1] + 2) >> 2
         const int X0 = even_upd(VL0, left, VH0);
         const int X2 = even_upd(VL1, VH0, VH1);
         const int right = __shfl_down_sync(0xffffffffu, X0, 1);
-        X[0] = X0;
-        X[1] = odd_upd(VH0, X0, X2);
-        X[2] = X2;
-        X[3] = (q == nq - 1) ? odd_last(VH1, X2) : odd_upd(VH1, X2, right);
+        const int t = odd_upd(VH1, X2, right);
+        V[0] = X0;
+        V[1] = odd_upd(VH0, X0, X2);
+        V[2] = X2;
+        V[3] = q_last ? odd_last(VH1, X2) : t;
     };
-    // level 1: a row held as (L, H) per lane -> 2 interleaved samples (level-1 rows are w1 = 2 * nq samples wide)
-    auto hsynth1 = [&](const int V[2], int X[2]) {
+    // level 1: a row held as (L, H) per lane -> 2 interleaved samples, in place (level-1 rows are 2 * nq samples wide)
+    auto hsynth1 = [&](int V[2]) {
         const int VL = V[0], VH = V[1];
         int left = __shfl_up_sync(0xffffffffu, VH, 1);
-        if (q == 0) left = VH;
+        left = q_first ? VH : left;
         const int X0 = even_upd(VL, left, VH);
         const int right = __shfl_down_sync(0xffffffffu, X0, 1);
-        X[0] = X0;
-        X[1] = (q == nq - 1) ? odd_last(VH, X0) : odd_upd(VH, X0, right);
+        const int t = odd_upd(VH, X0, right);
+        V[0] = X0;
+        V[1] = q_last ? odd_last(VH, X0) : t;
     };
 
     // ---- level 1 -----------------------------------------------------------------------------------------------
-    // band row rr of the level-1 image (rr < nly1: low-pass row, else high-pass row rr - nly1): (L, H) of this lane
-    auto l1_load = [&](int c, int rr, int v[2]) {
-        if (!qvalid) { v[0] = v[1] = 0; return; }
+    // band row pair j of the level-1 image: lo = row j, hi = row nly1 + j; v = lo (L, H), hi (L, H) of this lane
+    auto l1_load = [&](int j, int v[NC][4]) {
+        uint32_t o_lo, o_hi, o_p;          // element offsets of this lane's L element; the H element is nlx1 further
+        bool pL, pH;                       // lo L / lo H come from the level-2 output (int32) instead of the plane
         if (ISO) {
-            const CT *rowp = plane[c] + (size_t)((uint32_t)rr * uw);
-            v[1] = ld1(rowp + nlx1 + qc);
-            if (rr < nly1 && l2on) v[0] = __ldg(prev2[c] + (size_t)((uint32_t)rr * (uint32_t)nlx1 + (uint32_t)qc));
-            else v[0] = ld1(rowp + qc);
+            o_lo = (uint32_t)j * uw + (uint32_t)qc; o_hi = (uint32_t)(nly1 + j) * uw + (uint32_t)qc;
+            o_p = (uint32_t)j * (uint32_t)nlx1 + (uint32_t)qc;
+            pL = l2on; pH = false;
         } else {
-            const uint32_t lin = (uint32_t)rr * (uint32_t)w1 + (uint32_t)qc;
-            v[0] = (l2on && 2 * rr + 1 <= nly1) ? __ldg(prev2[c] + lin) : ld1(plane[c] + lin);
-            v[1] = (l2on && 2 * rr + 2 <= nly1) ? __ldg(prev2[c] + lin + nlx1) : ld1(plane[c] + lin + nlx1);
+            o_lo = (uint32_t)j * (uint32_t)nlx + (uint32_t)qc; o_hi = (uint32_t)(nly1 + j) * (uint32_t)nlx + (uint32_t)qc;
+            o_p = o_lo;
+            pL = l2on && 2 * j + 1 <= nly1; pH = l2on && 2 * j + 2 <= nly1;
+        }
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            v[c][0] = pL ? __ldg(prev2[c] + o_p) : ld1(plane[c] + o_lo);
+            v[c][1] = pH ? __ldg(prev2[c] + o_p + nlx1) : ld1(plane[c] + o_lo + nlx1);
+            v[c][2] = ld1(plane[c] + o_hi);
+            v[c][3] = ld1(plane[c] + o_hi + nlx1);
         }
     };
     int h1p[NC][2], e1p[NC][2];        // hi1[jn] and E1[jn] in the vertical-lifting domain
     int r1[2][NC][2];                  // the last emitted level-1 output row pair (rows 2(jn-1), 2(jn-1)+1), cols 2q, 2q+1
-    int pf1[NC][4];                    // prefetched band rows jn+1: lo (L,H), hi (L,H)
+    int pf1[NC][4];                    // prefetched band row pair jn+1
     int jn = 0, j1last = -1;           // next level-1 pair to emit; last pair this strip needs
 
-    auto l1_emit = [&]() {
+    // one level-1 step: consumes band row pair jn+1 (prefetched), emits output rows 2jn, 2jn+1 into r1, prefetches jn+2
+    auto l1_step = [&]() {
         int nx[NC][4];
         const bool pfnext = (jn + 1 <= j1last) && (jn + 2 < nly1);
-        if (pfnext) {
-#pragma unroll
-            for (int c = 0; c < NC; c++) { l1_load(c, jn + 2, &nx[c][0]); l1_load(c, nly1 + jn + 2, &nx[c][2]); }
-        }
+        if (pfnext) l1_load(jn + 2, nx);
         const bool inner = jn + 1 < nly1;
 #pragma unroll
         for (int c = 0; c < NC; c++) {
-            int o[2];
-            if (inner) {
-                int lo[2] = {pf1[c][0], pf1[c][1]}, hi[2] = {pf1[c][2], pf1[c][3]};
-                if (ISO) { int t[2]; hsynth1(lo, t); lo[0] = t[0]; lo[1] = t[1]; hsynth1(hi, t); hi[0] = t[0]; hi[1] = t[1]; }
+            int lo[2] = {pf1[c][0], pf1[c][1]}, hi[2] = {pf1[c][2], pf1[c][3]};
+            if (ISO) { hsynth1(lo); hsynth1(hi); }
 #pragma unroll
-                for (int j = 0; j < 2; j++) {
-                    const int e = even_upd(lo[j], h1p[c][j], hi[j]);
-                    o[j] = odd_upd(h1p[c][j], e1p[c][j], e);
-                    r1[0][c][j] = e1p[c][j];
-                    e1p[c][j] = e; h1p[c][j] = hi[j];
-                }
-            } else {                                                   // bottom edge (nly even): last odd row += x[n-2]
+            for (int j = 0; j < 2; j++) {
+                const int e = even_upd(lo[j], h1p[c][j], hi[j]);
+                const int o = inner ? odd_upd(h1p[c][j], e1p[c][j], e) : odd_last(h1p[c][j], e1p[c][j]);   // bottom edge
+                r1[0][c][j] = e1p[c][j]; r1[1][c][j] = o;
+                e1p[c][j] = e; h1p[c][j] = hi[j];
+            }
+            if (!ISO) { hsynth1(r1[0][c]); hsynth1(r1[1][c]); }
 #pragma unroll
-                for (int j = 0; j < 2; j++) { o[j] = odd_last(h1p[c][j], e1p[c][j]); r1[0][c][j] = e1p[c][j]; }
-            }
-            r1[1][c][0] = o[0]; r1[1][c][1] = o[1];
-            if (!ISO) {
-                int t[2];
-                hsynth1(r1[0][c], t); r1[0][c][0] = t[0]; r1[0][c][1] = t[1];
-                hsynth1(r1[1][c], t); r1[1][c][0] = t[0]; r1[1][c][1] = t[1];
-            }
-            if (pfnext) {
-#pragma unroll
-                for (int j = 0; j < 4; j++) pf1[c][j] = nx[c][j];
-            }
+            for (int j = 0; j < 4; j++) pf1[c][j] = nx[c][j];
         }
         jn++;
     };
 
-    // ---- prologue ------------------------------------------------------------------------------------------------
+    // ---- prologue: fill the ring, load the row above the strip; the first loop step then only builds E[ka] -----------
+    const int k0 = ka - 1;
+    o_iss = (uint32_t)ka * uw + col0;
 #pragma unroll
     for (int i = 1; i < kDepth; i++) {
-        if (ka + i <= rlast) issue_l0(ka + i);
+        if (qvalid && k0 + i <= rlast) issue_l0(k0 + i);
+        o_iss += uw;
         cp_commit();
     }
     bool l1need = false;
     if (l1on) {
-        if (ISO) { l1need = true; jn = ka >> 1; j1last = rlast >> 1; }
-        else if (ka < half0) { l1need = true; jn = ka; j1last = min(rlast, half0 - 1); }
+        if (ISO) { l1need = true; jn = (ka >> 1) - 1; j1last = rlast >> 1; }
+        else if (ka < half0) { l1need = true; jn = ka - 1; j1last = min(rlast, half0 - 1); }
     }
-    if (l1need) {
-        const int ja = jn;
+    if (l1need) {                                                      // hi1[max(jn, 0)] -> h1p, band row pair jn+1 -> pf1
+        int t[NC][4];
+        l1_load(jn < 0 ? 0 : jn, t);
 #pragma unroll
         for (int c = 0; c < NC; c++) {
-            int a[2], b[2], p[2];
-            l1_load(c, ja, a); l1_load(c, nly1 + ja, b);
-            if (ja > 0) l1_load(c, nly1 + ja - 1, p);
-            if (ISO) {
-                int t[2];
-                hsynth1(a, t); a[0] = t[0]; a[1] = t[1];
-                hsynth1(b, t); b[0] = t[0]; b[1] = t[1];
-                if (ja > 0) { hsynth1(p, t); p[0] = t[0]; p[1] = t[1]; }
-            }
-#pragma unroll
-            for (int j = 0; j < 2; j++) {
-                const int hprev = ja > 0 ? p[j] : b[j];                // top edge: Hi[-1] := Hi[0]
-                e1p[c][j] = even_upd(a[j], hprev, b[j]);
-                h1p[c][j] = b[j];
-            }
-            if (ja + 1 < nly1) { l1_load(c, ja + 1, &pf1[c][0]); l1_load(c, nly1 + ja + 1, &pf1[c][2]); }
+            int hi[2] = {t[c][2], t[c][3]};
+            if (ISO) hsynth1(hi);
+            h1p[c][0] = hi[0]; h1p[c][1] = hi[1];
+            e1p[c][0] = e1p[c][1] = 0;
         }
-        l1_emit();                                                     // the pair that holds level-0 row ka
+        l1_load(jn + 1, pf1);
     }
-
-    int hp[NC][4], ep[NC][4];          // Hi[k-1] and E[k-1] of the lane's 4 columns
+    int hp[NC][4], ep[NC][4];          // Hi[k] and E[k] of the lane's 4 columns
     {
-        const bool fl = l0_L_from_l1(ka), fh = l0_H_from_l1(ka);
+        const int rp = k0 < 0 ? 0 : k0;                                // top edge: Hi[-1] := Hi[0]
+        const uint32_t ohi = (uint32_t)(nly + rp) * uw + col0;
 #pragma unroll
         for (int c = 0; c < NC; c++) {
-            int lo[4], hi[4], pv[4];
-            if (qvalid) {
-                const CT *lop = plane[c] + (size_t)((uint32_t)ka * uw + col0);
-                const CT *hip = plane[c] + (size_t)((uint32_t)(nly + ka) * uw + col0);
-                int2 t;
-                if (fl) {
-                    const bool odd = ISO && (ka & 1);
-                    lo[0] = odd ? r1[1][c][0] : r1[0][c][0]; lo[1] = odd ? r1[1][c][1] : r1[0][c][1];
-                }
-                else { t = ldpair(lop); lo[0] = t.x; lo[1] = t.y; }
-                if (fh) { lo[2] = r1[1][c][0]; lo[3] = r1[1][c][1]; }
-                else { t = ldpair(lop + nlx); lo[2] = t.x; lo[3] = t.y; }
-                t = ldpair(hip); hi[0] = t.x; hi[1] = t.y;
-                t = ldpair(hip + nlx); hi[2] = t.x; hi[3] = t.y;
-                if (ka > 0) {
-                    t = ldpair(hip - uw); pv[0] = t.x; pv[1] = t.y;
-                    t = ldpair(hip - uw + nlx); pv[2] = t.x; pv[3] = t.y;
-                }
-            } else {
+            const int2 a = ldpair(plane[c] + ohi), b = ldpair(plane[c] + ohi + nlx);
+            hp[c][0] = a.x; hp[c][1] = a.y; hp[c][2] = b.x; hp[c][3] = b.y;
+            if (ISO) hsynth0(hp[c]);
 #pragma unroll
-                for (int j = 0; j < 4; j++) lo[j] = hi[j] = pv[j] = 0;
-            }
-            if (ISO) {
-                int t[4];
-                hsynth0(lo, t);
-#pragma unroll
-                for (int j = 0; j < 4; j++) lo[j] = t[j];
-                hsynth0(hi, t);
-#pragma unroll
-                for (int j = 0; j < 4; j++) hi[j] = t[j];
-                if (ka > 0) {
-                    hsynth0(pv, t);
-#pragma unroll
-                    for (int j = 0; j < 4; j++) pv[j] = t[j];
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int hprev = ka > 0 ? pv[j] : hi[j];              // top edge: Hi[-1] := Hi[0]
-                ep[c][j] = even_upd(lo[j], hprev, hi[j]);
-                hp[c][j] = hi[j];
-            }
+            for (int j = 0; j < 4; j++) ep[c][j] = 0;
         }
     }
 
-    // ---- pixel epilogue of one finished row (columns already interleaved) ---------------------------------------
+    // ---- pixel epilogue of one finished row (columns interleaved) ---------------------------------------------------
     const uint32_t gx0 = tile.img_x0 + 4u * (uint32_t)qc;
-    const bool fast_rgba8 = tp.fmt == J2KGPU_FMT_RGBA8 && NC == 3 && tp.prec[0] == 8 && tp.prec[1] == 8 && tp.prec[2] == 8 &&
-                            tp.mct && tp.reversible && !tp.sgnd[0] && !tp.sgnd[1] && !tp.sgnd[2] &&
-                            ((tile.out_stride & 15) == 0) && ((tile.img_x0 & 3) == 0) && (gx0 + 3 < tile.img_w);
     uint8_t *orow = pix + tile.out_off + (size_t)(tile.img_y0 + 2u * (uint32_t)ka) * tile.out_stride;
     uint32_t gy = tile.img_y0 + 2u * (uint32_t)ka;
     auto put_row = [&](int X[NC][4]) {
-        if (store_lane && gy < tile.img_h) {                           // decoder.go:398-410 clipping
-            if (fast_rgba8) {
+        if (FAST) {
+            if (store_lane) {
                 uint32_t px[4];
 #pragma unroll
                 for (int p = 0; p < 4; p++) {                          // mct.go:56-66, mct.go:113-118, decoder.go:468-487
@@ -343,118 +305,78 @@ k_idwt53_fused(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__ 
                     px[p] = pack_sat_u8(g8, r8, pack_sat_u8(255, b8, 0u));
                 }
                 __stcs(reinterpret_cast<uint4 *>(orow + 4 * (size_t)gx0), make_uint4(px[0], px[1], px[2], px[3]));
-            } else {
-#pragma unroll
-                for (int p = 0; p < 4; p++) {
-                    if (gx0 + p >= tile.img_w) continue;
-                    int32_t v[4] = {X[0][p], NC > 1 ? X[NC > 1 ? 1 : 0][p] : 0, NC > 2 ? X[NC > 2 ? 2 : 0][p] : 0,
-                                    NC > 3 ? X[NC > 3 ? 3 : 0][p] : 0};
-                    tail_mct_dc(v, tp);
-                    store_pixel(orow, gx0 + p, v, tp);
-                }
             }
+        } else {
+            if (store_lane && gy < tile.img_h) put_quad_generic<NC>(orow, gx0, tile.img_w, &X[0][0], tp);   // decoder.go:398-410
+            gy++;
         }
         orow += tile.out_stride;
-        gy++;
-    };
-    // REF: the finished row is in band-column order and still needs the horizontal synthesis; ISO: it is final
-    auto emit_row = [&](int V[NC][4]) {
-        if (ISO) {
-            put_row(V);
-        } else {
-            int X[NC][4];
-#pragma unroll
-            for (int c = 0; c < NC; c++) hsynth0(V[c], X[c]);
-            put_row(X);
-        }
     };
 
-    // ---- stream the strip: step k finishes output rows 2k (even) and 2k+1 (odd) --------------------------------------
-    for (int k = ka; k < kb; k++) {
-        if (k + kDepth <= rlast) issue_l0(k + kDepth);
+    // ---- stream the strip: step k consumes band row pair k+1 and finishes output rows 2k (even) and 2k+1 (odd) ------
+    for (int k = k0; k < kb; k++) {
+        if (qvalid && k + kDepth <= rlast) issue_l0(k + kDepth);
+        o_iss += uw;
         cp_commit();
-        int o[NC][4];
-        if (k + 1 < nly) {
-            const int r = k + 1;
-            const bool fl = l0_L_from_l1(r), fh = l0_H_from_l1(r);
-            if (fl && jn <= (ISO ? (r >> 1) : r)) l1_emit();           // warp-uniform
-            cp_wait<kDepth - 1>();
-            const int s = r & (kDepth - 1);
-            int e[NC][4];
-#pragma unroll
-            for (int c = 0; c < NC; c++) {
-                const uint2 *sl = ring + (size_t)((s * NC + c) * 4) * 32;
-                int lo[4], hi[4];
-                int2 t;
-                if (fl) {
-                    const bool odd = ISO && (r & 1);
-                    lo[0] = odd ? r1[1][c][0] : r1[0][c][0]; lo[1] = odd ? r1[1][c][1] : r1[0][c][1];
-                }
-                else { t = slot_pair(sl, CT()); lo[0] = t.x; lo[1] = t.y; }
-                if (fh) { lo[2] = r1[1][c][0]; lo[3] = r1[1][c][1]; }
-                else { t = slot_pair(sl + 32, CT()); lo[2] = t.x; lo[3] = t.y; }
-                t = slot_pair(sl + 64, CT()); hi[0] = t.x; hi[1] = t.y;
-                t = slot_pair(sl + 96, CT()); hi[2] = t.x; hi[3] = t.y;
-                if (!qvalid) {
-#pragma unroll
-                    for (int j = 0; j < 4; j++) lo[j] = hi[j] = 0;
-                }
-                if (ISO) {
-                    int x[4];
-                    hsynth0(lo, x);
-#pragma unroll
-                    for (int j = 0; j < 4; j++) lo[j] = x[j];
-                    hsynth0(hi, x);
-#pragma unroll
-                    for (int j = 0; j < 4; j++) hi[j] = x[j];
-                }
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    e[c][j] = even_upd(lo[j], hp[c][j], hi[j]);
-                    o[c][j] = odd_upd(hp[c][j], ep[c][j], e[c][j]);
-                    hp[c][j] = hi[j];
-                }
-            }
-            emit_row(ep);
-            emit_row(o);
-#pragma unroll
-            for (int c = 0; c < NC; c++)
-#pragma unroll
-                for (int j = 0; j < 4; j++) ep[c][j] = e[c][j];
-        } else {                                                       // bottom edge (h even): last odd row += x[n-2]
-#pragma unroll
-            for (int c = 0; c < NC; c++)
-#pragma unroll
-                for (int j = 0; j < 4; j++) o[c][j] = odd_last(hp[c][j], ep[c][j]);
-            emit_row(ep);
-            emit_row(o);
+        const int r = k + 1;
+        const bool inner = r < nly;                                    // false only below the last row pair of the tile
+        const bool fl = l1on && (ISO || r < half0), fh = l1on && !ISO && r < half0;
+        if (inner && fl) {
+            const int need = ISO ? (r >> 1) : r;                       // the level-1 pair that holds level-0 row r
+            while (jn <= need) l1_step();                              // warp-uniform; twice on the first step only
         }
+        cp_wait<kDepth - 1>();
+        const int s = r & (kDepth - 1);
+        const bool odd = ISO && (r & 1);
+        int evn[NC][4], o[NC][4];
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            const uint2 *sl = ring + (size_t)((s * NC + c) * 4) * 32;
+            int lo[4], hi[4];
+            int2 t;
+            t = slot_pair(sl, CT()); lo[0] = t.x; lo[1] = t.y;
+            t = slot_pair(sl + 32, CT()); lo[2] = t.x; lo[3] = t.y;
+            t = slot_pair(sl + 64, CT()); hi[0] = t.x; hi[1] = t.y;
+            t = slot_pair(sl + 96, CT()); hi[2] = t.x; hi[3] = t.y;
+            if (fl) { lo[0] = odd ? r1[1][c][0] : r1[0][c][0]; lo[1] = odd ? r1[1][c][1] : r1[0][c][1]; }
+            if (fh) { lo[2] = r1[1][c][0]; lo[3] = r1[1][c][1]; }
+            if (ISO) { hsynth0(lo); hsynth0(hi); }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int e = even_upd(lo[j], hp[c][j], hi[j]);
+                o[c][j] = inner ? odd_upd(hp[c][j], ep[c][j], e) : odd_last(hp[c][j], ep[c][j]);   // bottom edge (h even)
+                evn[c][j] = ep[c][j];
+                ep[c][j] = e; hp[c][j] = hi[j];
+            }
+            if (!ISO && k >= ka) { hsynth0(evn[c]); hsynth0(o[c]); }
+        }
+        if (k >= ka) { put_row(evn); put_row(o); }
     }
     cp_wait<0>();
 }
 
-template <int NC, typename CT>
+template <int NC, typename CT, bool FAST>
 cudaError_t run_ct(const IdwtLaunch &p, dim3 grid, int strip_pairs, cudaStream_t s)
 {
     const size_t smem = (size_t)kWarps * kDepth * NC * 4 * 32 * sizeof(uint2);
     const DevTile *tiles = p.d_tiles + p.tile_first;
     cudaError_t e;
     if (p.iso) {
-        if ((e = cudaFuncSetAttribute(k_idwt53_fused<NC, CT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        J2K_LAUNCH((k_idwt53_fused<NC, CT, true>), grid, kWarps * 32, smem, s, p.d_tcs, tiles, (const CT *)p.d_coef,
+        if ((e = cudaFuncSetAttribute(k_idwt53_fused<NC, CT, true, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        J2K_LAUNCH((k_idwt53_fused<NC, CT, true, FAST>), grid, kWarps * 32, smem, s, p.d_tcs, tiles, (const CT *)p.d_coef,
                    (const int32_t *)p.d_tmp, p.d_pix, p.nlevels, strip_pairs, p.tail);
     } else {
-        if ((e = cudaFuncSetAttribute(k_idwt53_fused<NC, CT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        J2K_LAUNCH((k_idwt53_fused<NC, CT, false>), grid, kWarps * 32, smem, s, p.d_tcs, tiles, (const CT *)p.d_coef,
+        if ((e = cudaFuncSetAttribute(k_idwt53_fused<NC, CT, false, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        J2K_LAUNCH((k_idwt53_fused<NC, CT, false, FAST>), grid, kWarps * 32, smem, s, p.d_tcs, tiles, (const CT *)p.d_coef,
                    (const int32_t *)p.d_tmp, p.d_pix, p.nlevels, strip_pairs, p.tail);
     }
     return cudaGetLastError();
 }
 
-template <int NC>
+template <int NC, bool FAST>
 cudaError_t run(const IdwtLaunch &p, dim3 grid, int strip_pairs, cudaStream_t s)
 {
-    return p.coef16 ? run_ct<NC, int16_t>(p, grid, strip_pairs, s) : run_ct<NC, int32_t>(p, grid, strip_pairs, s);
+    return p.coef16 ? run_ct<NC, int16_t, FAST>(p, grid, strip_pairs, s) : run_ct<NC, int32_t, FAST>(p, grid, strip_pairs, s);
 }
 
 }  // namespace
@@ -470,10 +392,11 @@ cudaError_t launch_idwt53_fused(const IdwtLaunch &p, cudaStream_t s)
     while (sp > 8 && (uint64_t)p.n_tiles * nwx * ((nly + sp - 1) / sp) < 148ull * 16 * 2) sp >>= 1;
     const uint32_t units = nwx * ((nly + sp - 1) / sp);
     dim3 grid((units + kWarps - 1) / kWarps, p.n_tiles, 1);
+    const bool fast = p.fast_epi && ((uintptr_t)p.d_pix & 15) == 0;
     switch (p.tail.ncomp) {
-    case 1: return run<1>(p, grid, sp, s);
-    case 3: return run<3>(p, grid, sp, s);
-    case 4: return run<4>(p, grid, sp, s);
+    case 1: return run<1, false>(p, grid, sp, s);
+    case 3: return fast ? run<3, true>(p, grid, sp, s) : run<3, false>(p, grid, sp, s);
+    case 4: return run<4, false>(p, grid, sp, s);
     }
     return cudaErrorInvalidValue;
 }

@@ -56,8 +56,12 @@ struct Src {
 };
 
 // REF (dense prefix): one linear index space, prev below nprev
-template <typename CT>
-__device__ __forceinline__ int2 ld2(const Src<CT> &s, uint32_t lin)
+__device__ __forceinline__ int2 ld2(const Src<int32_t> &s, uint32_t lin)
+{
+    const int32_t *p = lin < s.nprev ? s.prev : s.coef;          // one load, selected pointer
+    return ldpair(p + lin);
+}
+__device__ __forceinline__ int2 ld2(const Src<int16_t> &s, uint32_t lin)
 {
     return lin < s.nprev ? ldpair(s.prev + lin) : ldpair(s.coef + lin);
 }
