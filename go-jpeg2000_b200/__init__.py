@@ -25,6 +25,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libj2kgpu.so")
 
 MODE_REF, MODE_ISO = 0, 1
+PLAN_FUSED, PLAN_FAST_EPILOGUE, PLAN_WIDE, PLAN_COEF16 = 1, 2, 4, 8
 BAND_LL, BAND_HL, BAND_LH, BAND_HH = 0, 1, 2, 3
 FMT_AUTO, FMT_GRAY8, FMT_GRAY16, FMT_RGBA8, FMT_RGBA64 = 0, 1, 2, 3, 4
 E_ARG, E_RANGE, E_UNSUPPORTED, E_CUDA, E_NOMEM, E_NODEVICE = -1, -2, -3, -4, -5, -6
@@ -72,7 +73,7 @@ EXPORTS = [
     "j2kgpu_set_stream", "j2kgpu_launch_count", "j2kgpu_decode", "j2kgpu_decode_batch",
     "j2kgpu_job_create", "j2kgpu_job_destroy", "j2kgpu_job_blob_bytes", "j2kgpu_job_out_bytes",
     "j2kgpu_job_out_offset", "j2kgpu_job_run", "j2kgpu_job_run_entropy", "j2kgpu_job_run_dwt_mct",
-    "j2kgpu_job_run_level", "j2kgpu_job_fused_levels", "j2kgpu_job_coef_bytes",
+    "j2kgpu_job_run_level", "j2kgpu_job_fused_levels", "j2kgpu_job_coef_bytes", "j2kgpu_job_plan",
     "j2kgpu_job_run_host", "j2kgpu_sync", "j2kgpu_t1_decode_blocks", "j2kgpu_ht_decode_blocks",
     "j2kgpu_idwt53", "j2kgpu_idwt97", "j2kgpu_apply_inverse_dwt", "j2kgpu_inverse_rct",
     "j2kgpu_inverse_ict", "j2kgpu_dc_level_shift_inverse", "j2kgpu_mct_dc_pack",
@@ -121,6 +122,7 @@ def lib():
         L.j2kgpu_job_run_host.argtypes = [C.c_void_p, C.POINTER(BatchItem)]
         L.j2kgpu_job_fused_levels.argtypes = [C.c_void_p]
         L.j2kgpu_job_coef_bytes.argtypes = [C.c_void_p]
+        L.j2kgpu_job_plan.argtypes = [C.c_void_p]
         for name in ("j2kgpu_t1_decode_blocks", "j2kgpu_ht_decode_blocks"):
             getattr(L, name).argtypes = [C.c_void_p, C.c_int, C.POINTER(BlkJob), C.c_uint32, u8p, C.c_uint64,
                                          i32p, C.c_uint64]
@@ -303,6 +305,7 @@ class Job:
         self.n = len(items)
         self.fused_levels = int(lib().j2kgpu_job_fused_levels(self._h))
         self.coef_bytes = int(lib().j2kgpu_job_coef_bytes(self._h))
+        self.plan = int(lib().j2kgpu_job_plan(self._h))
 
     def out_offset(self, i):
         return int(lib().j2kgpu_job_out_offset(self._h, i))

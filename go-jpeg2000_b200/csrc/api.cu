@@ -384,6 +384,8 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
     for (int c = 0; c < 3; c++) if (tp.prec[c] != 8 || tp.sgnd[c]) job->fast_epi = 0;
     for (const DevTile &t : tiles)
         if ((t.out_stride & 15) || (t.out_off & 15) || (t.img_x0 & 3) || t.img_x0 + t.w > t.img_w || t.img_y0 + t.h > t.img_h) job->fast_epi = 0;
+    job->wide_ok = job->fast_epi && fused_ok && !env_flag("J2KGPU_NO_WIDE");
+    for (const DevTile &t : tiles) if (t.w & 15) job->wide_ok = 0;
     job->coef_elems = coef_elems; job->blob_bytes = blob_bytes; job->out_bytes = out_bytes; job->max_bps = max_bps;
     job->tmp_bytes = tmp_elems * (hdr.reversible ? 4 : 8);
     job->need_clear = need_clear;
@@ -451,7 +453,7 @@ static void fill_launch(const j2kgpu_job *job, IdwtLaunch &p, void *d_out, uint3
     p.d_tcs = job->d_tcs; p.d_tiles = job->d_tiles;
     p.tc_first = job->item_tc[ia]; p.n_tc = job->item_tc[ib] - p.tc_first;
     p.tile_first = job->item_tile[ia]; p.n_tiles = job->item_tile[ib] - p.tile_first;
-    p.d_coef = job->d_coef; p.coef16 = job->coef16; p.d_tmp = job->d_tmp; p.nlevels = job->nlevels; p.fast_epi = job->fast_epi;
+    p.d_coef = job->d_coef; p.coef16 = job->coef16; p.d_tmp = job->d_tmp; p.nlevels = job->nlevels; p.fast_epi = job->fast_epi; p.wide_ok = job->wide_ok;
     p.max_w = job->max_w; p.max_h = job->max_h; p.reversible = job->hdr.reversible != 0; p.f64_io = 0;
     p.d_plane_out = nullptr; p.d_pix = (uint8_t *)d_out; p.tail = job->tail; p.stream_levels = job->stream_levels; p.iso = job->iso;
 }
@@ -518,6 +520,12 @@ extern "C" int j2kgpu_job_run_level(j2kgpu_job *job, int lvl, void *d_out)
 
 extern "C" int j2kgpu_job_fused_levels(const j2kgpu_job *job) { return job ? (job->fused_ok ? 2 : 1) : 0; }
 extern "C" int j2kgpu_job_coef_bytes(const j2kgpu_job *job) { return job ? (job->coef16 ? 2 : 4) : 0; }
+extern "C" int j2kgpu_job_plan(const j2kgpu_job *job)
+{
+    if (!job) return 0;
+    return (job->fused_ok ? J2KGPU_PLAN_FUSED : 0) | (job->fused_ok && job->fast_epi ? J2KGPU_PLAN_FAST_EPILOGUE : 0) |
+           (job->fused_ok && job->wide_ok ? J2KGPU_PLAN_WIDE : 0) | (job->coef16 ? J2KGPU_PLAN_COEF16 : 0);
+}
 
 extern "C" int j2kgpu_job_run(j2kgpu_job *job, const void *d_blob, void *d_out)
 {

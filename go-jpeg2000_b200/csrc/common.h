@@ -105,6 +105,7 @@ struct j2kgpu_job {
     int coef16 = 0;                      // coefficient arena holds int16 (every magnitude provably < 2^15) instead of int32
     int fused_ok = 0;                    // levels 1 + 0 + pixel epilogue run as one kernel (idwt_fused.cu)
     int fast_epi = 0;                    // every tile qualifies for the fused kernel's fixed RGBA8 epilogue
+    int wide_ok = 0;                     // ... and for the 16-columns-per-lane variant (idwt_wide.cu)
     std::vector<uint32_t> item_cb, item_tc, item_tile;   // first block / tile-component / tile of each item (+ end)
     std::vector<uint64_t> tc_coef_off;                   // coefficient-arena offset of each tile-component (host copy)
     std::vector<cudaEvent_t> ev_in, ev_done;             // per chunk of the pipelined host-buffer run
@@ -151,6 +152,7 @@ struct IdwtLaunch {
     int coef16;
     uint32_t tc_first, tile_first;                  // sub-range of the tables this launch covers (batch pipelining)
     int fast_epi;                                   // fused kernel: 3 x 8-bit unsigned, RCT, RGBA8, tiles inside the image, aligned rows
+    int wide_ok;                                    // + every tile width a multiple of 16: the 16-columns-per-lane kernel (idwt_wide.cu)
     void *d_tmp;                                    // ping-pong arena (int32 for 5-3, double for 9-7)
     int nlevels, lvl;
     uint32_t max_w, max_h;                          // largest tile-component (grid sizing)
@@ -166,6 +168,7 @@ cudaError_t launch_idwt_level(const IdwtLaunch &p, cudaStream_t s, int *n_launch
 cudaError_t launch_idwt53_stream(const IdwtLaunch &p, cudaStream_t s);
 // levels 1 and 0 of every tile + inverse MCT + DC shift + clamp + pack in one kernel (5-3; see idwt_fused.cu)
 cudaError_t launch_idwt53_fused(const IdwtLaunch &p, cudaStream_t s);
+cudaError_t launch_idwt53_wide(const IdwtLaunch &p, cudaStream_t s);
 // a tile-component fits the fused kernel when its width is a multiple of 8 and its height a multiple of 4
 static inline bool j2k_fused_ok(uint32_t w, uint32_t h) { return w >= 8 && (w & 7) == 0 && h >= 4 && (h & 3) == 0; }
 // level l fits the streaming kernel when its width is a multiple of 4 and its height is even (>= 2)

@@ -393,6 +393,7 @@ cudaError_t launch_idwt53_fused(const IdwtLaunch &p, cudaStream_t s)
     const uint32_t units = nwx * ((nly + sp - 1) / sp);
     dim3 grid((units + kWarps - 1) / kWarps, p.n_tiles, 1);
     const bool fast = p.fast_epi && ((uintptr_t)p.d_pix & 15) == 0;
+    if (fast && p.wide_ok) return launch_idwt53_wide(p, s);
     switch (p.tail.ncomp) {
     case 1: return run<1, false>(p, grid, sp, s);
     case 3: return fast ? run<3, true>(p, grid, sp, s) : run<3, false>(p, grid, sp, s);

@@ -171,6 +171,12 @@ int      j2kgpu_job_run_level(j2kgpu_job *job, int lvl, void *d_out);
  * no-op and run_level(0) runs both), else 1; bytes per element of the coefficient planes in HBM (2 or 4) */
 int      j2kgpu_job_fused_levels(const j2kgpu_job *job);
 int      j2kgpu_job_coef_bytes(const j2kgpu_job *job);
+/* the kernels the job will use, as J2KGPU_PLAN_* bits (for tests and bench reports) */
+enum { J2KGPU_PLAN_FUSED = 1,          /* IDWT levels 1+0 + MCT + DC + pack in one kernel (idwt_fused.cu)          */
+       J2KGPU_PLAN_FAST_EPILOGUE = 2,  /* ... with the fixed 3 x 8-bit RCT -> RGBA8 epilogue                        */
+       J2KGPU_PLAN_WIDE = 4,           /* ... in the 16-columns-per-lane variant (idwt_wide.cu)                     */
+       J2KGPU_PLAN_COEF16 = 8 };       /* int16 coefficient planes                                                  */
+int      j2kgpu_job_plan(const j2kgpu_job *job);
 /* host-buffer run of a prepared job: H2D, kernels and D2H pipelined over chunks of the batch on three streams;
  * blocking.  Give pinned host buffers for the copies to overlap the kernels. */
 int      j2kgpu_job_run_host(j2kgpu_job *job, const j2k_batch_item_t *items);

@@ -147,7 +147,7 @@ def _run_items(j2k, ctx, jl, env=None, mode=0, coef_bits=0):
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
-    flags = (job.fused_levels, job.coef_bytes)
+    flags = (job.fused_levels, job.coef_bytes, job.plan)
     job.run_host()
     job.close()
     return outs, flags
@@ -161,6 +161,10 @@ def _run_items(j2k, ctx, jl, env=None, mode=0, coef_bits=0):
     (192, 96, 1, 8, 96, 96, 3, 0),         # 1 component, Gray8
     (160, 72, 4, 8, None, None, 3, 0),     # 4 components; 72 rows: strips shorter than the ring depth at the bottom
     (384, 256, 3, 12, 128, 128, 4, 0),     # RGBA64 epilogue
+    (1024, 64, 3, 8, None, None, 3, 1),    # wide kernel: 64 lanes' worth of columns -> 30 owned lanes + 1 halo lane each side
+    (1536, 40, 3, 8, None, None, 2, 0),    # wide kernel, three warps per row, int16 planes, short strip (20 row pairs)
+    (528, 136, 3, 8, None, None, 4, 0),    # wide kernel: 33 lanes' worth -> halo path with a nearly empty second warp
+    (512, 512, 3, 8, None, None, 5, 1),    # one warp per tile row, no halo lanes (the bench geometry)
 ])
 def test_fused_and_int16_variants_agree(j2k, gpu_ctx, w, h, ncomp, prec, tw, th, levels, ht):
     """the fused levels-1+0 kernel and the int16 coefficient planes are optimisations: every combination of
@@ -168,11 +172,17 @@ def test_fused_and_int16_variants_agree(j2k, gpu_ctx, w, h, ncomp, prec, tw, th,
     s = jobs.synth_image(w, h, ncomp, prec, seed=77 + w)
     job = jobs.build_ref_job(s, prec, tw, th, nlevels=levels, reversible=True, ht=bool(ht), threads=4)
     want = oracle_pixels(job)
-    seen = set()
-    for env in ({}, {"J2KGPU_NO_FUSE": "1"}, {"J2KGPU_COEF32": "1"}, {"J2KGPU_NO_FUSE": "1", "J2KGPU_COEF32": "1"}):
+    seen, plans = set(), set()
+    for env in ({}, {"J2KGPU_NO_FUSE": "1"}, {"J2KGPU_COEF32": "1"}, {"J2KGPU_NO_FUSE": "1", "J2KGPU_COEF32": "1"},
+                {"J2KGPU_NO_WIDE": "1"}, {"J2KGPU_NO_WIDE": "1", "J2KGPU_COEF32": "1"},
+                {"J2KGPU_NO_WIDE": "1", "J2KGPU_NO_FAST_EPI": "1"}):
         outs, flags = _run_items(j2k, gpu_ctx, [job], env)
         assert np.array_equal(outs[0], want), env
-        seen.add(flags)
+        seen.add(flags[:2])
+        plans.add(flags[2])
+    if ncomp == 3 and prec == 8 and w % 16 == 0 and (tw or w) % 16 == 0:
+        # the 16-columns-per-lane kernel, the 4-columns-per-lane kernel with the fast and with the generic epilogue
+        assert {p & 7 for p in plans} >= {7, 3, 1, 0}
     assert (2, 4) in seen and (1, 4) in seen
     if not ht:
         assert (2, 2) in seen and (1, 2) in seen      # EBCOT magnitudes are bounded by num_bps <= 15
