@@ -552,9 +552,15 @@ static int run_host_locked(j2kgpu_job *job, const j2k_batch_item_t *items)
         if (!items[i].out_pix) return j2k_set_err(ctx, J2KGPU_E_ARG, "item %u: null out_pix", i);
     int rc = j2k_ctx_copy_streams(ctx);
     if (rc) return rc;
-    // chunks of about 1/8 of the batch, at least one item each
+    // chunks of about 1/8 of the batch, at least one item each.  The thread-per-block HT decoder needs many blocks per
+    // launch (its run time is one block's serial chain whatever the count), so its chunks hold >= 16K blocks.
     const uint32_t n = job->n_img;
-    const uint32_t per = n >= 16 ? (n + 7) / 8 : 1;
+    uint32_t per = n >= 16 ? (n + 7) / 8 : 1;
+    if (job->iso && job->ht_map == 32 && job->n_cb) {
+        const uint64_t blocks_per_item = (job->n_cb + n - 1) / n;
+        const uint32_t need = (uint32_t)((16384 + blocks_per_item - 1) / blocks_per_item);
+        if (need > per) per = need < n ? need : n;
+    }
     const uint32_t nchunk = (n + per - 1) / per;
     if (job->ev_in.size() < nchunk) {
         const size_t old = job->ev_in.size();
