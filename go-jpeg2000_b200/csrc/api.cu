@@ -380,11 +380,17 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
         if (iso && hdr.reversible) job->coef16 = hdr.coef_bits >= 1 && hdr.coef_bits <= 14;
     }
     job->fused_ok = fused_ok;
-    job->fast_epi = tp.fmt == J2KGPU_FMT_RGBA8 && tp.ncomp == 3 && tp.mct && tp.reversible && !env_flag("J2KGPU_NO_FAST_EPI");
-    for (int c = 0; c < 3; c++) if (tp.prec[c] != 8 || tp.sgnd[c]) job->fast_epi = 0;
+    // fixed epilogues of the fused kernels: 3 x 8-bit unsigned + RCT -> RGBA8, or 1 x 8 / 16-bit unsigned -> Gray8 / Gray16
+    if (tp.ncomp == 3) {
+        job->fast_epi = tp.fmt == J2KGPU_FMT_RGBA8 && tp.mct && tp.reversible;
+        for (int c = 0; c < 3; c++) if (tp.prec[c] != 8 || tp.sgnd[c]) job->fast_epi = 0;
+    } else if (tp.ncomp == 1) {
+        job->fast_epi = (tp.prec[0] == 8 || tp.prec[0] == 16) && !tp.sgnd[0];
+    }
+    if (env_flag("J2KGPU_NO_FAST_EPI")) job->fast_epi = 0;
     for (const DevTile &t : tiles)
         if ((t.out_stride & 15) || (t.out_off & 15) || (t.img_x0 & 3) || t.img_x0 + t.w > t.img_w || t.img_y0 + t.h > t.img_h) job->fast_epi = 0;
-    job->wide_ok = job->fast_epi && fused_ok && !env_flag("J2KGPU_NO_WIDE");
+    job->wide_ok = job->fast_epi && fused_ok && tp.ncomp == 3 && !env_flag("J2KGPU_NO_WIDE");
     for (const DevTile &t : tiles) if (t.w & 15) job->wide_ok = 0;
     job->coef_elems = coef_elems; job->blob_bytes = blob_bytes; job->out_bytes = out_bytes; job->max_bps = max_bps;
     job->tmp_bytes = tmp_elems * (hdr.reversible ? 4 : 8);

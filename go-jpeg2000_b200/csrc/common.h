@@ -166,6 +166,7 @@ struct IdwtLaunch {
 };
 cudaError_t launch_idwt_level(const IdwtLaunch &p, cudaStream_t s, int *n_launches);
 cudaError_t launch_idwt53_stream(const IdwtLaunch &p, cudaStream_t s);
+cudaError_t launch_idwt97_stream(const IdwtLaunch &p, cudaStream_t s);     // 9-7 float64, REF semantics (idwt97_stream.cu)
 // levels 1 and 0 of every tile + inverse MCT + DC shift + clamp + pack in one kernel (5-3; see idwt_fused.cu)
 cudaError_t launch_idwt53_fused(const IdwtLaunch &p, cudaStream_t s);
 cudaError_t launch_idwt53_wide(const IdwtLaunch &p, cudaStream_t s);
@@ -183,6 +184,16 @@ cudaError_t launch_tail(const int32_t *const d_comps[4], int32_t *const d_planes
                         uint64_t out_stride, uint32_t width, uint32_t height, const TailParams &tp,
                         int apply_tail, cudaStream_t s);
 cudaError_t launch_inverse_ict_f64(double *y, double *cb, double *cr, uint64_t n, cudaStream_t s);
+
+// Go's int32(float64) as the reference runs it on amd64 (CVTTSD2SL): truncation, and 0x80000000 for NaN / out of range
+// (CUDA's cvt.rzi saturates instead, which differs for positive overflow)
+#if defined(__CUDACC__) || defined(J2K_EMU)
+__device__ __forceinline__ int32_t j2k_f64_to_i32(double v)
+{
+    const int32_t r = __double2int_rz(v);
+    return (v > -2147483649.0 && v < 2147483648.0) ? r : (int32_t)0x80000000u;
+}
+#endif
 
 int j2k_resolve_fmt(int ncomp, int prec, int fmt);
 int j2k_fmt_bpp(int fmt);

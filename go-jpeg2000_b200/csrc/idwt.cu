@@ -249,7 +249,7 @@ k_idwt_level(const DevTileComp *__restrict__ tcs, const void *__restrict__ coef,
         if (lvl > 0) {
             ((lvl & 1) ? pp1 : pp0)[o] = v;
         } else if (EPI == EPI_ROUND_I32) {
-            ((int32_t *)out_planes)[tc.coef_off + o] = __double2int_rz(__dadd_rn((double)v, 0.5));   // tcd.go:433-435
+            ((int32_t *)out_planes)[tc.coef_off + o] = j2k_f64_to_i32(__dadd_rn((double)v, 0.5));   // tcd.go:433-435
         } else {
             ((T *)out_planes)[tc.coef_off + o] = v;
         }
@@ -292,7 +292,7 @@ k_idwt_last_pixels(const DevTileComp *__restrict__ tcs, const DevTile *__restric
             int e = threadIdx.x + k * kThreads;
             int r = e / TW, cc = e - r * TW;
             T v = P[(r + HALO) * PP + cc + HALO];
-            if (sizeof(T) == 8) acc[c][k] = __double2int_rz(__dadd_rn((double)v, 0.5));   // tcd.go:433-435
+            if (sizeof(T) == 8) acc[c][k] = j2k_f64_to_i32(__dadd_rn((double)v, 0.5));   // tcd.go:433-435
             else acc[c][k] = (int32_t)v;
         }
         __syncthreads();
@@ -368,6 +368,8 @@ cudaError_t launch_idwt_level(const IdwtLaunch &p, cudaStream_t s, int *n_launch
     if (grid.z == 0) return cudaSuccess;
     if (p.reversible && p.nlevels > 0 && ((p.stream_levels >> lvl) & 1) && (lvl > 0 || pixels))
         return launch_idwt53_stream(p, s);
+    if (!p.reversible && !p.f64_io && !p.iso && p.nlevels > 0 && ((p.stream_levels >> lvl) & 1) && (lvl > 0 || pixels))
+        return launch_idwt97_stream(p, s);
     if (pixels) {
         if (p.reversible && p.iso)
             J2K_LAUNCH((k_idwt_last_pixels<Lift53, true>), grid, kThreads, patch_bytes<Lift53>(), s,

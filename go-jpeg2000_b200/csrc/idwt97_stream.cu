@@ -1,0 +1,255 @@
+// idwt97_stream.cu -- register-streaming inverse 9-7 DWT level in float64 (REF semantics), optionally fused with the
+// pixel epilogue (int32(v + 0.5) -> inverse ICT -> int32(v + 0.5) -> DC shift -> clamp -> pack).
+//
+// Replaces dwt.Inverse97 / Inverse2D97 / ReconstructMultiLevel97 (reference internal/dwt/dwt.go:213-262, 454-473,
+// 561-573) and tcd.ApplyInverseDWT's float path (tcd.go:428-435) on the whole-path route; arithmetic is the reference's
+// operation for operation (__dmul_rn / __dadd_rn / __dsub_rn, never an FMA: Go on amd64 does not fuse), so float64
+// parity is bit-exact.  The general tiled kernel in idwt.cu stays the fallback for odd shapes and for the stage API.
+//
+// Organisation = idwt_stream.cu (a warp owns 30 quads x a strip of row pairs, lanes 0 / 31 are halo lanes, no shared
+// memory, no barrier), with the 4-step lifting written as a vertical software pipeline: reading band row pair m
+// (L_m, H_m) advances, per column,
+//     A_m     = K L_m     - delta (Hs_{m-1} + Hs_m)        Hs = H / K            (even rows after step 1)
+//     B_{m-1} = Hs_{m-1}  - gamma (A_{m-1} + A_m)                                (odd rows after step 2)
+//     C_{m-1} = A_{m-1}   - beta  (B_{m-2} + B_{m-1})                            (even rows, final)
+//     D_{m-2} = B_{m-2}   - alpha (C_{m-2} + C_{m-1})                            (odd rows, final)
+// so output rows 2(m-2), 2(m-2)+1 leave two row pairs behind the loads; the state is 4 doubles per column.  Line ends
+// mirror the missing neighbour (the reference's 2c * neighbour is bit-identical to c * (n + n)).  A strip warms the
+// pipeline up over the two row pairs above it and reads two below.  Horizontal lifting of a finished row: the same
+// four steps across lanes, one double shuffle per step.
+// Eligibility (host, per level): width a multiple of 4, height even (same as idwt_stream.cu).
+#include "common.h"
+#include "tail.cuh"
+
+namespace {
+
+constexpr int kWarps = 4;
+constexpr double kK = 1.230174104914001, kInvK = 0.812893066115961;                       // dwt.go:150-157
+constexpr double kDelta = 0.443506852043971, kGamma = 0.882911075530934, kBeta = -0.052980118572961, kAlpha = -1.586134342059924;
+
+__device__ __forceinline__ int lvl_dim(int full, int lvl) { return (full + (1 << lvl) - 1) >> lvl; }
+// x - c * (l + r), three roundings like the reference (dwt.go:229-261)
+__device__ __forceinline__ double lift(double x, double c, double l, double r) { return __dsub_rn(x, __dmul_rn(c, __dadd_rn(l, r))); }
+
+// d = sat_u8(b) | sat_u8(a) << 8 | c << 16
+__device__ __forceinline__ uint32_t pack_sat_u8(int a, int b, uint32_t c)
+{
+#ifdef J2K_EMU
+    const uint32_t sa = (uint32_t)(a < 0 ? 0 : (a > 255 ? 255 : a)), sb = (uint32_t)(b < 0 ? 0 : (b > 255 ? 255 : b));
+    return sb | (sa << 8) | (c << 16);
+#else
+    uint32_t d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+#endif
+}
+
+__device__ __forceinline__ void ldpair_f64(const int32_t *p, double &a, double &b)
+{
+    const int2 v = __ldg(reinterpret_cast<const int2 *>(p));
+    a = (double)v.x; b = (double)v.y;                                                     // tcd.go:429-431
+}
+__device__ __forceinline__ void ldpair_f64(const int16_t *p, double &a, double &b)
+{
+    const uint32_t r = __ldg(reinterpret_cast<const uint32_t *>(p));
+    a = (double)(int)(int16_t)(r & 0xFFFFu); b = (double)((int)r >> 16);
+}
+__device__ __forceinline__ void ldpair_f64(const double *p, double &a, double &b)
+{
+    const double2 v = __ldg(reinterpret_cast<const double2 *>(p));
+    a = v.x; b = v.y;
+}
+
+template <int NC, bool PIXELS, typename CT>
+__global__ void __launch_bounds__(kWarps * 32, 2)
+k_idwt97_stream(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__ tiles, const CT *__restrict__ coef,
+                double *__restrict__ tmp, uint8_t *__restrict__ pix, int nlevels, int lvl, int strip_pairs, TailParams tp)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t tci[NC];
+    int W0, H0;
+    DevTile tile;
+    if (PIXELS) {
+        tile = tiles[blockIdx.y];
+#pragma unroll
+        for (int c = 0; c < NC; c++) tci[c] = tile.tc[c];
+        W0 = (int)tile.w; H0 = (int)tile.h;
+    } else {
+        tci[0] = blockIdx.y;
+        W0 = (int)tcs[blockIdx.y].w; H0 = (int)tcs[blockIdx.y].h;
+    }
+    const int w = lvl_dim(W0, lvl), h = lvl_dim(H0, lvl);
+    const int nlx = w >> 1, nly = h >> 1, nq = w >> 2;
+    const int nwx = (nq + 29) / 30;
+    const int nstrips = (nly + strip_pairs - 1) / strip_pairs;
+    const int unit = blockIdx.x * kWarps + warp;
+    if (unit >= nwx * nstrips) return;
+    const int strip = unit / nwx, wi = unit - strip * nwx;
+    const int q = wi * 30 - 1 + lane;
+    const bool qvalid = q >= 0 && q < nq;
+    const bool store_lane = qvalid && lane >= 1 && lane <= 30;
+    const bool q_first = q == 0, q_last = q == nq - 1;
+    const int qc = qvalid ? q : 0;
+    const int ka = strip * strip_pairs, kb = min(ka + strip_pairs, nly);
+
+    const double *prev[NC];
+    const CT *plane[NC];
+    double *dst = nullptr;
+    uint32_t nprev = 0;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        const DevTileComp tc = tcs[tci[c]];
+        double *pp0 = tmp + tc.tmp_off, *pp1 = pp0 + tc.tmp_elems;
+        prev[c] = ((lvl + 1) & 1) ? pp1 : pp0;
+        plane[c] = coef + tc.coef_off;
+        if (!PIXELS) dst = (lvl & 1) ? pp1 : pp0;
+    }
+    nprev = (lvl + 1 < nlevels) ? (uint32_t)nlx * (uint32_t)nly : 0u;      // dense prefix: elements below come from prev
+    const uint32_t uw = (uint32_t)w;
+    const uint32_t colL = 2u * (uint32_t)qc, colH = (uint32_t)nlx + colL;
+
+    // band row r of the level image (rows [0, nly) low-pass, [nly, h) high-pass) -> (L0, L1, H0, H1) of this lane
+    auto load_row = [&](int c, int r, double v[4]) {
+        const uint32_t lin = (uint32_t)r * uw;
+        if (lin + colL < nprev) ldpair_f64(prev[c] + lin + colL, v[0], v[1]); else ldpair_f64(plane[c] + lin + colL, v[0], v[1]);
+        if (lin + colH < nprev) ldpair_f64(prev[c] + lin + colH, v[2], v[3]); else ldpair_f64(plane[c] + lin + colH, v[2], v[3]);
+    };
+
+    // horizontal synthesis of a finished row (dwt.go:213-262 on the row), band order in, interleaved out
+    auto hsynth = [&](const double V[4], double X[4]) {
+        double e0 = __dmul_rn(V[0], kK), e1 = __dmul_rn(V[1], kK), o0 = __dmul_rn(V[2], kInvK), o1 = __dmul_rn(V[3], kInvK);
+        double ol = __shfl_up_sync(0xffffffffu, o1, 1);
+        ol = q_first ? o0 : ol;
+        e0 = lift(e0, kDelta, ol, o0); e1 = lift(e1, kDelta, o0, o1);
+        double er = __shfl_down_sync(0xffffffffu, e0, 1);
+        er = q_last ? e1 : er;
+        o0 = lift(o0, kGamma, e0, e1); o1 = lift(o1, kGamma, e1, er);
+        ol = __shfl_up_sync(0xffffffffu, o1, 1);
+        ol = q_first ? o0 : ol;
+        e0 = lift(e0, kBeta, ol, o0); e1 = lift(e1, kBeta, o0, o1);
+        er = __shfl_down_sync(0xffffffffu, e0, 1);
+        er = q_last ? e1 : er;
+        o0 = lift(o0, kAlpha, e0, e1); o1 = lift(o1, kAlpha, e1, er);
+        X[0] = e0; X[1] = o0; X[2] = e1; X[3] = o1;
+    };
+
+    const uint32_t gx0 = PIXELS ? tile.img_x0 + 4u * (uint32_t)qc : 0u;
+    const bool fast_rgba8 = PIXELS && NC == 3 && tp.fmt == J2KGPU_FMT_RGBA8 && tp.prec[0] == 8 && tp.prec[1] == 8 && tp.prec[2] == 8 &&
+                            tp.mct && !tp.sgnd[0] && !tp.sgnd[1] && !tp.sgnd[2] &&
+                            ((tile.out_stride & 15) == 0) && ((tile.out_off & 15) == 0) && ((tile.img_x0 & 3) == 0) &&
+                            (gx0 + 3 < tile.img_w) && (((uintptr_t)pix & 15) == 0);
+
+    // horizontal lifting of one finished row (all lanes take part in the shuffles) + store / epilogue
+    auto emit_row = [&](int y, double V[NC][4]) {
+        double X[NC][4];
+#pragma unroll
+        for (int c = 0; c < NC; c++) hsynth(V[c], X[c]);
+        if (!store_lane) return;
+        if (!PIXELS) {
+            double2 *o = reinterpret_cast<double2 *>(dst + (size_t)y * uw + 4u * (uint32_t)q);
+            o[0] = make_double2(X[0][0], X[0][1]);
+            o[1] = make_double2(X[0][2], X[0][3]);
+            return;
+        }
+        const uint32_t gy = tile.img_y0 + (uint32_t)y;
+        if (gy >= tile.img_h) return;                                  // decoder.go:398-410 clipping
+        uint8_t *row = pix + tile.out_off + (size_t)gy * tile.out_stride;
+        uint32_t px[4];
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            int32_t v[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) v[c] = c < NC ? j2k_f64_to_i32(__dadd_rn(X[c < NC ? c : 0][p], 0.5)) : 0;   // tcd.go:433-435
+            tail_mct_dc(v, tp);
+            if (fast_rgba8) px[p] = pack_sat_u8(v[1], v[0], pack_sat_u8(255, v[2], 0u));
+            else if (gx0 + p < tile.img_w) store_pixel(row, gx0 + p, v, tp);
+        }
+        if (fast_rgba8) __stcs(reinterpret_cast<uint4 *>(row + 4 * (size_t)gx0), make_uint4(px[0], px[1], px[2], px[3]));
+    };
+
+    // ---- vertical pipeline -------------------------------------------------------------------------------------------
+    double hs[NC][4], a[NC][4], b[NC][4], cc[NC][4];   // Hs_{m-1}, A_{m-1}, B_{m-2}, C_{m-2} on entry of step m
+#pragma unroll
+    for (int c = 0; c < NC; c++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) hs[c][j] = a[c][j] = b[c][j] = cc[c][j] = 0.0;
+    const int ms = ka >= 2 ? ka - 2 : 0;
+    const int me = min(kb + 1, nly + 1);
+    for (int m = ms; m <= me; m++) {
+        const bool have_in = m < nly;
+        const bool do_b = m >= 1 && m - 1 < nly, do_d = m >= 2 && m - 2 < nly;
+        double cur[NC][4], dd[NC][4];
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            double lo[4], hi[4];
+            if (have_in) { load_row(c, m, lo); load_row(c, nly + m, hi); }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                double A = a[c][j], Hs = hs[c][j];
+                if (have_in) {
+                    Hs = __dmul_rn(hi[j], kInvK);
+                    const double hl = m == 0 ? Hs : hs[c][j];
+                    A = lift(__dmul_rn(lo[j], kK), kDelta, hl, Hs);
+                }
+                double B = b[c][j], Cn = cc[c][j];
+                if (do_b) {
+                    B = lift(hs[c][j], kGamma, a[c][j], have_in ? A : a[c][j]);
+                    const double bl = m - 1 == 0 ? B : b[c][j];
+                    Cn = lift(a[c][j], kBeta, bl, B);
+                }
+                // D_{m-2} = B_{m-2} - alpha (C_{m-2} + C_{m-1}); below the last row pair C_{m-1} mirrors C_{m-2}
+                dd[c][j] = lift(b[c][j], kAlpha, cc[c][j], do_b ? Cn : cc[c][j]);
+                cur[c][j] = cc[c][j];
+                hs[c][j] = Hs; a[c][j] = A; b[c][j] = B; cc[c][j] = Cn;
+            }
+        }
+        if (do_d && m - 2 >= ka && m - 2 < kb) {
+            emit_row(2 * (m - 2), cur);
+            emit_row(2 * (m - 2) + 1, dd);
+        }
+    }
+}
+
+template <int NC, bool PIXELS, typename CT>
+cudaError_t run_ct(const IdwtLaunch &p, dim3 grid, int strip_pairs, cudaStream_t s)
+{
+    const DevTileComp *tcs = PIXELS ? p.d_tcs : p.d_tcs + p.tc_first;
+    const DevTile *tiles = p.d_tiles ? p.d_tiles + p.tile_first : nullptr;
+    J2K_LAUNCH((k_idwt97_stream<NC, PIXELS, CT>), grid, kWarps * 32, 0, s, tcs, tiles, (const CT *)p.d_coef,
+               (double *)p.d_tmp, p.d_pix, p.nlevels, p.lvl, strip_pairs, p.tail);
+    return cudaGetLastError();
+}
+
+template <int NC, bool PIXELS>
+cudaError_t run(const IdwtLaunch &p, dim3 grid, int strip_pairs, cudaStream_t s)
+{
+    return p.coef16 ? run_ct<NC, PIXELS, int16_t>(p, grid, strip_pairs, s) : run_ct<NC, PIXELS, int32_t>(p, grid, strip_pairs, s);
+}
+
+}  // namespace
+
+// Level p.lvl of every tile-component (or, with tiles, the last level fused with the pixel epilogue) of a 9-7 job whose
+// coefficient planes are int32 / int16 and whose intermediate levels are float64.  The caller has checked eligibility.
+cudaError_t launch_idwt97_stream(const IdwtLaunch &p, cudaStream_t s)
+{
+    const int lvl = p.lvl;
+    const uint32_t lw = (p.max_w + (1u << lvl) - 1) >> lvl, lh = (p.max_h + (1u << lvl) - 1) >> lvl;
+    const bool pixels = (lvl == 0 && p.d_tiles != nullptr);
+    const uint32_t nobj = pixels ? p.n_tiles : p.n_tc;
+    if (lw < 4 || lh < 2 || nobj == 0) return cudaSuccess;
+    const uint32_t nq = lw / 4, nwx = (nq + 29) / 30, nly = lh / 2;
+    // a strip costs 4 extra row pairs (pipeline warm-up above, look-ahead below): keep strips tall
+    int sp = 64;
+    while (sp > 4 && (uint64_t)nobj * nwx * ((nly + sp - 1) / sp) < 148ull * 8 * 3) sp >>= 1;
+    const uint32_t units = nwx * ((nly + sp - 1) / sp);
+    dim3 grid((units + kWarps - 1) / kWarps, nobj, 1);
+    if (pixels) {
+        switch (p.tail.ncomp) {
+        case 1: return run<1, true>(p, grid, sp, s);
+        case 3: return run<3, true>(p, grid, sp, s);
+        case 4: return run<4, true>(p, grid, sp, s);
+        }
+        return cudaErrorInvalidValue;
+    }
+    return run<1, false>(p, grid, sp, s);
+}

@@ -294,7 +294,26 @@ k_idwt53_fused(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__ 
     uint8_t *orow = pix + tile.out_off + (size_t)(tile.img_y0 + 2u * (uint32_t)ka) * tile.out_stride;
     uint32_t gy = tile.img_y0 + 2u * (uint32_t)ka;
     auto put_row = [&](int X[NC][4]) {
-        if (FAST) {
+        if (FAST && NC == 1) {
+            // one unsigned component of 8 or 16 bits: DC shift (mct.go:113-118), clamp + scale exactly as createImage
+            // (decoder.go:427-466; constant divisors), Gray8 or big-endian Gray16, one 4 / 8 byte store per lane and row
+            if (store_lane) {
+                if (tp.prec[0] == 8) {
+                    uint32_t px = 0;
+#pragma unroll
+                    for (int p = 0; p < 4; p++) px |= pack_value((int32_t)((uint32_t)X[0][p] + 128u), 8, 255, tp.iso) << (8 * p);
+                    __stcs(reinterpret_cast<uint32_t *>(orow + (size_t)gx0), px);
+                } else {
+                    uint32_t hv[4];
+#pragma unroll
+                    for (int p = 0; p < 4; p++) {
+                        const uint32_t t = pack_value((int32_t)((uint32_t)X[0][p] + 32768u), 16, 65535, tp.iso);
+                        hv[p] = (t >> 8) | ((t & 0xFFu) << 8);
+                    }
+                    __stcs(reinterpret_cast<uint2 *>(orow + 2 * (size_t)gx0), make_uint2(hv[0] | (hv[1] << 16), hv[2] | (hv[3] << 16)));
+                }
+            }
+        } else if (FAST) {
             if (store_lane) {
                 uint32_t px[4];
 #pragma unroll
@@ -395,7 +414,7 @@ cudaError_t launch_idwt53_fused(const IdwtLaunch &p, cudaStream_t s)
     const bool fast = p.fast_epi && ((uintptr_t)p.d_pix & 15) == 0;
     if (fast && p.wide_ok) return launch_idwt53_wide(p, s);
     switch (p.tail.ncomp) {
-    case 1: return run<1, false>(p, grid, sp, s);
+    case 1: return fast ? run<1, true>(p, grid, sp, s) : run<1, false>(p, grid, sp, s);
     case 3: return fast ? run<3, true>(p, grid, sp, s) : run<3, false>(p, grid, sp, s);
     case 4: return run<4, false>(p, grid, sp, s);
     }

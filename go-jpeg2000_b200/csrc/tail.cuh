@@ -18,9 +18,9 @@ __device__ __forceinline__ void tail_mct_dc(int32_t v[4], const TailParams &tp)
             double r = __dadd_rn(y, __dmul_rn(1.402, cr));
             double g = __dsub_rn(__dsub_rn(y, __dmul_rn(0.34413, cb)), __dmul_rn(0.71414, cr));
             double b = __dadd_rn(y, __dmul_rn(1.772, cb));
-            v[0] = __double2int_rz(__dadd_rn(r, 0.5));          // int32(v + 0.5) truncates toward zero
-            v[1] = __double2int_rz(__dadd_rn(g, 0.5));
-            v[2] = __double2int_rz(__dadd_rn(b, 0.5));
+            v[0] = j2k_f64_to_i32(__dadd_rn(r, 0.5));          // int32(v + 0.5) truncates toward zero
+            v[1] = j2k_f64_to_i32(__dadd_rn(g, 0.5));
+            v[2] = j2k_f64_to_i32(__dadd_rn(b, 0.5));
         }
     }
 #pragma unroll

@@ -79,6 +79,16 @@ void orc_decoder_tail(int32_t *const *comps, int ncomp, size_t n, int mct, int r
 int  orc_create_image(const int32_t *const *comps, int w, int h, int ncomp, int prec, uint8_t *pix);
 
 /* ---- whole-path driver used as the CPU baseline --------------------------- */
+/* Go float64 -> int32 conversion as the reference runs it on amd64 (CVTTSD2SL): truncation toward zero, and the
+ * "integer indefinite" value 0x80000000 for NaN and for anything outside the int32 range (the Go spec leaves the
+ * out-of-range result implementation-specific; REF parity is defined against amd64).  Written out instead of a C
+ * cast, which would be undefined behaviour out of range. */
+static inline int32_t orc_f64_to_i32(double v)
+{
+    if (!(v > -2147483649.0 && v < 2147483648.0)) return (int32_t)0x80000000u;
+    return (int32_t)v;
+}
+
 typedef struct {
     uint64_t data_off; uint32_t data_len;
     uint32_t tilecomp; uint16_t x0, y0, w, h;

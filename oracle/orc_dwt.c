@@ -131,6 +131,6 @@ void orc_apply_inverse_dwt(int32_t *d, int w, int h, int levels, int reversible)
     double *f = malloc(sizeof(double) * (n ? n : 1));
     for (size_t i = 0; i < n; i++) f[i] = (double)d[i];
     orc_reconstruct97(f, w, h, levels);
-    for (size_t i = 0; i < n; i++) d[i] = (int32_t)(f[i] + 0.5);
+    for (size_t i = 0; i < n; i++) d[i] = orc_f64_to_i32(f[i] + 0.5);
     free(f);
 }

@@ -54,7 +54,7 @@ void orc_decoder_tail(int32_t *const *comps, int ncomp, size_t n, int mct, int r
             }
             orc_inv_ict(f[0], f[1], f[2], n);
             for (int c = 0; c < 3; c++) {
-                for (size_t i = 0; i < n; i++) comps[c][i] = (int32_t)(f[c][i] + 0.5);  /* truncating */
+                for (size_t i = 0; i < n; i++) comps[c][i] = orc_f64_to_i32(f[c][i] + 0.5);  /* truncating */
                 free(f[c]);
             }
         }

@@ -50,6 +50,14 @@ CASES = [  # w, h, ncomp, prec, tile_w, tile_h, levels, reversible, ht
     (384, 256, 3, 12, 128, 128, 3, 1, 0),      # streaming kernel, RGBA64 epilogue
     (264, 136, 3, 8, 128, 128, 2, 1, 0),       # 8-wide / 8-high edge tiles (one active quad pair per warp)
     (1024, 192, 3, 8, None, None, 2, 1, 0),    # several warps across one tile row (30-quad ranges + halo lanes)
+    (480, 270, 3, 8, None, None, 5, 0, 1),     # cfg5 geometry / 4: reference HT coder + 9-7; its magnitudes overflow
+                                               # int32(float64): amd64 gives 0x80000000, not saturation
+    (512, 256, 1, 16, 256, 256, 4, 1, 1),      # cfg4 geometry / 16: Gray16, fast grayscale epilogue of the fused kernel
+    (256, 128, 1, 8, None, None, 3, 1, 1),     # Gray8 fast epilogue, int32 planes
+    (512, 256, 3, 12, 256, 256, 4, 0, 0),      # streaming 9-7 (float64) on every level, ICT, RGBA64
+    (1024, 96, 3, 8, None, None, 3, 0, 0),     # streaming 9-7, several warps per row, RGBA8 fast store
+    (384, 192, 1, 8, 192, 192, 2, 0, 0),       # streaming 9-7, one component
+    (256, 128, 4, 8, None, None, 3, 0, 1),     # streaming 9-7, four components, reference HT coder
 ]
 
 

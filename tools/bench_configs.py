@@ -1,0 +1,115 @@
+#!/usr/bin/env python3
+"""Side measurements of the other BASELINE.json configs (the bench.py line is configs[1]): each config is built in
+REF semantics with datagen/, decoded on cuda:0 through the C ABI (device-resident job), CHECKED bit-exactly against the
+CPU oracle on the full frame, and timed with CUDA events.  One JSON object per config on stdout.
+
+    python tools/bench_configs.py [cfg1 cfg3 cfg4 cfg5 ...] [--frames N]
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CONFIGS = {
+    # name: (W, H, ncomp, prec, tile, levels, reversible, ht, frames, note)
+    "cfg1": (512, 512, 3, 8, None, 5, 1, 0, 8, "512x512 RGB 8-bit lossless 5-3, 1 tile, 64x64 blocks, EBCOT"),
+    "cfg2": (3840, 2160, 3, 8, 512, 5, 1, 1, 2, "3840x2160 RGB 8-bit lossless, 512x512 tiles, RCT, reference HT coder"),
+    "cfg3": (3840, 2160, 3, 12, None, 5, 0, 0, 1, "3840x2160 RGB 12-bit lossy 9-7 EBCOT, ICT, 1 tile (REF: one quality layer)"),
+    "cfg4": (8192, 8192, 1, 16, 1024, 5, 1, 1, 1, "8192x8192 grayscale 16-bit lossless, 1024x1024 tiles, reference HT coder"),
+    "cfg5": (1920, 1080, 3, 8, None, 5, 0, 1, 32, "1920x1080 RGB 8-bit lossy 9-7 frames, reference HT coder (batch)"),
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("configs", nargs="*", default=["cfg1", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--frames", type=int, default=0)
+    ap.add_argument("--reps", type=int, default=5)
+    args = ap.parse_args()
+    import torch
+    import oracle_lib as O
+    from datagen import jobs
+    from __graft_entry__ import load_package
+    j2k = load_package()
+    ctx = j2k.Context(0)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    threads = os.cpu_count() or 1
+    for name in args.configs:
+        W, H, nc, prec, tile, lv, rev, ht, F, note = CONFIGS[name]
+        F = args.frames or F
+        t0 = time.perf_counter()
+        s = jobs.synth_image(W, H, nc, prec, seed=1000 + int(name[3:]))
+        job = jobs.build_ref_job(s, prec, tile, tile, nlevels=lv, reversible=bool(rev), ht=bool(ht), threads=threads)
+        t_gen = time.perf_counter() - t0
+        bpp = j2k.fmt_bpp(nc, prec)
+        stride = W * bpp
+        tcs, cbs = jobs.as_ctypes(job["tilecomps"], j2k.TileComp), jobs.as_ctypes(job["cblks"], j2k.CBlk)
+        blob = np.ascontiguousarray(job["blob"])
+        img = j2k.make_image(W, H, nc, prec, mct=job["mct"], reversible=rev, nlevels=lv, ht=ht)
+        outs = [np.zeros(stride * H, np.uint8) for _ in range(F)]
+        items = [j2k.BatchItem(img, tcs, len(tcs), cbs, len(cbs), blob.ctypes.data_as(j2k.u8p), blob.size,
+                               o.ctypes.data_as(j2k.u8p), stride) for o in outs]
+        J = j2k.Job(ctx, items)
+        d_blob = torch.cat([torch.from_numpy(blob)] * F + [torch.zeros(64, dtype=torch.uint8)]).cuda()
+        d_out = torch.empty(J.out_bytes, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        J.run(d_blob.data_ptr(), d_out.data_ptr())
+        stream.synchronize()
+        got = d_out[: stride * H].cpu().numpy()
+        # the checker: the oracle's whole REF path on the same job, full frame
+        oimg = O.Image()
+        oimg.width, oimg.height, oimg.ncomp = W, H, nc
+        for c in range(nc):
+            oimg.prec[c], oimg.sgnd[c] = prec, 0
+        oimg.mct, oimg.reversible, oimg.nlevels, oimg.ht = job["mct"], rev, lv, ht
+        t0 = time.perf_counter()
+        want = O.decode_image(oimg, jobs.as_ctypes(job["tilecomps"], O.TileComp), jobs.as_ctypes(job["cblks"], O.CBlk),
+                              job["blob"], stride, stride * H, threads=threads)
+        t_cpu = time.perf_counter() - t0
+        exact = bool(np.array_equal(got, want))
+        last = d_out[J.out_offset(F - 1): J.out_offset(F - 1) + stride * H].cpu().numpy()
+        exact = exact and bool(np.array_equal(last, want))
+
+        def timeit(fn):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ts = []
+            for _ in range(args.reps):
+                a.record(stream)
+                fn()
+                b.record(stream)
+                b.synchronize()
+                ts.append(a.elapsed_time(b))
+            return float(np.median(ts))
+
+        for _ in range(2):
+            J.run(d_blob.data_ptr(), d_out.data_ptr())
+        ms_all = timeit(lambda: J.run(d_blob.data_ptr(), d_out.data_ptr()))
+        ms_ent = timeit(lambda: J.run_entropy(d_blob.data_ptr()))
+        ms_dwt = timeit(lambda: J.run_dwt_mct(d_out.data_ptr()))
+        alg = (4 * W * H * nc + W * H * bpp) * F
+        print(json.dumps(dict(config=name, workload=note, frames=F, bit_exact_vs_oracle=exact, plan=J.plan,
+                              coef_plane_bytes=J.coef_bytes, code_blocks=len(job["cblks"]) * F,
+                              ms=dict(whole=round(ms_all, 3), entropy=round(ms_ent, 3), dwt_mct_pack=round(ms_dwt, 3)),
+                              mpixel_per_s=round(W * H * F / 1e3 / ms_all, 1),
+                              dwt_mct_gbs=round(alg / ms_dwt / 1e6, 1), dwt_mct_frac_of_hbm_peak=round(alg / ms_dwt / 1e6 / 6537.6, 3),
+                              cpu_oracle_mpixel_per_s=round(W * H / 1e6 / t_cpu, 1), cpu_threads=threads,
+                              datagen_s=round(t_gen, 1))), flush=True)
+        J.close()
+        del d_blob, d_out
+        torch.cuda.empty_cache()
+    ctx.set_stream(0)
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
