@@ -307,3 +307,155 @@ def write_htj2k(samples, prec, tile_w=None, tile_h=None, nlevels=5, mct=1, cb=64
     info = dict(width=W, height=H, ncomp=ncomp, prec=prec, nlevels=nlevels, mct=mct, tile_w=tile_w, tile_h=tile_h,
                 blocks=blocks_info, guard=guard, eps=eps, reversible=1, ht=1)
     return bytes(out), info
+
+
+# ------------------------------------------------------------------------------------------------ parser
+def _npasses(br):
+    """number of coding passes codeword (B.10.6)"""
+    if not br.get():
+        return 1
+    if not br.get():
+        return 2
+    v = br.bits(2)
+    if v != 3:
+        return 3 + v
+    v = br.bits(5)
+    if v != 31:
+        return 6 + v
+    return 37 + br.bits(7)
+
+
+def parse_codestream(data):
+    """main header + tile-parts + packet headers -> dict(width, height, ncomp, prec, sgnd, nlevels, reversible, mct,
+    layers, guard, tile_w, tile_h, blocks=[dict(tile, comp, res, band, level, px, py, w, h, data, passes, zbp, mb,
+    expn, mant)]).  Restrictions: see the module docstring; raises ValueError on anything else."""
+    d = bytes(data)
+    pos = 0
+
+    def u16(p):
+        return struct.unpack(">H", d[p:p + 2])[0]
+
+    if u16(0) != SOC:
+        raise ValueError("no SOC")
+    pos = 2
+    hdr = {}
+    qcd = None
+    while True:
+        m = u16(pos)
+        if m == SOT:
+            break
+        L = u16(pos + 2)
+        seg = d[pos + 4:pos + 2 + L]
+        if m == SIZ:
+            rsiz, xs, ys, xo, yo, xt, yt, xto, yto, nc = struct.unpack(">HIIIIIIIIH", seg[:36])
+            if xo or yo or xto or yto:
+                raise ValueError("non-zero image / tile origin")
+            comps = [struct.unpack(">BBB", seg[36 + 3 * i:39 + 3 * i]) for i in range(nc)]
+            if any(c[1] != 1 or c[2] != 1 for c in comps) or len({c[0] for c in comps}) != 1:
+                raise ValueError("sub-sampled or mixed-depth components")
+            hdr.update(width=xs, height=ys, tile_w=xt, tile_h=yt, ncomp=nc, prec=(comps[0][0] & 0x7F) + 1,
+                       sgnd=comps[0][0] >> 7)
+        elif m == COD:
+            scod, prog, layers, mct, nl, xcb, ycb, sty, xf = struct.unpack(">BBHBBBBBB", seg[:10])
+            if scod & 1:
+                raise ValueError("user precincts")
+            if scod & 6:
+                raise ValueError("SOP / EPH markers")
+            if prog not in (0, 1):
+                raise ValueError("progression order %d" % prog)
+            hdr.update(prog=prog, layers=layers, mct=mct, nlevels=nl, cbw=1 << (xcb + 2), cbh=1 << (ycb + 2),
+                       cblk_style=sty, reversible=int(xf == 1))
+        elif m == QCD:
+            sq = seg[0]
+            style, guard = sq & 31, sq >> 5
+            if style == 0:
+                qcd = [(b >> 3, 0) for b in seg[1:]]
+            elif style == 2:
+                qcd = [(u16(pos + 5 + 2 * i) >> 11, u16(pos + 5 + 2 * i) & 0x7FF) for i in range((L - 3) // 2)]
+            else:
+                raise ValueError("derived quantisation")
+            hdr.update(guard=guard, qstyle=style)
+        elif m in (0xFF53, 0xFF5D, 0xFF5E, 0xFF5F, 0xFF60, 0xFF61):       # COC QCC RGN POC PPM PPT
+            raise ValueError("marker %04X not supported" % m)
+        pos += 2 + L
+    nl, nc, W, H = hdr["nlevels"], hdr["ncomp"], hdr["width"], hdr["height"]
+    if hdr["cblk_style"] & ~0x40:
+        raise ValueError("code-block style %02X" % hdr["cblk_style"])
+    bands = band_list(nl)
+    ntx, nty = cdiv(W, hdr["tile_w"]), cdiv(H, hdr["tile_h"])
+    # per tile: concatenated packet bytes of its tile-parts
+    bodies = {}
+    while pos < len(d) and u16(pos) == SOT:
+        lsot, isot, psot, tp, tn = struct.unpack(">HHIBB", d[pos + 2:pos + 12])
+        end = pos + psot if psot else len(d) - 2
+        p = pos + 12
+        while u16(p) != SOD:
+            p += 2 + u16(p + 2)
+        bodies.setdefault(isot, bytearray()).extend(d[p + 2:end])
+        pos = end
+    blocks = []
+    for tidx in range(ntx * nty):
+        body = bytes(bodies.get(tidx, b""))
+        tx, ty = tidx % ntx, tidx // ntx
+        x0, y0 = tx * hdr["tile_w"], ty * hdr["tile_h"]
+        x1, y1 = min(x0 + hdr["tile_w"], W), min(y0 + hdr["tile_h"], H)
+        # code-block state per (comp, band index)
+        state = {}
+        for c in range(nc):
+            for bi, (r, b, lvl) in enumerate(bands):
+                bx0, by0, bx1, by1 = band_rect(x0, y0, x1, y1, b, lvl)
+                cbs, gw, gh = cblk_grid(bx0, by0, bx1, by1, hdr["cbw"], hdr["cbh"])
+                ox, oy = band_origin_in_plane(x0, y0, x1, y1, b, lvl)
+                expn, mant = qcd[bi]
+                ents = [dict(tile=tidx, comp=c, res=r, band=b, level=lvl, px=ox + cx0 - bx0, py=oy + cy0 - by0,
+                             w=cx1 - cx0, h=cy1 - cy0, data=bytearray(), passes=0, zbp=0, lblock=3, included=False,
+                             mb=hdr["guard"] + expn - 1, expn=expn, mant=mant)
+                        for (cx0, cy0, cx1, cy1) in cbs]
+                state[(c, bi)] = dict(ents=ents, gw=gw, gh=gh, incl=TagTree(gw, gh) if ents else None,
+                                      imsb=TagTree(gw, gh) if ents else None)
+        p = 0
+        order = [(l, r, c) for l in range(hdr["layers"]) for r in range(nl + 1) for c in range(nc)] if hdr["prog"] == 0 else \
+                [(l, r, c) for r in range(nl + 1) for l in range(hdr["layers"]) for c in range(nc)]
+        for (layer, r, c) in order:
+            if p >= len(body):
+                break
+            br = BitReader(body, p)
+            segs = []
+            if br.get():
+                for bi, (rr, b, lvl) in enumerate(bands):
+                    if rr != r:
+                        continue
+                    st = state[(c, bi)]
+                    for k, e in enumerate(st["ents"]):
+                        gx, gy = k % st["gw"], k // st["gw"]
+                        if not e["included"]:
+                            inc = st["incl"].decode(br, gx, gy, layer + 1)
+                        else:
+                            inc = bool(br.get())
+                        if not inc:
+                            continue
+                        if not e["included"]:
+                            t = 1
+                            while not st["imsb"].decode(br, gx, gy, t):
+                                t += 1
+                            e["zbp"] = int(st["imsb"].val[0][gy, gx])
+                            e["included"] = True
+                        n = _npasses(br)
+                        while br.get():
+                            e["lblock"] += 1
+                        nbits = e["lblock"] + (n.bit_length() - 1)
+                        ln = br.bits(nbits)
+                        e["passes"] += n
+                        segs.append((e, ln))
+            p = br.align()
+            for e, ln in segs:
+                e["data"] += body[p:p + ln]
+                p += ln
+        for key in sorted(state):
+            blocks += state[key]["ents"]
+    for e in blocks:
+        e["data"] = bytes(e["data"])
+        e["num_bps"] = max(e["mb"] - e["zbp"], 0)
+    hdr["blocks"] = blocks
+    hdr["qcd"] = qcd
+    return hdr

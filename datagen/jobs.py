@@ -145,3 +145,34 @@ def build_iso_job(samples, prec, tile_w=None, tile_h=None, nlevels=5, mct=1, cb=
                 nlevels=nlevels, ht=1, mode=1, tilecomps=np.array(tcs, TILECOMP_DT), cblks=cblks,
                 blob=np.frombuffer(bytes(blob), np.uint8).copy(), samples=samples, codestream=data,
                 coef_bits=max(info["eps"]) + info["guard"] - 1)      # max Mb over bands (QCD exponent + guard bits - 1)
+
+
+def build_iso_job_from_codestream(data):
+    """ISO-mode job tables from any codestream datagen.codestream.parse_codestream understands (e.g. one written by
+    OpenJPEG): classic EBCOT or HT blocks, any number of quality layers (the block's segments are concatenated and
+    num_passes says how many coding passes they hold), reversible or irreversible (step = dequantisation step)."""
+    from . import codestream as cs
+    h = cs.parse_codestream(data)
+    W, H, ncomp = h["width"], h["height"], h["ncomp"]
+    ntx = cs.cdiv(W, h["tile_w"])
+    tcs, tc_index = [], {}
+    for ty in range(cs.cdiv(H, h["tile_h"])):
+        for tx in range(ntx):
+            for c in range(ncomp):
+                tc_index[(ty * ntx + tx, c)] = len(tcs)
+                tcs.append((c, tx * h["tile_w"], ty * h["tile_h"], min((tx + 1) * h["tile_w"], W), min((ty + 1) * h["tile_h"], H), 0))
+    blks = h["blocks"]
+    cblks = np.zeros(len(blks), CBLK_DT)
+    blob = bytearray()
+    gain = {0: 0, 1: 1, 2: 1, 3: 2}
+    for i, b in enumerate(blks):
+        # Annex E.1: step = 2^(Rb - eps) * (1 + mu / 2^11), Rb = precision + band gain
+        step = 1.0 if h["reversible"] else 2.0 ** (h["prec"] + gain[b["band"]] - b["expn"]) * (1.0 + b["mant"] / 2048.0)
+        nb = b["num_bps"] if b["passes"] else 0
+        cblks[i] = (len(blob), len(b["data"]) if nb else 0, tc_index[(b["tile"], b["comp"])], b["px"], b["py"], b["w"], b["h"],
+                    b["band"], b["level"], nb, min(b["passes"], 255), step)
+        blob += b["data"]
+    return dict(width=W, height=H, ncomp=ncomp, prec=h["prec"], sgnd=h["sgnd"], mct=1 if (h["mct"] and ncomp >= 3) else 0,
+                reversible=h["reversible"], nlevels=h["nlevels"], ht=0, mode=1, tilecomps=np.array(tcs, TILECOMP_DT), cblks=cblks,
+                blob=np.frombuffer(bytes(blob) + bytes(8), np.uint8).copy(), codestream=bytes(data), layers=h["layers"],
+                coef_bits=max(e + h["guard"] - 1 for e, _ in h["qcd"]))

@@ -195,20 +195,22 @@ class Context:
 
     # ---- entropy stage ------------------------------------------------------------------------
     def _decode_blocks(self, fn, blocks, mode):
-        """blocks: list of (bytes, w, h, num_bps, band) -> list of int32 arrays (w*h each)"""
+        """blocks: list of (bytes, w, h, num_bps, band[, num_passes]) -> list of int32 arrays (w*h each)"""
         n = len(blocks)
         jobs = (BlkJob * max(n, 1))()
         blob = bytearray()
         off = 0
-        for i, (data, w, h, nbps, band) in enumerate(blocks):
-            jobs[i] = BlkJob(len(blob), len(data), off, w, h, band, nbps, 0, 0)
+        for i, blk in enumerate(blocks):
+            data, w, h, nbps, band = blk[:5]
+            jobs[i] = BlkJob(len(blob), len(data), off, w, h, band, nbps, blk[5] if len(blk) > 5 else 0, 0)
             blob += bytes(data)
             off += w * h
         blob_np = np.frombuffer(bytes(blob), np.uint8) if blob else np.zeros(1, np.uint8)
         out = np.zeros(max(off, 1), np.int32)
         self._check(fn(self._h, mode, jobs, n, _p(blob_np, u8p), len(blob), _p(out, i32p), off))
         res, o = [], 0
-        for (_, w, h, _, _) in blocks:
+        for blk in blocks:
+            w, h = blk[1], blk[2]
             res.append(out[o:o + w * h].copy())
             o += w * h
         return res

@@ -261,8 +261,6 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
     if (hdr.mode != J2KGPU_MODE_REF && hdr.mode != J2KGPU_MODE_ISO)
         return j2k_set_err(ctx, J2KGPU_E_ARG, "unknown mode %d", (int)hdr.mode);
     const bool iso = hdr.mode == J2KGPU_MODE_ISO;
-    if (iso && !hdr.ht)
-        return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "ISO mode: only HT code blocks (ISO/IEC 15444-15) are built in this revision");
     if (iso && !hdr.reversible)
         return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "ISO mode: only the reversible 5-3 path is built in this revision");
     if (hdr.nlevels > J2K_MAX_LEVELS) return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "nlevels %d > %d", (int)hdr.nlevels, J2K_MAX_LEVELS);
@@ -354,7 +352,7 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
             if ((uint32_t)cb.x0 + cb.w > d.w || (uint32_t)cb.y0 + cb.h > d.h) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_RANGE, "item %u block %u: outside its tile-component", ii, b); }
             if (cb.data_off > it.blob_len || cb.data_len > it.blob_len - cb.data_off) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_RANGE, "item %u block %u: data outside blob", ii, b); }
             if (iso && (cb.num_bps < 1 || cb.num_bps > 30) && cb.data_len) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "item %u block %u: num_bps %d outside 1..30", ii, b, (int)cb.num_bps); }
-            if (iso && cb.num_passes > 1) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "item %u block %u: HT SigProp/MagRef passes are not built in this revision", ii, b); }
+            if (iso && hdr.ht && cb.num_passes > 1) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "item %u block %u: HT SigProp/MagRef passes are not built in this revision", ii, b); }
             if (cb.num_bps > 31 || cb.band > 3) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "item %u block %u: num_bps %d / band %d", ii, b, (int)cb.num_bps, (int)cb.band); }
             DevCblk o{};
             o.data_off = blob_bytes + cb.data_off; o.data_len = cb.data_len;
@@ -445,7 +443,8 @@ static int run_entropy(j2kgpu_job *job, const void *d_blob, uint32_t ia, uint32_
     if (n == 0) return J2KGPU_OK;
     const DevCblk *cbs = job->d_cblks + ca;
     cudaError_t e;
-    if (job->iso) e = launch_ht_iso(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, job->d_steps, 0, job->hdr.coef_bits, job->ht_map, st);
+    if (job->iso && !job->hdr.ht) e = launch_t1_iso(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, job->d_steps, 0, job->max_bps, st);
+    else if (job->iso) e = launch_ht_iso(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, job->d_steps, 0, job->hdr.coef_bits, job->ht_map, st);
     else if (job->hdr.ht) e = launch_ht_ref(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, st);
     else e = launch_t1_ref(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, job->max_bps, st);
     if (e != cudaSuccess) return j2k_cuda_err(ctx, e, "entropy kernel launch");
@@ -644,7 +643,7 @@ static int stage_blocks(j2kgpu_ctx *ctx, int mode, int ht, const j2k_blkjob_t *j
 {
     if (!ctx) return J2KGPU_E_ARG;
     std::lock_guard<std::mutex> g(ctx->mu);
-    if (mode != J2KGPU_MODE_REF && !(mode == J2KGPU_MODE_ISO && ht)) return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "mode %d not built for this coder", mode);
+    if (mode != J2KGPU_MODE_REF && mode != J2KGPU_MODE_ISO) return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "mode %d not built for this coder", mode);
     if ((!jobs && n) || (!blob && blob_len) || (!out && out_len)) return j2k_set_err(ctx, J2KGPU_E_ARG, "null argument");
     if (n == 0) return J2KGPU_OK;
     cudaSetDevice(ctx->device);
@@ -659,7 +658,7 @@ static int stage_blocks(j2kgpu_ctx *ctx, int mode, int ht, const j2k_blkjob_t *j
         DevCblk &o = cbs[i];
         memset(&o, 0, sizeof o);
         o.data_off = j.data_off; o.data_len = j.data_len; o.out_off = j.out_off; o.out_stride = j.w;
-        o.w = j.w; o.h = j.h; o.band = j.band; o.num_bps = j.num_bps;
+        o.w = j.w; o.h = j.h; o.band = j.band; o.num_bps = j.num_bps; o.num_passes = j.rsv0;    // ISO EBCOT: coding passes (0 = all)
         if (j.num_bps > max_bps) max_bps = j.num_bps;
     }
     int rc;
@@ -673,6 +672,7 @@ static int stage_blocks(j2kgpu_ctx *ctx, int mode, int ht, const j2k_blkjob_t *j
     if (const char *ev = getenv("J2KGPU_HT_MAP")) ht_map = (atoi(ev) == 1) ? 1 : 32;
     cudaError_t e = (ht && mode == J2KGPU_MODE_ISO)
                         ? launch_ht_iso((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, nullptr, 0, 0, ht_map, ctx->stream)
+                    : mode == J2KGPU_MODE_ISO ? launch_t1_iso((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, nullptr, 0, max_bps, ctx->stream)
                     : ht ? launch_ht_ref((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, ctx->stream)
                        : launch_t1_ref_stage((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, (int32_t *)ctx->d_out.p, max_bps, ctx->stream);
     if (e != cudaSuccess) return j2k_cuda_err(ctx, e, "entropy kernel launch");

@@ -25,6 +25,9 @@ constexpr int kCtxZC = 0, kCtxSC = 9, kCtxMag = 14, kCtxRL = 17, kCtxUni = 18, k
 __constant__ uint32_t c_mq[94];          // qe | nmps << 16 | nlps << 24      (mqc.go:21-116)
 __constant__ uint8_t  c_zc9[4 * 512];    // band, 3x3 significance window -> ZC context (t1_luts.go:35-110)
 __constant__ uint8_t  c_sc[256];         // W,E,N,S (sig,neg) pairs -> (SC context - 9) << 1 | prediction (t1.go:387-460)
+// the same two tables filled from ISO/IEC 15444-1 Tables D.1 - D.3 (J2KGPU_MODE_ISO)
+__constant__ uint8_t  c_zc9_iso[4 * 512];
+__constant__ uint8_t  c_sc_iso[256];
 
 struct MQ {
     uint32_t A, C, CT;
@@ -93,13 +96,13 @@ __device__ __forceinline__ uint32_t win3(uint64_t row, int x)
 // decodeSign t1.go:1322-1328 with getSCContext t1.go:387-460; returns 1 for negative
 __device__ __forceinline__ uint32_t decode_sign(MQ &m, uint8_t *ctxs, int x,
                                                 uint64_t sup, uint64_t smid, uint64_t sdn,
-                                                uint64_t nup, uint64_t nmid, uint64_t ndn)
+                                                uint64_t nup, uint64_t nmid, uint64_t ndn, const uint8_t *sc = c_sc)
 {
     uint32_t ms = win3(smid, x), mn = win3(nmid, x);
     uint32_t idx = (ms & 1) | ((mn & 1) << 1) | ((ms >> 2) << 2) | ((mn >> 2) << 3) |
                    ((uint32_t)((sup >> x) & 1) << 4) | ((uint32_t)((nup >> x) & 1) << 5) |
                    ((uint32_t)((sdn >> x) & 1) << 6) | ((uint32_t)((ndn >> x) & 1) << 7);
-    uint32_t e = c_sc[idx];
+    uint32_t e = sc[idx];
     return mq_decode(m, ctxs, kCtxSC + (e >> 1)) ^ (e & 1);
 }
 
@@ -268,6 +271,230 @@ k_t1_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
     }
 }
 
+// ---- ISO/IEC 15444-1 Annex D block decoder (J2KGPU_MODE_ISO) -------------------------------------------------------
+// Same data structures as k_t1_ref (row bitmaps in shared memory, MQ state in registers, lanes in lock-step), with what
+// the standard prescribes and the reference does not: all three passes scan 4-row stripes column by
+// column, Tables D.1 - D.3 contexts, the initial states of Table D.7, and decoding stops after num_passes coding passes
+// (quality layers).  Output: sign * (2 * magnitude + mid-point of the last decoded bit-plane) / 2 as an integer for the
+// reversible path, or that twice-scale value * step / 2 as float32 bits for the irreversible one (the convention of the
+// CPU checker, which OpenJPEG pins).  Default code-block style only.
+template <typename OT>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_t1_iso(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob, OT *__restrict__ coef,
+         const float *__restrict__ steps, int irrev, int plane_words /* 64 * max_bps */)
+{
+    J2K_DYN_SMEM(uint64_t, smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t blk = blockIdx.x * kWarpsPerCta + warp;
+    if (blk >= n) return;
+    const DevCblk cb = cblks[blk];
+    const int w = cb.w, h = cb.h, nbps = cb.num_bps, band = cb.band & 3;
+    int npasses = cb.num_passes ? cb.num_passes : 3 * nbps - 2;
+    if (npasses > 3 * nbps - 2) npasses = 3 * nbps - 2;
+
+    const int words = 66 + 64 * 4 + plane_words + 4;
+    uint64_t *base = smem + (size_t)warp * words;
+    uint64_t *sig = base + 1;            // rows -1 .. 64
+    uint64_t *neg = base + 66;
+    uint64_t *visit = base + 130;
+    uint64_t *refine = base + 194;
+    uint64_t *lastc = base + 258;        // coded (became significant or refined) in the bit-plane decoded last
+    uint64_t *planes = base + 322;       // [bp][row]
+    uint8_t *ctxs = (uint8_t *)(base + 322 + plane_words);
+
+    OT *out = coef + cb.out_off;
+    const uint32_t ostride = cb.out_stride;
+    if (cb.data_len == 0 || nbps == 0 || npasses <= 0) {          // not included in any layer: all zero
+        for (int y = 0; y < h; y++)
+            for (int x = lane; x < w; x += 32) out[(size_t)y * ostride + x] = (OT)0;
+        return;
+    }
+    for (int i = lane; i < 322 + 64 * nbps; i += 32) base[i] = 0;
+    if (lane < kNumCtx) ctxs[lane] = (lane == kCtxUni) ? 92 : (lane == kCtxRL ? 6 : (lane == 0 ? 8 : 0));   // Table D.7
+    __syncwarp();
+
+    MQ mq;
+    mq_init(mq, blob + cb.data_off, (int)cb.data_len);
+    const uint64_t wmask = (w >= 64) ? ~0ull : ((1ull << w) - 1);
+    const uint8_t *zc = c_zc9_iso + band * 512;
+    int p_end = nbps - 1;
+
+    // pass sequence: cleanup of the top bit-plane, then (significance, refinement, cleanup) per lower bit-plane
+    int bp = nbps - 1, type = 2;
+    for (int pass = 0; pass < npasses && J2K_LOCKSTEP_LANE(lane); pass++) {
+        uint64_t *plane = planes + bp * 64;
+        p_end = bp;
+        for (int y0 = 0; y0 < h; y0 += 4) {
+            const bool full = (y0 + 4 <= h);
+            const int rows = full ? 4 : (h - y0);
+            uint64_t s[6], ng[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) { s[k] = sig[y0 - 1 + k]; ng[k] = neg[(y0 - 1 + k) & 63]; }
+            if (y0 == 0) ng[0] = 0;                               // neg[] has rows 0..63 only
+            if (y0 + 4 >= 64) ng[5] = 0;
+            if (type == 0) {
+                // ---- significance propagation (D.3.1): insignificant samples with a significant neighbour ----
+                uint64_t colmask = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (k >= rows) break;
+                    const uint64_t a = s[k], m = s[k + 1], c = s[k + 2];
+                    colmask |= ~m & (a | (a << 1) | (a >> 1) | (m << 1) | (m >> 1) | c | (c << 1) | (c >> 1));
+                }
+                colmask &= wmask;
+                if (!colmask) continue;
+                uint64_t v[4] = {0, 0, 0, 0}, pb[4] = {0, 0, 0, 0};
+                while (colmask) {
+                    const int x = __ffsll((long long)colmask) - 1;
+                    colmask &= colmask - 1;
+                    bool grew = false;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        if (k >= rows) break;
+                        if ((s[k + 1] >> x) & 1) continue;
+                        const uint32_t idx9 = win3(s[k], x) | (win3(s[k + 1], x) << 3) | (win3(s[k + 2], x) << 6);
+                        if ((idx9 & 0x1EF) == 0) continue;        // no significant neighbour (bit 4 is the sample itself)
+                        if (mq_decode(mq, ctxs, kCtxZC + zc[idx9])) {
+                            pb[k] |= 1ull << x;
+                            if (decode_sign(mq, ctxs, x, s[k], s[k + 1], s[k + 2], ng[k], ng[k + 1], ng[k + 2], c_sc_iso))
+                                ng[k + 1] |= 1ull << x;
+                            s[k + 1] |= 1ull << x;
+                            grew = true;
+                        }
+                        v[k] |= 1ull << x;
+                    }
+                    if (grew && x + 1 < w) colmask |= 1ull << (x + 1);    // the next column may have become a candidate
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (k < rows) {
+                        sig[y0 + k] = s[k + 1]; neg[y0 + k] = ng[k + 1]; visit[y0 + k] = v[k];
+                        if (pb[k]) { plane[y0 + k] |= pb[k]; lastc[y0 + k] |= pb[k]; }
+                    }
+            } else if (type == 1) {
+                // ---- magnitude refinement (D.3.3): significant samples not coded in this bit-plane's first pass ----
+                uint64_t cand[4], pb[4] = {0, 0, 0, 0}, rf[4], cols = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    cand[k] = k < rows ? (s[k + 1] & ~visit[(y0 + k) & 63]) : 0;
+                    rf[k] = refine[(y0 + k) & 63];
+                    cols |= cand[k];
+                }
+                if (!cols) continue;
+                while (cols) {
+                    const int x = __ffsll((long long)cols) - 1;
+                    cols &= cols - 1;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        if (!((cand[k] >> x) & 1)) continue;
+                        int ctx;
+                        if ((rf[k] >> x) & 1) ctx = kCtxMag + 2;
+                        else ctx = kCtxMag + ((win3(s[k], x) | win3(s[k + 2], x) | (win3(s[k + 1], x) & 5)) ? 1 : 0);
+                        if (mq_decode(mq, ctxs, ctx)) pb[k] |= 1ull << x;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (k < rows && cand[k]) {
+                        refine[y0 + k] = rf[k] | cand[k];
+                        lastc[y0 + k] |= cand[k];
+                        if (pb[k]) plane[y0 + k] |= pb[k];
+                    }
+            } else {
+                // ---- cleanup (D.3.4) ----
+                uint64_t v[4], pb[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) { v[k] = visit[(y0 + k) & 63]; pb[k] = 0; }
+                for (int x = 0; x < w; x++) {
+                    bool rl = false;
+                    int pos = 0;
+                    if (full) {
+                        const uint32_t any = win3(s[0], x) | win3(s[1], x) | win3(s[2], x) | win3(s[3], x) |
+                                             win3(s[4], x) | win3(s[5], x) |
+                                             (uint32_t)(((v[0] | v[1] | v[2] | v[3]) >> x) & 1);
+                        if (any == 0) {
+                            if (!mq_decode(mq, ctxs, kCtxRL)) continue;
+                            pos = (int)(mq_decode(mq, ctxs, kCtxUni) << 1);
+                            pos |= (int)mq_decode(mq, ctxs, kCtxUni);
+                            rl = true;
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        if (k >= rows) break;
+                        bool newsig;
+                        if (rl) {
+                            if (k < pos) continue;
+                            if (k == pos) newsig = true;
+                            else {
+                                const uint32_t idx9 = win3(s[k], x) | (win3(s[k + 1], x) << 3) | (win3(s[k + 2], x) << 6);
+                                newsig = mq_decode(mq, ctxs, kCtxZC + zc[idx9]) != 0;
+                            }
+                        } else {
+                            if ((v[k] >> x) & 1) continue;
+                            if ((s[k + 1] >> x) & 1) continue;
+                            const uint32_t idx9 = win3(s[k], x) | (win3(s[k + 1], x) << 3) | (win3(s[k + 2], x) << 6);
+                            newsig = mq_decode(mq, ctxs, kCtxZC + zc[idx9]) != 0;
+                        }
+                        if (newsig) {
+                            pb[k] |= 1ull << x;
+                            if (decode_sign(mq, ctxs, x, s[k], s[k + 1], s[k + 2], ng[k], ng[k + 1], ng[k + 2], c_sc_iso))
+                                ng[k + 1] |= 1ull << x;
+                            s[k + 1] |= 1ull << x;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (k < rows) {
+                        sig[y0 + k] = s[k + 1]; neg[y0 + k] = ng[k + 1]; visit[y0 + k] = 0;
+                        if (pb[k]) { plane[y0 + k] |= pb[k]; lastc[y0 + k] |= pb[k]; }
+                    }
+            }
+        }
+        if (type == 2) {
+            bp--;
+            if (pass + 1 < npasses)                                // the next bit-plane starts: nothing coded in it yet
+                for (int y = 0; y < h; y++) lastc[y] = 0;
+        }
+        type = type == 2 ? 0 : type + 1;
+    }
+#ifdef J2K_EMU
+    {   // lane 0 alone ran the passes: hand its p_end to the other lanes
+        p_end = __shfl_sync(0xffffffffu, p_end, 0);
+    }
+#endif
+    __syncwarp();
+
+    // ---- assemble: twice-scale magnitude with the mid-point of the last decoded bit-plane, sign, store ----
+    const float hstep = irrev ? 0.5f * steps[blk] : 0.0f;
+    for (int y = 0; y < h; y++) {
+        uint32_t m0 = 0, m1 = 0;
+        for (int b2 = 0; b2 < nbps; b2++) {
+            const uint64_t pr = planes[b2 * 64 + y];
+            m0 |= (uint32_t)((pr >> lane) & 1) << b2;
+            m1 |= (uint32_t)((pr >> (lane + 32)) & 1) << b2;
+        }
+        const uint64_t nr = neg[y], sr = sig[y], lr = lastc[y];
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const int x = lane + 32 * half;
+            if (x >= w) continue;
+            const uint32_t m = half ? m1 : m0;
+            uint32_t m2 = 0;
+            if ((sr >> x) & 1) m2 = (m << 1) | (1u << (((lr >> x) & 1) ? p_end : p_end + 1));
+            const bool ngt = (nr >> x) & 1;
+            if (irrev) {
+                const float f = (float)m2 * hstep;
+                out[(size_t)y * ostride + x] = (OT)__float_as_int(ngt ? -f : f);
+            } else {
+                const uint32_t v = m2 >> 1;
+                out[(size_t)y * ostride + x] = (OT)(int32_t)(ngt ? 0u - v : v);
+            }
+        }
+    }
+}
+
 // ---- host-side table construction -------------------------------------------------------------------
 // ISO/IEC 15444-1 Table C.2 rows (Qe, NMPS, NLPS, SWITCH); the reference's 94-entry table
 // (mqc.go:21-116) is this machine expanded to index 2*state + mps, entry 46 being UNI.
@@ -334,7 +561,45 @@ cudaError_t upload_tables()
         else if (hc == 2) ctx = 3;
         sc[i] = (uint8_t)((ctx << 1) | pred);
     }
+    // ISO/IEC 15444-1 Table D.1 (zero coding) and Tables D.2 / D.3 (sign coding) in the same index formats
+    uint8_t zci[4 * 512], sci[256];
+    for (int band = 0; band < 4; band++)
+        for (int i = 0; i < 512; i++) {
+            int nw = i & 1, n = (i >> 1) & 1, ne = (i >> 2) & 1, w = (i >> 3) & 1, e = (i >> 5) & 1,
+                sw = (i >> 6) & 1, s = (i >> 7) & 1, se = (i >> 8) & 1;
+            int hc = w + e, vc = n + s, dc = nw + ne + sw + se, ctx;
+            if (band == J2KGPU_BAND_HH) {
+                int hv = hc + vc;
+                if (dc >= 3) ctx = 8;
+                else if (dc == 2) ctx = hv >= 1 ? 7 : 6;
+                else if (dc == 1) ctx = hv >= 2 ? 5 : (hv == 1 ? 4 : 3);
+                else ctx = hv >= 2 ? 2 : (hv == 1 ? 1 : 0);
+            } else {
+                if (band == J2KGPU_BAND_HL) { int t = hc; hc = vc; vc = t; }
+                if (hc == 2) ctx = 8;
+                else if (hc == 1) ctx = vc >= 1 ? 7 : (dc >= 1 ? 6 : 5);
+                else if (vc == 2) ctx = 4;
+                else if (vc == 1) ctx = 3;
+                else ctx = dc >= 2 ? 2 : (dc == 1 ? 1 : 0);
+            }
+            zci[band * 512 + i] = (uint8_t)ctx;
+        }
+    for (int i = 0; i < 256; i++) {
+        int hc = 0, vc = 0;
+        if (i & 1)  hc += (i & 2) ? -1 : 1;
+        if (i & 4)  hc += (i & 8) ? -1 : 1;
+        if (i & 16) vc += (i & 32) ? -1 : 1;
+        if (i & 64) vc += (i & 128) ? -1 : 1;
+        hc = hc > 1 ? 1 : (hc < -1 ? -1 : hc);
+        vc = vc > 1 ? 1 : (vc < -1 ? -1 : vc);
+        int flip = 0;
+        if (hc < 0 || (hc == 0 && vc < 0)) { flip = 1; hc = -hc; vc = -vc; }
+        int ctx = hc == 1 ? (vc == 1 ? 4 : (vc == 0 ? 3 : 2)) : (vc == 1 ? 1 : 0);      // contexts 9..13, minus 9
+        sci[i] = (uint8_t)((ctx << 1) | flip);
+    }
     cudaError_t e;
+    if ((e = cudaMemcpyToSymbol(c_zc9_iso, zci, sizeof zci)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_sc_iso, sci, sizeof sci)) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(c_mq, mq, sizeof mq)) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(c_zc9, zc, sizeof zc)) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(c_sc, sc, sizeof sc)) != cudaSuccess) return e;
@@ -377,4 +642,26 @@ cudaError_t launch_t1_ref_stage(const DevCblk *d_cblks, uint32_t n, const uint8_
                                 int max_bps, cudaStream_t s)
 {
     return launch_t1_ref_impl(d_cblks, n, d_blob, d_coef, 0, max_bps, 0, s);
+}
+
+// ISO/IEC 15444-1 Annex D decoder (J2KGPU_MODE_ISO): num_bps magnitude bit-planes, num_passes coding passes per block
+// (0 = all); irrev: the planes receive float32 bits = value * steps[block]
+cudaError_t launch_t1_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
+                          const float *d_steps, int irrev, int max_bps, cudaStream_t s)
+{
+    if (n == 0) return cudaSuccess;
+    cudaError_t e = upload_tables();
+    if (e != cudaSuccess) return e;
+    if (max_bps < 1) max_bps = 1;
+    const int plane_words = 64 * max_bps;
+    const size_t smem = (size_t)kWarpsPerCta * (66 + 64 * 4 + plane_words + 4) * sizeof(uint64_t);
+    const uint32_t grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
+    if (coef16 && !irrev) {
+        if ((e = cudaFuncSetAttribute(k_t1_iso<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        J2K_LAUNCH((k_t1_iso<int16_t>), grid, kWarpsPerCta * 32, smem, s, d_cblks, n, d_blob, (int16_t *)d_coef, d_steps, irrev, plane_words);
+    } else {
+        if ((e = cudaFuncSetAttribute(k_t1_iso<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        J2K_LAUNCH((k_t1_iso<int32_t>), grid, kWarpsPerCta * 32, smem, s, d_cblks, n, d_blob, (int32_t *)d_coef, d_steps, irrev, plane_words);
+    }
+    return cudaGetLastError();
 }

@@ -118,7 +118,9 @@ typedef struct {
     uint64_t data_off;  uint32_t data_len;
     uint32_t out_off;           /* element offset into the int32 output array               */
     uint16_t w, h;
-    uint8_t  band, num_bps, rsv0, rsv1;
+    uint8_t  band, num_bps;
+    uint8_t  rsv0;              /* ISO mode, EBCOT: number of coding passes to decode (0 = all); else 0 */
+    uint8_t  rsv1;
 } j2k_blkjob_t;
 
 typedef struct j2kgpu_ctx j2kgpu_ctx;

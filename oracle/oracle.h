@@ -51,6 +51,9 @@ void orc_ht_decode(const uint8_t *data, int len, int w, int h, int32_t *out);
 /* ---- ISO-mode checkers (not restatements of the reference; see the file headers) ------ */
 /* ISO/IEC 15444-15 HT cleanup decoder: out = sign * (mu << (num_bps-1)); returns 0 or <0 if malformed */
 int  iso_ht_decode(const uint8_t *data, int len, int w, int h, int num_bps, int32_t *out);
+/* ISO/IEC 15444-1 Annex C/D code-block decoder (iso_t1.c): num_bps magnitude bit-planes, the first num_passes coding
+ * passes; out = sign * (2 * magnitude + mid-point of the last decoded bit-plane); band 0 LL, 1 HL, 2 LH, 3 HH */
+int  iso_t1_decode(const uint8_t *data, int len, int w, int h, int num_bps, int num_passes, int band, int32_t *out);
 
 /* ---- DWT (internal/dwt/dwt.go) ------------------------------------------ */
 void orc_inv53(int32_t *d, int n);                      /* dwt.go:122-147 */

@@ -95,6 +95,15 @@ def ht_decode(data, w, h):
     return out
 
 
+def iso_t1_decode(data, w, h, num_bps, num_passes, band):
+    """ISO EBCOT block decoder -> int32 [w*h] at twice scale with the mid-point (see oracle/iso_t1.c)"""
+    buf = np.frombuffer(bytes(data), np.uint8) if len(data) else np.zeros(1, np.uint8)
+    out = np.zeros(w * h, np.int32)
+    rc = lib().iso_t1_decode(_p(buf, u8p), len(data), w, h, num_bps, num_passes, band, _p(out, i32p))
+    assert rc == 0
+    return out
+
+
 def iso_ht_decode(data, w, h, num_bps=1):
     buf = np.frombuffer(bytes(data), np.uint8) if len(data) else np.zeros(1, np.uint8)
     out = np.zeros(w * h, np.int32)

@@ -129,3 +129,77 @@ def test_iso_coef_bits_violation_zeroes_blocks(j2k, gpu_ctx):
     job = jobs.build_iso_job(s, 8, None, None, 2)
     got = iso_pixels(j2k, gpu_ctx, job, coef_bits=2).reshape(128, 128)
     assert got.shape == (128, 128) and not np.array_equal(got, s[0].astype(np.uint8))
+
+
+# ---- classic EBCOT in ISO mode: real codestreams written by OpenJPEG ------------------------------------------------
+def opj_encode(s, **kw):
+    Image = pytest.importorskip("PIL.Image")
+    a = np.moveaxis(s, 0, 2).astype(np.uint8) if s.shape[0] == 3 else s[0].astype(np.uint8)
+    buf = io.BytesIO()
+    Image.fromarray(a).save(buf, format="JPEG2000", no_jp2=True, **kw)
+    return buf.getvalue()
+
+
+def test_iso_ebcot_blocks_vs_oracle(gpu_ctx):
+    """every code block of an OpenJPEG codestream, all passes and a random truncation, against oracle/iso_t1.c"""
+    from datagen import codestream as cs
+    s = jobs.synth_image(200, 150, 3, 8, seed=3)
+    h = cs.parse_codestream(opj_encode(s, irreversible=False, num_resolutions=4, mct=1))
+    rng = np.random.default_rng(0)
+    blocks, want = [], []
+    for b in h["blocks"]:
+        if not b["passes"]:
+            continue
+        for npass in (b["passes"], int(rng.integers(1, b["passes"] + 1))):
+            blocks.append((b["data"], b["w"], b["h"], b["num_bps"], b["band"], npass))
+            v = O.iso_t1_decode(b["data"], b["w"], b["h"], b["num_bps"], npass, b["band"])
+            want.append(np.sign(v) * (np.abs(v) >> 1))
+    assert len(blocks) > 100
+    for i, (g, w_) in enumerate(zip(gpu_ctx.t1_decode_blocks(blocks, mode=ISO), want)):
+        assert np.array_equal(g, w_), i
+
+
+def test_iso_ebcot_garbage_vs_oracle(gpu_ctx):
+    rng = np.random.default_rng(7)
+    blocks, want = [(b"", 8, 8, 5, 0, 0)], [np.zeros(64, np.int32)]
+    for _ in range(150):
+        n = int(rng.integers(1, 400))
+        d = rng.integers(0, 256, n).astype(np.uint8)
+        if rng.random() < 0.3:
+            d[rng.random(n) < 0.3] = 0xFF
+        w, h, nb, band = int(rng.integers(1, 65)), int(rng.integers(1, 65)), int(rng.integers(1, 13)), int(rng.integers(0, 4))
+        npass = int(rng.integers(0, 3 * nb))
+        blocks.append((d.tobytes(), w, h, nb, band, npass))
+        v = O.iso_t1_decode(d.tobytes(), w, h, nb, npass if npass else 3 * nb - 2, band)
+        want.append(np.sign(v) * (np.abs(v) >> 1))
+    for i, (g, w_) in enumerate(zip(gpu_ctx.t1_decode_blocks(blocks, mode=ISO), want)):
+        assert np.array_equal(g, w_), i
+
+
+@pytest.mark.parametrize("w,h,ncomp,kw", [
+    (200, 150, 3, dict(num_resolutions=4, mct=1)),
+    (512, 512, 3, dict(num_resolutions=6, mct=1)),                          # BASELINE configs[0] as a real codestream
+    (333, 211, 3, dict(num_resolutions=5, mct=1, tile_size=(128, 128))),
+    (300, 200, 1, dict(num_resolutions=3, codeblock_size=(32, 32))),
+    (256, 128, 3, dict(num_resolutions=4, mct=1, quality_mode="rates", quality_layers=[30, 10, 1])),
+    (256, 192, 3, dict(num_resolutions=5, mct=1, quality_mode="rates", quality_layers=[25])),          # truncated passes
+    (1024, 512, 3, dict(num_resolutions=6, mct=1, tile_size=(512, 512))),                               # wide fused kernel
+])
+def test_iso_whole_path_openjpeg_ebcot(j2k, gpu_ctx, w, h, ncomp, kw):
+    """a classic JPEG 2000 codestream written by OpenJPEG decodes to exactly OpenJPEG's own pixels (and to the source
+    image when lossless), with int32 and with int16 coefficient planes"""
+    Image = pytest.importorskip("PIL.Image")
+    s = jobs.synth_image(w, h, ncomp, 8, seed=w)
+    data = opj_encode(s, irreversible=False, **kw)
+    job = jobs.build_iso_job_from_codestream(data)
+    ref = np.array(Image.open(io.BytesIO(data)))
+    ref = ref[:, :, None] if ref.ndim == 2 else ref
+    for cb in (0, job["coef_bits"]):
+        img = j2k.make_image(w, h, ncomp, 8, mct=job["mct"], reversible=1, nlevels=job["nlevels"], ht=0, mode=ISO, coef_bits=cb)
+        got = gpu_ctx.decode_tiles(img, jobs.as_ctypes(job["tilecomps"], j2k.TileComp), jobs.as_ctypes(job["cblks"], j2k.CBlk),
+                                   job["blob"])
+        pix = got.reshape(h, w, -1)
+        assert np.array_equal(pix[:, :, :ncomp], ref), cb
+        if "quality_layers" not in kw or kw["quality_layers"][-1] <= 1:
+            for c in range(ncomp):
+                assert np.array_equal(pix[:, :, c], s[c].astype(np.uint8))

@@ -76,3 +76,92 @@ def test_iso_ht_oracle_rejects_malformed():
         scup = int(rng.integers(2, min(n, 4079) + 1))
         s[-1], s[-2] = scup >> 4, (s[-2] & 0xF0) | (scup & 0xF)
         O.iso_ht_decode(s.tobytes(), int(rng.integers(1, 65)), int(rng.integers(1, 65)), 1)
+
+
+# ---- classic EBCOT (ISO/IEC 15444-1 Annex C/D): tier-2 parser + oracle/iso_t1.c pinned by OpenJPEG -------------------
+def opj_encode(s, **kw):
+    a = np.moveaxis(s, 0, 2).astype(np.uint8) if s.shape[0] == 3 else s[0].astype(np.uint8)
+    buf = io.BytesIO()
+    PIL_Image.fromarray(a).save(buf, format="JPEG2000", no_jp2=True, **kw)
+    return buf.getvalue()
+
+
+def iso_inverse53(plane, w, h, levels):
+    """ISO 15444-1 inverse 5-3 on a Mallat plane: per level rows first, then columns = Inverse2D53 of the transpose"""
+    a = np.array(plane, np.int32).reshape(h, w).copy()
+    dims = [(w, h)]
+    for _ in range(levels - 1):
+        dims.append(((dims[-1][0] + 1) // 2, (dims[-1][1] + 1) // 2))
+    for (lw, lh) in (reversed(dims) if levels else []):
+        sub = np.ascontiguousarray(a[:lh, :lw].T)
+        a[:lh, :lw] = O.inv2d53(sub, lh, lw).reshape(lw, lh).T
+    return a.reshape(-1)
+
+
+def oracle_decode_reversible(data):
+    """parser -> iso_t1_decode per block -> Mallat planes -> ISO inverse 5-3 -> inverse RCT -> DC shift -> clamp"""
+    h = cs.parse_codestream(data)
+    W, H, nc, nl = h["width"], h["height"], h["ncomp"], h["nlevels"]
+    ntx = cs.cdiv(W, h["tile_w"])
+    out = np.zeros((nc, H, W), np.int64)
+    planes = {}
+    for b in h["blocks"]:
+        t = b["tile"]
+        x0, y0 = (t % ntx) * h["tile_w"], (t // ntx) * h["tile_h"]
+        x1, y1 = min(x0 + h["tile_w"], W), min(y0 + h["tile_h"], H)
+        key = (t, b["comp"])
+        if key not in planes:
+            planes[key] = (np.zeros((y1 - y0, x1 - x0), np.int32), (x0, y0, x1, y1))
+        if not b["passes"]:
+            continue
+        v = O.iso_t1_decode(b["data"], b["w"], b["h"], b["num_bps"], b["passes"], b["band"])
+        v = np.sign(v) * (np.abs(v) >> 1)                                  # reversible reconstruction: m2 / 2, truncating
+        planes[key][0][b["py"]:b["py"] + b["h"], b["px"]:b["px"] + b["w"]] = v.reshape(b["h"], b["w"])
+    for (t, c), (pl, (x0, y0, x1, y1)) in planes.items():
+        out[c, y0:y1, x0:x1] = iso_inverse53(pl.reshape(-1), x1 - x0, y1 - y0, nl).reshape(y1 - y0, x1 - x0)
+    if h["mct"] and nc >= 3:
+        y, u, v = out[0].copy(), out[1].copy(), out[2].copy()
+        g = y - ((u + v) >> 2)
+        out[0], out[1], out[2] = v + g, g, u + g
+    out += 1 << (h["prec"] - 1)
+    return np.clip(out, 0, (1 << h["prec"]) - 1), h
+
+
+EBCOT_CASES = [
+    (64, 64, 1, dict(num_resolutions=1)),
+    (200, 150, 3, dict(num_resolutions=4, mct=1)),
+    (512, 512, 3, dict(num_resolutions=6, mct=1)),                          # BASELINE configs[0] as a real codestream
+    (333, 211, 3, dict(num_resolutions=5, mct=1, tile_size=(128, 128))),
+    (300, 200, 1, dict(num_resolutions=3, codeblock_size=(32, 32))),
+    (256, 128, 3, dict(num_resolutions=4, mct=1, quality_mode="rates", quality_layers=[30, 10, 1])),   # 3 layers, lossless in total
+    (256, 192, 3, dict(num_resolutions=5, mct=1, quality_mode="rates", quality_layers=[25])),          # truncated passes (lossy 5-3)
+    (320, 240, 3, dict(num_resolutions=4, mct=1, progression="RLCP", quality_mode="rates", quality_layers=[40, 12])),
+]
+
+
+@pytest.mark.parametrize("w,h,ncomp,kw", EBCOT_CASES)
+def test_parser_and_iso_t1_oracle_match_openjpeg(w, h, ncomp, kw):
+    """OpenJPEG writes the codestream AND decodes it; our parser + ISO T1 oracle + ISO 5-3 + RCT must give the same
+    pixels (also when the stream is truncated: mid-point reconstruction m2 / 2 like OpenJPEG), and the source image
+    when the stream is lossless."""
+    s = jobs.synth_image(w, h, ncomp, 8, seed=w)
+    data = opj_encode(s, irreversible=False, **kw)
+    got, hdr = oracle_decode_reversible(data)
+    ref = opj_decode(data)
+    ref = ref[None] if ncomp == 1 else np.moveaxis(ref, 2, 0)
+    assert np.array_equal(got, ref)
+    lossless = "quality_layers" not in kw or kw["quality_layers"][-1] <= 1
+    assert np.array_equal(got, s) == lossless
+    if "quality_layers" in kw:
+        assert hdr["layers"] == len(kw["quality_layers"])
+
+
+def test_parser_reads_our_own_writer():
+    s = jobs.synth_image(200, 150, 3, 8, seed=3)
+    data, info = cs.write_htj2k(s, 8, 128, 128, 3)
+    h = cs.parse_codestream(data)
+    key = lambda e: (e["tile"], e["comp"], e["res"], e["band"], e["py"], e["px"])
+    a, b = sorted(h["blocks"], key=key), sorted(info["blocks"], key=key)
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        assert x["data"] == y["data"] and (x["px"], x["py"], x["w"], x["h"]) == (y["px"], y["py"], y["w"], y["h"])
