@@ -226,7 +226,7 @@ static void job_free(j2kgpu_job *job)
     if (!job) return;
     if (job->ctx) {
         cudaSetDevice(job->ctx->device);
-        void *ps[] = {job->d_cblks, job->d_tcs, job->d_tiles, job->d_coef, job->d_tmp, job->d_blob, job->d_pix};
+        void *ps[] = {job->d_cblks, job->d_tcs, job->d_tiles, job->d_coef, job->d_tmp, job->d_blob, job->d_pix, job->d_steps};
         for (void *p : ps) j2k_pool_free(job->ctx, p);
     }
     for (cudaEvent_t e : job->ev_in) if (e) cudaEventDestroy(e);
@@ -261,8 +261,6 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
     if (hdr.mode != J2KGPU_MODE_REF && hdr.mode != J2KGPU_MODE_ISO)
         return j2k_set_err(ctx, J2KGPU_E_ARG, "unknown mode %d", (int)hdr.mode);
     const bool iso = hdr.mode == J2KGPU_MODE_ISO;
-    if (iso && !hdr.reversible)
-        return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "ISO mode: only the reversible 5-3 path is built in this revision");
     if (hdr.nlevels > J2K_MAX_LEVELS) return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "nlevels %d > %d", (int)hdr.nlevels, J2K_MAX_LEVELS);
     const int bpp = j2k_fmt_bpp(tp.fmt);
 
@@ -274,6 +272,7 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
     std::vector<DevTileComp> tcs;
     std::vector<DevTile> tiles;
     std::vector<DevCblk> cbs;
+    std::vector<float> steps;                                  // ISO irreversible: dequantisation step per block
     uint64_t coef_elems = 0, tmp_elems = 0, blob_bytes = 0, out_bytes = 0;
     int max_bps = 0;
     bool need_clear = false;
@@ -359,6 +358,7 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
             o.out_off = d.coef_off + (uint64_t)cb.y0 * d.w + cb.x0; o.out_stride = d.w;
             o.w = cb.w; o.h = cb.h; o.band = cb.band; o.num_bps = cb.num_bps; o.level = cb.level; o.num_passes = cb.num_passes;
             cbs.push_back(o);
+            steps.push_back(cb.step);
             covered[cb.tilecomp] += (uint64_t)cb.w * cb.h;
             if (cb.data_len && cb.num_bps > max_bps) max_bps = cb.num_bps;
         }
@@ -391,7 +391,7 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
     job->wide_ok = job->fast_epi && fused_ok && tp.ncomp == 3 && !env_flag("J2KGPU_NO_WIDE");
     for (const DevTile &t : tiles) if (t.w & 15) job->wide_ok = 0;
     job->coef_elems = coef_elems; job->blob_bytes = blob_bytes; job->out_bytes = out_bytes; job->max_bps = max_bps;
-    job->tmp_bytes = tmp_elems * (hdr.reversible ? 4 : 8);
+    job->tmp_bytes = tmp_elems * ((hdr.reversible || iso) ? 4 : 8);     // int32 (5-3), float32 (ISO 9-7), float64 (REF 9-7)
     job->need_clear = need_clear;
     job->stream_levels = stream_levels;                  // some plane is not fully covered by its blocks
 
@@ -403,6 +403,7 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
         if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
     };
     up((void **)&job->d_cblks, cbs.data(), cbs.size() * sizeof(DevCblk));
+    if (iso && !hdr.reversible) up((void **)&job->d_steps, steps.data(), steps.size() * sizeof(float));
     up((void **)&job->d_tcs, tcs.data(), tcs.size() * sizeof(DevTileComp));
     up((void **)&job->d_tiles, tiles.data(), tiles.size() * sizeof(DevTile));
     if (e == cudaSuccess) job->d_coef = j2k_pool_alloc(ctx, coef_elems * (job->coef16 ? 2 : 4) + 64, &e);
@@ -443,8 +444,10 @@ static int run_entropy(j2kgpu_job *job, const void *d_blob, uint32_t ia, uint32_
     if (n == 0) return J2KGPU_OK;
     const DevCblk *cbs = job->d_cblks + ca;
     cudaError_t e;
-    if (job->iso && !job->hdr.ht) e = launch_t1_iso(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, job->d_steps, 0, job->max_bps, st);
-    else if (job->iso) e = launch_ht_iso(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, job->d_steps, 0, job->hdr.coef_bits, job->ht_map, st);
+    const int irrev = job->iso && !job->hdr.reversible;                  // ISO 9-7: the planes receive dequantised float32
+    const float *steps = job->d_steps ? job->d_steps + ca : nullptr;
+    if (job->iso && !job->hdr.ht) e = launch_t1_iso(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, steps, irrev, job->max_bps, st);
+    else if (job->iso) e = launch_ht_iso(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, steps, irrev, job->hdr.coef_bits, job->ht_map, st);
     else if (job->hdr.ht) e = launch_ht_ref(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, st);
     else e = launch_t1_ref(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, job->max_bps, st);
     if (e != cudaSuccess) return j2k_cuda_err(ctx, e, "entropy kernel launch");

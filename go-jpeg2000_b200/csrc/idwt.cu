@@ -78,6 +78,26 @@ struct Lift97 {
     }
 };
 
+// ISO mode, irreversible: float32 with OpenJPEG's constants and operation order (opj_v8dwt_decode: low-pass * K,
+// high-pass * 1.625732422 with the sub-band gain left out of the step size -- here the step carries the standard
+// gain, so the factor is 1.625732422 / 2; then x += (l + r) * c for -delta, -gamma, -beta, -alpha).  Powers of two
+// commute with float rounding, so the results are bit-identical to OpenJPEG's decoder.
+struct Lift97F {
+    typedef float T;
+    static constexpr int HALO = 4;
+    static constexpr int STEPS = 4;
+    static constexpr bool kScale = true;
+    static __device__ __forceinline__ T from_i32(int32_t v) { return __int_as_float(v); }       // planes hold float bits
+    static __device__ __forceinline__ T scale(T v, int odd) { return __fmul_rn(v, odd ? 0.8128662109375f : 1.230174105f); }
+    static __device__ __forceinline__ T apply(int step, T x, T l, T r, bool has_l, bool has_r)
+    {
+        const float c = step == 0 ? 0.443506852f : step == 1 ? 0.882911075f : step == 2 ? -0.052980118f : -1.586134342f;
+        if (!has_l) l = r;
+        if (!has_r) r = l;
+        return __fsub_rn(x, __fmul_rn(__fadd_rn(l, r), c));
+    }
+};
+
 // ---- one level of one tile-component into the shared patch -------------------------------------------
 struct LevelGeom {
     int w, h;          // level image size
@@ -278,6 +298,7 @@ k_idwt_last_pixels(const DevTileComp *__restrict__ tcs, const DevTile *__restric
     g.W = tile.w;
     g.coef16 = coef16;
 
+    constexpr bool kIsoIrrev = ISO && sizeof(T) == 4 && L::kScale;      // float32 samples stay float until after the ICT
     int32_t acc[4][PER];
 #pragma unroll
     for (int c = 0; c < 4; c++) {
@@ -293,6 +314,7 @@ k_idwt_last_pixels(const DevTileComp *__restrict__ tcs, const DevTile *__restric
             int r = e / TW, cc = e - r * TW;
             T v = P[(r + HALO) * PP + cc + HALO];
             if (sizeof(T) == 8) acc[c][k] = j2k_f64_to_i32(__dadd_rn((double)v, 0.5));   // tcd.go:433-435
+            else if (kIsoIrrev) acc[c][k] = __float_as_int((float)v);
             else acc[c][k] = (int32_t)v;
         }
         __syncthreads();
@@ -308,7 +330,12 @@ k_idwt_last_pixels(const DevTileComp *__restrict__ tcs, const DevTile *__restric
         if (gx >= tile.img_w || gy >= tile.img_h) continue;      // decoder.go:398-410 clipping
         int32_t v[4] = {acc[0][k], tp.ncomp > 1 ? acc[1][k] : 0, tp.ncomp > 2 ? acc[2][k] : 0,
                         tp.ncomp > 3 ? acc[3][k] : 0};
-        tail_mct_dc(v, tp);
+        if (kIsoIrrev) {
+            const float f[4] = {__int_as_float(v[0]), __int_as_float(v[1]), __int_as_float(v[2]), __int_as_float(v[3])};
+            tail_iso_irrev(f, v, tp);
+        } else {
+            tail_mct_dc(v, tp);
+        }
         store_pixel(img + (size_t)gy * tile.out_stride, gx, v, tp);
     }
 }
@@ -371,7 +398,10 @@ cudaError_t launch_idwt_level(const IdwtLaunch &p, cudaStream_t s, int *n_launch
     if (!p.reversible && !p.f64_io && !p.iso && p.nlevels > 0 && ((p.stream_levels >> lvl) & 1) && (lvl > 0 || pixels))
         return launch_idwt97_stream(p, s);
     if (pixels) {
-        if (p.reversible && p.iso)
+        if (!p.reversible && p.iso)
+            J2K_LAUNCH((k_idwt_last_pixels<Lift97F, true>), grid, kThreads, patch_bytes<Lift97F>(), s,
+                       p.d_tcs, p.d_tiles + p.tile_first, p.d_coef, (float *)p.d_tmp, p.d_pix, p.nlevels, p.tail, p.coef16);
+        else if (p.reversible && p.iso)
             J2K_LAUNCH((k_idwt_last_pixels<Lift53, true>), grid, kThreads, patch_bytes<Lift53>(), s,
                        p.d_tcs, p.d_tiles + p.tile_first, p.d_coef, (int32_t *)p.d_tmp, p.d_pix, p.nlevels, p.tail, p.coef16);
         else if (p.reversible)
@@ -383,6 +413,7 @@ cudaError_t launch_idwt_level(const IdwtLaunch &p, cudaStream_t s, int *n_launch
         return cudaGetLastError();
     }
     if (p.reversible) return run_level<Lift53, false, EPI_STORE>(p, grid, s);
+    if (p.iso)        return run_level<Lift97F, false, EPI_STORE>(p, grid, s);
     if (p.f64_io)     return run_level<Lift97, true, EPI_STORE>(p, grid, s);
     return run_level<Lift97, false, EPI_ROUND_I32>(p, grid, s);
 }

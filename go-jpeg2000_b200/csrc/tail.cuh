@@ -28,6 +28,27 @@ __device__ __forceinline__ void tail_mct_dc(int32_t v[4], const TailParams &tp)
         if (c < tp.ncomp && !tp.sgnd[c]) v[c] = (int32_t)((uint32_t)v[c] + (1u << (tp.prec[c] - 1)));   // mct.go:113-118
 }
 
+// ISO mode, irreversible path: float32 samples -> inverse ICT in float32 -> round to nearest even -> DC shift.
+// Operation order and constants are OpenJPEG's (opj_mct_decode_real, opj_tcd_dc_level_shift_decode), which the test
+// suite uses as the independent decoder: bit-identical output.  Clamping happens in store_pixel.
+__device__ __forceinline__ void tail_iso_irrev(const float f[4], int32_t v[4], const TailParams &tp)
+{
+    float y = f[0], u = f[1], w = f[2];
+    if (tp.mct) {
+        const float r = __fadd_rn(y, __fmul_rn(w, 1.402f));
+        const float g = __fsub_rn(__fsub_rn(y, __fmul_rn(u, 0.34413f)), __fmul_rn(w, 0.71414f));
+        const float b = __fadd_rn(y, __fmul_rn(u, 1.772f));
+        y = r; u = g; w = b;
+    }
+    const float o[4] = {y, u, w, f[3]};
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        int32_t q = __float2int_rn(o[c]);
+        if (c < tp.ncomp && !tp.sgnd[c]) q = (int32_t)((uint32_t)q + (1u << (tp.prec[c] - 1)));
+        v[c] = q;
+    }
+}
+
 // scaled sample value exactly as createImage computes it (int32 product wraps in REF mode)
 __device__ __forceinline__ uint32_t pack_value(int32_t v, int prec, int32_t maxv, bool iso)
 {

@@ -203,3 +203,29 @@ def test_iso_whole_path_openjpeg_ebcot(j2k, gpu_ctx, w, h, ncomp, kw):
         if "quality_layers" not in kw or kw["quality_layers"][-1] <= 1:
             for c in range(ncomp):
                 assert np.array_equal(pix[:, :, c], s[c].astype(np.uint8))
+
+
+@pytest.mark.parametrize("w,h,ncomp,kw", [
+    (256, 256, 1, dict(num_resolutions=4, quality_mode="rates", quality_layers=[10])),
+    (256, 256, 3, dict(num_resolutions=6, mct=1, quality_mode="rates", quality_layers=[20])),
+    (200, 150, 3, dict(num_resolutions=4, mct=1, quality_mode="rates", quality_layers=[40, 20, 8])),              # 3 layers
+    (333, 211, 3, dict(num_resolutions=5, mct=1, tile_size=(128, 128), quality_mode="dB", quality_layers=[38])),  # ragged tiles
+    (1024, 512, 3, dict(num_resolutions=6, mct=1, tile_size=(512, 512), quality_mode="rates", quality_layers=[12])),
+])
+def test_iso_whole_path_openjpeg_lossy_97(j2k, gpu_ctx, w, h, ncomp, kw):
+    """lossy 9-7 + ICT codestreams written by OpenJPEG decode to OpenJPEG's own pixels: max |delta| <= 1 LSB is the
+    north_star tolerance for the irreversible path; the kernels use OpenJPEG's constants and operation order in
+    float32, so the expected difference is zero"""
+    Image = pytest.importorskip("PIL.Image")
+    s = jobs.synth_image(w, h, ncomp, 8, seed=w)
+    data = opj_encode(s, irreversible=True, **kw)
+    job = jobs.build_iso_job_from_codestream(data)
+    img = j2k.make_image(w, h, ncomp, 8, mct=job["mct"], reversible=0, nlevels=job["nlevels"], ht=0, mode=ISO)
+    got = gpu_ctx.decode_tiles(img, jobs.as_ctypes(job["tilecomps"], j2k.TileComp), jobs.as_ctypes(job["cblks"], j2k.CBlk),
+                               job["blob"])
+    pix = got.reshape(h, w, -1)
+    ref = np.array(Image.open(io.BytesIO(data)))
+    ref = ref[:, :, None] if ref.ndim == 2 else ref
+    d = np.abs(pix[:, :, :ncomp].astype(np.int64) - ref.astype(np.int64))
+    assert d.max() <= 1                                                     # tolerance stated by north_star
+    assert d.max() == 0                                                     # what the design achieves
