@@ -395,7 +395,7 @@ cudaError_t launch_idwt_level(const IdwtLaunch &p, cudaStream_t s, int *n_launch
     if (grid.z == 0) return cudaSuccess;
     if (p.reversible && p.nlevels > 0 && ((p.stream_levels >> lvl) & 1) && (lvl > 0 || pixels))
         return launch_idwt53_stream(p, s);
-    if (!p.reversible && !p.f64_io && !p.iso && p.nlevels > 0 && ((p.stream_levels >> lvl) & 1) && (lvl > 0 || pixels))
+    if (!p.reversible && !p.f64_io && p.nlevels > 0 && ((p.stream_levels >> lvl) & 1) && (lvl > 0 || pixels))
         return launch_idwt97_stream(p, s);
     if (pixels) {
         if (!p.reversible && p.iso)

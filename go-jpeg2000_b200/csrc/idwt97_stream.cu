@@ -24,12 +24,30 @@
 namespace {
 
 constexpr int kWarps = 4;
-constexpr double kK = 1.230174104914001, kInvK = 0.812893066115961;                       // dwt.go:150-157
-constexpr double kDelta = 0.443506852043971, kGamma = 0.882911075530934, kBeta = -0.052980118572961, kAlpha = -1.586134342059924;
+
+// REF: float64, the reference's constants (dwt.go:150-157).  ISO: float32 with OpenJPEG's constants and operation order
+// (opj_v8dwt_decode; the high-pass factor is its 1.625732422 / 2 because the step sizes here carry the standard sub-band
+// gain) -- powers of two commute with float rounding, so the results are bit-identical to OpenJPEG's decoder.
+template <typename T> struct C97;
+template <> struct C97<double> {
+    static constexpr double K = 1.230174104914001, InvK = 0.812893066115961;
+    static constexpr double Delta = 0.443506852043971, Gamma = 0.882911075530934, Beta = -0.052980118572961, Alpha = -1.586134342059924;
+};
+template <> struct C97<float> {
+    static constexpr float K = 1.230174105f, InvK = 0.8128662109375f;
+    static constexpr float Delta = 0.443506852f, Gamma = 0.882911075f, Beta = -0.052980118f, Alpha = -1.586134342f;
+};
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
 
 __device__ __forceinline__ int lvl_dim(int full, int lvl) { return (full + (1 << lvl) - 1) >> lvl; }
-// x - c * (l + r), three roundings like the reference (dwt.go:229-261)
-__device__ __forceinline__ double lift(double x, double c, double l, double r) { return __dsub_rn(x, __dmul_rn(c, __dadd_rn(l, r))); }
+// x - c * (l + r), three roundings, never an FMA (dwt.go:229-261; OpenJPEG: x += (l + r) * -c, the same value)
+template <typename T>
+__device__ __forceinline__ T lift(T x, T c, T l, T r) { return sub_rn(x, mul_rn(c, add_rn(l, r))); }
 
 // d = sat_u8(b) | sat_u8(a) << 8 | c << 16
 __device__ __forceinline__ uint32_t pack_sat_u8(int a, int b, uint32_t c)
@@ -59,12 +77,20 @@ __device__ __forceinline__ void ldpair_f64(const double *p, double &a, double &b
     const double2 v = __ldg(reinterpret_cast<const double2 *>(p));
     a = v.x; b = v.y;
 }
+__device__ __forceinline__ void ldpair_f64(const float *p, float &a, float &b)          // ISO: planes and levels are float32
+{
+    const float2 v = __ldg(reinterpret_cast<const float2 *>(p));
+    a = v.x; b = v.y;
+}
 
-template <int NC, bool PIXELS, typename CT>
+// T = double, ISO = false: REF semantics (dense prefix, columns then rows, planes int32 / int16).
+// T = float,  ISO = true : ISO semantics (Mallat layout, rows then columns, planes hold dequantised float32).
+template <int NC, bool PIXELS, typename CT, typename T, bool ISO>
 __global__ void __launch_bounds__(kWarps * 32, 2)
 k_idwt97_stream(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__ tiles, const CT *__restrict__ coef,
-                double *__restrict__ tmp, uint8_t *__restrict__ pix, int nlevels, int lvl, int strip_pairs, TailParams tp)
+                T *__restrict__ tmp, uint8_t *__restrict__ pix, int nlevels, int lvl, int strip_pairs, TailParams tp)
 {
+    typedef C97<T> K;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t tci[NC];
     int W0, H0;
@@ -92,14 +118,14 @@ k_idwt97_stream(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__
     const int qc = qvalid ? q : 0;
     const int ka = strip * strip_pairs, kb = min(ka + strip_pairs, nly);
 
-    const double *prev[NC];
+    const T *prev[NC];
     const CT *plane[NC];
-    double *dst = nullptr;
+    T *dst = nullptr;
     uint32_t nprev = 0;
 #pragma unroll
     for (int c = 0; c < NC; c++) {
         const DevTileComp tc = tcs[tci[c]];
-        double *pp0 = tmp + tc.tmp_off, *pp1 = pp0 + tc.tmp_elems;
+        T *pp0 = tmp + tc.tmp_off, *pp1 = pp0 + tc.tmp_elems;
         prev[c] = ((lvl + 1) & 1) ? pp1 : pp0;
         plane[c] = coef + tc.coef_off;
         if (!PIXELS) dst = (lvl & 1) ? pp1 : pp0;
@@ -109,46 +135,66 @@ k_idwt97_stream(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__
     const uint32_t colL = 2u * (uint32_t)qc, colH = (uint32_t)nlx + colL;
 
     // band row r of the level image (rows [0, nly) low-pass, [nly, h) high-pass) -> (L0, L1, H0, H1) of this lane
-    auto load_row = [&](int c, int r, double v[4]) {
-        const uint32_t lin = (uint32_t)r * uw;
-        if (lin + colL < nprev) ldpair_f64(prev[c] + lin + colL, v[0], v[1]); else ldpair_f64(plane[c] + lin + colL, v[0], v[1]);
-        if (lin + colH < nprev) ldpair_f64(prev[c] + lin + colH, v[2], v[3]); else ldpair_f64(plane[c] + lin + colH, v[2], v[3]);
+    const uint32_t planeW = (uint32_t)W0;             // ISO: row stride of the Mallat plane
+    auto load_row = [&](int c, int r, T v[4]) {
+        if (ISO) {
+            const CT *rowp = plane[c] + (size_t)r * planeW;
+            if (r < nly && nprev) ldpair_f64(prev[c] + (size_t)r * (uint32_t)nlx + colL, v[0], v[1]);
+            else ldpair_f64(rowp + colL, v[0], v[1]);
+            ldpair_f64(rowp + colH, v[2], v[3]);
+        } else {
+            const uint32_t lin = (uint32_t)r * uw;
+            if (lin + colL < nprev) ldpair_f64(prev[c] + lin + colL, v[0], v[1]); else ldpair_f64(plane[c] + lin + colL, v[0], v[1]);
+            if (lin + colH < nprev) ldpair_f64(prev[c] + lin + colH, v[2], v[3]); else ldpair_f64(plane[c] + lin + colH, v[2], v[3]);
+        }
     };
 
     // horizontal synthesis of a finished row (dwt.go:213-262 on the row), band order in, interleaved out
-    auto hsynth = [&](const double V[4], double X[4]) {
-        double e0 = __dmul_rn(V[0], kK), e1 = __dmul_rn(V[1], kK), o0 = __dmul_rn(V[2], kInvK), o1 = __dmul_rn(V[3], kInvK);
-        double ol = __shfl_up_sync(0xffffffffu, o1, 1);
+    auto hsynth = [&](const T V[4], T X[4]) {
+        T e0 = mul_rn(V[0], (T)K::K), e1 = mul_rn(V[1], (T)K::K), o0 = mul_rn(V[2], (T)K::InvK), o1 = mul_rn(V[3], (T)K::InvK);
+        T ol = __shfl_up_sync(0xffffffffu, o1, 1);
         ol = q_first ? o0 : ol;
-        e0 = lift(e0, kDelta, ol, o0); e1 = lift(e1, kDelta, o0, o1);
-        double er = __shfl_down_sync(0xffffffffu, e0, 1);
+        e0 = lift<T>(e0, K::Delta, ol, o0); e1 = lift<T>(e1, K::Delta, o0, o1);
+        T er = __shfl_down_sync(0xffffffffu, e0, 1);
         er = q_last ? e1 : er;
-        o0 = lift(o0, kGamma, e0, e1); o1 = lift(o1, kGamma, e1, er);
+        o0 = lift<T>(o0, K::Gamma, e0, e1); o1 = lift<T>(o1, K::Gamma, e1, er);
         ol = __shfl_up_sync(0xffffffffu, o1, 1);
         ol = q_first ? o0 : ol;
-        e0 = lift(e0, kBeta, ol, o0); e1 = lift(e1, kBeta, o0, o1);
+        e0 = lift<T>(e0, K::Beta, ol, o0); e1 = lift<T>(e1, K::Beta, o0, o1);
         er = __shfl_down_sync(0xffffffffu, e0, 1);
         er = q_last ? e1 : er;
-        o0 = lift(o0, kAlpha, e0, e1); o1 = lift(o1, kAlpha, e1, er);
+        o0 = lift<T>(o0, K::Alpha, e0, e1); o1 = lift<T>(o1, K::Alpha, e1, er);
         X[0] = e0; X[1] = o0; X[2] = e1; X[3] = o1;
     };
 
     const uint32_t gx0 = PIXELS ? tile.img_x0 + 4u * (uint32_t)qc : 0u;
     const bool fast_rgba8 = PIXELS && NC == 3 && tp.fmt == J2KGPU_FMT_RGBA8 && tp.prec[0] == 8 && tp.prec[1] == 8 && tp.prec[2] == 8 &&
-                            tp.mct && !tp.sgnd[0] && !tp.sgnd[1] && !tp.sgnd[2] &&
+                            !tp.sgnd[0] && !tp.sgnd[1] && !tp.sgnd[2] && (ISO || tp.mct) &&
                             ((tile.out_stride & 15) == 0) && ((tile.out_off & 15) == 0) && ((tile.img_x0 & 3) == 0) &&
                             (gx0 + 3 < tile.img_w) && (((uintptr_t)pix & 15) == 0);
 
     // horizontal lifting of one finished row (all lanes take part in the shuffles) + store / epilogue
-    auto emit_row = [&](int y, double V[NC][4]) {
-        double X[NC][4];
+    // REF: the finished row is in band-column order and still needs the horizontal synthesis; ISO: it is final
+    auto emit_row = [&](int y, T V[NC][4]) {
+        T X[NC][4];
 #pragma unroll
-        for (int c = 0; c < NC; c++) hsynth(V[c], X[c]);
+        for (int c = 0; c < NC; c++) {
+            if (ISO) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) X[c][j] = V[c][j];
+            } else {
+                hsynth(V[c], X[c]);
+            }
+        }
         if (!store_lane) return;
         if (!PIXELS) {
-            double2 *o = reinterpret_cast<double2 *>(dst + (size_t)y * uw + 4u * (uint32_t)q);
-            o[0] = make_double2(X[0][0], X[0][1]);
-            o[1] = make_double2(X[0][2], X[0][3]);
+            T *o = dst + (size_t)y * uw + 4u * (uint32_t)q;
+            if (sizeof(T) == 8) {
+                reinterpret_cast<double2 *>(o)[0] = make_double2((double)X[0][0], (double)X[0][1]);
+                reinterpret_cast<double2 *>(o)[1] = make_double2((double)X[0][2], (double)X[0][3]);
+            } else {
+                *reinterpret_cast<float4 *>(o) = make_float4((float)X[0][0], (float)X[0][1], (float)X[0][2], (float)X[0][3]);
+            }
             return;
         }
         const uint32_t gy = tile.img_y0 + (uint32_t)y;
@@ -158,9 +204,15 @@ k_idwt97_stream(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__
 #pragma unroll
         for (int p = 0; p < 4; p++) {
             int32_t v[4];
+            if (ISO) {
+                const float f[4] = {(float)X[0][p], NC > 1 ? (float)X[NC > 1 ? 1 : 0][p] : 0.f, NC > 2 ? (float)X[NC > 2 ? 2 : 0][p] : 0.f,
+                                    NC > 3 ? (float)X[NC > 3 ? 3 : 0][p] : 0.f};
+                tail_iso_irrev(f, v, tp);
+            } else {
 #pragma unroll
-            for (int c = 0; c < 4; c++) v[c] = c < NC ? j2k_f64_to_i32(__dadd_rn(X[c < NC ? c : 0][p], 0.5)) : 0;   // tcd.go:433-435
-            tail_mct_dc(v, tp);
+                for (int c = 0; c < 4; c++) v[c] = c < NC ? j2k_f64_to_i32(__dadd_rn((double)X[c < NC ? c : 0][p], 0.5)) : 0;   // tcd.go:433-435
+                tail_mct_dc(v, tp);
+            }
             if (fast_rgba8) px[p] = pack_sat_u8(v[1], v[0], pack_sat_u8(255, v[2], 0u));
             else if (gx0 + p < tile.img_w) store_pixel(row, gx0 + p, v, tp);
         }
@@ -168,37 +220,48 @@ k_idwt97_stream(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__
     };
 
     // ---- vertical pipeline -------------------------------------------------------------------------------------------
-    double hs[NC][4], a[NC][4], b[NC][4], cc[NC][4];   // Hs_{m-1}, A_{m-1}, B_{m-2}, C_{m-2} on entry of step m
+    T hs[NC][4], a[NC][4], b[NC][4], cc[NC][4];   // Hs_{m-1}, A_{m-1}, B_{m-2}, C_{m-2} on entry of step m
 #pragma unroll
     for (int c = 0; c < NC; c++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) hs[c][j] = a[c][j] = b[c][j] = cc[c][j] = 0.0;
+        for (int j = 0; j < 4; j++) hs[c][j] = a[c][j] = b[c][j] = cc[c][j] = (T)0;
     const int ms = ka >= 2 ? ka - 2 : 0;
     const int me = min(kb + 1, nly + 1);
     for (int m = ms; m <= me; m++) {
         const bool have_in = m < nly;
         const bool do_b = m >= 1 && m - 1 < nly, do_d = m >= 2 && m - 2 < nly;
-        double cur[NC][4], dd[NC][4];
+        T cur[NC][4], dd[NC][4];
 #pragma unroll
         for (int c = 0; c < NC; c++) {
-            double lo[4], hi[4];
-            if (have_in) { load_row(c, m, lo); load_row(c, nly + m, hi); }
+            T lo[4], hi[4];
+            if (have_in) {
+                load_row(c, m, lo); load_row(c, nly + m, hi);
+                if (ISO) {                                             // rows first: both band rows become interleaved samples
+                    T x[4];
+                    hsynth(lo, x);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) lo[j] = x[j];
+                    hsynth(hi, x);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) hi[j] = x[j];
+                }
+            }
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                double A = a[c][j], Hs = hs[c][j];
+                T A = a[c][j], Hs = hs[c][j];
                 if (have_in) {
-                    Hs = __dmul_rn(hi[j], kInvK);
-                    const double hl = m == 0 ? Hs : hs[c][j];
-                    A = lift(__dmul_rn(lo[j], kK), kDelta, hl, Hs);
+                    Hs = mul_rn(hi[j], (T)K::InvK);
+                    const T hl = m == 0 ? Hs : hs[c][j];
+                    A = lift<T>(mul_rn(lo[j], (T)K::K), K::Delta, hl, Hs);
                 }
-                double B = b[c][j], Cn = cc[c][j];
+                T B = b[c][j], Cn = cc[c][j];
                 if (do_b) {
-                    B = lift(hs[c][j], kGamma, a[c][j], have_in ? A : a[c][j]);
-                    const double bl = m - 1 == 0 ? B : b[c][j];
-                    Cn = lift(a[c][j], kBeta, bl, B);
+                    B = lift<T>(hs[c][j], K::Gamma, a[c][j], have_in ? A : a[c][j]);
+                    const T bl = m - 1 == 0 ? B : b[c][j];
+                    Cn = lift<T>(a[c][j], K::Beta, bl, B);
                 }
                 // D_{m-2} = B_{m-2} - alpha (C_{m-2} + C_{m-1}); below the last row pair C_{m-1} mirrors C_{m-2}
-                dd[c][j] = lift(b[c][j], kAlpha, cc[c][j], do_b ? Cn : cc[c][j]);
+                dd[c][j] = lift<T>(b[c][j], K::Alpha, cc[c][j], do_b ? Cn : cc[c][j]);
                 cur[c][j] = cc[c][j];
                 hs[c][j] = Hs; a[c][j] = A; b[c][j] = B; cc[c][j] = Cn;
             }
@@ -210,20 +273,22 @@ k_idwt97_stream(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__
     }
 }
 
-template <int NC, bool PIXELS, typename CT>
+template <int NC, bool PIXELS, typename CT, typename T, bool ISO>
 cudaError_t run_ct(const IdwtLaunch &p, dim3 grid, int strip_pairs, cudaStream_t s)
 {
     const DevTileComp *tcs = PIXELS ? p.d_tcs : p.d_tcs + p.tc_first;
     const DevTile *tiles = p.d_tiles ? p.d_tiles + p.tile_first : nullptr;
-    J2K_LAUNCH((k_idwt97_stream<NC, PIXELS, CT>), grid, kWarps * 32, 0, s, tcs, tiles, (const CT *)p.d_coef,
-               (double *)p.d_tmp, p.d_pix, p.nlevels, p.lvl, strip_pairs, p.tail);
+    J2K_LAUNCH((k_idwt97_stream<NC, PIXELS, CT, T, ISO>), grid, kWarps * 32, 0, s, tcs, tiles, (const CT *)p.d_coef,
+               (T *)p.d_tmp, p.d_pix, p.nlevels, p.lvl, strip_pairs, p.tail);
     return cudaGetLastError();
 }
 
 template <int NC, bool PIXELS>
 cudaError_t run(const IdwtLaunch &p, dim3 grid, int strip_pairs, cudaStream_t s)
 {
-    return p.coef16 ? run_ct<NC, PIXELS, int16_t>(p, grid, strip_pairs, s) : run_ct<NC, PIXELS, int32_t>(p, grid, strip_pairs, s);
+    if (p.iso) return run_ct<NC, PIXELS, float, float, true>(p, grid, strip_pairs, s);
+    return p.coef16 ? run_ct<NC, PIXELS, int16_t, double, false>(p, grid, strip_pairs, s)
+                    : run_ct<NC, PIXELS, int32_t, double, false>(p, grid, strip_pairs, s);
 }
 
 }  // namespace

@@ -28,6 +28,81 @@ CONFIGS = {
 }
 
 
+ISO_CONFIGS = {
+    # name: (W, H, ncomp, Pillow/OpenJPEG encoder options, frames, note)
+    "iso_cfg1": (512, 512, 3, dict(irreversible=False, num_resolutions=6, mct=1), 8,
+                 "configs[0] as a real codestream: 512x512 RGB 8-bit lossless 5-3, 1 tile, 64x64 blocks, EBCOT, written by OpenJPEG"),
+    "iso_4k_ebcot": (3840, 2160, 3, dict(irreversible=False, num_resolutions=6, mct=1, tile_size=(512, 512)), 2,
+                     "3840x2160 RGB 8-bit lossless 5-3, 512x512 tiles, EBCOT, written by OpenJPEG"),
+    "iso_4k_lossy": (3840, 2160, 3, dict(irreversible=True, num_resolutions=6, mct=1, quality_mode="rates", quality_layers=[80, 40, 20, 10, 5]), 2,
+                     "3840x2160 RGB 8-bit lossy 9-7 EBCOT, ICT, 5 quality layers, LRCP, 1 tile, written by OpenJPEG (configs[2] at 8 bits)"),
+}
+
+
+def run_iso(name, args, j2k, ctx, stream):
+    """a codestream written by OpenJPEG (through Pillow) -> harness tier-2 -> GPU decode in J2KGPU_MODE_ISO, checked
+    against OpenJPEG's own decode of the same bytes"""
+    import io
+    import torch
+    from PIL import Image
+    from datagen import jobs
+    W, H, nc, kw, F, note = ISO_CONFIGS[name]
+    F = args.frames or F
+    s = jobs.synth_image(W, H, nc, 8, seed=77)
+    buf = io.BytesIO()
+    t0 = time.perf_counter()
+    Image.fromarray(np.moveaxis(s, 0, 2).astype(np.uint8)).save(buf, format="JPEG2000", no_jp2=True, **kw)
+    t_enc = time.perf_counter() - t0
+    data = buf.getvalue()
+    t0 = time.perf_counter()
+    job = jobs.build_iso_job_from_codestream(data)
+    t_parse = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    im = Image.open(io.BytesIO(data))
+    im.load()
+    t_opj = time.perf_counter() - t0
+    ref = np.array(im)
+    stride = W * 4
+    tcs, cbs = jobs.as_ctypes(job["tilecomps"], j2k.TileComp), jobs.as_ctypes(job["cblks"], j2k.CBlk)
+    blob = np.ascontiguousarray(job["blob"])
+    img = j2k.make_image(W, H, nc, 8, mct=job["mct"], reversible=job["reversible"], nlevels=job["nlevels"], ht=0, mode=1,
+                         coef_bits=job["coef_bits"])
+    outs = [np.zeros(stride * H, np.uint8) for _ in range(F)]
+    items = [j2k.BatchItem(img, tcs, len(tcs), cbs, len(cbs), blob.ctypes.data_as(j2k.u8p), blob.size,
+                           o.ctypes.data_as(j2k.u8p), stride) for o in outs]
+    J = j2k.Job(ctx, items)
+    d_blob = torch.cat([torch.from_numpy(blob)] * F + [torch.zeros(64, dtype=torch.uint8)]).cuda()
+    d_out = torch.empty(J.out_bytes, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    J.run(d_blob.data_ptr(), d_out.data_ptr())
+    stream.synchronize()
+    got = d_out[J.out_offset(F - 1): J.out_offset(F - 1) + stride * H].cpu().numpy().reshape(H, W, 4)
+    d = np.abs(got[:, :, :nc].astype(np.int64) - ref.astype(np.int64))
+
+    def timeit(fn):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ts = []
+        for _ in range(args.reps):
+            a.record(stream)
+            fn()
+            b.record(stream)
+            b.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+
+    ms_all = timeit(lambda: J.run(d_blob.data_ptr(), d_out.data_ptr()))
+    ms_ent = timeit(lambda: J.run_entropy(d_blob.data_ptr()))
+    ms_dwt = timeit(lambda: J.run_dwt_mct(d_out.data_ptr()))
+    print(json.dumps(dict(config=name, workload=note, frames=F, codestream_bytes=len(data), layers=job["layers"],
+                          max_abs_diff_vs_openjpeg=int(d.max()), plan=J.plan, coef_plane_bytes=J.coef_bytes,
+                          code_blocks=len(job["cblks"]) * F,
+                          ms=dict(whole=round(ms_all, 3), entropy=round(ms_ent, 3), dwt_mct_pack=round(ms_dwt, 3)),
+                          mpixel_per_s=round(W * H * F / 1e3 / ms_all, 1),
+                          openjpeg_cpu_mpixel_per_s=round(W * H / 1e6 / t_opj, 2),
+                          harness_s=dict(openjpeg_encode=round(t_enc, 2), python_tier2_parse=round(t_parse, 2)))), flush=True)
+    J.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("configs", nargs="*", default=["cfg1", "cfg3", "cfg4", "cfg5"])
@@ -45,6 +120,9 @@ def main():
     ctx.set_stream(stream.cuda_stream)
     threads = os.cpu_count() or 1
     for name in args.configs:
+        if name in ISO_CONFIGS:
+            run_iso(name, args, j2k, ctx, stream)
+            continue
         W, H, nc, prec, tile, lv, rev, ht, F, note = CONFIGS[name]
         F = args.frames or F
         t0 = time.perf_counter()
