@@ -564,7 +564,8 @@ static int run_host_locked(j2kgpu_job *job, const j2k_batch_item_t *items)
     // launch (its run time is one block's serial chain whatever the count), so its chunks hold >= 16K blocks.
     const uint32_t n = job->n_img;
     uint32_t per = n >= 16 ? (n + 7) / 8 : 1;
-    if (job->iso && job->ht_map == 32 && job->n_cb) {
+    const bool thread_per_block = job->hdr.ht && (job->iso ? job->ht_map == 32 : j2k_htref_map() == 32);
+    if (thread_per_block && job->n_cb) {
         const uint64_t blocks_per_item = (job->n_cb + n - 1) / n;
         const uint32_t need = (uint32_t)((16384 + blocks_per_item - 1) / blocks_per_item);
         if (need > per) per = need < n ? need : n;

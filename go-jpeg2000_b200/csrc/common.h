@@ -137,6 +137,7 @@ cudaError_t launch_t1_ref(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_b
                           int max_bps, cudaStream_t s);
 cudaError_t launch_ht_ref(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
                           cudaStream_t s);
+int j2k_htref_map();             // code blocks per warp of the reference-HT decoder: 32 (thread per block, default) or 1
 // ISO/IEC 15444-1 Annex D decoder (stripe-order passes, standard tables, pass truncation), one warp per block
 cudaError_t launch_t1_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
                           const float *d_steps, int irrev, int max_bps, cudaStream_t s);

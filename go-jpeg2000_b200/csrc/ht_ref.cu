@@ -12,6 +12,7 @@
 // Go semantics kept: uint32 shifts >= 32 give 0; the uint32 "bits" counters wrap when a MagSgn
 // field is longer than the buffered bits (emb up to 37, ht.go:668-669).
 #include "common.h"
+#include <cstdlib>
 
 namespace {
 
@@ -230,14 +231,40 @@ __device__ __forceinline__ int32_t magsgn_sample(Fwd &ms, uint32_t emb)
     return (int32_t)(sign ? 0u - m : m);
 }
 
-template <typename OT>
+// Mapping (template BPW = code blocks per warp), like ht_iso.cu: the block's bit streams are one serial chain, so
+//   BPW = 1   one warp per block: every lane runs the chain on uniform registers, lane 0 stores;
+//   BPW = 32  one thread per block: 32 independent chains per warp (short divergent branches), 32x fewer
+//             warp-instructions for the same work; the zero fill of the 32 blocks is done by the whole warp first.
+// The launcher picks by J2KGPU_HTREF_MAP (default thread per block).
+template <int BPW, typename OT>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 k_ht_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob,
          OT *__restrict__ coef)
 {
-    __shared__ uint8_t s_sigma[kWarpsPerCta][20];       // quadCols + 1 <= 17 for w <= 64
+    __shared__ uint8_t s_sigma[20][kWarpsPerCta * 32];      // quadCols + 1 <= 17 for w <= 64; one column per decoder
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t blk = blockIdx.x * kWarpsPerCta + warp;
+    uint32_t blk;
+    bool do_store;
+    uint8_t *sigma1;                                        // element i at sigma1[i * kWarpsPerCta * 32]
+    if (BPW == 32) {
+        // fresh decoder: output pre-zeroed (ht.go:81) -- the warp clears its 32 blocks together (coalesced rows)
+        const uint32_t first = (blockIdx.x * kWarpsPerCta + warp) * 32;
+        for (uint32_t bb = first; bb < first + 32 && bb < n; bb++) {
+            const DevCblk c0 = cblks[bb];
+            OT *o = coef + c0.out_off;
+            for (int y = 0; y < c0.h; y++)
+                for (int x = lane; x < c0.w; x += 32) o[(size_t)y * c0.out_stride + x] = 0;
+        }
+        __syncwarp();
+        blk = first + lane;
+        do_store = true;
+        sigma1 = &s_sigma[0][threadIdx.x];
+    } else {
+        blk = blockIdx.x * kWarpsPerCta + warp;
+        do_store = lane == 0;
+        sigma1 = &s_sigma[0][warp * 32];
+    }
+    constexpr int SS = kWarpsPerCta * 32;
     if (blk >= n) return;
     const DevCblk cb = cblks[blk];
     const int w = cb.w, h = cb.h, len = (int)cb.data_len;
@@ -245,11 +272,14 @@ k_ht_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
     const uint32_t ostride = cb.out_stride;
     const uint8_t *d = blob + cb.data_off;
 
-    // fresh decoder: output pre-zeroed (ht.go:81); lanes share the rows
-    for (int y = 0; y < h; y++)
-        for (int x = lane; x < w; x += 32) out[(size_t)y * ostride + x] = 0;
-    if (lane < 20) s_sigma[warp][lane] = 0;
-    __syncwarp();
+    if (BPW == 1) {
+        for (int y = 0; y < h; y++)
+            for (int x = lane; x < w; x += 32) out[(size_t)y * ostride + x] = 0;
+        if (lane < 20) sigma1[lane * SS] = 0;
+        __syncwarp();
+    } else {
+        for (int i = 0; i < 20; i++) sigma1[i * SS] = 0;
+    }
 
     if (len < 2) return;                                                    // ht.go:94-100
     int scup = (int)byte_at(d, len, len - 1) + (int)((byte_at(d, len, len - 2) & 0x0F) << 8);
@@ -260,7 +290,6 @@ k_ht_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
     vlc_init(vlc, d, len, lcup, scup);
     magsgn_init(ms, d, len, lcup - scup);
 
-    uint8_t *sigma1 = s_sigma[warp];
     const int quad_cols = (w + 3) / 4;
     for (int y = 0; y < h; y += 4) {                                        // ht.go:589
         const bool initial = (y == 0);
@@ -268,19 +297,19 @@ k_ht_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
         for (int qx = 0; qx < quad_cols; qx += 2) {
             uint32_t vv = rev_fetch(vlc);
             uint32_t ctx = 0;
-            if (initial) { if (qx > 0) ctx = sigma1[qx - 1] >> 4; }
-            else ctx = sigma1[qx] >> 4;                                     // lineState is never written: 0
+            if (initial) { if (qx > 0) ctx = sigma1[(qx - 1) * SS] >> 4; }
+            else ctx = sigma1[qx * SS] >> 4;                                // lineState is never written: 0
             uint32_t q1 = tbl[(ctx << 7) | (vv & 0x7F)];
             uint32_t len1 = q1 & 0x0F, rho1 = (q1 >> 4) & 0x0F, uoff1 = (q1 >> 3) & 1;
             rev_advance(vlc, len1);
             vv = rev_fetch(vlc);
-            uint32_t ctx2 = (rho1 >> 2) | (sigma1[qx + 1] >> 4);
+            uint32_t ctx2 = (rho1 >> 2) | (sigma1[(qx + 1) * SS] >> 4);
             uint32_t q2 = tbl[(ctx2 << 7) | (vv & 0x7F)];
             uint32_t len2 = q2 & 0x0F, rho2 = (q2 >> 4) & 0x0F, uoff2 = (q2 >> 3) & 1;
             rev_advance(vlc, len2);
-            __syncwarp();
-            if (lane == 0) { sigma1[qx] = (uint8_t)rho1; sigma1[qx + 1] = (uint8_t)rho2; }
-            __syncwarp();
+            if (BPW == 1) __syncwarp();
+            if (do_store) { sigma1[qx * SS] = (uint8_t)rho1; sigma1[(qx + 1) * SS] = (uint8_t)rho2; }
+            if (BPW == 1) __syncwarp();
 
             uint32_t u0 = 1, u1 = 1;
             uint32_t mode = (uoff1 << 1) | uoff2;
@@ -291,12 +320,12 @@ k_ht_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
             for (int i = 0; i < 4 && qx * 4 + i < w; i++)
                 if (rho1 & (1u << i)) {
                     int32_t v = magsgn_sample(ms, u0);
-                    if (lane == 0) out[(size_t)y * ostride + qx * 4 + i] = (OT)v;
+                    if (do_store) out[(size_t)y * ostride + qx * 4 + i] = (OT)v;
                 }
             for (int i = 0; i < 4 && (qx + 1) * 4 + i < w; i++)
                 if (rho2 & (1u << i)) {
                     int32_t v = magsgn_sample(ms, u1);
-                    if (lane == 0) out[(size_t)y * ostride + (qx + 1) * 4 + i] = (OT)v;
+                    if (do_store) out[(size_t)y * ostride + (qx + 1) * 4 + i] = (OT)v;
                 }
         }
     }
@@ -304,12 +333,26 @@ k_ht_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
 
 }  // namespace
 
+int j2k_htref_map()
+{
+    static int map = -1;
+    if (map < 0) { const char *e = getenv("J2KGPU_HTREF_MAP"); map = (e && atoi(e) == 1) ? 1 : 32; }
+    return map;
+}
+
 cudaError_t launch_ht_ref(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
                           cudaStream_t s)
 {
     if (n == 0) return cudaSuccess;
-    uint32_t grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
-    if (coef16) J2K_LAUNCH((k_ht_ref<int16_t>), grid, kWarpsPerCta * 32, 0, s, d_cblks, n, d_blob, (int16_t *)d_coef);
-    else J2K_LAUNCH((k_ht_ref<int32_t>), grid, kWarpsPerCta * 32, 0, s, d_cblks, n, d_blob, (int32_t *)d_coef);
+    const int map = j2k_htref_map();
+    if (map == 32) {
+        const uint32_t per = kWarpsPerCta * 32, grid = (n + per - 1) / per;
+        if (coef16) J2K_LAUNCH((k_ht_ref<32, int16_t>), grid, kWarpsPerCta * 32, 0, s, d_cblks, n, d_blob, (int16_t *)d_coef);
+        else J2K_LAUNCH((k_ht_ref<32, int32_t>), grid, kWarpsPerCta * 32, 0, s, d_cblks, n, d_blob, (int32_t *)d_coef);
+    } else {
+        const uint32_t grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
+        if (coef16) J2K_LAUNCH((k_ht_ref<1, int16_t>), grid, kWarpsPerCta * 32, 0, s, d_cblks, n, d_blob, (int16_t *)d_coef);
+        else J2K_LAUNCH((k_ht_ref<1, int32_t>), grid, kWarpsPerCta * 32, 0, s, d_cblks, n, d_blob, (int32_t *)d_coef);
+    }
     return cudaGetLastError();
 }
