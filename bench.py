@@ -12,9 +12,11 @@ buffers, H2D and D2H inside the timed region.  Timing: CUDA events on the launch
 synchronize on both sides, max over ranks.  The batch working set (F x (99.5 MB coefficients + 33 MB pixels))
 is larger than the 126 MB L2, so no explicit L2 flush is needed between steps.
 
-Extra objects on the JSON line: roofline (fused last-level IDWT+RCT+DC+pack kernel, algorithmic bytes
-4*W*H*C + W*H*bpp per frame over its CUDA-event time, against MEASURED_PEAKS.json), cpu_baseline (the C oracle,
-a restatement of the reference's Go stage functions, all host threads, bounded sample), clocks.
+Extra objects on the JSON line: roofline (the fused kernel "IDWT levels 1+0 + RCT + DC shift + clamp + RGBA pack",
+algorithmic bytes 4*W*H*C + W*H*bpp per frame over its CUDA-event time, against MEASURED_PEAKS.json), cpu_baseline
+(the C oracle, a restatement of the reference's Go stage functions, all host threads, bounded sample), clocks, and --
+unless --no-extra -- the same geometry as a conformant HTJ2K codestream in ISO mode (iso_htj2k, cross-checked with
+OpenJPEG) and with the reference's EBCOT coder (ebcot_ref).
 
 --impl reference times the CPU implementation alone (oracle port; the Go reference cannot run: no Go toolchain).
 """
@@ -243,7 +245,8 @@ def measure(args, ctx, j2k, jobs, frames, mode, stream, world, barrier, steps, c
     assert np.array_equal(host_out[0].numpy().reshape(H, W, 4), first), "host path differs from device path"
     res = dict(ms_total=ms_total, steps=steps, launches=int(launches), ent_ms=ent_ms, dwt_ms=dwt_ms, last_ms=last_ms,
                e2e_s=e2e_s, e2e_steps=e2e_steps, h2d=int(d_blob.numel()) - 64, d2h=stride * H * F,
-               n_blocks=sum(len(j["cblks"]) for j in frames), F=F, fused_levels=job.fused_levels, coef_bytes=job.coef_bytes)
+               n_blocks=sum(len(j["cblks"]) for j in frames), F=F, fused_levels=job.fused_levels, coef_bytes=job.coef_bytes,
+               plan=job.plan)
     job.close()
     return res
 
@@ -299,7 +302,9 @@ def run_ours(args):
                              d2h_bytes_per_step=m["d2h"], ms_per_step=round(1e3 * e2e_s / m["e2e_steps"], 3),
                              api="j2kgpu_job_run_host (pinned host buffers)"),
                     gpu_launches=m["launches"], code_blocks_per_step=m["n_blocks"] * world,
-                    plan=dict(idwt_levels_in_last_kernel=m["fused_levels"], coef_plane_bytes_per_sample=m["coef_bytes"]),
+                    plan=dict(idwt_levels_in_last_kernel=m["fused_levels"], coef_plane_bytes_per_sample=m["coef_bytes"],
+                              last_kernel="k_idwt53_wide (16 columns per lane)" if m["plan"] & 4 else
+                                          "k_idwt53_fused (4 columns per lane)" if m["plan"] & 1 else "k_idwt53_stream"),
                     stages_ms=dict(entropy=round(m["ent_ms"], 4), dwt_mct_pack=round(m["dwt_ms"], 4),
                                    last_level_fused=round(m["last_ms"], 4)),
                     roofline=dict(bound="hbm", achieved=round(ach, 1), peak=peak, unit="GB/s", frac=round(ach / peak, 4),
@@ -357,9 +362,9 @@ def run_ours(args):
                        "code_blocks_per_step": main["code_blocks_per_step"], "l2": "working set > L2 (no flush needed)",
                        "parallelism": "frames sharded across GPUs, no collective"},
             "e2e": main["e2e"], "gpu_launches": main["gpu_launches"], "stages_ms": main["stages_ms"], "plan": main["plan"],
-            "roofline": dict(main["roofline"], kernel="k_idwt53_fused<3> (IDWT levels 1+0 + RCT + DC + clamp + RGBA pack)"
-                             if main["plan"]["idwt_levels_in_last_kernel"] == 2 else
-                             "k_idwt53_stream<3,1> (last IDWT level + RCT + DC + clamp + RGBA pack)",
+            "roofline": dict(main["roofline"], kernel=main["plan"]["last_kernel"] +
+                             (": IDWT levels 1+0 + RCT + DC + clamp + RGBA pack" if main["plan"]["idwt_levels_in_last_kernel"] == 2
+                              else ": last IDWT level + RCT + DC + clamp + RGBA pack"),
                              peak_source=peak_src, algorithmic_bytes_per_launch=alg_bytes,
                              # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, from the ncu --set full capture
                              # in profiles/ (2-frame launch: 273.6 MB against 265.4 MB algorithmic), scaled to this launch
