@@ -197,7 +197,8 @@ static inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSu
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
-static inline cudaError_t cudaMalloc(void **p, size_t n) { *p = aligned_alloc(256, (n + 255) / 256 * 256 + 256); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+// exact size (posix_memalign): under AddressSanitizer (make asan) any access past the requested bytes is reported
+static inline cudaError_t cudaMalloc(void **p, size_t n) { return posix_memalign(p, 256, n ? n : 1) == 0 ? cudaSuccess : cudaErrorMemoryAllocation; }
 template <class T> static inline cudaError_t cudaMalloc(T **p, size_t n) { return cudaMalloc((void **)p, n); }
 static inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
 static inline cudaError_t cudaMallocHost(void **p, size_t n) { return cudaMalloc(p, n); }
