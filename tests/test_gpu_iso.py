@@ -229,3 +229,26 @@ def test_iso_whole_path_openjpeg_lossy_97(j2k, gpu_ctx, w, h, ncomp, kw):
     d = np.abs(pix[:, :, :ncomp].astype(np.int64) - ref.astype(np.int64))
     assert d.max() <= 1                                                     # tolerance stated by north_star
     assert d.max() == 0                                                     # what the design achieves
+
+
+@pytest.mark.parametrize("name", ["rgb_lossless", "rgb_lossless_layers_tiles", "rgb_truncated_53", "rgb_lossy_97",
+                                  "gray_lossy_97_odd", "gray16_lossless"])
+def test_iso_golden_openjpeg_vectors(j2k, gpu_ctx, name):
+    """committed codestreams written by OpenJPEG decode on the GPU to the committed pixels OpenJPEG decoded from them"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "iso_openjpeg.npz"))
+    data, ref = g[name + "_j2k"].tobytes(), g[name + "_pix"]
+    job = jobs.build_iso_job_from_codestream(data)
+    w, h, nc, prec = job["width"], job["height"], job["ncomp"], job["prec"]
+    img = j2k.make_image(w, h, nc, prec, mct=job["mct"], reversible=job["reversible"], nlevels=job["nlevels"], ht=0, mode=ISO,
+                         coef_bits=job["coef_bits"] if job["reversible"] else 0)
+    got = gpu_ctx.decode_tiles(img, jobs.as_ctypes(job["tilecomps"], j2k.TileComp), jobs.as_ctypes(job["cblks"], j2k.CBlk),
+                               job["blob"])
+    if prec > 8:
+        be = got.reshape(h, w, 2).astype(np.uint16)
+        pix = (be[:, :, 0] << 8) | be[:, :, 1]                                   # image.Gray16 is big-endian
+        assert np.array_equal(pix, ref)
+    elif nc == 1:
+        assert np.array_equal(got.reshape(h, w), ref)
+    else:
+        assert np.array_equal(got.reshape(h, w, 4)[:, :, :3], ref)

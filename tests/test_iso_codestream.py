@@ -244,3 +244,22 @@ def test_irreversible_model_matches_openjpeg(w, h, ncomp, kw):
     ref = ref[None] if ncomp == 1 else np.moveaxis(ref, 2, 0)
     assert np.array_equal(got, ref)
     assert 10 * np.log10(255.0 ** 2 / np.mean((got - s) ** 2.0)) > 30            # and it is a sensible image
+
+
+# ---- committed golden vectors: codestreams written by OpenJPEG + the pixels OpenJPEG decodes from them ----------------
+import os
+
+GOLD_ISO = os.path.join(os.path.dirname(__file__), "golden", "iso_openjpeg.npz")
+GOLD_NAMES = ["rgb_lossless", "rgb_lossless_layers_tiles", "rgb_truncated_53", "rgb_lossy_97", "gray_lossy_97_odd", "gray16_lossless"]
+
+
+@pytest.mark.parametrize("name", GOLD_NAMES)
+def test_iso_oracle_reproduces_openjpeg_golden_vectors(name):
+    """tests/golden/iso_openjpeg.npz (made by tests/golden/make_golden_iso.py): the parser + ISO oracle decode the stored
+    bytes to the stored pixels, bit for bit"""
+    g = np.load(GOLD_ISO)
+    data, pix = g[name + "_j2k"].tobytes(), g[name + "_pix"]
+    hdr = cs.parse_codestream(data)
+    got, _ = (oracle_decode_reversible if hdr["reversible"] else oracle_decode_irreversible)(data)
+    ref = pix[None] if pix.ndim == 2 else np.moveaxis(pix, 2, 0)
+    assert np.array_equal(got, ref.astype(np.int64))
