@@ -251,6 +251,33 @@ def measure(args, ctx, j2k, jobs, frames, mode, stream, world, barrier, steps, c
     return res
 
 
+def bind_to_gpu_numa_node(local):
+    """pin this rank (and therefore its pinned host buffers: first touch) to the CPUs of the NUMA node its GPU hangs off,
+    so that 8 ranks do not push their H2D / D2H traffic across the socket interconnect; returns a note for the JSON line"""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
+        dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local), "pci_device_id", 0)
+        if bus is None:
+            return "numa: unknown"
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return "numa: single node"
+        cpus = []
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return "numa: rank bound to node %d (%d cpus)" % (node, len(allowed))
+        return "numa: node %d has no allowed cpus" % node
+    except Exception as e:                       # best effort: never fail the bench over affinity
+        return "numa: not bound (%s)" % str(e)[:60]
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -264,6 +291,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
     torch.cuda.set_device(local)
+    numa_note = bind_to_gpu_numa_node(local) if world > 1 else "numa: single rank, not bound"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = j2k.Context(local)
@@ -360,7 +388,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": workload_name(args.coder, F), "mode": "REF", "frames_per_gpu_per_step": F,
                        "code_blocks_per_step": main["code_blocks_per_step"], "l2": "working set > L2 (no flush needed)",
-                       "parallelism": "frames sharded across GPUs, no collective"},
+                       "parallelism": "frames sharded across GPUs, no collective", "host": numa_note},
             "e2e": main["e2e"], "gpu_launches": main["gpu_launches"], "stages_ms": main["stages_ms"], "plan": main["plan"],
             "roofline": dict(main["roofline"], kernel=main["plan"]["last_kernel"] +
                              (": IDWT levels 1+0 + RCT + DC + clamp + RGBA pack" if main["plan"]["idwt_levels_in_last_kernel"] == 2
