@@ -147,21 +147,28 @@ def build_iso_job(samples, prec, tile_w=None, tile_h=None, nlevels=5, mct=1, cb=
                 coef_bits=max(info["eps"]) + info["guard"] - 1)      # max Mb over bands (QCD exponent + guard bits - 1)
 
 
-def build_iso_job_from_codestream(data):
+def build_iso_job_from_codestream(data, reduce=0):
     """ISO-mode job tables from any codestream datagen.codestream.parse_codestream understands (e.g. one written by
     OpenJPEG): classic EBCOT or HT blocks, any number of quality layers (the block's segments are concatenated and
-    num_passes says how many coding passes they hold), reversible or irreversible (step = dequantisation step)."""
+    num_passes says how many coding passes they hold), reversible or irreversible (step = dequantisation step).
+    reduce = Config.ReduceResolution (jpeg2000.go:205-207, decoder.go:289-295): the `reduce` finest resolutions are
+    left out -- purely a matter of which blocks the host hands over: in the Mallat plane the remaining bands keep
+    their positions, the image and tile bounds shrink by 2^reduce (ceil), nlevels drops by reduce."""
     from . import codestream as cs
     h = cs.parse_codestream(data)
-    W, H, ncomp = h["width"], h["height"], h["ncomp"]
-    ntx = cs.cdiv(W, h["tile_w"])
+    if reduce > h["nlevels"]:
+        raise ValueError("reduce > number of decomposition levels")
+    sc = 1 << reduce
+    W, H, ncomp = cs.cdiv(h["width"], sc), cs.cdiv(h["height"], sc), h["ncomp"]
+    ntx = cs.cdiv(h["width"], h["tile_w"])
     tcs, tc_index = [], {}
-    for ty in range(cs.cdiv(H, h["tile_h"])):
+    for ty in range(cs.cdiv(h["height"], h["tile_h"])):
         for tx in range(ntx):
             for c in range(ncomp):
                 tc_index[(ty * ntx + tx, c)] = len(tcs)
-                tcs.append((c, tx * h["tile_w"], ty * h["tile_h"], min((tx + 1) * h["tile_w"], W), min((ty + 1) * h["tile_h"], H), 0))
-    blks = h["blocks"]
+                tcs.append((c, cs.cdiv(tx * h["tile_w"], sc), cs.cdiv(ty * h["tile_h"], sc),
+                            cs.cdiv(min((tx + 1) * h["tile_w"], h["width"]), sc), cs.cdiv(min((ty + 1) * h["tile_h"], h["height"]), sc), 0))
+    blks = [b for b in h["blocks"] if b["res"] <= h["nlevels"] - reduce]
     cblks = np.zeros(len(blks), CBLK_DT)
     blob = bytearray()
     gain = {0: 0, 1: 1, 2: 1, 3: 2}
@@ -173,6 +180,6 @@ def build_iso_job_from_codestream(data):
                     b["band"], b["level"], nb, min(b["passes"], 255), step)
         blob += b["data"]
     return dict(width=W, height=H, ncomp=ncomp, prec=h["prec"], sgnd=h["sgnd"], mct=1 if (h["mct"] and ncomp >= 3) else 0,
-                reversible=h["reversible"], nlevels=h["nlevels"], ht=0, mode=1, tilecomps=np.array(tcs, TILECOMP_DT), cblks=cblks,
+                reversible=h["reversible"], nlevels=h["nlevels"] - reduce, ht=0, mode=1, tilecomps=np.array(tcs, TILECOMP_DT), cblks=cblks,
                 blob=np.frombuffer(bytes(blob) + bytes(8), np.uint8).copy(), codestream=bytes(data), layers=h["layers"],
                 coef_bits=max(e + h["guard"] - 1 for e, _ in h["qcd"]))

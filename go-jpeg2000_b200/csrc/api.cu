@@ -570,7 +570,12 @@ static int run_host_locked(j2kgpu_job *job, const j2k_batch_item_t *items)
         const uint32_t need = (uint32_t)((16384 + blocks_per_item - 1) / blocks_per_item);
         if (need > per) per = need < n ? need : n;
     }
-    const uint32_t nchunk = (n + per - 1) / per;
+    // the copy-out (the PCIe bottleneck of the path) can only start once the first chunk is decoded: keep that one small
+    std::vector<uint32_t> cuts;                             // chunk c = items [cuts[c], cuts[c + 1])
+    cuts.push_back(0);
+    if (n >= 4 && per > 1) cuts.push_back(1);
+    while (cuts.back() < n) cuts.push_back(cuts.back() + per < n ? cuts.back() + per : n);
+    const uint32_t nchunk = (uint32_t)cuts.size() - 1;
     if (job->ev_in.size() < nchunk) {
         const size_t old = job->ev_in.size();
         job->ev_in.resize(nchunk, nullptr); job->ev_done.resize(nchunk, nullptr);
@@ -584,7 +589,7 @@ static int run_host_locked(j2kgpu_job *job, const j2k_batch_item_t *items)
     J2K_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_start, 0));
     J2K_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_start, 0));
     for (uint32_t c = 0; c < nchunk; c++) {
-        const uint32_t ia = c * per, ib = ia + per < n ? ia + per : n;
+        const uint32_t ia = cuts[c], ib = cuts[c + 1];
         for (uint32_t i = ia; i < ib; i++)
             if (items[i].blob_len)
                 J2K_CUDA(ctx, cudaMemcpyAsync((uint8_t *)job->d_blob + job->blob_off[i], items[i].blob, items[i].blob_len,

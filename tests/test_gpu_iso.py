@@ -252,3 +252,27 @@ def test_iso_golden_openjpeg_vectors(j2k, gpu_ctx, name):
         assert np.array_equal(got.reshape(h, w), ref)
     else:
         assert np.array_equal(got.reshape(h, w, 4)[:, :, :3], ref)
+
+
+@pytest.mark.parametrize("w,h,kw", [
+    (256, 256, dict(irreversible=False, num_resolutions=6, mct=1)),
+    (320, 200, dict(irreversible=False, num_resolutions=4, mct=1)),
+    (256, 192, dict(irreversible=True, num_resolutions=5, mct=1, quality_mode="rates", quality_layers=[20])),
+])
+@pytest.mark.parametrize("reduce", [1, 2, 3])
+def test_iso_reduce_resolution_matches_openjpeg(j2k, gpu_ctx, w, h, kw, reduce):
+    """Config.ReduceResolution (jpeg2000.go:205-207): the host leaves out the finest resolutions when it builds the job
+    tables; no kernel knows about it.  The result equals OpenJPEG's reduced decode of the same codestream."""
+    Image = pytest.importorskip("PIL.Image")
+    s = jobs.synth_image(w, h, 3, 8, seed=w + reduce)
+    data = opj_encode(s, **kw)
+    job = jobs.build_iso_job_from_codestream(data, reduce=reduce)
+    W, H = job["width"], job["height"]
+    assert (W, H) == (-(-w // (1 << reduce)), -(-h // (1 << reduce)))             # decoder.go:289-295
+    img = j2k.make_image(W, H, 3, 8, mct=job["mct"], reversible=job["reversible"], nlevels=job["nlevels"], ht=0, mode=ISO)
+    got = gpu_ctx.decode_tiles(img, jobs.as_ctypes(job["tilecomps"], j2k.TileComp), jobs.as_ctypes(job["cblks"], j2k.CBlk),
+                               job["blob"]).reshape(H, W, 4)
+    im = Image.open(io.BytesIO(data))
+    im.reduce = reduce
+    im.load()
+    assert np.array_equal(got[:, :, :3], np.array(im))
