@@ -573,7 +573,8 @@ static int run_host_locked(j2kgpu_job *job, const j2k_batch_item_t *items)
     // the copy-out (the PCIe bottleneck of the path) can only start once the first chunk is decoded: keep that one small
     std::vector<uint32_t> cuts;                             // chunk c = items [cuts[c], cuts[c + 1])
     cuts.push_back(0);
-    if (n >= 4 && per > 1) cuts.push_back(1);
+    // (not for the ISO HT decoder: every launch of it costs one block's full serial chain, about 1.7 ms)
+    if (n >= 4 && per > 1 && !(job->iso && job->hdr.ht)) cuts.push_back(1);
     while (cuts.back() < n) cuts.push_back(cuts.back() + per < n ? cuts.back() + per : n);
     const uint32_t nchunk = (uint32_t)cuts.size() - 1;
     if (job->ev_in.size() < nchunk) {
