@@ -388,8 +388,8 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
     if (env_flag("J2KGPU_NO_FAST_EPI")) job->fast_epi = 0;
     for (const DevTile &t : tiles)
         if ((t.out_stride & 15) || (t.out_off & 15) || (t.img_x0 & 3) || t.img_x0 + t.w > t.img_w || t.img_y0 + t.h > t.img_h) job->fast_epi = 0;
-    job->wide_ok = job->fast_epi && fused_ok && tp.ncomp == 3 && !env_flag("J2KGPU_NO_WIDE");
-    for (const DevTile &t : tiles) if (t.w & 15) job->wide_ok = 0;
+    job->wide_ok = job->fast_epi && fused_ok && (tp.ncomp == 3 || tp.ncomp == 1) && !env_flag("J2KGPU_NO_WIDE");
+    for (const DevTile &t : tiles) if ((t.w & 15) || (tp.ncomp == 1 && (t.img_x0 & 15))) job->wide_ok = 0;   // 16-byte stores per lane
     job->coef_elems = coef_elems; job->blob_bytes = blob_bytes; job->out_bytes = out_bytes; job->max_bps = max_bps;
     job->tmp_bytes = tmp_elems * ((hdr.reversible || iso) ? 4 : 8);     // int32 (5-3), float32 (ISO 9-7), float64 (REF 9-7)
     job->need_clear = need_clear;

@@ -17,6 +17,7 @@
 //   * vertical lifting state (one row pair of delay) lives in registers: 144 per lane; the kernel runs 8 warps / SM.
 // Eligibility (host): fast RGBA8 epilogue conditions of idwt_fused.cu + every tile width % 16 == 0, height % 4 == 0.
 #include "common.h"
+#include "tail.cuh"
 
 namespace {
 
@@ -157,19 +158,21 @@ __device__ __forceinline__ void hsynth(int *V, bool first, bool last)
     for (int i = 0; i < N; i++) { V[2 * i] = E[i]; V[2 * i + 1] = O[i]; }
 }
 
-// shared memory of one warp (uint4 units)
-constexpr int kRing0 = 3 * 4 * 64;     // [comp][part loL, loH, hiL, hiH][2 halves][32 lanes]
-constexpr int kRing1 = 3 * 4 * 32;     // [comp][part][32 lanes]
-constexpr int kStage = 2 * 2 * 4 * 32; // [comp 0,1][row even, odd][quad][32 lanes]
-constexpr int kWarpSmem = kRing0 + kRing1 + kStage;   // 26 KB per warp: 2 CTAs of 4 warps per SM
+// shared memory of one warp (uint4 units), NC components
+__host__ __device__ constexpr int ring0_u4(int nc) { return nc * 4 * 64; }     // [comp][part loL, loH, hiL, hiH][2 halves][32 lanes]
+__host__ __device__ constexpr int ring1_u4(int nc) { return nc * 4 * 32; }     // [comp][part][32 lanes]
+__host__ __device__ constexpr int stage_u4(int nc) { return nc == 3 ? 2 * 2 * 4 * 32 : 0; }   // [comp 0,1][row even, odd][quad][32 lanes]
+__host__ __device__ constexpr int warp_smem_u4(int nc) { return ring0_u4(nc) + ring1_u4(nc) + stage_u4(nc); }   // 3 components: 26 KB per warp
 // ISO: the odd level-1 output row is wanted one step later; it waits in ring0's "lo L" part, which ISO never copies into
 // when level 1 exists (that part IS the level-1 output)
 
-template <typename CT, bool ISO>
+// NC = 3: RGB + RCT -> RGBA8.  NC = 1: one unsigned component of 8 or 16 bits -> Gray8 / big-endian Gray16.
+template <int NC, typename CT, bool ISO>
 __global__ void __launch_bounds__(kWarps * 32, 2)
 k_idwt53_wide(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__ tiles, const CT *__restrict__ coef,
-              const int32_t *__restrict__ tmp, uint8_t *__restrict__ pix, int nlevels, int strip_pairs)
+              const int32_t *__restrict__ tmp, uint8_t *__restrict__ pix, int nlevels, int strip_pairs, int prec, int iso_pack)
 {
+    constexpr int kRing0 = ring0_u4(NC), kRing1 = ring1_u4(NC), kWarpSmem = warp_smem_u4(NC);
     J2K_DYN_SMEM(uint4, smem_all);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const DevTile tile = tiles[blockIdx.y];
@@ -192,10 +195,10 @@ k_idwt53_wide(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__ t
     const int nlx1 = nlx >> 1, nly1 = nly >> 1;
     const int half0 = nly >> 1;
 
-    const CT *plane[3];
-    const int32_t *prev2[3];
+    const CT *plane[NC];
+    const int32_t *prev2[NC];
 #pragma unroll
-    for (int c = 0; c < 3; c++) {
+    for (int c = 0; c < NC; c++) {
         const DevTileComp tc = tcs[tile.tc[c]];
         plane[c] = coef + tc.coef_off;
         prev2[c] = tmp + tc.tmp_off;                  // level 2 wrote ping-pong buffer 0
@@ -252,12 +255,12 @@ k_idwt53_wide(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__ t
         part_read<4>(sl + 96, CT(), hi + 4);
     };
 
-    int hp[3][16], ep[3][16];          // level 0: Hi[k] and E[k] of the lane's 16 columns (REF: band order; ISO: interleaved)
+    int hp[NC][16], ep[NC][16];          // level 0: Hi[k] and E[k] of the lane's 16 columns (REF: band order; ISO: interleaved)
     // level 1: hi1[jn] and E1[jn] of the lane's 8 columns.  ISO keeps them in registers.  REF needs level 1 only while
     // the strip is in the top half of the tile, where ring0's two "lo" parts are never copied into (they ARE the
     // level-1 output): the state lives there (4 uint4 per lane and component) and 48 registers are saved -- without
     // this the REF variants spill their loop counters (ncu: 26 % of the stall samples were the spill reloads)
-    int h1[3][8], e1[3][8];
+    int h1[NC][8], e1[NC][8];
     auto l1_get = [&](int c, int *hh, int *ee) {
         if (ISO) {
 #pragma unroll
@@ -290,7 +293,7 @@ k_idwt53_wide(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__ t
         else if (ka < half0) { l1need = true; jn = ka - 1; j1last = min(rlast, half0 - 1); }
     }
 #pragma unroll
-    for (int c = 0; c < 3; c++) {                                      // group c: first level-0 row pair (+ level-1 pair jn+1)
+    for (int c = 0; c < NC; c++) {                                      // group c: first level-0 row pair (+ level-1 pair jn+1)
         if (lvalid) {
             issue_l0(c, k0 + 1);
             if (l1need) issue_l1(c, jn + 1);
@@ -301,7 +304,7 @@ k_idwt53_wide(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__ t
         const int jp = jn < 0 ? 0 : jn;
         const uint32_t o_hi = ISO ? (uint32_t)(nly1 + jp) * uw + col1 : (uint32_t)(nly1 + jp) * (uint32_t)nlx + col1;
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
+        for (int c = 0; c < NC; c++) {
             int hh[8], ee[8];
             part_ldg<4>(plane[c] + o_hi, &hh[0]);
             part_ldg<4>(plane[c] + o_hi + nlx1, &hh[4]);
@@ -315,7 +318,7 @@ k_idwt53_wide(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__ t
         const int rp = k0 < 0 ? 0 : k0;                                // top edge: Hi[-1] := Hi[0]
         const uint32_t ohi = (uint32_t)(nly + rp) * uw + col0;
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
+        for (int c = 0; c < NC; c++) {
             part_ldg<8>(plane[c] + ohi, &hp[c][0]);
             part_ldg<8>(plane[c] + ohi + nlx, &hp[c][8]);
             if (ISO) hsynth<8>(hp[c], first, last);
@@ -345,8 +348,8 @@ k_idwt53_wide(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__ t
 
     if (l1need) {                                                      // the silent level-1 step (outputs discarded)
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
-            cp_wait<2>();
+        for (int c = 0; c < NC; c++) {
+            cp_wait<NC - 1>();
             int a[8], b[8];
             l1_step(c, a, b);
             cp_commit();
@@ -355,8 +358,9 @@ k_idwt53_wide(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__ t
     }
 
     // ---- output addressing ------------------------------------------------------------------------------------------
+    const int bpp = NC == 3 ? 4 : (prec > 8 ? 2 : 1);
     uint8_t *orow = pix + tile.out_off + (size_t)(tile.img_y0 + 2u * (uint32_t)ka) * tile.out_stride +
-                    4 * (size_t)(tile.img_x0 + 16u * (uint32_t)lc);
+                    (size_t)bpp * (tile.img_x0 + 16u * (uint32_t)lc);
 
     // ---- stream the strip: step k consumes band row pair k+1 and finishes output rows 2k (even) and 2k+1 (odd) ------
     for (int k = k0; k < kb; k++) {
@@ -366,8 +370,8 @@ k_idwt53_wide(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__ t
         const bool do_l1 = fl && jn <= (ISO ? (r >> 1) : r);           // a new level-1 pair is due (warp-uniform)
         const bool emit = k >= ka;
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
-            cp_wait<2>();                                              // component c's copies of the previous step have landed
+        for (int c = 0; c < NC; c++) {
+            cp_wait<NC - 1>();                                         // component c's copies of the previous step have landed
             int lo[16], hi[16];
             if (fl) {
                 int rE[8], rO[8];
@@ -407,7 +411,43 @@ k_idwt53_wide(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__ t
             }
             if (emit) {
                 if (!ISO) { hsynth<8>(ev, first, last); hsynth<8>(od, first, last); }
-                if (c < 2) {                                           // park the two rows until component 2 is done
+                if (NC == 1) {
+                    // DC shift (mct.go:113-118), clamp + scale exactly as createImage (decoder.go:427-466), 16 pixels per row
+                    if (store_lane) {
+#pragma unroll
+                        for (int row = 0; row < 2; row++) {
+                            const int *X = row ? od : ev;
+                            uint8_t *o = orow + (size_t)row * tile.out_stride;
+                            if (prec <= 8) {
+                                uint32_t wd[4];
+#pragma unroll
+                                for (int g = 0; g < 4; g++) {
+                                    wd[g] = 0;
+#pragma unroll
+                                    for (int p2 = 0; p2 < 4; p2++)
+                                        wd[g] |= pack_value((int32_t)((uint32_t)X[4 * g + p2] + 128u), 8, 255, iso_pack != 0) << (8 * p2);
+                                }
+                                __stcs(reinterpret_cast<uint4 *>(o), make_uint4(wd[0], wd[1], wd[2], wd[3]));
+                            } else {
+#pragma unroll
+                                for (int half = 0; half < 2; half++) {
+                                    uint32_t wd[4];
+#pragma unroll
+                                    for (int g = 0; g < 4; g++) {
+                                        uint32_t hv[2];
+#pragma unroll
+                                        for (int p2 = 0; p2 < 2; p2++) {
+                                            const uint32_t t = pack_value((int32_t)((uint32_t)X[8 * half + 2 * g + p2] + 32768u), 16, 65535, iso_pack != 0);
+                                            hv[p2] = (t >> 8) | ((t & 0xFFu) << 8);                   // big-endian
+                                        }
+                                        wd[g] = hv[0] | (hv[1] << 16);
+                                    }
+                                    __stcs(reinterpret_cast<uint4 *>(o) + half, make_uint4(wd[0], wd[1], wd[2], wd[3]));
+                                }
+                            }
+                        }
+                    }
+                } else if (c < 2) {                                    // park the two rows until component 2 is done
                     uint4 *st = stage + c * 256;
 #pragma unroll
                     for (int g = 0; g < 4; g++) {
@@ -442,20 +482,20 @@ k_idwt53_wide(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__ t
     cp_wait<0>();
 }
 
-template <typename CT>
+template <int NC, typename CT>
 cudaError_t run_ct(const IdwtLaunch &p, dim3 grid, int strip_pairs, cudaStream_t s)
 {
-    const size_t smem = (size_t)kWarps * kWarpSmem * sizeof(uint4);
+    const size_t smem = (size_t)kWarps * warp_smem_u4(NC) * sizeof(uint4);
     const DevTile *tiles = p.d_tiles + p.tile_first;
     cudaError_t e;
     if (p.iso) {
-        if ((e = cudaFuncSetAttribute(k_idwt53_wide<CT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        J2K_LAUNCH((k_idwt53_wide<CT, true>), grid, kWarps * 32, smem, s, p.d_tcs, tiles, (const CT *)p.d_coef,
-                   (const int32_t *)p.d_tmp, p.d_pix, p.nlevels, strip_pairs);
+        if ((e = cudaFuncSetAttribute(k_idwt53_wide<NC, CT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        J2K_LAUNCH((k_idwt53_wide<NC, CT, true>), grid, kWarps * 32, smem, s, p.d_tcs, tiles, (const CT *)p.d_coef,
+                   (const int32_t *)p.d_tmp, p.d_pix, p.nlevels, strip_pairs, p.tail.prec[0], p.tail.iso);
     } else {
-        if ((e = cudaFuncSetAttribute(k_idwt53_wide<CT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        J2K_LAUNCH((k_idwt53_wide<CT, false>), grid, kWarps * 32, smem, s, p.d_tcs, tiles, (const CT *)p.d_coef,
-                   (const int32_t *)p.d_tmp, p.d_pix, p.nlevels, strip_pairs);
+        if ((e = cudaFuncSetAttribute(k_idwt53_wide<NC, CT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        J2K_LAUNCH((k_idwt53_wide<NC, CT, false>), grid, kWarps * 32, smem, s, p.d_tcs, tiles, (const CT *)p.d_coef,
+                   (const int32_t *)p.d_tmp, p.d_pix, p.nlevels, strip_pairs, p.tail.prec[0], p.tail.iso);
     }
     return cudaGetLastError();
 }
@@ -472,5 +512,6 @@ cudaError_t launch_idwt53_wide(const IdwtLaunch &p, cudaStream_t s)
     while (sp > 8 && (uint64_t)p.n_tiles * nwx * ((nly + sp - 1) / sp) < 148ull * 8 * 4) sp >>= 1;
     const uint32_t units = nwx * ((nly + sp - 1) / sp);
     dim3 grid((units + kWarps - 1) / kWarps, p.n_tiles, 1);
-    return p.coef16 ? run_ct<int16_t>(p, grid, sp, s) : run_ct<int32_t>(p, grid, sp, s);
+    if (p.tail.ncomp == 1) return p.coef16 ? run_ct<1, int16_t>(p, grid, sp, s) : run_ct<1, int32_t>(p, grid, sp, s);
+    return p.coef16 ? run_ct<3, int16_t>(p, grid, sp, s) : run_ct<3, int32_t>(p, grid, sp, s);
 }
