@@ -408,6 +408,12 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
     up((void **)&job->d_tiles, tiles.data(), tiles.size() * sizeof(DevTile));
     if (e == cudaSuccess) job->d_coef = j2k_pool_alloc(ctx, coef_elems * (job->coef16 ? 2 : 4) + 64, &e);
     if (e == cudaSuccess) job->d_tmp = j2k_pool_alloc(ctx, job->tmp_bytes, &e);
+    // reference HT coder: its decoder writes one row in four (ht.go:677, 701); zero the planes once, here, so that every
+    // run only has to clear the rows it may write (3/4 of the entropy stage's zero-fill traffic saved)
+    if (e == cudaSuccess && !iso && hdr.ht && !env_flag("J2KGPU_NO_PRECLEAR")) {
+        e = cudaMemsetAsync(job->d_coef, 0, coef_elems * (job->coef16 ? 2 : 4), ctx->stream);
+        job->precleared = 1;
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);          // tables are read from host vectors
     if (e != cudaSuccess) { job_free(job); return j2k_cuda_err(ctx, e, "job upload"); }
     *out = job;
@@ -448,7 +454,7 @@ static int run_entropy(j2kgpu_job *job, const void *d_blob, uint32_t ia, uint32_
     const float *steps = job->d_steps ? job->d_steps + ca : nullptr;
     if (job->iso && !job->hdr.ht) e = launch_t1_iso(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, steps, irrev, job->max_bps, st);
     else if (job->iso) e = launch_ht_iso(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, steps, irrev, job->hdr.coef_bits, job->ht_map, st);
-    else if (job->hdr.ht) e = launch_ht_ref(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, st);
+    else if (job->hdr.ht) e = launch_ht_ref(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, job->precleared, st);
     else e = launch_t1_ref(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, job->max_bps, st);
     if (e != cudaSuccess) return j2k_cuda_err(ctx, e, "entropy kernel launch");
     ctx->launches++;
@@ -683,7 +689,7 @@ static int stage_blocks(j2kgpu_ctx *ctx, int mode, int ht, const j2k_blkjob_t *j
     cudaError_t e = (ht && mode == J2KGPU_MODE_ISO)
                         ? launch_ht_iso((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, nullptr, 0, 0, ht_map, ctx->stream)
                     : mode == J2KGPU_MODE_ISO ? launch_t1_iso((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, nullptr, 0, max_bps, ctx->stream)
-                    : ht ? launch_ht_ref((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, ctx->stream)
+                    : ht ? launch_ht_ref((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, 0, ctx->stream)
                        : launch_t1_ref_stage((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, (int32_t *)ctx->d_out.p, max_bps, ctx->stream);
     if (e != cudaSuccess) return j2k_cuda_err(ctx, e, "entropy kernel launch");
     ctx->launches++;

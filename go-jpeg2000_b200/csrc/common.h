@@ -106,6 +106,7 @@ struct j2kgpu_job {
     int fused_ok = 0;                    // levels 1 + 0 + pixel epilogue run as one kernel (idwt_fused.cu)
     int fast_epi = 0;                    // every tile qualifies for the fused kernel's fixed RGBA8 epilogue
     int wide_ok = 0;                     // ... and for the 16-columns-per-lane variant (idwt_wide.cu)
+    int precleared = 0;                  // reference HT coder: planes zeroed at job creation, decoder clears every 4th row only
     std::vector<uint32_t> item_cb, item_tc, item_tile;   // first block / tile-component / tile of each item (+ end)
     std::vector<uint64_t> tc_coef_off;                   // coefficient-arena offset of each tile-component (host copy)
     std::vector<cudaEvent_t> ev_in, ev_done;             // per chunk of the pipelined host-buffer run
@@ -136,7 +137,7 @@ int j2k_ctx_copy_streams(j2kgpu_ctx *ctx);
 cudaError_t launch_t1_ref(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
                           int max_bps, cudaStream_t s);
 cudaError_t launch_ht_ref(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
-                          cudaStream_t s);
+                          int planes_precleared, cudaStream_t s);
 int j2k_htref_map();             // code blocks per warp of the reference-HT decoder: 32 (thread per block, default) or 1
 // ISO/IEC 15444-1 Annex D decoder (stripe-order passes, standard tables, pass truncation), one warp per block
 cudaError_t launch_t1_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,

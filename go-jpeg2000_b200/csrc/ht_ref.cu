@@ -236,7 +236,10 @@ __device__ __forceinline__ int32_t magsgn_sample(Fwd &ms, uint32_t emb)
 //   BPW = 32  one thread per block: 32 independent chains per warp (short divergent branches), 32x fewer
 //             warp-instructions for the same work; the zero fill of the 32 blocks is done by the whole warp first.
 // The launcher picks by J2KGPU_HTREF_MAP (default thread per block).
-template <int BPW, typename OT>
+// ZSTEP: rows of a block that are cleared before decoding.  The reference decoder only ever writes sample row y of each
+// 4-row stripe (ht.go:589-593, 677, 701), so inside a job -- whose planes were cleared once when the job was created and
+// are written by nothing else -- clearing every 4th row is enough (ZSTEP = 4); the stage API clears all rows (ZSTEP = 1).
+template <int BPW, typename OT, int ZSTEP>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 k_ht_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob,
          OT *__restrict__ coef)
@@ -252,7 +255,7 @@ k_ht_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
         for (uint32_t bb = first; bb < first + 32 && bb < n; bb++) {
             const DevCblk c0 = cblks[bb];
             OT *o = coef + c0.out_off;
-            for (int y = 0; y < c0.h; y++)
+            for (int y = 0; y < c0.h; y += ZSTEP)
                 for (int x = lane; x < c0.w; x += 32) o[(size_t)y * c0.out_stride + x] = 0;
         }
         __syncwarp();
@@ -273,7 +276,7 @@ k_ht_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
     const uint8_t *d = blob + cb.data_off;
 
     if (BPW == 1) {
-        for (int y = 0; y < h; y++)
+        for (int y = 0; y < h; y += ZSTEP)
             for (int x = lane; x < w; x += 32) out[(size_t)y * ostride + x] = 0;
         if (lane < 20) sigma1[lane * SS] = 0;
         __syncwarp();
@@ -340,19 +343,21 @@ int j2k_htref_map()
     return map;
 }
 
+// planes_precleared: the destination was zeroed once and only this decoder writes it (whole-path jobs): clear every 4th row
 cudaError_t launch_ht_ref(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
-                          cudaStream_t s)
+                          int planes_precleared, cudaStream_t s)
 {
     if (n == 0) return cudaSuccess;
     const int map = j2k_htref_map();
+    const uint32_t per = map == 32 ? kWarpsPerCta * 32 : kWarpsPerCta, grid = (n + per - 1) / per;
+#define J2K_HTREF_GO(BPW, OT, Z) J2K_LAUNCH((k_ht_ref<BPW, OT, Z>), grid, kWarpsPerCta * 32, 0, s, d_cblks, n, d_blob, (OT *)d_coef)
     if (map == 32) {
-        const uint32_t per = kWarpsPerCta * 32, grid = (n + per - 1) / per;
-        if (coef16) J2K_LAUNCH((k_ht_ref<32, int16_t>), grid, kWarpsPerCta * 32, 0, s, d_cblks, n, d_blob, (int16_t *)d_coef);
-        else J2K_LAUNCH((k_ht_ref<32, int32_t>), grid, kWarpsPerCta * 32, 0, s, d_cblks, n, d_blob, (int32_t *)d_coef);
+        if (coef16) { if (planes_precleared) J2K_HTREF_GO(32, int16_t, 4); else J2K_HTREF_GO(32, int16_t, 1); }
+        else { if (planes_precleared) J2K_HTREF_GO(32, int32_t, 4); else J2K_HTREF_GO(32, int32_t, 1); }
     } else {
-        const uint32_t grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
-        if (coef16) J2K_LAUNCH((k_ht_ref<1, int16_t>), grid, kWarpsPerCta * 32, 0, s, d_cblks, n, d_blob, (int16_t *)d_coef);
-        else J2K_LAUNCH((k_ht_ref<1, int32_t>), grid, kWarpsPerCta * 32, 0, s, d_cblks, n, d_blob, (int32_t *)d_coef);
+        if (coef16) { if (planes_precleared) J2K_HTREF_GO(1, int16_t, 4); else J2K_HTREF_GO(1, int16_t, 1); }
+        else { if (planes_precleared) J2K_HTREF_GO(1, int32_t, 4); else J2K_HTREF_GO(1, int32_t, 1); }
     }
+#undef J2K_HTREF_GO
     return cudaGetLastError();
 }
