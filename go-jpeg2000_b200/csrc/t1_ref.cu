@@ -11,9 +11,8 @@
 // shared memory (about 2 KB + 512 B per bit-plane per block instead of 21 KB).  Neighbourhood
 // tests are 64-bit shifts of three row words; the candidate set of a whole row is one boolean
 // expression; the zero-coding context is a 9-bit window (3 rows x 3 columns) indexing a 512-entry
-// table in constant memory.  The MQ decision chain is inherently serial, so the 32 lanes execute
-// it in lock-step on warp-uniform registers (no divergence, shared-memory loads are broadcasts);
-// the lanes split the work that IS parallel: clearing state, assembling magnitudes from the
+// table in constant memory.  The MQ decision chain is inherently serial: one lane of the warp runs
+// it; all lanes split the work that IS parallel: clearing state, assembling magnitudes from the
 // bit-plane bitmaps, applying signs and the coalesced store into the tile-component plane.
 #include "common.h"
 
@@ -146,8 +145,8 @@ k_t1_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
     const uint64_t wmask = (w >= 64) ? ~0ull : ((1ull << w) - 1);
     const uint8_t *zc = c_zc9 + band * 512;
 
-    // the serial MQ chain is executed redundantly by all 32 lanes in lock-step (idempotent shared-memory updates);
-    // the CPU fiber emulator (tools/emu) has no lock-step, so there lane 0 alone runs it
+    // the serial MQ chain: lane 0 runs it (J2K_T1_ONE_LANE, the default -- measured equal in speed to all 32 lanes running
+    // it redundantly in lock-step, and free of any reliance on implicit warp-synchronous shared-memory updates)
     for (int bp = nbps - 1; bp >= 0 && J2K_LOCKSTEP_LANE(lane); bp--) {
         uint64_t *plane = planes + bp * 64;
 
@@ -459,11 +458,7 @@ k_t1_iso(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
         }
         type = type == 2 ? 0 : type + 1;
     }
-#ifdef J2K_EMU
-    {   // lane 0 alone ran the passes: hand its p_end to the other lanes
-        p_end = __shfl_sync(0xffffffffu, p_end, 0);
-    }
-#endif
+    p_end = __shfl_sync(0xffffffffu, p_end, 0);                       // when lane 0 alone ran the passes
     __syncwarp();
 
     // ---- assemble: twice-scale magnitude with the mid-point of the last decoded bit-plane, sign, store ----
