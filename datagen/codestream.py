@@ -216,15 +216,61 @@ def forward_tile_iso(samples, prec, nlevels, mct):
     return [mallat53(p, nlevels) for p in c]
 
 
+def fwd97_1d(x, axis):
+    """one line direction of the forward 9-7 (Annex F.4.8, float64), interleaved in -> band order out (L first)"""
+    x = np.moveaxis(np.asarray(x, np.float64), axis, 0).copy()
+    n = x.shape[0]
+    if n < 2:
+        return np.moveaxis(x, 0, axis)
+    al, be, ga, de, K = -1.586134342059924, -0.052980118572961, 0.882911075530934, 0.443506852043971, 1.230174104914001
+    for par, c in ((1, al), (0, be), (1, ga), (0, de)):
+        idx = np.arange(par, n, 2)
+        l = np.where(idx - 1 >= 0, idx - 1, idx + 1)
+        r = np.where(idx + 1 < n, idx + 1, idx - 1)
+        x[idx] = x[idx] + c * (x[l] + x[r])
+    out = np.concatenate([x[0::2] / K, x[1::2] * K], axis=0)
+    return np.moveaxis(out, 0, axis)
+
+
+def forward_tile_iso_97(samples, prec, nlevels, mct):
+    """DC shift -> forward ICT -> multi-level forward 9-7 in Mallat layout (float64; vertical then horizontal)"""
+    ncomp = samples.shape[0]
+    c = [samples[i].astype(np.float64) - (1 << (prec - 1)) for i in range(ncomp)]
+    if mct and ncomp >= 3:
+        r, g, b = c[0], c[1], c[2]
+        c[0] = 0.299 * r + 0.587 * g + 0.114 * b
+        c[1] = -0.168736 * r - 0.331264 * g + 0.5 * b
+        c[2] = 0.5 * r - 0.418688 * g - 0.081312 * b
+    planes = []
+    for p in c:
+        out = p.copy()
+        h, w = out.shape
+        for _ in range(nlevels):
+            if w < 1 or h < 1:
+                break
+            out[:h, :w] = fwd97_1d(fwd97_1d(out[:h, :w], 0), 1)
+            w, h = (w + 1) // 2, (h + 1) // 2
+        planes.append(out)
+    return planes
+
+
 # ------------------------------------------------------------------------------------------------ writer
-def write_htj2k(samples, prec, tile_w=None, tile_h=None, nlevels=5, mct=1, cb=64, guard=2, extra_eps=1):
-    """samples int [ncomp, H, W] -> (codestream bytes, info dict with per-block tables for ISO jobs)"""
+def write_htj2k(samples, prec, tile_w=None, tile_h=None, nlevels=5, mct=1, cb=64, guard=2, extra_eps=1, lossy_step=None):
+    """samples int [ncomp, H, W] -> (codestream bytes, info dict with per-block tables for ISO jobs).
+    lossy_step = None: lossless 5-3 + RCT.  lossy_step = s (a power of two, e.g. 2.0 or 0.5): irreversible 9-7 + ICT with
+    the dead-zone quantiser of Annex E and the same step s in every band (scalar expounded QCD, mantissa 0)."""
     ncomp, H, W = samples.shape
     tile_w, tile_h = tile_w or W, tile_h or H
     ntx, nty = cdiv(W, tile_w), cdiv(H, tile_h)
     bands = band_list(nlevels)
     gain = {0: 0, 1: 1, 2: 1, 3: 2}
     eps = [prec + gain[b] + extra_eps for (_, b, _) in bands]
+    irrev = lossy_step is not None
+    if irrev:
+        k = int(round(np.log2(lossy_step)))
+        assert 2.0 ** k == lossy_step, "lossy_step must be a power of two"
+        eps = [prec + gain[b] - k for (_, b, _) in bands]            # step = 2^(Rb - eps) = 2^k, Rb = prec + gain
+        guard = max(guard, 3)
     out = bytearray()
     out += struct.pack(">H", SOC)
     out += struct.pack(">HHHIIIIIIIIH", SIZ, 38 + 3 * ncomp, 0x4000, W, H, 0, 0, tile_w, tile_h, 0, 0, ncomp)
@@ -232,16 +278,26 @@ def write_htj2k(samples, prec, tile_w=None, tile_h=None, nlevels=5, mct=1, cb=64
         out += struct.pack(">BBB", prec - 1, 1, 1)
     out += struct.pack(">HHIH", CAP, 8, 0x00020000, 0)
     xcb = cb.bit_length() - 1
-    out += struct.pack(">HHBBHBBBBBB", COD, 12, 0, 0, 1, 1 if (mct and ncomp >= 3) else 0, nlevels, xcb - 2, xcb - 2, 0x40, 1)
-    out += struct.pack(">HHB", QCD, 3 + len(bands), guard << 5)
-    for e in eps:
-        out += struct.pack(">B", e << 3)
+    out += struct.pack(">HHBBHBBBBBB", COD, 12, 0, 0, 1, 1 if (mct and ncomp >= 3) else 0, nlevels, xcb - 2, xcb - 2, 0x40,
+                       0 if irrev else 1)
+    if irrev:
+        out += struct.pack(">HHB", QCD, 3 + 2 * len(bands), (guard << 5) | 2)
+        for e in eps:
+            out += struct.pack(">H", e << 11)
+    else:
+        out += struct.pack(">HHB", QCD, 3 + len(bands), guard << 5)
+        for e in eps:
+            out += struct.pack(">B", e << 3)
     blocks_info = []
     for ty in range(nty):
         for tx in range(ntx):
             tidx = ty * ntx + tx
             x0, y0, x1, y1 = tx * tile_w, ty * tile_h, min((tx + 1) * tile_w, W), min((ty + 1) * tile_h, H)
-            planes = forward_tile_iso(samples[:, y0:y1, x0:x1], prec, nlevels, mct)
+            if irrev:
+                fp = forward_tile_iso_97(samples[:, y0:y1, x0:x1], prec, nlevels, mct)
+                planes = [(np.sign(p) * np.floor(np.abs(p) / lossy_step)).astype(np.int32) for p in fp]
+            else:
+                planes = forward_tile_iso(samples[:, y0:y1, x0:x1], prec, nlevels, mct)
             body = bytearray()
             for r in range(nlevels + 1):
                 for c in range(ncomp):
@@ -305,7 +361,7 @@ def write_htj2k(samples, prec, tile_w=None, tile_h=None, nlevels=5, mct=1, cb=64
             out += body
     out += struct.pack(">H", EOC)
     info = dict(width=W, height=H, ncomp=ncomp, prec=prec, nlevels=nlevels, mct=mct, tile_w=tile_w, tile_h=tile_h,
-                blocks=blocks_info, guard=guard, eps=eps, reversible=1, ht=1)
+                blocks=blocks_info, guard=guard, eps=eps, reversible=0 if irrev else 1, ht=1, lossy_step=lossy_step)
     return bytes(out), info
 
 
@@ -365,6 +421,8 @@ def parse_codestream(data):
                 raise ValueError("progression order %d" % prog)
             hdr.update(prog=prog, layers=layers, mct=mct, nlevels=nl, cbw=1 << (xcb + 2), cbh=1 << (ycb + 2),
                        cblk_style=sty, reversible=int(xf == 1))
+        elif m == CAP:
+            hdr["ht"] = 1
         elif m == QCD:
             sq = seg[0]
             style, guard = sq & 31, sq >> 5
@@ -378,6 +436,7 @@ def parse_codestream(data):
         elif m in (0xFF53, 0xFF5D, 0xFF5E, 0xFF5F, 0xFF60, 0xFF61):       # COC QCC RGN POC PPM PPT
             raise ValueError("marker %04X not supported" % m)
         pos += 2 + L
+    hdr.setdefault("ht", 0)
     nl, nc, W, H = hdr["nlevels"], hdr["ncomp"], hdr["width"], hdr["height"]
     if hdr["cblk_style"] & ~0x40:
         raise ValueError("code-block style %02X" % hdr["cblk_style"])

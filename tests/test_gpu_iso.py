@@ -276,3 +276,24 @@ def test_iso_reduce_resolution_matches_openjpeg(j2k, gpu_ctx, w, h, kw, reduce):
     im.reduce = reduce
     im.load()
     assert np.array_equal(got[:, :, :3], np.array(im))
+
+
+@pytest.mark.parametrize("w,h,ncomp,tw,nl,step", [(128, 128, 1, None, 3, 2.0), (256, 192, 3, None, 5, 1.0),
+                                                   (333, 211, 3, 128, 4, 4.0), (1024, 512, 3, 512, 5, 2.0),
+                                                   (480, 270, 3, None, 5, 1.0)])      # BASELINE cfg5 geometry / 4
+def test_iso_whole_path_lossy_htj2k(j2k, gpu_ctx, w, h, ncomp, tw, nl, step):
+    """lossy HTJ2K (9-7, ICT, HT cleanup blocks): the GPU path gives OpenJPEG's pixels for the same codestream
+    (north_star tolerance 1 LSB; achieved 0)"""
+    from datagen import codestream as cs
+    Image = pytest.importorskip("PIL.Image")
+    s = jobs.synth_image(w, h, ncomp, 8, seed=w)
+    data, _ = cs.write_htj2k(s, 8, tw, tw, nl, lossy_step=step)
+    job = jobs.build_iso_job_from_codestream(data)
+    assert job["ht"] == 1 and job["reversible"] == 0
+    img = j2k.make_image(w, h, ncomp, 8, mct=job["mct"], reversible=0, nlevels=nl, ht=1, mode=ISO)
+    got = gpu_ctx.decode_tiles(img, jobs.as_ctypes(job["tilecomps"], j2k.TileComp), jobs.as_ctypes(job["cblks"], j2k.CBlk),
+                               job["blob"]).reshape(h, w, -1)
+    ref = np.array(Image.open(io.BytesIO(data)))
+    ref = ref[:, :, None] if ref.ndim == 2 else ref
+    d = np.abs(got[:, :, :ncomp].astype(np.int64) - ref.astype(np.int64))
+    assert d.max() <= 1 and d.max() == 0

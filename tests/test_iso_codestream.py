@@ -263,3 +263,50 @@ def test_iso_oracle_reproduces_openjpeg_golden_vectors(name):
     got, _ = (oracle_decode_reversible if hdr["reversible"] else oracle_decode_irreversible)(data)
     ref = pix[None] if pix.ndim == 2 else np.moveaxis(pix, 2, 0)
     assert np.array_equal(got, ref.astype(np.int64))
+
+
+# ---- lossy HTJ2K (9-7 + ICT + dead-zone quantiser + HT cleanup blocks), written by datagen.codestream ------------------
+@pytest.mark.parametrize("w,h,ncomp,tw,nl,step", [(128, 128, 1, None, 3, 2.0), (256, 192, 3, None, 5, 1.0), (333, 211, 3, 128, 4, 4.0)])
+def test_openjpeg_decodes_our_lossy_htj2k_and_model_matches(w, h, ncomp, tw, nl, step):
+    """OpenJPEG decodes the lossy HTJ2K codestreams of our writer to a sensible image (the writer is conformant), and
+    the float32 model (parser + ISO HT oracle + mid-point dequantisation (|q| + 1/2) * step + OpenJPEG-order 9-7 / ICT)
+    reproduces OpenJPEG's pixels bit for bit"""
+    s = jobs.synth_image(w, h, ncomp, 8, seed=w)
+    data, _ = cs.write_htj2k(s, 8, tw, tw, nl, lossy_step=step)
+    ref = opj_decode(data)
+    ref = ref[None] if ncomp == 1 else np.moveaxis(ref, 2, 0)
+    assert 10 * np.log10(255.0 ** 2 / np.mean((ref.astype(np.float64) - s) ** 2)) > 33
+    hdr = cs.parse_codestream(data)
+    assert hdr["ht"] == 1 and hdr["reversible"] == 0
+    W, H, nc = hdr["width"], hdr["height"], hdr["ncomp"]
+    ntx = cs.cdiv(W, hdr["tile_w"])
+    out = np.zeros((nc, H, W), F32)
+    planes, gain = {}, {0: 0, 1: 1, 2: 1, 3: 2}
+    for b in hdr["blocks"]:
+        t = b["tile"]
+        x0, y0 = (t % ntx) * hdr["tile_w"], (t // ntx) * hdr["tile_h"]
+        x1, y1 = min(x0 + hdr["tile_w"], W), min(y0 + hdr["tile_h"], H)
+        key = (t, b["comp"])
+        if key not in planes:
+            planes[key] = (np.zeros((y1 - y0, x1 - x0), F32), (x0, y0, x1, y1))
+        if not b["passes"]:
+            continue
+        q, rc = O.iso_ht_decode(b["data"], b["w"], b["h"], b["num_bps"])
+        assert rc == 0
+        q = q.astype(np.int64)
+        stp = F32(2.0 ** (hdr["prec"] + gain[b["band"]] - b["expn"]) * (1.0 + b["mant"] / 2048.0))
+        f = (np.sign(q) * (2 * np.abs(q) + (q != 0))).astype(F32) * (F32(0.5) * stp)
+        planes[key][0][b["py"]:b["py"] + b["h"], b["px"]:b["px"] + b["w"]] = f.reshape(b["h"], b["w"])
+    for (t, c), (pl, (x0, y0, x1, y1)) in planes.items():
+        a = pl.copy()
+        dims = [(x1 - x0, y1 - y0)]
+        for _ in range(hdr["nlevels"] - 1):
+            dims.append(((dims[-1][0] + 1) // 2, (dims[-1][1] + 1) // 2))
+        for (lw, lh) in reversed(dims):
+            a[:lh, :lw] = inv97_1d_f32(inv97_1d_f32(a[:lh, :lw], 1), 0)
+        out[c, y0:y1, x0:x1] = a
+    if hdr["mct"] and nc >= 3:
+        y, u, v = out[0].copy(), out[1].copy(), out[2].copy()
+        out[0], out[1], out[2] = y + v * F32(1.402), (y - u * F32(0.34413)) - v * F32(0.71414), y + u * F32(1.772)
+    got = np.clip(np.rint(out).astype(np.int64) + 128, 0, 255)
+    assert np.array_equal(got, ref)

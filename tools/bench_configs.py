@@ -36,6 +36,11 @@ ISO_CONFIGS = {
                      "3840x2160 RGB 8-bit lossless 5-3, 512x512 tiles, EBCOT, written by OpenJPEG"),
     "iso_4k_lossy": (3840, 2160, 3, dict(irreversible=True, num_resolutions=6, mct=1, quality_mode="rates", quality_layers=[80, 40, 20, 10, 5]), 2,
                      "3840x2160 RGB 8-bit lossy 9-7 EBCOT, ICT, 5 quality layers, LRCP, 1 tile, written by OpenJPEG (configs[2] at 8 bits)"),
+    # written by datagen.codestream.write_htj2k (OpenJPEG 2.5 decodes HTJ2K but does not write it)
+    "iso_cfg5": (1920, 1080, 3, dict(htj2k=True, lossy_step=1.0, nlevels=5), 32,
+                 "configs[4] as a real codestream: 1920x1080 RGB 8-bit lossy 9-7 HTJ2K, ICT, 1 tile, 64x64 blocks (batch of frames)"),
+    "iso_cfg2": (3840, 2160, 3, dict(htj2k=True, lossy_step=None, nlevels=5, tile=512), 2,
+                 "configs[1] as a real codestream: 3840x2160 RGB 8-bit lossless HTJ2K, RCT, 512x512 tiles"),
 }
 
 
@@ -51,9 +56,13 @@ def run_iso(name, args, j2k, ctx, stream):
     s = jobs.synth_image(W, H, nc, 8, seed=77)
     buf = io.BytesIO()
     t0 = time.perf_counter()
-    Image.fromarray(np.moveaxis(s, 0, 2).astype(np.uint8)).save(buf, format="JPEG2000", no_jp2=True, **kw)
+    if kw.get("htj2k"):
+        from datagen import codestream as cs
+        data, _ = cs.write_htj2k(s, 8, kw.get("tile"), kw.get("tile"), kw["nlevels"], lossy_step=kw["lossy_step"])
+    else:
+        Image.fromarray(np.moveaxis(s, 0, 2).astype(np.uint8)).save(buf, format="JPEG2000", no_jp2=True, **kw)
+        data = buf.getvalue()
     t_enc = time.perf_counter() - t0
-    data = buf.getvalue()
     t0 = time.perf_counter()
     job = jobs.build_iso_job_from_codestream(data)
     t_parse = time.perf_counter() - t0
@@ -65,7 +74,7 @@ def run_iso(name, args, j2k, ctx, stream):
     stride = W * 4
     tcs, cbs = jobs.as_ctypes(job["tilecomps"], j2k.TileComp), jobs.as_ctypes(job["cblks"], j2k.CBlk)
     blob = np.ascontiguousarray(job["blob"])
-    img = j2k.make_image(W, H, nc, 8, mct=job["mct"], reversible=job["reversible"], nlevels=job["nlevels"], ht=0, mode=1,
+    img = j2k.make_image(W, H, nc, 8, mct=job["mct"], reversible=job["reversible"], nlevels=job["nlevels"], ht=job["ht"], mode=1,
                          coef_bits=job["coef_bits"])
     outs = [np.zeros(stride * H, np.uint8) for _ in range(F)]
     items = [j2k.BatchItem(img, tcs, len(tcs), cbs, len(cbs), blob.ctypes.data_as(j2k.u8p), blob.size,
@@ -99,7 +108,7 @@ def run_iso(name, args, j2k, ctx, stream):
                           ms=dict(whole=round(ms_all, 3), entropy=round(ms_ent, 3), dwt_mct_pack=round(ms_dwt, 3)),
                           mpixel_per_s=round(W * H * F / 1e3 / ms_all, 1),
                           openjpeg_cpu_mpixel_per_s=round(W * H / 1e6 / t_opj, 2),
-                          harness_s=dict(openjpeg_encode=round(t_enc, 2), python_tier2_parse=round(t_parse, 2)))), flush=True)
+                          harness_s=dict(encode=round(t_enc, 2), python_tier2_parse=round(t_parse, 2)))), flush=True)
     J.close()
 
 
