@@ -114,6 +114,7 @@ struct j2kgpu_job {
     std::vector<uint64_t> tc_coef_off;                   // coefficient-arena offset of each tile-component (host copy)
     std::vector<cudaEvent_t> ev_in, ev_done;             // per chunk of the pipelined host-buffer run
     float *d_steps = nullptr;            // ISO irreversible: dequantisation step per block
+    void *d_htscratch = nullptr;         // reference HT coder: quad table between its two kernels
     DevCblk *d_cblks = nullptr;
     DevTileComp *d_tcs = nullptr;
     DevTile *d_tiles = nullptr;
@@ -140,8 +141,10 @@ int j2k_ctx_copy_streams(j2kgpu_ctx *ctx);
 cudaError_t launch_t1_ref(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
                           int max_bps, cudaStream_t s);
 cudaError_t launch_ht_ref(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
-                          int planes_precleared, cudaStream_t s);
-int j2k_htref_map();             // code blocks per warp of the reference-HT decoder: 32 (thread per block, default) or 1
+                          int planes_precleared, void *d_scratch, cudaStream_t s);
+int j2k_htref_map();             // reference-HT decoder mapping: 2 (VLC kernel + MagSgn kernel, default), 32 (thread per block) or 1 (warp per block)
+size_t j2k_htref_scratch_bytes(uint32_t n_blocks);   // device scratch launch_ht_ref needs for n blocks
+int j2k_htref_launches();        // kernels per launch_ht_ref call
 // ISO/IEC 15444-1 Annex D decoder (stripe-order passes, standard tables, pass truncation), one warp per block
 cudaError_t launch_t1_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
                           const float *d_steps, int irrev, int max_bps, cudaStream_t s);

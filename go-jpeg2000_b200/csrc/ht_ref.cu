@@ -231,59 +231,17 @@ __device__ __forceinline__ int32_t magsgn_sample(Fwd &ms, uint32_t emb)
     return (int32_t)(sign ? 0u - m : m);
 }
 
-// Mapping (template BPW = code blocks per warp), like ht_iso.cu: the block's bit streams are one serial chain, so
-//   BPW = 1   one warp per block: every lane runs the chain on uniform registers, lane 0 stores;
-//   BPW = 32  one thread per block: 32 independent chains per warp (short divergent branches), 32x fewer
-//             warp-instructions for the same work; the zero fill of the 32 blocks is done by the whole warp first.
-// The launcher picks by J2KGPU_HTREF_MAP (default thread per block).
-// ZSTEP: rows of a block that are cleared before decoding.  The reference decoder only ever writes sample row y of each
-// 4-row stripe (ht.go:589-593, 677, 701), so inside a job -- whose planes were cleared once when the job was created and
-// are written by nothing else -- clearing every 4th row is enough (ZSTEP = 4); the stage API clears all rows (ZSTEP = 1).
-template <int BPW, typename OT, int ZSTEP>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
-k_ht_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob,
-         OT *__restrict__ coef)
+// The whole block, serially (the statement-level restatement; `do_store`: this thread performs the global stores).
+// The destination rows must have been cleared by the caller.  The reference's context lookups read sigma >> 4 where
+// sigma holds a 4-bit rho (ht.go:611-631), i.e. always 0: the first quad of a pair uses context 0 and the second
+// rho1 >> 2, and no significance state has to be kept.
+template <typename OT>
+__device__ void ht_ref_block_serial(const DevCblk &cb, const uint8_t *__restrict__ blob, OT *__restrict__ coef, bool do_store)
 {
-    __shared__ uint8_t s_sigma[20][kWarpsPerCta * 32];      // quadCols + 1 <= 17 for w <= 64; one column per decoder
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t blk;
-    bool do_store;
-    uint8_t *sigma1;                                        // element i at sigma1[i * kWarpsPerCta * 32]
-    if (BPW == 32) {
-        // fresh decoder: output pre-zeroed (ht.go:81) -- the warp clears its 32 blocks together (coalesced rows)
-        const uint32_t first = (blockIdx.x * kWarpsPerCta + warp) * 32;
-        for (uint32_t bb = first; bb < first + 32 && bb < n; bb++) {
-            const DevCblk c0 = cblks[bb];
-            OT *o = coef + c0.out_off;
-            for (int y = 0; y < c0.h; y += ZSTEP)
-                for (int x = lane; x < c0.w; x += 32) o[(size_t)y * c0.out_stride + x] = 0;
-        }
-        __syncwarp();
-        blk = first + lane;
-        do_store = true;
-        sigma1 = &s_sigma[0][threadIdx.x];
-    } else {
-        blk = blockIdx.x * kWarpsPerCta + warp;
-        do_store = lane == 0;
-        sigma1 = &s_sigma[0][warp * 32];
-    }
-    constexpr int SS = kWarpsPerCta * 32;
-    if (blk >= n) return;
-    const DevCblk cb = cblks[blk];
     const int w = cb.w, h = cb.h, len = (int)cb.data_len;
     OT *out = coef + cb.out_off;
     const uint32_t ostride = cb.out_stride;
     const uint8_t *d = blob + cb.data_off;
-
-    if (BPW == 1) {
-        for (int y = 0; y < h; y += ZSTEP)
-            for (int x = lane; x < w; x += 32) out[(size_t)y * ostride + x] = 0;
-        if (lane < 20) sigma1[lane * SS] = 0;
-        __syncwarp();
-    } else {
-        for (int i = 0; i < 20; i++) sigma1[i * SS] = 0;
-    }
-
     if (len < 2) return;                                                    // ht.go:94-100
     int scup = (int)byte_at(d, len, len - 1) + (int)((byte_at(d, len, len - 2) & 0x0F) << 8);
     if (scup < 2 || scup > len) return;                                     // ht.go:105-111
@@ -299,21 +257,13 @@ k_ht_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
         const uint16_t *tbl = initial ? d_vlc_tbl0 : d_vlc_tbl1;
         for (int qx = 0; qx < quad_cols; qx += 2) {
             uint32_t vv = rev_fetch(vlc);
-            uint32_t ctx = 0;
-            if (initial) { if (qx > 0) ctx = sigma1[(qx - 1) * SS] >> 4; }
-            else ctx = sigma1[qx * SS] >> 4;                                // lineState is never written: 0
-            uint32_t q1 = tbl[(ctx << 7) | (vv & 0x7F)];
+            uint32_t q1 = tbl[vv & 0x7F];
             uint32_t len1 = q1 & 0x0F, rho1 = (q1 >> 4) & 0x0F, uoff1 = (q1 >> 3) & 1;
             rev_advance(vlc, len1);
             vv = rev_fetch(vlc);
-            uint32_t ctx2 = (rho1 >> 2) | (sigma1[(qx + 1) * SS] >> 4);
-            uint32_t q2 = tbl[(ctx2 << 7) | (vv & 0x7F)];
+            uint32_t q2 = tbl[((rho1 >> 2) << 7) | (vv & 0x7F)];
             uint32_t len2 = q2 & 0x0F, rho2 = (q2 >> 4) & 0x0F, uoff2 = (q2 >> 3) & 1;
             rev_advance(vlc, len2);
-            if (BPW == 1) __syncwarp();
-            if (do_store) { sigma1[qx * SS] = (uint8_t)rho1; sigma1[(qx + 1) * SS] = (uint8_t)rho2; }
-            if (BPW == 1) __syncwarp();
-
             uint32_t u0 = 1, u1 = 1;
             uint32_t mode = (uoff1 << 1) | uoff2;
             if (mode > 0) {
@@ -334,21 +284,298 @@ k_ht_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
     }
 }
 
+// Single-kernel mappings (template BPW = code blocks per warp), kept for comparison (J2KGPU_HTREF_MAP = 1 / 32):
+//   BPW = 1   one warp per block: every lane runs the chain on uniform registers, lane 0 stores;
+//   BPW = 32  one thread per block: 32 independent chains per warp (divergent branches), 32x fewer
+//             warp-instructions for the same work; the zero fill of the 32 blocks is done by the whole warp first.
+// ZSTEP: rows of a block that are cleared before decoding.  The reference decoder only ever writes sample row y of each
+// 4-row stripe (ht.go:589-593, 677, 701), so inside a job -- whose planes were cleared once when the job was created and
+// are written by nothing else -- clearing every 4th row is enough (ZSTEP = 4); the stage API clears all rows (ZSTEP = 1).
+template <int BPW, typename OT, int ZSTEP>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_ht_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob,
+         OT *__restrict__ coef)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t blk;
+    if (BPW == 32) {
+        // fresh decoder: output pre-zeroed (ht.go:81) -- the warp clears its 32 blocks together (coalesced rows)
+        const uint32_t first = (blockIdx.x * kWarpsPerCta + warp) * 32;
+        for (uint32_t bb = first; bb < first + 32 && bb < n; bb++) {
+            const DevCblk c0 = cblks[bb];
+            OT *o = coef + c0.out_off;
+            for (int y = 0; y < c0.h; y += ZSTEP)
+                for (int x = lane; x < c0.w; x += 32) o[(size_t)y * c0.out_stride + x] = 0;
+        }
+        __syncwarp();
+        blk = first + lane;
+        if (blk >= n) return;
+        ht_ref_block_serial(cblks[blk], blob, coef, true);
+    } else {
+        blk = blockIdx.x * kWarpsPerCta + warp;
+        if (blk >= n) return;
+        const DevCblk cb = cblks[blk];
+        OT *out = coef + cb.out_off;
+        for (int y = 0; y < cb.h; y += ZSTEP)
+            for (int x = lane; x < cb.w; x += 32) out[(size_t)y * cb.out_stride + x] = 0;
+        __syncwarp();
+        ht_ref_block_serial(cb, blob, coef, lane == 0);
+    }
+}
+
+// ---- two-kernel mapping (default) ------------------------------------------------------------------------------------
+// The block's chain splits where its data dependencies do.  Both streams of the reference coder are pure functions of
+// the block's bytes: every byte contributes 8 bits, or 7 after a 0xFF (MagSgn) / after a byte > 0x8F when its low 7
+// bits are all ones (VLC); an exhausted MagSgn stream continues with 0xFF bytes, an exhausted VLC stream with zeros.
+// WHEN the reference refills its 64-bit buffers is therefore unobservable, with one exception that real inputs of the
+// reference's own encoder do hit: a MagSgn field wider than the 32 bits a fetch guarantees (emb = 33..37 from the
+// U-VLC) makes the uint32 bit counter wrap when fewer than emb bits are buffered (ht.go:668-669); from then on the
+// decoder never refills and reads zeros.  The buffered amount at a fetch is itself a pure function of the position:
+// refills come in 4-byte chunks, so it is (first chunk boundary >= P + 32) - P; the MagSgn kernel keeps the chunk
+// boundaries as a second bit string and finds the first wrapping sample of the block with a warp minimum.
+//   A  k_htref_vlc     one thread per block: the VLC / U-VLC chain only (context of a quad = 0 or rho1 >> 2, see
+//                      above), 128 quad pairs -> 16 bits per quad (rho | emb << 4) in a scratch table, and the
+//                      block's status (not coded / decodable / decodable with fields wider than 32 bits);
+//   B  k_htref_magsgn  one warp per block: bit length of every quad = popc(rho) * (emb + 1), warp prefix sums give
+//                      every quad's position in the MagSgn stream; the warp removes the stuffing once (prefix sum
+//                      of the byte widths, bytes OR-ed into a dense bit string in shared memory) and then every lane
+//                      extracts the 4 samples of one quad per step: 32 quads = two full sample rows per step,
+//                      written as 16-byte stores, zeros included (so no row has to be cleared first).
+constexpr int kQuadWords = 128;                         // 16 stripe rows x 8 quad pairs, one uint32 per pair
+constexpr int kWarpsB = 4;
+constexpr int kStreamWords = (1024 * 38 + 64) / 32 + 2; // 1024 samples x (37 + 1) bits, + the look-ahead windows
+enum { ST_ZERO = 0, ST_FAST = 1, ST_WIDE = 2 };
+
+__global__ void __launch_bounds__(128)
+k_htref_vlc(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob,
+            uint32_t *__restrict__ qinfo, uint8_t *__restrict__ status)
+{
+    __shared__ uint16_t s_tbl[2048];
+    for (int i = threadIdx.x; i < 1024; i += 128) { s_tbl[i] = d_vlc_tbl0[i]; s_tbl[1024 + i] = d_vlc_tbl1[i]; }
+    __syncthreads();
+    const uint32_t blk = blockIdx.x * 128 + threadIdx.x;
+    if (blk >= n) return;
+    const DevCblk cb = cblks[blk];
+    const int w = cb.w, h = cb.h, len = (int)cb.data_len;
+    const uint8_t *d = blob + cb.data_off;
+    int scup = 0;
+    bool ok = len >= 2;
+    if (ok) {
+        scup = (int)byte_at(d, len, len - 1) + (int)((byte_at(d, len, len - 2) & 0x0F) << 8);
+        ok = scup >= 2 && scup <= len && mel_init_ok(d, len, len, scup);
+    }
+    if (!ok) { status[blk] = ST_ZERO; return; }
+    Rev vlc;
+    vlc_init(vlc, d, len, len, scup);
+    uint32_t *qi = qinfo + (size_t)blk * kQuadWords;
+    const int quad_cols = (w + 3) >> 2, rows = (h + 3) >> 2;
+    uint32_t umax = 0;
+    for (int r = 0; r < rows; r++) {
+        const bool initial = (r == 0);
+        const uint16_t *tbl = s_tbl + (initial ? 0 : 1024);
+        for (int qx = 0; qx < quad_cols; qx += 2) {
+            uint32_t vv = rev_fetch(vlc);
+            const uint32_t q1 = tbl[vv & 0x7F];
+            const uint32_t rho1 = (q1 >> 4) & 0x0F;
+            rev_advance(vlc, q1 & 0x0F);
+            vv = rev_fetch(vlc);
+            const uint32_t q2 = tbl[((rho1 >> 2) << 7) | (vv & 0x7F)];
+            const uint32_t rho2 = (q2 >> 4) & 0x0F;
+            rev_advance(vlc, q2 & 0x0F);
+            uint32_t u0 = 1, u1 = 1;
+            const uint32_t mode = (((q1 >> 3) & 1) << 1) | ((q2 >> 3) & 1);
+            if (mode > 0) {
+                vv = rev_fetch(vlc);
+                rev_advance(vlc, uvlc_decode(vv, mode, initial, u0, u1));
+            }
+            umax = max(umax, max(u0, u1));
+            qi[r * 8 + (qx >> 1)] = rho1 | (u0 << 4) | ((rho2 | (u1 << 4)) << 16);
+        }
+    }
+    status[blk] = umax > 32 ? ST_WIDE : ST_FAST;
+}
+
+template <typename OT, int ZSTEP>
+__global__ void __launch_bounds__(kWarpsB * 32)
+k_htref_magsgn(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob,
+               const uint32_t *__restrict__ qinfo, const uint8_t *__restrict__ status, OT *__restrict__ coef)
+{
+    __shared__ uint32_t s_all[kWarpsB][2][kStreamWords];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t blk = blockIdx.x * kWarpsB + warp;
+    if (blk >= n) return;
+    const DevCblk cb = cblks[blk];
+    const int w = cb.w, h = cb.h, len = (int)cb.data_len;
+    OT *out = coef + cb.out_off;
+    const uint32_t ostride = cb.out_stride;
+    const uint8_t *d = blob + cb.data_off;
+    const int st = status[blk];
+    if (st == ST_ZERO) {
+        for (int y = 0; y < h; y += ZSTEP)
+            for (int x = lane; x < w; x += 32) out[(size_t)y * ostride + x] = 0;
+        return;
+    }
+    uint32_t *s = s_all[warp][0];                                       // the MagSgn bits
+    uint32_t *sb = s_all[warp][1];                                      // bit C set: a 4-byte refill chunk ends at bit C
+    const bool wide = (st == ST_WIDE);
+    const int quad_cols = (w + 3) >> 2, rows = (h + 3) >> 2;
+    const int qx = lane & 15;
+    const int ncols = min(4, w - qx * 4);                               // <= 0 for quads right of the block
+    const uint32_t colmask = ncols > 0 ? (1u << ncols) - 1u : 0u;
+    const uint16_t *q16 = reinterpret_cast<const uint16_t *>(qinfo + (size_t)blk * kQuadWords);
+
+    // ---- position of every quad in the MagSgn stream ----
+    uint32_t qv[8], P[8], T = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int row = 2 * j + (lane >> 4);
+        uint32_t q = 0;
+        if (row < rows && qx < quad_cols) q = q16[j * 32 + lane];
+        const uint32_t rho = q & colmask, emb = q >> 4;
+        const uint32_t bits = (uint32_t)__popc(rho) * (emb + 1);
+        uint32_t incl = bits;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        P[j] = T + incl - bits;
+        T += __shfl_sync(0xffffffffu, incl, 31);
+        qv[j] = rho | (emb << 4);
+    }
+
+    // ---- the MagSgn bytes (then 0xFF for ever) without their stuffing, as one dense little-endian bit string ----
+    const uint32_t need = T + 64;                                       // + the widest look-ahead (32-bit field, 5-bit window)
+    const int nW = (int)(need >> 5) + 2;
+    for (int i = lane; i < nW; i += 32) { s[i] = 0; if (wide) sb[i] = 0; }
+    __syncwarp();
+    const int scup = (int)byte_at(d, len, len - 1) + (int)((byte_at(d, len, len - 2) & 0x0F) << 8);
+    const int L = len - scup;
+    uint32_t base = 0, prev_ff = 0;
+    for (int k0 = 0; base < need; k0 += 128) {
+        const int k = k0 + 4 * lane;
+        uint32_t b[4], nb[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) b[i] = (k + i < L) ? (uint32_t)__ldg(d + k + i) : 0xFFu;
+        uint32_t pb = __shfl_up_sync(0xffffffffu, b[3], 1);
+        if (lane == 0) pb = prev_ff ? 0xFFu : 0u;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { nb[i] = pb == 0xFFu ? 7u : 8u; pb = b[i]; }
+        const uint32_t v = b[0] | (b[1] << nb[0]) | (b[2] << (nb[0] + nb[1])) | (b[3] << (nb[0] + nb[1] + nb[2]));
+        const uint32_t tot = nb[0] + nb[1] + nb[2] + nb[3];
+        uint32_t incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const uint32_t pos = base + incl - tot;
+        const int wi = (int)(pos >> 5);
+        const uint32_t sh = pos & 31;
+        if (wi < nW) {
+            atomicOr(&s[wi], v << sh);
+            const uint32_t hi = sh ? v >> (32 - sh) : 0u;
+            if (hi && wi + 1 < nW) atomicOr(&s[wi + 1], hi);
+        }
+        // the decoder starts with two chunks buffered (ht.go:399-429): the end of the first one never limits a fetch
+        const uint32_t cend = pos + tot;
+        if (wide && (k0 | lane) != 0 && (int)(cend >> 5) < nW) atomicOr(&sb[cend >> 5], 1u << (cend & 31));
+        base += __shfl_sync(0xffffffffu, incl, 31);
+        prev_ff = __shfl_sync(0xffffffffu, pb, 31) == 0xFFu;
+    }
+    __syncwarp();
+
+    // ---- first sample whose field is wider than the buffered bits (decode order = quad order, then sample order) ----
+    uint32_t wrap_at = 0xFFFFFFFFu;
+    if (wide) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint32_t rho = qv[j] & 15, emb = qv[j] >> 4;
+            if (emb < 33 || rho == 0) continue;
+            uint32_t p = P[j];
+            for (int i = 0; i < 4; i++)
+                if ((rho >> i) & 1) {
+                    const uint32_t a = p + 32;
+                    const uint32_t win = __funnelshift_r(sb[a >> 5], sb[(a >> 5) + 1], a & 31) & 0x1Fu;
+                    if (win && emb > 31u + (uint32_t)__ffs((int)win)) { wrap_at = min(wrap_at, (uint32_t)((j * 32 + lane) * 4 + i)); break; }
+                    p += emb + 1;
+                }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) wrap_at = min(wrap_at, __shfl_xor_sync(0xffffffffu, wrap_at, o));
+    }
+
+    // ---- 32 quads (two sample rows) per step ----
+    const bool vec_ok = ((cb.out_off | ostride) & 3) == 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int row = 2 * j + (lane >> 4);
+        if (row >= rows || ncols <= 0) continue;
+        const uint32_t rho = qv[j] & 15, emb = qv[j] >> 4;
+        uint32_t p = P[j];
+        int32_t v[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            v[i] = 0;
+            if ((rho >> i) & 1) {
+                const uint32_t idx = (uint32_t)((j * 32 + lane) * 4 + i);
+                uint32_t x = __funnelshift_r(s[p >> 5], s[(p >> 5) + 1], p & 31);
+                if (idx > wrap_at) x = 0;                               // after the wrap the decoder reads zeros
+                const uint32_t m = (emb >= 32 ? x : (x & ((1u << emb) - 1u))) + shl32(1u, emb - 1);
+                p += emb;
+                uint32_t sign = (s[p >> 5] >> (p & 31)) & 1u;
+                if (idx >= wrap_at) sign = 0;
+                p++;
+                v[i] = (int32_t)(sign ? 0u - m : m);
+            }
+        }
+        const int y = 4 * row;
+        OT *o = out + (size_t)y * ostride + qx * 4;
+        if (ncols == 4 && vec_ok) {
+            if (sizeof(OT) == 4) *reinterpret_cast<int4 *>(o) = make_int4(v[0], v[1], v[2], v[3]);
+            else *reinterpret_cast<uint2 *>(o) = make_uint2(((uint32_t)v[0] & 0xFFFFu) | ((uint32_t)v[1] << 16), ((uint32_t)v[2] & 0xFFFFu) | ((uint32_t)v[3] << 16));
+            if (ZSTEP == 1)
+                for (int yy = y + 1; yy < y + 4 && yy < h; yy++) {
+                    OT *z = out + (size_t)yy * ostride + qx * 4;
+                    if (sizeof(OT) == 4) *reinterpret_cast<int4 *>(z) = make_int4(0, 0, 0, 0);
+                    else *reinterpret_cast<uint2 *>(z) = make_uint2(0u, 0u);
+                }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (i < ncols) {
+                    o[i] = (OT)v[i];
+                    if (ZSTEP == 1)
+                        for (int yy = y + 1; yy < y + 4 && yy < h; yy++) out[(size_t)yy * ostride + qx * 4 + i] = 0;
+                }
+        }
+    }
+}
+
 }  // namespace
 
 int j2k_htref_map()
 {
     static int map = -1;
-    if (map < 0) { const char *e = getenv("J2KGPU_HTREF_MAP"); map = (e && atoi(e) == 1) ? 1 : 32; }
+    if (map < 0) { const char *e = getenv("J2KGPU_HTREF_MAP"); const int v = e ? atoi(e) : 2; map = (v == 1 || v == 32) ? v : 2; }
     return map;
 }
 
+size_t j2k_htref_scratch_bytes(uint32_t n) { return (size_t)n * (kQuadWords * 4 + 1) + 16; }
+int j2k_htref_launches() { return j2k_htref_map() == 2 ? 2 : 1; }
+
 // planes_precleared: the destination was zeroed once and only this decoder writes it (whole-path jobs): clear every 4th row
+// d_scratch: j2k_htref_scratch_bytes(n) bytes of device memory (the quad table between the two kernels)
 cudaError_t launch_ht_ref(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
-                          int planes_precleared, cudaStream_t s)
+                          int planes_precleared, void *d_scratch, cudaStream_t s)
 {
     if (n == 0) return cudaSuccess;
     const int map = j2k_htref_map();
+    if (map == 2) {
+        uint32_t *qinfo = (uint32_t *)d_scratch;
+        uint8_t *status = (uint8_t *)d_scratch + (size_t)n * kQuadWords * 4;
+        J2K_LAUNCH((k_htref_vlc), (n + 127) / 128, 128, 0, s, d_cblks, n, d_blob, qinfo, status);
+        const uint32_t grid = (n + kWarpsB - 1) / kWarpsB;
+#define J2K_HTREF_B(OT, Z) J2K_LAUNCH((k_htref_magsgn<OT, Z>), grid, kWarpsB * 32, 0, s, d_cblks, n, d_blob, qinfo, status, (OT *)d_coef)
+        if (coef16) { if (planes_precleared) J2K_HTREF_B(int16_t, 4); else J2K_HTREF_B(int16_t, 1); }
+        else { if (planes_precleared) J2K_HTREF_B(int32_t, 4); else J2K_HTREF_B(int32_t, 1); }
+#undef J2K_HTREF_B
+        return cudaGetLastError();
+    }
     const uint32_t per = map == 32 ? kWarpsPerCta * 32 : kWarpsPerCta, grid = (n + per - 1) / per;
 #define J2K_HTREF_GO(BPW, OT, Z) J2K_LAUNCH((k_ht_ref<BPW, OT, Z>), grid, kWarpsPerCta * 32, 0, s, d_cblks, n, d_blob, (OT *)d_coef)
     if (map == 32) {

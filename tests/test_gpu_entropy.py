@@ -129,6 +129,42 @@ def test_ht_garbage_vs_oracle(gpu_ctx):
         assert np.array_equal(got, O.ht_decode(s, w, h)), i
 
 
+def test_ht_corrupted_magsgn_vs_oracle(gpu_ctx):
+    """valid VLC segments (so the U-VLC values stay small and the blocks take the two-kernel path) over damaged MagSgn
+    segments: 0xFF runs (stuffing), random bytes, truncation (the exhausted stream continues with ones), empty"""
+    rng = np.random.default_rng(26)
+    blocks = []
+    for _ in range(300):
+        w, h = int(rng.integers(1, 65)), int(rng.integers(1, 65))
+        nb = int(rng.integers(1, 14))
+        d = rng.integers(-(1 << nb) + 1, 1 << nb, w * h).astype(np.int32)
+        d[rng.random(w * h) < rng.uniform(0, 0.9)] = 0
+        try:
+            s = np.frombuffer(O.ht_encode(d, w, h), np.uint8).copy()
+        except OverflowError:
+            continue
+        if s.size < 2:
+            continue
+        scup = int(s[-1]) + ((int(s[-2]) & 0x0F) << 8)
+        L = s.size - scup
+        if L > 0:
+            ms, tail = s[:L].copy(), s[L:]
+            mode = int(rng.integers(0, 4))
+            if mode == 0:
+                ms[rng.random(L) < 0.3] = 0xFF
+            elif mode == 1:
+                ms = rng.integers(0, 256, L).astype(np.uint8)
+            elif mode == 2:
+                ms = ms[: int(rng.integers(0, L))]            # scup stays: Lcup shrinks with the segment
+            else:
+                ms = np.concatenate([ms[: L // 2], np.full(L - L // 2, 0xFF, np.uint8)])
+            s = np.concatenate([ms, tail])
+        blocks.append((s.tobytes(), w, h, 0, 0))
+    assert len(blocks) > 200
+    for i, ((s, w, h, _, _), got) in enumerate(zip(blocks, gpu_ctx.ht_decode_blocks(blocks))):
+        assert np.array_equal(got, O.ht_decode(s, w, h)), i
+
+
 def test_block_argument_errors(gpu_ctx, j2k):
     with pytest.raises(j2k.J2KError) as e:
         gpu_ctx.t1_decode_blocks([(b"\x00", 65, 4, 8, 0)])
