@@ -346,9 +346,30 @@ constexpr int kWarpsB = 4;
 constexpr int kStreamWords = (1024 * 38 + 64) / 32 + 2; // 1024 samples x (37 + 1) bits, + the look-ahead windows
 enum { ST_ZERO = 0, ST_FAST = 1, ST_WIDE = 2 };
 
+// The VLC stream as the pure function it is (see above): bytes backwards from Lcup - 3, `left` of them, then zeros; no
+// inner branches, so the 32 chains of a warp diverge only on whether they refill.
+struct VlcStream { const uint8_t *d; int pos, left; uint64_t tmp; uint32_t bits; bool gt8f; };
+
+__device__ __forceinline__ void vlc_refill(VlcStream &v)
+{
+    if (v.bits < 32) {
+        uint32_t b[4], nb[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) b[i] = (i < v.left) ? (uint32_t)__ldg(v.d + v.pos - i) : 0u;
+        v.pos -= 4; v.left -= 4;
+        bool g = v.gt8f;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { nb[i] = (g && (b[i] & 0x7Fu) == 0x7Fu) ? 7u : 8u; g = b[i] > 0x8Fu; }
+        const uint32_t t = b[0] | (b[1] << nb[0]) | (b[2] << (nb[0] + nb[1])) | (b[3] << (nb[0] + nb[1] + nb[2]));
+        v.tmp |= (uint64_t)t << v.bits;
+        v.bits += nb[0] + nb[1] + nb[2] + nb[3];
+        v.gt8f = g;
+    }
+}
+
 __global__ void __launch_bounds__(128)
 k_htref_vlc(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob,
-            uint32_t *__restrict__ qinfo, uint8_t *__restrict__ status)
+            uint32_t *__restrict__ qinfo, uint32_t *__restrict__ status)
 {
     __shared__ uint16_t s_tbl[2048];
     for (int i = threadIdx.x; i < 1024; i += 128) { s_tbl[i] = d_vlc_tbl0[i]; s_tbl[1024 + i] = d_vlc_tbl1[i]; }
@@ -365,8 +386,15 @@ k_htref_vlc(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__rest
         ok = scup >= 2 && scup <= len && mel_init_ok(d, len, len, scup);
     }
     if (!ok) { status[blk] = ST_ZERO; return; }
-    Rev vlc;
-    vlc_init(vlc, d, len, len, scup);
+    VlcStream v;                                                        // initVLC ht.go:276-314
+    {
+        const uint32_t b = __ldg(d + len - 2);
+        v.d = d; v.pos = len - 3; v.left = scup - 2;
+        v.tmp = b >> 4;
+        v.bits = 4 - (uint32_t)((v.tmp & 7) >> 2);
+        v.gt8f = (b | 0x0F) > 0x8F;
+    }
+    vlc_refill(v);
     uint32_t *qi = qinfo + (size_t)blk * kQuadWords;
     const int quad_cols = (w + 3) >> 2, rows = (h + 3) >> 2;
     uint32_t umax = 0;
@@ -374,42 +402,47 @@ k_htref_vlc(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__rest
         const bool initial = (r == 0);
         const uint16_t *tbl = s_tbl + (initial ? 0 : 1024);
         for (int qx = 0; qx < quad_cols; qx += 2) {
-            uint32_t vv = rev_fetch(vlc);
-            const uint32_t q1 = tbl[vv & 0x7F];
-            const uint32_t rho1 = (q1 >> 4) & 0x0F;
-            rev_advance(vlc, q1 & 0x0F);
-            vv = rev_fetch(vlc);
-            const uint32_t q2 = tbl[((rho1 >> 2) << 7) | (vv & 0x7F)];
-            const uint32_t rho2 = (q2 >> 4) & 0x0F;
-            rev_advance(vlc, q2 & 0x0F);
+            vlc_refill(v);                                              // >= 32 bits: both codewords (<= 15 + 15)
+            const uint32_t q1 = tbl[(uint32_t)v.tmp & 0x7F];
+            const uint32_t rho1 = (q1 >> 4) & 0x0F, l1 = q1 & 0x0F;
+            const uint32_t q2 = tbl[((rho1 >> 2) << 7) | ((uint32_t)(v.tmp >> l1) & 0x7F)];
+            const uint32_t rho2 = (q2 >> 4) & 0x0F, l12 = l1 + (q2 & 0x0F);
+            v.tmp >>= l12; v.bits -= l12;
             uint32_t u0 = 1, u1 = 1;
             const uint32_t mode = (((q1 >> 3) & 1) << 1) | ((q2 >> 3) & 1);
             if (mode > 0) {
-                vv = rev_fetch(vlc);
-                rev_advance(vlc, uvlc_decode(vv, mode, initial, u0, u1));
+                vlc_refill(v);
+                const uint32_t c = uvlc_decode((uint32_t)v.tmp, mode, initial, u0, u1);
+                v.tmp >>= c; v.bits -= c;
             }
             umax = max(umax, max(u0, u1));
             qi[r * 8 + (qx >> 1)] = rho1 | (u0 << 4) | ((rho2 | (u1 << 4)) << 16);
         }
     }
-    status[blk] = umax > 32 ? ST_WIDE : ST_FAST;
+    status[blk] = (umax > 32 ? ST_WIDE : ST_FAST) | ((uint32_t)(len - scup) << 2);      // + the MagSgn segment length
 }
 
 template <typename OT, int ZSTEP>
 __global__ void __launch_bounds__(kWarpsB * 32)
 k_htref_magsgn(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob,
-               const uint32_t *__restrict__ qinfo, const uint8_t *__restrict__ status, OT *__restrict__ coef)
+               const uint32_t *__restrict__ qinfo, const uint32_t *__restrict__ status, OT *__restrict__ coef)
 {
     __shared__ uint32_t s_all[kWarpsB][2][kStreamWords];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t blk = blockIdx.x * kWarpsB + warp;
     if (blk >= n) return;
+    // three independent loads: the block, its status word and (below) its quad table
+    const uint32_t stw = status[blk];
+    const uint16_t *q16 = reinterpret_cast<const uint16_t *>(qinfo + (size_t)blk * kQuadWords);
+    uint32_t qraw[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) qraw[j] = q16[j * 32 + lane];           // entries the VLC kernel did not write are masked below
     const DevCblk cb = cblks[blk];
-    const int w = cb.w, h = cb.h, len = (int)cb.data_len;
+    const int w = cb.w, h = cb.h;
     OT *out = coef + cb.out_off;
     const uint32_t ostride = cb.out_stride;
     const uint8_t *d = blob + cb.data_off;
-    const int st = status[blk];
+    const int st = (int)(stw & 3);
     if (st == ST_ZERO) {
         for (int y = 0; y < h; y += ZSTEP)
             for (int x = lane; x < w; x += 32) out[(size_t)y * ostride + x] = 0;
@@ -422,15 +455,13 @@ k_htref_magsgn(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__r
     const int qx = lane & 15;
     const int ncols = min(4, w - qx * 4);                               // <= 0 for quads right of the block
     const uint32_t colmask = ncols > 0 ? (1u << ncols) - 1u : 0u;
-    const uint16_t *q16 = reinterpret_cast<const uint16_t *>(qinfo + (size_t)blk * kQuadWords);
 
     // ---- position of every quad in the MagSgn stream ----
     uint32_t qv[8], P[8], T = 0;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
         const int row = 2 * j + (lane >> 4);
-        uint32_t q = 0;
-        if (row < rows && qx < quad_cols) q = q16[j * 32 + lane];
+        const uint32_t q = (row < rows && qx < quad_cols) ? qraw[j] : 0u;
         const uint32_t rho = q & colmask, emb = q >> 4;
         const uint32_t bits = (uint32_t)__popc(rho) * (emb + 1);
         uint32_t incl = bits;
@@ -446,14 +477,16 @@ k_htref_magsgn(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__r
     const int nW = (int)(need >> 5) + 2;
     for (int i = lane; i < nW; i += 32) { s[i] = 0; if (wide) sb[i] = 0; }
     __syncwarp();
-    const int scup = (int)byte_at(d, len, len - 1) + (int)((byte_at(d, len, len - 2) & 0x0F) << 8);
-    const int L = len - scup;
+    const int L = (int)(stw >> 2);
     uint32_t base = 0, prev_ff = 0;
-    for (int k0 = 0; base < need; k0 += 128) {
-        const int k = k0 + 4 * lane;
-        uint32_t b[4], nb[4];
+    uint32_t bn[4];                                                     // the next chunk's bytes, loaded one iteration early
 #pragma unroll
-        for (int i = 0; i < 4; i++) b[i] = (k + i < L) ? (uint32_t)__ldg(d + k + i) : 0xFFu;
+    for (int i = 0; i < 4; i++) bn[i] = (4 * lane + i < L) ? (uint32_t)__ldg(d + 4 * lane + i) : 0xFFu;
+    for (int k0 = 0; base < need; k0 += 128) {
+        uint32_t b[4], nb[4];
+        const int kn = k0 + 128 + 4 * lane;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { b[i] = bn[i]; bn[i] = (kn + i < L) ? (uint32_t)__ldg(d + kn + i) : 0xFFu; }
         uint32_t pb = __shfl_up_sync(0xffffffffu, b[3], 1);
         if (lane == 0) pb = prev_ff ? 0xFFu : 0u;
 #pragma unroll
@@ -555,7 +588,7 @@ int j2k_htref_map()
     return map;
 }
 
-size_t j2k_htref_scratch_bytes(uint32_t n) { return (size_t)n * (kQuadWords * 4 + 1) + 16; }
+size_t j2k_htref_scratch_bytes(uint32_t n) { return (size_t)n * (kQuadWords * 4 + 4) + 16; }
 int j2k_htref_launches() { return j2k_htref_map() == 2 ? 2 : 1; }
 
 // planes_precleared: the destination was zeroed once and only this decoder writes it (whole-path jobs): clear every 4th row
@@ -567,7 +600,7 @@ cudaError_t launch_ht_ref(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_b
     const int map = j2k_htref_map();
     if (map == 2) {
         uint32_t *qinfo = (uint32_t *)d_scratch;
-        uint8_t *status = (uint8_t *)d_scratch + (size_t)n * kQuadWords * 4;
+        uint32_t *status = qinfo + (size_t)n * kQuadWords;
         J2K_LAUNCH((k_htref_vlc), (n + 127) / 128, 128, 0, s, d_cblks, n, d_blob, qinfo, status);
         const uint32_t grid = (n + kWarpsB - 1) / kWarpsB;
 #define J2K_HTREF_B(OT, Z) J2K_LAUNCH((k_htref_magsgn<OT, Z>), grid, kWarpsB * 32, 0, s, d_cblks, n, d_blob, qinfo, status, (OT *)d_coef)
