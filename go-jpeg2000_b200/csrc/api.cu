@@ -267,7 +267,7 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
     j2kgpu_job *job = new (std::nothrow) j2kgpu_job();
     if (!job) return j2k_set_err(ctx, J2KGPU_E_NOMEM, "job");
     job->ctx = ctx; job->n_img = n_img; job->hdr = hdr; job->tail = tp; job->nlevels = hdr.nlevels; job->iso = iso;
-    if (const char *e = getenv("J2KGPU_HT_MAP")) job->ht_map = (atoi(e) == 1) ? 1 : 32;
+    if (const char *e = getenv("J2KGPU_HT_MAP")) { const int v = atoi(e); job->ht_map = (v == 1 || v == 32) ? v : 2; }
 
     std::vector<DevTileComp> tcs;
     std::vector<DevTile> tiles;
@@ -408,7 +408,8 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
     up((void **)&job->d_tiles, tiles.data(), tiles.size() * sizeof(DevTile));
     if (e == cudaSuccess) job->d_coef = j2k_pool_alloc(ctx, coef_elems * (job->coef16 ? 2 : 4) + 64, &e);
     if (e == cudaSuccess) job->d_tmp = j2k_pool_alloc(ctx, job->tmp_bytes, &e);
-    if (e == cudaSuccess && !iso && hdr.ht) job->d_htscratch = j2k_pool_alloc(ctx, j2k_htref_scratch_bytes((uint32_t)cbs.size()), &e);
+    if (e == cudaSuccess && hdr.ht && (!iso || job->ht_map == 2))
+        job->d_htscratch = j2k_pool_alloc(ctx, iso ? j2k_htiso_scratch_bytes((uint32_t)cbs.size()) : j2k_htref_scratch_bytes((uint32_t)cbs.size()), &e);
     // reference HT coder: its decoder writes one row in four (ht.go:677, 701); zero the planes once, here, so that every
     // run only has to clear the rows it may write (3/4 of the entropy stage's zero-fill traffic saved)
     if (e == cudaSuccess && !iso && hdr.ht && !env_flag("J2KGPU_NO_PRECLEAR")) {
@@ -454,7 +455,11 @@ static int run_entropy(j2kgpu_job *job, const void *d_blob, uint32_t ia, uint32_
     const int irrev = job->iso && !job->hdr.reversible;                  // ISO 9-7: the planes receive dequantised float32
     const float *steps = job->d_steps ? job->d_steps + ca : nullptr;
     if (job->iso && !job->hdr.ht) e = launch_t1_iso(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, steps, irrev, job->max_bps, st);
-    else if (job->iso) e = launch_ht_iso(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, steps, irrev, job->hdr.coef_bits, job->ht_map, st);
+    else if (job->iso) {
+        e = launch_ht_iso(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, steps, irrev, job->hdr.coef_bits, job->ht_map,
+                          job->d_htscratch, st);
+        if (job->ht_map == 2) ctx->launches++;
+    }
     else if (job->hdr.ht) {
         // the scratch is indexed by the job-wide block number: chunks of a pipelined run never share entries
         e = launch_ht_ref(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, job->precleared,
@@ -576,7 +581,7 @@ static int run_host_locked(j2kgpu_job *job, const j2k_batch_item_t *items)
     // launch (its run time is one block's serial chain whatever the count), so its chunks hold >= 16K blocks.
     const uint32_t n = job->n_img;
     uint32_t per = n >= 16 ? (n + 7) / 8 : 1;
-    const bool thread_per_block = job->hdr.ht && (job->iso ? job->ht_map == 32 : j2k_htref_map() != 1);
+    const bool thread_per_block = job->hdr.ht && (job->iso ? job->ht_map != 1 : j2k_htref_map() != 1);
     if (thread_per_block && job->n_cb) {
         const uint64_t blocks_per_item = (job->n_cb + n - 1) / n;
         const uint32_t need = (uint32_t)((16384 + blocks_per_item - 1) / blocks_per_item);
@@ -691,10 +696,11 @@ static int stage_blocks(j2kgpu_ctx *ctx, int mode, int ht, const j2k_blkjob_t *j
     if (blob_len) J2K_CUDA(ctx, cudaMemcpyAsync(ctx->d_in.p, blob, blob_len, cudaMemcpyHostToDevice, ctx->stream));
     J2K_CUDA(ctx, cudaMemsetAsync(ctx->d_out.p, 0, out_len * sizeof(int32_t), ctx->stream));
     if (ht && mode != J2KGPU_MODE_ISO) { if ((rc = j2k_reserve(ctx, ctx->d_aux, j2k_htref_scratch_bytes(n), false))) return rc; ctx->launches += j2k_htref_launches() - 1; }
-    int ht_map = 32;
-    if (const char *ev = getenv("J2KGPU_HT_MAP")) ht_map = (atoi(ev) == 1) ? 1 : 32;
+    int ht_map = 2;
+    if (const char *ev = getenv("J2KGPU_HT_MAP")) { const int v = atoi(ev); ht_map = (v == 1 || v == 32) ? v : 2; }
+    if (ht && mode == J2KGPU_MODE_ISO && ht_map == 2) { if ((rc = j2k_reserve(ctx, ctx->d_aux, j2k_htiso_scratch_bytes(n), false))) return rc; ctx->launches++; }
     cudaError_t e = (ht && mode == J2KGPU_MODE_ISO)
-                        ? launch_ht_iso((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, nullptr, 0, 0, ht_map, ctx->stream)
+                        ? launch_ht_iso((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, nullptr, 0, 0, ht_map, ctx->d_aux.p, ctx->stream)
                     : mode == J2KGPU_MODE_ISO ? launch_t1_iso((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, nullptr, 0, max_bps, ctx->stream)
                     : ht ? launch_ht_ref((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, 0, ctx->d_aux.p, ctx->stream)
                        : launch_t1_ref_stage((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, (int32_t *)ctx->d_out.p, max_bps, ctx->stream);

@@ -104,7 +104,7 @@ struct j2kgpu_job {
     bool need_clear = false;
     uint32_t stream_levels = 0;
     int iso = 0;                         // J2KGPU_MODE_ISO
-    int ht_map = 32;                     // ISO HT: code blocks per warp (32 = thread per block, 1 = warp per block)
+    int ht_map = 2;                      // ISO HT mapping: 2 = VLC kernel + MagSgn kernel, 32 = thread per block, 1 = warp per block
     int coef16 = 0;                      // coefficient arena holds int16 (every magnitude provably < 2^15) instead of int32
     int fused_ok = 0;                    // levels 1 + 0 + pixel epilogue run as one kernel (idwt_fused.cu)
     int fast_epi = 0;                    // every tile qualifies for the fused kernel's fixed RGBA8 epilogue
@@ -150,7 +150,8 @@ cudaError_t launch_t1_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_b
                           const float *d_steps, int irrev, int max_bps, cudaStream_t s);
 // ISO/IEC 15444-15 cleanup decoder; blocks_per_warp = 1 (warp per block) or 32 (thread per block)
 cudaError_t launch_ht_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
-                          const float *d_steps, int irrev, int coef_bits, int blocks_per_warp, cudaStream_t s);
+                          const float *d_steps, int irrev, int coef_bits, int blocks_per_warp, void *d_scratch, cudaStream_t s);
+size_t j2k_htiso_scratch_bytes(uint32_t n_blocks);   // device scratch of the two-kernel mapping (blocks_per_warp == 2)
 
 // inverse DWT, REF (dense-prefix) addressing.  One call = one decomposition level of every
 // tile-component in the table.  `lvl` counts from 0 (full resolution).  For lvl > 0 the output goes to the

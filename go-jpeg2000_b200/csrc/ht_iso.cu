@@ -336,13 +336,300 @@ k_ht_iso(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
     ht_decode_block(cb, blob, coef, s_tbl, ex, kThreads, do_store, steps ? steps[blk] : 1.0f, irrev != 0, coef_bits);
 }
 
+// ---- two-kernel mapping (default) ------------------------------------------------------------------------------------
+// A block's chain splits where its data dependencies do (the same cut as in ht_ref.cu):
+//   A  k_htiso_vlc     one thread per block: MEL + CxtVLC + U-VLC only -- the context chain through the previous quad and
+//                      the previous quad row.  Output: 16 bits per quad in a scratch table, row-major 32 quads per quad
+//                      row: 2 bits per sample (0 insignificant, 1 significant, 2 + known EMB bit = 0, 3 + EMB bit = 1;
+//                      the CxtVLC tables satisfy e_1 <= e_k <= rho, so this loses nothing) and u_q << 8.
+//   B  k_htiso_magsgn  one warp per block, one lane per quad of a quad row: the exponent predictor needs the previous
+//                      row's exponents (two shuffles), then U_q, the four field widths, a warp prefix sum for the
+//                      position of every quad in the MagSgn stream, and the extraction of the row's 128 samples in
+//                      parallel; rows are written as contiguous 8-byte stores.  The stuffing is removed by the warp in
+//                      128-byte chunks (prefix sum of byte widths, bytes OR-ed into a dense bit string) into a 16 Kbit
+//                      shared-memory ring that runs at least one quad row (32 x 4 x 31 bits) ahead of the decoder.
+// The streams are pure functions of the block's bytes (see ht_ref.cu), so the result equals the single-chain decoder's
+// for every input, malformed ones included (same `bad` conditions, same zero block).
+constexpr int kQTabWords = 512;                         // 32 quad rows x 32 quads x 16 bits
+constexpr int kRingWords = 512;
+constexpr int kWarpsIsoB = 8;
+enum { ST_ZERO = 0, ST_OK = 1 };
+
+struct VlcStream { const uint8_t *d; int pos, left; uint64_t tmp; uint32_t bits; bool gt8f; };
+
+__device__ __forceinline__ void vlc_read4(VlcStream &v)
+{
+    uint32_t b[4], nb[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) b[i] = (i < v.left) ? (uint32_t)__ldg(v.d + v.pos - i) : 0u;
+    v.pos -= 4; v.left -= 4;
+    bool g = v.gt8f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { nb[i] = (g && (b[i] & 0x7Fu) == 0x7Fu) ? 7u : 8u; g = b[i] > 0x8Fu; }
+    const uint32_t t = b[0] | (b[1] << nb[0]) | (b[2] << (nb[0] + nb[1])) | (b[3] << (nb[0] + nb[1] + nb[2]));
+    v.tmp |= (uint64_t)t << v.bits;
+    v.bits += nb[0] + nb[1] + nb[2] + nb[3];
+    v.gt8f = g;
+}
+
+// at least 32 bits afterwards (four stuffed bytes give only 28: then a second read, which is rare)
+__device__ __forceinline__ void vlc_refill(VlcStream &v)
+{
+    if (v.bits < 32) {
+        vlc_read4(v);
+        if (v.bits < 32) vlc_read4(v);
+    }
+}
+
+// 4 bits -> the even bit positions of a byte
+__device__ __forceinline__ uint32_t spread4(uint32_t x) { return (x & 1) | ((x & 2) << 1) | ((x & 4) << 2) | ((x & 8) << 3); }
+
+__global__ void __launch_bounds__(kThreads)
+k_htiso_vlc(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob,
+            uint32_t *__restrict__ qtab, uint32_t *__restrict__ status)
+{
+    // table entries re-packed: len (3) | u_off (1) | rho (4) | sample states (8)
+    __shared__ uint16_t s_tbl[2048];
+    for (int i = threadIdx.x; i < 2048; i += kThreads) {
+        const uint32_t e = i < 1024 ? d_tbl0[i] : d_tbl1[i - 1024];
+        const uint32_t st8 = spread4((e >> 4) & 15) + spread4((e >> 12) & 15) + spread4((e >> 8) & 15);
+        s_tbl[i] = (uint16_t)((e & 0xFF) | (st8 << 8));
+    }
+    __syncthreads();
+    const uint32_t blk = blockIdx.x * kThreads + threadIdx.x;
+    if (blk >= n) return;
+    const DevCblk cb = cblks[blk];
+    const int w = cb.w, h = cb.h;
+    const uint8_t *d = blob + cb.data_off;
+    const int lcup = (int)cb.data_len;
+    bool ok = lcup >= 2 && cb.num_bps >= 1 && cb.num_bps <= 30;
+    int scup = 0;
+    if (ok) {
+        scup = ((int)__ldg(d + lcup - 1) << 4) + (int)(__ldg(d + lcup - 2) & 0x0F);
+        ok = scup >= 2 && scup <= lcup && scup <= 4079;
+    }
+    if (!ok) { status[blk] = ST_ZERO; return; }
+    Mel mel; mel.pos = lcup - scup; mel.left = scup - 1; mel.tmp = 0; mel.bits = 0; mel.unstuff = false;
+    mel.k = 0; mel.zeros = 0; mel.one_after = false;
+    VlcStream v;
+    {
+        const uint32_t b = __ldg(d + lcup - 2);
+        v.d = d; v.pos = lcup - 3; v.left = scup - 2;
+        v.tmp = b >> 4;
+        v.bits = 4 - (((v.tmp & 7) == 7) ? 1 : 0);
+        v.gt8f = (b | 0x0F) > 0x8F;
+    }
+    uint32_t *qt = qtab + (size_t)blk * kQTabWords;
+    const int nq = (w + 1) >> 1;
+    uint64_t sigprev = 0;
+    bool bad = false;
+    for (int y = 0; y < h; y += 2) {
+        const bool initial = (y == 0);
+        const uint16_t *tbl = s_tbl + (initial ? 0 : 1024);
+        const bool row2 = (y + 1 < h);
+        uint64_t signew = 0;
+        int cw = 0;
+        for (int q = 0; q < nq; q += 2) {
+            const bool pair = (q + 1 < nq);
+            vlc_refill(v);                               // >= 32 bits: two codewords (<= 7 each) and the U-VLC (<= 17)
+            uint32_t e0, e1 = 0;
+            {
+                int c_q = cw;
+                if (!initial) { const uint32_t s4 = win4(sigprev, 2 * q); c_q |= ((s4 | (s4 >> 1)) & 1) | ((((s4 >> 2) | (s4 >> 3)) & 1) << 2); }
+                uint32_t e = tbl[(c_q << 7) | ((uint32_t)v.tmp & 0x7F)];
+                if (c_q == 0 && !mel_event(mel, d)) e = 0;
+                v.tmp >>= (e & 7); v.bits -= (e & 7);
+                e0 = e;
+                const uint32_t rho = (e >> 4) & 0xF;
+                cw = initial ? (int)(((rho | (rho >> 1)) & 1) | (((rho >> 2) & 1) << 1) | (((rho >> 3) & 1) << 2))
+                             : (int)((((rho >> 2) | (rho >> 3)) & 1) << 1);
+            }
+            if (pair) {
+                int c_q = cw;
+                if (!initial) { const uint32_t s4 = win4(sigprev, 2 * q + 2); c_q |= ((s4 | (s4 >> 1)) & 1) | ((((s4 >> 2) | (s4 >> 3)) & 1) << 2); }
+                uint32_t e = tbl[(c_q << 7) | ((uint32_t)v.tmp & 0x7F)];
+                if (c_q == 0 && !mel_event(mel, d)) e = 0;
+                v.tmp >>= (e & 7); v.bits -= (e & 7);
+                e1 = e;
+                const uint32_t rho = (e >> 4) & 0xF;
+                cw = initial ? (int)(((rho | (rho >> 1)) & 1) | (((rho >> 2) & 1) << 1) | (((rho >> 3) & 1) << 2))
+                             : (int)((((rho >> 2) | (rho >> 3)) & 1) << 1);
+            }
+            int mode = (int)(((e0 >> 3) & 1) | (((e1 >> 3) & 1) << 1));
+            if (initial && mode == 3 && mel_event(mel, d)) mode = 4;
+            int u0 = 0, u1 = 0;
+            if (mode) { const int c = uvlc_decode((uint32_t)v.tmp, mode, initial, u0, u1); v.tmp >>= c; v.bits -= c; }
+            const int xq = 2 * q;
+            signew |= ((uint64_t)((e0 >> 5) & 1) << xq) | ((uint64_t)((e0 >> 7) & 1) << (xq + 1));
+            if (!row2 && (e0 & 0xA0)) bad = true;        // significance outside the block: malformed, the block is zero
+            if (xq + 1 >= w && (e0 & 0xC0)) bad = true;
+            if (pair) {
+                signew |= ((uint64_t)((e1 >> 5) & 1) << (xq + 2)) | ((uint64_t)((e1 >> 7) & 1) << (xq + 3));
+                if (!row2 && (e1 & 0xA0)) bad = true;
+                if (xq + 3 >= w && (e1 & 0xC0)) bad = true;
+            }
+            // u >= 31 makes U_q > 31 whatever the predictor says: malformed either way, 5 bits are enough
+            qt[(y >> 1) * 16 + (q >> 1)] = (e0 >> 8) | ((uint32_t)min(u0, 31) << 8) | (((e1 >> 8) | ((uint32_t)min(u1, 31) << 8)) << 16);
+        }
+        sigprev = signew;
+    }
+    status[blk] = bad ? (uint32_t)ST_ZERO : ((uint32_t)ST_OK | ((uint32_t)(lcup - scup) << 2));
+}
+
+template <typename OT>
+__global__ void __launch_bounds__(kWarpsIsoB * 32)
+k_htiso_magsgn(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob,
+               const uint32_t *__restrict__ qtab, const uint32_t *__restrict__ status, OT *__restrict__ coef,
+               const float *__restrict__ steps, int irrev_i, int coef_bits)
+{
+    __shared__ uint32_t s_ring[kWarpsIsoB][kRingWords];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t blk = blockIdx.x * kWarpsIsoB + warp;
+    if (blk >= n) return;
+    const uint32_t stw = status[blk];
+    const DevCblk cb = cblks[blk];
+    const int w = cb.w, h = cb.h;
+    OT *out = coef + cb.out_off;
+    const size_t ostride = cb.out_stride;
+    const uint8_t *d = blob + cb.data_off;
+    if ((stw & 3) == ST_ZERO) {
+        for (int y = 0; y < h; y++)
+            for (int x = lane; x < w; x += 32) out[(size_t)y * ostride + x] = 0;
+        return;
+    }
+    const bool irrev = irrev_i != 0;
+    const float step = steps ? steps[blk] : 1.0f;
+    const int L = (int)(stw >> 2);
+    const int shift = cb.num_bps - 1;
+    const int nq = (w + 1) >> 1, nrows = (h + 1) >> 1;
+    const bool active = lane < nq;
+    const bool colB = (2 * lane + 1 < w);
+    const bool vec_ok = ((cb.out_off | ostride) & 1) == 0;
+    const uint16_t *qt = reinterpret_cast<const uint16_t *>(qtab + (size_t)blk * kQTabWords);
+    uint32_t *ring = s_ring[warp];
+    for (int i = lane; i < kRingWords; i += 32) ring[i] = 0;
+    __syncwarp();
+    uint32_t built = 0, prev_ff = 0, P = 0;              // warp-uniform: bits in the ring, last byte was 0xFF, bits consumed
+    int kbyte = 0;
+    int Eb0 = 0, Eb1 = 0;                                // exponents of this quad's bottom samples in the previous quad row
+    bool bad = false;
+    uint32_t code_next = active ? (uint32_t)qt[lane] : 0u;
+    for (int r = 0; r < nrows; r++) {
+        const uint32_t code = code_next;
+        if (r + 1 < nrows) code_next = active ? (uint32_t)qt[(r + 1) * 32 + lane] : 0u;
+        // ---- keep the ring one full quad row ahead ----
+        while (built < P + 4096u) {
+            const int k = kbyte + 4 * lane;
+            uint32_t b[4], nb[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) b[i] = (k + i < L) ? (uint32_t)__ldg(d + k + i) : 0xFFu;
+            // the words this chunk reaches beyond the one `built` points into still hold bits 16 Kbit old
+            const uint32_t w0 = (built >> 5) + 1;
+            ring[(w0 + lane) & (kRingWords - 1)] = 0;
+            if (lane < 2) ring[(w0 + 32 + lane) & (kRingWords - 1)] = 0;
+            uint32_t pb = __shfl_up_sync(0xffffffffu, b[3], 1);
+            if (lane == 0) pb = prev_ff ? 0xFFu : 0u;
+#pragma unroll
+            for (int i = 0; i < 4; i++) { nb[i] = pb == 0xFFu ? 7u : 8u; pb = b[i]; }
+            const uint32_t v = b[0] | (b[1] << nb[0]) | (b[2] << (nb[0] + nb[1])) | (b[3] << (nb[0] + nb[1] + nb[2]));
+            const uint32_t tot = nb[0] + nb[1] + nb[2] + nb[3];
+            uint32_t incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            const uint32_t pos = built + incl - tot;
+            const uint32_t sh = pos & 31;
+            __syncwarp();
+            atomicOr(&ring[(pos >> 5) & (kRingWords - 1)], v << sh);
+            const uint32_t hi = sh ? v >> (32 - sh) : 0u;
+            if (hi) atomicOr(&ring[((pos >> 5) + 1) & (kRingWords - 1)], hi);
+            built += __shfl_sync(0xffffffffu, incl, 31);
+            prev_ff = __shfl_sync(0xffffffffu, pb, 31) == 0xFFu;
+            kbyte += 128;
+            __syncwarp();
+        }
+        // ---- U_q and the four field widths ----
+        const uint32_t st8 = code & 0xFF;
+        const int u = (int)(code >> 8);
+        const uint32_t sig = (st8 | (st8 >> 1)) & 0x55u;               // bit 2n: sample n significant
+        int U = u + 1;
+        if (r > 0) {
+            const int eL = __shfl_up_sync(0xffffffffu, Eb1, 1), eR = __shfl_down_sync(0xffffffffu, Eb0, 1);
+            if (sig & (sig - 1)) {
+                const int E = max(max(lane ? eL : 0, Eb0), max(Eb1, lane < 31 ? eR : 0));
+                U = u + max(1, E - 1);
+            }
+        }
+        if (U > 31) bad = true;
+        if (coef_bits && U + shift > coef_bits + 1) bad = true;
+        U = min(U, 31);
+        int m[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { const uint32_t s2 = (st8 >> (2 * i)) & 3; m[i] = s2 ? U - (int)(s2 >> 1) : 0; }
+        const uint32_t tot = (uint32_t)(m[0] + m[1] + m[2] + m[3]);
+        uint32_t incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        uint32_t p = P + incl - tot;
+        P += __shfl_sync(0xffffffffu, incl, 31);
+        // ---- the quad's samples: n = 0 (y, x), 1 (y + 1, x), 2 (y, x + 1), 3 (y + 1, x + 1) ----
+        int32_t val[4];
+        int en[2] = {0, 0};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t s2 = (st8 >> (2 * i)) & 3;
+            val[i] = 0;
+            if (s2) {
+                const uint32_t x = __funnelshift_r(ring[(p >> 5) & (kRingWords - 1)], ring[((p >> 5) + 1) & (kRingWords - 1)], p & 31);
+                uint32_t vv = x & ((1u << m[i]) - 1u);
+                const uint32_t sign = vv & 1;
+                vv |= (uint32_t)(s2 == 3) << m[i];
+                vv |= 1;
+                val[i] = sample_value((vv >> 1) + 1, sign, shift, step, irrev);
+                if (i & 1) en[i >> 1] = 32 - __clz((int)vv);
+                p += (uint32_t)m[i];
+            }
+        }
+        Eb0 = en[0]; Eb1 = en[1];
+        if (active) {
+            const int y = 2 * r;
+            const bool row2 = (y + 1 < h);
+            OT *p0 = out + (size_t)y * ostride + 2 * lane;
+            if (colB && vec_ok) {
+                if (sizeof(OT) == 4) {
+                    *reinterpret_cast<int2 *>(p0) = make_int2(val[0], val[2]);
+                    if (row2) *reinterpret_cast<int2 *>(p0 + ostride) = make_int2(val[1], val[3]);
+                } else {
+                    *reinterpret_cast<uint32_t *>(p0) = ((uint32_t)val[0] & 0xFFFFu) | ((uint32_t)val[2] << 16);
+                    if (row2) *reinterpret_cast<uint32_t *>(p0 + ostride) = ((uint32_t)val[1] & 0xFFFFu) | ((uint32_t)val[3] << 16);
+                }
+            } else {
+                p0[0] = (OT)val[0];
+                if (colB) p0[1] = (OT)val[2];
+                if (row2) { p0[ostride] = (OT)val[1]; if (colB) p0[ostride + 1] = (OT)val[3]; }
+            }
+        }
+    }
+    if (__any_sync(0xffffffffu, bad)) {
+        __syncwarp();
+        for (int y = 0; y < h; y++)
+            for (int x = lane; x < w; x += 32) out[(size_t)y * ostride + x] = 0;
+    }
+}
+
 }  // namespace
+
+size_t j2k_htiso_scratch_bytes(uint32_t n) { return (size_t)n * (kQTabWords * 4 + 4) + 16; }
 
 template <typename OT>
 static void launch_ht_iso_t(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, OT *d_coef,
-                            const float *d_steps, int irrev, int coef_bits, int blocks_per_warp, cudaStream_t s)
+                            const float *d_steps, int irrev, int coef_bits, int blocks_per_warp, void *d_scratch, cudaStream_t s)
 {
-    if (blocks_per_warp == 32) {
+    if (blocks_per_warp == 2) {
+        uint32_t *qtab = (uint32_t *)d_scratch, *status = qtab + (size_t)n * kQTabWords;
+        J2K_LAUNCH((k_htiso_vlc), (n + kThreads - 1) / kThreads, kThreads, 0, s, d_cblks, n, d_blob, qtab, status);
+        J2K_LAUNCH((k_htiso_magsgn<OT>), (n + kWarpsIsoB - 1) / kWarpsIsoB, kWarpsIsoB * 32, 0, s, d_cblks, n, d_blob, qtab, status,
+                   d_coef, d_steps, irrev, coef_bits);
+    } else if (blocks_per_warp == 32) {
         J2K_LAUNCH((k_ht_iso<32, OT>), (n + kThreads - 1) / kThreads, kThreads, 0, s, d_cblks, n, d_blob, d_coef, d_steps, irrev, coef_bits);
     } else {
         const uint32_t per = kThreads / 32;
@@ -350,11 +637,12 @@ static void launch_ht_iso_t(const DevCblk *d_cblks, uint32_t n, const uint8_t *d
     }
 }
 
+// blocks_per_warp: 2 = the two-kernel mapping (needs d_scratch of j2k_htiso_scratch_bytes(n)), 32 / 1 = single kernel
 cudaError_t launch_ht_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
-                          const float *d_steps, int irrev, int coef_bits, int blocks_per_warp, cudaStream_t s)
+                          const float *d_steps, int irrev, int coef_bits, int blocks_per_warp, void *d_scratch, cudaStream_t s)
 {
     if (n == 0) return cudaSuccess;
-    if (coef16 && !irrev) launch_ht_iso_t<int16_t>(d_cblks, n, d_blob, (int16_t *)d_coef, d_steps, irrev, coef_bits, blocks_per_warp, s);
-    else launch_ht_iso_t<int32_t>(d_cblks, n, d_blob, (int32_t *)d_coef, d_steps, irrev, coef_bits, blocks_per_warp, s);
+    if (coef16 && !irrev) launch_ht_iso_t<int16_t>(d_cblks, n, d_blob, (int16_t *)d_coef, d_steps, irrev, coef_bits, blocks_per_warp, d_scratch, s);
+    else launch_ht_iso_t<int32_t>(d_cblks, n, d_blob, (int32_t *)d_coef, d_steps, irrev, coef_bits, blocks_per_warp, d_scratch, s);
     return cudaGetLastError();
 }

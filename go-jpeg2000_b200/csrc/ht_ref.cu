@@ -350,20 +350,27 @@ enum { ST_ZERO = 0, ST_FAST = 1, ST_WIDE = 2 };
 // inner branches, so the 32 chains of a warp diverge only on whether they refill.
 struct VlcStream { const uint8_t *d; int pos, left; uint64_t tmp; uint32_t bits; bool gt8f; };
 
+__device__ __forceinline__ void vlc_read4(VlcStream &v)
+{
+    uint32_t b[4], nb[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) b[i] = (i < v.left) ? (uint32_t)__ldg(v.d + v.pos - i) : 0u;
+    v.pos -= 4; v.left -= 4;
+    bool g = v.gt8f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { nb[i] = (g && (b[i] & 0x7Fu) == 0x7Fu) ? 7u : 8u; g = b[i] > 0x8Fu; }
+    const uint32_t t = b[0] | (b[1] << nb[0]) | (b[2] << (nb[0] + nb[1])) | (b[3] << (nb[0] + nb[1] + nb[2]));
+    v.tmp |= (uint64_t)t << v.bits;
+    v.bits += nb[0] + nb[1] + nb[2] + nb[3];
+    v.gt8f = g;
+}
+
+// at least 32 bits afterwards (four stuffed bytes give only 28: then a second read, which is rare)
 __device__ __forceinline__ void vlc_refill(VlcStream &v)
 {
     if (v.bits < 32) {
-        uint32_t b[4], nb[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) b[i] = (i < v.left) ? (uint32_t)__ldg(v.d + v.pos - i) : 0u;
-        v.pos -= 4; v.left -= 4;
-        bool g = v.gt8f;
-#pragma unroll
-        for (int i = 0; i < 4; i++) { nb[i] = (g && (b[i] & 0x7Fu) == 0x7Fu) ? 7u : 8u; g = b[i] > 0x8Fu; }
-        const uint32_t t = b[0] | (b[1] << nb[0]) | (b[2] << (nb[0] + nb[1])) | (b[3] << (nb[0] + nb[1] + nb[2]));
-        v.tmp |= (uint64_t)t << v.bits;
-        v.bits += nb[0] + nb[1] + nb[2] + nb[3];
-        v.gt8f = g;
+        vlc_read4(v);
+        if (v.bits < 32) vlc_read4(v);
     }
 }
 

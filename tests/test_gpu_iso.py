@@ -27,9 +27,9 @@ def test_iso_ht_blocks_vs_oracle(gpu_ctx):
         nbps = int(rng.integers(1, 4))
         blocks.append((enc, w, h, nbps, 0))
         want.append(d << (nbps - 1))
-    for mp in ("32", "1"):
+    for mp in ("2", "32", "1"):
         import os
-        os.environ["J2KGPU_HT_MAP"] = mp                       # thread-per-block and warp-per-block mappings
+        os.environ["J2KGPU_HT_MAP"] = mp                       # two-kernel (default), thread-per-block and warp-per-block mappings
         for i, (got, w_) in enumerate(zip(gpu_ctx.ht_decode_blocks(blocks, mode=ISO), want)):
             assert np.array_equal(got, w_), (mp, i)
     os.environ.pop("J2KGPU_HT_MAP", None)
@@ -47,6 +47,39 @@ def test_iso_ht_garbage_vs_oracle(gpu_ctx):
         scup = int(rng.integers(2, min(n, 4079) + 1))
         s[-1], s[-2] = scup >> 4, (s[-2] & 0xF0) | (scup & 0xF)
         blocks.append((s.tobytes(), int(rng.integers(1, 65)), int(rng.integers(1, 65)), 1, 0))
+    for i, ((s, w, h, nb, _), got) in enumerate(zip(blocks, gpu_ctx.ht_decode_blocks(blocks, mode=ISO))):
+        assert np.array_equal(got, O.iso_ht_decode(s, w, h, nb)[0]), i
+
+
+def test_iso_ht_corrupted_magsgn_vs_oracle(gpu_ctx):
+    """valid MEL / VLC segments over damaged MagSgn segments (0xFF runs, random bytes, truncation): the exponent
+    predictor, the U_q > 31 and Mb bounds and the stuffing all see values no encoder produces"""
+    rng = np.random.default_rng(33)
+    blocks = []
+    for _ in range(300):
+        w, h = int(rng.integers(1, 65)), int(rng.integers(1, 65))
+        nb = int(rng.integers(1, 16))
+        d = rng.integers(-(1 << nb) + 1, 1 << nb, w * h).astype(np.int32)
+        d[rng.random(w * h) < rng.uniform(0, 0.9)] = 0
+        s = np.frombuffer(iso_ht_encode(d, w, h), np.uint8).copy()
+        if s.size < 2:
+            continue
+        scup = (int(s[-1]) << 4) + (int(s[-2]) & 0x0F)
+        L = s.size - scup
+        if L > 0:
+            ms, tail = s[:L].copy(), s[L:]
+            mode = int(rng.integers(0, 4))
+            if mode == 0:
+                ms[rng.random(L) < 0.3] = 0xFF
+            elif mode == 1:
+                ms = rng.integers(0, 256, L).astype(np.uint8)
+            elif mode == 2:
+                ms = ms[: int(rng.integers(0, L))]
+            else:
+                ms = np.concatenate([ms[: L // 2], np.full(L - L // 2, 0xFF, np.uint8)])
+            s = np.concatenate([ms, tail])
+        blocks.append((s.tobytes(), w, h, int(rng.integers(1, 4)), 0))
+    assert len(blocks) > 200
     for i, ((s, w, h, nb, _), got) in enumerate(zip(blocks, gpu_ctx.ht_decode_blocks(blocks, mode=ISO))):
         assert np.array_equal(got, O.iso_ht_decode(s, w, h, nb)[0]), i
 
