@@ -384,6 +384,35 @@ __device__ __forceinline__ void vlc_refill(VlcStream &v)
 // 4 bits -> the even bit positions of a byte
 __device__ __forceinline__ uint32_t spread4(uint32_t x) { return (x & 1) | ((x & 2) << 1) | ((x & 4) << 2) | ((x & 8) << 3); }
 
+// U-VLC of a quad pair from a 192-entry table built at kernel start: kind (0 one code, 1 two codes, 2 two codes in the
+// initial row: when the first prefix is the long one the second code is a single bit) x the next 6 bits ->
+// prefix bits (3) | first suffix length (3) | second suffix length (3) | first base (3) | second base (3).
+__device__ __forceinline__ uint16_t uvlc_entry(int kind, uint32_t bits6)
+{
+    const uint32_t t1 = uvlc_row(bits6 & 7);
+    const uint32_t p1 = t1 & 3, s1 = (t1 >> 2) & 7, b1 = t1 >> 5;
+    if (kind == 0) return (uint16_t)(p1 | (s1 << 3) | (b1 << 9));
+    const uint32_t rest = bits6 >> p1;
+    if (kind == 2 && p1 > 2) return (uint16_t)((p1 + 1) | (s1 << 3) | (b1 << 9) | (((rest & 1) + 1) << 12));
+    const uint32_t t2 = uvlc_row(rest & 7);
+    return (uint16_t)((p1 + (t2 & 3)) | (s1 << 3) | (((t2 >> 2) & 7) << 6) | (b1 << 9) | ((t2 >> 5) << 12));
+}
+
+__device__ __forceinline__ int uvlc_pair(const uint16_t *utab, uint32_t vlc, int mode, bool initial, int &u0, int &u1)
+{
+    const int kind = mode < 3 ? 0 : ((mode == 3 && initial) ? 2 : 1);
+    const uint32_t t = utab[kind * 64 + (vlc & 63)];
+    const int pl = t & 7, s1 = (t >> 3) & 7, s2 = (t >> 6) & 7;
+    vlc >>= pl;
+    const int ua = (int)(((t >> 9) & 7) + (vlc & ((1u << s1) - 1)));
+    vlc >>= s1;
+    const int ub = (int)((t >> 12) + (vlc & ((1u << s2) - 1)));
+    const int add = (mode == 4) ? 2 : 0;
+    u0 = (mode == 2) ? 0 : ua + add;
+    u1 = (mode == 1) ? 0 : (mode == 2 ? ua : ub + add);
+    return pl + s1 + s2;
+}
+
 __global__ void __launch_bounds__(kThreads)
 k_htiso_vlc(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob,
             uint32_t *__restrict__ qtab, uint32_t *__restrict__ status)
@@ -395,6 +424,8 @@ k_htiso_vlc(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__rest
         const uint32_t st8 = spread4((e >> 4) & 15) + spread4((e >> 12) & 15) + spread4((e >> 8) & 15);
         s_tbl[i] = (uint16_t)((e & 0xFF) | (st8 << 8));
     }
+    __shared__ uint16_t s_utab[192];
+    for (int i = threadIdx.x; i < 192; i += kThreads) s_utab[i] = uvlc_entry(i >> 6, (uint32_t)i & 63);
     __syncthreads();
     const uint32_t blk = blockIdx.x * kThreads + threadIdx.x;
     if (blk >= n) return;
@@ -421,66 +452,68 @@ k_htiso_vlc(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__rest
     }
     uint32_t *qt = qtab + (size_t)blk * kQTabWords;
     const int nq = (w + 1) >> 1;
-    uint64_t sigprev = 0;
-    bool bad = false;
+    uint64_t sigprev = 0;                                // bottom-row significance of the previous quad row, bit c = column c
+    uint32_t badbits = 0;
     for (int y = 0; y < h; y += 2) {
         const bool initial = (y == 0);
         const uint16_t *tbl = s_tbl + (initial ? 0 : 1024);
-        const bool row2 = (y + 1 < h);
-        uint64_t signew = 0;
-        int cw = 0;
-        for (int q = 0; q < nq; q += 2) {
+        const uint32_t rowmask = (y + 1 < h) ? 0u : 0xA0u;              // rho bits of samples below the block
+        uint64_t sp = sigprev;                           // bit 0 = column 2q of the current pair
+        uint32_t spc = 0;                                // column 2q - 1
+        uint64_t sn = 0;                                 // new significance, shifted in from the top, 4 columns per pair
+        int cw = 0, iters = 0;
+        uint32_t *qrow = qt + (y >> 1) * 16;
+        for (int q = 0; q < nq; q += 2, iters++) {
             const bool pair = (q + 1 < nq);
-            vlc_refill(v);                               // >= 32 bits: two codewords (<= 7 each) and the U-VLC (<= 17)
+            vlc_refill(v);                               // >= 32 bits: two codewords (<= 7 each) and the U-VLC (<= 16)
+            const uint32_t s6 = (((uint32_t)sp & 0x1F) << 1) | spc;     // columns 2q - 1 .. 2q + 4 (zero in the initial row)
+            spc = ((uint32_t)sp >> 3) & 1;
+            sp >>= 4;
             uint32_t e0, e1 = 0;
             {
-                int c_q = cw;
-                if (!initial) { const uint32_t s4 = win4(sigprev, 2 * q); c_q |= ((s4 | (s4 >> 1)) & 1) | ((((s4 >> 2) | (s4 >> 3)) & 1) << 2); }
+                const int c_q = cw | (int)((s6 & 3) != 0) | ((int)((s6 & 0xC) != 0) << 2);
                 uint32_t e = tbl[(c_q << 7) | ((uint32_t)v.tmp & 0x7F)];
                 if (c_q == 0 && !mel_event(mel, d)) e = 0;
                 v.tmp >>= (e & 7); v.bits -= (e & 7);
                 e0 = e;
                 const uint32_t rho = (e >> 4) & 0xF;
-                cw = initial ? (int)(((rho | (rho >> 1)) & 1) | (((rho >> 2) & 1) << 1) | (((rho >> 3) & 1) << 2))
-                             : (int)((((rho >> 2) | (rho >> 3)) & 1) << 1);
+                cw = initial ? (int)(((rho & 3) != 0) | (((rho >> 2) & 3) << 1))
+                             : (int)((rho >> 2) != 0) << 1;
             }
             if (pair) {
-                int c_q = cw;
-                if (!initial) { const uint32_t s4 = win4(sigprev, 2 * q + 2); c_q |= ((s4 | (s4 >> 1)) & 1) | ((((s4 >> 2) | (s4 >> 3)) & 1) << 2); }
+                const int c_q = cw | (int)((s6 & 0xC) != 0) | ((int)((s6 & 0x30) != 0) << 2);
                 uint32_t e = tbl[(c_q << 7) | ((uint32_t)v.tmp & 0x7F)];
                 if (c_q == 0 && !mel_event(mel, d)) e = 0;
                 v.tmp >>= (e & 7); v.bits -= (e & 7);
                 e1 = e;
                 const uint32_t rho = (e >> 4) & 0xF;
-                cw = initial ? (int)(((rho | (rho >> 1)) & 1) | (((rho >> 2) & 1) << 1) | (((rho >> 3) & 1) << 2))
-                             : (int)((((rho >> 2) | (rho >> 3)) & 1) << 1);
+                cw = initial ? (int)(((rho & 3) != 0) | (((rho >> 2) & 3) << 1))
+                             : (int)((rho >> 2) != 0) << 1;
             }
             int mode = (int)(((e0 >> 3) & 1) | (((e1 >> 3) & 1) << 1));
             if (initial && mode == 3 && mel_event(mel, d)) mode = 4;
             int u0 = 0, u1 = 0;
-            if (mode) { const int c = uvlc_decode((uint32_t)v.tmp, mode, initial, u0, u1); v.tmp >>= c; v.bits -= c; }
+            if (mode) { const int c = uvlc_pair(s_utab, (uint32_t)v.tmp, mode, initial, u0, u1); v.tmp >>= c; v.bits -= c; }
+            // bottom samples (rho bits 1 and 3) of both quads: columns 2q .. 2q + 3
+            const uint32_t nb4 = ((e0 >> 5) & 1) | (((e0 >> 7) & 1) << 1) | (((e1 >> 5) & 1) << 2) | (((e1 >> 7) & 1) << 3);
+            sn = (sn >> 4) | ((uint64_t)nb4 << 60);
+            // significance outside the block: malformed, the block is zero
             const int xq = 2 * q;
-            signew |= ((uint64_t)((e0 >> 5) & 1) << xq) | ((uint64_t)((e0 >> 7) & 1) << (xq + 1));
-            if (!row2 && (e0 & 0xA0)) bad = true;        // significance outside the block: malformed, the block is zero
-            if (xq + 1 >= w && (e0 & 0xC0)) bad = true;
-            if (pair) {
-                signew |= ((uint64_t)((e1 >> 5) & 1) << (xq + 2)) | ((uint64_t)((e1 >> 7) & 1) << (xq + 3));
-                if (!row2 && (e1 & 0xA0)) bad = true;
-                if (xq + 3 >= w && (e1 & 0xC0)) bad = true;
-            }
+            badbits |= e0 & (rowmask | (xq + 1 >= w ? 0xC0u : 0u));
+            badbits |= e1 & (rowmask | (xq + 3 >= w ? 0xC0u : 0u));
             // u >= 31 makes U_q > 31 whatever the predictor says: malformed either way, 5 bits are enough
-            qt[(y >> 1) * 16 + (q >> 1)] = (e0 >> 8) | ((uint32_t)min(u0, 31) << 8) | (((e1 >> 8) | ((uint32_t)min(u1, 31) << 8)) << 16);
+            qrow[q >> 1] = (e0 >> 8) | ((uint32_t)min(u0, 31) << 8) | (((e1 >> 8) | ((uint32_t)min(u1, 31) << 8)) << 16);
         }
-        sigprev = signew;
+        sigprev = sn >> (64 - 4 * iters);
     }
-    status[blk] = bad ? (uint32_t)ST_ZERO : ((uint32_t)ST_OK | ((uint32_t)(lcup - scup) << 2));
+    status[blk] = badbits ? (uint32_t)ST_ZERO : ((uint32_t)ST_OK | ((uint32_t)(lcup - scup) << 2));
 }
 
-template <typename OT>
+template <typename OT, bool IRREV>
 __global__ void __launch_bounds__(kWarpsIsoB * 32)
 k_htiso_magsgn(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob,
                const uint32_t *__restrict__ qtab, const uint32_t *__restrict__ status, OT *__restrict__ coef,
-               const float *__restrict__ steps, int irrev_i, int coef_bits)
+               const float *__restrict__ steps, int coef_bits)
 {
     __shared__ uint32_t s_ring[kWarpsIsoB][kRingWords];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -497,8 +530,7 @@ k_htiso_magsgn(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__r
             for (int x = lane; x < w; x += 32) out[(size_t)y * ostride + x] = 0;
         return;
     }
-    const bool irrev = irrev_i != 0;
-    const float step = steps ? steps[blk] : 1.0f;
+    const float step = (IRREV && steps) ? steps[blk] : 1.0f;
     const int L = (int)(stw >> 2);
     const int shift = cb.num_bps - 1;
     const int nq = (w + 1) >> 1, nrows = (h + 1) >> 1;
@@ -519,32 +551,38 @@ k_htiso_magsgn(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__r
         if (r + 1 < nrows) code_next = active ? (uint32_t)qt[(r + 1) * 32 + lane] : 0u;
         // ---- keep the ring one full quad row ahead ----
         while (built < P + 4096u) {
-            const int k = kbyte + 4 * lane;
-            uint32_t b[4], nb[4];
+            const int k = kbyte + 8 * lane;
+            uint32_t b[8], nb[8];
 #pragma unroll
-            for (int i = 0; i < 4; i++) b[i] = (k + i < L) ? (uint32_t)__ldg(d + k + i) : 0xFFu;
+            for (int i = 0; i < 8; i++) b[i] = (k + i < L) ? (uint32_t)__ldg(d + k + i) : 0xFFu;
             // the words this chunk reaches beyond the one `built` points into still hold bits 16 Kbit old
             const uint32_t w0 = (built >> 5) + 1;
             ring[(w0 + lane) & (kRingWords - 1)] = 0;
-            if (lane < 2) ring[(w0 + 32 + lane) & (kRingWords - 1)] = 0;
-            uint32_t pb = __shfl_up_sync(0xffffffffu, b[3], 1);
+            ring[(w0 + 32 + lane) & (kRingWords - 1)] = 0;
+            if (lane < 2) ring[(w0 + 64 + lane) & (kRingWords - 1)] = 0;
+            uint32_t pb = __shfl_up_sync(0xffffffffu, b[7], 1);
             if (lane == 0) pb = prev_ff ? 0xFFu : 0u;
 #pragma unroll
-            for (int i = 0; i < 4; i++) { nb[i] = pb == 0xFFu ? 7u : 8u; pb = b[i]; }
-            const uint32_t v = b[0] | (b[1] << nb[0]) | (b[2] << (nb[0] + nb[1])) | (b[3] << (nb[0] + nb[1] + nb[2]));
-            const uint32_t tot = nb[0] + nb[1] + nb[2] + nb[3];
+            for (int i = 0; i < 8; i++) { nb[i] = pb == 0xFFu ? 7u : 8u; pb = b[i]; }
+            const uint32_t va = b[0] | (b[1] << nb[0]) | (b[2] << (nb[0] + nb[1])) | (b[3] << (nb[0] + nb[1] + nb[2]));
+            const uint32_t vb = b[4] | (b[5] << nb[4]) | (b[6] << (nb[4] + nb[5])) | (b[7] << (nb[4] + nb[5] + nb[6]));
+            const uint32_t ta = nb[0] + nb[1] + nb[2] + nb[3], tot = ta + nb[4] + nb[5] + nb[6] + nb[7];
             uint32_t incl = tot;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
             const uint32_t pos = built + incl - tot;
-            const uint32_t sh = pos & 31;
             __syncwarp();
-            atomicOr(&ring[(pos >> 5) & (kRingWords - 1)], v << sh);
-            const uint32_t hi = sh ? v >> (32 - sh) : 0u;
-            if (hi) atomicOr(&ring[((pos >> 5) + 1) & (kRingWords - 1)], hi);
+#pragma unroll
+            for (int g = 0; g < 2; g++) {
+                const uint32_t pg = g ? pos + ta : pos, vg = g ? vb : va;
+                const uint32_t sh = pg & 31, wi = pg >> 5;
+                atomicOr(&ring[wi & (kRingWords - 1)], vg << sh);
+                const uint32_t hi = sh ? vg >> (32 - sh) : 0u;
+                if (hi) atomicOr(&ring[(wi + 1) & (kRingWords - 1)], hi);
+            }
             built += __shfl_sync(0xffffffffu, incl, 31);
             prev_ff = __shfl_sync(0xffffffffu, pb, 31) == 0xFFu;
-            kbyte += 128;
+            kbyte += 256;
             __syncwarp();
         }
         // ---- U_q and the four field widths ----
@@ -579,12 +617,13 @@ k_htiso_magsgn(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__r
             const uint32_t s2 = (st8 >> (2 * i)) & 3;
             val[i] = 0;
             if (s2) {
-                const uint32_t x = __funnelshift_r(ring[(p >> 5) & (kRingWords - 1)], ring[((p >> 5) + 1) & (kRingWords - 1)], p & 31);
+                const uint32_t wi = p >> 5;
+                const uint32_t x = __funnelshift_r(ring[wi & (kRingWords - 1)], ring[(wi + 1) & (kRingWords - 1)], p & 31);
                 uint32_t vv = x & ((1u << m[i]) - 1u);
                 const uint32_t sign = vv & 1;
                 vv |= (uint32_t)(s2 == 3) << m[i];
                 vv |= 1;
-                val[i] = sample_value((vv >> 1) + 1, sign, shift, step, irrev);
+                val[i] = sample_value((vv >> 1) + 1, sign, shift, step, IRREV);
                 if (i & 1) en[i >> 1] = 32 - __clz((int)vv);
                 p += (uint32_t)m[i];
             }
@@ -627,8 +666,9 @@ static void launch_ht_iso_t(const DevCblk *d_cblks, uint32_t n, const uint8_t *d
     if (blocks_per_warp == 2) {
         uint32_t *qtab = (uint32_t *)d_scratch, *status = qtab + (size_t)n * kQTabWords;
         J2K_LAUNCH((k_htiso_vlc), (n + kThreads - 1) / kThreads, kThreads, 0, s, d_cblks, n, d_blob, qtab, status);
-        J2K_LAUNCH((k_htiso_magsgn<OT>), (n + kWarpsIsoB - 1) / kWarpsIsoB, kWarpsIsoB * 32, 0, s, d_cblks, n, d_blob, qtab, status,
-                   d_coef, d_steps, irrev, coef_bits);
+        const uint32_t grid = (n + kWarpsIsoB - 1) / kWarpsIsoB;
+        if (irrev) J2K_LAUNCH((k_htiso_magsgn<OT, true>), grid, kWarpsIsoB * 32, 0, s, d_cblks, n, d_blob, qtab, status, d_coef, d_steps, coef_bits);
+        else J2K_LAUNCH((k_htiso_magsgn<OT, false>), grid, kWarpsIsoB * 32, 0, s, d_cblks, n, d_blob, qtab, status, d_coef, d_steps, coef_bits);
     } else if (blocks_per_warp == 32) {
         J2K_LAUNCH((k_ht_iso<32, OT>), (n + kThreads - 1) / kThreads, kThreads, 0, s, d_cblks, n, d_blob, d_coef, d_steps, irrev, coef_bits);
     } else {
