@@ -115,6 +115,7 @@ def iso_pixels(j2k, ctx, job, coef_bits=0):
     (64, 64, 1, 8, None, None, 0), (128, 128, 1, 8, None, None, 2), (256, 256, 3, 8, None, None, 5),
     (200, 150, 3, 8, None, None, 3), (512, 512, 3, 8, 256, 256, 5), (333, 211, 3, 8, 128, 128, 4),
     (640, 360, 1, 12, None, None, 5), (300, 200, 3, 16, None, None, 4), (1024, 512, 3, 8, 512, 512, 5),
+    (328, 140, 3, 8, None, None, 5), (488, 508, 1, 8, None, None, 4),        # odd level sizes above the fused pair
 ])
 def test_iso_whole_path_lossless_htj2k(j2k, gpu_ctx, w, h, ncomp, prec, tw, th, nl):
     s = jobs.synth_image(w, h, ncomp, prec, seed=w + 3 * h)

@@ -173,6 +173,8 @@ def _run_items(j2k, ctx, jl, env=None, mode=0, coef_bits=0):
     (1536, 40, 3, 8, None, None, 2, 0),    # wide kernel, three warps per row, int16 planes, short strip (20 row pairs)
     (528, 136, 3, 8, None, None, 4, 0),    # wide kernel: 33 lanes' worth -> halo path with a nearly empty second warp
     (512, 512, 3, 8, None, None, 5, 1),    # one warp per tile row, no halo lanes (the bench geometry)
+    (328, 140, 3, 8, None, None, 5, 0),    # odd level sizes above the fused pair (82x35, 41x18, 21x9)
+    (488, 508, 1, 8, None, None, 4, 1),    # level-2 image 122x127
 ])
 def test_fused_and_int16_variants_agree(j2k, gpu_ctx, w, h, ncomp, prec, tw, th, levels, ht):
     """the fused levels-1+0 kernel and the int16 coefficient planes are optimisations: every combination of
