@@ -323,8 +323,10 @@ def run_ours(args):
 
     def summarize(m):
         ms_total, e2e_s = reduce_max(m["ms_total"], m["e2e_s"])
-        ach = alg_bytes / (m["last_ms"] / 1e3) / 1e9
-        stg = alg_bytes / (m["dwt_ms"] / 1e3) / 1e9
+        # bytes this variant's fused kernel has to move: its coefficient planes (int32, or int16 when the plan says so) + pixels
+        vb = (m["coef_bytes"] * W * H * NCOMP + W * H * 4) * F
+        ach = vb / (m["last_ms"] / 1e3) / 1e9
+        stg = vb / (m["dwt_ms"] / 1e3) / 1e9
         return dict(value=round(mpix_step * m["steps"] / (ms_total / 1e3), 1), ms_per_step=round(ms_total / m["steps"], 4),
                     e2e=dict(value=round(mpix_step * m["e2e_steps"] / e2e_s, 1), unit=UNIT, h2d_bytes_per_step=m["h2d"],
                              d2h_bytes_per_step=m["d2h"], ms_per_step=round(1e3 * e2e_s / m["e2e_steps"], 3),
@@ -336,7 +338,8 @@ def run_ours(args):
                     stages_ms=dict(entropy=round(m["ent_ms"], 4), dwt_mct_pack=round(m["dwt_ms"], 4),
                                    last_level_fused=round(m["last_ms"], 4)),
                     roofline=dict(bound="hbm", achieved=round(ach, 1), peak=peak, unit="GB/s", frac=round(ach / peak, 4),
-                                  dwt_mct_stage_gbs=round(stg, 1), dwt_mct_stage_frac=round(stg / peak, 4)))
+                                  dwt_mct_stage_gbs=round(stg, 1), dwt_mct_stage_frac=round(stg / peak, 4),
+                                  bytes_per_launch=vb))
 
     sampler = ClockSampler(local)
     # ---- headline: REF semantics (bit-identical to the reference's stage functions) -----------------------------------
