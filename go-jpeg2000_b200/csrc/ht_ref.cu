@@ -374,12 +374,42 @@ __device__ __forceinline__ void vlc_refill(VlcStream &v)
     }
 }
 
+// U-VLC of a quad pair (ht.go:716-864) from a 192-entry table built at kernel start: kind (0 one code, 1 two codes,
+// 2 two codes in the initial row: when the first prefix is the long one the second value is one bit + 2) x the next
+// 6 bits -> prefix bits (3) | first suffix length (3) | second suffix length (3) | first base (3) | second base (3).
+__device__ __forceinline__ uint16_t uvlc_entry(int kind, uint32_t bits6)
+{
+    const uint32_t t1 = c_uvlc_dec[bits6 & 7];
+    const uint32_t p1 = t1 & 3, s1 = (t1 >> 2) & 7, b1 = t1 >> 5;
+    if (kind == 0) return (uint16_t)(p1 | (s1 << 3) | (b1 << 9));
+    const uint32_t rest = bits6 >> p1;
+    if (kind == 2 && p1 > 2) return (uint16_t)((p1 + 1) | (s1 << 3) | (b1 << 9) | (((rest & 1) + 1) << 12));
+    const uint32_t t2 = c_uvlc_dec[rest & 7];
+    return (uint16_t)((p1 + (t2 & 3)) | (s1 << 3) | (((t2 >> 2) & 7) << 6) | (b1 << 9) | ((t2 >> 5) << 12));
+}
+
+__device__ __forceinline__ uint32_t uvlc_pair(const uint16_t *utab, uint32_t vlc, uint32_t mode, bool initial, uint32_t &u0, uint32_t &u1)
+{
+    const uint32_t kind = mode < 3 ? 0u : (initial ? 2u : 1u);
+    const uint32_t t = utab[kind * 64 + (vlc & 63)];
+    const uint32_t pl = t & 7, s1 = (t >> 3) & 7, s2 = (t >> 6) & 7;
+    vlc >>= pl;
+    const uint32_t ua = ((t >> 9) & 7) + (vlc & ((1u << s1) - 1)) + 1;
+    vlc >>= s1;
+    const uint32_t ub = (t >> 12) + (vlc & ((1u << s2) - 1)) + 1;
+    u0 = (mode == 2) ? 1u : ua;
+    u1 = (mode == 1) ? 1u : (mode == 2 ? ua : ub);
+    return pl + s1 + s2;
+}
+
 __global__ void __launch_bounds__(128)
 k_htref_vlc(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob,
             uint32_t *__restrict__ qinfo, uint32_t *__restrict__ status)
 {
     __shared__ uint16_t s_tbl[2048];
+    __shared__ uint16_t s_utab[192];
     for (int i = threadIdx.x; i < 1024; i += 128) { s_tbl[i] = d_vlc_tbl0[i]; s_tbl[1024 + i] = d_vlc_tbl1[i]; }
+    for (int i = threadIdx.x; i < 192; i += 128) s_utab[i] = uvlc_entry(i >> 6, (uint32_t)i & 63);
     __syncthreads();
     const uint32_t blk = blockIdx.x * 128 + threadIdx.x;
     if (blk >= n) return;
@@ -419,7 +449,7 @@ k_htref_vlc(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__rest
             const uint32_t mode = (((q1 >> 3) & 1) << 1) | ((q2 >> 3) & 1);
             if (mode > 0) {
                 vlc_refill(v);
-                const uint32_t c = uvlc_decode((uint32_t)v.tmp, mode, initial, u0, u1);
+                const uint32_t c = uvlc_pair(s_utab, (uint32_t)v.tmp, mode, initial, u0, u1);
                 v.tmp >>= c; v.bits -= c;
             }
             umax = max(umax, max(u0, u1));
