@@ -562,6 +562,56 @@ extern "C" int j2kgpu_job_run(j2kgpu_job *job, const void *d_blob, void *d_out)
     return run_dwt_mct(job, d_out, 0, job->n_img, job->ctx->stream);
 }
 
+// Chunk plan of the host-buffer run.  The device->host copy of the pixels is the bottleneck of the path (4 bytes per
+// pixel out against about 2 in), and on a Gen5 x16 link under bidirectional load the host->device direction is not
+// faster per frame than the device->host one (measured: 53 GB/s out, about 35 GB/s in, tools/pcie_probe.py), so chunks
+// cannot grow along the batch without starving the copy-out engine.  The plan is therefore: the smallest possible first
+// chunk (its copy-in + decode is the only exposed latency), then equal chunks, as many as the decoder's per-launch
+// latency floor (one code block's serial chain per launch sequence) allows inside the copy-out time; compute-bound
+// coders (EBCOT) get four chunks.  Measured on the bench batch (16 x 4K): 16 chunks of one frame 11.16 ms, (1,3,3,3,3,3)
+// 11.72 ms, (4,4,4,4) 12.26 ms, one chunk 16.6 ms.
+static std::vector<uint32_t> plan_chunks(const j2kgpu_job *job, const j2k_batch_item_t *items)
+{
+    const uint32_t n = job->n_img;
+    if (const char *e = getenv("J2KGPU_CHUNKS")) {       // experiments: explicit chunk sizes, e.g. "1,1,2,4"; the rest in one chunk
+        std::vector<uint32_t> cuts(1, 0u);
+        while (*e && cuts.back() < n) {
+            const uint32_t k = (uint32_t)strtoul(e, (char **)&e, 10);
+            if (k == 0) break;
+            cuts.push_back(cuts.back() + k < n ? cuts.back() + k : n);
+            if (*e == ',') e++;
+        }
+        if (cuts.back() < n) cuts.push_back(n);
+        return cuts;
+    }
+    double lat, r_cmp;                                   // seconds per launch sequence, output bytes per second
+    if (!job->hdr.ht) { lat = 5e-3; r_cmp = 2.4e9; }                    // EBCOT / MQ
+    else if (job->iso) { lat = 1.1e-3; r_cmp = 400e9; }
+    else { lat = 0.4e-3; r_cmp = 800e9; }
+    const double t_out = (double)job->out_bytes / 53e9, t_thr = (double)job->out_bytes / r_cmp;
+    uint32_t nchunks = t_thr > 0.5 * t_out ? 4u : (uint32_t)((0.8 * t_out - t_thr) / lat);
+    if (nchunks > 16) nchunks = 16;
+    if (nchunks > n) nchunks = n;
+    if (nchunks < 1) nchunks = 1;
+    std::vector<uint32_t> cuts(1, 0u);
+    if (nchunks >= 3 && t_thr <= 0.5 * t_out) {          // small first chunk, the rest in nchunks - 1 equal parts
+        const uint32_t k0 = (n + 15) / 16;
+        cuts.push_back(k0);
+        const uint32_t rest = n - k0, parts = nchunks - 1;
+        for (uint32_t c = 1; c <= parts; c++) {
+            const uint32_t end = k0 + (uint32_t)(((uint64_t)rest * c) / parts);
+            if (end > cuts.back()) cuts.push_back(end);
+        }
+    } else {
+        for (uint32_t c = 1; c <= nchunks; c++) {
+            const uint32_t end = (uint32_t)(((uint64_t)n * c) / nchunks);
+            if (end > cuts.back()) cuts.push_back(end);
+        }
+    }
+    if (getenv("J2KGPU_DEBUG_PLAN")) { fprintf(stderr, "j2kgpu chunk plan:"); for (uint32_t c : cuts) fprintf(stderr, " %u", c); fprintf(stderr, "\n"); }
+    return cuts;
+}
+
 // Host-buffer run.  The batch is cut into chunks of whole items; chunk c's host->device copy runs on the copy-in
 // stream, its kernels on the ctx stream and its device->host copy on the copy-out stream, chained by events, so
 // that the PCIe transfers of neighbouring chunks overlap the kernels (the two copy engines work in both directions
@@ -577,22 +627,7 @@ static int run_host_locked(j2kgpu_job *job, const j2k_batch_item_t *items)
         if (!items[i].out_pix) return j2k_set_err(ctx, J2KGPU_E_ARG, "item %u: null out_pix", i);
     int rc = j2k_ctx_copy_streams(ctx);
     if (rc) return rc;
-    // chunks of about 1/8 of the batch, at least one item each.  The thread-per-block HT decoder needs many blocks per
-    // launch (its run time is one block's serial chain whatever the count), so its chunks hold >= 16K blocks.
-    const uint32_t n = job->n_img;
-    uint32_t per = n >= 16 ? (n + 7) / 8 : 1;
-    const bool thread_per_block = job->hdr.ht && (job->iso ? job->ht_map != 1 : j2k_htref_map() != 1);
-    if (thread_per_block && job->n_cb) {
-        const uint64_t blocks_per_item = (job->n_cb + n - 1) / n;
-        const uint32_t need = (uint32_t)((16384 + blocks_per_item - 1) / blocks_per_item);
-        if (need > per) per = need < n ? need : n;
-    }
-    // the copy-out (the PCIe bottleneck of the path) can only start once the first chunk is decoded: keep that one small
-    std::vector<uint32_t> cuts;                             // chunk c = items [cuts[c], cuts[c + 1])
-    cuts.push_back(0);
-    // (not for the ISO HT decoder: every launch of it costs one block's full serial chain, about 1.7 ms)
-    if (n >= 4 && per > 1 && !(job->iso && job->hdr.ht)) cuts.push_back(1);
-    while (cuts.back() < n) cuts.push_back(cuts.back() + per < n ? cuts.back() + per : n);
+    const std::vector<uint32_t> cuts = plan_chunks(job, items);          // chunk c = items [cuts[c], cuts[c + 1])
     const uint32_t nchunk = (uint32_t)cuts.size() - 1;
     if (job->ev_in.size() < nchunk) {
         const size_t old = job->ev_in.size();
