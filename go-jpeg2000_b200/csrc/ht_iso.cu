@@ -16,6 +16,7 @@
 // column mask; previous-row exponents as 64 bytes of shared memory, updated in place with a one-column carry.
 // Every sample of the block is written exactly once (zeros included), two rows x two columns per quad.
 #include "common.h"
+#include <cstdlib>
 
 namespace {
 
@@ -655,6 +656,178 @@ k_htiso_magsgn(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__r
     }
 }
 
+// B', the default: TWO blocks per warp, one per half-warp, each lane two neighbouring quads (4 columns) of a quad row.
+// Kernel B spends about as many instructions per quad row on what is per row (loop, ring upkeep, predictor shuffles,
+// prefix sum) as on the samples; with two quads per lane and two blocks per instruction stream that fixed part is
+// shared by four times as many samples.  Same arithmetic, same ring (one per block, 128-byte chunks), same results.
+constexpr int kWarpsIsoB2 = 8;
+
+template <typename OT, bool IRREV>
+__global__ void __launch_bounds__(kWarpsIsoB2 * 32)
+k_htiso_magsgn2(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob,
+                const uint32_t *__restrict__ qtab, const uint32_t *__restrict__ status, OT *__restrict__ coef,
+                const float *__restrict__ steps, int coef_bits)
+{
+    constexpr uint32_t FULL = 0xffffffffu;
+    __shared__ uint32_t s_ring[kWarpsIsoB2 * 2][kRingWords];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4, sl = lane & 15;
+    const uint32_t blk0 = (blockIdx.x * kWarpsIsoB2 + warp) * 2;
+    if (blk0 >= n) return;
+    const bool have = blk0 + half < n;
+    const uint32_t blk = have ? blk0 + half : blk0;
+    const uint32_t stw = status[blk];
+    const DevCblk cb = cblks[blk];
+    const int w = cb.w, h = cb.h;
+    OT *out = coef + cb.out_off;
+    const size_t ostride = cb.out_stride;
+    const uint8_t *d = blob + cb.data_off;
+    const bool zero = (stw & 3) == ST_ZERO;
+    if (have && zero)
+        for (int y = 0; y < h; y++)
+            for (int x = sl; x < w; x += 16) out[(size_t)y * ostride + x] = 0;
+    const bool live = have && !zero;                     // this half-warp decodes a block
+    const float step = (IRREV && steps) ? steps[blk] : 1.0f;
+    const int L = (int)(stw >> 2);
+    const int shift = cb.num_bps - 1;
+    const int nq = (w + 1) >> 1, nrows = live ? (h + 1) >> 1 : 0;
+    const bool active = live && 2 * sl < nq;             // the lane's first quad exists
+    const int ncols = w - 4 * sl;                        // columns of the block right of (and including) the lane's first
+    const bool vec_ok = ((cb.out_off | ostride) & 3) == 0;
+    const uint32_t *qt = qtab + (size_t)blk * kQTabWords;
+    uint32_t *ring = s_ring[warp * 2 + half];
+    for (int i = sl; i < kRingWords; i += 16) ring[i] = 0;
+    __syncwarp();
+    uint32_t built = 0, prev_ff = 0, P = 0;              // uniform per half-warp
+    int kbyte = 0;
+    int Eb[4] = {0, 0, 0, 0};                            // bottom-sample exponents of the lane's 4 columns, previous quad row
+    bool bad = false;
+    const int nrows_max = max(__shfl_sync(FULL, nrows, 0), __shfl_sync(FULL, nrows, 16));
+    uint32_t code_next = (active && nrows > 0) ? qt[sl] : 0u;
+    for (int r = 0; r < nrows_max; r++) {
+        const bool row_on = r < nrows;
+        const uint32_t code2 = row_on ? code_next : 0u;
+        if (r + 1 < nrows) code_next = active ? qt[(r + 1) * 16 + sl] : 0u;
+        // ---- keep each ring one full quad row ahead ----
+        bool need = row_on && built < P + 4096u;
+        while (__any_sync(FULL, need)) {
+            const int k = kbyte + 8 * sl;
+            uint32_t b[8], nb[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) b[i] = (need && k + i < L) ? (uint32_t)__ldg(d + k + i) : 0xFFu;
+            if (need) {                                  // words beyond the one `built` points into hold bits 16 Kbit old
+                const uint32_t w0 = (built >> 5) + 1;
+                ring[(w0 + sl) & (kRingWords - 1)] = 0;
+                ring[(w0 + 16 + sl) & (kRingWords - 1)] = 0;
+                if (sl < 2) ring[(w0 + 32 + sl) & (kRingWords - 1)] = 0;
+            }
+            uint32_t pb = __shfl_up_sync(FULL, b[7], 1, 16);
+            if (sl == 0) pb = prev_ff ? 0xFFu : 0u;
+#pragma unroll
+            for (int i = 0; i < 8; i++) { nb[i] = pb == 0xFFu ? 7u : 8u; pb = b[i]; }
+            const uint32_t va = b[0] | (b[1] << nb[0]) | (b[2] << (nb[0] + nb[1])) | (b[3] << (nb[0] + nb[1] + nb[2]));
+            const uint32_t vb = b[4] | (b[5] << nb[4]) | (b[6] << (nb[4] + nb[5])) | (b[7] << (nb[4] + nb[5] + nb[6]));
+            const uint32_t ta = nb[0] + nb[1] + nb[2] + nb[3], tot = ta + nb[4] + nb[5] + nb[6] + nb[7];
+            uint32_t incl = tot;
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL, incl, o, 16); if (sl >= o) incl += t; }
+            const uint32_t pos = built + incl - tot;
+            __syncwarp();
+            if (need) {
+#pragma unroll
+                for (int g = 0; g < 2; g++) {
+                    const uint32_t pg = g ? pos + ta : pos, vg = g ? vb : va;
+                    const uint32_t sh = pg & 31, wi = pg >> 5;
+                    atomicOr(&ring[wi & (kRingWords - 1)], vg << sh);
+                    const uint32_t hi = sh ? vg >> (32 - sh) : 0u;
+                    if (hi) atomicOr(&ring[(wi + 1) & (kRingWords - 1)], hi);
+                }
+            }
+            const uint32_t total = __shfl_sync(FULL, incl, 15, 16);
+            const uint32_t lastb = __shfl_sync(FULL, pb, 15, 16);
+            if (need) { built += total; prev_ff = lastb == 0xFFu; kbyte += 128; }
+            __syncwarp();
+            need = row_on && built < P + 4096u;
+        }
+        // ---- U_q and the field widths of the lane's two quads ----
+        const int eL = __shfl_up_sync(FULL, Eb[3], 1, 16), eR = __shfl_down_sync(FULL, Eb[0], 1, 16);
+        const int eLeft = sl ? eL : 0, eRight = sl < 15 ? eR : 0;
+        uint32_t st8[2];
+        int U[2], m[8];
+#pragma unroll
+        for (int qd = 0; qd < 2; qd++) {
+            const uint32_t code = (code2 >> (16 * qd)) & 0xFFFFu;
+            st8[qd] = code & 0xFF;
+            const int u = (int)(code >> 8);
+            const uint32_t sig = (st8[qd] | (st8[qd] >> 1)) & 0x55u;
+            int Uq = u + 1;
+            if (r > 0 && (sig & (sig - 1))) {
+                const int E = qd == 0 ? max(max(eLeft, Eb[0]), max(Eb[1], Eb[2])) : max(max(Eb[1], Eb[2]), max(Eb[3], eRight));
+                Uq = u + max(1, E - 1);
+            }
+            if (Uq > 31) bad = true;
+            if (coef_bits && Uq + shift > coef_bits + 1) bad = true;
+            U[qd] = min(Uq, 31);
+#pragma unroll
+            for (int i = 0; i < 4; i++) { const uint32_t s2 = (st8[qd] >> (2 * i)) & 3; m[4 * qd + i] = s2 ? U[qd] - (int)(s2 >> 1) : 0; }
+        }
+        const uint32_t tot = (uint32_t)(m[0] + m[1] + m[2] + m[3] + m[4] + m[5] + m[6] + m[7]);
+        uint32_t incl = tot;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL, incl, o, 16); if (sl >= o) incl += t; }
+        uint32_t p = P + incl - tot;
+        P += __shfl_sync(FULL, incl, 15, 16);
+        // ---- samples: per quad n = 0 (y, x), 1 (y + 1, x), 2 (y, x + 1), 3 (y + 1, x + 1) ----
+        int32_t val[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t s2 = (st8[i >> 2] >> (2 * (i & 3))) & 3;
+            val[i] = 0;
+            if (i & 1) Eb[i >> 1] = 0;
+            if (s2) {
+                const uint32_t wi = p >> 5;
+                const uint32_t x = __funnelshift_r(ring[wi & (kRingWords - 1)], ring[(wi + 1) & (kRingWords - 1)], p & 31);
+                uint32_t vv = x & ((1u << m[i]) - 1u);
+                const uint32_t sign = vv & 1;
+                vv |= (uint32_t)(s2 == 3) << m[i];
+                vv |= 1;
+                val[i] = sample_value((vv >> 1) + 1, sign, shift, step, IRREV);
+                if (i & 1) Eb[i >> 1] = 32 - __clz((int)vv);
+                p += (uint32_t)m[i];
+            }
+        }
+        if (active && row_on) {
+            const int y = 2 * r;
+            const bool row2 = (y + 1 < h);
+            OT *p0 = out + (size_t)y * ostride + 4 * sl;
+            if (ncols >= 4 && vec_ok) {
+                if (sizeof(OT) == 4) {
+                    *reinterpret_cast<int4 *>(p0) = make_int4(val[0], val[2], val[4], val[6]);
+                    if (row2) *reinterpret_cast<int4 *>(p0 + ostride) = make_int4(val[1], val[3], val[5], val[7]);
+                } else {
+                    *reinterpret_cast<uint2 *>(p0) = make_uint2(((uint32_t)val[0] & 0xFFFFu) | ((uint32_t)val[2] << 16),
+                                                                ((uint32_t)val[4] & 0xFFFFu) | ((uint32_t)val[6] << 16));
+                    if (row2) *reinterpret_cast<uint2 *>(p0 + ostride) = make_uint2(((uint32_t)val[1] & 0xFFFFu) | ((uint32_t)val[3] << 16),
+                                                                                     ((uint32_t)val[5] & 0xFFFFu) | ((uint32_t)val[7] << 16));
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    if (c < ncols) {
+                        p0[c] = (OT)val[2 * c];
+                        if (row2) p0[ostride + c] = (OT)val[2 * c + 1];
+                    }
+            }
+        }
+    }
+    // a malformed block is zero as a whole
+    bad = bad && live;
+    const uint32_t badm = __ballot_sync(FULL, bad);
+    if (have && !zero && (badm & (half ? 0xFFFF0000u : 0x0000FFFFu))) {
+        for (int y = 0; y < h; y++)
+            for (int x = sl; x < w; x += 16) out[(size_t)y * ostride + x] = 0;
+    }
+}
+
 }  // namespace
 
 size_t j2k_htiso_scratch_bytes(uint32_t n) { return (size_t)n * (kQTabWords * 4 + 4) + 16; }
@@ -666,9 +839,16 @@ static void launch_ht_iso_t(const DevCblk *d_cblks, uint32_t n, const uint8_t *d
     if (blocks_per_warp == 2) {
         uint32_t *qtab = (uint32_t *)d_scratch, *status = qtab + (size_t)n * kQTabWords;
         J2K_LAUNCH((k_htiso_vlc), (n + kThreads - 1) / kThreads, kThreads, 0, s, d_cblks, n, d_blob, qtab, status);
-        const uint32_t grid = (n + kWarpsIsoB - 1) / kWarpsIsoB;
-        if (irrev) J2K_LAUNCH((k_htiso_magsgn<OT, true>), grid, kWarpsIsoB * 32, 0, s, d_cblks, n, d_blob, qtab, status, d_coef, d_steps, coef_bits);
-        else J2K_LAUNCH((k_htiso_magsgn<OT, false>), grid, kWarpsIsoB * 32, 0, s, d_cblks, n, d_blob, qtab, status, d_coef, d_steps, coef_bits);
+        static const bool one_block_per_warp = getenv("J2KGPU_HT_B1") != nullptr;       // the first version of kernel B, for A/B runs
+        if (one_block_per_warp) {
+            const uint32_t grid = (n + kWarpsIsoB - 1) / kWarpsIsoB;
+            if (irrev) J2K_LAUNCH((k_htiso_magsgn<OT, true>), grid, kWarpsIsoB * 32, 0, s, d_cblks, n, d_blob, qtab, status, d_coef, d_steps, coef_bits);
+            else J2K_LAUNCH((k_htiso_magsgn<OT, false>), grid, kWarpsIsoB * 32, 0, s, d_cblks, n, d_blob, qtab, status, d_coef, d_steps, coef_bits);
+        } else {
+            const uint32_t grid = (n + 2 * kWarpsIsoB2 - 1) / (2 * kWarpsIsoB2);
+            if (irrev) J2K_LAUNCH((k_htiso_magsgn2<OT, true>), grid, kWarpsIsoB2 * 32, 0, s, d_cblks, n, d_blob, qtab, status, d_coef, d_steps, coef_bits);
+            else J2K_LAUNCH((k_htiso_magsgn2<OT, false>), grid, kWarpsIsoB2 * 32, 0, s, d_cblks, n, d_blob, qtab, status, d_coef, d_steps, coef_bits);
+        }
     } else if (blocks_per_warp == 32) {
         J2K_LAUNCH((k_ht_iso<32, OT>), (n + kThreads - 1) / kThreads, kThreads, 0, s, d_cblks, n, d_blob, d_coef, d_steps, irrev, coef_bits);
     } else {
