@@ -457,13 +457,13 @@ static int run_entropy(j2kgpu_job *job, const void *d_blob, uint32_t ia, uint32_
     if (job->iso && !job->hdr.ht) e = launch_t1_iso(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, steps, irrev, job->max_bps, st);
     else if (job->iso) {
         e = launch_ht_iso(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, steps, irrev, job->hdr.coef_bits, job->ht_map,
-                          job->d_htscratch, st);
+                          job->d_htscratch, job->blob_bytes, st);
         if (job->ht_map == 2) ctx->launches++;
     }
     else if (job->hdr.ht) {
         // the scratch is indexed by the job-wide block number: chunks of a pipelined run never share entries
         e = launch_ht_ref(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, job->precleared,
-                          (uint8_t *)job->d_htscratch, st);
+                          (uint8_t *)job->d_htscratch, job->blob_bytes, st);
         ctx->launches += j2k_htref_launches() - 1;
     }
     else e = launch_t1_ref(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, job->max_bps, st);
@@ -735,9 +735,9 @@ static int stage_blocks(j2kgpu_ctx *ctx, int mode, int ht, const j2k_blkjob_t *j
     if (const char *ev = getenv("J2KGPU_HT_MAP")) { const int v = atoi(ev); ht_map = (v == 1 || v == 32) ? v : 2; }
     if (ht && mode == J2KGPU_MODE_ISO && ht_map == 2) { if ((rc = j2k_reserve(ctx, ctx->d_aux, j2k_htiso_scratch_bytes(n), false))) return rc; ctx->launches++; }
     cudaError_t e = (ht && mode == J2KGPU_MODE_ISO)
-                        ? launch_ht_iso((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, nullptr, 0, 0, ht_map, ctx->d_aux.p, ctx->stream)
+                        ? launch_ht_iso((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, nullptr, 0, 0, ht_map, ctx->d_aux.p, blob_len, ctx->stream)
                     : mode == J2KGPU_MODE_ISO ? launch_t1_iso((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, nullptr, 0, max_bps, ctx->stream)
-                    : ht ? launch_ht_ref((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, 0, ctx->d_aux.p, ctx->stream)
+                    : ht ? launch_ht_ref((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, 0, ctx->d_aux.p, blob_len, ctx->stream)
                        : launch_t1_ref_stage((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, (int32_t *)ctx->d_out.p, max_bps, ctx->stream);
     if (e != cudaSuccess) return j2k_cuda_err(ctx, e, "entropy kernel launch");
     ctx->launches++;

@@ -141,7 +141,7 @@ int j2k_ctx_copy_streams(j2kgpu_ctx *ctx);
 cudaError_t launch_t1_ref(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
                           int max_bps, cudaStream_t s);
 cudaError_t launch_ht_ref(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
-                          int planes_precleared, void *d_scratch, cudaStream_t s);
+                          int planes_precleared, void *d_scratch, uint64_t blob_bytes, cudaStream_t s);
 int j2k_htref_map();             // reference-HT decoder mapping: 2 (VLC kernel + MagSgn kernel, default), 32 (thread per block) or 1 (warp per block)
 size_t j2k_htref_scratch_bytes(uint32_t n_blocks);   // device scratch launch_ht_ref needs for n blocks
 int j2k_htref_launches();        // kernels per launch_ht_ref call
@@ -150,7 +150,8 @@ cudaError_t launch_t1_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_b
                           const float *d_steps, int irrev, int max_bps, cudaStream_t s);
 // ISO/IEC 15444-15 cleanup decoder; blocks_per_warp = 1 (warp per block) or 32 (thread per block)
 cudaError_t launch_ht_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
-                          const float *d_steps, int irrev, int coef_bits, int blocks_per_warp, void *d_scratch, cudaStream_t s);
+                          const float *d_steps, int irrev, int coef_bits, int blocks_per_warp, void *d_scratch, uint64_t blob_bytes,
+                          cudaStream_t s);
 size_t j2k_htiso_scratch_bytes(uint32_t n_blocks);   // device scratch of the two-kernel mapping (blocks_per_warp == 2)
 
 // inverse DWT, REF (dense-prefix) addressing.  One call = one decomposition level of every

@@ -358,11 +358,22 @@ enum { ST_ZERO = 0, ST_OK = 1 };
 
 struct VlcStream { const uint8_t *d; int pos, left; uint64_t tmp; uint32_t bits; bool gt8f; };
 
-__device__ __forceinline__ void vlc_read4(VlcStream &v)
+// `lim` = the blob and its size (0 when the blob is not 4-byte aligned): inside it the four bytes come from two
+// aligned 32-bit loads instead of four byte loads
+struct BlobLim { const uint8_t *base; uint64_t bytes; };
+
+__device__ __forceinline__ void vlc_read4(VlcStream &v, const BlobLim &lim)
 {
     uint32_t b[4], nb[4];
+    const uint64_t off = (uint64_t)(v.d + v.pos - 3 - lim.base);
+    if (v.left >= 4 && off + 8 <= lim.bytes) {
+        const uint32_t *a = reinterpret_cast<const uint32_t *>(lim.base + (off & ~(uint64_t)3));
+        const uint32_t x = __funnelshift_r(__ldg(a), __ldg(a + 1), (uint32_t)(off & 3) * 8);      // bytes pos-3 .. pos
+        b[0] = x >> 24; b[1] = (x >> 16) & 0xFFu; b[2] = (x >> 8) & 0xFFu; b[3] = x & 0xFFu;
+    } else {
 #pragma unroll
-    for (int i = 0; i < 4; i++) b[i] = (i < v.left) ? (uint32_t)__ldg(v.d + v.pos - i) : 0u;
+        for (int i = 0; i < 4; i++) b[i] = (i < v.left) ? (uint32_t)__ldg(v.d + v.pos - i) : 0u;
+    }
     v.pos -= 4; v.left -= 4;
     bool g = v.gt8f;
 #pragma unroll
@@ -374,11 +385,11 @@ __device__ __forceinline__ void vlc_read4(VlcStream &v)
 }
 
 // at least 32 bits afterwards (four stuffed bytes give only 28: then a second read, which is rare)
-__device__ __forceinline__ void vlc_refill(VlcStream &v)
+__device__ __forceinline__ void vlc_refill(VlcStream &v, const BlobLim &lim)
 {
     if (v.bits < 32) {
-        vlc_read4(v);
-        if (v.bits < 32) vlc_read4(v);
+        vlc_read4(v, lim);
+        if (v.bits < 32) vlc_read4(v, lim);
     }
 }
 
@@ -415,9 +426,10 @@ __device__ __forceinline__ int uvlc_pair(const uint16_t *utab, uint32_t vlc, int
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_htiso_vlc(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob,
+k_htiso_vlc(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob, uint64_t blob_bytes,
             uint32_t *__restrict__ qtab, uint32_t *__restrict__ status)
 {
+    const BlobLim lim = {blob, blob_bytes};
     // table entries re-packed: len (3) | u_off (1) | rho (4) | sample states (8)
     __shared__ uint16_t s_tbl[2048];
     for (int i = threadIdx.x; i < 2048; i += kThreads) {
@@ -466,16 +478,17 @@ k_htiso_vlc(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__rest
         uint32_t *qrow = qt + (y >> 1) * 16;
         for (int q = 0; q < nq; q += 2, iters++) {
             const bool pair = (q + 1 < nq);
-            vlc_refill(v);                               // >= 32 bits: two codewords (<= 7 each) and the U-VLC (<= 16)
+            vlc_refill(v, lim);                               // >= 32 bits: two codewords (<= 7 each) and the U-VLC (<= 16)
+            uint32_t win = (uint32_t)v.tmp, used = 0;    // the pair decodes from one 32-bit window; one 64-bit shift at the end
             const uint32_t s6 = (((uint32_t)sp & 0x1F) << 1) | spc;     // columns 2q - 1 .. 2q + 4 (zero in the initial row)
             spc = ((uint32_t)sp >> 3) & 1;
             sp >>= 4;
             uint32_t e0, e1 = 0;
             {
                 const int c_q = cw | (int)((s6 & 3) != 0) | ((int)((s6 & 0xC) != 0) << 2);
-                uint32_t e = tbl[(c_q << 7) | ((uint32_t)v.tmp & 0x7F)];
+                uint32_t e = tbl[(c_q << 7) | (win & 0x7F)];
                 if (c_q == 0 && !mel_event(mel, d)) e = 0;
-                v.tmp >>= (e & 7); v.bits -= (e & 7);
+                win >>= (e & 7); used += (e & 7);
                 e0 = e;
                 const uint32_t rho = (e >> 4) & 0xF;
                 cw = initial ? (int)(((rho & 3) != 0) | (((rho >> 2) & 3) << 1))
@@ -483,9 +496,9 @@ k_htiso_vlc(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__rest
             }
             if (pair) {
                 const int c_q = cw | (int)((s6 & 0xC) != 0) | ((int)((s6 & 0x30) != 0) << 2);
-                uint32_t e = tbl[(c_q << 7) | ((uint32_t)v.tmp & 0x7F)];
+                uint32_t e = tbl[(c_q << 7) | (win & 0x7F)];
                 if (c_q == 0 && !mel_event(mel, d)) e = 0;
-                v.tmp >>= (e & 7); v.bits -= (e & 7);
+                win >>= (e & 7); used += (e & 7);
                 e1 = e;
                 const uint32_t rho = (e >> 4) & 0xF;
                 cw = initial ? (int)(((rho & 3) != 0) | (((rho >> 2) & 3) << 1))
@@ -494,14 +507,17 @@ k_htiso_vlc(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__rest
             int mode = (int)(((e0 >> 3) & 1) | (((e1 >> 3) & 1) << 1));
             if (initial && mode == 3 && mel_event(mel, d)) mode = 4;
             int u0 = 0, u1 = 0;
-            if (mode) { const int c = uvlc_pair(s_utab, (uint32_t)v.tmp, mode, initial, u0, u1); v.tmp >>= c; v.bits -= c; }
+            if (mode) used += (uint32_t)uvlc_pair(s_utab, win, mode, initial, u0, u1);
+            v.tmp >>= used; v.bits -= used;
             // bottom samples (rho bits 1 and 3) of both quads: columns 2q .. 2q + 3
-            const uint32_t nb4 = ((e0 >> 5) & 1) | (((e0 >> 7) & 1) << 1) | (((e1 >> 5) & 1) << 2) | (((e1 >> 7) & 1) << 3);
+            const uint32_t nb4 = ((e0 >> 5) & 1) | ((e0 >> 6) & 2) | ((e1 >> 3) & 4) | ((e1 >> 4) & 8);
             sn = (sn >> 4) | ((uint64_t)nb4 << 60);
-            // significance outside the block: malformed, the block is zero
+            // significance outside the block: malformed, the block is zero (only the last row / last pair can have it)
             const int xq = 2 * q;
-            badbits |= e0 & (rowmask | (xq + 1 >= w ? 0xC0u : 0u));
-            badbits |= e1 & (rowmask | (xq + 3 >= w ? 0xC0u : 0u));
+            if (rowmask | (uint32_t)(xq + 3 >= w)) {
+                badbits |= e0 & (rowmask | (xq + 1 >= w ? 0xC0u : 0u));
+                badbits |= e1 & (rowmask | (xq + 3 >= w ? 0xC0u : 0u));
+            }
             // u >= 31 makes U_q > 31 whatever the predictor says: malformed either way, 5 bits are enough
             qrow[q >> 1] = (e0 >> 8) | ((uint32_t)min(u0, 31) << 8) | (((e1 >> 8) | ((uint32_t)min(u1, 31) << 8)) << 16);
         }
@@ -834,11 +850,12 @@ size_t j2k_htiso_scratch_bytes(uint32_t n) { return (size_t)n * (kQTabWords * 4 
 
 template <typename OT>
 static void launch_ht_iso_t(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, OT *d_coef,
-                            const float *d_steps, int irrev, int coef_bits, int blocks_per_warp, void *d_scratch, cudaStream_t s)
+                            const float *d_steps, int irrev, int coef_bits, int blocks_per_warp, void *d_scratch, uint64_t blob_bytes, cudaStream_t s)
 {
+    if ((uintptr_t)d_blob & 3) blob_bytes = 0;           // unaligned blob: byte loads only
     if (blocks_per_warp == 2) {
         uint32_t *qtab = (uint32_t *)d_scratch, *status = qtab + (size_t)n * kQTabWords;
-        J2K_LAUNCH((k_htiso_vlc), (n + kThreads - 1) / kThreads, kThreads, 0, s, d_cblks, n, d_blob, qtab, status);
+        J2K_LAUNCH((k_htiso_vlc), (n + kThreads - 1) / kThreads, kThreads, 0, s, d_cblks, n, d_blob, blob_bytes, qtab, status);
         static const bool one_block_per_warp = getenv("J2KGPU_HT_B1") != nullptr;       // the first version of kernel B, for A/B runs
         if (one_block_per_warp) {
             const uint32_t grid = (n + kWarpsIsoB - 1) / kWarpsIsoB;
@@ -859,10 +876,11 @@ static void launch_ht_iso_t(const DevCblk *d_cblks, uint32_t n, const uint8_t *d
 
 // blocks_per_warp: 2 = the two-kernel mapping (needs d_scratch of j2k_htiso_scratch_bytes(n)), 32 / 1 = single kernel
 cudaError_t launch_ht_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
-                          const float *d_steps, int irrev, int coef_bits, int blocks_per_warp, void *d_scratch, cudaStream_t s)
+                          const float *d_steps, int irrev, int coef_bits, int blocks_per_warp, void *d_scratch, uint64_t blob_bytes,
+                          cudaStream_t s)
 {
     if (n == 0) return cudaSuccess;
-    if (coef16 && !irrev) launch_ht_iso_t<int16_t>(d_cblks, n, d_blob, (int16_t *)d_coef, d_steps, irrev, coef_bits, blocks_per_warp, d_scratch, s);
-    else launch_ht_iso_t<int32_t>(d_cblks, n, d_blob, (int32_t *)d_coef, d_steps, irrev, coef_bits, blocks_per_warp, d_scratch, s);
+    if (coef16 && !irrev) launch_ht_iso_t<int16_t>(d_cblks, n, d_blob, (int16_t *)d_coef, d_steps, irrev, coef_bits, blocks_per_warp, d_scratch, blob_bytes, s);
+    else launch_ht_iso_t<int32_t>(d_cblks, n, d_blob, (int32_t *)d_coef, d_steps, irrev, coef_bits, blocks_per_warp, d_scratch, blob_bytes, s);
     return cudaGetLastError();
 }

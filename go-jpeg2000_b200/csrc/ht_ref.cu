@@ -350,11 +350,22 @@ enum { ST_ZERO = 0, ST_FAST = 1, ST_WIDE = 2 };
 // inner branches, so the 32 chains of a warp diverge only on whether they refill.
 struct VlcStream { const uint8_t *d; int pos, left; uint64_t tmp; uint32_t bits; bool gt8f; };
 
-__device__ __forceinline__ void vlc_read4(VlcStream &v)
+// `lim` = the blob and its size (0 when the blob is not 4-byte aligned): inside it the four bytes come from two
+// aligned 32-bit loads instead of four byte loads
+struct BlobLim { const uint8_t *base; uint64_t bytes; };
+
+__device__ __forceinline__ void vlc_read4(VlcStream &v, const BlobLim &lim)
 {
     uint32_t b[4], nb[4];
+    const uint64_t off = (uint64_t)(v.d + v.pos - 3 - lim.base);
+    if (v.left >= 4 && off + 8 <= lim.bytes) {
+        const uint32_t *a = reinterpret_cast<const uint32_t *>(lim.base + (off & ~(uint64_t)3));
+        const uint32_t x = __funnelshift_r(__ldg(a), __ldg(a + 1), (uint32_t)(off & 3) * 8);      // bytes pos-3 .. pos
+        b[0] = x >> 24; b[1] = (x >> 16) & 0xFFu; b[2] = (x >> 8) & 0xFFu; b[3] = x & 0xFFu;
+    } else {
 #pragma unroll
-    for (int i = 0; i < 4; i++) b[i] = (i < v.left) ? (uint32_t)__ldg(v.d + v.pos - i) : 0u;
+        for (int i = 0; i < 4; i++) b[i] = (i < v.left) ? (uint32_t)__ldg(v.d + v.pos - i) : 0u;
+    }
     v.pos -= 4; v.left -= 4;
     bool g = v.gt8f;
 #pragma unroll
@@ -366,11 +377,11 @@ __device__ __forceinline__ void vlc_read4(VlcStream &v)
 }
 
 // at least 32 bits afterwards (four stuffed bytes give only 28: then a second read, which is rare)
-__device__ __forceinline__ void vlc_refill(VlcStream &v)
+__device__ __forceinline__ void vlc_refill(VlcStream &v, const BlobLim &lim)
 {
     if (v.bits < 32) {
-        vlc_read4(v);
-        if (v.bits < 32) vlc_read4(v);
+        vlc_read4(v, lim);
+        if (v.bits < 32) vlc_read4(v, lim);
     }
 }
 
@@ -403,9 +414,10 @@ __device__ __forceinline__ uint32_t uvlc_pair(const uint16_t *utab, uint32_t vlc
 }
 
 __global__ void __launch_bounds__(128)
-k_htref_vlc(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob,
+k_htref_vlc(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob, uint64_t blob_bytes,
             uint32_t *__restrict__ qinfo, uint32_t *__restrict__ status)
 {
+    const BlobLim lim = {blob, blob_bytes};
     __shared__ uint16_t s_tbl[2048];
     __shared__ uint16_t s_utab[192];
     for (int i = threadIdx.x; i < 1024; i += 128) { s_tbl[i] = d_vlc_tbl0[i]; s_tbl[1024 + i] = d_vlc_tbl1[i]; }
@@ -431,7 +443,7 @@ k_htref_vlc(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__rest
         v.bits = 4 - (uint32_t)((v.tmp & 7) >> 2);
         v.gt8f = (b | 0x0F) > 0x8F;
     }
-    vlc_refill(v);
+    vlc_refill(v, lim);
     uint32_t *qi = qinfo + (size_t)blk * kQuadWords;
     const int quad_cols = (w + 3) >> 2, rows = (h + 3) >> 2;
     uint32_t umax = 0;
@@ -439,7 +451,7 @@ k_htref_vlc(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__rest
         const bool initial = (r == 0);
         const uint16_t *tbl = s_tbl + (initial ? 0 : 1024);
         for (int qx = 0; qx < quad_cols; qx += 2) {
-            vlc_refill(v);                                              // >= 32 bits: both codewords (<= 15 + 15)
+            vlc_refill(v, lim);                                              // >= 32 bits: both codewords (<= 15 + 15)
             const uint32_t q1 = tbl[(uint32_t)v.tmp & 0x7F];
             const uint32_t rho1 = (q1 >> 4) & 0x0F, l1 = q1 & 0x0F;
             const uint32_t q2 = tbl[((rho1 >> 2) << 7) | ((uint32_t)(v.tmp >> l1) & 0x7F)];
@@ -448,7 +460,7 @@ k_htref_vlc(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__rest
             uint32_t u0 = 1, u1 = 1;
             const uint32_t mode = (((q1 >> 3) & 1) << 1) | ((q2 >> 3) & 1);
             if (mode > 0) {
-                vlc_refill(v);
+                vlc_refill(v, lim);
                 const uint32_t c = uvlc_pair(s_utab, (uint32_t)v.tmp, mode, initial, u0, u1);
                 v.tmp >>= c; v.bits -= c;
             }
@@ -631,14 +643,15 @@ int j2k_htref_launches() { return j2k_htref_map() == 2 ? 2 : 1; }
 // planes_precleared: the destination was zeroed once and only this decoder writes it (whole-path jobs): clear every 4th row
 // d_scratch: j2k_htref_scratch_bytes(n) bytes of device memory (the quad table between the two kernels)
 cudaError_t launch_ht_ref(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
-                          int planes_precleared, void *d_scratch, cudaStream_t s)
+                          int planes_precleared, void *d_scratch, uint64_t blob_bytes, cudaStream_t s)
 {
+    if ((uintptr_t)d_blob & 3) blob_bytes = 0;           // unaligned blob: byte loads only
     if (n == 0) return cudaSuccess;
     const int map = j2k_htref_map();
     if (map == 2) {
         uint32_t *qinfo = (uint32_t *)d_scratch;
         uint32_t *status = qinfo + (size_t)n * kQuadWords;
-        J2K_LAUNCH((k_htref_vlc), (n + 127) / 128, 128, 0, s, d_cblks, n, d_blob, qinfo, status);
+        J2K_LAUNCH((k_htref_vlc), (n + 127) / 128, 128, 0, s, d_cblks, n, d_blob, blob_bytes, qinfo, status);
         const uint32_t grid = (n + kWarpsB - 1) / kWarpsB;
 #define J2K_HTREF_B(OT, Z) J2K_LAUNCH((k_htref_magsgn<OT, Z>), grid, kWarpsB * 32, 0, s, d_cblks, n, d_blob, qinfo, status, (OT *)d_coef)
         if (coef16) { if (planes_precleared) J2K_HTREF_B(int16_t, 4); else J2K_HTREF_B(int16_t, 1); }
