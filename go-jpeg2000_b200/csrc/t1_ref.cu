@@ -206,14 +206,23 @@ k_t1_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
             for (int k = 0; k < 4; k++) { v[k] = visit[(y0 + k) & 63]; pb[k] = 0; }
             const bool full = (y0 + 4 <= h);
             const int rows = full ? 4 : (h - y0);
-            for (int x = 0; x < w; x++) {
+            // only columns with a sample that is neither significant nor already coded in this bit-plane have anything
+            // to decode (elsewhere the run-length test fails and every row is skipped); the set can only shrink
+            uint64_t need = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) if (k < rows) need |= ~(s[k + 1] | v[k]);
+            need &= wmask;
+            // run-length test of a column (canUseRunLength t1.go:1195-1208) = no significant sample in the 6 x 3 window and
+            // nothing coded in the column: kept as a column mask, updated when a sample turns significant
+            uint64_t anym = 0;
+            if (full) { const uint64_t a = s[0] | s[1] | s[2] | s[3] | s[4] | s[5]; anym = a | (a << 1) | (a >> 1) | v[0] | v[1] | v[2] | v[3]; }
+            while (need) {
+                const int x = __ffsll((long long)need) - 1;
+                need &= need - 1;
                 bool rl = false;
                 int pos = 0;
                 if (full) {
-                    uint32_t any = win3(s[0], x) | win3(s[1], x) | win3(s[2], x) | win3(s[3], x) |
-                                   win3(s[4], x) | win3(s[5], x) |
-                                   (uint32_t)(((v[0] | v[1] | v[2] | v[3]) >> x) & 1);
-                    if (any == 0) {                               // canUseRunLength t1.go:1195-1208
+                    if (!((anym >> x) & 1)) {
                         if (!mq_decode(mq, ctxs, kCtxRL)) continue;
                         pos = (int)(mq_decode(mq, ctxs, kCtxUni) << 1);
                         pos |= (int)mq_decode(mq, ctxs, kCtxUni);
@@ -242,6 +251,7 @@ k_t1_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
                         if (decode_sign(mq, ctxs, x, s[k], s[k + 1], s[k + 2], ng[k], ng[k + 1], ng[k + 2]))
                             ng[k + 1] |= 1ull << x;
                         s[k + 1] |= 1ull << x;
+                        anym |= x ? (7ull << (x - 1)) : 3ull;
                     }
                 }
             }
@@ -404,14 +414,21 @@ k_t1_iso(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
                 uint64_t v[4], pb[4];
 #pragma unroll
                 for (int k = 0; k < 4; k++) { v[k] = visit[(y0 + k) & 63]; pb[k] = 0; }
-                for (int x = 0; x < w; x++) {
+                // only columns with a sample that is neither significant nor coded in this bit-plane have work left
+                uint64_t need = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) if (k < rows) need |= ~(s[k + 1] | v[k]);
+                need &= wmask;
+                // run-length columns: no significant sample in the 6 x 3 window and nothing coded in the column yet
+                uint64_t anym = 0;
+                if (full) { const uint64_t a = s[0] | s[1] | s[2] | s[3] | s[4] | s[5]; anym = a | (a << 1) | (a >> 1) | v[0] | v[1] | v[2] | v[3]; }
+                while (need) {
+                    const int x = __ffsll((long long)need) - 1;
+                    need &= need - 1;
                     bool rl = false;
                     int pos = 0;
                     if (full) {
-                        const uint32_t any = win3(s[0], x) | win3(s[1], x) | win3(s[2], x) | win3(s[3], x) |
-                                             win3(s[4], x) | win3(s[5], x) |
-                                             (uint32_t)(((v[0] | v[1] | v[2] | v[3]) >> x) & 1);
-                        if (any == 0) {
+                        if (!((anym >> x) & 1)) {
                             if (!mq_decode(mq, ctxs, kCtxRL)) continue;
                             pos = (int)(mq_decode(mq, ctxs, kCtxUni) << 1);
                             pos |= (int)mq_decode(mq, ctxs, kCtxUni);
@@ -440,6 +457,7 @@ k_t1_iso(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
                             if (decode_sign(mq, ctxs, x, s[k], s[k + 1], s[k + 2], ng[k], ng[k + 1], ng[k + 2], c_sc_iso))
                                 ng[k + 1] |= 1ull << x;
                             s[k + 1] |= 1ull << x;
+                            anym |= x ? (7ull << (x - 1)) : 3ull;
                         }
                     }
                 }
