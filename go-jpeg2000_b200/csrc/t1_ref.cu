@@ -181,14 +181,14 @@ k_t1_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
             uint64_t cand = mid & ~visit[y];
             if (!cand) continue;
             const uint64_t up = sig[y - 1], dn = sig[y + 1], ref = refine[y];
+            // significance does not change during this pass: "has a significant neighbour" is one mask per row
+            const uint64_t nbm = up | (up << 1) | (up >> 1) | dn | (dn << 1) | (dn >> 1) | (mid << 1) | (mid >> 1);
             uint64_t bits = 0;
             refine[y] = ref | cand;
             while (cand) {
                 int x = __ffsll((long long)cand) - 1;
                 cand &= cand - 1;
-                int ctx;
-                if ((ref >> x) & 1) ctx = kCtxMag + 2;
-                else ctx = kCtxMag + ((win3(up, x) | win3(dn, x) | (win3(mid, x) & 5)) ? 1 : 0);
+                const int ctx = kCtxMag + (((ref >> x) & 1) ? 2 : (int)((nbm >> x) & 1));
                 if (mq_decode(mq, ctxs, ctx)) bits |= 1ull << x;
             }
             if (bits) plane[y] |= bits;
@@ -390,15 +390,19 @@ k_t1_iso(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
                     cols |= cand[k];
                 }
                 if (!cols) continue;
+                uint64_t nbm[4];                                  // significance is fixed during this pass: one neighbour mask per row
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint64_t a = s[k], m = s[k + 1], c = s[k + 2];
+                    nbm[k] = a | (a << 1) | (a >> 1) | c | (c << 1) | (c >> 1) | (m << 1) | (m >> 1);
+                }
                 while (cols) {
                     const int x = __ffsll((long long)cols) - 1;
                     cols &= cols - 1;
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
                         if (!((cand[k] >> x) & 1)) continue;
-                        int ctx;
-                        if ((rf[k] >> x) & 1) ctx = kCtxMag + 2;
-                        else ctx = kCtxMag + ((win3(s[k], x) | win3(s[k + 2], x) | (win3(s[k + 1], x) & 5)) ? 1 : 0);
+                        const int ctx = kCtxMag + (((rf[k] >> x) & 1) ? 2 : (int)((nbm[k] >> x) & 1));
                         if (mq_decode(mq, ctxs, ctx)) pb[k] |= 1ull << x;
                     }
                 }
