@@ -212,6 +212,27 @@ def test_pipelined_host_run_many_items(j2k, gpu_ctx):
         assert np.array_equal(o, oracle_pixels(j))
 
 
+@pytest.mark.parametrize("ht", [0, 1])
+def test_host_run_is_independent_of_the_chunk_plan(j2k, gpu_ctx, ht):
+    """the pipelined host-buffer run gives the same pixels whatever its chunk plan (planner default, one chunk, one item
+    per chunk, uneven chunks): the HT scratch tables are indexed by job-wide block numbers, the arenas by item"""
+    import os
+    jl = [jobs.build_ref_job(jobs.synth_image(96, 64, 3, 8, seed=900 + i), 8, 32, 32, nlevels=2, reversible=True,
+                             ht=bool(ht), threads=2) for i in range(7)]
+    want = [oracle_pixels(j) for j in jl]
+    try:
+        for plan in (None, "7", "1,1,1,1,1,1,1", "2,4,1", "3"):
+            if plan is None:
+                os.environ.pop("J2KGPU_CHUNKS", None)
+            else:
+                os.environ["J2KGPU_CHUNKS"] = plan
+            outs, _ = _run_items(j2k, gpu_ctx, jl)
+            for o, wnt in zip(outs, want):
+                assert np.array_equal(o, wnt), plan
+    finally:
+        os.environ.pop("J2KGPU_CHUNKS", None)
+
+
 def test_path_argument_errors(j2k, gpu_ctx):
     s = jobs.synth_image(64, 64, 3, 8, seed=9)
     job = jobs.build_ref_job(s, 8, nlevels=2, reversible=True, threads=2)
