@@ -6,12 +6,12 @@
 // in pairs, CxtVLC tables, U-VLC, exponent predictor from the previous quad row.  Checked in the test suite against
 // a CPU statement of the same algorithm that is itself pinned by OpenJPEG decoding the same streams.
 //
-// Mapping.  The three bit streams of a block are strictly sequential, so a block is one serial chain of about
-// 50 instructions per quad whatever the mapping.  Two mappings of the same device function are built:
-//   BLOCKS_PER_WARP = 1   one warp per code block: all lanes run the chain on uniform registers, lane 0 stores;
-//   BLOCKS_PER_WARP = 32  one thread per code block: 32 independent chains per warp (divergent but short
+// Mapping.  Default (J2KGPU_HT_MAP unset or 2): two kernels, k_htiso_vlc (one thread per block: the MEL / VLC context
+// chain) and k_htiso_magsgn2 (half a warp per block: the MagSgn rows in parallel) -- second half of this file.
+// First half: the single-chain decoder, a block as one serial chain of about 50 instructions per quad, in two mappings:
+//   J2KGPU_HT_MAP = 1     one warp per code block: all lanes run the chain on uniform registers, lane 0 stores;
+//   J2KGPU_HT_MAP = 32    one thread per code block: 32 independent chains per warp (divergent but short
 //                         branches), 32x fewer warp-instructions for the same work.
-// The launcher picks by J2KGPU_HT_MAP (default: thread-per-block; see DESIGN.md for the ncu comparison).
 // Per-block state: stream cursors and 64-bit bit buffers in registers; previous-row significance as a 64-bit
 // column mask; previous-row exponents as 64 bytes of shared memory, updated in place with a one-column carry.
 // Every sample of the block is written exactly once (zeros included), two rows x two columns per quad.

@@ -1,4 +1,5 @@
-// ht_ref.cu -- "HT" block decoder, REF semantics, one warp per code block (sm_100a).
+// ht_ref.cu -- "HT" block decoder, REF semantics (sm_100a): a per-thread VLC kernel + a warp-per-block MagSgn kernel
+// (default), and the statement-level single-kernel decoder they are checked against.
 //
 // Replaces entropy.HTDecoder.Decode (reference internal/entropy/ht.go:93-150): MEL init check
 // (ht.go:153-195), backward VLC reader (ht.go:276-396), forward MagSgn reader (ht.go:399-519),
@@ -7,8 +8,8 @@
 // the MEL stream is never consumed, the VLC length field is read with mask 0x0F.  REF mode
 // reproduces exactly that; the conformant decoder is the ISO-mode kernel.
 //
-// The bit readers are serial, so the warp runs them lock-step on uniform registers; the lanes
-// share the parallel part (zero-filling the block in the tile-component plane, coalesced).
+// First part of the file: the statement-level restatement (bit readers as in the reference, one serial chain per
+// block: ht_ref_block_serial, mappings J2KGPU_HTREF_MAP = 1 / 32).  Second part: the two-kernel mapping (see there).
 // Go semantics kept: uint32 shifts >= 32 give 0; the uint32 "bits" counters wrap when a MagSgn
 // field is longer than the buffered bits (emb up to 37, ht.go:668-669).
 #include "common.h"
