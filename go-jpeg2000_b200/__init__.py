@@ -77,6 +77,7 @@ EXPORTS = [
     "j2kgpu_job_run_host", "j2kgpu_sync", "j2kgpu_t1_decode_blocks", "j2kgpu_ht_decode_blocks",
     "j2kgpu_idwt53", "j2kgpu_idwt97", "j2kgpu_apply_inverse_dwt", "j2kgpu_inverse_rct",
     "j2kgpu_inverse_ict", "j2kgpu_dc_level_shift_inverse", "j2kgpu_mct_dc_pack",
+    "j2kgpu_host_alloc", "j2kgpu_host_free", "j2kgpu_host_register", "j2kgpu_host_unregister",
 ]
 
 _lib = None
@@ -192,6 +193,27 @@ class Context:
 
     def sync(self):
         self._check(lib().j2kgpu_sync(self._h))
+
+    # ---- page-locked host memory (j2kgpu_host_*) ----------------------------------------------
+    def host_alloc(self, nbytes):
+        """a uint8 numpy array over `nbytes` of page-locked memory; release it with host_free(array)"""
+        p = C.c_void_p()
+        self._check(lib().j2kgpu_host_alloc(self._h, C.c_uint64(nbytes), C.byref(p)))
+        a = np.ctypeslib.as_array(C.cast(p, u8p), shape=(max(int(nbytes), 1),))[:nbytes]
+        self._pinned = getattr(self, "_pinned", {})
+        self._pinned[a.ctypes.data] = p
+        return a
+
+    def host_free(self, a):
+        p = self._pinned.pop(a.ctypes.data)
+        self._check(lib().j2kgpu_host_free(self._h, p))
+
+    def host_register(self, a):
+        """page-lock a contiguous numpy array the caller owns (until host_unregister)"""
+        self._check(lib().j2kgpu_host_register(self._h, C.c_void_p(a.ctypes.data), C.c_uint64(a.nbytes)))
+
+    def host_unregister(self, a):
+        self._check(lib().j2kgpu_host_unregister(self._h, C.c_void_p(a.ctypes.data)))
 
     # ---- entropy stage ------------------------------------------------------------------------
     def _decode_blocks(self, fn, blocks, mode):

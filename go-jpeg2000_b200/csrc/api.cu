@@ -671,6 +671,45 @@ extern "C" int j2kgpu_job_run_host(j2kgpu_job *job, const j2k_batch_item_t *item
     return run_host_locked(job, items);
 }
 
+// ---- page-locked host memory -------------------------------------------------------------------------------
+extern "C" int j2kgpu_host_alloc(j2kgpu_ctx *ctx, uint64_t bytes, void **out)
+{
+    if (!ctx || !out) return J2KGPU_E_ARG;
+    *out = nullptr;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    cudaSetDevice(ctx->device);
+    J2K_CUDA(ctx, cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return J2KGPU_OK;
+}
+
+extern "C" int j2kgpu_host_free(j2kgpu_ctx *ctx, void *p)
+{
+    if (!ctx) return J2KGPU_E_ARG;
+    if (!p) return J2KGPU_OK;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    cudaSetDevice(ctx->device);
+    J2K_CUDA(ctx, cudaFreeHost(p));
+    return J2KGPU_OK;
+}
+
+extern "C" int j2kgpu_host_register(j2kgpu_ctx *ctx, void *p, uint64_t bytes)
+{
+    if (!ctx || !p || !bytes) return J2KGPU_E_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    cudaSetDevice(ctx->device);
+    J2K_CUDA(ctx, cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return J2KGPU_OK;
+}
+
+extern "C" int j2kgpu_host_unregister(j2kgpu_ctx *ctx, void *p)
+{
+    if (!ctx || !p) return J2KGPU_E_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    cudaSetDevice(ctx->device);
+    J2K_CUDA(ctx, cudaHostUnregister(p));
+    return J2KGPU_OK;
+}
+
 extern "C" int j2kgpu_decode_batch(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *items)
 {
     if (!ctx) return J2KGPU_E_ARG;

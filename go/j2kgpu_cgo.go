@@ -87,6 +87,13 @@ func (d *decoder) decodeTilesGPU(job *gpuJob) (image.Image, error) {
 	if len(job.blob) > 0 {
 		blob = (*C.uint8_t)(unsafe.Pointer(&job.blob[0]))
 	}
+	// Page-lock the pixel buffer for the call (ABI v3): the device->host copy of the pixels is the slowest step of the
+	// path and runs at link speed, overlapped with the kernels, only into page-locked memory.  The Go heap does not
+	// move objects, and cgo keeps pix alive for the duration of the call; a decoder that recycles its images would
+	// register each buffer once instead.  Failure to register is not an error: the copy is then staged by the driver.
+	if C.j2kgpu_host_register(ctx.h, unsafe.Pointer(&pix[0]), C.uint64_t(len(pix))) == 0 {
+		defer C.j2kgpu_host_unregister(ctx.h, unsafe.Pointer(&pix[0]))
+	}
 	rc := C.j2kgpu_decode(ctx.h, &job.img, tc, C.uint32_t(len(job.tilecomps)), cb, C.uint32_t(len(job.cblks)),
 		blob, C.uint64_t(len(job.blob)), (*C.uint8_t)(unsafe.Pointer(&pix[0])), C.uint64_t(stride))
 	if rc != 0 {

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define J2KGPU_ABI_VERSION 2
+#define J2KGPU_ABI_VERSION 3
 
 /* ---- status codes ---------------------------------------------------------- */
 enum {
@@ -183,6 +183,19 @@ int      j2kgpu_job_plan(const j2kgpu_job *job);
  * blocking.  Give pinned host buffers for the copies to overlap the kernels. */
 int      j2kgpu_job_run_host(j2kgpu_job *job, const j2k_batch_item_t *items);
 int      j2kgpu_sync(j2kgpu_ctx *ctx);
+
+/* ---- page-locked host memory (ABI v3) --------------------------------------- *
+ * The host-buffer entry points copy asynchronously, overlapped with the kernels,
+ * only from / to page-locked memory; pageable memory (a Go slice, malloc) still
+ * works but every copy is staged by the driver and blocks.  Either allocate the
+ * blob / pixel buffers here, or page-lock memory the caller already owns (the
+ * Pix of an image.RGBA, kept alive and unmoved for the duration: runtime.Pinner)
+ * and release it before the memory is freed.  The reference has no counterpart:
+ * its buffers are plain Go slices (decoder.go:296-305, 417-588).                */
+int      j2kgpu_host_alloc(j2kgpu_ctx *ctx, uint64_t bytes, void **out);
+int      j2kgpu_host_free(j2kgpu_ctx *ctx, void *p);
+int      j2kgpu_host_register(j2kgpu_ctx *ctx, void *p, uint64_t bytes);
+int      j2kgpu_host_unregister(j2kgpu_ctx *ctx, void *p);
 
 /* ---- per-stage entry points (differential tests against the oracle) --------- */
 /* entropy.T1.Decode (t1.go:1261) over n blocks; out = concatenated w*h int32 */

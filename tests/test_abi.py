@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol(j2k):
     for n in names:
         assert hasattr(L, n), n
     assert sorted(j2k.EXPORTS) == names
-    assert L.j2kgpu_abi_version() == 2
+    assert L.j2kgpu_abi_version() == 3
 
 
 def test_struct_layouts(j2k):

@@ -233,6 +233,35 @@ def test_host_run_is_independent_of_the_chunk_plan(j2k, gpu_ctx, ht):
         os.environ.pop("J2KGPU_CHUNKS", None)
 
 
+def test_page_locked_host_buffers(j2k, gpu_ctx):
+    """j2kgpu_host_alloc / j2kgpu_host_register (ABI v3): decoding from a page-locked blob into page-locked pixels gives
+    the pixels of the pageable call; the calls fail as values on bad arguments"""
+    j = jobs.build_ref_job(jobs.synth_image(96, 64, 3, 8, seed=41), 8, 32, 32, nlevels=2, reversible=True, ht=True, threads=2)
+    want = oracle_pixels(j)
+    tcs, cbs = jobs.as_ctypes(j["tilecomps"], j2k.TileComp), jobs.as_ctypes(j["cblks"], j2k.CBlk)
+    blob = np.ascontiguousarray(j["blob"])
+    img = j2k.make_image(96, 64, 3, 8, mct=j["mct"], reversible=1, nlevels=2, ht=1)
+    pin_blob = gpu_ctx.host_alloc(blob.size)                         # allocated by the library
+    pin_blob[:] = blob
+    out = np.zeros(96 * 64 * 4, np.uint8)
+    gpu_ctx.host_register(out)                                       # owned by the caller, page-locked in place
+    try:
+        item = j2k.BatchItem(img, tcs, len(tcs), cbs, len(cbs), pin_blob.ctypes.data_as(j2k.u8p), blob.size,
+                             out.ctypes.data_as(j2k.u8p), 96 * 4)
+        job = j2k.Job(gpu_ctx, [item])
+        job.run_host()
+        job.close()
+        assert np.array_equal(out, want)
+    finally:
+        gpu_ctx.host_unregister(out)
+        gpu_ctx.host_free(pin_blob)
+    L = j2k.lib()
+    import ctypes as C
+    assert L.j2kgpu_host_alloc(None, C.c_uint64(16), C.byref(C.c_void_p())) == j2k.E_ARG
+    assert L.j2kgpu_host_register(gpu_ctx._h, None, C.c_uint64(16)) == j2k.E_ARG
+    assert L.j2kgpu_host_free(gpu_ctx._h, None) == 0
+
+
 def test_path_argument_errors(j2k, gpu_ctx):
     s = jobs.synth_image(64, 64, 3, 8, seed=9)
     job = jobs.build_ref_job(s, 8, nlevels=2, reversible=True, threads=2)
