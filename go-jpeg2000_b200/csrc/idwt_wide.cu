@@ -17,6 +17,7 @@
 //   * vertical lifting state (one row pair of delay) lives in registers: 144 per lane; the kernel runs 8 warps / SM.
 // Eligibility (host): fast RGBA8 epilogue conditions of idwt_fused.cu + every tile width % 16 == 0, height % 4 == 0.
 #include "common.h"
+#include <cstdlib>
 #include "tail.cuh"
 
 namespace {
@@ -507,9 +508,13 @@ cudaError_t launch_idwt53_wide(const IdwtLaunch &p, cudaStream_t s)
 {
     if (p.n_tiles == 0 || p.max_w < 16 || p.max_h < 4) return cudaSuccess;
     const uint32_t nl = p.max_w / 16, own = nl > 32 ? 30 : 32, nwx = (nl + own - 1) / own, nly = p.max_h / 2;
-    // strip height: tall strips amortise the two silent prologue steps; keep ~4 waves of 8 warps per SM for balance
+    // strip height: tall strips amortise the two silent prologue steps, short ones even out the last wave of 8 warps per
+    // SM.  Measured on the bench batch (640 tiles of 512 x 512): REF order 64 / 32 / 16 row pairs -> 0.626 / 0.533 / 0.515 ms
+    // (int32 planes), ISO order 0.419 / 0.359 / 0.367 ms (int16): at least 8 waves for REF, 4 for ISO.
+    const uint64_t min_warps = 148ull * 8 * (p.iso ? 4 : 8);
     int sp = 64;
-    while (sp > 8 && (uint64_t)p.n_tiles * nwx * ((nly + sp - 1) / sp) < 148ull * 8 * 4) sp >>= 1;
+    while (sp > 8 && (uint64_t)p.n_tiles * nwx * ((nly + sp - 1) / sp) < min_warps) sp >>= 1;
+    if (const char *e = getenv("J2KGPU_WIDE_SP")) { const int v = atoi(e); if (v >= 2) sp = v & ~1; }
     const uint32_t units = nwx * ((nly + sp - 1) / sp);
     dim3 grid((units + kWarps - 1) / kWarps, p.n_tiles, 1);
     if (p.tail.ncomp == 1) return p.coef16 ? run_ct<1, int16_t>(p, grid, sp, s) : run_ct<1, int32_t>(p, grid, sp, s);
