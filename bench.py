@@ -36,7 +36,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 W, H, NCOMP, PREC, TILE, LEVELS = 3840, 2160, 3, 8, 512, 5
-NCU_TRAFFIC_RATIO = {4: 1.031}     # measured DRAM bytes / algorithmic bytes of the fused kernel (ncu capture, see profiles/)
+NCU_TRAFFIC_RATIO = {4: 1.069}     # measured DRAM bytes / algorithmic bytes of the fused kernel (ncu capture, see profiles/)
 METRIC = "decoded_mpixels_per_s"
 UNIT = "Mpixel/s"
 
@@ -398,9 +398,9 @@ def run_ours(args):
                               else ": last IDWT level + RCT + DC + clamp + RGBA pack"),
                              peak_source=peak_src, algorithmic_bytes_per_launch=alg_bytes,
                              # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, from the ncu --set full capture
-                             # in profiles/ (2-frame launch: 273.6 MB against 265.4 MB algorithmic), scaled to this launch
+                             # in profiles/ (the bench's own 16-frame launch: 1.763 GB read + 0.507 GB written against 2.123 GB algorithmic)
                              traffic=int(alg_bytes * NCU_TRAFFIC_RATIO.get(main["plan"]["coef_plane_bytes_per_sample"], 1.0)),
-                             traffic_source="profiles/r1_ncu_idwt53_wide_int32.txt (ratio measured / algorithmic = 1.031)"),
+                             traffic_source="profiles/r1_ncu_idwt53_wide_int32_final.txt (16-frame launch: 2.270 GB measured / 2.123 GB algorithmic = 1.069)"),
             "cpu_baseline": {"value": round(cpu_val, 2), "unit": UNIT, "cores": cpu_threads, "kind": "port",
                              "sample": "1 frame of the batch, whole path, all host threads",
                              "note": "C restatement of the reference's Go stage functions (oracle/); Go itself is absent"},
