@@ -29,6 +29,7 @@ PLAN_FUSED, PLAN_FAST_EPILOGUE, PLAN_WIDE, PLAN_COEF16 = 1, 2, 4, 8
 BAND_LL, BAND_HL, BAND_LH, BAND_HH = 0, 1, 2, 3
 FMT_AUTO, FMT_GRAY8, FMT_GRAY16, FMT_RGBA8, FMT_RGBA64 = 0, 1, 2, 3, 4
 E_ARG, E_RANGE, E_UNSUPPORTED, E_CUDA, E_NOMEM, E_NODEVICE = -1, -2, -3, -4, -5, -6
+CS_NONE, CS_YCC709, CS_YCC601 = 0, 1, 2          # J2KGPU_CS_*
 
 u8p = C.POINTER(C.c_uint8)
 i32p = C.POINTER(C.c_int32)
@@ -39,7 +40,8 @@ class Image(C.Structure):          # j2k_image_t
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("ncomp", C.c_uint16),
                 ("prec", C.c_uint8 * 4), ("sgnd", C.c_uint8 * 4), ("mct", C.c_uint8),
                 ("reversible", C.c_uint8), ("nlevels", C.c_uint8), ("ht", C.c_uint8),
-                ("mode", C.c_uint8), ("out_fmt", C.c_uint8), ("coef_bits", C.c_uint8), ("rsv", C.c_uint8 * 3)]
+                ("mode", C.c_uint8), ("out_fmt", C.c_uint8), ("coef_bits", C.c_uint8), ("colorspace", C.c_uint8),
+                ("rsv", C.c_uint8 * 2)]
 
 
 class TileComp(C.Structure):       # j2k_tilecomp_t
@@ -143,7 +145,8 @@ def fmt_bpp(ncomp, prec):
     return (1 if prec <= 8 else 2) if ncomp == 1 else (4 if prec <= 8 else 8)
 
 
-def make_image(width, height, ncomp, prec, sgnd=0, mct=1, reversible=1, nlevels=5, ht=0, mode=MODE_REF, coef_bits=0):
+def make_image(width, height, ncomp, prec, sgnd=0, mct=1, reversible=1, nlevels=5, ht=0, mode=MODE_REF, coef_bits=0,
+               colorspace=0):
     im = Image()
     im.width, im.height, im.ncomp = width, height, ncomp
     precs = list(prec) if isinstance(prec, (list, tuple)) else [prec] * ncomp
@@ -153,6 +156,7 @@ def make_image(width, height, ncomp, prec, sgnd=0, mct=1, reversible=1, nlevels=
         im.sgnd[c] = sg[c]
     im.mct, im.reversible, im.nlevels, im.ht, im.mode, im.out_fmt = mct, reversible, nlevels, ht, mode, FMT_AUTO
     im.coef_bits = coef_bits
+    im.colorspace = colorspace
     return im
 
 

@@ -142,6 +142,9 @@ static int make_tail(j2kgpu_ctx *ctx, const j2k_image_t &im, TailParams &tp)
     tp.mct = (im.mct != 0 && im.ncomp >= 3);                                            // decoder.go:322
     tp.reversible = im.reversible != 0;
     tp.iso = im.mode == J2KGPU_MODE_ISO;
+    if (im.colorspace > J2KGPU_CS_YCC601)
+        return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "colour conversion %d is not built (YCbCr family only)", (int)im.colorspace);
+    tp.cconv = im.ncomp >= 3 ? im.colorspace : 0;                                       // colorspace.go:93-95: fewer than 3 components -> no-op
     tp.fmt = j2k_resolve_fmt(im.ncomp, im.prec[0], im.out_fmt);
     if (tp.fmt < 0) return j2k_set_err(ctx, J2KGPU_E_ARG, "out_fmt %d does not match ncomp/precision", (int)im.out_fmt);
     return J2KGPU_OK;
@@ -247,7 +250,7 @@ static bool same_header(const j2k_image_t &a, const j2k_image_t &b)
 {
     return a.ncomp == b.ncomp && !memcmp(a.prec, b.prec, 4) && !memcmp(a.sgnd, b.sgnd, 4) && a.mct == b.mct &&
            a.reversible == b.reversible && a.nlevels == b.nlevels && a.ht == b.ht && a.mode == b.mode &&
-           a.out_fmt == b.out_fmt;
+           a.out_fmt == b.out_fmt && a.colorspace == b.colorspace;
 }
 
 static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *items, j2kgpu_job **out)
@@ -380,7 +383,7 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
     job->fused_ok = fused_ok;
     // fixed epilogues of the fused kernels: 3 x 8-bit unsigned + RCT -> RGBA8, or 1 x 8 / 16-bit unsigned -> Gray8 / Gray16
     if (tp.ncomp == 3) {
-        job->fast_epi = tp.fmt == J2KGPU_FMT_RGBA8 && tp.mct && tp.reversible;
+        job->fast_epi = tp.fmt == J2KGPU_FMT_RGBA8 && tp.mct && tp.reversible && !tp.cconv;
         for (int c = 0; c < 3; c++) if (tp.prec[c] != 8 || tp.sgnd[c]) job->fast_epi = 0;
     } else if (tp.ncomp == 1) {
         job->fast_epi = (tp.prec[0] == 8 || tp.prec[0] == 16) && !tp.sgnd[0];

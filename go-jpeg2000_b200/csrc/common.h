@@ -68,6 +68,7 @@ struct TailParams {              // image-wide constants of the MCT / DC / pack 
     int reversible;
     int fmt;                     // J2KGPU_FMT_* (resolved, never AUTO)
     int iso;                     // 1: ISO packing (no int32-overflow quirk)
+    int cconv;                   // J2KGPU_CS_*: colour conversion to sRGB after the DC shift (0 = none)
 };
 
 // ---- context -----------------------------------------------------------------------------------

@@ -6,6 +6,29 @@
 // ---- pixel epilogue: decoder.go:321-348 + createImage decoder.go:417-588 ----------------------------
 __device__ __forceinline__ int32_t clampi(int32_t v, int32_t lo, int32_t hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+// clampToInt32 colorspace.go:483-491: below 0 -> 0, above max -> max, else int32(v + 0.5) (truncating)
+__device__ __forceinline__ int32_t cs_clamp_round(double v, double maxv)
+{
+    if (v < 0.0) return 0;
+    if (v > maxv) return (int32_t)maxv;
+    return j2k_f64_to_i32(__dadd_rn(v, 0.5));
+}
+
+// colour conversion to sRGB (decoder.go:350-356 -> getColorConversion colorspace.go:54-88), YCbCr family: convertSYCCToRGB /
+// convertYPbPr709ToRGB (colorspace.go:90-114, 429-452) and convertYCbCr601ToRGB (:116-140).  float64, no FMA (Go on amd64).
+__device__ __forceinline__ void tail_colour(int32_t v[4], const TailParams &tp)
+{
+    if (tp.cconv == 0 || tp.ncomp < 3) return;
+    const int prec = tp.prec[0];
+    const double maxv = (double)(int32_t)((1u << prec) - 1u), half = (double)(int32_t)(1u << (prec - 1));
+    const bool bt709 = tp.cconv == J2KGPU_CS_YCC709;
+    const double y = (double)v[0], cb = __dsub_rn((double)v[1], half), cr = __dsub_rn((double)v[2], half);
+    const double r = __dadd_rn(y, __dmul_rn(bt709 ? 1.5748 : 1.402, cr));
+    const double g = __dsub_rn(__dsub_rn(y, __dmul_rn(bt709 ? 0.1873 : 0.344136, cb)), __dmul_rn(bt709 ? 0.4681 : 0.714136, cr));
+    const double b = __dadd_rn(y, __dmul_rn(bt709 ? 1.8556 : 1.772, cb));
+    v[0] = cs_clamp_round(r, maxv); v[1] = cs_clamp_round(g, maxv); v[2] = cs_clamp_round(b, maxv);
+}
+
 __device__ __forceinline__ void tail_mct_dc(int32_t v[4], const TailParams &tp)
 {
     if (tp.mct) {
@@ -26,6 +49,7 @@ __device__ __forceinline__ void tail_mct_dc(int32_t v[4], const TailParams &tp)
 #pragma unroll
     for (int c = 0; c < 4; c++)
         if (c < tp.ncomp && !tp.sgnd[c]) v[c] = (int32_t)((uint32_t)v[c] + (1u << (tp.prec[c] - 1)));   // mct.go:113-118
+    tail_colour(v, tp);
 }
 
 // ISO mode, irreversible path: float32 samples -> inverse ICT in float32 -> round to nearest even -> DC shift.
@@ -47,6 +71,7 @@ __device__ __forceinline__ void tail_iso_irrev(const float f[4], int32_t v[4], c
         if (c < tp.ncomp && !tp.sgnd[c]) q = (int32_t)((uint32_t)q + (1u << (tp.prec[c] - 1)));
         v[c] = q;
     }
+    tail_colour(v, tp);
 }
 
 // scaled sample value exactly as createImage computes it (int32 product wraps in REF mode)

@@ -28,6 +28,12 @@
 extern "C" {
 #endif
 
+/* colour conversions of the reference that are built (colorspace.go): the YCbCr family.  Components 1 and 2 are centred
+ * at 2^(prec-1); result = clamp(round(matrix * (Y, Cb, Cr)), 0, 2^prec - 1) in float64, as convertSYCCToRGB does. */
+#define J2KGPU_CS_NONE   0   /* sRGB, greyscale, unspecified: no conversion                                          */
+#define J2KGPU_CS_YCC709 1   /* ITU-R BT.709 matrix: ColorSpaceSYCC, YPbPr60, YPbPr50 (colorspace.go:90-114, 429-452) */
+#define J2KGPU_CS_YCC601 2   /* ITU-R BT.601 matrix: ColorSpaceYCbCr2, YCbCr3 (colorspace.go:116-140)                 */
+
 #define J2KGPU_ABI_VERSION 3
 
 /* ---- status codes ---------------------------------------------------------- */
@@ -79,7 +85,9 @@ typedef struct {
                                  * a block whose decoded magnitudes exceed the bound is malformed and decodes to
                                  * zero.  REF mode ignores it (EBCOT bounds come from num_bps, the reference HT
                                  * coder has no bound).                                                       */
-    uint8_t  rsv[3];            /* set 0                                                      */
+    uint8_t  colorspace;        /* J2KGPU_CS_*: conversion to sRGB after the DC shift, the step of decoder.go:350-356
+                                 * (getColorConversion, colorspace.go:54-88); 0 = none (sRGB, grey, unknown)    */
+    uint8_t  rsv[2];            /* set 0                                                      */
 } j2k_image_t;
 
 /* one tile-component (tcd.TileComponent, tcd.go:272-283): bounds in image

@@ -106,12 +106,16 @@ typedef struct {
     uint32_t width, height;
     uint16_t ncomp; uint8_t prec[4]; uint8_t sgnd[4];
     uint8_t mct, reversible, nlevels, ht, mode, out_fmt;
+    uint8_t coef_bits, colorspace, rsv[2];
 } orc_image_t;                /* same layout as j2k_image_t */
 
 /* REF-mode whole path with `threads` host threads: per block T1.Decode /
  * HTDecoder.Decode into the tile-component plane, ApplyInverseDWT per
  * tile-component, copy into image planes (decoder.go:398-410), decoder tail,
  * createImage.  Returns 0, or negative on bad arguments. */
+/* colour conversion to sRGB, YCbCr family (colorspace.go:90-140, 429-452): cs 1 = BT.709 matrix, 2 = BT.601 matrix */
+void orc_colour_convert(int32_t *const *comps, int ncomp, size_t n, int prec, int cs);
+
 int orc_decode_image(const orc_image_t *img, const orc_tilecomp_t *tcs, uint32_t n_tc,
                      const orc_cblk_t *cbs, uint32_t n_cb, const uint8_t *blob, uint64_t blob_len,
                      uint8_t *out_pix, uint64_t out_stride, int threads);

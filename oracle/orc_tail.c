@@ -63,6 +63,33 @@ void orc_decoder_tail(int32_t *const *comps, int ncomp, size_t n, int mct, int r
         if (!sgnd[c]) orc_dc_shift_inverse(comps[c], n, prec[c]);
 }
 
+/* clampToInt32 colorspace.go:483-491 */
+static inline int32_t cs_clamp_round(double v, double maxv)
+{
+    if (v < 0.0) return 0;
+    if (v > maxv) return (int32_t)maxv;
+    return orc_f64_to_i32(v + 0.5);
+}
+
+/* decoder.go:350-356 -> getColorConversion (colorspace.go:54-88), the YCbCr family: convertSYCCToRGB (:90-114) and
+ * convertYPbPr709ToRGB (:429-452) share the BT.709 matrix (cs 1); convertYCbCr601ToRGB (:116-140) is cs 2 */
+void orc_colour_convert(int32_t *const *comps, int ncomp, size_t n, int prec, int cs)
+{
+    if (cs == 0 || ncomp < 3) return;
+    const double maxv = (double)(int32_t)(((uint32_t)1 << prec) - 1), half = (double)(int32_t)((uint32_t)1 << (prec - 1));
+    const double kr = cs == 1 ? 1.5748 : 1.402, kgb = cs == 1 ? 0.1873 : 0.344136, kgr = cs == 1 ? 0.4681 : 0.714136,
+                 kb = cs == 1 ? 1.8556 : 1.772;
+    for (size_t i = 0; i < n; i++) {
+        const double y = (double)comps[0][i], cb = (double)comps[1][i] - half, cr = (double)comps[2][i] - half;
+        const double r = y + kr * cr;
+        const double g = y - kgb * cb - kgr * cr;
+        const double b = y + kb * cb;
+        comps[0][i] = cs_clamp_round(r, maxv);
+        comps[1][i] = cs_clamp_round(g, maxv);
+        comps[2][i] = cs_clamp_round(b, maxv);
+    }
+}
+
 static inline int32_t clamp_i32(int32_t v, int32_t lo, int32_t hi)   /* decoder.go:591-599 */
 {
     return v < lo ? lo : (v > hi ? hi : v);
@@ -143,6 +170,7 @@ static void *worker(void *arg)
             int32_t *c[4] = {0, 0, 0, 0};
             for (int k = 0; k < j->img->ncomp; k++) c[k] = j->comps[k] + y0 * W;
             orc_decoder_tail(c, j->img->ncomp, rows * W, j->img->mct, j->img->reversible, j->img->prec, j->img->sgnd);
+            orc_colour_convert(c, j->img->ncomp, rows * W, j->img->prec[0], j->img->colorspace);   /* decoder.go:350-356 */
             if (j->out_stride == W * (size_t)j->bpp) {
                 if (orc_create_image((const int32_t *const *)c, (int)W, (int)rows, j->img->ncomp, j->img->prec[0],
                                      j->out_pix + y0 * j->out_stride) < 0) j->rc = -3;

@@ -40,7 +40,8 @@ class Image(C.Structure):  # == j2k_image_t
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("ncomp", C.c_uint16),
                 ("prec", C.c_uint8 * 4), ("sgnd", C.c_uint8 * 4), ("mct", C.c_uint8),
                 ("reversible", C.c_uint8), ("nlevels", C.c_uint8), ("ht", C.c_uint8),
-                ("mode", C.c_uint8), ("out_fmt", C.c_uint8)]
+                ("mode", C.c_uint8), ("out_fmt", C.c_uint8), ("coef_bits", C.c_uint8), ("colorspace", C.c_uint8),
+                ("rsv", C.c_uint8 * 2)]
 
 
 def build(force=False):
@@ -155,6 +156,14 @@ def decoder_tail(comps, mct, reversible, prec, sgnd):
     pr = (C.c_uint8 * 4)(*(list(prec) + [0] * (4 - len(prec))))
     sg = (C.c_uint8 * 4)(*(list(sgnd) + [0] * (4 - len(sgnd))))
     lib().orc_decoder_tail(arr, len(comps), C.c_size_t(comps[0].size), int(mct), int(reversible), pr, sg)
+    return comps
+
+
+def colour_convert(comps, prec, cs):
+    """colorspace.go conversions of the YCbCr family (cs 1 = BT.709 matrix, 2 = BT.601), in place on copies"""
+    comps = [np.array(c, np.int32).reshape(-1) for c in comps]
+    arr = (i32p * len(comps))(*[_p(c, i32p) for c in comps])
+    lib().orc_colour_convert(arr, len(comps), C.c_size_t(comps[0].size), int(prec), int(cs))
     return comps
 
 

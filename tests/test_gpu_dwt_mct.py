@@ -107,3 +107,26 @@ def test_decoder_tail_then_pack(gpu_ctx, j2k, ncomp, prec, rev, sgnd):
     after = O.decoder_tail(comps, 1, rev, [prec] * ncomp, [sgnd] * ncomp)
     want, _ = O.create_image(after, w, h, prec)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("ncomp,prec,cs,mct,rev", [(3, 8, 1, 0, 1), (3, 8, 2, 0, 1), (3, 12, 1, 0, 0), (4, 8, 2, 0, 1), (3, 16, 2, 1, 0),
+                                                   (1, 8, 1, 0, 1)])
+def test_colour_conversion_then_pack(gpu_ctx, j2k, ncomp, prec, cs, mct, rev):
+    """decoder.go:321-356 followed by createImage: the YCbCr-family conversions of colorspace.go run in the same epilogue
+    (values outside the nominal range included: the conversion clamps)"""
+    rng = np.random.default_rng(10 * ncomp + prec + cs)
+    w, h = 61, 7
+    comps = [rng.integers(-(1 << (prec - 1)) - 90, (1 << (prec - 1)) + 90, w * h).astype(np.int32) for _ in range(ncomp)]
+    img = j2k.make_image(w, h, ncomp, prec, sgnd=0, mct=mct, reversible=rev, colorspace=cs)
+    got = gpu_ctx.mct_dc_pack(img, comps, apply_tail=True)
+    after = O.decoder_tail(comps, mct, rev, [prec] * ncomp, [0] * ncomp)
+    after = O.colour_convert(after, prec, cs)
+    want, _ = O.create_image(after, w, h, prec)
+    assert np.array_equal(got, want)
+
+
+def test_colour_conversion_not_built(gpu_ctx, j2k):
+    img = j2k.make_image(8, 8, 3, 8, colorspace=9)
+    with pytest.raises(j2k.J2KError) as e:
+        gpu_ctx.mct_dc_pack(img, [np.zeros(64, np.int32)] * 3)
+    assert e.value.code == j2k.E_UNSUPPORTED

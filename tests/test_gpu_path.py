@@ -233,6 +233,32 @@ def test_host_run_is_independent_of_the_chunk_plan(j2k, gpu_ctx, ht):
         os.environ.pop("J2KGPU_CHUNKS", None)
 
 
+@pytest.mark.parametrize("w,h,prec,tw,levels,rev,ht,cs", [
+    (96, 80, 8, None, 3, 1, 0, 1),        # fused kernels, generic epilogue (the fast RGBA8 one has no conversion)
+    (512, 256, 8, 256, 4, 1, 1, 2),       # would take the 16-columns-per-lane kernel without the conversion
+    (200, 120, 12, 128, 4, 0, 0, 1),      # 9-7, RGBA64
+    (130, 70, 8, 64, 2, 1, 0, 2),         # ragged tiles, tiled per-level path
+])
+def test_whole_path_with_colour_conversion(j2k, gpu_ctx, w, h, prec, tw, levels, rev, ht, cs):
+    """j2k_image_t.colorspace: sYCC / YCbCr images come out as sRGB exactly as decoder.go:350-356 + colorspace.go would"""
+    s = jobs.synth_image(w, h, 3, prec, seed=7 * w + cs)
+    job = jobs.build_ref_job(s, prec, tw, tw, nlevels=levels, reversible=bool(rev), ht=bool(ht), threads=2)
+    img = O.Image()
+    img.width, img.height, img.ncomp = w, h, 3
+    for c in range(3):
+        img.prec[c], img.sgnd[c] = prec, 0
+    img.mct, img.reversible, img.nlevels, img.ht, img.colorspace = job["mct"], rev, levels, ht, cs
+    bpp = 4 if prec <= 8 else 8
+    want = O.decode_image(img, jobs.as_ctypes(job["tilecomps"], O.TileComp), jobs.as_ctypes(job["cblks"], O.CBlk),
+                          job["blob"], w * bpp, w * bpp * h, threads=2)
+    gimg = j2k.make_image(w, h, 3, prec, mct=job["mct"], reversible=rev, nlevels=levels, ht=ht, colorspace=cs)
+    got = gpu_ctx.decode_tiles(gimg, jobs.as_ctypes(job["tilecomps"], j2k.TileComp), jobs.as_ctypes(job["cblks"], j2k.CBlk), job["blob"])
+    assert np.array_equal(got, want)
+    plain = gpu_ctx.decode_tiles(j2k.make_image(w, h, 3, prec, mct=job["mct"], reversible=rev, nlevels=levels, ht=ht),
+                                 jobs.as_ctypes(job["tilecomps"], j2k.TileComp), jobs.as_ctypes(job["cblks"], j2k.CBlk), job["blob"])
+    assert not np.array_equal(plain, got)
+
+
 def test_page_locked_host_buffers(j2k, gpu_ctx):
     """j2kgpu_host_alloc / j2kgpu_host_register (ABI v3): decoding from a page-locked blob into page-locked pixels gives
     the pixels of the pageable call; the calls fail as values on bad arguments"""
