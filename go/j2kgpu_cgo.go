@@ -46,6 +46,19 @@ type gpuJob struct {
 	blob      []byte
 }
 
+// gpuColorSpace maps the colour spaces whose conversion to sRGB the library applies in its pixel epilogue
+// (decoder.go:350-356, colorspace.go:54-88).  The other conversions of colorspace.go are not built: for those the
+// caller keeps the reference's CPU path.
+func gpuColorSpace(cs ColorSpace) (C.uint8_t, bool) {
+	switch cs {
+	case ColorSpaceSYCC, ColorSpaceYPbPr60, ColorSpaceYPbPr50:
+		return C.J2KGPU_CS_YCC709, true
+	case ColorSpaceYCbCr2, ColorSpaceYCbCr3:
+		return C.J2KGPU_CS_YCC601, true
+	}
+	return C.J2KGPU_CS_NONE, getColorConversion(cs) == nil
+}
+
 // decodeTilesGPU is decoder.decodeTiles on the GPU: it returns the same image types createImage would
 // (decoder.go:417-588) with Pix filled by the library; errors are wrapped like decoder.go:47.
 func (d *decoder) decodeTilesGPU(job *gpuJob) (image.Image, error) {
