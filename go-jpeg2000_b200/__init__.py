@@ -29,7 +29,7 @@ PLAN_FUSED, PLAN_FAST_EPILOGUE, PLAN_WIDE, PLAN_COEF16 = 1, 2, 4, 8
 BAND_LL, BAND_HL, BAND_LH, BAND_HH = 0, 1, 2, 3
 FMT_AUTO, FMT_GRAY8, FMT_GRAY16, FMT_RGBA8, FMT_RGBA64 = 0, 1, 2, 3, 4
 E_ARG, E_RANGE, E_UNSUPPORTED, E_CUDA, E_NOMEM, E_NODEVICE = -1, -2, -3, -4, -5, -6
-CS_NONE, CS_YCC709, CS_YCC601 = 0, 1, 2          # J2KGPU_CS_*
+CS_NONE, CS_YCC709, CS_YCC601, CS_PHOTOYCC, CS_CMY, CS_CMYK, CS_YCCK = 0, 1, 2, 3, 4, 5, 6          # J2KGPU_CS_*
 
 u8p = C.POINTER(C.c_uint8)
 i32p = C.POINTER(C.c_int32)

@@ -142,8 +142,8 @@ static int make_tail(j2kgpu_ctx *ctx, const j2k_image_t &im, TailParams &tp)
     tp.mct = (im.mct != 0 && im.ncomp >= 3);                                            // decoder.go:322
     tp.reversible = im.reversible != 0;
     tp.iso = im.mode == J2KGPU_MODE_ISO;
-    if (im.colorspace > J2KGPU_CS_YCC601)
-        return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "colour conversion %d is not built (YCbCr family only)", (int)im.colorspace);
+    if (im.colorspace > J2KGPU_CS_YCCK)
+        return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "colour conversion %d is not built", (int)im.colorspace);
     tp.cconv = im.ncomp >= 3 ? im.colorspace : 0;                                       // colorspace.go:93-95: fewer than 3 components -> no-op
     tp.fmt = j2k_resolve_fmt(im.ncomp, im.prec[0], im.out_fmt);
     if (tp.fmt < 0) return j2k_set_err(ctx, J2KGPU_E_ARG, "out_fmt %d does not match ncomp/precision", (int)im.out_fmt);
@@ -281,6 +281,9 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
     bool need_clear = false;
     uint32_t stream_levels = hdr.nlevels ? ((1u << hdr.nlevels) - 1) : 0;
     bool fused_ok = hdr.reversible && hdr.nlevels >= 1 && !env_flag("J2KGPU_NO_FUSE");
+    // a colour conversion (j2k_image_t.colorspace) lives in the epilogue of the general tiled kernel only: the last level
+    // takes neither the fused nor the streaming kernels (their epilogues stay free of it, see tail.cuh)
+    if (tp.cconv) { fused_ok = false; stream_levels &= ~1u; }
 
     for (uint32_t ii = 0; ii < n_img; ii++) {
         const j2k_batch_item_t &it = items[ii];

@@ -277,7 +277,7 @@ k_idwt_level(const DevTileComp *__restrict__ tcs, const void *__restrict__ coef,
 }
 
 // ---- kernel: last level of every tile, fused with inverse MCT + DC shift + clamp + pack ---------------
-template <class L, bool ISO>
+template <class L, bool ISO, bool CC>
 __global__ void __launch_bounds__(kThreads)
 k_idwt_last_pixels(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__ tiles,
                    const void *__restrict__ coef, typename L::T *tmp, uint8_t *pix, int nlevels,
@@ -336,6 +336,7 @@ k_idwt_last_pixels(const DevTileComp *__restrict__ tcs, const DevTile *__restric
         } else {
             tail_mct_dc(v, tp);
         }
+        if (CC) tail_colour(v, tp);                              // decoder.go:350-356
         store_pixel(img + (size_t)gy * tile.out_stride, gx, v, tp);
     }
 }
@@ -348,7 +349,7 @@ __global__ void k_tail(const int32_t *c0, const int32_t *c1, const int32_t *c2, 
     uint64_t n = (uint64_t)width * height;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         int32_t v[4] = {c0[i], tp.ncomp > 1 ? c1[i] : 0, tp.ncomp > 2 ? c2[i] : 0, tp.ncomp > 3 ? c3[i] : 0};
-        if (apply_tail) tail_mct_dc(v, tp);
+        if (apply_tail) { tail_mct_dc(v, tp); tail_colour(v, tp); }
         if (o0) { o0[i] = v[0]; if (tp.ncomp > 1) o1[i] = v[1]; if (tp.ncomp > 2) o2[i] = v[2]; if (tp.ncomp > 3) o3[i] = v[3]; }
         if (pix) {
             uint32_t y = (uint32_t)(i / width), x = (uint32_t)(i - (uint64_t)y * width);
@@ -398,18 +399,20 @@ cudaError_t launch_idwt_level(const IdwtLaunch &p, cudaStream_t s, int *n_launch
     if (!p.reversible && !p.f64_io && p.nlevels > 0 && ((p.stream_levels >> lvl) & 1) && (lvl > 0 || pixels))
         return launch_idwt97_stream(p, s);
     if (pixels) {
-        if (!p.reversible && p.iso)
-            J2K_LAUNCH((k_idwt_last_pixels<Lift97F, true>), grid, kThreads, patch_bytes<Lift97F>(), s,
-                       p.d_tcs, p.d_tiles + p.tile_first, p.d_coef, (float *)p.d_tmp, p.d_pix, p.nlevels, p.tail, p.coef16);
-        else if (p.reversible && p.iso)
-            J2K_LAUNCH((k_idwt_last_pixels<Lift53, true>), grid, kThreads, patch_bytes<Lift53>(), s,
-                       p.d_tcs, p.d_tiles + p.tile_first, p.d_coef, (int32_t *)p.d_tmp, p.d_pix, p.nlevels, p.tail, p.coef16);
-        else if (p.reversible)
-            J2K_LAUNCH((k_idwt_last_pixels<Lift53, false>), grid, kThreads, patch_bytes<Lift53>(), s,
-                       p.d_tcs, p.d_tiles + p.tile_first, p.d_coef, (int32_t *)p.d_tmp, p.d_pix, p.nlevels, p.tail, p.coef16);
-        else
-            J2K_LAUNCH((k_idwt_last_pixels<Lift97, false>), grid, kThreads, patch_bytes<Lift97>(), s,
-                       p.d_tcs, p.d_tiles + p.tile_first, p.d_coef, (double *)p.d_tmp, p.d_pix, p.nlevels, p.tail, p.coef16);
+#define J2K_LAST_PIXELS(L, ISO_, TT)                                                                                             \
+        do {                                                                                                                     \
+            if (p.tail.cconv)                                                                                                    \
+                J2K_LAUNCH((k_idwt_last_pixels<L, ISO_, true>), grid, kThreads, patch_bytes<L>(), s, p.d_tcs,                     \
+                           p.d_tiles + p.tile_first, p.d_coef, (TT *)p.d_tmp, p.d_pix, p.nlevels, p.tail, p.coef16);              \
+            else                                                                                                                 \
+                J2K_LAUNCH((k_idwt_last_pixels<L, ISO_, false>), grid, kThreads, patch_bytes<L>(), s, p.d_tcs,                    \
+                           p.d_tiles + p.tile_first, p.d_coef, (TT *)p.d_tmp, p.d_pix, p.nlevels, p.tail, p.coef16);              \
+        } while (0)
+        if (!p.reversible && p.iso) J2K_LAST_PIXELS(Lift97F, true, float);
+        else if (p.reversible && p.iso) J2K_LAST_PIXELS(Lift53, true, int32_t);
+        else if (p.reversible) J2K_LAST_PIXELS(Lift53, false, int32_t);
+        else J2K_LAST_PIXELS(Lift97, false, double);
+#undef J2K_LAST_PIXELS
         return cudaGetLastError();
     }
     if (p.reversible) return run_level<Lift53, false, EPI_STORE>(p, grid, s);

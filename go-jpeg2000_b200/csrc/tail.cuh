@@ -14,19 +14,56 @@ __device__ __forceinline__ int32_t cs_clamp_round(double v, double maxv)
     return j2k_f64_to_i32(__dadd_rn(v, 0.5));
 }
 
-// colour conversion to sRGB (decoder.go:350-356 -> getColorConversion colorspace.go:54-88), YCbCr family: convertSYCCToRGB /
-// convertYPbPr709ToRGB (colorspace.go:90-114, 429-452) and convertYCbCr601ToRGB (:116-140).  float64, no FMA (Go on amd64).
+// colour conversion to sRGB (decoder.go:350-356 -> getColorConversion colorspace.go:54-88), float64 with Go's evaluation
+// order and no FMA.  cs 1 / 2: the YCbCr family -- convertSYCCToRGB / convertYPbPr709ToRGB / convertEYCCToRGB
+// (colorspace.go:90-114, 429-482) and convertYCbCr601ToRGB (:116-140); cs 3: convertPhotoYCCToRGB (:142-168); cs 4:
+// convertCMYToRGB (:170-189); cs 5: convertCMYKToRGB (:191-217); cs 6: convertYCCKToRGB (:219-250).
+// Out of line and by value, and called only by the two kernels jobs with a conversion are routed to (k_idwt_last_pixels<.., CC = true>
+// and k_tail): measured, even an untaken call in the epilogue of the register-heavy streaming kernels cost them 7 to 30 %.
+static __device__ J2K_NOINLINE int3 tail_colour_rgb(int32_t v0, int32_t v1, int32_t v2, int32_t v3, int cconv, int ncomp, int prec)
+{
+    const int32_t maxi = (int32_t)((1u << prec) - 1u);
+    const double maxv = (double)maxi;
+    if (cconv == J2KGPU_CS_YCC709 || cconv == J2KGPU_CS_YCC601) {
+        const bool bt709 = cconv == J2KGPU_CS_YCC709;
+        const double half = (double)(int32_t)(1u << (prec - 1));
+        const double y = (double)v0, cb = __dsub_rn((double)v1, half), cr = __dsub_rn((double)v2, half);
+        const double r = __dadd_rn(y, __dmul_rn(bt709 ? 1.5748 : 1.402, cr));
+        const double g = __dsub_rn(__dsub_rn(y, __dmul_rn(bt709 ? 0.1873 : 0.344136, cb)), __dmul_rn(bt709 ? 0.4681 : 0.714136, cr));
+        const double b = __dadd_rn(y, __dmul_rn(bt709 ? 1.8556 : 1.772, cb));
+        return make_int3(cs_clamp_round(r, maxv), cs_clamp_round(g, maxv), cs_clamp_round(b, maxv));
+    }
+    if (cconv == J2KGPU_CS_CMY)
+        return make_int3((int32_t)((uint32_t)maxi - (uint32_t)v0), (int32_t)((uint32_t)maxi - (uint32_t)v1), (int32_t)((uint32_t)maxi - (uint32_t)v2));
+    if (cconv == J2KGPU_CS_CMYK) {
+        if (ncomp < 4) return make_int3(v0, v1, v2);
+        const double c = __ddiv_rn((double)v0, maxv), m = __ddiv_rn((double)v1, maxv), y = __ddiv_rn((double)v2, maxv),
+                     k1 = __dsub_rn(1.0, __ddiv_rn((double)v3, maxv));
+        return make_int3(cs_clamp_round(__dmul_rn(__dmul_rn(__dsub_rn(1.0, c), k1), maxv), maxv),
+                         cs_clamp_round(__dmul_rn(__dmul_rn(__dsub_rn(1.0, m), k1), maxv), maxv),
+                         cs_clamp_round(__dmul_rn(__dmul_rn(__dsub_rn(1.0, y), k1), maxv), maxv));
+    }
+    const bool ycck = cconv == J2KGPU_CS_YCCK;                          // else PhotoYCC
+    if (ycck && ncomp < 4) return make_int3(v0, v1, v2);
+    const double scale = __ddiv_rn(maxv, 255.0);
+    const double y = __ddiv_rn((double)v0, scale), c1 = __dsub_rn(__ddiv_rn((double)v1, scale), 156.0),
+                 c2 = __dsub_rn(__ddiv_rn((double)v2, scale), 156.0);
+    double r = __dadd_rn(y, __dmul_rn(1.3584, c2));
+    double g = __dsub_rn(__dsub_rn(y, __dmul_rn(0.4302, c1)), __dmul_rn(0.7915, c2));
+    double b = __dadd_rn(y, __dmul_rn(2.2179, c1));
+    r = __dmul_rn(r, scale); g = __dmul_rn(g, scale); b = __dmul_rn(b, scale);
+    if (ycck) {
+        const double k1 = __dsub_rn(1.0, __ddiv_rn((double)v3, maxv));
+        r = __dmul_rn(r, k1); g = __dmul_rn(g, k1); b = __dmul_rn(b, k1);
+    }
+    return make_int3(cs_clamp_round(r, maxv), cs_clamp_round(g, maxv), cs_clamp_round(b, maxv));
+}
+
 __device__ __forceinline__ void tail_colour(int32_t v[4], const TailParams &tp)
 {
-    if (tp.cconv == 0 || tp.ncomp < 3) return;
-    const int prec = tp.prec[0];
-    const double maxv = (double)(int32_t)((1u << prec) - 1u), half = (double)(int32_t)(1u << (prec - 1));
-    const bool bt709 = tp.cconv == J2KGPU_CS_YCC709;
-    const double y = (double)v[0], cb = __dsub_rn((double)v[1], half), cr = __dsub_rn((double)v[2], half);
-    const double r = __dadd_rn(y, __dmul_rn(bt709 ? 1.5748 : 1.402, cr));
-    const double g = __dsub_rn(__dsub_rn(y, __dmul_rn(bt709 ? 0.1873 : 0.344136, cb)), __dmul_rn(bt709 ? 0.4681 : 0.714136, cr));
-    const double b = __dadd_rn(y, __dmul_rn(bt709 ? 1.8556 : 1.772, cb));
-    v[0] = cs_clamp_round(r, maxv); v[1] = cs_clamp_round(g, maxv); v[2] = cs_clamp_round(b, maxv);
+    if (tp.cconv == 0) return;                                          // make_tail: 0 unless ncomp >= 3
+    const int3 c = tail_colour_rgb(v[0], v[1], v[2], v[3], tp.cconv, tp.ncomp, tp.prec[0]);
+    v[0] = c.x; v[1] = c.y; v[2] = c.z;
 }
 
 __device__ __forceinline__ void tail_mct_dc(int32_t v[4], const TailParams &tp)
@@ -49,7 +86,6 @@ __device__ __forceinline__ void tail_mct_dc(int32_t v[4], const TailParams &tp)
 #pragma unroll
     for (int c = 0; c < 4; c++)
         if (c < tp.ncomp && !tp.sgnd[c]) v[c] = (int32_t)((uint32_t)v[c] + (1u << (tp.prec[c] - 1)));   // mct.go:113-118
-    tail_colour(v, tp);
 }
 
 // ISO mode, irreversible path: float32 samples -> inverse ICT in float32 -> round to nearest even -> DC shift.
@@ -71,7 +107,6 @@ __device__ __forceinline__ void tail_iso_irrev(const float f[4], int32_t v[4], c
         if (c < tp.ncomp && !tp.sgnd[c]) q = (int32_t)((uint32_t)q + (1u << (tp.prec[c] - 1)));
         v[c] = q;
     }
-    tail_colour(v, tp);
 }
 
 // scaled sample value exactly as createImage computes it (int32 product wraps in REF mode)

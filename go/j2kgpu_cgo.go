@@ -47,16 +47,23 @@ type gpuJob struct {
 }
 
 // gpuColorSpace maps the colour spaces whose conversion to sRGB the library applies in its pixel epilogue
-// (decoder.go:350-356, colorspace.go:54-88).  The other conversions of colorspace.go are not built: for those the
-// caller keeps the reference's CPU path.
+// (decoder.go:350-356, colorspace.go:54-88): every conversion that needs no math.Pow.
 func gpuColorSpace(cs ColorSpace) (C.uint8_t, bool) {
 	switch cs {
-	case ColorSpaceSYCC, ColorSpaceYPbPr60, ColorSpaceYPbPr50:
+	case ColorSpaceSYCC, ColorSpaceEYCC, ColorSpaceYPbPr60, ColorSpaceYPbPr50:
 		return C.J2KGPU_CS_YCC709, true
 	case ColorSpaceYCbCr2, ColorSpaceYCbCr3:
 		return C.J2KGPU_CS_YCC601, true
+	case ColorSpacePhotoYCC:
+		return C.J2KGPU_CS_PHOTOYCC, true
+	case ColorSpaceCMY:
+		return C.J2KGPU_CS_CMY, true
+	case ColorSpaceCMYK:
+		return C.J2KGPU_CS_CMYK, true
+	case ColorSpaceYCCK:
+		return C.J2KGPU_CS_YCCK, true
 	}
-	return C.J2KGPU_CS_NONE, getColorConversion(cs) == nil
+	return C.J2KGPU_CS_NONE, getColorConversion(cs) == nil // false: CIELab, CIEJab, e-sRGB, ROMM-RGB stay on the CPU path
 }
 
 // decodeTilesGPU is decoder.decodeTiles on the GPU: it returns the same image types createImage would

@@ -28,11 +28,16 @@
 extern "C" {
 #endif
 
-/* colour conversions of the reference that are built (colorspace.go): the YCbCr family.  Components 1 and 2 are centred
- * at 2^(prec-1); result = clamp(round(matrix * (Y, Cb, Cr)), 0, 2^prec - 1) in float64, as convertSYCCToRGB does. */
+/* colour conversions of the reference that are built (colorspace.go), float64 with the reference's evaluation order and its
+ * clampToInt32 rounding.  A job with a conversion decodes its last IDWT level with the general tiled kernel. */
 #define J2KGPU_CS_NONE   0   /* sRGB, greyscale, unspecified: no conversion                                          */
-#define J2KGPU_CS_YCC709 1   /* ITU-R BT.709 matrix: ColorSpaceSYCC, YPbPr60, YPbPr50 (colorspace.go:90-114, 429-452) */
+#define J2KGPU_CS_YCC709 1   /* ITU-R BT.709 matrix: ColorSpaceSYCC, EYCC, YPbPr60, YPbPr50 (colorspace.go:90-114, 429-482) */
 #define J2KGPU_CS_YCC601 2   /* ITU-R BT.601 matrix: ColorSpaceYCbCr2, YCbCr3 (colorspace.go:116-140)                 */
+#define J2KGPU_CS_PHOTOYCC 3 /* ColorSpacePhotoYCC (colorspace.go:142-168)                                           */
+#define J2KGPU_CS_CMY    4   /* ColorSpaceCMY: maxVal - v (colorspace.go:170-189)                                    */
+#define J2KGPU_CS_CMYK   5   /* ColorSpaceCMYK, 4 components; the 4th stays and becomes alpha (colorspace.go:191-217) */
+#define J2KGPU_CS_YCCK   6   /* ColorSpaceYCCK, 4 components (colorspace.go:219-250)                                 */
+/* not built (they need pow / cube roots whose last bit differs between libms): CIELab, CIEJab, e-sRGB, ROMM-RGB */
 
 #define J2KGPU_ABI_VERSION 3
 

@@ -71,12 +71,49 @@ static inline int32_t cs_clamp_round(double v, double maxv)
     return orc_f64_to_i32(v + 0.5);
 }
 
-/* decoder.go:350-356 -> getColorConversion (colorspace.go:54-88), the YCbCr family: convertSYCCToRGB (:90-114) and
- * convertYPbPr709ToRGB (:429-452) share the BT.709 matrix (cs 1); convertYCbCr601ToRGB (:116-140) is cs 2 */
+/* decoder.go:350-356 -> getColorConversion (colorspace.go:54-88).  cs 1: convertSYCCToRGB (:90-114), convertYPbPr709ToRGB
+ * (:429-452), convertEYCCToRGB (:454-482) -- the BT.709 matrix; cs 2: convertYCbCr601ToRGB (:116-140); cs 3:
+ * convertPhotoYCCToRGB (:142-168); cs 4: convertCMYToRGB (:170-189); cs 5: convertCMYKToRGB (:191-217); cs 6:
+ * convertYCCKToRGB (:219-250).  The pow-based ones (CIELab, CIEJab, e-sRGB, ROMM) are not restated. */
 void orc_colour_convert(int32_t *const *comps, int ncomp, size_t n, int prec, int cs)
 {
     if (cs == 0 || ncomp < 3) return;
-    const double maxv = (double)(int32_t)(((uint32_t)1 << prec) - 1), half = (double)(int32_t)((uint32_t)1 << (prec - 1));
+    const int32_t maxi = (int32_t)(((uint32_t)1 << prec) - 1);
+    const double maxv = (double)maxi, half = (double)(int32_t)((uint32_t)1 << (prec - 1));
+    if (cs == 4) {
+        for (size_t i = 0; i < n; i++)
+            for (int c = 0; c < 3; c++) comps[c][i] = (int32_t)((uint32_t)maxi - (uint32_t)comps[c][i]);
+        return;
+    }
+    if (cs == 5) {
+        if (ncomp < 4) return;
+        for (size_t i = 0; i < n; i++) {
+            const double c = (double)comps[0][i] / maxv, m = (double)comps[1][i] / maxv, y = (double)comps[2][i] / maxv,
+                         k = (double)comps[3][i] / maxv;
+            const double r = (1 - c) * (1 - k) * maxv, g = (1 - m) * (1 - k) * maxv, b = (1 - y) * (1 - k) * maxv;
+            comps[0][i] = cs_clamp_round(r, maxv); comps[1][i] = cs_clamp_round(g, maxv); comps[2][i] = cs_clamp_round(b, maxv);
+        }
+        return;
+    }
+    if (cs == 3 || cs == 6) {
+        if (cs == 6 && ncomp < 4) return;
+        const double scale = maxv / 255.0;
+        for (size_t i = 0; i < n; i++) {
+            const double y = (double)comps[0][i] / scale, c1 = (double)comps[1][i] / scale - 156.0,
+                         c2 = (double)comps[2][i] / scale - 156.0;
+            double r = y + 1.3584 * c2;
+            double g = y - 0.4302 * c1 - 0.7915 * c2;
+            double b = y + 2.2179 * c1;
+            if (cs == 6) {
+                const double k = (double)comps[3][i] / maxv;
+                r = r * scale * (1 - k); g = g * scale * (1 - k); b = b * scale * (1 - k);
+            } else {
+                r = r * scale; g = g * scale; b = b * scale;
+            }
+            comps[0][i] = cs_clamp_round(r, maxv); comps[1][i] = cs_clamp_round(g, maxv); comps[2][i] = cs_clamp_round(b, maxv);
+        }
+        return;
+    }
     const double kr = cs == 1 ? 1.5748 : 1.402, kgb = cs == 1 ? 0.1873 : 0.344136, kgr = cs == 1 ? 0.4681 : 0.714136,
                  kb = cs == 1 ? 1.8556 : 1.772;
     for (size_t i = 0; i < n; i++) {

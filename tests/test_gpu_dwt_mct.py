@@ -110,10 +110,11 @@ def test_decoder_tail_then_pack(gpu_ctx, j2k, ncomp, prec, rev, sgnd):
 
 
 @pytest.mark.parametrize("ncomp,prec,cs,mct,rev", [(3, 8, 1, 0, 1), (3, 8, 2, 0, 1), (3, 12, 1, 0, 0), (4, 8, 2, 0, 1), (3, 16, 2, 1, 0),
-                                                   (1, 8, 1, 0, 1)])
+                                                   (1, 8, 1, 0, 1), (3, 8, 3, 0, 1), (3, 12, 3, 0, 0), (3, 8, 4, 0, 1), (4, 8, 5, 0, 1),
+                                                   (4, 12, 6, 0, 0), (3, 8, 5, 0, 1), (3, 8, 6, 0, 1)])
 def test_colour_conversion_then_pack(gpu_ctx, j2k, ncomp, prec, cs, mct, rev):
-    """decoder.go:321-356 followed by createImage: the YCbCr-family conversions of colorspace.go run in the same epilogue
-    (values outside the nominal range included: the conversion clamps)"""
+    """decoder.go:321-356 followed by createImage: the conversions of colorspace.go that need no pow() run in the same
+    epilogue (values outside the nominal range included: the conversions clamp; CMYK / YCCK with 3 components: no-op)"""
     rng = np.random.default_rng(10 * ncomp + prec + cs)
     w, h = 61, 7
     comps = [rng.integers(-(1 << (prec - 1)) - 90, (1 << (prec - 1)) + 90, w * h).astype(np.int32) for _ in range(ncomp)]

@@ -31,6 +31,8 @@
 
 // ---- vector types ----------------------------------------------------------------------------------------
 struct uint3 { unsigned x, y, z; };
+struct int3 { int x, y, z; };
+static inline int3 make_int3(int x, int y, int z) { int3 r; r.x = x; r.y = y; r.z = z; return r; }
 struct dim3 {
     unsigned x, y, z;
     dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
@@ -126,6 +128,7 @@ template <class T> static inline T __ldcg(const T *p) { return *p; }
 template <class T> static inline void __stcs(T *p, T v) { *p = v; }
 template <class T> static inline void __stcg(T *p, T v) { *p = v; }
 static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+static inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
 static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 static inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
