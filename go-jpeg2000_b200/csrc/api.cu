@@ -281,9 +281,9 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
     bool need_clear = false;
     uint32_t stream_levels = hdr.nlevels ? ((1u << hdr.nlevels) - 1) : 0;
     bool fused_ok = hdr.reversible && hdr.nlevels >= 1 && !env_flag("J2KGPU_NO_FUSE");
-    // a colour conversion (j2k_image_t.colorspace) lives in the epilogue of the general tiled kernel only: the last level
-    // takes neither the fused nor the streaming kernels (their epilogues stay free of it, see tail.cuh)
-    if (tp.cconv) { fused_ok = false; stream_levels &= ~1u; }
+    // a colour conversion (j2k_image_t.colorspace) lives in two out-of-line epilogues only: the fused kernel's generic one
+    // (put_quad_generic) and the general tiled kernel's; the streaming kernels stay free of it (see tail.cuh)
+    if (tp.cconv) stream_levels &= ~1u;
 
     for (uint32_t ii = 0; ii < n_img; ii++) {
         const j2k_batch_item_t &it = items[ii];

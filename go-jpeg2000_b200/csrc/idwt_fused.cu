@@ -107,6 +107,7 @@ __device__ J2K_NOINLINE void put_quad_generic(uint8_t *orow, uint32_t gx0, uint3
         int32_t v[4] = {X[p], NC > 1 ? X[(NC > 1 ? 4 : 0) + p] : 0, NC > 2 ? X[(NC > 2 ? 8 : 0) + p] : 0,
                         NC > 3 ? X[(NC > 3 ? 12 : 0) + p] : 0};
         tail_mct_dc(v, tp);
+        if (NC >= 3) tail_colour(v, tp);                         // decoder.go:350-356 (a call only when the job has a conversion)
         store_pixel(orow, gx0 + p, v, tp);
     }
 }

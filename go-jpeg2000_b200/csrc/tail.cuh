@@ -18,8 +18,9 @@ __device__ __forceinline__ int32_t cs_clamp_round(double v, double maxv)
 // order and no FMA.  cs 1 / 2: the YCbCr family -- convertSYCCToRGB / convertYPbPr709ToRGB / convertEYCCToRGB
 // (colorspace.go:90-114, 429-482) and convertYCbCr601ToRGB (:116-140); cs 3: convertPhotoYCCToRGB (:142-168); cs 4:
 // convertCMYToRGB (:170-189); cs 5: convertCMYKToRGB (:191-217); cs 6: convertYCCKToRGB (:219-250).
-// Out of line and by value, and called only by the two kernels jobs with a conversion are routed to (k_idwt_last_pixels<.., CC = true>
-// and k_tail): measured, even an untaken call in the epilogue of the register-heavy streaming kernels cost them 7 to 30 %.
+// Out of line and by value, and called only from epilogues that are out of line or rarely used themselves (put_quad_generic of
+// the fused kernel, k_idwt_last_pixels<.., CC = true>, k_tail): measured, even an untaken call inlined into the epilogue of the
+// register-heavy streaming kernels cost them 7 to 30 %.
 static __device__ J2K_NOINLINE int3 tail_colour_rgb(int32_t v0, int32_t v1, int32_t v2, int32_t v3, int cconv, int ncomp, int prec)
 {
     const int32_t maxi = (int32_t)((1u << prec) - 1u);
