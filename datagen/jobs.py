@@ -22,10 +22,10 @@ from . import (dc_shift_forward, decompose53, decompose97, encode_blocks, fwd_ic
 
 CBLK_DT = np.dtype([("data_off", "<u8"), ("data_len", "<u4"), ("tilecomp", "<u4"), ("x0", "<u2"), ("y0", "<u2"),
                     ("w", "<u2"), ("h", "<u2"), ("band", "u1"), ("level", "u1"), ("num_bps", "u1"),
-                    ("num_passes", "u1"), ("step", "<f4")], align=True)
+                    ("num_passes", "u1"), ("step", "<f4"), ("len_cleanup", "<u4"), ("rsv", "<u4")], align=True)
 TILECOMP_DT = np.dtype([("comp", "<u4"), ("x0", "<u4"), ("y0", "<u4"), ("x1", "<u4"), ("y1", "<u4"),
                         ("coeff_off", "<u8")], align=True)
-assert CBLK_DT.itemsize == 32 and TILECOMP_DT.itemsize == 32
+assert CBLK_DT.itemsize == 40 and TILECOMP_DT.itemsize == 32
 
 
 def synth_image(width, height, ncomp, prec, seed):
@@ -139,7 +139,7 @@ def build_iso_job(samples, prec, tile_w=None, tile_h=None, nlevels=5, mct=1, cb=
     blob = bytearray()
     for i, b in enumerate(blks):
         cblks[i] = (len(blob), len(b["data"]), tc_index[(b["tile"], b["comp"])], b["px"], b["py"], b["w"], b["h"],
-                    b["band"], b["level"], 1, 1, 1.0)
+                    b["band"], b["level"], 1, 1, 1.0, 0, 0)
         blob += b["data"]
     return dict(width=W, height=H, ncomp=ncomp, prec=prec, sgnd=0, mct=1 if (mct and ncomp >= 3) else 0, reversible=1,
                 nlevels=nlevels, ht=1, mode=1, tilecomps=np.array(tcs, TILECOMP_DT), cblks=cblks,
@@ -177,7 +177,7 @@ def build_iso_job_from_codestream(data, reduce=0):
         step = 1.0 if h["reversible"] else 2.0 ** (h["prec"] + gain[b["band"]] - b["expn"]) * (1.0 + b["mant"] / 2048.0)
         nb = b["num_bps"] if b["passes"] else 0
         cblks[i] = (len(blob), len(b["data"]) if nb else 0, tc_index[(b["tile"], b["comp"])], b["px"], b["py"], b["w"], b["h"],
-                    b["band"], b["level"], nb, min(b["passes"], 255), step)
+                    b["band"], b["level"], nb, min(b["passes"], 255), step, b.get("lcup", 0), 0)
         blob += b["data"]
     return dict(width=W, height=H, ncomp=ncomp, prec=h["prec"], sgnd=h["sgnd"], mct=1 if (h["mct"] and ncomp >= 3) else 0,
                 reversible=h["reversible"], nlevels=h["nlevels"] - reduce, ht=h["ht"], mode=1, tilecomps=np.array(tcs, TILECOMP_DT), cblks=cblks,

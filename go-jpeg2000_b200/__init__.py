@@ -53,7 +53,7 @@ class CBlk(C.Structure):           # j2k_cblk_t
     _fields_ = [("data_off", C.c_uint64), ("data_len", C.c_uint32), ("tilecomp", C.c_uint32),
                 ("x0", C.c_uint16), ("y0", C.c_uint16), ("w", C.c_uint16), ("h", C.c_uint16),
                 ("band", C.c_uint8), ("level", C.c_uint8), ("num_bps", C.c_uint8), ("num_passes", C.c_uint8),
-                ("step", C.c_float)]
+                ("step", C.c_float), ("len_cleanup", C.c_uint32), ("rsv", C.c_uint32)]
 
 
 class BatchItem(C.Structure):      # j2k_batch_item_t
@@ -61,18 +61,21 @@ class BatchItem(C.Structure):      # j2k_batch_item_t
                 ("tilecomps", C.POINTER(TileComp)), ("n_tilecomps", C.c_uint32),
                 ("cblks", C.POINTER(CBlk)), ("n_cblks", C.c_uint32),
                 ("blob", u8p), ("blob_len", C.c_uint64),
-                ("out_pix", u8p), ("out_stride", C.c_uint64)]
+                ("out_pix", u8p), ("out_stride", C.c_uint64), ("flags", C.c_uint32), ("rsv", C.c_uint32)]
+
+
+ITEM_TILES_ONLY = 1                # J2KGPU_ITEM_TILES_ONLY
 
 
 class BlkJob(C.Structure):         # j2k_blkjob_t
     _fields_ = [("data_off", C.c_uint64), ("data_len", C.c_uint32), ("out_off", C.c_uint32),
                 ("w", C.c_uint16), ("h", C.c_uint16), ("band", C.c_uint8), ("num_bps", C.c_uint8),
-                ("rsv0", C.c_uint8), ("rsv1", C.c_uint8)]
+                ("rsv0", C.c_uint8), ("rsv1", C.c_uint8), ("len_cleanup", C.c_uint32), ("rsv2", C.c_uint32)]
 
 
 EXPORTS = [
     "j2kgpu_abi_version", "j2kgpu_create", "j2kgpu_destroy", "j2kgpu_strerror", "j2kgpu_last_error",
-    "j2kgpu_set_stream", "j2kgpu_launch_count", "j2kgpu_decode", "j2kgpu_decode_batch",
+    "j2kgpu_set_stream", "j2kgpu_set_option", "j2kgpu_launch_count", "j2kgpu_decode", "j2kgpu_decode_batch",
     "j2kgpu_job_create", "j2kgpu_job_destroy", "j2kgpu_job_blob_bytes", "j2kgpu_job_out_bytes",
     "j2kgpu_job_out_offset", "j2kgpu_job_run", "j2kgpu_job_run_entropy", "j2kgpu_job_run_dwt_mct",
     "j2kgpu_job_run_level", "j2kgpu_job_fused_levels", "j2kgpu_job_coef_bytes", "j2kgpu_job_plan",
@@ -113,6 +116,7 @@ def lib():
         L.j2kgpu_destroy.argtypes = [C.c_void_p]
         L.j2kgpu_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         L.j2kgpu_sync.argtypes = [C.c_void_p]
+        L.j2kgpu_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
         L.j2kgpu_decode.argtypes = [C.c_void_p, C.POINTER(Image), C.POINTER(TileComp), C.c_uint32,
                                     C.POINTER(CBlk), C.c_uint32, u8p, C.c_uint64, u8p, C.c_uint64]
         L.j2kgpu_decode_batch.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(BatchItem)]
@@ -198,6 +202,24 @@ class Context:
     def sync(self):
         self._check(lib().j2kgpu_sync(self._h))
 
+    def set_option(self, name, value):
+        """A/B switch / test hook (j2kgpu_set_option): e.g. set_option("no_fuse", "1"), set_option("chunks", "1,1,2")"""
+        self._check(lib().j2kgpu_set_option(self._h, name.encode(), str(value).encode()))
+
+    def options(self, **kw):
+        """context manager: set the given options, restore the defaults ("0" / "") afterwards"""
+        ctx = self
+
+        class _Scope:
+            def __enter__(self_):
+                for k, v in kw.items():
+                    ctx.set_option(k, v)
+
+            def __exit__(self_, *a):
+                for k in kw:
+                    ctx.set_option(k, "" if k == "chunks" else "0")
+        return _Scope()
+
     # ---- page-locked host memory (j2kgpu_host_*) ----------------------------------------------
     def host_alloc(self, nbytes):
         """a uint8 numpy array over `nbytes` of page-locked memory; release it with host_free(array)"""
@@ -221,14 +243,15 @@ class Context:
 
     # ---- entropy stage ------------------------------------------------------------------------
     def _decode_blocks(self, fn, blocks, mode):
-        """blocks: list of (bytes, w, h, num_bps, band[, num_passes]) -> list of int32 arrays (w*h each)"""
+        """blocks: list of (bytes, w, h, num_bps, band[, num_passes[, len_cleanup]]) -> list of int32 arrays (w*h each)"""
         n = len(blocks)
         jobs = (BlkJob * max(n, 1))()
         blob = bytearray()
         off = 0
         for i, blk in enumerate(blocks):
             data, w, h, nbps, band = blk[:5]
-            jobs[i] = BlkJob(len(blob), len(data), off, w, h, band, nbps, blk[5] if len(blk) > 5 else 0, 0)
+            jobs[i] = BlkJob(len(blob), len(data), off, w, h, band, nbps, blk[5] if len(blk) > 5 else 0, 0,
+                             blk[6] if len(blk) > 6 else 0, 0)
             blob += bytes(data)
             off += w * h
         blob_np = np.frombuffer(bytes(blob), np.uint8) if blob else np.zeros(1, np.uint8)

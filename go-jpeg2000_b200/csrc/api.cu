@@ -4,6 +4,8 @@
 // returns an error.
 #include "common.h"
 
+#include <algorithm>
+#include <cctype>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstdio>
@@ -14,8 +16,6 @@
 
 cudaError_t launch_t1_ref_stage(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, int32_t *d_coef,
                                 int max_bps, cudaStream_t s);
-
-static bool env_flag(const char *name) { const char *e = getenv(name); return e && *e && *e != '0'; }
 
 // ---- errors ------------------------------------------------------------------------------------------
 int j2k_set_err(j2kgpu_ctx *ctx, int code, const char *fmt, ...)
@@ -59,14 +59,14 @@ int j2k_ctx_copy_streams(j2kgpu_ctx *ctx)
     return J2KGPU_OK;
 }
 
-// ---- ctx-level device buffer pool (grow-only cache) ------------------------------------------------------
-struct PoolTag { size_t cap; };
+// ---- ctx-level buffer pools (grow-only caches: repeated decode calls neither cudaMalloc nor cudaHostAlloc) --------
 static std::map<void *, size_t> &pool_sizes()
 {
     static std::map<void *, size_t> m;
     return m;
 }
 static std::mutex g_pool_mu;
+static constexpr size_t kPoolEntries = 1024;
 
 void *j2k_pool_alloc(j2kgpu_ctx *ctx, size_t bytes, cudaError_t *err)
 {
@@ -100,7 +100,7 @@ void j2k_pool_free(j2kgpu_ctx *ctx, void *p)
     if (!p) return;
     size_t cap = 0;
     { std::lock_guard<std::mutex> g(g_pool_mu); auto it = pool_sizes().find(p); if (it != pool_sizes().end()) cap = it->second; }
-    if (cap == 0 || ctx->pool.size() >= 64) {
+    if (cap == 0 || ctx->pool.size() >= kPoolEntries) {
         std::lock_guard<std::mutex> g(g_pool_mu);
         pool_sizes().erase(p);
         cudaFree(p);
@@ -108,6 +108,43 @@ void j2k_pool_free(j2kgpu_ctx *ctx, void *p)
     }
     DevBuf b; b.p = p; b.cap = cap;
     ctx->pool.push_back(b);
+}
+
+// page-locked host blocks (the table staging of pipelined batch calls)
+void *j2k_hpool_alloc(j2kgpu_ctx *ctx, size_t bytes, size_t *cap, cudaError_t *err)
+{
+    *err = cudaSuccess;
+    if (bytes == 0) bytes = 16;
+    int best = -1;
+    for (size_t i = 0; i < ctx->hpool.size(); i++)
+        if (ctx->hpool[i].cap >= bytes && (best < 0 || ctx->hpool[i].cap < ctx->hpool[best].cap)) best = (int)i;
+    if (best >= 0) {
+        void *p = ctx->hpool[best].p;
+        *cap = ctx->hpool[best].cap;
+        ctx->hpool.erase(ctx->hpool.begin() + best);
+        return p;
+    }
+    void *p = nullptr;
+    *cap = (bytes + bytes / 8 + 4095) / 4096 * 4096;
+    *err = cudaHostAlloc(&p, *cap, cudaHostAllocDefault);
+    return *err == cudaSuccess ? p : nullptr;
+}
+
+void j2k_hpool_free(j2kgpu_ctx *ctx, void *p, size_t cap)
+{
+    if (!p) return;
+    if (ctx->hpool.size() >= 64) { cudaFreeHost(p); return; }
+    DevBuf b; b.p = p; b.cap = cap;
+    ctx->hpool.push_back(b);
+}
+
+static cudaEvent_t ctx_event(j2kgpu_ctx *ctx, cudaError_t *err)
+{
+    *err = cudaSuccess;
+    if (!ctx->events.empty()) { cudaEvent_t e = ctx->events.back(); ctx->events.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    *err = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    return e;
 }
 
 int j2k_resolve_fmt(int ncomp, int prec, int fmt)
@@ -167,6 +204,24 @@ extern "C" const char *j2kgpu_strerror(int code)
     return "unknown error";
 }
 
+// option names = the J2KGPU_<NAME> environment switches, lower case, without the prefix
+static int set_option(J2kOpts &o, const char *name, const char *value)
+{
+    const std::string k = name ? name : "", v = value ? value : "";
+    const int iv = atoi(v.c_str());
+    const int on = !v.empty() && v != "0";
+    if (k == "no_fuse") o.no_fuse = on;
+    else if (k == "no_wide") o.no_wide = on;
+    else if (k == "no_fast_epi") o.no_fast_epi = on;
+    else if (k == "coef32") o.coef32 = on;
+    else if (k == "no_preclear") o.no_preclear = on;
+    else if (k == "wide_sp") o.wide_sp = iv;
+    else if (k == "debug_plan") o.debug_plan = on;
+    else if (k == "chunks") o.chunks = v;
+    else return J2KGPU_E_ARG;
+    return J2KGPU_OK;
+}
+
 extern "C" int j2kgpu_create(int device, j2kgpu_ctx **out)
 {
     if (!out) return J2KGPU_E_ARG;
@@ -178,9 +233,25 @@ extern "C" int j2kgpu_create(int device, j2kgpu_ctx **out)
     j2kgpu_ctx *ctx = new (std::nothrow) j2kgpu_ctx();
     if (!ctx) return J2KGPU_E_NOMEM;
     ctx->device = device;
+    // the environment is read here, once per context, and nowhere else
+    static const char *const names[] = {"no_fuse", "no_wide", "no_fast_epi", "coef32", "no_preclear", "wide_sp", "debug_plan", "chunks"};
+    for (const char *nm : names) {
+        std::string env = "J2KGPU_";
+        for (const char *c = nm; *c; c++) env += (char)toupper((unsigned char)*c);
+        if (const char *e = getenv(env.c_str())) set_option(ctx->opt, nm, e);
+    }
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return J2KGPU_E_CUDA; }
     ctx->stream = ctx->own_stream;
     *out = ctx;
+    return J2KGPU_OK;
+}
+
+extern "C" int j2kgpu_set_option(j2kgpu_ctx *ctx, const char *name, const char *value)
+{
+    if (!ctx || !name) return J2KGPU_E_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    const int rc = set_option(ctx->opt, name, value);
+    if (rc) return j2k_set_err(ctx, rc, "unknown option '%s'", name);
     return J2KGPU_OK;
 }
 
@@ -195,6 +266,10 @@ extern "C" void j2kgpu_destroy(j2kgpu_ctx *ctx)
     free_buf(ctx->h_in, true); free_buf(ctx->h_out, true);
     for (auto &b : ctx->pool) { { std::lock_guard<std::mutex> g(g_pool_mu); pool_sizes().erase(b.p); } cudaFree(b.p); }
     ctx->pool.clear();
+    for (auto &b : ctx->hpool) cudaFreeHost(b.p);
+    ctx->hpool.clear();
+    for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
+    ctx->events.clear();
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
@@ -229,11 +304,13 @@ static void job_free(j2kgpu_job *job)
     if (!job) return;
     if (job->ctx) {
         cudaSetDevice(job->ctx->device);
-        void *ps[] = {job->d_cblks, job->d_tcs, job->d_tiles, job->d_coef, job->d_tmp, job->d_blob, job->d_pix, job->d_steps, job->d_htscratch};
+        void *ps[] = {job->d_cblks, job->d_tcs, job->d_tiles, job->d_coef, job->d_tmp, job->d_blob, job->d_pix, job->d_steps,
+                      job->d_htscratch, job->d_fillpix};
         for (void *p : ps) j2k_pool_free(job->ctx, p);
+        for (cudaEvent_t e : job->ev_in) if (e) job->ctx->events.push_back(e);
+        for (cudaEvent_t e : job->ev_done) if (e) job->ctx->events.push_back(e);
+        if (job->h_tables) j2k_hpool_free(job->ctx, job->h_tables, job->h_tables_cap);
     }
-    for (cudaEvent_t e : job->ev_in) if (e) cudaEventDestroy(e);
-    for (cudaEvent_t e : job->ev_done) if (e) cudaEventDestroy(e);
     if (job->h_blob) cudaFreeHost(job->h_blob);
     if (job->h_pix) cudaFreeHost(job->h_pix);
     delete job;
@@ -253,11 +330,40 @@ static bool same_header(const j2k_image_t &a, const j2k_image_t &b)
            a.out_fmt == b.out_fmt && a.colorspace == b.colorspace;
 }
 
-static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *items, j2kgpu_job **out)
+// a table built in place in page-locked memory
+template <class T>
+struct Fixed {
+    T *p = nullptr; size_t n = 0;
+    void push_back(const T &v) { p[n++] = v; }
+    T &operator[](size_t i) { return p[i]; }
+    size_t size() const { return n; }
+};
+
+struct Rect { uint32_t x0, y0, x1, y1; };
+
+// do the rectangles (all inside a w x h plane) cover it exactly once?  Their areas must add up to the plane and no two
+// may overlap; the overlap test is a sweep over the rectangles sorted by their top edge.
+static bool tiles_exactly(std::vector<Rect> &r, uint32_t w, uint32_t h)
+{
+    uint64_t area = 0;
+    for (const Rect &q : r) area += (uint64_t)(q.x1 - q.x0) * (q.y1 - q.y0);
+    if (area != (uint64_t)w * h) return false;
+    std::sort(r.begin(), r.end(), [](const Rect &a, const Rect &b) { return a.y0 != b.y0 ? a.y0 < b.y0 : a.x0 < b.x0; });
+    for (size_t i = 0; i < r.size(); i++)
+        for (size_t j = i + 1; j < r.size() && r[j].y0 < r[i].y1; j++)
+            if (r[j].x0 < r[i].x1 && r[i].x0 < r[j].x1) return false;
+    return true;
+}
+
+// async_stream != nullptr: the tables are staged in page-locked memory owned by the job and uploaded on that stream
+// without any synchronisation (pipelined batch calls: the host builds the next chunk's tables while the device decodes
+// this one); nullptr: uploaded on the ctx stream and synchronised before returning.
+static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *items, j2kgpu_job **out, cudaStream_t async_stream)
 {
     if (!ctx || !out || !items || n_img == 0) return j2k_set_err(ctx, J2KGPU_E_ARG, "null or empty batch");
     *out = nullptr;
     const j2k_image_t &hdr = items[0].image;
+    const J2kOpts &opt = ctx->opt;
     TailParams tp;
     int rc = make_tail(ctx, hdr, tp);
     if (rc) return rc;
@@ -267,35 +373,50 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
     if (hdr.nlevels > J2K_MAX_LEVELS) return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "nlevels %d > %d", (int)hdr.nlevels, J2K_MAX_LEVELS);
     const int bpp = j2k_fmt_bpp(tp.fmt);
 
+    uint64_t tot_cb = 0, tot_tc = 0;
+    for (uint32_t ii = 0; ii < n_img; ii++) { tot_cb += items[ii].n_cblks; tot_tc += items[ii].n_tilecomps; }
+    if (tot_cb > 0xFFFFFFF0ull || tot_tc > 0xFFFFFFF0ull) return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "batch too large");
+
     j2kgpu_job *job = new (std::nothrow) j2kgpu_job();
     if (!job) return j2k_set_err(ctx, J2KGPU_E_NOMEM, "job");
     job->ctx = ctx; job->n_img = n_img; job->hdr = hdr; job->tail = tp; job->nlevels = hdr.nlevels; job->iso = iso;
-    if (const char *e = getenv("J2KGPU_HT_MAP")) { const int v = atoi(e); job->ht_map = (v == 1 || v == 32) ? v : 2; }
+    cudaSetDevice(ctx->device);
 
-    std::vector<DevTileComp> tcs;
-    std::vector<DevTile> tiles;
-    std::vector<DevCblk> cbs;
-    std::vector<float> steps;                                  // ISO irreversible: dequantisation step per block
+    // one page-locked block for all tables: [DevCblk x tot_cb][float x tot_cb][DevTileComp x tot_tc][DevTile x tot_tc]
+    const size_t off_steps = align_up(tot_cb * sizeof(DevCblk), 256), off_tcs = align_up(off_steps + tot_cb * sizeof(float), 256),
+                 off_tiles = align_up(off_tcs + tot_tc * sizeof(DevTileComp), 256), tab_bytes = align_up(off_tiles + tot_tc * sizeof(DevTile), 256);
+    cudaError_t e = cudaSuccess;
+    job->h_tables = j2k_hpool_alloc(ctx, tab_bytes, &job->h_tables_cap, &e);
+    if (e != cudaSuccess) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_NOMEM, "table staging: %s", cudaGetErrorString(e)); }
+    uint8_t *hb = (uint8_t *)job->h_tables;
+    Fixed<DevCblk> cbs;       cbs.p = (DevCblk *)hb;
+    Fixed<float> steps;       steps.p = (float *)(hb + off_steps);          // ISO irreversible: dequantisation step per block
+    Fixed<DevTileComp> tcs;   tcs.p = (DevTileComp *)(hb + off_tcs);
+    Fixed<DevTile> tiles;     tiles.p = (DevTile *)(hb + off_tiles);
+    job->h_tiles_host = tiles.p;
+
     uint64_t coef_elems = 0, tmp_elems = 0, blob_bytes = 0, out_bytes = 0;
     int max_bps = 0;
     bool need_clear = false;
     uint32_t stream_levels = hdr.nlevels ? ((1u << hdr.nlevels) - 1) : 0;
-    bool fused_ok = hdr.reversible && hdr.nlevels >= 1 && !env_flag("J2KGPU_NO_FUSE");
+    bool fused_ok = hdr.reversible && hdr.nlevels >= 1 && !opt.no_fuse;
     // a colour conversion (j2k_image_t.colorspace) lives in two out-of-line epilogues only: the fused kernel's generic one
     // (put_quad_generic) and the general tiled kernel's; the streaming kernels stay free of it (see tail.cuh)
     if (tp.cconv) stream_levels &= ~1u;
+    const bool will_coef16 = !opt.coef32 && iso && hdr.reversible && hdr.coef_bits >= 1 && hdr.coef_bits <= 14;
+    std::vector<Rect> rects;
+    std::vector<std::vector<Rect>> blk_rects;
 
+#define J2K_FAIL(...) do { const int rc__ = j2k_set_err(__VA_ARGS__); job_free(job); return rc__; } while (0)
     for (uint32_t ii = 0; ii < n_img; ii++) {
         const j2k_batch_item_t &it = items[ii];
         const j2k_image_t &im = it.image;
-        if (!same_header(im, hdr)) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_ARG, "item %u: header differs from item 0", ii); }
-        if (im.width == 0 || im.height == 0) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_ARG, "item %u: empty image", ii); }
-        if ((!it.tilecomps && it.n_tilecomps) || (!it.cblks && it.n_cblks) || (!it.blob && it.blob_len)) {
-            job_free(job); return j2k_set_err(ctx, J2KGPU_E_ARG, "item %u: null table", ii);
-        }
-        if (it.out_stride < (uint64_t)im.width * bpp || it.out_stride % bpp) {
-            job_free(job); return j2k_set_err(ctx, J2KGPU_E_ARG, "item %u: out_stride %llu too small or not a multiple of %d", ii, (unsigned long long)it.out_stride, bpp);
-        }
+        if (!same_header(im, hdr)) J2K_FAIL(ctx, J2KGPU_E_ARG, "item %u: header differs from item 0", ii);
+        if (im.width == 0 || im.height == 0) J2K_FAIL(ctx, J2KGPU_E_ARG, "item %u: empty image", ii);
+        if ((!it.tilecomps && it.n_tilecomps) || (!it.cblks && it.n_cblks) || (!it.blob && it.blob_len))
+            J2K_FAIL(ctx, J2KGPU_E_ARG, "item %u: null table", ii);
+        if (it.out_stride < (uint64_t)im.width * bpp || it.out_stride % bpp)
+            J2K_FAIL(ctx, J2KGPU_E_ARG, "item %u: out_stride %llu too small or not a multiple of %d", ii, (unsigned long long)it.out_stride, bpp);
         const uint32_t tc_base = (uint32_t)tcs.size();
         job->item_cb.push_back((uint32_t)cbs.size());
         job->item_tc.push_back(tc_base);
@@ -303,15 +424,17 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
         job->blob_off.push_back(blob_bytes);
         job->out_off.push_back(out_bytes);
         job->out_size.push_back(it.out_stride * im.height);
+        job->row_bytes.push_back(im.width * (uint32_t)bpp);
+        job->out_stride.push_back(it.out_stride);
+        job->img_h.push_back(im.height);
 
         std::map<std::tuple<uint32_t, uint32_t, uint32_t, uint32_t>, uint32_t> tile_of;
-        std::vector<uint64_t> covered(it.n_tilecomps, 0);
         for (uint32_t t = 0; t < it.n_tilecomps; t++) {
             const j2k_tilecomp_t &tc = it.tilecomps[t];
-            if (tc.comp >= im.ncomp || tc.x1 <= tc.x0 || tc.y1 <= tc.y0) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_ARG, "item %u tile-component %u: bad bounds/component", ii, t); }
+            if (tc.comp >= im.ncomp || tc.x1 <= tc.x0 || tc.y1 <= tc.y0) J2K_FAIL(ctx, J2KGPU_E_ARG, "item %u tile-component %u: bad bounds/component", ii, t);
             DevTileComp d{};
             d.w = tc.x1 - tc.x0; d.h = tc.y1 - tc.y0;
-            if ((uint64_t)d.w * d.h > (1ull << 31)) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "tile-component too large"); }
+            if ((uint64_t)d.w * d.h > (1ull << 31)) J2K_FAIL(ctx, J2KGPU_E_UNSUPPORTED, "tile-component too large");
             d.coef_off = coef_elems;
             job->tc_coef_off.push_back(coef_elems);
             coef_elems = align_up(coef_elems + (uint64_t)d.w * d.h, 32);
@@ -322,10 +445,8 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
             for (int l = 0; l < hdr.nlevels; l++)
                 if (!j2k_stream_ok(d.w, d.h, l)) stream_levels &= ~(1u << l);
             if (!j2k_fused_ok(d.w, d.h)) fused_ok = false;
-            if (iso && ((tc.x0 | tc.y0) & ((1u << hdr.nlevels) - 1))) {
-                job_free(job);
-                return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "ISO mode: tile origin (%u,%u) is not a multiple of 2^nlevels", tc.x0, tc.y0);
-            }
+            if (iso && ((tc.x0 | tc.y0) & ((1u << hdr.nlevels) - 1)))
+                J2K_FAIL(ctx, J2KGPU_E_UNSUPPORTED, "ISO mode: tile origin (%u,%u) is not a multiple of 2^nlevels", tc.x0, tc.y0);
             if (iso && (d.w & 3)) stream_levels = 0;          // Mallat rows must stay 8-byte aligned for the streaming kernel
             if (d.w > job->max_w) job->max_w = d.w;
             if (d.h > job->max_h) job->max_h = d.h;
@@ -341,45 +462,63 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
                 tiles.push_back(tl);
                 tile_of[key] = ti;
             } else ti = f->second;
-            if (tiles[ti].tc[tc.comp] != 0xFFFFFFFFu) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_ARG, "item %u: duplicate tile-component", ii); }
+            if (tiles[ti].tc[tc.comp] != 0xFFFFFFFFu) J2K_FAIL(ctx, J2KGPU_E_ARG, "item %u: duplicate tile-component", ii);
             tiles[ti].tc[tc.comp] = tc_base + t;
         }
         for (auto &kv : tile_of)
             for (int c = 0; c < im.ncomp; c++)
-                if (tiles[kv.second].tc[c] == 0xFFFFFFFFu) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_ARG, "item %u: a tile lacks component %d (subsampled components are not supported)", ii, c); }
+                if (tiles[kv.second].tc[c] == 0xFFFFFFFFu) J2K_FAIL(ctx, J2KGPU_E_ARG, "item %u: a tile lacks component %d (subsampled components are not supported)", ii, c);
+        // pixels no tile covers keep what the reference's zero-initialised planes decode to (decoder.go:305-309): if the
+        // tiles, clipped to the image, do not cover it exactly once, the pixel buffer is pre-filled with that value
+        rects.clear();
+        for (auto &kv : tile_of) {
+            const DevTile &t = tiles[kv.second];
+            Rect q = {t.img_x0, t.img_y0, t.img_x0 + t.w < im.width ? t.img_x0 + t.w : im.width, t.img_y0 + t.h < im.height ? t.img_y0 + t.h : im.height};
+            if (q.x0 < q.x1 && q.y0 < q.y1) rects.push_back(q);
+        }
+        const bool fill = !tiles_exactly(rects, im.width, im.height);
+        job->item_fill.push_back(fill ? 1 : 0);
+        if (fill) job->pix_fill = 1;
 
+        blk_rects.assign(it.n_tilecomps, std::vector<Rect>());
         for (uint32_t b = 0; b < it.n_cblks; b++) {
             const j2k_cblk_t &cb = it.cblks[b];
-            if (cb.tilecomp >= it.n_tilecomps) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_RANGE, "item %u block %u: tile-component %u out of range", ii, b, cb.tilecomp); }
+            if (cb.tilecomp >= it.n_tilecomps) J2K_FAIL(ctx, J2KGPU_E_RANGE, "item %u block %u: tile-component %u out of range", ii, b, cb.tilecomp);
             const DevTileComp &d = tcs[tc_base + cb.tilecomp];
             if (cb.w == 0 || cb.h == 0) continue;
-            if (cb.w > 64 || cb.h > 64) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "item %u block %u: %ux%u exceeds 64x64", ii, b, cb.w, cb.h); }
-            if ((uint32_t)cb.x0 + cb.w > d.w || (uint32_t)cb.y0 + cb.h > d.h) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_RANGE, "item %u block %u: outside its tile-component", ii, b); }
-            if (cb.data_off > it.blob_len || cb.data_len > it.blob_len - cb.data_off) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_RANGE, "item %u block %u: data outside blob", ii, b); }
-            if (iso && (cb.num_bps < 1 || cb.num_bps > 30) && cb.data_len) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "item %u block %u: num_bps %d outside 1..30", ii, b, (int)cb.num_bps); }
-            if (iso && hdr.ht && cb.num_passes > 1) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "item %u block %u: HT SigProp/MagRef passes are not built in this revision", ii, b); }
-            if (cb.num_bps > 31 || cb.band > 3) { job_free(job); return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "item %u block %u: num_bps %d / band %d", ii, b, (int)cb.num_bps, (int)cb.band); }
+            if (cb.w > 64 || cb.h > 64) J2K_FAIL(ctx, J2KGPU_E_UNSUPPORTED, "item %u block %u: %ux%u exceeds 64x64", ii, b, cb.w, cb.h);
+            if ((uint32_t)cb.x0 + cb.w > d.w || (uint32_t)cb.y0 + cb.h > d.h) J2K_FAIL(ctx, J2KGPU_E_RANGE, "item %u block %u: outside its tile-component", ii, b);
+            if (cb.data_off > it.blob_len || cb.data_len > it.blob_len - cb.data_off) J2K_FAIL(ctx, J2KGPU_E_RANGE, "item %u block %u: data outside blob", ii, b);
+            if (iso && (cb.num_bps < 1 || cb.num_bps > 30) && cb.data_len) J2K_FAIL(ctx, J2KGPU_E_UNSUPPORTED, "item %u block %u: num_bps %d outside 1..30", ii, b, (int)cb.num_bps);
+            if (iso && hdr.ht && cb.num_passes > 3) J2K_FAIL(ctx, J2KGPU_E_UNSUPPORTED, "item %u block %u: %d HT coding passes (one HT set = cleanup, SigProp, MagRef)", ii, b, (int)cb.num_passes);
+            if (cb.num_bps > 31 || cb.band > 3) J2K_FAIL(ctx, J2KGPU_E_UNSUPPORTED, "item %u block %u: num_bps %d / band %d", ii, b, (int)cb.num_bps, (int)cb.band);
+            // int16 planes hold what coef_bits promises; an EBCOT block that claims more bit-planes than that would be truncated
+            if (will_coef16 && !hdr.ht && cb.data_len && cb.num_bps > hdr.coef_bits)
+                J2K_FAIL(ctx, J2KGPU_E_RANGE, "item %u block %u: num_bps %d exceeds the declared coef_bits %d", ii, b, (int)cb.num_bps, (int)hdr.coef_bits);
             DevCblk o{};
             o.data_off = blob_bytes + cb.data_off; o.data_len = cb.data_len;
             o.out_off = d.coef_off + (uint64_t)cb.y0 * d.w + cb.x0; o.out_stride = d.w;
             o.w = cb.w; o.h = cb.h; o.band = cb.band; o.num_bps = cb.num_bps; o.level = cb.level; o.num_passes = cb.num_passes;
+            o.len_cup = (cb.len_cleanup && cb.len_cleanup <= cb.data_len) ? cb.len_cleanup : cb.data_len;
             cbs.push_back(o);
             steps.push_back(cb.step);
-            covered[cb.tilecomp] += (uint64_t)cb.w * cb.h;
+            blk_rects[cb.tilecomp].push_back(Rect{cb.x0, cb.y0, (uint32_t)cb.x0 + cb.w, (uint32_t)cb.y0 + cb.h});
             if (cb.data_len && cb.num_bps > max_bps) max_bps = cb.num_bps;
         }
-        for (uint32_t t = 0; t < it.n_tilecomps; t++)
-            if (covered[t] != (uint64_t)tcs[tc_base + t].w * tcs[tc_base + t].h) need_clear = true;
+        // a plane its blocks do not tile exactly (holes, or overlaps hiding holes) is cleared before the entropy stage
+        for (uint32_t t = 0; t < it.n_tilecomps && !need_clear; t++)
+            if (!tiles_exactly(blk_rects[t], tcs[tc_base + t].w, tcs[tc_base + t].h)) need_clear = true;
         blob_bytes += it.blob_len;
         out_bytes = align_up(out_bytes + it.out_stride * im.height, 256);
     }
+#undef J2K_FAIL
     job->item_cb.push_back((uint32_t)cbs.size());
     job->item_tc.push_back((uint32_t)tcs.size());
     job->item_tile.push_back((uint32_t)tiles.size());
     job->n_tc = (uint32_t)tcs.size(); job->n_tiles = (uint32_t)tiles.size(); job->n_cb = (uint32_t)cbs.size();
     // int16 coefficient planes when every magnitude provably fits: EBCOT magnitudes are < 2^num_bps; a conformant
     // codestream bounds them by coef_bits (Mb); the reference's HT coder has no bound (ht.go:664-684) and stays int32
-    if (!env_flag("J2KGPU_COEF32")) {
+    if (!opt.coef32) {
         if (!iso && !hdr.ht) job->coef16 = max_bps <= 15;
         if (iso && hdr.reversible) job->coef16 = hdr.coef_bits >= 1 && hdr.coef_bits <= 14;
     }
@@ -391,39 +530,55 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
     } else if (tp.ncomp == 1) {
         job->fast_epi = (tp.prec[0] == 8 || tp.prec[0] == 16) && !tp.sgnd[0];
     }
-    if (env_flag("J2KGPU_NO_FAST_EPI")) job->fast_epi = 0;
-    for (const DevTile &t : tiles)
+    if (opt.no_fast_epi) job->fast_epi = 0;
+    for (size_t i = 0; i < tiles.size(); i++) {
+        const DevTile &t = tiles[i];
         if ((t.out_stride & 15) || (t.out_off & 15) || (t.img_x0 & 3) || t.img_x0 + t.w > t.img_w || t.img_y0 + t.h > t.img_h) job->fast_epi = 0;
-    job->wide_ok = job->fast_epi && fused_ok && (tp.ncomp == 3 || tp.ncomp == 1) && !env_flag("J2KGPU_NO_WIDE");
-    for (const DevTile &t : tiles) if ((t.w & 15) || (tp.ncomp == 1 && (t.img_x0 & 15))) job->wide_ok = 0;   // 16-byte stores per lane
+    }
+    job->wide_ok = job->fast_epi && fused_ok && (tp.ncomp == 3 || tp.ncomp == 1) && !opt.no_wide;
+    for (size_t i = 0; i < tiles.size(); i++) if ((tiles[i].w & 15) || (tp.ncomp == 1 && (tiles[i].img_x0 & 15))) job->wide_ok = 0;   // 16-byte stores per lane
     job->coef_elems = coef_elems; job->blob_bytes = blob_bytes; job->out_bytes = out_bytes; job->max_bps = max_bps;
     job->tmp_bytes = tmp_elems * ((hdr.reversible || iso) ? 4 : 8);     // int32 (5-3), float32 (ISO 9-7), float64 (REF 9-7)
-    job->need_clear = need_clear;
-    job->stream_levels = stream_levels;                  // some plane is not fully covered by its blocks
+    job->need_clear = need_clear;                        // some plane is not tiled exactly by its blocks
+    job->stream_levels = stream_levels;
 
-    cudaSetDevice(ctx->device);
-    cudaError_t e = cudaSuccess;
+    const cudaStream_t up_stream = async_stream ? async_stream : ctx->stream;
     auto up = [&](void **dst, const void *src, size_t bytes) {
         if (e != cudaSuccess) return;
         *dst = j2k_pool_alloc(ctx, bytes, &e);
-        if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, up_stream);
     };
-    up((void **)&job->d_cblks, cbs.data(), cbs.size() * sizeof(DevCblk));
-    if (iso && !hdr.reversible) up((void **)&job->d_steps, steps.data(), steps.size() * sizeof(float));
-    up((void **)&job->d_tcs, tcs.data(), tcs.size() * sizeof(DevTileComp));
-    up((void **)&job->d_tiles, tiles.data(), tiles.size() * sizeof(DevTile));
+    up((void **)&job->d_cblks, cbs.p, cbs.size() * sizeof(DevCblk));
+    if (iso && !hdr.reversible) up((void **)&job->d_steps, steps.p, steps.size() * sizeof(float));
+    up((void **)&job->d_tcs, tcs.p, tcs.size() * sizeof(DevTileComp));
+    up((void **)&job->d_tiles, tiles.p, tiles.size() * sizeof(DevTile));
     if (e == cudaSuccess) job->d_coef = j2k_pool_alloc(ctx, coef_elems * (job->coef16 ? 2 : 4) + 64, &e);
     if (e == cudaSuccess) job->d_tmp = j2k_pool_alloc(ctx, job->tmp_bytes, &e);
-    if (e == cudaSuccess && hdr.ht && (!iso || job->ht_map == 2))
+    if (e == cudaSuccess && hdr.ht)
         job->d_htscratch = j2k_pool_alloc(ctx, iso ? j2k_htiso_scratch_bytes((uint32_t)cbs.size()) : j2k_htref_scratch_bytes((uint32_t)cbs.size()), &e);
     // reference HT coder: its decoder writes one row in four (ht.go:677, 701); zero the planes once, here, so that every
     // run only has to clear the rows it may write (3/4 of the entropy stage's zero-fill traffic saved)
-    if (e == cudaSuccess && !iso && hdr.ht && !env_flag("J2KGPU_NO_PRECLEAR")) {
+    if (e == cudaSuccess && !iso && hdr.ht && !opt.no_preclear) {
         e = cudaMemsetAsync(job->d_coef, 0, coef_elems * (job->coef16 ? 2 : 4), ctx->stream);
         job->precleared = 1;
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);          // tables are read from host vectors
-    if (e != cudaSuccess) { job_free(job); return j2k_cuda_err(ctx, e, "job upload"); }
+    // the pixel that all-zero coefficients decode to (inverse MCT, DC shift, colour conversion, clamp, pack of zeros)
+    if (e == cudaSuccess && job->pix_fill) {
+        job->d_fillpix = j2k_pool_alloc(ctx, 64, &e);
+        if (e == cudaSuccess) e = cudaMemsetAsync(job->d_fillpix, 0, 64, ctx->stream);
+        if (e == cudaSuccess) {
+            const int32_t *z = (const int32_t *)((uint8_t *)job->d_fillpix + 16);
+            const int32_t *zc[4] = {z, z + 1, z + 2, z + 3};
+            e = launch_tail(zc, nullptr, (uint8_t *)job->d_fillpix, 16, 1, 1, tp, 1, ctx->stream);
+            ctx->launches++;
+        }
+    }
+    if (e == cudaSuccess && !async_stream) {
+        e = cudaStreamSynchronize(ctx->stream);              // the tables have left the staging block
+        j2k_hpool_free(ctx, job->h_tables, job->h_tables_cap);
+        job->h_tables = nullptr; job->h_tiles_host = nullptr;
+    }
+    if (e != cudaSuccess) { if (async_stream) cudaStreamSynchronize(async_stream); job_free(job); return j2k_cuda_err(ctx, e, "job upload"); }
     *out = job;
     return J2KGPU_OK;
 }
@@ -432,7 +587,7 @@ extern "C" int j2kgpu_job_create(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batc
 {
     if (!ctx) return J2KGPU_E_ARG;
     std::lock_guard<std::mutex> g(ctx->mu);
-    return job_build(ctx, n_img, items, out);
+    return job_build(ctx, n_img, items, out, nullptr);
 }
 
 extern "C" uint64_t j2kgpu_job_blob_bytes(const j2kgpu_job *job) { return job ? job->blob_bytes : 0; }
@@ -462,14 +617,14 @@ static int run_entropy(j2kgpu_job *job, const void *d_blob, uint32_t ia, uint32_
     const float *steps = job->d_steps ? job->d_steps + ca : nullptr;
     if (job->iso && !job->hdr.ht) e = launch_t1_iso(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, steps, irrev, job->max_bps, st);
     else if (job->iso) {
-        e = launch_ht_iso(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, steps, irrev, job->hdr.coef_bits, job->ht_map,
+        // chunks of a pipelined run share the scratch: their kernels are ordered on one stream
+        e = launch_ht_iso(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, steps, irrev, job->hdr.coef_bits,
                           job->d_htscratch, job->blob_bytes, st);
-        if (job->ht_map == 2) ctx->launches++;
+        ctx->launches += j2k_htiso_launches() - 1;
     }
     else if (job->hdr.ht) {
-        // the scratch is indexed by the job-wide block number: chunks of a pipelined run never share entries
         e = launch_ht_ref(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, job->precleared,
-                          (uint8_t *)job->d_htscratch, job->blob_bytes, st);
+                          job->d_htscratch, job->blob_bytes, st);
         ctx->launches += j2k_htref_launches() - 1;
     }
     else e = launch_t1_ref(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, job->max_bps, st);
@@ -487,6 +642,7 @@ static void fill_launch(const j2kgpu_job *job, IdwtLaunch &p, void *d_out, uint3
     p.d_coef = job->d_coef; p.coef16 = job->coef16; p.d_tmp = job->d_tmp; p.nlevels = job->nlevels; p.fast_epi = job->fast_epi; p.wide_ok = job->wide_ok;
     p.max_w = job->max_w; p.max_h = job->max_h; p.reversible = job->hdr.reversible != 0; p.f64_io = 0;
     p.d_plane_out = nullptr; p.d_pix = (uint8_t *)d_out; p.tail = job->tail; p.stream_levels = job->stream_levels; p.iso = job->iso;
+    p.wide_sp = job->ctx->opt.wide_sp;
 }
 
 // one level of the reconstruction; with the fused kernel, level 1 is part of the level-0 launch
@@ -512,6 +668,15 @@ static int run_level(j2kgpu_job *job, const IdwtLaunch &base, int lvl, cudaStrea
 
 static int run_dwt_mct(j2kgpu_job *job, void *d_out, uint32_t ia, uint32_t ib, cudaStream_t st)
 {
+    j2kgpu_ctx *ctx = job->ctx;
+    if (job->pix_fill)
+        for (uint32_t i = ia; i < ib; i++)
+            if (job->item_fill[i]) {
+                cudaError_t e = launch_fill_pixels((uint8_t *)d_out + job->out_off[i], job->out_stride[i], job->row_bytes[i], job->img_h[i],
+                                                   j2k_fmt_bpp(job->tail.fmt), (const uint8_t *)job->d_fillpix, st);
+                if (e != cudaSuccess) return j2k_cuda_err(ctx, e, "pixel fill launch");
+                ctx->launches++;
+            }
     IdwtLaunch p;
     fill_launch(job, p, d_out, ia, ib);
     if (p.n_tiles == 0) return J2KGPU_OK;
@@ -576,10 +741,10 @@ extern "C" int j2kgpu_job_run(j2kgpu_job *job, const void *d_blob, void *d_out)
 // latency floor (one code block's serial chain per launch sequence) allows inside the copy-out time; compute-bound
 // coders (EBCOT) get four chunks.  Measured on the bench batch (16 x 4K): 16 chunks of one frame 11.16 ms, (1,3,3,3,3,3)
 // 11.72 ms, (4,4,4,4) 12.26 ms, one chunk 16.6 ms.
-static std::vector<uint32_t> plan_chunks(const j2kgpu_job *job, const j2k_batch_item_t *items)
+static std::vector<uint32_t> plan_chunks(const j2kgpu_ctx *ctx, uint32_t n, const j2k_image_t &hdr, uint64_t out_bytes)
 {
-    const uint32_t n = job->n_img;
-    if (const char *e = getenv("J2KGPU_CHUNKS")) {       // experiments: explicit chunk sizes, e.g. "1,1,2,4"; the rest in one chunk
+    if (!ctx->opt.chunks.empty()) {                      // experiments: explicit chunk sizes, e.g. "1,1,2,4"; the rest in one chunk
+        const char *e = ctx->opt.chunks.c_str();
         std::vector<uint32_t> cuts(1, 0u);
         while (*e && cuts.back() < n) {
             const uint32_t k = (uint32_t)strtoul(e, (char **)&e, 10);
@@ -591,10 +756,10 @@ static std::vector<uint32_t> plan_chunks(const j2kgpu_job *job, const j2k_batch_
         return cuts;
     }
     double lat, r_cmp;                                   // seconds per launch sequence, output bytes per second
-    if (!job->hdr.ht) { lat = 5e-3; r_cmp = 2.4e9; }                    // EBCOT / MQ
-    else if (job->iso) { lat = 1.1e-3; r_cmp = 400e9; }
+    if (!hdr.ht) { lat = 5e-3; r_cmp = 2.4e9; }                         // EBCOT / MQ
+    else if (hdr.mode == J2KGPU_MODE_ISO) { lat = 1.1e-3; r_cmp = 400e9; }
     else { lat = 0.4e-3; r_cmp = 800e9; }
-    const double t_out = (double)job->out_bytes / 53e9, t_thr = (double)job->out_bytes / r_cmp;
+    const double t_out = (double)out_bytes / 53e9, t_thr = (double)out_bytes / r_cmp;
     uint32_t nchunks = t_thr > 0.5 * t_out ? 4u : (uint32_t)((0.8 * t_out - t_thr) / lat);
     if (nchunks > 16) nchunks = 16;
     if (nchunks > n) nchunks = n;
@@ -614,13 +779,51 @@ static std::vector<uint32_t> plan_chunks(const j2kgpu_job *job, const j2k_batch_
             if (end > cuts.back()) cuts.push_back(end);
         }
     }
-    if (getenv("J2KGPU_DEBUG_PLAN")) { fprintf(stderr, "j2kgpu chunk plan:"); for (uint32_t c : cuts) fprintf(stderr, " %u", c); fprintf(stderr, "\n"); }
+    if (ctx->opt.debug_plan) { fprintf(stderr, "j2kgpu chunk plan:"); for (uint32_t c : cuts) fprintf(stderr, " %u", c); fprintf(stderr, "\n"); }
     return cuts;
 }
 
-// Host-buffer run.  The batch is cut into chunks of whole items; chunk c's host->device copy runs on the copy-in
-// stream, its kernels on the ctx stream and its device->host copy on the copy-out stream, chained by events, so
-// that the PCIe transfers of neighbouring chunks overlap the kernels (the two copy engines work in both directions
+// pixels of item i (job numbering) back to the caller.  Rows go without their padding (the bytes between width * bpp and
+// out_stride belong to the caller and are left alone).  J2KGPU_ITEM_TILES_ONLY: only the rectangles this item's tiles
+// cover are copied, so that several contexts (GPUs) given disjoint tile subsets of ONE image fill one host buffer.
+static int copy_out_item(j2kgpu_job *job, uint32_t i, const j2k_batch_item_t &it, const DevTile *h_tiles, cudaStream_t st)
+{
+    j2kgpu_ctx *ctx = job->ctx;
+    const uint8_t *src = (const uint8_t *)job->d_pix + job->out_off[i];
+    const uint64_t stride = job->out_stride[i];
+    const uint32_t rb = job->row_bytes[i];
+    if (!(it.flags & J2KGPU_ITEM_TILES_ONLY)) {
+        if (stride == rb) J2K_CUDA(ctx, cudaMemcpyAsync(it.out_pix, src, job->out_size[i], cudaMemcpyDeviceToHost, st));
+        else J2K_CUDA(ctx, cudaMemcpy2DAsync(it.out_pix, stride, src, stride, rb, job->img_h[i], cudaMemcpyDeviceToHost, st));
+        return J2KGPU_OK;
+    }
+    const int bpp = j2k_fmt_bpp(job->tail.fmt);
+    const uint32_t width = rb / (uint32_t)bpp;
+    // horizontally adjacent tiles with the same rows are merged; a run of full-width rows is one contiguous copy
+    std::vector<Rect> rs;
+    for (uint32_t t = job->item_tile[i]; t < job->item_tile[i + 1]; t++) {
+        const DevTile &tl = h_tiles[t];
+        Rect q = {tl.img_x0, tl.img_y0, tl.img_x0 + tl.w < width ? tl.img_x0 + tl.w : width,
+                  tl.img_y0 + tl.h < job->img_h[i] ? tl.img_y0 + tl.h : job->img_h[i]};
+        if (q.x0 < q.x1 && q.y0 < q.y1) rs.push_back(q);
+    }
+    std::sort(rs.begin(), rs.end(), [](const Rect &a, const Rect &b) { return a.y0 != b.y0 ? a.y0 < b.y0 : a.x0 < b.x0; });
+    for (size_t k = 0; k < rs.size();) {
+        Rect q = rs[k++];
+        while (k < rs.size() && rs[k].y0 == q.y0 && rs[k].y1 == q.y1 && rs[k].x0 == q.x1) q.x1 = rs[k++].x1;
+        const size_t off = (size_t)q.y0 * stride + (size_t)q.x0 * bpp;
+        if (q.x0 == 0 && q.x1 == width && stride == rb)
+            J2K_CUDA(ctx, cudaMemcpyAsync(it.out_pix + off, src + off, (size_t)(q.y1 - q.y0) * stride, cudaMemcpyDeviceToHost, st));
+        else
+            J2K_CUDA(ctx, cudaMemcpy2DAsync(it.out_pix + off, stride, src + off, stride, (size_t)(q.x1 - q.x0) * bpp, q.y1 - q.y0,
+                                            cudaMemcpyDeviceToHost, st));
+    }
+    return J2KGPU_OK;
+}
+
+// Host-buffer run of a prepared job.  The batch is cut into chunks of whole items; chunk c's host->device copy runs on
+// the copy-in stream, its kernels on the ctx stream and its device->host copy on the copy-out stream, chained by events,
+// so that the PCIe transfers of neighbouring chunks overlap the kernels (the two copy engines work in both directions
 // at once).  A single-item batch degenerates to copy, compute, copy.
 static int run_host_locked(j2kgpu_job *job, const j2k_batch_item_t *items)
 {
@@ -629,19 +832,23 @@ static int run_host_locked(j2kgpu_job *job, const j2k_batch_item_t *items)
     cudaError_t pe = cudaSuccess;
     if (!job->d_blob) { job->d_blob = j2k_pool_alloc(ctx, job->blob_bytes + 64, &pe); if (pe != cudaSuccess) return j2k_cuda_err(ctx, pe, "blob staging"); }
     if (!job->d_pix) { job->d_pix = j2k_pool_alloc(ctx, job->out_bytes, &pe); if (pe != cudaSuccess) return j2k_cuda_err(ctx, pe, "pixel staging"); }
-    for (uint32_t i = 0; i < job->n_img; i++)
+    std::vector<DevTile> h_tiles;
+    for (uint32_t i = 0; i < job->n_img; i++) {
         if (!items[i].out_pix) return j2k_set_err(ctx, J2KGPU_E_ARG, "item %u: null out_pix", i);
+        if ((items[i].flags & J2KGPU_ITEM_TILES_ONLY) && h_tiles.empty()) {
+            h_tiles.resize(job->n_tiles);
+            J2K_CUDA(ctx, cudaMemcpy(h_tiles.data(), job->d_tiles, job->n_tiles * sizeof(DevTile), cudaMemcpyDeviceToHost));
+        }
+    }
     int rc = j2k_ctx_copy_streams(ctx);
     if (rc) return rc;
-    const std::vector<uint32_t> cuts = plan_chunks(job, items);          // chunk c = items [cuts[c], cuts[c + 1])
+    const std::vector<uint32_t> cuts = plan_chunks(ctx, job->n_img, job->hdr, job->out_bytes);   // chunk c = items [cuts[c], cuts[c + 1])
     const uint32_t nchunk = (uint32_t)cuts.size() - 1;
-    if (job->ev_in.size() < nchunk) {
-        const size_t old = job->ev_in.size();
-        job->ev_in.resize(nchunk, nullptr); job->ev_done.resize(nchunk, nullptr);
-        for (size_t c = old; c < nchunk; c++) {
-            J2K_CUDA(ctx, cudaEventCreateWithFlags(&job->ev_in[c], cudaEventDisableTiming));
-            J2K_CUDA(ctx, cudaEventCreateWithFlags(&job->ev_done[c], cudaEventDisableTiming));
-        }
+    while (job->ev_in.size() < nchunk) {
+        cudaError_t e1, e2;
+        job->ev_in.push_back(ctx_event(ctx, &e1));
+        job->ev_done.push_back(ctx_event(ctx, &e2));
+        if (e1 != cudaSuccess || e2 != cudaSuccess) return j2k_cuda_err(ctx, e1 != cudaSuccess ? e1 : e2, "event");
     }
     // the copy streams start after whatever the caller queued on the ctx stream
     J2K_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
@@ -662,8 +869,7 @@ static int run_host_locked(j2kgpu_job *job, const j2k_batch_item_t *items)
         J2K_CUDA(ctx, cudaEventRecord(job->ev_done[c], ctx->stream));
         J2K_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, job->ev_done[c], 0));
         for (uint32_t i = ia; i < ib; i++)
-            J2K_CUDA(ctx, cudaMemcpyAsync(items[i].out_pix, (uint8_t *)job->d_pix + job->out_off[i], job->out_size[i],
-                                          cudaMemcpyDeviceToHost, ctx->s_out));
+            if ((rc = copy_out_item(job, i, items[i], h_tiles.data(), ctx->s_out))) return rc;
     }
     J2K_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
     J2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -716,16 +922,69 @@ extern "C" int j2kgpu_host_unregister(j2kgpu_ctx *ctx, void *p)
     return J2KGPU_OK;
 }
 
+// The plugin call.  The batch is cut into chunks of whole images and every chunk is a job of its own: its tables are
+// validated and flattened on the host into page-locked staging and uploaded on the copy-in stream together with its
+// compressed bytes, its kernels run on the ctx stream, its pixels leave on the copy-out stream.  Nothing synchronises
+// until the last chunk is queued, so the host builds chunk c + 1 while the device decodes chunk c and the link carries
+// chunk c - 1 out: table building, both PCIe directions and the SMs all overlap.
 extern "C" int j2kgpu_decode_batch(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *items)
 {
     if (!ctx) return J2KGPU_E_ARG;
     std::lock_guard<std::mutex> g(ctx->mu);
-    j2kgpu_job *job = nullptr;
-    int rc = job_build(ctx, n_img, items, &job);
+    if (!items || n_img == 0) return j2k_set_err(ctx, J2KGPU_E_ARG, "null or empty batch");
+    cudaSetDevice(ctx->device);
+    int rc = j2k_ctx_copy_streams(ctx);
     if (rc) return rc;
-    rc = run_host_locked(job, items);
-    cudaStreamSynchronize(ctx->stream);
-    job_free(job);
+    TailParams tp;
+    if ((rc = make_tail(ctx, items[0].image, tp))) return rc;
+    uint64_t out_bytes = 0;
+    for (uint32_t i = 0; i < n_img; i++) {
+        if (!items[i].out_pix) return j2k_set_err(ctx, J2KGPU_E_ARG, "item %u: null out_pix", i);
+        if (!same_header(items[i].image, items[0].image)) return j2k_set_err(ctx, J2KGPU_E_ARG, "item %u: header differs from item 0", i);
+        out_bytes += items[i].out_stride * items[i].image.height;
+    }
+    const std::vector<uint32_t> cuts = plan_chunks(ctx, n_img, items[0].image, out_bytes);
+    const uint32_t nchunk = (uint32_t)cuts.size() - 1;
+    std::vector<j2kgpu_job *> jobs(nchunk, nullptr);
+    std::vector<DevTile> h_tiles;
+    cudaError_t ce = cudaSuccess;
+    ce = cudaEventRecord(ctx->ev_start, ctx->stream);
+    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->s_in, ctx->ev_start, 0);
+    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->s_out, ctx->ev_start, 0);
+    if (ce != cudaSuccess) rc = j2k_cuda_err(ctx, ce, "stream setup");
+    for (uint32_t c = 0; c < nchunk && rc == J2KGPU_OK; c++) {
+        const uint32_t ia = cuts[c], ib = cuts[c + 1];
+        const j2k_batch_item_t *its = items + ia;
+        j2kgpu_job *job = nullptr;
+        if ((rc = job_build(ctx, ib - ia, its, &job, ctx->s_in))) break;
+        jobs[c] = job;
+        job->d_blob = j2k_pool_alloc(ctx, job->blob_bytes + 64, &ce);
+        if (ce == cudaSuccess) job->d_pix = j2k_pool_alloc(ctx, job->out_bytes, &ce);
+        cudaEvent_t ev_in = nullptr, ev_done = nullptr;
+        if (ce == cudaSuccess) { ev_in = ctx_event(ctx, &ce); job->ev_in.push_back(ev_in); }
+        if (ce == cudaSuccess) { ev_done = ctx_event(ctx, &ce); job->ev_done.push_back(ev_done); }
+        for (uint32_t i = 0; i < ib - ia && ce == cudaSuccess; i++)
+            if (its[i].blob_len)
+                ce = cudaMemcpyAsync((uint8_t *)job->d_blob + job->blob_off[i], its[i].blob, its[i].blob_len, cudaMemcpyHostToDevice, ctx->s_in);
+        if (ce == cudaSuccess) ce = cudaEventRecord(ev_in, ctx->s_in);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->stream, ev_in, 0);
+        if (ce != cudaSuccess) { rc = j2k_cuda_err(ctx, ce, "chunk upload"); break; }
+        if ((rc = run_entropy(job, job->d_blob, 0, ib - ia, ctx->stream))) break;
+        if ((rc = run_dwt_mct(job, job->d_pix, 0, ib - ia, ctx->stream))) break;
+        ce = cudaEventRecord(ev_done, ctx->stream);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->s_out, ev_done, 0);
+        if (ce != cudaSuccess) { rc = j2k_cuda_err(ctx, ce, "chunk events"); break; }
+        bool subset = false;
+        for (uint32_t i = 0; i < ib - ia; i++) subset |= (its[i].flags & J2KGPU_ITEM_TILES_ONLY) != 0;
+        if (subset) h_tiles.assign(job->h_tiles_host, job->h_tiles_host + job->n_tiles);   // still in the page-locked staging block
+        for (uint32_t i = 0; i < ib - ia && rc == J2KGPU_OK; i++)
+            rc = copy_out_item(job, i, its[i], h_tiles.data(), ctx->s_out);
+    }
+    // everything queued (or failed): drain, then give the chunks' buffers back to the pools
+    cudaStreamSynchronize(ctx->s_in);
+    cudaError_t e1 = cudaStreamSynchronize(ctx->stream), e2 = cudaStreamSynchronize(ctx->s_out);
+    for (j2kgpu_job *j : jobs) job_free(j);
+    if (rc == J2KGPU_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) rc = j2k_cuda_err(ctx, e1 != cudaSuccess ? e1 : e2, "decode_batch");
     return rc;
 }
 
@@ -765,7 +1024,8 @@ static int stage_blocks(j2kgpu_ctx *ctx, int mode, int ht, const j2k_blkjob_t *j
         DevCblk &o = cbs[i];
         memset(&o, 0, sizeof o);
         o.data_off = j.data_off; o.data_len = j.data_len; o.out_off = j.out_off; o.out_stride = j.w;
-        o.w = j.w; o.h = j.h; o.band = j.band; o.num_bps = j.num_bps; o.num_passes = j.rsv0;    // ISO EBCOT: coding passes (0 = all)
+        o.w = j.w; o.h = j.h; o.band = j.band; o.num_bps = j.num_bps; o.num_passes = j.rsv0;    // ISO: coding passes (0 = all)
+        o.len_cup = (j.len_cleanup && j.len_cleanup <= j.data_len) ? j.len_cleanup : j.data_len;
         if (j.num_bps > max_bps) max_bps = j.num_bps;
     }
     int rc;
@@ -776,11 +1036,9 @@ static int stage_blocks(j2kgpu_ctx *ctx, int mode, int ht, const j2k_blkjob_t *j
     if (blob_len) J2K_CUDA(ctx, cudaMemcpyAsync(ctx->d_in.p, blob, blob_len, cudaMemcpyHostToDevice, ctx->stream));
     J2K_CUDA(ctx, cudaMemsetAsync(ctx->d_out.p, 0, out_len * sizeof(int32_t), ctx->stream));
     if (ht && mode != J2KGPU_MODE_ISO) { if ((rc = j2k_reserve(ctx, ctx->d_aux, j2k_htref_scratch_bytes(n), false))) return rc; ctx->launches += j2k_htref_launches() - 1; }
-    int ht_map = 2;
-    if (const char *ev = getenv("J2KGPU_HT_MAP")) { const int v = atoi(ev); ht_map = (v == 1 || v == 32) ? v : 2; }
-    if (ht && mode == J2KGPU_MODE_ISO && ht_map == 2) { if ((rc = j2k_reserve(ctx, ctx->d_aux, j2k_htiso_scratch_bytes(n), false))) return rc; ctx->launches++; }
+    if (ht && mode == J2KGPU_MODE_ISO) { if ((rc = j2k_reserve(ctx, ctx->d_aux, j2k_htiso_scratch_bytes(n), false))) return rc; ctx->launches += j2k_htiso_launches() - 1; }
     cudaError_t e = (ht && mode == J2KGPU_MODE_ISO)
-                        ? launch_ht_iso((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, nullptr, 0, 0, ht_map, ctx->d_aux.p, blob_len, ctx->stream)
+                        ? launch_ht_iso((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, nullptr, 0, 0, ctx->d_aux.p, blob_len, ctx->stream)
                     : mode == J2KGPU_MODE_ISO ? launch_t1_iso((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, nullptr, 0, max_bps, ctx->stream)
                     : ht ? launch_ht_ref((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, 0, ctx->d_aux.p, blob_len, ctx->stream)
                        : launch_t1_ref_stage((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, (int32_t *)ctx->d_out.p, max_bps, ctx->stream);

@@ -34,13 +34,15 @@
 #endif
 
 // ---- device-side tables (uploaded once per job) ---------------------------------------------
-struct DevCblk {                 // one code block, 32 bytes
+struct DevCblk {                 // one code block, 40 bytes
     uint64_t data_off;           // into the job blob
     uint64_t out_off;            // int32 element offset of sample (0,0) in the coefficient arena
     uint32_t data_len;
     uint32_t out_stride;         // row stride of the destination plane, in elements
     uint16_t w, h;
     uint8_t  band, num_bps, level, num_passes;
+    uint32_t len_cup;            // ISO HT: bytes of the cleanup segment (the refinement segment follows); 0 = data_len
+    uint32_t pad;
 };
 
 struct DevTileComp {             // one tile-component plane
@@ -76,8 +78,22 @@ struct DevBuf {
     void *p = nullptr; size_t cap = 0;
 };
 
+// A/B switches and test hooks: seeded from the environment (J2KGPU_<NAME>) ONCE, in j2kgpu_create, and changed only through
+// j2kgpu_set_option; no launch path reads the environment
+struct J2kOpts {
+    int no_fuse = 0;        // per-level IDWT launches instead of the fused levels-1+0 kernels
+    int no_wide = 0;        // 4-columns-per-lane fused kernel instead of the 16-columns-per-lane one
+    int no_fast_epi = 0;    // generic pixel epilogue
+    int coef32 = 0;         // int32 coefficient planes everywhere
+    int no_preclear = 0;    // reference HT coder: clear every row on every run
+    int wide_sp = 0;        // strip height of the wide IDWT kernel in row pairs (0 = planner)
+    int debug_plan = 0;     // print the chunk plan of host-buffer runs
+    std::string chunks;     // explicit chunk sizes of host-buffer runs, e.g. "1,1,2,4"
+};
+
 struct j2kgpu_ctx {
     int device = 0;
+    J2kOpts opt;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;       // stream in use (own or external)
     cudaStream_t s_in = nullptr, s_out = nullptr;   // copy-in / copy-out streams of the pipelined host-buffer run
@@ -90,9 +106,13 @@ struct j2kgpu_ctx {
     DevBuf h_in, h_out;                  // pinned staging
     // device buffers released by finished jobs, reused by the next job (repeated decode calls do not cudaMalloc)
     std::vector<DevBuf> pool;
+    std::vector<DevBuf> hpool;           // page-locked host blocks (table staging of pipelined batch calls), same policy
+    std::vector<cudaEvent_t> events;     // timing-disabled events, reused across calls
 };
 void *j2k_pool_alloc(j2kgpu_ctx *ctx, size_t bytes, cudaError_t *err);
 void j2k_pool_free(j2kgpu_ctx *ctx, void *p);
+void *j2k_hpool_alloc(j2kgpu_ctx *ctx, size_t bytes, size_t *cap, cudaError_t *err);
+void j2k_hpool_free(j2kgpu_ctx *ctx, void *p, size_t cap);
 
 struct j2kgpu_job {
     j2kgpu_ctx *ctx = nullptr;
@@ -105,12 +125,19 @@ struct j2kgpu_job {
     bool need_clear = false;
     uint32_t stream_levels = 0;
     int iso = 0;                         // J2KGPU_MODE_ISO
-    int ht_map = 2;                      // ISO HT mapping: 2 = VLC kernel + MagSgn kernel, 32 = thread per block, 1 = warp per block
     int coef16 = 0;                      // coefficient arena holds int16 (every magnitude provably < 2^15) instead of int32
     int fused_ok = 0;                    // levels 1 + 0 + pixel epilogue run as one kernel (idwt_fused.cu)
     int fast_epi = 0;                    // every tile qualifies for the fused kernel's fixed RGBA8 epilogue
     int wide_ok = 0;                     // ... and for the 16-columns-per-lane variant (idwt_wide.cu)
     int precleared = 0;                  // reference HT coder: planes zeroed at job creation, decoder clears every 4th row only
+    int pix_fill = 0;                    // some pixel of some image is covered by no tile: pre-fill with the pixel of zero coefficients
+    std::vector<uint8_t> item_fill;      // per item: needs the pre-fill
+    std::vector<uint32_t> row_bytes;     // per item: width * bytes per pixel (rows are copied back without their padding)
+    std::vector<uint64_t> out_stride;    // per item
+    std::vector<uint32_t> img_h;         // per item
+    const DevTile *h_tiles_host = nullptr;               // the tile table inside h_tables (valid while h_tables is)
+    void *h_tables = nullptr; size_t h_tables_cap = 0;   // page-locked staging of the tables while their upload is in flight
+    void *d_fillpix = nullptr;           // 16 bytes: the packed pixel an all-zero coefficient decodes to
     std::vector<uint32_t> item_cb, item_tc, item_tile;   // first block / tile-component / tile of each item (+ end)
     std::vector<uint64_t> tc_coef_off;                   // coefficient-arena offset of each tile-component (host copy)
     std::vector<cudaEvent_t> ev_in, ev_done;             // per chunk of the pipelined host-buffer run
@@ -143,17 +170,17 @@ cudaError_t launch_t1_ref(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_b
                           int max_bps, cudaStream_t s);
 cudaError_t launch_ht_ref(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
                           int planes_precleared, void *d_scratch, uint64_t blob_bytes, cudaStream_t s);
-int j2k_htref_map();             // reference-HT decoder mapping: 2 (VLC kernel + MagSgn kernel, default), 32 (thread per block) or 1 (warp per block)
 size_t j2k_htref_scratch_bytes(uint32_t n_blocks);   // device scratch launch_ht_ref needs for n blocks
 int j2k_htref_launches();        // kernels per launch_ht_ref call
 // ISO/IEC 15444-1 Annex D decoder (stripe-order passes, standard tables, pass truncation), one warp per block
 cudaError_t launch_t1_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
                           const float *d_steps, int irrev, int max_bps, cudaStream_t s);
-// ISO/IEC 15444-15 cleanup decoder; blocks_per_warp = 1 (warp per block) or 32 (thread per block)
+// ISO/IEC 15444-15 block decoder (VLC kernel + MagSgn kernel)
 cudaError_t launch_ht_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
-                          const float *d_steps, int irrev, int coef_bits, int blocks_per_warp, void *d_scratch, uint64_t blob_bytes,
+                          const float *d_steps, int irrev, int coef_bits, void *d_scratch, uint64_t blob_bytes,
                           cudaStream_t s);
-size_t j2k_htiso_scratch_bytes(uint32_t n_blocks);   // device scratch of the two-kernel mapping (blocks_per_warp == 2)
+size_t j2k_htiso_scratch_bytes(uint32_t n_blocks);   // device scratch between the two kernels
+int j2k_htiso_launches();        // kernels per launch_ht_iso call
 
 // inverse DWT, REF (dense-prefix) addressing.  One call = one decomposition level of every
 // tile-component in the table.  `lvl` counts from 0 (full resolution).  For lvl > 0 the output goes to the
@@ -173,6 +200,7 @@ struct IdwtLaunch {
     int reversible;
     int f64_io;                                     // 9-7 stage API: coefficient arena and output planes are double
     int iso;                                        // 1: Mallat addressing + ISO order (rows, then columns)
+    int wide_sp;                                    // J2kOpts.wide_sp
     uint32_t stream_levels;                         // bit l set: level l of every tile-component fits the streaming kernel
     int32_t *d_plane_out;                           // lvl == 0 without tiles: output planes (same offsets as coef)
     uint8_t *d_pix;                                 // lvl == 0 with tiles: packed pixels
@@ -198,6 +226,9 @@ cudaError_t launch_tail(const int32_t *const d_comps[4], int32_t *const d_planes
                         uint64_t out_stride, uint32_t width, uint32_t height, const TailParams &tp,
                         int apply_tail, cudaStream_t s);
 cudaError_t launch_inverse_ict_f64(double *y, double *cb, double *cr, uint64_t n, cudaStream_t s);
+// rows x row_bytes of d_pix (row pitch out_stride) <- the bpp-byte pixel at d_pattern, repeated
+cudaError_t launch_fill_pixels(uint8_t *d_pix, uint64_t out_stride, uint32_t row_bytes, uint32_t rows, int bpp,
+                               const uint8_t *d_pattern, cudaStream_t s);
 
 // Go's int32(float64) as the reference runs it on amd64 (CVTTSD2SL): truncation, and 0x80000000 for NaN / out of range
 // (CUDA's cvt.rzi saturates instead, which differs for positive overflow)

@@ -6,15 +6,9 @@
 // in pairs, CxtVLC tables, U-VLC, exponent predictor from the previous quad row.  Checked in the test suite against
 // a CPU statement of the same algorithm that is itself pinned by OpenJPEG decoding the same streams.
 //
-// Mapping.  Default (J2KGPU_HT_MAP unset or 2): two kernels, k_htiso_vlc (one thread per block: the MEL / VLC context
-// chain) and k_htiso_magsgn2 (half a warp per block: the MagSgn rows in parallel) -- second half of this file.
-// First half: the single-chain decoder, a block as one serial chain of about 50 instructions per quad, in two mappings:
-//   J2KGPU_HT_MAP = 1     one warp per code block: all lanes run the chain on uniform registers, lane 0 stores;
-//   J2KGPU_HT_MAP = 32    one thread per code block: 32 independent chains per warp (divergent but short
-//                         branches), 32x fewer warp-instructions for the same work.
-// Per-block state: stream cursors and 64-bit bit buffers in registers; previous-row significance as a 64-bit
-// column mask; previous-row exponents as 64 bytes of shared memory, updated in place with a one-column carry.
-// Every sample of the block is written exactly once (zeros included), two rows x two columns per quad.
+// Mapping: two kernels, k_htiso_vlc (one thread per block: the MEL / VLC context chain) and k_htiso_magsgn2 (half a
+// warp per block: the MagSgn rows in parallel).  The single-chain statement of the same algorithm is the CPU checker
+// (test side).
 #include "common.h"
 #include <cstdlib>
 
@@ -30,8 +24,6 @@ struct Mel {
     int pos, left; uint32_t tmp; int bits; bool unstuff;
     int k, zeros; bool one_after;
 };
-struct Vlc { int pos, left; uint64_t tmp; int bits; bool unstuff; };
-struct Ms  { int pos, left; uint64_t tmp; int bits; bool unstuff; };
 
 __device__ __forceinline__ int mel_exp(int k)
 {
@@ -74,79 +66,11 @@ __device__ __forceinline__ int mel_event(Mel &m, const uint8_t *d)
     return 1;
 }
 
-__device__ __forceinline__ uint32_t vlc_peek(Vlc &v, const uint8_t *d)
-{
-    while (v.bits <= 32) {
-        uint32_t b = 0;
-        if (v.left > 0) { b = __ldg(d + v.pos); v.pos--; v.left--; }
-        const int nb = (v.unstuff && (b & 0x7F) == 0x7F) ? 7 : 8;
-        v.tmp |= (uint64_t)b << v.bits;
-        v.bits += nb;
-        v.unstuff = b > 0x8F;
-    }
-    return (uint32_t)v.tmp;
-}
-__device__ __forceinline__ void vlc_skip(Vlc &v, int n) { v.tmp >>= n; v.bits -= n; }
-
-__device__ __forceinline__ uint32_t ms_get(Ms &s, const uint8_t *d, int n)
-{
-    while (s.bits <= 32) {
-        uint32_t b = 0xFF;
-        if (s.left > 0) { b = __ldg(d + s.pos); s.pos++; s.left--; }
-        const int nb = s.unstuff ? 7 : 8;
-        s.tmp |= (uint64_t)b << s.bits;
-        s.bits += nb;
-        s.unstuff = (b == 0xFF);
-    }
-    const uint32_t v = (uint32_t)s.tmp & ((n >= 32) ? 0xFFFFFFFFu : ((1u << n) - 1u));
-    s.tmp >>= n; s.bits -= n;
-    return v;
-}
-
 // U-VLC prefix rows (T.814 Table 3): prefix_len | suffix_len << 2 | base << 5, indexed by the 3 LSBs
 __device__ __forceinline__ uint32_t uvlc_row(uint32_t b3)
 {
     // {183, 33, 66, 33, 103, 33, 66, 33}
     return (uint32_t)((0x2142216721422100ull | 0xB7ull) >> (8 * b3)) & 0xFF;
-}
-
-__device__ int uvlc_decode(uint32_t vlc, int mode, bool initial, int &u0, int &u1)
-{
-    u0 = 0; u1 = 0;
-    if (mode == 0) return 0;
-    if (mode == 1 || mode == 2) {
-        const uint32_t t = uvlc_row(vlc & 7);
-        const int pl = t & 3, sl = (t >> 2) & 7;
-        vlc >>= pl;
-        const int u = (int)((t >> 5) + (vlc & ((1u << sl) - 1)));
-        if (mode == 1) u0 = u; else u1 = u;
-        return pl + sl;
-    }
-    const uint32_t t1 = uvlc_row(vlc & 7);
-    const int p1 = t1 & 3;
-    vlc >>= p1;
-    if (mode == 3 && initial && p1 > 2) {                 // u0 > 2, so u1 is 1 or 2: a single bit
-        u1 = (int)(vlc & 1) + 1;
-        vlc >>= 1;
-        const int sl = (t1 >> 2) & 7;
-        u0 = (int)((t1 >> 5) + (vlc & ((1u << sl) - 1)));
-        return p1 + 1 + sl;
-    }
-    const uint32_t t2 = uvlc_row(vlc & 7);
-    const int p2 = t2 & 3;
-    vlc >>= p2;
-    const int s1 = (t1 >> 2) & 7, s2 = (t2 >> 2) & 7;
-    u0 = (int)((t1 >> 5) + (vlc & ((1u << s1) - 1)));
-    vlc >>= s1;
-    u1 = (int)((t2 >> 5) + (vlc & ((1u << s2) - 1)));
-    if (mode == 4) { u0 += 2; u1 += 2; }
-    return p1 + p2 + s1 + s2;
-}
-
-// columns (c-1, c, c+1, c+2) of a 64-bit column mask as 4 bits; columns outside 0..63 read 0
-__device__ __forceinline__ uint32_t win4(uint64_t m, int c)
-{
-    return (uint32_t)(c ? (m >> (c - 1)) : (m << 1)) & 0xF;
 }
 
 // value written for one decoded sample: reversible -> integer; irreversible -> dequantised float bits
@@ -159,182 +83,6 @@ __device__ __forceinline__ int32_t sample_value(uint32_t mu, uint32_t sign, int 
     // mid-point reconstruction: (mu + 1/2) * 2^shift * step
     const float f = ((float)mu + 0.5f) * (float)(1u << shift) * step;
     return __float_as_int(sign ? -f : f);
-}
-
-// One block, one thread's worth of control flow.  `ex` = 64 exponent bytes of the previous quad row's bottom
-// samples (element c at ex[c * ex_stride]).  `do_store`: this thread performs the global stores.
-template <typename OT>
-__device__ void ht_decode_block(const DevCblk &cb, const uint8_t *__restrict__ blob, OT *__restrict__ coef,
-                                const uint16_t *s_tbl, uint8_t *ex, int ex_stride, bool do_store, float step, bool irrev, int coef_bits)
-{
-    const int w = cb.w, h = cb.h;
-    OT *out = coef + cb.out_off;
-    const size_t ostride = cb.out_stride;
-    const uint8_t *d = blob + cb.data_off;
-    const int lcup = (int)cb.data_len;
-    bool ok = lcup >= 2 && cb.num_bps >= 1 && cb.num_bps <= 30;
-    int scup = 0;
-    if (ok) {
-        scup = ((int)__ldg(d + lcup - 1) << 4) + (int)(__ldg(d + lcup - 2) & 0x0F);
-        ok = scup >= 2 && scup <= lcup && scup <= 4079;
-    }
-    if (!ok) {                                               // not coded or malformed: the block is zero
-        if (do_store)
-            for (int y = 0; y < h; y++)
-                for (int x = 0; x < w; x++) out[(size_t)y * ostride + x] = 0;
-        return;
-    }
-    const int shift = cb.num_bps - 1;
-    Mel mel; mel.pos = lcup - scup; mel.left = scup - 1; mel.tmp = 0; mel.bits = 0; mel.unstuff = false;
-    mel.k = 0; mel.zeros = 0; mel.one_after = false;
-    Vlc vlc;
-    {
-        const uint32_t b = __ldg(d + lcup - 2);
-        vlc.pos = lcup - 3; vlc.left = scup - 2;
-        vlc.tmp = b >> 4;
-        vlc.bits = 4 - (((vlc.tmp & 7) == 7) ? 1 : 0);
-        vlc.unstuff = (b | 0x0F) > 0x8F;
-    }
-    Ms ms; ms.pos = 0; ms.left = lcup - scup; ms.tmp = 0; ms.bits = 0; ms.unstuff = false;
-
-    const int nq = (w + 1) >> 1;
-    for (int c = 0; c < 64; c++) ex[c * ex_stride] = 0;
-    uint64_t sigprev = 0;
-    bool bad = false;
-    const bool vec_ok = ((cb.out_off | ostride) & 1) == 0;
-
-    for (int y = 0; y < h; y += 2) {
-        const bool initial = (y == 0);
-        const uint16_t *tbl = s_tbl + (initial ? 0 : 1024);
-        const bool row2 = (y + 1 < h);
-        uint64_t signew = 0;
-        int cw = 0;
-        int e_carry = 0;                                     // previous-row exponent of column 2q-1
-        for (int q = 0; q < nq; q += 2) {
-            const bool pair = (q + 1 < nq);
-            uint32_t qinf0 = 0, qinf1 = 0;
-            // ---- CxtVLC of the two quads ----
-            {
-                int c_q = cw;
-                if (!initial) { const uint32_t s4 = win4(sigprev, 2 * q); c_q |= ((s4 | (s4 >> 1)) & 1) | ((((s4 >> 2) | (s4 >> 3)) & 1) << 2); }
-                uint32_t e = tbl[(c_q << 7) | (vlc_peek(vlc, d) & 0x7F)];
-                if (c_q == 0 && !mel_event(mel, d)) e = 0;
-                vlc_skip(vlc, e & 7);
-                qinf0 = e;
-                const uint32_t rho = (e >> 4) & 0xF;
-                cw = initial ? (int)(((rho | (rho >> 1)) & 1) | (((rho >> 2) & 1) << 1) | (((rho >> 3) & 1) << 2))
-                             : (int)((((rho >> 2) | (rho >> 3)) & 1) << 1);
-            }
-            if (pair) {
-                int c_q = cw;
-                if (!initial) { const uint32_t s4 = win4(sigprev, 2 * q + 2); c_q |= ((s4 | (s4 >> 1)) & 1) | ((((s4 >> 2) | (s4 >> 3)) & 1) << 2); }
-                uint32_t e = tbl[(c_q << 7) | (vlc_peek(vlc, d) & 0x7F)];
-                if (c_q == 0 && !mel_event(mel, d)) e = 0;
-                vlc_skip(vlc, e & 7);
-                qinf1 = e;
-                const uint32_t rho = (e >> 4) & 0xF;
-                cw = initial ? (int)(((rho | (rho >> 1)) & 1) | (((rho >> 2) & 1) << 1) | (((rho >> 3) & 1) << 2))
-                             : (int)((((rho >> 2) | (rho >> 3)) & 1) << 1);
-            }
-            // ---- U-VLC ----
-            int mode = (int)(((qinf0 >> 3) & 1) | (((qinf1 >> 3) & 1) << 1));
-            if (initial && mode == 3 && mel_event(mel, d)) mode = 4;
-            int u0 = 0, u1 = 0;
-            if (mode) vlc_skip(vlc, uvlc_decode(vlc_peek(vlc, d), mode, initial, u0, u1));
-            // ---- exponent predictor kappa from the previous quad row (columns 2q-1 .. 2q+4) ----
-            const int c0 = 2 * q;
-            const int eA = e_carry, eB = ex[c0 * ex_stride], eC = (c0 + 1 < 64) ? ex[(c0 + 1) * ex_stride] : 0,
-                      eD = (c0 + 2 < 64) ? ex[(c0 + 2) * ex_stride] : 0, eE = (c0 + 3 < 64) ? ex[(c0 + 3) * ex_stride] : 0,
-                      eF = (c0 + 4 < 64) ? ex[(c0 + 4) * ex_stride] : 0;
-            int U0 = u0 + 1, U1 = u1 + 1;
-            if (!initial) {
-                const uint32_t r0 = (qinf0 >> 4) & 0xF, r1 = (qinf1 >> 4) & 0xF;
-                if (r0 & (r0 - 1)) { const int E = max(max(eA, eB), max(eC, eD)); U0 = u0 + max(1, E - 1); }
-                if (r1 & (r1 - 1)) { const int E = max(max(eC, eD), max(eE, eF)); U1 = u1 + max(1, E - 1); }
-            }
-            e_carry = eE;                                    // column 2(q+2)-1 before this pair overwrites it
-            if (U0 > 31 || U1 > 31) bad = true;
-            // magnitude bound of the codestream (Mb = coef_bits): every decoded mu is <= 2^(U-1), and a conformant
-            // encoder never needs U > Mb - p + 1; beyond that the block is malformed (and would not fit the int16 arena)
-            if (coef_bits && (U0 + shift > coef_bits + 1 || U1 + shift > coef_bits + 1)) bad = true;
-            U0 = min(U0, 31); U1 = min(U1, 31);
-            // ---- MagSgn + store, quad by quad ----
-#pragma unroll
-            for (int i = 0; i < 2; i++) {
-                if (i == 1 && !pair) break;
-                const uint32_t e = i ? qinf1 : qinf0;
-                const int U = i ? U1 : U0;
-                const int xq = c0 + 2 * i;
-                int32_t v[4];
-                int enew[2] = {0, 0};
-#pragma unroll
-                for (int n = 0; n < 4; n++) {
-                    v[n] = 0;
-                    if ((e >> (4 + n)) & 1) {
-                        const int m = U - (int)((e >> (12 + n)) & 1);
-                        uint32_t val = ms_get(ms, d, m);
-                        const uint32_t sign = val & 1;
-                        val |= ((e >> (8 + n)) & 1) << m;
-                        val |= 1;
-                        v[n] = sample_value((val >> 1) + 1, sign, shift, step, irrev);
-                        if (n & 1) enew[n >> 1] = 32 - __clz((int)val);
-                    }
-                }
-                const bool colB = (xq + 1 < w);
-                ex[xq * ex_stride] = (uint8_t)enew[0];
-                if (xq + 1 < 64) ex[(xq + 1) * ex_stride] = (uint8_t)enew[1];
-                signew |= ((uint64_t)((e >> 5) & 1) << xq) | ((uint64_t)((e >> 7) & 1) << (xq + 1));
-                // significance outside the block is a malformed stream: the whole block decodes to zero
-                if ((!colB && (e & 0xC0)) || (!row2 && (e & 0xA0))) bad = true;
-                if (do_store) {
-                    OT *p0 = out + (size_t)y * ostride + xq;
-                    if (colB && vec_ok) {
-                        if (sizeof(OT) == 4) {
-                            *reinterpret_cast<int2 *>(p0) = make_int2(v[0], v[2]);
-                            if (row2) *reinterpret_cast<int2 *>(p0 + ostride) = make_int2(v[1], v[3]);
-                        } else {
-                            *reinterpret_cast<uint32_t *>(p0) = ((uint32_t)v[0] & 0xFFFFu) | ((uint32_t)v[2] << 16);
-                            if (row2) *reinterpret_cast<uint32_t *>(p0 + ostride) = ((uint32_t)v[1] & 0xFFFFu) | ((uint32_t)v[3] << 16);
-                        }
-                    } else {
-                        p0[0] = (OT)v[0];
-                        if (colB) p0[1] = (OT)v[2];
-                        if (row2) { p0[ostride] = (OT)v[1]; if (colB) p0[ostride + 1] = (OT)v[3]; }
-                    }
-                }
-            }
-        }
-        sigprev = signew;
-    }
-    if (bad && do_store)
-        for (int y = 0; y < h; y++)
-            for (int x = 0; x < w; x++) out[(size_t)y * ostride + x] = 0;
-}
-
-template <int BLOCKS_PER_WARP, typename OT>
-__global__ void __launch_bounds__(kThreads)
-k_ht_iso(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob,
-         OT *__restrict__ coef, const float *__restrict__ steps, int irrev, int coef_bits)
-{
-    __shared__ uint16_t s_tbl[2048];
-    __shared__ uint8_t s_ex[64 * kThreads];
-    for (int i = threadIdx.x; i < 1024; i += kThreads) { s_tbl[i] = d_tbl0[i]; s_tbl[1024 + i] = d_tbl1[i]; }
-    __syncthreads();
-    uint32_t blk;
-    bool do_store;
-    uint8_t *ex;
-    if (BLOCKS_PER_WARP == 32) {
-        blk = blockIdx.x * kThreads + threadIdx.x;
-        do_store = true;
-        ex = s_ex + threadIdx.x;                              // column-major: element c at ex[c * kThreads]
-    } else {
-        blk = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-        do_store = (threadIdx.x & 31) == 0;
-        ex = s_ex + (threadIdx.x >> 5);                       // lanes of a warp share one column (same values)
-    }
-    if (blk >= n) return;
-    const DevCblk cb = cblks[blk];
-    ht_decode_block(cb, blob, coef, s_tbl, ex, kThreads, do_store, steps ? steps[blk] : 1.0f, irrev != 0, coef_bits);
 }
 
 // ---- two-kernel mapping (default) ------------------------------------------------------------------------------------
@@ -353,7 +101,6 @@ k_ht_iso(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
 // for every input, malformed ones included (same `bad` conditions, same zero block).
 constexpr int kQTabWords = 512;                         // 32 quad rows x 32 quads x 16 bits
 constexpr int kRingWords = 512;
-constexpr int kWarpsIsoB = 8;
 enum { ST_ZERO = 0, ST_OK = 1 };
 
 struct VlcStream { const uint8_t *d; int pos, left; uint64_t tmp; uint32_t bits; bool gt8f; };
@@ -524,152 +271,6 @@ k_htiso_vlc(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__rest
         sigprev = sn >> (64 - 4 * iters);
     }
     status[blk] = badbits ? (uint32_t)ST_ZERO : ((uint32_t)ST_OK | ((uint32_t)(lcup - scup) << 2));
-}
-
-template <typename OT, bool IRREV>
-__global__ void __launch_bounds__(kWarpsIsoB * 32)
-k_htiso_magsgn(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob,
-               const uint32_t *__restrict__ qtab, const uint32_t *__restrict__ status, OT *__restrict__ coef,
-               const float *__restrict__ steps, int coef_bits)
-{
-    __shared__ uint32_t s_ring[kWarpsIsoB][kRingWords];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t blk = blockIdx.x * kWarpsIsoB + warp;
-    if (blk >= n) return;
-    const uint32_t stw = status[blk];
-    const DevCblk cb = cblks[blk];
-    const int w = cb.w, h = cb.h;
-    OT *out = coef + cb.out_off;
-    const size_t ostride = cb.out_stride;
-    const uint8_t *d = blob + cb.data_off;
-    if ((stw & 3) == ST_ZERO) {
-        for (int y = 0; y < h; y++)
-            for (int x = lane; x < w; x += 32) out[(size_t)y * ostride + x] = 0;
-        return;
-    }
-    const float step = (IRREV && steps) ? steps[blk] : 1.0f;
-    const int L = (int)(stw >> 2);
-    const int shift = cb.num_bps - 1;
-    const int nq = (w + 1) >> 1, nrows = (h + 1) >> 1;
-    const bool active = lane < nq;
-    const bool colB = (2 * lane + 1 < w);
-    const bool vec_ok = ((cb.out_off | ostride) & 1) == 0;
-    const uint16_t *qt = reinterpret_cast<const uint16_t *>(qtab + (size_t)blk * kQTabWords);
-    uint32_t *ring = s_ring[warp];
-    for (int i = lane; i < kRingWords; i += 32) ring[i] = 0;
-    __syncwarp();
-    uint32_t built = 0, prev_ff = 0, P = 0;              // warp-uniform: bits in the ring, last byte was 0xFF, bits consumed
-    int kbyte = 0;
-    int Eb0 = 0, Eb1 = 0;                                // exponents of this quad's bottom samples in the previous quad row
-    bool bad = false;
-    uint32_t code_next = active ? (uint32_t)qt[lane] : 0u;
-    for (int r = 0; r < nrows; r++) {
-        const uint32_t code = code_next;
-        if (r + 1 < nrows) code_next = active ? (uint32_t)qt[(r + 1) * 32 + lane] : 0u;
-        // ---- keep the ring one full quad row ahead ----
-        while (built < P + 4096u) {
-            const int k = kbyte + 8 * lane;
-            uint32_t b[8], nb[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) b[i] = (k + i < L) ? (uint32_t)__ldg(d + k + i) : 0xFFu;
-            // the words this chunk reaches beyond the one `built` points into still hold bits 16 Kbit old
-            const uint32_t w0 = (built >> 5) + 1;
-            ring[(w0 + lane) & (kRingWords - 1)] = 0;
-            ring[(w0 + 32 + lane) & (kRingWords - 1)] = 0;
-            if (lane < 2) ring[(w0 + 64 + lane) & (kRingWords - 1)] = 0;
-            uint32_t pb = __shfl_up_sync(0xffffffffu, b[7], 1);
-            if (lane == 0) pb = prev_ff ? 0xFFu : 0u;
-#pragma unroll
-            for (int i = 0; i < 8; i++) { nb[i] = pb == 0xFFu ? 7u : 8u; pb = b[i]; }
-            const uint32_t va = b[0] | (b[1] << nb[0]) | (b[2] << (nb[0] + nb[1])) | (b[3] << (nb[0] + nb[1] + nb[2]));
-            const uint32_t vb = b[4] | (b[5] << nb[4]) | (b[6] << (nb[4] + nb[5])) | (b[7] << (nb[4] + nb[5] + nb[6]));
-            const uint32_t ta = nb[0] + nb[1] + nb[2] + nb[3], tot = ta + nb[4] + nb[5] + nb[6] + nb[7];
-            uint32_t incl = tot;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-            const uint32_t pos = built + incl - tot;
-            __syncwarp();
-#pragma unroll
-            for (int g = 0; g < 2; g++) {
-                const uint32_t pg = g ? pos + ta : pos, vg = g ? vb : va;
-                const uint32_t sh = pg & 31, wi = pg >> 5;
-                atomicOr(&ring[wi & (kRingWords - 1)], vg << sh);
-                const uint32_t hi = sh ? vg >> (32 - sh) : 0u;
-                if (hi) atomicOr(&ring[(wi + 1) & (kRingWords - 1)], hi);
-            }
-            built += __shfl_sync(0xffffffffu, incl, 31);
-            prev_ff = __shfl_sync(0xffffffffu, pb, 31) == 0xFFu;
-            kbyte += 256;
-            __syncwarp();
-        }
-        // ---- U_q and the four field widths ----
-        const uint32_t st8 = code & 0xFF;
-        const int u = (int)(code >> 8);
-        const uint32_t sig = (st8 | (st8 >> 1)) & 0x55u;               // bit 2n: sample n significant
-        int U = u + 1;
-        if (r > 0) {
-            const int eL = __shfl_up_sync(0xffffffffu, Eb1, 1), eR = __shfl_down_sync(0xffffffffu, Eb0, 1);
-            if (sig & (sig - 1)) {
-                const int E = max(max(lane ? eL : 0, Eb0), max(Eb1, lane < 31 ? eR : 0));
-                U = u + max(1, E - 1);
-            }
-        }
-        if (U > 31) bad = true;
-        if (coef_bits && U + shift > coef_bits + 1) bad = true;
-        U = min(U, 31);
-        int m[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) { const uint32_t s2 = (st8 >> (2 * i)) & 3; m[i] = s2 ? U - (int)(s2 >> 1) : 0; }
-        const uint32_t tot = (uint32_t)(m[0] + m[1] + m[2] + m[3]);
-        uint32_t incl = tot;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        uint32_t p = P + incl - tot;
-        P += __shfl_sync(0xffffffffu, incl, 31);
-        // ---- the quad's samples: n = 0 (y, x), 1 (y + 1, x), 2 (y, x + 1), 3 (y + 1, x + 1) ----
-        int32_t val[4];
-        int en[2] = {0, 0};
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const uint32_t s2 = (st8 >> (2 * i)) & 3;
-            val[i] = 0;
-            if (s2) {
-                const uint32_t wi = p >> 5;
-                const uint32_t x = __funnelshift_r(ring[wi & (kRingWords - 1)], ring[(wi + 1) & (kRingWords - 1)], p & 31);
-                uint32_t vv = x & ((1u << m[i]) - 1u);
-                const uint32_t sign = vv & 1;
-                vv |= (uint32_t)(s2 == 3) << m[i];
-                vv |= 1;
-                val[i] = sample_value((vv >> 1) + 1, sign, shift, step, IRREV);
-                if (i & 1) en[i >> 1] = 32 - __clz((int)vv);
-                p += (uint32_t)m[i];
-            }
-        }
-        Eb0 = en[0]; Eb1 = en[1];
-        if (active) {
-            const int y = 2 * r;
-            const bool row2 = (y + 1 < h);
-            OT *p0 = out + (size_t)y * ostride + 2 * lane;
-            if (colB && vec_ok) {
-                if (sizeof(OT) == 4) {
-                    *reinterpret_cast<int2 *>(p0) = make_int2(val[0], val[2]);
-                    if (row2) *reinterpret_cast<int2 *>(p0 + ostride) = make_int2(val[1], val[3]);
-                } else {
-                    *reinterpret_cast<uint32_t *>(p0) = ((uint32_t)val[0] & 0xFFFFu) | ((uint32_t)val[2] << 16);
-                    if (row2) *reinterpret_cast<uint32_t *>(p0 + ostride) = ((uint32_t)val[1] & 0xFFFFu) | ((uint32_t)val[3] << 16);
-                }
-            } else {
-                p0[0] = (OT)val[0];
-                if (colB) p0[1] = (OT)val[2];
-                if (row2) { p0[ostride] = (OT)val[1]; if (colB) p0[ostride + 1] = (OT)val[3]; }
-            }
-        }
-    }
-    if (__any_sync(0xffffffffu, bad)) {
-        __syncwarp();
-        for (int y = 0; y < h; y++)
-            for (int x = lane; x < w; x += 32) out[(size_t)y * ostride + x] = 0;
-    }
 }
 
 // B', the default: TWO blocks per warp, one per half-warp, each lane two neighbouring quads (4 columns) of a quad row.
@@ -847,40 +448,27 @@ k_htiso_magsgn2(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__
 }  // namespace
 
 size_t j2k_htiso_scratch_bytes(uint32_t n) { return (size_t)n * (kQTabWords * 4 + 4) + 16; }
+int j2k_htiso_launches() { return 2; }
 
 template <typename OT>
 static void launch_ht_iso_t(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, OT *d_coef,
-                            const float *d_steps, int irrev, int coef_bits, int blocks_per_warp, void *d_scratch, uint64_t blob_bytes, cudaStream_t s)
+                            const float *d_steps, int irrev, int coef_bits, void *d_scratch, uint64_t blob_bytes, cudaStream_t s)
 {
     if ((uintptr_t)d_blob & 3) blob_bytes = 0;           // unaligned blob: byte loads only
-    if (blocks_per_warp == 2) {
-        uint32_t *qtab = (uint32_t *)d_scratch, *status = qtab + (size_t)n * kQTabWords;
-        J2K_LAUNCH((k_htiso_vlc), (n + kThreads - 1) / kThreads, kThreads, 0, s, d_cblks, n, d_blob, blob_bytes, qtab, status);
-        static const bool one_block_per_warp = getenv("J2KGPU_HT_B1") != nullptr;       // the first version of kernel B, for A/B runs
-        if (one_block_per_warp) {
-            const uint32_t grid = (n + kWarpsIsoB - 1) / kWarpsIsoB;
-            if (irrev) J2K_LAUNCH((k_htiso_magsgn<OT, true>), grid, kWarpsIsoB * 32, 0, s, d_cblks, n, d_blob, qtab, status, d_coef, d_steps, coef_bits);
-            else J2K_LAUNCH((k_htiso_magsgn<OT, false>), grid, kWarpsIsoB * 32, 0, s, d_cblks, n, d_blob, qtab, status, d_coef, d_steps, coef_bits);
-        } else {
-            const uint32_t grid = (n + 2 * kWarpsIsoB2 - 1) / (2 * kWarpsIsoB2);
-            if (irrev) J2K_LAUNCH((k_htiso_magsgn2<OT, true>), grid, kWarpsIsoB2 * 32, 0, s, d_cblks, n, d_blob, qtab, status, d_coef, d_steps, coef_bits);
-            else J2K_LAUNCH((k_htiso_magsgn2<OT, false>), grid, kWarpsIsoB2 * 32, 0, s, d_cblks, n, d_blob, qtab, status, d_coef, d_steps, coef_bits);
-        }
-    } else if (blocks_per_warp == 32) {
-        J2K_LAUNCH((k_ht_iso<32, OT>), (n + kThreads - 1) / kThreads, kThreads, 0, s, d_cblks, n, d_blob, d_coef, d_steps, irrev, coef_bits);
-    } else {
-        const uint32_t per = kThreads / 32;
-        J2K_LAUNCH((k_ht_iso<1, OT>), (n + per - 1) / per, kThreads, 0, s, d_cblks, n, d_blob, d_coef, d_steps, irrev, coef_bits);
-    }
+    uint32_t *qtab = (uint32_t *)d_scratch, *status = qtab + (size_t)n * kQTabWords;
+    J2K_LAUNCH((k_htiso_vlc), (n + kThreads - 1) / kThreads, kThreads, 0, s, d_cblks, n, d_blob, blob_bytes, qtab, status);
+    const uint32_t grid = (n + 2 * kWarpsIsoB2 - 1) / (2 * kWarpsIsoB2);
+    if (irrev) J2K_LAUNCH((k_htiso_magsgn2<OT, true>), grid, kWarpsIsoB2 * 32, 0, s, d_cblks, n, d_blob, qtab, status, d_coef, d_steps, coef_bits);
+    else J2K_LAUNCH((k_htiso_magsgn2<OT, false>), grid, kWarpsIsoB2 * 32, 0, s, d_cblks, n, d_blob, qtab, status, d_coef, d_steps, coef_bits);
 }
 
-// blocks_per_warp: 2 = the two-kernel mapping (needs d_scratch of j2k_htiso_scratch_bytes(n)), 32 / 1 = single kernel
+// d_scratch: j2k_htiso_scratch_bytes(n) bytes of device memory (quad table + status between the two kernels)
 cudaError_t launch_ht_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
-                          const float *d_steps, int irrev, int coef_bits, int blocks_per_warp, void *d_scratch, uint64_t blob_bytes,
+                          const float *d_steps, int irrev, int coef_bits, void *d_scratch, uint64_t blob_bytes,
                           cudaStream_t s)
 {
     if (n == 0) return cudaSuccess;
-    if (coef16 && !irrev) launch_ht_iso_t<int16_t>(d_cblks, n, d_blob, (int16_t *)d_coef, d_steps, irrev, coef_bits, blocks_per_warp, d_scratch, blob_bytes, s);
-    else launch_ht_iso_t<int32_t>(d_cblks, n, d_blob, (int32_t *)d_coef, d_steps, irrev, coef_bits, blocks_per_warp, d_scratch, blob_bytes, s);
+    if (coef16 && !irrev) launch_ht_iso_t<int16_t>(d_cblks, n, d_blob, (int16_t *)d_coef, d_steps, irrev, coef_bits, d_scratch, blob_bytes, s);
+    else launch_ht_iso_t<int32_t>(d_cblks, n, d_blob, (int32_t *)d_coef, d_steps, irrev, coef_bits, d_scratch, blob_bytes, s);
     return cudaGetLastError();
 }

@@ -368,6 +368,20 @@ __global__ void k_inverse_ict_f64(double *y, double *cb, double *cr, uint64_t n)
     }
 }
 
+// pixels no tile covers: the reference's planes are zero there (decoder.go:305-309), so they hold the pixel that zero
+// coefficients decode to; `pattern` = that pixel (bpp bytes, produced by k_tail on a 1 x 1 zero image)
+__global__ void k_fill_pixels(uint8_t *pix, uint64_t out_stride, uint32_t row_bytes, uint32_t rows, int bpp, const uint8_t *pattern)
+{
+    const uint8_t p0 = pattern[0], p1 = pattern[1 % bpp], p2 = pattern[2 % bpp], p3 = pattern[3 % bpp],
+                  p4 = pattern[4 % bpp], p5 = pattern[5 % bpp], p6 = pattern[6 % bpp], p7 = pattern[7 % bpp];
+    const uint8_t pat[8] = {p0, p1, p2, p3, p4, p5, p6, p7};
+    const uint64_t n = (uint64_t)row_bytes * rows;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t y = (uint32_t)(i / row_bytes), x = (uint32_t)(i - (uint64_t)y * row_bytes);
+        pix[(size_t)y * out_stride + x] = pat[x % (uint32_t)bpp];
+    }
+}
+
 template <class L>
 constexpr size_t patch_bytes() { return sizeof(typename L::T) * (size_t)(TH + 2 * L::HALO) * (TW + 2 * L::HALO + 1); }
 
@@ -433,6 +447,17 @@ cudaError_t launch_tail(const int32_t *const d_comps[4], int32_t *const d_planes
                                   d_planes_out ? d_planes_out[0] : nullptr, d_planes_out ? d_planes_out[1] : nullptr,
                                   d_planes_out ? d_planes_out[2] : nullptr, d_planes_out ? d_planes_out[3] : nullptr,
                                   d_pix, out_stride, width, height, tp, apply_tail);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fill_pixels(uint8_t *d_pix, uint64_t out_stride, uint32_t row_bytes, uint32_t rows, int bpp,
+                               const uint8_t *d_pattern, cudaStream_t s)
+{
+    const uint64_t n = (uint64_t)row_bytes * rows;
+    if (n == 0) return cudaSuccess;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    J2K_LAUNCH((k_fill_pixels), blocks, 256, 0, s, d_pix, out_stride, row_bytes, rows, bpp, d_pattern);
     return cudaGetLastError();
 }
 

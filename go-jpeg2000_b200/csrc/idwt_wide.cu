@@ -514,7 +514,7 @@ cudaError_t launch_idwt53_wide(const IdwtLaunch &p, cudaStream_t s)
     const uint64_t min_warps = 148ull * 8 * (p.iso ? 4 : 8);
     int sp = 64;
     while (sp > 8 && (uint64_t)p.n_tiles * nwx * ((nly + sp - 1) / sp) < min_warps) sp >>= 1;
-    if (const char *e = getenv("J2KGPU_WIDE_SP")) { const int v = atoi(e); if (v >= 2) sp = v & ~1; }
+    if (p.wide_sp >= 2) sp = p.wide_sp & ~1;             // J2kOpts.wide_sp: A/B runs
     const uint32_t units = nwx * ((nly + sp - 1) / sp);
     dim3 grid((units + kWarps - 1) / kWarps, p.n_tiles, 1);
     if (p.tail.ncomp == 1) return p.coef16 ? run_ct<1, int16_t>(p, grid, sp, s) : run_ct<1, int32_t>(p, grid, sp, s);

@@ -543,12 +543,20 @@ int zc_context(int band, int hc, int vc, int dc)                 // t1_luts.go:5
     return dc >= 2 ? 1 : 0;
 }
 
-cudaError_t upload_tables()
+// __constant__ symbols exist once per device: the tables are uploaded once per device of the process, on the launching
+// stream (ordered before the first kernel that reads them; later launches on other streams of the same device happen
+// after this call has returned, and the copies out of the pageable host arrays below are staged before it returns --
+// the final synchronise makes the first upload visible to every stream)
+cudaError_t upload_tables(cudaStream_t s)
 {
-    static bool done = false;
+    static bool done[64] = {};
     static std::mutex mu;
     std::lock_guard<std::mutex> g(mu);
-    if (done) return cudaSuccess;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (done[dev]) return cudaSuccess;
     uint32_t mq[94];
     for (int i = 0; i < 47; i++)
         for (int m = 0; m < 2; m++) {
@@ -614,13 +622,13 @@ cudaError_t upload_tables()
         int ctx = hc == 1 ? (vc == 1 ? 4 : (vc == 0 ? 3 : 2)) : (vc == 1 ? 1 : 0);      // contexts 9..13, minus 9
         sci[i] = (uint8_t)((ctx << 1) | flip);
     }
-    cudaError_t e;
-    if ((e = cudaMemcpyToSymbol(c_zc9_iso, zci, sizeof zci)) != cudaSuccess) return e;
-    if ((e = cudaMemcpyToSymbol(c_sc_iso, sci, sizeof sci)) != cudaSuccess) return e;
-    if ((e = cudaMemcpyToSymbol(c_mq, mq, sizeof mq)) != cudaSuccess) return e;
-    if ((e = cudaMemcpyToSymbol(c_zc9, zc, sizeof zc)) != cudaSuccess) return e;
-    if ((e = cudaMemcpyToSymbol(c_sc, sc, sizeof sc)) != cudaSuccess) return e;
-    done = true;
+    if ((e = cudaMemcpyToSymbolAsync(c_zc9_iso, zci, sizeof zci, 0, cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbolAsync(c_sc_iso, sci, sizeof sci, 0, cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbolAsync(c_mq, mq, sizeof mq, 0, cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbolAsync(c_zc9, zc, sizeof zc, 0, cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbolAsync(c_sc, sc, sizeof sc, 0, cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+    done[dev] = true;
     return cudaSuccess;
 }
 
@@ -630,7 +638,7 @@ static cudaError_t launch_t1_ref_impl(const DevCblk *d_cblks, uint32_t n, const 
                                       int max_bps, int skip_empty, cudaStream_t s)
 {
     if (n == 0) return cudaSuccess;
-    cudaError_t e = upload_tables();
+    cudaError_t e = upload_tables(s);
     if (e != cudaSuccess) return e;
     if (max_bps < 1) max_bps = 1;
     int plane_words = 64 * max_bps;
@@ -667,7 +675,7 @@ cudaError_t launch_t1_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_b
                           const float *d_steps, int irrev, int max_bps, cudaStream_t s)
 {
     if (n == 0) return cudaSuccess;
-    cudaError_t e = upload_tables();
+    cudaError_t e = upload_tables(s);
     if (e != cudaSuccess) return e;
     if (max_bps < 1) max_bps = 1;
     const int plane_words = 64 * max_bps;

@@ -39,7 +39,7 @@ extern "C" {
 #define J2KGPU_CS_YCCK   6   /* ColorSpaceYCCK, 4 components (colorspace.go:219-250)                                 */
 /* not built (they need pow / cube roots whose last bit differs between libms): CIELab, CIEJab, e-sRGB, ROMM-RGB */
 
-#define J2KGPU_ABI_VERSION 3
+#define J2KGPU_ABI_VERSION 4
 
 /* ---- status codes ---------------------------------------------------------- */
 enum {
@@ -113,8 +113,13 @@ typedef struct {
     uint8_t  band;              /* J2KGPU_BAND_*                                             */
     uint8_t  level;             /* decomposition level of the band (ISO mode)                */
     uint8_t  num_bps;           /* CodeBlock.TotalBitPlanes: bit length of max|x|            */
-    uint8_t  num_passes;        /* ISO mode: coding passes present (0 = all); REF: ignored   */
+    uint8_t  num_passes;        /* ISO mode: coding passes present (0 = all); REF: ignored.  HT blocks: 1 = cleanup,
+                                 * 2 = + SigProp, 3 = + SigProp + MagRef (one HT set, T.814 clause 7)           */
     float    step;              /* ISO mode dequantisation step; REF: ignored                */
+    uint32_t len_cleanup;       /* ISO mode, HT blocks with num_passes > 1 (ABI v4): the data is the cleanup segment
+                                 * (Lcup = len_cleanup bytes) followed by the refinement segment (SigProp bytes
+                                 * forward, MagRef bytes backward; data_len - len_cleanup bytes).  0 = data_len  */
+    uint32_t rsv;               /* set 0                                                     */
 } j2k_cblk_t;
 
 /* one image of a batch (cfg5: many frames, one call) */
@@ -124,7 +129,17 @@ typedef struct {
     const j2k_cblk_t     *cblks;      uint32_t n_cblks;
     const uint8_t        *blob;       uint64_t blob_len;
     uint8_t              *out_pix;    uint64_t out_stride;   /* bytes per output row          */
+    uint32_t              flags;      /* J2KGPU_ITEM_* (ABI v4)                               */
+    uint32_t              rsv;        /* set 0                                                 */
 } j2k_batch_item_t;
+
+/* j2k_batch_item_t.flags */
+/* The item carries only SOME tiles of its image (large-image tile sharding, SURVEY.md 8e: the tile loop of
+ * decoder.go:315-319 split over several contexts / GPUs).  Only the pixel rectangles those tiles cover are written to
+ * out_pix (decoder.go:398-410 copies tile by tile); the rest of the buffer is not touched, so that contexts given
+ * disjoint tile subsets of ONE image fill one shared host buffer.  Without the flag a call writes the whole image and
+ * pixels no tile covers hold what the reference's zero-initialised planes decode to (decoder.go:305-309). */
+#define J2KGPU_ITEM_TILES_ONLY 1u
 
 /* stage-level block job (entropy stage in isolation) */
 typedef struct {
@@ -132,8 +147,10 @@ typedef struct {
     uint32_t out_off;           /* element offset into the int32 output array               */
     uint16_t w, h;
     uint8_t  band, num_bps;
-    uint8_t  rsv0;              /* ISO mode, EBCOT: number of coding passes to decode (0 = all); else 0 */
+    uint8_t  rsv0;              /* ISO mode: number of coding passes to decode (0 = all; HT: 1..3); else 0 */
     uint8_t  rsv1;
+    uint32_t len_cleanup;       /* ISO mode, HT, passes > 1: Lcup (see j2k_cblk_t.len_cleanup); 0 = data_len */
+    uint32_t rsv2;              /* set 0 */
 } j2k_blkjob_t;
 
 typedef struct j2kgpu_ctx j2kgpu_ctx;
@@ -148,6 +165,10 @@ const char *j2kgpu_last_error(const j2kgpu_ctx *ctx);
 /* Use an externally owned CUDA stream (cudaStream_t, e.g. torch's current stream)
  * for all work of this ctx; NULL restores the ctx's own stream. */
 int         j2kgpu_set_stream(j2kgpu_ctx *ctx, void *cuda_stream);
+/* A/B switches and test hooks (no_fuse, no_wide, no_fast_epi, coef32, no_preclear, wide_sp, debug_plan, chunks).  Their
+ * initial values come from the environment variables J2KGPU_<NAME>, read once in j2kgpu_create; nothing else in the
+ * library reads the environment. */
+int         j2kgpu_set_option(j2kgpu_ctx *ctx, const char *name, const char *value);
 /* kernels launched by this ctx since creation (bench.py's gpu_launches) */
 uint64_t    j2kgpu_launch_count(const j2kgpu_ctx *ctx);
 

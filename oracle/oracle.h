@@ -97,6 +97,7 @@ typedef struct {
     uint32_t tilecomp; uint16_t x0, y0, w, h;
     uint8_t band, level, num_bps, num_passes;
     float step;
+    uint32_t len_cleanup, rsv;
 } orc_cblk_t;                 /* same layout as j2k_cblk_t (include/j2kgpu.h) */
 typedef struct {
     uint32_t comp, x0, y0, x1, y1;

@@ -28,7 +28,7 @@ class CBlk(C.Structure):  # == j2k_cblk_t
     _fields_ = [("data_off", C.c_uint64), ("data_len", C.c_uint32), ("tilecomp", C.c_uint32),
                 ("x0", C.c_uint16), ("y0", C.c_uint16), ("w", C.c_uint16), ("h", C.c_uint16),
                 ("band", C.c_uint8), ("level", C.c_uint8), ("num_bps", C.c_uint8), ("num_passes", C.c_uint8),
-                ("step", C.c_float)]
+                ("step", C.c_float), ("len_cleanup", C.c_uint32), ("rsv", C.c_uint32)]
 
 
 class TileComp(C.Structure):  # == j2k_tilecomp_t

@@ -22,15 +22,15 @@ def test_library_exports_every_declared_symbol(j2k):
     for n in names:
         assert hasattr(L, n), n
     assert sorted(j2k.EXPORTS) == names
-    assert L.j2kgpu_abi_version() == 3
+    assert L.j2kgpu_abi_version() == 4
 
 
 def test_struct_layouts(j2k):
     assert C.sizeof(j2k.Image) == 28 and j2k.Image.coef_bits.offset == 24
     assert C.sizeof(j2k.TileComp) == 32 and j2k.TileComp.coeff_off.offset == 24
-    assert C.sizeof(j2k.CBlk) == 32 and j2k.CBlk.step.offset == 28 and j2k.CBlk.band.offset == 24
-    assert C.sizeof(j2k.BlkJob) == 24
-    assert C.sizeof(j2k.BatchItem) == 96 and j2k.BatchItem.out_stride.offset == 88
+    assert C.sizeof(j2k.CBlk) == 40 and j2k.CBlk.step.offset == 28 and j2k.CBlk.band.offset == 24 and j2k.CBlk.len_cleanup.offset == 32
+    assert C.sizeof(j2k.BlkJob) == 32 and j2k.BlkJob.len_cleanup.offset == 24
+    assert C.sizeof(j2k.BatchItem) == 104 and j2k.BatchItem.out_stride.offset == 88 and j2k.BatchItem.flags.offset == 96
 
 
 def test_strerror(j2k):

@@ -27,12 +27,8 @@ def test_iso_ht_blocks_vs_oracle(gpu_ctx):
         nbps = int(rng.integers(1, 4))
         blocks.append((enc, w, h, nbps, 0))
         want.append(d << (nbps - 1))
-    for mp in ("2", "32", "1"):
-        import os
-        os.environ["J2KGPU_HT_MAP"] = mp                       # two-kernel (default), thread-per-block and warp-per-block mappings
-        for i, (got, w_) in enumerate(zip(gpu_ctx.ht_decode_blocks(blocks, mode=ISO), want)):
-            assert np.array_equal(got, w_), (mp, i)
-    os.environ.pop("J2KGPU_HT_MAP", None)
+    for i, (got, w_) in enumerate(zip(gpu_ctx.ht_decode_blocks(blocks, mode=ISO), want)):
+        assert np.array_equal(got, w_), i
 
 
 def test_iso_ht_garbage_vs_oracle(gpu_ctx):

@@ -145,19 +145,11 @@ def _run_items(j2k, ctx, jl, env=None, mode=0, coef_bits=0):
                              reversible=j["reversible"], nlevels=j["nlevels"], ht=j["ht"], mode=mode, coef_bits=coef_bits)
         items.append(j2k.BatchItem(img, tcs, len(tcs), cbs, len(cbs), blob.ctypes.data_as(j2k.u8p), blob.size,
                                    out.ctypes.data_as(j2k.u8p), j["width"] * bpp))
-    old = {k: os.environ.get(k) for k in (env or {})}
-    os.environ.update(env or {})
-    try:
+    with ctx.options(**{k[len("J2KGPU_"):].lower(): v for k, v in (env or {}).items()}):
         job = j2k.Job(ctx, items)
-    finally:
-        for k, v in old.items():
-            if v is None:
-                os.environ.pop(k, None)
-            else:
-                os.environ[k] = v
-    flags = (job.fused_levels, job.coef_bytes, job.plan)
-    job.run_host()
-    job.close()
+        flags = (job.fused_levels, job.coef_bytes, job.plan)
+        job.run_host()
+        job.close()
     return outs, flags
 
 
@@ -220,17 +212,10 @@ def test_host_run_is_independent_of_the_chunk_plan(j2k, gpu_ctx, ht):
     jl = [jobs.build_ref_job(jobs.synth_image(96, 64, 3, 8, seed=900 + i), 8, 32, 32, nlevels=2, reversible=True,
                              ht=bool(ht), threads=2) for i in range(7)]
     want = [oracle_pixels(j) for j in jl]
-    try:
-        for plan in (None, "7", "1,1,1,1,1,1,1", "2,4,1", "3"):
-            if plan is None:
-                os.environ.pop("J2KGPU_CHUNKS", None)
-            else:
-                os.environ["J2KGPU_CHUNKS"] = plan
-            outs, _ = _run_items(j2k, gpu_ctx, jl)
-            for o, wnt in zip(outs, want):
-                assert np.array_equal(o, wnt), plan
-    finally:
-        os.environ.pop("J2KGPU_CHUNKS", None)
+    for plan in ("", "7", "1,1,1,1,1,1,1", "2,4,1", "3"):
+        outs, _ = _run_items(j2k, gpu_ctx, jl, {"J2KGPU_CHUNKS": plan})
+        for o, wnt in zip(outs, want):
+            assert np.array_equal(o, wnt), plan
 
 
 @pytest.mark.parametrize("w,h,prec,tw,levels,rev,ht,cs", [

@@ -63,6 +63,6 @@ def test_lossy_path_is_close():
 
 
 def test_job_tables_are_abi_sized():
-    assert jobs.CBLK_DT.itemsize == C.sizeof(O.CBlk) == 32
+    assert jobs.CBLK_DT.itemsize == C.sizeof(O.CBlk) == 40
     assert jobs.TILECOMP_DT.itemsize == C.sizeof(O.TileComp) == 32
     assert C.sizeof(O.Image) == 28                      # == j2k_image_t (include/j2kgpu.h)

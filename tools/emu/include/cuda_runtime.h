@@ -189,7 +189,7 @@ template <class T> static inline T atomicOr(T *p, T v) { T o = *p; *p = o | v; r
 
 // ---- runtime API (synchronous, host memory) ---------------------------------------------------------------
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2 };
+enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2, cudaErrorInvalidDevice = 101 };
 typedef struct emu_stream *cudaStream_t;
 typedef struct emu_event *cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
@@ -200,6 +200,7 @@ static inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSu
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+static inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
 // exact size (posix_memalign): under AddressSanitizer (make asan) any access past the requested bytes is reported
 static inline cudaError_t cudaMalloc(void **p, size_t n) { return posix_memalign(p, 256, n ? n : 1) == 0 ? cudaSuccess : cudaErrorMemoryAllocation; }
 template <class T> static inline cudaError_t cudaMalloc(T **p, size_t n) { return cudaMalloc((void **)p, n); }
@@ -223,4 +224,11 @@ static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cuda
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
 template <class T> static inline cudaError_t cudaMemcpyToSymbol(T &sym, const void *src, size_t n) { memcpy(&sym, src, n); return cudaSuccess; }
+template <class T> static inline cudaError_t cudaMemcpyToSymbolAsync(T &sym, const void *src, size_t n, size_t, cudaMemcpyKind, cudaStream_t) { memcpy(&sym, src, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpy2DAsync(void *d, size_t dp, const void *s, size_t sp, size_t w, size_t h, cudaMemcpyKind, cudaStream_t = nullptr)
+{
+    for (size_t y = 0; y < h; y++) memmove((char *)d + y * dp, (const char *)s + y * sp, w);
+    return cudaSuccess;
+}
+enum { cudaHostAllocDefault = 0 };
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
