@@ -41,6 +41,7 @@ def lib():
         _lib.gen_ht_encode.restype = C.c_int
         _lib.gen_encode_blocks.restype = C.c_int64
         _lib.gen_iso_ht_encode.restype = C.c_int
+        _lib.gen_iso_ht_encode_passes.restype = C.c_int
     return _lib
 
 
@@ -87,6 +88,20 @@ def iso_ht_encode(coeffs, w, h):
     if n < 0:
         raise ValueError("HT encode failed (magnitude too large?)")
     return out[:n].tobytes()
+
+
+def iso_ht_encode_passes(coeffs, w, h, P, npasses):
+    """one HT set (T.814): cleanup at bit-plane P, SigProp (npasses >= 2) and MagRef (npasses == 3) at bit-plane P - 1
+    -> (bytes = cleanup segment + refinement segment, Lcup, expected reconstruction in quarter units, signed)"""
+    c = np.ascontiguousarray(coeffs, np.int32).reshape(-1)
+    assert c.size == w * h
+    out = np.zeros(w * h * 6 + 8192, np.uint8)
+    recon = np.zeros(w * h, np.int32)
+    lcup = C.c_int(0)
+    n = lib().gen_iso_ht_encode_passes(_p(c, i32p), w, h, P, npasses, _p(out, u8p), len(out), C.byref(lcup), _p(recon, i32p))
+    if n < 0:
+        raise ValueError("HT encode failed")
+    return out[:n].tobytes(), lcup.value, recon
 
 
 def _inplace(fn, arr, *args):

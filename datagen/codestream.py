@@ -15,7 +15,7 @@ import struct
 
 import numpy as np
 
-from . import fwd2d53, iso_ht_encode
+from . import fwd2d53, iso_ht_encode, iso_ht_encode_passes
 
 SOC, SIZ, CAP, COD, QCD, SOT, SOD, EOC, COM = 0xFF4F, 0xFF51, 0xFF50, 0xFF52, 0xFF5C, 0xFF90, 0xFF93, 0xFFD9, 0xFF64
 
@@ -255,10 +255,25 @@ def forward_tile_iso_97(samples, prec, nlevels, mct):
 
 
 # ------------------------------------------------------------------------------------------------ writer
-def write_htj2k(samples, prec, tile_w=None, tile_h=None, nlevels=5, mct=1, cb=64, guard=2, extra_eps=1, lossy_step=None):
+def _put_npasses(bw, n):
+    """number of coding passes codeword (B.10.6), n = 1..5"""
+    if n == 1:
+        bw.put(0)
+    elif n == 2:
+        bw.bits(2, 2)
+    else:
+        bw.bits(0b1100 + (n - 3), 4)
+
+
+def write_htj2k(samples, prec, tile_w=None, tile_h=None, nlevels=5, mct=1, cb=64, guard=2, extra_eps=1, lossy_step=None,
+                ht_passes=1, ht_plane=0):
     """samples int [ncomp, H, W] -> (codestream bytes, info dict with per-block tables for ISO jobs).
     lossy_step = None: lossless 5-3 + RCT.  lossy_step = s (a power of two, e.g. 2.0 or 0.5): irreversible 9-7 + ICT with
-    the dead-zone quantiser of Annex E and the same step s in every band (scalar expounded QCD, mantissa 0)."""
+    the dead-zone quantiser of Annex E and the same step s in every band (scalar expounded QCD, mantissa 0).
+    ht_passes = 2 or 3 with ht_plane = P >= 1: every block is one HT set of a cleanup pass at bit-plane P plus SigProp
+    (and MagRef) passes at bit-plane P - 1; the packet header then carries two lengths (cleanup segment, refinement
+    segment) and P fewer missing bit-planes.  Such a stream is lossy by up to 2^(P-1) in the coefficient domain (isolated
+    small coefficients belong to no pass of the set)."""
     ncomp, H, W = samples.shape
     tile_w, tile_h = tile_w or W, tile_h or H
     ntx, nty = cdiv(W, tile_w), cdiv(H, tile_h)
@@ -313,9 +328,14 @@ def write_htj2k(samples, prec, tile_w=None, tile_h=None, nlevels=5, mct=1, cb=64
                         for (cx0, cy0, cx1, cy1) in cbs:
                             px, py = ox + cx0 - bx0, oy + cy0 - by0
                             blk = planes[c][py:py + cy1 - cy0, px:px + cx1 - cx0]
-                            data = iso_ht_encode(blk, cx1 - cx0, cy1 - cy0)
+                            lcup = 0
+                            if ht_passes > 1 or ht_plane:
+                                data, lcup, _ = iso_ht_encode_passes(blk, cx1 - cx0, cy1 - cy0, ht_plane, ht_passes)
+                            else:
+                                data = iso_ht_encode(blk, cx1 - cx0, cy1 - cy0)
                             entries.append(dict(data=data, px=px, py=py, w=cx1 - cx0, h=cy1 - cy0, band=b, level=l,
-                                                mb=mb, comp=c, tile=tidx, res=r))
+                                                mb=mb, comp=c, tile=tidx, res=r, lcup=lcup or len(data),
+                                                passes=(ht_passes if len(data) > (lcup or len(data)) else 1) if data else 0))
                         per_band.append((entries, gw, gh, mb, bx0 // cb, by0 // cb, cbs))
                     bw = BitWriter()
                     if not any(e["data"] for pb in per_band for e in pb[0]):
@@ -334,7 +354,7 @@ def write_htj2k(samples, prec, tile_w=None, tile_h=None, nlevels=5, mct=1, cb=64
                         for k, e in enumerate(entries):
                             gx, gy = k % gw, k // gw
                             iv[gy, gx] = 0 if e["data"] else 1
-                            mv[gy, gx] = mb - 1                # HT cleanup carries every magnitude bit: P = Mb - 1
+                            mv[gy, gx] = mb - 1 - ht_plane     # HT cleanup at bit-plane P carries every bit above it: Mb - 1 - P missing
                         incl.set_values(iv)
                         imsb.set_values(mv)
                         for k, e in enumerate(entries):
@@ -343,14 +363,19 @@ def write_htj2k(samples, prec, tile_w=None, tile_h=None, nlevels=5, mct=1, cb=64
                             if not e["data"]:
                                 continue
                             imsb.encode(bw, gx, gy, 1 << 20)
-                            bw.put(0)                          # one coding pass
-                            n = len(e["data"])
+                            npass = e["passes"]
+                            _put_npasses(bw, npass)
+                            # HT: the cleanup pass is one codeword segment, SigProp + MagRef together the second (T.814 B.10.7)
+                            n1, n2 = e["lcup"], len(e["data"]) - e["lcup"]
+                            x2 = (npass - 1).bit_length() - 1 if npass > 1 else 0
                             lblock = 3
-                            while n >= (1 << lblock):
+                            while n1 >= (1 << lblock) or (npass > 1 and n2 >= (1 << (lblock + x2))):
                                 bw.put(1)
                                 lblock += 1
                             bw.put(0)
-                            bw.bits(n, lblock)
+                            bw.bits(n1, lblock)
+                            if npass > 1:
+                                bw.bits(n2, lblock + x2)
                             pkt_blocks.append(e["data"])
                         blocks_info += entries
                     body += bw.finish()
@@ -502,8 +527,18 @@ def parse_codestream(data):
                         n = _npasses(br)
                         while br.get():
                             e["lblock"] += 1
-                        nbits = e["lblock"] + (n.bit_length() - 1)
-                        ln = br.bits(nbits)
+                        if hdr["ht"]:
+                            # HT (T.814 B.10.7): the cleanup pass is a codeword segment of its own, the SigProp and MagRef
+                            # passes share the second one
+                            if e["passes"] or n > 3:
+                                raise ValueError("more than one HT set per code block")
+                            ln = br.bits(e["lblock"])
+                            e["lcup"] = ln
+                            if n > 1:
+                                ln += br.bits(e["lblock"] + ((n - 1).bit_length() - 1))
+                        else:
+                            nbits = e["lblock"] + (n.bit_length() - 1)
+                            ln = br.bits(nbits)
                         e["passes"] += n
                         segs.append((e, ln))
             p = br.align()

@@ -22,6 +22,10 @@ int  gen_t1_encode(const int32_t *coeffs, int w, int h, int band, uint8_t *out, 
 int  gen_ht_encode(const int32_t *coeffs, int w, int h, int band, uint8_t *out, int cap);
 /* ISO/IEC 15444-15 HT cleanup-pass encoder (conformant; see gen_iso_ht.c) */
 int  gen_iso_ht_encode(const int32_t *coeffs, int w, int h, uint8_t *out, int cap);
+/* one HT set: cleanup at bit-plane P, + SigProp (npasses >= 2) + MagRef (npasses == 3) at bit-plane P - 1; returns
+ * Lcup + Lref (0: nothing significant at bit-plane P), *lcup = Lcup; see gen_iso_ht.c */
+int  gen_iso_ht_encode_passes(const int32_t *coeffs, int w, int h, int P, int npasses, uint8_t *out, int cap,
+                              int *lcup, int32_t *recon);
 void gen_fwd53(int32_t *d, int n);                              /* dwt.go:73-118  */
 void gen_fwd97(double *d, int n);                               /* dwt.go:161-210 */
 void gen_fwd2d53(int32_t *d, int w, int h);                     /* dwt.go:356-407 */

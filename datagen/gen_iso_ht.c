@@ -298,3 +298,94 @@ int gen_iso_ht_encode(const int32_t *coef, int w, int h, uint8_t *out, int cap)
     free(msb); free(melb); free(vlcb); free(sg); free(ex); free(nsg); free(nex);
     return ret;
 }
+
+/* ---- HT refinement passes (T.814 clause 7.4 SigProp, 7.5 MagRef) -------------------------------------------------
+ * One HT set: the cleanup pass codes mu = |x| >> P (all bit-planes >= P), the SigProp and MagRef passes code
+ * bit-plane P - 1.  SigProp: 4-row stripes, groups of 4 columns, column by column, top to bottom; a sample that is
+ * insignificant after the cleanup pass and has a significant neighbour (cleanup significance of all 8 neighbours,
+ * plus SigProp significance of the ones already visited) gets one bit; the sign bits of the samples that turned
+ * significant follow after the group's (up to 16) significance bits.  Bits go LSB first into a forward-growing
+ * stream with 7 bits after a 0xFF byte.  MagRef: one bit per cleanup-significant sample in stripe scan order, LSB
+ * first into a stream that grows backward from the end of the refinement segment (the VLC stuffing rule, with the
+ * byte after the end of the segment taken as 0xFF).  The refinement segment = SigProp bytes, then MagRef bytes.
+ * recon (optional, w * h): what a conformant decoder reconstructs, in quarter units (integer LSB = bit 2) with the
+ * mid-point bit below the last decoded bit-plane, signed: the writer's own statement of the expected result. */
+int gen_iso_ht_encode_passes(const int32_t *coef, int w, int h, int P, int npasses, uint8_t *out, int cap,
+                             int *lcup_out, int32_t *recon)
+{
+    if (npasses < 1 || npasses > 3 || P < 0 || P > 20 || (npasses > 1 && P < 1)) return -1;
+    const int n = w * h;
+    int32_t *mu = malloc(sizeof(int32_t) * (size_t)n);
+    for (int i = 0; i < n; i++) {
+        const int32_t a = coef[i] < 0 ? -coef[i] : coef[i];
+        mu[i] = coef[i] < 0 ? -(a >> P) : (a >> P);
+    }
+    const int lcup = gen_iso_ht_encode(mu, w, h, out, cap);
+    if (lcup_out) *lcup_out = lcup > 0 ? lcup : 0;
+    if (recon) memset(recon, 0, sizeof(int32_t) * (size_t)n);
+    if (lcup <= 0) { free(mu); return lcup; }
+    if (recon)
+        for (int i = 0; i < n; i++)
+            if (mu[i]) {
+                const int32_t m = mu[i] < 0 ? -mu[i] : mu[i];
+                const int32_t q = (2 * m + 1) << (P + 1);
+                recon[i] = mu[i] < 0 ? -q : q;
+            }
+    if (npasses == 1) { free(mu); return lcup; }
+
+    const int seg = n / 2 + 64;
+    uint8_t *sppb = malloc((size_t)seg), *mrpb = malloc((size_t)seg);
+    uint8_t *sspp = calloc((size_t)n, 1);
+    msw_t spp = {sppb, seg, 0, 0, 0, 8, 0};
+    vlcw_t mrp = {mrpb + seg - 1, seg, 0, 0, 0, 1, 0};
+    for (int y0 = 0; y0 < h; y0 += 4)
+        for (int x0 = 0; x0 < w; x0 += 4) {
+            int newi[16], nnew = 0;
+            for (int x = x0; x < x0 + 4 && x < w; x++)
+                for (int y = y0; y < y0 + 4 && y < h; y++) {
+                    const int i = y * w + x;
+                    if (mu[i]) continue;
+                    int mbr = 0;
+                    for (int dy = -1; dy <= 1; dy++)
+                        for (int dx = -1; dx <= 1; dx++) {
+                            const int yy = y + dy, xx = x + dx;
+                            if ((dy || dx) && yy >= 0 && yy < h && xx >= 0 && xx < w && (mu[yy * w + xx] || sspp[yy * w + xx])) mbr = 1;
+                        }
+                    if (!mbr) continue;
+                    const int32_t a = coef[i] < 0 ? -coef[i] : coef[i];
+                    const int bit = (a >> (P - 1)) & 1;
+                    ms_put(&spp, (uint32_t)bit, 1);
+                    if (bit) { sspp[i] = 1; newi[nnew++] = i; }
+                }
+            for (int k = 0; k < nnew; k++) {
+                ms_put(&spp, coef[newi[k]] < 0 ? 1u : 0u, 1);
+                if (recon) recon[newi[k]] = coef[newi[k]] < 0 ? -(3 << P) : (3 << P);
+            }
+        }
+    if (spp.used) { spp.buf[spp.pos++] = (uint8_t)spp.tmp; }                 /* partial byte, zero padded */
+    if (spp.pos == 0 || spp.buf[spp.pos - 1] == 0xFF) spp.buf[spp.pos++] = 0;  /* never empty, never ends in 0xFF */
+    if (npasses == 3) {
+        for (int y0 = 0; y0 < h; y0 += 4)
+            for (int x = 0; x < w; x++)
+                for (int y = y0; y < y0 + 4 && y < h; y++) {
+                    const int i = y * w + x;
+                    if (!mu[i]) continue;
+                    const int32_t a = coef[i] < 0 ? -coef[i] : coef[i];
+                    const int bit = (a >> (P - 1)) & 1;
+                    vlc_put(&mrp, (uint32_t)bit, 1);
+                    if (recon) {
+                        const int32_t q = ((a >> P) << (P + 2)) | (bit << (P + 1)) | (1 << P);
+                        recon[i] = coef[i] < 0 ? -q : q;
+                    }
+                }
+        if (mrp.used > 0) { *(mrp.end - mrp.pos) = (uint8_t)mrp.tmp; mrp.pos++; }
+    }
+    int ret = -1;
+    if (!spp.ovf && !mrp.ovf && spp.pos < seg - 2 && lcup + spp.pos + mrp.pos <= cap) {
+        memcpy(out + lcup, sppb, (size_t)spp.pos);
+        memcpy(out + lcup + spp.pos, mrp.end - mrp.pos + 1, (size_t)mrp.pos);
+        ret = lcup + spp.pos + mrp.pos;
+    }
+    free(mu); free(sppb); free(mrpb); free(sspp);
+    return ret;
+}

@@ -118,7 +118,7 @@ def as_ctypes(arr, ctype):
     return buf
 
 
-def build_iso_job(samples, prec, tile_w=None, tile_h=None, nlevels=5, mct=1, cb=64):
+def build_iso_job(samples, prec, tile_w=None, tile_h=None, nlevels=5, mct=1, cb=64, ht_passes=1, ht_plane=0):
     """ISO-mode (J2KGPU_MODE_ISO) job: the same source image as a conformant HTJ2K codestream (lossless 5-3, RCT,
     HT cleanup-only blocks) plus the flat tables a tier-2 parser would hand to j2kgpu_decode.  Block placement
     (x0, y0) is in the tile-component's Mallat plane; num_bps = Mb - missing_msbs = 1 (HT cleanup carries every
@@ -126,7 +126,7 @@ def build_iso_job(samples, prec, tile_w=None, tile_h=None, nlevels=5, mct=1, cb=
     from . import codestream as cs
     ncomp, H, W = samples.shape
     tile_w, tile_h = tile_w or W, tile_h or H
-    data, info = cs.write_htj2k(samples, prec, tile_w, tile_h, nlevels, mct=mct, cb=cb)
+    data, info = cs.write_htj2k(samples, prec, tile_w, tile_h, nlevels, mct=mct, cb=cb, ht_passes=ht_passes, ht_plane=ht_plane)
     ntx = cs.cdiv(W, tile_w)
     tcs, tc_index = [], {}
     for ty in range(cs.cdiv(H, tile_h)):
@@ -139,7 +139,7 @@ def build_iso_job(samples, prec, tile_w=None, tile_h=None, nlevels=5, mct=1, cb=
     blob = bytearray()
     for i, b in enumerate(blks):
         cblks[i] = (len(blob), len(b["data"]), tc_index[(b["tile"], b["comp"])], b["px"], b["py"], b["w"], b["h"],
-                    b["band"], b["level"], 1, 1, 1.0, 0, 0)
+                    b["band"], b["level"], 1 + ht_plane, max(b["passes"], 1), 1.0, b["lcup"] if b["passes"] > 1 else 0, 0)
         blob += b["data"]
     return dict(width=W, height=H, ncomp=ncomp, prec=prec, sgnd=0, mct=1 if (mct and ncomp >= 3) else 0, reversible=1,
                 nlevels=nlevels, ht=1, mode=1, tilecomps=np.array(tcs, TILECOMP_DT), cblks=cblks,

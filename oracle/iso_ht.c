@@ -10,8 +10,15 @@
  * Pinned by: OpenJPEG 2.5.4 decodes the streams of datagen/gen_iso_ht.c to the source image
  * (tests/test_iso_codestream.py), and this decoder inverts the same streams.
  *
- * Output: out[y*w+x] = sign * (mu << (num_bps-1)) where mu is the decoded magnitude index at the
- * cleanup bit-plane (num_bps = Mb - missing_msbs, so num_bps = 1 for a lossless cleanup-only block).
+ * plus the SigProp and MagRef passes of the same HT set (clause 7.4 / 7.5), pinned the same way by OpenJPEG
+ * decoding multi-pass streams of the extended writer.
+ *
+ * Reconstruction follows OpenJPEG (the pin): the cleanup pass at bit-plane P = num_bps - 1 (num_bps = Mb - missing
+ * MSBs) gives magnitude index mu; a mid-point bit sits below the last decoded bit-plane.  iso_ht_decode_passes
+ * returns sign * Q in QUARTER units (integer LSB = bit 2), so that the refinement of bit-plane P - 1 = -1 and its
+ * mid-point are still integers: cleanup only Q = (2 mu + 1) << (P + 1); MagRef'ed Q = mu << (P + 2) | bit << (P + 1)
+ * | 1 << P; newly significant in SigProp Q = 3 << P.  Reversible value = sign * (Q >> 2); irreversible =
+ * sign * Q * step / 4.  iso_ht_decode = cleanup only, reversible value.
  * Returns 0, or a negative value for a malformed segment (out is then all zero).
  */
 #include "oracle.h"
@@ -161,14 +168,15 @@ static int uvlc_decode(uint32_t vlc, int mode, int initial, int u[2])
 
 static inline int bitlen32(uint32_t v) { return v ? 32 - __builtin_clz(v) : 0; }
 
-int iso_ht_decode(const uint8_t *data, int len, int w, int h, int num_bps, int32_t *out)
+/* cleanup pass: mu (>= 1 for every significant sample, 0 elsewhere) and sign per sample */
+static int ht_cleanup(const uint8_t *data, int len, int w, int h, uint32_t *out, uint8_t *sgn)
 {
-    memset(out, 0, sizeof(int32_t) * (size_t)w * h);
-    if (len < 2 || num_bps < 1 || num_bps > 30) return -1;
+    memset(out, 0, sizeof(uint32_t) * (size_t)w * h);
+    memset(sgn, 0, (size_t)w * h);
+    if (len < 2) return -1;
     const int lcup = len;
     const int scup = ((int)data[lcup - 1] << 4) + (data[lcup - 2] & 0x0F);
     if (scup < 2 || scup > lcup || scup > 4079) return -2;
-    const int shift = num_bps - 1;
 
     mel_t mel; memset(&mel, 0, sizeof mel);
     mel.d = data; mel.pos = lcup - scup; mel.left = scup - 1;
@@ -244,8 +252,8 @@ int iso_ht_decode(const uint8_t *data, int len, int w, int h, int num_bps, int32
                     v |= ((e >> (8 + n)) & 1) << m;
                     v |= 1;
                     const uint32_t mu = (v >> 1) + 1;
-                    const uint32_t mag = mu << shift;
-                    out[yy * w + x] = (int32_t)(sign ? 0u - mag : mag);
+                    out[yy * w + x] = mu;
+                    sgn[yy * w + x] = (uint8_t)sign;
                     if (n & 1) { NSG[x] = 1; NEX[x] = (uint8_t)bitlen32(v); }
                 }
             }
@@ -255,6 +263,102 @@ int iso_ht_decode(const uint8_t *data, int len, int w, int h, int num_bps, int32
         SG = sg + 2; EX = ex + 2; NSG = nsg + 2; NEX = nex + 2;
     }
     free(sg); free(ex); free(nsg); free(nex);
-    if (rc) memset(out, 0, sizeof(int32_t) * (size_t)w * h);
+    if (rc) memset(out, 0, sizeof(uint32_t) * (size_t)w * h);
+    return rc;
+}
+
+/* forward bit reader of the SigProp stream: LSB first, a byte after 0xFF carries 7 bits, zeros when exhausted */
+typedef struct { const uint8_t *d; int pos, left; uint32_t tmp; int bits; int unstuff; } spp_t;
+static int spp_bit(spp_t *s)
+{
+    if (s->bits == 0) {
+        uint32_t b = 0;
+        if (s->left > 0) { b = s->d[s->pos++]; s->left--; }
+        s->bits = s->unstuff ? 7 : 8;
+        s->tmp = b;
+        s->unstuff = (b == 0xFF);
+    }
+    const int v = (int)(s->tmp & 1);
+    s->tmp >>= 1; s->bits--;
+    return v;
+}
+/* backward bit reader of the MagRef stream: LSB first, from the last byte of the refinement segment; a byte whose low
+ * 7 bits are all ones after a byte > 0x8F carries 7 bits (the byte after the segment counts as > 0x8F); then zeros */
+typedef struct { const uint8_t *d; int pos, left; uint32_t tmp; int bits; int unstuff; } mrp_t;
+static int mrp_bit(mrp_t *s)
+{
+    if (s->bits == 0) {
+        uint32_t b = 0;
+        if (s->left > 0) { b = s->d[s->pos--]; s->left--; }
+        s->bits = (s->unstuff && (b & 0x7F) == 0x7F) ? 7 : 8;
+        s->tmp = b;
+        s->unstuff = b > 0x8F;
+    }
+    const int v = (int)(s->tmp & 1);
+    s->tmp >>= 1; s->bits--;
+    return v;
+}
+
+int iso_ht_decode_passes(const uint8_t *data, int lcup, int lref, int w, int h, int num_bps, int num_passes, int32_t *out)
+{
+    const int n = w * h;
+    memset(out, 0, sizeof(int32_t) * (size_t)n);
+    if (num_bps < 1 || num_bps > 30 || num_passes < 1 || num_passes > 3 || lref < 0) return -1;
+    uint32_t *mu = malloc(sizeof(uint32_t) * (size_t)n);
+    uint8_t *sgn = malloc((size_t)n), *snew = calloc((size_t)n, 1);
+    const int rc = ht_cleanup(data, lcup, w, h, mu, sgn);
+    if (rc) { free(mu); free(sgn); free(snew); return rc; }
+    const int P = num_bps - 1;
+    if (num_passes > 1 && lref == 0) num_passes = 1;             /* no refinement bytes: cleanup only (as OpenJPEG) */
+    if (num_passes >= 2) {
+        spp_t sp = {data + lcup, 0, lref, 0, 0, 0};
+        for (int y0 = 0; y0 < h; y0 += 4)
+            for (int x0 = 0; x0 < w; x0 += 4) {
+                int newi[16], nnew = 0;
+                for (int x = x0; x < x0 + 4 && x < w; x++)
+                    for (int y = y0; y < y0 + 4 && y < h; y++) {
+                        const int i = y * w + x;
+                        if (mu[i]) continue;
+                        int mbr = 0;
+                        for (int dy = -1; dy <= 1; dy++)
+                            for (int dx = -1; dx <= 1; dx++) {
+                                const int yy = y + dy, xx = x + dx;
+                                if ((dy || dx) && yy >= 0 && yy < h && xx >= 0 && xx < w && (mu[yy * w + xx] || snew[yy * w + xx])) mbr = 1;
+                            }
+                        if (mbr && spp_bit(&sp)) { snew[i] = 1; newi[nnew++] = i; }
+                    }
+                for (int k = 0; k < nnew; k++) snew[newi[k]] = (uint8_t)(1 + 2 * spp_bit(&sp));   /* 1 positive, 3 negative */
+            }
+    }
+    /* all arithmetic is uint32 (wraps on absurd inputs exactly like the device code) */
+    mrp_t mr = {data + lcup, lref - 1, lref, 0, 0, 1};
+    for (int y0 = 0; y0 < h; y0 += 4)
+        for (int x = 0; x < w; x++)
+            for (int y = y0; y < y0 + 4 && y < h; y++) {
+                const int i = y * w + x;
+                uint32_t q = 0, neg = 0;
+                if (mu[i]) {
+                    if (num_passes == 3) q = (mu[i] << (P + 2)) | ((uint32_t)mrp_bit(&mr) << (P + 1)) | (1u << P);
+                    else q = (2u * mu[i] + 1u) << (P + 1);
+                    neg = sgn[i];
+                } else if (snew[i]) {
+                    q = 3u << P;
+                    neg = snew[i] & 2;
+                }
+                out[i] = (int32_t)(neg ? 0u - q : q);
+            }
+    free(mu); free(sgn); free(snew);
+    return 0;
+}
+
+/* cleanup only, reversible value sign * (Q >> 2) (uint32 arithmetic) */
+int iso_ht_decode(const uint8_t *data, int len, int w, int h, int num_bps, int32_t *out)
+{
+    const int rc = iso_ht_decode_passes(data, len, 0, w, h, num_bps, 1, out);
+    for (int i = 0; i < w * h; i++) {
+        const uint32_t u = (uint32_t)out[i];
+        const uint32_t q = (out[i] < 0) ? 0u - u : u;
+        out[i] = (int32_t)((out[i] < 0) ? 0u - (q >> 2) : (q >> 2));
+    }
     return rc;
 }

@@ -49,7 +49,11 @@ const uint8_t *orc_t1_zc_lut(void);
 void orc_ht_decode(const uint8_t *data, int len, int w, int h, int32_t *out);
 
 /* ---- ISO-mode checkers (not restatements of the reference; see the file headers) ------ */
-/* ISO/IEC 15444-15 HT cleanup decoder: out = sign * (mu << (num_bps-1)); returns 0 or <0 if malformed */
+/* ISO/IEC 15444-15 HT block decoder, one HT set: data = cleanup segment (lcup bytes) + refinement segment (lref bytes),
+ * num_passes 1..3 (cleanup, + SigProp, + MagRef), cleanup bit-plane P = num_bps - 1.  out = sign * Q in quarter units
+ * (integer LSB = bit 2, mid-point bit below the last decoded bit-plane, as OpenJPEG reconstructs); 0 or <0 if malformed */
+int  iso_ht_decode_passes(const uint8_t *data, int lcup, int lref, int w, int h, int num_bps, int num_passes, int32_t *out);
+/* cleanup only, reversible value: out = sign * (Q >> 2) */
 int  iso_ht_decode(const uint8_t *data, int len, int w, int h, int num_bps, int32_t *out);
 /* ISO/IEC 15444-1 Annex C/D code-block decoder (iso_t1.c): num_bps magnitude bit-planes, the first num_passes coding
  * passes; out = sign * (2 * magnitude + mid-point of the last decoded bit-plane); band 0 LL, 1 HL, 2 LH, 3 HH */
@@ -118,6 +122,11 @@ typedef struct {
 void orc_colour_convert(int32_t *const *comps, int ncomp, size_t n, int prec, int cs);
 
 int orc_decode_image(const orc_image_t *img, const orc_tilecomp_t *tcs, uint32_t n_tc,
+                     const orc_cblk_t *cbs, uint32_t n_cb, const uint8_t *blob, uint64_t blob_len,
+                     uint8_t *out_pix, uint64_t out_stride, int threads);
+
+/* ISO-mode (J2KGPU_MODE_ISO) whole path, see iso_path.c: same tables, OpenJPEG's arithmetic */
+int iso_decode_image(const orc_image_t *img, const orc_tilecomp_t *tcs, uint32_t n_tc,
                      const orc_cblk_t *cbs, uint32_t n_cb, const uint8_t *blob, uint64_t blob_len,
                      uint8_t *out_pix, uint64_t out_stride, int threads);
 

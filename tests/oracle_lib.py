@@ -61,6 +61,7 @@ def lib():
         L.orc_decode_image.restype = C.c_int
         L.orc_t1_zc_lut.restype = u8p
         L.iso_ht_decode.restype = C.c_int
+        L.iso_ht_decode_passes.restype = C.c_int
     return _lib
 
 
@@ -109,6 +110,14 @@ def iso_ht_decode(data, w, h, num_bps=1):
     buf = np.frombuffer(bytes(data), np.uint8) if len(data) else np.zeros(1, np.uint8)
     out = np.zeros(w * h, np.int32)
     rc = lib().iso_ht_decode(_p(buf, u8p), len(data), w, h, num_bps, _p(out, i32p))
+    return out, rc
+
+
+def iso_ht_decode_passes(data, lcup, w, h, num_bps, num_passes):
+    """one HT set: cleanup segment (lcup bytes) + refinement segment -> (sign * Q in quarter units, rc)"""
+    buf = np.frombuffer(bytes(data), np.uint8) if len(data) else np.zeros(1, np.uint8)
+    out = np.zeros(w * h, np.int32)
+    rc = lib().iso_ht_decode_passes(_p(buf, u8p), lcup, len(data) - lcup, w, h, num_bps, num_passes, _p(out, i32p))
     return out, rc
 
 
@@ -185,4 +194,28 @@ def decode_image(img, tcs, cbs, blob, out_stride, out_size, threads=1):
                                 C.c_uint64(blob.size), _p(out, u8p), C.c_uint64(out_stride), threads)
     if rc != 0:
         raise RuntimeError("orc_decode_image rc=%d" % rc)
+    return out
+
+
+def iso_decode_job(job, threads=4, out=None):
+    """the ISO-mode whole path (oracle/iso_path.c) on a job dict of datagen.jobs (build_iso_job / build_iso_job_from_codestream)
+    -> packed pixels (uint8, width * bpp per row)"""
+    from datagen import jobs as J
+    img = Image()
+    img.width, img.height, img.ncomp = job["width"], job["height"], job["ncomp"]
+    for c in range(job["ncomp"]):
+        img.prec[c], img.sgnd[c] = job["prec"], job["sgnd"]
+    img.mct, img.reversible, img.nlevels, img.ht, img.mode = job["mct"], job["reversible"], job["nlevels"], job["ht"], 1
+    bpp = (1 if job["prec"] <= 8 else 2) if job["ncomp"] == 1 else (4 if job["prec"] <= 8 else 8)
+    stride = job["width"] * bpp
+    if out is None:
+        out = np.zeros(stride * job["height"], np.uint8)
+    tcs, cbs = J.as_ctypes(job["tilecomps"], TileComp), J.as_ctypes(job["cblks"], CBlk)
+    blob = np.ascontiguousarray(job["blob"], np.uint8)
+    L = lib()
+    L.iso_decode_image.restype = C.c_int
+    rc = L.iso_decode_image(C.byref(img), tcs, len(tcs), cbs, len(cbs), _p(blob, u8p), C.c_uint64(blob.size),
+                            _p(out, u8p), C.c_uint64(stride), threads)
+    if rc != 0:
+        raise RuntimeError("iso_decode_image rc=%d" % rc)
     return out
