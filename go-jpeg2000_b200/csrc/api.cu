@@ -504,6 +504,7 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
             steps.push_back(cb.step);
             blk_rects[cb.tilecomp].push_back(Rect{cb.x0, cb.y0, (uint32_t)cb.x0 + cb.w, (uint32_t)cb.y0 + cb.h});
             if (cb.data_len && cb.num_bps > max_bps) max_bps = cb.num_bps;
+            if (iso && hdr.ht && cb.num_passes > 1) job->ht_refine = 1;
         }
         // a plane its blocks do not tile exactly (holes, or overlaps hiding holes) is cleared before the entropy stage
         for (uint32_t t = 0; t < it.n_tilecomps && !need_clear; t++)
@@ -555,7 +556,7 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
     if (e == cudaSuccess) job->d_coef = j2k_pool_alloc(ctx, coef_elems * (job->coef16 ? 2 : 4) + 64, &e);
     if (e == cudaSuccess) job->d_tmp = j2k_pool_alloc(ctx, job->tmp_bytes, &e);
     if (e == cudaSuccess && hdr.ht)
-        job->d_htscratch = j2k_pool_alloc(ctx, iso ? j2k_htiso_scratch_bytes((uint32_t)cbs.size()) : j2k_htref_scratch_bytes((uint32_t)cbs.size()), &e);
+        job->d_htscratch = j2k_pool_alloc(ctx, iso ? j2k_htiso_scratch_bytes((uint32_t)cbs.size(), job->ht_refine) : j2k_htref_scratch_bytes((uint32_t)cbs.size()), &e);
     // reference HT coder: its decoder writes one row in four (ht.go:677, 701); zero the planes once, here, so that every
     // run only has to clear the rows it may write (3/4 of the entropy stage's zero-fill traffic saved)
     if (e == cudaSuccess && !iso && hdr.ht && !opt.no_preclear) {
@@ -619,8 +620,8 @@ static int run_entropy(j2kgpu_job *job, const void *d_blob, uint32_t ia, uint32_
     else if (job->iso) {
         // chunks of a pipelined run share the scratch: their kernels are ordered on one stream
         e = launch_ht_iso(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, steps, irrev, job->hdr.coef_bits,
-                          job->d_htscratch, job->blob_bytes, st);
-        ctx->launches += j2k_htiso_launches() - 1;
+                          job->ht_refine, job->d_htscratch, job->blob_bytes, st);
+        ctx->launches += j2k_htiso_launches(job->ht_refine) - 1;
     }
     else if (job->hdr.ht) {
         e = launch_ht_ref(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, job->precleared,
@@ -1036,9 +1037,17 @@ static int stage_blocks(j2kgpu_ctx *ctx, int mode, int ht, const j2k_blkjob_t *j
     if (blob_len) J2K_CUDA(ctx, cudaMemcpyAsync(ctx->d_in.p, blob, blob_len, cudaMemcpyHostToDevice, ctx->stream));
     J2K_CUDA(ctx, cudaMemsetAsync(ctx->d_out.p, 0, out_len * sizeof(int32_t), ctx->stream));
     if (ht && mode != J2KGPU_MODE_ISO) { if ((rc = j2k_reserve(ctx, ctx->d_aux, j2k_htref_scratch_bytes(n), false))) return rc; ctx->launches += j2k_htref_launches() - 1; }
-    if (ht && mode == J2KGPU_MODE_ISO) { if ((rc = j2k_reserve(ctx, ctx->d_aux, j2k_htiso_scratch_bytes(n), false))) return rc; ctx->launches += j2k_htiso_launches() - 1; }
+    int refine = 0;
+    if (ht && mode == J2KGPU_MODE_ISO) {
+        for (uint32_t i = 0; i < n; i++) {
+            if (cbs[i].num_passes > 3) return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "block %u: %d HT coding passes", i, (int)cbs[i].num_passes);
+            if (cbs[i].num_passes > 1) refine = 1;
+        }
+        if ((rc = j2k_reserve(ctx, ctx->d_aux, j2k_htiso_scratch_bytes(n, refine), false))) return rc;
+        ctx->launches += j2k_htiso_launches(refine) - 1;
+    }
     cudaError_t e = (ht && mode == J2KGPU_MODE_ISO)
-                        ? launch_ht_iso((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, nullptr, 0, 0, ctx->d_aux.p, blob_len, ctx->stream)
+                        ? launch_ht_iso((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, nullptr, 0, 0, refine, ctx->d_aux.p, blob_len, ctx->stream)
                     : mode == J2KGPU_MODE_ISO ? launch_t1_iso((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, nullptr, 0, max_bps, ctx->stream)
                     : ht ? launch_ht_ref((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, 0, ctx->d_aux.p, blob_len, ctx->stream)
                        : launch_t1_ref_stage((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, (int32_t *)ctx->d_out.p, max_bps, ctx->stream);

@@ -129,6 +129,7 @@ struct j2kgpu_job {
     int fused_ok = 0;                    // levels 1 + 0 + pixel epilogue run as one kernel (idwt_fused.cu)
     int fast_epi = 0;                    // every tile qualifies for the fused kernel's fixed RGBA8 epilogue
     int wide_ok = 0;                     // ... and for the 16-columns-per-lane variant (idwt_wide.cu)
+    int ht_refine = 0;                   // ISO HT: some block has SigProp / MagRef passes
     int precleared = 0;                  // reference HT coder: planes zeroed at job creation, decoder clears every 4th row only
     int pix_fill = 0;                    // some pixel of some image is covered by no tile: pre-fill with the pixel of zero coefficients
     std::vector<uint8_t> item_fill;      // per item: needs the pre-fill
@@ -176,11 +177,12 @@ int j2k_htref_launches();        // kernels per launch_ht_ref call
 cudaError_t launch_t1_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
                           const float *d_steps, int irrev, int max_bps, cudaStream_t s);
 // ISO/IEC 15444-15 block decoder (VLC kernel + MagSgn kernel)
+// refine: some block carries SigProp / MagRef passes (num_passes > 1): the refinement kernel runs between the two
 cudaError_t launch_ht_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
-                          const float *d_steps, int irrev, int coef_bits, void *d_scratch, uint64_t blob_bytes,
+                          const float *d_steps, int irrev, int coef_bits, int refine, void *d_scratch, uint64_t blob_bytes,
                           cudaStream_t s);
-size_t j2k_htiso_scratch_bytes(uint32_t n_blocks);   // device scratch between the two kernels
-int j2k_htiso_launches();        // kernels per launch_ht_iso call
+size_t j2k_htiso_scratch_bytes(uint32_t n_blocks, int refine);   // device scratch between the kernels
+int j2k_htiso_launches(int refine);                              // kernels per launch_ht_iso call
 
 // inverse DWT, REF (dense-prefix) addressing.  One call = one decomposition level of every
 // tile-component in the table.  `lvl` counts from 0 (full resolution).  For lvl > 0 the output goes to the

@@ -1,13 +1,15 @@
-// ht_iso.cu -- ISO/IEC 15444-15 (ITU-T T.814) HT cleanup-pass block decoder for J2KGPU_MODE_ISO (sm_100a).
+// ht_iso.cu -- ISO/IEC 15444-15 (ITU-T T.814) HT block decoder for J2KGPU_MODE_ISO (sm_100a): cleanup, SigProp, MagRef.
 //
-// What north_star calls "HTJ2K cleanup decoding (MEL, VLC and MagSgn bitstreams)".  The reference's ht.go is
+// What north_star calls "HTJ2K cleanup/SigProp/MagRef decoding (MEL, VLC and MagSgn bitstreams)".  The reference's ht.go is
 // not conformant and is covered by ht_ref.cu; this kernel follows the published algorithm
 // (T.814 clause 7): MagSgn forward from byte 0, MEL forward from Lcup-Scup, VLC backward from Lcup-2, 2x2 quads
 // in pairs, CxtVLC tables, U-VLC, exponent predictor from the previous quad row.  Checked in the test suite against
 // a CPU statement of the same algorithm that is itself pinned by OpenJPEG decoding the same streams.
 //
-// Mapping: two kernels, k_htiso_vlc (one thread per block: the MEL / VLC context chain) and k_htiso_magsgn2 (half a
-// warp per block: the MagSgn rows in parallel).  The single-chain statement of the same algorithm is the CPU checker
+// Mapping: k_htiso_vlc (one thread per block: the MEL / VLC context chain), then -- only when some block of the launch
+// carries SigProp / MagRef passes -- k_htiso_refine (one warp per block: significance propagation and the MagRef bits,
+// left as three row bitmaps per block), then k_htiso_magsgn2 (half a warp per block: the MagSgn rows in parallel and
+// the final value of every sample, written once).  The single-chain statement of the same algorithm is the CPU checker
 // (test side).
 #include "common.h"
 #include <cstdlib>
@@ -73,16 +75,18 @@ __device__ __forceinline__ uint32_t uvlc_row(uint32_t b3)
     return (uint32_t)((0x2142216721422100ull | 0xB7ull) >> (8 * b3)) & 0xFF;
 }
 
-// value written for one decoded sample: reversible -> integer; irreversible -> dequantised float bits
-__device__ __forceinline__ int32_t sample_value(uint32_t mu, uint32_t sign, int shift, float step, bool irrev)
+// Value written for one decoded sample.  q = magnitude in QUARTER units (integer LSB = bit 2) including the mid-point
+// bit below the last decoded bit-plane, the reconstruction OpenJPEG uses (the pin of the CPU checker):
+// cleanup only (2 mu + 1) << (P + 1); after MagRef mu << (P + 2) | bit << (P + 1) | 1 << P; new in SigProp 3 << P.
+// Reversible -> sign * (q >> 2); irreversible -> dequantised float bits sign * q * step / 4.  uint32 arithmetic throughout.
+__device__ __forceinline__ int32_t sample_value(uint32_t q, uint32_t sign, float qstep, bool irrev)
 {
     if (!irrev) {
-        const uint32_t mag = mu << shift;
+        const uint32_t mag = q >> 2;
         return (int32_t)(sign ? 0u - mag : mag);
     }
-    // mid-point reconstruction: (mu + 1/2) * 2^shift * step
-    const float f = ((float)mu + 0.5f) * (float)(1u << shift) * step;
-    return __float_as_int(sign ? -f : f);
+    const float f = (float)(int32_t)(sign ? 0u - q : q) * qstep;          // qstep = 0.25 * step
+    return __float_as_int(f);
 }
 
 // ---- two-kernel mapping (default) ------------------------------------------------------------------------------------
@@ -192,7 +196,7 @@ k_htiso_vlc(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__rest
     const DevCblk cb = cblks[blk];
     const int w = cb.w, h = cb.h;
     const uint8_t *d = blob + cb.data_off;
-    const int lcup = (int)cb.data_len;
+    const int lcup = (int)cb.len_cup;                    // the cleanup segment; a refinement segment may follow it
     bool ok = lcup >= 2 && cb.num_bps >= 1 && cb.num_bps <= 30;
     int scup = 0;
     if (ok) {
@@ -273,17 +277,214 @@ k_htiso_vlc(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__rest
     status[blk] = badbits ? (uint32_t)ST_ZERO : ((uint32_t)ST_OK | ((uint32_t)(lcup - scup) << 2));
 }
 
+// ---- SigProp + MagRef (T.814 clause 7.4 / 7.5) -----------------------------------------------------------------------
+// k_htiso_refine, one warp per block, between the VLC kernel and the MagSgn kernel; only blocks with num_passes > 1 and
+// a non-empty refinement segment do anything.  Both passes refine bit-plane P - 1 below the cleanup pass:
+//   * SigProp: 4-row stripes, column by column; an insignificant sample with a significant neighbour (cleanup
+//     significance of all eight neighbours, SigProp significance of the ones visited before it) takes one bit from a
+//     forward-growing stream (LSB first, 7 bits after 0xFF, zeros when exhausted); the sign bits of the samples that
+//     turned significant come after the (up to 16) significance bits of each group of 4 stripe columns.  The chain of
+//     decisions is serial (every bit's meaning depends on the ones before): lane 0 walks it on 64-bit row bitmaps with
+//     the candidate-column mask of the EBCOT kernel; the warp first removes the stuffing in parallel so that the chain
+//     reads bit i of a dense bit string.
+//   * MagRef: one bit per cleanup-significant sample in stripe scan order from a backward-growing stream -- no chain:
+//     a sample's bit index is the number of significant samples before it, i.e. popcounts and a warp prefix sum.
+// Output: three 64 x 64 bitmaps per block (new in SigProp, its sign, the MagRef bit) that the MagSgn kernel folds into
+// the values it writes.  Input significance comes from the VLC kernel's quad table.
+constexpr int kRefWarps = 4;
+constexpr int kRefWords = 192;                          // u64 per block in the scratch: 64 rows x (new, sign, magref)
+constexpr int kSppWords = 304;                          // SigProp bits: at most 2 per sample
+constexpr int kMrpWords = 152;                          // MagRef bits: at most 1 per sample
+constexpr int kSppBytes = 1184, kMrpBytes = 592;        // bytes that can hold them, stuffing included
+
+__device__ __forceinline__ uint64_t spread_even(uint32_t x)          // bit i -> bit 2 i
+{
+    uint64_t v = x;
+    v = (v | (v << 16)) & 0x0000FFFF0000FFFFull;
+    v = (v | (v << 8)) & 0x00FF00FF00FF00FFull;
+    v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0Full;
+    v = (v | (v << 2)) & 0x3333333333333333ull;
+    v = (v | (v << 1)) & 0x5555555555555555ull;
+    return v;
+}
+
+__device__ __forceinline__ uint32_t win3r(uint64_t row, int x) { return (uint32_t)(x ? (row >> (x - 1)) : (row << 1)) & 7u; }
+
+// the warp unstuffs `nbytes` bytes of a stream into a dense LSB-first bit string in shared memory (zeroed before).
+// FWD: bytes d[0], d[1], ...; a byte after 0xFF carries 7 bits.  !FWD: bytes d[0], d[-1], ...; a byte whose low 7 bits are
+// all ones after a byte > 0x8F carries 7 bits, and the byte before the first counts as > 0x8F.  Returns the bit count.
+template <bool FWD>
+__device__ uint32_t unstuff_stream(const uint8_t *d, int nbytes, uint32_t *bits, int lane)
+{
+    uint32_t total = 0;
+    uint32_t carry = FWD ? 0u : 0xFFu;                   // the byte before this chunk, as stored
+    for (int k0 = 0; k0 < nbytes; k0 += 128) {
+        uint32_t ob[4], nb[4], val[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { const int k = k0 + 4 * lane + i; ob[i] = k < nbytes ? (uint32_t)__ldg(FWD ? d + k : d - k) : 0u; }
+        uint32_t prev = __shfl_up_sync(0xffffffffu, ob[3], 1);
+        if (lane == 0) prev = carry;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const bool seven = FWD ? (prev == 0xFFu) : (prev > 0x8Fu && (ob[i] & 0x7Fu) == 0x7Fu);
+            nb[i] = (k0 + 4 * lane + i < nbytes) ? (seven ? 7u : 8u) : 0u;
+            val[i] = seven ? (ob[i] & 0x7Fu) : ob[i];
+            prev = ob[i];
+        }
+        const uint32_t v = val[0] | (val[1] << nb[0]) | (val[2] << (nb[0] + nb[1])) | (val[3] << (nb[0] + nb[1] + nb[2]));
+        const uint32_t tot = nb[0] + nb[1] + nb[2] + nb[3];
+        uint32_t incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const uint32_t pos = total + incl - tot;
+        if (tot) {
+            const uint32_t sh = pos & 31, wi = pos >> 5;
+            atomicOr(&bits[wi], v << sh);
+            const uint32_t hi = sh ? v >> (32 - sh) : 0u;
+            if (hi) atomicOr(&bits[wi + 1], hi);
+        }
+        total += __shfl_sync(0xffffffffu, incl, 31);
+        carry = __shfl_sync(0xffffffffu, ob[3], 31);
+    }
+    __syncwarp();
+    return total;
+}
+
+__global__ void __launch_bounds__(kRefWarps * 32)
+k_htiso_refine(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob,
+               const uint32_t *__restrict__ qtab, const uint32_t *__restrict__ status, uint64_t *__restrict__ ref)
+{
+    __shared__ uint64_t s_sg[kRefWarps][66];             // cleanup significance, rows -1 .. 64
+    __shared__ uint64_t s_out[kRefWarps][kRefWords];     // new, sign, magref rows
+    __shared__ uint32_t s_spp[kRefWarps][kSppWords];
+    __shared__ uint32_t s_mrp[kRefWarps][kMrpWords];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t blk = blockIdx.x * kRefWarps + warp;
+    if (blk >= n) return;
+    const DevCblk cb = cblks[blk];
+    const int lcup = (int)cb.len_cup, lref = (int)cb.data_len - lcup;
+    if (cb.num_passes < 2 || lref <= 0 || (status[blk] & 3) == ST_ZERO) return;
+    const int w = cb.w, h = cb.h;
+    const int np = cb.num_passes > 3 ? 3 : cb.num_passes;
+    uint64_t *sg = s_sg[warp] + 1, *onew = s_out[warp], *osgn = s_out[warp] + 64, *omr = s_out[warp] + 128;
+    uint32_t *spp = s_spp[warp], *mrp = s_mrp[warp];
+    for (int i = lane; i < 66; i += 32) s_sg[warp][i] = 0;
+    for (int i = lane; i < kRefWords; i += 32) s_out[warp][i] = 0;
+    for (int i = lane; i < kSppWords; i += 32) spp[i] = 0;
+    for (int i = lane; i < kMrpWords; i += 32) mrp[i] = 0;
+    __syncwarp();
+    // ---- cleanup significance from the quad table: lane = quad of a quad row ----
+    const uint16_t *qt = reinterpret_cast<const uint16_t *>(qtab + (size_t)blk * kQTabWords);
+    const int nq = (w + 1) >> 1, nrows = (h + 1) >> 1;
+    for (int r = 0; r < nrows; r++) {
+        const uint32_t st8 = lane < nq ? ((uint32_t)qt[r * 32 + lane] & 0xFFu) : 0u;
+        const uint32_t b0 = __ballot_sync(0xffffffffu, (st8 & 0x03u) != 0), b1 = __ballot_sync(0xffffffffu, (st8 & 0x0Cu) != 0),
+                       b2 = __ballot_sync(0xffffffffu, (st8 & 0x30u) != 0), b3 = __ballot_sync(0xffffffffu, (st8 & 0xC0u) != 0);
+        if (lane == 0) {
+            sg[2 * r] = spread_even(b0) | (spread_even(b2) << 1);
+            if (2 * r + 1 < 64) sg[2 * r + 1] = spread_even(b1) | (spread_even(b3) << 1);
+        }
+    }
+    const uint8_t *dref = blob + cb.data_off + lcup;
+    const uint32_t nspp = unstuff_stream<true>(dref, lref < kSppBytes ? lref : kSppBytes, spp, lane);
+    uint32_t nmrp = 0;
+    if (np == 3) nmrp = unstuff_stream<false>(dref + lref - 1, lref < kMrpBytes ? lref : kMrpBytes, mrp, lane);
+    __syncwarp();
+    const uint64_t wmask = (w >= 64) ? ~0ull : ((1ull << w) - 1);
+    // ---- SigProp: the serial chain, lane 0 ----
+    if (lane == 0) {
+        uint32_t pos = 0;
+        uint64_t above = 0;                                  // row y0 - 1: cleanup or SigProp significance
+        for (int y0 = 0; y0 < h; y0 += 4) {
+            const int rows = (y0 + 4 <= h) ? 4 : (h - y0);
+            uint64_t a[6], nw[4] = {0, 0, 0, 0}, sn[4] = {0, 0, 0, 0};
+            a[0] = above;
+#pragma unroll
+            for (int k = 1; k < 6; k++) a[k] = (k <= rows || k == rows + 1) ? sg[y0 + k - 1] : 0;
+            if (y0 + rows >= h) a[rows + 1] = 0;
+            uint64_t colmask = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (k >= rows) break;
+                const uint64_t u = a[k], m = a[k + 1], c = a[k + 2];
+                colmask |= ~m & (u | (u << 1) | (u >> 1) | (m << 1) | (m >> 1) | c | (c << 1) | (c >> 1));
+            }
+            colmask &= wmask;
+            int grp = -1;
+            while (true) {
+                const int x = colmask ? __ffsll((long long)colmask) - 1 : 64;
+                if ((x >> 2) != grp) {
+                    if (grp >= 0) {                              // the signs of the group just finished
+                        for (int c = 4 * grp; c < 4 * grp + 4; c++)
+#pragma unroll
+                            for (int k = 0; k < 4; k++)
+                                if ((nw[k] >> c) & 1) {
+                                    const uint32_t i = pos++;
+                                    if (i < nspp && ((spp[i >> 5] >> (i & 31)) & 1)) sn[k] |= 1ull << c;
+                                }
+                    }
+                    grp = x >> 2;
+                }
+                if (x >= 64) break;
+                colmask &= colmask - 1;
+                bool grew = false;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (k >= rows) break;
+                    if ((a[k + 1] >> x) & 1) continue;
+                    const uint32_t idx9 = win3r(a[k], x) | (win3r(a[k + 1], x) << 3) | (win3r(a[k + 2], x) << 6);
+                    if ((idx9 & 0x1EFu) == 0) continue;          // no significant neighbour (bit 4 is the sample itself)
+                    const uint32_t i = pos++;
+                    if (i < nspp && ((spp[i >> 5] >> (i & 31)) & 1)) { a[k + 1] |= 1ull << x; nw[k] |= 1ull << x; grew = true; }
+                }
+                if (grew && x + 1 < w) colmask |= 1ull << (x + 1);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) if (k < rows) { onew[y0 + k] = nw[k]; osgn[y0 + k] = sn[k]; }
+            above = a[rows];
+        }
+    }
+    // ---- MagRef: lane = columns 2 lane, 2 lane + 1 of a stripe ----
+    if (np == 3) {
+        uint32_t base = 0;
+        for (int y0 = 0; y0 < h; y0 += 4) {
+            uint32_t c0 = 0, c1 = 0;                             // the column's 4 significance bits, top to bottom
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (y0 + k < h) { const uint64_t rw = sg[y0 + k]; c0 |= (uint32_t)((rw >> (2 * lane)) & 1) << k; c1 |= (uint32_t)((rw >> (2 * lane + 1)) & 1) << k; }
+            const uint32_t n0 = __popc(c0), tot = n0 + __popc(c1);
+            uint32_t incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            const uint32_t off = base + incl - tot;
+            base += __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                uint32_t bit0 = 0, bit1 = 0;
+                if ((c0 >> k) & 1) { const uint32_t i = off + __popc(c0 & ((1u << k) - 1)); bit0 = i < nmrp ? (mrp[i >> 5] >> (i & 31)) & 1 : 0; }
+                if ((c1 >> k) & 1) { const uint32_t i = off + n0 + __popc(c1 & ((1u << k) - 1)); bit1 = i < nmrp ? (mrp[i >> 5] >> (i & 31)) & 1 : 0; }
+                const uint32_t e = __ballot_sync(0xffffffffu, bit0), o = __ballot_sync(0xffffffffu, bit1);
+                if (lane == 0 && y0 + k < h) omr[y0 + k] = spread_even(e) | (spread_even(o) << 1);
+            }
+        }
+    }
+    __syncwarp();
+    uint64_t *dst = ref + (size_t)blk * kRefWords;
+    for (int i = lane; i < kRefWords; i += 32) dst[i] = s_out[warp][i];
+}
+
 // B', the default: TWO blocks per warp, one per half-warp, each lane two neighbouring quads (4 columns) of a quad row.
 // Kernel B spends about as many instructions per quad row on what is per row (loop, ring upkeep, predictor shuffles,
 // prefix sum) as on the samples; with two quads per lane and two blocks per instruction stream that fixed part is
 // shared by four times as many samples.  Same arithmetic, same ring (one per block, 128-byte chunks), same results.
 constexpr int kWarpsIsoB2 = 8;
 
-template <typename OT, bool IRREV>
+// REFINE: some block of the launch has SigProp / MagRef passes; their bitmaps (k_htiso_refine) are folded in here.
+template <typename OT, bool IRREV, bool REFINE>
 __global__ void __launch_bounds__(kWarpsIsoB2 * 32)
 k_htiso_magsgn2(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob,
                 const uint32_t *__restrict__ qtab, const uint32_t *__restrict__ status, OT *__restrict__ coef,
-                const float *__restrict__ steps, int coef_bits)
+                const float *__restrict__ steps, int coef_bits, const uint64_t *__restrict__ ref)
 {
     constexpr uint32_t FULL = 0xffffffffu;
     __shared__ uint32_t s_ring[kWarpsIsoB2 * 2][kRingWords];
@@ -303,9 +504,12 @@ k_htiso_magsgn2(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__
         for (int y = 0; y < h; y++)
             for (int x = sl; x < w; x += 16) out[(size_t)y * ostride + x] = 0;
     const bool live = have && !zero;                     // this half-warp decodes a block
-    const float step = (IRREV && steps) ? steps[blk] : 1.0f;
+    const float qstep = (IRREV && steps) ? 0.25f * steps[blk] : 0.25f;
     const int L = (int)(stw >> 2);
-    const int shift = cb.num_bps - 1;
+    const int shift = cb.num_bps - 1;                    // P: bit-plane of the cleanup pass
+    // passes of the HT set that are decoded: 1 = cleanup, 2 = + SigProp, 3 = + MagRef (none without refinement bytes)
+    const int np = (REFINE && cb.num_passes > 1 && cb.data_len > cb.len_cup) ? (cb.num_passes > 3 ? 3 : (int)cb.num_passes) : 1;
+    const uint64_t *rf = REFINE ? ref + (size_t)blk * kRefWords : nullptr;
     const int nq = (w + 1) >> 1, nrows = live ? (h + 1) >> 1 : 0;
     const bool active = live && 2 * sl < nq;             // the lane's first quad exists
     const int ncols = w - 4 * sl;                        // columns of the block right of (and including) the lane's first
@@ -381,7 +585,7 @@ k_htiso_magsgn2(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__
                 const int E = qd == 0 ? max(max(eLeft, Eb[0]), max(Eb[1], Eb[2])) : max(max(Eb[1], Eb[2]), max(Eb[3], eRight));
                 Uq = u + max(1, E - 1);
             }
-            if (Uq > 31) bad = true;
+            if (Uq + shift > 28) bad = true;             // a magnitude would not fit 31 bits in quarter units: malformed
             if (coef_bits && Uq + shift > coef_bits + 1) bad = true;
             U[qd] = min(Uq, 31);
 #pragma unroll
@@ -394,12 +598,26 @@ k_htiso_magsgn2(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__
         uint32_t p = P + incl - tot;
         P += __shfl_sync(FULL, incl, 15, 16);
         // ---- samples: per quad n = 0 (y, x), 1 (y + 1, x), 2 (y, x + 1), 3 (y + 1, x + 1) ----
+        // refinement bitmaps of the two sample rows: the lane's 4 columns are bits 4 sl .. 4 sl + 3
+        uint32_t rnew[2] = {0, 0}, rsgn[2] = {0, 0}, rmr[2] = {0, 0};
+        if (REFINE && np > 1 && row_on) {
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
+                const int y = 2 * r + t;
+                if (y < h) {
+                    rnew[t] = (uint32_t)(__ldg(rf + y) >> (4 * sl)) & 0xFu;
+                    rsgn[t] = (uint32_t)(__ldg(rf + 64 + y) >> (4 * sl)) & 0xFu;
+                    if (np == 3) rmr[t] = (uint32_t)(__ldg(rf + 128 + y) >> (4 * sl)) & 0xFu;
+                }
+            }
+        }
         int32_t val[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const uint32_t s2 = (st8[i >> 2] >> (2 * (i & 3))) & 3;
             val[i] = 0;
             if (i & 1) Eb[i >> 1] = 0;
+            const int col = 2 * (i >> 2) + ((i >> 1) & 1), rowt = i & 1;       // position inside the lane's 4 x 2 patch
             if (s2) {
                 const uint32_t wi = p >> 5;
                 const uint32_t x = __funnelshift_r(ring[wi & (kRingWords - 1)], ring[(wi + 1) & (kRingWords - 1)], p & 31);
@@ -407,9 +625,14 @@ k_htiso_magsgn2(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__
                 const uint32_t sign = vv & 1;
                 vv |= (uint32_t)(s2 == 3) << m[i];
                 vv |= 1;
-                val[i] = sample_value((vv >> 1) + 1, sign, shift, step, IRREV);
+                const uint32_t mu = (vv >> 1) + 1;
+                uint32_t q = (2u * mu + 1u) << (shift + 1);
+                if (REFINE && np == 3) q = (mu << (shift + 2)) | (((rmr[rowt] >> col) & 1u) << (shift + 1)) | (1u << shift);
+                val[i] = sample_value(q, sign, qstep, IRREV);
                 if (i & 1) Eb[i >> 1] = 32 - __clz((int)vv);
                 p += (uint32_t)m[i];
+            } else if (REFINE && ((rnew[rowt] >> col) & 1u)) {
+                val[i] = sample_value(3u << shift, (rsgn[rowt] >> col) & 1u, qstep, IRREV);
             }
         }
         if (active && row_on) {
@@ -447,28 +670,36 @@ k_htiso_magsgn2(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__
 
 }  // namespace
 
-size_t j2k_htiso_scratch_bytes(uint32_t n) { return (size_t)n * (kQTabWords * 4 + 4) + 16; }
-int j2k_htiso_launches() { return 2; }
+// quad table + status (+ the refinement bitmaps when some block has SigProp / MagRef passes)
+size_t j2k_htiso_scratch_bytes(uint32_t n, int refine)
+{
+    return (size_t)n * (kQTabWords * 4 + 4) + 64 + (refine ? (size_t)n * kRefWords * 8 : 0);
+}
+int j2k_htiso_launches(int refine) { return refine ? 3 : 2; }
 
 template <typename OT>
 static void launch_ht_iso_t(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, OT *d_coef,
-                            const float *d_steps, int irrev, int coef_bits, void *d_scratch, uint64_t blob_bytes, cudaStream_t s)
+                            const float *d_steps, int irrev, int coef_bits, int refine, void *d_scratch, uint64_t blob_bytes, cudaStream_t s)
 {
     if ((uintptr_t)d_blob & 3) blob_bytes = 0;           // unaligned blob: byte loads only
     uint32_t *qtab = (uint32_t *)d_scratch, *status = qtab + (size_t)n * kQTabWords;
+    uint64_t *ref = (uint64_t *)(((uintptr_t)(status + n) + 63) & ~(uintptr_t)63);
     J2K_LAUNCH((k_htiso_vlc), (n + kThreads - 1) / kThreads, kThreads, 0, s, d_cblks, n, d_blob, blob_bytes, qtab, status);
+    if (refine) J2K_LAUNCH((k_htiso_refine), (n + kRefWarps - 1) / kRefWarps, kRefWarps * 32, 0, s, d_cblks, n, d_blob, qtab, status, ref);
     const uint32_t grid = (n + 2 * kWarpsIsoB2 - 1) / (2 * kWarpsIsoB2);
-    if (irrev) J2K_LAUNCH((k_htiso_magsgn2<OT, true>), grid, kWarpsIsoB2 * 32, 0, s, d_cblks, n, d_blob, qtab, status, d_coef, d_steps, coef_bits);
-    else J2K_LAUNCH((k_htiso_magsgn2<OT, false>), grid, kWarpsIsoB2 * 32, 0, s, d_cblks, n, d_blob, qtab, status, d_coef, d_steps, coef_bits);
+#define J2K_HTISO_B(IRR, REF) J2K_LAUNCH((k_htiso_magsgn2<OT, IRR, REF>), grid, kWarpsIsoB2 * 32, 0, s, d_cblks, n, d_blob, qtab, status, d_coef, d_steps, coef_bits, ref)
+    if (irrev) { if (refine) J2K_HTISO_B(true, true); else J2K_HTISO_B(true, false); }
+    else { if (refine) J2K_HTISO_B(false, true); else J2K_HTISO_B(false, false); }
+#undef J2K_HTISO_B
 }
 
-// d_scratch: j2k_htiso_scratch_bytes(n) bytes of device memory (quad table + status between the two kernels)
+// d_scratch: j2k_htiso_scratch_bytes(n, refine) bytes of device memory; refine: some block has num_passes > 1
 cudaError_t launch_ht_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
-                          const float *d_steps, int irrev, int coef_bits, void *d_scratch, uint64_t blob_bytes,
+                          const float *d_steps, int irrev, int coef_bits, int refine, void *d_scratch, uint64_t blob_bytes,
                           cudaStream_t s)
 {
     if (n == 0) return cudaSuccess;
-    if (coef16 && !irrev) launch_ht_iso_t<int16_t>(d_cblks, n, d_blob, (int16_t *)d_coef, d_steps, irrev, coef_bits, d_scratch, blob_bytes, s);
-    else launch_ht_iso_t<int32_t>(d_cblks, n, d_blob, (int32_t *)d_coef, d_steps, irrev, coef_bits, d_scratch, blob_bytes, s);
+    if (coef16 && !irrev) launch_ht_iso_t<int16_t>(d_cblks, n, d_blob, (int16_t *)d_coef, d_steps, irrev, coef_bits, refine, d_scratch, blob_bytes, s);
+    else launch_ht_iso_t<int32_t>(d_cblks, n, d_blob, (int32_t *)d_coef, d_steps, irrev, coef_bits, refine, d_scratch, blob_bytes, s);
     return cudaGetLastError();
 }

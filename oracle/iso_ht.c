@@ -169,7 +169,7 @@ static int uvlc_decode(uint32_t vlc, int mode, int initial, int u[2])
 static inline int bitlen32(uint32_t v) { return v ? 32 - __builtin_clz(v) : 0; }
 
 /* cleanup pass: mu (>= 1 for every significant sample, 0 elsewhere) and sign per sample */
-static int ht_cleanup(const uint8_t *data, int len, int w, int h, uint32_t *out, uint8_t *sgn)
+static int ht_cleanup(const uint8_t *data, int len, int w, int h, int P, uint32_t *out, uint8_t *sgn)
 {
     memset(out, 0, sizeof(uint32_t) * (size_t)w * h);
     memset(sgn, 0, (size_t)w * h);
@@ -237,7 +237,9 @@ static int ht_cleanup(const uint8_t *data, int len, int w, int h, uint32_t *out,
                     if (E - 1 > kappa) kappa = E - 1;
                 }
                 U[i] = u[i] + kappa;
-                if (U[i] > 31) { rc = -3; U[i] = 31; }
+                /* every magnitude must fit 31 bits in quarter units: (2 mu + 1) << (P + 1) with mu <= 2^U */
+                if (U[i] + P > 28) rc = -3;
+                if (U[i] > 31) U[i] = 31;
             }
             for (int i = 0; i < npair; i++) {
                 const int qq = q + i;
@@ -306,9 +308,9 @@ int iso_ht_decode_passes(const uint8_t *data, int lcup, int lref, int w, int h, 
     if (num_bps < 1 || num_bps > 30 || num_passes < 1 || num_passes > 3 || lref < 0) return -1;
     uint32_t *mu = malloc(sizeof(uint32_t) * (size_t)n);
     uint8_t *sgn = malloc((size_t)n), *snew = calloc((size_t)n, 1);
-    const int rc = ht_cleanup(data, lcup, w, h, mu, sgn);
-    if (rc) { free(mu); free(sgn); free(snew); return rc; }
     const int P = num_bps - 1;
+    const int rc = ht_cleanup(data, lcup, w, h, P, mu, sgn);
+    if (rc) { free(mu); free(sgn); free(snew); return rc; }
     if (num_passes > 1 && lref == 0) num_passes = 1;             /* no refinement bytes: cleanup only (as OpenJPEG) */
     if (num_passes >= 2) {
         spp_t sp = {data + lcup, 0, lref, 0, 0, 0};

@@ -26,9 +26,77 @@ def test_iso_ht_blocks_vs_oracle(gpu_ctx):
         enc = iso_ht_encode(d, w, h)
         nbps = int(rng.integers(1, 4))
         blocks.append((enc, w, h, nbps, 0))
-        want.append(d << (nbps - 1))
+        # cleanup at bit-plane P = nbps - 1 with the mid-point bit below it (OpenJPEG's reconstruction)
+        want.append((d << (nbps - 1)) + np.sign(d) * ((1 << (nbps - 1)) >> 1))
     for i, (got, w_) in enumerate(zip(gpu_ctx.ht_decode_blocks(blocks, mode=ISO), want)):
         assert np.array_equal(got, w_), i
+        assert np.array_equal(got, O.iso_ht_decode(blocks[i][0], blocks[i][1], blocks[i][2], blocks[i][3])[0]), i
+
+
+def _rev(q):
+    """quarter units -> reversible value: sign * (|Q| >> 2)"""
+    q = q.astype(np.int64)
+    return (np.sign(q) * (np.abs(q) >> 2)).astype(np.int32)
+
+
+def test_iso_ht_sigprop_magref_blocks_vs_oracle(gpu_ctx):
+    """one HT set of 1, 2 or 3 passes (cleanup at bit-plane P, SigProp / MagRef at P - 1), streams of the extended
+    writer: the GPU equals the CPU checker (itself identical to OpenJPEG on whole codestreams) and the writer's own
+    statement of the reconstruction"""
+    from datagen import iso_ht_encode_passes
+    rng = np.random.default_rng(41)
+    blocks, want = [], []
+    for t in range(500):
+        w, h = int(rng.integers(1, 65)), int(rng.integers(1, 65))
+        nb = int(rng.integers(2, 12))
+        d = rng.integers(-(1 << nb) + 1, 1 << nb, w * h).astype(np.int32)
+        d[rng.random(w * h) < rng.uniform(0, 0.97)] = 0
+        small = rng.random(w * h) < rng.uniform(0, 0.5)
+        d[small] = rng.integers(-3, 4, int(small.sum()))
+        P, npass = int(rng.integers(1, 4)), int(rng.integers(1, 4))
+        enc, lcup, recon = iso_ht_encode_passes(d, w, h, P, npass)
+        if not enc:
+            continue
+        q, rc = O.iso_ht_decode_passes(enc, lcup, w, h, P + 1, npass)
+        assert rc == 0 and np.array_equal(q, recon)
+        blocks.append((enc, w, h, P + 1, 0, npass, lcup))
+        want.append(_rev(q))
+    assert len(blocks) > 400
+    for i, (got, w_) in enumerate(zip(gpu_ctx.ht_decode_blocks(blocks, mode=ISO), want)):
+        assert np.array_equal(got, w_), (i, blocks[i][1:])
+
+
+def test_iso_ht_damaged_refinement_segments_vs_oracle(gpu_ctx):
+    """valid cleanup segments followed by refinement segments no encoder produces (random bytes, 0xFF runs, too short,
+    too long, empty): same values as the checker, nothing faults"""
+    from datagen import iso_ht_encode_passes
+    rng = np.random.default_rng(42)
+    blocks, want = [], []
+    for t in range(300):
+        w, h = int(rng.integers(1, 65)), int(rng.integers(1, 65))
+        d = rng.integers(-200, 201, w * h).astype(np.int32)
+        d[rng.random(w * h) < rng.uniform(0.2, 0.95)] = 0
+        P, npass = int(rng.integers(1, 3)), int(rng.integers(2, 4))
+        enc, lcup, _ = iso_ht_encode_passes(d, w, h, P, npass)
+        if not enc:
+            continue
+        ref = np.frombuffer(enc[lcup:], np.uint8).copy()
+        mode = int(rng.integers(0, 5))
+        if mode == 0:
+            ref = rng.integers(0, 256, ref.size).astype(np.uint8)
+        elif mode == 1:
+            ref[rng.random(ref.size) < 0.4] = 0xFF
+        elif mode == 2:
+            ref = ref[: int(rng.integers(0, ref.size + 1))]
+        elif mode == 3:
+            ref = np.concatenate([ref, rng.integers(0, 256, int(rng.integers(1, 2000))).astype(np.uint8)])
+        else:
+            ref = np.full(int(rng.integers(1, 1500)), 0xFF, np.uint8)
+        data = enc[:lcup] + ref.tobytes()
+        blocks.append((data, w, h, P + 1, 0, npass, lcup))
+        want.append(_rev(O.iso_ht_decode_passes(data, lcup, w, h, P + 1, npass)[0]))
+    for i, (got, w_) in enumerate(zip(gpu_ctx.ht_decode_blocks(blocks, mode=ISO), want)):
+        assert np.array_equal(got, w_), (i, blocks[i][1:])
 
 
 def test_iso_ht_garbage_vs_oracle(gpu_ctx):
@@ -136,6 +204,30 @@ def test_iso_whole_path_lossless_htj2k(j2k, gpu_ctx, w, h, ncomp, prec, tw, th, 
         maxv = (1 << prec) - 1
         for c in range(ncomp):
             assert np.array_equal(val[:, :, c], s[c].astype(np.int64) * 65535 // maxv)   # ISO packing: no int32 wrap
+
+
+@pytest.mark.parametrize("w,h,ncomp,tw,nl,passes,P", [
+    (200, 150, 1, None, 3, 3, 1), (256, 256, 3, None, 5, 3, 1), (333, 211, 3, 128, 4, 2, 1), (512, 512, 3, 256, 5, 3, 2),
+    (640, 360, 3, None, 5, 2, 3), (328, 140, 3, None, 5, 1, 2), (1024, 512, 3, 512, 5, 3, 1), (96, 80, 1, 32, 2, 3, 3),
+    (300, 200, 3, None, 4, 3, 1), (1024, 256, 3, 512, 5, 2, 2),
+])
+def test_iso_whole_path_sigprop_magref_equals_openjpeg(j2k, gpu_ctx, w, h, ncomp, tw, nl, passes, P):
+    """multi-pass HTJ2K codestreams (cleanup + SigProp [+ MagRef]) through the whole path: the pixels OpenJPEG decodes
+    from the same bytes, and the C checker's; with and without int16 coefficient planes"""
+    Image = pytest.importorskip("PIL.Image")
+    s = jobs.synth_image(w, h, ncomp, 8, seed=w + 7 * h)
+    job = jobs.build_iso_job(s, 8, tw, tw, nl, ht_passes=passes, ht_plane=P)
+    assert (job["cblks"]["num_passes"] == passes).any()
+    im = Image.open(io.BytesIO(job["codestream"]))
+    im.load()
+    a = np.array(im).reshape(h, w, ncomp)
+    want = O.iso_decode_job(job)
+    assert np.array_equal(want.reshape(h, w, -1)[:, :, :ncomp], a)
+    for cbits in (0, job["coef_bits"]):
+        got = iso_pixels(j2k, gpu_ctx, job, coef_bits=cbits)
+        assert np.array_equal(got, want), cbits
+    if passes == 3 and P == 1:                                     # only isolated +-1 coefficients are lost
+        assert np.abs(a.astype(int) - np.moveaxis(s, 0, 2)).max() <= 3
 
 
 @pytest.mark.parametrize("w,h,ncomp,tw,th,nl", [(256, 256, 3, None, None, 5), (1024, 512, 3, 512, 512, 5),
