@@ -60,8 +60,49 @@ def test_iso_ht_oracle_inverts_encoder_random_blocks():
             continue
         out, rc = O.iso_ht_decode(enc, w, h, 1)
         assert rc == 0 and np.array_equal(out, d), t
-        out3, rc = O.iso_ht_decode(enc, w, h, 3)                   # cleanup at bit-plane 2: magnitudes shifted
-        assert rc == 0 and np.array_equal(out3, d * 4)
+        out3, rc = O.iso_ht_decode(enc, w, h, 3)                   # cleanup at bit-plane 2: magnitudes shifted, mid-point below
+        assert rc == 0 and np.array_equal(out3, d * 4 + 2 * np.sign(d))
+
+
+@pytest.mark.parametrize("w,h,ncomp,tw,nl,passes,P", [
+    (200, 150, 1, None, 3, 1, 1), (200, 150, 1, None, 3, 2, 1), (200, 150, 1, None, 3, 3, 1), (256, 256, 3, None, 5, 3, 2),
+    (333, 211, 3, 128, 4, 2, 3), (333, 211, 3, 128, 4, 3, 1), (70, 5, 1, None, 2, 3, 1), (5, 90, 3, None, 3, 2, 2),
+])
+def test_openjpeg_pins_sigprop_magref(w, h, ncomp, tw, nl, passes, P):
+    """HT SigProp / MagRef (T.814 7.4, 7.5): OpenJPEG decodes the multi-pass codestreams of the extended writer, and the
+    CPU checker (tier-2 parser -> oracle/iso_ht.c refinement passes -> oracle/iso_path.c) reproduces OpenJPEG's pixels
+    bit for bit -- including the mid-point reconstruction of a cleanup pass that stops above bit-plane 0"""
+    s = jobs.synth_image(w, h, ncomp, 8, seed=w + h)
+    job = jobs.build_iso_job(s, 8, tw, tw, nl, ht_passes=passes, ht_plane=P)
+    ref = opj_decode(job["codestream"]).reshape(h, w, ncomp)
+    got = O.iso_decode_job(job).reshape(h, w, -1)[:, :, :ncomp]
+    assert np.array_equal(got, ref)
+    via_parser = O.iso_decode_job(jobs.build_iso_job_from_codestream(job["codestream"])).reshape(h, w, -1)[:, :, :ncomp]
+    assert np.array_equal(via_parser, ref)
+    err = np.abs(ref.astype(int) - np.moveaxis(s, 0, 2)).max()
+    assert err <= (3 if (passes, P) == (3, 1) else 40)             # (3, 1): only isolated +-1 coefficients are lost
+
+
+def test_iso_ht_refinement_checker_matches_writer_statement():
+    """block level: the checker's SigProp / MagRef decode equals the reconstruction the writer states for its own stream"""
+    from datagen import iso_ht_encode_passes
+    rng = np.random.default_rng(5)
+    n = 0
+    for t in range(400):
+        w, h = int(rng.integers(1, 65)), int(rng.integers(1, 65))
+        nb = int(rng.integers(2, 12))
+        d = rng.integers(-(1 << nb) + 1, 1 << nb, w * h).astype(np.int32)
+        d[rng.random(w * h) < rng.uniform(0, 0.97)] = 0
+        sm = rng.random(w * h) < 0.3
+        d[sm] = rng.integers(-3, 4, int(sm.sum()))
+        P, npass = int(rng.integers(1, 4)), int(rng.integers(1, 4))
+        enc, lcup, recon = iso_ht_encode_passes(d, w, h, P, npass)
+        if not enc:
+            continue
+        out, rc = O.iso_ht_decode_passes(enc, lcup, w, h, P + 1, npass)
+        assert rc == 0 and np.array_equal(out, recon), t
+        n += 1
+    assert n > 300
 
 
 def test_iso_ht_oracle_rejects_malformed():
