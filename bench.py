@@ -1,28 +1,35 @@
 #!/usr/bin/env python3
 """bench.py -- decoded Mpixels/s of the B200 JPEG 2000 tile-component decode path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--coder ht|ebcot] [--frames F]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--frames F] [--no-extra]
 
-One "step" = one pass of the whole hot path (block entropy decode -> inverse DWT -> inverse RCT -> DC shift ->
-clamp -> RGBA pack) over one batch of F frames of BASELINE configs[1]: 3840x2160 RGB 8-bit lossless,
-5 decomposition levels (6 resolutions), 512x512 tiles, RCT, 64x64 code blocks, block bitstreams produced by the
-reference encoder restated in datagen/ (REF semantics).  Inputs are resident in HBM when the
-timed region starts (`value`); `e2e` times the same batch through the host-buffer C-ABI call with pinned host
-buffers, H2D and D2H inside the timed region.  Timing: CUDA events on the launching stream, barrier +
-synchronize on both sides, max over ranks.  The batch working set (F x (99.5 MB coefficients + 33 MB pixels))
-is larger than the 126 MB L2, so no explicit L2 flush is needed between steps.
+Headline workload = BASELINE configs[1] as a CONFORMANT HTJ2K codestream (ISO/IEC 15444-15; J2KGPU_MODE_ISO):
+3840x2160 RGB 8-bit lossless 5-3, 5 decomposition levels (6 resolutions), 512x512 tiles, RCT, 64x64 code blocks,
+HT cleanup-only blocks, F DISTINCT frames per step.  One "step" = one pass of the whole hot path (HT block decode ->
+inverse 5-3 DWT -> inverse RCT -> DC shift -> clamp -> RGBA pack) over that batch.
 
-Extra objects on the JSON line: roofline (the fused kernel "IDWT levels 1+0 + RCT + DC shift + clamp + RGBA pack",
-algorithmic bytes 4*W*H*C + W*H*bpp per frame over its CUDA-event time, against MEASURED_PEAKS.json), cpu_baseline
-(the C oracle, a restatement of the reference's Go stage functions, all host threads, bounded sample), clocks, and --
-unless --no-extra -- the same geometry as a conformant HTJ2K codestream in ISO mode (iso_htj2k, cross-checked with
-OpenJPEG) and with the reference's EBCOT coder (ebcot_ref).
+  value      device-resident: inputs in HBM when the timed region starts, CUDA events on the launching stream, barrier +
+             synchronize on both sides, max over ranks, EXACTLY --steps steps (`sustained` repeats it over >= 200 steps).
+  e2e        the plugin call j2kgpu_decode_batch with pinned HOST buffers: table validation / flattening / upload, H2D of the
+             compressed bytes, kernels and D2H of the pixels all inside the clock (`e2e.prebuilt_job` = the same batch through a
+             job whose tables were uploaded beforehand, j2kgpu_job_run_host).
+  guard      before anything is timed every frame of every timed workload is decoded once and compared: lossless frames with
+             their source image, frame 0 additionally with the CPU checker (oracle/) and, for the headline, with OpenJPEG.
+  roofline   the HBM-bound kernel of the path (IDWT levels 1+0 + RCT + DC + clamp + RGBA pack): ALGORITHMIC bytes per launch
+             (4*W*H*C + W*H*bpp per frame -- the reference's int32 coefficients, whatever the plane type in HBM)
+             over its CUDA-event time, against MEASURED_PEAKS.json; `moved_*` = the bytes the kernel really has to move.
+  side       the same geometry in REF semantics: the reference's own (non-conformant, one row in four) HT coder and its
+             EBCOT coder (ref_ht, ebcot_ref); cfg4 (8192^2 16-bit grey, 1024^2 tiles) decoded as ONE image whose tiles are
+             sharded over the ranks into one shared host buffer (cfg4_tile_sharded).
+The batch working set (F x (50-100 MB coefficients + 33 MB pixels)) is larger than the 126 MB L2: no L2 flush needed.
 
---impl reference times the CPU implementation alone (oracle port; the Go reference cannot run: no Go toolchain).
+--impl reference times the CPU implementation of the same workload (the C checker of oracle/ with all host threads; the Go
+reference cannot run: no Go toolchain, and its own decodeTile is a placeholder -- SURVEY.md F1/F5).
 """
 import argparse
 import ctypes as C
 import json
+import mmap
 import os
 import subprocess
 import sys
@@ -36,21 +43,49 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 W, H, NCOMP, PREC, TILE, LEVELS = 3840, 2160, 3, 8, 512, 5
-NCU_TRAFFIC_RATIO = {4: 1.069}     # measured DRAM bytes / algorithmic bytes of the fused kernel (ncu capture, see profiles/)
 METRIC = "decoded_mpixels_per_s"
 UNIT = "Mpixel/s"
+# dram__bytes_read.sum + dram__bytes_write.sum of the roofline kernel over its algorithmic bytes, from the ncu --set full
+# captures committed under profiles/ (an OFFLINE capture of this same command; the bench cannot run ncu on itself)
+NCU_TRAFFIC = {4: (1.069, "profiles/r1_ncu_idwt53_wide_int32_final.txt"), 2: (None, None)}
 
 
-def workload_name(coder, frames):
-    return ("cfg2: %dx%d RGB 8-bit lossless 5-3, %d levels, %dx%d tiles, RCT, 64x64 blocks, %s block coder "
-            "(REF semantics), batch of %d frames" % (W, H, LEVELS, TILE, TILE,
-                                                    "reference HT" if coder == "ht" else "EBCOT/MQ", frames))
+def workload_name(frames):
+    return ("cfg2 as a conformant HTJ2K codestream: %dx%d RGB 8-bit lossless 5-3, %d levels, %dx%d tiles, RCT, 64x64 blocks, "
+            "HT cleanup-only code blocks (ISO/IEC 15444-15), batch of %d distinct frames" % (W, H, LEVELS, TILE, TILE, frames))
 
 
-def build_frame(coder, seed, threads):
+# ---- input generation (CPU, before CUDA is touched: worker processes are forked) ---------------------------------------------
+def _make_frame(spec):
+    kind, seed, keep_cs = spec
     from datagen import jobs
-    s = jobs.synth_image(W, H, NCOMP, PREC, seed=seed)
-    return jobs.build_ref_job(s, PREC, TILE, TILE, nlevels=LEVELS, reversible=True, ht=(coder == "ht"), threads=threads)
+    s = jobs.synth_image_fast(W, H, NCOMP, PREC, seed=seed)
+    if kind == "iso":
+        j = jobs.build_iso_job(s, PREC, TILE, TILE, LEVELS)
+        if not keep_cs:
+            j.pop("codestream", None)
+    else:
+        j = jobs.build_ref_job(s, PREC, TILE, TILE, nlevels=LEVELS, reversible=True, ht=(kind == "ref_ht"), threads=2)
+        j.pop("planes", None)
+    j["samples"] = s.astype(np.uint8)
+    return j
+
+
+def _make_cfg4_tile(spec):
+    seed, tx, ty, tile, prec, nlevels = spec
+    from datagen import jobs
+    s = jobs.synth_image_fast(tile, tile, 1, prec, seed=seed)
+    j = jobs.build_iso_job(s, prec, None, None, nlevels)
+    j.pop("codestream", None)
+    return j
+
+
+def build_many(fn, specs, workers):
+    if workers <= 1 or len(specs) <= 1:
+        return [fn(s) for s in specs]
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(min(workers, len(specs))) as pool:
+        return pool.map(fn, specs, chunksize=1)
 
 
 def peaks():
@@ -94,67 +129,63 @@ class ClockSampler:
                 self.proc.kill()
         sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        pw = [float(r[3]) for r in self.rows if len(r) >= 9 and r[3].replace(".", "").isdigit()]
+        busy = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] if pw else sm       # samples taken under load
         reasons = set()
         for r in self.rows:
             if len(r) >= 9:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+        return {"sm_mhz": float(np.median(busy or sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def oracle_image(O, job):
-    img = O.Image()
-    img.width, img.height, img.ncomp = job["width"], job["height"], job["ncomp"]
-    for c in range(job["ncomp"]):
-        img.prec[c], img.sgnd[c] = job["prec"], job["sgnd"]
-    img.mct, img.reversible, img.nlevels, img.ht = job["mct"], job["reversible"], job["nlevels"], job["ht"]
-    return img
-
-
-def cpu_decode_time(job, threads, reps):
-    """seconds per frame of the oracle's whole path (orc_decode_image) with `threads` host threads"""
+def oracle_pixels(job, threads):
+    """frame through the CPU checker: ISO jobs -> oracle/iso_path.c, REF jobs -> orc_decode_image; returns (pixels, seconds)"""
     import oracle_lib as O
     from datagen import jobs
-    img = oracle_image(O, job)
-    tcs, cbs = jobs.as_ctypes(job["tilecomps"], O.TileComp), jobs.as_ctypes(job["cblks"], O.CBlk)
-    blob = np.ascontiguousarray(job["blob"])
-    out = np.zeros(W * H * 4, np.uint8)
-    fn = O.lib().orc_decode_image
-    best = None
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        rc = fn(C.byref(img), tcs, len(tcs), cbs, len(cbs), blob.ctypes.data_as(O.u8p), C.c_uint64(blob.size),
-                out.ctypes.data_as(O.u8p), C.c_uint64(W * 4), threads)
-        dt = time.perf_counter() - t0
-        assert rc == 0
-        best = dt if best is None else min(best, dt)
-    return best, out
+    t0 = time.perf_counter()
+    if job.get("mode") == 1:
+        out = O.iso_decode_job(job, threads=threads)
+    else:
+        img = O.Image()
+        img.width, img.height, img.ncomp = job["width"], job["height"], job["ncomp"]
+        for c in range(job["ncomp"]):
+            img.prec[c], img.sgnd[c] = job["prec"], job["sgnd"]
+        img.mct, img.reversible, img.nlevels, img.ht = job["mct"], job["reversible"], job["nlevels"], job["ht"]
+        out = O.decode_image(img, jobs.as_ctypes(job["tilecomps"], O.TileComp), jobs.as_ctypes(job["cblks"], O.CBlk),
+                             job["blob"], job["width"] * 4, job["width"] * job["height"] * 4, threads=threads)
+    return out, time.perf_counter() - t0
 
 
 def run_reference(args):
-    """--impl reference: the CPU implementation of the path on the host cores (oracle port, all threads)."""
+    """--impl reference: the CPU implementation of the headline workload on the host cores (all threads), one frame of the
+    batch per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    job = build_frame(args.coder, 1002, threads)
-    for _ in range(min(args.warmup, 1)):
-        cpu_decode_time(job, threads, 1)
+    job = _make_frame(("iso", 2002, False))
+    warm = min(args.warmup, 1)
+    for _ in range(warm):
+        oracle_pixels(job, threads)
     times = []
     for _ in range(max(1, args.steps)):
-        t, _ = cpu_decode_time(job, threads, 1)
-        times.append(t)
+        out, dt = oracle_pixels(job, threads)
+        times.append(dt)
+    pix = out.reshape(H, W, 4)
+    assert all(np.array_equal(pix[:, :, c], job["samples"][c]) for c in range(3)), "the CPU arm decodes its input incorrectly"
     tot = sum(times)
     val = (W * H / 1e6) * len(times) / tot
-    sample = "1 frame of the workload per step (of %d in the GPU arm's batch)" % args.frames
+    sample = "1 frame of the workload per step (of %d in the GPU arm's batch), all host threads" % args.frames
     line = {"impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": UNIT, "n_gpus": args.gpus,
-            "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": round(1e3 * tot / len(times), 3),
+            "steps": len(times), "warmup": warm, "ms_per_step": round(1e3 * tot / len(times), 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": workload_name(args.coder, args.frames), "mode": "REF", "sample": sample},
+            "config": {"workload": workload_name(args.frames), "mode": "ISO", "sample": sample},
             "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                             "note": "C restatement of the reference's Go stage functions (oracle/), not Go: no Go toolchain on the box"},
+                             "note": "C statement of the same ISO-mode path (oracle/iso_path.c, bit-identical to OpenJPEG 2.5.4); "
+                                     "the Go reference cannot run here (no Go toolchain) and its decodeTile is a placeholder"},
             "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -162,21 +193,23 @@ def run_reference(args):
 def build_items(j2k, jobs, frames, mode):
     """pinned host buffers + batch items for a list of frame jobs"""
     import torch
-    stride = W * 4
     keep, items, host_out = [], [], []
     for j in frames:
+        bpp = j2k.fmt_bpp(j["ncomp"], j["prec"])
+        stride = j["width"] * bpp
         tcs, cbs = jobs.as_ctypes(j["tilecomps"], j2k.TileComp), jobs.as_ctypes(j["cblks"], j2k.CBlk)
         hb = torch.from_numpy(np.ascontiguousarray(j["blob"])).pin_memory()
-        ho = torch.empty(stride * H, dtype=torch.uint8).pin_memory()
+        ho = torch.empty(stride * j["height"], dtype=torch.uint8).pin_memory()
         keep += [tcs, cbs, hb]
         host_out.append(ho)
-        img = j2k.make_image(W, H, NCOMP, PREC, nlevels=LEVELS, ht=j["ht"], mode=mode, coef_bits=j.get("coef_bits", 0))
+        img = j2k.make_image(j["width"], j["height"], j["ncomp"], j["prec"], nlevels=j["nlevels"], ht=j["ht"], mode=mode,
+                             coef_bits=j.get("coef_bits", 0))
         items.append(j2k.BatchItem(img, tcs, len(tcs), cbs, len(cbs), C.cast(hb.data_ptr(), j2k.u8p), hb.numel(),
-                                   C.cast(ho.data_ptr(), j2k.u8p), stride))
+                                   C.cast(ho.data_ptr(), j2k.u8p), stride, 0, 0))
     return items, host_out, keep
 
 
-def measure(args, ctx, j2k, jobs, frames, mode, stream, world, barrier, steps, check_lossless):
+def measure(args, ctx, j2k, jobs, frames, mode, stream, barrier, steps, e2e_steps, long_steps, rank0_checks):
     """device-resident and end-to-end timing of one workload; returns a dict of raw measurements"""
     import torch
     stride = W * 4
@@ -186,31 +219,61 @@ def measure(args, ctx, j2k, jobs, frames, mode, stream, world, barrier, steps, c
     d_blob = torch.cat([torch.from_numpy(np.ascontiguousarray(j["blob"])) for j in frames] + [torch.zeros(64, dtype=torch.uint8)]).cuda()
     d_out = torch.empty(job.out_bytes, dtype=torch.uint8, device="cuda")
     torch.cuda.synchronize()
-    # correctness guard on the exact bench inputs
+    # ---- correctness guard on the exact inputs that are timed: every frame against its source image (all three
+    # workloads are lossless where the coder decodes every sample), frame 0 against the CPU checker / OpenJPEG ----
     job.run(d_blob.data_ptr(), d_out.data_ptr())
     stream.synchronize()
-    first = d_out[: stride * H].cpu().numpy().reshape(H, W, 4)
-    if check_lossless:
-        src = frames[0]["samples"]
-        for c in range(3):
-            assert np.array_equal(first[:, :, c], src[c].astype(np.uint8)), "bench inputs decode incorrectly"
+    lossless = not (mode == 0 and frames[0]["ht"])               # the reference's HT coder decodes one row in four (ht.go:677)
+    firsts = []
+    for i, fr in enumerate(frames):
+        off = job.out_offset(i)
+        pix = d_out[off: off + stride * H].cpu().numpy().reshape(H, W, 4)
+        if lossless:
+            for c in range(3):
+                assert np.array_equal(pix[:, :, c], fr["samples"][c]), "bench input %d decodes incorrectly" % i
+        if i == 0:
+            firsts = pix.copy()
+    guard = {"frames_equal_source": F if lossless else 0}
+    if rank0_checks:
+        want, cpu_s = oracle_pixels(frames[0], os.cpu_count() or 1)
+        assert np.array_equal(firsts.reshape(-1), want), "frame 0 differs from the CPU checker"
+        guard["frame0_equals_cpu_checker"] = True
+        guard["cpu_s"] = cpu_s
+        if frames[0].get("codestream"):
+            try:
+                import io
+                from PIL import Image
+                t0 = time.perf_counter()
+                im = Image.open(io.BytesIO(frames[0]["codestream"]))
+                im.load()
+                guard["openjpeg_s"] = time.perf_counter() - t0
+                assert np.array_equal(np.array(im), firsts[:, :, :3]), "frame 0 differs from OpenJPEG's decode"
+                guard["frame0_equals_openjpeg"] = True
+            except ImportError:
+                pass
     for _ in range(args.warmup):
         job.run(d_blob.data_ptr(), d_out.data_ptr())
-    barrier()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    l0 = ctx.launches
-    ev[0].record(stream)
-    for _ in range(steps):
-        job.run(d_blob.data_ptr(), d_out.data_ptr())
-    ev[1].record(stream)
-    barrier()
-    ms_total = ev[0].elapsed_time(ev[1])
-    launches = ctx.launches - l0
 
-    def time_fn(fn, reps):
+    def timed(n):
+        barrier()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        l0 = ctx.launches
+        ev[0].record(stream)
+        for _ in range(n):
+            job.run(d_blob.data_ptr(), d_out.data_ptr())
+        ev[1].record(stream)
+        barrier()
+        return ev[0].elapsed_time(ev[1]), ctx.launches - l0
+
+    ms_total, launches = timed(steps)
+    ms_long, _ = timed(long_steps) if long_steps else (0.0, 0)
+
+    def time_fn(fn, reps, pre=None):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ts = []
         for _ in range(reps):
+            if pre:
+                pre()
             a.record(stream)
             fn()
             b.record(stream)
@@ -218,35 +281,35 @@ def measure(args, ctx, j2k, jobs, frames, mode, stream, world, barrier, steps, c
             ts.append(a.elapsed_time(b))
         return float(np.mean(ts))
 
-    reps = max(3, min(steps, 10))
+    reps = max(5, min(steps, 20))
     ent_ms = time_fn(lambda: job.run_entropy(d_blob.data_ptr()), reps)
     dwt_ms = time_fn(lambda: job.run_dwt_mct(d_out.data_ptr()), reps)
-    last_ts = []
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for _ in range(reps):                      # the dominant kernel alone: coarser levels refill the ping-pong buffers first
-        for lvl in range(LEVELS - 1, 0, -1):
-            job.run_level(lvl)
-        a.record(stream)
-        job.run_level(0, d_out.data_ptr())
-        b.record(stream)
-        b.synchronize()
-        last_ts.append(a.elapsed_time(b))
-    last_ms = float(np.mean(last_ts))
-    # end to end through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timed region)
+    nl = frames[0]["nlevels"]
+    # the roofline kernel alone: the coarser levels refill the ping-pong buffers first
+    last_ms = time_fn(lambda: job.run_level(0, d_out.data_ptr()), reps, pre=lambda: [job.run_level(l) for l in range(nl - 1, 0, -1)])
+    # ---- end to end: the plugin call (tables built inside), and the prebuilt job beside it ----
+    for _ in range(2):
+        ctx.decode_batch(items)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.decode_batch(items)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    assert np.array_equal(host_out[0].numpy().reshape(H, W, 4), firsts), "plugin call differs from the device path"
     for _ in range(2):
         job.run_host()
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(1, min(steps, 5))
-    for _ in range(e2e_steps):
+    pre_steps = max(1, min(e2e_steps, 10))
+    for _ in range(pre_steps):
         job.run_host()
     barrier()
-    e2e_s = time.perf_counter() - t0
-    assert np.array_equal(host_out[0].numpy().reshape(H, W, 4), first), "host path differs from device path"
-    res = dict(ms_total=ms_total, steps=steps, launches=int(launches), ent_ms=ent_ms, dwt_ms=dwt_ms, last_ms=last_ms,
-               e2e_s=e2e_s, e2e_steps=e2e_steps, h2d=int(d_blob.numel()) - 64, d2h=stride * H * F,
-               n_blocks=sum(len(j["cblks"]) for j in frames), F=F, fused_levels=job.fused_levels, coef_bytes=job.coef_bytes,
-               plan=job.plan)
+    pre_s = time.perf_counter() - t0
+    res = dict(ms_total=ms_total, steps=steps, launches=int(launches), ms_long=ms_long, long_steps=long_steps, ent_ms=ent_ms,
+               dwt_ms=dwt_ms, last_ms=last_ms, e2e_s=e2e_s, e2e_steps=e2e_steps, pre_s=pre_s, pre_steps=pre_steps,
+               h2d=int(d_blob.numel()) - 64, d2h=stride * H * F, n_blocks=sum(len(j["cblks"]) for j in frames), F=F,
+               fused_levels=job.fused_levels, coef_bytes=job.coef_bytes, plan=job.plan, guard=guard)
     job.close()
     return res
 
@@ -256,9 +319,10 @@ def bind_to_gpu_numa_node(local):
     so that 8 ranks do not push their H2D / D2H traffic across the socket interconnect; returns a note for the JSON line"""
     try:
         import torch
-        bus = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
-        dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
-        dev = getattr(torch.cuda.get_device_properties(local), "pci_device_id", 0)
+        props = torch.cuda.get_device_properties(local)
+        bus = getattr(props, "pci_bus_id", None)
+        dom = getattr(props, "pci_domain_id", 0)
+        dev = getattr(props, "pci_device_id", 0)
         if bus is None:
             return "numa: unknown"
         path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
@@ -278,16 +342,102 @@ def bind_to_gpu_numa_node(local):
         return "numa: not bound (%s)" % str(e)[:60]
 
 
-def run_ours(args):
+def run_cfg4_tile_sharded(ctx, j2k, jobs, shard, tile_jobs, my_tiles, world, rank, barrier, reduce_max, steps):
+    """BASELINE configs[3]: ONE 8192x8192 16-bit grey image, 1024x1024 tiles, its 64 tiles sharded over the ranks (LPT on
+    compressed bytes, go-jpeg2000_b200/shard.py); every rank decodes its tiles and copies ONLY their pixel rectangles
+    (J2KGPU_ITEM_TILES_ONLY) into ONE host image shared by all ranks (a page-locked /dev/shm mapping); rank 0 checks the
+    assembled image against the sources.  No collective on the data path."""
     import torch
-    import torch.distributed as dist
-    from datagen import jobs
-    from __graft_entry__ import load_package
-    j2k = load_package()
+    G, T, prec, nl = 8192, 1024, 16, 5
+    ntx = G // T
+    stride = G * 2
+    path = "/dev/shm/j2kgpu_cfg4_%s.pix" % os.environ.get("MASTER_PORT", "0")
+    if rank == 0:
+        with open(path, "wb") as f:
+            f.truncate(stride * G)
+    barrier()
+    fd = os.open(path, os.O_RDWR)
+    mm = mmap.mmap(fd, stride * G)
+    host = np.frombuffer(mm, np.uint8)
+    ctx.host_register(host)
+    tcs, cbs, blobs, boff = [], [], [], 0
+    for t in my_tiles:
+        j = tile_jobs[t]
+        tx, ty = t % ntx, t // ntx
+        tc = j["tilecomps"].copy()
+        tc["x0"] += tx * T; tc["x1"] += tx * T; tc["y0"] += ty * T; tc["y1"] += ty * T
+        cb = j["cblks"].copy()
+        cb["tilecomp"] += sum(len(a) for a in tcs)
+        cb["data_off"] += boff
+        tcs.append(tc)
+        cbs.append(cb)
+        blobs.append(j["blob"])
+        boff += j["blob"].size
+    tc_arr = np.concatenate(tcs) if tcs else np.zeros(0, jobs.TILECOMP_DT)
+    cb_arr = np.concatenate(cbs) if cbs else np.zeros(0, jobs.CBLK_DT)
+    blob = torch.from_numpy(np.concatenate(blobs) if blobs else np.zeros(8, np.uint8)).pin_memory()
+    c_tcs, c_cbs = jobs.as_ctypes(tc_arr, j2k.TileComp), jobs.as_ctypes(cb_arr, j2k.CBlk)
+    cbits = max(tile_jobs[t]["coef_bits"] for t in my_tiles) if my_tiles else 0
+    img = j2k.make_image(G, G, 1, prec, nlevels=nl, ht=1, mode=1, coef_bits=cbits)
+    item = j2k.BatchItem(img, c_tcs, len(tc_arr), c_cbs, len(cb_arr), C.cast(blob.data_ptr(), j2k.u8p), blob.numel(),
+                         C.cast(host.ctypes.data, j2k.u8p), stride, j2k.ITEM_TILES_ONLY, 0)
+    for _ in range(2):
+        ctx.decode_batch([item])
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ctx.decode_batch([item])
+    barrier()
+    (dt,) = reduce_max(time.perf_counter() - t0)
+    ok = True
+    if rank == 0:                                            # the assembled image, every tile, against its source
+        img16 = host.reshape(G, G, 2)
+        val = (img16[:, :, 0].astype(np.uint16) << 8) | img16[:, :, 1]
+        for t, j in enumerate(tile_jobs):
+            tx, ty = t % ntx, t // ntx
+            ok &= bool(np.array_equal(val[ty * T:(ty + 1) * T, tx * T:(tx + 1) * T], j["samples"][0].astype(np.uint16)))
+    barrier()
+    ctx.host_unregister(host)
+    del host
+    mm.close()
+    os.close(fd)
+    barrier()
+    if rank == 0:
+        os.unlink(path)
+    return dict(value=round(G * G / 1e6 * steps / dt, 1), unit=UNIT, ms_per_image=round(1e3 * dt / steps, 3), steps=steps,
+                tiles_per_rank=[len(p) for p in shard.shard_units([tile_jobs[t]["blob"].size for t in range(len(tile_jobs))], world)],
+                assembled_image_equals_source=ok, api="j2kgpu_decode_batch, J2KGPU_ITEM_TILES_ONLY, one shared page-locked host image",
+                workload="cfg4: 8192x8192 grey 16-bit lossless HTJ2K, 1024x1024 tiles, ONE image, tiles sharded over %d rank(s), "
+                         "end to end (H2D + kernels + D2H of the owned tile rectangles)" % world)
 
+
+def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    F = args.frames
+    # ---- which frames are this rank's: the batch of world * F frames is sharded with the package's planner (equal costs:
+    # the frames do not exist yet; every rank derives the same plan without talking to the others) ----
+    from __graft_entry__ import load_package
+    j2k = load_package()
+    from go_jpeg2000_b200 import shard
+    mine = shard.shard_units([W * H] * (world * F), world, rank)
+    assert len(mine) == F
+    workers = max(1, min(16, (os.cpu_count() or 1) // max(1, world)))
+    t_gen = time.perf_counter()
+    specs = [("iso", 2002 + g, i == 0 and rank == 0) for i, g in enumerate(mine)]
+    n_ref, n_eb = (min(F, 4), min(F, 2)) if not args.no_extra else (0, 0)
+    specs += [("ref_ht", 1002 + mine[i], False) for i in range(n_ref)] + [("ebcot", 3002 + mine[i], False) for i in range(n_eb)]
+    built = build_many(_make_frame, specs, workers)
+    iso_frames, ref_frames, eb_frames = built[:F], built[F:F + n_ref], built[F + n_ref:]
+    tile_jobs = []
+    if not args.no_extra:
+        tile_jobs = build_many(_make_cfg4_tile, [(4004 + t, t % 8, t // 8, 1024, 16, 5) for t in range(64)], workers)
+    t_gen = time.perf_counter() - t_gen
+
+    import torch
+    import torch.distributed as dist
+    from datagen import jobs
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
     torch.cuda.set_device(local)
@@ -315,97 +465,89 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return tuple(float(x) for x in t)
 
-    threads = max(1, (os.cpu_count() or 1) // max(1, world))
-    F = args.frames
-    mpix_step = W * H * F * world / 1e6
-    alg_bytes = (4 * W * H * NCOMP + W * H * 4) * F               # SURVEY.md 8(d), per launch of the fused kernel
     peak, peak_src = peaks()
 
     def summarize(m):
-        ms_total, e2e_s = reduce_max(m["ms_total"], m["e2e_s"])
-        # bytes this variant's fused kernel has to move: its coefficient planes (int32, or int16 when the plan says so) + pixels
-        vb = (m["coef_bytes"] * W * H * NCOMP + W * H * 4) * F
-        ach = vb / (m["last_ms"] / 1e3) / 1e9
-        stg = vb / (m["dwt_ms"] / 1e3) / 1e9
-        return dict(value=round(mpix_step * m["steps"] / (ms_total / 1e3), 1), ms_per_step=round(ms_total / m["steps"], 4),
-                    e2e=dict(value=round(mpix_step * m["e2e_steps"] / e2e_s, 1), unit=UNIT, h2d_bytes_per_step=m["h2d"],
-                             d2h_bytes_per_step=m["d2h"], ms_per_step=round(1e3 * e2e_s / m["e2e_steps"], 3),
-                             api="j2kgpu_job_run_host (pinned host buffers)"),
-                    gpu_launches=m["launches"], code_blocks_per_step=m["n_blocks"] * world,
-                    plan=dict(idwt_levels_in_last_kernel=m["fused_levels"], coef_plane_bytes_per_sample=m["coef_bytes"],
-                              last_kernel="k_idwt53_wide (16 columns per lane)" if m["plan"] & 4 else
-                                          "k_idwt53_fused (4 columns per lane)" if m["plan"] & 1 else "k_idwt53_stream"),
-                    stages_ms=dict(entropy=round(m["ent_ms"], 4), dwt_mct_pack=round(m["dwt_ms"], 4),
-                                   last_level_fused=round(m["last_ms"], 4)),
-                    roofline=dict(bound="hbm", achieved=round(ach, 1), peak=peak, unit="GB/s", frac=round(ach / peak, 4),
-                                  dwt_mct_stage_gbs=round(stg, 1), dwt_mct_stage_frac=round(stg / peak, 4),
-                                  bytes_per_launch=vb))
+        Fm = m["F"]
+        mpix_step = W * H * Fm * world / 1e6
+        alg = (4 * W * H * NCOMP + W * H * 4) * Fm                  # SURVEY.md 8(d), per launch of the roofline kernel
+        moved = (m["coef_bytes"] * W * H * NCOMP + W * H * 4) * Fm   # what this variant's kernel has to move (int16 planes: less)
+        ms_total, ms_long, e2e_s, pre_s = reduce_max(m["ms_total"], m["ms_long"], m["e2e_s"], m["pre_s"])
+        ach, stg = alg / (m["last_ms"] / 1e3) / 1e9, alg / (m["dwt_ms"] / 1e3) / 1e9
+        last_kernel = ("k_idwt53_wide (16 columns per lane)" if m["plan"] & 4 else
+                       "k_idwt53_fused (4 columns per lane)" if m["plan"] & 1 else "k_idwt53_stream")
+        ratio, src = NCU_TRAFFIC.get(m["coef_bytes"], (None, None))
+        out = dict(value=round(mpix_step * m["steps"] / (ms_total / 1e3), 1), ms_per_step=round(ms_total / m["steps"], 4),
+                   frames_per_gpu_per_step=Fm,
+                   e2e=dict(value=round(mpix_step * m["e2e_steps"] / e2e_s, 1), unit=UNIT, h2d_bytes_per_step=m["h2d"],
+                            d2h_bytes_per_step=m["d2h"], ms_per_step=round(1e3 * e2e_s / m["e2e_steps"], 3), steps=m["e2e_steps"],
+                            api="j2kgpu_decode_batch (tables validated, flattened and uploaded inside the call; pinned host buffers)",
+                            prebuilt_job=dict(value=round(mpix_step * m["pre_steps"] / pre_s, 1), unit=UNIT,
+                                              ms_per_step=round(1e3 * pre_s / m["pre_steps"], 3), api="j2kgpu_job_run_host")),
+                   gpu_launches=m["launches"], code_blocks_per_step=m["n_blocks"] * world,
+                   plan=dict(idwt_levels_in_last_kernel=m["fused_levels"], coef_plane_bytes_per_sample=m["coef_bytes"], last_kernel=last_kernel),
+                   stages_ms=dict(entropy=round(m["ent_ms"], 4), dwt_mct_pack=round(m["dwt_ms"], 4), last_level_fused=round(m["last_ms"], 4)),
+                   roofline=dict(bound="hbm", achieved=round(ach, 1), peak=peak, unit="GB/s", frac=round(ach / peak, 4),
+                                 kernel=last_kernel + ": IDWT levels 1+0 + RCT + DC shift + clamp + RGBA pack" if m["fused_levels"] == 2 else
+                                        last_kernel + ": last IDWT level + RCT + DC shift + clamp + RGBA pack",
+                                 peak_source=peak_src, algorithmic_bytes_per_launch=alg, duration_ms=round(m["last_ms"], 4),
+                                 moved_bytes_per_launch=moved, moved_gbs=round(moved / (m["last_ms"] / 1e3) / 1e9, 1),
+                                 moved_frac=round(moved / (m["last_ms"] / 1e3) / 1e9 / peak, 4),
+                                 dwt_mct_stage_gbs=round(stg, 1), dwt_mct_stage_frac=round(stg / peak, 4),
+                                 dwt_mct_stage_moved_frac=round(moved / (m["dwt_ms"] / 1e3) / 1e9 / peak, 4),
+                                 traffic=int(alg * ratio) if ratio else None,
+                                 traffic_source=("offline ncu --set full capture of this command, " + src) if ratio else
+                                                "no ncu capture of this variant is wired in: see profiles/"),
+                   guard=m["guard"])
+        if m["long_steps"]:
+            out["sustained"] = dict(steps=m["long_steps"], value=round(mpix_step * m["long_steps"] / (ms_long / 1e3), 1),
+                                    ms_per_step=round(ms_long / m["long_steps"], 4))
+        return out
 
     sampler = ClockSampler(local)
-    # ---- headline: REF semantics (bit-identical to the reference's stage functions) -----------------------------------
-    base = [build_frame(args.coder, 1002 + 17 * rank + i, threads) for i in range(min(2, F))]
-    frames = [base[i % len(base)] for i in range(F)]
     if rank == 0:
         sampler.start()
-    m_ref = measure(args, ctx, j2k, jobs, frames, 0, stream, world, barrier, args.steps, args.coder == "ebcot")
+    e2e_steps = max(args.steps, 20) if not args.quick else args.steps
+    long_steps = 0 if args.quick else max(200, args.steps)
+    m_iso = measure(args, ctx, j2k, jobs, iso_frames, 1, stream, barrier, args.steps, e2e_steps, long_steps, rank == 0)
     clocks = sampler.stop() if rank == 0 else None
-    main = summarize(m_ref)
+    main = summarize(m_iso)
 
     extra = {}
     if not args.no_extra:
-        # ---- real HTJ2K (ISO/IEC 15444-15), same geometry: conformant codestream, cross-checked with OpenJPEG ----
-        iso_base = [jobs.build_iso_job(jobs.synth_image(W, H, NCOMP, PREC, seed=2002 + 17 * rank + i), PREC, TILE, TILE, LEVELS)
-                    for i in range(min(2, F))]
-        iso_frames = [iso_base[i % len(iso_base)] for i in range(F)]
-        m_iso = measure(args, ctx, j2k, jobs, iso_frames, 1, stream, world, barrier, args.steps, True)
-        extra["iso_htj2k"] = summarize(m_iso)
-        extra["iso_htj2k"]["workload"] = ("configs[1] as a conformant HTJ2K codestream (lossless 5-3, RCT, HT cleanup-only blocks), "
-                                          "J2KGPU_MODE_ISO, %d frames; pixels == source image == OpenJPEG decode" % F)
-        if rank == 0:
-            try:
-                import io
-                from PIL import Image
-                t0 = time.perf_counter()
-                im = Image.open(io.BytesIO(iso_base[0]["codestream"]))
-                im.load()
-                dt = time.perf_counter() - t0
-                extra["iso_htj2k"]["openjpeg_cpu"] = dict(value=round(W * H / 1e6 / dt, 2), unit=UNIT,
-                                                          note="OpenJPEG 2.5.4 via Pillow, same codestream, 1 frame, context only")
-            except Exception as e:  # pragma: no cover
-                extra["iso_htj2k"]["openjpeg_cpu"] = dict(error=str(e)[:100])
-        # ---- classic EBCOT/MQ, REF semantics ----------------------------------------------------------------
-        if args.coder != "ebcot":
-            eb = [build_frame("ebcot", 3002 + 17 * rank, threads)]
-            eb_frames = [eb[0]] * F
-            m_eb = measure(args, ctx, j2k, jobs, eb_frames, 0, stream, world, barrier, max(2, min(args.steps, 3)), True)
-            extra["ebcot_ref"] = summarize(m_eb)
-            extra["ebcot_ref"]["workload"] = workload_name("ebcot", F)
+        s_side = max(3, min(args.steps, 10))
+        m_ref = measure(args, ctx, j2k, jobs, ref_frames, 0, stream, barrier, s_side, s_side, 0, rank == 0)
+        extra["ref_ht"] = summarize(m_ref)
+        extra["ref_ht"]["workload"] = ("cfg2 geometry, REF semantics, the reference's own HT coder (ht.go: not ISO/IEC 15444-15, decodes one "
+                                       "sample row in four, parity unpinned) -- kept OUT of the headline; %d distinct frames" % len(ref_frames))
+        m_eb = measure(args, ctx, j2k, jobs, eb_frames, 0, stream, barrier, 3, 3, 0, rank == 0)
+        extra["ebcot_ref"] = summarize(m_eb)
+        extra["ebcot_ref"]["workload"] = "cfg2 geometry, REF semantics, the reference's EBCOT/MQ coder (t1.go), %d distinct frames" % len(eb_frames)
+        costs = [j["blob"].size for j in tile_jobs]
+        extra["cfg4_tile_sharded"] = run_cfg4_tile_sharded(ctx, j2k, jobs, shard, tile_jobs, shard.shard_units(costs, world, rank),
+                                                           world, rank, barrier, reduce_max, 5)
 
     if rank == 0:
+        g = m_iso["guard"]
         cpu_threads = os.cpu_count() or 1
-        cpu_t, _ = cpu_decode_time(frames[0], cpu_threads, 1 if args.coder == "ebcot" else 2)
-        cpu_val = (W * H / 1e6) / cpu_t
         line = {
             "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": workload_name(args.coder, F), "mode": "REF", "frames_per_gpu_per_step": F,
+            "config": {"workload": workload_name(F), "mode": "ISO", "frames_per_gpu_per_step": F, "distinct_frames": F,
                        "code_blocks_per_step": main["code_blocks_per_step"], "l2": "working set > L2 (no flush needed)",
-                       "parallelism": "frames sharded across GPUs, no collective", "host": numa_note},
+                       "parallelism": "frames sharded across GPUs (go-jpeg2000_b200/shard.py), no collective", "host": numa_note,
+                       "input_generation_s": round(t_gen, 1)},
             "e2e": main["e2e"], "gpu_launches": main["gpu_launches"], "stages_ms": main["stages_ms"], "plan": main["plan"],
-            "roofline": dict(main["roofline"], kernel=main["plan"]["last_kernel"] +
-                             (": IDWT levels 1+0 + RCT + DC + clamp + RGBA pack" if main["plan"]["idwt_levels_in_last_kernel"] == 2
-                              else ": last IDWT level + RCT + DC + clamp + RGBA pack"),
-                             peak_source=peak_src, algorithmic_bytes_per_launch=alg_bytes,
-                             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, from the ncu --set full capture
-                             # in profiles/ (the bench's own 16-frame launch: 1.763 GB read + 0.507 GB written against 2.123 GB algorithmic)
-                             traffic=int(alg_bytes * NCU_TRAFFIC_RATIO.get(main["plan"]["coef_plane_bytes_per_sample"], 1.0)),
-                             traffic_source="profiles/r1_ncu_idwt53_wide_int32_final.txt (16-frame launch: 2.270 GB measured / 2.123 GB algorithmic = 1.069)"),
-            "cpu_baseline": {"value": round(cpu_val, 2), "unit": UNIT, "cores": cpu_threads, "kind": "port",
-                             "sample": "1 frame of the batch, whole path, all host threads",
-                             "note": "C restatement of the reference's Go stage functions (oracle/); Go itself is absent"},
+            "roofline": main["roofline"], "sustained": main.get("sustained"), "guard": {k: v for k, v in g.items() if not k.endswith("_s")},
+            "cpu_baseline": {"value": round((W * H / 1e6) / g["cpu_s"], 2), "unit": UNIT, "cores": cpu_threads, "kind": "port",
+                             "sample": "frame 0 of the batch, whole path, all host threads",
+                             "note": "C statement of the same ISO-mode path (oracle/iso_path.c, bit-identical to OpenJPEG); Go is absent"},
             "clocks": clocks,
         }
+        if "openjpeg_s" in g:
+            line["openjpeg_cpu"] = dict(value=round(W * H / 1e6 / g["openjpeg_s"], 2), unit=UNIT,
+                                        note="OpenJPEG 2.5.4 via Pillow decoding frame 0's codestream (context; same pixels)")
         line.update(extra)
         print(json.dumps(line))
     ctx.set_stream(0)
@@ -417,12 +559,12 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--coder", default="ht", choices=["ht", "ebcot"])
     ap.add_argument("--frames", type=int, default=16, help="frames per GPU per step (the metric is quoted on a batch)")
-    ap.add_argument("--no-extra", action="store_true", help="skip the ISO HTJ2K and EBCOT side measurements")
+    ap.add_argument("--no-extra", action="store_true", help="skip the REF-mode and cfg4 side measurements")
+    ap.add_argument("--quick", action="store_true", help="profiling runs: no sustained loop, e2e steps = --steps")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

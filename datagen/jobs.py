@@ -45,6 +45,30 @@ def synth_image(width, height, ncomp, prec, seed):
     return out
 
 
+def synth_image_fast(width, height, ncomp, prec, seed):
+    """the same kind of content as synth_image (three low-frequency cosines per channel + 2 % noise), about 5x cheaper:
+    each cosine is built from two outer products (cos(a + b) = cos a cos b - sin a sin b).  Used where many large frames
+    are needed (bench.py, full-size tests); NOT bit-identical to synth_image for the same seed."""
+    rng = np.random.default_rng(seed)
+    maxv = (1 << prec) - 1
+    x = np.arange(width, dtype=np.float32)
+    y = np.arange(height, dtype=np.float32)
+    out = np.empty((ncomp, height, width), np.int32)
+    for c in range(ncomp):
+        acc = np.zeros((height, width), np.float32)
+        for _ in range(3):
+            fx, fy = rng.uniform(0.5, 4.0, 2) * 2 * np.pi / max(width, height)
+            ph = rng.uniform(0, 2 * np.pi)
+            acc += np.outer(np.cos(fy * y), np.cos(fx * x + ph)).astype(np.float32)
+            acc -= np.outer(np.sin(fy * y), np.sin(fx * x + ph)).astype(np.float32)
+        acc *= np.float32(0.1 * maxv * 0.6 / 0.8)
+        acc += np.float32(0.5 * maxv * 0.6 / 0.8)
+        acc += rng.standard_normal((height, width), dtype=np.float32) * np.float32(0.02 * maxv)
+        np.rint(acc, out=acc)
+        out[c] = np.clip(acc, 0, maxv).astype(np.int32)
+    return out
+
+
 def forward_tile(samples, prec, reversible, nlevels, quality=1.0, sgnd=0, mct=1):
     """samples: int32 [ncomp, h, w] -> list of int32 coefficient planes (dense-prefix layout), flat"""
     ncomp, h, w = samples.shape

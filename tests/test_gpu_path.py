@@ -297,3 +297,65 @@ def test_path_argument_errors(j2k, gpu_ctx):
     blob[::7] ^= 0xA5
     job["blob"] = blob
     assert np.array_equal(gpu_pixels(j2k, gpu_ctx, job), oracle_pixels(job))
+
+
+def test_padded_stride_and_partial_tile_set(j2k, gpu_ctx):
+    """out_stride > width * bpp: the padding bytes belong to the caller and are left alone; tiles that do not cover the image:
+    the uncovered pixels hold what the reference's zero-initialised planes decode to (decoder.go:305-309: mid-grey after the DC
+    shift), never stale device memory -- also right after a call that left other pixels in the pooled buffers"""
+    w, h = 160, 96
+    s = jobs.synth_image(w, h, 3, 8, seed=61)
+    job = jobs.build_ref_job(s, 8, 64, 32, nlevels=2, reversible=True, threads=2)
+    full = oracle_pixels(job).reshape(h, w, 4)
+    gpu_pixels(j2k, gpu_ctx, job)                                # fills the pooled device buffers with this image
+    # keep only the tiles whose index is not a multiple of 3
+    tcs = job["tilecomps"]
+    tile_id = (tcs["y0"] // 32) * 3 + tcs["x0"] // 64
+    keep_tc = tile_id % 3 != 0
+    remap = np.cumsum(keep_tc) - 1
+    cb = job["cblks"][keep_tc[job["cblks"]["tilecomp"]]].copy()
+    cb["tilecomp"] = remap[cb["tilecomp"]]
+    part = dict(job, tilecomps=tcs[keep_tc].copy(), cblks=cb)
+    stride = w * 4 + 48
+    img = hdr(j2k, part)
+    out = gpu_ctx.decode_tiles(img, jobs.as_ctypes(part["tilecomps"], j2k.TileComp), jobs.as_ctypes(part["cblks"], j2k.CBlk),
+                               part["blob"], out_stride=stride).reshape(h, stride)
+    assert not out[:, w * 4:].any()                              # decode_tiles hands over a zeroed buffer: padding untouched
+    pix = out[:, :w * 4].reshape(h, w, 4)
+    covered = np.zeros((h, w), bool)
+    for t in part["tilecomps"]:
+        covered[t["y0"]:t["y1"], t["x0"]:t["x1"]] = True
+    assert covered.any() and not covered.all()
+    assert np.array_equal(pix[covered], full[covered])
+    assert (pix[~covered] == np.array([128, 128, 128, 255], np.uint8)).all()
+    # the CPU checker agrees on the whole picture (its planes are zero-initialised like the reference's)
+    assert np.array_equal(pix, oracle_pixels(part).reshape(h, w, 4))
+
+
+def test_overlapping_blocks_are_not_mistaken_for_full_coverage(j2k, gpu_ctx):
+    """block areas that add up to the plane while leaving a hole (one block duplicated, one dropped): the hole reads zero
+    coefficients, never uninitialised pool memory"""
+    s = jobs.synth_image(128, 64, 1, 8, seed=62)
+    job = jobs.build_ref_job(s, 8, nlevels=1, reversible=True, threads=2)
+    gpu_pixels(j2k, gpu_ctx, job)
+    cb = job["cblks"].copy()
+    assert len(cb) == 2 and cb["w"][0] == cb["w"][1]
+    cb[1] = cb[0]                                                # block 0 twice, block 1 missing: the areas still sum to w * h
+    dup = dict(job, cblks=cb)
+    assert np.array_equal(gpu_pixels(j2k, gpu_ctx, dup), oracle_pixels(dup))
+
+
+def test_two_devices_in_one_process(j2k):
+    """a second context on another device of the same process gets its own constant tables (EBCOT contexts, MQ states)"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("one CUDA device")
+    s = jobs.synth_image(96, 80, 3, 8, seed=63)
+    job = jobs.build_ref_job(s, 8, nlevels=3, reversible=True, threads=2)
+    want = oracle_pixels(job)
+    for dev in (1, 0):
+        ctx = j2k.Context(dev)
+        try:
+            assert np.array_equal(gpu_pixels(j2k, ctx, job), want), dev
+        finally:
+            ctx.close()
