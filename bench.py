@@ -396,10 +396,14 @@ def run_cfg4_tile_sharded(ctx, j2k, jobs, shard, tile_jobs, my_tiles, world, ran
         for t, j in enumerate(tile_jobs):
             tx, ty = t % ntx, t // ntx
             ok &= bool(np.array_equal(val[ty * T:(ty + 1) * T, tx * T:(tx + 1) * T], j["samples"][0].astype(np.uint16)))
+        del img16, val
     barrier()
     ctx.host_unregister(host)
-    del host
-    mm.close()
+    del host, item                                           # every view of the mapping has to go before it can be closed
+    try:
+        mm.close()
+    except BufferError:                                      # a stray view keeps it alive until exit: harmless
+        pass
     os.close(fd)
     barrier()
     if rank == 0:

@@ -406,12 +406,15 @@ def _npasses(br):
     return 37 + br.bits(7)
 
 
-def parse_codestream(data):
+def parse_codestream(data, keep_packets=False):
     """main header + tile-parts + packet headers -> dict(width, height, ncomp, prec, sgnd, nlevels, reversible, mct,
     layers, guard, tile_w, tile_h, blocks=[dict(tile, comp, res, band, level, px, py, w, h, data, passes, zbp, mb,
-    expn, mant)]).  Restrictions: see the module docstring; raises ValueError on anything else."""
+    expn, mant)]).  Restrictions: see the module docstring; raises ValueError on anything else.
+    keep_packets: also return main_segments = [(marker, segment bytes)] and packets[tile] = [(header bytes, body bytes)]
+    for reassemble()."""
     d = bytes(data)
     pos = 0
+    main_segments, packets = [], {}
 
     def u16(p):
         return struct.unpack(">H", d[p:p + 2])[0]
@@ -427,6 +430,7 @@ def parse_codestream(data):
             break
         L = u16(pos + 2)
         seg = d[pos + 4:pos + 2 + L]
+        main_segments.append((m, seg))
         if m == SIZ:
             rsiz, xs, ys, xo, yo, xt, yt, xto, yto, nc = struct.unpack(">HIIIIIIIIH", seg[:36])
             if xo or yo or xto or yto:
@@ -541,10 +545,13 @@ def parse_codestream(data):
                             ln = br.bits(nbits)
                         e["passes"] += n
                         segs.append((e, ln))
-            p = br.align()
+            p0, p = p, br.align()
+            p1 = p
             for e, ln in segs:
                 e["data"] += body[p:p + ln]
                 p += ln
+            if keep_packets:
+                packets.setdefault(tidx, []).append((body[p0:p1], body[p1:p]))
         for key in sorted(state):
             blocks += state[key]["ents"]
     for e in blocks:
@@ -552,4 +559,67 @@ def parse_codestream(data):
         e["num_bps"] = max(e["mb"] - e["zbp"], 0)
     hdr["blocks"] = blocks
     hdr["qcd"] = qcd
+    if keep_packets:
+        hdr["main_segments"], hdr["packets"] = main_segments, packets
     return hdr
+
+
+def reassemble(h, sop=False, eph=False, tlm=False, split=False, plt=False):
+    """Re-emit a codestream parsed with keep_packets=True in another legal shape: SOP marker segments before and / or EPH
+    markers after every packet header (A.8), a TLM marker segment in the main header (A.7.1), PLT marker segments in the
+    tile-part headers (A.7.3), every tile cut into two tile-parts at a packet boundary.  Packet bytes are untouched."""
+    ntiles = cdiv(h["width"], h["tile_w"]) * cdiv(h["height"], h["tile_h"])
+    parts = []                                               # (tile, tile-part index, number of tile-parts, [packet bytes])
+    for t in range(ntiles):
+        pk = []
+        for i, (hd, body) in enumerate(h["packets"].get(t, [])):
+            b = bytearray()
+            if sop:
+                b += struct.pack(">HHH", 0xFF91, 4, i & 0xFFFF)
+            b += hd
+            if eph:
+                b += struct.pack(">H", 0xFF92)
+            b += body
+            pk.append(bytes(b))
+        if split and len(pk) >= 2:
+            k = len(pk) // 2
+            parts += [(t, 0, 2, pk[:k]), (t, 1, 2, pk[k:])]
+        else:
+            parts.append((t, 0, 1, pk))
+    tps = []
+    for (t, tp, ntp, pk) in parts:
+        hdrs = bytearray()
+        if plt:
+            lens = bytearray()
+            for b in pk:
+                n, enc = len(b), []
+                while True:
+                    enc.append(n & 0x7F)
+                    n >>= 7
+                    if not n:
+                        break
+                for j, v in enumerate(reversed(enc)):
+                    lens.append(v | (0x80 if j < len(enc) - 1 else 0))
+            z = 0
+            while lens or z == 0:                            # a PLT segment holds at most 65535 - 3 bytes of lengths
+                chunk, lens = lens[:60000], lens[60000:]
+                while lens and chunk[-1] & 0x80:             # never cut inside a length
+                    chunk.append(lens.pop(0))
+                hdrs += struct.pack(">HHB", 0xFF58, 3 + len(chunk), z) + chunk
+                z += 1
+        body = b"".join(pk)
+        tps.append(struct.pack(">HHHIBB", SOT, 10, t, 12 + len(hdrs) + 2 + len(body), tp, ntp) + hdrs + struct.pack(">H", SOD) + body)
+    out = bytearray(struct.pack(">H", SOC))
+    for (m, seg) in h["main_segments"]:
+        if m in (0xFF55, 0xFF57):                            # existing TLM / PLM: lengths change
+            continue
+        if m == COD:
+            seg = bytes([(seg[0] & ~6) | (2 if sop else 0) | (4 if eph else 0)]) + seg[1:]
+        out += struct.pack(">HH", m, len(seg) + 2) + seg
+    if tlm:                                                  # Stlm: ST = 2 (16-bit tile index), SP = 1 (32-bit lengths)
+        ent = b"".join(struct.pack(">HI", t, len(b)) for (t, _, _, _), b in zip(parts, tps))
+        out += struct.pack(">HHBB", 0xFF55, 4 + len(ent), 0, 0x60) + ent
+    for b in tps:
+        out += b
+    out += struct.pack(">H", EOC)
+    return bytes(out)

@@ -201,7 +201,7 @@ def build_iso_job_from_codestream(data, reduce=0):
         step = 1.0 if h["reversible"] else 2.0 ** (h["prec"] + gain[b["band"]] - b["expn"]) * (1.0 + b["mant"] / 2048.0)
         nb = b["num_bps"] if b["passes"] else 0
         cblks[i] = (len(blob), len(b["data"]) if nb else 0, tc_index[(b["tile"], b["comp"])], b["px"], b["py"], b["w"], b["h"],
-                    b["band"], b["level"], nb, min(b["passes"], 255), step, b.get("lcup", 0), 0)
+                    b["band"], max(b["level"] - reduce, 0), nb, min(b["passes"], 255), step, b.get("lcup", 0), 0)
         blob += b["data"]
     return dict(width=W, height=H, ncomp=ncomp, prec=h["prec"], sgnd=h["sgnd"], mct=1 if (h["mct"] and ncomp >= 3) else 0,
                 reversible=h["reversible"], nlevels=h["nlevels"] - reduce, ht=h["ht"], mode=1, tilecomps=np.array(tcs, TILECOMP_DT), cblks=cblks,

@@ -83,6 +83,8 @@ EXPORTS = [
     "j2kgpu_idwt53", "j2kgpu_idwt97", "j2kgpu_apply_inverse_dwt", "j2kgpu_inverse_rct",
     "j2kgpu_inverse_ict", "j2kgpu_dc_level_shift_inverse", "j2kgpu_mct_dc_pack",
     "j2kgpu_host_alloc", "j2kgpu_host_free", "j2kgpu_host_register", "j2kgpu_host_unregister",
+    "j2kgpu_parse_codestream", "j2kgpu_parsed_free", "j2kgpu_parsed_error", "j2kgpu_parsed_item", "j2kgpu_parsed_info",
+    "j2kgpu_decode_codestream", "j2kgpu_decode_codestreams",
 ]
 
 _lib = None
@@ -140,6 +142,16 @@ def lib():
         L.j2kgpu_inverse_ict.argtypes = [C.c_void_p, f64p, f64p, f64p, C.c_uint64]
         L.j2kgpu_dc_level_shift_inverse.argtypes = [C.c_void_p, i32p, C.c_uint64, C.c_int]
         L.j2kgpu_mct_dc_pack.argtypes = [C.c_void_p, C.POINTER(Image), C.POINTER(i32p), C.c_int, u8p, C.c_uint64]
+        L.j2kgpu_parse_codestream.argtypes = [u8p, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
+        L.j2kgpu_parsed_free.argtypes = [C.c_void_p]
+        L.j2kgpu_parsed_free.restype = None
+        L.j2kgpu_parsed_error.argtypes = [C.c_void_p]
+        L.j2kgpu_parsed_error.restype = C.c_char_p
+        L.j2kgpu_parsed_item.argtypes = [C.c_void_p, C.POINTER(BatchItem)]
+        L.j2kgpu_parsed_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
+        L.j2kgpu_decode_codestream.argtypes = [C.c_void_p, u8p, C.c_uint64, C.c_uint32, u8p, C.c_uint64]
+        L.j2kgpu_decode_codestreams.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(u8p), C.POINTER(C.c_uint64), C.c_uint32,
+                                                C.POINTER(u8p), C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
 
@@ -341,6 +353,79 @@ class Context:
     def decode_batch(self, items):
         arr = (BatchItem * len(items))(*items)
         self._check(lib().j2kgpu_decode_batch(self._h, len(items), arr))
+
+    def decode_codestreams(self, streams, reduce=0, outs=None):
+        """raw codestreams -> pixels (j2kgpu_decode_codestreams): tier-2 of the frames runs on host threads inside the
+        library, overlapped with the copy / kernel / copy pipeline.  -> list of uint8 arrays (stride = width * bpp);
+        `outs` (e.g. page-locked arrays from host_alloc) is filled instead when given."""
+        n = len(streams)
+        bufs = [s if isinstance(s, np.ndarray) else np.frombuffer(bytes(s), np.uint8) for s in streams]
+        dims = [siz_of(b, reduce) for b in bufs]
+        strides = [w * fmt_bpp(nc, pr) for (w, h, nc, pr) in dims]
+        if outs is None:
+            outs = [np.zeros(max(st * d[1], 1), np.uint8) for st, d in zip(strides, dims)]
+        cs = (u8p * n)(*[_p(b, u8p) for b in bufs])
+        lens = (C.c_uint64 * n)(*[b.size for b in bufs])
+        po = (u8p * n)(*[_p(o, u8p) for o in outs])
+        so = (C.c_uint64 * n)(*strides)
+        self._check(lib().j2kgpu_decode_codestreams(self._h, n, cs, lens, reduce, po, so))
+        return [o[: st * d[1]] for o, st, d in zip(outs, strides, dims)]
+
+    def decode_codestream(self, data, reduce=0):
+        """jpeg2000.Decode of one raw codestream, device path (j2kgpu_decode_codestream)"""
+        return self.decode_codestreams([data], reduce)[0]
+
+
+class Parsed:
+    """j2kgpu_parse_codestream: the codestream front door's host half (main header, tile-part index, tier-2) -- what the
+    Go side's buildGPUJob does in the reference layout (codestream.Parser.ReadHeader parser.go:44, ReadTilePartHeader
+    parser.go:894, the missing tier-2 of decoder.go:375).  Needs no device.  Keeps `data` alive: the tables point into it."""
+    INFO = ("layers", "tiles", "tile_parts", "packets", "progression", "plt_packets", "tlm_tile_parts", "zero_copy")
+
+    def __init__(self, data, reduce=0, threads=0):
+        self.data = np.frombuffer(bytes(data), np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, np.uint8)
+        self._h = C.c_void_p()
+        buf = self.data if self.data.size else np.zeros(1, np.uint8)
+        rc = lib().j2kgpu_parse_codestream(_p(buf, u8p), self.data.size, reduce, threads, C.byref(self._h))
+        if rc != 0:
+            msg = lib().j2kgpu_parsed_error(self._h).decode() if self._h else ""
+            self.close()
+            raise J2KError(rc, msg)
+        self.item = BatchItem()
+        lib().j2kgpu_parsed_item(self._h, C.byref(self.item))
+        info = (C.c_uint32 * 8)()
+        lib().j2kgpu_parsed_info(self._h, info)
+        self.info = dict(zip(self.INFO, (int(v) for v in info)))
+        self.image = self.item.image
+
+    def tables(self):
+        """(tilecomps, cblks, blob) as numpy copies (structured arrays with the C field names)"""
+        it = self.item
+        tcs = np.ctypeslib.as_array(it.tilecomps, shape=(it.n_tilecomps,)).copy() if it.n_tilecomps else np.zeros(0, TileComp)
+        cbs = np.ctypeslib.as_array(it.cblks, shape=(it.n_cblks,)).copy() if it.n_cblks else np.zeros(0, CBlk)
+        blob = np.ctypeslib.as_array(it.blob, shape=(int(it.blob_len),)).copy() if it.blob_len else np.zeros(0, np.uint8)
+        return tcs, cbs, blob
+
+    def close(self):
+        if self._h:
+            lib().j2kgpu_parsed_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def siz_of(data, reduce=0):
+    """(width, height, ncomp, precision) from the SIZ marker segment, which directly follows SOC (A.5.1); reduce as in Parsed"""
+    d = bytes(data[:64])
+    if len(d) < 43 or d[:4] != b"\xff\x4f\xff\x51":
+        raise J2KError(E_ARG, "not a codestream (no SOC + SIZ)")
+    be = lambda o, n: int.from_bytes(d[o:o + n], "big")
+    sc = 1 << reduce
+    return -(-be(8, 4) // sc), -(-be(12, 4) // sc), be(40, 2), (d[42] & 0x7F) + 1
 
 
 class Job:

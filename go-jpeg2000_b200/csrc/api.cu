@@ -3,6 +3,7 @@
 // There is no CPU fallback anywhere in this file: every entry point either runs CUDA kernels or
 // returns an error.
 #include "common.h"
+#include "../host/tier2.h"
 
 #include <algorithm>
 #include <cctype>
@@ -10,6 +11,9 @@
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <thread>
 #include <map>
 #include <new>
 #include <tuple>
@@ -928,16 +932,79 @@ extern "C" int j2kgpu_host_unregister(j2kgpu_ctx *ctx, void *p)
 // compressed bytes, its kernels run on the ctx stream, its pixels leave on the copy-out stream.  Nothing synchronises
 // until the last chunk is queued, so the host builds chunk c + 1 while the device decodes chunk c and the link carries
 // chunk c - 1 out: table building, both PCIe directions and the SMs all overlap.
+struct BatchPipe {
+    j2kgpu_ctx *ctx = nullptr;
+    std::vector<j2kgpu_job *> jobs;
+    std::vector<DevTile> h_tiles;
+    int rc = J2KGPU_OK;
+};
+
+static int pipe_begin(BatchPipe &bp, j2kgpu_ctx *ctx)
+{
+    bp.ctx = ctx;
+    cudaSetDevice(ctx->device);
+    int rc = j2k_ctx_copy_streams(ctx);
+    if (rc) return bp.rc = rc;
+    cudaError_t ce = cudaEventRecord(ctx->ev_start, ctx->stream);
+    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->s_in, ctx->ev_start, 0);
+    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->s_out, ctx->ev_start, 0);
+    if (ce != cudaSuccess) bp.rc = j2k_cuda_err(ctx, ce, "stream setup");
+    return bp.rc;
+}
+
+// queue one chunk: tables + compressed bytes in, kernels, pixels out; returns without waiting for any of it
+static int pipe_submit(BatchPipe &bp, const j2k_batch_item_t *its, uint32_t n)
+{
+    if (bp.rc || n == 0) return bp.rc;
+    j2kgpu_ctx *ctx = bp.ctx;
+    j2kgpu_job *job = nullptr;
+    if ((bp.rc = job_build(ctx, n, its, &job, ctx->s_in))) return bp.rc;
+    bp.jobs.push_back(job);
+    cudaError_t ce = cudaSuccess;
+    job->d_blob = j2k_pool_alloc(ctx, job->blob_bytes + 64, &ce);
+    if (ce == cudaSuccess) job->d_pix = j2k_pool_alloc(ctx, job->out_bytes, &ce);
+    cudaEvent_t ev_in = nullptr, ev_done = nullptr;
+    if (ce == cudaSuccess) { ev_in = ctx_event(ctx, &ce); job->ev_in.push_back(ev_in); }
+    if (ce == cudaSuccess) { ev_done = ctx_event(ctx, &ce); job->ev_done.push_back(ev_done); }
+    for (uint32_t i = 0; i < n && ce == cudaSuccess; i++)
+        if (its[i].blob_len)
+            ce = cudaMemcpyAsync((uint8_t *)job->d_blob + job->blob_off[i], its[i].blob, its[i].blob_len, cudaMemcpyHostToDevice, ctx->s_in);
+    if (ce == cudaSuccess) ce = cudaEventRecord(ev_in, ctx->s_in);
+    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->stream, ev_in, 0);
+    if (ce != cudaSuccess) return bp.rc = j2k_cuda_err(ctx, ce, "chunk upload");
+    if ((bp.rc = run_entropy(job, job->d_blob, 0, n, ctx->stream))) return bp.rc;
+    if ((bp.rc = run_dwt_mct(job, job->d_pix, 0, n, ctx->stream))) return bp.rc;
+    ce = cudaEventRecord(ev_done, ctx->stream);
+    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->s_out, ev_done, 0);
+    if (ce != cudaSuccess) return bp.rc = j2k_cuda_err(ctx, ce, "chunk events");
+    bool subset = false;
+    for (uint32_t i = 0; i < n; i++) subset |= (its[i].flags & J2KGPU_ITEM_TILES_ONLY) != 0;
+    if (subset) bp.h_tiles.assign(job->h_tiles_host, job->h_tiles_host + job->n_tiles);   // still in the page-locked staging block
+    for (uint32_t i = 0; i < n && bp.rc == J2KGPU_OK; i++)
+        bp.rc = copy_out_item(job, i, its[i], bp.h_tiles.data(), ctx->s_out);
+    return bp.rc;
+}
+
+// everything queued (or failed): drain, then give the chunks' buffers back to the pools
+static int pipe_finish(BatchPipe &bp)
+{
+    j2kgpu_ctx *ctx = bp.ctx;
+    if (ctx->s_in) cudaStreamSynchronize(ctx->s_in);
+    cudaError_t e1 = cudaStreamSynchronize(ctx->stream), e2 = ctx->s_out ? cudaStreamSynchronize(ctx->s_out) : cudaSuccess;
+    for (j2kgpu_job *j : bp.jobs) job_free(j);
+    bp.jobs.clear();
+    if (bp.rc == J2KGPU_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) bp.rc = j2k_cuda_err(ctx, e1 != cudaSuccess ? e1 : e2, "decode_batch");
+    return bp.rc;
+}
+
 extern "C" int j2kgpu_decode_batch(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *items)
 {
     if (!ctx) return J2KGPU_E_ARG;
     std::lock_guard<std::mutex> g(ctx->mu);
     if (!items || n_img == 0) return j2k_set_err(ctx, J2KGPU_E_ARG, "null or empty batch");
-    cudaSetDevice(ctx->device);
-    int rc = j2k_ctx_copy_streams(ctx);
-    if (rc) return rc;
     TailParams tp;
-    if ((rc = make_tail(ctx, items[0].image, tp))) return rc;
+    int rc = make_tail(ctx, items[0].image, tp);
+    if (rc) return rc;
     uint64_t out_bytes = 0;
     for (uint32_t i = 0; i < n_img; i++) {
         if (!items[i].out_pix) return j2k_set_err(ctx, J2KGPU_E_ARG, "item %u: null out_pix", i);
@@ -945,48 +1012,103 @@ extern "C" int j2kgpu_decode_batch(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_ba
         out_bytes += items[i].out_stride * items[i].image.height;
     }
     const std::vector<uint32_t> cuts = plan_chunks(ctx, n_img, items[0].image, out_bytes);
-    const uint32_t nchunk = (uint32_t)cuts.size() - 1;
-    std::vector<j2kgpu_job *> jobs(nchunk, nullptr);
-    std::vector<DevTile> h_tiles;
-    cudaError_t ce = cudaSuccess;
-    ce = cudaEventRecord(ctx->ev_start, ctx->stream);
-    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->s_in, ctx->ev_start, 0);
-    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->s_out, ctx->ev_start, 0);
-    if (ce != cudaSuccess) rc = j2k_cuda_err(ctx, ce, "stream setup");
-    for (uint32_t c = 0; c < nchunk && rc == J2KGPU_OK; c++) {
-        const uint32_t ia = cuts[c], ib = cuts[c + 1];
-        const j2k_batch_item_t *its = items + ia;
-        j2kgpu_job *job = nullptr;
-        if ((rc = job_build(ctx, ib - ia, its, &job, ctx->s_in))) break;
-        jobs[c] = job;
-        job->d_blob = j2k_pool_alloc(ctx, job->blob_bytes + 64, &ce);
-        if (ce == cudaSuccess) job->d_pix = j2k_pool_alloc(ctx, job->out_bytes, &ce);
-        cudaEvent_t ev_in = nullptr, ev_done = nullptr;
-        if (ce == cudaSuccess) { ev_in = ctx_event(ctx, &ce); job->ev_in.push_back(ev_in); }
-        if (ce == cudaSuccess) { ev_done = ctx_event(ctx, &ce); job->ev_done.push_back(ev_done); }
-        for (uint32_t i = 0; i < ib - ia && ce == cudaSuccess; i++)
-            if (its[i].blob_len)
-                ce = cudaMemcpyAsync((uint8_t *)job->d_blob + job->blob_off[i], its[i].blob, its[i].blob_len, cudaMemcpyHostToDevice, ctx->s_in);
-        if (ce == cudaSuccess) ce = cudaEventRecord(ev_in, ctx->s_in);
-        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->stream, ev_in, 0);
-        if (ce != cudaSuccess) { rc = j2k_cuda_err(ctx, ce, "chunk upload"); break; }
-        if ((rc = run_entropy(job, job->d_blob, 0, ib - ia, ctx->stream))) break;
-        if ((rc = run_dwt_mct(job, job->d_pix, 0, ib - ia, ctx->stream))) break;
-        ce = cudaEventRecord(ev_done, ctx->stream);
-        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->s_out, ev_done, 0);
-        if (ce != cudaSuccess) { rc = j2k_cuda_err(ctx, ce, "chunk events"); break; }
-        bool subset = false;
-        for (uint32_t i = 0; i < ib - ia; i++) subset |= (its[i].flags & J2KGPU_ITEM_TILES_ONLY) != 0;
-        if (subset) h_tiles.assign(job->h_tiles_host, job->h_tiles_host + job->n_tiles);   // still in the page-locked staging block
-        for (uint32_t i = 0; i < ib - ia && rc == J2KGPU_OK; i++)
-            rc = copy_out_item(job, i, its[i], h_tiles.data(), ctx->s_out);
+    BatchPipe bp;
+    pipe_begin(bp, ctx);
+    for (size_t c = 0; c + 1 < cuts.size() && bp.rc == J2KGPU_OK; c++) pipe_submit(bp, items + cuts[c], cuts[c + 1] - cuts[c]);
+    return pipe_finish(bp);
+}
+
+// ---- codestream front door: tier-2 on the host (host/tier2.cpp), then the same pipeline --------------------------------
+extern "C" int j2kgpu_parse_codestream(const uint8_t *cs, uint64_t len, uint32_t reduce, uint32_t threads, j2kgpu_parsed **out)
+{
+    if (!out) return J2KGPU_E_ARG;
+    j2kgpu_parsed *p = new (std::nothrow) j2kgpu_parsed();
+    *out = p;
+    if (!p) return J2KGPU_E_NOMEM;
+    return j2k_tier2_parse(cs, len, reduce, threads, *p);
+}
+
+extern "C" void j2kgpu_parsed_free(j2kgpu_parsed *p) { delete p; }
+extern "C" const char *j2kgpu_parsed_error(const j2kgpu_parsed *p) { return p ? p->err.c_str() : "null"; }
+
+extern "C" int j2kgpu_parsed_item(const j2kgpu_parsed *p, j2k_batch_item_t *item)
+{
+    if (!p || !item) return J2KGPU_E_ARG;
+    memset(item, 0, sizeof *item);
+    item->image = p->image;
+    item->tilecomps = p->tilecomps.data(); item->n_tilecomps = (uint32_t)p->tilecomps.size();
+    item->cblks = p->cblks.data(); item->n_cblks = (uint32_t)p->cblks.size();
+    item->blob = p->blob; item->blob_len = p->blob_len;
+    return J2KGPU_OK;
+}
+
+extern "C" int j2kgpu_parsed_info(const j2kgpu_parsed *p, uint32_t info[8])
+{
+    if (!p || !info) return J2KGPU_E_ARG;
+    info[0] = p->layers; info[1] = p->tiles; info[2] = p->tile_parts; info[3] = p->packets; info[4] = p->progression;
+    info[5] = p->plt_packets; info[6] = p->tlm_tile_parts; info[7] = p->owned.empty() ? 1u : 0u;   // 1: blocks point into the caller's bytes
+    return J2KGPU_OK;
+}
+
+// n codestreams -> n images.  Worker threads run the tier-2 of the frames (one frame per thread at a time) while this
+// thread submits finished frames, in order and in chunks, to the copy / kernel / copy pipeline: host parsing of frame
+// i + k overlaps the device's work on frame i.  All frames must share the header fields j2kgpu_decode_batch requires.
+extern "C" int j2kgpu_decode_codestreams(j2kgpu_ctx *ctx, uint32_t n, const uint8_t *const *cs, const uint64_t *lens, uint32_t reduce,
+                                         uint8_t *const *out_pix, const uint64_t *out_stride)
+{
+    if (!ctx) return J2KGPU_E_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!n || !cs || !lens || !out_pix || !out_stride) return j2k_set_err(ctx, J2KGPU_E_ARG, "null or empty batch");
+    std::vector<j2kgpu_parsed> parsed(n);
+    std::vector<int> prc(n, 0);
+    std::vector<std::atomic<int>> done(n);
+    for (auto &d : done) d.store(0);
+    std::atomic<uint32_t> next{0};
+    std::mutex mu;
+    std::condition_variable cv;
+    const uint32_t hw = std::max(1u, std::thread::hardware_concurrency());
+    const uint32_t nthreads = n == 1 ? 1 : std::min<uint32_t>({hw, n, 32u});
+    auto worker = [&]() {
+        for (;;) {
+            const uint32_t i = next.fetch_add(1);
+            if (i >= n) break;
+            prc[i] = j2k_tier2_parse(cs[i], lens[i], reduce, n == 1 ? 0 : 1, parsed[i]);
+            { std::lock_guard<std::mutex> lk(mu); done[i].store(1); }
+            cv.notify_all();
+        }
+    };
+    std::vector<std::thread> th;
+    for (uint32_t t = 0; t < nthreads; t++) th.emplace_back(worker);
+    auto wait_for = [&](uint32_t i) { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return done[i].load() != 0; }); };
+    BatchPipe bp;
+    int rc = J2KGPU_OK;
+    std::vector<j2k_batch_item_t> items(n);
+    std::vector<uint32_t> cuts;
+    uint32_t submitted = 0, ci = 1;
+    for (uint32_t i = 0; i < n && rc == J2KGPU_OK; i++) {
+        wait_for(i);
+        if (prc[i]) { rc = j2k_set_err(ctx, prc[i], "codestream %u: %s", i, parsed[i].err.c_str()); break; }
+        j2kgpu_parsed_item(&parsed[i], &items[i]);
+        items[i].out_pix = out_pix[i]; items[i].out_stride = out_stride[i];
+        if (!out_pix[i]) { rc = j2k_set_err(ctx, J2KGPU_E_ARG, "codestream %u: null out_pix", i); break; }
+        if (i == 0) {                                    // chunk plan from the first frame (frames of a batch are alike)
+            cuts = plan_chunks(ctx, n, items[0].image, (uint64_t)n * out_stride[0] * items[0].image.height);
+            rc = pipe_begin(bp, ctx);
+        }
+        if (rc == J2KGPU_OK && i + 1 == cuts[ci]) {
+            rc = pipe_submit(bp, items.data() + submitted, i + 1 - submitted);
+            submitted = i + 1; ci++;
+        }
     }
-    // everything queued (or failed): drain, then give the chunks' buffers back to the pools
-    cudaStreamSynchronize(ctx->s_in);
-    cudaError_t e1 = cudaStreamSynchronize(ctx->stream), e2 = cudaStreamSynchronize(ctx->s_out);
-    for (j2kgpu_job *j : jobs) job_free(j);
-    if (rc == J2KGPU_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) rc = j2k_cuda_err(ctx, e1 != cudaSuccess ? e1 : e2, "decode_batch");
+    next.store(n);                                       // on error: stop handing out frames
+    for (auto &t : th) t.join();
+    if (bp.ctx) { bp.rc = bp.rc ? bp.rc : rc; return pipe_finish(bp); }
     return rc;
+}
+
+extern "C" int j2kgpu_decode_codestream(j2kgpu_ctx *ctx, const uint8_t *cs, uint64_t len, uint32_t reduce, uint8_t *out_pix, uint64_t out_stride)
+{
+    return j2kgpu_decode_codestreams(ctx, 1, &cs, &len, reduce, &out_pix, &out_stride);
 }
 
 extern "C" int j2kgpu_decode(j2kgpu_ctx *ctx, const j2k_image_t *img,

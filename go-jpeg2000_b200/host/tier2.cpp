@@ -1,0 +1,550 @@
+// tier2.cpp -- see tier2.h.  Main header (SIZ, CAP, COD, QCD, TLM, COM), tile-part index (SOT / Psot, TLM cross-check), packet
+// headers (tag trees, number of passes, Lblock, segment lengths; SOP / EPH; PLT cross-check) for all five progression orders
+// with maximal precincts, any number of quality layers, classic and HT code blocks (one HT set: the cleanup length and the
+// SigProp + MagRef length are separate codeword segments, T.814 B.10.7).  Tiles are parsed concurrently.
+// Everything is bounds-checked: malformed bytes give an error code, never a fault (the reference's fuzz contract).
+#include "tier2.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <thread>
+
+namespace {
+
+constexpr uint16_t SOC = 0xFF4F, SIZ = 0xFF51, CAP = 0xFF50, COD = 0xFF52, COC = 0xFF53, QCD = 0xFF5C, QCC = 0xFF5D, RGN = 0xFF5E,
+                   POC = 0xFF5F, TLM = 0xFF55, PLM = 0xFF57, PLT = 0xFF58, PPM = 0xFF60, PPT = 0xFF61, SOT = 0xFF90, SOP = 0xFF91,
+                   EPH = 0xFF92, SOD = 0xFF93, EOC = 0xFFD9;
+
+struct Err {
+    int code = 0;
+    std::string msg;
+    int fail(int c, const char *fmt, ...)
+    {
+        if (code) return code;
+        char buf[256];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        code = c; msg = buf;
+        return c;
+    }
+};
+
+inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+inline int64_t cdiv64(int64_t a, int64_t b) { return a >= 0 ? (a + b - 1) / b : -((-a) / b); }
+
+struct Header {
+    uint32_t W = 0, H = 0, tile_w = 0, tile_h = 0, ncomp = 0, prec = 0, sgnd = 0;
+    uint32_t prog = 0, layers = 0, mct = 0, nlevels = 0, cbw = 0, cbh = 0, style = 0, reversible = 0, sop = 0, eph = 0, ht = 0;
+    uint32_t guard = 0;
+    bool have_siz = false, have_cod = false, have_qcd = false;
+    std::vector<std::pair<uint32_t, uint32_t>> q;      // per band in codestream order: exponent, mantissa
+};
+
+struct BandId { uint32_t res, band, lvl; };
+
+std::vector<BandId> band_list(uint32_t nl)
+{
+    std::vector<BandId> out;
+    out.push_back({0, 0, nl});
+    for (uint32_t r = 1; r <= nl; r++) {
+        const uint32_t lvl = nl - r + 1;
+        out.push_back({r, 1, lvl}); out.push_back({r, 2, lvl}); out.push_back({r, 3, lvl});
+    }
+    return out;
+}
+
+struct Rect { int64_t x0, y0, x1, y1; };
+
+// band bounds in band coordinates (ISO/IEC 15444-1 B.15): HL / HH are offset in x, LH / HH in y
+Rect band_rect(int64_t tx0, int64_t ty0, int64_t tx1, int64_t ty1, uint32_t band, uint32_t lvl)
+{
+    const int64_t s = (int64_t)1 << lvl;
+    if (band == 0 || lvl == 0) return {cdiv64(tx0, s), cdiv64(ty0, s), cdiv64(tx1, s), cdiv64(ty1, s)};
+    const int64_t hs = (int64_t)1 << (lvl - 1), xo = band & 1, yo = band >> 1;
+    return {cdiv64(tx0 - hs * xo, s), cdiv64(ty0 - hs * yo, s), cdiv64(tx1 - hs * xo, s), cdiv64(ty1 - hs * yo, s)};
+}
+
+// packet-header bit reader: MSB first, the byte after 0xFF carries 7 bits (B.10.1); reads past `end` give zeros and set bad
+struct BitReader {
+    const uint8_t *d; size_t pos, end;
+    uint32_t cur = 0; int left = 0; bool prev_ff = false, bad = false;
+    BitReader(const uint8_t *d_, size_t pos_, size_t end_) : d(d_), pos(pos_), end(end_) {}
+    uint32_t get()
+    {
+        if (left == 0) {
+            if (pos >= end) { bad = true; return 0; }
+            cur = d[pos++];
+            left = prev_ff ? 7 : 8;
+            prev_ff = cur == 0xFF;
+        }
+        left--;
+        return (cur >> left) & 1u;
+    }
+    uint32_t bits(int n) { uint32_t v = 0; for (int i = 0; i < n; i++) v = (v << 1) | get(); return v; }
+    size_t align()
+    {
+        if (prev_ff && left == 0) pos++;                 // a header may not end in 0xFF: the stuffed byte follows
+        left = 0; prev_ff = false;
+        return pos;
+    }
+};
+
+struct TagTree {
+    struct Lvl { uint32_t w, h; size_t off; };
+    std::vector<Lvl> lv;
+    std::vector<int32_t> val, low;
+    std::vector<uint8_t> known;
+    void init(uint32_t w, uint32_t h)
+    {
+        lv.clear();
+        size_t off = 0;
+        for (;;) {
+            lv.push_back({w, h, off});
+            off += (size_t)w * h;
+            if (w <= 1 && h <= 1) break;
+            w = cdiv(w, 2); h = cdiv(h, 2);
+        }
+        val.assign(off, 1 << 30); low.assign(off, 0); known.assign(off, 0);
+    }
+    // -> true when value(x, y) < threshold is established
+    bool decode(BitReader &br, uint32_t x, uint32_t y, int32_t threshold)
+    {
+        int32_t lo = 0;
+        for (int l = (int)lv.size() - 1; l >= 0; l--) {
+            const size_t i = lv[l].off + (size_t)(y >> l) * lv[l].w + (x >> l);
+            if (lo > low[i]) low[i] = lo; else lo = low[i];
+            while (lo < threshold && !known[i]) {
+                if (br.bad) return false;
+                if (br.get()) { known[i] = 1; val[i] = lo; }
+                else lo++;
+            }
+            low[i] = lo;
+            if (known[i] && l) lo = std::max(lo, val[i]);
+        }
+        const size_t i0 = lv[0].off + (size_t)y * lv[0].w + x;
+        return known[i0] && val[i0] < threshold;
+    }
+    int32_t value(uint32_t x, uint32_t y) const { return val[lv[0].off + (size_t)y * lv[0].w + x]; }
+};
+
+uint32_t read_npasses(BitReader &br)                      // B.10.6
+{
+    if (!br.get()) return 1;
+    if (!br.get()) return 2;
+    uint32_t v = br.bits(2);
+    if (v != 3) return 3 + v;
+    v = br.bits(5);
+    if (v != 31) return 6 + v;
+    return 37 + br.bits(7);
+}
+
+inline int floorlog2(uint32_t v) { int r = 0; while (v >>= 1) r++; return r; }
+
+struct Blk {
+    uint32_t px, py, w, h;             // placement in the tile-component's Mallat plane
+    uint32_t passes = 0, zbp = 0, lblock = 3, lcup = 0;
+    bool included = false;
+    uint64_t off = 0; uint32_t len = 0; // first contribution (offset into the tile body)
+    uint32_t npieces = 0;
+    std::vector<std::pair<uint64_t, uint32_t>> more;   // further contributions (quality layers)
+};
+
+struct BandState {
+    uint32_t comp, bidx, gw = 0, gh = 0, first = 0, count = 0;   // blocks [first, first + count) of the tile's block list
+    TagTree incl, imsb;
+};
+
+struct TilePart { uint64_t body, end; };
+
+struct TileOut {
+    std::vector<j2k_tilecomp_t> tcs;
+    std::vector<j2k_cblk_t> cbs;
+    std::vector<uint8_t> extra;                       // concatenated bytes of blocks that are not contiguous in the codestream
+    std::vector<uint8_t> is_extra;                    // per block: data_off is relative to `extra`
+    uint32_t packets = 0, plt_checked = 0;
+    Err err;
+};
+
+// truncated: the codestream ends inside this tile's data -- its last, incomplete packet is dropped instead of being an error
+void parse_tile(const uint8_t *cs, const Header &h, uint32_t tidx, const std::vector<TilePart> &parts,
+                const std::vector<uint32_t> &plt, uint32_t reduce, bool truncated, TileOut &out)
+{
+    const uint32_t ntx = cdiv(h.W, h.tile_w);
+    const uint32_t tx = tidx % ntx, ty = tidx / ntx;
+    const int64_t x0 = (int64_t)tx * h.tile_w, y0 = (int64_t)ty * h.tile_h;
+    const int64_t x1 = std::min<int64_t>(x0 + h.tile_w, h.W), y1 = std::min<int64_t>(y0 + h.tile_h, h.H);
+    const std::vector<BandId> bands = band_list(h.nlevels);
+    const uint32_t nl = h.nlevels, nc = h.ncomp;
+    // the tile body: one tile-part -> parsed in place; several -> concatenated (their blocks then go through `extra`)
+    std::vector<uint8_t> joined;
+    const uint8_t *body;
+    size_t blen;
+    int64_t abs_off;
+    if (parts.size() == 1) { body = cs + parts[0].body; blen = (size_t)(parts[0].end - parts[0].body); abs_off = (int64_t)parts[0].body; }
+    else {
+        for (const TilePart &p : parts) joined.insert(joined.end(), cs + p.body, cs + p.end);
+        body = joined.data(); blen = joined.size(); abs_off = -1;
+    }
+    // code blocks of every (component, band), raster order inside the band
+    std::vector<Blk> blks;
+    std::vector<BandState> bst(nc * bands.size());
+    for (uint32_t c = 0; c < nc; c++)
+        for (size_t bi = 0; bi < bands.size(); bi++) {
+            const BandId &b = bands[bi];
+            BandState &st = bst[c * bands.size() + bi];
+            st.comp = c; st.bidx = (uint32_t)bi; st.first = (uint32_t)blks.size();
+            const Rect br = band_rect(x0, y0, x1, y1, b.band, b.lvl);
+            if (br.x1 <= br.x0 || br.y1 <= br.y0) continue;
+            const int64_t gx0 = br.x0 / h.cbw, gy0 = br.y0 / h.cbh, gx1 = cdiv64(br.x1, h.cbw), gy1 = cdiv64(br.y1, h.cbh);
+            st.gw = (uint32_t)(gx1 - gx0); st.gh = (uint32_t)(gy1 - gy0);
+            // origin of the band inside the Mallat plane: LL_lvl top-left, HL to the right, LH below
+            const int64_t s = (int64_t)1 << b.lvl;
+            const int64_t lw = cdiv64(x1, s) - cdiv64(x0, s), lh = cdiv64(y1, s) - cdiv64(y0, s);
+            const int64_t ox = (b.band & 1) ? lw : 0, oy = (b.band >> 1) ? lh : 0;
+            for (int64_t gy = gy0; gy < gy1; gy++)
+                for (int64_t gx = gx0; gx < gx1; gx++) {
+                    const int64_t cx0 = std::max(br.x0, gx * h.cbw), cy0 = std::max(br.y0, gy * h.cbh);
+                    const int64_t cx1 = std::min(br.x1, (gx + 1) * h.cbw), cy1 = std::min(br.y1, (gy + 1) * h.cbh);
+                    Blk k;
+                    k.px = (uint32_t)(ox + cx0 - br.x0); k.py = (uint32_t)(oy + cy0 - br.y0);
+                    k.w = (uint32_t)(cx1 - cx0); k.h = (uint32_t)(cy1 - cy0);
+                    blks.push_back(k);
+                }
+            st.count = (uint32_t)blks.size() - st.first;
+            st.incl.init(st.gw, st.gh); st.imsb.init(st.gw, st.gh);
+        }
+    // packet sequence: one precinct per resolution, so the position loops of RPCL / PCRL / CPRL collapse
+    struct Pk { uint32_t l, r, c; };
+    std::vector<Pk> order;
+    order.reserve((size_t)h.layers * (nl + 1) * nc);
+    auto push = [&](uint32_t l, uint32_t r, uint32_t c) { order.push_back({l, r, c}); };
+    switch (h.prog) {
+    case 0: for (uint32_t l = 0; l < h.layers; l++) for (uint32_t r = 0; r <= nl; r++) for (uint32_t c = 0; c < nc; c++) push(l, r, c); break;
+    case 1: for (uint32_t r = 0; r <= nl; r++) for (uint32_t l = 0; l < h.layers; l++) for (uint32_t c = 0; c < nc; c++) push(l, r, c); break;
+    case 2: for (uint32_t r = 0; r <= nl; r++) for (uint32_t c = 0; c < nc; c++) for (uint32_t l = 0; l < h.layers; l++) push(l, r, c); break;
+    default: for (uint32_t c = 0; c < nc; c++) for (uint32_t r = 0; r <= nl; r++) for (uint32_t l = 0; l < h.layers; l++) push(l, r, c); break;
+    }
+    size_t p = 0;
+    std::vector<std::pair<uint32_t, uint32_t>> segs;   // (block, length) of this packet
+    struct Undo { uint32_t blk, passes, zbp, lblock, lcup; bool included; };
+    std::vector<Undo> undo;                            // state of the blocks this packet's header touched (truncated tiles only)
+    bool cut = false;
+    for (const Pk &pk : order) {
+        if (p >= blen) break;                            // truncated codestream: the remaining packets are absent
+        const size_t pk_start = p;
+        if (h.sop && p + 6 <= blen && body[p] == 0xFF && body[p + 1] == 0x91) p += 6;
+        BitReader br(body, p, blen);
+        segs.clear();
+        undo.clear();
+        if (br.get()) {
+            for (size_t bi = 0; bi < bands.size(); bi++) {
+                if (bands[bi].res != pk.r) continue;
+                BandState &st = bst[pk.c * bands.size() + bi];
+                for (uint32_t k = 0; k < st.count; k++) {
+                    Blk &e = blks[st.first + k];
+                    const uint32_t gx = k % st.gw, gy = k / st.gw;
+                    bool inc;
+                    if (!e.included) inc = st.incl.decode(br, gx, gy, (int32_t)pk.l + 1);
+                    else inc = br.get() != 0;
+                    if (br.bad) { if (truncated) { cut = true; goto packet_done; } out.err.fail(J2KGPU_E_RANGE, "tile %u: packet header runs past the tile data", tidx); return; }
+                    if (!inc) continue;
+                    if (truncated) undo.push_back({st.first + k, e.passes, e.zbp, e.lblock, e.lcup, e.included});
+                    if (!e.included) {
+                        int32_t t = 1;
+                        while (!st.imsb.decode(br, gx, gy, t)) {
+                            if (br.bad && truncated) { cut = true; goto packet_done; }
+                            if (br.bad || t > 64) { out.err.fail(J2KGPU_E_RANGE, "tile %u: bad zero-bit-plane tag tree", tidx); return; }
+                            t++;
+                        }
+                        e.zbp = (uint32_t)st.imsb.value(gx, gy);
+                        e.included = true;
+                    }
+                    const uint32_t n = read_npasses(br);
+                    while (br.get()) {
+                        if (++e.lblock > 32 || br.bad) {
+                            if (br.bad && truncated) { cut = true; goto packet_done; }
+                            out.err.fail(J2KGPU_E_RANGE, "tile %u: bad Lblock", tidx); return;
+                        }
+                    }
+                    uint32_t ln;
+                    if (h.ht) {
+                        // HT (T.814 B.10.7): the cleanup pass is a codeword segment of its own, SigProp + MagRef share the second
+                        if (e.passes || n > 3) { out.err.fail(J2KGPU_E_UNSUPPORTED, "tile %u: more than one HT set per code block", tidx); return; }
+                        ln = br.bits((int)e.lblock);
+                        e.lcup = ln;
+                        if (n > 1) ln += br.bits((int)e.lblock + floorlog2(n - 1));
+                    } else {
+                        const int nb = (int)e.lblock + floorlog2(n);
+                        if (nb > 32) { out.err.fail(J2KGPU_E_RANGE, "tile %u: segment length field too wide", tidx); return; }
+                        ln = br.bits(nb);
+                    }
+                    if (br.bad) { if (truncated) { cut = true; goto packet_done; } out.err.fail(J2KGPU_E_RANGE, "tile %u: packet header runs past the tile data", tidx); return; }
+                    e.passes += n;
+                    segs.push_back({st.first + k, ln});
+                }
+            }
+        }
+        p = br.align();
+        if (h.eph && p + 2 <= blen && body[p] == 0xFF && body[p + 1] == 0x92) p += 2;
+        {
+            uint64_t total = 0;
+            for (auto &sg : segs) total += sg.second;
+            if (total > blen - std::min(p, blen)) {
+                if (truncated) cut = true;
+                else { out.err.fail(J2KGPU_E_RANGE, "tile %u: code-block data runs past the tile data", tidx); return; }
+            }
+        }
+    packet_done:
+        if (cut) {                                       // the codestream ended inside this packet: forget it and stop
+            for (const Undo &u : undo) { Blk &e = blks[u.blk]; e.passes = u.passes; e.zbp = u.zbp; e.lblock = u.lblock; e.lcup = u.lcup; e.included = u.included; }
+            break;
+        }
+        for (auto &sg : segs) {
+            Blk &e = blks[sg.first];
+            if (e.npieces == 0) { e.off = p; e.len = sg.second; }
+            else e.more.push_back({p, sg.second});
+            e.npieces++;
+            p += sg.second;
+        }
+        if (out.packets < plt.size()) {                  // PLT announced this packet's length: it must agree
+            if (plt[out.packets] != p - pk_start) { out.err.fail(J2KGPU_E_RANGE, "tile %u packet %u: PLT length %u, parsed %zu", tidx, out.packets, plt[out.packets], p - pk_start); return; }
+            out.plt_checked++;
+        }
+        out.packets++;
+    }
+    // ---- tables ----
+    const uint32_t sc = reduce;
+    auto red = [&](int64_t v) { return (uint32_t)cdiv64(v, (int64_t)1 << sc); };
+    for (uint32_t c = 0; c < nc; c++) {
+        j2k_tilecomp_t tc{};
+        tc.comp = c; tc.x0 = red(x0); tc.y0 = red(y0); tc.x1 = red(x1); tc.y1 = red(y1);
+        out.tcs.push_back(tc);
+    }
+    static const int gain[4] = {0, 1, 1, 2};
+    for (uint32_t c = 0; c < nc; c++)
+        for (size_t bi = 0; bi < bands.size(); bi++) {
+            const BandId &b = bands[bi];
+            if (b.res > nl - reduce) continue;             // ReduceResolution: the finest resolutions are not handed over
+            const BandState &st = bst[c * bands.size() + bi];
+            const uint32_t expn = h.q[bi].first, mant = h.q[bi].second;
+            const int mb = (int)h.guard + (int)expn - 1;
+            for (uint32_t k = 0; k < st.count; k++) {
+                const Blk &e = blks[st.first + k];
+                j2k_cblk_t cb{};
+                cb.tilecomp = c; cb.x0 = (uint16_t)e.px; cb.y0 = (uint16_t)e.py; cb.w = (uint16_t)e.w; cb.h = (uint16_t)e.h;
+                cb.band = (uint8_t)b.band; cb.level = (uint8_t)(b.lvl > reduce ? b.lvl - reduce : 0);
+                // Annex E.1: step = 2^(Rb - eps) * (1 + mu / 2^11), Rb = precision + band gain
+                cb.step = h.reversible ? 1.0f : (float)(std::ldexp(1.0, (int)h.prec + gain[b.band] - (int)expn) * (1.0 + mant / 2048.0));
+                const int nb = mb - (int)e.zbp;
+                uint32_t total = e.len;
+                for (auto &m : e.more) total += m.second;
+                if (!e.passes || nb <= 0 || total == 0) { cb.num_bps = 0; cb.num_passes = 0; cb.data_len = 0; cb.data_off = 0; out.is_extra.push_back(0); out.cbs.push_back(cb); continue; }
+                if (nb > 31) { out.err.fail(J2KGPU_E_UNSUPPORTED, "tile %u: %d magnitude bit-planes", tidx, nb); return; }
+                cb.num_bps = (uint8_t)nb;
+                cb.num_passes = (uint8_t)std::min<uint32_t>(e.passes, 255);
+                cb.data_len = total;
+                cb.len_cleanup = (h.ht && e.passes > 1) ? e.lcup : 0;
+                if (e.more.empty() && abs_off >= 0) { cb.data_off = (uint64_t)abs_off + e.off; out.is_extra.push_back(0); }
+                else {
+                    cb.data_off = out.extra.size();
+                    out.extra.insert(out.extra.end(), body + e.off, body + e.off + e.len);
+                    for (auto &m : e.more) out.extra.insert(out.extra.end(), body + m.first, body + m.first + m.second);
+                    out.is_extra.push_back(1);
+                }
+                out.cbs.push_back(cb);
+            }
+        }
+}
+
+inline uint32_t be16(const uint8_t *p) { return ((uint32_t)p[0] << 8) | p[1]; }
+inline uint32_t be32(const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+
+}  // namespace
+
+int j2k_tier2_parse(const uint8_t *d, uint64_t len, uint32_t reduce, uint32_t threads, j2kgpu_parsed &out)
+{
+    Err err;
+    Header h;
+#define T2_FAIL(...) do { err.fail(__VA_ARGS__); out.err = err.msg; return err.code; } while (0)
+    if (!d || len < 4 || be16(d) != SOC) T2_FAIL(J2KGPU_E_ARG, "not a codestream (no SOC)");
+    uint64_t pos = 2;
+    std::vector<uint32_t> tlm;                          // tile-part lengths announced by TLM, in codestream order
+    // ---- main header: codestream.Parser.ReadHeader (parser.go:44-124) ----
+    for (;;) {
+        if (pos + 4 > len) T2_FAIL(J2KGPU_E_RANGE, "main header truncated");
+        const uint32_t m = be16(d + pos);
+        if (m == SOT) break;
+        if (m == EOC) T2_FAIL(J2KGPU_E_RANGE, "no tile-part");
+        const uint32_t L = be16(d + pos + 2);
+        if (L < 2 || pos + 2 + L > len) T2_FAIL(J2KGPU_E_RANGE, "marker %04X: bad length", m);
+        const uint8_t *seg = d + pos + 4;
+        const uint32_t sl = L - 2;
+        if (m == SIZ) {                                   // readSIZ parser.go:193-285
+            if (sl < 36) T2_FAIL(J2KGPU_E_RANGE, "SIZ too short");
+            const uint32_t xs = be32(seg + 2), ys = be32(seg + 6), xo = be32(seg + 10), yo = be32(seg + 14), xt = be32(seg + 18),
+                           yt = be32(seg + 22), xto = be32(seg + 26), yto = be32(seg + 30), nc = be16(seg + 34);
+            if (xo || yo || xto || yto) T2_FAIL(J2KGPU_E_UNSUPPORTED, "non-zero image / tile origin");
+            if (nc < 1 || nc > 4 || sl < 36 + 3 * nc) T2_FAIL(J2KGPU_E_UNSUPPORTED, "unsupported number of components: %u", nc);   // decoder.go:585
+            for (uint32_t c = 0; c < nc; c++) {
+                const uint8_t *q = seg + 36 + 3 * c;
+                if (q[1] != 1 || q[2] != 1) T2_FAIL(J2KGPU_E_UNSUPPORTED, "sub-sampled components");
+                if (q[0] != seg[36]) T2_FAIL(J2KGPU_E_UNSUPPORTED, "components of different depth");
+            }
+            if (!xs || !ys || !xt || !yt || xs > 32768 || ys > 32768) T2_FAIL(J2KGPU_E_UNSUPPORTED, "image %ux%u", xs, ys);
+            h.W = xs; h.H = ys; h.tile_w = xt; h.tile_h = yt; h.ncomp = nc; h.prec = (seg[36] & 0x7F) + 1; h.sgnd = seg[36] >> 7;
+            if (h.prec > 16) T2_FAIL(J2KGPU_E_UNSUPPORTED, "precision %u", h.prec);
+            h.have_siz = true;
+        } else if (m == COD) {                            // readCOD parser.go:288-370
+            if (sl < 10) T2_FAIL(J2KGPU_E_RANGE, "COD too short");
+            const uint32_t scod = seg[0];
+            if (scod & 1) T2_FAIL(J2KGPU_E_UNSUPPORTED, "user-defined precincts");
+            h.sop = (scod >> 1) & 1; h.eph = (scod >> 2) & 1;
+            h.prog = seg[1]; h.layers = be16(seg + 2); h.mct = seg[4]; h.nlevels = seg[5];
+            h.cbw = 1u << (seg[6] + 2); h.cbh = 1u << (seg[7] + 2); h.style = seg[8]; h.reversible = seg[9] == 1;
+            if (h.prog > 4) T2_FAIL(J2KGPU_E_RANGE, "progression order %u", h.prog);
+            if (h.nlevels > 10) T2_FAIL(J2KGPU_E_UNSUPPORTED, "%u decomposition levels", h.nlevels);
+            if (h.cbw > 64 || h.cbh > 64 || h.cbw * h.cbh > 4096) T2_FAIL(J2KGPU_E_UNSUPPORTED, "code blocks %ux%u", h.cbw, h.cbh);
+            if (h.style & ~0x40u) T2_FAIL(J2KGPU_E_UNSUPPORTED, "code-block style %02X (bypass / reset / termination / causal / segmentation symbols)", h.style);
+            if (!h.layers) T2_FAIL(J2KGPU_E_RANGE, "zero quality layers");
+            h.have_cod = true;
+        } else if (m == CAP) {
+            h.ht = 1;                                     // Part 15 capability (Header.IsHTJ2K header.go:241-257)
+        } else if (m == QCD) {                            // readQCD parser.go:459-519
+            if (sl < 1) T2_FAIL(J2KGPU_E_RANGE, "QCD too short");
+            const uint32_t style = seg[0] & 31;
+            h.guard = seg[0] >> 5;
+            h.q.clear();
+            if (style == 0) for (uint32_t i = 1; i < sl; i++) h.q.push_back({(uint32_t)seg[i] >> 3, 0u});
+            else if (style == 1 || style == 2) for (uint32_t i = 1; i + 1 < sl; i += 2) h.q.push_back({be16(seg + i) >> 11, be16(seg + i) & 0x7FFu});
+            else T2_FAIL(J2KGPU_E_RANGE, "quantisation style %u", style);
+            if (style == 1) h.q.resize(1);
+            h.have_qcd = true;
+            if (style == 1) h.q.push_back({0xFFFFFFFFu, 0});   // marks "derived": expanded once nlevels is known
+        } else if (m == TLM) {                            // parser.go:671-775: Stlm, then (Ttlm, Ptlm) pairs
+            if (sl >= 2) {
+                const uint32_t st = (seg[1] >> 4) & 3, sp = (seg[1] >> 6) & 1;
+                const uint32_t esz = st + (sp ? 4 : 2);
+                if (st <= 2) for (uint32_t i = 2; i + esz <= sl; i += esz) tlm.push_back(sp ? be32(seg + i + st) : be16(seg + i + st));
+            }
+        } else if (m == COC || m == QCC || m == RGN || m == POC || m == PPM || m == PLM) {
+            T2_FAIL(J2KGPU_E_UNSUPPORTED, "marker %04X", m);
+        }
+        pos += 2 + L;
+    }
+    if (!h.have_siz || !h.have_cod || !h.have_qcd) T2_FAIL(J2KGPU_E_RANGE, "SIZ / COD / QCD missing");
+    if (h.style & 0x40) h.ht = 1;
+    const std::vector<BandId> bands = band_list(h.nlevels);
+    if (h.q.size() == 2 && h.q[1].first == 0xFFFFFFFFu) {   // scalar derived (E-5): eps_b = eps_0 - N_L + n_b, mu_b = mu_0
+        const auto q0 = h.q[0];
+        h.q.clear();
+        for (const BandId &b : bands) h.q.push_back({q0.first + b.lvl >= h.nlevels ? q0.first + b.lvl - h.nlevels : 0u, q0.second});
+    }
+    if (h.q.size() < bands.size()) T2_FAIL(J2KGPU_E_RANGE, "QCD lists %zu bands, %zu needed", h.q.size(), bands.size());
+    if (reduce > h.nlevels) T2_FAIL(J2KGPU_E_ARG, "reduce %u > %u decomposition levels", reduce, h.nlevels);
+    const uint32_t ntx = cdiv(h.W, h.tile_w), nty = cdiv(h.H, h.tile_h);
+    if ((uint64_t)ntx * nty > 65535) T2_FAIL(J2KGPU_E_UNSUPPORTED, "too many tiles");
+    if (ntx * nty > 1 && ((h.tile_w | h.tile_h) & ((1u << h.nlevels) - 1)))
+        T2_FAIL(J2KGPU_E_UNSUPPORTED, "tile size %ux%u is not a multiple of 2^nlevels", h.tile_w, h.tile_h);
+    // ---- tile-part index: ReadTilePartHeader (parser.go:894-982), hopping by Psot ----
+    const uint32_t ntiles = ntx * nty;
+    std::vector<std::vector<TilePart>> parts(ntiles);
+    std::vector<std::vector<uint32_t>> plt(ntiles);
+    uint32_t ntp = 0;
+    int64_t truncated_tile = -1;
+    while (pos + 12 <= len && be16(d + pos) == SOT) {
+        const uint32_t isot = be16(d + pos + 4), psot = be32(d + pos + 6);
+        if (isot >= ntiles) T2_FAIL(J2KGPU_E_RANGE, "tile index %u out of range", isot);
+        uint64_t end = psot ? pos + psot : len - 2;
+        if (end > len) { end = len; truncated_tile = (int64_t)isot; }     // the file ends inside this tile-part: decode what is there
+        if (end < pos + 14) T2_FAIL(J2KGPU_E_RANGE, "tile-part %u: bad Psot", ntp);
+        if (ntp < tlm.size() && psot && tlm[ntp] != psot) T2_FAIL(J2KGPU_E_RANGE, "tile-part %u: TLM says %u bytes, Psot %u", ntp, tlm[ntp], psot);
+        uint64_t p = pos + 12;
+        for (;;) {
+            if (p + 2 > end) T2_FAIL(J2KGPU_E_RANGE, "tile-part %u: no SOD", ntp);
+            const uint32_t m = be16(d + p);
+            if (m == SOD) break;
+            if (p + 4 > end) T2_FAIL(J2KGPU_E_RANGE, "tile-part header truncated");
+            const uint32_t L = be16(d + p + 2);
+            if (L < 2 || p + 2 + L > end) T2_FAIL(J2KGPU_E_RANGE, "tile-part marker %04X: bad length", m);
+            if (m == PLT) {                               // packet lengths, 7 bits per byte, MSB = continuation
+                uint32_t v = 0;
+                for (uint32_t i = 5; i < 2 + L; i++) {
+                    const uint8_t b = d[p + i];
+                    v = (v << 7) | (b & 0x7F);
+                    if (!(b & 0x80)) { plt[isot].push_back(v); v = 0; }
+                }
+            } else if (m == COD || m == COC || m == QCD || m == QCC || m == RGN || m == POC || m == PPT) {
+                T2_FAIL(J2KGPU_E_UNSUPPORTED, "marker %04X in a tile-part header", m);
+            }
+            p += 2 + L;
+        }
+        parts[isot].push_back({p + 2, end});
+        pos = end;
+        ntp++;
+    }
+    // ---- tier-2 per tile, tiles in parallel ----
+    std::vector<TileOut> touts(ntiles);
+    uint32_t nthreads = threads ? threads : std::max(1u, std::thread::hardware_concurrency());
+    nthreads = std::min<uint32_t>({nthreads, ntiles, 64u});
+    std::atomic<uint32_t> next{0};
+    auto worker = [&]() {
+        for (;;) {
+            const uint32_t t = next.fetch_add(1);
+            if (t >= ntiles) break;
+            if (parts[t].empty()) { std::vector<TilePart> none{{0, 0}}; parse_tile(d, h, t, none, plt[t], reduce, false, touts[t]); }
+            else parse_tile(d, h, t, parts[t], plt[t], reduce, (int64_t)t == truncated_tile, touts[t]);
+        }
+    };
+    if (nthreads <= 1) worker();
+    else {
+        std::vector<std::thread> th;
+        for (uint32_t i = 0; i < nthreads; i++) th.emplace_back(worker);
+        for (auto &t : th) t.join();
+    }
+    // ---- merge ----
+    uint64_t extra_total = 0;
+    size_t ncb = 0;
+    for (uint32_t t = 0; t < ntiles; t++) {
+        if (touts[t].err.code) { out.err = touts[t].err.msg; return touts[t].err.code; }
+        extra_total += touts[t].extra.size();
+        ncb += touts[t].cbs.size();
+    }
+    out.tilecomps.clear(); out.cblks.clear(); out.owned.clear();
+    out.cblks.reserve(ncb);
+    if (extra_total) { out.owned.reserve(len + extra_total + 8); out.owned.assign(d, d + len); }
+    for (uint32_t t = 0; t < ntiles; t++) {
+        TileOut &to = touts[t];
+        const uint32_t tc_base = (uint32_t)out.tilecomps.size();
+        const uint64_t ex_base = out.owned.size();
+        out.tilecomps.insert(out.tilecomps.end(), to.tcs.begin(), to.tcs.end());
+        if (!to.extra.empty()) out.owned.insert(out.owned.end(), to.extra.begin(), to.extra.end());
+        for (size_t i = 0; i < to.cbs.size(); i++) {
+            j2k_cblk_t cb = to.cbs[i];
+            cb.tilecomp += tc_base;
+            if (to.is_extra[i]) cb.data_off += ex_base;
+            out.cblks.push_back(cb);
+        }
+        out.packets += to.packets; out.plt_packets += to.plt_checked;
+    }
+    if (extra_total) { out.blob = out.owned.data(); out.blob_len = out.owned.size(); }
+    else { out.blob = d; out.blob_len = len; }
+    j2k_image_t &im = out.image;
+    memset(&im, 0, sizeof im);
+    im.width = (uint32_t)cdiv64(h.W, (int64_t)1 << reduce); im.height = (uint32_t)cdiv64(h.H, (int64_t)1 << reduce);
+    im.ncomp = (uint16_t)h.ncomp;
+    for (uint32_t c = 0; c < h.ncomp; c++) { im.prec[c] = (uint8_t)h.prec; im.sgnd[c] = (uint8_t)h.sgnd; }
+    im.mct = (h.mct && h.ncomp >= 3) ? 1 : 0; im.reversible = (uint8_t)h.reversible; im.nlevels = (uint8_t)(h.nlevels - reduce);
+    im.ht = (uint8_t)h.ht; im.mode = J2KGPU_MODE_ISO; im.out_fmt = J2KGPU_FMT_AUTO;
+    uint32_t cbits = 0;
+    for (size_t bi = 0; bi < bands.size(); bi++) cbits = std::max(cbits, h.q[bi].first + h.guard - 1);
+    im.coef_bits = (uint8_t)std::min(cbits, 255u);
+    out.layers = h.layers; out.tiles = ntiles; out.tile_parts = ntp; out.progression = h.prog; out.tlm_tile_parts = (uint32_t)tlm.size();
+    return J2KGPU_OK;
+#undef T2_FAIL
+}

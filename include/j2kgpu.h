@@ -185,6 +185,30 @@ int j2kgpu_decode(j2kgpu_ctx *ctx, const j2k_image_t *img,
  * nlevels/ht/mode (geometry may differ). */
 int j2kgpu_decode_batch(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *items);
 
+/* ---- codestream front door (ABI v4): tier-2 inside the library ----------------- *
+ * The reference keeps codestream parsing in Go (internal/codestream) but has no working tier-2: decodeTile is a
+ * placeholder (decoder.go:375-380), internal/tcd/t2.go a toy.  These entry points do what the Go-side `buildGPUJob`
+ * of INTEGRATION.md has to do -- main header (parser.go:44-124), tile-part index (parser.go:894-982, Psot / TLM), packet
+ * headers (tag trees, passes, Lblock, lengths; SOP / EPH; PLT cross-check; all five progression orders, quality layers,
+ * classic and HT blocks) -- and fill the tables above in J2KGPU_MODE_ISO, tiles parsed concurrently on host threads.
+ * Raw codestreams only (the JP2 box walk stays with decoder.readJP2, decoder.go:206-253).  reduce =
+ * Config.ReduceResolution (jpeg2000.go:205-207).  Unsupported features (precincts, sub-sampling, COC/QCC/POC/PPM/PPT,
+ * non-default block styles) return J2KGPU_E_UNSUPPORTED. */
+typedef struct j2kgpu_parsed j2kgpu_parsed;
+/* *out is always set (free it with j2kgpu_parsed_free); on failure j2kgpu_parsed_error(*out) says why.  No CUDA involved. */
+int         j2kgpu_parse_codestream(const uint8_t *cs, uint64_t len, uint32_t reduce, uint32_t threads, j2kgpu_parsed **out);
+void        j2kgpu_parsed_free(j2kgpu_parsed *p);
+const char *j2kgpu_parsed_error(const j2kgpu_parsed *p);
+/* item <- image header, tables and blob of the parsed codestream (pointers into p, and into cs when every block's bytes
+ * are contiguous there: cs must then outlive the decode call); out_pix / out_stride are left for the caller */
+int         j2kgpu_parsed_item(const j2kgpu_parsed *p, j2k_batch_item_t *item);
+/* info: layers, tiles, tile-parts, packets, progression order, packets checked against PLT, tile-parts listed by TLM, zero-copy */
+int         j2kgpu_parsed_info(const j2kgpu_parsed *p, uint32_t info[8]);
+/* parse + decode; for n codestreams the tier-2 of later frames runs on host threads while the device decodes earlier ones */
+int         j2kgpu_decode_codestream(j2kgpu_ctx *ctx, const uint8_t *cs, uint64_t len, uint32_t reduce, uint8_t *out_pix, uint64_t out_stride);
+int         j2kgpu_decode_codestreams(j2kgpu_ctx *ctx, uint32_t n, const uint8_t *const *cs, const uint64_t *lens, uint32_t reduce,
+                                      uint8_t *const *out_pix, const uint64_t *out_stride);
+
 /* ---- device-resident form (inputs and outputs stay in HBM) ------------------ *
  * A job is a batch whose tables have been validated, flattened and uploaded.
  * j2kgpu_job_run launches the whole path on the ctx stream with DEVICE pointers
