@@ -8,7 +8,7 @@
 //
 // Mapping: k_htiso_vlc (one thread per block: the MEL / VLC context chain), then -- only when some block of the launch
 // carries SigProp / MagRef passes -- k_htiso_refine (one warp per block: significance propagation and the MagRef bits,
-// left as three row bitmaps per block), then k_htiso_magsgn2 (half a warp per block: the MagSgn rows in parallel and
+// left as three row bitmaps per block), then k_htiso_magsgn4 (eight lanes per block: the MagSgn rows in parallel and
 // the final value of every sample, written once).  The single-chain statement of the same algorithm is the CPU checker
 // (test side).
 #include "common.h"
@@ -473,26 +473,52 @@ k_htiso_refine(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__r
     for (int i = lane; i < kRefWords; i += 32) dst[i] = s_out[warp][i];
 }
 
-// B', the default: TWO blocks per warp, one per half-warp, each lane two neighbouring quads (4 columns) of a quad row.
-// Kernel B spends about as many instructions per quad row on what is per row (loop, ring upkeep, predictor shuffles,
-// prefix sum) as on the samples; with two quads per lane and two blocks per instruction stream that fixed part is
-// shared by four times as many samples.  Same arithmetic, same ring (one per block, 128-byte chunks), same results.
-constexpr int kWarpsIsoB2 = 8;
+// B (k_htiso_magsgn4): FOUR blocks per warp, eight lanes per block, each lane four neighbouring quads (8 columns, 16
+// samples) of a quad row.  The MagSgn work is issue-bound, so the mapping is chosen for instructions per sample:
+//   * what is per quad row and not per sample (loop, ring upkeep, predictor shuffles, prefix sum over 8 lanes instead of 32)
+//     is shared by 512 samples per warp step;
+//   * a sample costs ~20 straight-line instructions: no branch per sample (an insignificant sample is a zero-width field),
+//     one funnel shift over two ring words (the ring keeps a copy of word 0 behind its last word, so the second load needs
+//     no wrap), reconstruction as one add and one shift;
+//   * the stuffing is removed 16 bytes per lane (two aligned 16-byte loads funnelled to the stream position): 0xFF bytes are
+//     found with three word-wide operations per 4 bytes and the rare bit removals run in a short loop; blocks of a warp
+//     refill together once one of them has to (hysteresis), so the refill runs about every other quad row.
+// Same arithmetic as the single-chain checker for every input, malformed ones included: a byte after 0xFF contributes 7 bits
+// and its top bit is OR-ed onto the next byte's first bit, an exhausted stream continues with 0xFF.
+constexpr int kWarpsB4 = 4;
+constexpr uint32_t kRingMask = kRingWords - 1;
+
+// 4 stream bytes (x, little endian) -> dense bits; *nbits = 32 - number of bytes that follow a 0xFF byte; prev_ff: the byte
+// before x was 0xFF; *last_ff: the last byte of x is 0xFF
+__device__ __forceinline__ uint32_t unstuff_word(uint32_t x, uint32_t prev_ff, uint32_t *nbits, uint32_t *last_ff)
+{
+    const uint32_t ff = ((x & 0x7F7F7F7Fu) + 0x01010101u) & x & 0x80808080u;      // bit 7 of every byte that is 0xFF
+    uint32_t st = (ff << 8) | (prev_ff ? 0x80u : 0u);                            // bit 7 of every byte that carries 7 bits
+    *nbits = 32u - (uint32_t)__popc(st);
+    *last_ff = ff >> 31;
+    while (st) {                                                                 // top down, so that lower positions stay valid
+        const uint32_t pos = 31u - (uint32_t)__clz((int)st);
+        const uint32_t low = (1u << pos) - 1u;
+        x = (x & ((low << 1) | 1u)) | ((x >> 1) & ~low);                         // bit pos stays and the bits above close onto it
+        st &= low;
+    }
+    return x;
+}
 
 // REFINE: some block of the launch has SigProp / MagRef passes; their bitmaps (k_htiso_refine) are folded in here.
 template <typename OT, bool IRREV, bool REFINE>
-__global__ void __launch_bounds__(kWarpsIsoB2 * 32)
-k_htiso_magsgn2(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob,
+__global__ void __launch_bounds__(kWarpsB4 * 32)
+k_htiso_magsgn4(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob, const uint8_t *blob_end,
                 const uint32_t *__restrict__ qtab, const uint32_t *__restrict__ status, OT *__restrict__ coef,
                 const float *__restrict__ steps, int coef_bits, const uint64_t *__restrict__ ref)
 {
     constexpr uint32_t FULL = 0xffffffffu;
-    __shared__ uint32_t s_ring[kWarpsIsoB2 * 2][kRingWords];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4, sl = lane & 15;
-    const uint32_t blk0 = (blockIdx.x * kWarpsIsoB2 + warp) * 2;
+    __shared__ uint32_t s_ring[kWarpsB4 * 4][kRingWords + 1];            // [kRingWords] mirrors word 0
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, grp = lane >> 3, sl = lane & 7;
+    const uint32_t blk0 = (blockIdx.x * kWarpsB4 + warp) * 4;
     if (blk0 >= n) return;
-    const bool have = blk0 + half < n;
-    const uint32_t blk = have ? blk0 + half : blk0;
+    const bool have = blk0 + grp < n;
+    const uint32_t blk = have ? blk0 + grp : blk0;
     const uint32_t stw = status[blk];
     const DevCblk cb = cblks[blk];
     const int w = cb.w, h = cb.h;
@@ -502,156 +528,183 @@ k_htiso_magsgn2(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__
     const bool zero = (stw & 3) == ST_ZERO;
     if (have && zero)
         for (int y = 0; y < h; y++)
-            for (int x = sl; x < w; x += 16) out[(size_t)y * ostride + x] = 0;
-    const bool live = have && !zero;                     // this half-warp decodes a block
+            for (int x = sl; x < w; x += 8) out[(size_t)y * ostride + x] = 0;
+    const bool live = have && !zero;                     // these eight lanes decode a block
     const float qstep = (IRREV && steps) ? 0.25f * steps[blk] : 0.25f;
-    const int L = (int)(stw >> 2);
+    const int L = (int)(stw >> 2);                       // bytes of the MagSgn stream
     const int shift = cb.num_bps - 1;                    // P: bit-plane of the cleanup pass
     // passes of the HT set that are decoded: 1 = cleanup, 2 = + SigProp, 3 = + MagRef (none without refinement bytes)
     const int np = (REFINE && cb.num_passes > 1 && cb.data_len > cb.len_cup) ? (cb.num_passes > 3 ? 3 : (int)cb.num_passes) : 1;
     const uint64_t *rf = REFINE ? ref + (size_t)blk * kRefWords : nullptr;
     const int nq = (w + 1) >> 1, nrows = live ? (h + 1) >> 1 : 0;
-    const bool active = live && 2 * sl < nq;             // the lane's first quad exists
-    const int ncols = w - 4 * sl;                        // columns of the block right of (and including) the lane's first
-    const bool vec_ok = ((cb.out_off | ostride) & 3) == 0;
-    const uint32_t *qt = qtab + (size_t)blk * kQTabWords;
-    uint32_t *ring = s_ring[warp * 2 + half];
-    for (int i = sl; i < kRingWords; i += 16) ring[i] = 0;
+    const uint32_t pairA = (live && 4 * sl < nq) ? ~0u : 0u, pairB = (live && 4 * sl + 2 < nq) ? ~0u : 0u;   // the lane's quad pairs exist
+    const int ncols = w - 8 * sl;                        // columns of the block right of (and including) the lane's first
+    const bool vec_ok = ((cb.out_off | ostride) & (sizeof(OT) == 2 ? 7 : 3)) == 0;
+    const int ulimit = min(28, coef_bits ? coef_bits + 1 : 28) - shift;   // a wider field would not fit 31 bits in quarter units / the plane
+    const uint2 *qt = reinterpret_cast<const uint2 *>(qtab + (size_t)blk * kQTabWords) + sl;
+    uint32_t *ring = s_ring[warp * 4 + grp];
+    for (int i = sl; i <= kRingWords; i += 8) ring[i] = 0;
     __syncwarp();
-    uint32_t built = 0, prev_ff = 0, P = 0;              // uniform per half-warp
+    const uint32_t mis = (uint32_t)((uintptr_t)d & 3u);  // byte 0 of the stream inside its aligned word
+    uint32_t built = 0, prev_ff = 0, P = 0;              // uniform over the block's lanes
     int kbyte = 0;
-    int Eb[4] = {0, 0, 0, 0};                            // bottom-sample exponents of the lane's 4 columns, previous quad row
+    int Eb[8] = {0, 0, 0, 0, 0, 0, 0, 0};                // bottom-sample exponents of the lane's 8 columns, previous quad row
     bool bad = false;
-    const int nrows_max = max(__shfl_sync(FULL, nrows, 0), __shfl_sync(FULL, nrows, 16));
-    uint32_t code_next = (active && nrows > 0) ? qt[sl] : 0u;
+    int nrows_max = nrows;
+    nrows_max = max(nrows_max, __shfl_xor_sync(FULL, nrows_max, 8));
+    nrows_max = max(nrows_max, __shfl_xor_sync(FULL, nrows_max, 16));
+    uint2 code_next = make_uint2(0u, 0u);
+    if (nrows > 0) { code_next = __ldg(qt); code_next.x &= pairA; code_next.y &= pairB; }
     for (int r = 0; r < nrows_max; r++) {
         const bool row_on = r < nrows;
-        const uint32_t code2 = row_on ? code_next : 0u;
-        if (r + 1 < nrows) code_next = active ? qt[(r + 1) * 16 + sl] : 0u;
-        // ---- keep each ring one full quad row ahead ----
-        bool need = row_on && built < P + 4096u;
-        while (__any_sync(FULL, need)) {
-            const int k = kbyte + 8 * sl;
-            uint32_t b[8], nb[8];
+        const uint2 code = row_on ? code_next : make_uint2(0u, 0u);
+        if (r + 1 < nrows) { code_next = __ldg(qt + (r + 1) * 8); code_next.x &= pairA; code_next.y &= pairB; }
+        // ---- keep each ring one full quad row (32 x 4 x 31 bits) ahead; when one block has to refill, every block that is
+        // less than 7 Kbit ahead refills with it ----
+        if (__any_sync(FULL, row_on && built < P + 4096u)) {
+            bool join = row_on && built < P + 7168u;
+            while (__any_sync(FULL, join)) {
+                if (join) {                              // words beyond the one `built` points into hold bits 16 Kbit old
+                    const uint32_t w0 = (built >> 5) + 1 + sl;
 #pragma unroll
-            for (int i = 0; i < 8; i++) b[i] = (need && k + i < L) ? (uint32_t)__ldg(d + k + i) : 0xFFu;
-            if (need) {                                  // words beyond the one `built` points into hold bits 16 Kbit old
-                const uint32_t w0 = (built >> 5) + 1;
-                ring[(w0 + sl) & (kRingWords - 1)] = 0;
-                ring[(w0 + 16 + sl) & (kRingWords - 1)] = 0;
-                if (sl < 2) ring[(w0 + 32 + sl) & (kRingWords - 1)] = 0;
-            }
-            uint32_t pb = __shfl_up_sync(FULL, b[7], 1, 16);
-            if (sl == 0) pb = prev_ff ? 0xFFu : 0u;
-#pragma unroll
-            for (int i = 0; i < 8; i++) { nb[i] = pb == 0xFFu ? 7u : 8u; pb = b[i]; }
-            const uint32_t va = b[0] | (b[1] << nb[0]) | (b[2] << (nb[0] + nb[1])) | (b[3] << (nb[0] + nb[1] + nb[2]));
-            const uint32_t vb = b[4] | (b[5] << nb[4]) | (b[6] << (nb[4] + nb[5])) | (b[7] << (nb[4] + nb[5] + nb[6]));
-            const uint32_t ta = nb[0] + nb[1] + nb[2] + nb[3], tot = ta + nb[4] + nb[5] + nb[6] + nb[7];
-            uint32_t incl = tot;
-#pragma unroll
-            for (int o = 1; o < 16; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL, incl, o, 16); if (sl >= o) incl += t; }
-            const uint32_t pos = built + incl - tot;
-            __syncwarp();
-            if (need) {
-#pragma unroll
-                for (int g = 0; g < 2; g++) {
-                    const uint32_t pg = g ? pos + ta : pos, vg = g ? vb : va;
-                    const uint32_t sh = pg & 31, wi = pg >> 5;
-                    atomicOr(&ring[wi & (kRingWords - 1)], vg << sh);
-                    const uint32_t hi = sh ? vg >> (32 - sh) : 0u;
-                    if (hi) atomicOr(&ring[(wi + 1) & (kRingWords - 1)], hi);
+                    for (int i = 0; i < 5; i++) ring[(w0 + 8 * i) & kRingMask] = 0;
                 }
-            }
-            const uint32_t total = __shfl_sync(FULL, incl, 15, 16);
-            const uint32_t lastb = __shfl_sync(FULL, pb, 15, 16);
-            if (need) { built += total; prev_ff = lastb == 0xFFu; kbyte += 128; }
-            __syncwarp();
-            need = row_on && built < P + 4096u;
-        }
-        // ---- U_q and the field widths of the lane's two quads ----
-        const int eL = __shfl_up_sync(FULL, Eb[3], 1, 16), eR = __shfl_down_sync(FULL, Eb[0], 1, 16);
-        const int eLeft = sl ? eL : 0, eRight = sl < 15 ? eR : 0;
-        uint32_t st8[2];
-        int U[2], m[8];
+                __syncwarp();
+                const int k = kbyte + 16 * sl;           // the lane's stream bytes k .. k + 15
+                uint32_t x[4] = {FULL, FULL, FULL, FULL};
+                if (join && k < L) {
+                    // five aligned words that hold the 16 bytes; a word is read only if it starts inside the blob
+                    const uint8_t *a = d + k - mis;
+                    uint32_t wd[5];
+                    if (a + 20 <= blob_end) {
 #pragma unroll
-        for (int qd = 0; qd < 2; qd++) {
-            const uint32_t code = (code2 >> (16 * qd)) & 0xFFFFu;
-            st8[qd] = code & 0xFF;
-            const int u = (int)(code >> 8);
-            const uint32_t sig = (st8[qd] | (st8[qd] >> 1)) & 0x55u;
+                        for (int j = 0; j < 5; j++) wd[j] = __ldg(reinterpret_cast<const uint32_t *>(a) + j);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 5; j++) wd[j] = (a + 4 * j < blob_end) ? __ldg(reinterpret_cast<const uint32_t *>(a) + j) : FULL;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) x[j] = __funnelshift_r(wd[j], wd[j + 1], mis * 8);
+                    if (k + 16 > L) {                    // past the end of the stream: 0xFF
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const int vb = L - (k + 4 * j);
+                            if (vb < 4) x[j] |= vb <= 0 ? FULL : (FULL << (8 * vb));
+                        }
+                    }
+                }
+                uint32_t pf = __shfl_up_sync(FULL, x[3] >> 24, 1, 8) == 0xFFu;
+                if (sl == 0) pf = prev_ff;
+                uint32_t nb[4], v[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) v[j] = unstuff_word(x[j], pf, &nb[j], &pf);
+                const uint32_t tot = nb[0] + nb[1] + nb[2] + nb[3];
+                uint32_t incl = tot;
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL, incl, o, 8); if (sl >= o) incl += t; }
+                uint32_t pos = built + incl - tot;
+                if (join) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t wi = pos >> 5;
+                        atomicOr(&ring[wi & kRingMask], v[j] << (pos & 31));
+                        atomicOr(&ring[(wi + 1) & kRingMask], __funnelshift_l(v[j], 0u, pos));   // the bits that spill over (none at pos % 32 == 0)
+                        pos += nb[j];
+                    }
+                }
+                const uint32_t total = __shfl_sync(FULL, incl, 7, 8);
+                const uint32_t lastff = __shfl_sync(FULL, pf, 7, 8);
+                if (join) { built += total; prev_ff = lastff; kbyte += 128; }
+                __syncwarp();
+                if (sl == 0) ring[kRingWords] = ring[0];  // the word behind the last mirrors word 0: readers take two words without a wrap
+                __syncwarp();
+                join = row_on && built < P + 4096u;      // (a second round only if 1024 bits were not enough)
+            }
+        }
+        // ---- U_q and the field widths of the lane's four quads ----
+        const int eL = __shfl_up_sync(FULL, Eb[7], 1, 8), eR = __shfl_down_sync(FULL, Eb[0], 1, 8);
+        const int c_m1 = max(sl ? eL : 0, Eb[0]), c_1 = max(Eb[1], Eb[2]), c_3 = max(Eb[3], Eb[4]), c_5 = max(Eb[5], Eb[6]),
+                  c_7 = max(Eb[7], sl < 7 ? eR : 0);
+        const int Eq[4] = {max(c_m1, c_1), max(c_1, c_3), max(c_3, c_5), max(c_5, c_7)};
+        uint32_t sigm[4], e1m[4];
+        int m[16];
+        uint32_t tot = 0;
+#pragma unroll
+        for (int qd = 0; qd < 4; qd++) {
+            const uint32_t c16 = (qd & 1) ? ((qd >> 1) ? code.y : code.x) >> 16 : ((qd >> 1) ? code.y : code.x) & 0xFFFFu;
+            const uint32_t st8 = c16 & 0xFFu;
+            const int u = (int)(c16 >> 8);
+            const uint32_t sig = (st8 | (st8 >> 1)) & 0x55u, ek = (st8 >> 1) & 0x55u;
+            sigm[qd] = sig; e1m[qd] = st8 & ek;
             int Uq = u + 1;
-            if (r > 0 && (sig & (sig - 1))) {
-                const int E = qd == 0 ? max(max(eLeft, Eb[0]), max(Eb[1], Eb[2])) : max(max(Eb[1], Eb[2]), max(Eb[3], eRight));
-                Uq = u + max(1, E - 1);
-            }
-            if (Uq + shift > 28) bad = true;             // a magnitude would not fit 31 bits in quarter units: malformed
-            if (coef_bits && Uq + shift > coef_bits + 1) bad = true;
-            U[qd] = min(Uq, 31);
+            if (r > 0 && (sig & (sig - 1))) Uq = u + max(1, Eq[qd] - 1);
+            bad |= Uq > ulimit;
+            const int U = min(Uq, 31);
 #pragma unroll
-            for (int i = 0; i < 4; i++) { const uint32_t s2 = (st8[qd] >> (2 * i)) & 3; m[4 * qd + i] = s2 ? U[qd] - (int)(s2 >> 1) : 0; }
+            for (int i = 0; i < 4; i++) {
+                const int mi = ((sig >> (2 * i)) & 1u) ? U - (int)((ek >> (2 * i)) & 1u) : 0;
+                m[4 * qd + i] = mi;
+                tot += (uint32_t)mi;
+            }
         }
-        const uint32_t tot = (uint32_t)(m[0] + m[1] + m[2] + m[3] + m[4] + m[5] + m[6] + m[7]);
         uint32_t incl = tot;
 #pragma unroll
-        for (int o = 1; o < 16; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL, incl, o, 16); if (sl >= o) incl += t; }
+        for (int o = 1; o < 8; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL, incl, o, 8); if (sl >= o) incl += t; }
         uint32_t p = P + incl - tot;
-        P += __shfl_sync(FULL, incl, 15, 16);
+        P += __shfl_sync(FULL, incl, 7, 8);
         // ---- samples: per quad n = 0 (y, x), 1 (y + 1, x), 2 (y, x + 1), 3 (y + 1, x + 1) ----
-        // refinement bitmaps of the two sample rows: the lane's 4 columns are bits 4 sl .. 4 sl + 3
+        // refinement bitmaps of the two sample rows: the lane's 8 columns are bits 8 sl .. 8 sl + 7
         uint32_t rnew[2] = {0, 0}, rsgn[2] = {0, 0}, rmr[2] = {0, 0};
         if (REFINE && np > 1 && row_on) {
 #pragma unroll
             for (int t = 0; t < 2; t++) {
                 const int y = 2 * r + t;
                 if (y < h) {
-                    rnew[t] = (uint32_t)(__ldg(rf + y) >> (4 * sl)) & 0xFu;
-                    rsgn[t] = (uint32_t)(__ldg(rf + 64 + y) >> (4 * sl)) & 0xFu;
-                    if (np == 3) rmr[t] = (uint32_t)(__ldg(rf + 128 + y) >> (4 * sl)) & 0xFu;
+                    rnew[t] = (uint32_t)(__ldg(rf + y) >> (8 * sl)) & 0xFFu;
+                    rsgn[t] = (uint32_t)(__ldg(rf + 64 + y) >> (8 * sl)) & 0xFFu;
+                    if (np == 3) rmr[t] = (uint32_t)(__ldg(rf + 128 + y) >> (8 * sl)) & 0xFFu;
                 }
             }
         }
-        int32_t val[8];
+        int32_t val[16];
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const uint32_t s2 = (st8[i >> 2] >> (2 * (i & 3))) & 3;
-            val[i] = 0;
-            if (i & 1) Eb[i >> 1] = 0;
-            const int col = 2 * (i >> 2) + ((i >> 1) & 1), rowt = i & 1;       // position inside the lane's 4 x 2 patch
-            if (s2) {
-                const uint32_t wi = p >> 5;
-                const uint32_t x = __funnelshift_r(ring[wi & (kRingWords - 1)], ring[(wi + 1) & (kRingWords - 1)], p & 31);
-                uint32_t vv = x & ((1u << m[i]) - 1u);
-                const uint32_t sign = vv & 1;
-                vv |= (uint32_t)(s2 == 3) << m[i];
-                vv |= 1;
-                const uint32_t mu = (vv >> 1) + 1;
-                uint32_t q = (2u * mu + 1u) << (shift + 1);
-                if (REFINE && np == 3) q = (mu << (shift + 2)) | (((rmr[rowt] >> col) & 1u) << (shift + 1)) | (1u << shift);
-                val[i] = sample_value(q, sign, qstep, IRREV);
-                if (i & 1) Eb[i >> 1] = 32 - __clz((int)vv);
-                p += (uint32_t)m[i];
-            } else if (REFINE && ((rnew[rowt] >> col) & 1u)) {
-                val[i] = sample_value(3u << shift, (rsgn[rowt] >> col) & 1u, qstep, IRREV);
-            }
+        for (int i = 0; i < 16; i++) {
+            const int qd = i >> 2, sn = i & 3;
+            const uint32_t sigb = (sigm[qd] >> (2 * sn)) & 1u, e1 = (e1m[qd] >> (2 * sn)) & 1u;
+            const uint32_t *rw = ring + ((p >> 5) & kRingMask);
+            const uint32_t xb = __funnelshift_r(rw[0], rw[1], p);
+            const uint32_t fld = xb & ((1u << m[i]) - 1u);
+            const uint32_t vv = fld | (e1 << m[i]) | sigb;               // 2 (mu - 1) + 1, or 0 for an insignificant sample
+            p += (uint32_t)m[i];
+            if (sn & 1) Eb[2 * qd + (sn >> 1)] = 32 - __clz((int)vv);
+            const int col = 2 * qd + (sn >> 1), rowt = sn & 1;           // position inside the lane's 8 x 2 patch
+            uint32_t q = (vv + 2u * sigb) << (shift + 1);                // (2 mu + 1) << (P + 1)
+            if (REFINE && np == 3) q = sigb ? ((((vv >> 1) + 1u) << (shift + 2)) | (((rmr[rowt] >> col) & 1u) << (shift + 1)) | (1u << shift)) : 0u;
+            uint32_t sign = fld & 1u;
+            if (REFINE && !sigb && ((rnew[rowt] >> col) & 1u)) { q = 3u << shift; sign = (rsgn[rowt] >> col) & 1u; }
+            val[i] = sample_value(q, sign, qstep, IRREV);
         }
-        if (active && row_on) {
+        if (row_on && ncols > 0) {
             const int y = 2 * r;
             const bool row2 = (y + 1 < h);
-            OT *p0 = out + (size_t)y * ostride + 4 * sl;
-            if (ncols >= 4 && vec_ok) {
+            OT *p0 = out + (size_t)y * ostride + 8 * sl;
+            if (ncols >= 8 && vec_ok) {
                 if (sizeof(OT) == 4) {
                     *reinterpret_cast<int4 *>(p0) = make_int4(val[0], val[2], val[4], val[6]);
-                    if (row2) *reinterpret_cast<int4 *>(p0 + ostride) = make_int4(val[1], val[3], val[5], val[7]);
+                    *reinterpret_cast<int4 *>(p0 + 4) = make_int4(val[8], val[10], val[12], val[14]);
+                    if (row2) {
+                        *reinterpret_cast<int4 *>(p0 + ostride) = make_int4(val[1], val[3], val[5], val[7]);
+                        *reinterpret_cast<int4 *>(p0 + ostride + 4) = make_int4(val[9], val[11], val[13], val[15]);
+                    }
                 } else {
-                    *reinterpret_cast<uint2 *>(p0) = make_uint2(((uint32_t)val[0] & 0xFFFFu) | ((uint32_t)val[2] << 16),
-                                                                ((uint32_t)val[4] & 0xFFFFu) | ((uint32_t)val[6] << 16));
-                    if (row2) *reinterpret_cast<uint2 *>(p0 + ostride) = make_uint2(((uint32_t)val[1] & 0xFFFFu) | ((uint32_t)val[3] << 16),
-                                                                                     ((uint32_t)val[5] & 0xFFFFu) | ((uint32_t)val[7] << 16));
+#define J2K_PK16(a, b) (((uint32_t)(a) & 0xFFFFu) | ((uint32_t)(b) << 16))
+                    *reinterpret_cast<uint4 *>(p0) = make_uint4(J2K_PK16(val[0], val[2]), J2K_PK16(val[4], val[6]), J2K_PK16(val[8], val[10]), J2K_PK16(val[12], val[14]));
+                    if (row2) *reinterpret_cast<uint4 *>(p0 + ostride) = make_uint4(J2K_PK16(val[1], val[3]), J2K_PK16(val[5], val[7]), J2K_PK16(val[9], val[11]), J2K_PK16(val[13], val[15]));
+#undef J2K_PK16
                 }
             } else {
 #pragma unroll
-                for (int c = 0; c < 4; c++)
+                for (int c = 0; c < 8; c++)
                     if (c < ncols) {
                         p0[c] = (OT)val[2 * c];
                         if (row2) p0[ostride + c] = (OT)val[2 * c + 1];
@@ -662,9 +715,9 @@ k_htiso_magsgn2(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__
     // a malformed block is zero as a whole
     bad = bad && live;
     const uint32_t badm = __ballot_sync(FULL, bad);
-    if (have && !zero && (badm & (half ? 0xFFFF0000u : 0x0000FFFFu))) {
+    if (live && (badm & (0xFFu << (8 * grp)))) {
         for (int y = 0; y < h; y++)
-            for (int x = sl; x < w; x += 16) out[(size_t)y * ostride + x] = 0;
+            for (int x = sl; x < w; x += 8) out[(size_t)y * ostride + x] = 0;
     }
 }
 
@@ -681,13 +734,15 @@ template <typename OT>
 static void launch_ht_iso_t(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, OT *d_coef,
                             const float *d_steps, int irrev, int coef_bits, int refine, void *d_scratch, uint64_t blob_bytes, cudaStream_t s)
 {
+    const uint64_t blob_total = blob_bytes;
     if ((uintptr_t)d_blob & 3) blob_bytes = 0;           // unaligned blob: byte loads only
     uint32_t *qtab = (uint32_t *)d_scratch, *status = qtab + (size_t)n * kQTabWords;
     uint64_t *ref = (uint64_t *)(((uintptr_t)(status + n) + 63) & ~(uintptr_t)63);
     J2K_LAUNCH((k_htiso_vlc), (n + kThreads - 1) / kThreads, kThreads, 0, s, d_cblks, n, d_blob, blob_bytes, qtab, status);
     if (refine) J2K_LAUNCH((k_htiso_refine), (n + kRefWarps - 1) / kRefWarps, kRefWarps * 32, 0, s, d_cblks, n, d_blob, qtab, status, ref);
-    const uint32_t grid = (n + 2 * kWarpsIsoB2 - 1) / (2 * kWarpsIsoB2);
-#define J2K_HTISO_B(IRR, REF) J2K_LAUNCH((k_htiso_magsgn2<OT, IRR, REF>), grid, kWarpsIsoB2 * 32, 0, s, d_cblks, n, d_blob, qtab, status, d_coef, d_steps, coef_bits, ref)
+    const uint32_t grid = (n + 4 * kWarpsB4 - 1) / (4 * kWarpsB4);
+    const uint8_t *blob_end = d_blob + blob_total;
+#define J2K_HTISO_B(IRR, REF) J2K_LAUNCH((k_htiso_magsgn4<OT, IRR, REF>), grid, kWarpsB4 * 32, 0, s, d_cblks, n, d_blob, blob_end, qtab, status, d_coef, d_steps, coef_bits, ref)
     if (irrev) { if (refine) J2K_HTISO_B(true, true); else J2K_HTISO_B(true, false); }
     else { if (refine) J2K_HTISO_B(false, true); else J2K_HTISO_B(false, false); }
 #undef J2K_HTISO_B

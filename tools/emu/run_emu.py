@@ -38,4 +38,5 @@ if __name__ == "__main__":
     subprocess.check_call(["make", "-s", "-j8", "-C", HERE])
     os.chdir(ROOT)
     args = sys.argv[1:] or ["-x", "-q"]
-    sys.exit(pytest.main(["tests", "-m", "gpu", "-p", "no:cacheprovider"] + args, plugins=[EmuPlugin()]))
+    paths = [] if any(a.startswith("tests") for a in args) else ["tests"]       # explicit test paths replace the whole suite
+    sys.exit(pytest.main(paths + ["-m", "gpu", "-p", "no:cacheprovider"] + args, plugins=[EmuPlugin()]))
