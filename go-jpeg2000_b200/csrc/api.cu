@@ -362,6 +362,22 @@ static bool tiles_exactly(std::vector<Rect> &r, uint32_t w, uint32_t h)
 // async_stream != nullptr: the tables are staged in page-locked memory owned by the job and uploaded on that stream
 // without any synchronisation (pipelined batch calls: the host builds the next chunk's tables while the device decodes
 // this one); nullptr: uploaded on the ctx stream and synchronised before returning.
+// Blocks of one image in order of falling height, then width (counting sort, stable): the entropy kernels give a block
+// to a thread or to a few lanes of a warp and run as long as the tallest block of the warp, so neighbours in the table
+// should be alike; the tallest first also keeps the last wave short.  The table order carries no meaning otherwise.
+static void sort_blocks_by_shape(DevCblk *cb, float *step, size_t n, std::vector<DevCblk> &tmp, std::vector<float> &stmp)
+{
+    if (n < 2) return;
+    uint32_t count[65 * 65 + 1] = {0};
+    auto key = [](const DevCblk &c) { return (uint32_t)(64 - c.h) * 65u + (uint32_t)(64 - c.w); };
+    bool sorted = true;
+    for (size_t i = 0; i < n; i++) { count[key(cb[i]) + 1]++; if (i && key(cb[i]) < key(cb[i - 1])) sorted = false; }
+    if (sorted) return;
+    for (int k = 0; k < 65 * 65; k++) count[k + 1] += count[k];
+    tmp.assign(cb, cb + n); stmp.assign(step, step + n);
+    for (size_t i = 0; i < n; i++) { const uint32_t d = count[key(tmp[i])]++; cb[d] = tmp[i]; step[d] = stmp[i]; }
+}
+
 static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *items, j2kgpu_job **out, cudaStream_t async_stream)
 {
     if (!ctx || !out || !items || n_img == 0) return j2k_set_err(ctx, J2KGPU_E_ARG, "null or empty batch");
@@ -410,6 +426,8 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
     const bool will_coef16 = !opt.coef32 && iso && hdr.reversible && hdr.coef_bits >= 1 && hdr.coef_bits <= 14;
     std::vector<Rect> rects;
     std::vector<std::vector<Rect>> blk_rects;
+    std::vector<DevCblk> shape_tmp;
+    std::vector<float> step_tmp;
 
 #define J2K_FAIL(...) do { const int rc__ = j2k_set_err(__VA_ARGS__); job_free(job); return rc__; } while (0)
     for (uint32_t ii = 0; ii < n_img; ii++) {
@@ -485,6 +503,7 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
         if (fill) job->pix_fill = 1;
 
         blk_rects.assign(it.n_tilecomps, std::vector<Rect>());
+        const size_t cb_first = cbs.size();
         for (uint32_t b = 0; b < it.n_cblks; b++) {
             const j2k_cblk_t &cb = it.cblks[b];
             if (cb.tilecomp >= it.n_tilecomps) J2K_FAIL(ctx, J2KGPU_E_RANGE, "item %u block %u: tile-component %u out of range", ii, b, cb.tilecomp);
@@ -510,6 +529,7 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
             if (cb.data_len && cb.num_bps > max_bps) max_bps = cb.num_bps;
             if (iso && hdr.ht && cb.num_passes > 1) job->ht_refine = 1;
         }
+        sort_blocks_by_shape(cbs.p + cb_first, steps.p + cb_first, cbs.size() - cb_first, shape_tmp, step_tmp);
         // a plane its blocks do not tile exactly (holes, or overlaps hiding holes) is cleared before the entropy stage
         for (uint32_t t = 0; t < it.n_tilecomps && !need_clear; t++)
             if (!tiles_exactly(blk_rects[t], tcs[tc_base + t].w, tcs[tc_base + t].h)) need_clear = true;

@@ -107,40 +107,60 @@ constexpr int kQTabWords = 512;                         // 32 quad rows x 32 qua
 constexpr int kRingWords = 512;
 enum { ST_ZERO = 0, ST_OK = 1 };
 
-struct VlcStream { const uint8_t *d; int pos, left; uint64_t tmp; uint32_t bits; bool gt8f; };
+// The VLC stream is read backwards, four bytes at a time, from aligned words: `hi` holds the word of the next byte to read,
+// `lo` the word below it (loaded one read ahead, so that its latency is off the chain), `wp` the word below that.
+// Words that start below `floor` (the blob's first word) are not read; bytes beyond the segment (`left`) are zeros.
+struct VlcStream { const uint32_t *wp, *floor; uint32_t hi, lo, sh; int left; uint64_t tmp; uint32_t bits; bool gt8f; };
 
-// `lim` = the blob and its size (0 when the blob is not 4-byte aligned): inside it the four bytes come from two
-// aligned 32-bit loads instead of four byte loads
-struct BlobLim { const uint8_t *base; uint64_t bytes; };
+__device__ __forceinline__ uint32_t vlc_word(const uint32_t *p, const uint32_t *floor) { return p >= floor ? __ldg(p) : 0u; }
 
-__device__ __forceinline__ void vlc_read4(VlcStream &v, const BlobLim &lim)
+// next byte to read: d[pos]
+__device__ __forceinline__ void vlc_open(VlcStream &v, const uint8_t *d, int pos, const uint8_t *blob)
 {
-    uint32_t b[4], nb[4];
-    const uint64_t off = (uint64_t)(v.d + v.pos - 3 - lim.base);
-    if (v.left >= 4 && off + 8 <= lim.bytes) {
-        const uint32_t *a = reinterpret_cast<const uint32_t *>(lim.base + (off & ~(uint64_t)3));
-        const uint32_t x = __funnelshift_r(__ldg(a), __ldg(a + 1), (uint32_t)(off & 3) * 8);      // bytes pos-3 .. pos
-        b[0] = x >> 24; b[1] = (x >> 16) & 0xFFu; b[2] = (x >> 8) & 0xFFu; b[3] = x & 0xFFu;
-    } else {
+    const uintptr_t a = (uintptr_t)(d + pos);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+    v.floor = reinterpret_cast<const uint32_t *>((uintptr_t)blob & ~(uintptr_t)3);
+    v.sh = ((uint32_t)(a & 3) + 1) * 8;                  // d[pos - 3 .. pos] = (hi : lo) >> sh, sh = 8 .. 32
+    v.hi = (pos >= 0) ? vlc_word(w, v.floor) : 0u;
+    v.lo = vlc_word(w - 1, v.floor);
+    v.wp = w - 2;
+}
+
+__device__ __forceinline__ void vlc_read4(VlcStream &v)
+{
+#ifdef J2K_EMU
+    const uint32_t x = v.sh == 32 ? v.hi : (uint32_t)((((uint64_t)v.hi << 32) | v.lo) >> v.sh);
+#else
+    uint32_t x;
+    asm("shf.r.clamp.b32 %0, %1, %2, %3;" : "=r"(x) : "r"(v.lo), "r"(v.hi), "r"(v.sh));
+#endif
+    v.hi = v.lo; v.lo = vlc_word(v.wp, v.floor); v.wp--;
+    uint32_t y = __byte_perm(x, 0, 0x0123);              // stream order: the first byte read is bits 0 .. 7
+    if (v.left < 4) y = v.left <= 0 ? 0u : (y & ((1u << (8 * v.left)) - 1u));
+    v.left -= 4;
+    uint32_t t = y, nbits = 32;
+    if (((y & 0x7F7F7F7Fu) + 0x01010101u) & 0x80808080u) {   // some byte has its low 7 bits all ones: it carries 7 bits after a byte > 0x8F
+        bool g = v.gt8f;
+        t = 0; nbits = 0;
 #pragma unroll
-        for (int i = 0; i < 4; i++) b[i] = (i < v.left) ? (uint32_t)__ldg(v.d + v.pos - i) : 0u;
+        for (int i = 0; i < 4; i++) {
+            const uint32_t bi = (y >> (8 * i)) & 0xFFu;
+            t |= bi << nbits;
+            nbits += (g && (bi & 0x7Fu) == 0x7Fu) ? 7u : 8u;
+            g = bi > 0x8Fu;
+        }
     }
-    v.pos -= 4; v.left -= 4;
-    bool g = v.gt8f;
-#pragma unroll
-    for (int i = 0; i < 4; i++) { nb[i] = (g && (b[i] & 0x7Fu) == 0x7Fu) ? 7u : 8u; g = b[i] > 0x8Fu; }
-    const uint32_t t = b[0] | (b[1] << nb[0]) | (b[2] << (nb[0] + nb[1])) | (b[3] << (nb[0] + nb[1] + nb[2]));
+    v.gt8f = (y >> 24) > 0x8Fu;
     v.tmp |= (uint64_t)t << v.bits;
-    v.bits += nb[0] + nb[1] + nb[2] + nb[3];
-    v.gt8f = g;
+    v.bits += nbits;
 }
 
 // at least 32 bits afterwards (four stuffed bytes give only 28: then a second read, which is rare)
-__device__ __forceinline__ void vlc_refill(VlcStream &v, const BlobLim &lim)
+__device__ __forceinline__ void vlc_refill(VlcStream &v)
 {
     if (v.bits < 32) {
-        vlc_read4(v, lim);
-        if (v.bits < 32) vlc_read4(v, lim);
+        vlc_read4(v);
+        if (v.bits < 32) vlc_read4(v);
     }
 }
 
@@ -177,10 +197,9 @@ __device__ __forceinline__ int uvlc_pair(const uint16_t *utab, uint32_t vlc, int
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_htiso_vlc(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob, uint64_t blob_bytes,
+k_htiso_vlc(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob,
             uint32_t *__restrict__ qtab, uint32_t *__restrict__ status)
 {
-    const BlobLim lim = {blob, blob_bytes};
     // table entries re-packed: len (3) | u_off (1) | rho (4) | sample states (8)
     __shared__ uint16_t s_tbl[2048];
     for (int i = threadIdx.x; i < 2048; i += kThreads) {
@@ -209,7 +228,8 @@ k_htiso_vlc(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__rest
     VlcStream v;
     {
         const uint32_t b = __ldg(d + lcup - 2);
-        v.d = d; v.pos = lcup - 3; v.left = scup - 2;
+        vlc_open(v, d, lcup - 3, blob);
+        v.left = scup - 2;
         v.tmp = b >> 4;
         v.bits = 4 - (((v.tmp & 7) == 7) ? 1 : 0);
         v.gt8f = (b | 0x0F) > 0x8F;
@@ -229,7 +249,7 @@ k_htiso_vlc(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__rest
         uint32_t *qrow = qt + (y >> 1) * 16;
         for (int q = 0; q < nq; q += 2, iters++) {
             const bool pair = (q + 1 < nq);
-            vlc_refill(v, lim);                               // >= 32 bits: two codewords (<= 7 each) and the U-VLC (<= 16)
+            vlc_refill(v);                                    // >= 32 bits: two codewords (<= 7 each) and the U-VLC (<= 16)
             uint32_t win = (uint32_t)v.tmp, used = 0;    // the pair decodes from one 32-bit window; one 64-bit shift at the end
             const uint32_t s6 = (((uint32_t)sp & 0x1F) << 1) | spc;     // columns 2q - 1 .. 2q + 4 (zero in the initial row)
             spc = ((uint32_t)sp >> 3) & 1;
@@ -735,10 +755,9 @@ static void launch_ht_iso_t(const DevCblk *d_cblks, uint32_t n, const uint8_t *d
                             const float *d_steps, int irrev, int coef_bits, int refine, void *d_scratch, uint64_t blob_bytes, cudaStream_t s)
 {
     const uint64_t blob_total = blob_bytes;
-    if ((uintptr_t)d_blob & 3) blob_bytes = 0;           // unaligned blob: byte loads only
     uint32_t *qtab = (uint32_t *)d_scratch, *status = qtab + (size_t)n * kQTabWords;
     uint64_t *ref = (uint64_t *)(((uintptr_t)(status + n) + 63) & ~(uintptr_t)63);
-    J2K_LAUNCH((k_htiso_vlc), (n + kThreads - 1) / kThreads, kThreads, 0, s, d_cblks, n, d_blob, blob_bytes, qtab, status);
+    J2K_LAUNCH((k_htiso_vlc), (n + kThreads - 1) / kThreads, kThreads, 0, s, d_cblks, n, d_blob, qtab, status);
     if (refine) J2K_LAUNCH((k_htiso_refine), (n + kRefWarps - 1) / kRefWarps, kRefWarps * 32, 0, s, d_cblks, n, d_blob, qtab, status, ref);
     const uint32_t grid = (n + 4 * kWarpsB4 - 1) / (4 * kWarpsB4);
     const uint8_t *blob_end = d_blob + blob_total;
