@@ -107,23 +107,23 @@ constexpr int kQTabWords = 512;                         // 32 quad rows x 32 qua
 constexpr int kRingWords = 512;
 enum { ST_ZERO = 0, ST_OK = 1 };
 
-// The VLC stream is read backwards, four bytes at a time, from aligned words: `hi` holds the word of the next byte to read,
-// `lo` the word below it (loaded one read ahead, so that its latency is off the chain), `wp` the word below that.
-// Words that start below `floor` (the blob's first word) are not read; bytes beyond the segment (`left`) are zeros.
-struct VlcStream { const uint32_t *wp, *floor; uint32_t hi, lo, sh; int left; uint64_t tmp; uint32_t bits; bool gt8f; };
+// The VLC stream is read backwards, four bytes at a time, from aligned words of the blob: `hi` holds the word of the next
+// byte to read, `lo` the word below it, `nx` the word below that -- loaded two reads ahead, so that no instruction of a
+// read touches a word that is still in flight -- and `wi` the index of the word after `nx`.  Words below the blob's first
+// are not read (index clamped: such bytes lie outside the segment and are masked by `left`); bytes beyond the segment are zeros.
+struct VlcStream { const uint32_t *base; int wi; uint32_t hi, lo, nx, sh; int left; uint64_t tmp; uint32_t bits; bool gt8f; };
 
-__device__ __forceinline__ uint32_t vlc_word(const uint32_t *p, const uint32_t *floor) { return p >= floor ? __ldg(p) : 0u; }
+__device__ __forceinline__ uint32_t vlc_word(const VlcStream &v, int wi) { return __ldg(v.base + max(wi, 0)); }
 
 // next byte to read: d[pos]
 __device__ __forceinline__ void vlc_open(VlcStream &v, const uint8_t *d, int pos, const uint8_t *blob)
 {
-    const uintptr_t a = (uintptr_t)(d + pos);
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
-    v.floor = reinterpret_cast<const uint32_t *>((uintptr_t)blob & ~(uintptr_t)3);
+    v.base = reinterpret_cast<const uint32_t *>((uintptr_t)blob & ~(uintptr_t)3);
+    const int64_t a = (int64_t)((d + pos) - reinterpret_cast<const uint8_t *>(v.base));       // -1 at the least (then nothing is left to read)
+    const int w = (int)(a >> 2);
     v.sh = ((uint32_t)(a & 3) + 1) * 8;                  // d[pos - 3 .. pos] = (hi : lo) >> sh, sh = 8 .. 32
-    v.hi = (pos >= 0) ? vlc_word(w, v.floor) : 0u;
-    v.lo = vlc_word(w - 1, v.floor);
-    v.wp = w - 2;
+    v.hi = vlc_word(v, w); v.lo = vlc_word(v, w - 1); v.nx = vlc_word(v, w - 2);
+    v.wi = w - 3;
 }
 
 __device__ __forceinline__ void vlc_read4(VlcStream &v)
@@ -134,7 +134,11 @@ __device__ __forceinline__ void vlc_read4(VlcStream &v)
     uint32_t x;
     asm("shf.r.clamp.b32 %0, %1, %2, %3;" : "=r"(x) : "r"(v.lo), "r"(v.hi), "r"(v.sh));
 #endif
-    v.hi = v.lo; v.lo = vlc_word(v.wp, v.floor); v.wp--;
+    v.hi = v.lo; v.lo = v.nx; v.nx = vlc_word(v, v.wi);
+#ifndef J2K_EMU
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(v.base + max(v.wi - 12, 0)));     // the sector after next, on its way while this one is used
+#endif
+    v.wi--;
     uint32_t y = __byte_perm(x, 0, 0x0123);              // stream order: the first byte read is bits 0 .. 7
     if (v.left < 4) y = v.left <= 0 ? 0u : (y & ((1u << (8 * v.left)) - 1u));
     v.left -= 4;
@@ -167,36 +171,37 @@ __device__ __forceinline__ void vlc_refill(VlcStream &v)
 // 4 bits -> the even bit positions of a byte
 __device__ __forceinline__ uint32_t spread4(uint32_t x) { return (x & 1) | ((x & 2) << 1) | ((x & 4) << 2) | ((x & 8) << 3); }
 
-// U-VLC of a quad pair from a 192-entry table built at kernel start: kind (0 one code, 1 two codes, 2 two codes in the
-// initial row: when the first prefix is the long one the second code is a single bit) x the next 6 bits ->
-// prefix bits (3) | first suffix length (3) | second suffix length (3) | first base (3) | second base (3).
+// U-VLC of a quad pair from a 320-entry table built at kernel start: kind (0 only the first quad has a code, 1 only the
+// second, 2 both, 3 both in the initial row: when the first prefix is the long one the second code is a single bit,
+// 4 both in the initial row with the MEL offset: u + 2) x the next 6 bits ->
+// prefix bits (3) | first suffix length (3) | second suffix length (3) | first base (3) | second base (3); an absent code has
+// length 0 and base 0, so that u = base + suffix needs no selection.
 __device__ __forceinline__ uint16_t uvlc_entry(int kind, uint32_t bits6)
 {
     const uint32_t t1 = uvlc_row(bits6 & 7);
     const uint32_t p1 = t1 & 3, s1 = (t1 >> 2) & 7, b1 = t1 >> 5;
     if (kind == 0) return (uint16_t)(p1 | (s1 << 3) | (b1 << 9));
+    if (kind == 1) return (uint16_t)(p1 | (s1 << 6) | (b1 << 12));
     const uint32_t rest = bits6 >> p1;
-    if (kind == 2 && p1 > 2) return (uint16_t)((p1 + 1) | (s1 << 3) | (b1 << 9) | (((rest & 1) + 1) << 12));
-    const uint32_t t2 = uvlc_row(rest & 7);
-    return (uint16_t)((p1 + (t2 & 3)) | (s1 << 3) | (((t2 >> 2) & 7) << 6) | (b1 << 9) | ((t2 >> 5) << 12));
+    if (kind == 3 && p1 > 2) return (uint16_t)((p1 + 1) | (s1 << 3) | (b1 << 9) | (((rest & 1) + 1) << 12));
+    const uint32_t t2 = uvlc_row(rest & 7), add = kind == 4 ? 2u : 0u;
+    return (uint16_t)((p1 + (t2 & 3)) | (s1 << 3) | (((t2 >> 2) & 7) << 6) | ((b1 + add) << 9) | (((t2 >> 5) + add) << 12));
 }
 
+// mode: 1 first quad, 2 second quad, 3 both, 4 both + MEL offset (initial row)
 __device__ __forceinline__ int uvlc_pair(const uint16_t *utab, uint32_t vlc, int mode, bool initial, int &u0, int &u1)
 {
-    const int kind = mode < 3 ? 0 : ((mode == 3 && initial) ? 2 : 1);
+    const int kind = (initial && mode == 3) ? 3 : (mode == 4 ? 4 : mode - 1);
     const uint32_t t = utab[kind * 64 + (vlc & 63)];
     const int pl = t & 7, s1 = (t >> 3) & 7, s2 = (t >> 6) & 7;
     vlc >>= pl;
-    const int ua = (int)(((t >> 9) & 7) + (vlc & ((1u << s1) - 1)));
+    u0 = (int)(((t >> 9) & 7) + (vlc & ((1u << s1) - 1)));
     vlc >>= s1;
-    const int ub = (int)((t >> 12) + (vlc & ((1u << s2) - 1)));
-    const int add = (mode == 4) ? 2 : 0;
-    u0 = (mode == 2) ? 0 : ua + add;
-    u1 = (mode == 1) ? 0 : (mode == 2 ? ua : ub + add);
+    u1 = (int)((t >> 12) + (vlc & ((1u << s2) - 1)));
     return pl + s1 + s2;
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 6)
 k_htiso_vlc(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob,
             uint32_t *__restrict__ qtab, uint32_t *__restrict__ status)
 {
@@ -207,8 +212,8 @@ k_htiso_vlc(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__rest
         const uint32_t st8 = spread4((e >> 4) & 15) + spread4((e >> 12) & 15) + spread4((e >> 8) & 15);
         s_tbl[i] = (uint16_t)((e & 0xFF) | (st8 << 8));
     }
-    __shared__ uint16_t s_utab[192];
-    for (int i = threadIdx.x; i < 192; i += kThreads) s_utab[i] = uvlc_entry(i >> 6, (uint32_t)i & 63);
+    __shared__ uint16_t s_utab[320];
+    for (int i = threadIdx.x; i < 320; i += kThreads) s_utab[i] = uvlc_entry(i >> 6, (uint32_t)i & 63);
     __syncthreads();
     const uint32_t blk = blockIdx.x * kThreads + threadIdx.x;
     if (blk >= n) return;
@@ -773,6 +778,7 @@ cudaError_t launch_ht_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_b
                           cudaStream_t s)
 {
     if (n == 0) return cudaSuccess;
+    if (blob_bytes >> 33) return cudaErrorInvalidValue;  // the VLC reader indexes the blob's words with an int
     if (coef16 && !irrev) launch_ht_iso_t<int16_t>(d_cblks, n, d_blob, (int16_t *)d_coef, d_steps, irrev, coef_bits, refine, d_scratch, blob_bytes, s);
     else launch_ht_iso_t<int32_t>(d_cblks, n, d_blob, (int32_t *)d_coef, d_steps, irrev, coef_bits, refine, d_scratch, blob_bytes, s);
     return cudaGetLastError();
