@@ -107,38 +107,53 @@ constexpr int kQTabWords = 512;                         // 32 quad rows x 32 qua
 constexpr int kRingWords = 512;
 enum { ST_ZERO = 0, ST_OK = 1 };
 
-// The VLC stream is read backwards, four bytes at a time, from aligned words of the blob: `hi` holds the word of the next
-// byte to read, `lo` the word below it, `nx` the word below that -- loaded two reads ahead, so that no instruction of a
-// read touches a word that is still in flight -- and `wi` the index of the word after `nx`.  Words below the blob's first
-// are not read (index clamped: such bytes lie outside the segment and are masked by `left`); bytes beyond the segment are zeros.
-struct VlcStream { const uint32_t *base; int wi; uint32_t hi, lo, nx, sh; int left; uint64_t tmp; uint32_t bits; bool gt8f; };
+// The VLC stream is read backwards, four bytes at a time, from aligned words of the blob that travel through a thread-private
+// ring of eight words in shared memory: a read takes the word below `hi` (the word of the next byte to read) from the ring
+// and asks for the word seven below it with a 4-byte cp.async, so a word has seven reads' time to arrive and nothing
+// loop-carried ever waits on global memory (a register-held read-ahead made the compiler copy the word in flight at the
+// loop's merge point: one third of all stall samples).  Words below the blob's first are not read (index clamped: such
+// bytes lie outside the segment and are masked by `left`); bytes beyond the segment are zeros.
+struct VlcStream { const uint32_t *base; uint32_t *ring; int wi; uint32_t hi, sh; int left; uint64_t tmp; uint32_t bits; bool gt8f; };
 
-__device__ __forceinline__ uint32_t vlc_word(const VlcStream &v, int wi) { return __ldg(v.base + max(wi, 0)); }
+__device__ __forceinline__ void vlc_fetch(const VlcStream &v, int wi)     // word wi -> ring slot wi % 8, one commit group
+{
+    const uint32_t *src = v.base + max(wi, 0);
+    uint32_t *dst = v.ring + (wi & 7) * kThreads;
+#ifdef J2K_EMU
+    *dst = *src;
+#else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n\tcp.async.commit_group;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+#endif
+}
 
-// next byte to read: d[pos]
-__device__ __forceinline__ void vlc_open(VlcStream &v, const uint8_t *d, int pos, const uint8_t *blob)
+// next byte to read: d[pos]; ring: this thread's column of the CTA's [8][kThreads] words
+__device__ __forceinline__ void vlc_open(VlcStream &v, const uint8_t *d, int pos, const uint8_t *blob, uint32_t *ring)
 {
     v.base = reinterpret_cast<const uint32_t *>((uintptr_t)blob & ~(uintptr_t)3);
+    v.ring = ring;
     const int64_t a = (int64_t)((d + pos) - reinterpret_cast<const uint8_t *>(v.base));       // -1 at the least (then nothing is left to read)
     const int w = (int)(a >> 2);
     v.sh = ((uint32_t)(a & 3) + 1) * 8;                  // d[pos - 3 .. pos] = (hi : lo) >> sh, sh = 8 .. 32
-    v.hi = vlc_word(v, w); v.lo = vlc_word(v, w - 1); v.nx = vlc_word(v, w - 2);
-    v.wi = w - 3;
+    v.hi = __ldg(v.base + max(w, 0));
+    v.wi = w - 1;
+#pragma unroll
+    for (int i = 0; i < 7; i++) vlc_fetch(v, v.wi - i);
 }
 
 __device__ __forceinline__ void vlc_read4(VlcStream &v)
 {
+#ifndef J2K_EMU
+    asm volatile("cp.async.wait_group 6;" ::: "memory");  // all but the six youngest requests have landed: word wi is there
+#endif
+    const uint32_t lo = v.ring[(v.wi & 7) * kThreads];
+    vlc_fetch(v, v.wi - 7);                              // into the slot the previous read emptied
 #ifdef J2K_EMU
-    const uint32_t x = v.sh == 32 ? v.hi : (uint32_t)((((uint64_t)v.hi << 32) | v.lo) >> v.sh);
+    const uint32_t x = v.sh == 32 ? v.hi : (uint32_t)((((uint64_t)v.hi << 32) | lo) >> v.sh);
 #else
     uint32_t x;
-    asm("shf.r.clamp.b32 %0, %1, %2, %3;" : "=r"(x) : "r"(v.lo), "r"(v.hi), "r"(v.sh));
+    asm("shf.r.clamp.b32 %0, %1, %2, %3;" : "=r"(x) : "r"(lo), "r"(v.hi), "r"(v.sh));
 #endif
-    v.hi = v.lo; v.lo = v.nx; v.nx = vlc_word(v, v.wi);
-#ifndef J2K_EMU
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(v.base + max(v.wi - 12, 0)));     // the sector after next, on its way while this one is used
-#endif
-    v.wi--;
+    v.hi = lo; v.wi--;
     uint32_t y = __byte_perm(x, 0, 0x0123);              // stream order: the first byte read is bits 0 .. 7
     if (v.left < 4) y = v.left <= 0 ? 0u : (y & ((1u << (8 * v.left)) - 1u));
     v.left -= 4;
@@ -212,6 +227,7 @@ k_htiso_vlc(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__rest
         const uint32_t st8 = spread4((e >> 4) & 15) + spread4((e >> 12) & 15) + spread4((e >> 8) & 15);
         s_tbl[i] = (uint16_t)((e & 0xFF) | (st8 << 8));
     }
+    __shared__ uint32_t s_vring[8 * kThreads];
     __shared__ uint16_t s_utab[320];
     for (int i = threadIdx.x; i < 320; i += kThreads) s_utab[i] = uvlc_entry(i >> 6, (uint32_t)i & 63);
     __syncthreads();
@@ -233,7 +249,7 @@ k_htiso_vlc(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__rest
     VlcStream v;
     {
         const uint32_t b = __ldg(d + lcup - 2);
-        vlc_open(v, d, lcup - 3, blob);
+        vlc_open(v, d, lcup - 3, blob, s_vring + threadIdx.x);
         v.left = scup - 2;
         v.tmp = b >> 4;
         v.bits = 4 - (((v.tmp & 7) == 7) ? 1 : 0);
