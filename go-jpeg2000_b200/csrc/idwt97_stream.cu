@@ -62,24 +62,55 @@ __device__ __forceinline__ uint32_t pack_sat_u8(int a, int b, uint32_t c)
 #endif
 }
 
-__device__ __forceinline__ void ldpair_f64(const int32_t *p, double &a, double &b)
+// ---- band samples travel global -> shared with cp.async into warp-private slots (16 bytes per lane and part), one row
+// pair ahead of the arithmetic; every lane reads back only what it copied itself, so the kernel has no barrier ----
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void *smem_dst, const void *gsrc)
 {
-    const int2 v = __ldg(reinterpret_cast<const int2 *>(p));
+#ifdef J2K_EMU
+    memcpy(smem_dst, gsrc, BYTES);
+#else
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gsrc), "n"(BYTES) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_commit()
+{
+#ifndef J2K_EMU
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+__device__ __forceinline__ void cp_wait()
+{
+#ifndef J2K_EMU
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+// two neighbouring elements: copy, and read back as T
+__device__ __forceinline__ void pair_copy(uint4 *slot, const int32_t *g) { cp_async<8>(slot, g); }
+__device__ __forceinline__ void pair_copy(uint4 *slot, const int16_t *g) { cp_async<4>(slot, g); }
+__device__ __forceinline__ void pair_copy(uint4 *slot, const float *g) { cp_async<8>(slot, g); }
+__device__ __forceinline__ void pair_copy(uint4 *slot, const double *g) { cp_async<16>(slot, g); }
+__device__ __forceinline__ void pair_read(const uint4 *slot, int32_t, double &a, double &b)
+{
+    const int2 v = *reinterpret_cast<const int2 *>(slot);
     a = (double)v.x; b = (double)v.y;                                                     // tcd.go:429-431
 }
-__device__ __forceinline__ void ldpair_f64(const int16_t *p, double &a, double &b)
+__device__ __forceinline__ void pair_read(const uint4 *slot, int16_t, double &a, double &b)
 {
-    const uint32_t r = __ldg(reinterpret_cast<const uint32_t *>(p));
+    const uint32_t r = *reinterpret_cast<const uint32_t *>(slot);
     a = (double)(int)(int16_t)(r & 0xFFFFu); b = (double)((int)r >> 16);
 }
-__device__ __forceinline__ void ldpair_f64(const double *p, double &a, double &b)
+__device__ __forceinline__ void pair_read(const uint4 *slot, double, double &a, double &b)
 {
-    const double2 v = __ldg(reinterpret_cast<const double2 *>(p));
+    const double2 v = *reinterpret_cast<const double2 *>(slot);
     a = v.x; b = v.y;
 }
-__device__ __forceinline__ void ldpair_f64(const float *p, float &a, float &b)          // ISO: planes and levels are float32
+__device__ __forceinline__ void pair_read(const uint4 *slot, float, float &a, float &b)  // ISO: planes and levels are float32
 {
-    const float2 v = __ldg(reinterpret_cast<const float2 *>(p));
+    const float2 v = *reinterpret_cast<const float2 *>(slot);
     a = v.x; b = v.y;
 }
 
@@ -91,7 +122,9 @@ k_idwt97_stream(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__
                 T *__restrict__ tmp, uint8_t *__restrict__ pix, int nlevels, int lvl, int strip_pairs, TailParams tp)
 {
     typedef C97<T> K;
+    __shared__ uint4 s_slots[kWarps][NC * 4][32];        // [component][L, H of the low row; L, H of the high row][lane]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint4 *slots = &s_slots[warp][0][lane];              // part i of component c: slots[(4 c + i) * 32]
     uint32_t tci[NC];
     int W0, H0;
     DevTile tile;
@@ -134,20 +167,34 @@ k_idwt97_stream(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__
     const uint32_t uw = (uint32_t)w;
     const uint32_t colL = 2u * (uint32_t)qc, colH = (uint32_t)nlx + colL;
 
-    // band row r of the level image (rows [0, nly) low-pass, [nly, h) high-pass) -> (L0, L1, H0, H1) of this lane
+    // band row r of the level image (rows [0, nly) low-pass, [nly, h) high-pass) -> (L0, L1, H0, H1) of this lane:
+    // issue_row starts the copy into parts `part`, `part + 1` of component c's slots, read_row takes it out
     const uint32_t planeW = (uint32_t)W0;             // ISO: row stride of the Mallat plane
-    auto load_row = [&](int c, int r, T v[4]) {
+    auto issue_row = [&](int c, int r, int part) {
+        uint4 *sl = slots + (4 * c + part) * 32;
         if (ISO) {
             const CT *rowp = plane[c] + (size_t)r * planeW;
-            if (r < nly && nprev) ldpair_f64(prev[c] + (size_t)r * (uint32_t)nlx + colL, v[0], v[1]);
-            else ldpair_f64(rowp + colL, v[0], v[1]);
-            ldpair_f64(rowp + colH, v[2], v[3]);
+            if (r < nly && nprev) pair_copy(sl, prev[c] + (size_t)r * (uint32_t)nlx + colL);
+            else pair_copy(sl, rowp + colL);
+            pair_copy(sl + 32, rowp + colH);
         } else {
             const uint32_t lin = (uint32_t)r * uw;
-            if (lin + colL < nprev) ldpair_f64(prev[c] + lin + colL, v[0], v[1]); else ldpair_f64(plane[c] + lin + colL, v[0], v[1]);
-            if (lin + colH < nprev) ldpair_f64(prev[c] + lin + colH, v[2], v[3]); else ldpair_f64(plane[c] + lin + colH, v[2], v[3]);
+            if (lin + colL < nprev) pair_copy(sl, prev[c] + lin + colL); else pair_copy(sl, plane[c] + lin + colL);
+            if (lin + colH < nprev) pair_copy(sl + 32, prev[c] + lin + colH); else pair_copy(sl + 32, plane[c] + lin + colH);
         }
     };
+    auto read_row = [&](int c, int r, int part, T v[4]) {
+        const uint4 *sl = slots + (4 * c + part) * 32;
+        if (ISO) {
+            pair_read(sl, T(), v[0], v[1]);              // previous level and plane are both float32
+            pair_read(sl + 32, T(), v[2], v[3]);
+        } else {
+            const uint32_t lin = (uint32_t)r * uw;
+            if (lin + colL < nprev) pair_read(sl, T(), v[0], v[1]); else pair_read(sl, CT(), v[0], v[1]);
+            if (lin + colH < nprev) pair_read(sl + 32, T(), v[2], v[3]); else pair_read(sl + 32, CT(), v[2], v[3]);
+        }
+    };
+    auto issue_pair = [&](int c, int m) { issue_row(c, m, 0); issue_row(c, nly + m, 2); };
 
     // horizontal synthesis of a finished row (dwt.go:213-262 on the row), band order in, interleaved out
     auto hsynth = [&](const T V[4], T X[4]) {
@@ -227,6 +274,11 @@ k_idwt97_stream(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__
         for (int j = 0; j < 4; j++) hs[c][j] = a[c][j] = b[c][j] = cc[c][j] = (T)0;
     const int ms = ka >= 2 ? ka - 2 : 0;
     const int me = min(kb + 1, nly + 1);
+#pragma unroll
+    for (int c = 0; c < NC; c++) {                       // group c: component c's first band row pair
+        if (ms < nly) issue_pair(c, ms);
+        cp_commit();
+    }
     for (int m = ms; m <= me; m++) {
         const bool have_in = m < nly;
         const bool do_b = m >= 1 && m - 1 < nly, do_d = m >= 2 && m - 2 < nly;
@@ -235,7 +287,10 @@ k_idwt97_stream(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__
         for (int c = 0; c < NC; c++) {
             T lo[4], hi[4];
             if (have_in) {
-                load_row(c, m, lo); load_row(c, nly + m, hi);
+                cp_wait<NC - 1>();                       // component c's copies of this row pair have landed
+                read_row(c, m, 0, lo); read_row(c, nly + m, 2, hi);
+                if (m + 1 < nly && m + 1 <= me) issue_pair(c, m + 1);   // refill the slots: one full step to land
+                cp_commit();
                 if (ISO) {                                             // rows first: both band rows become interleaved samples
                     T x[4];
                     hsynth(lo, x);
@@ -271,6 +326,7 @@ k_idwt97_stream(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__
             emit_row(2 * (m - 2) + 1, dd);
         }
     }
+    cp_wait<0>();
 }
 
 template <int NC, bool PIXELS, typename CT, typename T, bool ISO>
