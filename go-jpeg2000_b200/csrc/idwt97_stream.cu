@@ -114,10 +114,20 @@ __device__ __forceinline__ void pair_read(const uint4 *slot, float, float &a, fl
     a = v.x; b = v.y;
 }
 
+// the general pixel epilogue of four neighbouring pixels, out of line (any component count, precision, signedness, format,
+// colour conversion); mct_dc: REF semantics still need the inverse MCT + DC shift (ISO values arrive with both applied)
+static __device__ J2K_NOINLINE void store_quad_generic(uint8_t *row, uint32_t gx0, uint32_t img_w, int32_t (*v)[4], const TailParams &tp, bool mct_dc)
+{
+    for (int p = 0; p < 4; p++) {
+        if (mct_dc) tail_mct_dc(v[p], tp);
+        if (gx0 + p < img_w) store_pixel(row, gx0 + p, v[p], tp);
+    }
+}
+
 // T = double, ISO = false: REF semantics (dense prefix, columns then rows, planes int32 / int16).
 // T = float,  ISO = true : ISO semantics (Mallat layout, rows then columns, planes hold dequantised float32).
 template <int NC, bool PIXELS, typename CT, typename T, bool ISO>
-__global__ void __launch_bounds__(kWarps * 32, 2)
+__global__ void __launch_bounds__(kWarps * 32, sizeof(T) == 4 ? 3 : 2)
 k_idwt97_stream(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__ tiles, const CT *__restrict__ coef,
                 T *__restrict__ tmp, uint8_t *__restrict__ pix, int nlevels, int lvl, int strip_pairs, TailParams tp)
 {
@@ -216,7 +226,7 @@ k_idwt97_stream(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__
 
     const uint32_t gx0 = PIXELS ? tile.img_x0 + 4u * (uint32_t)qc : 0u;
     const bool fast_rgba8 = PIXELS && NC == 3 && tp.fmt == J2KGPU_FMT_RGBA8 && tp.prec[0] == 8 && tp.prec[1] == 8 && tp.prec[2] == 8 &&
-                            !tp.sgnd[0] && !tp.sgnd[1] && !tp.sgnd[2] && (ISO || tp.mct) &&
+                            !tp.sgnd[0] && !tp.sgnd[1] && !tp.sgnd[2] && (ISO || (tp.mct && !tp.reversible)) && !tp.cconv &&
                             ((tile.out_stride & 15) == 0) && ((tile.out_off & 15) == 0) && ((tile.img_x0 & 3) == 0) &&
                             (gx0 + 3 < tile.img_w) && (((uintptr_t)pix & 15) == 0);
 
@@ -247,23 +257,49 @@ k_idwt97_stream(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__
         const uint32_t gy = tile.img_y0 + (uint32_t)y;
         if (gy >= tile.img_h) return;                                  // decoder.go:398-410 clipping
         uint8_t *row = pix + tile.out_off + (size_t)gy * tile.out_stride;
-        uint32_t px[4];
+        if (fast_rgba8) {
+            // three unsigned 8-bit components -> RGBA8: the epilogue with everything constant folded in (the general one
+            // below is out of line: inlined eight times it made the kernel 150 KB of code, beyond the instruction cache)
+            uint32_t px[4];
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                int r8, g8, b8;
+                if (ISO) {                                             // opj_mct_decode_real, round to nearest even, DC shift
+                    float yv = (float)X[0][p], u = (float)X[NC > 1 ? 1 : 0][p], wv = (float)X[NC > 2 ? 2 : 0][p];
+                    if (tp.mct) {
+                        const float r = __fadd_rn(yv, __fmul_rn(wv, 1.402f));
+                        const float g = __fsub_rn(__fsub_rn(yv, __fmul_rn(u, 0.34413f)), __fmul_rn(wv, 0.71414f));
+                        const float b = __fadd_rn(yv, __fmul_rn(u, 1.772f));
+                        yv = r; u = g; wv = b;
+                    }
+                    r8 = (int)((uint32_t)__float2int_rn(yv) + 128u); g8 = (int)((uint32_t)__float2int_rn(u) + 128u); b8 = (int)((uint32_t)__float2int_rn(wv) + 128u);
+                } else {                                               // tcd.go:433-435, mct.go:43-53 via decoder.go:326-340, mct.go:113-118
+                    const double yv = (double)j2k_f64_to_i32(__dadd_rn((double)X[0][p], 0.5)), cb = (double)j2k_f64_to_i32(__dadd_rn((double)X[NC > 1 ? 1 : 0][p], 0.5)),
+                                 cr = (double)j2k_f64_to_i32(__dadd_rn((double)X[NC > 2 ? 2 : 0][p], 0.5));
+                    const double r = __dadd_rn(yv, __dmul_rn(1.402, cr));
+                    const double g = __dsub_rn(__dsub_rn(yv, __dmul_rn(0.34413, cb)), __dmul_rn(0.71414, cr));
+                    const double b = __dadd_rn(yv, __dmul_rn(1.772, cb));
+                    r8 = (int)((uint32_t)j2k_f64_to_i32(__dadd_rn(r, 0.5)) + 128u); g8 = (int)((uint32_t)j2k_f64_to_i32(__dadd_rn(g, 0.5)) + 128u);
+                    b8 = (int)((uint32_t)j2k_f64_to_i32(__dadd_rn(b, 0.5)) + 128u);
+                }
+                px[p] = pack_sat_u8(g8, r8, pack_sat_u8(255, b8, 0u));
+            }
+            __stcs(reinterpret_cast<uint4 *>(row + 4 * (size_t)gx0), make_uint4(px[0], px[1], px[2], px[3]));
+            return;
+        }
+        int32_t v[4][4];
 #pragma unroll
         for (int p = 0; p < 4; p++) {
-            int32_t v[4];
             if (ISO) {
                 const float f[4] = {(float)X[0][p], NC > 1 ? (float)X[NC > 1 ? 1 : 0][p] : 0.f, NC > 2 ? (float)X[NC > 2 ? 2 : 0][p] : 0.f,
                                     NC > 3 ? (float)X[NC > 3 ? 3 : 0][p] : 0.f};
-                tail_iso_irrev(f, v, tp);
+                tail_iso_irrev(f, v[p], tp);
             } else {
 #pragma unroll
-                for (int c = 0; c < 4; c++) v[c] = c < NC ? j2k_f64_to_i32(__dadd_rn((double)X[c < NC ? c : 0][p], 0.5)) : 0;   // tcd.go:433-435
-                tail_mct_dc(v, tp);
+                for (int c = 0; c < 4; c++) v[p][c] = c < NC ? j2k_f64_to_i32(__dadd_rn((double)X[c < NC ? c : 0][p], 0.5)) : 0;   // tcd.go:433-435
             }
-            if (fast_rgba8) px[p] = pack_sat_u8(v[1], v[0], pack_sat_u8(255, v[2], 0u));
-            else if (gx0 + p < tile.img_w) store_pixel(row, gx0 + p, v, tp);
         }
-        if (fast_rgba8) __stcs(reinterpret_cast<uint4 *>(row + 4 * (size_t)gx0), make_uint4(px[0], px[1], px[2], px[3]));
+        store_quad_generic(row, gx0, tile.img_w, v, tp, !ISO);
     };
 
     // ---- vertical pipeline -------------------------------------------------------------------------------------------
