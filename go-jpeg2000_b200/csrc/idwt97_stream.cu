@@ -20,6 +20,7 @@
 // Eligibility (host, per level): width a multiple of 4, height even (same as idwt_stream.cu).
 #include "common.h"
 #include "tail.cuh"
+#include <type_traits>
 
 namespace {
 
@@ -177,34 +178,41 @@ k_idwt97_stream(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__
     const uint32_t uw = (uint32_t)w;
     const uint32_t colL = 2u * (uint32_t)qc, colH = (uint32_t)nlx + colL;
 
-    // band row r of the level image (rows [0, nly) low-pass, [nly, h) high-pass) -> (L0, L1, H0, H1) of this lane:
-    // issue_row starts the copy into parts `part`, `part + 1` of component c's slots, read_row takes it out
+    // band row pair m of the level image (row m of [0, nly) low-pass, row nly + m high-pass) -> (L0, L1, H0, H1) of this
+    // lane for both rows.  issue_pair starts the copies into the four parts of component c's slots, read_pair takes them
+    // out.  Addresses: one 64-bit base per component and source, one 32-bit element offset per part.
     const uint32_t planeW = (uint32_t)W0;             // ISO: row stride of the Mallat plane
-    auto issue_row = [&](int c, int r, int part) {
-        uint4 *sl = slots + (4 * c + part) * 32;
+    const uint32_t rs = ISO ? planeW : uw;            // row stride of the coefficient plane at this level
+    const uint32_t hi_row0 = (uint32_t)nly * rs;
+    auto issue_pair = [&](int c, int m) {
+        uint4 *sl = slots + 4 * c * 32;
+        const uint32_t lo = (uint32_t)m * rs, hi = hi_row0 + lo;
         if (ISO) {
-            const CT *rowp = plane[c] + (size_t)r * planeW;
-            if (r < nly && nprev) pair_copy(sl, prev[c] + (size_t)r * (uint32_t)nlx + colL);
-            else pair_copy(sl, rowp + colL);
-            pair_copy(sl + 32, rowp + colH);
+            if (nprev) pair_copy(sl, prev[c] + ((uint32_t)m * (uint32_t)nlx + colL));
+            else pair_copy(sl, plane[c] + (lo + colL));
+            pair_copy(sl + 32, plane[c] + (lo + colH));
+            pair_copy(sl + 64, plane[c] + (hi + colL));
+            pair_copy(sl + 96, plane[c] + (hi + colH));
         } else {
-            const uint32_t lin = (uint32_t)r * uw;
-            if (lin + colL < nprev) pair_copy(sl, prev[c] + lin + colL); else pair_copy(sl, plane[c] + lin + colL);
-            if (lin + colH < nprev) pair_copy(sl + 32, prev[c] + lin + colH); else pair_copy(sl + 32, plane[c] + lin + colH);
+            if (lo + colL < nprev) pair_copy(sl, prev[c] + (lo + colL)); else pair_copy(sl, plane[c] + (lo + colL));
+            if (lo + colH < nprev) pair_copy(sl + 32, prev[c] + (lo + colH)); else pair_copy(sl + 32, plane[c] + (lo + colH));
+            if (hi + colL < nprev) pair_copy(sl + 64, prev[c] + (hi + colL)); else pair_copy(sl + 64, plane[c] + (hi + colL));
+            if (hi + colH < nprev) pair_copy(sl + 96, prev[c] + (hi + colH)); else pair_copy(sl + 96, plane[c] + (hi + colH));
         }
     };
-    auto read_row = [&](int c, int r, int part, T v[4]) {
-        const uint4 *sl = slots + (4 * c + part) * 32;
-        if (ISO) {
-            pair_read(sl, T(), v[0], v[1]);              // previous level and plane are both float32
-            pair_read(sl + 32, T(), v[2], v[3]);
+    auto read_pair = [&](int c, int m, T lo4[4], T hi4[4]) {
+        const uint4 *sl = slots + 4 * c * 32;
+        if (ISO) {                                       // previous level and plane are both float32
+            pair_read(sl, T(), lo4[0], lo4[1]); pair_read(sl + 32, T(), lo4[2], lo4[3]);
+            pair_read(sl + 64, T(), hi4[0], hi4[1]); pair_read(sl + 96, T(), hi4[2], hi4[3]);
         } else {
-            const uint32_t lin = (uint32_t)r * uw;
-            if (lin + colL < nprev) pair_read(sl, T(), v[0], v[1]); else pair_read(sl, CT(), v[0], v[1]);
-            if (lin + colH < nprev) pair_read(sl + 32, T(), v[2], v[3]); else pair_read(sl + 32, CT(), v[2], v[3]);
+            const uint32_t lo = (uint32_t)m * rs, hi = hi_row0 + lo;
+            if (lo + colL < nprev) pair_read(sl, T(), lo4[0], lo4[1]); else pair_read(sl, CT(), lo4[0], lo4[1]);
+            if (lo + colH < nprev) pair_read(sl + 32, T(), lo4[2], lo4[3]); else pair_read(sl + 32, CT(), lo4[2], lo4[3]);
+            if (hi + colL < nprev) pair_read(sl + 64, T(), hi4[0], hi4[1]); else pair_read(sl + 64, CT(), hi4[0], hi4[1]);
+            if (hi + colH < nprev) pair_read(sl + 96, T(), hi4[2], hi4[3]); else pair_read(sl + 96, CT(), hi4[2], hi4[3]);
         }
     };
-    auto issue_pair = [&](int c, int m) { issue_row(c, m, 0); issue_row(c, nly + m, 2); };
 
     // horizontal synthesis of a finished row (dwt.go:213-262 on the row), band order in, interleaved out
     auto hsynth = [&](const T V[4], T X[4]) {
@@ -315,16 +323,20 @@ k_idwt97_stream(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__
         if (ms < nly) issue_pair(c, ms);
         cp_commit();
     }
-    for (int m = ms; m <= me; m++) {
-        const bool have_in = m < nly;
-        const bool do_b = m >= 1 && m - 1 < nly, do_d = m >= 2 && m - 2 < nly;
+    // one step of the pipeline.  STEADY: 2 <= m < nly, i.e. a band row pair comes in and no line end is in reach -- the
+    // flags fold away and the steady state of a strip (all but its first and last two steps) runs without selections
+    auto step = [&](int m, auto steady_tag) {
+        constexpr bool STEADY = decltype(steady_tag)::value;
+        const bool have_in = STEADY || m < nly;
+        const bool do_b = STEADY || (m >= 1 && m - 1 < nly), do_d = STEADY || (m >= 2 && m - 2 < nly);
+        const bool top0 = !STEADY && m == 0, top1 = !STEADY && m == 1;
         T cur[NC][4], dd[NC][4];
 #pragma unroll
         for (int c = 0; c < NC; c++) {
             T lo[4], hi[4];
             if (have_in) {
                 cp_wait<NC - 1>();                       // component c's copies of this row pair have landed
-                read_row(c, m, 0, lo); read_row(c, nly + m, 2, hi);
+                read_pair(c, m, lo, hi);
                 if (m + 1 < nly && m + 1 <= me) issue_pair(c, m + 1);   // refill the slots: one full step to land
                 cp_commit();
                 if (ISO) {                                             // rows first: both band rows become interleaved samples
@@ -342,13 +354,13 @@ k_idwt97_stream(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__
                 T A = a[c][j], Hs = hs[c][j];
                 if (have_in) {
                     Hs = mul_rn(hi[j], (T)K::InvK);
-                    const T hl = m == 0 ? Hs : hs[c][j];
+                    const T hl = top0 ? Hs : hs[c][j];
                     A = lift<T>(mul_rn(lo[j], (T)K::K), K::Delta, hl, Hs);
                 }
                 T B = b[c][j], Cn = cc[c][j];
                 if (do_b) {
                     B = lift<T>(hs[c][j], K::Gamma, a[c][j], have_in ? A : a[c][j]);
-                    const T bl = m - 1 == 0 ? B : b[c][j];
+                    const T bl = top1 ? B : b[c][j];
                     Cn = lift<T>(a[c][j], K::Beta, bl, B);
                 }
                 // D_{m-2} = B_{m-2} - alpha (C_{m-2} + C_{m-1}); below the last row pair C_{m-1} mirrors C_{m-2}
@@ -361,6 +373,10 @@ k_idwt97_stream(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__
             emit_row(2 * (m - 2), cur);
             emit_row(2 * (m - 2) + 1, dd);
         }
+    };
+    for (int m = ms; m <= me; m++) {
+        if (m >= 2 && m < nly) step(m, std::true_type());
+        else step(m, std::false_type());
     }
     cp_wait<0>();
 }

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Per-source-line instruction counts of one kernel of an .ncu-rep (captured with --import-source on, built with -lineinfo):
-    python tools/ncu_lines.py report.ncu-rep <kernel regex> [top N]"""
+    python tools/ncu_lines.py report.ncu-rep <kernel regex> [top N] [launches of that kernel to skip]"""
 import csv
 import io
 import subprocess
@@ -10,8 +10,9 @@ import sys
 def main():
     rep, pat = sys.argv[1], sys.argv[2]
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+    skip = sys.argv[4] if len(sys.argv) > 4 else "0"
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name",
-                          "regex:" + pat, "--launch-skip", "0", "--launch-count", "1"], capture_output=True, text=True).stdout
+                          "regex:" + pat, "--launch-skip", skip, "--launch-count", "1"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hi = [i for i, r in enumerate(rows) if r and r[0] == "Line No"][0]
     hdr = rows[hi]
