@@ -19,7 +19,7 @@
 #include <tuple>
 
 cudaError_t launch_t1_ref_stage(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, int32_t *d_coef,
-                                int max_bps, cudaStream_t s);
+                                int max_bps, int group, cudaStream_t s);
 
 // ---- errors ------------------------------------------------------------------------------------------
 int j2k_set_err(j2kgpu_ctx *ctx, int code, const char *fmt, ...)
@@ -220,6 +220,7 @@ static int set_option(J2kOpts &o, const char *name, const char *value)
     else if (k == "coef32") o.coef32 = on;
     else if (k == "no_preclear") o.no_preclear = on;
     else if (k == "wide_sp") o.wide_sp = iv;
+    else if (k == "t1_group") o.t1_group = iv;
     else if (k == "debug_plan") o.debug_plan = on;
     else if (k == "chunks") o.chunks = v;
     else return J2KGPU_E_ARG;
@@ -238,7 +239,7 @@ extern "C" int j2kgpu_create(int device, j2kgpu_ctx **out)
     if (!ctx) return J2KGPU_E_NOMEM;
     ctx->device = device;
     // the environment is read here, once per context, and nowhere else
-    static const char *const names[] = {"no_fuse", "no_wide", "no_fast_epi", "coef32", "no_preclear", "wide_sp", "debug_plan", "chunks"};
+    static const char *const names[] = {"no_fuse", "no_wide", "no_fast_epi", "coef32", "no_preclear", "wide_sp", "t1_group", "debug_plan", "chunks"};
     for (const char *nm : names) {
         std::string env = "J2KGPU_";
         for (const char *c = nm; *c; c++) env += (char)toupper((unsigned char)*c);
@@ -345,19 +346,19 @@ struct Fixed {
 
 struct Rect { uint32_t x0, y0, x1, y1; };
 
-// do the rectangles (all inside a w x h plane) cover it exactly once?  Their areas must add up to the plane and no two
-// may overlap; the overlap test is a sweep over the rectangles sorted by their top edge.
-static bool tiles_exactly(std::vector<Rect> &r, uint32_t w, uint32_t h)
+// how do the rectangles (all inside a w x h plane) cover it?  0: exactly once; 1: without overlap but with holes;
+// 2: two of them overlap.  The overlap test is a sweep over the rectangles sorted by their top edge.
+static int rect_cover(std::vector<Rect> &r, uint32_t w, uint32_t h)
 {
     uint64_t area = 0;
     for (const Rect &q : r) area += (uint64_t)(q.x1 - q.x0) * (q.y1 - q.y0);
-    if (area != (uint64_t)w * h) return false;
     std::sort(r.begin(), r.end(), [](const Rect &a, const Rect &b) { return a.y0 != b.y0 ? a.y0 < b.y0 : a.x0 < b.x0; });
     for (size_t i = 0; i < r.size(); i++)
         for (size_t j = i + 1; j < r.size() && r[j].y0 < r[i].y1; j++)
-            if (r[j].x0 < r[i].x1 && r[i].x0 < r[j].x1) return false;
-    return true;
+            if (r[j].x0 < r[i].x1 && r[i].x0 < r[j].x1) return 2;
+    return area == (uint64_t)w * h ? 0 : 1;
 }
+static bool tiles_exactly(std::vector<Rect> &r, uint32_t w, uint32_t h) { return rect_cover(r, w, h) == 0; }
 
 // async_stream != nullptr: the tables are staged in page-locked memory owned by the job and uploaded on that stream
 // without any synchronisation (pipelined batch calls: the host builds the next chunk's tables while the device decodes
@@ -530,9 +531,13 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
             if (iso && hdr.ht && cb.num_passes > 1) job->ht_refine = 1;
         }
         sort_blocks_by_shape(cbs.p + cb_first, steps.p + cb_first, cbs.size() - cb_first, shape_tmp, step_tmp);
-        // a plane its blocks do not tile exactly (holes, or overlaps hiding holes) is cleared before the entropy stage
-        for (uint32_t t = 0; t < it.n_tilecomps && !need_clear; t++)
-            if (!tiles_exactly(blk_rects[t], tcs[tc_base + t].w, tcs[tc_base + t].h)) need_clear = true;
+        // a plane its blocks leave holes in is cleared before the entropy stage; blocks that overlap are refused (no
+        // codestream has them, and the EBCOT kernels accumulate a block's bit-planes in place: its samples are its own)
+        for (uint32_t t = 0; t < it.n_tilecomps; t++) {
+            const int cover = rect_cover(blk_rects[t], tcs[tc_base + t].w, tcs[tc_base + t].h);
+            if (cover == 2) J2K_FAIL(ctx, J2KGPU_E_ARG, "item %u: code blocks of tile-component %u overlap", ii, t);
+            if (cover == 1) need_clear = true;
+        }
         blob_bytes += it.blob_len;
         out_bytes = align_up(out_bytes + it.out_stride * im.height, 256);
     }
@@ -640,7 +645,7 @@ static int run_entropy(j2kgpu_job *job, const void *d_blob, uint32_t ia, uint32_
     cudaError_t e;
     const int irrev = job->iso && !job->hdr.reversible;                  // ISO 9-7: the planes receive dequantised float32
     const float *steps = job->d_steps ? job->d_steps + ca : nullptr;
-    if (job->iso && !job->hdr.ht) e = launch_t1_iso(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, steps, irrev, job->max_bps, st);
+    if (job->iso && !job->hdr.ht) e = launch_t1_iso(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, steps, irrev, job->max_bps, ctx->opt.t1_group, st);
     else if (job->iso) {
         // chunks of a pipelined run share the scratch: their kernels are ordered on one stream
         e = launch_ht_iso(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, steps, irrev, job->hdr.coef_bits,
@@ -652,7 +657,7 @@ static int run_entropy(j2kgpu_job *job, const void *d_blob, uint32_t ia, uint32_
                           job->d_htscratch, job->blob_bytes, st);
         ctx->launches += j2k_htref_launches() - 1;
     }
-    else e = launch_t1_ref(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, job->max_bps, st);
+    else e = launch_t1_ref(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, job->max_bps, ctx->opt.t1_group, st);
     if (e != cudaSuccess) return j2k_cuda_err(ctx, e, "entropy kernel launch");
     ctx->launches++;
     return J2KGPU_OK;
@@ -1190,9 +1195,9 @@ static int stage_blocks(j2kgpu_ctx *ctx, int mode, int ht, const j2k_blkjob_t *j
     }
     cudaError_t e = (ht && mode == J2KGPU_MODE_ISO)
                         ? launch_ht_iso((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, nullptr, 0, 0, refine, ctx->d_aux.p, blob_len, ctx->stream)
-                    : mode == J2KGPU_MODE_ISO ? launch_t1_iso((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, nullptr, 0, max_bps, ctx->stream)
+                    : mode == J2KGPU_MODE_ISO ? launch_t1_iso((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, nullptr, 0, max_bps, ctx->opt.t1_group, ctx->stream)
                     : ht ? launch_ht_ref((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, 0, ctx->d_aux.p, blob_len, ctx->stream)
-                       : launch_t1_ref_stage((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, (int32_t *)ctx->d_out.p, max_bps, ctx->stream);
+                       : launch_t1_ref_stage((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, (int32_t *)ctx->d_out.p, max_bps, ctx->opt.t1_group, ctx->stream);
     if (e != cudaSuccess) return j2k_cuda_err(ctx, e, "entropy kernel launch");
     ctx->launches++;
     J2K_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_out.p, out_len * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));

@@ -87,6 +87,7 @@ struct J2kOpts {
     int coef32 = 0;         // int32 coefficient planes everywhere
     int no_preclear = 0;    // reference HT coder: clear every row on every run
     int wide_sp = 0;        // strip height of the wide IDWT kernel in row pairs (0 = planner)
+    int t1_group = 0;       // EBCOT kernels: lanes per code block (4, 8, 16, 32; 0 = default 8)
     int debug_plan = 0;     // print the chunk plan of host-buffer runs
     std::string chunks;     // explicit chunk sizes of host-buffer runs, e.g. "1,1,2,4"
 };
@@ -167,15 +168,16 @@ int j2k_ctx_copy_streams(j2kgpu_ctx *ctx);
 // ---- kernel launchers (each returns a cudaError_t; all asynchronous on `s`) ---------------------
 // entropy stage: one warp per code block
 // d_coef: coefficient arena, int16 elements when coef16 else int32
+// group: lanes per code block (4, 8, 16, 32; 0 = default), i.e. 32 / group blocks share a warp's instruction stream
 cudaError_t launch_t1_ref(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
-                          int max_bps, cudaStream_t s);
+                          int max_bps, int group, cudaStream_t s);
 cudaError_t launch_ht_ref(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
                           int planes_precleared, void *d_scratch, uint64_t blob_bytes, cudaStream_t s);
 size_t j2k_htref_scratch_bytes(uint32_t n_blocks);   // device scratch launch_ht_ref needs for n blocks
 int j2k_htref_launches();        // kernels per launch_ht_ref call
-// ISO/IEC 15444-1 Annex D decoder (stripe-order passes, standard tables, pass truncation), one warp per block
+// ISO/IEC 15444-1 Annex D decoder (stripe-order passes, standard tables, pass truncation)
 cudaError_t launch_t1_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
-                          const float *d_steps, int irrev, int max_bps, cudaStream_t s);
+                          const float *d_steps, int irrev, int max_bps, int group, cudaStream_t s);
 // ISO/IEC 15444-15 block decoder (VLC kernel + MagSgn kernel)
 // refine: some block carries SigProp / MagRef passes (num_passes > 1): the refinement kernel runs between the two
 cudaError_t launch_ht_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,

@@ -15,11 +15,15 @@
 // it; all lanes split the work that IS parallel: clearing state, assembling magnitudes from the
 // bit-plane bitmaps, applying signs and the coalesced store into the tile-component plane.
 #include "common.h"
+#include <type_traits>
 
 namespace {
 
 constexpr int kWarpsPerCta = 4;
 constexpr int kCtxZC = 0, kCtxSC = 9, kCtxMag = 14, kCtxRL = 17, kCtxUni = 18, kNumCtx = 19;
+// shared memory per block in 64-bit words: significance rows -1 .. 64, sign, visited, refined (+ coded-last for ISO), one
+// magnitude bit-plane, the 19 context states
+constexpr int kRefWords = 66 + 64 * 4 + 4, kIsoWords = 66 + 64 * 5 + 4;
 
 __constant__ uint32_t c_mq[94];          // qe | nmps << 16 | nlps << 24      (mqc.go:21-116)
 __constant__ uint8_t  c_zc9[4 * 512];    // band, 3x3 significance window -> ZC context (t1_luts.go:35-110)
@@ -105,39 +109,75 @@ __device__ __forceinline__ uint32_t decode_sign(MQ &m, uint8_t *ctxs, int x,
     return mq_decode(m, ctxs, kCtxSC + (e >> 1)) ^ (e & 1);
 }
 
-// OT = element type of the coefficient arena: int32_t, or int16_t when every block of the job has num_bps <= 15
-template <typename OT>
+// One magnitude bit-plane lives in shared memory; when it is complete the group's lanes OR it into the block's samples in
+// the coefficient plane (which therefore hold plain magnitudes until the final pass applies signs / mid-points) and
+// clear it.  Lane sl owns columns sl * 64 / G ... of every row.  Keeping all num_bps planes in shared memory (512 bytes
+// each) allowed 24 blocks per SM; one plane allows about 80 chains per SM inside the register budget of 25 warps.
+template <typename OT, int G>
+__device__ __forceinline__ void t1_flush_plane(uint64_t *plane, OT *out, uint32_t ostride, int h, int sl, int bp, uint32_t gmask)
+{
+    constexpr int W = 64 / G;
+    typedef typename std::conditional<sizeof(OT) == 2, uint16_t, uint32_t>::type UT;
+    for (int y = 0; y < h; y++) {
+        uint32_t bits = (uint32_t)(plane[y] >> (sl * W)) & (uint32_t)((1ull << W) - 1);
+        UT *row = reinterpret_cast<UT *>(out + (size_t)y * ostride + sl * W);
+        while (bits) {
+            const int j = __ffs((int)bits) - 1;
+            bits &= bits - 1;
+            row[j] = (UT)(row[j] | (UT)(1u << bp));
+        }
+    }
+    __syncwarp(gmask);                                   // every lane has read the plane
+    for (int y = sl; y < 64; y += G) plane[y] = 0;
+    __syncwarp(gmask);
+}
+
+// OT = element type of the coefficient arena: int32_t, or int16_t when every block of the job has num_bps <= 15.
+// G = lanes per code block: a warp decodes 32 / G blocks at once.  The MQ decision chain of a block is serial and runs in
+// the first lane of its group; with one block per warp every issued instruction did one lane's worth of work.  With
+// several chains per warp the SIMT hardware issues an instruction once for all the chains that are at it -- the passes are
+// loops over rows, candidate columns and the MQ routine, so the chains of a warp walk the same code and mostly meet --
+// and the group's lanes share the parallel parts (clearing state, assembling magnitudes, stores).
+template <typename OT, int G>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 k_t1_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob,
-         OT *__restrict__ coef, int plane_words /* 64 * max_bps */, int skip_empty)
+         OT *__restrict__ coef, int skip_empty)
 {
     J2K_DYN_SMEM(uint64_t, smem);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t blk = blockIdx.x * kWarpsPerCta + warp;
-    if (blk >= n) return;
+    constexpr int BPW = 32 / G, W = 64 / G;              // blocks per warp, columns per lane
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, grp = lane / G, sl = lane % G;
+    const uint32_t gmask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (grp * G));
+    const uint32_t blk_raw = (blockIdx.x * (blockDim.x >> 5) + warp) * BPW + grp;
+    const bool have = blk_raw < n;
+    const uint32_t blk = have ? blk_raw : n - 1;         // lanes without a block follow along and write nothing
     const DevCblk cb = cblks[blk];
     const int w = cb.w, h = cb.h, nbps = cb.num_bps, band = cb.band & 3;
 
-    const int words = 66 + 64 * 3 + plane_words + 4;
-    uint64_t *base = smem + (size_t)warp * words;
+    uint64_t *base = smem + (size_t)(warp * BPW + grp) * kRefWords;
     uint64_t *sig = base + 1;            // rows -1 .. 64
     uint64_t *neg = base + 66;
     uint64_t *visit = base + 130;
     uint64_t *refine = base + 194;
-    uint64_t *planes = base + 258;       // [bp][row]
-    uint8_t *ctxs = (uint8_t *)(base + 258 + plane_words);
+    uint64_t *plane = base + 258;        // the bit-plane being decoded
+    uint8_t *ctxs = (uint8_t *)(base + 322);
 
     OT *out = coef + cb.out_off;
     const uint32_t ostride = cb.out_stride;
 
-    if ((cb.data_len == 0 && skip_empty) || nbps == 0) {          // tcd.go:394-396: not coded -> zeros
+    const bool coded = !((cb.data_len == 0 && skip_empty) || nbps == 0);
+    if (have && !coded) {                                          // tcd.go:394-396: not coded -> zeros
         for (int y = 0; y < h; y++)
-            for (int x = lane; x < w; x += 32) out[(size_t)y * ostride + x] = 0;
-        return;
+            for (int x = sl; x < w; x += G) out[(size_t)y * ostride + x] = 0;
     }
-
-    for (int i = lane; i < 258 + 64 * nbps; i += 32) base[i] = 0;
-    if (lane < kNumCtx) ctxs[lane] = (lane == kCtxUni) ? 92 : 0;   // mqc.go:378-383
+    const bool run = have && coded;
+    if (run) {
+        for (int i = sl; i < 322; i += G) base[i] = 0;
+        for (int i = sl; i < kNumCtx; i += G) ctxs[i] = (i == kCtxUni) ? 92 : 0;   // mqc.go:378-383
+        for (int y = 0; y < h; y++)                                    // the samples collect their magnitude bits plane by plane
+#pragma unroll
+            for (int j = 0; j < W; j++)
+                if (sl * W + j < w) out[(size_t)y * ostride + sl * W + j] = 0;
+    }
     __syncwarp();
 
     MQ mq;
@@ -145,10 +185,9 @@ k_t1_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
     const uint64_t wmask = (w >= 64) ? ~0ull : ((1ull << w) - 1);
     const uint8_t *zc = c_zc9 + band * 512;
 
-    // the serial MQ chain: lane 0 runs it (J2K_T1_ONE_LANE, the default -- measured equal in speed to all 32 lanes running
-    // it redundantly in lock-step, and free of any reliance on implicit warp-synchronous shared-memory updates)
-    for (int bp = nbps - 1; bp >= 0 && J2K_LOCKSTEP_LANE(lane); bp--) {
-        uint64_t *plane = planes + bp * 64;
+    // the serial MQ chain: the first lane of the group runs it, the others wait for the plane
+    for (int bp = nbps - 1; bp >= 0 && run; bp--) {
+      if (sl == 0) {
 
         // ---- significance propagation, raster order (t1.go:1295-1319) ----
         for (int y = 0; y < h; y++) {
@@ -263,20 +302,21 @@ k_t1_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
                 }
             }
         }
+      }
+        __syncwarp(gmask);
+        t1_flush_plane<OT, G>(plane, out, ostride, h, sl, bp, gmask);
     }
     __syncwarp();
 
-    // ---- assemble magnitudes, apply signs (t1.go:1282-1289), coalesced store ----
-    for (int y = 0; y < h; y++) {
-        uint32_t m0 = 0, m1 = 0;
-        for (int bp = 0; bp < nbps; bp++) {
-            uint64_t pr = planes[bp * 64 + y];
-            m0 |= (uint32_t)((pr >> lane) & 1) << bp;
-            m1 |= (uint32_t)((pr >> (lane + 32)) & 1) << bp;
+    // ---- apply signs (t1.go:1282-1289) ----
+    for (int y = 0; run && y < h; y++) {
+        uint32_t nb = (uint32_t)(neg[y] >> (sl * W)) & (uint32_t)((1ull << W) - 1);
+        OT *row = out + (size_t)y * ostride + sl * W;
+        while (nb) {
+            const int j = __ffs((int)nb) - 1;
+            nb &= nb - 1;
+            row[j] = (OT)(0 - row[j]);
         }
-        uint64_t nr = neg[y];
-        if (lane < w)      out[(size_t)y * ostride + lane]      = (OT)(int32_t)(((nr >> lane) & 1) ? 0u - m0 : m0);
-        if (lane + 32 < w) out[(size_t)y * ostride + lane + 32] = (OT)(int32_t)(((nr >> (lane + 32)) & 1) ? 0u - m1 : m1);
     }
 }
 
@@ -287,39 +327,48 @@ k_t1_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
 // (quality layers).  Output: sign * (2 * magnitude + mid-point of the last decoded bit-plane) / 2 as an integer for the
 // reversible path, or that twice-scale value * step / 2 as float32 bits for the irreversible one (the convention of the
 // CPU checker, which OpenJPEG pins).  Default code-block style only.
-template <typename OT>
+template <typename OT, int G>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 k_t1_iso(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob, OT *__restrict__ coef,
-         const float *__restrict__ steps, int irrev, int plane_words /* 64 * max_bps */)
+         const float *__restrict__ steps, int irrev)
 {
     J2K_DYN_SMEM(uint64_t, smem);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t blk = blockIdx.x * kWarpsPerCta + warp;
-    if (blk >= n) return;
+    constexpr int BPW = 32 / G, W = 64 / G;              // blocks per warp, columns per lane (see k_t1_ref)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, grp = lane / G, sl = lane % G;
+    const uint32_t gmask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (grp * G));
+    const uint32_t blk_raw = (blockIdx.x * (blockDim.x >> 5) + warp) * BPW + grp;
+    const bool have = blk_raw < n;
+    const uint32_t blk = have ? blk_raw : n - 1;
     const DevCblk cb = cblks[blk];
     const int w = cb.w, h = cb.h, nbps = cb.num_bps, band = cb.band & 3;
     int npasses = cb.num_passes ? cb.num_passes : 3 * nbps - 2;
     if (npasses > 3 * nbps - 2) npasses = 3 * nbps - 2;
 
-    const int words = 66 + 64 * 4 + plane_words + 4;
-    uint64_t *base = smem + (size_t)warp * words;
+    uint64_t *base = smem + (size_t)(warp * BPW + grp) * kIsoWords;
     uint64_t *sig = base + 1;            // rows -1 .. 64
     uint64_t *neg = base + 66;
     uint64_t *visit = base + 130;
     uint64_t *refine = base + 194;
     uint64_t *lastc = base + 258;        // coded (became significant or refined) in the bit-plane decoded last
-    uint64_t *planes = base + 322;       // [bp][row]
-    uint8_t *ctxs = (uint8_t *)(base + 322 + plane_words);
+    uint64_t *plane = base + 322;        // the bit-plane being decoded
+    uint8_t *ctxs = (uint8_t *)(base + 386);
 
     OT *out = coef + cb.out_off;
     const uint32_t ostride = cb.out_stride;
-    if (cb.data_len == 0 || nbps == 0 || npasses <= 0) {          // not included in any layer: all zero
+    const bool coded = !(cb.data_len == 0 || nbps == 0 || npasses <= 0);
+    if (have && !coded) {                                         // not included in any layer: all zero
         for (int y = 0; y < h; y++)
-            for (int x = lane; x < w; x += 32) out[(size_t)y * ostride + x] = (OT)0;
-        return;
+            for (int x = sl; x < w; x += G) out[(size_t)y * ostride + x] = (OT)0;
     }
-    for (int i = lane; i < 322 + 64 * nbps; i += 32) base[i] = 0;
-    if (lane < kNumCtx) ctxs[lane] = (lane == kCtxUni) ? 92 : (lane == kCtxRL ? 6 : (lane == 0 ? 8 : 0));   // Table D.7
+    const bool run = have && coded;
+    if (run) {
+        for (int i = sl; i < 386; i += G) base[i] = 0;
+        for (int i = sl; i < kNumCtx; i += G) ctxs[i] = (i == kCtxUni) ? 92 : (i == kCtxRL ? 6 : (i == 0 ? 8 : 0));   // Table D.7
+        for (int y = 0; y < h; y++)                                    // the samples collect their magnitude bits plane by plane
+#pragma unroll
+            for (int j = 0; j < W; j++)
+                if (sl * W + j < w) out[(size_t)y * ostride + sl * W + j] = (OT)0;
+    }
     __syncwarp();
 
     MQ mq;
@@ -330,9 +379,9 @@ k_t1_iso(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
 
     // pass sequence: cleanup of the top bit-plane, then (significance, refinement, cleanup) per lower bit-plane
     int bp = nbps - 1, type = 2;
-    for (int pass = 0; pass < npasses && J2K_LOCKSTEP_LANE(lane); pass++) {
-        uint64_t *plane = planes + bp * 64;
+    for (int pass = 0; pass < npasses && run; pass++) {
         p_end = bp;
+      if (sl == 0) {
         for (int y0 = 0; y0 < h; y0 += 4) {
             const bool full = (y0 + 4 <= h);
             const int rows = full ? 4 : (h - y0);
@@ -473,40 +522,37 @@ k_t1_iso(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
                     }
             }
         }
-        if (type == 2) {
-            bp--;
-            if (pass + 1 < npasses)                                // the next bit-plane starts: nothing coded in it yet
-                for (int y = 0; y < h; y++) lastc[y] = 0;
+        if (type == 2 && pass + 1 < npasses)                        // the next bit-plane starts: nothing coded in it yet
+            for (int y = 0; y < h; y++) lastc[y] = 0;
+      }
+        if (type == 2 || pass + 1 == npasses) {                     // the bit-plane is complete (or the block's passes end in it)
+            __syncwarp(gmask);
+            t1_flush_plane<OT, G>(plane, out, ostride, h, sl, bp, gmask);
         }
+        if (type == 2) bp--;
         type = type == 2 ? 0 : type + 1;
     }
-    p_end = __shfl_sync(0xffffffffu, p_end, 0);                       // when lane 0 alone ran the passes
     __syncwarp();
 
-    // ---- assemble: twice-scale magnitude with the mid-point of the last decoded bit-plane, sign, store ----
+    // ---- final values: twice-scale magnitude with the mid-point of the last decoded bit-plane, sign, dequantisation ----
     const float hstep = irrev ? 0.5f * steps[blk] : 0.0f;
-    for (int y = 0; y < h; y++) {
-        uint32_t m0 = 0, m1 = 0;
-        for (int b2 = 0; b2 < nbps; b2++) {
-            const uint64_t pr = planes[b2 * 64 + y];
-            m0 |= (uint32_t)((pr >> lane) & 1) << b2;
-            m1 |= (uint32_t)((pr >> (lane + 32)) & 1) << b2;
-        }
-        const uint64_t nr = neg[y], sr = sig[y], lr = lastc[y];
-#pragma unroll
-        for (int half = 0; half < 2; half++) {
-            const int x = lane + 32 * half;
-            if (x >= w) continue;
-            const uint32_t m = half ? m1 : m0;
-            uint32_t m2 = 0;
-            if ((sr >> x) & 1) m2 = (m << 1) | (1u << (((lr >> x) & 1) ? p_end : p_end + 1));
-            const bool ngt = (nr >> x) & 1;
+    typedef typename std::conditional<sizeof(OT) == 2, uint16_t, uint32_t>::type UT;
+    for (int y = 0; run && y < h; y++) {
+        uint32_t sb = (uint32_t)(sig[y] >> (sl * W)) & (uint32_t)((1ull << W) - 1);
+        const uint32_t nb = (uint32_t)(neg[y] >> (sl * W)), lb = (uint32_t)(lastc[y] >> (sl * W));
+        OT *row = out + (size_t)y * ostride + sl * W;
+        while (sb) {
+            const int j = __ffs((int)sb) - 1;
+            sb &= sb - 1;
+            const uint32_t m = (uint32_t)*reinterpret_cast<UT *>(row + j);
+            const uint32_t m2 = (m << 1) | (1u << (((lb >> j) & 1) ? p_end : p_end + 1));
+            const bool ngt = (nb >> j) & 1;
             if (irrev) {
                 const float f = (float)m2 * hstep;
-                out[(size_t)y * ostride + x] = (OT)__float_as_int(ngt ? -f : f);
+                row[j] = (OT)__float_as_int(ngt ? -f : f);
             } else {
                 const uint32_t v = m2 >> 1;
-                out[(size_t)y * ostride + x] = (OT)(int32_t)(ngt ? 0u - v : v);
+                row[j] = (OT)(int32_t)(ngt ? 0u - v : v);
             }
         }
     }
@@ -634,59 +680,105 @@ cudaError_t upload_tables(cudaStream_t s)
 
 }  // namespace
 
+// warps per CTA and dynamic shared memory for 32 / G blocks per warp of `block_words` 64-bit words each: as many warps
+// (at most kWarpsPerCta) as leave room for two CTAs per SM; 0 when even one warp does not fit (the caller takes a wider group)
+static int t1_warps_per_cta(int G, size_t block_words, size_t *smem)
+{
+    const size_t per_warp = (size_t)(32 / G) * block_words * sizeof(uint64_t);
+    int wpc = kWarpsPerCta;
+    while (wpc > 1 && (size_t)wpc * per_warp > 48 * 1024) wpc >>= 1;
+    *smem = (size_t)wpc * per_warp;
+    return *smem <= 220 * 1024 ? wpc : 0;
+}
+
+template <typename OT, int G>
+static cudaError_t launch_t1_ref_g(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, OT *d_coef, int skip_empty, cudaStream_t s)
+{
+    size_t smem;
+    const int wpc = t1_warps_per_cta(G, kRefWords, &smem);
+    if (!wpc) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(k_t1_ref<OT, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const uint32_t per_cta = (uint32_t)wpc * (32 / G);
+    J2K_LAUNCH((k_t1_ref<OT, G>), (n + per_cta - 1) / per_cta, wpc * 32, smem, s, d_cblks, n, d_blob, d_coef, skip_empty);
+    return cudaGetLastError();
+}
+
+template <typename OT, int G>
+static cudaError_t launch_t1_iso_g(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, OT *d_coef, const float *d_steps, int irrev,
+                                   cudaStream_t s)
+{
+    size_t smem;
+    const int wpc = t1_warps_per_cta(G, kIsoWords, &smem);
+    if (!wpc) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(k_t1_iso<OT, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const uint32_t per_cta = (uint32_t)wpc * (32 / G);
+    J2K_LAUNCH((k_t1_iso<OT, G>), (n + per_cta - 1) / per_cta, wpc * 32, smem, s, d_cblks, n, d_blob, d_coef, d_steps, irrev);
+    return cudaGetLastError();
+}
+
+// Lanes per block.  A chain issues an instruction every 8 cycles or so (dependent latency), so an SM wants as many chains
+// in flight as it can hold; registers allow 25 warps, shared memory about 80 blocks.  With few blocks per SM one chain
+// per warp finishes first (no chain waits for a diverged neighbour): measured on B200, ms per launch for 32 / 16 / 8 / 4
+// lanes per block: 1 536 blocks 6.6 / 8.7 / 11.9 / 16.8; 12 240 blocks 22.9 / 16.3 / 18.7 / 23.4; 14 010 blocks
+// 44.0 / 33.1 / 32.8 / 36.5.
+static int t1_group(int opt, uint32_t n)
+{
+    if (opt == 4 || opt == 8 || opt == 16 || opt == 32) return opt;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint32_t per_sm = n / (uint32_t)(sms > 0 ? sms : 148);
+    return per_sm < 28 ? 32 : (per_sm < 120 ? 16 : 8);
+}
+
 static cudaError_t launch_t1_ref_impl(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
-                                      int max_bps, int skip_empty, cudaStream_t s)
+                                      int max_bps, int skip_empty, int group, cudaStream_t s)
 {
     if (n == 0) return cudaSuccess;
     cudaError_t e = upload_tables(s);
     if (e != cudaSuccess) return e;
-    if (max_bps < 1) max_bps = 1;
-    int plane_words = 64 * max_bps;
-    size_t smem = (size_t)kWarpsPerCta * (66 + 64 * 3 + plane_words + 4) * sizeof(uint64_t);
-    if (smem > 48 * 1024) {
-        e = coef16 ? cudaFuncSetAttribute(k_t1_ref<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                   : cudaFuncSetAttribute(k_t1_ref<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
+    (void)max_bps;
+#define J2K_T1_REF(G) (coef16 ? launch_t1_ref_g<int16_t, G>(d_cblks, n, d_blob, (int16_t *)d_coef, skip_empty, s) \
+                              : launch_t1_ref_g<int32_t, G>(d_cblks, n, d_blob, (int32_t *)d_coef, skip_empty, s))
+    switch (t1_group(group, n)) {
+    case 4: return J2K_T1_REF(4);
+    case 8: return J2K_T1_REF(8);
+    case 16: return J2K_T1_REF(16);
+    default: return J2K_T1_REF(32);
     }
-    uint32_t grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
-    if (coef16)
-        J2K_LAUNCH((k_t1_ref<int16_t>), grid, kWarpsPerCta * 32, smem, s, d_cblks, n, d_blob, (int16_t *)d_coef, plane_words, skip_empty);
-    else
-        J2K_LAUNCH((k_t1_ref<int32_t>), grid, kWarpsPerCta * 32, smem, s, d_cblks, n, d_blob, (int32_t *)d_coef, plane_words, skip_empty);
-    return cudaGetLastError();
+#undef J2K_T1_REF
 }
 
 cudaError_t launch_t1_ref(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
-                          int max_bps, cudaStream_t s)
+                          int max_bps, int group, cudaStream_t s)
 {
-    return launch_t1_ref_impl(d_cblks, n, d_blob, d_coef, coef16, max_bps, 1, s);
+    return launch_t1_ref_impl(d_cblks, n, d_blob, d_coef, coef16, max_bps, 1, group, s);
 }
 
 // stage API form: T1.Decode is also defined for empty data (decodes the 0xFF fill, mqc.go:387-388)
 cudaError_t launch_t1_ref_stage(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, int32_t *d_coef,
-                                int max_bps, cudaStream_t s)
+                                int max_bps, int group, cudaStream_t s)
 {
-    return launch_t1_ref_impl(d_cblks, n, d_blob, d_coef, 0, max_bps, 0, s);
+    return launch_t1_ref_impl(d_cblks, n, d_blob, d_coef, 0, max_bps, 0, group, s);
 }
 
 // ISO/IEC 15444-1 Annex D decoder (J2KGPU_MODE_ISO): num_bps magnitude bit-planes, num_passes coding passes per block
 // (0 = all); irrev: the planes receive float32 bits = value * steps[block]
 cudaError_t launch_t1_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
-                          const float *d_steps, int irrev, int max_bps, cudaStream_t s)
+                          const float *d_steps, int irrev, int max_bps, int group, cudaStream_t s)
 {
     if (n == 0) return cudaSuccess;
     cudaError_t e = upload_tables(s);
     if (e != cudaSuccess) return e;
-    if (max_bps < 1) max_bps = 1;
-    const int plane_words = 64 * max_bps;
-    const size_t smem = (size_t)kWarpsPerCta * (66 + 64 * 4 + plane_words + 4) * sizeof(uint64_t);
-    const uint32_t grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
-    if (coef16 && !irrev) {
-        if ((e = cudaFuncSetAttribute(k_t1_iso<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        J2K_LAUNCH((k_t1_iso<int16_t>), grid, kWarpsPerCta * 32, smem, s, d_cblks, n, d_blob, (int16_t *)d_coef, d_steps, irrev, plane_words);
-    } else {
-        if ((e = cudaFuncSetAttribute(k_t1_iso<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        J2K_LAUNCH((k_t1_iso<int32_t>), grid, kWarpsPerCta * 32, smem, s, d_cblks, n, d_blob, (int32_t *)d_coef, d_steps, irrev, plane_words);
+    (void)max_bps;
+#define J2K_T1_ISO(G) ((coef16 && !irrev) ? launch_t1_iso_g<int16_t, G>(d_cblks, n, d_blob, (int16_t *)d_coef, d_steps, irrev, s) \
+                                          : launch_t1_iso_g<int32_t, G>(d_cblks, n, d_blob, (int32_t *)d_coef, d_steps, irrev, s))
+    switch (t1_group(group, n)) {
+    case 4: return J2K_T1_ISO(4);
+    case 8: return J2K_T1_ISO(8);
+    case 16: return J2K_T1_ISO(16);
+    default: return J2K_T1_ISO(32);
     }
-    return cudaGetLastError();
+#undef J2K_T1_ISO
 }

@@ -332,17 +332,22 @@ def test_padded_stride_and_partial_tile_set(j2k, gpu_ctx):
     assert np.array_equal(pix, oracle_pixels(part).reshape(h, w, 4))
 
 
-def test_overlapping_blocks_are_not_mistaken_for_full_coverage(j2k, gpu_ctx):
-    """block areas that add up to the plane while leaving a hole (one block duplicated, one dropped): the hole reads zero
-    coefficients, never uninitialised pool memory"""
+def test_overlapping_blocks_are_refused(j2k, gpu_ctx):
+    """block areas that add up to the plane while leaving a hole (one block duplicated, one dropped) are not mistaken for
+    full coverage: overlapping blocks are an argument error (a block's samples are its own while its bit-planes
+    accumulate), and the context keeps working"""
     s = jobs.synth_image(128, 64, 1, 8, seed=62)
     job = jobs.build_ref_job(s, 8, nlevels=1, reversible=True, threads=2)
-    gpu_pixels(j2k, gpu_ctx, job)
+    want = gpu_pixels(j2k, gpu_ctx, job)
     cb = job["cblks"].copy()
     assert len(cb) == 2 and cb["w"][0] == cb["w"][1]
     cb[1] = cb[0]                                                # block 0 twice, block 1 missing: the areas still sum to w * h
-    dup = dict(job, cblks=cb)
-    assert np.array_equal(gpu_pixels(j2k, gpu_ctx, dup), oracle_pixels(dup))
+    with pytest.raises(j2k.J2KError) as e:
+        gpu_pixels(j2k, gpu_ctx, dict(job, cblks=cb))
+    assert e.value.code == j2k.E_ARG and "overlap" in str(e.value)
+    hole = dict(job, cblks=job["cblks"][:1].copy())              # block 1 missing, no overlap: the hole reads zero coefficients
+    assert np.array_equal(gpu_pixels(j2k, gpu_ctx, hole), oracle_pixels(hole))
+    assert np.array_equal(gpu_pixels(j2k, gpu_ctx, job), want)
 
 
 def test_two_devices_in_one_process(j2k):
