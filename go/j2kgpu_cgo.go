@@ -20,23 +20,49 @@ import (
 	"fmt"
 	"image"
 	"os"
+	"runtime"
 	"strconv"
-	"sync"
 	"unsafe"
 )
 
-// gpuCtx is one j2kgpu_ctx (one GPU, one stream).  A ctx serialises its calls, so a pool keeps one per
-// concurrently decoding goroutine; J2KGPU_DEVICE selects the device.
+// gpuCtx is one j2kgpu_ctx (one GPU, one stream, pooled device buffers, pinned staging).  A ctx serialises its calls, so
+// a bounded free list keeps one per concurrently decoding goroutine; J2KGPU_DEVICE selects the device.  A ctx that the
+// list has no room for is destroyed at once, and a finalizer destroys whatever the collector finds unreferenced: a
+// sync.Pool would drop contexts at any GC without ever calling j2kgpu_destroy.
 type gpuCtx struct{ h *C.j2kgpu_ctx }
 
-var gpuPool = sync.Pool{New: func() interface{} {
+var gpuFree = make(chan *gpuCtx, 16)
+
+func (c *gpuCtx) Close() {
+	if c.h != nil {
+		C.j2kgpu_destroy(c.h)
+		c.h = nil
+	}
+}
+
+func getGPUCtx() (*gpuCtx, error) {
+	select {
+	case c := <-gpuFree:
+		return c, nil
+	default:
+	}
 	dev, _ := strconv.Atoi(os.Getenv("J2KGPU_DEVICE"))
 	var h *C.j2kgpu_ctx
 	if rc := C.j2kgpu_create(C.int(dev), &h); rc != 0 {
-		return fmt.Errorf("j2kgpu_create: %s", C.GoString(C.j2kgpu_strerror(rc)))
+		return nil, fmt.Errorf("j2kgpu_create: %s", C.GoString(C.j2kgpu_strerror(rc)))
 	}
-	return &gpuCtx{h}
-}}
+	c := &gpuCtx{h}
+	runtime.SetFinalizer(c, (*gpuCtx).Close)
+	return c, nil
+}
+
+func putGPUCtx(c *gpuCtx) {
+	select {
+	case gpuFree <- c:
+	default:
+		c.Close()
+	}
+}
 
 // gpuJob is what the Go tier-2 walk produces: flat tables (no Go pointers inside) plus one blob.
 type gpuJob struct {
@@ -69,14 +95,16 @@ func gpuColorSpace(cs ColorSpace) (C.uint8_t, bool) {
 // decodeTilesGPU is decoder.decodeTiles on the GPU: it returns the same image types createImage would
 // (decoder.go:417-588) with Pix filled by the library; errors are wrapped like decoder.go:47.
 func (d *decoder) decodeTilesGPU(job *gpuJob) (image.Image, error) {
-	v := gpuPool.Get()
-	ctx, ok := v.(*gpuCtx)
-	if !ok {
-		return nil, fmt.Errorf("decoding tiles: %w", v.(error))
+	ctx, err := getGPUCtx()
+	if err != nil {
+		return nil, fmt.Errorf("decoding tiles: %w", err)
 	}
-	defer gpuPool.Put(ctx)
+	defer putGPUCtx(ctx)
 
 	w, h := int(job.img.width), int(job.img.height)
+	if w <= 0 || h <= 0 {
+		return nil, fmt.Errorf("decoding tiles: empty image") // &pix[0] below needs at least one pixel
+	}
 	var out image.Image
 	var pix []uint8
 	var stride int
@@ -108,9 +136,13 @@ func (d *decoder) decodeTilesGPU(job *gpuJob) (image.Image, error) {
 		blob = (*C.uint8_t)(unsafe.Pointer(&job.blob[0]))
 	}
 	// Page-lock the pixel buffer for the call (ABI v3): the device->host copy of the pixels is the slowest step of the
-	// path and runs at link speed, overlapped with the kernels, only into page-locked memory.  The Go heap does not
-	// move objects, and cgo keeps pix alive for the duration of the call; a decoder that recycles its images would
-	// register each buffer once instead.  Failure to register is not an error: the copy is then staged by the driver.
+	// path and runs at link speed, overlapped with the kernels, only into page-locked memory.  The driver keeps the
+	// address while the buffer is registered, so the buffer is pinned in the Go sense too (runtime.Pinner, Go 1.21) until
+	// it is unregistered; a decoder that recycles its images would take them from j2kgpu_host_alloc instead.  Failure
+	// to register is not an error: the copy is then staged by the driver.
+	var pin runtime.Pinner
+	pin.Pin(&pix[0])
+	defer pin.Unpin()
 	if C.j2kgpu_host_register(ctx.h, unsafe.Pointer(&pix[0]), C.uint64_t(len(pix))) == 0 {
 		defer C.j2kgpu_host_unregister(ctx.h, unsafe.Pointer(&pix[0]))
 	}
@@ -121,4 +153,24 @@ func (d *decoder) decodeTilesGPU(job *gpuJob) (image.Image, error) {
 			C.GoString(C.j2kgpu_last_error(ctx.h)))
 	}
 	return out, nil
+}
+
+// decodeCodestreamGPU hands the raw codestream (what readJP2 or the SOC check found) to the library's own front door:
+// main header, tile-part index and tier-2 run on host threads inside libj2kgpu.so (host/tier2.cpp), so no Go tier-2 is
+// needed.  pix / stride belong to the image.* the caller allocated as createImage would; reduce = Config.ReduceResolution.
+func decodeCodestreamGPU(cs []byte, reduce int, pix []uint8, stride int) error {
+	if len(cs) == 0 || len(pix) == 0 {
+		return fmt.Errorf("decoding tiles: empty input")
+	}
+	ctx, err := getGPUCtx()
+	if err != nil {
+		return fmt.Errorf("decoding tiles: %w", err)
+	}
+	defer putGPUCtx(ctx)
+	rc := C.j2kgpu_decode_codestream(ctx.h, (*C.uint8_t)(unsafe.Pointer(&cs[0])), C.uint64_t(len(cs)), C.uint32_t(reduce),
+		(*C.uint8_t)(unsafe.Pointer(&pix[0])), C.uint64_t(stride))
+	if rc != 0 {
+		return fmt.Errorf("decoding tiles: %s: %s", C.GoString(C.j2kgpu_strerror(rc)), C.GoString(C.j2kgpu_last_error(ctx.h)))
+	}
+	return nil
 }
