@@ -769,8 +769,9 @@ extern "C" int j2kgpu_job_run(j2kgpu_job *job, const void *d_blob, void *d_out)
 // cannot grow along the batch without starving the copy-out engine.  The plan is therefore: the smallest possible first
 // chunk (its copy-in + decode is the only exposed latency), then equal chunks, as many as the decoder's per-launch
 // latency floor (one code block's serial chain per launch sequence) allows inside the copy-out time; compute-bound
-// coders (EBCOT) get four chunks.  Measured on the bench batch (16 x 4K): 16 chunks of one frame 11.16 ms, (1,3,3,3,3,3)
-// 11.72 ms, (4,4,4,4) 12.26 ms, one chunk 16.6 ms.
+// coders (EBCOT) get four chunks.  Measured on the bench batch (16 x 4K, reference HT coder): 16 chunks of one frame 11.16 ms,
+// (1,3,3,3,3,3) 11.72 ms, (4,4,4,4) 12.26 ms, one chunk 16.6 ms; conformant HTJ2K with the round-2 kernels: 16 x 1 11.17 ms,
+// (1,1,2,2,...) 11.28, (1,2,2,...,3) 11.44, 8 x 2 11.69, (1,3,3,3,3,3) 12.02, (1,3,4,4,4) 12.28.
 static std::vector<uint32_t> plan_chunks(const j2kgpu_ctx *ctx, uint32_t n, const j2k_image_t &hdr, uint64_t out_bytes)
 {
     if (!ctx->opt.chunks.empty()) {                      // experiments: explicit chunk sizes, e.g. "1,1,2,4"; the rest in one chunk
@@ -787,7 +788,7 @@ static std::vector<uint32_t> plan_chunks(const j2kgpu_ctx *ctx, uint32_t n, cons
     }
     double lat, r_cmp;                                   // seconds per launch sequence, output bytes per second
     if (!hdr.ht) { lat = 5e-3; r_cmp = 2.4e9; }                         // EBCOT / MQ
-    else if (hdr.mode == J2KGPU_MODE_ISO) { lat = 1.1e-3; r_cmp = 400e9; }
+    else if (hdr.mode == J2KGPU_MODE_ISO) { lat = 0.4e-3; r_cmp = 400e9; }     // round-2 kernels: one frame per chunk pays
     else { lat = 0.4e-3; r_cmp = 800e9; }
     const double t_out = (double)out_bytes / 53e9, t_thr = (double)out_bytes / r_cmp;
     uint32_t nchunks = t_thr > 0.5 * t_out ? 4u : (uint32_t)((0.8 * t_out - t_thr) / lat);
