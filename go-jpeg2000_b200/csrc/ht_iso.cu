@@ -589,6 +589,20 @@ k_htiso_magsgn4(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__
     const uint32_t mis = (uint32_t)((uintptr_t)d & 3u);  // byte 0 of the stream inside its aligned word
     uint32_t built = 0, prev_ff = 0, P = 0;              // uniform over the block's lanes
     int kbyte = 0;
+    // the five aligned words that hold the lane's 16 stream bytes from k on; a word is read only if it starts inside the blob
+    uint32_t pre[5] = {FULL, FULL, FULL, FULL, FULL};
+    auto load5 = [&](int k) {
+        if (k >= L) return;
+        const uint8_t *a = d + k - mis;
+        if (a + 20 <= blob_end) {
+#pragma unroll
+            for (int j = 0; j < 5; j++) pre[j] = __ldg(reinterpret_cast<const uint32_t *>(a) + j);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 5; j++) pre[j] = (a + 4 * j < blob_end) ? __ldg(reinterpret_cast<const uint32_t *>(a) + j) : FULL;
+        }
+    };
+    if (live) load5(16 * sl);
     int Eb[8] = {0, 0, 0, 0, 0, 0, 0, 0};                // bottom-sample exponents of the lane's 8 columns, previous quad row
     bool bad = false;
     int nrows_max = nrows;
@@ -611,21 +625,11 @@ k_htiso_magsgn4(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__
                     for (int i = 0; i < 5; i++) ring[(w0 + 8 * i) & kRingMask] = 0;
                 }
                 __syncwarp();
-                const int k = kbyte + 16 * sl;           // the lane's stream bytes k .. k + 15
+                const int k = kbyte + 16 * sl;           // the lane's stream bytes k .. k + 15: loaded one refill ahead (pre[])
                 uint32_t x[4] = {FULL, FULL, FULL, FULL};
                 if (join && k < L) {
-                    // five aligned words that hold the 16 bytes; a word is read only if it starts inside the blob
-                    const uint8_t *a = d + k - mis;
-                    uint32_t wd[5];
-                    if (a + 20 <= blob_end) {
 #pragma unroll
-                        for (int j = 0; j < 5; j++) wd[j] = __ldg(reinterpret_cast<const uint32_t *>(a) + j);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 5; j++) wd[j] = (a + 4 * j < blob_end) ? __ldg(reinterpret_cast<const uint32_t *>(a) + j) : FULL;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; j++) x[j] = __funnelshift_r(wd[j], wd[j + 1], mis * 8);
+                    for (int j = 0; j < 4; j++) x[j] = __funnelshift_r(pre[j], pre[j + 1], mis * 8);
                     if (k + 16 > L) {                    // past the end of the stream: 0xFF
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
@@ -634,6 +638,7 @@ k_htiso_magsgn4(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__
                         }
                     }
                 }
+                if (join) load5(k + 128);                // the next refill's bytes are on their way while these are used
                 uint32_t pf = __shfl_up_sync(FULL, x[3] >> 24, 1, 8) == 0xFFu;
                 if (sl == 0) pf = prev_ff;
                 uint32_t nb[4], v[4];
