@@ -582,6 +582,14 @@ k_htiso_magsgn4(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__
     const int ncols = w - 8 * sl;                        // columns of the block right of (and including) the lane's first
     const bool vec_ok = ((cb.out_off | ostride) & (sizeof(OT) == 2 ? 7 : 3)) == 0;
     const int ulimit = min(28, coef_bits ? coef_bits + 1 : 28) - shift;   // a wider field would not fit 31 bits in quarter units / the plane
+    // The sample path is bound by the integer ALU pipe (LOP3 / SHF / ISETP issue every other cycle per scheduler) while the
+    // FMA pipe, which executes IMAD at the same rate, idles: shifts by a per-block amount are multiplies by a power of two,
+    // the sign is applied as a multiply, and additions are written as a * one + b with `one` opaque to the compiler.
+    const uint32_t one = min(n, 1u), minus2 = 0u - (one + one);
+    uint32_t mulq = 1u << (shift + 1);
+#ifndef J2K_EMU
+    asm volatile("" : "+r"(mulq));                       // keep it a multiplier (the compiler would turn the product back into a shift)
+#endif
     const uint2 *qt = reinterpret_cast<const uint2 *>(qtab + (size_t)blk * kQTabWords) + sl;
     uint32_t *ring = s_ring[warp * 4 + grp];
     for (int i = sl; i <= kRingWords; i += 8) ring[i] = 0;
@@ -603,7 +611,7 @@ k_htiso_magsgn4(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__
         }
     };
     if (live) load5(16 * sl);
-    int Eb[8] = {0, 0, 0, 0, 0, 0, 0, 0};                // bottom-sample exponents of the lane's 8 columns, previous quad row
+    int Eb[8] = {-1, -1, -1, -1, -1, -1, -1, -1};        // bottom-sample exponents - 1 of the lane's 8 columns, previous quad row
     bool bad = false;
     int nrows_max = nrows;
     nrows_max = max(nrows_max, __shfl_xor_sync(FULL, nrows_max, 8));
@@ -669,8 +677,8 @@ k_htiso_magsgn4(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__
         }
         // ---- U_q and the field widths of the lane's four quads ----
         const int eL = __shfl_up_sync(FULL, Eb[7], 1, 8), eR = __shfl_down_sync(FULL, Eb[0], 1, 8);
-        const int c_m1 = max(sl ? eL : 0, Eb[0]), c_1 = max(Eb[1], Eb[2]), c_3 = max(Eb[3], Eb[4]), c_5 = max(Eb[5], Eb[6]),
-                  c_7 = max(Eb[7], sl < 7 ? eR : 0);
+        const int c_m1 = max(sl ? eL : -1, Eb[0]), c_1 = max(Eb[1], Eb[2]), c_3 = max(Eb[3], Eb[4]), c_5 = max(Eb[5], Eb[6]),
+                  c_7 = max(Eb[7], sl < 7 ? eR : -1);
         const int Eq[4] = {max(c_m1, c_1), max(c_1, c_3), max(c_3, c_5), max(c_5, c_7)};
         uint32_t sigm[4], e1m[4];
         int m[16];
@@ -683,14 +691,15 @@ k_htiso_magsgn4(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__
             const uint32_t sig = (st8 | (st8 >> 1)) & 0x55u, ek = (st8 >> 1) & 0x55u;
             sigm[qd] = sig; e1m[qd] = st8 & ek;
             int Uq = u + 1;
-            if (r > 0 && (sig & (sig - 1))) Uq = u + max(1, Eq[qd] - 1);
+            if (r > 0 && (sig & (sig - 1))) Uq = u + max(1, Eq[qd]);      // Eq holds E - 1
             bad |= Uq > ulimit;
             const int U = min(Uq, 31);
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const int mi = ((sig >> (2 * i)) & 1u) ? U - (int)((ek >> (2 * i)) & 1u) : 0;
-                m[4 * qd + i] = mi;
-                tot += (uint32_t)mi;
+                // width = significant ? U - e_k : 0, as multiply-adds (e_k is set only where the sample is significant)
+                const uint32_t mi = ((sig >> (2 * i)) & 1u) * (uint32_t)U - ((ek >> (2 * i)) & 1u);
+                m[4 * qd + i] = (int)mi;
+                tot = mi * one + tot;
             }
         }
         uint32_t incl = tot;
@@ -719,15 +728,17 @@ k_htiso_magsgn4(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__
             const uint32_t sigb = (sigm[qd] >> (2 * sn)) & 1u, e1 = (e1m[qd] >> (2 * sn)) & 1u;
             const uint32_t *rw = ring + ((p >> 5) & kRingMask);
             const uint32_t xb = __funnelshift_r(rw[0], rw[1], p);
-            const uint32_t fld = xb & ((1u << m[i]) - 1u);
-            const uint32_t vv = fld | (e1 << m[i]) | sigb;               // 2 (mu - 1) + 1, or 0 for an insignificant sample
-            p += (uint32_t)m[i];
-            if (sn & 1) Eb[2 * qd + (sn >> 1)] = 32 - __clz((int)vv);
+            const uint32_t pw = 1u << m[i];
+            const uint32_t fld = xb & (pw * one - 1u);
+            const uint32_t vv = fld | (e1 * pw + sigb);                  // 2 (mu - 1) + 1, or 0 for an insignificant sample
+            p = (uint32_t)m[i] * one + p;
+            if (sn & 1) Eb[2 * qd + (sn >> 1)] = 31 - __clz((int)vv);     // exponent - 1 (-1 for an insignificant sample)
             const int col = 2 * qd + (sn >> 1), rowt = sn & 1;           // position inside the lane's 8 x 2 patch
-            uint32_t q = (vv + 2u * sigb) << (shift + 1);                // (2 mu + 1) << (P + 1)
+            uint32_t q = (sigb * 2u + vv) * mulq;                        // (2 mu + 1) << (P + 1)
             if (REFINE && np == 3) q = sigb ? ((((vv >> 1) + 1u) << (shift + 2)) | (((rmr[rowt] >> col) & 1u) << (shift + 1)) | (1u << shift)) : 0u;
             uint32_t sign = fld & 1u;
             if (REFINE && !sigb && ((rnew[rowt] >> col) & 1u)) { q = 3u << shift; sign = (rsgn[rowt] >> col) & 1u; }
+            if (!IRREV) { val[i] = (int32_t)((q >> 2) * (sign * minus2 + one)); continue; }   // magnitude * (1 - 2 sign)
             val[i] = sample_value(q, sign, qstep, IRREV);
         }
         if (row_on && ncols > 0) {

@@ -1,6 +1,6 @@
 // tier2.cpp -- see tier2.h.  Main header (SIZ, CAP, COD, QCD, TLM, COM), tile-part index (SOT / Psot, TLM cross-check), packet
 // headers (tag trees, number of passes, Lblock, segment lengths; SOP / EPH; PLT cross-check) for all five progression orders
-// with maximal precincts, any number of quality layers, classic and HT code blocks (one HT set: the cleanup length and the
+// with maximal or user-defined precincts, any number of quality layers, classic and HT code blocks (one HT set: the cleanup length and the
 // SigProp + MagRef length are separate codeword segments, T.814 B.10.7).  Tiles are parsed concurrently.
 // Everything is bounds-checked: malformed bytes give an error code, never a fault (the reference's fuzz contract).
 #include "tier2.h"
@@ -42,6 +42,7 @@ struct Header {
     uint32_t W = 0, H = 0, tile_w = 0, tile_h = 0, ncomp = 0, prec = 0, sgnd = 0;
     uint32_t prog = 0, layers = 0, mct = 0, nlevels = 0, cbw = 0, cbh = 0, style = 0, reversible = 0, sop = 0, eph = 0, ht = 0;
     uint32_t guard = 0;
+    uint8_t ppx[33], ppy[33];                            // precinct size exponents per resolution (15 = maximal)
     bool have_siz = false, have_cod = false, have_qcd = false;
     std::vector<std::pair<uint32_t, uint32_t>> q;      // per band in codestream order: exponent, mantissa
 };
@@ -147,6 +148,7 @@ uint32_t read_npasses(BitReader &br)                      // B.10.6
 inline int floorlog2(uint32_t v) { int r = 0; while (v >>= 1) r++; return r; }
 
 struct Blk {
+    uint32_t comp, bidx;               // component, index into the band list
     uint32_t px, py, w, h;             // placement in the tile-component's Mallat plane
     uint32_t passes = 0, zbp = 0, lblock = 3, lcup = 0;
     bool included = false;
@@ -155,9 +157,16 @@ struct Blk {
     std::vector<std::pair<uint64_t, uint32_t>> more;   // further contributions (quality layers)
 };
 
-struct BandState {
-    uint32_t comp, bidx, gw = 0, gh = 0, first = 0, count = 0;   // blocks [first, first + count) of the tile's block list
+// the code blocks of one band that lie in one precinct: their own grid and tag trees (B.10.2)
+struct PrecBand {
+    uint32_t gw = 0, gh = 0, first = 0, count = 0;       // blocks [first, first + count) of the tile's block list, raster order
     TagTree incl, imsb;
+};
+struct Prec {
+    uint32_t c, r, idx;                // component, resolution, raster index among the resolution's precincts
+    int64_t x, y;                      // top-left corner on the reference grid (clamped to the tile): position of its packets
+    uint32_t nb = 0;                   // bands at this resolution: 1 (LL) or 3
+    PrecBand pb[3];
 };
 
 struct TilePart { uint64_t body, end; };
@@ -191,45 +200,83 @@ void parse_tile(const uint8_t *cs, const Header &h, uint32_t tidx, const std::ve
         for (const TilePart &p : parts) joined.insert(joined.end(), cs + p.body, cs + p.end);
         body = joined.data(); blen = joined.size(); abs_off = -1;
     }
-    // code blocks of every (component, band), raster order inside the band
+    // precincts of every (component, resolution) and, per precinct and band, the code blocks inside it (B.6, B.7)
     std::vector<Blk> blks;
-    std::vector<BandState> bst(nc * bands.size());
+    std::vector<Prec> precs;
     for (uint32_t c = 0; c < nc; c++)
-        for (size_t bi = 0; bi < bands.size(); bi++) {
-            const BandId &b = bands[bi];
-            BandState &st = bst[c * bands.size() + bi];
-            st.comp = c; st.bidx = (uint32_t)bi; st.first = (uint32_t)blks.size();
-            const Rect br = band_rect(x0, y0, x1, y1, b.band, b.lvl);
-            if (br.x1 <= br.x0 || br.y1 <= br.y0) continue;
-            const int64_t gx0 = br.x0 / h.cbw, gy0 = br.y0 / h.cbh, gx1 = cdiv64(br.x1, h.cbw), gy1 = cdiv64(br.y1, h.cbh);
-            st.gw = (uint32_t)(gx1 - gx0); st.gh = (uint32_t)(gy1 - gy0);
-            // origin of the band inside the Mallat plane: LL_lvl top-left, HL to the right, LH below
-            const int64_t s = (int64_t)1 << b.lvl;
-            const int64_t lw = cdiv64(x1, s) - cdiv64(x0, s), lh = cdiv64(y1, s) - cdiv64(y0, s);
-            const int64_t ox = (b.band & 1) ? lw : 0, oy = (b.band >> 1) ? lh : 0;
-            for (int64_t gy = gy0; gy < gy1; gy++)
-                for (int64_t gx = gx0; gx < gx1; gx++) {
-                    const int64_t cx0 = std::max(br.x0, gx * h.cbw), cy0 = std::max(br.y0, gy * h.cbh);
-                    const int64_t cx1 = std::min(br.x1, (gx + 1) * h.cbw), cy1 = std::min(br.y1, (gy + 1) * h.cbh);
-                    Blk k;
-                    k.px = (uint32_t)(ox + cx0 - br.x0); k.py = (uint32_t)(oy + cy0 - br.y0);
-                    k.w = (uint32_t)(cx1 - cx0); k.h = (uint32_t)(cy1 - cy0);
-                    blks.push_back(k);
+        for (uint32_t r = 0; r <= nl; r++) {
+            const int64_t rs = (int64_t)1 << (nl - r);
+            const int64_t trx0 = cdiv64(x0, rs), try0 = cdiv64(y0, rs), trx1 = cdiv64(x1, rs), try1 = cdiv64(y1, rs);
+            if (trx1 <= trx0 || try1 <= try0) continue;
+            const uint32_t ppx = h.ppx[r], ppy = h.ppy[r];
+            const int64_t pw = (int64_t)1 << ppx, ph = (int64_t)1 << ppy;
+            const int64_t pxa0 = trx0 >> ppx, pya0 = try0 >> ppy, pxa1 = cdiv64(trx1, pw), pya1 = cdiv64(try1, ph);
+            if ((uint64_t)(pxa1 - pxa0) * (uint64_t)(pya1 - pya0) > 65536) { out.err.fail(J2KGPU_E_UNSUPPORTED, "tile %u: too many precincts", tidx); return; }
+            uint32_t pidx = 0;
+            for (int64_t pya = pya0; pya < pya1; pya++)
+                for (int64_t pxa = pxa0; pxa < pxa1; pxa++, pidx++) {
+                    Prec pr;
+                    pr.c = c; pr.r = r; pr.idx = pidx;
+                    pr.x = std::max(x0, pxa * pw * rs); pr.y = std::max(y0, pya * ph * rs);
+                    pr.nb = r ? 3 : 1;
+                    for (uint32_t k = 0; k < pr.nb; k++) {
+                        const size_t bi = r ? 1 + 3 * (r - 1) + k : 0;
+                        const BandId &b = bands[bi];
+                        PrecBand &pb = pr.pb[k];
+                        pb.first = (uint32_t)blks.size();
+                        const Rect br = band_rect(x0, y0, x1, y1, b.band, b.lvl);
+                        // the precinct in band coordinates (half the resolution's above resolution 0) and the block size it allows
+                        const uint32_t sx = r ? ppx - 1 : ppx, sy = r ? ppy - 1 : ppy;
+                        const int64_t cbw = std::min<int64_t>(h.cbw, (int64_t)1 << sx), cbh = std::min<int64_t>(h.cbh, (int64_t)1 << sy);
+                        const int64_t qx0 = std::max(br.x0, pxa << sx), qy0 = std::max(br.y0, pya << sy);
+                        const int64_t qx1 = std::min(br.x1, (pxa + 1) << sx), qy1 = std::min(br.y1, (pya + 1) << sy);
+                        if (qx1 > qx0 && qy1 > qy0) {
+                            const int64_t gx0 = qx0 / cbw, gy0 = qy0 / cbh, gx1 = cdiv64(qx1, cbw), gy1 = cdiv64(qy1, cbh);
+                            pb.gw = (uint32_t)(gx1 - gx0); pb.gh = (uint32_t)(gy1 - gy0);
+                            // origin of the band inside the Mallat plane: LL_lvl top-left, HL to the right, LH below
+                            const int64_t s = (int64_t)1 << b.lvl;
+                            const int64_t lw = cdiv64(x1, s) - cdiv64(x0, s), lh = cdiv64(y1, s) - cdiv64(y0, s);
+                            const int64_t ox = (b.band & 1) ? lw : 0, oy = (b.band >> 1) ? lh : 0;
+                            for (int64_t gy = gy0; gy < gy1; gy++)
+                                for (int64_t gx = gx0; gx < gx1; gx++) {
+                                    const int64_t cx0 = std::max(qx0, gx * cbw), cy0 = std::max(qy0, gy * cbh);
+                                    const int64_t cx1 = std::min(qx1, (gx + 1) * cbw), cy1 = std::min(qy1, (gy + 1) * cbh);
+                                    Blk k2;
+                                    k2.comp = c; k2.bidx = (uint32_t)bi;
+                                    k2.px = (uint32_t)(ox + cx0 - br.x0); k2.py = (uint32_t)(oy + cy0 - br.y0);
+                                    k2.w = (uint32_t)(cx1 - cx0); k2.h = (uint32_t)(cy1 - cy0);
+                                    blks.push_back(k2);
+                                }
+                        }
+                        pb.count = (uint32_t)blks.size() - pb.first;
+                        pb.incl.init(pb.gw, pb.gh); pb.imsb.init(pb.gw, pb.gh);
+                    }
+                    precs.push_back(std::move(pr));
                 }
-            st.count = (uint32_t)blks.size() - st.first;
-            st.incl.init(st.gw, st.gh); st.imsb.init(st.gw, st.gh);
         }
-    // packet sequence: one precinct per resolution, so the position loops of RPCL / PCRL / CPRL collapse
-    struct Pk { uint32_t l, r, c; };
+    // packet sequence (B.12): one packet per layer, resolution, component and precinct; the position-driven orders visit a
+    // precinct when the scan over the reference grid reaches its top-left corner, i.e. in the order of (y, x)
+    struct Pk { uint32_t l, pi; };
     std::vector<Pk> order;
-    order.reserve((size_t)h.layers * (nl + 1) * nc);
-    auto push = [&](uint32_t l, uint32_t r, uint32_t c) { order.push_back({l, r, c}); };
-    switch (h.prog) {
-    case 0: for (uint32_t l = 0; l < h.layers; l++) for (uint32_t r = 0; r <= nl; r++) for (uint32_t c = 0; c < nc; c++) push(l, r, c); break;
-    case 1: for (uint32_t r = 0; r <= nl; r++) for (uint32_t l = 0; l < h.layers; l++) for (uint32_t c = 0; c < nc; c++) push(l, r, c); break;
-    case 2: for (uint32_t r = 0; r <= nl; r++) for (uint32_t c = 0; c < nc; c++) for (uint32_t l = 0; l < h.layers; l++) push(l, r, c); break;
-    default: for (uint32_t c = 0; c < nc; c++) for (uint32_t r = 0; r <= nl; r++) for (uint32_t l = 0; l < h.layers; l++) push(l, r, c); break;
-    }
+    order.reserve((size_t)h.layers * precs.size());
+    for (uint32_t l = 0; l < h.layers; l++)
+        for (uint32_t i = 0; i < precs.size(); i++) order.push_back({l, i});
+    auto key = [&](const Pk &k, int64_t out5[5]) {
+        const Prec &q = precs[k.pi];
+        switch (h.prog) {
+        case 0: out5[0] = k.l; out5[1] = q.r; out5[2] = q.c; out5[3] = q.idx; out5[4] = 0; break;            // LRCP
+        case 1: out5[0] = q.r; out5[1] = k.l; out5[2] = q.c; out5[3] = q.idx; out5[4] = 0; break;            // RLCP
+        case 2: out5[0] = q.r; out5[1] = q.y; out5[2] = q.x; out5[3] = q.c; out5[4] = k.l; break;            // RPCL
+        case 3: out5[0] = q.y; out5[1] = q.x; out5[2] = q.c; out5[3] = q.r; out5[4] = k.l; break;            // PCRL
+        default: out5[0] = q.c; out5[1] = q.y; out5[2] = q.x; out5[3] = q.r; out5[4] = k.l; break;           // CPRL
+        }
+    };
+    std::stable_sort(order.begin(), order.end(), [&](const Pk &a2, const Pk &b2) {
+        int64_t ka[5], kb[5];
+        key(a2, ka); key(b2, kb);
+        for (int i = 0; i < 5; i++) if (ka[i] != kb[i]) return ka[i] < kb[i];
+        return false;
+    });
     size_t p = 0;
     std::vector<std::pair<uint32_t, uint32_t>> segs;   // (block, length) of this packet
     struct Undo { uint32_t blk, passes, zbp, lblock, lcup; bool included; };
@@ -243,9 +290,9 @@ void parse_tile(const uint8_t *cs, const Header &h, uint32_t tidx, const std::ve
         segs.clear();
         undo.clear();
         if (br.get()) {
-            for (size_t bi = 0; bi < bands.size(); bi++) {
-                if (bands[bi].res != pk.r) continue;
-                BandState &st = bst[pk.c * bands.size() + bi];
+            Prec &pq = precs[pk.pi];
+            for (uint32_t kb = 0; kb < pq.nb; kb++) {
+                PrecBand &st = pq.pb[kb];
                 for (uint32_t k = 0; k < st.count; k++) {
                     Blk &e = blks[st.first + k];
                     const uint32_t gx = k % st.gw, gy = k / st.gw;
@@ -327,39 +374,34 @@ void parse_tile(const uint8_t *cs, const Header &h, uint32_t tidx, const std::ve
         out.tcs.push_back(tc);
     }
     static const int gain[4] = {0, 1, 1, 2};
-    for (uint32_t c = 0; c < nc; c++)
-        for (size_t bi = 0; bi < bands.size(); bi++) {
-            const BandId &b = bands[bi];
-            if (b.res > nl - reduce) continue;             // ReduceResolution: the finest resolutions are not handed over
-            const BandState &st = bst[c * bands.size() + bi];
-            const uint32_t expn = h.q[bi].first, mant = h.q[bi].second;
-            const int mb = (int)h.guard + (int)expn - 1;
-            for (uint32_t k = 0; k < st.count; k++) {
-                const Blk &e = blks[st.first + k];
-                j2k_cblk_t cb{};
-                cb.tilecomp = c; cb.x0 = (uint16_t)e.px; cb.y0 = (uint16_t)e.py; cb.w = (uint16_t)e.w; cb.h = (uint16_t)e.h;
-                cb.band = (uint8_t)b.band; cb.level = (uint8_t)(b.lvl > reduce ? b.lvl - reduce : 0);
-                // Annex E.1: step = 2^(Rb - eps) * (1 + mu / 2^11), Rb = precision + band gain
-                cb.step = h.reversible ? 1.0f : (float)(std::ldexp(1.0, (int)h.prec + gain[b.band] - (int)expn) * (1.0 + mant / 2048.0));
-                const int nb = mb - (int)e.zbp;
-                uint32_t total = e.len;
-                for (auto &m : e.more) total += m.second;
-                if (!e.passes || nb <= 0 || total == 0) { cb.num_bps = 0; cb.num_passes = 0; cb.data_len = 0; cb.data_off = 0; out.is_extra.push_back(0); out.cbs.push_back(cb); continue; }
-                if (nb > 31) { out.err.fail(J2KGPU_E_UNSUPPORTED, "tile %u: %d magnitude bit-planes", tidx, nb); return; }
-                cb.num_bps = (uint8_t)nb;
-                cb.num_passes = (uint8_t)std::min<uint32_t>(e.passes, 255);
-                cb.data_len = total;
-                cb.len_cleanup = (h.ht && e.passes > 1) ? e.lcup : 0;
-                if (e.more.empty() && abs_off >= 0) { cb.data_off = (uint64_t)abs_off + e.off; out.is_extra.push_back(0); }
-                else {
-                    cb.data_off = out.extra.size();
-                    out.extra.insert(out.extra.end(), body + e.off, body + e.off + e.len);
-                    for (auto &m : e.more) out.extra.insert(out.extra.end(), body + m.first, body + m.first + m.second);
-                    out.is_extra.push_back(1);
-                }
-                out.cbs.push_back(cb);
-            }
+    for (const Blk &e : blks) {
+        const BandId &b = bands[e.bidx];
+        if (b.res > nl - reduce) continue;                 // ReduceResolution: the finest resolutions are not handed over
+        const uint32_t expn = h.q[e.bidx].first, mant = h.q[e.bidx].second;
+        const int mb = (int)h.guard + (int)expn - 1;
+        j2k_cblk_t cb{};
+        cb.tilecomp = e.comp; cb.x0 = (uint16_t)e.px; cb.y0 = (uint16_t)e.py; cb.w = (uint16_t)e.w; cb.h = (uint16_t)e.h;
+        cb.band = (uint8_t)b.band; cb.level = (uint8_t)(b.lvl > reduce ? b.lvl - reduce : 0);
+        // Annex E.1: step = 2^(Rb - eps) * (1 + mu / 2^11), Rb = precision + band gain
+        cb.step = h.reversible ? 1.0f : (float)(std::ldexp(1.0, (int)h.prec + gain[b.band] - (int)expn) * (1.0 + mant / 2048.0));
+        const int nb = mb - (int)e.zbp;
+        uint32_t total = e.len;
+        for (auto &m : e.more) total += m.second;
+        if (!e.passes || nb <= 0 || total == 0) { cb.num_bps = 0; cb.num_passes = 0; cb.data_len = 0; cb.data_off = 0; out.is_extra.push_back(0); out.cbs.push_back(cb); continue; }
+        if (nb > 31) { out.err.fail(J2KGPU_E_UNSUPPORTED, "tile %u: %d magnitude bit-planes", tidx, nb); return; }
+        cb.num_bps = (uint8_t)nb;
+        cb.num_passes = (uint8_t)std::min<uint32_t>(e.passes, 255);
+        cb.data_len = total;
+        cb.len_cleanup = (h.ht && e.passes > 1) ? e.lcup : 0;
+        if (e.more.empty() && abs_off >= 0) { cb.data_off = (uint64_t)abs_off + e.off; out.is_extra.push_back(0); }
+        else {
+            cb.data_off = out.extra.size();
+            out.extra.insert(out.extra.end(), body + e.off, body + e.off + e.len);
+            for (auto &m : e.more) out.extra.insert(out.extra.end(), body + m.first, body + m.first + m.second);
+            out.is_extra.push_back(1);
         }
+        out.cbs.push_back(cb);
+    }
 }
 
 inline uint32_t be16(const uint8_t *p) { return ((uint32_t)p[0] << 8) | p[1]; }
@@ -403,7 +445,6 @@ int j2k_tier2_parse(const uint8_t *d, uint64_t len, uint32_t reduce, uint32_t th
         } else if (m == COD) {                            // readCOD parser.go:288-370
             if (sl < 10) T2_FAIL(J2KGPU_E_RANGE, "COD too short");
             const uint32_t scod = seg[0];
-            if (scod & 1) T2_FAIL(J2KGPU_E_UNSUPPORTED, "user-defined precincts");
             h.sop = (scod >> 1) & 1; h.eph = (scod >> 2) & 1;
             h.prog = seg[1]; h.layers = be16(seg + 2); h.mct = seg[4]; h.nlevels = seg[5];
             h.cbw = 1u << (seg[6] + 2); h.cbh = 1u << (seg[7] + 2); h.style = seg[8]; h.reversible = seg[9] == 1;
@@ -412,6 +453,14 @@ int j2k_tier2_parse(const uint8_t *d, uint64_t len, uint32_t reduce, uint32_t th
             if (h.cbw > 64 || h.cbh > 64 || h.cbw * h.cbh > 4096) T2_FAIL(J2KGPU_E_UNSUPPORTED, "code blocks %ux%u", h.cbw, h.cbh);
             if (h.style & ~0x40u) T2_FAIL(J2KGPU_E_UNSUPPORTED, "code-block style %02X (bypass / reset / termination / causal / segmentation symbols)", h.style);
             if (!h.layers) T2_FAIL(J2KGPU_E_RANGE, "zero quality layers");
+            for (uint32_t r = 0; r <= 32; r++) h.ppx[r] = h.ppy[r] = 15;
+            if (scod & 1) {                               // user-defined precincts: one byte per resolution, PPx | PPy << 4 (A.6.1)
+                if (sl < 10 + h.nlevels + 1) T2_FAIL(J2KGPU_E_RANGE, "COD too short for its precinct sizes");
+                for (uint32_t r = 0; r <= h.nlevels; r++) {
+                    h.ppx[r] = seg[10 + r] & 15; h.ppy[r] = seg[10 + r] >> 4;
+                    if (r && (h.ppx[r] == 0 || h.ppy[r] == 0)) T2_FAIL(J2KGPU_E_RANGE, "precinct size 1 above resolution 0");
+                }
+            }
             h.have_cod = true;
         } else if (m == CAP) {
             h.ht = 1;                                     // Part 15 capability (Header.IsHTJ2K header.go:241-257)

@@ -40,6 +40,9 @@ def pixels(got, h, w, nc):
     (256, 192, 3, dict(num_resolutions=4, mct=1, progression="RPCL", quality_layers=[20, 5, 1])),
     (256, 192, 3, dict(num_resolutions=4, mct=1, progression="CPRL", quality_layers=[20, 1], tile_size=(128, 64))),
     (200, 150, 3, dict(num_resolutions=4, mct=1, plt=True, tile_size=(64, 64))),
+    (333, 211, 3, dict(num_resolutions=5, mct=1, precinct_size=(128, 128), quality_layers=[20, 5, 1])),                       # user-defined precincts
+    (333, 211, 3, dict(num_resolutions=4, mct=1, precinct_size=(64, 32), progression="PCRL", tile_size=(128, 128), quality_layers=[20, 1])),
+    (300, 200, 3, dict(num_resolutions=4, mct=1, precinct_size=(64, 64), irreversible=True, progression="RPCL", quality_layers=[30, 10])),
 ])
 def test_openjpeg_codestream_in_pixels_out(j2k, gpu_ctx, w, h, nc, kw):
     s = jobs.synth_image(w, h, nc, 8, seed=w + 1)

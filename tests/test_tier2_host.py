@@ -186,11 +186,48 @@ def test_plt_and_tlm_disagreements_are_errors(j2k):
     assert "TLM" in str(e.value)
 
 
+PRECINCT_CASES = [
+    dict(w=256, h=192, nc=3, kw=dict(num_resolutions=4, mct=1, precinct_size=(64, 64))),
+    dict(w=333, h=211, nc=3, kw=dict(num_resolutions=5, mct=1, precinct_size=(128, 128), quality_layers=[20, 5, 1])),
+    dict(w=333, h=211, nc=3, kw=dict(num_resolutions=4, mct=1, precinct_size=(64, 128), tile_size=(128, 128), quality_layers=[10, 1])),
+    dict(w=256, h=256, nc=1, kw=dict(num_resolutions=6, precinct_size=(64, 64), codeblock_size=(32, 32))),
+    dict(w=200, h=150, nc=3, kw=dict(num_resolutions=3, mct=1, precinct_size=(32, 32), codeblock_size=(16, 16))),
+    dict(w=300, h=200, nc=3, kw=dict(num_resolutions=4, mct=1, precinct_size=(64, 64), irreversible=True, quality_layers=[30, 10])),
+    dict(w=256, h=192, nc=3, kw=dict(num_resolutions=4, mct=1, precinct_size=(64, 64), progression="RLCP", quality_layers=[20, 1])),
+    dict(w=256, h=192, nc=3, kw=dict(num_resolutions=4, mct=1, precinct_size=(64, 64), progression="RPCL", quality_layers=[20, 1])),
+    dict(w=333, h=211, nc=3, kw=dict(num_resolutions=4, mct=1, precinct_size=(64, 32), progression="PCRL", quality_layers=[20, 1])),
+    dict(w=333, h=211, nc=3, kw=dict(num_resolutions=5, mct=1, precinct_size=(32, 64), progression="CPRL", tile_size=(128, 128))),
+    dict(w=256, h=192, nc=3, kw=dict(num_resolutions=4, mct=1, precinct_size=(128, 128), progression="RPCL", plt=True)),
+]
+
+
+@pytest.mark.parametrize("case", PRECINCT_CASES, ids=lambda c: "%dx%dx%d-%s" % (c["w"], c["h"], c["nc"], "-".join(
+    "%s" % (v if not isinstance(v, (list, tuple)) else "x".join(map(str, v))) for v in c["kw"].values())))
+def test_user_defined_precincts(j2k, case):
+    """COD with precinct sizes (A.6.1, B.6): blocks are cut by the precinct grid, every precinct-band has its own tag trees,
+    a layer has one packet per precinct, and the position-driven progressions visit precincts by their reference-grid
+    corner -- the tables decode (CPU checker) to OpenJPEG's pixels of the same bytes"""
+    s = jobs.synth_image(case["w"], case["h"], case["nc"], 8, seed=case["w"] + 7)
+    data = opj_encode(s, **case["kw"])
+    p = j2k.Parsed(data)
+    assert p.info["packets"] > p.info["layers"] * (case["kw"]["num_resolutions"]) * case["nc"] * p.info["tiles"]   # more than one precinct somewhere
+    if case["kw"].get("plt"):
+        assert p.info["plt_packets"] == p.info["packets"]
+    mine = job_from_parsed(p, data)
+    got = O.iso_decode_job(mine).reshape(case["h"], case["w"], -1)[:, :, :case["nc"]]
+    assert np.array_equal(got, opj_decode(data).reshape(case["h"], case["w"], case["nc"]))
+    if not case["kw"].get("irreversible") and len(case["kw"].get("quality_layers", [1])) == 1:
+        assert np.array_equal(got, np.moveaxis(s, 0, 2).reshape(case["h"], case["w"], case["nc"]))
+
+
 def test_unsupported_features_are_reported(j2k):
     s = jobs.synth_image(128, 128, 3, 8, seed=3)
+    good = opj_encode(s, num_resolutions=3, mct=1)
+    i = good.index(b"\xff\x5c")                                   # a COC marker segment in front of QCD: component-specific coding style
+    coc = b"\xff\x53" + (9).to_bytes(2, "big") + bytes([0, 0, 2, 4, 4, 0, 1])
     with pytest.raises(j2k.J2KError) as e:
-        j2k.Parsed(opj_encode(s, num_resolutions=3, precinct_size=(64, 64)))
-    assert e.value.code == j2k.E_UNSUPPORTED and "precinct" in str(e.value)
+        j2k.Parsed(good[:i] + coc + good[i:])
+    assert e.value.code == j2k.E_UNSUPPORTED and "FF53" in str(e.value)
     with pytest.raises(j2k.J2KError) as e:
         j2k.Parsed(b"\x00\x01\x02\x03")
     assert e.value.code == j2k.E_ARG
