@@ -97,8 +97,9 @@ def test_errors_surface_and_the_context_survives(j2k, gpu_ctx):
     with pytest.raises(j2k.J2KError) as e:
         gpu_ctx.decode_codestreams([good, bytes(bad)])
     assert "codestream 1" in str(e.value)
+    i = good.index(b"\xff\x5c")                                   # a COC marker segment (component-specific coding style) is not handled
     with pytest.raises(j2k.J2KError) as e:
-        gpu_ctx.decode_codestream(opj_encode(s, num_resolutions=3, precinct_size=(64, 64)))
+        gpu_ctx.decode_codestream(good[:i] + b"\xff\x53" + (9).to_bytes(2, "big") + bytes([0, 0, 2, 4, 4, 0, 1]) + good[i:])
     assert e.value.code == j2k.E_UNSUPPORTED
     trunc = good[: len(good) * 2 // 3]                             # truncated: remaining packets absent, still decodes
     gpu_ctx.decode_codestream(trunc)
