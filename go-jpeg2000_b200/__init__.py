@@ -421,6 +421,9 @@ class Parsed:
 def siz_of(data, reduce=0):
     """(width, height, ncomp, precision) from the SIZ marker segment, which directly follows SOC (A.5.1); reduce as in Parsed"""
     d = bytes(data[:64])
+    if d[4:8] == b"jP  ":                              # a JP2 file: the codestream sits in its jp2c box
+        i = bytes(data).find(b"jp2c\xff\x4f\xff\x51")
+        d = bytes(data[i + 4:i + 68]) if i >= 0 else b""
     if len(d) < 43 or d[:4] != b"\xff\x4f\xff\x51":
         raise J2KError(E_ARG, "not a codestream (no SOC + SIZ)")
     be = lambda o, n: int.from_bytes(d[o:o + n], "big")

@@ -414,6 +414,22 @@ int j2k_tier2_parse(const uint8_t *d, uint64_t len, uint32_t reduce, uint32_t th
     Err err;
     Header h;
 #define T2_FAIL(...) do { err.fail(__VA_ARGS__); out.err = err.msg; return err.code; } while (0)
+    // a JP2 file (ISO/IEC 15444-1 Annex I: signature box first): walk the top-level boxes to the contiguous codestream box.
+    // Everything else in the container (colour specification, palette, resolution ...) stays with the caller (box.go).
+    if (d && len >= 12 && be32(d) == 12 && be32(d + 4) == 0x6A502020u) {
+        uint64_t bp = 0;
+        bool found = false;
+        while (bp + 8 <= len) {
+            uint64_t bl = be32(d + bp), hl = 8;
+            const uint32_t bt = be32(d + bp + 4);
+            if (bl == 1) { if (bp + 16 > len) break; bl = ((uint64_t)be32(d + bp + 8) << 32) | be32(d + bp + 12); hl = 16; }
+            else if (bl == 0) bl = len - bp;              // the box runs to the end of the file
+            if (bl < hl || bl > len - bp) break;
+            if (bt == 0x6A703263u) { d += bp + hl; len = bl - hl; found = true; break; }   // 'jp2c'
+            bp += bl;
+        }
+        if (!found) T2_FAIL(J2KGPU_E_RANGE, "JP2 file without a codestream box");
+    }
     if (!d || len < 4 || be16(d) != SOC) T2_FAIL(J2KGPU_E_ARG, "not a codestream (no SOC)");
     uint64_t pos = 2;
     std::vector<uint32_t> tlm;                          // tile-part lengths announced by TLM, in codestream order

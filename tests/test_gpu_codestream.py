@@ -89,6 +89,16 @@ def test_page_locked_output_and_gray16(j2k, gpu_ctx):
         gpu_ctx.host_free(out)
 
 
+def test_jp2_file_and_alpha(j2k, gpu_ctx):
+    """a JP2 file (container + RGBA codestream) straight into the front door"""
+    s = jobs.synth_image(200, 150, 4, 8, seed=5)
+    buf = io.BytesIO()
+    PIL_Image.fromarray(np.moveaxis(s, 0, 2).astype(np.uint8), "RGBA").save(buf, format="JPEG2000", num_resolutions=4)
+    data = buf.getvalue()
+    assert data[4:8] == b"jP  "
+    assert np.array_equal(gpu_ctx.decode_codestream(data).reshape(150, 200, 4), np.moveaxis(s, 0, 2))
+
+
 def test_errors_surface_and_the_context_survives(j2k, gpu_ctx):
     s = jobs.synth_image(128, 128, 3, 8, seed=8)
     good = opj_encode(s, num_resolutions=3, mct=1)

@@ -220,6 +220,24 @@ def test_user_defined_precincts(j2k, case):
         assert np.array_equal(got, np.moveaxis(s, 0, 2).reshape(case["h"], case["w"], case["nc"]))
 
 
+def test_jp2_container_and_rgba(j2k):
+    """a JP2 file is accepted as it is (the codestream box is located; the other boxes stay with the Go side), and a fourth
+    component becomes the alpha channel as in createImage (decoder.go:489-523)"""
+    s = jobs.synth_image(200, 150, 4, 8, seed=5)
+    for no_jp2 in (True, False):
+        buf = io.BytesIO()
+        PIL_Image.fromarray(np.moveaxis(s, 0, 2).astype(np.uint8), "RGBA").save(buf, format="JPEG2000", no_jp2=no_jp2, num_resolutions=4)
+        data = buf.getvalue()
+        assert (data[4:8] == b"jP  ") == (not no_jp2)
+        p = j2k.Parsed(data)
+        assert p.image.ncomp == 4 and p.info["zero_copy"] == 1
+        got = O.iso_decode_job(job_from_parsed(p, data)).reshape(150, 200, 4)
+        assert np.array_equal(got, np.moveaxis(s, 0, 2)) and np.array_equal(got, opj_decode(data))
+    with pytest.raises(j2k.J2KError) as e:
+        j2k.Parsed(data[:40])                                      # signature + file type boxes only
+    assert "codestream box" in str(e.value)
+
+
 def test_unsupported_features_are_reported(j2k):
     s = jobs.synth_image(128, 128, 3, 8, seed=3)
     good = opj_encode(s, num_resolutions=3, mct=1)
