@@ -139,7 +139,7 @@ __device__ __forceinline__ void t1_flush_plane(uint64_t *plane, OT *out, uint32_
 // loops over rows, candidate columns and the MQ routine, so the chains of a warp walk the same code and mostly meet --
 // and the group's lanes share the parallel parts (clearing state, assembling magnitudes, stores).
 template <typename OT, int G>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 6)
 k_t1_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob,
          OT *__restrict__ coef, int skip_empty)
 {
@@ -224,11 +224,21 @@ k_t1_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
             const uint64_t nbm = up | (up << 1) | (up >> 1) | dn | (dn << 1) | (dn >> 1) | (mid << 1) | (mid >> 1);
             uint64_t bits = 0;
             refine[y] = ref | cand;
-            while (cand) {
-                int x = __ffsll((long long)cand) - 1;
-                cand &= cand - 1;
-                const int ctx = kCtxMag + (((ref >> x) & 1) ? 2 : (int)((nbm >> x) & 1));
-                if (mq_decode(mq, ctxs, ctx)) bits |= 1ull << x;
+            // the masks are fixed during the loop: walk the row as two 32-bit halves (64-bit find-first-set, clear-lowest and
+            // variable shifts cost twice the instructions)
+#pragma unroll 1
+            for (int half = 0; half < 2; half++) {
+                uint32_t c32 = (uint32_t)(cand >> (32 * half));
+                if (!c32) continue;
+                const uint32_t r32 = (uint32_t)(ref >> (32 * half)), n32 = (uint32_t)(nbm >> (32 * half));
+                uint32_t b32 = 0;
+                while (c32) {
+                    const int x = __ffs((int)c32) - 1;
+                    c32 &= c32 - 1;
+                    const int ctx = kCtxMag + (((r32 >> x) & 1) ? 2 : (int)((n32 >> x) & 1));
+                    if (mq_decode(mq, ctxs, ctx)) b32 |= 1u << x;
+                }
+                bits |= (uint64_t)b32 << (32 * half);
             }
             if (bits) plane[y] |= bits;
         }
