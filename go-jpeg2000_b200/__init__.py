@@ -229,7 +229,7 @@ class Context:
 
             def __exit__(self_, *a):
                 for k in kw:
-                    ctx.set_option(k, "" if k == "chunks" else "0")
+                    ctx.set_option(k, "" if k == "chunks" else ("-1" if k == "host_alpha" else "0"))
         return _Scope()
 
     # ---- page-locked host memory (j2kgpu_host_*) ----------------------------------------------

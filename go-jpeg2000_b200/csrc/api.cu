@@ -221,6 +221,7 @@ static int set_option(J2kOpts &o, const char *name, const char *value)
     else if (k == "no_preclear") o.no_preclear = on;
     else if (k == "wide_sp") o.wide_sp = iv;
     else if (k == "t1_group") o.t1_group = iv;
+    else if (k == "host_alpha") o.host_alpha = iv;
     else if (k == "debug_plan") o.debug_plan = on;
     else if (k == "chunks") o.chunks = v;
     else return J2KGPU_E_ARG;
@@ -239,7 +240,7 @@ extern "C" int j2kgpu_create(int device, j2kgpu_ctx **out)
     if (!ctx) return J2KGPU_E_NOMEM;
     ctx->device = device;
     // the environment is read here, once per context, and nowhere else
-    static const char *const names[] = {"no_fuse", "no_wide", "no_fast_epi", "coef32", "no_preclear", "wide_sp", "t1_group", "debug_plan", "chunks"};
+    static const char *const names[] = {"no_fuse", "no_wide", "no_fast_epi", "coef32", "no_preclear", "wide_sp", "t1_group", "host_alpha", "debug_plan", "chunks"};
     for (const char *nm : names) {
         std::string env = "J2KGPU_";
         for (const char *c = nm; *c; c++) env += (char)toupper((unsigned char)*c);
@@ -273,6 +274,8 @@ extern "C" void j2kgpu_destroy(j2kgpu_ctx *ctx)
     ctx->pool.clear();
     for (auto &b : ctx->hpool) cudaFreeHost(b.p);
     ctx->hpool.clear();
+    delete ctx->expand;
+    ctx->expand = nullptr;
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     ctx->events.clear();
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
@@ -315,6 +318,7 @@ static void job_free(j2kgpu_job *job)
         for (cudaEvent_t e : job->ev_in) if (e) job->ctx->events.push_back(e);
         for (cudaEvent_t e : job->ev_done) if (e) job->ctx->events.push_back(e);
         if (job->h_tables) j2k_hpool_free(job->ctx, job->h_tables, job->h_tables_cap);
+        if (job->h_rgb) j2k_hpool_free(job->ctx, job->h_rgb, job->h_rgb_cap);
     }
     if (job->h_blob) cudaFreeHost(job->h_blob);
     if (job->h_pix) cudaFreeHost(job->h_pix);
@@ -567,6 +571,10 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
     }
     job->wide_ok = job->fast_epi && fused_ok && (tp.ncomp == 3 || tp.ncomp == 1) && !opt.no_wide;
     for (size_t i = 0; i < tiles.size(); i++) if ((tiles[i].w & 15) || (tp.ncomp == 1 && (tiles[i].img_x0 & 15))) job->wide_ok = 0;   // 16-byte stores per lane
+    // packed-RGB transfer (rgb_expand.h): the 16-columns-per-lane kernel writes the pixels of every tile, rows of 16 pixels are
+    // 48 aligned bytes in the packed layout, and nothing else (pre-fill of uncovered pixels) writes the pixel buffer
+    job->rgb24_ok = job->wide_ok && job->fused_ok && tp.ncomp == 3 && tp.fmt == J2KGPU_FMT_RGBA8 && !job->pix_fill;
+    for (size_t i = 0; i < tiles.size(); i++) if ((tiles[i].img_x0 & 15) || (tiles[i].out_stride & 63)) job->rgb24_ok = 0;
     job->coef_elems = coef_elems; job->blob_bytes = blob_bytes; job->out_bytes = out_bytes; job->max_bps = max_bps;
     job->tmp_bytes = tmp_elems * ((hdr.reversible || iso) ? 4 : 8);     // int32 (5-3), float32 (ISO 9-7), float64 (REF 9-7)
     job->need_clear = need_clear;                        // some plane is not tiled exactly by its blocks
@@ -673,6 +681,7 @@ static void fill_launch(const j2kgpu_job *job, IdwtLaunch &p, void *d_out, uint3
     p.max_w = job->max_w; p.max_h = job->max_h; p.reversible = job->hdr.reversible != 0; p.f64_io = 0;
     p.d_plane_out = nullptr; p.d_pix = (uint8_t *)d_out; p.tail = job->tail; p.stream_levels = job->stream_levels; p.iso = job->iso;
     p.wide_sp = job->ctx->opt.wide_sp;
+    p.rgb24 = job->rgb24;
 }
 
 // one level of the reconstruction; with the fused kernel, level 1 is part of the level-0 launch
@@ -814,6 +823,58 @@ static std::vector<uint32_t> plan_chunks(const j2kgpu_ctx *ctx, uint32_t n, cons
     return cuts;
 }
 
+// ---- packed-RGB transfer of host-buffer runs (host/rgb_expand.h) ---------------------------------------------------------
+static bool rgb24_wanted(const j2kgpu_ctx *ctx)
+{
+    if (ctx->opt.host_alpha >= 0) return ctx->opt.host_alpha != 0;
+    int ndev = 1;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) ndev = 1;
+    return std::thread::hardware_concurrency() / (unsigned)ndev >= 8;    // the widening needs host cores: eight per GPU or more
+}
+
+// decides whether this host-buffer run of `job` moves packed RGB, and prepares the staging block and the worker threads
+static int rgb24_begin(j2kgpu_job *job, const j2k_batch_item_t *items, uint32_t n)
+{
+    j2kgpu_ctx *ctx = job->ctx;
+    job->rgb24 = 0;
+    job->rgb_tasks.clear();
+    if (!job->rgb24_ok || !rgb24_wanted(ctx)) return J2KGPU_OK;
+    for (uint32_t i = 0; i < n; i++) if (items[i].flags & J2KGPU_ITEM_TILES_ONLY) return J2KGPU_OK;
+    uint64_t tot = 0;
+    job->rgb_off.resize(n);
+    for (uint32_t i = 0; i < n; i++) { job->rgb_off[i] = tot; tot = align_up(tot + (uint64_t)job->img_h[i] * (job->out_stride[i] / 4 * 3), 256); }
+    if (!job->h_rgb || job->h_rgb_cap < tot) {
+        if (job->h_rgb) j2k_hpool_free(ctx, job->h_rgb, job->h_rgb_cap);
+        cudaError_t e = cudaSuccess;
+        job->h_rgb = j2k_hpool_alloc(ctx, tot, &job->h_rgb_cap, &e);
+        if (e != cudaSuccess) { job->h_rgb = nullptr; return j2k_cuda_err(ctx, e, "packed-RGB staging"); }
+    }
+    if (!ctx->expand) ctx->expand = new (std::nothrow) J2kExpandPool();
+    if (!ctx->expand) return J2KGPU_OK;                  // (no pool: plain RGBA transfer)
+    int ndev = 1;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) ndev = 1;
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency()) / (unsigned)ndev;
+    ctx->expand->start(std::min(8u, std::max(2u, hw / 2)));
+    job->rgb24 = 1;
+    if (ctx->opt.debug_plan) fprintf(stderr, "j2kgpu packed-RGB transfer: %u image(s), %u host thread(s)\n", n, ctx->expand->threads());
+    return J2KGPU_OK;
+}
+
+static void CUDART_CB rgb24_callback(void *ud)
+{
+    J2kRgbCb *cb = static_cast<J2kRgbCb *>(ud);
+    cb->pool->submit(cb->t);
+}
+
+// after the copy-out stream has drained: every row has been widened; the job returns to plain RGBA
+static void rgb24_end(j2kgpu_job *job)
+{
+    if (!job->rgb24) return;
+    job->ctx->expand->wait_idle();
+    job->rgb24 = 0;
+    job->rgb_tasks.clear();
+}
+
 // pixels of item i (job numbering) back to the caller.  Rows go without their padding (the bytes between width * bpp and
 // out_stride belong to the caller and are left alone).  J2KGPU_ITEM_TILES_ONLY: only the rectangles this item's tiles
 // cover are copied, so that several contexts (GPUs) given disjoint tile subsets of ONE image fill one host buffer.
@@ -823,6 +884,14 @@ static int copy_out_item(j2kgpu_job *job, uint32_t i, const j2k_batch_item_t &it
     const uint8_t *src = (const uint8_t *)job->d_pix + job->out_off[i];
     const uint64_t stride = job->out_stride[i];
     const uint32_t rb = job->row_bytes[i];
+    if (job->rgb24) {                                    // packed rows into the staging block, widened by the pool once they are there
+        const uint64_t s3 = stride / 4 * 3;
+        uint8_t *stage = (uint8_t *)job->h_rgb + job->rgb_off[i];
+        J2K_CUDA(ctx, cudaMemcpyAsync(stage, src, (size_t)job->img_h[i] * s3, cudaMemcpyDeviceToHost, st));
+        job->rgb_tasks.push_back(J2kRgbCb{ctx->expand, J2kExpandTask{stage, it.out_pix, s3, it.out_stride, rb / 4, job->img_h[i]}});
+        J2K_CUDA(ctx, cudaLaunchHostFunc(st, rgb24_callback, &job->rgb_tasks.back()));
+        return J2KGPU_OK;
+    }
     if (!(it.flags & J2KGPU_ITEM_TILES_ONLY)) {
         if (stride == rb) J2K_CUDA(ctx, cudaMemcpyAsync(it.out_pix, src, job->out_size[i], cudaMemcpyDeviceToHost, st));
         else J2K_CUDA(ctx, cudaMemcpy2DAsync(it.out_pix, stride, src, stride, rb, job->img_h[i], cudaMemcpyDeviceToHost, st));
@@ -856,10 +925,9 @@ static int copy_out_item(j2kgpu_job *job, uint32_t i, const j2k_batch_item_t &it
 // the copy-in stream, its kernels on the ctx stream and its device->host copy on the copy-out stream, chained by events,
 // so that the PCIe transfers of neighbouring chunks overlap the kernels (the two copy engines work in both directions
 // at once).  A single-item batch degenerates to copy, compute, copy.
-static int run_host_locked(j2kgpu_job *job, const j2k_batch_item_t *items)
+static int run_host_body(j2kgpu_job *job, const j2k_batch_item_t *items)
 {
     j2kgpu_ctx *ctx = job->ctx;
-    cudaSetDevice(ctx->device);
     cudaError_t pe = cudaSuccess;
     if (!job->d_blob) { job->d_blob = j2k_pool_alloc(ctx, job->blob_bytes + 64, &pe); if (pe != cudaSuccess) return j2k_cuda_err(ctx, pe, "blob staging"); }
     if (!job->d_pix) { job->d_pix = j2k_pool_alloc(ctx, job->out_bytes, &pe); if (pe != cudaSuccess) return j2k_cuda_err(ctx, pe, "pixel staging"); }
@@ -905,6 +973,19 @@ static int run_host_locked(j2kgpu_job *job, const j2k_batch_item_t *items)
     J2K_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
     J2K_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return J2KGPU_OK;
+}
+
+static int run_host_locked(j2kgpu_job *job, const j2k_batch_item_t *items)
+{
+    j2kgpu_ctx *ctx = job->ctx;
+    cudaSetDevice(ctx->device);
+    int rc = rgb24_begin(job, items, job->n_img);
+    if (rc == J2KGPU_OK) rc = run_host_body(job, items);
+    if (job->rgb24) {                                    // also after an error: no callback may outlive the run
+        if (ctx->s_out) cudaStreamSynchronize(ctx->s_out);
+        rgb24_end(job);
+    }
+    return rc;
 }
 
 extern "C" int j2kgpu_job_run_host(j2kgpu_job *job, const j2k_batch_item_t *items)
@@ -986,6 +1067,7 @@ static int pipe_submit(BatchPipe &bp, const j2k_batch_item_t *its, uint32_t n)
     j2kgpu_job *job = nullptr;
     if ((bp.rc = job_build(ctx, n, its, &job, ctx->s_in))) return bp.rc;
     bp.jobs.push_back(job);
+    if ((bp.rc = rgb24_begin(job, its, n))) return bp.rc;
     cudaError_t ce = cudaSuccess;
     job->d_blob = j2k_pool_alloc(ctx, job->blob_bytes + 64, &ce);
     if (ce == cudaSuccess) job->d_pix = j2k_pool_alloc(ctx, job->out_bytes, &ce);
@@ -1017,7 +1099,7 @@ static int pipe_finish(BatchPipe &bp)
     j2kgpu_ctx *ctx = bp.ctx;
     if (ctx->s_in) cudaStreamSynchronize(ctx->s_in);
     cudaError_t e1 = cudaStreamSynchronize(ctx->stream), e2 = ctx->s_out ? cudaStreamSynchronize(ctx->s_out) : cudaSuccess;
-    for (j2kgpu_job *j : bp.jobs) job_free(j);
+    for (j2kgpu_job *j : bp.jobs) { rgb24_end(j); job_free(j); }
     bp.jobs.clear();
     if (bp.rc == J2KGPU_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) bp.rc = j2k_cuda_err(ctx, e1 != cudaSuccess ? e1 : e2, "decode_batch");
     return bp.rc;

@@ -10,6 +10,7 @@
 #include <mutex>
 
 #include "../../include/j2kgpu.h"
+#include "../host/rgb_expand.h"
 
 #define J2K_MAX_LEVELS 10
 #ifndef J2K_T1_ONE_LANE
@@ -88,9 +89,12 @@ struct J2kOpts {
     int no_preclear = 0;    // reference HT coder: clear every row on every run
     int wide_sp = 0;        // strip height of the wide IDWT kernel in row pairs (0 = planner)
     int t1_group = 0;       // EBCOT kernels: lanes per code block (4, 8, 16, 32; 0 = default 8)
+    int host_alpha = -1;    // host-buffer runs of RGBA8 images: packed R G B over PCIe, alpha filled in by host threads (-1 = auto)
     int debug_plan = 0;     // print the chunk plan of host-buffer runs
     std::string chunks;     // explicit chunk sizes of host-buffer runs, e.g. "1,1,2,4"
 };
+
+struct J2kRgbCb { J2kExpandPool *pool; J2kExpandTask t; };   // what a copy-out stream callback hands to the pool
 
 struct j2kgpu_ctx {
     int device = 0;
@@ -109,6 +113,7 @@ struct j2kgpu_ctx {
     std::vector<DevBuf> pool;
     std::vector<DevBuf> hpool;           // page-locked host blocks (table staging of pipelined batch calls), same policy
     std::vector<cudaEvent_t> events;     // timing-disabled events, reused across calls
+    J2kExpandPool *expand = nullptr;     // host threads that widen packed RGB rows to RGBA8 (created on first use)
 };
 void *j2k_pool_alloc(j2kgpu_ctx *ctx, size_t bytes, cudaError_t *err);
 void j2k_pool_free(j2kgpu_ctx *ctx, void *p);
@@ -156,6 +161,11 @@ struct j2kgpu_job {
     // staging for run_host
     void *d_blob = nullptr; void *d_pix = nullptr;
     void *h_blob = nullptr; void *h_pix = nullptr;
+    // packed-RGB transfer of host-buffer runs (rgb_expand.h): possible for this job / in use by the current run
+    int rgb24_ok = 0, rgb24 = 0;
+    void *h_rgb = nullptr; size_t h_rgb_cap = 0;         // page-locked staging of the packed rows
+    std::vector<uint64_t> rgb_off;                       // per item: offset in h_rgb
+    std::deque<J2kRgbCb> rgb_tasks;                      // one per item of the current run (stable addresses for the stream callbacks)
 };
 
 // ---- error helpers -----------------------------------------------------------------------------
@@ -205,6 +215,7 @@ struct IdwtLaunch {
     int f64_io;                                     // 9-7 stage API: coefficient arena and output planes are double
     int iso;                                        // 1: Mallat addressing + ISO order (rows, then columns)
     int wide_sp;                                    // J2kOpts.wide_sp
+    int rgb24;                                      // wide kernel, 3 components: packed R G B out (3 bytes per pixel, stride 3/4 of the table's)
     uint32_t stream_levels;                         // bit l set: level l of every tile-component fits the streaming kernel
     int32_t *d_plane_out;                           // lvl == 0 without tiles: output planes (same offsets as coef)
     uint8_t *d_pix;                                 // lvl == 0 with tiles: packed pixels

@@ -168,7 +168,10 @@ __host__ __device__ constexpr int warp_smem_u4(int nc) { return ring0_u4(nc) + r
 // when level 1 exists (that part IS the level-1 output)
 
 // NC = 3: RGB + RCT -> RGBA8.  NC = 1: one unsigned component of 8 or 16 bits -> Gray8 / big-endian Gray16.
-template <int NC, typename CT, bool ISO>
+// RGB24 (NC = 3, host-buffer runs): the pixels are written as packed R G B, 3 bytes each, row stride 3/4 of the tile
+// table's -- the alpha byte of an RGBA8 image is the constant 255, so it does not cross the PCIe link; the host side
+// of the library widens the rows to RGBA8 while the next chunk is in flight (api.cu).
+template <int NC, typename CT, bool ISO, bool RGB24>
 __global__ void __launch_bounds__(kWarps * 32, 2)
 k_idwt53_wide(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__ tiles, const CT *__restrict__ coef,
               const int32_t *__restrict__ tmp, uint8_t *__restrict__ pix, int nlevels, int strip_pairs, int prec, int iso_pack)
@@ -359,8 +362,9 @@ k_idwt53_wide(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__ t
     }
 
     // ---- output addressing ------------------------------------------------------------------------------------------
-    const int bpp = NC == 3 ? 4 : (prec > 8 ? 2 : 1);
-    uint8_t *orow = pix + tile.out_off + (size_t)(tile.img_y0 + 2u * (uint32_t)ka) * tile.out_stride +
+    const int bpp = NC == 3 ? (RGB24 ? 3 : 4) : (prec > 8 ? 2 : 1);
+    const size_t ostride = RGB24 ? (size_t)(tile.out_stride >> 2) * 3 : (size_t)tile.out_stride;
+    uint8_t *orow = pix + tile.out_off + (size_t)(tile.img_y0 + 2u * (uint32_t)ka) * ostride +
                     (size_t)bpp * (tile.img_x0 + 16u * (uint32_t)lc);
 
     // ---- stream the strip: step k consumes band row pair k+1 and finishes output rows 2k (even) and 2k+1 (odd) ------
@@ -418,7 +422,7 @@ k_idwt53_wide(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__ t
 #pragma unroll
                         for (int row = 0; row < 2; row++) {
                             const int *X = row ? od : ev;
-                            uint8_t *o = orow + (size_t)row * tile.out_stride;
+                            uint8_t *o = orow + (size_t)row * ostride;
                             if (prec <= 8) {
                                 uint32_t wd[4];
 #pragma unroll
@@ -459,6 +463,7 @@ k_idwt53_wide(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__ t
 #pragma unroll
                     for (int row = 0; row < 2; row++) {
                         const int *X2 = row ? od : ev;
+                        uint32_t w3[12];                               // RGB24: the row's 16 pixels as 48 packed bytes
 #pragma unroll
                         for (int g = 0; g < 4; g++) {
                             const uint4 a = stage[row * 128 + g * 32], b = stage[256 + row * 128 + g * 32];
@@ -471,34 +476,46 @@ k_idwt53_wide(const DevTileComp *__restrict__ tcs, const DevTile *__restrict__ t
                                 const int r8 = (int)(v + gg + 128u), g8 = (int)(gg + 128u), b8 = (int)(U[p] + gg + 128u);
                                 px[p] = pack_sat_u8(g8, r8, pack_sat_u8(255, b8, 0u));
                             }
-                            __stcs(reinterpret_cast<uint4 *>(orow + (size_t)row * tile.out_stride) + g, make_uint4(px[0], px[1], px[2], px[3]));
+                            if (RGB24) {                               // R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
+                                w3[3 * g] = __byte_perm(px[0], px[1], 0x4210);
+                                w3[3 * g + 1] = __byte_perm(px[1], px[2], 0x5421);
+                                w3[3 * g + 2] = __byte_perm(px[2], px[3], 0x6542);
+                            } else {
+                                __stcs(reinterpret_cast<uint4 *>(orow + (size_t)row * ostride) + g, make_uint4(px[0], px[1], px[2], px[3]));
+                            }
+                        }
+                        if (RGB24) {
+#pragma unroll
+                            for (int g = 0; g < 3; g++)
+                                __stcs(reinterpret_cast<uint4 *>(orow + (size_t)row * ostride) + g, make_uint4(w3[4 * g], w3[4 * g + 1], w3[4 * g + 2], w3[4 * g + 3]));
                         }
                     }
                 }
             }
         }
         if (do_l1) jn++;
-        if (emit) orow += 2 * tile.out_stride;
+        if (emit) orow += 2 * ostride;
     }
     cp_wait<0>();
+}
+
+template <int NC, typename CT, bool ISO, bool RGB24>
+cudaError_t run_k(const IdwtLaunch &p, dim3 grid, int strip_pairs, cudaStream_t s)
+{
+    const size_t smem = (size_t)kWarps * warp_smem_u4(NC) * sizeof(uint4);
+    const DevTile *tiles = p.d_tiles + p.tile_first;
+    cudaError_t e = cudaFuncSetAttribute(k_idwt53_wide<NC, CT, ISO, RGB24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    J2K_LAUNCH((k_idwt53_wide<NC, CT, ISO, RGB24>), grid, kWarps * 32, smem, s, p.d_tcs, tiles, (const CT *)p.d_coef,
+               (const int32_t *)p.d_tmp, p.d_pix, p.nlevels, strip_pairs, p.tail.prec[0], p.tail.iso);
+    return cudaGetLastError();
 }
 
 template <int NC, typename CT>
 cudaError_t run_ct(const IdwtLaunch &p, dim3 grid, int strip_pairs, cudaStream_t s)
 {
-    const size_t smem = (size_t)kWarps * warp_smem_u4(NC) * sizeof(uint4);
-    const DevTile *tiles = p.d_tiles + p.tile_first;
-    cudaError_t e;
-    if (p.iso) {
-        if ((e = cudaFuncSetAttribute(k_idwt53_wide<NC, CT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        J2K_LAUNCH((k_idwt53_wide<NC, CT, true>), grid, kWarps * 32, smem, s, p.d_tcs, tiles, (const CT *)p.d_coef,
-                   (const int32_t *)p.d_tmp, p.d_pix, p.nlevels, strip_pairs, p.tail.prec[0], p.tail.iso);
-    } else {
-        if ((e = cudaFuncSetAttribute(k_idwt53_wide<NC, CT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        J2K_LAUNCH((k_idwt53_wide<NC, CT, false>), grid, kWarps * 32, smem, s, p.d_tcs, tiles, (const CT *)p.d_coef,
-                   (const int32_t *)p.d_tmp, p.d_pix, p.nlevels, strip_pairs, p.tail.prec[0], p.tail.iso);
-    }
-    return cudaGetLastError();
+    if (NC == 3 && p.rgb24) return p.iso ? run_k<3, CT, true, true>(p, grid, strip_pairs, s) : run_k<3, CT, false, true>(p, grid, strip_pairs, s);
+    return p.iso ? run_k<NC, CT, true, false>(p, grid, strip_pairs, s) : run_k<NC, CT, false, false>(p, grid, strip_pairs, s);
 }
 
 }  // namespace

@@ -350,6 +350,45 @@ def test_overlapping_blocks_are_refused(j2k, gpu_ctx):
     assert np.array_equal(gpu_pixels(j2k, gpu_ctx, job), want)
 
 
+def test_packed_rgb_transfer_equals_rgba_transfer(j2k, gpu_ctx):
+    """host-buffer runs of RGBA8 images move packed R G B over the link and host threads of the library fill in the alpha
+    byte (host/rgb_expand.h): same bytes as the plain RGBA transfer, for one image, a batch in several chunks, a padded
+    stride, and the codestream front door; padding bytes of the caller's rows stay untouched"""
+    for (w, h, tile) in ((256, 128, 128), (512, 192, None)):
+        srcs = [jobs.synth_image(w, h, 3, 8, seed=70 + i) for i in range(5)]
+        isos = [jobs.build_iso_job(s, 8, tile, tile, 3) for s in srcs]
+        for pad in (0, 64):
+            stride = w * 4 + pad
+            outs = {}
+            for mode in (0, 1):
+                bufs = [np.full(stride * h, 0xA5, np.uint8) for _ in isos]
+                items = []
+                keep = []
+                for ij, buf in zip(isos, bufs):
+                    img = j2k.make_image(w, h, 3, 8, nlevels=3, ht=1, mode=j2k.MODE_ISO, coef_bits=ij["coef_bits"])
+                    tcs, cbs = jobs.as_ctypes(ij["tilecomps"], j2k.TileComp), jobs.as_ctypes(ij["cblks"], j2k.CBlk)
+                    blob = np.ascontiguousarray(ij["blob"], np.uint8)
+                    keep += [tcs, cbs, blob]
+                    items.append(j2k.BatchItem(img, tcs, len(tcs), cbs, len(cbs), blob.ctypes.data_as(j2k.u8p), blob.size,
+                                               buf.ctypes.data_as(j2k.u8p), stride, 0, 0))
+                with gpu_ctx.options(host_alpha=mode, chunks="1,2,2"):
+                    gpu_ctx.decode_batch(items)
+                outs[mode] = bufs
+            for a, b, s in zip(outs[0], outs[1], srcs):
+                assert np.array_equal(a, b)
+                px = b.reshape(h, stride)[:, :w * 4].reshape(h, w, 4)
+                assert np.array_equal(px[:, :, :3], np.moveaxis(s, 0, 2)) and (px[:, :, 3] == 255).all()
+                if pad:
+                    assert (b.reshape(h, stride)[:, w * 4:] == 0xA5).all()
+    s = jobs.synth_image(256, 128, 3, 8, seed=80)
+    data = jobs.build_iso_job(s, 8, 128, 128, 3)["codestream"]
+    with gpu_ctx.options(host_alpha=1):
+        a = gpu_ctx.decode_codestreams([data, data])
+    with gpu_ctx.options(host_alpha=0):
+        b = gpu_ctx.decode_codestreams([data, data])
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and np.array_equal(a[0].reshape(128, 256, 4)[:, :, :3], np.moveaxis(s, 0, 2))
+
+
 def test_two_devices_in_one_process(j2k):
     """a second context on another device of the same process gets its own constant tables (EBCOT contexts, MQ states)"""
     import torch

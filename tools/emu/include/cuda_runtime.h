@@ -201,6 +201,9 @@ static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
+#define CUDART_CB
+typedef void (*cudaHostFn_t)(void *);
+static inline cudaError_t cudaLaunchHostFunc(cudaStream_t, cudaHostFn_t fn, void *ud) { fn(ud); return cudaSuccess; }
 enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
 static inline cudaError_t cudaDeviceGetAttribute(int *v, int, int) { *v = 148; return cudaSuccess; }
 // exact size (posix_memalign): under AddressSanitizer (make asan) any access past the requested bytes is reported
