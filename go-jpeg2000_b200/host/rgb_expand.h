@@ -5,6 +5,8 @@
 // such images the device writes packed R G B (idwt_wide.cu, RGB24), the copy engine moves 3 bytes per pixel into a
 // page-locked staging block of the library, and the worker threads of this pool widen finished rows into the caller's
 // RGBA buffer while the next chunk is decoded and copied.  The caller sees exactly the bytes it would have received.
+// Whether it pays is a property of the host: the threads must store 4 bytes per pixel faster than the link delivers 3
+// (option host_alpha; off on hosts with fewer than 32 hardware threads per GPU, where it measured slower: DESIGN.md 5).
 #pragma once
 #include <stdint.h>
 #include <condition_variable>
