@@ -503,7 +503,8 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
             Rect q = {t.img_x0, t.img_y0, t.img_x0 + t.w < im.width ? t.img_x0 + t.w : im.width, t.img_y0 + t.h < im.height ? t.img_y0 + t.h : im.height};
             if (q.x0 < q.x1 && q.y0 < q.y1) rects.push_back(q);
         }
-        const bool fill = !tiles_exactly(rects, im.width, im.height);
+        // (an item whose copy-out is restricted to its tiles' rectangles never shows the uncovered pixels: no pre-fill)
+        const bool fill = !(it.flags & J2KGPU_ITEM_TILES_ONLY) && !tiles_exactly(rects, im.width, im.height);
         job->item_fill.push_back(fill ? 1 : 0);
         if (fill) job->pix_fill = 1;
 

@@ -138,7 +138,9 @@ typedef struct {
  * decoder.go:315-319 split over several contexts / GPUs).  Only the pixel rectangles those tiles cover are written to
  * out_pix (decoder.go:398-410 copies tile by tile); the rest of the buffer is not touched, so that contexts given
  * disjoint tile subsets of ONE image fill one shared host buffer.  Without the flag a call writes the whole image and
- * pixels no tile covers hold what the reference's zero-initialised planes decode to (decoder.go:305-309). */
+ * pixels no tile covers hold what the reference's zero-initialised planes decode to (decoder.go:305-309); with the flag
+ * those pixels are left undefined in the device buffer as well (device-resident runs of such an item).  Several items of
+ * one batch call may name the same out_pix with disjoint tile subsets: the call then pipelines the groups of tiles. */
 #define J2KGPU_ITEM_TILES_ONLY 1u
 
 /* stage-level block job (entropy stage in isolation) */
