@@ -1109,6 +1109,72 @@ static int pipe_finish(BatchPipe &bp)
     return bp.rc;
 }
 
+// One image of many tiles as several items of one batch: groups of tiles (in the order of the table) whose copy-in, decode
+// and copy-out then overlap like the images of a batch do (every group's item names the same out_pix and carries
+// J2KGPU_ITEM_TILES_ONLY; its blob is the byte range its blocks lie in).  Only when the tiles cover the image exactly
+// (otherwise the uncovered pixels need the whole-image pre-fill) and the image is large enough for the split to pay.
+struct SplitItems {
+    std::vector<j2k_batch_item_t> items;
+    std::vector<std::vector<j2k_tilecomp_t>> tcs;
+    std::vector<std::vector<j2k_cblk_t>> cbs;
+};
+
+static bool split_by_tiles(const j2k_batch_item_t &it, SplitItems &sp)
+{
+    const j2k_image_t &im = it.image;
+    if ((it.flags & J2KGPU_ITEM_TILES_ONLY) || (uint64_t)im.width * im.height < (1u << 20) || it.n_tilecomps < 4u * im.ncomp || !im.ncomp) return false;
+    // tiles = distinct bounds, numbered in order of first appearance
+    std::map<std::tuple<uint32_t, uint32_t, uint32_t, uint32_t>, uint32_t> tile_of;
+    std::vector<uint32_t> tc_tile(it.n_tilecomps);
+    std::vector<Rect> rects;
+    for (uint32_t t = 0; t < it.n_tilecomps; t++) {
+        const j2k_tilecomp_t &tc = it.tilecomps[t];
+        if (tc.x1 <= tc.x0 || tc.y1 <= tc.y0 || tc.x0 >= im.width || tc.y0 >= im.height) return false;
+        auto key = std::make_tuple(tc.x0, tc.y0, tc.x1, tc.y1);
+        auto f = tile_of.find(key);
+        if (f == tile_of.end()) {
+            f = tile_of.emplace(key, (uint32_t)tile_of.size()).first;
+            rects.push_back(Rect{tc.x0, tc.y0, tc.x1 < im.width ? tc.x1 : im.width, tc.y1 < im.height ? tc.y1 : im.height});
+        }
+        tc_tile[t] = f->second;
+    }
+    const uint32_t ntiles = (uint32_t)tile_of.size();
+    if (ntiles < 4 || !tiles_exactly(rects, im.width, im.height)) return false;
+    const uint32_t K = ntiles < 8 ? ntiles : 8;
+    sp.items.assign(K, it);
+    sp.tcs.assign(K, {});
+    sp.cbs.assign(K, {});
+    std::vector<uint32_t> tc_new(it.n_tilecomps);
+    for (uint32_t t = 0; t < it.n_tilecomps; t++) {
+        const uint32_t g = (uint32_t)((uint64_t)tc_tile[t] * K / ntiles);
+        tc_new[t] = (uint32_t)sp.tcs[g].size();
+        sp.tcs[g].push_back(it.tilecomps[t]);
+    }
+    std::vector<uint64_t> lo(K, ~0ull), hi(K, 0);
+    for (uint32_t b = 0; b < it.n_cblks; b++) {
+        const j2k_cblk_t &cb = it.cblks[b];
+        if (cb.tilecomp >= it.n_tilecomps) return false;                 // (the plain path reports it)
+        const uint32_t g = (uint32_t)((uint64_t)tc_tile[cb.tilecomp] * K / ntiles);
+        j2k_cblk_t c2 = cb;
+        c2.tilecomp = tc_new[cb.tilecomp];
+        sp.cbs[g].push_back(c2);
+        if (cb.data_len) {
+            if (cb.data_off > it.blob_len || cb.data_len > it.blob_len - cb.data_off) return false;
+            lo[g] = std::min(lo[g], cb.data_off); hi[g] = std::max(hi[g], cb.data_off + cb.data_len);
+        }
+    }
+    for (uint32_t g = 0; g < K; g++) {
+        j2k_batch_item_t &o = sp.items[g];
+        if (lo[g] > hi[g]) { lo[g] = hi[g] = 0; }
+        for (j2k_cblk_t &c : sp.cbs[g]) c.data_off = c.data_len ? c.data_off - lo[g] : 0;
+        o.tilecomps = sp.tcs[g].data(); o.n_tilecomps = (uint32_t)sp.tcs[g].size();
+        o.cblks = sp.cbs[g].data(); o.n_cblks = (uint32_t)sp.cbs[g].size();
+        o.blob = it.blob ? it.blob + lo[g] : nullptr; o.blob_len = hi[g] - lo[g];
+        o.flags |= J2KGPU_ITEM_TILES_ONLY;
+    }
+    return true;
+}
+
 extern "C" int j2kgpu_decode_batch(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *items)
 {
     if (!ctx) return J2KGPU_E_ARG;
@@ -1117,6 +1183,12 @@ extern "C" int j2kgpu_decode_batch(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_ba
     TailParams tp;
     int rc = make_tail(ctx, items[0].image, tp);
     if (rc) return rc;
+    SplitItems sp;                                       // one large image of many tiles: its groups of tiles are the batch
+    if (n_img == 1 && items[0].out_pix && (items[0].tilecomps || !items[0].n_tilecomps) && (items[0].cblks || !items[0].n_cblks) &&
+        ctx->opt.chunks.empty() && split_by_tiles(items[0], sp)) {
+        items = sp.items.data();
+        n_img = (uint32_t)sp.items.size();
+    }
     uint64_t out_bytes = 0;
     for (uint32_t i = 0; i < n_img; i++) {
         if (!items[i].out_pix) return j2k_set_err(ctx, J2KGPU_E_ARG, "item %u: null out_pix", i);

@@ -389,6 +389,24 @@ def test_packed_rgb_transfer_equals_rgba_transfer(j2k, gpu_ctx):
     assert all(np.array_equal(x, y) for x, y in zip(a, b)) and np.array_equal(a[0].reshape(128, 256, 4)[:, :, :3], np.moveaxis(s, 0, 2))
 
 
+def test_one_large_image_is_pipelined_by_tile_groups(j2k, gpu_ctx):
+    """a single image of many tiles goes through the batch pipeline as groups of tiles (copy-in, decode and copy-out of
+    neighbouring groups overlap): same pixels as the one-chunk run, for ISO HT, REF EBCOT and a padded stride"""
+    s = jobs.synth_image(1280, 1024, 3, 8, seed=91)
+    for kind in ("iso", "ref"):
+        job = jobs.build_iso_job(s, 8, 256, 256, 4) if kind == "iso" else jobs.build_ref_job(s, 8, tile_w=256, tile_h=256, nlevels=3, reversible=True, threads=4)
+        mode = j2k.MODE_ISO if kind == "iso" else j2k.MODE_REF
+        img = j2k.make_image(1280, 1024, 3, 8, nlevels=job["nlevels"], ht=job["ht"], mode=mode, coef_bits=job.get("coef_bits", 0))
+        tcs, cbs = jobs.as_ctypes(job["tilecomps"], j2k.TileComp), jobs.as_ctypes(job["cblks"], j2k.CBlk)
+        for stride in (None, 1280 * 4 + 128):
+            split = gpu_ctx.decode_tiles(img, tcs, cbs, job["blob"], out_stride=stride)
+            with gpu_ctx.options(chunks="1"):                      # an explicit chunk plan keeps the image in one piece
+                whole = gpu_ctx.decode_tiles(img, tcs, cbs, job["blob"], out_stride=stride)
+            assert np.array_equal(split, whole)
+            st = stride or 1280 * 4
+            assert np.array_equal(split.reshape(1024, st)[:, :1280 * 4].reshape(1024, 1280, 4)[:, :, :3], np.moveaxis(s, 0, 2))
+
+
 def test_two_devices_in_one_process(j2k):
     """a second context on another device of the same process gets its own constant tables (EBCOT contexts, MQ states)"""
     import torch
