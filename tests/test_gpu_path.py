@@ -399,7 +399,8 @@ def test_one_large_image_is_pipelined_by_tile_groups(j2k, gpu_ctx):
         img = j2k.make_image(1280, 1024, 3, 8, nlevels=job["nlevels"], ht=job["ht"], mode=mode, coef_bits=job.get("coef_bits", 0))
         tcs, cbs = jobs.as_ctypes(job["tilecomps"], j2k.TileComp), jobs.as_ctypes(job["cblks"], j2k.CBlk)
         for stride in (None, 1280 * 4 + 128):
-            split = gpu_ctx.decode_tiles(img, tcs, cbs, job["blob"], out_stride=stride)
+            with gpu_ctx.options(split_min_mpixel=1):              # (the default threshold is 24 Mpixel)
+                split = gpu_ctx.decode_tiles(img, tcs, cbs, job["blob"], out_stride=stride)
             with gpu_ctx.options(chunks="1"):                      # an explicit chunk plan keeps the image in one piece
                 whole = gpu_ctx.decode_tiles(img, tcs, cbs, job["blob"], out_stride=stride)
             assert np.array_equal(split, whole)
