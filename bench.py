@@ -307,7 +307,26 @@ def measure(args, ctx, j2k, jobs, frames, mode, stream, barrier, steps, e2e_step
         job.run_host()
     barrier()
     pre_s = time.perf_counter() - t0
-    res = dict(ms_total=ms_total, steps=steps, launches=int(launches), ms_long=ms_long, long_steps=long_steps, ent_ms=ent_ms,
+    # ---- the codestream front door: raw codestream bytes in (page-locked), tier-2 on host threads inside the library ----
+    cs_s, cs_steps, cs_bytes = 0.0, 0, 0
+    if all(fr.get("codestream") for fr in frames):
+        cs_host = [torch.from_numpy(np.frombuffer(fr["codestream"], np.uint8).copy()).pin_memory() for fr in frames]
+        cs_arrs = [t.numpy() for t in cs_host]
+        outs = [t.numpy() for t in host_out]
+        for t in host_out:
+            t.zero_()
+        for _ in range(2):
+            ctx.decode_codestreams(cs_arrs, outs=outs)
+        assert np.array_equal(host_out[0].numpy().reshape(H, W, 4), firsts), "codestream front door differs from the device path"
+        barrier()
+        t0 = time.perf_counter()
+        cs_steps = max(1, min(e2e_steps, 10))
+        for _ in range(cs_steps):
+            ctx.decode_codestreams(cs_arrs, outs=outs)
+        barrier()
+        cs_s = time.perf_counter() - t0
+        cs_bytes = int(sum(a.size for a in cs_arrs))
+    res = dict(cs_s=cs_s, cs_steps=cs_steps, cs_bytes=cs_bytes, ms_total=ms_total, steps=steps, launches=int(launches), ms_long=ms_long, long_steps=long_steps, ent_ms=ent_ms,
                dwt_ms=dwt_ms, last_ms=last_ms, e2e_s=e2e_s, e2e_steps=e2e_steps, pre_s=pre_s, pre_steps=pre_steps,
                h2d=int(d_blob.numel()) - 64, d2h=stride * H * F, n_blocks=sum(len(j["cblks"]) for j in frames), F=F,
                fused_levels=job.fused_levels, coef_bytes=job.coef_bytes, plan=job.plan, guard=guard)
@@ -438,7 +457,7 @@ def run_ours(args):
     assert len(mine) == F
     workers = max(1, min(16, (os.cpu_count() or 1) // max(1, world)))
     t_gen = time.perf_counter()
-    specs = [("iso", 2002 + g, i == 0 and rank == 0) for i, g in enumerate(mine)]
+    specs = [("iso", 2002 + g, True) for i, g in enumerate(mine)]      # every frame keeps its codestream (front-door e2e)
     n_ref, n_eb = (min(F, 4), min(F, 2)) if not args.no_extra else (0, 0)
     specs += [("ref_ht", 1002 + mine[i], False) for i in range(n_ref)] + [("ebcot", 3002 + mine[i], False) for i in range(n_eb)]
     built = build_many(_make_frame, specs, workers)
@@ -485,7 +504,7 @@ def run_ours(args):
         mpix_step = W * H * Fm * world / 1e6
         alg = (4 * W * H * NCOMP + W * H * 4) * Fm                  # SURVEY.md 8(d), per launch of the roofline kernel
         moved = (m["coef_bytes"] * W * H * NCOMP + W * H * 4) * Fm   # what this variant's kernel has to move (int16 planes: less)
-        ms_total, ms_long, e2e_s, pre_s = reduce_max(m["ms_total"], m["ms_long"], m["e2e_s"], m["pre_s"])
+        ms_total, ms_long, e2e_s, pre_s, cs_s = reduce_max(m["ms_total"], m["ms_long"], m["e2e_s"], m["pre_s"], m["cs_s"])
         ach, stg = alg / (m["last_ms"] / 1e3) / 1e9, alg / (m["dwt_ms"] / 1e3) / 1e9
         last_kernel = ("k_idwt53_wide (16 columns per lane)" if m["plan"] & 4 else
                        "k_idwt53_fused (4 columns per lane)" if m["plan"] & 1 else "k_idwt53_stream")
@@ -518,6 +537,11 @@ def run_ours(args):
                                                  "of the kernel, as a ratio to its bytes), " + src) if ratio else
                                                 "no ncu capture of this variant is wired in: see profiles/"),
                    guard=m["guard"])
+        if m["cs_steps"]:
+            out["e2e"]["codestream_front_door"] = dict(value=round(mpix_step * m["cs_steps"] / cs_s, 1), unit=UNIT,
+                                                       ms_per_step=round(1e3 * cs_s / m["cs_steps"], 3), h2d_bytes_per_step=m["cs_bytes"],
+                                                       api="j2kgpu_decode_codestreams (raw codestream bytes in: main header, tile-part index "
+                                                           "and tier-2 on host threads inside the call, overlapped with the device)")
         if m["long_steps"]:
             out["sustained"] = dict(steps=m["long_steps"], value=round(mpix_step * m["long_steps"] / (ms_long / 1e3), 1),
                                     ms_per_step=round(ms_long / m["long_steps"], 4))

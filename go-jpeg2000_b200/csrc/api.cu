@@ -1260,7 +1260,8 @@ extern "C" int j2kgpu_decode_codestreams(j2kgpu_ctx *ctx, uint32_t n, const uint
         for (;;) {
             const uint32_t i = next.fetch_add(1);
             if (i >= n) break;
-            prc[i] = j2k_tier2_parse(cs[i], lens[i], reduce, n == 1 ? 0 : 1, parsed[i]);
+            // the first frame gates the start of the device pipeline: its tiles are parsed on all threads, the others' on one
+            prc[i] = j2k_tier2_parse(cs[i], lens[i], reduce, (n == 1 || i == 0) ? 0 : 1, parsed[i]);
             { std::lock_guard<std::mutex> lk(mu); done[i].store(1); }
             cv.notify_all();
         }

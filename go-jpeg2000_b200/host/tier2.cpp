@@ -96,42 +96,57 @@ struct BitReader {
     }
 };
 
-struct TagTree {
-    struct Lvl { uint32_t w, h; size_t off; };
-    std::vector<Lvl> lv;
+// Tag tree (B.10.2) whose nodes live in an arena shared by all the trees of a tile (a 4K frame has some 13 000 of them:
+// one heap block per tree and array made the parser spend its time in malloc)
+struct TagArena {
     std::vector<int32_t> val, low;
     std::vector<uint8_t> known;
-    void init(uint32_t w, uint32_t h)
+    size_t grab(size_t n)
     {
-        lv.clear();
-        size_t off = 0;
+        const size_t off = val.size();
+        val.resize(off + n, 1 << 30); low.resize(off + n, 0); known.resize(off + n, 0);
+        return off;
+    }
+};
+
+struct TagTree {
+    struct Lvl { uint32_t w, h; uint32_t off; };
+    Lvl lv[17];
+    uint32_t nlv = 0;
+    void init(TagArena &ar, uint32_t w, uint32_t h)
+    {
+        nlv = 0;
+        if (!w || !h) return;
+        size_t n = 0;
+        uint32_t ww = w, hh = h;
         for (;;) {
-            lv.push_back({w, h, off});
-            off += (size_t)w * h;
-            if (w <= 1 && h <= 1) break;
-            w = cdiv(w, 2); h = cdiv(h, 2);
+            lv[nlv++] = {ww, hh, (uint32_t)n};
+            n += (size_t)ww * hh;
+            if ((ww <= 1 && hh <= 1) || nlv == 17) break;
+            ww = cdiv(ww, 2); hh = cdiv(hh, 2);
         }
-        val.assign(off, 1 << 30); low.assign(off, 0); known.assign(off, 0);
+        const size_t base = ar.grab(n);
+        for (uint32_t l = 0; l < nlv; l++) lv[l].off += (uint32_t)base;
     }
     // -> true when value(x, y) < threshold is established
-    bool decode(BitReader &br, uint32_t x, uint32_t y, int32_t threshold)
+    bool decode(TagArena &ar, BitReader &br, uint32_t x, uint32_t y, int32_t threshold)
     {
         int32_t lo = 0;
-        for (int l = (int)lv.size() - 1; l >= 0; l--) {
+        for (int l = (int)nlv - 1; l >= 0; l--) {
             const size_t i = lv[l].off + (size_t)(y >> l) * lv[l].w + (x >> l);
-            if (lo > low[i]) low[i] = lo; else lo = low[i];
-            while (lo < threshold && !known[i]) {
+            if (lo > ar.low[i]) ar.low[i] = lo; else lo = ar.low[i];
+            while (lo < threshold && !ar.known[i]) {
                 if (br.bad) return false;
-                if (br.get()) { known[i] = 1; val[i] = lo; }
+                if (br.get()) { ar.known[i] = 1; ar.val[i] = lo; }
                 else lo++;
             }
-            low[i] = lo;
-            if (known[i] && l) lo = std::max(lo, val[i]);
+            ar.low[i] = lo;
+            if (ar.known[i] && l) lo = std::max(lo, ar.val[i]);
         }
         const size_t i0 = lv[0].off + (size_t)y * lv[0].w + x;
-        return known[i0] && val[i0] < threshold;
+        return ar.known[i0] && ar.val[i0] < threshold;
     }
-    int32_t value(uint32_t x, uint32_t y) const { return val[lv[0].off + (size_t)y * lv[0].w + x]; }
+    int32_t value(const TagArena &ar, uint32_t x, uint32_t y) const { return ar.val[lv[0].off + (size_t)y * lv[0].w + x]; }
 };
 
 uint32_t read_npasses(BitReader &br)                      // B.10.6
@@ -154,8 +169,9 @@ struct Blk {
     bool included = false;
     uint64_t off = 0; uint32_t len = 0; // first contribution (offset into the tile body)
     uint32_t npieces = 0;
-    std::vector<std::pair<uint64_t, uint32_t>> more;   // further contributions (quality layers)
+    int32_t more_head = -1, more_tail = -1;            // further contributions (quality layers): list in the tile's `pieces`
 };
+struct Piece { uint64_t off; uint32_t len; int32_t next; };
 
 // the code blocks of one band that lie in one precinct: their own grid and tag trees (B.10.2)
 struct PrecBand {
@@ -203,6 +219,8 @@ void parse_tile(const uint8_t *cs, const Header &h, uint32_t tidx, const std::ve
     // precincts of every (component, resolution) and, per precinct and band, the code blocks inside it (B.6, B.7)
     std::vector<Blk> blks;
     std::vector<Prec> precs;
+    std::vector<Piece> pieces;
+    TagArena arena;
     for (uint32_t c = 0; c < nc; c++)
         for (uint32_t r = 0; r <= nl; r++) {
             const int64_t rs = (int64_t)1 << (nl - r);
@@ -249,9 +267,9 @@ void parse_tile(const uint8_t *cs, const Header &h, uint32_t tidx, const std::ve
                                 }
                         }
                         pb.count = (uint32_t)blks.size() - pb.first;
-                        pb.incl.init(pb.gw, pb.gh); pb.imsb.init(pb.gw, pb.gh);
+                        pb.incl.init(arena, pb.gw, pb.gh); pb.imsb.init(arena, pb.gw, pb.gh);
                     }
-                    precs.push_back(std::move(pr));
+                    precs.push_back(pr);
                 }
         }
     // packet sequence (B.12): one packet per layer, resolution, component and precinct; the position-driven orders visit a
@@ -297,19 +315,19 @@ void parse_tile(const uint8_t *cs, const Header &h, uint32_t tidx, const std::ve
                     Blk &e = blks[st.first + k];
                     const uint32_t gx = k % st.gw, gy = k / st.gw;
                     bool inc;
-                    if (!e.included) inc = st.incl.decode(br, gx, gy, (int32_t)pk.l + 1);
+                    if (!e.included) inc = st.incl.decode(arena, br, gx, gy, (int32_t)pk.l + 1);
                     else inc = br.get() != 0;
                     if (br.bad) { if (truncated) { cut = true; goto packet_done; } out.err.fail(J2KGPU_E_RANGE, "tile %u: packet header runs past the tile data", tidx); return; }
                     if (!inc) continue;
                     if (truncated) undo.push_back({st.first + k, e.passes, e.zbp, e.lblock, e.lcup, e.included});
                     if (!e.included) {
                         int32_t t = 1;
-                        while (!st.imsb.decode(br, gx, gy, t)) {
+                        while (!st.imsb.decode(arena, br, gx, gy, t)) {
                             if (br.bad && truncated) { cut = true; goto packet_done; }
                             if (br.bad || t > 64) { out.err.fail(J2KGPU_E_RANGE, "tile %u: bad zero-bit-plane tag tree", tidx); return; }
                             t++;
                         }
-                        e.zbp = (uint32_t)st.imsb.value(gx, gy);
+                        e.zbp = (uint32_t)st.imsb.value(arena, gx, gy);
                         e.included = true;
                     }
                     const uint32_t n = read_npasses(br);
@@ -355,7 +373,11 @@ void parse_tile(const uint8_t *cs, const Header &h, uint32_t tidx, const std::ve
         for (auto &sg : segs) {
             Blk &e = blks[sg.first];
             if (e.npieces == 0) { e.off = p; e.len = sg.second; }
-            else e.more.push_back({p, sg.second});
+            else {
+                pieces.push_back({p, sg.second, -1});
+                if (e.more_tail >= 0) pieces[e.more_tail].next = (int32_t)pieces.size() - 1; else e.more_head = (int32_t)pieces.size() - 1;
+                e.more_tail = (int32_t)pieces.size() - 1;
+            }
             e.npieces++;
             p += sg.second;
         }
@@ -386,18 +408,18 @@ void parse_tile(const uint8_t *cs, const Header &h, uint32_t tidx, const std::ve
         cb.step = h.reversible ? 1.0f : (float)(std::ldexp(1.0, (int)h.prec + gain[b.band] - (int)expn) * (1.0 + mant / 2048.0));
         const int nb = mb - (int)e.zbp;
         uint32_t total = e.len;
-        for (auto &m : e.more) total += m.second;
+        for (int32_t m = e.more_head; m >= 0; m = pieces[m].next) total += pieces[m].len;
         if (!e.passes || nb <= 0 || total == 0) { cb.num_bps = 0; cb.num_passes = 0; cb.data_len = 0; cb.data_off = 0; out.is_extra.push_back(0); out.cbs.push_back(cb); continue; }
         if (nb > 31) { out.err.fail(J2KGPU_E_UNSUPPORTED, "tile %u: %d magnitude bit-planes", tidx, nb); return; }
         cb.num_bps = (uint8_t)nb;
         cb.num_passes = (uint8_t)std::min<uint32_t>(e.passes, 255);
         cb.data_len = total;
         cb.len_cleanup = (h.ht && e.passes > 1) ? e.lcup : 0;
-        if (e.more.empty() && abs_off >= 0) { cb.data_off = (uint64_t)abs_off + e.off; out.is_extra.push_back(0); }
+        if (e.more_head < 0 && abs_off >= 0) { cb.data_off = (uint64_t)abs_off + e.off; out.is_extra.push_back(0); }
         else {
             cb.data_off = out.extra.size();
             out.extra.insert(out.extra.end(), body + e.off, body + e.off + e.len);
-            for (auto &m : e.more) out.extra.insert(out.extra.end(), body + m.first, body + m.first + m.second);
+            for (int32_t m = e.more_head; m >= 0; m = pieces[m].next) out.extra.insert(out.extra.end(), body + pieces[m].off, body + pieces[m].off + pieces[m].len);
             out.is_extra.push_back(1);
         }
         out.cbs.push_back(cb);
