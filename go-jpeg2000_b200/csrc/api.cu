@@ -1247,27 +1247,49 @@ extern "C" int j2kgpu_decode_codestreams(j2kgpu_ctx *ctx, uint32_t n, const uint
     if (!ctx) return J2KGPU_E_ARG;
     std::lock_guard<std::mutex> g(ctx->mu);
     if (!n || !cs || !lens || !out_pix || !out_stride) return j2k_set_err(ctx, J2KGPU_E_ARG, "null or empty batch");
+    // Host side: the main header and tile-part index of every frame are read here (microseconds each); the tiles of all
+    // frames then form one task list in frame order, worked off by one set of threads, so the first frame is ready after
+    // 1 / threads of its tier-2 time and the frames finish in the order the device pipeline wants them.  The thread that
+    // parses a frame's last tile merges its tables.
     std::vector<j2kgpu_parsed> parsed(n);
     std::vector<int> prc(n, 0);
     std::vector<std::atomic<int>> done(n);
     for (auto &d : done) d.store(0);
+    std::vector<j2k_t2_frame *> frames(n, nullptr);
+    std::vector<uint32_t> first_task(n + 1, 0);
+    for (uint32_t i = 0; i < n; i++) {
+        prc[i] = j2k_tier2_begin(cs[i], lens[i], reduce, &frames[i], parsed[i].err);
+        first_task[i + 1] = first_task[i] + (prc[i] ? 0 : j2k_tier2_tiles(frames[i]));
+        if (prc[i] || j2k_tier2_tiles(frames[i]) == 0) {  // failed, or nothing to parse: finished as it is
+            if (!prc[i]) prc[i] = j2k_tier2_finish(frames[i], parsed[i]);
+            frames[i] = nullptr;
+            done[i].store(1);
+        }
+    }
+    const uint32_t ntasks = first_task[n];
+    std::vector<std::atomic<uint32_t>> left(n);
+    for (uint32_t i = 0; i < n; i++) left[i].store(first_task[i + 1] - first_task[i]);
     std::atomic<uint32_t> next{0};
     std::mutex mu;
     std::condition_variable cv;
     const uint32_t hw = std::max(1u, std::thread::hardware_concurrency());
-    const uint32_t nthreads = n == 1 ? 1 : std::min<uint32_t>({hw, n, 32u});
+    const uint32_t nthreads = std::max(1u, std::min<uint32_t>({hw, ntasks, 32u}));
     auto worker = [&]() {
+        uint32_t f = 0;
         for (;;) {
-            const uint32_t i = next.fetch_add(1);
-            if (i >= n) break;
-            // the first frame gates the start of the device pipeline: its tiles are parsed on all threads, the others' on one
-            prc[i] = j2k_tier2_parse(cs[i], lens[i], reduce, (n == 1 || i == 0) ? 0 : 1, parsed[i]);
-            { std::lock_guard<std::mutex> lk(mu); done[i].store(1); }
-            cv.notify_all();
+            const uint32_t k = next.fetch_add(1);
+            if (k >= ntasks) break;
+            while (k >= first_task[f + 1]) f++;
+            j2k_tier2_tile(frames[f], k - first_task[f]);
+            if (left[f].fetch_sub(1) == 1) {             // the frame's last tile: merge, publish
+                prc[f] = j2k_tier2_finish(frames[f], parsed[f]);
+                { std::lock_guard<std::mutex> lk(mu); done[f].store(1); }
+                cv.notify_all();
+            }
         }
     };
     std::vector<std::thread> th;
-    for (uint32_t t = 0; t < nthreads; t++) th.emplace_back(worker);
+    for (uint32_t t = 0; t < nthreads && ntasks; t++) th.emplace_back(worker);
     auto wait_for = [&](uint32_t i) { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return done[i].load() != 0; }); };
     BatchPipe bp;
     int rc = J2KGPU_OK;
@@ -1289,8 +1311,7 @@ extern "C" int j2kgpu_decode_codestreams(j2kgpu_ctx *ctx, uint32_t n, const uint
             submitted = i + 1; ci++;
         }
     }
-    next.store(n);                                       // on error: stop handing out frames
-    for (auto &t : th) t.join();
+    for (auto &t : th) t.join();                         // (after an error the remaining tiles are still parsed: their frames are freed by finish)
     if (bp.ctx) { bp.rc = bp.rc ? bp.rc : rc; return pipe_finish(bp); }
     return rc;
 }

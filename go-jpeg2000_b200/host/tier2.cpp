@@ -11,6 +11,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <memory>
+#include <new>
 #include <thread>
 
 namespace {
@@ -431,11 +433,27 @@ inline uint32_t be32(const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint3
 
 }  // namespace
 
-int j2k_tier2_parse(const uint8_t *d, uint64_t len, uint32_t reduce, uint32_t threads, j2kgpu_parsed &out)
-{
-    Err err;
+// a codestream whose main header and tile-part index have been read: its tiles can then be parsed independently
+struct j2k_t2_frame {
+    const uint8_t *d = nullptr; uint64_t len = 0; uint32_t reduce = 0;
     Header h;
-#define T2_FAIL(...) do { err.fail(__VA_ARGS__); out.err = err.msg; return err.code; } while (0)
+    std::vector<BandId> bands;
+    uint32_t ntiles = 0, ntp = 0, ntlm = 0;
+    int64_t truncated_tile = -1;
+    std::vector<std::vector<TilePart>> parts;
+    std::vector<std::vector<uint32_t>> plt;
+    std::vector<TileOut> touts;
+};
+
+int j2k_tier2_begin(const uint8_t *d, uint64_t len, uint32_t reduce, j2k_t2_frame **fout, std::string &errmsg)
+{
+    *fout = nullptr;
+    j2k_t2_frame *F = new (std::nothrow) j2k_t2_frame();
+    if (!F) { errmsg = "out of memory"; return J2KGPU_E_NOMEM; }
+    std::unique_ptr<j2k_t2_frame> guard(F);
+    Err err;
+    Header &h = F->h;
+#define T2_FAIL(...) do { err.fail(__VA_ARGS__); errmsg = err.msg; return err.code; } while (0)
     // a JP2 file (ISO/IEC 15444-1 Annex I: signature box first): walk the top-level boxes to the contiguous codestream box.
     // Everything else in the container (colour specification, palette, resolution ...) stays with the caller (box.go).
     if (d && len >= 12 && be32(d) == 12 && be32(d + 4) == 0x6A502020u) {
@@ -526,7 +544,8 @@ int j2k_tier2_parse(const uint8_t *d, uint64_t len, uint32_t reduce, uint32_t th
     }
     if (!h.have_siz || !h.have_cod || !h.have_qcd) T2_FAIL(J2KGPU_E_RANGE, "SIZ / COD / QCD missing");
     if (h.style & 0x40) h.ht = 1;
-    const std::vector<BandId> bands = band_list(h.nlevels);
+    F->bands = band_list(h.nlevels);
+    const std::vector<BandId> &bands = F->bands;
     if (h.q.size() == 2 && h.q[1].first == 0xFFFFFFFFu) {   // scalar derived (E-5): eps_b = eps_0 - N_L + n_b, mu_b = mu_0
         const auto q0 = h.q[0];
         h.q.clear();
@@ -540,8 +559,9 @@ int j2k_tier2_parse(const uint8_t *d, uint64_t len, uint32_t reduce, uint32_t th
         T2_FAIL(J2KGPU_E_UNSUPPORTED, "tile size %ux%u is not a multiple of 2^nlevels", h.tile_w, h.tile_h);
     // ---- tile-part index: ReadTilePartHeader (parser.go:894-982), hopping by Psot ----
     const uint32_t ntiles = ntx * nty;
-    std::vector<std::vector<TilePart>> parts(ntiles);
-    std::vector<std::vector<uint32_t>> plt(ntiles);
+    std::vector<std::vector<TilePart>> &parts = F->parts;
+    std::vector<std::vector<uint32_t>> &plt = F->plt;
+    parts.assign(ntiles, {}); plt.assign(ntiles, {});
     uint32_t ntp = 0;
     int64_t truncated_tile = -1;
     while (pos + 12 <= len && be16(d + pos) == SOT) {
@@ -575,25 +595,35 @@ int j2k_tier2_parse(const uint8_t *d, uint64_t len, uint32_t reduce, uint32_t th
         pos = end;
         ntp++;
     }
-    // ---- tier-2 per tile, tiles in parallel ----
-    std::vector<TileOut> touts(ntiles);
-    uint32_t nthreads = threads ? threads : std::max(1u, std::thread::hardware_concurrency());
-    nthreads = std::min<uint32_t>({nthreads, ntiles, 64u});
-    std::atomic<uint32_t> next{0};
-    auto worker = [&]() {
-        for (;;) {
-            const uint32_t t = next.fetch_add(1);
-            if (t >= ntiles) break;
-            if (parts[t].empty()) { std::vector<TilePart> none{{0, 0}}; parse_tile(d, h, t, none, plt[t], reduce, false, touts[t]); }
-            else parse_tile(d, h, t, parts[t], plt[t], reduce, (int64_t)t == truncated_tile, touts[t]);
-        }
-    };
-    if (nthreads <= 1) worker();
-    else {
-        std::vector<std::thread> th;
-        for (uint32_t i = 0; i < nthreads; i++) th.emplace_back(worker);
-        for (auto &t : th) t.join();
-    }
+    F->d = d; F->len = len; F->reduce = reduce; F->ntiles = ntiles; F->ntp = ntp; F->ntlm = (uint32_t)tlm.size();
+    F->truncated_tile = truncated_tile;
+    F->touts.assign(ntiles, TileOut());
+    *fout = guard.release();
+    return J2KGPU_OK;
+#undef T2_FAIL
+}
+
+uint32_t j2k_tier2_tiles(const j2k_t2_frame *F) { return F ? F->ntiles : 0; }
+void j2k_tier2_free(j2k_t2_frame *F) { delete F; }
+
+// tier-2 of tile t (callable concurrently for distinct tiles)
+void j2k_tier2_tile(j2k_t2_frame *F, uint32_t t)
+{
+    if (t >= F->ntiles) return;
+    if (F->parts[t].empty()) { std::vector<TilePart> none{{0, 0}}; parse_tile(F->d, F->h, t, none, F->plt[t], F->reduce, false, F->touts[t]); }
+    else parse_tile(F->d, F->h, t, F->parts[t], F->plt[t], F->reduce, (int64_t)t == F->truncated_tile, F->touts[t]);
+}
+
+// every tile parsed: merge into the flat tables; the frame is freed
+int j2k_tier2_finish(j2k_t2_frame *F, j2kgpu_parsed &out)
+{
+    std::unique_ptr<j2k_t2_frame> guard(F);
+    const Header &h = F->h;
+    const uint8_t *d = F->d;
+    const uint64_t len = F->len;
+    const uint32_t ntiles = F->ntiles, reduce = F->reduce;
+    std::vector<TileOut> &touts = F->touts;
+    const std::vector<BandId> &bands = F->bands;
     // ---- merge ----
     uint64_t extra_total = 0;
     size_t ncb = 0;
@@ -631,7 +661,31 @@ int j2k_tier2_parse(const uint8_t *d, uint64_t len, uint32_t reduce, uint32_t th
     uint32_t cbits = 0;
     for (size_t bi = 0; bi < bands.size(); bi++) cbits = std::max(cbits, h.q[bi].first + h.guard - 1);
     im.coef_bits = (uint8_t)std::min(cbits, 255u);
-    out.layers = h.layers; out.tiles = ntiles; out.tile_parts = ntp; out.progression = h.prog; out.tlm_tile_parts = (uint32_t)tlm.size();
+    out.layers = h.layers; out.tiles = ntiles; out.tile_parts = F->ntp; out.progression = h.prog; out.tlm_tile_parts = F->ntlm;
     return J2KGPU_OK;
-#undef T2_FAIL
+}
+
+int j2k_tier2_parse(const uint8_t *d, uint64_t len, uint32_t reduce, uint32_t threads, j2kgpu_parsed &out)
+{
+    j2k_t2_frame *F = nullptr;
+    const int rc = j2k_tier2_begin(d, len, reduce, &F, out.err);
+    if (rc) return rc;
+    const uint32_t ntiles = F->ntiles;
+    uint32_t nthreads = threads ? threads : std::max(1u, std::thread::hardware_concurrency());
+    nthreads = std::min<uint32_t>({nthreads, ntiles, 64u});
+    std::atomic<uint32_t> next{0};
+    auto worker = [&]() {
+        for (;;) {
+            const uint32_t t = next.fetch_add(1);
+            if (t >= ntiles) break;
+            j2k_tier2_tile(F, t);
+        }
+    };
+    if (nthreads <= 1) worker();
+    else {
+        std::vector<std::thread> th;
+        for (uint32_t i = 0; i < nthreads; i++) th.emplace_back(worker);
+        for (auto &t : th) t.join();
+    }
+    return j2k_tier2_finish(F, out);
 }

@@ -27,5 +27,15 @@ struct j2kgpu_parsed {
     std::string err;
 };
 
+// The same in steps, for callers that spread the tiles of several codestreams over one set of threads: begin reads the main
+// header and the tile-part index, tile(t) runs tier-2 of one tile (thread-safe for distinct tiles), finish merges the tiles
+// into the tables and frees the frame (free: without merging).
+struct j2k_t2_frame;
+int j2k_tier2_begin(const uint8_t *cs, uint64_t len, uint32_t reduce, j2k_t2_frame **f, std::string &err);
+uint32_t j2k_tier2_tiles(const j2k_t2_frame *f);
+void j2k_tier2_tile(j2k_t2_frame *f, uint32_t t);
+int j2k_tier2_finish(j2k_t2_frame *f, j2kgpu_parsed &out);
+void j2k_tier2_free(j2k_t2_frame *f);
+
 // threads = tiles parsed concurrently (0 = hardware concurrency).  Returns J2KGPU_OK or a J2KGPU_E_* code with out.err set.
 int j2k_tier2_parse(const uint8_t *cs, uint64_t len, uint32_t reduce, uint32_t threads, j2kgpu_parsed &out);
