@@ -76,6 +76,32 @@ def test_t1_garbage_and_truncated_vs_oracle(gpu_ctx):
         assert np.array_equal(got, O.t1_decode(s, w, h, nbps, band))
 
 
+@pytest.mark.parametrize("group", [4, 8, 16, 32])
+def test_t1_every_lanes_per_block_variant(gpu_ctx, group):
+    """k_t1_ref<OT, G>: 32 / G blocks share a warp (one MQ chain per group of G lanes, finished bit-planes merged into the
+    samples in place): every G against the oracle on encoder streams of all shapes, garbage, and a block count that
+    leaves the last warp partly empty"""
+    rng = np.random.default_rng(40 + group)
+    blocks, want = [], []
+    for k in range(75):
+        w, h = int(rng.integers(1, 65)), int(rng.integers(1, 65))
+        band, nb = int(rng.integers(0, 4)), int(rng.integers(1, 15))
+        if k % 5 == 4:                                               # arbitrary bytes
+            s = rng.integers(0, 256, int(rng.integers(1, 300))).astype(np.uint8).tobytes()
+            blocks.append((s, w, h, nb, band))
+            want.append(O.t1_decode(s, w, h, nb, band))
+            continue
+        d = rng.integers(-(1 << nb) + 1, 1 << nb, w * h).astype(np.int32)
+        d[rng.random(w * h) < rng.uniform(0, 0.95)] = 0
+        enc, nbps = O.t1_encode(d, w, h, band)
+        blocks.append((enc, w, h, nbps, band))
+        want.append(d if d.any() else O.t1_decode(enc, w, h, nbps, band))
+    with gpu_ctx.options(t1_group=group):
+        got = gpu_ctx.t1_decode_blocks(blocks)
+    for i, (g, w_) in enumerate(zip(got, want)):
+        assert np.array_equal(g, w_), i
+
+
 def test_t1_wide_dynamic_range(gpu_ctx):
     """num_bps up to 31 (int32 magnitudes)"""
     rng = np.random.default_rng(23)

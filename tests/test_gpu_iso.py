@@ -281,6 +281,32 @@ def test_iso_ebcot_blocks_vs_oracle(gpu_ctx):
         assert np.array_equal(g, w_), i
 
 
+@pytest.mark.parametrize("group", [4, 8, 16, 32])
+def test_iso_ebcot_every_lanes_per_block_variant(j2k, gpu_ctx, group):
+    """k_t1_iso<OT, G> for every G: block level (all passes and truncations, int32) and whole path (int16 planes, 3 layers
+    and a lossy 9-7 stream with float32 planes) against the oracle / OpenJPEG"""
+    from datagen import codestream as cs
+    s = jobs.synth_image(160, 120, 3, 8, seed=13)
+    h = cs.parse_codestream(opj_encode(s, irreversible=False, num_resolutions=3, mct=1))
+    rng = np.random.default_rng(group)
+    blocks, want = [], []
+    for b in h["blocks"]:
+        if not b["passes"]:
+            continue
+        npass = int(rng.integers(1, b["passes"] + 1))
+        blocks.append((b["data"], b["w"], b["h"], b["num_bps"], b["band"], npass))
+        v = O.iso_t1_decode(b["data"], b["w"], b["h"], b["num_bps"], npass, b["band"])
+        want.append(np.sign(v) * (np.abs(v) >> 1))
+    with gpu_ctx.options(t1_group=group):
+        got = gpu_ctx.t1_decode_blocks(blocks, mode=ISO)
+        for i, (g, w_) in enumerate(zip(got, want)):
+            assert np.array_equal(g, w_), i
+        for kw in (dict(num_resolutions=4, mct=1, quality_layers=[20, 5, 1]), dict(num_resolutions=4, mct=1, irreversible=True, quality_layers=[15])):
+            data = opj_encode(s, **kw)
+            got_px = gpu_ctx.decode_codestream(data).reshape(120, 160, 4)[:, :, :3]
+            assert np.array_equal(got_px, np.array(pytest.importorskip("PIL.Image").open(io.BytesIO(data))))
+
+
 def test_iso_ebcot_garbage_vs_oracle(gpu_ctx):
     rng = np.random.default_rng(7)
     blocks, want = [(b"", 8, 8, 5, 0, 0)], [np.zeros(64, np.int32)]
