@@ -13,9 +13,6 @@
 #include "../host/rgb_expand.h"
 
 #define J2K_MAX_LEVELS 10
-#ifndef J2K_T1_ONE_LANE
-#define J2K_T1_ONE_LANE 1      /* EBCOT kernels: lane 0 alone runs the serial MQ chain (1) or all lanes run it in lock-step (0) */
-#endif
 
 // Kernel launch / dynamic shared memory spelled as macros so that tools/emu can build these same sources for the
 // CPU fiber emulator (a debugging aid; the product is the nvcc build below).
@@ -23,13 +20,11 @@
 #ifdef J2K_EMU
 #define J2K_LAUNCH(K, G, B, SM, ST, ...) emu::launch(dim3(G), dim3(B), (SM), [&]() { J2K_UNPAREN K(__VA_ARGS__); })
 #define J2K_DYN_SMEM(T, name) T *name = reinterpret_cast<T *>(emu::dyn_smem)
-#define J2K_LOCKSTEP_LANE(lane) ((lane) == 0)
 #define J2K_NOINLINE __attribute__((noinline))
 #define J2K_OPAQUE_PTR(p) ((void)0)
 #else
 #define J2K_OPAQUE_PTR(p) asm volatile("" : "+l"(p))
 #define J2K_NOINLINE __noinline__
-#define J2K_LOCKSTEP_LANE(lane) (J2K_T1_ONE_LANE ? (lane) == 0 : true)
 #define J2K_LAUNCH(K, G, B, SM, ST, ...) J2K_UNPAREN K<<<(G), (B), (SM), (ST)>>>(__VA_ARGS__)
 #define J2K_DYN_SMEM(T, name) extern __shared__ __align__(16) unsigned char j2k_dyn_smem_[]; T *name = reinterpret_cast<T *>(j2k_dyn_smem_)
 #endif

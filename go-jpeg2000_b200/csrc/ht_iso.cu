@@ -95,12 +95,9 @@ __device__ __forceinline__ int32_t sample_value(uint32_t q, uint32_t sign, float
 //                      the previous quad row.  Output: 16 bits per quad in a scratch table, row-major 32 quads per quad
 //                      row: 2 bits per sample (0 insignificant, 1 significant, 2 + known EMB bit = 0, 3 + EMB bit = 1;
 //                      the CxtVLC tables satisfy e_1 <= e_k <= rho, so this loses nothing) and u_q << 8.
-//   B  k_htiso_magsgn  one warp per block, one lane per quad of a quad row: the exponent predictor needs the previous
-//                      row's exponents (two shuffles), then U_q, the four field widths, a warp prefix sum for the
-//                      position of every quad in the MagSgn stream, and the extraction of the row's 128 samples in
-//                      parallel; rows are written as contiguous 8-byte stores.  The stuffing is removed by the warp in
-//                      128-byte chunks (prefix sum of byte widths, bytes OR-ed into a dense bit string) into a 16 Kbit
-//                      shared-memory ring that runs at least one quad row (32 x 4 x 31 bits) ahead of the decoder.
+//   B  k_htiso_magsgn4 eight lanes per block, four blocks per warp (below): exponent predictor from the previous quad row,
+//                      U_q, field widths, prefix sum for the positions in the MagSgn stream, the samples of a quad row in
+//                      parallel out of a shared-memory ring that holds the stream with its stuffing removed.
 // The streams are pure functions of the block's bytes (see ht_ref.cu), so the result equals the single-chain decoder's
 // for every input, malformed ones included (same `bad` conditions, same zero block).
 constexpr int kQTabWords = 512;                         // 32 quad rows x 32 quads x 16 bits
