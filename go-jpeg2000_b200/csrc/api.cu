@@ -222,8 +222,6 @@ static int set_option(J2kOpts &o, const char *name, const char *value)
     else if (k == "wide_sp") o.wide_sp = iv;
     else if (k == "t1_group") o.t1_group = iv;
     else if (k == "host_alpha") o.host_alpha = iv;
-    else if (k == "no_ht_overlap") o.no_ht_overlap = iv;
-    else if (k == "ht_overlap_min") o.ht_overlap_min = iv;
     else if (k == "split_min_mpixel") o.split_min_mpixel = iv;
     else if (k == "debug_plan") o.debug_plan = on;
     else if (k == "chunks") o.chunks = v;
@@ -243,7 +241,7 @@ extern "C" int j2kgpu_create(int device, j2kgpu_ctx **out)
     if (!ctx) return J2KGPU_E_NOMEM;
     ctx->device = device;
     // the environment is read here, once per context, and nowhere else
-    static const char *const names[] = {"no_fuse", "no_wide", "no_fast_epi", "coef32", "no_preclear", "wide_sp", "t1_group", "host_alpha", "no_ht_overlap", "ht_overlap_min", "split_min_mpixel", "debug_plan", "chunks"};
+    static const char *const names[] = {"no_fuse", "no_wide", "no_fast_epi", "coef32", "no_preclear", "wide_sp", "t1_group", "host_alpha", "split_min_mpixel", "debug_plan", "chunks"};
     for (const char *nm : names) {
         std::string env = "J2KGPU_";
         for (const char *c = nm; *c; c++) env += (char)toupper((unsigned char)*c);
@@ -279,9 +277,6 @@ extern "C" void j2kgpu_destroy(j2kgpu_ctx *ctx)
     ctx->hpool.clear();
     delete ctx->expand;
     ctx->expand = nullptr;
-    if (ctx->s_aux) cudaStreamDestroy(ctx->s_aux);
-    if (ctx->ev_aux1) cudaEventDestroy(ctx->ev_aux1);
-    if (ctx->ev_aux2) cudaEventDestroy(ctx->ev_aux2);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     ctx->events.clear();
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
@@ -663,19 +658,9 @@ static int run_entropy(j2kgpu_job *job, const void *d_blob, uint32_t ia, uint32_
     if (job->iso && !job->hdr.ht) e = launch_t1_iso(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, steps, irrev, job->max_bps, ctx->opt.t1_group, st);
     else if (job->iso) {
         // chunks of a pipelined run share the scratch: their kernels are ordered on one stream
-        const uint32_t ov_min = ctx->opt.ht_overlap_min > 0 ? (uint32_t)ctx->opt.ht_overlap_min : 60000u;
-        HtIsoOverlap ov{nullptr, nullptr, nullptr, ov_min};
-        if (!ctx->opt.no_ht_overlap && n >= ov_min && n >= 256u) {    // a second stream for the halves of a large launch (created once)
-            if (!ctx->s_aux) {
-                if (cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking) != cudaSuccess ||
-                    cudaEventCreateWithFlags(&ctx->ev_aux1, cudaEventDisableTiming) != cudaSuccess ||
-                    cudaEventCreateWithFlags(&ctx->ev_aux2, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); ctx->s_aux = nullptr; }
-            }
-            if (ctx->s_aux && ctx->ev_aux1 && ctx->ev_aux2) ov = HtIsoOverlap{ctx->s_aux, ctx->ev_aux1, ctx->ev_aux2, ov_min};
-        }
         e = launch_ht_iso(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, steps, irrev, job->hdr.coef_bits,
-                          job->ht_refine, job->d_htscratch, job->blob_bytes, st, ov.aux ? &ov : nullptr);
-        ctx->launches += j2k_htiso_launches(job->ht_refine, ov.aux != nullptr) - 1;
+                          job->ht_refine, job->d_htscratch, job->blob_bytes, st);
+        ctx->launches += j2k_htiso_launches(job->ht_refine) - 1;
     }
     else if (job->hdr.ht) {
         e = launch_ht_ref(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, job->precleared,
@@ -1391,10 +1376,10 @@ static int stage_blocks(j2kgpu_ctx *ctx, int mode, int ht, const j2k_blkjob_t *j
             if (cbs[i].num_passes > 1) refine = 1;
         }
         if ((rc = j2k_reserve(ctx, ctx->d_aux, j2k_htiso_scratch_bytes(n, refine), false))) return rc;
-        ctx->launches += j2k_htiso_launches(refine, 0) - 1;
+        ctx->launches += j2k_htiso_launches(refine) - 1;
     }
     cudaError_t e = (ht && mode == J2KGPU_MODE_ISO)
-                        ? launch_ht_iso((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, nullptr, 0, 0, refine, ctx->d_aux.p, blob_len, ctx->stream, nullptr)
+                        ? launch_ht_iso((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, nullptr, 0, 0, refine, ctx->d_aux.p, blob_len, ctx->stream)
                     : mode == J2KGPU_MODE_ISO ? launch_t1_iso((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, nullptr, 0, max_bps, ctx->opt.t1_group, ctx->stream)
                     : ht ? launch_ht_ref((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, 0, ctx->d_aux.p, blob_len, ctx->stream)
                        : launch_t1_ref_stage((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, (int32_t *)ctx->d_out.p, max_bps, ctx->opt.t1_group, ctx->stream);

@@ -782,67 +782,33 @@ size_t j2k_htiso_scratch_bytes(uint32_t n, int refine)
 {
     return (size_t)n * (kQTabWords * 4 + 4) + 64 + (refine ? (size_t)n * kRefWords * 8 : 0);
 }
-int j2k_htiso_launches(int refine, int halves) { return (refine ? 3 : 2) * (halves ? 2 : 1); }
-
-// the kernels of blocks [first, first + n) of a launch of n_all blocks (the scratch is laid out for n_all)
-template <typename OT>
-static void launch_ht_iso_vlc(const DevCblk *d_cblks, uint32_t first, uint32_t n, uint32_t n_all, const uint8_t *d_blob, void *d_scratch, cudaStream_t s)
-{
-    uint32_t *qtab = (uint32_t *)d_scratch, *status = qtab + (size_t)n_all * kQTabWords;
-    J2K_LAUNCH((k_htiso_vlc), (n + kThreads - 1) / kThreads, kThreads, 0, s, d_cblks + first, n, d_blob, qtab + (size_t)first * kQTabWords, status + first);
-}
+int j2k_htiso_launches(int refine) { return refine ? 3 : 2; }
 
 template <typename OT>
-static void launch_ht_iso_rest(const DevCblk *d_cblks, uint32_t first, uint32_t n, uint32_t n_all, const uint8_t *d_blob, OT *d_coef,
-                               const float *d_steps, int irrev, int coef_bits, int refine, void *d_scratch, uint64_t blob_bytes, cudaStream_t s)
+static void launch_ht_iso_t(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, OT *d_coef,
+                            const float *d_steps, int irrev, int coef_bits, int refine, void *d_scratch, uint64_t blob_bytes, cudaStream_t s)
 {
-    uint32_t *qtab = (uint32_t *)d_scratch, *status = qtab + (size_t)n_all * kQTabWords;
-    uint64_t *ref = (uint64_t *)(((uintptr_t)(status + n_all) + 63) & ~(uintptr_t)63);
-    const DevCblk *cb = d_cblks + first;
-    qtab += (size_t)first * kQTabWords; status += first; ref += (size_t)first * kRefWords;
-    const float *steps = d_steps ? d_steps + first : nullptr;
-    if (refine) J2K_LAUNCH((k_htiso_refine), (n + kRefWarps - 1) / kRefWarps, kRefWarps * 32, 0, s, cb, n, d_blob, qtab, status, ref);
+    const uint64_t blob_total = blob_bytes;
+    uint32_t *qtab = (uint32_t *)d_scratch, *status = qtab + (size_t)n * kQTabWords;
+    uint64_t *ref = (uint64_t *)(((uintptr_t)(status + n) + 63) & ~(uintptr_t)63);
+    J2K_LAUNCH((k_htiso_vlc), (n + kThreads - 1) / kThreads, kThreads, 0, s, d_cblks, n, d_blob, qtab, status);
+    if (refine) J2K_LAUNCH((k_htiso_refine), (n + kRefWarps - 1) / kRefWarps, kRefWarps * 32, 0, s, d_cblks, n, d_blob, qtab, status, ref);
     const uint32_t grid = (n + 4 * kWarpsB4 - 1) / (4 * kWarpsB4);
-    const uint8_t *blob_end = d_blob + blob_bytes;
-#define J2K_HTISO_B(IRR, REF) J2K_LAUNCH((k_htiso_magsgn4<OT, IRR, REF>), grid, kWarpsB4 * 32, 0, s, cb, n, d_blob, blob_end, qtab, status, d_coef, steps, coef_bits, ref)
+    const uint8_t *blob_end = d_blob + blob_total;
+#define J2K_HTISO_B(IRR, REF) J2K_LAUNCH((k_htiso_magsgn4<OT, IRR, REF>), grid, kWarpsB4 * 32, 0, s, d_cblks, n, d_blob, blob_end, qtab, status, d_coef, d_steps, coef_bits, ref)
     if (irrev) { if (refine) J2K_HTISO_B(true, true); else J2K_HTISO_B(true, false); }
     else { if (refine) J2K_HTISO_B(false, true); else J2K_HTISO_B(false, false); }
 #undef J2K_HTISO_B
 }
 
-// The VLC kernel is a chain per thread that leaves issue slots and most of the register file idle; the MagSgn kernel is
-// bound by the integer pipe.  A large launch is therefore cut in two halves: the VLC kernel of the second half runs on a
-// second stream next to the MagSgn kernel of the first (s: VLC 1, MagSgn 1, MagSgn 2; aux: VLC 2 between the two events).
-template <typename OT>
-static cudaError_t launch_ht_iso_t(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, OT *d_coef, const float *d_steps, int irrev,
-                                   int coef_bits, int refine, void *d_scratch, uint64_t blob_bytes, cudaStream_t s, const HtIsoOverlap *ov)
-{
-    if (!ov || !ov->aux || n < ov->min_blocks || n < 256u) {
-        launch_ht_iso_vlc<OT>(d_cblks, 0, n, n, d_blob, d_scratch, s);
-        launch_ht_iso_rest<OT>(d_cblks, 0, n, n, d_blob, d_coef, d_steps, irrev, coef_bits, refine, d_scratch, blob_bytes, s);
-        return cudaGetLastError();
-    }
-    const uint32_t n1 = ((n / 2) + 127u) & ~127u;
-    cudaError_t e;
-    launch_ht_iso_vlc<OT>(d_cblks, 0, n1, n, d_blob, d_scratch, s);
-    if ((e = cudaEventRecord(ov->ev1, s)) != cudaSuccess) return e;
-    if ((e = cudaStreamWaitEvent(ov->aux, ov->ev1, 0)) != cudaSuccess) return e;
-    launch_ht_iso_vlc<OT>(d_cblks, n1, n - n1, n, d_blob, d_scratch, ov->aux);
-    if ((e = cudaEventRecord(ov->ev2, ov->aux)) != cudaSuccess) return e;
-    launch_ht_iso_rest<OT>(d_cblks, 0, n1, n, d_blob, d_coef, d_steps, irrev, coef_bits, refine, d_scratch, blob_bytes, s);
-    if ((e = cudaStreamWaitEvent(s, ov->ev2, 0)) != cudaSuccess) return e;
-    launch_ht_iso_rest<OT>(d_cblks, n1, n - n1, n, d_blob, d_coef, d_steps, irrev, coef_bits, refine, d_scratch, blob_bytes, s);
-    return cudaGetLastError();
-}
-
-// d_scratch: j2k_htiso_scratch_bytes(n, refine) bytes of device memory; refine: some block has num_passes > 1;
-// ov: a second stream and two events for the overlap of large launches (may be null)
+// d_scratch: j2k_htiso_scratch_bytes(n, refine) bytes of device memory; refine: some block has num_passes > 1
 cudaError_t launch_ht_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
                           const float *d_steps, int irrev, int coef_bits, int refine, void *d_scratch, uint64_t blob_bytes,
-                          cudaStream_t s, const HtIsoOverlap *ov)
+                          cudaStream_t s)
 {
     if (n == 0) return cudaSuccess;
     if (blob_bytes >> 33) return cudaErrorInvalidValue;  // the VLC reader indexes the blob's words with an int
-    if (coef16 && !irrev) return launch_ht_iso_t<int16_t>(d_cblks, n, d_blob, (int16_t *)d_coef, d_steps, irrev, coef_bits, refine, d_scratch, blob_bytes, s, ov);
-    return launch_ht_iso_t<int32_t>(d_cblks, n, d_blob, (int32_t *)d_coef, d_steps, irrev, coef_bits, refine, d_scratch, blob_bytes, s, ov);
+    if (coef16 && !irrev) launch_ht_iso_t<int16_t>(d_cblks, n, d_blob, (int16_t *)d_coef, d_steps, irrev, coef_bits, refine, d_scratch, blob_bytes, s);
+    else launch_ht_iso_t<int32_t>(d_cblks, n, d_blob, (int32_t *)d_coef, d_steps, irrev, coef_bits, refine, d_scratch, blob_bytes, s);
+    return cudaGetLastError();
 }

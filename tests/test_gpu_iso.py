@@ -281,30 +281,6 @@ def test_iso_ebcot_blocks_vs_oracle(gpu_ctx):
         assert np.array_equal(g, w_), i
 
 
-@pytest.mark.parametrize("passes,step", [(1, None), (3, None), (1, 2.0)])
-def test_iso_ht_large_launch_in_two_halves(j2k, gpu_ctx, passes, step):
-    """a large HT launch is cut in two halves whose VLC and MagSgn kernels overlap on two streams (second half of the quad
-    table, status words, refinement bitmaps and step sizes addressed by offset): same pixels as the single launch"""
-    from datagen import codestream as cs
-    s = jobs.synth_image(768, 512, 3, 8, seed=31)
-    if step:
-        data, _ = cs.write_htj2k(s, 8, 256, 256, 4, lossy_step=step)
-    else:
-        data = jobs.build_iso_job(s, 8, 256, 256, 4, ht_passes=passes, ht_plane=1 if passes > 1 else 0)["codestream"]
-    with gpu_ctx.options(ht_overlap_min=300):
-        n0 = gpu_ctx.launches
-        a = gpu_ctx.decode_codestreams([data, data])
-        halves = gpu_ctx.launches - n0
-    with gpu_ctx.options(no_ht_overlap=1):
-        n0 = gpu_ctx.launches
-        b = gpu_ctx.decode_codestreams([data, data])
-        whole = gpu_ctx.launches - n0
-    assert halves > whole                                          # the entropy kernels ran twice per call
-    assert all(np.array_equal(x, y) for x, y in zip(a, b))
-    ref = np.array(pytest.importorskip("PIL.Image").open(io.BytesIO(data)))
-    assert np.array_equal(a[0].reshape(512, 768, 4)[:, :, :3], ref)
-
-
 @pytest.mark.parametrize("group", [4, 8, 16, 32])
 def test_iso_ebcot_every_lanes_per_block_variant(j2k, gpu_ctx, group):
     """k_t1_iso<OT, G> for every G: block level (all passes and truncations, int32) and whole path (int16 planes, 3 layers
