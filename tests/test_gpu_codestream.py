@@ -99,6 +99,20 @@ def test_jp2_file_and_alpha(j2k, gpu_ctx):
     assert np.array_equal(gpu_ctx.decode_codestream(data).reshape(150, 200, 4), np.moveaxis(s, 0, 2))
 
 
+@pytest.mark.parametrize("rate", [0, 150])
+def test_16_bit_rgb_written_by_opencv(j2k, gpu_ctx, rate):
+    """16-bit RGB EBCOT (int32 planes, RGBA64 output) from a JP2 file written by OpenCV: OpenCV's own decode"""
+    cv2 = pytest.importorskip("cv2")
+    s = jobs.synth_image(300, 200, 3, 16, seed=6)
+    bgr = np.ascontiguousarray(np.moveaxis(s, 0, 2).astype(np.uint16)[:, :, ::-1])
+    ok, enc = cv2.imencode(".jp2", bgr, [cv2.IMWRITE_JPEG2000_COMPRESSION_X1000, rate] if rate else [])
+    assert ok
+    data = enc.tobytes()
+    got = gpu_ctx.decode_codestream(data).reshape(200, 300, 4, 2)
+    val = (got[..., 0].astype(np.uint16) << 8) | got[..., 1]
+    assert np.array_equal(val[:, :, :3], cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_UNCHANGED)[:, :, ::-1])   # (OpenCV returns B G R)
+
+
 def test_errors_surface_and_the_context_survives(j2k, gpu_ctx):
     s = jobs.synth_image(128, 128, 3, 8, seed=8)
     good = opj_encode(s, num_resolutions=3, mct=1)

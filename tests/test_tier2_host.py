@@ -238,6 +238,24 @@ def test_jp2_container_and_rgba(j2k):
     assert "codestream box" in str(e.value)
 
 
+@pytest.mark.parametrize("rate", [0, 150])
+def test_16_bit_rgb_written_by_opencv(j2k, rate):
+    """three 16-bit components in a JP2 file written by OpenCV's OpenJPEG encoder (lossless, and truncated by a rate target):
+    tier-2 + CPU checker give OpenCV's own decode (RGBA64, big-endian channels)"""
+    cv2 = pytest.importorskip("cv2")
+    s = jobs.synth_image(300, 200, 3, 16, seed=6)
+    bgr = np.ascontiguousarray(np.moveaxis(s, 0, 2).astype(np.uint16)[:, :, ::-1])
+    ok, enc = cv2.imencode(".jp2", bgr, [cv2.IMWRITE_JPEG2000_COMPRESSION_X1000, rate] if rate else [])
+    assert ok
+    data = enc.tobytes()
+    p = j2k.Parsed(data)
+    assert p.image.prec[0] == 16 and p.image.ncomp == 3 and p.image.coef_bits > 14
+    got = O.iso_decode_job(job_from_parsed(p, data)).reshape(200, 300, 4, 2)
+    val = (got[..., 0].astype(np.uint16) << 8) | got[..., 1]
+    ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_UNCHANGED)
+    assert np.array_equal(val[:, :, :3], ref[:, :, ::-1]) and (val[:, :, 3] == 65535).all()   # (OpenCV returns B G R)
+
+
 def test_unsupported_features_are_reported(j2k):
     s = jobs.synth_image(128, 128, 3, 8, seed=3)
     good = opj_encode(s, num_resolutions=3, mct=1)
