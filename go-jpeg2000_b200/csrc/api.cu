@@ -222,8 +222,6 @@ static int set_option(J2kOpts &o, const char *name, const char *value)
     else if (k == "wide_sp") o.wide_sp = iv;
     else if (k == "t1_group") o.t1_group = iv;
     else if (k == "host_alpha") o.host_alpha = iv;
-    else if (k == "no_coarse_overlap") o.no_coarse_overlap = iv;
-    else if (k == "coarse_overlap_min") o.coarse_overlap_min = iv;
     else if (k == "split_min_mpixel") o.split_min_mpixel = iv;
     else if (k == "debug_plan") o.debug_plan = on;
     else if (k == "chunks") o.chunks = v;
@@ -243,7 +241,7 @@ extern "C" int j2kgpu_create(int device, j2kgpu_ctx **out)
     if (!ctx) return J2KGPU_E_NOMEM;
     ctx->device = device;
     // the environment is read here, once per context, and nowhere else
-    static const char *const names[] = {"no_fuse", "no_wide", "no_fast_epi", "coef32", "no_preclear", "wide_sp", "t1_group", "host_alpha", "no_coarse_overlap", "coarse_overlap_min", "split_min_mpixel", "debug_plan", "chunks"};
+    static const char *const names[] = {"no_fuse", "no_wide", "no_fast_epi", "coef32", "no_preclear", "wide_sp", "t1_group", "host_alpha", "split_min_mpixel", "debug_plan", "chunks"};
     for (const char *nm : names) {
         std::string env = "J2KGPU_";
         for (const char *c = nm; *c; c++) env += (char)toupper((unsigned char)*c);
@@ -279,9 +277,6 @@ extern "C" void j2kgpu_destroy(j2kgpu_ctx *ctx)
     ctx->hpool.clear();
     delete ctx->expand;
     ctx->expand = nullptr;
-    if (ctx->s_coarse) cudaStreamDestroy(ctx->s_coarse);
-    if (ctx->ev_coarse_in) cudaEventDestroy(ctx->ev_coarse_in);
-    if (ctx->ev_coarse_out) cudaEventDestroy(ctx->ev_coarse_out);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     ctx->events.clear();
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
@@ -379,13 +374,12 @@ static bool tiles_exactly(std::vector<Rect> &r, uint32_t w, uint32_t h) { return
 static void sort_blocks_by_shape(DevCblk *cb, float *step, size_t n, std::vector<DevCblk> &tmp, std::vector<float> &stmp)
 {
     if (n < 2) return;
-    uint32_t count[2 * 65 * 65 + 1] = {0};
-    // (blocks of decomposition level >= 3 first: the MagSgn kernel of a large HT job runs over them in a launch of its own)
-    auto key = [](const DevCblk &c) { return (c.level >= 3 ? 0u : 65u * 65u) + (uint32_t)(64 - c.h) * 65u + (uint32_t)(64 - c.w); };
+    uint32_t count[65 * 65 + 1] = {0};
+    auto key = [](const DevCblk &c) { return (uint32_t)(64 - c.h) * 65u + (uint32_t)(64 - c.w); };
     bool sorted = true;
     for (size_t i = 0; i < n; i++) { count[key(cb[i]) + 1]++; if (i && key(cb[i]) < key(cb[i - 1])) sorted = false; }
     if (sorted) return;
-    for (int k = 0; k < 2 * 65 * 65; k++) count[k + 1] += count[k];
+    for (int k = 0; k < 65 * 65; k++) count[k + 1] += count[k];
     tmp.assign(cb, cb + n); stmp.assign(step, step + n);
     for (size_t i = 0; i < n; i++) { const uint32_t d = count[key(tmp[i])]++; cb[d] = tmp[i]; step[d] = stmp[i]; }
 }
@@ -644,7 +638,7 @@ extern "C" uint64_t j2kgpu_job_out_offset(const j2kgpu_job *job, uint32_t item)
 }
 
 // ---- launch sequences over the items [ia, ib) of a job, on stream `st` ------------------------------------------------
-static int run_entropy(j2kgpu_job *job, const void *d_blob, uint32_t ia, uint32_t ib, cudaStream_t st, cudaEvent_t coarse_done = nullptr)
+static int run_entropy(j2kgpu_job *job, const void *d_blob, uint32_t ia, uint32_t ib, cudaStream_t st)
 {
     j2kgpu_ctx *ctx = job->ctx;
     const size_t esz = job->coef16 ? 2 : 4;
@@ -665,8 +659,8 @@ static int run_entropy(j2kgpu_job *job, const void *d_blob, uint32_t ia, uint32_
     else if (job->iso) {
         // chunks of a pipelined run share the scratch: their kernels are ordered on one stream
         e = launch_ht_iso(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, steps, irrev, job->hdr.coef_bits,
-                          job->ht_refine, job->d_htscratch, job->blob_bytes, st, coarse_done);
-        ctx->launches += j2k_htiso_launches(job->ht_refine) - 1 + (coarse_done ? 1 : 0);
+                          job->ht_refine, job->d_htscratch, job->blob_bytes, st);
+        ctx->launches += j2k_htiso_launches(job->ht_refine) - 1;
     }
     else if (job->hdr.ht) {
         e = launch_ht_ref(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, job->precleared,
@@ -713,10 +707,7 @@ static int run_level(j2kgpu_job *job, const IdwtLaunch &base, int lvl, cudaStrea
     return J2KGPU_OK;
 }
 
-// coarse != nullptr: the entropy stage recorded ev_coarse_in once the blocks of decomposition level >= 3 were decoded; the
-// inverse-DWT levels >= 2 then run on the coarse stream (beside the MagSgn kernel of the fine blocks) and the fused kernel
-// of levels 1 + 0 waits for them
-static int run_dwt_mct(j2kgpu_job *job, void *d_out, uint32_t ia, uint32_t ib, cudaStream_t st, cudaStream_t coarse = nullptr)
+static int run_dwt_mct(j2kgpu_job *job, void *d_out, uint32_t ia, uint32_t ib, cudaStream_t st)
 {
     j2kgpu_ctx *ctx = job->ctx;
     if (job->pix_fill)
@@ -730,35 +721,11 @@ static int run_dwt_mct(j2kgpu_job *job, void *d_out, uint32_t ia, uint32_t ib, c
     IdwtLaunch p;
     fill_launch(job, p, d_out, ia, ib);
     if (p.n_tiles == 0) return J2KGPU_OK;
-    if (coarse) J2K_CUDA(ctx, cudaStreamWaitEvent(coarse, ctx->ev_coarse_in, 0));
     for (int lvl = job->nlevels ? job->nlevels - 1 : 0; lvl >= 0; lvl--) {
-        if (coarse && lvl == 1) {                        // the coarse levels are queued: the rest waits for them on the main stream
-            J2K_CUDA(ctx, cudaEventRecord(ctx->ev_coarse_out, coarse));
-            J2K_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_coarse_out, 0));
-        }
-        int rc = run_level(job, p, lvl, (coarse && lvl >= 2) ? coarse : st);
+        int rc = run_level(job, p, lvl, st);
         if (rc) return rc;
     }
     return J2KGPU_OK;
-}
-
-// a large conformant-HT job whose last two levels run fused: its coarse levels can run beside the fine blocks' MagSgn kernel
-static cudaStream_t coarse_stream(j2kgpu_job *job, uint32_t ia, uint32_t ib)
-{
-    j2kgpu_ctx *ctx = job->ctx;
-    if (ctx->opt.no_coarse_overlap || !job->iso || !job->hdr.ht || !job->fused_ok || job->nlevels < 3) return nullptr;
-    if (job->item_cb[ib] - job->item_cb[ia] < (ctx->opt.coarse_overlap_min > 0 ? (uint32_t)ctx->opt.coarse_overlap_min : 50000u)) return nullptr;
-    if (!ctx->s_coarse) {
-        int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);      // its small kernels take the first slots that come free
-        if (cudaStreamCreateWithPriority(&ctx->s_coarse, cudaStreamNonBlocking, hi) != cudaSuccess ||
-            cudaEventCreateWithFlags(&ctx->ev_coarse_in, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&ctx->ev_coarse_out, cudaEventDisableTiming) != cudaSuccess) {
-            cudaGetLastError();
-            return nullptr;
-        }
-    }
-    return ctx->s_coarse;
 }
 
 extern "C" int j2kgpu_job_run_entropy(j2kgpu_job *job, const void *d_blob)
@@ -802,10 +769,9 @@ extern "C" int j2kgpu_job_run(j2kgpu_job *job, const void *d_blob, void *d_out)
     if (!job || !d_out || (!d_blob && job->blob_bytes)) return J2KGPU_E_ARG;
     std::lock_guard<std::mutex> g(job->ctx->mu);
     cudaSetDevice(job->ctx->device);
-    cudaStream_t coarse = coarse_stream(job, 0, job->n_img);
-    int rc = run_entropy(job, d_blob, 0, job->n_img, job->ctx->stream, coarse ? job->ctx->ev_coarse_in : nullptr);
+    int rc = run_entropy(job, d_blob, 0, job->n_img, job->ctx->stream);
     if (rc) return rc;
-    return run_dwt_mct(job, d_out, 0, job->n_img, job->ctx->stream, coarse);
+    return run_dwt_mct(job, d_out, 0, job->n_img, job->ctx->stream);
 }
 
 // Chunk plan of the host-buffer run.  The device->host copy of the pixels is the bottleneck of the path (4 bytes per
@@ -1413,7 +1379,7 @@ static int stage_blocks(j2kgpu_ctx *ctx, int mode, int ht, const j2k_blkjob_t *j
         ctx->launches += j2k_htiso_launches(refine) - 1;
     }
     cudaError_t e = (ht && mode == J2KGPU_MODE_ISO)
-                        ? launch_ht_iso((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, nullptr, 0, 0, refine, ctx->d_aux.p, blob_len, ctx->stream, nullptr)
+                        ? launch_ht_iso((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, nullptr, 0, 0, refine, ctx->d_aux.p, blob_len, ctx->stream)
                     : mode == J2KGPU_MODE_ISO ? launch_t1_iso((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, nullptr, 0, max_bps, ctx->opt.t1_group, ctx->stream)
                     : ht ? launch_ht_ref((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, 0, ctx->d_aux.p, blob_len, ctx->stream)
                        : launch_t1_ref_stage((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, (int32_t *)ctx->d_out.p, max_bps, ctx->opt.t1_group, ctx->stream);

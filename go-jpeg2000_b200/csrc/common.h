@@ -85,8 +85,6 @@ struct J2kOpts {
     int wide_sp = 0;        // strip height of the wide IDWT kernel in row pairs (0 = planner)
     int t1_group = 0;       // EBCOT kernels: lanes per code block (4, 8, 16, 32; 0 = default 8)
     int split_min_mpixel = 0; // a single image of at least this many Mpixel is pipelined by groups of tiles (0 = 24)
-    int no_coarse_overlap = 0; // ISO HT jobs: coarse IDWT levels on the ctx stream, after the whole entropy stage
-    int coarse_overlap_min = 0; // ... the overlap starts at this many code blocks per run (0 = 50 000)
     int host_alpha = -1;    // host-buffer runs of RGBA8 images: packed R G B over PCIe, alpha filled in by host threads (-1 = auto)
     int debug_plan = 0;     // print the chunk plan of host-buffer runs
     std::string chunks;     // explicit chunk sizes of host-buffer runs, e.g. "1,1,2,4"
@@ -112,9 +110,6 @@ struct j2kgpu_ctx {
     std::vector<DevBuf> hpool;           // page-locked host blocks (table staging of pipelined batch calls), same policy
     std::vector<cudaEvent_t> events;     // timing-disabled events, reused across calls
     J2kExpandPool *expand = nullptr;     // host threads that widen packed RGB rows to RGBA8 (created on first use)
-    // the coarse inverse-DWT levels of a large HT job run on this stream beside the MagSgn kernel of the fine blocks
-    cudaStream_t s_coarse = nullptr;
-    cudaEvent_t ev_coarse_in = nullptr, ev_coarse_out = nullptr;
 };
 void *j2k_pool_alloc(j2kgpu_ctx *ctx, size_t bytes, cudaError_t *err);
 void j2k_pool_free(j2kgpu_ctx *ctx, void *p);
@@ -193,7 +188,7 @@ cudaError_t launch_t1_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_b
 // refine: some block carries SigProp / MagRef passes (num_passes > 1): the refinement kernel runs between the two
 cudaError_t launch_ht_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
                           const float *d_steps, int irrev, int coef_bits, int refine, void *d_scratch, uint64_t blob_bytes,
-                          cudaStream_t s, cudaEvent_t coarse_done);
+                          cudaStream_t s);
 size_t j2k_htiso_scratch_bytes(uint32_t n_blocks, int refine);   // device scratch between the kernels
 int j2k_htiso_launches(int refine);                              // kernels per launch_ht_iso call
 

@@ -548,20 +548,17 @@ template <typename OT, bool IRREV, bool REFINE>
 __global__ void __launch_bounds__(kWarpsB4 * 32)
 k_htiso_magsgn4(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob, const uint8_t *blob_end,
                 const uint32_t *__restrict__ qtab, const uint32_t *__restrict__ status, OT *__restrict__ coef,
-                const float *__restrict__ steps, int coef_bits, const uint64_t *__restrict__ ref, int cls)
+                const float *__restrict__ steps, int coef_bits, const uint64_t *__restrict__ ref)
 {
     constexpr uint32_t FULL = 0xffffffffu;
     __shared__ uint32_t s_ring[kWarpsB4 * 4][kRingWords + 1];            // [kRingWords] mirrors word 0
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, grp = lane >> 3, sl = lane & 7;
     const uint32_t blk0 = (blockIdx.x * kWarpsB4 + warp) * 4;
     if (blk0 >= n) return;
-    const uint32_t blk = blk0 + grp < n ? blk0 + grp : blk0;
-    const DevCblk cb = cblks[blk];
-    // cls: 0 every block; 1 only the blocks the coarse inverse-DWT levels read (decomposition level >= 3, LL included);
-    // 2 only the others -- the launch is then made twice, so that the coarse levels can run beside the second (api.cu)
-    const bool have = blk0 + grp < n && (cls == 0 || (cb.level >= 3) == (cls == 1));
-    if (!__any_sync(FULL, have)) return;
+    const bool have = blk0 + grp < n;
+    const uint32_t blk = have ? blk0 + grp : blk0;
     const uint32_t stw = status[blk];
+    const DevCblk cb = cblks[blk];
     const int w = cb.w, h = cb.h;
     OT *out = coef + cb.out_off;
     const size_t ostride = cb.out_stride;
@@ -789,8 +786,7 @@ int j2k_htiso_launches(int refine) { return refine ? 3 : 2; }
 
 template <typename OT>
 static void launch_ht_iso_t(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, OT *d_coef,
-                            const float *d_steps, int irrev, int coef_bits, int refine, void *d_scratch, uint64_t blob_bytes, cudaStream_t s,
-                            cudaEvent_t coarse_done)
+                            const float *d_steps, int irrev, int coef_bits, int refine, void *d_scratch, uint64_t blob_bytes, cudaStream_t s)
 {
     const uint64_t blob_total = blob_bytes;
     uint32_t *qtab = (uint32_t *)d_scratch, *status = qtab + (size_t)n * kQTabWords;
@@ -799,29 +795,20 @@ static void launch_ht_iso_t(const DevCblk *d_cblks, uint32_t n, const uint8_t *d
     if (refine) J2K_LAUNCH((k_htiso_refine), (n + kRefWarps - 1) / kRefWarps, kRefWarps * 32, 0, s, d_cblks, n, d_blob, qtab, status, ref);
     const uint32_t grid = (n + 4 * kWarpsB4 - 1) / (4 * kWarpsB4);
     const uint8_t *blob_end = d_blob + blob_total;
-#define J2K_HTISO_B(IRR, REF, CLS) J2K_LAUNCH((k_htiso_magsgn4<OT, IRR, REF>), grid, kWarpsB4 * 32, 0, s, d_cblks, n, d_blob, blob_end, qtab, status, d_coef, d_steps, coef_bits, ref, CLS)
-#define J2K_HTISO_B4(CLS) do { if (irrev) { if (refine) J2K_HTISO_B(true, true, CLS); else J2K_HTISO_B(true, false, CLS); } \
-                               else { if (refine) J2K_HTISO_B(false, true, CLS); else J2K_HTISO_B(false, false, CLS); } } while (0)
-    if (!coarse_done) J2K_HTISO_B4(0);
-    else {                                               // coarse-level blocks first; the caller starts the coarse IDWT levels at the event
-        J2K_HTISO_B4(1);
-        cudaEventRecord(coarse_done, s);
-        J2K_HTISO_B4(2);
-    }
-#undef J2K_HTISO_B4
+#define J2K_HTISO_B(IRR, REF) J2K_LAUNCH((k_htiso_magsgn4<OT, IRR, REF>), grid, kWarpsB4 * 32, 0, s, d_cblks, n, d_blob, blob_end, qtab, status, d_coef, d_steps, coef_bits, ref)
+    if (irrev) { if (refine) J2K_HTISO_B(true, true); else J2K_HTISO_B(true, false); }
+    else { if (refine) J2K_HTISO_B(false, true); else J2K_HTISO_B(false, false); }
 #undef J2K_HTISO_B
 }
 
-// d_scratch: j2k_htiso_scratch_bytes(n, refine) bytes of device memory; refine: some block has num_passes > 1;
-// coarse_done (may be null): the MagSgn kernel runs twice, first over the blocks of decomposition level >= 3, and the event
-// is recorded between the two
+// d_scratch: j2k_htiso_scratch_bytes(n, refine) bytes of device memory; refine: some block has num_passes > 1
 cudaError_t launch_ht_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
                           const float *d_steps, int irrev, int coef_bits, int refine, void *d_scratch, uint64_t blob_bytes,
-                          cudaStream_t s, cudaEvent_t coarse_done)
+                          cudaStream_t s)
 {
     if (n == 0) return cudaSuccess;
     if (blob_bytes >> 33) return cudaErrorInvalidValue;  // the VLC reader indexes the blob's words with an int
-    if (coef16 && !irrev) launch_ht_iso_t<int16_t>(d_cblks, n, d_blob, (int16_t *)d_coef, d_steps, irrev, coef_bits, refine, d_scratch, blob_bytes, s, coarse_done);
-    else launch_ht_iso_t<int32_t>(d_cblks, n, d_blob, (int32_t *)d_coef, d_steps, irrev, coef_bits, refine, d_scratch, blob_bytes, s, coarse_done);
+    if (coef16 && !irrev) launch_ht_iso_t<int16_t>(d_cblks, n, d_blob, (int16_t *)d_coef, d_steps, irrev, coef_bits, refine, d_scratch, blob_bytes, s);
+    else launch_ht_iso_t<int32_t>(d_cblks, n, d_blob, (int32_t *)d_coef, d_steps, irrev, coef_bits, refine, d_scratch, blob_bytes, s);
     return cudaGetLastError();
 }

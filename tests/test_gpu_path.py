@@ -350,50 +350,6 @@ def test_overlapping_blocks_are_refused(j2k, gpu_ctx):
     assert np.array_equal(gpu_pixels(j2k, gpu_ctx, job), want)
 
 
-def test_coarse_levels_beside_the_fine_blocks(j2k, gpu_ctx):
-    """device-resident run of a conformant-HT job with the coarse inverse-DWT levels on their own stream (the MagSgn kernel
-    runs first over the blocks of decomposition level >= 3, then over the rest): same pixels as the single-stream run, for
-    cleanup-only, 3-pass and lossy blocks, and repeated runs keep agreeing (no stale event, no race on the level buffers)"""
-    import torch
-    from datagen import codestream as cs
-    srcs = [jobs.synth_image(768, 512, 3, 8, seed=50 + i) for i in range(3)]
-    for kind in ("lossless", "passes3", "lossy"):
-        if kind == "lossy":
-            jl = [jobs.build_iso_job_from_codestream(cs.write_htj2k(s, 8, 256, 256, 4, lossy_step=2.0)[0]) for s in srcs]
-        else:
-            jl = [jobs.build_iso_job(s, 8, 256, 256, 4, ht_passes=3 if kind == "passes3" else 1, ht_plane=1 if kind == "passes3" else 0) for s in srcs]
-        keep, items = [], []
-        for j in jl:
-            tcs, cbs = jobs.as_ctypes(j["tilecomps"], j2k.TileComp), jobs.as_ctypes(j["cblks"], j2k.CBlk)
-            blob = np.ascontiguousarray(j["blob"])
-            out = np.zeros(768 * 512 * 4, np.uint8)
-            keep += [tcs, cbs, blob, out]
-            img = j2k.make_image(768, 512, 3, 8, mct=j["mct"], reversible=j["reversible"], nlevels=4, ht=1, mode=j2k.MODE_ISO,
-                                 coef_bits=j.get("coef_bits", 0) if j["reversible"] else 0)
-            items.append(j2k.BatchItem(img, tcs, len(tcs), cbs, len(cbs), blob.ctypes.data_as(j2k.u8p), blob.size,
-                                       out.ctypes.data_as(j2k.u8p), 768 * 4))
-        job = j2k.Job(gpu_ctx, items)
-        d_blob = torch.from_numpy(np.concatenate([np.ascontiguousarray(j["blob"]) for j in jl] + [np.zeros(64, np.uint8)])).cuda()
-        d_a = torch.zeros(job.out_bytes, dtype=torch.uint8, device="cuda")
-        d_b = torch.zeros(job.out_bytes, dtype=torch.uint8, device="cuda")
-        torch.cuda.synchronize()
-        with gpu_ctx.options(no_coarse_overlap=1):
-            n0 = gpu_ctx.launches
-            job.run(d_blob.data_ptr(), d_b.data_ptr())
-            gpu_ctx.sync()
-            plain = gpu_ctx.launches - n0
-        with gpu_ctx.options(coarse_overlap_min=100):
-            for rep in range(4):
-                d_a.zero_()
-                torch.cuda.synchronize()
-                n0 = gpu_ctx.launches
-                job.run(d_blob.data_ptr(), d_a.data_ptr())
-                gpu_ctx.sync()
-                assert gpu_ctx.launches - n0 == plain + 1          # the MagSgn kernel ran twice
-                assert torch.equal(d_a, d_b), (kind, rep)
-        job.close()
-
-
 def test_packed_rgb_transfer_equals_rgba_transfer(j2k, gpu_ctx):
     """host-buffer runs of RGBA8 images move packed R G B over the link and host threads of the library fill in the alpha
     byte (host/rgb_expand.h): same bytes as the plain RGBA transfer, for one image, a batch in several chunks, a padded
