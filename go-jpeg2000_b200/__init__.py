@@ -18,6 +18,7 @@ __graft_entry__.py -- under the module name go_jpeg2000_b200.)
 """
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -185,12 +186,15 @@ class Context:
 
     def __init__(self, device=0):
         self._h = C.c_void_p()
+        self._jobs = weakref.WeakSet()                           # live Job objects: a job must not outlive its context
         rc = lib().j2kgpu_create(device, C.byref(self._h))
         if rc != 0:
             raise J2KError(rc, lib().j2kgpu_strerror(rc).decode())
 
     def close(self):
         if self._h:
+            for job in list(self._jobs):
+                job.close()
             lib().j2kgpu_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -439,6 +443,7 @@ class Job:
         self._items = (BatchItem * len(items))(*items)
         self._h = C.c_void_p()
         ctx._check(lib().j2kgpu_job_create(ctx._h, len(items), self._items, C.byref(self._h)))
+        ctx._jobs.add(self)
         self.blob_bytes = int(lib().j2kgpu_job_blob_bytes(self._h))
         self.out_bytes = int(lib().j2kgpu_job_out_bytes(self._h))
         self.n = len(items)

@@ -422,3 +422,21 @@ def test_two_devices_in_one_process(j2k):
             assert np.array_equal(gpu_pixels(j2k, ctx, job), want), dev
         finally:
             ctx.close()
+
+
+def test_closing_a_context_retires_its_jobs(j2k):
+    """Context.close() destroys the jobs still alive on it first; their later close / finaliser is then a no-op"""
+    j = jobs.build_ref_job(jobs.synth_image(64, 64, 1, 8, seed=64), 8, nlevels=2, reversible=True, threads=1)
+    tcs, cbs = jobs.as_ctypes(j["tilecomps"], j2k.TileComp), jobs.as_ctypes(j["cblks"], j2k.CBlk)
+    blob = np.ascontiguousarray(j["blob"])
+    out = np.zeros(64 * 64, np.uint8)
+    item = j2k.BatchItem(hdr(j2k, j), tcs, len(tcs), cbs, len(cbs), blob.ctypes.data_as(j2k.u8p), blob.size,
+                         out.ctypes.data_as(j2k.u8p), 64)
+    ctx = j2k.Context(0)
+    job = j2k.Job(ctx, [item])
+    job.run_host()
+    assert np.array_equal(out, oracle_pixels(j))
+    ctx.close()
+    assert not job._h
+    job.close()
+    del job
