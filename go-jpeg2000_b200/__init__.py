@@ -29,7 +29,7 @@ MODE_REF, MODE_ISO = 0, 1
 PLAN_FUSED, PLAN_FAST_EPILOGUE, PLAN_WIDE, PLAN_COEF16 = 1, 2, 4, 8
 BAND_LL, BAND_HL, BAND_LH, BAND_HH = 0, 1, 2, 3
 FMT_AUTO, FMT_GRAY8, FMT_GRAY16, FMT_RGBA8, FMT_RGBA64 = 0, 1, 2, 3, 4
-E_ARG, E_RANGE, E_UNSUPPORTED, E_CUDA, E_NOMEM, E_NODEVICE = -1, -2, -3, -4, -5, -6
+E_ARG, E_RANGE, E_UNSUPPORTED, E_CUDA, E_NOMEM, E_NODEVICE, E_INTERNAL = -1, -2, -3, -4, -5, -6, -7
 CS_NONE, CS_YCC709, CS_YCC601, CS_PHOTOYCC, CS_CMY, CS_CMYK, CS_YCCK = 0, 1, 2, 3, 4, 5, 6          # J2KGPU_CS_*
 
 u8p = C.POINTER(C.c_uint8)
@@ -65,6 +65,16 @@ class BatchItem(C.Structure):      # j2k_batch_item_t
                 ("out_pix", u8p), ("out_stride", C.c_uint64), ("flags", C.c_uint32), ("rsv", C.c_uint32)]
 
 
+class EncodeParams(C.Structure):
+    """j2k_encode_t: the reference encoder's Options as its forward path reads them (encoder.go:197-281, 597-673)"""
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("ncomp", C.c_uint16), ("pix_bits", C.c_uint8),
+                ("precision", C.c_uint8), ("lossless", C.c_uint8), ("num_resolutions", C.c_uint8), ("cb_x", C.c_uint8),
+                ("cb_y", C.c_uint8), ("quality", C.c_int32), ("flags", C.c_uint32), ("rsv", C.c_uint32 * 2)]
+
+
+ENC_DEVICE_PTRS = 1
+
+
 ITEM_TILES_ONLY = 1                # J2KGPU_ITEM_TILES_ONLY
 
 
@@ -86,6 +96,7 @@ EXPORTS = [
     "j2kgpu_host_alloc", "j2kgpu_host_free", "j2kgpu_host_register", "j2kgpu_host_unregister",
     "j2kgpu_parse_codestream", "j2kgpu_parsed_free", "j2kgpu_parsed_error", "j2kgpu_parsed_item", "j2kgpu_parsed_info",
     "j2kgpu_decode_codestream", "j2kgpu_decode_codestreams",
+    "j2kgpu_encode_block_count", "j2kgpu_encode_preprocess", "j2kgpu_encode_tile",
 ]
 
 _lib = None
@@ -143,6 +154,11 @@ def lib():
         L.j2kgpu_inverse_ict.argtypes = [C.c_void_p, f64p, f64p, f64p, C.c_uint64]
         L.j2kgpu_dc_level_shift_inverse.argtypes = [C.c_void_p, i32p, C.c_uint64, C.c_int]
         L.j2kgpu_mct_dc_pack.argtypes = [C.c_void_p, C.POINTER(Image), C.POINTER(i32p), C.c_int, u8p, C.c_uint64]
+        L.j2kgpu_encode_block_count.argtypes = [C.POINTER(EncodeParams)]
+        L.j2kgpu_encode_block_count.restype = C.c_uint32
+        L.j2kgpu_encode_preprocess.argtypes = [C.c_void_p, C.POINTER(EncodeParams), C.c_void_p, C.c_uint64, C.c_void_p]
+        L.j2kgpu_encode_tile.argtypes = [C.c_void_p, C.POINTER(EncodeParams), C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
+                                         C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), u8p, C.c_uint32]
         L.j2kgpu_parse_codestream.argtypes = [u8p, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
         L.j2kgpu_parsed_free.argtypes = [C.c_void_p]
         L.j2kgpu_parsed_free.restype = None
@@ -342,6 +358,30 @@ class Context:
         """decoder.createImage (decoder.go:417): planar components -> Pix; raises for a bad component count"""
         img = make_image(width, height, len(comps), prec, sgnd=1, mct=0)
         return self.mct_dc_pack(img, comps, apply_tail=False)
+
+    # ---- forward path (encoder.go:79-281, 597-743) --------------------------------------------------
+    def encode_preprocess(self, params, pix, stride=None):
+        """extractImageData + preprocess: Go image bytes -> encoder.componentData (ncomp x height x width int32)"""
+        pix = np.ascontiguousarray(pix, np.uint8).reshape(-1)
+        bpp = (1 if params.ncomp == 1 else 4) * (params.pix_bits // 8)
+        stride = stride or params.width * bpp
+        planes = np.zeros((params.ncomp, params.height, params.width), np.int32)
+        self._check(lib().j2kgpu_encode_preprocess(self._h, C.byref(params), pix.ctypes.data, stride, planes.ctypes.data))
+        return planes
+
+    def encode_tile(self, params, pix, stride=None):
+        """... + encodeTile up to createTileHeader -> (tileData bytes, bytes per block, bit planes per block)"""
+        pix = np.ascontiguousarray(pix, np.uint8).reshape(-1)
+        bpp = (1 if params.ncomp == 1 else 4) * (params.pix_bits // 8)
+        stride = stride or params.width * bpp
+        n = int(lib().j2kgpu_encode_block_count(C.byref(params)))
+        lens, bps = np.zeros(max(n, 1), np.uint32), np.zeros(max(n, 1), np.uint8)
+        cap = params.width * params.height * params.ncomp * 4 + 65536
+        out = np.zeros(cap, np.uint8)
+        got = C.c_uint64(0)
+        self._check(lib().j2kgpu_encode_tile(self._h, C.byref(params), pix.ctypes.data, stride, out.ctypes.data, cap, C.byref(got),
+                                             lens.ctypes.data_as(C.POINTER(C.c_uint32)), _p(bps, u8p), n))
+        return out[: got.value].copy(), lens[:n], bps[:n]
 
     # ---- whole path -------------------------------------------------------------------------------
     def decode_tiles(self, img, tilecomps, cblks, blob, out_stride=None):

@@ -204,6 +204,7 @@ extern "C" const char *j2kgpu_strerror(int code)
     case J2KGPU_E_CUDA: return "CUDA error";
     case J2KGPU_E_NOMEM: return "out of memory";
     case J2KGPU_E_NODEVICE: return "no CUDA device";
+    case J2KGPU_E_INTERNAL: return "internal bound exceeded";
     }
     return "unknown error";
 }

@@ -49,7 +49,8 @@ enum {
     J2KGPU_E_UNSUPPORTED = -3,   /* component count (decoder.go:585), block > 64x64, ... */
     J2KGPU_E_CUDA        = -4,   /* CUDA runtime error, see j2kgpu_last_error()          */
     J2KGPU_E_NOMEM       = -5,
-    J2KGPU_E_NODEVICE    = -6
+    J2KGPU_E_NODEVICE    = -6,
+    J2KGPU_E_INTERNAL    = -7    /* an internal bound was exceeded (reported, never silent)   */
 };
 
 /* conformance mode */
@@ -217,7 +218,9 @@ int         j2kgpu_decode_codestreams(j2kgpu_ctx *ctx, uint32_t n, const uint8_t
  * j2kgpu_job_run launches the whole path on the ctx stream with DEVICE pointers
  * and returns without synchronising (CUDA-graph friendly).  d_blob holds the
  * items' blobs back to back in item order; d_out holds the items' pixel buffers
- * back to back (item i at byte offset j2kgpu_job_out_offset(job, i)).          */
+ * back to back (item i at byte offset j2kgpu_job_out_offset(job, i)).
+ * Lifetime: a job belongs to its context and must be destroyed before it
+ * (j2kgpu_job_destroy after j2kgpu_destroy of the owning context is undefined). */
 int      j2kgpu_job_create(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *items, j2kgpu_job **out);
 void     j2kgpu_job_destroy(j2kgpu_job *job);
 uint64_t j2kgpu_job_blob_bytes(const j2kgpu_job *job);
@@ -280,6 +283,40 @@ int j2kgpu_dc_level_shift_inverse(j2kgpu_ctx *ctx, int32_t *data, uint64_t n, in
  * apply_tail != 0 runs inverse MCT + DC shift first; 0 packs the planes as they are. */
 int j2kgpu_mct_dc_pack(j2kgpu_ctx *ctx, const j2k_image_t *img, const int32_t *const *comps,
                        int apply_tail, uint8_t *out_pix, uint64_t out_stride);
+
+/* ---- forward path ------------------------------------------------------------------------------ *
+ * What encoder.encode does between extractImageData and createTileHeader (encoder.go:79-281, 597-743), byte for byte:
+ * Go image bytes -> component planes (Options.Precision rescale, encoder.go:197-211) -> DC shift, ForwardRCT / ForwardICT
+ * (rounded half away from zero), DecomposeMultiLevel53 / 97 (rows then columns, dense-prefix levels), v / stepSize +- 0.5
+ * -> encodeTile's code-block list (component, resolution, band, block row, block column; blocks cut from the top-left
+ * corner of the component plane whatever the band, encoder.go:763-796, kept as written) -> T1.SetData + T1.Encode per
+ * block -> the blocks' bytes appended in list order (`tileData`, the argument of createTileHeader).  Marker segments,
+ * the tile-part header and the JP2 boxes stay in Go. */
+typedef struct {
+    uint32_t width, height;     /* img.Bounds().Dx() / Dy()                                                        */
+    uint16_t ncomp;             /* 1: image.Gray / Gray16; 3: image.RGBA / RGBA64 (alpha ignored, encoder.go:109,126);
+                                 * 4: image.NRGBA / NRGBA64 (alpha is component 3)                                  */
+    uint8_t  pix_bits;          /* 8 or 16: sample size of the Go image type (16-bit samples big-endian); pixels are
+                                 * ncomp == 1 ? 1 : 4 samples wide                                                  */
+    uint8_t  precision;         /* Options.Precision (0 = keep)                                                     */
+    uint8_t  lossless;          /* Options.Lossless: 5-3 + RCT, else 9-7 + ICT + Quality                            */
+    uint8_t  num_resolutions;   /* Options.NumResolutions; 0 -> 6 (and <= 1 -> 5 decomposition levels, encoder.go:249-252) */
+    uint8_t  cb_x, cb_y;        /* Options.CodeBlockSize: blocks of 1 << (v + 2) samples (encoder.go:606-607), v <= 6 */
+    int32_t  quality;           /* Options.Quality; <= 0 -> 100 (encoder.go:265-268)                                */
+    uint32_t flags;             /* J2KGPU_ENC_*                                                                     */
+    uint32_t rsv[2];            /* set 0                                                                            */
+} j2k_encode_t;
+#define J2KGPU_ENC_DEVICE_PTRS 1u   /* pix and out (planes) are device pointers; blk_len / blk_bps stay host arrays   */
+/* number of entries of encodeTile's job list for these options (0: invalid options) */
+uint32_t j2kgpu_encode_block_count(const j2k_encode_t *p);
+/* extractImageData + preprocess: planes receives ncomp planes of width x height int32 (encoder.componentData) */
+int j2kgpu_encode_preprocess(j2kgpu_ctx *ctx, const j2k_encode_t *p, const uint8_t *pix, uint64_t pix_stride, int32_t *planes);
+/* ... + encodeTile up to createTileHeader: out receives *out_len bytes (J2KGPU_E_ARG with *out_len = the size needed when
+ * out_cap is too small).  blk_len / blk_bps (optional, n_blk >= the block count): bytes per block (0 = the reference's
+ * nil: all-zero block) and the bit-plane count T1.Encode derived (t1_fast5.go:23-27), which the reference leaves out of
+ * its codestream although its decoder needs it (t1.go:1261). */
+int j2kgpu_encode_tile(j2kgpu_ctx *ctx, const j2k_encode_t *p, const uint8_t *pix, uint64_t pix_stride, uint8_t *out,
+                       uint64_t out_cap, uint64_t *out_len, uint32_t *blk_len, uint8_t *blk_bps, uint32_t n_blk);
 
 #ifdef __cplusplus
 }

@@ -130,6 +130,16 @@ int iso_decode_image(const orc_image_t *img, const orc_tilecomp_t *tcs, uint32_t
                      const orc_cblk_t *cbs, uint32_t n_cb, const uint8_t *blob, uint64_t blob_len,
                      uint8_t *out_pix, uint64_t out_stride, int threads);
 
+/* forward path (orc_enc.c): encoder.extractImageData + preprocess + encodeTile's tileData (encoder.go:79-281, 597-743) */
+typedef struct {
+    uint32_t width, height; uint16_t ncomp; uint8_t pix_bits, precision, lossless, num_resolutions, cb_x, cb_y;
+    int32_t quality; uint32_t flags; uint32_t rsv[2];
+} orc_encode_t;               /* same layout as j2k_encode_t */
+uint32_t orc_encode_block_count(const orc_encode_t *p);
+int orc_encode_preprocess(const orc_encode_t *p, const uint8_t *pix, uint64_t stride, int32_t *planes);
+int64_t orc_encode_tile(const orc_encode_t *p, const uint8_t *pix, uint64_t stride, uint8_t *out, uint64_t cap,
+                        uint32_t *blk_len, uint8_t *blk_bps, int threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -219,3 +219,49 @@ def iso_decode_job(job, threads=4, out=None):
     if rc != 0:
         raise RuntimeError("iso_decode_image rc=%d" % rc)
     return out
+
+
+# ---- forward path checker (oracle/orc_enc.c) ---------------------------------------------------------------------------
+class EncodeParams(C.Structure):  # == j2k_encode_t / orc_encode_t
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("ncomp", C.c_uint16), ("pix_bits", C.c_uint8),
+                ("precision", C.c_uint8), ("lossless", C.c_uint8), ("num_resolutions", C.c_uint8), ("cb_x", C.c_uint8),
+                ("cb_y", C.c_uint8), ("quality", C.c_int32), ("flags", C.c_uint32), ("rsv", C.c_uint32 * 2)]
+
+
+def _enc_params(p):
+    q = EncodeParams()
+    for name, _ in EncodeParams._fields_[:-1]:
+        setattr(q, name, getattr(p, name))
+    return q
+
+
+def encode_block_count(p):
+    lib().orc_encode_block_count.restype = C.c_uint32
+    return int(lib().orc_encode_block_count(C.byref(_enc_params(p))))
+
+
+def encode_preprocess(p, pix, stride=None):
+    """encoder.extractImageData + preprocess -> componentData (ncomp, height, width) int32"""
+    pix = np.ascontiguousarray(pix, np.uint8).reshape(-1)
+    stride = stride or p.width * (1 if p.ncomp == 1 else 4) * (p.pix_bits // 8)
+    planes = np.zeros((p.ncomp, p.height, p.width), np.int32)
+    rc = lib().orc_encode_preprocess(C.byref(_enc_params(p)), _p(pix, u8p), C.c_uint64(stride), _p(planes, i32p))
+    if rc != 0:
+        raise ValueError("bad encoder options")
+    return planes
+
+
+def encode_tile(p, pix, stride=None, threads=4):
+    """... + encodeTile's tileData -> (bytes, bytes per block, bit planes per block)"""
+    pix = np.ascontiguousarray(pix, np.uint8).reshape(-1)
+    stride = stride or p.width * (1 if p.ncomp == 1 else 4) * (p.pix_bits // 8)
+    n = encode_block_count(p)
+    lens, bps = np.zeros(max(n, 1), np.uint32), np.zeros(max(n, 1), np.uint8)
+    cap = p.width * p.height * p.ncomp * 4 + 65536
+    out = np.zeros(cap, np.uint8)
+    lib().orc_encode_tile.restype = C.c_int64
+    got = lib().orc_encode_tile(C.byref(_enc_params(p)), _p(pix, u8p), C.c_uint64(stride), _p(out, u8p), C.c_uint64(cap),
+                                lens.ctypes.data_as(C.POINTER(C.c_uint32)), _p(bps, u8p), threads)
+    if got < 0:
+        raise ValueError("orc_encode_tile rc=%d" % got)
+    return out[:got].copy(), lens[:n], bps[:n]

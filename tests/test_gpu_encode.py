@@ -1,0 +1,133 @@
+"""GPU: the forward path (j2kgpu_encode_preprocess / j2kgpu_encode_tile; encoder.go:79-281, 597-743) against the CPU checker
+(oracle/orc_enc.c) -- planes, tile bytes, bytes per block and bit planes per block, all bit-exact -- and back through the
+GPU's own block decoder."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from enc_cases import CASES, go_image
+
+pytestmark = pytest.mark.gpu
+
+
+def params(j2k, case, flags=0):
+    w, h, nc, bits, ll, nr, cbx, cby, q, prec = case
+    return j2k.EncodeParams(width=w, height=h, ncomp=nc, pix_bits=bits, precision=prec, lossless=ll, num_resolutions=nr,
+                            cb_x=cbx, cb_y=cby, quality=q, flags=flags)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_forward_path_equals_the_checker(j2k, gpu_ctx, case):
+    p = params(j2k, case)
+    pix = go_image(p.width, p.height, p.ncomp, p.pix_bits, seed=p.width * 3 + p.height)
+    assert np.array_equal(gpu_ctx.encode_preprocess(p, pix), O.encode_preprocess(p, pix))
+    data, lens, bps = gpu_ctx.encode_tile(p, pix)
+    want, wlens, wbps = O.encode_tile(p, pix)
+    assert np.array_equal(lens, wlens) and np.array_equal(bps, wbps)
+    assert np.array_equal(data, want)
+
+
+def test_padded_rows_and_constant_images(j2k, gpu_ctx):
+    case = (90, 50, 3, 8, 1, 5, 4, 4, 0, 0)
+    p = params(j2k, case)
+    pix = go_image(90, 50, 3, 8, seed=9).reshape(50, 360)
+    padded = np.full((50, 512), 0xA5, np.uint8)
+    padded[:, :360] = pix
+    a = gpu_ctx.encode_tile(p, padded, stride=512)
+    b = O.encode_tile(p, pix)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    # mid-grey: every coefficient zero after the DC shift -> every block nil, an empty tile (t1_fast5.go:20-22)
+    data, lens, bps = gpu_ctx.encode_tile(p, np.full(90 * 50 * 4, 128, np.uint8))
+    assert len(data) == 0 and not lens.any() and not bps.any()
+    # white: only the blocks that reach the plane's top-left corner values are coded
+    a = gpu_ctx.encode_tile(p, np.full(90 * 50 * 4, 255, np.uint8))
+    b = O.encode_tile(p, np.full(90 * 50 * 4, 255, np.uint8))
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and len(a[0]) > 0
+
+
+def test_blocks_decode_on_the_gpu(j2k, gpu_ctx):
+    """encode on the GPU, decode the blocks with the GPU's reference-mode EBCOT decoder (given the bit-plane counts the
+    reference leaves out of its codestream): the planes come back"""
+    case = (192, 128, 3, 8, 1, 6, 4, 4, 0, 0)
+    p = params(j2k, case)
+    pix = go_image(192, 128, 3, 8, seed=4)
+    planes = gpu_ctx.encode_preprocess(p, pix)
+    data, lens, bps = gpu_ctx.encode_tile(p, pix)
+    import test_oracle_encode as T
+    blocks = T.block_list(p)
+    jobs, off = [], 0
+    for (c, sx, sy, w, h, band), n, nb in zip(blocks, lens, bps):
+        jobs.append((data[off:off + int(n)].tobytes(), w, h, int(nb), band))
+        off += int(n)
+    got = gpu_ctx.t1_decode_blocks(jobs)
+    for (c, sx, sy, w, h, band), g in zip(blocks, got):
+        want = np.zeros((h, w), np.int32)
+        src = planes[c, sy:sy + h, sx:sx + w]
+        want[:src.shape[0], :src.shape[1]] = src
+        assert np.array_equal(np.asarray(g).reshape(h, w), want)
+
+
+def test_device_pointers(j2k, gpu_ctx):
+    import torch
+    case = (160, 96, 3, 8, 0, 5, 4, 4, 60, 0)
+    p = params(j2k, case, flags=j2k.ENC_DEVICE_PTRS)
+    pix = go_image(160, 96, 3, 8, seed=5)
+    want, wlens, wbps = O.encode_tile(params(j2k, case), pix)
+    d_pix = torch.from_numpy(pix).cuda()
+    d_out = torch.zeros(len(want) + 64, dtype=torch.uint8, device="cuda")
+    n = j2k.lib().j2kgpu_encode_block_count(C.byref(p))
+    lens, bps = np.zeros(n, np.uint32), np.zeros(n, np.uint8)
+    got = C.c_uint64(0)
+    torch.cuda.synchronize()
+    rc = j2k.lib().j2kgpu_encode_tile(gpu_ctx._h, C.byref(p), d_pix.data_ptr(), 160 * 4, d_out.data_ptr(), d_out.numel(), C.byref(got),
+                                      lens.ctypes.data_as(C.POINTER(C.c_uint32)), bps.ctypes.data_as(j2k.u8p), n)
+    assert rc == 0 and got.value == len(want)
+    assert np.array_equal(d_out[: got.value].cpu().numpy(), want)
+    assert np.array_equal(lens, wlens) and np.array_equal(bps, wbps)
+    d_planes = torch.zeros(3 * 160 * 96, dtype=torch.int32, device="cuda")
+    rc = j2k.lib().j2kgpu_encode_preprocess(gpu_ctx._h, C.byref(p), d_pix.data_ptr(), 160 * 4, d_planes.data_ptr())
+    assert rc == 0
+    assert np.array_equal(d_planes.cpu().numpy().reshape(3, 96, 160), O.encode_preprocess(params(j2k, case), pix))
+
+
+def test_argument_errors(j2k, gpu_ctx):
+    pix = go_image(64, 64, 3, 8, seed=6)
+    ok = (64, 64, 3, 8, 1, 6, 4, 4, 0, 0)
+    for bad, code in [((0, 64) + ok[2:], j2k.E_ARG), ((64, 64, 2) + ok[3:], j2k.E_ARG), ((64, 64, 3, 12) + ok[4:], j2k.E_ARG),
+                      (ok[:6] + (7, 4, 0, 0), j2k.E_UNSUPPORTED), ((20000, 4) + ok[2:], j2k.E_UNSUPPORTED)]:
+        with pytest.raises(j2k.J2KError) as e:
+            gpu_ctx.encode_tile(params(j2k, bad), pix)
+        assert e.value.code == code, bad
+    p = params(j2k, ok)
+    with pytest.raises(j2k.J2KError):
+        gpu_ctx.encode_tile(p, pix, stride=100)                    # stride below the row size
+    got = C.c_uint64(0)
+    out = np.zeros(16, np.uint8)
+    rc = j2k.lib().j2kgpu_encode_tile(gpu_ctx._h, C.byref(p), pix.ctypes.data, 256, out.ctypes.data, 16, C.byref(got), None, None, 0)
+    assert rc == j2k.E_ARG and got.value == len(O.encode_tile(p, pix)[0])   # too small: the size needed is reported
+    assert j2k.lib().j2kgpu_encode_block_count(C.byref(params(j2k, (64, 64, 2) + ok[3:]))) == 0
+    a = gpu_ctx.encode_tile(p, pix)                                 # the context still works
+    assert np.array_equal(a[0], O.encode_tile(p, pix)[0])
+
+
+def test_full_size_4k_rgb_lossless(j2k, gpu_ctx):
+    """BASELINE configs[1]'s image through the forward path: 3840 x 2160 RGB 8-bit, lossless, 6 resolutions, 64 x 64 blocks"""
+    case = (3840, 2160, 3, 8, 1, 6, 4, 4, 0, 0)
+    p = params(j2k, case)
+    pix = go_image(3840, 2160, 3, 8, seed=7)
+    data, lens, bps = gpu_ctx.encode_tile(p, pix)
+    want, wlens, wbps = O.encode_tile(p, pix, threads=16)
+    assert np.array_equal(lens, wlens) and np.array_equal(bps, wbps) and np.array_equal(data, want)
+    assert np.array_equal(gpu_ctx.encode_preprocess(p, pix), O.encode_preprocess(p, pix))
+
+
+def test_full_size_1080p_lossy(j2k, gpu_ctx):
+    """BASELINE configs[4]'s frame shape, 9-7 + ICT + Quality 75 in float64"""
+    case = (1920, 1080, 3, 8, 0, 6, 4, 4, 75, 0)
+    p = params(j2k, case)
+    pix = go_image(1920, 1080, 3, 8, seed=8)
+    a = gpu_ctx.encode_tile(p, pix)
+    b = O.encode_tile(p, pix, threads=16)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
