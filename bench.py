@@ -443,6 +443,66 @@ def run_cfg4_tile_sharded(ctx, j2k, jobs, shard, tile_jobs, my_tiles, world, ran
                          "end to end (H2D + kernels + D2H of the owned tile rectangles)" % world)
 
 
+def run_forward_path(ctx, j2k, stream, steps):
+    """side object: the forward path (encoder.go:79-281, 597-743) on one 4K RGB frame, lossless, 6 resolutions,
+    64 x 64 blocks -- device-resident (pixels and tile bytes in HBM), end to end from page-locked host pixels, and the CPU
+    checker (oracle/orc_enc.c, all host threads) on the same frame; the three outputs are compared"""
+    import ctypes as C
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    w, h = W, H
+    rgb = jobs.synth_image_fast(w, h, 3, 8, seed=4242)
+    pix = np.full((h, w, 4), 255, np.uint8)
+    pix[:, :, :3] = np.moveaxis(rgb, 0, 2)
+    pix = pix.reshape(-1)
+    kw = dict(width=w, height=h, ncomp=3, pix_bits=8, lossless=1, num_resolutions=6, cb_x=4, cb_y=4)
+    p_dev, p_host = j2k.EncodeParams(flags=j2k.ENC_DEVICE_PTRS, **kw), j2k.EncodeParams(**kw)
+    L = j2k.lib()
+    n = int(L.j2kgpu_encode_block_count(C.byref(p_host)))
+    lens, bps = np.zeros(n, np.uint32), np.zeros(n, np.uint8)
+    cap = w * h * 3 * 2
+    got = C.c_uint64(0)
+    d_pix = torch.from_numpy(pix).cuda()
+    d_out = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+    h_pix = torch.from_numpy(pix).pin_memory()
+    h_out = torch.zeros(cap, dtype=torch.uint8).pin_memory()
+    torch.cuda.synchronize()
+
+    def call(params, src, dst):
+        rc = L.j2kgpu_encode_tile(ctx._h, C.byref(params), src.data_ptr(), w * 4, dst.data_ptr(), cap, C.byref(got),
+                                  lens.ctypes.data_as(C.POINTER(C.c_uint32)), bps.ctypes.data_as(j2k.u8p), n)
+        if rc:
+            raise RuntimeError("j2kgpu_encode_tile rc=%d" % rc)
+
+    def timed(params, src, dst):
+        for _ in range(2):
+            call(params, src, dst)
+        n0 = ctx.launches
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            call(params, src, dst)
+        return (time.perf_counter() - t0) / steps, (ctx.launches - n0) // steps
+
+    dev_s, launches = timed(p_dev, d_pix, d_out)
+    dev_bytes = d_out[: got.value].cpu().numpy().copy()
+    e2e_s, _ = timed(p_host, h_pix, h_out)
+    host_bytes = h_out[: got.value].numpy().copy()
+    t0 = time.perf_counter()
+    want, wlens, wbps = O.encode_tile(p_host, pix, threads=os.cpu_count() or 1)
+    cpu_s = time.perf_counter() - t0
+    same = bool(np.array_equal(dev_bytes, want) and np.array_equal(host_bytes, want) and np.array_equal(lens, wlens) and np.array_equal(bps, wbps))
+    mp = w * h / 1e6
+    return dict(workload="one 3840x2160 RGB 8-bit frame, lossless 5-3 + RCT, 6 resolutions, 64x64 blocks, the reference encoder's EBCOT / MQ coder",
+                value=round(mp / dev_s, 1), unit=UNIT, ms_per_frame=round(dev_s * 1e3, 3), code_blocks=n, tile_bytes=int(got.value),
+                gpu_launches=int(launches), timing="wall clock around the blocking call (it synchronises before it returns)",
+                e2e=dict(value=round(mp / e2e_s, 1), unit=UNIT, ms_per_frame=round(e2e_s * 1e3, 3), h2d_bytes_per_step=int(pix.size),
+                         d2h_bytes_per_step=int(got.value) + 5 * n, api="j2kgpu_encode_tile, page-locked host pixels in, tile bytes out"),
+                cpu_baseline=dict(value=round(mp / cpu_s, 2), unit=UNIT, cores=os.cpu_count() or 1, kind="port",
+                                  sample="the same frame, oracle/orc_enc.c on all host threads"),
+                bytes_equal_checker=same)
+
+
 def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -567,6 +627,8 @@ def run_ours(args):
         extra["ebcot_ref"] = summarize(m_eb)
         extra["ebcot_ref"]["workload"] = "cfg2 geometry, REF semantics, the reference's EBCOT/MQ coder (t1.go), %d distinct frames" % len(eb_frames)
         costs = [j["blob"].size for j in tile_jobs]
+        if rank == 0 and world == 1:
+            extra["forward_path"] = run_forward_path(ctx, j2k, stream, 5)
         extra["cfg4_tile_sharded"] = run_cfg4_tile_sharded(ctx, j2k, jobs, shard, tile_jobs, shard.shard_units(costs, world, rank),
                                                            world, rank, barrier, reduce_max, 5)
 

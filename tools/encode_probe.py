@@ -1,0 +1,52 @@
+#!/usr/bin/env python
+"""Forward path alone (for launch lists / ncu): one 4K RGB lossless frame and one 1080p lossy frame through
+j2kgpu_encode_tile with device pointers, per-stage device times from CUDA events on the context's stream."""
+import ctypes as C
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from __graft_entry__ import load_package  # noqa: E402
+from datagen import jobs  # noqa: E402
+
+
+def main():
+    import torch
+    j2k = load_package()
+    ctx = j2k.Context(0)
+    L = j2k.lib()
+    for (w, h, lossless, q) in ((3840, 2160, 1, 0), (1920, 1080, 0, 75)):
+        rgb = jobs.synth_image_fast(w, h, 3, 8, seed=11)
+        pix = np.full((h, w, 4), 255, np.uint8)
+        pix[:, :, :3] = np.moveaxis(rgb, 0, 2)
+        p = j2k.EncodeParams(width=w, height=h, ncomp=3, pix_bits=8, lossless=lossless, num_resolutions=6, cb_x=4, cb_y=4, quality=q,
+                             flags=j2k.ENC_DEVICE_PTRS)
+        n = int(L.j2kgpu_encode_block_count(C.byref(p)))
+        d_pix = torch.from_numpy(pix.reshape(-1)).cuda()
+        d_out = torch.zeros(w * h * 6, dtype=torch.uint8, device="cuda")
+        d_planes = torch.zeros(3 * w * h, dtype=torch.int32, device="cuda")
+        got = C.c_uint64(0)
+        torch.cuda.synchronize()
+        for name, fn in (("preprocess (pixels -> planes, DWT, quantiser)",
+                          lambda: L.j2kgpu_encode_preprocess(ctx._h, C.byref(p), d_pix.data_ptr(), w * 4, d_planes.data_ptr())),
+                         ("whole forward path",
+                          lambda: L.j2kgpu_encode_tile(ctx._h, C.byref(p), d_pix.data_ptr(), w * 4, d_out.data_ptr(), d_out.numel(),
+                                                       C.byref(got), None, None, 0))):
+            for _ in range(2):
+                assert fn() == 0
+            t0 = time.perf_counter()
+            reps = 5
+            for _ in range(reps):
+                assert fn() == 0
+            dt = (time.perf_counter() - t0) / reps
+            print("%dx%d %s: %s %.3f ms (%.1f Mpixel/s), %d blocks, %d bytes" %
+                  (w, h, "lossless" if lossless else "lossy q=%d" % q, name, dt * 1e3, w * h / 1e6 / dt, n, got.value), flush=True)
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
