@@ -451,6 +451,7 @@ def run_forward_path(ctx, j2k, stream, steps):
     import torch
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
+    from datagen import jobs
     w, h = W, H
     rgb = jobs.synth_image_fast(w, h, 3, 8, seed=4242)
     pix = np.full((h, w, 4), 255, np.uint8)

@@ -174,3 +174,47 @@ func decodeCodestreamGPU(cs []byte, reduce int, pix []uint8, stride int) error {
 	}
 	return nil
 }
+
+// encodeTileGPU replaces encoder.preprocess (encoder.go:216-281) and the body of encoder.encodeTile up to
+// createTileHeader (encoder.go:597-743): it takes the Pix bytes of the image.Gray / Gray16 / RGBA / RGBA64 / NRGBA /
+// NRGBA64 the encoder was given (extractImageData, encoder.go:79-214, happens on the device as well) and returns
+// tileData, byte for byte what the goroutine pool produces.  The caller keeps generateSIZ / COD / QCD, createTileHeader
+// and writeJP2.  ncomp / pixBits follow the type switch of extractImageData (RGBA: 3 components, alpha ignored).
+func encodeTileGPU(pix []uint8, stride, width, height, ncomp, pixBits int, o *Options) ([]byte, error) {
+	if len(pix) == 0 || width <= 0 || height <= 0 {
+		return nil, fmt.Errorf("preprocessing: empty image")
+	}
+	ctx, err := getGPUCtx()
+	if err != nil {
+		return nil, fmt.Errorf("preprocessing: %w", err)
+	}
+	defer putGPUCtx(ctx)
+	var p C.j2k_encode_t
+	p.width, p.height = C.uint32_t(width), C.uint32_t(height)
+	p.ncomp, p.pix_bits = C.uint16_t(ncomp), C.uint8_t(pixBits)
+	if o.Precision > 0 && o.Precision <= 16 {
+		p.precision = C.uint8_t(o.Precision)
+	}
+	if o.Lossless {
+		p.lossless = 1
+	}
+	if o.NumResolutions > 0 && o.NumResolutions < 256 {
+		p.num_resolutions = C.uint8_t(o.NumResolutions)
+	}
+	p.cb_x, p.cb_y = C.uint8_t(o.CodeBlockSize.X), C.uint8_t(o.CodeBlockSize.Y)
+	p.quality = C.int32_t(o.Quality)
+	out := make([]byte, width*height*ncomp*2+65536)
+	var n C.uint64_t
+	for {
+		rc := C.j2kgpu_encode_tile(ctx.h, &p, (*C.uint8_t)(unsafe.Pointer(&pix[0])), C.uint64_t(stride),
+			(*C.uint8_t)(unsafe.Pointer(&out[0])), C.uint64_t(len(out)), &n, nil, nil, 0)
+		if rc == C.J2KGPU_E_ARG && uint64(n) > uint64(len(out)) { // the size needed was reported: once more
+			out = make([]byte, n)
+			continue
+		}
+		if rc != 0 {
+			return nil, fmt.Errorf("encoding tile: %s: %s", C.GoString(C.j2kgpu_strerror(rc)), C.GoString(C.j2kgpu_last_error(ctx.h)))
+		}
+		return out[:n], nil
+	}
+}
