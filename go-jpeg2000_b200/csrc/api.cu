@@ -224,6 +224,7 @@ static int set_option(J2kOpts &o, const char *name, const char *value)
     else if (k == "t1_group") o.t1_group = iv;
     else if (k == "host_alpha") o.host_alpha = iv;
     else if (k == "split_min_mpixel") o.split_min_mpixel = iv;
+    else if (k == "enc_bytes") o.enc_bytes = on;
     else if (k == "debug_plan") o.debug_plan = on;
     else if (k == "chunks") o.chunks = v;
     else return J2KGPU_E_ARG;
@@ -242,7 +243,7 @@ extern "C" int j2kgpu_create(int device, j2kgpu_ctx **out)
     if (!ctx) return J2KGPU_E_NOMEM;
     ctx->device = device;
     // the environment is read here, once per context, and nowhere else
-    static const char *const names[] = {"no_fuse", "no_wide", "no_fast_epi", "coef32", "no_preclear", "wide_sp", "t1_group", "host_alpha", "split_min_mpixel", "debug_plan", "chunks"};
+    static const char *const names[] = {"no_fuse", "no_wide", "no_fast_epi", "coef32", "no_preclear", "wide_sp", "t1_group", "host_alpha", "split_min_mpixel", "enc_bytes", "debug_plan", "chunks"};
     for (const char *nm : names) {
         std::string env = "J2KGPU_";
         for (const char *c = nm; *c; c++) env += (char)toupper((unsigned char)*c);

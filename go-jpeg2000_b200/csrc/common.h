@@ -86,6 +86,7 @@ struct J2kOpts {
     int t1_group = 0;       // EBCOT kernels: lanes per code block (4, 8, 16, 32; 0 = default 8)
     int split_min_mpixel = 0; // a single image of at least this many Mpixel is pipelined by groups of tiles (0 = 24)
     int host_alpha = -1;    // host-buffer runs of RGBA8 images: packed R G B over PCIe, alpha filled in by host threads (-1 = auto)
+    int enc_bytes = 0;      // forward path: the flag-byte tier-1 coder also for blocks at most 64 wide (A/B, tests)
     int debug_plan = 0;     // print the chunk plan of host-buffer runs
     std::string chunks;     // explicit chunk sizes of host-buffer runs, e.g. "1,1,2,4"
 };

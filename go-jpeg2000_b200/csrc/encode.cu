@@ -21,6 +21,8 @@ namespace {
 
 __constant__ uint32_t c_emq[94];          // qe | nmps << 16 | nlps << 24 (mqc.go:21-116)
 __constant__ uint8_t  c_ezc[4 * 256];     // band, 8 neighbour bits -> zero-coding context (t1_luts.go:35-110)
+__constant__ uint8_t  c_ezc9[4 * 512];    // band, 3 x 3 significance window (row above | row << 3 | row below << 6) -> the same
+__constant__ uint8_t  c_esc[256];         // W, E, N, S (significant, negative) pairs -> (context - 9) << 1 | prediction (t1.go:387-460)
 
 struct EncBlk {                           // one entry of encodeTile's job list
     uint64_t plane_off;                   // element offset of the component plane
@@ -364,13 +366,117 @@ __device__ J2K_NOINLINE void t1_plane(T1Enc &t, MqEnc &mq)
         }
 }
 
-// shared memory of one warp: flag bytes, the bit-plane bitmap, the context states
-__host__ __device__ constexpr size_t t1enc_flag_bytes(int cbw, int cbh) { return ((size_t)(cbw + 2) * (cbh + 2) + 15) & ~(size_t)15; }
-__host__ __device__ constexpr size_t t1enc_warp_bytes(int cbw, int cbh)
+// ---- blocks at most 64 samples wide: the coder's state as one 64-bit mask per row -----------------------------------------
+// sig / neg / vis / ref hold rows -1 .. h (index y + 1; the two border rows stay zero).  Instead of visiting every sample,
+// each pass computes the set of samples that take part (candidates of the row, or of the stripe's columns) with a few
+// logic operations and walks its set bits in coding order; a sample that becomes significant adds its right-hand neighbour
+// to the row's candidates (SPP) or takes the next column out of run-length mode (cleanup), which is all that the
+// reference's visit-time tests (t1.go:349-384, 1087-1092, 1195-1208) can see of it.
+struct T1Narrow {
+    uint64_t *sig, *neg, *vis, *ref;
+    const uint64_t *bits;
+    uint64_t rowmask;
+    int w, h, band;
+};
+__device__ __forceinline__ uint32_t win3(uint64_t row, int x) { return (uint32_t)(x ? row >> (x - 1) : row << 1) & 7u; }
+__device__ __forceinline__ uint64_t spread3(uint64_t r) { return r | (r << 1) | (r >> 1); }
+__device__ __forceinline__ uint64_t nb_mask(const T1Narrow &t, int y)      // samples of row y with a significant neighbour
 {
-    return t1enc_flag_bytes(cbw, cbh) + (size_t)cbh * ((cbw + 63) / 64) * 8 + 32;
+    const uint64_t s = t.sig[y + 1];
+    return (spread3(t.sig[y]) | spread3(t.sig[y + 2]) | (s << 1) | (s >> 1)) & t.rowmask;
+}
+__device__ __forceinline__ void nr_sign(const T1Narrow &t, MqEnc &mq, int x, int y)
+{
+    const uint32_t sm = win3(t.sig[y + 1], x), nm = win3(t.neg[y + 1], x);
+    const uint32_t idx = (sm & 1u) | (nm & 1u) << 1 | (sm & 4u) | (nm & 4u) << 1 |
+                         (uint32_t)((t.sig[y] >> x) & 1u) << 4 | (uint32_t)((t.neg[y] >> x) & 1u) << 5 |
+                         (uint32_t)((t.sig[y + 2] >> x) & 1u) << 6 | (uint32_t)((t.neg[y + 2] >> x) & 1u) << 7;
+    const uint32_t e = c_esc[idx];
+    mq_encode(mq, CX_SC0 + (int)(e >> 1), (int)(((t.neg[y + 1] >> x) & 1u) ^ (e & 1u)));
+}
+// zero coding of sample (x, y) with bit `sig`; returns sig after coding the sign and marking the sample significant
+__device__ __forceinline__ int nr_zc_and_sign(const T1Narrow &t, MqEnc &mq, int x, int y, int sig)
+{
+    const uint32_t idx = win3(t.sig[y], x) | win3(t.sig[y + 1], x) << 3 | win3(t.sig[y + 2], x) << 6;
+    mq_encode(mq, c_ezc9[t.band * 512 + idx], sig);
+    if (sig) { nr_sign(t, mq, x, y); t.sig[y + 1] |= (uint64_t)1 << x; }
+    return sig;
+}
+__device__ J2K_NOINLINE void t1_plane_narrow(T1Narrow &t, MqEnc &mq)
+{
+    const int h = t.h;
+    for (int y = 0; y < h; y++) {                                  // significance propagation, t1.go:558-639
+        uint64_t cand = ~t.sig[y + 1] & nb_mask(t, y), seen = 0;
+        const uint64_t plane = t.bits[y];
+        while (cand) {
+            const int x = __ffsll((long long)cand) - 1;
+            const uint64_t bit = (uint64_t)1 << x;
+            cand &= ~bit; seen |= bit;
+            if (nr_zc_and_sign(t, mq, x, y, (int)((plane >> x) & 1u)))
+                cand |= (bit << 1) & ~t.sig[y + 1] & t.rowmask;    // its right-hand neighbour has a significant neighbour now
+        }
+        t.vis[y + 1] |= seen;
+    }
+    for (int y = 0; y < h; y++) {                                  // magnitude refinement, t1.go:642-683
+        uint64_t cand = t.sig[y + 1] & ~t.vis[y + 1];
+        if (!cand) continue;
+        const uint64_t plane = t.bits[y], nb = nb_mask(t, y), ref = t.ref[y + 1];
+        t.ref[y + 1] = ref | cand;
+        while (cand) {
+            const int x = __ffsll((long long)cand) - 1;
+            cand &= cand - 1;
+            const int cx = ((ref >> x) & 1u) ? CX_MAG0 + 2 : (((nb >> x) & 1u) ? CX_MAG0 + 1 : CX_MAG0);
+            mq_encode(mq, cx, (int)((plane >> x) & 1u));
+        }
+    }
+    for (int y = 0; y < h; y += 4) {                               // cleanup, t1.go:686-770, 816-914
+        const int rows = min(4, h - y);
+        uint64_t todo = 0, busy = 0;
+        for (int k = 0; k < rows; k++) {
+            const uint64_t sv = t.sig[y + k + 1] | t.vis[y + k + 1];
+            todo |= ~sv & t.rowmask;
+            busy |= sv | nb_mask(t, y + k);
+        }
+        uint64_t rl = rows == 4 ? ~busy & t.rowmask : 0;            // columns in run-length mode (t1.go:1195-1208)
+        while (todo) {
+            const int x = __ffsll((long long)todo) - 1;
+            const uint64_t bit = (uint64_t)1 << x;
+            todo &= ~bit;
+            int k = 0, grew = 0;
+            if (rl & bit) {
+                const uint32_t col = (uint32_t)((t.bits[y] >> x) & 1u) | (uint32_t)((t.bits[y + 1] >> x) & 1u) << 1 |
+                                     (uint32_t)((t.bits[y + 2] >> x) & 1u) << 2 | (uint32_t)((t.bits[y + 3] >> x) & 1u) << 3;
+                if (!col) { mq_encode(mq, CX_RL, 0); continue; }
+                const int first = __ffs((int)col) - 1;
+                mq_encode(mq, CX_RL, 1);
+                mq_encode(mq, CX_UNI, (first >> 1) & 1);
+                mq_encode(mq, CX_UNI, first & 1);
+                nr_sign(t, mq, x, y + first);
+                t.sig[y + first + 1] |= bit;
+                grew = 1;
+                k = first + 1;
+            }
+            for (; k < rows; k++) {
+                if ((t.sig[y + k + 1] | t.vis[y + k + 1]) & bit) continue;
+                grew |= nr_zc_and_sign(t, mq, x, y + k, (int)((t.bits[y + k] >> x) & 1u));
+            }
+            if (grew) rl &= ~(bit << 1);
+        }
+        for (int k = 0; k < rows; k++) t.vis[y + k + 1] = 0;
+    }
 }
 
+// shared memory of one warp: flag bytes (or row masks), the bit-plane bitmap, the context states
+__host__ __device__ constexpr size_t t1enc_flag_bytes(int cbw, int cbh, bool narrow)
+{
+    return narrow ? (size_t)4 * (cbh + 2) * 8 : (((size_t)(cbw + 2) * (cbh + 2) + 15) & ~(size_t)15);
+}
+__host__ __device__ constexpr size_t t1enc_warp_bytes(int cbw, int cbh, bool narrow)
+{
+    return t1enc_flag_bytes(cbw, cbh, narrow) + (size_t)cbh * ((cbw + 63) / 64) * 8 + 32;
+}
+
+template <bool NARROW>
 __global__ void k_t1_enc(const EncBlk *__restrict__ blks, uint32_t n, const int32_t *__restrict__ planes, int W, int H,
                          int cbw, int cbh, uint8_t *__restrict__ slab, uint32_t cap, uint32_t *__restrict__ lens,
                          uint8_t *__restrict__ bps, int *__restrict__ err)
@@ -380,14 +486,16 @@ __global__ void k_t1_enc(const EncBlk *__restrict__ blks, uint32_t n, const int3
     const uint32_t bi = blockIdx.x * (blockDim.x >> 5) + (uint32_t)warp;
     if (bi >= n) return;
     const EncBlk blk = blks[bi];
-    uint8_t *base = smem + (size_t)warp * t1enc_warp_bytes(cbw, cbh);
-    uint8_t *flags = base;
-    uint64_t *bits = reinterpret_cast<uint64_t *>(base + t1enc_flag_bytes(cbw, cbh));
+    uint8_t *base = smem + (size_t)warp * t1enc_warp_bytes(cbw, cbh, NARROW);
+    uint8_t *flags = base;                                         // wide blocks: flag bytes; narrow: four arrays of row masks
+    uint64_t *rows = reinterpret_cast<uint64_t *>(base);
+    uint64_t *bits = reinterpret_cast<uint64_t *>(base + t1enc_flag_bytes(cbw, cbh, NARROW));
     const int w = blk.w, h = blk.h, stride = w + 2, words = (w + 63) >> 6;
     uint8_t *cx = reinterpret_cast<uint8_t *>(bits + (size_t)cbh * ((cbw + 63) / 64));
     const int32_t *plane = planes + blk.plane_off;
     // extractCodeBlockData + SetData: sign flags, largest magnitude
-    for (int i = lane; i < stride * (h + 2); i += 32) flags[i] = 0;
+    if (NARROW) { for (int i = lane; i < 4 * (cbh + 2); i += 32) rows[i] = 0; }
+    else { for (int i = lane; i < stride * (h + 2); i += 32) flags[i] = 0; }
     if (lane < CX_N) cx[lane] = lane == CX_UNI ? 92 : 0;           // mqc.go:194-199
     __syncwarp();
     auto sample = [&](int x, int y) -> int32_t {
@@ -395,12 +503,25 @@ __global__ void k_t1_enc(const EncBlk *__restrict__ blks, uint32_t n, const int3
         return (gx < (uint32_t)W && gy < (uint32_t)H) ? plane[(uint64_t)gy * W + gx] : 0;
     };
     int32_t maxv = 0;
-    for (int y = 0; y < h; y++)
-        for (int x = lane; x < w; x += 32) {
-            int32_t v = sample(x, y);
-            if (v < 0) { v = (int32_t)(0u - (uint32_t)v); flags[(y + 1) * stride + x + 1] = F_NEG; }
-            maxv = v > maxv ? v : maxv;
+    if (NARROW) {
+        uint64_t *neg = rows + (cbh + 2);
+        for (int y = 0; y < h; y++) {
+            int32_t v0 = lane < w ? sample(lane, y) : 0, v1 = lane + 32 < w ? sample(lane + 32, y) : 0;
+            const uint32_t lo = __ballot_sync(0xffffffffu, v0 < 0), hi = __ballot_sync(0xffffffffu, v1 < 0);
+            if (lane == 0) neg[y + 1] = (uint64_t)lo | ((uint64_t)hi << 32);
+            v0 = v0 < 0 ? (int32_t)(0u - (uint32_t)v0) : v0;
+            v1 = v1 < 0 ? (int32_t)(0u - (uint32_t)v1) : v1;
+            maxv = v0 > maxv ? v0 : maxv;
+            maxv = v1 > maxv ? v1 : maxv;
         }
+    } else {
+        for (int y = 0; y < h; y++)
+            for (int x = lane; x < w; x += 32) {
+                int32_t v = sample(x, y);
+                if (v < 0) { v = (int32_t)(0u - (uint32_t)v); flags[(y + 1) * stride + x + 1] = F_NEG; }
+                maxv = v > maxv ? v : maxv;
+            }
+    }
     for (int o = 16; o; o >>= 1) { const int32_t m = __shfl_xor_sync(0xffffffffu, maxv, o); maxv = m > maxv ? m : maxv; }
     int nbps = 0;
     for (int32_t m = maxv; m > 0; m >>= 1) nbps++;                 // t1_fast5.go:23-27
@@ -412,6 +533,8 @@ __global__ void k_t1_enc(const EncBlk *__restrict__ blks, uint32_t n, const int3
     mq.A = 0x8000u; mq.C = 0; mq.CT = 12; mq.bp = 0; mq.cur = 0; mq.ovf = 0;
     mq.out = slab + (uint64_t)bi * cap; mq.cap = cap; mq.cx = cx;
     T1Enc t{flags, bits, w, h, stride, words, (int)blk.band};
+    T1Narrow tn{rows, rows + (cbh + 2), rows + 2 * (cbh + 2), rows + 3 * (cbh + 2), bits,
+                w >= 64 ? ~(uint64_t)0 : (((uint64_t)1 << w) - 1), w, h, (int)blk.band};
     for (int bp = nbps - 1; bp >= 0; bp--) {
         __syncwarp();
         for (int y = 0; y < h; y++)
@@ -425,7 +548,9 @@ __global__ void k_t1_enc(const EncBlk *__restrict__ blks, uint32_t n, const int3
                 if (lane == 0) bits[y * words + wd] = (uint64_t)lo | ((uint64_t)hi << 32);
             }
         __syncwarp();
-        if (lane == 0) t1_plane(t, mq);
+        if (lane == 0) {
+            if (NARROW) t1_plane_narrow(tn, mq); else t1_plane(t, mq);
+        }
     }
     if (lane == 0) {
         const int len = mq_flush(mq);                              // t1_fast5.go:878-898
@@ -513,6 +638,28 @@ cudaError_t upload_enc_tables(cudaStream_t s)
             }
             zc[band * 256 + p] = (uint8_t)cx;
         }
+    uint8_t zc9[4 * 512], sc[256];
+    for (int band = 0; band < 4; band++)
+        for (int i = 0; i < 512; i++) {                            // window bits: (row above, row, row below) x (x - 1, x, x + 1)
+            const int p = ((i >> 3) & 1) | ((i >> 5) & 1) << 1 | ((i >> 1) & 1) << 2 | ((i >> 7) & 1) << 3 | (i & 1) << 4 |
+                          ((i >> 2) & 1) << 5 | ((i >> 6) & 1) << 6 | ((i >> 8) & 1) << 7;
+            zc9[band * 512 + i] = zc[band * 256 + p];
+        }
+    for (int i = 0; i < 256; i++) {                                // t1.go:387-460
+        int hc = 0, vc = 0, pred = 0, cx = 0;
+        if (i & 1) hc += (i & 2) ? -1 : 1;
+        if (i & 4) hc += (i & 8) ? -1 : 1;
+        if (i & 16) vc += (i & 32) ? -1 : 1;
+        if (i & 64) vc += (i & 128) ? -1 : 1;
+        if (hc < 0) { pred = 1; hc = -hc; }
+        if (hc == 0 && vc < 0) { pred = 1; vc = -vc; }
+        if (hc == 1) cx = vc == 1 ? 4 : (vc == 0 ? 2 : 1);
+        else if (hc == 0) cx = vc == 1 ? 1 : 0;
+        else if (hc == 2) cx = 3;
+        sc[i] = (uint8_t)(cx << 1 | pred);
+    }
+    if ((e = cudaMemcpyToSymbolAsync(c_ezc9, zc9, sizeof zc9, 0, cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbolAsync(c_esc, sc, sizeof sc, 0, cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbolAsync(c_emq, mq, sizeof mq, 0, cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbolAsync(c_ezc, zc, sizeof zc, 0, cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
@@ -702,16 +849,19 @@ extern "C" int j2kgpu_encode_tile(j2kgpu_ctx *ctx, const j2k_encode_t *p, const 
     e = cudaMemsetAsync(d_err, 0, 8, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_blks, blks.data(), (size_t)n * sizeof(EncBlk), cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) { cudaStreamSynchronize(s); return j2k_cuda_err(ctx, e, "block table upload"); }
-    const size_t per_warp = t1enc_warp_bytes(g.cbw, g.cbh);
+    const bool narrow = g.cbw <= 64 && !ctx->opt.enc_bytes;        // row-mask coder; option enc_bytes forces the flag-byte coder (tests)
+    const size_t per_warp = t1enc_warp_bytes(g.cbw, g.cbh, narrow);
     int wpc = 8;
     while (wpc > 1 && (size_t)wpc * per_warp > 96 * 1024) wpc >>= 1;
     const size_t smem = (size_t)wpc * per_warp;
     if (smem > 48 * 1024) {
-        e = cudaFuncSetAttribute((const void *)k_t1_enc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(narrow ? (const void *)k_t1_enc<true> : (const void *)k_t1_enc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { cudaStreamSynchronize(s); return j2k_cuda_err(ctx, e, "k_t1_enc shared memory"); }
     }
-    J2K_LAUNCH((k_t1_enc), (n + wpc - 1) / wpc, wpc * 32, smem, s, (const EncBlk *)d_blks, n, (const int32_t *)d_planes, g.w, g.h, g.cbw,
-               g.cbh, d_slab, cap, d_lens, d_bps, d_err);
+    if (narrow) J2K_LAUNCH((k_t1_enc<true>), (n + wpc - 1) / wpc, wpc * 32, smem, s, (const EncBlk *)d_blks, n, (const int32_t *)d_planes, g.w, g.h,
+                           g.cbw, g.cbh, d_slab, cap, d_lens, d_bps, d_err);
+    else J2K_LAUNCH((k_t1_enc<false>), (n + wpc - 1) / wpc, wpc * 32, smem, s, (const EncBlk *)d_blks, n, (const int32_t *)d_planes, g.w, g.h,
+                    g.cbw, g.cbh, d_slab, cap, d_lens, d_bps, d_err);
     J2K_LAUNCH((k_enc_scan), 1, 1024, 0, s, (const uint32_t *)d_lens, n, d_offs);
     ctx->launches += 2;
     e = cudaGetLastError();

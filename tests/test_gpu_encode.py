@@ -23,10 +23,45 @@ def test_forward_path_equals_the_checker(j2k, gpu_ctx, case):
     p = params(j2k, case)
     pix = go_image(p.width, p.height, p.ncomp, p.pix_bits, seed=p.width * 3 + p.height)
     assert np.array_equal(gpu_ctx.encode_preprocess(p, pix), O.encode_preprocess(p, pix))
-    data, lens, bps = gpu_ctx.encode_tile(p, pix)
     want, wlens, wbps = O.encode_tile(p, pix)
-    assert np.array_equal(lens, wlens) and np.array_equal(bps, wbps)
-    assert np.array_equal(data, want)
+    for enc_bytes in (0, 1):                                       # row-mask coder (blocks <= 64 wide) / flag-byte coder
+        with gpu_ctx.options(enc_bytes=enc_bytes):
+            data, lens, bps = gpu_ctx.encode_tile(p, pix)
+        assert np.array_equal(lens, wlens) and np.array_equal(bps, wbps)
+        assert np.array_equal(data, want)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_options_and_contents(j2k, gpu_ctx, seed):
+    """random sizes, component counts, block shapes, qualities; noise / sparse / ramps / near-constant contents"""
+    rng = np.random.default_rng(1000 + seed)
+    w, h = int(rng.integers(1, 200)), int(rng.integers(1, 200))
+    nc, bits = int(rng.choice([1, 3, 4])), int(rng.choice([8, 16]))
+    case = (w, h, nc, bits, int(rng.integers(0, 2)), int(rng.integers(0, 7)), int(rng.integers(0, 7)), int(rng.integers(0, 7)),
+            int(rng.choice([0, 1, 30, 75, 100])), int(rng.choice([0, 0, 5, 12])))
+    ch, m = (1 if nc == 1 else 4), (1 << bits) - 1
+    kind = seed % 4
+    if kind == 0:
+        v = rng.integers(0, m + 1, (h, w, ch))
+    elif kind == 1:
+        v = (rng.random((h, w, ch)) < 0.02) * rng.integers(0, m + 1, (h, w, ch))
+    elif kind == 2:
+        yy, xx = np.mgrid[0:h, 0:w]
+        v = np.stack([(xx * 3 + yy * 5 + c * 17) % (m + 1) for c in range(ch)], axis=2)
+    else:
+        v = np.full((h, w, ch), m // 2 + 1) + rng.integers(-2, 3, (h, w, ch))
+    v = np.clip(v, 0, m).astype(np.uint32)
+    if bits == 8:
+        pix = v.astype(np.uint8).reshape(-1)
+    else:
+        o = np.zeros((h, w, ch, 2), np.uint8)
+        o[..., 0], o[..., 1] = v >> 8, v & 255
+        pix = o.reshape(-1)
+    p = params(j2k, case)
+    want = O.encode_tile(p, pix)
+    assert all(np.array_equal(x, y) for x, y in zip(gpu_ctx.encode_tile(p, pix), want)), case
+    with gpu_ctx.options(enc_bytes=1):
+        assert all(np.array_equal(x, y) for x, y in zip(gpu_ctx.encode_tile(p, pix), want)), case
 
 
 def test_padded_rows_and_constant_images(j2k, gpu_ctx):

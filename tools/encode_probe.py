@@ -31,11 +31,13 @@ def main():
         d_planes = torch.zeros(3 * w * h, dtype=torch.int32, device="cuda")
         got = C.c_uint64(0)
         torch.cuda.synchronize()
-        for name, fn in (("preprocess (pixels -> planes, DWT, quantiser)",
-                          lambda: L.j2kgpu_encode_preprocess(ctx._h, C.byref(p), d_pix.data_ptr(), w * 4, d_planes.data_ptr())),
-                         ("whole forward path",
-                          lambda: L.j2kgpu_encode_tile(ctx._h, C.byref(p), d_pix.data_ptr(), w * 4, d_out.data_ptr(), d_out.numel(),
-                                                       C.byref(got), None, None, 0))):
+        whole = lambda: L.j2kgpu_encode_tile(ctx._h, C.byref(p), d_pix.data_ptr(), w * 4, d_out.data_ptr(), d_out.numel(),  # noqa: E731
+                                             C.byref(got), None, None, 0)
+        for name, fn, opt in (("preprocess (pixels -> planes, DWT, quantiser)",
+                               lambda: L.j2kgpu_encode_preprocess(ctx._h, C.byref(p), d_pix.data_ptr(), w * 4, d_planes.data_ptr()), 0),
+                              ("whole forward path, flag-byte tier-1 coder", whole, 1),
+                              ("whole forward path, row-mask tier-1 coder", whole, 0)):
+            ctx.set_option("enc_bytes", opt)
             for _ in range(2):
                 assert fn() == 0
             t0 = time.perf_counter()

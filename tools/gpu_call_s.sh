@@ -5,8 +5,10 @@ cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
 TAG=${1:-s}
 (time timeout 900 python -m pytest tests/test_gpu_encode.py -m gpu -x -q) > gpurun_out/${TAG}_pytest_enc.log 2>&1; tail -3 gpurun_out/${TAG}_pytest_enc.log
+if [ "$2" = full ]; then
 (time timeout 1500 python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_encode.py) > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest.log
 tail -4 gpurun_out/${TAG}_pytest.log
+fi
 timeout 300 python __graft_entry__.py smoke > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/${TAG}_smoke.log
 (time timeout 900 python bench.py --steps 20 --warmup 5) > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
 python - <<PY
