@@ -440,3 +440,48 @@ def test_closing_a_context_retires_its_jobs(j2k):
     assert not job._h
     job.close()
     del job
+
+
+@pytest.mark.parametrize("mode", ["ref_ebcot", "iso_ht"])
+def test_job_run_replays_from_a_cuda_graph(j2k, gpu_ctx, mode):
+    """j2kgpu_job_run only enqueues work on the context's stream (no allocation, no synchronisation, no host copy once the
+    job exists), so a caller can capture it into a CUDA graph and replay the whole path with one launch"""
+    import torch
+    s = jobs.synth_image(256, 192, 3, 8, seed=71)
+    if mode == "ref_ebcot":
+        j = jobs.build_ref_job(s, 8, 128, 64, nlevels=3, reversible=True, threads=2)
+        img = hdr(j2k, j)
+    else:
+        j = jobs.build_iso_job(s, 8, 128, 64, 3, ht_passes=3, ht_plane=1)
+        img = j2k.make_image(256, 192, 3, 8, nlevels=3, ht=1, mode=j2k.MODE_ISO, coef_bits=j["coef_bits"])
+    tcs, cbs = jobs.as_ctypes(j["tilecomps"], j2k.TileComp), jobs.as_ctypes(j["cblks"], j2k.CBlk)
+    blob = np.ascontiguousarray(j["blob"])
+    out = np.zeros(256 * 192 * 4, np.uint8)
+    item = j2k.BatchItem(img, tcs, len(tcs), cbs, len(cbs), blob.ctypes.data_as(j2k.u8p), blob.size, out.ctypes.data_as(j2k.u8p), 256 * 4)
+    job = j2k.Job(gpu_ctx, [item])
+    try:
+        job.run_host()
+        want = out.copy()
+        assert np.array_equal(want.reshape(192, 256, 4)[:, :, :3], np.moveaxis(s, 0, 2)) or mode == "iso_ht"
+        d_blob = torch.from_numpy(blob).cuda()
+        d_out = torch.zeros(job.out_bytes, dtype=torch.uint8, device="cuda")
+        stream = torch.cuda.Stream()
+        gpu_ctx.set_stream(stream.cuda_stream)
+        torch.cuda.synchronize()
+        job.run(d_blob.data_ptr(), d_out.data_ptr())                 # warm: tables, attributes
+        stream.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        n0 = gpu_ctx.launches
+        with torch.cuda.graph(graph, stream=stream):
+            job.run(d_blob.data_ptr(), d_out.data_ptr())
+        launches = gpu_ctx.launches - n0
+        assert launches >= 3
+        for _ in range(3):
+            d_out.zero_()
+            torch.cuda.synchronize()
+            graph.replay()
+            torch.cuda.synchronize()
+            assert np.array_equal(d_out.cpu().numpy()[: want.size], want)
+    finally:
+        gpu_ctx.set_stream(0)
+        job.close()
