@@ -166,3 +166,17 @@ def test_full_size_1080p_lossy(j2k, gpu_ctx):
     a = gpu_ctx.encode_tile(p, pix)
     b = O.encode_tile(p, pix, threads=16)
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_full_size_8192_grey16(j2k, gpu_ctx):
+    """BASELINE configs[3]'s image through the forward path: 8192 x 8192 Gray16, lossless (two waves of code blocks)"""
+    w = h = 8192
+    rng = np.random.default_rng(84)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    v = ((np.sin(xx / 37.0) + np.cos(yy / 53.0) + 2.0) * 12000.0 + rng.integers(0, 600, (h, w))).astype(np.uint32)
+    pix = np.zeros((h, w, 2), np.uint8)
+    pix[..., 0], pix[..., 1] = v >> 8, v & 255
+    p = params(j2k, (w, h, 1, 16, 1, 6, 4, 4, 0, 0))
+    a = gpu_ctx.encode_tile(p, pix)
+    b = O.encode_tile(p, pix, threads=16)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))

@@ -47,6 +47,39 @@ def main():
             dt = (time.perf_counter() - t0) / reps
             print("%dx%d %s: %s %.3f ms (%.1f Mpixel/s), %d blocks, %d bytes" %
                   (w, h, "lossless" if lossless else "lossy q=%d" % q, name, dt * 1e3, w * h / 1e6 / dt, n, got.value), flush=True)
+    # several encoders at once, one context (and stream) per caller as the Go binding keeps them: blocks of different images
+    # share the machine, so the calls overlap where one call alone leaves SMs idle behind its longest chains
+    import threading
+    w, h = 3840, 2160
+    rgb = jobs.synth_image_fast(w, h, 3, 8, seed=12)
+    pix = np.full((h, w, 4), 255, np.uint8)
+    pix[:, :, :3] = np.moveaxis(rgb, 0, 2)
+    d_pix = torch.from_numpy(pix.reshape(-1)).cuda()
+    torch.cuda.synchronize()
+    for nthreads in (1, 2, 4, 8):
+        ctxs = [j2k.Context(0) for _ in range(nthreads)]
+        outs = [torch.zeros(w * h * 6, dtype=torch.uint8, device="cuda") for _ in range(nthreads)]
+        torch.cuda.synchronize()
+        reps = 4
+
+        def work(i):
+            p = j2k.EncodeParams(width=w, height=h, ncomp=3, pix_bits=8, lossless=1, num_resolutions=6, cb_x=4, cb_y=4, flags=j2k.ENC_DEVICE_PTRS)
+            got = C.c_uint64(0)
+            for _ in range(reps + 1):
+                assert L.j2kgpu_encode_tile(ctxs[i]._h, C.byref(p), d_pix.data_ptr(), w * 4, outs[i].data_ptr(), outs[i].numel(), C.byref(got), None, None, 0) == 0
+
+        work(0)                                                         # warm
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=work, args=(i,)) for i in range(nthreads)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        dt = time.perf_counter() - t0
+        print("%d contexts at once, 4K lossless: %.1f Mpixel/s in total (%.2f ms per frame and context)" %
+              (nthreads, nthreads * (reps + 1) * w * h / 1e6 / dt, dt / (reps + 1) * 1e3), flush=True)
+        for c in ctxs:
+            c.close()
     ctx.close()
 
 
