@@ -230,7 +230,7 @@ __device__ __forceinline__ void mq_put(MqEnc &e, uint32_t b)
     e.bp++;
     e.cur = b & 0xFFu;
 }
-__device__ J2K_NOINLINE void mq_byte_out(MqEnc &e)                 // mqc.go:270-310
+__device__ __forceinline__ void mq_byte_out(MqEnc &e)                 // mqc.go:270-310
 {
     if (e.cur == 0xFFu) { mq_put(e, e.C >> 20); e.C &= 0xFFFFFu; e.CT = 7; }
     else if ((e.C & 0x8000000u) == 0) { mq_put(e, e.C >> 19); e.C &= 0x7FFFFu; e.CT = 8; }
@@ -263,7 +263,7 @@ __device__ __forceinline__ void mq_encode(MqEnc &e, int cx, int d) // mqc.go:224
         mq_renorm(e);
     }
 }
-__device__ int mq_flush(MqEnc &e)                                  // mqc.go:313-341 -> number of bytes
+__device__ __forceinline__ int mq_flush(MqEnc &e)                                  // mqc.go:313-341 -> number of bytes
 {
     const uint32_t tc = e.C + e.A;
     e.C |= 0xFFFFu;
@@ -315,7 +315,7 @@ __device__ __forceinline__ void t1_zc_and_sign(T1Enc &t, MqEnc &mq, int i, int s
     if (sig) { t1_sign(t, mq, i); t.f[i] |= F_SIG; }
 }
 // the three passes of one bit-plane (t1.go:558-770, 816-914), run by one lane
-__device__ J2K_NOINLINE void t1_plane(T1Enc &t, MqEnc &mq)
+__device__ __forceinline__ void t1_plane(T1Enc &t, MqEnc &mq)
 {
     const int w = t.w, h = t.h, s = t.stride;
     for (int y = 0; y < h; y++)                                    // significance propagation: raster order
@@ -402,7 +402,7 @@ __device__ __forceinline__ int nr_zc_and_sign(const T1Narrow &t, MqEnc &mq, int 
     if (sig) { nr_sign(t, mq, x, y); t.sig[y + 1] |= (uint64_t)1 << x; }
     return sig;
 }
-__device__ J2K_NOINLINE void t1_plane_narrow(T1Narrow &t, MqEnc &mq)
+__device__ __forceinline__ void t1_plane_narrow(T1Narrow &t, MqEnc &mq)
 {
     const int h = t.h;
     for (int y = 0; y < h; y++) {                                  // significance propagation, t1.go:558-639
