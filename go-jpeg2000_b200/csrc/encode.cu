@@ -418,16 +418,21 @@ __device__ __forceinline__ void t1_plane_narrow(T1Narrow &t, MqEnc &mq)
         t.vis[y + 1] |= seen;
     }
     for (int y = 0; y < h; y++) {                                  // magnitude refinement, t1.go:642-683
-        uint64_t cand = t.sig[y + 1] & ~t.vis[y + 1];
+        const uint64_t cand = t.sig[y + 1] & ~t.vis[y + 1];
         if (!cand) continue;
         const uint64_t plane = t.bits[y], nb = nb_mask(t, y), ref = t.ref[y + 1];
         t.ref[y + 1] = ref | cand;
-        while (cand) {
-            const int x = __ffsll((long long)cand) - 1;
-            cand &= cand - 1;
-            const int cx = ((ref >> x) & 1u) ? CX_MAG0 + 2 : (((nb >> x) & 1u) ? CX_MAG0 + 1 : CX_MAG0);
-            mq_encode(mq, cx, (int)((plane >> x) & 1u));
-        }
+        // a row as two 32-bit halves: find-first-set, clear-lowest and variable shifts of 64-bit words cost twice the instructions
+        auto half = [&](uint32_t c, uint32_t refh, uint32_t nbh, uint32_t pl) {
+            while (c) {
+                const int x = __ffs((int)c) - 1;
+                c &= c - 1;
+                const int cx = ((refh >> x) & 1u) ? CX_MAG0 + 2 : CX_MAG0 + (int)((nbh >> x) & 1u);   // t1.go:463-479
+                mq_encode(mq, cx, (int)((pl >> x) & 1u));
+            }
+        };
+        half((uint32_t)cand, (uint32_t)ref, (uint32_t)nb, (uint32_t)plane);
+        half((uint32_t)(cand >> 32), (uint32_t)(ref >> 32), (uint32_t)(nb >> 32), (uint32_t)(plane >> 32));
     }
     for (int y = 0; y < h; y += 4) {                               // cleanup, t1.go:686-770, 816-914
         const int rows = min(4, h - y);
@@ -476,15 +481,61 @@ __host__ __device__ constexpr size_t t1enc_warp_bytes(int cbw, int cbh, bool nar
     return t1enc_flag_bytes(cbw, cbh, narrow) + (size_t)cbh * ((cbw + 63) / 64) * 8 + 32;
 }
 
+// longest chains first: a warp per block finds the block's bit-plane count (the length of its chain, to first order), one CTA
+// then lists the blocks by falling count; k_t1_enc takes them in that order, so that the tail of the launch is made of the
+// short chains (the reference's own pool hands its jobs out in list order; the bytes of a block do not depend on when it runs)
+__global__ void k_enc_bps(const EncBlk *__restrict__ blks, uint32_t n, const int32_t *__restrict__ planes, int W, int H,
+                          uint8_t *__restrict__ bps)
+{
+    const uint32_t bi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = (int)threadIdx.x & 31;
+    if (bi >= n) return;
+    const EncBlk blk = blks[bi];
+    const int32_t *plane = planes + blk.plane_off;
+    int32_t maxv = 0;
+    for (int y = 0; y < blk.h; y++) {
+        const uint32_t gy = blk.sy + (uint32_t)y;
+        if (gy >= (uint32_t)H) break;
+        for (int x = lane; x < blk.w; x += 32) {
+            const uint32_t gx = blk.sx + (uint32_t)x;
+            int32_t v = gx < (uint32_t)W ? plane[(uint64_t)gy * W + gx] : 0;
+            v = v < 0 ? (int32_t)(0u - (uint32_t)v) : v;
+            maxv = v > maxv ? v : maxv;
+        }
+    }
+    for (int o = 16; o; o >>= 1) { const int32_t m = __shfl_xor_sync(0xffffffffu, maxv, o); maxv = m > maxv ? m : maxv; }
+    int nbps = 0;
+    for (int32_t m = maxv; m > 0; m >>= 1) nbps++;
+    if (lane == 0) bps[bi] = (uint8_t)nbps;
+}
+
+__global__ void k_enc_order(const uint8_t *__restrict__ bps, uint32_t n, uint32_t *__restrict__ order)
+{
+    __shared__ uint32_t hist[33], cursor[33];
+    const uint32_t t = threadIdx.x;
+    if (t < 33) hist[t] = 0;
+    __syncthreads();
+    for (uint32_t i = t; i < n; i += blockDim.x) atomicAdd(&hist[min((uint32_t)bps[i], 32u)], 1u);
+    __syncthreads();
+    if (t == 0) {
+        uint32_t run = 0;
+        for (int b = 32; b >= 0; b--) { cursor[b] = run; run += hist[b]; }
+    }
+    __syncthreads();
+    for (uint32_t i = t; i < n; i += blockDim.x) order[atomicAdd(&cursor[min((uint32_t)bps[i], 32u)], 1u)] = i;
+}
+
 template <bool NARROW>
-__global__ void k_t1_enc(const EncBlk *__restrict__ blks, uint32_t n, const int32_t *__restrict__ planes, int W, int H,
+__global__ void k_t1_enc(const EncBlk *__restrict__ blks, const uint32_t *__restrict__ order, uint32_t n,
+                         const int32_t *__restrict__ planes, int W, int H,
                          int cbw, int cbh, uint8_t *__restrict__ slab, uint32_t cap, uint32_t *__restrict__ lens,
                          uint8_t *__restrict__ bps, int *__restrict__ err)
 {
     J2K_DYN_SMEM(uint8_t, smem);
     const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
-    const uint32_t bi = blockIdx.x * (blockDim.x >> 5) + (uint32_t)warp;
-    if (bi >= n) return;
+    const uint32_t slot = blockIdx.x * (blockDim.x >> 5) + (uint32_t)warp;
+    if (slot >= n) return;
+    const uint32_t bi = order[slot];
     const EncBlk blk = blks[bi];
     uint8_t *base = smem + (size_t)warp * t1enc_warp_bytes(cbw, cbh, NARROW);
     uint8_t *flags = base;                                         // wide blocks: flag bytes; narrow: four arrays of row masks
@@ -843,6 +894,7 @@ extern "C" int j2kgpu_encode_tile(j2kgpu_ctx *ctx, const j2k_encode_t *p, const 
     uint32_t *d_lens = e == cudaSuccess ? (uint32_t *)mem.get((size_t)n * 4, &e) : nullptr;
     uint8_t *d_bps = e == cudaSuccess ? (uint8_t *)mem.get((size_t)n, &e) : nullptr;
     uint64_t *d_offs = e == cudaSuccess ? (uint64_t *)mem.get((size_t)(n + 1) * 8 + 16, &e) : nullptr;
+    uint32_t *d_order = e == cudaSuccess ? (uint32_t *)mem.get((size_t)n * 4, &e) : nullptr;
     if (e != cudaSuccess) { cudaStreamSynchronize(s); return j2k_set_err(ctx, J2KGPU_E_NOMEM, "tier-1 encoder buffers: %s", cudaGetErrorString(e)); }
     int *d_err = (int *)(d_offs + n + 1);
     uint64_t h_tail[2] = {0, 0};                                   // total bytes, error flag
@@ -858,12 +910,14 @@ extern "C" int j2kgpu_encode_tile(j2kgpu_ctx *ctx, const j2k_encode_t *p, const 
         e = cudaFuncSetAttribute(narrow ? (const void *)k_t1_enc<true> : (const void *)k_t1_enc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { cudaStreamSynchronize(s); return j2k_cuda_err(ctx, e, "k_t1_enc shared memory"); }
     }
-    if (narrow) J2K_LAUNCH((k_t1_enc<true>), (n + wpc - 1) / wpc, wpc * 32, smem, s, (const EncBlk *)d_blks, n, (const int32_t *)d_planes, g.w, g.h,
-                           g.cbw, g.cbh, d_slab, cap, d_lens, d_bps, d_err);
-    else J2K_LAUNCH((k_t1_enc<false>), (n + wpc - 1) / wpc, wpc * 32, smem, s, (const EncBlk *)d_blks, n, (const int32_t *)d_planes, g.w, g.h,
-                    g.cbw, g.cbh, d_slab, cap, d_lens, d_bps, d_err);
+    J2K_LAUNCH((k_enc_bps), (n + 7) / 8, 256, 0, s, (const EncBlk *)d_blks, n, (const int32_t *)d_planes, g.w, g.h, d_bps);
+    J2K_LAUNCH((k_enc_order), 1, 1024, 0, s, (const uint8_t *)d_bps, n, d_order);
+    if (narrow) J2K_LAUNCH((k_t1_enc<true>), (n + wpc - 1) / wpc, wpc * 32, smem, s, (const EncBlk *)d_blks, (const uint32_t *)d_order, n,
+                           (const int32_t *)d_planes, g.w, g.h, g.cbw, g.cbh, d_slab, cap, d_lens, d_bps, d_err);
+    else J2K_LAUNCH((k_t1_enc<false>), (n + wpc - 1) / wpc, wpc * 32, smem, s, (const EncBlk *)d_blks, (const uint32_t *)d_order, n,
+                    (const int32_t *)d_planes, g.w, g.h, g.cbw, g.cbh, d_slab, cap, d_lens, d_bps, d_err);
     J2K_LAUNCH((k_enc_scan), 1, 1024, 0, s, (const uint32_t *)d_lens, n, d_offs);
-    ctx->launches += 2;
+    ctx->launches += 4;
     e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(h_tail, d_offs + n, 16, cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess && blk_len) e = cudaMemcpyAsync(blk_len, d_lens, (size_t)n * 4, cudaMemcpyDeviceToHost, s);

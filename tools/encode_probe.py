@@ -68,7 +68,10 @@ def main():
             for _ in range(reps + 1):
                 assert L.j2kgpu_encode_tile(ctxs[i]._h, C.byref(p), d_pix.data_ptr(), w * 4, outs[i].data_ptr(), outs[i].numel(), C.byref(got), None, None, 0) == 0
 
-        work(0)                                                         # warm
+        reps = 0
+        for i in range(nthreads):                                       # warm every context: its pool allocates on the first call
+            work(i)
+        reps = 4
         t0 = time.perf_counter()
         th = [threading.Thread(target=work, args=(i,)) for i in range(nthreads)]
         for t in th:
