@@ -1,8 +1,8 @@
 #!/bin/bash
-# forward path: the 8192^2 test, the probe (both coders, several contexts at once)
+# forward path: its tests, the probe (both coders, several contexts at once)
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
 TAG=${1:-t}
-(time timeout 900 python -m pytest tests/test_gpu_encode.py -m gpu -x -q -k "8192 or full_size") > gpurun_out/${TAG}_pytest_enc.log 2>&1; grep -n "passed\|failed" gpurun_out/${TAG}_pytest_enc.log
+(time timeout 900 python -m pytest tests/test_gpu_encode.py -m gpu -x -q) > gpurun_out/${TAG}_pytest_enc.log 2>&1; grep -n "passed\|failed" gpurun_out/${TAG}_pytest_enc.log
 timeout 900 python tools/encode_probe.py > gpurun_out/${TAG}_encode_probe.log 2>&1; echo "probe rc=$?"
 cat gpurun_out/${TAG}_encode_probe.log
