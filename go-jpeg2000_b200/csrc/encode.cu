@@ -366,119 +366,160 @@ __device__ __forceinline__ void t1_plane(T1Enc &t, MqEnc &mq)
         }
 }
 
-// ---- blocks at most 64 samples wide: the coder's state as one 64-bit mask per row -----------------------------------------
-// sig / neg / vis / ref hold rows -1 .. h (index y + 1; the two border rows stay zero).  Instead of visiting every sample,
-// each pass computes the set of samples that take part (candidates of the row, or of the stripe's columns) with a few
-// logic operations and walks its set bits in coding order; a sample that becomes significant adds its right-hand neighbour
-// to the row's candidates (SPP) or takes the next column out of run-length mode (cleanup), which is all that the
-// reference's visit-time tests (t1.go:349-384, 1087-1092, 1195-1208) can see of it.
-struct T1Narrow {
+// ---- the coder's state as 64-bit masks per row -------------------------------------------------------------------------------
+// sig / neg / vis / ref hold rows -1 .. h (index y + 1; the two border rows stay zero), `ws` words per row (M = false: blocks
+// at most 64 samples wide, one word, every word loop and carry below folds away; M = true: up to four words).  Instead of
+// visiting every sample, each pass computes the set of samples that take part (candidates of a row word, or of a stripe's
+// columns) with a few logic operations and walks its set bits in coding order; a sample that becomes significant adds its
+// right-hand neighbour to the candidates (SPP) or takes the next column out of run-length mode (cleanup), which is all
+// that the reference's visit-time tests (t1.go:349-384, 1087-1092, 1195-1208) can see of it.  Words are taken left to right
+// and a word's sets are computed when the walk reaches it, so what happened in the word before is already in the masks.
+struct T1Mask {
     uint64_t *sig, *neg, *vis, *ref;
-    const uint64_t *bits;
-    uint64_t rowmask;
-    int w, h, band;
+    const uint64_t *bits;                 // current bit-plane, nw words per row
+    uint64_t lastmask;                    // valid columns of the last word
+    int w, h, band, ws, nw;               // ws = words per row of the state arrays (launch-wide), nw = words this block uses
 };
-__device__ __forceinline__ uint32_t win3(uint64_t row, int x) { return (uint32_t)(x ? row >> (x - 1) : row << 1) & 7u; }
-__device__ __forceinline__ uint64_t spread3(uint64_t r) { return r | (r << 1) | (r >> 1); }
-__device__ __forceinline__ uint64_t nb_mask(const T1Narrow &t, int y)      // samples of row y with a significant neighbour
+template <bool M> __device__ __forceinline__ int mk_ws(const T1Mask &t) { return M ? t.ws : 1; }
+template <bool M> __device__ __forceinline__ int mk_nw(const T1Mask &t) { return M ? t.nw : 1; }
+template <bool M> __device__ __forceinline__ uint64_t mk_mask(const T1Mask &t, int k) { return (M && k + 1 < t.nw) ? ~(uint64_t)0 : t.lastmask; }
+template <bool M> __device__ __forceinline__ uint64_t mk_shl(const T1Mask &t, const uint64_t *a, int r, int k)   // column x <- x - 1
 {
-    const uint64_t s = t.sig[y + 1];
-    return (spread3(t.sig[y]) | spread3(t.sig[y + 2]) | (s << 1) | (s >> 1)) & t.rowmask;
+    const uint64_t *p = a + r * mk_ws<M>(t) + k;
+    return (p[0] << 1) | ((M && k > 0) ? p[-1] >> 63 : 0);
 }
-__device__ __forceinline__ void nr_sign(const T1Narrow &t, MqEnc &mq, int x, int y)
+template <bool M> __device__ __forceinline__ uint64_t mk_shr(const T1Mask &t, const uint64_t *a, int r, int k)   // column x <- x + 1
 {
-    const uint32_t sm = win3(t.sig[y + 1], x), nm = win3(t.neg[y + 1], x);
+    const uint64_t *p = a + r * mk_ws<M>(t) + k;
+    return (p[0] >> 1) | ((M && k + 1 < t.nw) ? p[1] << 63 : 0);
+}
+template <bool M> __device__ __forceinline__ uint64_t mk_spread(const T1Mask &t, const uint64_t *a, int r, int k)
+{
+    return a[r * mk_ws<M>(t) + k] | mk_shl<M>(t, a, r, k) | mk_shr<M>(t, a, r, k);
+}
+template <bool M> __device__ __forceinline__ uint64_t mk_nb(const T1Mask &t, int y, int k)      // samples of row y, word k, with a significant neighbour
+{
+    return (mk_spread<M>(t, t.sig, y, k) | mk_spread<M>(t, t.sig, y + 2, k) | mk_shl<M>(t, t.sig, y + 1, k) | mk_shr<M>(t, t.sig, y + 1, k)) &
+           mk_mask<M>(t, k);
+}
+// columns x - 1, x, x + 1 of row r (x = 64 k + b) as bits 0..2
+template <bool M> __device__ __forceinline__ uint32_t mk_win(const T1Mask &t, const uint64_t *a, int r, int k, int b)
+{
+    const uint64_t *p = a + r * mk_ws<M>(t) + k;
+    uint32_t u = (uint32_t)(b ? p[0] >> (b - 1) : p[0] << 1) & 7u;
+    if (M) {
+        if (b == 0 && k > 0) u |= (uint32_t)(p[-1] >> 63);
+        if (b == 63 && k + 1 < t.nw) u |= (uint32_t)(p[1] & 1u) << 2;
+    }
+    return u;
+}
+template <bool M> __device__ __forceinline__ uint32_t mk_bit(const T1Mask &t, const uint64_t *a, int r, int k, int b)
+{
+    return (uint32_t)(a[r * mk_ws<M>(t) + k] >> b) & 1u;
+}
+template <bool M> __device__ __forceinline__ void mk_sign(const T1Mask &t, MqEnc &mq, int y, int k, int b)
+{
+    const uint32_t sm = mk_win<M>(t, t.sig, y + 1, k, b), nm = mk_win<M>(t, t.neg, y + 1, k, b);
     const uint32_t idx = (sm & 1u) | (nm & 1u) << 1 | (sm & 4u) | (nm & 4u) << 1 |
-                         (uint32_t)((t.sig[y] >> x) & 1u) << 4 | (uint32_t)((t.neg[y] >> x) & 1u) << 5 |
-                         (uint32_t)((t.sig[y + 2] >> x) & 1u) << 6 | (uint32_t)((t.neg[y + 2] >> x) & 1u) << 7;
+                         mk_bit<M>(t, t.sig, y, k, b) << 4 | mk_bit<M>(t, t.neg, y, k, b) << 5 |
+                         mk_bit<M>(t, t.sig, y + 2, k, b) << 6 | mk_bit<M>(t, t.neg, y + 2, k, b) << 7;
     const uint32_t e = c_esc[idx];
-    mq_encode(mq, CX_SC0 + (int)(e >> 1), (int)(((t.neg[y + 1] >> x) & 1u) ^ (e & 1u)));
+    mq_encode(mq, CX_SC0 + (int)(e >> 1), (int)(mk_bit<M>(t, t.neg, y + 1, k, b) ^ (e & 1u)));
 }
-// zero coding of sample (x, y) with bit `sig`; returns sig after coding the sign and marking the sample significant
-__device__ __forceinline__ int nr_zc_and_sign(const T1Narrow &t, MqEnc &mq, int x, int y, int sig)
+// zero coding of sample (64 k + b, y) with bit `sig`; returns sig after coding the sign and marking the sample significant
+template <bool M> __device__ __forceinline__ int mk_zc_and_sign(const T1Mask &t, MqEnc &mq, int y, int k, int b, int sig)
 {
-    const uint32_t idx = win3(t.sig[y], x) | win3(t.sig[y + 1], x) << 3 | win3(t.sig[y + 2], x) << 6;
+    const uint32_t idx = mk_win<M>(t, t.sig, y, k, b) | mk_win<M>(t, t.sig, y + 1, k, b) << 3 | mk_win<M>(t, t.sig, y + 2, k, b) << 6;
     mq_encode(mq, c_ezc9[t.band * 512 + idx], sig);
-    if (sig) { nr_sign(t, mq, x, y); t.sig[y + 1] |= (uint64_t)1 << x; }
+    if (sig) { mk_sign<M>(t, mq, y, k, b); t.sig[(y + 1) * mk_ws<M>(t) + k] |= (uint64_t)1 << b; }
     return sig;
 }
-__device__ __forceinline__ void t1_plane_narrow(T1Narrow &t, MqEnc &mq)
+template <bool M>
+__device__ __forceinline__ void t1_plane_masks(T1Mask &t, MqEnc &mq)
 {
-    const int h = t.h;
-    for (int y = 0; y < h; y++) {                                  // significance propagation, t1.go:558-639
-        uint64_t cand = ~t.sig[y + 1] & nb_mask(t, y), seen = 0;
-        const uint64_t plane = t.bits[y];
-        while (cand) {
-            const int x = __ffsll((long long)cand) - 1;
-            const uint64_t bit = (uint64_t)1 << x;
-            cand &= ~bit; seen |= bit;
-            if (nr_zc_and_sign(t, mq, x, y, (int)((plane >> x) & 1u)))
-                cand |= (bit << 1) & ~t.sig[y + 1] & t.rowmask;    // its right-hand neighbour has a significant neighbour now
-        }
-        t.vis[y + 1] |= seen;
-    }
-    for (int y = 0; y < h; y++) {                                  // magnitude refinement, t1.go:642-683
-        const uint64_t cand = t.sig[y + 1] & ~t.vis[y + 1];
-        if (!cand) continue;
-        const uint64_t plane = t.bits[y], nb = nb_mask(t, y), ref = t.ref[y + 1];
-        t.ref[y + 1] = ref | cand;
-        // a row as two 32-bit halves: find-first-set, clear-lowest and variable shifts of 64-bit words cost twice the instructions
-        auto half = [&](uint32_t c, uint32_t refh, uint32_t nbh, uint32_t pl) {
-            while (c) {
-                const int x = __ffs((int)c) - 1;
-                c &= c - 1;
-                const int cx = ((refh >> x) & 1u) ? CX_MAG0 + 2 : CX_MAG0 + (int)((nbh >> x) & 1u);   // t1.go:463-479
-                mq_encode(mq, cx, (int)((pl >> x) & 1u));
+    const int h = t.h, ws = mk_ws<M>(t), nw = mk_nw<M>(t);
+    for (int y = 0; y < h; y++)                                    // significance propagation, t1.go:558-639
+        for (int k = 0; k < nw; k++) {
+            uint64_t *srow = t.sig + (y + 1) * ws + k;
+            const uint64_t mask = mk_mask<M>(t, k), plane = t.bits[y * nw + k];
+            uint64_t cand = ~*srow & mk_nb<M>(t, y, k), seen = 0;
+            while (cand) {
+                const int b = __ffsll((long long)cand) - 1;
+                const uint64_t bit = (uint64_t)1 << b;
+                cand &= ~bit; seen |= bit;
+                if (mk_zc_and_sign<M>(t, mq, y, k, b, (int)((plane >> b) & 1u)))
+                    cand |= (bit << 1) & ~*srow & mask;            // its right-hand neighbour has a significant neighbour now
             }
-        };
-        half((uint32_t)cand, (uint32_t)ref, (uint32_t)nb, (uint32_t)plane);
-        half((uint32_t)(cand >> 32), (uint32_t)(ref >> 32), (uint32_t)(nb >> 32), (uint32_t)(plane >> 32));
-    }
+            t.vis[(y + 1) * ws + k] |= seen;
+        }
+    for (int y = 0; y < h; y++)                                    // magnitude refinement, t1.go:642-683
+        for (int k = 0; k < nw; k++) {
+            const int i = (y + 1) * ws + k;
+            const uint64_t cand = t.sig[i] & ~t.vis[i];
+            if (!cand) continue;
+            const uint64_t plane = t.bits[y * nw + k], nb = mk_nb<M>(t, y, k), ref = t.ref[i];
+            t.ref[i] = ref | cand;
+            // a word as two 32-bit halves: find-first-set, clear-lowest and variable shifts of 64-bit words cost twice the instructions
+            auto half = [&](uint32_t c, uint32_t refh, uint32_t nbh, uint32_t pl) {
+                while (c) {
+                    const int x = __ffs((int)c) - 1;
+                    c &= c - 1;
+                    const int cx = ((refh >> x) & 1u) ? CX_MAG0 + 2 : CX_MAG0 + (int)((nbh >> x) & 1u);   // t1.go:463-479
+                    mq_encode(mq, cx, (int)((pl >> x) & 1u));
+                }
+            };
+            half((uint32_t)cand, (uint32_t)ref, (uint32_t)nb, (uint32_t)plane);
+            half((uint32_t)(cand >> 32), (uint32_t)(ref >> 32), (uint32_t)(nb >> 32), (uint32_t)(plane >> 32));
+        }
     for (int y = 0; y < h; y += 4) {                               // cleanup, t1.go:686-770, 816-914
         const int rows = min(4, h - y);
-        uint64_t todo = 0, busy = 0;
-        for (int k = 0; k < rows; k++) {
-            const uint64_t sv = t.sig[y + k + 1] | t.vis[y + k + 1];
-            todo |= ~sv & t.rowmask;
-            busy |= sv | nb_mask(t, y + k);
-        }
-        uint64_t rl = rows == 4 ? ~busy & t.rowmask : 0;            // columns in run-length mode (t1.go:1195-1208)
-        while (todo) {
-            const int x = __ffsll((long long)todo) - 1;
-            const uint64_t bit = (uint64_t)1 << x;
-            todo &= ~bit;
-            int k = 0, grew = 0;
-            if (rl & bit) {
-                const uint32_t col = (uint32_t)((t.bits[y] >> x) & 1u) | (uint32_t)((t.bits[y + 1] >> x) & 1u) << 1 |
-                                     (uint32_t)((t.bits[y + 2] >> x) & 1u) << 2 | (uint32_t)((t.bits[y + 3] >> x) & 1u) << 3;
-                if (!col) { mq_encode(mq, CX_RL, 0); continue; }
-                const int first = __ffs((int)col) - 1;
-                mq_encode(mq, CX_RL, 1);
-                mq_encode(mq, CX_UNI, (first >> 1) & 1);
-                mq_encode(mq, CX_UNI, first & 1);
-                nr_sign(t, mq, x, y + first);
-                t.sig[y + first + 1] |= bit;
-                grew = 1;
-                k = first + 1;
+        for (int k = 0; k < nw; k++) {
+            const uint64_t mask = mk_mask<M>(t, k);
+            uint64_t todo = 0, busy = 0;
+            for (int j = 0; j < rows; j++) {
+                const uint64_t sv = t.sig[(y + j + 1) * ws + k] | t.vis[(y + j + 1) * ws + k];
+                todo |= ~sv & mask;
+                busy |= sv | mk_nb<M>(t, y + j, k);
             }
-            for (; k < rows; k++) {
-                if ((t.sig[y + k + 1] | t.vis[y + k + 1]) & bit) continue;
-                grew |= nr_zc_and_sign(t, mq, x, y + k, (int)((t.bits[y + k] >> x) & 1u));
+            uint64_t rl = rows == 4 ? ~busy & mask : 0;             // columns in run-length mode (t1.go:1195-1208)
+            while (todo) {
+                const int b = __ffsll((long long)todo) - 1;
+                const uint64_t bit = (uint64_t)1 << b;
+                todo &= ~bit;
+                int j = 0, grew = 0;
+                if (rl & bit) {
+                    const uint32_t col = (uint32_t)((t.bits[y * nw + k] >> b) & 1u) | (uint32_t)((t.bits[(y + 1) * nw + k] >> b) & 1u) << 1 |
+                                         (uint32_t)((t.bits[(y + 2) * nw + k] >> b) & 1u) << 2 | (uint32_t)((t.bits[(y + 3) * nw + k] >> b) & 1u) << 3;
+                    if (!col) { mq_encode(mq, CX_RL, 0); continue; }
+                    const int first = __ffs((int)col) - 1;
+                    mq_encode(mq, CX_RL, 1);
+                    mq_encode(mq, CX_UNI, (first >> 1) & 1);
+                    mq_encode(mq, CX_UNI, first & 1);
+                    mk_sign<M>(t, mq, y + first, k, b);
+                    t.sig[(y + first + 1) * ws + k] |= bit;
+                    grew = 1;
+                    j = first + 1;
+                }
+                for (; j < rows; j++) {
+                    if ((t.sig[(y + j + 1) * ws + k] | t.vis[(y + j + 1) * ws + k]) & bit) continue;
+                    grew |= mk_zc_and_sign<M>(t, mq, y + j, k, b, (int)((t.bits[(y + j) * nw + k] >> b) & 1u));
+                }
+                if (grew) rl &= ~(bit << 1);
             }
-            if (grew) rl &= ~(bit << 1);
         }
-        for (int k = 0; k < rows; k++) t.vis[y + k + 1] = 0;
+        for (int j = 0; j < rows; j++)
+            for (int k = 0; k < nw; k++) t.vis[(y + j + 1) * ws + k] = 0;
     }
 }
 
 // shared memory of one warp: flag bytes (or row masks), the bit-plane bitmap, the context states
-__host__ __device__ constexpr size_t t1enc_flag_bytes(int cbw, int cbh, bool narrow)
+__host__ __device__ constexpr size_t t1enc_flag_bytes(int cbw, int cbh, bool masks)
 {
-    return narrow ? (size_t)4 * (cbh + 2) * 8 : (((size_t)(cbw + 2) * (cbh + 2) + 15) & ~(size_t)15);
+    return masks ? (size_t)4 * (cbh + 2) * ((cbw + 63) / 64) * 8 : (((size_t)(cbw + 2) * (cbh + 2) + 15) & ~(size_t)15);
 }
-__host__ __device__ constexpr size_t t1enc_warp_bytes(int cbw, int cbh, bool narrow)
+__host__ __device__ constexpr size_t t1enc_warp_bytes(int cbw, int cbh, bool masks)
 {
-    return t1enc_flag_bytes(cbw, cbh, narrow) + (size_t)cbh * ((cbw + 63) / 64) * 8 + 32;
+    return t1enc_flag_bytes(cbw, cbh, masks) + (size_t)cbh * ((cbw + 63) / 64) * 8 + 32;
 }
 
 // longest chains first: a warp per block finds the block's bit-plane count (the length of its chain, to first order), one CTA
@@ -525,27 +566,30 @@ __global__ void k_enc_order(const uint8_t *__restrict__ bps, uint32_t n, uint32_
     for (uint32_t i = t; i < n; i += blockDim.x) order[atomicAdd(&cursor[min((uint32_t)bps[i], 32u)], 1u)] = i;
 }
 
-template <bool NARROW>
+// MODE 0: flag bytes (A/B and tests: option enc_bytes); 1: row masks, blocks at most 64 wide; 2: row masks, several words per row
+template <int MODE>
 __global__ void k_t1_enc(const EncBlk *__restrict__ blks, const uint32_t *__restrict__ order, uint32_t n,
                          const int32_t *__restrict__ planes, int W, int H,
                          int cbw, int cbh, uint8_t *__restrict__ slab, uint32_t cap, uint32_t *__restrict__ lens,
                          uint8_t *__restrict__ bps, int *__restrict__ err)
 {
+    constexpr bool MASKS = MODE != 0;
     J2K_DYN_SMEM(uint8_t, smem);
     const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
     const uint32_t slot = blockIdx.x * (blockDim.x >> 5) + (uint32_t)warp;
     if (slot >= n) return;
     const uint32_t bi = order[slot];
     const EncBlk blk = blks[bi];
-    uint8_t *base = smem + (size_t)warp * t1enc_warp_bytes(cbw, cbh, NARROW);
-    uint8_t *flags = base;                                         // wide blocks: flag bytes; narrow: four arrays of row masks
+    uint8_t *base = smem + (size_t)warp * t1enc_warp_bytes(cbw, cbh, MASKS);
+    uint8_t *flags = base;                                         // MODE 0: flag bytes; else four arrays of row masks
     uint64_t *rows = reinterpret_cast<uint64_t *>(base);
-    uint64_t *bits = reinterpret_cast<uint64_t *>(base + t1enc_flag_bytes(cbw, cbh, NARROW));
+    uint64_t *bits = reinterpret_cast<uint64_t *>(base + t1enc_flag_bytes(cbw, cbh, MASKS));
     const int w = blk.w, h = blk.h, stride = w + 2, words = (w + 63) >> 6;
+    const int ws = MODE == 1 ? 1 : (cbw + 63) >> 6, arr = (cbh + 2) * ws;   // words per row / per array of the mask state
     uint8_t *cx = reinterpret_cast<uint8_t *>(bits + (size_t)cbh * ((cbw + 63) / 64));
     const int32_t *plane = planes + blk.plane_off;
     // extractCodeBlockData + SetData: sign flags, largest magnitude
-    if (NARROW) { for (int i = lane; i < 4 * (cbh + 2); i += 32) rows[i] = 0; }
+    if (MASKS) { for (int i = lane; i < 4 * arr; i += 32) rows[i] = 0; }
     else { for (int i = lane; i < stride * (h + 2); i += 32) flags[i] = 0; }
     if (lane < CX_N) cx[lane] = lane == CX_UNI ? 92 : 0;           // mqc.go:194-199
     __syncwarp();
@@ -554,17 +598,19 @@ __global__ void k_t1_enc(const EncBlk *__restrict__ blks, const uint32_t *__rest
         return (gx < (uint32_t)W && gy < (uint32_t)H) ? plane[(uint64_t)gy * W + gx] : 0;
     };
     int32_t maxv = 0;
-    if (NARROW) {
-        uint64_t *neg = rows + (cbh + 2);
-        for (int y = 0; y < h; y++) {
-            int32_t v0 = lane < w ? sample(lane, y) : 0, v1 = lane + 32 < w ? sample(lane + 32, y) : 0;
-            const uint32_t lo = __ballot_sync(0xffffffffu, v0 < 0), hi = __ballot_sync(0xffffffffu, v1 < 0);
-            if (lane == 0) neg[y + 1] = (uint64_t)lo | ((uint64_t)hi << 32);
-            v0 = v0 < 0 ? (int32_t)(0u - (uint32_t)v0) : v0;
-            v1 = v1 < 0 ? (int32_t)(0u - (uint32_t)v1) : v1;
-            maxv = v0 > maxv ? v0 : maxv;
-            maxv = v1 > maxv ? v1 : maxv;
-        }
+    if (MASKS) {
+        uint64_t *neg = rows + arr;
+        for (int y = 0; y < h; y++)
+            for (int wd = 0; wd < words; wd++) {
+                const int x0 = wd * 64 + lane, x1 = x0 + 32;
+                int32_t v0 = x0 < w ? sample(x0, y) : 0, v1 = x1 < w ? sample(x1, y) : 0;
+                const uint32_t lo = __ballot_sync(0xffffffffu, v0 < 0), hi = __ballot_sync(0xffffffffu, v1 < 0);
+                if (lane == 0) neg[(y + 1) * ws + wd] = (uint64_t)lo | ((uint64_t)hi << 32);
+                v0 = v0 < 0 ? (int32_t)(0u - (uint32_t)v0) : v0;
+                v1 = v1 < 0 ? (int32_t)(0u - (uint32_t)v1) : v1;
+                maxv = v0 > maxv ? v0 : maxv;
+                maxv = v1 > maxv ? v1 : maxv;
+            }
     } else {
         for (int y = 0; y < h; y++)
             for (int x = lane; x < w; x += 32) {
@@ -584,8 +630,9 @@ __global__ void k_t1_enc(const EncBlk *__restrict__ blks, const uint32_t *__rest
     mq.A = 0x8000u; mq.C = 0; mq.CT = 12; mq.bp = 0; mq.cur = 0; mq.ovf = 0;
     mq.out = slab + (uint64_t)bi * cap; mq.cap = cap; mq.cx = cx;
     T1Enc t{flags, bits, w, h, stride, words, (int)blk.band};
-    T1Narrow tn{rows, rows + (cbh + 2), rows + 2 * (cbh + 2), rows + 3 * (cbh + 2), bits,
-                w >= 64 ? ~(uint64_t)0 : (((uint64_t)1 << w) - 1), w, h, (int)blk.band};
+    const int wl = w - 64 * (words - 1);                           // columns of the last word
+    T1Mask tm{rows, rows + arr, rows + 2 * arr, rows + 3 * arr, bits, wl >= 64 ? ~(uint64_t)0 : (((uint64_t)1 << wl) - 1),
+              w, h, (int)blk.band, ws, words};
     for (int bp = nbps - 1; bp >= 0; bp--) {
         __syncwarp();
         for (int y = 0; y < h; y++)
@@ -600,7 +647,9 @@ __global__ void k_t1_enc(const EncBlk *__restrict__ blks, const uint32_t *__rest
             }
         __syncwarp();
         if (lane == 0) {
-            if (NARROW) t1_plane_narrow(tn, mq); else t1_plane(t, mq);
+            if (MODE == 1) t1_plane_masks<false>(tm, mq);
+            else if (MODE == 2) t1_plane_masks<true>(tm, mq);
+            else t1_plane(t, mq);
         }
     }
     if (lane == 0) {
@@ -901,21 +950,24 @@ extern "C" int j2kgpu_encode_tile(j2kgpu_ctx *ctx, const j2k_encode_t *p, const 
     e = cudaMemsetAsync(d_err, 0, 8, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_blks, blks.data(), (size_t)n * sizeof(EncBlk), cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) { cudaStreamSynchronize(s); return j2k_cuda_err(ctx, e, "block table upload"); }
-    const bool narrow = g.cbw <= 64 && !ctx->opt.enc_bytes;        // row-mask coder; option enc_bytes forces the flag-byte coder (tests)
-    const size_t per_warp = t1enc_warp_bytes(g.cbw, g.cbh, narrow);
+    const int mode = ctx->opt.enc_bytes ? 0 : (g.cbw <= 64 ? 1 : 2);   // option enc_bytes forces the flag-byte coder (A/B, tests)
+    const size_t per_warp = t1enc_warp_bytes(g.cbw, g.cbh, mode != 0);
     int wpc = 8;
     while (wpc > 1 && (size_t)wpc * per_warp > 96 * 1024) wpc >>= 1;
     const size_t smem = (size_t)wpc * per_warp;
+    const void *kfn = mode == 0 ? (const void *)k_t1_enc<0> : (mode == 1 ? (const void *)k_t1_enc<1> : (const void *)k_t1_enc<2>);
     if (smem > 48 * 1024) {
-        e = cudaFuncSetAttribute(narrow ? (const void *)k_t1_enc<true> : (const void *)k_t1_enc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { cudaStreamSynchronize(s); return j2k_cuda_err(ctx, e, "k_t1_enc shared memory"); }
     }
     J2K_LAUNCH((k_enc_bps), (n + 7) / 8, 256, 0, s, (const EncBlk *)d_blks, n, (const int32_t *)d_planes, g.w, g.h, d_bps);
     J2K_LAUNCH((k_enc_order), 1, 1024, 0, s, (const uint8_t *)d_bps, n, d_order);
-    if (narrow) J2K_LAUNCH((k_t1_enc<true>), (n + wpc - 1) / wpc, wpc * 32, smem, s, (const EncBlk *)d_blks, (const uint32_t *)d_order, n,
-                           (const int32_t *)d_planes, g.w, g.h, g.cbw, g.cbh, d_slab, cap, d_lens, d_bps, d_err);
-    else J2K_LAUNCH((k_t1_enc<false>), (n + wpc - 1) / wpc, wpc * 32, smem, s, (const EncBlk *)d_blks, (const uint32_t *)d_order, n,
-                    (const int32_t *)d_planes, g.w, g.h, g.cbw, g.cbh, d_slab, cap, d_lens, d_bps, d_err);
+#define J2K_T1ENC(MODE_) J2K_LAUNCH((k_t1_enc<MODE_>), (n + wpc - 1) / wpc, wpc * 32, smem, s, (const EncBlk *)d_blks, (const uint32_t *)d_order, n, \
+                                    (const int32_t *)d_planes, g.w, g.h, g.cbw, g.cbh, d_slab, cap, d_lens, d_bps, d_err)
+    if (mode == 0) J2K_T1ENC(0);
+    else if (mode == 1) J2K_T1ENC(1);
+    else J2K_T1ENC(2);
+#undef J2K_T1ENC
     J2K_LAUNCH((k_enc_scan), 1, 1024, 0, s, (const uint32_t *)d_lens, n, d_offs);
     ctx->launches += 4;
     e = cudaGetLastError();

@@ -64,6 +64,48 @@ def test_random_options_and_contents(j2k, gpu_ctx, seed):
         assert all(np.array_equal(x, y) for x, y in zip(gpu_ctx.encode_tile(p, pix), want)), case
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_blocks_wider_than_64(j2k, gpu_ctx, seed):
+    """128- and 256-wide blocks: the row-mask coder with several words per row (neighbourhoods and run-length columns
+    across word boundaries), noise / sparse / word-aligned steps / near-constant contents"""
+    rng = np.random.default_rng(2000 + seed)
+    w, h = int(rng.integers(60, 400)), int(rng.integers(1, 90))
+    nc, bits = int(rng.choice([1, 3])), int(rng.choice([8, 16]))
+    case = (w, h, nc, bits, int(rng.integers(0, 2)), int(rng.integers(1, 4)), int(rng.choice([5, 6])), int(rng.integers(0, 5)),
+            int(rng.choice([0, 3, 75])), 0)
+    ch, m = (1 if nc == 1 else 4), (1 << bits) - 1
+    kind = seed % 4
+    if kind == 0:
+        v = rng.integers(0, m + 1, (h, w, ch))
+    elif kind == 1:
+        v = (rng.random((h, w, ch)) < 0.05) * rng.integers(0, m + 1, (h, w, ch))
+    elif kind == 2:
+        yy, xx = np.mgrid[0:h, 0:w]
+        v = np.stack([((xx // 63) * 977 + yy * 5 + c * 17) % (m + 1) for c in range(ch)], axis=2)
+    else:
+        v = np.full((h, w, ch), m // 2 + 1) + rng.integers(-3, 4, (h, w, ch))
+    v = np.clip(v, 0, m).astype(np.uint32)
+    if bits == 8:
+        pix = v.astype(np.uint8).reshape(-1)
+    else:
+        o = np.zeros((h, w, ch, 2), np.uint8)
+        o[..., 0], o[..., 1] = v >> 8, v & 255
+        pix = o.reshape(-1)
+    p = params(j2k, case)
+    want = O.encode_tile(p, pix)
+    assert all(np.array_equal(x, y) for x, y in zip(gpu_ctx.encode_tile(p, pix), want)), case
+
+
+def test_default_options_4k(j2k, gpu_ctx):
+    """DefaultOptions() (jpeg2000.go:305-320) on a 4K RGB frame: lossy, Quality 75, 6 resolutions, 256 x 256 blocks"""
+    case = (3840, 2160, 3, 8, 0, 6, 6, 6, 75, 0)
+    p = params(j2k, case)
+    pix = go_image(3840, 2160, 3, 8, seed=10)
+    a = gpu_ctx.encode_tile(p, pix)
+    b = O.encode_tile(p, pix, threads=16)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
 def test_padded_rows_and_constant_images(j2k, gpu_ctx):
     case = (90, 50, 3, 8, 1, 5, 4, 4, 0, 0)
     p = params(j2k, case)

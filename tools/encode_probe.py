@@ -19,6 +19,25 @@ def main():
     j2k = load_package()
     ctx = j2k.Context(0)
     L = j2k.lib()
+    import sys as _sys
+    _sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    # DefaultOptions() (jpeg2000.go:305-320): lossy, Quality 75, 6 resolutions, CodeBlockSize {6, 6} = 256 x 256 blocks
+    w, h = 3840, 2160
+    rgb = jobs.synth_image_fast(w, h, 3, 8, seed=13)
+    pix = np.full((h, w, 4), 255, np.uint8)
+    pix[:, :, :3] = np.moveaxis(rgb, 0, 2)
+    p = j2k.EncodeParams(width=w, height=h, ncomp=3, pix_bits=8, lossless=0, num_resolutions=6, cb_x=6, cb_y=6, quality=75)
+    t0 = time.perf_counter()
+    a = ctx.encode_tile(p, pix.reshape(-1))
+    t1 = time.perf_counter()
+    a = ctx.encode_tile(p, pix.reshape(-1))
+    t2 = time.perf_counter()
+    b = O.encode_tile(p, pix.reshape(-1), threads=os.cpu_count() or 1)
+    t3 = time.perf_counter()
+    print("DefaultOptions (lossy q=75, 256x256 blocks) 4K: GPU %.1f ms (first call %.1f), %d blocks, %d bytes; CPU checker %d threads %.1f ms; equal %s" %
+          ((t2 - t1) * 1e3, (t1 - t0) * 1e3, len(a[1]), len(a[0]), os.cpu_count() or 1, (t3 - t2) * 1e3,
+           all(np.array_equal(x, y) for x, y in zip(a, b))), flush=True)
     for (w, h, lossless, q) in ((3840, 2160, 1, 0), (1920, 1080, 0, 75)):
         rgb = jobs.synth_image_fast(w, h, 3, 8, seed=11)
         pix = np.full((h, w, 4), 255, np.uint8)
