@@ -19,7 +19,7 @@
 
 namespace {
 
-__constant__ uint32_t c_emq[94];          // qe | nmps << 16 | nlps << 24 (mqc.go:21-116)
+__constant__ uint32_t c_emq[94];          // qe (15 bits) | MPS << 15 | nmps << 16 | nlps << 24 (mqc.go:21-116)
 __constant__ uint8_t  c_ezc[4 * 256];     // band, 8 neighbour bits -> zero-coding context (t1_luts.go:35-110)
 __constant__ uint8_t  c_ezc9[4 * 512];    // band, 3 x 3 significance window (row above | row << 3 | row below << 6) -> the same
 __constant__ uint8_t  c_esc[256];         // W, E, N, S (significant, negative) pairs -> (context - 9) << 1 | prediction (t1.go:387-460)
@@ -220,7 +220,14 @@ struct MqEnc {                            // mqc.go:169-201; the byte at bp live
     uint32_t A, C, cur, cap;
     int CT, bp, ovf;
     uint8_t *out;                         // out[i] = the reference's buf[i + 1] (buf[0] is its dummy byte)
+#ifndef J2K_ENC_CXROW
+#define J2K_ENC_CXROW 1                   // a context holds its table row, not its state index: one load per decision on the chain
+#endif
+#if J2K_ENC_CXROW
+    uint32_t *cx;                         // 19 contexts, shared memory: the table row of the context's state
+#else
     uint8_t *cx;                          // 19 context states, shared memory
+#endif
 };
 __device__ __forceinline__ void mq_put(MqEnc &e, uint32_t b)
 {
@@ -249,17 +256,29 @@ __device__ __forceinline__ void mq_renorm(MqEnc &e)                // mqc.go:258
 }
 __device__ __forceinline__ void mq_encode(MqEnc &e, int cx, int d) // mqc.go:224-255
 {
-    const uint32_t s = e.cx[cx], row = c_emq[s], qe = row & 0xFFFFu;
+#if J2K_ENC_CXROW
+    const uint32_t row = e.cx[cx], qe = row & 0x7FFFu, mps = (row >> 15) & 1u;
+#else
+    const uint32_t s = e.cx[cx], row = c_emq[s], qe = row & 0x7FFFu, mps = s & 1u;
+#endif
     e.A -= qe;
-    if ((uint32_t)(d & 1) == (s & 1u)) {
+    if ((uint32_t)(d & 1) == mps) {
         if ((e.A & 0x8000u) == 0) {
             if (e.A < qe) e.A = qe; else e.C += qe;
+#if J2K_ENC_CXROW
+            e.cx[cx] = c_emq[(row >> 16) & 0xFFu];
+#else
             e.cx[cx] = (uint8_t)((row >> 16) & 0xFFu);
+#endif
             mq_renorm(e);
         } else e.C += qe;
     } else {
         if (e.A < qe) e.C += qe; else e.A = qe;
+#if J2K_ENC_CXROW
+        e.cx[cx] = c_emq[row >> 24];
+#else
         e.cx[cx] = (uint8_t)(row >> 24);
+#endif
         mq_renorm(e);
     }
 }
@@ -519,7 +538,7 @@ __host__ __device__ constexpr size_t t1enc_flag_bytes(int cbw, int cbh, bool mas
 }
 __host__ __device__ constexpr size_t t1enc_warp_bytes(int cbw, int cbh, bool masks)
 {
-    return t1enc_flag_bytes(cbw, cbh, masks) + (size_t)cbh * ((cbw + 63) / 64) * 8 + 32;
+    return t1enc_flag_bytes(cbw, cbh, masks) + (size_t)cbh * ((cbw + 63) / 64) * 8 + 96;
 }
 
 // longest chains first: a warp per block finds the block's bit-plane count (the length of its chain, to first order), one CTA
@@ -586,12 +605,20 @@ __global__ void k_t1_enc(const EncBlk *__restrict__ blks, const uint32_t *__rest
     uint64_t *bits = reinterpret_cast<uint64_t *>(base + t1enc_flag_bytes(cbw, cbh, MASKS));
     const int w = blk.w, h = blk.h, stride = w + 2, words = (w + 63) >> 6;
     const int ws = MODE == 1 ? 1 : (cbw + 63) >> 6, arr = (cbh + 2) * ws;   // words per row / per array of the mask state
+#if J2K_ENC_CXROW
+    uint32_t *cx = reinterpret_cast<uint32_t *>(bits + (size_t)cbh * ((cbw + 63) / 64));
+#else
     uint8_t *cx = reinterpret_cast<uint8_t *>(bits + (size_t)cbh * ((cbw + 63) / 64));
+#endif
     const int32_t *plane = planes + blk.plane_off;
     // extractCodeBlockData + SetData: sign flags, largest magnitude
     if (MASKS) { for (int i = lane; i < 4 * arr; i += 32) rows[i] = 0; }
     else { for (int i = lane; i < stride * (h + 2); i += 32) flags[i] = 0; }
+#if J2K_ENC_CXROW
+    if (lane < CX_N) cx[lane] = c_emq[lane == CX_UNI ? 92 : 0];    // mqc.go:194-199
+#else
     if (lane < CX_N) cx[lane] = lane == CX_UNI ? 92 : 0;           // mqc.go:194-199
+#endif
     __syncwarp();
     auto sample = [&](int x, int y) -> int32_t {
         const uint32_t gx = blk.sx + (uint32_t)x, gy = blk.sy + (uint32_t)y;
@@ -715,7 +742,7 @@ cudaError_t upload_enc_tables(cudaStream_t s)
     uint32_t mq[94];
     for (int i = 0; i < 47; i++)
         for (int m = 0; m < 2; m++)
-            mq[2 * i + m] = qe[i] | (uint32_t)(2 * nmps[i] + m) << 16 | (uint32_t)(2 * nlps[i] + (m ^ sw[i])) << 24;
+            mq[2 * i + m] = qe[i] | (uint32_t)m << 15 | (uint32_t)(2 * nmps[i] + m) << 16 | (uint32_t)(2 * nlps[i] + (m ^ sw[i])) << 24;
     uint8_t zc[4 * 256];
     for (int band = 0; band < 4; band++)
         for (int p = 0; p < 256; p++) {                            // t1_luts.go:35-110

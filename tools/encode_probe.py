@@ -17,6 +17,9 @@ from datagen import jobs  # noqa: E402
 def main():
     import torch
     j2k = load_package()
+    if os.environ.get("J2K_PROBE_LIB"):                              # A/B builds of the library
+        j2k.LIB_PATH = os.environ["J2K_PROBE_LIB"]
+        print("library:", j2k.LIB_PATH, flush=True)
     ctx = j2k.Context(0)
     L = j2k.lib()
     import sys as _sys
