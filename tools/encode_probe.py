@@ -78,14 +78,17 @@ def main():
     pix[:, :, :3] = np.moveaxis(rgb, 0, 2)
     d_pix = torch.from_numpy(pix.reshape(-1)).cuda()
     torch.cuda.synchronize()
-    for nthreads in (1, 2, 4, 8):
+    for nthreads, cb, lossless, q, label in ((1, 4, 1, 0, "4K lossless"), (2, 4, 1, 0, "4K lossless"), (4, 4, 1, 0, "4K lossless"),
+                                             (8, 4, 1, 0, "4K lossless"), (1, 6, 0, 75, "4K DefaultOptions"), (4, 6, 0, 75, "4K DefaultOptions"),
+                                             (8, 6, 0, 75, "4K DefaultOptions"), (16, 6, 0, 75, "4K DefaultOptions")):
         ctxs = [j2k.Context(0) for _ in range(nthreads)]
         outs = [torch.zeros(w * h * 6, dtype=torch.uint8, device="cuda") for _ in range(nthreads)]
         torch.cuda.synchronize()
-        reps = 4
+        reps = 0
 
         def work(i):
-            p = j2k.EncodeParams(width=w, height=h, ncomp=3, pix_bits=8, lossless=1, num_resolutions=6, cb_x=4, cb_y=4, flags=j2k.ENC_DEVICE_PTRS)
+            p = j2k.EncodeParams(width=w, height=h, ncomp=3, pix_bits=8, lossless=lossless, num_resolutions=6, cb_x=cb, cb_y=cb, quality=q,
+                                 flags=j2k.ENC_DEVICE_PTRS)
             got = C.c_uint64(0)
             for _ in range(reps + 1):
                 assert L.j2kgpu_encode_tile(ctxs[i]._h, C.byref(p), d_pix.data_ptr(), w * 4, outs[i].data_ptr(), outs[i].numel(), C.byref(got), None, None, 0) == 0
@@ -93,7 +96,7 @@ def main():
         reps = 0
         for i in range(nthreads):                                       # warm every context: its pool allocates on the first call
             work(i)
-        reps = 4
+        reps = 4 if cb == 4 else 2
         t0 = time.perf_counter()
         th = [threading.Thread(target=work, args=(i,)) for i in range(nthreads)]
         for t in th:
@@ -101,8 +104,8 @@ def main():
         for t in th:
             t.join()
         dt = time.perf_counter() - t0
-        print("%d contexts at once, 4K lossless: %.1f Mpixel/s in total (%.2f ms per frame and context)" %
-              (nthreads, nthreads * (reps + 1) * w * h / 1e6 / dt, dt / (reps + 1) * 1e3), flush=True)
+        print("%d contexts at once, %s: %.1f Mpixel/s in total (%.2f ms per frame and context)" %
+              (nthreads, label, nthreads * (reps + 1) * w * h / 1e6 / dt, dt / (reps + 1) * 1e3), flush=True)
         for c in ctxs:
             c.close()
     ctx.close()
