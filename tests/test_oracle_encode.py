@@ -80,3 +80,20 @@ def test_frozen_digest():
 
 
 FROZEN = "9c92a3286d026c0f301176f080922f2708af3821d6bcf61e41e3ddf48abd6b0e"
+
+
+def test_product_block_count_without_a_gpu(j2k):
+    """j2kgpu_encode_block_count is host logic (encodeTile's job list, encoder.go:615-673): same count as the checker and as the
+    Python restatement above, for the fixed cases and a sweep of sizes / block shapes; 0 for options the library refuses"""
+    import ctypes as C
+    L = j2k.lib()
+    rng = np.random.default_rng(9)
+    cases = list(CASES) + [(int(rng.integers(1, 5000)), int(rng.integers(1, 5000)), int(rng.choice([1, 3, 4])), 8, 1,
+                            int(rng.integers(0, 9)), int(rng.integers(0, 7)), int(rng.integers(0, 7)), 0, 0) for _ in range(40)]
+    for case in cases:
+        p = params(case)
+        q = j2k.EncodeParams(width=p.width, height=p.height, ncomp=p.ncomp, pix_bits=p.pix_bits, lossless=p.lossless,
+                             num_resolutions=p.num_resolutions, cb_x=p.cb_x, cb_y=p.cb_y)
+        assert L.j2kgpu_encode_block_count(C.byref(q)) == O.encode_block_count(p) == len(block_list(p)), case
+    for bad in (dict(width=0, height=4, ncomp=1), dict(width=4, height=4, ncomp=2), dict(width=4, height=4, ncomp=1, cb_x=7)):
+        assert L.j2kgpu_encode_block_count(C.byref(j2k.EncodeParams(pix_bits=8, **bad))) == 0
