@@ -222,3 +222,22 @@ def test_full_size_8192_grey16(j2k, gpu_ctx):
     a = gpu_ctx.encode_tile(p, pix)
     b = O.encode_tile(p, pix, threads=16)
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize("w,bits,q,cb", [(64, 16, 30000, 4), (64, 16, 2000000, 4), (40, 8, 2000000000, 3), (200, 16, 40000, 6)])
+def test_out_of_range_quality(j2k, gpu_ctx, w, bits, q, cb):
+    """Options.Quality is not validated by the reference: huge values drive the quantised coefficients to 31 bit planes and
+    past int32 (Go's int32(float64) gives 0x80000000 there); noise input, the densest blocks the coder can meet"""
+    rng = np.random.default_rng(q % 1000 + w)
+    m = (1 << bits) - 1
+    v = rng.integers(0, m + 1, (w, w, 1)).astype(np.uint32)
+    if bits == 8:
+        pix = v.astype(np.uint8).reshape(-1)
+    else:
+        o = np.zeros((w, w, 1, 2), np.uint8)
+        o[..., 0], o[..., 1] = v >> 8, v & 255
+        pix = o.reshape(-1)
+    p = params(j2k, (w, w, 1, bits, 0, 1, cb, cb, q, 0))
+    a, b = gpu_ctx.encode_tile(p, pix), O.encode_tile(p, pix)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    assert int(a[2].max()) == 31
