@@ -467,7 +467,7 @@ def parse_codestream(data, keep_packets=False):
         pos += 2 + L
     hdr.setdefault("ht", 0)
     nl, nc, W, H = hdr["nlevels"], hdr["ncomp"], hdr["width"], hdr["height"]
-    if hdr["cblk_style"] & ~0x40:
+    if hdr["cblk_style"] & ~0x7A or (hdr["cblk_style"] & 0x40 and hdr["cblk_style"] & 0x3F):     # not BYPASS / TERMALL
         raise ValueError("code-block style %02X" % hdr["cblk_style"])
     bands = band_list(nl)
     ntx, nty = cdiv(W, hdr["tile_w"]), cdiv(H, hdr["tile_h"])

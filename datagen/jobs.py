@@ -206,4 +206,4 @@ def build_iso_job_from_codestream(data, reduce=0):
     return dict(width=W, height=H, ncomp=ncomp, prec=h["prec"], sgnd=h["sgnd"], mct=1 if (h["mct"] and ncomp >= 3) else 0,
                 reversible=h["reversible"], nlevels=h["nlevels"] - reduce, ht=h["ht"], mode=1, tilecomps=np.array(tcs, TILECOMP_DT), cblks=cblks,
                 blob=np.frombuffer(bytes(blob) + bytes(8), np.uint8).copy(), codestream=bytes(data), layers=h["layers"],
-                coef_bits=max(e + h["guard"] - 1 for e, _ in h["qcd"]))
+                coef_bits=max(e + h["guard"] - 1 for e, _ in h["qcd"]), cblk_style=0 if h["ht"] else h["cblk_style"] & 0x3F)

@@ -42,7 +42,7 @@ class Image(C.Structure):          # j2k_image_t
                 ("prec", C.c_uint8 * 4), ("sgnd", C.c_uint8 * 4), ("mct", C.c_uint8),
                 ("reversible", C.c_uint8), ("nlevels", C.c_uint8), ("ht", C.c_uint8),
                 ("mode", C.c_uint8), ("out_fmt", C.c_uint8), ("coef_bits", C.c_uint8), ("colorspace", C.c_uint8),
-                ("rsv", C.c_uint8 * 2)]
+                ("cblk_style", C.c_uint8), ("rsv", C.c_uint8)]
 
 
 class TileComp(C.Structure):       # j2k_tilecomp_t
@@ -179,7 +179,7 @@ def fmt_bpp(ncomp, prec):
 
 
 def make_image(width, height, ncomp, prec, sgnd=0, mct=1, reversible=1, nlevels=5, ht=0, mode=MODE_REF, coef_bits=0,
-               colorspace=0):
+               colorspace=0, cblk_style=0):
     im = Image()
     im.width, im.height, im.ncomp = width, height, ncomp
     precs = list(prec) if isinstance(prec, (list, tuple)) else [prec] * ncomp
@@ -190,6 +190,7 @@ def make_image(width, height, ncomp, prec, sgnd=0, mct=1, reversible=1, nlevels=
     im.mct, im.reversible, im.nlevels, im.ht, im.mode, im.out_fmt = mct, reversible, nlevels, ht, mode, FMT_AUTO
     im.coef_bits = coef_bits
     im.colorspace = colorspace
+    im.cblk_style = cblk_style
     return im
 
 
@@ -274,15 +275,16 @@ class Context:
         self._check(lib().j2kgpu_host_unregister(self._h, C.c_void_p(a.ctypes.data)))
 
     # ---- entropy stage ------------------------------------------------------------------------
-    def _decode_blocks(self, fn, blocks, mode):
-        """blocks: list of (bytes, w, h, num_bps, band[, num_passes[, len_cleanup]]) -> list of int32 arrays (w*h each)"""
+    def _decode_blocks(self, fn, blocks, mode, style=0):
+        """blocks: list of (bytes, w, h, num_bps, band[, num_passes[, len_cleanup]]) -> list of int32 arrays (w*h each);
+        style: code-block style bits (ISO mode, classic blocks)"""
         n = len(blocks)
         jobs = (BlkJob * max(n, 1))()
         blob = bytearray()
         off = 0
         for i, blk in enumerate(blocks):
             data, w, h, nbps, band = blk[:5]
-            jobs[i] = BlkJob(len(blob), len(data), off, w, h, band, nbps, blk[5] if len(blk) > 5 else 0, 0,
+            jobs[i] = BlkJob(len(blob), len(data), off, w, h, band, nbps, blk[5] if len(blk) > 5 else 0, style,
                              blk[6] if len(blk) > 6 else 0, 0)
             blob += bytes(data)
             off += w * h
@@ -296,8 +298,8 @@ class Context:
             o += w * h
         return res
 
-    def t1_decode_blocks(self, blocks, mode=MODE_REF):
-        return self._decode_blocks(lib().j2kgpu_t1_decode_blocks, blocks, mode)
+    def t1_decode_blocks(self, blocks, mode=MODE_REF, style=0):
+        return self._decode_blocks(lib().j2kgpu_t1_decode_blocks, blocks, mode, style)
 
     def ht_decode_blocks(self, blocks, mode=MODE_REF):
         return self._decode_blocks(lib().j2kgpu_ht_decode_blocks, blocks, mode)

@@ -443,6 +443,11 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
         const j2k_image_t &im = it.image;
         if (!same_header(im, hdr)) J2K_FAIL(ctx, J2KGPU_E_ARG, "item %u: header differs from item 0", ii);
         if (im.width == 0 || im.height == 0) J2K_FAIL(ctx, J2KGPU_E_ARG, "item %u: empty image", ii);
+        // classic blocks: RESET / VCAUSAL / PREDTERM / SEGSYM are decoded (one codeword segment per block); selective bypass and
+        // termination on every pass need per-segment lengths the block table does not carry
+        const uint32_t cstyle = (iso && !im.ht) ? im.cblk_style : 0u;
+        if (cstyle & ~(J2KGPU_CBLK_RESET | J2KGPU_CBLK_VCAUSAL | J2KGPU_CBLK_PREDTERM | J2KGPU_CBLK_SEGSYM))
+            J2K_FAIL(ctx, J2KGPU_E_UNSUPPORTED, "item %u: code-block style %02X (selective bypass / termination on each pass)", ii, cstyle);
         if ((!it.tilecomps && it.n_tilecomps) || (!it.cblks && it.n_cblks) || (!it.blob && it.blob_len))
             J2K_FAIL(ctx, J2KGPU_E_ARG, "item %u: null table", ii);
         if (it.out_stride < (uint64_t)im.width * bpp || it.out_stride % bpp)
@@ -532,6 +537,7 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
             o.out_off = d.coef_off + (uint64_t)cb.y0 * d.w + cb.x0; o.out_stride = d.w;
             o.w = cb.w; o.h = cb.h; o.band = cb.band; o.num_bps = cb.num_bps; o.level = cb.level; o.num_passes = cb.num_passes;
             o.len_cup = (cb.len_cleanup && cb.len_cleanup <= cb.data_len) ? cb.len_cleanup : cb.data_len;
+            o.pad = cstyle;                                          // k_t1_iso reads the style per block
             cbs.push_back(o);
             steps.push_back(cb.step);
             blk_rects[cb.tilecomp].push_back(Rect{cb.x0, cb.y0, (uint32_t)cb.x0 + cb.w, (uint32_t)cb.y0 + cb.h});
@@ -1361,6 +1367,11 @@ static int stage_blocks(j2kgpu_ctx *ctx, int mode, int ht, const j2k_blkjob_t *j
         o.data_off = j.data_off; o.data_len = j.data_len; o.out_off = j.out_off; o.out_stride = j.w;
         o.w = j.w; o.h = j.h; o.band = j.band; o.num_bps = j.num_bps; o.num_passes = j.rsv0;    // ISO: coding passes (0 = all)
         o.len_cup = (j.len_cleanup && j.len_cleanup <= j.data_len) ? j.len_cleanup : j.data_len;
+        if (mode == J2KGPU_MODE_ISO && !ht) {
+            if (j.rsv1 & ~(J2KGPU_CBLK_RESET | J2KGPU_CBLK_VCAUSAL | J2KGPU_CBLK_PREDTERM | J2KGPU_CBLK_SEGSYM))
+                return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "block %u: code-block style %02X", i, (unsigned)j.rsv1);
+            o.pad = j.rsv1;
+        }
         if (j.num_bps > max_bps) max_bps = j.num_bps;
     }
     int rc;

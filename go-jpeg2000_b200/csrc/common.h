@@ -38,7 +38,7 @@ struct DevCblk {                 // one code block, 40 bytes
     uint16_t w, h;
     uint8_t  band, num_bps, level, num_passes;
     uint32_t len_cup;            // ISO HT: bytes of the cleanup segment (the refinement segment follows); 0 = data_len
-    uint32_t pad;
+    uint32_t pad;                // k_t1_iso: code-block style bits (J2KGPU_CBLK_*); 0 elsewhere
 };
 
 struct DevTileComp {             // one tile-component plane

@@ -336,7 +336,8 @@ k_t1_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
 // column, Tables D.1 - D.3 contexts, the initial states of Table D.7, and decoding stops after num_passes coding passes
 // (quality layers).  Output: sign * (2 * magnitude + mid-point of the last decoded bit-plane) / 2 as an integer for the
 // reversible path, or that twice-scale value * step / 2 as float32 bits for the irreversible one (the convention of the
-// CPU checker, which OpenJPEG pins).  Default code-block style only.
+// CPU checker, which OpenJPEG pins).  Code-block styles RESET, VCAUSAL and SEGSYM (DevCblk.pad) are decoded, PREDTERM needs
+// nothing from a decoder; BYPASS / TERMALL blocks never get here (job_build refuses them).
 template <typename OT, int G>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 k_t1_iso(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob, OT *__restrict__ coef,
@@ -351,6 +352,8 @@ k_t1_iso(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
     const uint32_t blk = have ? blk_raw : n - 1;
     const DevCblk cb = cblks[blk];
     const int w = cb.w, h = cb.h, nbps = cb.num_bps, band = cb.band & 3;
+    const uint32_t style = cb.pad;                       // code-block style bits (Table A.19): RESET, VCAUSAL, SEGSYM matter here
+    const bool vcausal = (style & 0x08u) != 0;
     int npasses = cb.num_passes ? cb.num_passes : 3 * nbps - 2;
     if (npasses > 3 * nbps - 2) npasses = 3 * nbps - 2;
 
@@ -392,6 +395,8 @@ k_t1_iso(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
     for (int pass = 0; pass < npasses && run; pass++) {
         p_end = bp;
       if (sl == 0) {
+        if (pass && (style & 0x02u))                                   // RESET: every pass starts from Table D.7
+            for (int i = 0; i < kNumCtx; i++) ctxs[i] = (i == kCtxUni) ? 92 : (i == kCtxRL ? 6 : (i == 0 ? 8 : 0));
         for (int y0 = 0; y0 < h; y0 += 4) {
             const bool full = (y0 + 4 <= h);
             const int rows = full ? 4 : (h - y0);
@@ -400,6 +405,7 @@ k_t1_iso(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
             for (int k = 0; k < 6; k++) { s[k] = sig[y0 - 1 + k]; ng[k] = neg[(y0 - 1 + k) & 63]; }
             if (y0 == 0) ng[0] = 0;                               // neg[] has rows 0..63 only
             if (y0 + 4 >= 64) ng[5] = 0;
+            if (vcausal) { s[5] = 0; ng[5] = 0; }                 // D.7: the stripe below does not exist for context formation
             if (type == 0) {
                 // ---- significance propagation (D.3.1): insignificant samples with a significant neighbour ----
                 uint64_t colmask = 0;
@@ -532,6 +538,8 @@ k_t1_iso(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
                     }
             }
         }
+        if (type == 2 && (style & 0x20u))                           // SEGSYM: four UNIFORM decisions (1010) close a cleanup pass (D.5)
+            for (int i = 0; i < 4; i++) (void)mq_decode(mq, ctxs, kCtxUni);
         if (type == 2 && pass + 1 < npasses)                        // the next bit-plane starts: nothing coded in it yet
             for (int y = 0; y < h; y++) lastc[y] = 0;
       }

@@ -507,7 +507,10 @@ int j2k_tier2_begin(const uint8_t *d, uint64_t len, uint32_t reduce, j2k_t2_fram
             if (h.prog > 4) T2_FAIL(J2KGPU_E_RANGE, "progression order %u", h.prog);
             if (h.nlevels > 10) T2_FAIL(J2KGPU_E_UNSUPPORTED, "%u decomposition levels", h.nlevels);
             if (h.cbw > 64 || h.cbh > 64 || h.cbw * h.cbh > 4096) T2_FAIL(J2KGPU_E_UNSUPPORTED, "code blocks %ux%u", h.cbw, h.cbh);
-            if (h.style & ~0x40u) T2_FAIL(J2KGPU_E_UNSUPPORTED, "code-block style %02X (bypass / reset / termination / causal / segmentation symbols)", h.style);
+            // RESET, VCAUSAL, PREDTERM, SEGSYM keep one codeword segment per block: the block decoder handles them;
+            // BYPASS and TERMALL change the length signalling of the packet headers (B.10.7.2) and are refused
+            if ((h.style & ~0x7Au) || ((h.style & 0x40u) && (h.style & 0x3Fu)))
+                T2_FAIL(J2KGPU_E_UNSUPPORTED, "code-block style %02X (selective bypass / termination on each pass; HT with a classic style bit)", h.style);
             if (!h.layers) T2_FAIL(J2KGPU_E_RANGE, "zero quality layers");
             for (uint32_t r = 0; r <= 32; r++) h.ppx[r] = h.ppy[r] = 15;
             if (scod & 1) {                               // user-defined precincts: one byte per resolution, PPx | PPy << 4 (A.6.1)
@@ -661,6 +664,7 @@ int j2k_tier2_finish(j2k_t2_frame *F, j2kgpu_parsed &out)
     uint32_t cbits = 0;
     for (size_t bi = 0; bi < bands.size(); bi++) cbits = std::max(cbits, h.q[bi].first + h.guard - 1);
     im.coef_bits = (uint8_t)std::min(cbits, 255u);
+    im.cblk_style = h.ht ? 0 : (uint8_t)(h.style & 0x3Fu);
     out.layers = h.layers; out.tiles = ntiles; out.tile_parts = F->ntp; out.progression = h.prog; out.tlm_tile_parts = F->ntlm;
     return J2KGPU_OK;
 }

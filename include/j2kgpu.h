@@ -93,8 +93,17 @@ typedef struct {
                                  * coder has no bound).                                                       */
     uint8_t  colorspace;        /* J2KGPU_CS_*: conversion to sRGB after the DC shift, the step of decoder.go:350-356
                                  * (getColorConversion, colorspace.go:54-88); 0 = none (sRGB, grey, unknown)    */
-    uint8_t  rsv[2];            /* set 0                                                      */
+    uint8_t  cblk_style;        /* ISO mode, classic (non-HT) blocks: code-block style bits of COD SPcod (Table A.19).
+                                 * Decoded: J2KGPU_CBLK_RESET | _VCAUSAL | _PREDTERM | _SEGSYM; _BYPASS and _TERMALL
+                                 * (several codeword segments per block) return J2KGPU_E_UNSUPPORTED.  REF: set 0 */
+    uint8_t  rsv;               /* set 0                                                      */
 } j2k_image_t;
+#define J2KGPU_CBLK_BYPASS   0x01u
+#define J2KGPU_CBLK_RESET    0x02u
+#define J2KGPU_CBLK_TERMALL  0x04u
+#define J2KGPU_CBLK_VCAUSAL  0x08u
+#define J2KGPU_CBLK_PREDTERM 0x10u
+#define J2KGPU_CBLK_SEGSYM   0x20u
 
 /* one tile-component (tcd.TileComponent, tcd.go:272-283): bounds in image
  * coordinates relative to the image origin; the coefficient plane is
@@ -151,7 +160,7 @@ typedef struct {
     uint16_t w, h;
     uint8_t  band, num_bps;
     uint8_t  rsv0;              /* ISO mode: number of coding passes to decode (0 = all; HT: 1..3); else 0 */
-    uint8_t  rsv1;
+    uint8_t  rsv1;              /* ISO mode, classic blocks: code-block style (j2k_image_t.cblk_style); else 0 */
     uint32_t len_cleanup;       /* ISO mode, HT, passes > 1: Lcup (see j2k_cblk_t.len_cleanup); 0 = data_len */
     uint32_t rsv2;              /* set 0 */
 } j2k_blkjob_t;
@@ -197,7 +206,8 @@ int j2kgpu_decode_batch(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t 
  * Raw codestreams, or JP2 files whose contiguous codestream box is located here (every other box -- colour specification,
  * palette, resolution -- stays with decoder.readJP2, decoder.go:206-253).  reduce =
  * Config.ReduceResolution (jpeg2000.go:205-207).  Unsupported features (sub-sampling, COC/QCC/POC/PPM/PPT,
- * non-default block styles) return J2KGPU_E_UNSUPPORTED. */
+ * the code-block styles selective bypass and termination on each pass) return J2KGPU_E_UNSUPPORTED; RESET, VCAUSAL,
+ * PREDTERM and SEGSYM blocks are decoded (j2k_image_t.cblk_style). */
 typedef struct j2kgpu_parsed j2kgpu_parsed;
 /* *out is always set (free it with j2kgpu_parsed_free); on failure j2kgpu_parsed_error(*out) says why.  No CUDA involved. */
 int         j2kgpu_parse_codestream(const uint8_t *cs, uint64_t len, uint32_t reduce, uint32_t threads, j2kgpu_parsed **out);

@@ -106,8 +106,8 @@ static void *iso_worker(void *arg)
                 shift = 2;
             } else {
                 const int all = 3 * cb->num_bps - 2;
-                iso_t1_decode(j->blob + cb->data_off, (int)cb->data_len, cb->w, cb->h, cb->num_bps,
-                              cb->num_passes && cb->num_passes < all ? cb->num_passes : all, cb->band, buf);
+                iso_t1_decode_style(j->blob + cb->data_off, (int)cb->data_len, cb->w, cb->h, cb->num_bps,
+                                    cb->num_passes && cb->num_passes < all ? cb->num_passes : all, cb->band, im->cblk_style, buf);
                 shift = 1;
             }
             const float sc = cb->step * (shift == 2 ? 0.25f : (shift == 1 ? 0.5f : 1.0f));

@@ -6,7 +6,11 @@
  * context tables, all contexts starting in state 0) and is restated in orc_t1.c; this file follows the published
  * algorithm instead and is pinned by OpenJPEG: tests/test_iso_codestream.py decodes codestreams written by OpenJPEG
  * (through Pillow) with this decoder + the ISO inverse transform and compares with OpenJPEG's own output.
- * Default code-block style only (no bypass, reset, termination, vertical-causal context, segmentation symbols).
+ * Code-block styles (COD SPcod, Table A.19): RESET (0x02: contexts back to Table D.7 at every pass boundary), VCAUSAL
+ * (0x08: the row below a stripe counts as insignificant, D.4.3... D.7) and SEGSYM (0x20: four UNIFORM symbols after each
+ * cleanup pass, D.5) are decoded; PREDTERM (0x10) needs nothing from a decoder; BYPASS (0x01) and TERMALL (0x04) split
+ * the block into several codeword segments and are not handled (the caller refuses them).  Pinned by streams OpenJPEG
+ * wrote with those styles (datagen/opj_direct.py) and decodes itself.
  *
  * Output convention (what the CUDA kernel reproduces): out[y*w+x] = sign * m2, where m2 is the magnitude at TWICE
  * scale with the mid-point of the last decoded bit-plane added: m2 = 2 * (decoded magnitude bits) + (1 << p_last),
@@ -46,11 +50,17 @@ static void mq_bytein(mq_t *m)
     } else { m->bp++; m->C += mq_byte(m, m->bp) << 8; m->CT = 8; }
 }
 
+static void mq_reset_contexts(mq_t *m)                       /* Table D.7: ZC context 0, run-length, uniform */
+{
+    memset(m->idx, 0, sizeof m->idx); memset(m->mps, 0, sizeof m->mps);
+    m->idx[0] = 4; m->idx[17] = 3; m->idx[18] = 46;
+}
+
 static void mq_init(mq_t *m, const uint8_t *d, int len)
 {
     memset(m, 0, sizeof *m);
     m->d = d; m->len = len; m->bp = 0;
-    m->idx[0] = 4; m->idx[17] = 3; m->idx[18] = 46;          /* Table D.7: ZC context 0, run-length, uniform */
+    mq_reset_contexts(m);
     m->C = mq_byte(m, 0) << 16;
     mq_bytein(m);
     m->C <<= 7; m->CT -= 7; m->A = 0x8000;
@@ -99,11 +109,14 @@ static int zc_ctx(int band, int h, int v, int d)
 typedef struct {
     int w, h, sw;                 /* sw = w + 2 */
     uint8_t *sig, *neg, *pi, *ref;
+    int vsc;                      /* vertically causal context formation */
     int32_t *mag;                 /* magnitude bits decoded so far */
     int8_t *plast;                /* lowest bit-plane at which the sample was coded */
 } blk_t;
 
 #define AT(a, x, y) ((a)[((y) + 1) * b->sw + (x) + 1])
+/* the row below sample (x, y): with the vertically causal style a stripe never looks into the next one */
+#define BELOW(a, xx, y) ((b->vsc && ((y) & 3) == 3) ? 0 : AT(a, xx, (y) + 1))
 
 static int sign_decode(mq_t *m, const blk_t *b, int x, int y)      /* Table D.2 / D.3 */
 {
@@ -111,7 +124,7 @@ static int sign_decode(mq_t *m, const blk_t *b, int x, int y)      /* Table D.2 
     if (AT(b->sig, x - 1, y)) hc += AT(b->neg, x - 1, y) ? -1 : 1;
     if (AT(b->sig, x + 1, y)) hc += AT(b->neg, x + 1, y) ? -1 : 1;
     if (AT(b->sig, x, y - 1)) vc += AT(b->neg, x, y - 1) ? -1 : 1;
-    if (AT(b->sig, x, y + 1)) vc += AT(b->neg, x, y + 1) ? -1 : 1;
+    if (BELOW(b->sig, x, y)) vc += AT(b->neg, x, y + 1) ? -1 : 1;
     hc = hc > 1 ? 1 : (hc < -1 ? -1 : hc);
     vc = vc > 1 ? 1 : (vc < -1 ? -1 : vc);
     int flip = 0;
@@ -125,15 +138,15 @@ static int sign_decode(mq_t *m, const blk_t *b, int x, int y)      /* Table D.2 
 static int zc_of(const blk_t *b, int band, int x, int y)
 {
     const int h = AT(b->sig, x - 1, y) + AT(b->sig, x + 1, y);
-    const int v = AT(b->sig, x, y - 1) + AT(b->sig, x, y + 1);
-    const int d = AT(b->sig, x - 1, y - 1) + AT(b->sig, x + 1, y - 1) + AT(b->sig, x - 1, y + 1) + AT(b->sig, x + 1, y + 1);
+    const int v = AT(b->sig, x, y - 1) + BELOW(b->sig, x, y);
+    const int d = AT(b->sig, x - 1, y - 1) + AT(b->sig, x + 1, y - 1) + BELOW(b->sig, x - 1, y) + BELOW(b->sig, x + 1, y);
     return zc_ctx(band, h, v, d);
 }
 
 static int any_neighbour(const blk_t *b, int x, int y)
 {
-    return AT(b->sig, x - 1, y) | AT(b->sig, x + 1, y) | AT(b->sig, x, y - 1) | AT(b->sig, x, y + 1) |
-           AT(b->sig, x - 1, y - 1) | AT(b->sig, x + 1, y - 1) | AT(b->sig, x - 1, y + 1) | AT(b->sig, x + 1, y + 1);
+    return AT(b->sig, x - 1, y) | AT(b->sig, x + 1, y) | AT(b->sig, x, y - 1) | BELOW(b->sig, x, y) |
+           AT(b->sig, x - 1, y - 1) | AT(b->sig, x + 1, y - 1) | BELOW(b->sig, x - 1, y) | BELOW(b->sig, x + 1, y);
 }
 
 static void become_sig(mq_t *m, blk_t *b, int x, int y, int bp)
@@ -146,13 +159,19 @@ static void become_sig(mq_t *m, blk_t *b, int x, int y, int bp)
 
 int iso_t1_decode(const uint8_t *data, int len, int w, int h, int num_bps, int num_passes, int band, int32_t *out)
 {
+    return iso_t1_decode_style(data, len, w, h, num_bps, num_passes, band, 0, out);
+}
+
+int iso_t1_decode_style(const uint8_t *data, int len, int w, int h, int num_bps, int num_passes, int band, int style, int32_t *out)
+{
+    if (style & (0x01 | 0x04)) return -2;                        /* BYPASS, TERMALL: several codeword segments */
     memset(out, 0, sizeof(int32_t) * (size_t)w * h);
     if (w < 1 || h < 1 || w > 1024 || h > 1024 || num_bps < 0 || num_bps > 30) return -1;
     if (num_bps == 0 || num_passes <= 0) return 0;
     const int max_passes = 3 * num_bps - 2;
     if (num_passes > max_passes) num_passes = max_passes;
     blk_t blk, *b = &blk;
-    b->w = w; b->h = h; b->sw = w + 2;
+    b->w = w; b->h = h; b->sw = w + 2; b->vsc = (style & 0x08) != 0;
     const size_t fl = (size_t)(w + 2) * (h + 2);
     b->sig = calloc(4 * fl, 1); b->neg = b->sig + fl; b->pi = b->neg + fl; b->ref = b->pi + fl;
     b->mag = calloc((size_t)w * h, sizeof(int32_t));
@@ -161,6 +180,7 @@ int iso_t1_decode(const uint8_t *data, int len, int w, int h, int num_bps, int n
     mq_init(&mq, data, len);
     int bp = num_bps - 1, type = 2;                              /* the first pass is a cleanup pass */
     for (int pass = 0; pass < num_passes; pass++) {
+        if (pass && (style & 0x02)) mq_reset_contexts(&mq);
         for (int y0 = 0; y0 < h; y0 += 4)
             for (int x = 0; x < w; x++) {
                 const int rows = y0 + 4 <= h ? 4 : h - y0;
@@ -201,6 +221,8 @@ int iso_t1_decode(const uint8_t *data, int len, int w, int h, int num_bps, int n
                     }
                 }
             }
+        if (type == 2 && (style & 0x20))                                               /* segmentation symbol 1010 (D.5) */
+            for (int i = 0; i < 4; i++) mq_decode(&mq, 18);
         if (type == 2) {                                                               /* end of the bit-plane */
             memset(b->pi, 0, fl);
             bp--;

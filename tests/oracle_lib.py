@@ -41,7 +41,7 @@ class Image(C.Structure):  # == j2k_image_t
                 ("prec", C.c_uint8 * 4), ("sgnd", C.c_uint8 * 4), ("mct", C.c_uint8),
                 ("reversible", C.c_uint8), ("nlevels", C.c_uint8), ("ht", C.c_uint8),
                 ("mode", C.c_uint8), ("out_fmt", C.c_uint8), ("coef_bits", C.c_uint8), ("colorspace", C.c_uint8),
-                ("rsv", C.c_uint8 * 2)]
+                ("cblk_style", C.c_uint8), ("rsv", C.c_uint8)]
 
 
 def build(force=False):
@@ -97,11 +97,11 @@ def ht_decode(data, w, h):
     return out
 
 
-def iso_t1_decode(data, w, h, num_bps, num_passes, band):
+def iso_t1_decode(data, w, h, num_bps, num_passes, band, style=0):
     """ISO EBCOT block decoder -> int32 [w*h] at twice scale with the mid-point (see oracle/iso_t1.c)"""
     buf = np.frombuffer(bytes(data), np.uint8) if len(data) else np.zeros(1, np.uint8)
     out = np.zeros(w * h, np.int32)
-    rc = lib().iso_t1_decode(_p(buf, u8p), len(data), w, h, num_bps, num_passes, band, _p(out, i32p))
+    rc = lib().iso_t1_decode_style(_p(buf, u8p), len(data), w, h, num_bps, num_passes, band, style, _p(out, i32p))
     assert rc == 0
     return out
 
@@ -206,6 +206,7 @@ def iso_decode_job(job, threads=4, out=None):
     for c in range(job["ncomp"]):
         img.prec[c], img.sgnd[c] = job["prec"], job["sgnd"]
     img.mct, img.reversible, img.nlevels, img.ht, img.mode = job["mct"], job["reversible"], job["nlevels"], job["ht"], 1
+    img.cblk_style = job.get("cblk_style", 0)
     bpp = (1 if job["prec"] <= 8 else 2) if job["ncomp"] == 1 else (4 if job["prec"] <= 8 else 8)
     stride = job["width"] * bpp
     if out is None:

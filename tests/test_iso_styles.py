@@ -1,0 +1,92 @@
+"""CPU: code-block styles of ISO/IEC 15444-1 Table A.19 in the ISO-mode checker (oracle/iso_t1.c) and in the product's
+tier-2 (host code, no GPU).  The streams are written by OpenJPEG itself through its C API (datagen/opj_direct.py: Pillow
+does not pass the style byte through) and OpenJPEG's own decode of them is the expected image."""
+import io
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from datagen import jobs
+
+PIL_Image = pytest.importorskip("PIL.Image")
+opj = pytest.importorskip("datagen.opj_direct")
+
+RESET, VCAUSAL, PREDTERM, SEGSYM = 0x02, 0x08, 0x10, 0x20
+STYLES = [RESET, VCAUSAL, SEGSYM, PREDTERM, RESET | VCAUSAL, VCAUSAL | SEGSYM, RESET | VCAUSAL | PREDTERM | SEGSYM]
+
+
+def opj_decode(data):
+    im = PIL_Image.open(io.BytesIO(data))
+    im.load()
+    a = np.array(im)
+    return a[None] if a.ndim == 2 else np.moveaxis(a, 2, 0)
+
+
+def test_direct_encoder_writes_what_was_asked():
+    s = jobs.synth_image(96, 80, 3, 8, seed=1)
+    for mode, mct in ((0, 0), (RESET | SEGSYM, 1)):
+        d = opj.encode(s, mode=mode, num_resolutions=3, mct=mct)
+        k = d.index(b"\xff\x52")
+        assert d[k + 8] == mct and d[k + 9] == 2 and d[k + 12] == mode
+        assert np.array_equal(opj_decode(d), s)
+
+
+@pytest.mark.parametrize("style", STYLES)
+@pytest.mark.parametrize("w,h,nc,kw", [
+    (200, 150, 3, dict(num_resolutions=4)),
+    (131, 77, 1, dict(num_resolutions=3, cblk=(32, 32))),
+    (256, 192, 3, dict(num_resolutions=5, tile=(128, 128), rates=[30, 8, 1])),
+])
+def test_styles_reversible_checker_equals_openjpeg(style, w, h, nc, kw):
+    s = jobs.synth_image(w, h, nc, 8, seed=style + w)
+    data = opj.encode(s, mode=style, **kw)
+    job = jobs.build_iso_job_from_codestream(data)
+    assert job["cblk_style"] == style
+    got = O.iso_decode_job(job).reshape(h, w, -1)[:, :, :nc]
+    assert np.array_equal(np.moveaxis(got, 2, 0), opj_decode(data))
+    if kw.get("rates", [1])[-1] == 1:
+        assert np.array_equal(np.moveaxis(got, 2, 0), s)
+
+
+@pytest.mark.parametrize("style", [RESET, VCAUSAL | SEGSYM, RESET | VCAUSAL | PREDTERM | SEGSYM])
+def test_styles_irreversible_checker_equals_openjpeg(style):
+    w, h = 240, 160
+    s = jobs.synth_image(w, h, 3, 8, seed=style)
+    data = opj.encode(s, mode=style, irreversible=True, num_resolutions=4, rates=[25, 6])
+    job = jobs.build_iso_job_from_codestream(data)
+    got = O.iso_decode_job(job).reshape(h, w, -1)[:, :, :3]
+    assert np.abs(np.moveaxis(got, 2, 0).astype(int) - opj_decode(data).astype(int)).max() == 0
+
+
+def test_style_matters():
+    """decoding a RESET / VCAUSAL / SEGSYM stream as the default style gives another image: the tests above are not vacuous"""
+    s = jobs.synth_image(128, 128, 1, 8, seed=5)
+    for style in (RESET, VCAUSAL, SEGSYM):
+        job = jobs.build_iso_job_from_codestream(opj.encode(s, mode=style, num_resolutions=3))
+        job["cblk_style"] = 0
+        assert not np.array_equal(O.iso_decode_job(job).reshape(128, 128), s[0])
+
+
+@pytest.mark.parametrize("style", STYLES)
+def test_product_tier2_carries_the_style(style):
+    import importlib
+    j2k = importlib.import_module("go-jpeg2000_b200")
+    s = jobs.synth_image(150, 100, 3, 8, seed=2)
+    data = opj.encode(s, mode=style, num_resolutions=3)
+    p = j2k.Parsed(data)
+    try:
+        assert p.image.cblk_style == style and p.image.ht == 0
+    finally:
+        p.close()
+
+
+@pytest.mark.parametrize("style", [0x01, 0x04, 0x05])
+def test_product_tier2_refuses_segmented_styles(style):
+    import importlib
+    j2k = importlib.import_module("go-jpeg2000_b200")
+    s = jobs.synth_image(64, 64, 1, 8, seed=2)
+    data = opj.encode(s, mode=style, num_resolutions=2)
+    with pytest.raises(j2k.J2KError) as e:
+        j2k.Parsed(data)
+    assert "style" in str(e.value)
