@@ -183,7 +183,7 @@ static int make_tail(j2kgpu_ctx *ctx, const j2k_image_t &im, TailParams &tp)
     tp.mct = (im.mct != 0 && im.ncomp >= 3);                                            // decoder.go:322
     tp.reversible = im.reversible != 0;
     tp.iso = im.mode == J2KGPU_MODE_ISO;
-    if (im.colorspace > J2KGPU_CS_YCCK)
+    if (im.colorspace > J2KGPU_CS_ROMM)
         return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "colour conversion %d is not built", (int)im.colorspace);
     tp.cconv = im.ncomp >= 3 ? im.colorspace : 0;                                       // colorspace.go:93-95: fewer than 3 components -> no-op
     tp.fmt = j2k_resolve_fmt(im.ncomp, im.prec[0], im.out_fmt);

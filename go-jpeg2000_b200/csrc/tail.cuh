@@ -18,9 +18,38 @@ __device__ __forceinline__ int32_t cs_clamp_round(double v, double maxv)
 // order and no FMA.  cs 1 / 2: the YCbCr family -- convertSYCCToRGB / convertYPbPr709ToRGB / convertEYCCToRGB
 // (colorspace.go:90-114, 429-482) and convertYCbCr601ToRGB (:116-140); cs 3: convertPhotoYCCToRGB (:142-168); cs 4:
 // convertCMYToRGB (:170-189); cs 5: convertCMYKToRGB (:191-217); cs 6: convertYCCKToRGB (:219-250).
+// cs 7 / 8: convertCIELabToRGB / convertCIEJabToRGB (:250-292, :319-359: the same arithmetic); cs 9: convertESRGBToRGB (:363-389);
+// cs 10: convertROMMRGBToRGB (:393-427) -- CUDA's pow() where Go has math.Pow, everything else in Go's order (1 LSB tolerance).
 // Out of line and by value, and called only from epilogues that are out of line or rarely used themselves (put_quad_generic of
 // the fused kernel, k_idwt_last_pixels<.., CC = true>, k_tail): measured, even an untaken call inlined into the epilogue of the
 // register-heavy streaming kernels cost them 7 to 30 %.
+// labInverseF colorspace.go:294-301 (6/29, 4/29 and 3 * (6/29)^2 are Go's exact constants rounded to float64)
+__device__ __forceinline__ double cs_lab_inverse_f(double t)
+{
+    if (t > 6.0 / 29.0) return __dmul_rn(__dmul_rn(t, t), t);
+    return __dmul_rn(3 * (6.0 / 29.0) * (6.0 / 29.0), __dsub_rn(t, 4.0 / 29.0));
+}
+
+// srgbGamma colorspace.go:303-309
+__device__ __forceinline__ double cs_srgb_gamma(double lin)
+{
+    if (lin <= 0.0031308) return __dmul_rn(12.92, lin);
+    return __dsub_rn(__dmul_rn(1.055, pow(lin, 1.0 / 2.4)), 0.055);
+}
+
+__device__ __forceinline__ double cs_clampf(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }   // colorspace.go:494-502
+
+// XYZ -> linear sRGB (colorspace.go:277-279) -> gamma -> integer; clamp01: convertROMMRGBToRGB clamps before the gamma
+static __device__ J2K_NOINLINE int3 cs_xyz_to_srgb(double x, double y, double z, bool clamp01, double maxv)
+{
+    double rl = __dsub_rn(__dsub_rn(__dmul_rn(3.2404542, x), __dmul_rn(1.5371385, y)), __dmul_rn(0.4985314, z));
+    double gl = __dadd_rn(__dadd_rn(__dmul_rn(-0.9692660, x), __dmul_rn(1.8760108, y)), __dmul_rn(0.0415560, z));
+    double bl = __dadd_rn(__dsub_rn(__dmul_rn(0.0556434, x), __dmul_rn(0.2040259, y)), __dmul_rn(1.0572252, z));
+    if (clamp01) { rl = cs_clampf(rl, 0.0, 1.0); gl = cs_clampf(gl, 0.0, 1.0); bl = cs_clampf(bl, 0.0, 1.0); }
+    return make_int3(cs_clamp_round(__dmul_rn(cs_srgb_gamma(rl), maxv), maxv), cs_clamp_round(__dmul_rn(cs_srgb_gamma(gl), maxv), maxv),
+                     cs_clamp_round(__dmul_rn(cs_srgb_gamma(bl), maxv), maxv));
+}
+
 static __device__ J2K_NOINLINE int3 tail_colour_rgb(int32_t v0, int32_t v1, int32_t v2, int32_t v3, int cconv, int ncomp, int prec)
 {
     const int32_t maxi = (int32_t)((1u << prec) - 1u);
@@ -33,6 +62,31 @@ static __device__ J2K_NOINLINE int3 tail_colour_rgb(int32_t v0, int32_t v1, int3
         const double g = __dsub_rn(__dsub_rn(y, __dmul_rn(bt709 ? 0.1873 : 0.344136, cb)), __dmul_rn(bt709 ? 0.4681 : 0.714136, cr));
         const double b = __dadd_rn(y, __dmul_rn(bt709 ? 1.8556 : 1.772, cb));
         return make_int3(cs_clamp_round(r, maxv), cs_clamp_round(g, maxv), cs_clamp_round(b, maxv));
+    }
+    if (cconv == J2KGPU_CS_CIELAB || cconv == J2KGPU_CS_CIEJAB) {
+        const double L = __dmul_rn(__ddiv_rn((double)v0, maxv), 100.0);
+        const double a = __dsub_rn(__dmul_rn(__ddiv_rn((double)v1, maxv), 255.0), 128.0);
+        const double b = __dsub_rn(__dmul_rn(__ddiv_rn((double)v2, maxv), 255.0), 128.0);
+        const double fy = __ddiv_rn(__dadd_rn(L, 16.0), 116.0);
+        const double fx = __dadd_rn(__ddiv_rn(a, 500.0), fy), fz = __dsub_rn(fy, __ddiv_rn(b, 200.0));
+        return cs_xyz_to_srgb(__dmul_rn(0.96422, cs_lab_inverse_f(fx)), cs_lab_inverse_f(fy), __dmul_rn(0.82521, cs_lab_inverse_f(fz)), false, maxv);
+    }
+    if (cconv == J2KGPU_CS_ESRGB) {
+        int32_t o[3];
+        const int32_t in[3] = {v0, v1, v2};
+#pragma unroll 1
+        for (int c = 0; c < 3; c++) {
+            const double v = __dsub_rn(__dmul_rn(__ddiv_rn((double)in[c], maxv), 1.25), 0.25);
+            o[c] = cs_clamp_round(__dmul_rn(cs_srgb_gamma(cs_clampf(v, 0.0, 1.0)), maxv), maxv);
+        }
+        return make_int3(o[0], o[1], o[2]);
+    }
+    if (cconv == J2KGPU_CS_ROMM) {
+        const double rr = pow(__ddiv_rn((double)v0, maxv), 1.8), gr = pow(__ddiv_rn((double)v1, maxv), 1.8), br = pow(__ddiv_rn((double)v2, maxv), 1.8);
+        const double x = __dadd_rn(__dadd_rn(__dmul_rn(0.7977, rr), __dmul_rn(0.1352, gr)), __dmul_rn(0.0313, br));
+        const double y = __dadd_rn(__dadd_rn(__dmul_rn(0.2880, rr), __dmul_rn(0.7119, gr)), __dmul_rn(0.0001, br));
+        const double z = __dadd_rn(__dadd_rn(__dmul_rn(0.0, rr), __dmul_rn(0.0, gr)), __dmul_rn(0.8249, br));
+        return cs_xyz_to_srgb(x, y, z, true, maxv);
     }
     if (cconv == J2KGPU_CS_CMY)
         return make_int3((int32_t)((uint32_t)maxi - (uint32_t)v0), (int32_t)((uint32_t)maxi - (uint32_t)v1), (int32_t)((uint32_t)maxi - (uint32_t)v2));

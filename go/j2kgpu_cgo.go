@@ -73,7 +73,7 @@ type gpuJob struct {
 }
 
 // gpuColorSpace maps the colour spaces whose conversion to sRGB the library applies in its pixel epilogue
-// (decoder.go:350-356, colorspace.go:54-88): every conversion that needs no math.Pow.
+// (decoder.go:350-356, colorspace.go:54-88): all of getColorConversion's cases.
 func gpuColorSpace(cs ColorSpace) (C.uint8_t, bool) {
 	switch cs {
 	case ColorSpaceSYCC, ColorSpaceEYCC, ColorSpaceYPbPr60, ColorSpaceYPbPr50:
@@ -88,8 +88,16 @@ func gpuColorSpace(cs ColorSpace) (C.uint8_t, bool) {
 		return C.J2KGPU_CS_CMYK, true
 	case ColorSpaceYCCK:
 		return C.J2KGPU_CS_YCCK, true
+	case ColorSpaceCIELab: // the four math.Pow conversions: CUDA's pow(), 1 LSB tolerance (include/j2kgpu.h)
+		return C.J2KGPU_CS_CIELAB, true
+	case ColorSpaceCIEJab:
+		return C.J2KGPU_CS_CIEJAB, true
+	case ColorSpaceESRGB:
+		return C.J2KGPU_CS_ESRGB, true
+	case ColorSpaceROMMRGB:
+		return C.J2KGPU_CS_ROMM, true
 	}
-	return C.J2KGPU_CS_NONE, getColorConversion(cs) == nil // false: CIELab, CIEJab, e-sRGB, ROMM-RGB stay on the CPU path
+	return C.J2KGPU_CS_NONE, getColorConversion(cs) == nil // false: a conversion this library does not know
 }
 
 // decodeTilesGPU is decoder.decodeTiles on the GPU: it returns the same image types createImage would

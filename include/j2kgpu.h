@@ -37,7 +37,13 @@ extern "C" {
 #define J2KGPU_CS_CMY    4   /* ColorSpaceCMY: maxVal - v (colorspace.go:170-189)                                    */
 #define J2KGPU_CS_CMYK   5   /* ColorSpaceCMYK, 4 components; the 4th stays and becomes alpha (colorspace.go:191-217) */
 #define J2KGPU_CS_YCCK   6   /* ColorSpaceYCCK, 4 components (colorspace.go:219-250)                                 */
-/* not built (they need pow / cube roots whose last bit differs between libms): CIELab, CIEJab, e-sRGB, ROMM-RGB */
+/* The four conversions that go through math.Pow.  Everything but the power function itself is evaluated in the reference's
+ * order in float64; CUDA's pow() (<= 2 ulp) stands where Go has math.Pow, so a result can differ from the reference's by
+ * 1 LSB when the real value lies within ~1e-13 of a rounding boundary (tolerance in the tests: 1 LSB; measured: 0). */
+#define J2KGPU_CS_CIELAB 7   /* ColorSpaceCIELab (colorspace.go:250-292)                                             */
+#define J2KGPU_CS_CIEJAB 8   /* ColorSpaceCIEJab: the reference treats J as L* (colorspace.go:319-359), same arithmetic */
+#define J2KGPU_CS_ESRGB  9   /* ColorSpaceESRGB (colorspace.go:363-389)                                              */
+#define J2KGPU_CS_ROMM   10  /* ColorSpaceROMMRGB (colorspace.go:393-427)                                            */
 
 #define J2KGPU_ABI_VERSION 4
 

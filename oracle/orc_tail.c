@@ -6,6 +6,7 @@
  * used as the CPU baseline.  Oracle / test infrastructure only.
  */
 #include "oracle.h"
+#include <math.h>
 #include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
@@ -71,10 +72,43 @@ static inline int32_t cs_clamp_round(double v, double maxv)
     return orc_f64_to_i32(v + 0.5);
 }
 
+/* labInverseF colorspace.go:294-301; the constants are Go's exact untyped constants rounded to float64 (6/29, 4/29,
+ * 3 * (6/29)^2 = 108/841: the C constant expressions below round to the same doubles, tests/test_oracle_tail.py) */
+static inline double lab_inverse_f(double t)
+{
+    if (t > 6.0 / 29.0) return t * t * t;
+    return (3 * (6.0 / 29.0) * (6.0 / 29.0)) * (t - 4.0 / 29.0);
+}
+
+/* srgbGamma colorspace.go:303-309.  pow() is the libm's where Go has math.Pow: the only place this restatement can
+ * differ from the reference, in the last bit of the power before the rounding to an integer ("parity unpinned at 1 LSB"
+ * for conversions 7-10; there is no Go here to run). */
+static inline double srgb_gamma(double lin)
+{
+    if (lin <= 0.0031308) return 12.92 * lin;
+    return 1.055 * pow(lin, 1.0 / 2.4) - 0.055;
+}
+
+static inline double clampf(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }   /* colorspace.go:494-502 */
+
+/* XYZ -> linear sRGB -> gamma -> integer: the common tail of convertCIELabToRGB / convertCIEJabToRGB (no clamp before the
+ * gamma, colorspace.go:277-289) and convertROMMRGBToRGB (clamped to [0, 1], :416-424) */
+static inline void xyz_to_srgb(double x, double y, double z, int clamp01, double maxv, int32_t out[3])
+{
+    double rl = 3.2404542 * x - 1.5371385 * y - 0.4985314 * z;
+    double gl = -0.9692660 * x + 1.8760108 * y + 0.0415560 * z;
+    double bl = 0.0556434 * x - 0.2040259 * y + 1.0572252 * z;
+    if (clamp01) { rl = clampf(rl, 0, 1); gl = clampf(gl, 0, 1); bl = clampf(bl, 0, 1); }
+    out[0] = cs_clamp_round(srgb_gamma(rl) * maxv, maxv);
+    out[1] = cs_clamp_round(srgb_gamma(gl) * maxv, maxv);
+    out[2] = cs_clamp_round(srgb_gamma(bl) * maxv, maxv);
+}
+
 /* decoder.go:350-356 -> getColorConversion (colorspace.go:54-88).  cs 1: convertSYCCToRGB (:90-114), convertYPbPr709ToRGB
  * (:429-452), convertEYCCToRGB (:454-482) -- the BT.709 matrix; cs 2: convertYCbCr601ToRGB (:116-140); cs 3:
  * convertPhotoYCCToRGB (:142-168); cs 4: convertCMYToRGB (:170-189); cs 5: convertCMYKToRGB (:191-217); cs 6:
- * convertYCCKToRGB (:219-250).  The pow-based ones (CIELab, CIEJab, e-sRGB, ROMM) are not restated. */
+ * convertYCCKToRGB (:219-250); cs 7 / 8: convertCIELabToRGB (:250-292) / convertCIEJabToRGB (:319-359, the same arithmetic);
+ * cs 9: convertESRGBToRGB (:363-389); cs 10: convertROMMRGBToRGB (:393-427). */
 void orc_colour_convert(int32_t *const *comps, int ncomp, size_t n, int prec, int cs)
 {
     if (cs == 0 || ncomp < 3) return;
@@ -92,6 +126,38 @@ void orc_colour_convert(int32_t *const *comps, int ncomp, size_t n, int prec, in
                          k = (double)comps[3][i] / maxv;
             const double r = (1 - c) * (1 - k) * maxv, g = (1 - m) * (1 - k) * maxv, b = (1 - y) * (1 - k) * maxv;
             comps[0][i] = cs_clamp_round(r, maxv); comps[1][i] = cs_clamp_round(g, maxv); comps[2][i] = cs_clamp_round(b, maxv);
+        }
+        return;
+    }
+    if (cs == 7 || cs == 8) {
+        for (size_t i = 0; i < n; i++) {
+            const double L = (double)comps[0][i] / maxv * 100.0;
+            const double a = (double)comps[1][i] / maxv * 255.0 - 128.0, b = (double)comps[2][i] / maxv * 255.0 - 128.0;
+            const double fy = (L + 16.0) / 116.0, fx = a / 500.0 + fy, fz = fy - b / 200.0;
+            int32_t o[3];
+            xyz_to_srgb(0.96422 * lab_inverse_f(fx), 1.0 * lab_inverse_f(fy), 0.82521 * lab_inverse_f(fz), 0, maxv, o);
+            comps[0][i] = o[0]; comps[1][i] = o[1]; comps[2][i] = o[2];
+        }
+        return;
+    }
+    if (cs == 9) {
+        for (size_t i = 0; i < n; i++)
+            for (int c = 0; c < 3; c++) {
+                const double v = (double)comps[c][i] / maxv * 1.25 - 0.25;
+                comps[c][i] = cs_clamp_round(srgb_gamma(clampf(v, 0, 1)) * maxv, maxv);
+            }
+        return;
+    }
+    if (cs == 10) {
+        for (size_t i = 0; i < n; i++) {
+            const double rr = pow((double)comps[0][i] / maxv, 1.8), gr = pow((double)comps[1][i] / maxv, 1.8),
+                         br = pow((double)comps[2][i] / maxv, 1.8);
+            const double x = 0.7977 * rr + 0.1352 * gr + 0.0313 * br;
+            const double y = 0.2880 * rr + 0.7119 * gr + 0.0001 * br;
+            const double z = 0.0000 * rr + 0.0000 * gr + 0.8249 * br;
+            int32_t o[3];
+            xyz_to_srgb(x, y, z, 1, maxv, o);
+            comps[0][i] = o[0]; comps[1][i] = o[1]; comps[2][i] = o[2];
         }
         return;
     }

@@ -126,8 +126,33 @@ def test_colour_conversion_then_pack(gpu_ctx, j2k, ncomp, prec, cs, mct, rev):
     assert np.array_equal(got, want)
 
 
+def _unpack(pix, prec):
+    a = np.asarray(pix, np.uint8).astype(np.int32)
+    return a if prec <= 8 else (a[0::2] << 8) | a[1::2]
+
+
+@pytest.mark.parametrize("ncomp,prec,cs,mct,rev", [(3, 8, 7, 0, 1), (3, 12, 7, 0, 0), (3, 16, 8, 0, 1), (4, 8, 8, 0, 1), (3, 8, 9, 0, 1),
+                                                   (3, 12, 9, 1, 0), (3, 8, 10, 0, 1), (3, 16, 10, 0, 1), (4, 8, 10, 1, 1), (1, 8, 7, 0, 1)])
+def test_pow_colour_conversion_then_pack(gpu_ctx, j2k, ncomp, prec, cs, mct, rev):
+    """CIELab / CIEJab / e-sRGB / ROMM-RGB (colorspace.go:250-427) in the pixel epilogue: CUDA's pow() where Go has math.Pow,
+    so the tolerance is 1 LSB (north_star's floating-point tolerance); every other operation is in the reference's order"""
+    rng = np.random.default_rng(10 * ncomp + prec + cs)
+    w, h = 97, 61
+    comps = [rng.integers(-(1 << (prec - 1)) - 30, (1 << (prec - 1)) + 30, w * h).astype(np.int32) for _ in range(ncomp)]
+    img = j2k.make_image(w, h, ncomp, prec, sgnd=0, mct=mct, reversible=rev, colorspace=cs)
+    got = gpu_ctx.mct_dc_pack(img, comps, apply_tail=True)
+    after = O.decoder_tail(comps, mct, rev, [prec] * ncomp, [0] * ncomp)
+    after = O.colour_convert(after, prec, cs)
+    want, _ = O.create_image(after, w, h, prec)
+    g, w_ = _unpack(got, prec), _unpack(want, prec)
+    d = np.abs(g - w_)
+    # a NaN of the ROMM conversion (negative input) packs to the same bytes on both sides; everything else within 1 LSB
+    assert d.max() <= 1, (int(d.max()), int((d > 0).sum()))
+    assert (d > 0).sum() <= max(1, d.size // 10000)
+
+
 def test_colour_conversion_not_built(gpu_ctx, j2k):
-    img = j2k.make_image(8, 8, 3, 8, colorspace=9)
+    img = j2k.make_image(8, 8, 3, 8, colorspace=11)
     with pytest.raises(j2k.J2KError) as e:
         gpu_ctx.mct_dc_pack(img, [np.zeros(64, np.int32)] * 3)
     assert e.value.code == j2k.E_UNSUPPORTED
