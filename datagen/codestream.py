@@ -623,3 +623,20 @@ def reassemble(h, sop=False, eph=False, tlm=False, split=False, plt=False):
         out += b
     out += struct.pack(">H", EOC)
     return bytes(out)
+
+
+def wrap_jp2(codestream, enumcs=16, width=0, height=0, ncomp=3, bpc=7, colr_method=1, extra_colr=None, header_after=False):
+    """TEST HARNESS: a minimal JP2 file (ISO/IEC 15444-1 Annex I) around a codestream: signature, file type, JP2 header
+    (image header + colour specification box[es]) and contiguous codestream box.  extra_colr: EnumCS values of further colr
+    boxes (the reference keeps the last, box.go:427-431); header_after: the header box behind the codestream box."""
+    def box(t, payload):
+        return struct.pack(">I4s", 8 + len(payload), t) + payload
+    def colr(cs):
+        if colr_method == 1:
+            return box(b"colr", struct.pack(">BBBI", 1, 0, 0, cs))
+        return box(b"colr", struct.pack(">BBB", colr_method, 0, 0) + bytes(16))          # an (empty) ICC profile
+    ihdr = box(b"ihdr", struct.pack(">IIHBBBB", height, width, ncomp, bpc, 7, 0, 0))
+    jp2h = box(b"jp2h", ihdr + b"".join(colr(c) for c in [enumcs] + list(extra_colr or [])))
+    head = box(b"jP  ", b"\r\n\x87\n") + box(b"ftyp", b"jp2 " + struct.pack(">I", 0) + b"jp2 ")
+    body = box(b"jp2c", bytes(codestream))
+    return head + (body + jp2h if header_after else jp2h + body)

@@ -44,6 +44,7 @@ struct Header {
     uint32_t W = 0, H = 0, tile_w = 0, tile_h = 0, ncomp = 0, prec = 0, sgnd = 0;
     uint32_t prog = 0, layers = 0, mct = 0, nlevels = 0, cbw = 0, cbh = 0, style = 0, reversible = 0, sop = 0, eph = 0, ht = 0;
     uint32_t guard = 0;
+    uint32_t colorspace = 0;                             // J2KGPU_CS_* from the JP2 colour specification box (0: none / raw codestream)
     uint8_t ppx[33], ppy[33];                            // precinct size exponents per resolution (15 = maximal)
     bool have_siz = false, have_cod = false, have_qcd = false;
     std::vector<std::pair<uint32_t, uint32_t>> q;      // per band in codestream order: exponent, mantissa
@@ -454,8 +455,11 @@ int j2k_tier2_begin(const uint8_t *d, uint64_t len, uint32_t reduce, j2k_t2_fram
     Err err;
     Header &h = F->h;
 #define T2_FAIL(...) do { err.fail(__VA_ARGS__); errmsg = err.msg; return err.code; } while (0)
-    // a JP2 file (ISO/IEC 15444-1 Annex I: signature box first): walk the top-level boxes to the contiguous codestream box.
-    // Everything else in the container (colour specification, palette, resolution ...) stays with the caller (box.go).
+    // a JP2 file (ISO/IEC 15444-1 Annex I: signature box first): walk the top-level boxes to the contiguous codestream box
+    // (decoder.readJP2, decoder.go:206-253).  Of the JP2 header box only the colour specification is read here: its enumerated
+    // colour space selects the conversion to sRGB the pixel epilogue applies (decoder.getColorSpace decoder.go:135-178 ->
+    // getColorConversion colorspace.go:54-88); the last colr box wins and a header box behind the codestream box is never
+    // seen, as in box.ParseJP2Header / readJP2.  Palette, channel definition, resolution stay with the caller (box.go).
     if (d && len >= 12 && be32(d) == 12 && be32(d + 4) == 0x6A502020u) {
         uint64_t bp = 0;
         bool found = false;
@@ -466,6 +470,41 @@ int j2k_tier2_begin(const uint8_t *d, uint64_t len, uint32_t reduce, j2k_t2_fram
             else if (bl == 0) bl = len - bp;              // the box runs to the end of the file
             if (bl < hl || bl > len - bp) break;
             if (bt == 0x6A703263u) { d += bp + hl; len = bl - hl; found = true; break; }   // 'jp2c'
+            if (bt == 0x6A703268u) {                                                       // 'jp2h': a superbox
+                uint64_t sp = bp + hl;
+                const uint64_t se = bp + bl;
+                while (sp + 8 <= se) {
+                    uint64_t sl = be32(d + sp), shl = 8;
+                    const uint32_t st = be32(d + sp + 4);
+                    if (sl == 1) { if (sp + 16 > se) break; sl = ((uint64_t)be32(d + sp + 8) << 32) | be32(d + sp + 12); shl = 16; }
+                    else if (sl == 0) sl = se - sp;
+                    if (sl < shl || sl > se - sp) break;
+                    if (st == 0x636F6C72u) {                                               // 'colr' (box.go:287-307)
+                        const uint8_t *c = d + sp + shl;
+                        const uint64_t cl = sl - shl;
+                        if (cl < 3) T2_FAIL(J2KGPU_E_RANGE, "color specification box too short");
+                        uint32_t enumcs = 0;                                               // ICC methods leave it 0 (bi-level: no conversion)
+                        if (c[0] == 1) {
+                            if (cl < 7) T2_FAIL(J2KGPU_E_RANGE, "color specification box too short for enumerated CS");
+                            enumcs = be32(c + 3);
+                        }
+                        switch (enumcs) {                                                  // box.go:265-283 -> decoder.go:140-177 -> colorspace.go:54-88
+                        case 1: case 18: case 22: case 23: case 24: h.colorspace = J2KGPU_CS_YCC709; break;   // YCbCr(1), sYCC, YPbPr 1125 / 1250, e-sYCC
+                        case 3: case 4: h.colorspace = J2KGPU_CS_YCC601; break;            // YCbCr(2), YCbCr(3)
+                        case 9: h.colorspace = J2KGPU_CS_PHOTOYCC; break;
+                        case 11: h.colorspace = J2KGPU_CS_CMY; break;
+                        case 12: h.colorspace = J2KGPU_CS_CMYK; break;
+                        case 13: h.colorspace = J2KGPU_CS_YCCK; break;
+                        case 14: h.colorspace = J2KGPU_CS_CIELAB; break;
+                        case 19: h.colorspace = J2KGPU_CS_CIEJAB; break;
+                        case 20: h.colorspace = J2KGPU_CS_ESRGB; break;
+                        case 21: h.colorspace = J2KGPU_CS_ROMM; break;
+                        default: h.colorspace = J2KGPU_CS_NONE; break;                    // bi-level, sRGB, grey, unknown
+                        }
+                    }
+                    sp += sl;
+                }
+            }
             bp += bl;
         }
         if (!found) T2_FAIL(J2KGPU_E_RANGE, "JP2 file without a codestream box");
@@ -665,6 +704,7 @@ int j2k_tier2_finish(j2k_t2_frame *F, j2kgpu_parsed &out)
     for (size_t bi = 0; bi < bands.size(); bi++) cbits = std::max(cbits, h.q[bi].first + h.guard - 1);
     im.coef_bits = (uint8_t)std::min(cbits, 255u);
     im.cblk_style = h.ht ? 0 : (uint8_t)(h.style & 0x3Fu);
+    im.colorspace = (uint8_t)h.colorspace;
     out.layers = h.layers; out.tiles = ntiles; out.tile_parts = F->ntp; out.progression = h.prog; out.tlm_tile_parts = F->ntlm;
     return J2KGPU_OK;
 }

@@ -209,8 +209,10 @@ int j2kgpu_decode_batch(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t 
  * of INTEGRATION.md has to do -- main header (parser.go:44-124), tile-part index (parser.go:894-982, Psot / TLM), packet
  * headers (tag trees, passes, Lblock, lengths; SOP / EPH; PLT cross-check; all five progression orders, maximal or
  * user-defined precincts, quality layers, classic and HT blocks) -- and fill the tables above in J2KGPU_MODE_ISO, tiles parsed concurrently on host threads.
- * Raw codestreams, or JP2 files whose contiguous codestream box is located here (every other box -- colour specification,
- * palette, resolution -- stays with decoder.readJP2, decoder.go:206-253).  reduce =
+ * Raw codestreams, or JP2 files: the contiguous codestream box is located here and the enumerated colour space of the JP2
+ * header's colour specification box selects j2k_image_t.colorspace (decoder.getColorSpace decoder.go:135-178, applied as in
+ * decoder.go:350-356); every other box -- palette, channel definition, resolution -- stays with decoder.readJP2
+ * (decoder.go:206-253).  reduce =
  * Config.ReduceResolution (jpeg2000.go:205-207).  Unsupported features (sub-sampling, COC/QCC/POC/PPM/PPT,
  * the code-block styles selective bypass and termination on each pass) return J2KGPU_E_UNSUPPORTED; RESET, VCAUSAL,
  * PREDTERM and SEGSYM blocks are decoded (j2k_image_t.cblk_style). */

@@ -173,6 +173,10 @@ static void *iso_worker(void *arg)
                         }
                     }
                     for (int c = 0; c < nc; c++) if (!im->sgnd[c]) v[c] = (int32_t)((uint32_t)v[c] + (1u << (im->prec[c] - 1)));
+                    if (im->colorspace && nc >= 3) {                                   /* decoder.go:350-356 */
+                        int32_t *cp[4] = {&v[0], &v[1], &v[2], &v[3]};
+                        orc_colour_convert(cp, nc, 1, im->prec[0], im->colorspace);
+                    }
                     uint8_t *o = j->out + (size_t)(tc->y0 + (uint32_t)y) * j->out_stride + (size_t)(tc->x0 + (uint32_t)x) * (size_t)bpp;
                     if (bpp == 1) o[0] = (uint8_t)pack_value(v[0], prec);
                     else if (bpp == 2) { const uint32_t p = pack_value(v[0], prec); o[0] = (uint8_t)(p >> 8); o[1] = (uint8_t)p; }

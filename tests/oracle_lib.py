@@ -207,6 +207,7 @@ def iso_decode_job(job, threads=4, out=None):
         img.prec[c], img.sgnd[c] = job["prec"], job["sgnd"]
     img.mct, img.reversible, img.nlevels, img.ht, img.mode = job["mct"], job["reversible"], job["nlevels"], job["ht"], 1
     img.cblk_style = job.get("cblk_style", 0)
+    img.colorspace = job.get("colorspace", 0)
     bpp = (1 if job["prec"] <= 8 else 2) if job["ncomp"] == 1 else (4 if job["prec"] <= 8 else 8)
     stride = job["width"] * bpp
     if out is None:

@@ -6,6 +6,7 @@ import io
 import numpy as np
 import pytest
 
+import oracle_lib as O
 from datagen import jobs
 
 pytestmark = pytest.mark.gpu
@@ -140,3 +141,30 @@ def test_full_size_4k_htj2k_codestream(j2k, gpu_ctx):
     got = gpu_ctx.decode_codestreams([data, data])
     for g in got:
         assert np.array_equal(pixels(g, h, w, 3), np.moveaxis(s, 0, 2))
+
+
+@pytest.mark.parametrize("enumcs,cconv,kw", [
+    (18, 1, dict(num_resolutions=4, mct=0)),                                   # sYCC, lossless 5-3
+    (3, 2, dict(num_resolutions=3, mct=0, tile_size=(128, 128))),              # YCbCr(2)
+    (14, 7, dict(num_resolutions=4, mct=0, irreversible=True, quality_layers=[10])),   # CIELab, 9-7
+    (21, 10, dict(num_resolutions=4, mct=0)),                                  # ROMM-RGB
+    (9, 3, dict(num_resolutions=4, mct=0)),                                    # PhotoYCC
+    (16, 0, dict(num_resolutions=4, mct=1)),                                   # sRGB: no conversion
+])
+def test_jp2_file_with_colour_specification(j2k, gpu_ctx, enumcs, cconv, kw):
+    """a JP2 file through the front door: the colr box's enumerated colour space selects the conversion to sRGB that
+    decoder.go:350-356 applies; the pixels equal the CPU checker's with that conversion (1 LSB for the pow-based ones) and the
+    raw codestream decodes to OpenJPEG's unconverted samples"""
+    from datagen import codestream as cs
+    w, h = 300, 200
+    s = jobs.synth_image(w, h, 3, 8, seed=enumcs)
+    data = opj_encode(s, **kw)
+    got = pixels(gpu_ctx.decode_codestream(cs.wrap_jp2(data, enumcs, w, h)), h, w, 3)
+    plain = pixels(gpu_ctx.decode_codestream(data), h, w, 3)
+    assert np.array_equal(plain, opj_decode(data).reshape(h, w, 3))
+    job = jobs.build_iso_job_from_codestream(data)
+    job["colorspace"] = cconv
+    want = pixels(O.iso_decode_job(job), h, w, 3)
+    d = np.abs(got.astype(int) - want.astype(int))
+    assert d.max() <= (1 if cconv >= 7 else 0)
+    assert np.array_equal(got, plain) == (cconv == 0)

@@ -69,9 +69,7 @@ def test_style_matters():
 
 
 @pytest.mark.parametrize("style", STYLES)
-def test_product_tier2_carries_the_style(style):
-    import importlib
-    j2k = importlib.import_module("go-jpeg2000_b200")
+def test_product_tier2_carries_the_style(j2k, style):
     s = jobs.synth_image(150, 100, 3, 8, seed=2)
     data = opj.encode(s, mode=style, num_resolutions=3)
     p = j2k.Parsed(data)
@@ -82,9 +80,7 @@ def test_product_tier2_carries_the_style(style):
 
 
 @pytest.mark.parametrize("style", [0x01, 0x04, 0x05])
-def test_product_tier2_refuses_segmented_styles(style):
-    import importlib
-    j2k = importlib.import_module("go-jpeg2000_b200")
+def test_product_tier2_refuses_segmented_styles(j2k, style):
     s = jobs.synth_image(64, 64, 1, 8, seed=2)
     data = opj.encode(s, mode=style, num_resolutions=2)
     with pytest.raises(j2k.J2KError) as e:

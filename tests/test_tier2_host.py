@@ -305,3 +305,45 @@ def test_many_tiles_parsed_concurrently_equal_serial(j2k):
     a, b = j2k.Parsed(data, threads=1), j2k.Parsed(data, threads=8)
     ta, tb = a.tables(), b.tables()
     assert a.info["tiles"] == 48 and all(np.array_equal(x, y) for x, y in zip(ta, tb))
+
+
+# ---- JP2 container: the colour specification box selects the conversion to sRGB (decoder.go:135-178, 350-356) ------------
+ENUMCS_TO_CS = {0: 0, 15: 0, 16: 0, 17: 0, 99: 0,              # bi-level, sRGB, grey, unknown: no conversion
+                1: 1, 18: 1, 22: 1, 23: 1, 24: 1,              # YCbCr(1), sYCC, YPbPr 1125/60 and 1250/50, e-sYCC: BT.709 matrix
+                3: 2, 4: 2, 9: 3, 11: 4, 12: 5, 13: 6, 14: 7, 19: 8, 20: 9, 21: 10}
+
+
+def test_jp2_colour_specification_box(j2k):
+    s = jobs.synth_image(64, 48, 3, 8, seed=4)
+    data = opj_encode(s, num_resolutions=3, mct=0)
+    for enumcs, want in ENUMCS_TO_CS.items():
+        p = j2k.Parsed(cs.wrap_jp2(data, enumcs, 64, 48))
+        assert p.image.colorspace == want, enumcs
+        assert (p.image.width, p.image.height, p.image.ncomp) == (64, 48, 3)
+        p.close()
+    assert j2k.Parsed(data).image.colorspace == 0                                          # raw codestream: unspecified
+    assert j2k.Parsed(cs.wrap_jp2(data, 18, 64, 48, extra_colr=[16])).image.colorspace == 0  # the last colr box wins (box.go:427-431)
+    assert j2k.Parsed(cs.wrap_jp2(data, 16, 64, 48, extra_colr=[14])).image.colorspace == 7
+    assert j2k.Parsed(cs.wrap_jp2(data, 18, 64, 48, colr_method=2)).image.colorspace == 0    # ICC profile: EnumCS stays 0
+    assert j2k.Parsed(cs.wrap_jp2(data, 18, 64, 48, header_after=True)).image.colorspace == 0  # readJP2 stops at the codestream box
+    bad = cs.wrap_jp2(data, 18, 64, 48)
+    k = bad.index(b"colr")
+    short = bad[:k - 4] + (8 + 5).to_bytes(4, "big") + b"colr" + bytes([1, 0, 0, 0, 0]) + bad[k + 4 + 7:]
+    short = short[:short.index(b"jp2h") - 4] + (int.from_bytes(bad[bad.index(b"jp2h") - 4:bad.index(b"jp2h")], "big") - 2).to_bytes(4, "big") + short[short.index(b"jp2h"):]
+    with pytest.raises(j2k.J2KError) as e:
+        j2k.Parsed(short)
+    assert "color specification box too short" in str(e.value)
+
+
+def test_pillow_jp2_file_parses_like_its_codestream(j2k):
+    s = jobs.synth_image(80, 60, 3, 8, seed=6)
+    a = np.moveaxis(s, 0, 2).astype(np.uint8)
+    buf = io.BytesIO()
+    PIL_Image.fromarray(a).save(buf, format="JPEG2000", num_resolutions=3)
+    p = j2k.Parsed(buf.getvalue())
+    assert p.image.colorspace == 0 and (p.image.width, p.image.height) == (80, 60)
+    buf = io.BytesIO()
+    PIL_Image.fromarray(a).convert("YCbCr").save(buf, format="JPEG2000", num_resolutions=3)
+    data = buf.getvalue()
+    if b"colr" in data and data[data.index(b"colr") + 4] == 1 and int.from_bytes(data[data.index(b"colr") + 7:data.index(b"colr") + 11], "big") == 18:
+        assert j2k.Parsed(data).image.colorspace == 1                                       # Pillow writes YCbCr images as sYCC
