@@ -99,3 +99,15 @@ def test_4k_rgb_all_styles_lossless(j2k, gpu_ctx):
     data = opj.encode(s, mode=RESET | VCAUSAL | PREDTERM | SEGSYM, num_resolutions=6, tile=(1024, 1024))
     got = gpu_ctx.decode_codestream(data).reshape(2160, 3840, -1)[:, :, :3]
     assert np.array_equal(got, np.moveaxis(s, 0, 2))
+
+
+@pytest.mark.parametrize("name", ["reset", "vcausal", "segsym", "all_four_layers_tiles", "all_four_lossy_97"])
+def test_golden_styled_streams(gpu_ctx, name):
+    """committed bytes OpenJPEG wrote with each style -> front door -> the committed pixels OpenJPEG decoded from them"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "iso_styles.npz"))
+    data, ref = g[name + "_j2k"].tobytes(), g[name + "_pix"]
+    h, w = ref.shape[:2]
+    nc = 1 if ref.ndim == 2 else ref.shape[2]
+    got = gpu_ctx.decode_codestream(data).reshape(h, w, -1)[:, :, :nc]
+    assert np.array_equal(got, ref.reshape(h, w, nc))

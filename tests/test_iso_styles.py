@@ -86,3 +86,18 @@ def test_product_tier2_refuses_segmented_styles(j2k, style):
     with pytest.raises(j2k.J2KError) as e:
         j2k.Parsed(data)
     assert "style" in str(e.value)
+
+
+GOLD = ["reset", "vcausal", "segsym", "all_four_layers_tiles", "all_four_lossy_97"]
+
+
+@pytest.mark.parametrize("name", GOLD)
+def test_golden_styled_streams_checker(name):
+    """tests/golden/iso_styles.npz (tests/golden/make_golden_styles.py): bytes OpenJPEG wrote, pixels OpenJPEG decoded"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "iso_styles.npz"))
+    data, ref = g[name + "_j2k"].tobytes(), g[name + "_pix"]
+    job = jobs.build_iso_job_from_codestream(data)
+    h, w, nc = job["height"], job["width"], job["ncomp"]
+    got = O.iso_decode_job(job).reshape(h, w, -1)[:, :, :nc]
+    assert np.array_equal(got, ref.reshape(h, w, nc))
