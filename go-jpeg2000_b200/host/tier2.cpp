@@ -173,7 +173,25 @@ struct Blk {
     uint64_t off = 0; uint32_t len = 0; // first contribution (offset into the tile body)
     uint32_t npieces = 0;
     int32_t more_head = -1, more_tail = -1;            // further contributions (quality layers): list in the tile's `pieces`
+    std::vector<uint32_t> segl;                        // BYPASS / TERMALL blocks: bytes of each codeword segment so far
 };
+
+// Codeword segments of a classic block whose style terminates inside the block (B.10.7.2, D.4, D.6): with TERMALL every coding
+// pass is a segment; with selective bypass alone the first ten passes share one, then each (significance + refinement) pair
+// is a raw segment and each cleanup pass an MQ segment.  -> segment index of pass i, and how many passes a segment may hold.
+inline uint32_t seg_of_pass(uint32_t style, uint32_t i)
+{
+    if (style & 0x04u) return i;
+    if (i < 10) return 0;
+    const uint32_t j = i - 10;
+    return 1 + 2 * (j / 3) + (j % 3 == 2 ? 1 : 0);
+}
+inline uint32_t seg_capacity(uint32_t style, uint32_t seg)
+{
+    if (style & 0x04u) return 1;
+    if (seg == 0) return 10;
+    return (seg & 1) ? 2 : 1;
+}
 struct Piece { uint64_t off; uint32_t len; int32_t next; };
 
 // the code blocks of one band that lie in one precinct: their own grid and tag trees (B.10.2)
@@ -300,7 +318,7 @@ void parse_tile(const uint8_t *cs, const Header &h, uint32_t tidx, const std::ve
     });
     size_t p = 0;
     std::vector<std::pair<uint32_t, uint32_t>> segs;   // (block, length) of this packet
-    struct Undo { uint32_t blk, passes, zbp, lblock, lcup; bool included; };
+    struct Undo { uint32_t blk, passes, zbp, lblock, lcup; bool included; std::vector<uint32_t> segl; };
     std::vector<Undo> undo;                            // state of the blocks this packet's header touched (truncated tiles only)
     bool cut = false;
     for (const Pk &pk : order) {
@@ -322,7 +340,7 @@ void parse_tile(const uint8_t *cs, const Header &h, uint32_t tidx, const std::ve
                     else inc = br.get() != 0;
                     if (br.bad) { if (truncated) { cut = true; goto packet_done; } out.err.fail(J2KGPU_E_RANGE, "tile %u: packet header runs past the tile data", tidx); return; }
                     if (!inc) continue;
-                    if (truncated) undo.push_back({st.first + k, e.passes, e.zbp, e.lblock, e.lcup, e.included});
+                    if (truncated) undo.push_back({st.first + k, e.passes, e.zbp, e.lblock, e.lcup, e.included, e.segl});
                     if (!e.included) {
                         int32_t t = 1;
                         while (!st.imsb.decode(arena, br, gx, gy, t)) {
@@ -347,6 +365,23 @@ void parse_tile(const uint8_t *cs, const Header &h, uint32_t tidx, const std::ve
                         ln = br.bits((int)e.lblock);
                         e.lcup = ln;
                         if (n > 1) ln += br.bits((int)e.lblock + floorlog2(n - 1));
+                    } else if (h.style & 0x05u) {
+                        // several codeword segments: one length per segment the new passes touch, each Lblock + floor(log2(passes
+                        // of that segment in this packet)) bits wide (B.10.7.2)
+                        ln = 0;
+                        for (uint32_t done = 0; done < n;) {
+                            const uint32_t i = e.passes + done, sg = seg_of_pass(h.style, i);
+                            uint32_t first = i;                                    // passes of segment sg that came before
+                            while (first > 0 && seg_of_pass(h.style, first - 1) == sg) first--;
+                            const uint32_t m = std::min(n - done, seg_capacity(h.style, sg) - (i - first));
+                            const int nb = (int)e.lblock + floorlog2(m);
+                            if (nb > 32) { out.err.fail(J2KGPU_E_RANGE, "tile %u: segment length field too wide", tidx); return; }
+                            const uint32_t l = br.bits(nb);
+                            if (e.segl.size() <= sg) e.segl.resize(sg + 1, 0);
+                            e.segl[sg] += l;
+                            ln += l;
+                            done += m;
+                        }
                     } else {
                         const int nb = (int)e.lblock + floorlog2(n);
                         if (nb > 32) { out.err.fail(J2KGPU_E_RANGE, "tile %u: segment length field too wide", tidx); return; }
@@ -370,7 +405,7 @@ void parse_tile(const uint8_t *cs, const Header &h, uint32_t tidx, const std::ve
         }
     packet_done:
         if (cut) {                                       // the codestream ended inside this packet: forget it and stop
-            for (const Undo &u : undo) { Blk &e = blks[u.blk]; e.passes = u.passes; e.zbp = u.zbp; e.lblock = u.lblock; e.lcup = u.lcup; e.included = u.included; }
+            for (const Undo &u : undo) { Blk &e = blks[u.blk]; e.passes = u.passes; e.zbp = u.zbp; e.lblock = u.lblock; e.lcup = u.lcup; e.included = u.included; e.segl = u.segl; }
             break;
         }
         for (auto &sg : segs) {
@@ -418,11 +453,20 @@ void parse_tile(const uint8_t *cs, const Header &h, uint32_t tidx, const std::ve
         cb.num_passes = (uint8_t)std::min<uint32_t>(e.passes, 255);
         cb.data_len = total;
         cb.len_cleanup = (h.ht && e.passes > 1) ? e.lcup : 0;
-        if (e.more_head < 0 && abs_off >= 0) { cb.data_off = (uint64_t)abs_off + e.off; out.is_extra.push_back(0); }
+        if (e.more_head < 0 && abs_off >= 0 && e.segl.empty()) { cb.data_off = (uint64_t)abs_off + e.off; out.is_extra.push_back(0); }
         else {
             cb.data_off = out.extra.size();
             out.extra.insert(out.extra.end(), body + e.off, body + e.off + e.len);
             for (int32_t m = e.more_head; m >= 0; m = pieces[m].next) out.extra.insert(out.extra.end(), body + pieces[m].off, body + pieces[m].off + pieces[m].len);
+            if (h.style & 0x05u) {
+                // the segment lengths follow the block's bytes as little-endian 32-bit words, one per segment its passes touch
+                // (include/j2kgpu.h, j2k_image_t.cblk_style)
+                const uint32_t nseg = seg_of_pass(h.style, e.passes - 1) + 1;
+                for (uint32_t s = 0; s < nseg; s++) {
+                    const uint32_t l = s < e.segl.size() ? e.segl[s] : 0;
+                    for (int k = 0; k < 4; k++) out.extra.push_back((uint8_t)(l >> (8 * k)));
+                }
+            }
             out.is_extra.push_back(1);
         }
         out.cbs.push_back(cb);
@@ -548,8 +592,8 @@ int j2k_tier2_begin(const uint8_t *d, uint64_t len, uint32_t reduce, j2k_t2_fram
             if (h.cbw > 64 || h.cbh > 64 || h.cbw * h.cbh > 4096) T2_FAIL(J2KGPU_E_UNSUPPORTED, "code blocks %ux%u", h.cbw, h.cbh);
             // RESET, VCAUSAL, PREDTERM, SEGSYM keep one codeword segment per block: the block decoder handles them;
             // BYPASS and TERMALL change the length signalling of the packet headers (B.10.7.2) and are refused
-            if ((h.style & ~0x7Au) || ((h.style & 0x40u) && (h.style & 0x3Fu)))
-                T2_FAIL(J2KGPU_E_UNSUPPORTED, "code-block style %02X (selective bypass / termination on each pass; HT with a classic style bit)", h.style);
+            if ((h.style & ~0x7Fu) || ((h.style & 0x40u) && (h.style & 0x3Fu)))
+                T2_FAIL(J2KGPU_E_UNSUPPORTED, "code-block style %02X (HT with a classic style bit)", h.style);
             if (!h.layers) T2_FAIL(J2KGPU_E_RANGE, "zero quality layers");
             for (uint32_t r = 0; r <= 32; r++) h.ppx[r] = h.ppy[r] = 15;
             if (scod & 1) {                               // user-defined precincts: one byte per resolution, PPx | PPy << 4 (A.6.1)

@@ -211,6 +211,9 @@ int iso_decode_image(const orc_image_t *img, const orc_tilecomp_t *tcs, uint32_t
         const orc_tilecomp_t *tc = &tcs[cb->tilecomp];
         if (cb->x0 + cb->w > tc->x1 - tc->x0 || cb->y0 + cb->h > tc->y1 - tc->y0 || cb->w > 64 || cb->h > 64) return -2;
         if (cb->data_off > blob_len || cb->data_len > blob_len - cb->data_off) return -2;
+        if (!img->ht && (img->cblk_style & 0x05) && cb->data_len &&           /* the segment-length table behind the code bytes */
+            4ull * (uint64_t)iso_t1_num_segments(img->cblk_style, cb->num_passes ? cb->num_passes : 3 * cb->num_bps - 2) >
+                blob_len - cb->data_off - cb->data_len) return -2;
     }
     int32_t **planes = calloc(n_tc ? n_tc : 1, sizeof(int32_t *));
     for (uint32_t t = 0; t < n_tc; t++)

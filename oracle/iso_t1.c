@@ -8,9 +8,11 @@
  * (through Pillow) with this decoder + the ISO inverse transform and compares with OpenJPEG's own output.
  * Code-block styles (COD SPcod, Table A.19): RESET (0x02: contexts back to Table D.7 at every pass boundary), VCAUSAL
  * (0x08: the row below a stripe counts as insignificant, D.4.3... D.7) and SEGSYM (0x20: four UNIFORM symbols after each
- * cleanup pass, D.5) are decoded; PREDTERM (0x10) needs nothing from a decoder; BYPASS (0x01) and TERMALL (0x04) split
- * the block into several codeword segments and are not handled (the caller refuses them).  Pinned by streams OpenJPEG
- * wrote with those styles (datagen/opj_direct.py) and decodes itself.
+ * cleanup pass, D.5) are decoded; PREDTERM (0x10) needs nothing from a decoder; BYPASS (0x01, D.6: from the fifth
+ * bit-plane on the significance and refinement passes are raw bits) and TERMALL (0x04: every pass its own terminated
+ * codeword) split the block into several codeword segments: their byte counts follow the block's data_len bytes as
+ * little-endian 32-bit words (seglens; the job-table convention of include/j2kgpu.h).  Pinned by streams OpenJPEG wrote
+ * with those styles (datagen/opj_direct.py) and decodes itself.
  *
  * Output convention (what the CUDA kernel reproduces): out[y*w+x] = sign * m2, where m2 is the magnitude at TWICE
  * scale with the mid-point of the last decoded bit-plane added: m2 = 2 * (decoded magnitude bits) + (1 << p_last),
@@ -66,6 +68,30 @@ static void mq_init(mq_t *m, const uint8_t *d, int len)
     m->C <<= 7; m->CT -= 7; m->A = 0x8000;
 }
 
+/* raw (bypass) bit, D.6: bytes are read MSB first, the byte after an 0xFF carries 7 bits; past the end: 0xFF */
+static int raw_decode(mq_t *m)
+{
+    if (m->CT == 0) {
+        if (m->C == 0xFF) {
+            if (mq_byte(m, m->bp) > 0x8F) { m->C = 0xFF; m->CT = 8; }
+            else { m->C = mq_byte(m, m->bp); m->bp++; m->CT = 7; }
+        } else { m->C = mq_byte(m, m->bp); m->bp++; m->CT = 8; }
+    }
+    m->CT--;
+    return (int)((m->C >> m->CT) & 1);
+}
+
+/* a new codeword segment: the contexts survive (unless RESET), the arithmetic / raw state starts over */
+static void seg_start(mq_t *m, const uint8_t *d, int len, int raw)
+{
+    m->d = d; m->len = len; m->bp = 0;
+    if (raw) { m->C = 0; m->CT = 0; return; }
+    m->C = mq_byte(m, 0) << 16;
+    m->CT = 0;
+    mq_bytein(m);
+    m->C <<= 7; m->CT -= 7; m->A = 0x8000;
+}
+
 static int mq_decode(mq_t *m, int cx)
 {
     const uint32_t qe = QE[m->idx[cx]];
@@ -108,6 +134,7 @@ static int zc_ctx(int band, int h, int v, int d)
 
 typedef struct {
     int w, h, sw;                 /* sw = w + 2 */
+    int raw;                      /* the current pass reads raw bits (selective bypass) */
     uint8_t *sig, *neg, *pi, *ref;
     int vsc;                      /* vertically causal context formation */
     int32_t *mag;                 /* magnitude bits decoded so far */
@@ -120,6 +147,7 @@ typedef struct {
 
 static int sign_decode(mq_t *m, const blk_t *b, int x, int y)      /* Table D.2 / D.3 */
 {
+    if (b->raw) return raw_decode(m);                               /* D.6: the sign bit itself, no prediction */
     int hc = 0, vc = 0;
     if (AT(b->sig, x - 1, y)) hc += AT(b->neg, x - 1, y) ? -1 : 1;
     if (AT(b->sig, x + 1, y)) hc += AT(b->neg, x + 1, y) ? -1 : 1;
@@ -157,6 +185,16 @@ static void become_sig(mq_t *m, blk_t *b, int x, int y, int bp)
     b->plast[y * b->w + x] = (int8_t)bp;
 }
 
+/* codeword segments that num_passes coding passes touch (1 unless the style has BYPASS or TERMALL) */
+int iso_t1_num_segments(int style, int num_passes)
+{
+    if (num_passes <= 0 || !(style & 0x05)) return 1;
+    const int i = num_passes - 1;
+    if (style & 0x04) return i + 1;
+    if (i < 10) return 1;
+    return 1 + 2 * ((i - 10) / 3) + ((i - 10) % 3 == 2 ? 1 : 0) + 1;
+}
+
 int iso_t1_decode(const uint8_t *data, int len, int w, int h, int num_bps, int num_passes, int band, int32_t *out)
 {
     return iso_t1_decode_style(data, len, w, h, num_bps, num_passes, band, 0, out);
@@ -164,7 +202,7 @@ int iso_t1_decode(const uint8_t *data, int len, int w, int h, int num_bps, int n
 
 int iso_t1_decode_style(const uint8_t *data, int len, int w, int h, int num_bps, int num_passes, int band, int style, int32_t *out)
 {
-    if (style & (0x01 | 0x04)) return -2;                        /* BYPASS, TERMALL: several codeword segments */
+
     memset(out, 0, sizeof(int32_t) * (size_t)w * h);
     if (w < 1 || h < 1 || w > 1024 || h > 1024 || num_bps < 0 || num_bps > 30) return -1;
     if (num_bps == 0 || num_passes <= 0) return 0;
@@ -179,8 +217,26 @@ int iso_t1_decode_style(const uint8_t *data, int len, int w, int h, int num_bps,
     mq_t mq;
     mq_init(&mq, data, len);
     int bp = num_bps - 1, type = 2;                              /* the first pass is a cleanup pass */
+    const int segmented = style & (0x01 | 0x04);
+    const uint8_t *seglens = data + len;                         /* segmented styles: the table behind the code bytes */
+    int seg = 0, seg_pos = 0, seg_left = 0;
+    b->raw = 0;
     for (int pass = 0; pass < num_passes; pass++) {
         if (pass && (style & 0x02)) mq_reset_contexts(&mq);
+        if (segmented) {
+            const int raw = (style & 0x01) && pass >= 10 && type != 2;
+            if (seg_left == 0) {
+                const int sl = (int)((uint32_t)seglens[4 * seg] | (uint32_t)seglens[4 * seg + 1] << 8 | (uint32_t)seglens[4 * seg + 2] << 16 |
+                                     (uint32_t)seglens[4 * seg + 3] << 24);
+                const int avail = sl < 0 || sl > len - seg_pos ? len - seg_pos : sl;
+                seg_start(&mq, data + seg_pos, avail, raw);
+                seg_pos += avail;
+                seg_left = (style & 0x04) ? 1 : (seg == 0 ? 10 : ((seg & 1) ? 2 : 1));
+                seg++;
+            }
+            seg_left--;
+            b->raw = raw;
+        }
         for (int y0 = 0; y0 < h; y0 += 4)
             for (int x = 0; x < w; x++) {
                 const int rows = y0 + 4 <= h ? 4 : h - y0;
@@ -188,7 +244,7 @@ int iso_t1_decode_style(const uint8_t *data, int len, int w, int h, int num_bps,
                     for (int k = 0; k < rows; k++) {
                         const int y = y0 + k;
                         if (AT(b->sig, x, y) || !any_neighbour(b, x, y)) continue;
-                        if (mq_decode(&mq, zc_of(b, band, x, y))) become_sig(&mq, b, x, y, bp);
+                        if (b->raw ? raw_decode(&mq) : mq_decode(&mq, zc_of(b, band, x, y))) become_sig(&mq, b, x, y, bp);
                         AT(b->pi, x, y) = 1;
                     }
                 } else if (type == 1) {                                                /* magnitude refinement, D.3.3 */
@@ -196,7 +252,7 @@ int iso_t1_decode_style(const uint8_t *data, int len, int w, int h, int num_bps,
                         const int y = y0 + k;
                         if (!AT(b->sig, x, y) || AT(b->pi, x, y)) continue;
                         const int cx = AT(b->ref, x, y) ? 16 : (any_neighbour(b, x, y) ? 15 : 14);
-                        if (mq_decode(&mq, cx)) b->mag[y * w + x] |= 1 << bp;
+                        if (b->raw ? raw_decode(&mq) : mq_decode(&mq, cx)) b->mag[y * w + x] |= 1 << bp;
                         AT(b->ref, x, y) = 1;
                         b->plast[y * w + x] = (int8_t)bp;
                     }

@@ -58,6 +58,7 @@ int  iso_ht_decode(const uint8_t *data, int len, int w, int h, int num_bps, int3
 /* ISO/IEC 15444-1 Annex C/D code-block decoder (iso_t1.c): num_bps magnitude bit-planes, the first num_passes coding
  * passes; out = sign * (2 * magnitude + mid-point of the last decoded bit-plane); band 0 LL, 1 HL, 2 LH, 3 HH */
 int  iso_t1_decode(const uint8_t *data, int len, int w, int h, int num_bps, int num_passes, int band, int32_t *out);
+int  iso_t1_num_segments(int style, int num_passes);
 int  iso_t1_decode_style(const uint8_t *data, int len, int w, int h, int num_bps, int num_passes, int band, int style, int32_t *out);
 
 /* ---- DWT (internal/dwt/dwt.go) ------------------------------------------ */
