@@ -335,6 +335,16 @@ extern "C" void j2kgpu_job_destroy(j2kgpu_job *job)
     job_free(job);
 }
 
+// codeword segments that np coding passes of a classic block touch (B.10.7.2, D.4, D.6); 1 without BYPASS / TERMALL
+static uint32_t t1_num_segments(uint32_t style, uint32_t np)
+{
+    if (np == 0 || !(style & (J2KGPU_CBLK_BYPASS | J2KGPU_CBLK_TERMALL))) return 1;
+    const uint32_t i = np - 1;
+    if (style & J2KGPU_CBLK_TERMALL) return i + 1;
+    if (i < 10) return 1;
+    return 1 + 2 * ((i - 10) / 3) + ((i - 10) % 3 == 2 ? 1 : 0) + 1;
+}
+
 static bool same_header(const j2k_image_t &a, const j2k_image_t &b)
 {
     return a.ncomp == b.ncomp && !memcmp(a.prec, b.prec, 4) && !memcmp(a.sgnd, b.sgnd, 4) && a.mct == b.mct &&
@@ -443,11 +453,11 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
         const j2k_image_t &im = it.image;
         if (!same_header(im, hdr)) J2K_FAIL(ctx, J2KGPU_E_ARG, "item %u: header differs from item 0", ii);
         if (im.width == 0 || im.height == 0) J2K_FAIL(ctx, J2KGPU_E_ARG, "item %u: empty image", ii);
-        // classic blocks: RESET / VCAUSAL / PREDTERM / SEGSYM are decoded (one codeword segment per block); selective bypass and
-        // termination on every pass need per-segment lengths the block table does not carry
+        // classic blocks: all six style bits of Table A.19.  BYPASS / TERMALL blocks carry several codeword segments: their
+        // byte counts follow the block's bytes in the blob (j2k_image_t.cblk_style)
         const uint32_t cstyle = (iso && !im.ht) ? im.cblk_style : 0u;
-        if (cstyle & ~(J2KGPU_CBLK_RESET | J2KGPU_CBLK_VCAUSAL | J2KGPU_CBLK_PREDTERM | J2KGPU_CBLK_SEGSYM))
-            J2K_FAIL(ctx, J2KGPU_E_UNSUPPORTED, "item %u: code-block style %02X (selective bypass / termination on each pass)", ii, cstyle);
+        if (cstyle & ~0x3Fu) J2K_FAIL(ctx, J2KGPU_E_UNSUPPORTED, "item %u: code-block style %02X", ii, cstyle);
+        if (cstyle) job->t1_segmented = 1;                   // the styled instantiation of k_t1_iso
         if ((!it.tilecomps && it.n_tilecomps) || (!it.cblks && it.n_cblks) || (!it.blob && it.blob_len))
             J2K_FAIL(ctx, J2KGPU_E_ARG, "item %u: null table", ii);
         if (it.out_stride < (uint64_t)im.width * bpp || it.out_stride % bpp)
@@ -532,6 +542,11 @@ static int job_build(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t *it
             // int16 planes hold what coef_bits promises; an EBCOT block that claims more bit-planes than that would be truncated
             if (will_coef16 && !hdr.ht && cb.data_len && cb.num_bps > hdr.coef_bits)
                 J2K_FAIL(ctx, J2KGPU_E_RANGE, "item %u block %u: num_bps %d exceeds the declared coef_bits %d", ii, b, (int)cb.num_bps, (int)hdr.coef_bits);
+            if ((cstyle & (J2KGPU_CBLK_BYPASS | J2KGPU_CBLK_TERMALL)) && cb.data_len && cb.num_bps) {
+                const uint32_t np = cb.num_passes ? cb.num_passes : 3u * cb.num_bps - 2u;
+                if (4ull * t1_num_segments(cstyle, np) > it.blob_len - cb.data_off - cb.data_len)
+                    J2K_FAIL(ctx, J2KGPU_E_RANGE, "item %u block %u: segment-length table outside blob", ii, b);
+            }
             DevCblk o{};
             o.data_off = blob_bytes + cb.data_off; o.data_len = cb.data_len;
             o.out_off = d.coef_off + (uint64_t)cb.y0 * d.w + cb.x0; o.out_stride = d.w;
@@ -663,7 +678,7 @@ static int run_entropy(j2kgpu_job *job, const void *d_blob, uint32_t ia, uint32_
     cudaError_t e;
     const int irrev = job->iso && !job->hdr.reversible;                  // ISO 9-7: the planes receive dequantised float32
     const float *steps = job->d_steps ? job->d_steps + ca : nullptr;
-    if (job->iso && !job->hdr.ht) e = launch_t1_iso(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, steps, irrev, job->max_bps, ctx->opt.t1_group, st);
+    if (job->iso && !job->hdr.ht) e = launch_t1_iso(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, steps, irrev, job->t1_segmented, ctx->opt.t1_group, st);
     else if (job->iso) {
         // chunks of a pipelined run share the scratch: their kernels are ordered on one stream
         e = launch_ht_iso(cbs, n, (const uint8_t *)d_blob, job->d_coef, job->coef16, steps, irrev, job->hdr.coef_bits,
@@ -1355,7 +1370,7 @@ static int stage_blocks(j2kgpu_ctx *ctx, int mode, int ht, const j2k_blkjob_t *j
     if (n == 0) return J2KGPU_OK;
     cudaSetDevice(ctx->device);
     std::vector<DevCblk> cbs(n);
-    int max_bps = 1;
+    int max_bps = 1, segmented = 0;
     for (uint32_t i = 0; i < n; i++) {
         const j2k_blkjob_t &j = jobs[i];
         if (j.w == 0 || j.h == 0 || j.w > 64 || j.h > 64) return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "block %u: size %ux%u", i, j.w, j.h);
@@ -1368,8 +1383,13 @@ static int stage_blocks(j2kgpu_ctx *ctx, int mode, int ht, const j2k_blkjob_t *j
         o.w = j.w; o.h = j.h; o.band = j.band; o.num_bps = j.num_bps; o.num_passes = j.rsv0;    // ISO: coding passes (0 = all)
         o.len_cup = (j.len_cleanup && j.len_cleanup <= j.data_len) ? j.len_cleanup : j.data_len;
         if (mode == J2KGPU_MODE_ISO && !ht) {
-            if (j.rsv1 & ~(J2KGPU_CBLK_RESET | J2KGPU_CBLK_VCAUSAL | J2KGPU_CBLK_PREDTERM | J2KGPU_CBLK_SEGSYM))
-                return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "block %u: code-block style %02X", i, (unsigned)j.rsv1);
+            if (j.rsv1 & ~0x3Fu) return j2k_set_err(ctx, J2KGPU_E_UNSUPPORTED, "block %u: code-block style %02X", i, (unsigned)j.rsv1);
+            if ((j.rsv1 & (J2KGPU_CBLK_BYPASS | J2KGPU_CBLK_TERMALL)) && j.data_len && j.num_bps) {
+                const uint32_t np = j.rsv0 ? j.rsv0 : 3u * j.num_bps - 2u;
+                if (4ull * t1_num_segments(j.rsv1, np) > blob_len - j.data_off - j.data_len)
+                    return j2k_set_err(ctx, J2KGPU_E_RANGE, "block %u: segment-length table outside blob", i);
+            }
+            if (j.rsv1) segmented = 1;
             o.pad = j.rsv1;
         }
         if (j.num_bps > max_bps) max_bps = j.num_bps;
@@ -1393,7 +1413,7 @@ static int stage_blocks(j2kgpu_ctx *ctx, int mode, int ht, const j2k_blkjob_t *j
     }
     cudaError_t e = (ht && mode == J2KGPU_MODE_ISO)
                         ? launch_ht_iso((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, nullptr, 0, 0, refine, ctx->d_aux.p, blob_len, ctx->stream)
-                    : mode == J2KGPU_MODE_ISO ? launch_t1_iso((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, nullptr, 0, max_bps, ctx->opt.t1_group, ctx->stream)
+                    : mode == J2KGPU_MODE_ISO ? launch_t1_iso((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, nullptr, 0, segmented, ctx->opt.t1_group, ctx->stream)
                     : ht ? launch_ht_ref((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, ctx->d_out.p, 0, 0, ctx->d_aux.p, blob_len, ctx->stream)
                        : launch_t1_ref_stage((const DevCblk *)ctx->d_tab.p, n, (const uint8_t *)ctx->d_in.p, (int32_t *)ctx->d_out.p, max_bps, ctx->opt.t1_group, ctx->stream);
     if (e != cudaSuccess) return j2k_cuda_err(ctx, e, "entropy kernel launch");

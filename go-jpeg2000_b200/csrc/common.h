@@ -133,6 +133,7 @@ struct j2kgpu_job {
     int fast_epi = 0;                    // every tile qualifies for the fused kernel's fixed RGBA8 epilogue
     int wide_ok = 0;                     // ... and for the 16-columns-per-lane variant (idwt_wide.cu)
     int ht_refine = 0;                   // ISO HT: some block has SigProp / MagRef passes
+    int t1_segmented = 0;                // ISO EBCOT: some item has a non-default code-block style (styled instantiation of k_t1_iso)
     int precleared = 0;                  // reference HT coder: planes zeroed at job creation, decoder clears every 4th row only
     int pix_fill = 0;                    // some pixel of some image is covered by no tile: pre-fill with the pixel of zero coefficients
     std::vector<uint8_t> item_fill;      // per item: needs the pre-fill
@@ -184,7 +185,7 @@ size_t j2k_htref_scratch_bytes(uint32_t n_blocks);   // device scratch launch_ht
 int j2k_htref_launches();        // kernels per launch_ht_ref call
 // ISO/IEC 15444-1 Annex D decoder (stripe-order passes, standard tables, pass truncation)
 cudaError_t launch_t1_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
-                          const float *d_steps, int irrev, int max_bps, int group, cudaStream_t s);
+                          const float *d_steps, int irrev, int segmented, int group, cudaStream_t s);
 // ISO/IEC 15444-15 block decoder (VLC kernel + MagSgn kernel)
 // refine: some block carries SigProp / MagRef passes (num_passes > 1): the refinement kernel runs between the two
 cudaError_t launch_ht_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,

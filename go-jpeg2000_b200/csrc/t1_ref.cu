@@ -338,7 +338,25 @@ k_t1_ref(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
 // reversible path, or that twice-scale value * step / 2 as float32 bits for the irreversible one (the convention of the
 // CPU checker, which OpenJPEG pins).  Code-block styles RESET, VCAUSAL and SEGSYM (DevCblk.pad) are decoded, PREDTERM needs
 // nothing from a decoder; BYPASS / TERMALL blocks never get here (job_build refuses them).
-template <typename OT, int G>
+// raw (selective bypass) bit, D.6: MSB first, the byte after an 0xFF carries 7 bits, 0xFF past the end of the segment.
+// The MQ struct is reused: C = current byte, CT = bits left in it, bp = next byte.
+__device__ __forceinline__ uint32_t raw_decode(MQ &m)
+{
+    if (m.CT == 0) {
+        const uint32_t nb = m.bp < m.len ? (uint32_t)__ldg(m.d + m.bp) : 0xFFu;
+        if (m.C == 0xFF) {
+            if (nb > 0x8F) { m.C = 0xFF; m.CT = 8; }
+            else { m.C = nb; m.bp++; m.CT = 7; }
+        } else { m.C = nb; m.bp++; m.CT = 8; }
+    }
+    m.CT--;
+    return (m.C >> m.CT) & 1u;
+}
+
+// SEG: the job has blocks with a non-default code-block style (DevCblk.pad).  BYPASS / TERMALL blocks consist of several
+// codeword segments whose byte counts follow the block's data_len bytes as little-endian 32-bit words.  A separate
+// instantiation, so that the kernel of the default style carries none of it (measured: 3 % on 4K EBCOT frames).
+template <typename OT, int G, bool SEG>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 k_t1_iso(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restrict__ blob, OT *__restrict__ coef,
          const float *__restrict__ steps, int irrev)
@@ -352,7 +370,7 @@ k_t1_iso(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
     const uint32_t blk = have ? blk_raw : n - 1;
     const DevCblk cb = cblks[blk];
     const int w = cb.w, h = cb.h, nbps = cb.num_bps, band = cb.band & 3;
-    const uint32_t style = cb.pad;                       // code-block style bits (Table A.19): RESET, VCAUSAL, SEGSYM matter here
+    const uint32_t style = SEG ? cb.pad : 0u;            // code-block style bits (Table A.19); the plain instantiation has none
     const bool vcausal = (style & 0x08u) != 0;
     int npasses = cb.num_passes ? cb.num_passes : 3 * nbps - 2;
     if (npasses > 3 * nbps - 2) npasses = 3 * nbps - 2;
@@ -392,9 +410,26 @@ k_t1_iso(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
 
     // pass sequence: cleanup of the top bit-plane, then (significance, refinement, cleanup) per lower bit-plane
     int bp = nbps - 1, type = 2;
+    int seg = 0, seg_pos = 0, seg_left = 0;
+    bool raw = false;
     for (int pass = 0; pass < npasses && run; pass++) {
         p_end = bp;
       if (sl == 0) {
+        if (SEG && (style & 0x05u)) {
+            raw = (style & 0x01u) && pass >= 10 && type != 2;          // D.6: raw significance / refinement passes from the 5th bit-plane on
+            if (seg_left == 0) {                                       // this pass opens a codeword segment
+                const uint8_t *t = blob + cb.data_off + cb.data_len + 4 * seg;
+                const uint32_t sl32 = (uint32_t)__ldg(t) | ((uint32_t)__ldg(t + 1) << 8) | ((uint32_t)__ldg(t + 2) << 16) | ((uint32_t)__ldg(t + 3) << 24);
+                const int left = (int)cb.data_len - seg_pos;
+                const int avail = sl32 > (uint32_t)left ? left : (int)sl32;
+                if (raw) { mq.d = blob + cb.data_off + seg_pos; mq.len = avail; mq.bp = 0; mq.C = 0; mq.CT = 0; }
+                else mq_init(mq, blob + cb.data_off + seg_pos, avail);
+                seg_pos += avail;
+                seg_left = (style & 0x04u) ? 1 : (seg == 0 ? 10 : ((seg & 1) ? 2 : 1));
+                seg++;
+            }
+            seg_left--;
+        }
         if (pass && (style & 0x02u))                                   // RESET: every pass starts from Table D.7
             for (int i = 0; i < kNumCtx; i++) ctxs[i] = (i == kCtxUni) ? 92 : (i == kCtxRL ? 6 : (i == 0 ? 8 : 0));
         for (int y0 = 0; y0 < h; y0 += 4) {
@@ -428,9 +463,10 @@ k_t1_iso(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
                         if ((s[k + 1] >> x) & 1) continue;
                         const uint32_t idx9 = win3(s[k], x) | (win3(s[k + 1], x) << 3) | (win3(s[k + 2], x) << 6);
                         if ((idx9 & 0x1EF) == 0) continue;        // no significant neighbour (bit 4 is the sample itself)
-                        if (mq_decode(mq, ctxs, kCtxZC + zc[idx9])) {
+                        if ((SEG && raw) ? raw_decode(mq) : mq_decode(mq, ctxs, kCtxZC + zc[idx9])) {
                             pb[k] |= 1ull << x;
-                            if (decode_sign(mq, ctxs, x, s[k], s[k + 1], s[k + 2], ng[k], ng[k + 1], ng[k + 2], c_sc_iso))
+                            if ((SEG && raw) ? raw_decode(mq)
+                                             : decode_sign(mq, ctxs, x, s[k], s[k + 1], s[k + 2], ng[k], ng[k + 1], ng[k + 2], c_sc_iso))
                                 ng[k + 1] |= 1ull << x;
                             s[k + 1] |= 1ull << x;
                             grew = true;
@@ -468,7 +504,7 @@ k_t1_iso(const DevCblk *__restrict__ cblks, uint32_t n, const uint8_t *__restric
                     for (int k = 0; k < 4; k++) {
                         if (!((cand[k] >> x) & 1)) continue;
                         const int ctx = kCtxMag + (((rf[k] >> x) & 1) ? 2 : (int)((nbm[k] >> x) & 1));
-                        if (mq_decode(mq, ctxs, ctx)) pb[k] |= 1ull << x;
+                        if ((SEG && raw) ? raw_decode(mq) : mq_decode(mq, ctxs, ctx)) pb[k] |= 1ull << x;
                     }
                 }
 #pragma unroll
@@ -722,17 +758,17 @@ static cudaError_t launch_t1_ref_g(const DevCblk *d_cblks, uint32_t n, const uin
     return cudaGetLastError();
 }
 
-template <typename OT, int G>
+template <typename OT, int G, bool SEG>
 static cudaError_t launch_t1_iso_g(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, OT *d_coef, const float *d_steps, int irrev,
                                    cudaStream_t s)
 {
     size_t smem;
     const int wpc = t1_warps_per_cta(G, kIsoWords, &smem);
     if (!wpc) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(k_t1_iso<OT, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_t1_iso<OT, G, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const uint32_t per_cta = (uint32_t)wpc * (32 / G);
-    J2K_LAUNCH((k_t1_iso<OT, G>), (n + per_cta - 1) / per_cta, wpc * 32, smem, s, d_cblks, n, d_blob, d_coef, d_steps, irrev);
+    J2K_LAUNCH((k_t1_iso<OT, G, SEG>), (n + per_cta - 1) / per_cta, wpc * 32, smem, s, d_cblks, n, d_blob, d_coef, d_steps, irrev);
     return cudaGetLastError();
 }
 
@@ -784,14 +820,14 @@ cudaError_t launch_t1_ref_stage(const DevCblk *d_cblks, uint32_t n, const uint8_
 // ISO/IEC 15444-1 Annex D decoder (J2KGPU_MODE_ISO): num_bps magnitude bit-planes, num_passes coding passes per block
 // (0 = all); irrev: the planes receive float32 bits = value * steps[block]
 cudaError_t launch_t1_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_blob, void *d_coef, int coef16,
-                          const float *d_steps, int irrev, int max_bps, int group, cudaStream_t s)
+                          const float *d_steps, int irrev, int segmented, int group, cudaStream_t s)
 {
     if (n == 0) return cudaSuccess;
     cudaError_t e = upload_tables(s);
     if (e != cudaSuccess) return e;
-    (void)max_bps;
-#define J2K_T1_ISO(G) ((coef16 && !irrev) ? launch_t1_iso_g<int16_t, G>(d_cblks, n, d_blob, (int16_t *)d_coef, d_steps, irrev, s) \
-                                          : launch_t1_iso_g<int32_t, G>(d_cblks, n, d_blob, (int32_t *)d_coef, d_steps, irrev, s))
+#define J2K_T1_ISO_S(G, S) ((coef16 && !irrev) ? launch_t1_iso_g<int16_t, G, S>(d_cblks, n, d_blob, (int16_t *)d_coef, d_steps, irrev, s) \
+                                               : launch_t1_iso_g<int32_t, G, S>(d_cblks, n, d_blob, (int32_t *)d_coef, d_steps, irrev, s))
+#define J2K_T1_ISO(G) (segmented ? J2K_T1_ISO_S(G, true) : J2K_T1_ISO_S(G, false))
     switch (t1_group(group, n)) {
     case 4: return J2K_T1_ISO(4);
     case 8: return J2K_T1_ISO(8);
@@ -799,4 +835,5 @@ cudaError_t launch_t1_iso(const DevCblk *d_cblks, uint32_t n, const uint8_t *d_b
     default: return J2K_T1_ISO(32);
     }
 #undef J2K_T1_ISO
+#undef J2K_T1_ISO_S
 }

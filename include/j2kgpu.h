@@ -99,9 +99,14 @@ typedef struct {
                                  * coder has no bound).                                                       */
     uint8_t  colorspace;        /* J2KGPU_CS_*: conversion to sRGB after the DC shift, the step of decoder.go:350-356
                                  * (getColorConversion, colorspace.go:54-88); 0 = none (sRGB, grey, unknown)    */
-    uint8_t  cblk_style;        /* ISO mode, classic (non-HT) blocks: code-block style bits of COD SPcod (Table A.19).
-                                 * Decoded: J2KGPU_CBLK_RESET | _VCAUSAL | _PREDTERM | _SEGSYM; _BYPASS and _TERMALL
-                                 * (several codeword segments per block) return J2KGPU_E_UNSUPPORTED.  REF: set 0 */
+    uint8_t  cblk_style;        /* ISO mode, classic (non-HT) blocks: code-block style bits of COD SPcod (Table A.19),
+                                 * all six decoded.  With J2KGPU_CBLK_BYPASS or _TERMALL a block consists of several
+                                 * codeword segments (with TERMALL one per coding pass; with BYPASS alone passes 0..9,
+                                 * then per bit-plane one raw segment for significance + refinement and one MQ segment
+                                 * for the cleanup pass): the block's data_len bytes are the segments back to back, and
+                                 * they are FOLLOWED in the blob by one little-endian uint32 byte count per segment its
+                                 * num_passes touch (not counted in data_len; B.10.7.2 signals these lengths in the
+                                 * packet headers).  REF: set 0 */
     uint8_t  rsv;               /* set 0                                                      */
 } j2k_image_t;
 #define J2KGPU_CBLK_BYPASS   0x01u
@@ -214,8 +219,8 @@ int j2kgpu_decode_batch(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t 
  * decoder.go:350-356); every other box -- palette, channel definition, resolution -- stays with decoder.readJP2
  * (decoder.go:206-253).  reduce =
  * Config.ReduceResolution (jpeg2000.go:205-207).  Unsupported features (sub-sampling, COC/QCC/POC/PPM/PPT,
- * the code-block styles selective bypass and termination on each pass) return J2KGPU_E_UNSUPPORTED; RESET, VCAUSAL,
- * PREDTERM and SEGSYM blocks are decoded (j2k_image_t.cblk_style). */
+ * HT blocks with classic style bits) return J2KGPU_E_UNSUPPORTED; all six classic code-block styles are decoded
+ * (j2k_image_t.cblk_style). */
 typedef struct j2kgpu_parsed j2kgpu_parsed;
 /* *out is always set (free it with j2kgpu_parsed_free); on failure j2kgpu_parsed_error(*out) says why.  No CUDA involved. */
 int         j2kgpu_parse_codestream(const uint8_t *cs, uint64_t len, uint32_t reduce, uint32_t threads, j2kgpu_parsed **out);

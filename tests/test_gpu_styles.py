@@ -80,23 +80,57 @@ def test_batch_of_frames_with_different_styles(j2k, gpu_ctx):
         assert np.array_equal(got.reshape(h, w, -1)[:, :, :3], np.moveaxis(s, 0, 2))
 
 
-@pytest.mark.parametrize("style", [0x01, 0x04, 0x40 | 0x02])
-def test_segmented_styles_are_refused(j2k, gpu_ctx, style):
-    img = j2k.make_image(64, 64, 1, 8, mct=0, nlevels=0, ht=0, mode=ISO, cblk_style=style & 0x3F)
+BYPASS, TERMALL = 0x01, 0x04
+SEGMENTED = [TERMALL, BYPASS, BYPASS | TERMALL, TERMALL | RESET, BYPASS | VCAUSAL | SEGSYM, 0x3F, BYPASS | TERMALL | PREDTERM]
+
+
+@pytest.mark.parametrize("style", SEGMENTED)
+@pytest.mark.parametrize("w,h,nc,kw", [
+    (200, 150, 3, dict(num_resolutions=4)),
+    (131, 77, 1, dict(num_resolutions=3, cblk=(32, 32))),
+    (256, 192, 3, dict(num_resolutions=5, tile=(128, 128), rates=[30, 8, 1])),
+    (240, 160, 3, dict(num_resolutions=4, irreversible=True, rates=[25, 6])),
+])
+def test_segmented_styles_codestream_in_pixels_out(j2k, gpu_ctx, style, w, h, nc, kw):
+    """selective bypass / termination on each pass (several codeword segments per block, raw passes): front door == OpenJPEG,
+    for every lanes-per-block variant of the kernel and with int32 planes as well"""
+    s = jobs.synth_image(w, h, nc, 8, seed=style + w)
+    data = opj.encode(s, mode=style, **kw)
+    ref = opj_decode(data)
+    assert np.array_equal(gpu_ctx.decode_codestream(data).reshape(h, w, -1)[:, :, :nc], ref)
+    for opts in (dict(t1_group=4), dict(t1_group=32), dict(coef32=1)):
+        with gpu_ctx.options(**opts):
+            assert np.array_equal(gpu_ctx.decode_codestream(data).reshape(h, w, -1)[:, :, :nc], ref), opts
+
+
+def test_segment_table_outside_blob_is_refused(j2k, gpu_ctx):
+    img = j2k.make_image(64, 64, 1, 8, mct=0, nlevels=0, ht=0, mode=ISO, cblk_style=TERMALL)
     tcs = (j2k.TileComp * 1)(j2k.TileComp(0, 0, 0, 64, 64, 0))
     cbs = (j2k.CBlk * 1)()
     cbs[0].w = cbs[0].h = 64
-    if style & 0x40:
-        return                                                    # HT + classic style bits is a tier-2 matter (CPU test)
+    cbs[0].num_bps, cbs[0].num_passes, cbs[0].data_len, cbs[0].step = 3, 7, 8, 1.0
+    with pytest.raises(j2k.J2KError) as e:
+        gpu_ctx.decode_tiles(img, tcs, cbs, np.zeros(16, np.uint8))          # 8 code bytes + 7 x 4 table bytes do not fit in 16
+    assert e.value.code == j2k.E_RANGE
+    img = j2k.make_image(64, 64, 1, 8, mct=0, nlevels=0, ht=0, mode=ISO, cblk_style=0x40)
     with pytest.raises(j2k.J2KError):
-        gpu_ctx.decode_tiles(img, tcs, cbs, np.zeros(8, np.uint8))
+        gpu_ctx.decode_tiles(img, tcs, cbs, np.zeros(64, np.uint8))
+
+
+def test_batch_with_segmented_and_plain_frames(j2k, gpu_ctx):
+    w, h = 192, 128
+    modes = [0, TERMALL, BYPASS, 0x3F, 0x02, BYPASS | TERMALL]
+    srcs = [jobs.synth_image(w, h, 3, 8, seed=70 + i) for i in range(len(modes))]
+    streams = [opj.encode(s, mode=m, num_resolutions=4) for s, m in zip(srcs, modes)]
+    for s, got in zip(srcs, gpu_ctx.decode_codestreams(streams)):
+        assert np.array_equal(got.reshape(h, w, -1)[:, :, :3], np.moveaxis(s, 0, 2))
 
 
 def test_4k_rgb_all_styles_lossless(j2k, gpu_ctx):
-    """BASELINE cfg2's geometry (3840x2160 RGB, 5 levels, 64x64 blocks) written by OpenJPEG with RESET | VCAUSAL | PREDTERM |
-    SEGSYM: the front door returns the source"""
+    """BASELINE cfg2's geometry (3840x2160 RGB, 5 levels, 64x64 blocks) written by OpenJPEG with all six style bits (BYPASS |
+    RESET | TERMALL | VCAUSAL | PREDTERM | SEGSYM): the front door returns the source"""
     s = jobs.synth_image(3840, 2160, 3, 8, seed=9)
-    data = opj.encode(s, mode=RESET | VCAUSAL | PREDTERM | SEGSYM, num_resolutions=6, tile=(1024, 1024))
+    data = opj.encode(s, mode=0x3F, num_resolutions=6, tile=(1024, 1024))
     got = gpu_ctx.decode_codestream(data).reshape(2160, 3840, -1)[:, :, :3]
     assert np.array_equal(got, np.moveaxis(s, 0, 2))
 

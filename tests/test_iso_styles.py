@@ -79,13 +79,47 @@ def test_product_tier2_carries_the_style(j2k, style):
         p.close()
 
 
-@pytest.mark.parametrize("style", [0x01, 0x04, 0x05])
-def test_product_tier2_refuses_segmented_styles(j2k, style):
-    s = jobs.synth_image(64, 64, 1, 8, seed=2)
-    data = opj.encode(s, mode=style, num_resolutions=2)
-    with pytest.raises(j2k.J2KError) as e:
-        j2k.Parsed(data)
-    assert "style" in str(e.value)
+BYPASS, TERMALL = 0x01, 0x04
+SEGMENTED = [TERMALL, BYPASS, BYPASS | TERMALL, TERMALL | RESET, BYPASS | VCAUSAL | SEGSYM, 0x3F, BYPASS | TERMALL | PREDTERM]
+
+
+def checker_from_product_tier2(j2k, data):
+    """the product's tier-2 (host code) fills the tables, the CPU checker decodes them"""
+    p = j2k.Parsed(data)
+    try:
+        im = p.image
+        tcs, cbs, blob = p.tables()
+        job = dict(width=im.width, height=im.height, ncomp=im.ncomp, prec=im.prec[0], sgnd=im.sgnd[0], mct=im.mct, reversible=im.reversible,
+                   nlevels=im.nlevels, ht=im.ht, tilecomps=tcs, cblks=cbs, blob=np.concatenate([blob, np.zeros(8, np.uint8)]),
+                   cblk_style=im.cblk_style, colorspace=im.colorspace)
+        return O.iso_decode_job(job).reshape(im.height, im.width, -1)[:, :, :im.ncomp], im.cblk_style
+    finally:
+        p.close()
+
+
+@pytest.mark.parametrize("style", SEGMENTED)
+@pytest.mark.parametrize("w,h,nc,kw", [
+    (200, 150, 3, dict(num_resolutions=4)),
+    (131, 77, 1, dict(num_resolutions=3, cblk=(32, 32))),
+    (256, 192, 3, dict(num_resolutions=5, tile=(128, 128), rates=[30, 8, 1])),
+    (240, 160, 3, dict(num_resolutions=4, irreversible=True, rates=[25, 6])),
+])
+def test_segmented_styles_tier2_and_checker_equal_openjpeg(j2k, style, w, h, nc, kw):
+    """selective arithmetic-coding bypass and termination on each coding pass: several codeword segments per block, their
+    lengths signalled per segment in the packet headers (B.10.7.2) -- product tier-2 + checker == OpenJPEG's own decode"""
+    s = jobs.synth_image(w, h, nc, 8, seed=style + w)
+    data = opj.encode(s, mode=style, **kw)
+    got, st = checker_from_product_tier2(j2k, data)
+    assert st == style
+    assert np.array_equal(np.moveaxis(got, 2, 0), opj_decode(data))
+
+
+def test_segment_count():
+    L = O.lib()
+    assert [L.iso_t1_num_segments(0, n) for n in (1, 10, 40)] == [1, 1, 1]
+    assert [L.iso_t1_num_segments(TERMALL, n) for n in (1, 2, 10, 11)] == [1, 2, 10, 11]
+    # bypass: passes 0..9 | (10, 11) raw | 12 cleanup | (13, 14) raw | 15 cleanup ...
+    assert [L.iso_t1_num_segments(BYPASS, n) for n in (1, 10, 11, 12, 13, 14, 15, 16)] == [1, 1, 2, 2, 3, 4, 4, 5]
 
 
 GOLD = ["reset", "vcausal", "segsym", "all_four_layers_tiles", "all_four_lossy_97"]
