@@ -135,7 +135,8 @@ def test_4k_rgb_all_styles_lossless(j2k, gpu_ctx):
     assert np.array_equal(got, np.moveaxis(s, 0, 2))
 
 
-@pytest.mark.parametrize("name", ["reset", "vcausal", "segsym", "all_four_layers_tiles", "all_four_lossy_97"])
+@pytest.mark.parametrize("name", ["reset", "vcausal", "segsym", "all_four_layers_tiles", "all_four_lossy_97", "termall", "bypass",
+        "all_six_layers_tiles", "bypass_termall_lossy_97"])
 def test_golden_styled_streams(gpu_ctx, name):
     """committed bytes OpenJPEG wrote with each style -> front door -> the committed pixels OpenJPEG decoded from them"""
     import os

@@ -122,16 +122,16 @@ def test_segment_count():
     assert [L.iso_t1_num_segments(BYPASS, n) for n in (1, 10, 11, 12, 13, 14, 15, 16)] == [1, 1, 2, 2, 3, 4, 4, 5]
 
 
-GOLD = ["reset", "vcausal", "segsym", "all_four_layers_tiles", "all_four_lossy_97"]
+GOLD = ["reset", "vcausal", "segsym", "all_four_layers_tiles", "all_four_lossy_97", "termall", "bypass",
+        "all_six_layers_tiles", "bypass_termall_lossy_97"]
 
 
 @pytest.mark.parametrize("name", GOLD)
-def test_golden_styled_streams_checker(name):
-    """tests/golden/iso_styles.npz (tests/golden/make_golden_styles.py): bytes OpenJPEG wrote, pixels OpenJPEG decoded"""
+def test_golden_styled_streams_checker(j2k, name):
+    """tests/golden/iso_styles.npz (tests/golden/make_golden_styles.py): bytes OpenJPEG wrote, pixels OpenJPEG decoded;
+    the product's tier-2 fills the tables, the CPU checker decodes them"""
     import os
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "iso_styles.npz"))
     data, ref = g[name + "_j2k"].tobytes(), g[name + "_pix"]
-    job = jobs.build_iso_job_from_codestream(data)
-    h, w, nc = job["height"], job["width"], job["ncomp"]
-    got = O.iso_decode_job(job).reshape(h, w, -1)[:, :, :nc]
-    assert np.array_equal(got, ref.reshape(h, w, nc))
+    got, _ = checker_from_product_tier2(j2k, data)
+    assert np.array_equal(got, ref.reshape(got.shape))

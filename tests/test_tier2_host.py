@@ -276,6 +276,11 @@ def test_fuzz_contract_never_faults(j2k):
     s = jobs.synth_image(96, 80, 3, 8, seed=4)
     streams = [opj_encode(s, num_resolutions=3, mct=1, quality_layers=[10, 1], tile_size=(64, 64)),
                jobs.build_iso_job(s, 8, 64, 64, 2, ht_passes=3, ht_plane=1)["codestream"]]
+    try:                                                  # a stream with several codeword segments per block (BYPASS | TERMALL)
+        from datagen import opj_direct
+        streams.append(opj_direct.encode(s, mode=0x05, num_resolutions=3, tile=(64, 64), rates=[10, 1]))
+    except OSError:
+        pass
     rng = np.random.default_rng(11)
     for data in streams:
         ok = 0
