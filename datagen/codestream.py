@@ -640,3 +640,35 @@ def wrap_jp2(codestream, enumcs=16, width=0, height=0, ncomp=3, bpc=7, colr_meth
     head = box(b"jP  ", b"\r\n\x87\n") + box(b"ftyp", b"jp2 " + struct.pack(">I", 0) + b"jp2 ")
     body = box(b"jp2c", bytes(codestream))
     return head + (body + jp2h if header_after else jp2h + body)
+
+
+def with_qcc(data, scramble_qcd=True):
+    """TEST HARNESS: the same codestream with a QCC marker segment per component that repeats what QCD says, and (scramble_qcd)
+    a QCD rewritten to other guard bits / exponents -- every component then takes its quantisation from its QCC, so a decoder
+    that honours QCC (A.6.5) reproduces the original image and one that does not cannot."""
+    data = bytes(data)
+    pos, ncomp, out, qcd_at = 2, None, None, None
+    while True:
+        m, L = struct.unpack(">HH", data[pos:pos + 4])
+        if m == SOT:
+            break
+        if m == SIZ:
+            ncomp = struct.unpack(">H", data[pos + 38:pos + 40])[0]
+        if m == QCD:
+            qcd_at = (pos, L)
+        pos += 2 + L
+    p, L = qcd_at
+    body = data[p + 4:p + 2 + L]                                     # Sqcd + SPqcd
+    qccs = b"".join(struct.pack(">HH", 0xFF5D, 2 + 1 + len(body)) + bytes([c]) + body for c in range(ncomp))
+    qcd = bytearray(data[p:p + 2 + L])
+    if scramble_qcd:
+        style = body[0] & 31
+        qcd[4] = (((body[0] >> 5) + 1) & 7) << 5 | style              # another number of guard bits
+        if style == 0:
+            for i in range(5, len(qcd)):
+                qcd[i] = (((qcd[i] >> 3) + 2) & 31) << 3
+        else:
+            for i in range(5, len(qcd) - 1, 2):
+                v = struct.unpack(">H", qcd[i:i + 2])[0]
+                qcd[i:i + 2] = struct.pack(">H", ((((v >> 11) + 1) & 31) << 11) | ((v + 77) & 0x7FF))
+    return data[:p] + bytes(qcd) + qccs + data[p + 2 + L:]

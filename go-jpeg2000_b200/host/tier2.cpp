@@ -1,4 +1,4 @@
-// tier2.cpp -- see tier2.h.  Main header (SIZ, CAP, COD, QCD, TLM, COM), tile-part index (SOT / Psot, TLM cross-check), packet
+// tier2.cpp -- see tier2.h.  Main header (SIZ, CAP, COD, QCD, QCC, TLM, COM), tile-part index (SOT / Psot, TLM cross-check), packet
 // headers (tag trees, number of passes, Lblock, segment lengths; SOP / EPH; PLT cross-check) for all five progression orders
 // with maximal or user-defined precincts, any number of quality layers, classic and HT code blocks (one HT set: the cleanup length and the
 // SigProp + MagRef length are separate codeword segments, T.814 B.10.7).  Tiles are parsed concurrently.
@@ -48,6 +48,11 @@ struct Header {
     uint8_t ppx[33], ppy[33];                            // precinct size exponents per resolution (15 = maximal)
     bool have_siz = false, have_cod = false, have_qcd = false;
     std::vector<std::pair<uint32_t, uint32_t>> q;      // per band in codestream order: exponent, mantissa
+    // QCC (A.6.5): a component's own guard bits and step sizes override QCD's for that component
+    struct QComp { bool set = false; uint32_t guard = 0; std::vector<std::pair<uint32_t, uint32_t>> q; };
+    std::vector<QComp> qc;                             // per component (empty: no QCC in the main header)
+    uint32_t guard_of(uint32_t c) const { return c < qc.size() && qc[c].set ? qc[c].guard : guard; }
+    const std::vector<std::pair<uint32_t, uint32_t>> &q_of(uint32_t c) const { return c < qc.size() && qc[c].set ? qc[c].q : q; }
 };
 
 struct BandId { uint32_t res, band, lvl; };
@@ -437,8 +442,8 @@ void parse_tile(const uint8_t *cs, const Header &h, uint32_t tidx, const std::ve
     for (const Blk &e : blks) {
         const BandId &b = bands[e.bidx];
         if (b.res > nl - reduce) continue;                 // ReduceResolution: the finest resolutions are not handed over
-        const uint32_t expn = h.q[e.bidx].first, mant = h.q[e.bidx].second;
-        const int mb = (int)h.guard + (int)expn - 1;
+        const uint32_t expn = h.q_of(e.comp)[e.bidx].first, mant = h.q_of(e.comp)[e.bidx].second;
+        const int mb = (int)h.guard_of(e.comp) + (int)expn - 1;
         j2k_cblk_t cb{};
         cb.tilecomp = e.comp; cb.x0 = (uint16_t)e.px; cb.y0 = (uint16_t)e.py; cb.w = (uint16_t)e.w; cb.h = (uint16_t)e.h;
         cb.band = (uint8_t)b.band; cb.level = (uint8_t)(b.lvl > reduce ? b.lvl - reduce : 0);
@@ -623,7 +628,22 @@ int j2k_tier2_begin(const uint8_t *d, uint64_t len, uint32_t reduce, j2k_t2_fram
                 const uint32_t esz = st + (sp ? 4 : 2);
                 if (st <= 2) for (uint32_t i = 2; i + esz <= sl; i += esz) tlm.push_back(sp ? be32(seg + i + st) : be16(seg + i + st));
             }
-        } else if (m == COC || m == QCC || m == RGN || m == POC || m == PPM || m == PLM) {
+        } else if (m == QCC) {                            // A.6.5: Cqcc (1 byte below 257 components, else 2), then as QCD
+            if (!h.have_siz) T2_FAIL(J2KGPU_E_RANGE, "QCC before SIZ");
+            const uint32_t cw = h.ncomp < 257 ? 1 : 2;
+            if (sl < cw + 1) T2_FAIL(J2KGPU_E_RANGE, "QCC too short");
+            const uint32_t c = cw == 1 ? seg[0] : be16(seg);
+            if (c >= h.ncomp) T2_FAIL(J2KGPU_E_RANGE, "QCC for component %u of %u", c, h.ncomp);
+            const uint8_t *qs = seg + cw;
+            const uint32_t ql = sl - cw, style = qs[0] & 31;
+            if (h.qc.empty()) h.qc.resize(h.ncomp);
+            Header::QComp &qc = h.qc[c];
+            qc.set = true; qc.guard = qs[0] >> 5; qc.q.clear();
+            if (style == 0) for (uint32_t i = 1; i < ql; i++) qc.q.push_back({(uint32_t)qs[i] >> 3, 0u});
+            else if (style == 1 || style == 2) for (uint32_t i = 1; i + 1 < ql; i += 2) qc.q.push_back({be16(qs + i) >> 11, be16(qs + i) & 0x7FFu});
+            else T2_FAIL(J2KGPU_E_RANGE, "quantisation style %u", style);
+            if (style == 1) { qc.q.resize(1); qc.q.push_back({0xFFFFFFFFu, 0}); }
+        } else if (m == COC || m == RGN || m == POC || m == PPM || m == PLM) {
             T2_FAIL(J2KGPU_E_UNSUPPORTED, "marker %04X", m);
         }
         pos += 2 + L;
@@ -638,6 +658,15 @@ int j2k_tier2_begin(const uint8_t *d, uint64_t len, uint32_t reduce, j2k_t2_fram
         for (const BandId &b : bands) h.q.push_back({q0.first + b.lvl >= h.nlevels ? q0.first + b.lvl - h.nlevels : 0u, q0.second});
     }
     if (h.q.size() < bands.size()) T2_FAIL(J2KGPU_E_RANGE, "QCD lists %zu bands, %zu needed", h.q.size(), bands.size());
+    for (Header::QComp &qc : h.qc) {
+        if (!qc.set) continue;
+        if (qc.q.size() == 2 && qc.q[1].first == 0xFFFFFFFFu) {
+            const auto q0 = qc.q[0];
+            qc.q.clear();
+            for (const BandId &b : bands) qc.q.push_back({q0.first + b.lvl >= h.nlevels ? q0.first + b.lvl - h.nlevels : 0u, q0.second});
+        }
+        if (qc.q.size() < bands.size()) T2_FAIL(J2KGPU_E_RANGE, "QCC lists %zu bands, %zu needed", qc.q.size(), bands.size());
+    }
     if (reduce > h.nlevels) T2_FAIL(J2KGPU_E_ARG, "reduce %u > %u decomposition levels", reduce, h.nlevels);
     const uint32_t ntx = cdiv(h.W, h.tile_w), nty = cdiv(h.H, h.tile_h);
     if ((uint64_t)ntx * nty > 65535) T2_FAIL(J2KGPU_E_UNSUPPORTED, "too many tiles");
@@ -745,7 +774,8 @@ int j2k_tier2_finish(j2k_t2_frame *F, j2kgpu_parsed &out)
     im.mct = (h.mct && h.ncomp >= 3) ? 1 : 0; im.reversible = (uint8_t)h.reversible; im.nlevels = (uint8_t)(h.nlevels - reduce);
     im.ht = (uint8_t)h.ht; im.mode = J2KGPU_MODE_ISO; im.out_fmt = J2KGPU_FMT_AUTO;
     uint32_t cbits = 0;
-    for (size_t bi = 0; bi < bands.size(); bi++) cbits = std::max(cbits, h.q[bi].first + h.guard - 1);
+    for (uint32_t c = 0; c < h.ncomp; c++)
+        for (size_t bi = 0; bi < bands.size(); bi++) cbits = std::max(cbits, h.q_of(c)[bi].first + h.guard_of(c) - 1);
     im.coef_bits = (uint8_t)std::min(cbits, 255u);
     im.cblk_style = h.ht ? 0 : (uint8_t)(h.style & 0x3Fu);
     im.colorspace = (uint8_t)h.colorspace;

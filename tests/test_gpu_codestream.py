@@ -168,3 +168,13 @@ def test_jp2_file_with_colour_specification(j2k, gpu_ctx, enumcs, cconv, kw):
     d = np.abs(got.astype(int) - want.astype(int))
     assert d.max() <= (1 if cconv >= 7 else 0)
     assert np.array_equal(got, plain) == (cconv == 0)
+
+
+@pytest.mark.parametrize("kw", [dict(num_resolutions=4, mct=1), dict(num_resolutions=4, mct=1, irreversible=True, quality_layers=[20, 5])])
+def test_qcc_marker_segments(j2k, gpu_ctx, kw):
+    """per-component quantisation (QCC) with a QCD that says something else: the front door decodes to OpenJPEG's pixels"""
+    from datagen import codestream as cs
+    w, h = 200, 150
+    s = jobs.synth_image(w, h, 3, 8, seed=3)
+    data = cs.with_qcc(opj_encode(s, **kw))
+    assert np.array_equal(pixels(gpu_ctx.decode_codestream(data), h, w, 3), opj_decode(data).reshape(h, w, 3))

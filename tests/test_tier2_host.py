@@ -352,3 +352,27 @@ def test_pillow_jp2_file_parses_like_its_codestream(j2k):
     data = buf.getvalue()
     if b"colr" in data and data[data.index(b"colr") + 4] == 1 and int.from_bytes(data[data.index(b"colr") + 7:data.index(b"colr") + 11], "big") == 18:
         assert j2k.Parsed(data).image.colorspace == 1                                       # Pillow writes YCbCr images as sYCC
+
+
+@pytest.mark.parametrize("kw", [dict(num_resolutions=4, mct=1), dict(num_resolutions=4, mct=1, irreversible=True, quality_layers=[20, 5]),
+                                dict(num_resolutions=3, mct=1, irreversible=True, tile_size=(64, 64))])
+def test_qcc_overrides_qcd(j2k, kw):
+    """QCC (A.6.5): datagen.codestream.with_qcc gives every component a QCC that repeats the stream's QCD and rewrites QCD to
+    other guard bits / exponents.  OpenJPEG decodes both streams to the same pixels, and the product's tier-2 fills the same
+    tables (bit-plane counts, steps, coef_bits) from both; the rewritten QCD alone gives other tables."""
+    s = jobs.synth_image(200, 150, 3, 8, seed=3)
+    d0 = opj_encode(s, **kw)
+    d1 = cs.with_qcc(d0)
+    assert np.array_equal(opj_decode(d0), opj_decode(d1))
+    p0, p1 = j2k.Parsed(d0), j2k.Parsed(d1)
+    (_, c0, _), (_, c1, _) = p0.tables(), p1.tables()
+    for f in ("data_len", "num_bps", "num_passes", "step", "band", "level", "x0", "y0", "w", "h", "tilecomp"):
+        assert np.array_equal(c0[f], c1[f]), f
+    assert p0.image.coef_bits == p1.image.coef_bits
+    k = d1.index(b"\xff\x5d")
+    no_qcc = d1[:k] + d1[k + 3 * (d1[k + 2] * 256 + d1[k + 3] + 2):]                 # the scrambled QCD without the three QCCs
+    p2 = j2k.Parsed(no_qcc)
+    c2 = p2.tables()[1]
+    assert not (np.array_equal(c0["num_bps"], c2["num_bps"]) and np.array_equal(c0["step"], c2["step"]))
+    for p in (p0, p1, p2):
+        p.close()
