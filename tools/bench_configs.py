@@ -36,6 +36,11 @@ ISO_CONFIGS = {
                      "3840x2160 RGB 8-bit lossless 5-3, 512x512 tiles, EBCOT, written by OpenJPEG"),
     "iso_4k_lossy": (3840, 2160, 3, dict(irreversible=True, num_resolutions=6, mct=1, quality_mode="rates", quality_layers=[80, 40, 20, 10, 5]), 2,
                      "3840x2160 RGB 8-bit lossy 9-7 EBCOT, ICT, 5 quality layers, LRCP, 1 tile, written by OpenJPEG (configs[2] at 8 bits)"),
+    # code-block styles: OpenJPEG's encoder through its C API (datagen/opj_direct.py), tables from the product's tier-2
+    "iso_4k_bypass": (3840, 2160, 3, dict(opj_mode=0x01, num_resolutions=6, mct=1, tile=(512, 512)), 2,
+                      "iso_4k_ebcot written with selective arithmetic-coding bypass (raw significance / refinement passes from the 5th bit-plane on)"),
+    "iso_4k_all_styles": (3840, 2160, 3, dict(opj_mode=0x3F, num_resolutions=6, mct=1, tile=(512, 512)), 2,
+                          "iso_4k_ebcot written with all six code-block styles (BYPASS RESET TERMALL VCAUSAL PREDTERM SEGSYM)"),
     # written by datagen.codestream.write_htj2k (OpenJPEG 2.5 decodes HTJ2K but does not write it)
     "iso_cfg5": (1920, 1080, 3, dict(htj2k=True, lossy_step=1.0, nlevels=5), 32,
                  "configs[4] as a real codestream: 1920x1080 RGB 8-bit lossy 9-7 HTJ2K, ICT, 1 tile, 64x64 blocks (batch of frames)"),
@@ -56,15 +61,26 @@ def run_iso(name, args, j2k, ctx, stream):
     s = jobs.synth_image(W, H, nc, 8, seed=77)
     buf = io.BytesIO()
     t0 = time.perf_counter()
+    parsed = None
     if kw.get("htj2k"):
         from datagen import codestream as cs
         data, _ = cs.write_htj2k(s, 8, kw.get("tile"), kw.get("tile"), kw["nlevels"], lossy_step=kw["lossy_step"])
+    elif "opj_mode" in kw:
+        from datagen import opj_direct
+        data = opj_direct.encode(s, mode=kw["opj_mode"], num_resolutions=kw["num_resolutions"], mct=kw["mct"], tile=kw["tile"])
     else:
         Image.fromarray(np.moveaxis(s, 0, 2).astype(np.uint8)).save(buf, format="JPEG2000", no_jp2=True, **kw)
         data = buf.getvalue()
     t_enc = time.perf_counter() - t0
     t0 = time.perf_counter()
-    job = jobs.build_iso_job_from_codestream(data)
+    if "opj_mode" in kw:                                   # the harness's Python tier-2 does not read segmented blocks: product tier-2
+        parsed = j2k.Parsed(data)
+        tcs_np, cbs_np, blob_np = parsed.tables()
+        pim = parsed.image
+        job = dict(mct=pim.mct, reversible=pim.reversible, nlevels=pim.nlevels, ht=pim.ht, coef_bits=pim.coef_bits, layers=parsed.info["layers"],
+                   tilecomps=tcs_np, cblks=cbs_np, blob=np.concatenate([blob_np, np.zeros(8, np.uint8)]), cblk_style=pim.cblk_style)
+    else:
+        job = jobs.build_iso_job_from_codestream(data)
     t_parse = time.perf_counter() - t0
     t0 = time.perf_counter()
     im = Image.open(io.BytesIO(data))
@@ -75,7 +91,7 @@ def run_iso(name, args, j2k, ctx, stream):
     tcs, cbs = jobs.as_ctypes(job["tilecomps"], j2k.TileComp), jobs.as_ctypes(job["cblks"], j2k.CBlk)
     blob = np.ascontiguousarray(job["blob"])
     img = j2k.make_image(W, H, nc, 8, mct=job["mct"], reversible=job["reversible"], nlevels=job["nlevels"], ht=job["ht"], mode=1,
-                         coef_bits=job["coef_bits"])
+                         coef_bits=job["coef_bits"], cblk_style=job.get("cblk_style", 0))
     outs = [np.zeros(stride * H, np.uint8) for _ in range(F)]
     items = [j2k.BatchItem(img, tcs, len(tcs), cbs, len(cbs), blob.ctypes.data_as(j2k.u8p), blob.size,
                            o.ctypes.data_as(j2k.u8p), stride) for o in outs]
