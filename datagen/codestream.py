@@ -672,3 +672,26 @@ def with_qcc(data, scramble_qcd=True):
                 v = struct.unpack(">H", qcd[i:i + 2])[0]
                 qcd[i:i + 2] = struct.pack(">H", ((((v >> 11) + 1) & 31) << 11) | ((v + 77) & 0x7FF))
     return data[:p] + bytes(qcd) + qccs + data[p + 2 + L:]
+
+
+def with_coc(data, scramble_cod=True):
+    """TEST HARNESS: the same codestream with a COC marker segment per component that repeats COD's SPcod, and (scramble_cod) a
+    COD that announces other code-block dimensions -- every component then takes its coding parameters from its COC (A.6.2)."""
+    data = bytes(data)
+    pos, ncomp, cod_at = 2, None, None
+    while True:
+        m, L = struct.unpack(">HH", data[pos:pos + 4])
+        if m == SOT:
+            break
+        if m == SIZ:
+            ncomp = struct.unpack(">H", data[pos + 38:pos + 40])[0]
+        if m == COD:
+            cod_at = (pos, L)
+        pos += 2 + L
+    p, L = cod_at
+    scod, spcod = data[p + 4], data[p + 9:p + 2 + L]                 # SPcod: levels, xcb, ycb, style, transform[, precincts]
+    cocs = b"".join(struct.pack(">HH", 0xFF53, 2 + 1 + 1 + len(spcod)) + bytes([c, scod & 1]) + spcod for c in range(ncomp))
+    cod = bytearray(data[p:p + 2 + L])
+    if scramble_cod:
+        cod[10] = cod[11] = 3 if cod[10] != 3 else 2                  # 32 x 32 (or 16 x 16) code blocks, says COD
+    return data[:p] + bytes(cod) + cocs + data[p + 2 + L:]

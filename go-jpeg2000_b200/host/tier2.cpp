@@ -1,4 +1,4 @@
-// tier2.cpp -- see tier2.h.  Main header (SIZ, CAP, COD, QCD, QCC, TLM, COM), tile-part index (SOT / Psot, TLM cross-check), packet
+// tier2.cpp -- see tier2.h.  Main header (SIZ, CAP, COD, COC, QCD, QCC, TLM, COM), tile-part index (SOT / Psot, TLM cross-check), packet
 // headers (tag trees, number of passes, Lblock, segment lengths; SOP / EPH; PLT cross-check) for all five progression orders
 // with maximal or user-defined precincts, any number of quality layers, classic and HT code blocks (one HT set: the cleanup length and the
 // SigProp + MagRef length are separate codeword segments, T.814 B.10.7).  Tiles are parsed concurrently.
@@ -51,6 +51,11 @@ struct Header {
     // QCC (A.6.5): a component's own guard bits and step sizes override QCD's for that component
     struct QComp { bool set = false; uint32_t guard = 0; std::vector<std::pair<uint32_t, uint32_t>> q; };
     std::vector<QComp> qc;                             // per component (empty: no QCC in the main header)
+    // COC (A.6.2): a component's own decomposition levels, code-block size / style, transform and precinct sizes.  The device
+    // path wants the components of a tile to share one geometry, so COC is accepted when every component ends up with the same
+    // parameters (each from its COC, or from COD); they then replace COD's.
+    struct CComp { bool set = false; uint32_t nlevels = 0, cbw = 0, cbh = 0, style = 0, reversible = 0; uint8_t ppx[33], ppy[33]; };
+    std::vector<CComp> cc;
     uint32_t guard_of(uint32_t c) const { return c < qc.size() && qc[c].set ? qc[c].guard : guard; }
     const std::vector<std::pair<uint32_t, uint32_t>> &q_of(uint32_t c) const { return c < qc.size() && qc[c].set ? qc[c].q : q; }
 };
@@ -643,12 +648,47 @@ int j2k_tier2_begin(const uint8_t *d, uint64_t len, uint32_t reduce, j2k_t2_fram
             else if (style == 1 || style == 2) for (uint32_t i = 1; i + 1 < ql; i += 2) qc.q.push_back({be16(qs + i) >> 11, be16(qs + i) & 0x7FFu});
             else T2_FAIL(J2KGPU_E_RANGE, "quantisation style %u", style);
             if (style == 1) { qc.q.resize(1); qc.q.push_back({0xFFFFFFFFu, 0}); }
-        } else if (m == COC || m == RGN || m == POC || m == PPM || m == PLM) {
+        } else if (m == COC) {                            // A.6.2: Ccoc, Scoc, then SPcoc laid out like SPcod
+            if (!h.have_siz) T2_FAIL(J2KGPU_E_RANGE, "COC before SIZ");
+            const uint32_t cw = h.ncomp < 257 ? 1 : 2;
+            if (sl < cw + 6) T2_FAIL(J2KGPU_E_RANGE, "COC too short");
+            const uint32_t c = cw == 1 ? seg[0] : be16(seg);
+            if (c >= h.ncomp) T2_FAIL(J2KGPU_E_RANGE, "COC for component %u of %u", c, h.ncomp);
+            const uint8_t *sp = seg + cw + 1;
+            if (h.cc.empty()) h.cc.resize(h.ncomp);
+            Header::CComp &q = h.cc[c];
+            q.set = true; q.nlevels = sp[0]; q.cbw = 1u << ((sp[1] & 15) + 2); q.cbh = 1u << ((sp[2] & 15) + 2); q.style = sp[3]; q.reversible = sp[4] == 1;
+            if (q.nlevels > 10) T2_FAIL(J2KGPU_E_UNSUPPORTED, "%u decomposition levels", q.nlevels);
+            for (uint32_t r = 0; r <= 32; r++) q.ppx[r] = q.ppy[r] = 15;
+            if (seg[cw] & 1) {
+                if (sl < cw + 6 + q.nlevels + 1) T2_FAIL(J2KGPU_E_RANGE, "COC too short for its precinct sizes");
+                for (uint32_t r = 0; r <= q.nlevels; r++) {
+                    q.ppx[r] = sp[5 + r] & 15; q.ppy[r] = sp[5 + r] >> 4;
+                    if (r && (q.ppx[r] == 0 || q.ppy[r] == 0)) T2_FAIL(J2KGPU_E_RANGE, "precinct size 1 above resolution 0");
+                }
+            }
+        } else if (m == RGN || m == POC || m == PPM || m == PLM) {
             T2_FAIL(J2KGPU_E_UNSUPPORTED, "marker %04X", m);
         }
         pos += 2 + L;
     }
     if (!h.have_siz || !h.have_cod || !h.have_qcd) T2_FAIL(J2KGPU_E_RANGE, "SIZ / COD / QCD missing");
+    if (!h.cc.empty()) {                                  // COC: every component must end up with the same coding parameters
+        Header::CComp cod;
+        cod.nlevels = h.nlevels; cod.cbw = h.cbw; cod.cbh = h.cbh; cod.style = h.style; cod.reversible = h.reversible;
+        memcpy(cod.ppx, h.ppx, sizeof cod.ppx); memcpy(cod.ppy, h.ppy, sizeof cod.ppy);
+        const Header::CComp &e0 = h.cc[0].set ? h.cc[0] : cod;
+        for (uint32_t c = 1; c < h.ncomp; c++) {
+            const Header::CComp &e = h.cc[c].set ? h.cc[c] : cod;
+            if (e.nlevels != e0.nlevels || e.cbw != e0.cbw || e.cbh != e0.cbh || e.style != e0.style || e.reversible != e0.reversible ||
+                memcmp(e.ppx, e0.ppx, e0.nlevels + 1) || memcmp(e.ppy, e0.ppy, e0.nlevels + 1))
+                T2_FAIL(J2KGPU_E_UNSUPPORTED, "COC: component %u is coded with other parameters than component 0", c);
+        }
+        if (e0.cbw > 64 || e0.cbh > 64 || e0.cbw * e0.cbh > 4096) T2_FAIL(J2KGPU_E_UNSUPPORTED, "code blocks %ux%u", e0.cbw, e0.cbh);
+        if ((e0.style & ~0x7Fu) || ((e0.style & 0x40u) && (e0.style & 0x3Fu))) T2_FAIL(J2KGPU_E_UNSUPPORTED, "code-block style %02X", e0.style);
+        h.nlevels = e0.nlevels; h.cbw = e0.cbw; h.cbh = e0.cbh; h.style = e0.style; h.reversible = e0.reversible;
+        memcpy(h.ppx, e0.ppx, sizeof h.ppx); memcpy(h.ppy, e0.ppy, sizeof h.ppy);
+    }
     if (h.style & 0x40) h.ht = 1;
     F->bands = band_list(h.nlevels);
     const std::vector<BandId> &bands = F->bands;

@@ -218,7 +218,7 @@ int j2kgpu_decode_batch(j2kgpu_ctx *ctx, uint32_t n_img, const j2k_batch_item_t 
  * header's colour specification box selects j2k_image_t.colorspace (decoder.getColorSpace decoder.go:135-178, applied as in
  * decoder.go:350-356); every other box -- palette, channel definition, resolution -- stays with decoder.readJP2
  * (decoder.go:206-253).  reduce =
- * Config.ReduceResolution (jpeg2000.go:205-207).  Unsupported features (sub-sampling, COC/POC/PPM/PPT,
+ * Config.ReduceResolution (jpeg2000.go:205-207).  Unsupported features (sub-sampling, POC/PPM/PPT, COC with differing components,
  * HT blocks with classic style bits) return J2KGPU_E_UNSUPPORTED; all six classic code-block styles are decoded
  * (j2k_image_t.cblk_style). */
 typedef struct j2kgpu_parsed j2kgpu_parsed;

@@ -178,3 +178,5 @@ def test_qcc_marker_segments(j2k, gpu_ctx, kw):
     s = jobs.synth_image(w, h, 3, 8, seed=3)
     data = cs.with_qcc(opj_encode(s, **kw))
     assert np.array_equal(pixels(gpu_ctx.decode_codestream(data), h, w, 3), opj_decode(data).reshape(h, w, 3))
+    data = cs.with_coc(data)                                              # and per-component coding parameters (COC) on top
+    assert np.array_equal(pixels(gpu_ctx.decode_codestream(data), h, w, 3), opj_decode(data).reshape(h, w, 3))

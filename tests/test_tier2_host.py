@@ -259,11 +259,17 @@ def test_16_bit_rgb_written_by_opencv(j2k, rate):
 def test_unsupported_features_are_reported(j2k):
     s = jobs.synth_image(128, 128, 3, 8, seed=3)
     good = opj_encode(s, num_resolutions=3, mct=1)
-    i = good.index(b"\xff\x5c")                                   # a COC marker segment in front of QCD: component-specific coding style
-    coc = b"\xff\x53" + (9).to_bytes(2, "big") + bytes([0, 0, 2, 4, 4, 0, 1])
+    i = good.index(b"\xff\x5c")                                   # a COC marker segment in front of QCD: component 0 with one level less
+    coc = b"\xff\x53" + (9).to_bytes(2, "big") + bytes([0, 0, 1, 4, 4, 0, 1])
     with pytest.raises(j2k.J2KError) as e:
         j2k.Parsed(good[:i] + coc + good[i:])
-    assert e.value.code == j2k.E_UNSUPPORTED and "FF53" in str(e.value)
+    assert e.value.code == j2k.E_UNSUPPORTED and "COC" in str(e.value)
+    same = b"\xff\x53" + (9).to_bytes(2, "big") + bytes([0, 0, 2, 4, 4, 0, 1])   # what COD says anyway: accepted
+    j2k.Parsed(good[:i] + same + good[i:]).close()
+    poc = b"\xff\x5f" + (9).to_bytes(2, "big") + bytes([0, 0, 0, 1, 3, 3, 0])       # progression order change
+    with pytest.raises(j2k.J2KError) as e:
+        j2k.Parsed(good[:i] + poc + good[i:])
+    assert e.value.code == j2k.E_UNSUPPORTED and "FF5F" in str(e.value)
     with pytest.raises(j2k.J2KError) as e:
         j2k.Parsed(b"\x00\x01\x02\x03")
     assert e.value.code == j2k.E_ARG
@@ -376,3 +382,29 @@ def test_qcc_overrides_qcd(j2k, kw):
     assert not (np.array_equal(c0["num_bps"], c2["num_bps"]) and np.array_equal(c0["step"], c2["step"]))
     for p in (p0, p1, p2):
         p.close()
+
+
+@pytest.mark.parametrize("kw", [dict(num_resolutions=4, mct=1), dict(num_resolutions=4, mct=1, irreversible=True, quality_layers=[20, 5], precinct_size=(64, 64)),
+                                dict(num_resolutions=3, mct=1, tile_size=(64, 64))])
+def test_coc_overrides_cod(j2k, kw):
+    """COC (A.6.2): datagen.codestream.with_coc gives every component a COC that repeats the stream's SPcod while COD announces
+    other code-block dimensions.  OpenJPEG decodes both streams to the same pixels and the product's tier-2 fills the same
+    tables from both; components that end up with different parameters are refused by name."""
+    s = jobs.synth_image(200, 150, 3, 8, seed=3)
+    d0 = opj_encode(s, **kw)
+    d1 = cs.with_coc(d0)
+    assert np.array_equal(opj_decode(d0), opj_decode(d1))
+    p0, p1 = j2k.Parsed(d0), j2k.Parsed(d1)
+    (_, c0, _), (_, c1, _) = p0.tables(), p1.tables()
+    assert len(c0) == len(c1)
+    for f in ("data_len", "num_bps", "num_passes", "step", "band", "level", "x0", "y0", "w", "h", "tilecomp"):
+        assert np.array_equal(c0[f], c1[f]), f
+    k = d1.index(b"\xff\x53")
+    for _ in range(2):                                                    # hop to the COC of component 2
+        k += 2 + d1[k + 2] * 256 + d1[k + 3]
+    assert d1[k:k + 2] == b"\xff\x53" and d1[k + 4] == 2
+    mixed = d1[:k] + d1[k + 2 + d1[k + 2] * 256 + d1[k + 3]:]             # component 2 falls back to the (other) COD parameters
+    with pytest.raises(j2k.J2KError) as e:
+        j2k.Parsed(mixed)
+    assert e.value.code == j2k.E_UNSUPPORTED and "component 2" in str(e.value)
+    p0.close(); p1.close()
