@@ -122,10 +122,12 @@ def test_errors_surface_and_the_context_survives(j2k, gpu_ctx):
     with pytest.raises(j2k.J2KError) as e:
         gpu_ctx.decode_codestreams([good, bytes(bad)])
     assert "codestream 1" in str(e.value)
-    i = good.index(b"\xff\x5c")                                   # a COC marker segment (component-specific coding style) is not handled
+    i = good.index(b"\xff\x5c")                                   # a COC that gives component 0 one level less than the others: not handled
     with pytest.raises(j2k.J2KError) as e:
-        gpu_ctx.decode_codestream(good[:i] + b"\xff\x53" + (9).to_bytes(2, "big") + bytes([0, 0, 2, 4, 4, 0, 1]) + good[i:])
+        gpu_ctx.decode_codestream(good[:i] + b"\xff\x53" + (9).to_bytes(2, "big") + bytes([0, 0, 1, 4, 4, 0, 1]) + good[i:])
     assert e.value.code == j2k.E_UNSUPPORTED
+    same = good[:i] + b"\xff\x53" + (9).to_bytes(2, "big") + bytes([0, 0, 2, 4, 4, 0, 1]) + good[i:]   # a COC that repeats COD: decoded
+    assert np.array_equal(pixels(gpu_ctx.decode_codestream(same), 128, 128, 3), np.moveaxis(s, 0, 2))
     trunc = good[: len(good) * 2 // 3]                             # truncated: remaining packets absent, still decodes
     gpu_ctx.decode_codestream(trunc)
     assert np.array_equal(pixels(gpu_ctx.decode_codestream(good), 128, 128, 3), np.moveaxis(s, 0, 2))
